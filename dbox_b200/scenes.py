@@ -1,0 +1,195 @@
+"""Scene generators for BASELINE.json's configs, written against the b2World mirror API (dbox_b200.world) exactly
+as the reference programs are written against dbox, so one function builds the same scene on the GPU library and
+(in the tests) on the CPU oracle.
+
+ config 1  hello_world   examples/hello_world/hello_world.d:31-103
+ config 2  pyramid       examples/demo/tests/pyramid.d:39-78 (+ the demo base class's empty body, framework/test.d:160-161)
+ config 3  tumbler       examples/demo/tests/tumbler.d:40-97 (mixed boxes/circles, scalable container)
+ config 4  pile          SURVEY.md 8(d): jittered box/circle grid on a chain floor with revolute + distance chains
+"""
+import ctypes as C
+import random
+
+from .world import (b2BodyDef, b2ChainShape, b2CircleShape, b2DistanceJointDef, b2EdgeShape, b2FixtureDef,
+                    b2PolygonShape, b2RevoluteJointDef, b2Vec2, b2World, b2_dynamicBody, b2_pi)
+
+
+def f32(x):
+    return C.c_float(x).value
+
+
+def hello_world(api=None, **kw):
+    world = b2World((0.0, -10.0), api=api, **kw)
+    groundBodyDef = b2BodyDef()
+    groundBodyDef.position.Set(0.0, -10.0)
+    groundBody = world.CreateBody(groundBodyDef)
+    groundBox = b2PolygonShape(world._api)
+    groundBox.SetAsBox(50.0, 10.0)
+    groundBody.CreateFixture(groundBox, 0.0)
+    bodyDef = b2BodyDef()
+    bodyDef.type = b2_dynamicBody
+    bodyDef.position.Set(0.0, 4.0)
+    body = world.CreateBody(bodyDef)
+    dynamicBox = b2PolygonShape(world._api)
+    dynamicBox.SetAsBox(1.0, 1.0)
+    fixtureDef = b2FixtureDef()
+    fixtureDef.shape = dynamicBox
+    fixtureDef.density = 1.0
+    fixtureDef.friction = 0.3
+    body.CreateFixture(fixtureDef)
+    return world, body
+
+
+def pyramid(api=None, count=20, demo_ground_body=True, world=None, offset=(0.0, 0.0), **kw):
+    if world is None:
+        world = b2World((0.0, -10.0), api=api, **kw)
+    ox, oy = offset
+    if demo_ground_body:
+        world.CreateBody(b2BodyDef())  # framework/test.d:160-161: fixture-less static body created by every demo
+    bd = b2BodyDef()
+    bd.position.Set(ox, oy)
+    ground = world.CreateBody(bd)
+    shape = b2EdgeShape(world._api)
+    shape.Set((-40.0, 0.0), (40.0, 0.0))
+    ground.CreateFixture(shape, 0.0)
+    a = 0.5
+    box = b2PolygonShape(world._api)
+    box.SetAsBox(a, a)
+    x = [f32(-7.0), f32(0.75)]
+    deltaX = (0.5625, 1.25)
+    deltaY = (1.125, 0.0)
+    bodies = []
+    for i in range(count):
+        y = list(x)
+        for j in range(i, count):
+            bd = b2BodyDef()
+            bd.type = b2_dynamicBody
+            bd.position.Set(f32(y[0] + ox), f32(y[1] + oy))
+            body = world.CreateBody(bd)
+            body.CreateFixture(box, 5.0)
+            bodies.append(body)
+            y = [f32(y[0] + deltaY[0]), f32(y[1] + deltaY[1])]
+        x = [f32(x[0] + deltaX[0]), f32(x[1] + deltaX[1])]
+    return world, bodies
+
+
+class Tumbler:
+    """tumbler.d:40-97.  `scale` grows the container (SURVEY.md 8(d) uses 5 for the 20k-body case);
+    `mixed` alternates boxes and circles."""
+
+    def __init__(self, api=None, count=800, scale=1.0, mixed=True, **kw):
+        self.world = world = b2World((0.0, -10.0), api=api, **kw)
+        self.count, self.m_count, self.mixed = count, 0, mixed
+        s = scale
+        world.CreateBody(b2BodyDef())  # demo base-class body
+        ground = world.CreateBody(b2BodyDef())
+        bd = b2BodyDef()
+        bd.type = b2_dynamicBody
+        bd.allowSleep = False
+        bd.position.Set(0.0, 10.0 * s)
+        body = world.CreateBody(bd)
+        shape = b2PolygonShape(world._api)
+        for (hx, hy, c) in ((0.5 * s, 10.0 * s, (10.0 * s, 0.0)), (0.5 * s, 10.0 * s, (-10.0 * s, 0.0)),
+                            (10.0 * s, 0.5 * s, (0.0, 10.0 * s)), (10.0 * s, 0.5 * s, (0.0, -10.0 * s))):
+            shape.SetAsBox(hx, hy, c, 0.0)
+            body.CreateFixture(shape, 5.0)
+        jd = b2RevoluteJointDef()
+        jd.bodyA, jd.bodyB = ground, body
+        jd.localAnchorA.Set(0.0, 10.0 * s)
+        jd.localAnchorB.Set(0.0, 0.0)
+        jd.referenceAngle = 0.0
+        jd.motorSpeed = f32(f32(0.05) * f32(b2_pi))
+        jd.maxMotorTorque = 1e8
+        jd.enableMotor = True
+        self.joint = world.CreateJoint(jd)
+        self.container = body
+        self.scale = s
+        self.bodies = []
+
+    def Step(self, dt=1.0 / 60.0, vi=8, pi=3, spawn_per_step=1):
+        self.world.Step(dt, vi, pi)
+        for _ in range(spawn_per_step):
+            if self.m_count < self.count:
+                bd = b2BodyDef()
+                bd.type = b2_dynamicBody
+                bd.position.Set(0.0, 10.0 * self.scale)
+                body = self.world.CreateBody(bd)
+                if self.mixed and (self.m_count & 1):
+                    shape = b2CircleShape(self.world._api)
+                    shape.m_radius = 0.125
+                else:
+                    shape = b2PolygonShape(self.world._api)
+                    shape.SetAsBox(0.125, 0.125)
+                body.CreateFixture(shape, 1.0)
+                self.bodies.append(body)
+                self.m_count += 1
+
+
+def pile(api=None, n=100000, columns=1000, joints=True, circles=True, seed=12345, world=None, **kw):
+    """Config 4: `n` dynamic bodies in a jittered grid `columns` wide above a static chain floor with
+    two edge walls; 70 % boxes (half-extent 0.5, density 1, friction 0.3), 30 % circles r=0.5; every 10th column is
+    linked upward into 25-body revolute chains and every 10th row sideways into 25-body rigid distance chains."""
+    if world is None:
+        world = b2World((0.0, -10.0), api=api, **kw)
+    rng = random.Random(seed)
+    half_w = f32(1.05 * columns * 0.5 + 5.0)
+    rows = (n + columns - 1) // columns
+    ground = world.CreateBody(b2BodyDef())
+    floor = b2ChainShape(world._api)
+    segs = max(2, columns // 50)
+    floor.CreateChain([(f32(-half_w + 2.0 * half_w * k / segs), 0.0) for k in range(segs + 1)])
+    ground.CreateFixture(floor, 0.0)
+    wall = b2EdgeShape(world._api)
+    top = f32(1.05 * rows + 20.0)
+    wall.Set((-half_w, 0.0), (-half_w, top))
+    ground.CreateFixture(wall, 0.0)
+    wall.Set((half_w, 0.0), (half_w, top))
+    ground.CreateFixture(wall, 0.0)
+
+    box = b2PolygonShape(world._api)
+    box.SetAsBox(0.5, 0.5)
+    circle = b2CircleShape(world._api)
+    circle.m_radius = 0.5
+    fd = b2FixtureDef()
+    fd.density, fd.friction = 1.0, 0.3
+    bodies = []
+    x0 = f32(-1.05 * columns * 0.5 + 0.525)
+    for i in range(n):
+        col, row = i % columns, i // columns
+        bd = b2BodyDef()
+        bd.type = b2_dynamicBody
+        bd.position.Set(f32(x0 + 1.05 * col + rng.uniform(-0.01, 0.01)), f32(0.55 + 1.05 * row + rng.uniform(-0.01, 0.01)))
+        body = world.CreateBody(bd)
+        fd.shape = circle if (circles and rng.random() < 0.3) else box
+        body.CreateFixture(fd)
+        bodies.append(body)
+    njoints = 0
+    if joints:
+        # revolute chains: column c (c % 10 == 0), rows r..r+24 linked pairwise at the midpoint, collideConnected=false
+        for col in range(0, columns, 10):
+            for row in range(rows - 1):
+                if row % 25 == 24:
+                    continue
+                i, j = row * columns + col, (row + 1) * columns + col
+                if j >= n:
+                    continue
+                jd = b2RevoluteJointDef()
+                pa, pb = bodies[i].GetPosition(), bodies[j].GetPosition()
+                jd.Initialize(bodies[i], bodies[j], (f32(0.5 * (pa.x + pb.x)), f32(0.5 * (pa.y + pb.y))))
+                world.CreateJoint(jd)
+                njoints += 1
+        # rigid distance chains: row r (r % 10 == 5), columns linked pairwise centre to centre
+        for row in range(5, rows, 10):
+            for col in range(columns - 1):
+                if col % 25 == 24 or col % 10 == 0 or (col + 1) % 10 == 0:
+                    continue
+                i, j = row * columns + col, row * columns + col + 1
+                if j >= n:
+                    continue
+                jd = b2DistanceJointDef()
+                pa, pb = bodies[i].GetPosition(), bodies[j].GetPosition()
+                jd.Initialize(bodies[i], bodies[j], (pa.x, pa.y), (pb.x, pb.y))
+                jd.collideConnected = True
+                world.CreateJoint(jd)
+                njoints += 1
+    return world, bodies, njoints

@@ -1,0 +1,501 @@
+"""Host-side mirror of the reference's public API for the hot path, over the C ABI.
+
+Same names and argument meaning as dbox's D API (dynamics/b2world.d, b2body.d, b2fixture.d,
+collision/shapes/*.d, dynamics/joints/b2revolutejoint.d, b2distancejoint.d) so that scene code and the parity
+tests read like the reference's own programs (examples/hello_world/hello_world.d:31-103).  Every method is a
+thin forward to one `dbx_*` entry point of include/dbox_b200.h — no physics runs in Python, and there is no CPU
+fallback: `b2World()` raises if the CUDA library cannot create a device world.
+
+`b2World(gravity, api=...)` takes the ABI binding to drive; the default is the product library
+(dbox_b200.lib.api()).  The tests pass the CPU oracle's binding to build the *same* scene on both sides.
+"""
+import ctypes as C
+import math
+
+from . import _abi as A
+
+
+class b2Vec2:
+    __slots__ = ("x", "y")
+
+    def __init__(self, x=0.0, y=0.0):
+        self.x, self.y = float(x), float(y)
+
+    def Set(self, x, y):
+        self.x, self.y = float(x), float(y)
+
+    def __iter__(self):
+        yield self.x
+        yield self.y
+
+    def __repr__(self):
+        return "b2Vec2(%r, %r)" % (self.x, self.y)
+
+
+def _v(v):
+    x, y = v
+    return A.Vec2(x, y)
+
+
+b2_staticBody, b2_kinematicBody, b2_dynamicBody = A.STATIC_BODY, A.KINEMATIC_BODY, A.DYNAMIC_BODY
+b2_pi = 3.14159265359
+b2_linearSlop = 0.005
+b2_polygonRadius = 2.0 * b2_linearSlop
+
+
+class b2BodyDef:
+    """dynamics/b2body.d:51-104"""
+
+    def __init__(self):
+        self.type = b2_staticBody
+        self.position = b2Vec2(0, 0)
+        self.angle = 0.0
+        self.linearVelocity = b2Vec2(0, 0)
+        self.angularVelocity = 0.0
+        self.linearDamping = 0.0
+        self.angularDamping = 0.0
+        self.allowSleep = True
+        self.awake = True
+        self.fixedRotation = False
+        self.bullet = False
+        self.active = True
+        self.userData = 0
+        self.gravityScale = 1.0
+
+    def _pod(self):
+        d = A.BodyDef()
+        d.type = self.type
+        d.position = _v(self.position)
+        d.angle = self.angle
+        d.linearVelocity = _v(self.linearVelocity)
+        d.angularVelocity = self.angularVelocity
+        d.linearDamping, d.angularDamping = self.linearDamping, self.angularDamping
+        d.allowSleep, d.awake, d.fixedRotation = int(self.allowSleep), int(self.awake), int(self.fixedRotation)
+        d.bullet, d.active, d.gravityScale, d.userData = int(self.bullet), int(self.active), self.gravityScale, self.userData
+        return d
+
+
+class b2Filter:
+    """dynamics/b2fixture.d:32-45"""
+
+    def __init__(self):
+        self.categoryBits, self.maskBits, self.groupIndex = 0x0001, 0xFFFF, 0
+
+
+class b2FixtureDef:
+    """dynamics/b2fixture.d:49-73"""
+
+    def __init__(self):
+        self.shape = None
+        self.userData = 0
+        self.friction = 0.2
+        self.restitution = 0.0
+        self.density = 0.0
+        self.isSensor = False
+        self.filter = b2Filter()
+
+    def _pod(self):
+        d = A.FixtureDef()
+        d.friction, d.restitution, d.density, d.isSensor = self.friction, self.restitution, self.density, int(self.isSensor)
+        d.categoryBits, d.maskBits, d.groupIndex = self.filter.categoryBits, self.filter.maskBits, self.filter.groupIndex
+        d.userData = self.userData
+        return d
+
+
+class b2Shape:
+    """collision/shapes/b2shape.d:43-100.  Setup-time geometry helpers run in the library (host side)."""
+    e_circle, e_edge, e_polygon, e_chain = 0, 1, 2, 3
+
+    def __init__(self, api=None):
+        if api is None:
+            from . import lib
+            api = lib.api()
+        self._api = api
+        self._pod = A.Shape()
+        self._keep = None
+
+    def GetType(self):
+        return self._pod.type
+
+    @property
+    def m_radius(self):
+        return self._pod.radius
+
+    @m_radius.setter
+    def m_radius(self, r):
+        self._pod.radius = r
+
+
+class b2CircleShape(b2Shape):
+    def __init__(self, api=None):
+        super().__init__(api)
+        self._api.shape_set_circle(C.byref(self._pod), 0.0, 0.0, 0.0)
+
+    @property
+    def m_p(self):
+        return b2Vec2(self._pod.p.x, self._pod.p.y)
+
+    @m_p.setter
+    def m_p(self, v):
+        self._pod.p = _v(v)
+
+
+class b2EdgeShape(b2Shape):
+    def __init__(self, api=None):
+        super().__init__(api)
+        self._api.shape_set_edge(C.byref(self._pod), A.Vec2(0, 0), A.Vec2(0, 0))
+
+    def Set(self, v1, v2):
+        self._api.shape_set_edge(C.byref(self._pod), _v(v1), _v(v2))
+
+
+class b2PolygonShape(b2Shape):
+    def __init__(self, api=None):
+        super().__init__(api)
+        self._pod.type = A.SHAPE_POLYGON
+        self._pod.radius = b2_polygonRadius
+
+    def SetAsBox(self, hx, hy, center=None, angle=0.0):
+        if center is None:
+            self._api.shape_set_box(C.byref(self._pod), hx, hy)
+        else:
+            self._api.shape_set_box_at(C.byref(self._pod), hx, hy, _v(center), angle)
+
+    def Set(self, vertices):
+        arr = (A.Vec2 * len(vertices))(*[_v(p) for p in vertices])
+        self._api.shape_set_polygon(C.byref(self._pod), arr, len(vertices))
+
+    @property
+    def m_count(self):
+        return self._pod.count
+
+
+class b2ChainShape(b2Shape):
+    def __init__(self, api=None):
+        super().__init__(api)
+        self._pod.type = A.SHAPE_CHAIN
+        self._pod.radius = b2_polygonRadius
+
+    def CreateChain(self, vertices):
+        self._keep = (A.Vec2 * len(vertices))(*[_v(p) for p in vertices])
+        self._api.shape_set_chain(C.byref(self._pod), self._keep, len(vertices), 0)
+
+    def CreateLoop(self, vertices):
+        vs = list(vertices) + [vertices[0]]
+        self._keep = (A.Vec2 * len(vs))(*[_v(p) for p in vs])
+        self._api.shape_set_chain(C.byref(self._pod), self._keep, len(vs), 1)
+
+
+class b2JointDef:
+    def __init__(self):
+        self.userData, self.bodyA, self.bodyB, self.collideConnected = 0, None, None, False
+
+
+class b2RevoluteJointDef(b2JointDef):
+    """dynamics/joints/b2revolutejoint.d:39-107"""
+    type = A.JOINT_REVOLUTE
+
+    def __init__(self):
+        super().__init__()
+        self.localAnchorA, self.localAnchorB = b2Vec2(), b2Vec2()
+        self.referenceAngle = self.lowerAngle = self.upperAngle = self.maxMotorTorque = self.motorSpeed = 0.0
+        self.enableLimit = self.enableMotor = False
+
+    def Initialize(self, bA, bB, anchor):
+        self.bodyA, self.bodyB = bA, bB
+        self.localAnchorA = bA.GetLocalPoint(anchor)
+        self.localAnchorB = bB.GetLocalPoint(anchor)
+        self.referenceAngle = _f32(bB.GetAngle() - bA.GetAngle())
+
+    def _pod(self):
+        d = A.JointDef()
+        d.type, d.bodyA, d.bodyB, d.collideConnected = self.type, self.bodyA.id, self.bodyB.id, int(self.collideConnected)
+        d.localAnchorA, d.localAnchorB = _v(self.localAnchorA), _v(self.localAnchorB)
+        d.referenceAngle, d.enableLimit, d.lowerAngle, d.upperAngle = self.referenceAngle, int(self.enableLimit), self.lowerAngle, self.upperAngle
+        d.enableMotor, d.motorSpeed, d.maxMotorTorque, d.userData = int(self.enableMotor), self.motorSpeed, self.maxMotorTorque, self.userData
+        return d
+
+
+class b2DistanceJointDef(b2JointDef):
+    """dynamics/joints/b2distancejoint.d:36-90"""
+    type = A.JOINT_DISTANCE
+
+    def __init__(self):
+        super().__init__()
+        self.localAnchorA, self.localAnchorB = b2Vec2(), b2Vec2()
+        self.length, self.frequencyHz, self.dampingRatio = 1.0, 0.0, 0.0
+
+    def Initialize(self, b1, b2, anchor1, anchor2):
+        self.bodyA, self.bodyB = b1, b2
+        self.localAnchorA = b1.GetLocalPoint(anchor1)
+        self.localAnchorB = b2.GetLocalPoint(anchor2)
+        a1, a2 = _v(anchor1), _v(anchor2)
+        dx, dy = _f32(a2.x - a1.x), _f32(a2.y - a1.y)
+        self.length = _f32(math.sqrt(_f32(_f32(dx * dx) + _f32(dy * dy))))
+
+    def _pod(self):
+        d = A.JointDef()
+        d.type, d.bodyA, d.bodyB, d.collideConnected = self.type, self.bodyA.id, self.bodyB.id, int(self.collideConnected)
+        d.localAnchorA, d.localAnchorB = _v(self.localAnchorA), _v(self.localAnchorB)
+        d.length, d.frequencyHz, d.dampingRatio, d.userData = self.length, self.frequencyHz, self.dampingRatio, self.userData
+        return d
+
+
+def _f32(x):
+    return C.c_float(x).value
+
+
+class b2Fixture:
+    def __init__(self, body, fid):
+        self.body, self.id = body, fid
+
+    def GetBody(self):
+        return self.body
+
+
+class b2Joint:
+    def __init__(self, world, jid, bodyA, bodyB):
+        self.world, self.id, self.bodyA, self.bodyB = world, jid, bodyA, bodyB
+
+
+class b2Body:
+    """dynamics/b2body.d:107-1219 (the accessors and mutators the hot path's callers use)"""
+
+    def __init__(self, world, bid):
+        self.world, self.id = world, bid
+        self.fixtures = []
+
+    def _state(self):
+        s = A.BodyState()
+        self.world._ck(self.world._api.body_get_state(self.world._w, self.id, C.byref(s)))
+        return s
+
+    def CreateFixture(self, shape_or_def, density=None):
+        """b2body.d:116-170: CreateFixture(&fixtureDef) or CreateFixture(shape, density)."""
+        if isinstance(shape_or_def, b2FixtureDef):
+            fd, shape = shape_or_def, shape_or_def.shape
+        else:
+            fd, shape = b2FixtureDef(), shape_or_def
+            fd.density = 0.0 if density is None else density
+        pod = fd._pod()
+        fid = self.world._ck(self.world._api.fixture_create(self.world._w, self.id, C.byref(pod), C.byref(shape._pod)))
+        f = b2Fixture(self, fid)
+        self.fixtures.append(f)
+        self.world._fixtures[fid] = f
+        return f
+
+    def GetPosition(self):
+        s = self._state()
+        return b2Vec2(s.p.x, s.p.y)
+
+    def GetAngle(self):
+        return self._state().a
+
+    def GetWorldCenter(self):
+        s = self._state()
+        return b2Vec2(s.c.x, s.c.y)
+
+    def GetLinearVelocity(self):
+        s = self._state()
+        return b2Vec2(s.v.x, s.v.y)
+
+    def GetAngularVelocity(self):
+        return self._state().w
+
+    def GetMass(self):
+        return self._state().mass
+
+    def IsAwake(self):
+        return bool(self._state().flags & A.BODY_AWAKE)
+
+    def GetLocalPoint(self, worldPoint):
+        """b2body.d GetLocalPoint = b2MulT(m_xf, p) (common/b2math.d:738-746), evaluated in fp32."""
+        s = self._state()
+        wx, wy = worldPoint
+        px, py = _f32(_f32(wx) - s.p.x), _f32(_f32(wy) - s.p.y)
+        x = _f32(_f32(s.qc * px) + _f32(s.qs * py))
+        y = _f32(_f32(-s.qs * px) + _f32(s.qc * py))
+        return b2Vec2(x, y)
+
+    def SetTransform(self, position, angle):
+        x, y = position
+        self.world._ck(self.world._api.body_set_transform(self.world._w, self.id, x, y, angle))
+
+    def SetLinearVelocity(self, v):
+        x, y = v
+        self.world._ck(self.world._api.body_set_linear_velocity(self.world._w, self.id, x, y))
+
+    def SetAngularVelocity(self, w):
+        self.world._ck(self.world._api.body_set_angular_velocity(self.world._w, self.id, w))
+
+    def ApplyForce(self, force, point, wake=True):
+        (fx, fy), (px, py) = force, point
+        self.world._ck(self.world._api.body_apply_force(self.world._w, self.id, fx, fy, px, py, int(wake)))
+
+    def ApplyTorque(self, torque, wake=True):
+        self.world._ck(self.world._api.body_apply_torque(self.world._w, self.id, torque, int(wake)))
+
+    def ApplyLinearImpulse(self, impulse, point, wake=True):
+        (ix, iy), (px, py) = impulse, point
+        self.world._ck(self.world._api.body_apply_linear_impulse(self.world._w, self.id, ix, iy, px, py, int(wake)))
+
+    def ApplyAngularImpulse(self, impulse, wake=True):
+        self.world._ck(self.world._api.body_apply_angular_impulse(self.world._w, self.id, impulse, int(wake)))
+
+    def SetAwake(self, flag):
+        self.world._ck(self.world._api.body_set_awake(self.world._w, self.id, int(flag)))
+
+    def SetBullet(self, flag):
+        self.world._ck(self.world._api.body_set_bullet(self.world._w, self.id, int(flag)))
+
+    def SetSleepingAllowed(self, flag):
+        self.world._ck(self.world._api.body_set_sleeping_allowed(self.world._w, self.id, int(flag)))
+
+
+class b2World:
+    """dynamics/b2world.d:34-1591 — construction, factories, Step, toggles and bulk state access."""
+
+    def __init__(self, gravity, api=None, device=0, caps=None):
+        if api is None:
+            from . import lib
+            api = lib.api()
+        self._api = api
+        gx, gy = gravity
+        if api.prefix == "dbx_":
+            self._w = api.world_create(gx, gy, device, C.byref(caps) if caps is not None else None)
+            if not self._w:
+                raise RuntimeError("dbx_world_create failed: %s" % api.last_error().decode())
+        else:
+            self._w = api.world_create(gx, gy)
+        self._bodies, self._fixtures, self._joints = {}, {}, {}
+        self._flags = A.WORLD_DEFAULT_FLAGS
+
+    def close(self):
+        if self._w:
+            self._api.world_destroy(self._w)
+            self._w = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc < 0:
+            msg = self._api.last_error().decode() if hasattr(self._api, "last_error") else ""
+            raise RuntimeError("ABI call failed with %d %s" % (rc, msg))
+        return rc
+
+    # factories ---------------------------------------------------------------------------------------------
+    def CreateBody(self, bodyDef):
+        pod = bodyDef._pod()
+        bid = self._ck(self._api.body_create(self._w, C.byref(pod)))
+        b = b2Body(self, bid)
+        self._bodies[bid] = b
+        return b
+
+    def DestroyBody(self, body):
+        self._ck(self._api.body_destroy(self._w, body.id))
+        self._bodies.pop(body.id, None)
+
+    def CreateJoint(self, jointDef):
+        pod = jointDef._pod()
+        jid = self._ck(self._api.joint_create(self._w, C.byref(pod)))
+        j = b2Joint(self, jid, jointDef.bodyA, jointDef.bodyB)
+        self._joints[jid] = j
+        return j
+
+    def DestroyJoint(self, joint):
+        self._ck(self._api.joint_destroy(self._w, joint.id))
+        self._joints.pop(joint.id, None)
+
+    # stepping ----------------------------------------------------------------------------------------------
+    def Step(self, dt, velocityIterations, positionIterations):
+        self._ck(self._api.world_step(self._w, dt, velocityIterations, positionIterations))
+
+    def StepN(self, dt, velocityIterations, positionIterations, n):
+        self._ck(self._api.world_step_n(self._w, dt, velocityIterations, positionIterations, n))
+
+    def _set_flag(self, bit, on):
+        self._flags = (self._flags | bit) if on else (self._flags & ~bit)
+        self._ck(self._api.world_set_flags(self._w, self._flags))
+
+    def SetAllowSleeping(self, flag):
+        self._set_flag(A.WORLD_ALLOW_SLEEP, flag)
+
+    def SetWarmStarting(self, flag):
+        self._set_flag(A.WORLD_WARM_STARTING, flag)
+
+    def SetContinuousPhysics(self, flag):
+        self._set_flag(A.WORLD_CONTINUOUS, flag)
+
+    def SetSubStepping(self, flag):
+        self._set_flag(A.WORLD_SUB_STEPPING, flag)
+
+    def SetAutoClearForces(self, flag):
+        self._set_flag(A.WORLD_AUTO_CLEAR_FORCES, flag)
+
+    def SetGravity(self, g):
+        gx, gy = g
+        self._ck(self._api.world_set_gravity(self._w, gx, gy))
+
+    # counts / profile (b2world.d:677-716, 789-792) ------------------------------------------------------------
+    def counts(self):
+        c = A.Counts()
+        self._ck(self._api.world_counts(self._w, C.byref(c)))
+        return c
+
+    def GetBodyCount(self):
+        return self.counts().bodies
+
+    def GetContactCount(self):
+        return self.counts().contacts
+
+    def GetJointCount(self):
+        return self.counts().joints
+
+    def GetProxyCount(self):
+        return self.counts().proxies
+
+    def GetProfile(self):
+        p = A.Profile()
+        self._ck(self._api.world_profile(self._w, C.byref(p)))
+        return p
+
+    # bulk state ----------------------------------------------------------------------------------------------
+    def _read(self, fn, typ, n_hint=0):
+        n = fn(self._w, None, 0) if n_hint <= 0 else n_hint
+        self._ck(n)
+        buf = (typ * max(n, 1))()
+        n2 = self._ck(fn(self._w, buf, n))
+        return buf, min(n, n2)
+
+    def read_bodies(self):
+        return self._read(self._api.world_read_bodies, A.BodyState)
+
+    def read_contacts(self):
+        return self._read(self._api.world_read_contacts, A.ContactRec)
+
+    def read_proxies(self):
+        return self._read(self._api.world_read_proxies, A.ProxyRec)
+
+    def read_joints(self):
+        return self._read(self._api.world_read_joints, A.JointState)
+
+    def read_moves(self):
+        n = self._ck(self._api.world_read_moves(self._w, None, 0))
+        buf = (C.c_int32 * max(2 * n, 2))()
+        n = self._ck(self._api.world_read_moves(self._w, buf, n))
+        return [(buf[2 * i], buf[2 * i + 1]) for i in range(n)]
+
+    def read_pairs(self):
+        n = self._ck(self._api.world_read_pairs(self._w, None, 0))
+        buf = (C.c_int32 * max(4 * n, 4))()
+        n = self._ck(self._api.world_read_pairs(self._w, buf, n))
+        return [tuple(buf[4 * i:4 * i + 4]) for i in range(n)]
+
+    def get_inv_dt0(self):
+        f = C.c_float()
+        self._ck(self._api.world_get_inv_dt0(self._w, C.byref(f)))
+        return f.value

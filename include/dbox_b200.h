@@ -1,0 +1,277 @@
+/* dbox_b200.h — the drop-in boundary: a C ABI for dbox's per-step world pipeline on one B200.
+ *
+ * The reference (d-gamedev-team/dbox, a D port of Box2D 2.3.1) has no FFI seam: D user code calls
+ * methods on b2World / b2Body / b2Fixture / b2Joint directly.  The seam is therefore introduced one
+ * level below that public API: the D classes keep their signatures and forward to these functions
+ * (the `extern(C)` block a maintainer adds is shown in INTEGRATION.md).  Each entry point cites the
+ * reference method it stands in for, relative to /root/reference/src/dbox/.
+ *
+ * Conventions
+ *  - plain C: opaque world pointer, int32 handles (ids are dense, never reused while alive), POD
+ *    structs, caller-owned buffers; no C++/torch types.
+ *  - status returns: >= 0 success (often an id or a count), < 0 a DBX_E_* code.  The reference
+ *    asserts / silently returns null when the world is locked (dynamics/b2world.d:77-82); here the
+ *    same calls return DBX_E_LOCKED.
+ *  - one CUDA stream per world; calls are synchronous with respect to the host unless noted.
+ *  - all world state (bodies, fixtures, proxies, contacts, manifolds, joints, constraints) lives in
+ *    SoA device buffers; there is NO CPU fallback: without a CUDA device dbx_world_create fails with
+ *    DBX_E_NO_DEVICE and every other call on a null world returns DBX_E_INVALID.
+ */
+#ifndef DBOX_B200_H_
+#define DBOX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBX_ABI_VERSION 1
+
+typedef struct dbx_world dbx_world; /* opaque */
+
+enum {
+  DBX_OK = 0,
+  DBX_E_INVALID = -1,    /* bad handle / argument */
+  DBX_E_LOCKED = -2,     /* world is inside Step (reference: IsLocked()) */
+  DBX_E_NO_DEVICE = -3,  /* no usable CUDA device */
+  DBX_E_CUDA = -4,       /* a CUDA call failed; see dbx_last_error() */
+  DBX_E_CAPACITY = -5,   /* a device pool overflowed (pairs / contacts); see dbx_world_caps */
+  DBX_E_UNSUPPORTED = -6 /* feature outside the hot-path scope of this build */
+};
+
+/* common/b2math.d:60-190 */
+typedef struct { float x, y; } dbx_vec2;
+typedef struct { dbx_vec2 lo, hi; } dbx_aabb; /* collision/b2collision.d:283-409 */
+
+/* dynamics/b2body.d:35-43 */
+enum { DBX_STATIC_BODY = 0, DBX_KINEMATIC_BODY = 1, DBX_DYNAMIC_BODY = 2 };
+/* dynamics/b2body.d:1118-1127 */
+enum {
+  DBX_BODY_ISLAND = 0x0001, DBX_BODY_AWAKE = 0x0002, DBX_BODY_AUTOSLEEP = 0x0004, DBX_BODY_BULLET = 0x0008,
+  DBX_BODY_FIXED_ROTATION = 0x0010, DBX_BODY_ACTIVE = 0x0020, DBX_BODY_TOI = 0x0040
+};
+/* dynamics/contacts/b2contact.d:242-261 */
+enum {
+  DBX_CONTACT_ISLAND = 0x0001, DBX_CONTACT_TOUCHING = 0x0002, DBX_CONTACT_ENABLED = 0x0004,
+  DBX_CONTACT_FILTER = 0x0008, DBX_CONTACT_BULLET_HIT = 0x0010, DBX_CONTACT_TOI = 0x0020
+};
+/* collision/shapes/b2shape.d:45-52 */
+enum { DBX_SHAPE_CIRCLE = 0, DBX_SHAPE_EDGE = 1, DBX_SHAPE_POLYGON = 2, DBX_SHAPE_CHAIN = 3 };
+/* collision/b2collision.d:98-103 */
+enum { DBX_MANIFOLD_CIRCLES = 0, DBX_MANIFOLD_FACE_A = 1, DBX_MANIFOLD_FACE_B = 2 };
+/* dynamics/joints/b2joint.d:28-42 */
+enum {
+  DBX_JOINT_UNKNOWN = 0, DBX_JOINT_REVOLUTE = 1, DBX_JOINT_PRISMATIC = 2, DBX_JOINT_DISTANCE = 3, DBX_JOINT_PULLEY = 4,
+  DBX_JOINT_MOUSE = 5, DBX_JOINT_GEAR = 6, DBX_JOINT_WHEEL = 7, DBX_JOINT_WELD = 8, DBX_JOINT_FRICTION = 9,
+  DBX_JOINT_ROPE = 10, DBX_JOINT_MOTOR = 11
+};
+/* world toggles: dynamics/b2world.d:622-753 (SetAllowSleeping / SetWarmStarting / SetContinuousPhysics /
+ * SetSubStepping / SetAutoClearForces) */
+enum {
+  DBX_WORLD_ALLOW_SLEEP = 0x01, DBX_WORLD_WARM_STARTING = 0x02, DBX_WORLD_CONTINUOUS = 0x04,
+  DBX_WORLD_SUB_STEPPING = 0x08, DBX_WORLD_AUTO_CLEAR_FORCES = 0x10,
+  DBX_WORLD_DEFAULT_FLAGS = 0x01 | 0x02 | 0x04 | 0x10 /* dynamics/b2world.d:876-885 */
+};
+
+/* dynamics/b2body.d:51-104 (b2BodyDef; same defaults via dbx_default_body_def) */
+typedef struct {
+  int32_t type;
+  dbx_vec2 position;
+  float angle;
+  dbx_vec2 linearVelocity;
+  float angularVelocity;
+  float linearDamping, angularDamping;
+  int32_t allowSleep, awake, fixedRotation, bullet, active;
+  float gravityScale;
+  uint64_t userData;
+} dbx_body_def;
+
+/* One POD for the four shape classes (collision/shapes/b2circleshape.d:158, b2edgeshape.d:189-193,
+ * b2polygonshape.d:562-565, b2chainshape.d:257-263).  Polygon vertices/normals/centroid are the
+ * already-processed values (b2PolygonShape.Set / SetAsBox run on the caller's side; helpers below). */
+typedef struct {
+  int32_t type;
+  float radius;
+  dbx_vec2 p;                 /* circle centre */
+  dbx_vec2 v0, v1, v2, v3;    /* edge: v1-v2 with optional ghost vertices */
+  int32_t hasV0, hasV3;
+  dbx_vec2 centroid;          /* polygon */
+  dbx_vec2 vertices[8];
+  dbx_vec2 normals[8];
+  int32_t count;
+  const dbx_vec2* chainVertices; /* chain: chainCount vertices (a loop repeats vertex 0 at the end) */
+  int32_t chainCount;
+  dbx_vec2 prevVertex, nextVertex;
+  int32_t hasPrev, hasNext;
+} dbx_shape;
+
+/* dynamics/b2fixture.d:32-73 (b2Filter + b2FixtureDef) */
+typedef struct {
+  float friction, restitution, density;
+  int32_t isSensor;
+  uint16_t categoryBits, maskBits;
+  int16_t groupIndex;
+  uint16_t _pad;
+  uint64_t userData;
+} dbx_fixture_def;
+
+/* dynamics/joints/b2joint.d:77-93 + b2revolutejoint.d:39-107 + b2distancejoint.d:36-90 */
+typedef struct {
+  int32_t type;
+  int32_t bodyA, bodyB;
+  int32_t collideConnected;
+  dbx_vec2 localAnchorA, localAnchorB;
+  /* revolute */
+  float referenceAngle;
+  int32_t enableLimit;
+  float lowerAngle, upperAngle;
+  int32_t enableMotor;
+  float motorSpeed, maxMotorTorque;
+  /* distance */
+  float length, frequencyHz, dampingRatio;
+  uint64_t userData;
+} dbx_joint_def;
+
+/* full per-body state (dynamics/b2body.d:1182-1218) */
+typedef struct {
+  int32_t type;
+  uint32_t flags;
+  dbx_vec2 p;            /* m_xf.p */
+  float qs, qc;          /* m_xf.q */
+  dbx_vec2 localCenter, c0, c; /* m_sweep */
+  float a0, a, alpha0;
+  dbx_vec2 v;            /* m_linearVelocity */
+  float w;               /* m_angularVelocity */
+  dbx_vec2 force;
+  float torque;
+  float mass, invMass, I, invI;
+  float linearDamping, angularDamping, gravityScale;
+  float sleepTime;
+} dbx_body_state;
+
+/* collision/b2collision.d:72-114 (b2ManifoldPoint, b2Manifold) */
+typedef struct { dbx_vec2 localPoint; float normalImpulse, tangentImpulse; uint32_t key; } dbx_manifold_point;
+typedef struct {
+  dbx_manifold_point points[2];
+  dbx_vec2 localNormal, localPoint;
+  int32_t type, pointCount;
+} dbx_manifold;
+
+/* one persistent contact (dynamics/contacts/b2contact.d:441-465), identified by (fixture, child) pairs */
+typedef struct {
+  int32_t fixtureA, fixtureB, childA, childB;
+  uint32_t flags;
+  dbx_manifold manifold;
+  float friction, restitution, tangentSpeed;
+  int32_t toiCount;
+  float toi;
+} dbx_contact_rec;
+
+/* one broadphase proxy (dynamics/b2fixture.d:76-82 + the tree's fat AABB, collision/b2dynamictree.d:146-180) */
+typedef struct {
+  int32_t fixture, child;
+  int32_t proxyId;  /* reference tree-node id: decides A/B order of pairs (collision/b2broadphase.d:289-290) */
+  dbx_aabb aabb;    /* tight swept AABB */
+  dbx_aabb fat;     /* persistent fat AABB */
+} dbx_proxy_rec;
+
+/* joint solver state that persists across steps */
+typedef struct { int32_t type; float impulse[3]; float motorImpulse; int32_t limitState; } dbx_joint_state;
+
+/* dynamics/b2world.d:677-716 counts */
+typedef struct { int32_t bodies, fixtures, proxies, contacts, touching, joints, awakeBodies, colours, islands, moves, pairs; } dbx_counts;
+
+/* dynamics/b2timestep.d:37-47 (b2Profile, ms) — filled from CUDA events per phase */
+typedef struct { float step, collide, solve, solveInit, solveVelocity, solvePosition, broadphase, solveTOI; } dbx_profile;
+
+/* pool sizing (0 = default).  All pools are device-resident; overflow => DBX_E_CAPACITY. */
+typedef struct {
+  int32_t maxBodies, maxProxies, maxContacts, maxJoints, maxPairs;
+} dbx_caps;
+
+/* ---- library ---- */
+int32_t dbx_abi_version(void);
+const char* dbx_last_error(void);
+int32_t dbx_device_count(void);
+
+/* ---- defaults: dynamics/b2body.d:55-103, dynamics/b2fixture.d:59-72, joint def ctors ---- */
+void dbx_default_body_def(dbx_body_def* out);
+void dbx_default_fixture_def(dbx_fixture_def* out);
+void dbx_default_joint_def(dbx_joint_def* out, int32_t type);
+
+/* ---- shape helpers (host side of the shim; run at setup time) ---- */
+void dbx_shape_set_circle(dbx_shape* out, float px, float py, float radius);               /* b2circleshape.d */
+void dbx_shape_set_edge(dbx_shape* out, dbx_vec2 v1, dbx_vec2 v2);                         /* b2edgeshape.d:47-53 */
+void dbx_shape_set_box(dbx_shape* out, float hx, float hy);                                /* b2polygonshape.d:220-232 */
+void dbx_shape_set_box_at(dbx_shape* out, float hx, float hy, dbx_vec2 center, float angle); /* :239-262 */
+int32_t dbx_shape_set_polygon(dbx_shape* out, const dbx_vec2* pts, int32_t n);             /* :74-209 */
+void dbx_shape_set_chain(dbx_shape* out, const dbx_vec2* pts, int32_t n, int32_t loop);    /* b2chainshape.d:64-117; pts must outlive fixture creation */
+
+/* ---- world lifecycle: dynamics/b2world.d:865-919 ---- */
+dbx_world* dbx_world_create(float gx, float gy, int32_t device, const dbx_caps* caps);
+void dbx_world_destroy(dbx_world* w);
+int32_t dbx_world_set_flags(dbx_world* w, uint32_t flags);            /* b2world.d:622-753 */
+uint32_t dbx_world_get_flags(dbx_world* w);
+int32_t dbx_world_set_gravity(dbx_world* w, float gx, float gy);      /* b2world.d:719-728 */
+
+/* ---- object lifecycle ---- */
+int32_t dbx_body_create(dbx_world* w, const dbx_body_def* def);                                   /* b2world.d:75-99 */
+int32_t dbx_body_destroy(dbx_world* w, int32_t body);                                             /* b2world.d:105-191 */
+int32_t dbx_fixture_create(dbx_world* w, int32_t body, const dbx_fixture_def* def, const dbx_shape* shape); /* b2body.d:116-155 */
+int32_t dbx_fixture_destroy(dbx_world* w, int32_t fixture);                                       /* b2body.d:179-247 */
+int32_t dbx_joint_create(dbx_world* w, const dbx_joint_def* def);                                 /* b2world.d:196-261 */
+int32_t dbx_joint_destroy(dbx_world* w, int32_t joint);                                           /* b2world.d:265-360 */
+
+/* ---- the hot path: dynamics/b2world.d:367-434 (Collide -> Solve -> SolveTOI -> ClearForces) ---- */
+int32_t dbx_world_step(dbx_world* w, float dt, int32_t velocityIterations, int32_t positionIterations);
+/* n consecutive steps without returning to the host in between (RL / benchmark loops) */
+int32_t dbx_world_step_n(dbx_world* w, float dt, int32_t velocityIterations, int32_t positionIterations, int32_t n);
+int32_t dbx_world_clear_forces(dbx_world* w);                          /* b2world.d:443-450 */
+
+/* ---- body accessors / mutators: dynamics/b2body.d ---- */
+int32_t dbx_body_get_state(dbx_world* w, int32_t body, dbx_body_state* out);
+int32_t dbx_body_set_transform(dbx_world* w, int32_t body, float x, float y, float angle);   /* b2body.d:261-285 */
+int32_t dbx_body_set_linear_velocity(dbx_world* w, int32_t body, float vx, float vy);       /* :322-335 */
+int32_t dbx_body_set_angular_velocity(dbx_world* w, int32_t body, float omega);             /* :346-359 */
+int32_t dbx_body_apply_force(dbx_world* w, int32_t body, float fx, float fy, float px, float py, int32_t wake); /* :367-385 */
+int32_t dbx_body_apply_torque(dbx_world* w, int32_t body, float torque, int32_t wake);      /* :414-431 */
+int32_t dbx_body_apply_linear_impulse(dbx_world* w, int32_t body, float ix, float iy, float px, float py, int32_t wake); /* :439-457 */
+int32_t dbx_body_apply_angular_impulse(dbx_world* w, int32_t body, float impulse, int32_t wake); /* :462-479 */
+int32_t dbx_body_set_awake(dbx_world* w, int32_t body, int32_t flag);                       /* :827-846 */
+int32_t dbx_body_set_bullet(dbx_world* w, int32_t body, int32_t flag);                      /* :784-794 */
+int32_t dbx_body_set_sleeping_allowed(dbx_world* w, int32_t body, int32_t flag);            /* :804-815 */
+
+/* ---- bulk state access (one D2H / H2D copy each; also the checkpoint / parity-injection path) ---- */
+int32_t dbx_world_counts(dbx_world* w, dbx_counts* out);
+int32_t dbx_world_profile(dbx_world* w, dbx_profile* out);                                    /* b2world.d:789-792 */
+int32_t dbx_world_read_bodies(dbx_world* w, dbx_body_state* out, int32_t cap);                /* index = body id */
+int32_t dbx_world_write_bodies(dbx_world* w, const dbx_body_state* in, int32_t n);
+int32_t dbx_world_read_contacts(dbx_world* w, dbx_contact_rec* out, int32_t cap);             /* b2world.d:610-613 (GetContactList) */
+int32_t dbx_world_write_contacts(dbx_world* w, const dbx_contact_rec* in, int32_t n);         /* replaces the pair cache */
+int32_t dbx_world_read_proxies(dbx_world* w, dbx_proxy_rec* out, int32_t cap);
+int32_t dbx_world_write_proxies(dbx_world* w, const dbx_proxy_rec* in, int32_t n);            /* fat/tight AABBs by (fixture, child) */
+int32_t dbx_world_read_joints(dbx_world* w, dbx_joint_state* out, int32_t cap);
+int32_t dbx_world_write_joints(dbx_world* w, const dbx_joint_state* in, int32_t n);
+int32_t dbx_world_read_moves(dbx_world* w, int32_t* fixture_child_pairs, int32_t cap);        /* pending move buffer (b2broadphase.d:244-257) */
+int32_t dbx_world_write_moves(dbx_world* w, const int32_t* fixture_child_pairs, int32_t n);
+int32_t dbx_world_get_inv_dt0(dbx_world* w, float* out);                                      /* b2world.d:421-424 */
+int32_t dbx_world_set_inv_dt0(dbx_world* w, float inv_dt0);
+
+/* ---- staged stepping for parity tests and listener round-trips (same kernels as dbx_world_step) ---- */
+int32_t dbx_world_stage_find_new_contacts(dbx_world* w);   /* b2contactmanager.d:178-181 */
+int32_t dbx_world_stage_collide(dbx_world* w);             /* b2contactmanager.d:251-317 */
+int32_t dbx_world_read_pairs(dbx_world* w, int32_t* fixA_childA_fixB_childB, int32_t cap); /* last UpdatePairs' unique pair set */
+/* override the constraint colouring with a caller-supplied schedule: level[i] for contact rec i of the last
+ * dbx_world_read_contacts order; lets a test replay the reference's exact sequential order. n=0 clears. */
+int32_t dbx_world_debug_set_contact_levels(dbx_world* w, const int32_t* levels, int32_t n);
+
+/* ---- batched independent worlds (config 5): replicas of a template share one device world ---- */
+int32_t dbx_world_replicate(dbx_world* w, int32_t copies);  /* world becomes `copies` disjoint replicas of its current content */
+int32_t dbx_world_replica_count(dbx_world* w);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBOX_B200_H_ */

@@ -1,0 +1,396 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.h header).  PARITY UNPINNED.
+//
+// C API over the oracle world.  It deliberately has the same shape as the product's C ABI
+// (include/dbox_b200.h: same POD structs, `orc_` prefix instead of `dbx_`) so that one Python scene
+// builder can drive either side in the parity tests.  Only the struct *definitions* are shared with the
+// product header; no product code is linked here.
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <thread>
+#include <vector>
+#include "../include/dbox_b200.h"
+#include "orc_world.h"
+
+using namespace orc;
+
+struct orc_world {
+  World w;
+  std::vector<std::unique_ptr<std::vector<V2>>> keep;  // nothing retained from defs; placeholder
+  explicit orc_world(V2 g) : w(g) {}
+};
+
+static V2 v2(dbx_vec2 a) { return V2(a.x, a.y); }
+static dbx_vec2 d2(V2 a) { dbx_vec2 r; r.x = a.x; r.y = a.y; return r; }
+
+static Shape toShape(const dbx_shape* s) {
+  Shape o;
+  o.type = s->type;
+  o.radius = s->radius;
+  switch (s->type) {
+    case kCircle: o.p = v2(s->p); break;
+    case kEdge: o.v0 = v2(s->v0); o.v1 = v2(s->v1); o.v2 = v2(s->v2); o.v3 = v2(s->v3); o.hasV0 = s->hasV0 != 0; o.hasV3 = s->hasV3 != 0; break;
+    case kPolygon:
+      o.centroid = v2(s->centroid); o.count = s->count;
+      for (int i = 0; i < s->count; ++i) { o.verts[i] = v2(s->vertices[i]); o.normals[i] = v2(s->normals[i]); }
+      break;
+    case kChain:
+      for (int i = 0; i < s->chainCount; ++i) o.chain.push_back(v2(s->chainVertices[i]));
+      o.prevVertex = v2(s->prevVertex); o.nextVertex = v2(s->nextVertex); o.hasPrev = s->hasPrev != 0; o.hasNext = s->hasNext != 0;
+      break;
+  }
+  return o;
+}
+static void fromShape(const Shape& o, dbx_shape* s) {
+  std::memset(s, 0, sizeof(*s));
+  s->type = o.type; s->radius = o.radius; s->p = d2(o.p);
+  s->v0 = d2(o.v0); s->v1 = d2(o.v1); s->v2 = d2(o.v2); s->v3 = d2(o.v3); s->hasV0 = o.hasV0; s->hasV3 = o.hasV3;
+  s->centroid = d2(o.centroid); s->count = o.count;
+  for (int i = 0; i < o.count; ++i) { s->vertices[i] = d2(o.verts[i]); s->normals[i] = d2(o.normals[i]); }
+}
+
+extern "C" {
+
+// ---- shape helpers (the oracle's restatement of the shape setup functions) ----
+void orc_shape_set_circle(dbx_shape* out, float px, float py, float r) { fromShape(Shape::circle(V2(px, py), r), out); }
+void orc_shape_set_edge(dbx_shape* out, dbx_vec2 a, dbx_vec2 b) { fromShape(Shape::edge(v2(a), v2(b)), out); }
+void orc_shape_set_box(dbx_shape* out, float hx, float hy) { fromShape(Shape::box(hx, hy), out); }
+void orc_shape_set_box_at(dbx_shape* out, float hx, float hy, dbx_vec2 c, float angle) { fromShape(Shape::box(hx, hy, v2(c), angle), out); }
+int32_t orc_shape_set_polygon(dbx_shape* out, const dbx_vec2* pts, int32_t n) {
+  std::vector<V2> p(n);
+  for (int i = 0; i < n; ++i) p[i] = v2(pts[i]);
+  fromShape(Shape::polygon(p.data(), n), out);
+  return out->count;
+}
+void orc_shape_set_chain(dbx_shape* out, const dbx_vec2* pts, int32_t n, int32_t loop) {
+  std::memset(out, 0, sizeof(*out));
+  out->type = kChain; out->radius = kPolygonRadius;
+  out->chainVertices = pts; out->chainCount = n;  // caller's array; a loop must already repeat vertex 0
+  if (loop) { out->prevVertex = pts[n - 2]; out->nextVertex = pts[1]; out->hasPrev = out->hasNext = 1; }
+}
+void orc_shape_mass(const dbx_shape* s, float density, float* mass, dbx_vec2* center, float* I) {
+  MassData md; toShape(s).computeMass(&md, density);
+  *mass = md.mass; *center = d2(md.center); *I = md.I;
+}
+void orc_shape_aabb(const dbx_shape* s, float px, float py, float angle, int32_t child, dbx_aabb* out) {
+  Xf xf; xf.set(V2(px, py), angle);
+  AABB a; toShape(s).computeAABB(&a, xf, child);
+  out->lo = d2(a.lo); out->hi = d2(a.hi);
+}
+
+// ---- world ----
+orc_world* orc_world_create(float gx, float gy) { return new orc_world(V2(gx, gy)); }
+void orc_world_destroy(orc_world* w) { delete w; }
+int32_t orc_world_set_flags(orc_world* w, uint32_t f) {
+  w->w.allowSleep = (f & DBX_WORLD_ALLOW_SLEEP) != 0;
+  if (!w->w.allowSleep) for (Body* b = w->w.bodyList; b; b = b->next) b->setAwake(true);  // b2world.d:622-640
+  w->w.warmStarting = (f & DBX_WORLD_WARM_STARTING) != 0;
+  w->w.continuousPhysics = (f & DBX_WORLD_CONTINUOUS) != 0;
+  w->w.subStepping = (f & DBX_WORLD_SUB_STEPPING) != 0;
+  w->w.clearForcesFlag = (f & DBX_WORLD_AUTO_CLEAR_FORCES) != 0;
+  return 0;
+}
+int32_t orc_world_set_gravity(orc_world* w, float gx, float gy) { w->w.gravity = V2(gx, gy); return 0; }
+
+int32_t orc_body_create(orc_world* w, const dbx_body_def* d) {
+  BodyDef bd;
+  bd.type = d->type; bd.position = v2(d->position); bd.angle = d->angle; bd.linearVelocity = v2(d->linearVelocity);
+  bd.angularVelocity = d->angularVelocity; bd.linearDamping = d->linearDamping; bd.angularDamping = d->angularDamping;
+  bd.allowSleep = d->allowSleep != 0; bd.awake = d->awake != 0; bd.fixedRotation = d->fixedRotation != 0;
+  bd.bullet = d->bullet != 0; bd.active = d->active != 0; bd.gravityScale = d->gravityScale; bd.userData = d->userData;
+  Body* b = w->w.createBody(bd);
+  return b ? b->id : DBX_E_LOCKED;
+}
+int32_t orc_body_destroy(orc_world* w, int32_t body) {
+  if (body < 0 || body >= (int)w->w.bodiesById.size() || !w->w.bodiesById[body]) return DBX_E_INVALID;
+  w->w.destroyBody(w->w.bodiesById[body]);
+  return 0;
+}
+int32_t orc_fixture_create(orc_world* w, int32_t body, const dbx_fixture_def* d, const dbx_shape* s) {
+  if (body < 0 || body >= (int)w->w.bodiesById.size() || !w->w.bodiesById[body]) return DBX_E_INVALID;
+  Shape shape = toShape(s);
+  FixtureDef fd;
+  fd.shape = &shape; fd.friction = d->friction; fd.restitution = d->restitution; fd.density = d->density;
+  fd.isSensor = d->isSensor != 0; fd.filter.categoryBits = d->categoryBits; fd.filter.maskBits = d->maskBits; fd.filter.groupIndex = d->groupIndex;
+  fd.userData = d->userData;
+  Fixture* f = w->w.createFixture(w->w.bodiesById[body], fd);
+  return f ? f->id : DBX_E_LOCKED;
+}
+int32_t orc_fixture_destroy(orc_world* w, int32_t fixture) {
+  if (fixture < 0 || fixture >= (int)w->w.fixturesById.size() || !w->w.fixturesById[fixture]) return DBX_E_INVALID;
+  w->w.destroyFixture(w->w.fixturesById[fixture]);
+  return 0;
+}
+int32_t orc_joint_create(orc_world* w, const dbx_joint_def* d) {
+  auto& B = w->w.bodiesById;
+  if (d->bodyA < 0 || d->bodyB < 0 || d->bodyA >= (int)B.size() || d->bodyB >= (int)B.size() || !B[d->bodyA] || !B[d->bodyB]) return DBX_E_INVALID;
+  Joint* j = nullptr;
+  if (d->type == jRevolute) {
+    // b2revolutejoint.d:118-137
+    RevoluteJoint* r = new RevoluteJoint();
+    r->localAnchorA = v2(d->localAnchorA); r->localAnchorB = v2(d->localAnchorB); r->referenceAngle = d->referenceAngle;
+    r->lowerAngle = d->lowerAngle; r->upperAngle = d->upperAngle; r->maxMotorTorque = d->maxMotorTorque; r->motorSpeed = d->motorSpeed;
+    r->enableLimit = d->enableLimit != 0; r->enableMotor = d->enableMotor != 0; r->limitState = kInactiveLimit;
+    j = r;
+  } else if (d->type == jDistance) {
+    // b2distancejoint.d:98-109
+    DistanceJoint* dj = new DistanceJoint();
+    dj->localAnchorA = v2(d->localAnchorA); dj->localAnchorB = v2(d->localAnchorB); dj->length = d->length;
+    dj->frequencyHz = d->frequencyHz; dj->dampingRatio = d->dampingRatio;
+    j = dj;
+  } else {
+    return DBX_E_UNSUPPORTED;
+  }
+  j->type = d->type; j->bodyA = B[d->bodyA]; j->bodyB = B[d->bodyB]; j->collideConnected = d->collideConnected != 0; j->userData = d->userData;
+  Joint* r = w->w.addJoint(j);
+  return r ? r->id : DBX_E_LOCKED;
+}
+int32_t orc_joint_destroy(orc_world* w, int32_t joint) {
+  if (joint < 0 || joint >= (int)w->w.jointsById.size() || !w->w.jointsById[joint]) return DBX_E_INVALID;
+  w->w.destroyJoint(w->w.jointsById[joint]);
+  return 0;
+}
+
+int32_t orc_world_step(orc_world* w, float dt, int32_t vi, int32_t pi) { w->w.step(dt, vi, pi); return 0; }
+int32_t orc_world_step_n(orc_world* w, float dt, int32_t vi, int32_t pi, int32_t n) { for (int i = 0; i < n; ++i) w->w.step(dt, vi, pi); return 0; }
+
+// ---- body access ----
+static void fillBody(const Body* b, dbx_body_state* o) {
+  o->type = b->type; o->flags = b->flags; o->p = d2(b->xf.p); o->qs = b->xf.q.s; o->qc = b->xf.q.c;
+  o->localCenter = d2(b->sweep.localCenter); o->c0 = d2(b->sweep.c0); o->c = d2(b->sweep.c);
+  o->a0 = b->sweep.a0; o->a = b->sweep.a; o->alpha0 = b->sweep.alpha0;
+  o->v = d2(b->linearVelocity); o->w = b->angularVelocity; o->force = d2(b->force); o->torque = b->torque;
+  o->mass = b->mass; o->invMass = b->invMass; o->I = b->I; o->invI = b->invI;
+  o->linearDamping = b->linearDamping; o->angularDamping = b->angularDamping; o->gravityScale = b->gravityScale; o->sleepTime = b->sleepTime;
+}
+static Body* getBody(orc_world* w, int32_t id) { return (id >= 0 && id < (int)w->w.bodiesById.size()) ? w->w.bodiesById[id] : nullptr; }
+int32_t orc_body_get_state(orc_world* w, int32_t body, dbx_body_state* out) { Body* b = getBody(w, body); if (!b) return DBX_E_INVALID; fillBody(b, out); return 0; }
+int32_t orc_world_read_bodies(orc_world* w, dbx_body_state* out, int32_t cap) {
+  int n = (int)w->w.bodiesById.size();
+  for (int i = 0; i < n && i < cap; ++i) { if (w->w.bodiesById[i]) fillBody(w->w.bodiesById[i], out + i); else std::memset(out + i, 0, sizeof(*out)); }
+  return n;
+}
+// b2body.d:261-285
+int32_t orc_body_set_transform(orc_world* w, int32_t body, float x, float y, float angle) {
+  Body* b = getBody(w, body); if (!b) return DBX_E_INVALID;
+  b->xf.q.set(angle); b->xf.p = V2(x, y);
+  b->sweep.c = mul(b->xf, b->sweep.localCenter); b->sweep.a = angle;
+  b->sweep.c0 = b->sweep.c; b->sweep.a0 = angle;
+  for (Fixture* f = b->fixtureList; f; f = f->next) {
+    for (int i = 0; i < f->proxyCount; ++i) {
+      FixtureProxy* p = &f->proxies[i];
+      AABB a1, a2; f->shape.computeAABB(&a1, b->xf, p->childIndex); f->shape.computeAABB(&a2, b->xf, p->childIndex);
+      p->aabb.combine(a1, a2);
+      w->w.broadPhase.moveProxy(p->proxyId, p->aabb, b->xf.p - b->xf.p);
+    }
+  }
+  return 0;
+}
+int32_t orc_body_set_linear_velocity(orc_world* w, int32_t body, float vx, float vy) {
+  Body* b = getBody(w, body); if (!b) return DBX_E_INVALID;
+  if (b->type == kStatic) return 0;
+  V2 v(vx, vy);
+  if (dot(v, v) > 0.0f) b->setAwake(true);
+  b->linearVelocity = v; return 0;
+}
+int32_t orc_body_set_angular_velocity(orc_world* w, int32_t body, float om) {
+  Body* b = getBody(w, body); if (!b) return DBX_E_INVALID;
+  if (b->type == kStatic) return 0;
+  if (om * om > 0.0f) b->setAwake(true);
+  b->angularVelocity = om; return 0;
+}
+int32_t orc_body_apply_force(orc_world* w, int32_t body, float fx, float fy, float px, float py, int32_t wake) {
+  Body* b = getBody(w, body); if (!b) return DBX_E_INVALID;
+  if (b->type != kDynamic) return 0;
+  if (wake && (b->flags & bAwake) == 0) b->setAwake(true);
+  if (b->flags & bAwake) { b->force += V2(fx, fy); b->torque += cross(V2(px, py) - b->sweep.c, V2(fx, fy)); }
+  return 0;
+}
+int32_t orc_body_apply_torque(orc_world* w, int32_t body, float t, int32_t wake) {
+  Body* b = getBody(w, body); if (!b) return DBX_E_INVALID;
+  if (b->type != kDynamic) return 0;
+  if (wake && (b->flags & bAwake) == 0) b->setAwake(true);
+  if (b->flags & bAwake) b->torque += t;
+  return 0;
+}
+int32_t orc_body_apply_linear_impulse(orc_world* w, int32_t body, float ix, float iy, float px, float py, int32_t wake) {
+  Body* b = getBody(w, body); if (!b) return DBX_E_INVALID;
+  if (b->type != kDynamic) return 0;
+  if (wake && (b->flags & bAwake) == 0) b->setAwake(true);
+  if (b->flags & bAwake) { b->linearVelocity += b->invMass * V2(ix, iy); b->angularVelocity += b->invI * cross(V2(px, py) - b->sweep.c, V2(ix, iy)); }
+  return 0;
+}
+int32_t orc_body_apply_angular_impulse(orc_world* w, int32_t body, float imp, int32_t wake) {
+  Body* b = getBody(w, body); if (!b) return DBX_E_INVALID;
+  if (b->type != kDynamic) return 0;
+  if (wake && (b->flags & bAwake) == 0) b->setAwake(true);
+  if (b->flags & bAwake) b->angularVelocity += b->invI * imp;
+  return 0;
+}
+int32_t orc_body_set_awake(orc_world* w, int32_t body, int32_t flag) { Body* b = getBody(w, body); if (!b) return DBX_E_INVALID; b->setAwake(flag != 0); return 0; }
+int32_t orc_body_set_bullet(orc_world* w, int32_t body, int32_t flag) { Body* b = getBody(w, body); if (!b) return DBX_E_INVALID; if (flag) b->flags |= bBullet; else b->flags &= ~bBullet; return 0; }
+int32_t orc_body_set_sleeping_allowed(orc_world* w, int32_t body, int32_t flag) {
+  Body* b = getBody(w, body); if (!b) return DBX_E_INVALID;
+  if (flag) b->flags |= bAutoSleep; else { b->flags &= ~bAutoSleep; b->setAwake(true); }
+  return 0;
+}
+
+// ---- bulk state ----
+int32_t orc_world_counts(orc_world* w, dbx_counts* o) {
+  std::memset(o, 0, sizeof(*o));
+  o->bodies = w->w.bodyCount; o->joints = w->w.jointCount; o->contacts = w->w.contactCount; o->proxies = w->w.broadPhase.proxyCount();
+  for (Fixture* f : w->w.fixturesById) if (f) ++o->fixtures;
+  for (Contact* c = w->w.contactList; c; c = c->next) if (c->isTouching()) ++o->touching;
+  for (Body* b = w->w.bodyList; b; b = b->next) if (b->isAwake() && b->type != kStatic) ++o->awakeBodies;
+  o->islands = w->w.lastIslandCount; o->moves = (int)w->w.broadPhase.moveBuffer().size(); o->pairs = (int)w->w.lastPairs.size();
+  o->colours = w->w.toiEvents;  // oracle has no colouring; slot reused for the cumulative TOI event count (tests)
+  return 0;
+}
+int32_t orc_world_profile(orc_world* w, dbx_profile* o) {
+  const Profile& p = w->w.profile;
+  o->step = p.step; o->collide = p.collide; o->solve = p.solve; o->solveInit = p.solveInit; o->solveVelocity = p.solveVelocity;
+  o->solvePosition = p.solvePosition; o->broadphase = p.broadphase; o->solveTOI = p.solveTOI;
+  return 0;
+}
+static void fillContact(const Contact* c, dbx_contact_rec* o) {
+  o->fixtureA = c->fixtureA->id; o->fixtureB = c->fixtureB->id; o->childA = c->indexA; o->childB = c->indexB; o->flags = c->flags;
+  for (int i = 0; i < 2; ++i) {
+    o->manifold.points[i].localPoint = d2(c->manifold.points[i].localPoint);
+    o->manifold.points[i].normalImpulse = c->manifold.points[i].normalImpulse;
+    o->manifold.points[i].tangentImpulse = c->manifold.points[i].tangentImpulse;
+    o->manifold.points[i].key = c->manifold.points[i].id.key;
+  }
+  o->manifold.localNormal = d2(c->manifold.localNormal); o->manifold.localPoint = d2(c->manifold.localPoint);
+  o->manifold.type = c->manifold.type; o->manifold.pointCount = c->manifold.pointCount;
+  o->friction = c->friction; o->restitution = c->restitution; o->tangentSpeed = c->tangentSpeed; o->toiCount = c->toiCount; o->toi = c->toi;
+}
+// world contact list order (newest first), as GetContactList would traverse it (b2world.d:610-613)
+int32_t orc_world_read_contacts(orc_world* w, dbx_contact_rec* out, int32_t cap) {
+  int n = 0;
+  for (Contact* c = w->w.contactList; c; c = c->next) { if (n < cap) fillContact(c, out + n); ++n; }
+  return n;
+}
+// contacts in the order the islands solved them during the last Step (sequential Gauss-Seidel order)
+int32_t orc_world_read_solve_order(orc_world* w, int32_t* fixA_childA_fixB_childB, int32_t cap) {
+  int n = 0;
+  for (Contact* c : w->w.lastSolveOrder) {
+    if (n < cap) { int32_t* o = fixA_childA_fixB_childB + 4 * n; o[0] = c->fixtureA->id; o[1] = c->indexA; o[2] = c->fixtureB->id; o[3] = c->indexB; }
+    ++n;
+  }
+  return n;
+}
+int32_t orc_world_read_proxies(orc_world* w, dbx_proxy_rec* out, int32_t cap) {
+  int n = 0;
+  for (Fixture* f : w->w.fixturesById) {
+    if (!f) continue;
+    for (int i = 0; i < f->proxyCount; ++i) {
+      if (n < cap) {
+        dbx_proxy_rec* o = out + n;
+        o->fixture = f->id; o->child = f->proxies[i].childIndex; o->proxyId = f->proxies[i].proxyId;
+        o->aabb.lo = d2(f->proxies[i].aabb.lo); o->aabb.hi = d2(f->proxies[i].aabb.hi);
+        const AABB& fat = w->w.broadPhase.fatAABB(f->proxies[i].proxyId);
+        o->fat.lo = d2(fat.lo); o->fat.hi = d2(fat.hi);
+      }
+      ++n;
+    }
+  }
+  return n;
+}
+int32_t orc_world_read_joints(orc_world* w, dbx_joint_state* out, int32_t cap) {
+  int n = (int)w->w.jointsById.size();
+  for (int i = 0; i < n && i < cap; ++i) {
+    dbx_joint_state* o = out + i; std::memset(o, 0, sizeof(*o));
+    Joint* j = w->w.jointsById[i]; if (!j) continue;
+    o->type = j->type;
+    if (j->type == jRevolute) { auto* r = (RevoluteJoint*)j; o->impulse[0] = r->impulse.x; o->impulse[1] = r->impulse.y; o->impulse[2] = r->impulse.z; o->motorImpulse = r->motorImpulse; o->limitState = r->limitState; }
+    else if (j->type == jDistance) { auto* d = (DistanceJoint*)j; o->impulse[0] = d->impulse; }
+  }
+  return n;
+}
+int32_t orc_world_read_moves(orc_world* w, int32_t* out, int32_t cap) {
+  int n = 0;
+  for (int id : w->w.broadPhase.moveBuffer()) {
+    if (id == kNullNode) continue;
+    FixtureProxy* p = (FixtureProxy*)w->w.broadPhase.userData(id);
+    if (n < cap) { out[2 * n] = p->fixture->id; out[2 * n + 1] = p->childIndex; }
+    ++n;
+  }
+  return n;
+}
+int32_t orc_world_read_pairs(orc_world* w, int32_t* out, int32_t cap) {
+  int n = 0;
+  for (auto& pr : w->w.lastPairs) {
+    if (n < cap) { int32_t* o = out + 4 * n; o[0] = pr.first->fixture->id; o[1] = pr.first->childIndex; o[2] = pr.second->fixture->id; o[3] = pr.second->childIndex; }
+    ++n;
+  }
+  return n;
+}
+int32_t orc_world_get_inv_dt0(orc_world* w, float* out) { *out = w->w.inv_dt0; return 0; }
+int32_t orc_world_stage_find_new_contacts(orc_world* w) { w->w.findNewContacts(); w->w.newFixture = false; return 0; }
+int32_t orc_world_stage_collide(orc_world* w) { w->w.collide(); return 0; }
+int32_t orc_world_tree_height(orc_world* w) { return w->w.broadPhase.treeHeight(); }
+int32_t orc_world_tree_validate(orc_world* w) { return w->w.broadPhase.tree().validate() ? 1 : 0; }
+
+// ---- pure-function entry points for known-answer fixtures (polycollision.d, distancetest.d, timeofimpact.d) ----
+int32_t orc_collide(const dbx_shape* sA, float ax, float ay, float aa, int32_t childA, const dbx_shape* sB, float bx, float by, float ba, int32_t childB, dbx_manifold* out) {
+  Shape A = toShape(sA), B = toShape(sB);
+  Fixture fA, fB; fA.shape = A; fB.shape = B;
+  Contact c; c.fixtureA = &fA; c.fixtureB = &fB; c.indexA = childA; c.indexB = childB;
+  Xf xfA, xfB; xfA.set(V2(ax, ay), aa); xfB.set(V2(bx, by), ba);
+  Manifold m;
+  c.evaluate(&m, xfA, xfB);
+  std::memset(out, 0, sizeof(*out));
+  out->type = m.type; out->pointCount = m.pointCount; out->localNormal = d2(m.localNormal); out->localPoint = d2(m.localPoint);
+  for (int i = 0; i < m.pointCount; ++i) { out->points[i].localPoint = d2(m.points[i].localPoint); out->points[i].key = m.points[i].id.key; }
+  return m.pointCount;
+}
+// same, with explicit rotation (sin, cos) so device-vs-libm sinf/cosf differences cannot leak into a bit-exact compare
+int32_t orc_collide_xf(const dbx_shape* sA, const float* xfa, int32_t childA, const dbx_shape* sB, const float* xfb, int32_t childB, dbx_manifold* out) {
+  Shape A = toShape(sA), B = toShape(sB);
+  Fixture fA, fB; fA.shape = A; fB.shape = B;
+  Contact c; c.fixtureA = &fA; c.fixtureB = &fB; c.indexA = childA; c.indexB = childB;
+  Xf xfA, xfB; xfA.p = V2(xfa[0], xfa[1]); xfA.q.s = xfa[2]; xfA.q.c = xfa[3]; xfB.p = V2(xfb[0], xfb[1]); xfB.q.s = xfb[2]; xfB.q.c = xfb[3];
+  Manifold m;
+  c.evaluate(&m, xfA, xfB);
+  std::memset(out, 0, sizeof(*out));
+  out->type = m.type; out->pointCount = m.pointCount; out->localNormal = d2(m.localNormal); out->localPoint = d2(m.localPoint);
+  for (int i = 0; i < m.pointCount; ++i) { out->points[i].localPoint = d2(m.points[i].localPoint); out->points[i].key = m.points[i].id.key; }
+  return m.pointCount;
+}
+float orc_distance(const dbx_shape* sA, float ax, float ay, float aa, int32_t childA, const dbx_shape* sB, float bx, float by, float ba, int32_t childB,
+                   int32_t useRadii, dbx_vec2* pA, dbx_vec2* pB, int32_t* iterations) {
+  Shape A = toShape(sA), B = toShape(sB);
+  DistanceInput in; in.proxyA.set(A, childA); in.proxyB.set(B, childB);
+  in.transformA.set(V2(ax, ay), aa); in.transformB.set(V2(bx, by), ba); in.useRadii = useRadii != 0;
+  SimplexCache cache; cache.count = 0;
+  DistanceOutput o; distance(&o, &cache, &in);
+  *pA = d2(o.pointA); *pB = d2(o.pointB); *iterations = o.iterations;
+  return o.distance;
+}
+// sweeps given as {localCenter.x, localCenter.y, c0.x, c0.y, c.x, c.y, a0, a, alpha0}
+int32_t orc_time_of_impact(const dbx_shape* sA, const float* sweepA, int32_t childA, const dbx_shape* sB, const float* sweepB, int32_t childB, float tMax, float* t) {
+  Shape A = toShape(sA), B = toShape(sB);
+  TOIInput in; in.proxyA.set(A, childA); in.proxyB.set(B, childB);
+  auto rd = [](const float* s) { Sweep w; w.localCenter = V2(s[0], s[1]); w.c0 = V2(s[2], s[3]); w.c = V2(s[4], s[5]); w.a0 = s[6]; w.a = s[7]; w.alpha0 = s[8]; return w; };
+  in.sweepA = rd(sweepA); in.sweepB = rd(sweepB); in.tMax = tMax;
+  TOIOutput o; timeOfImpact(&o, &in);
+  *t = o.t;
+  return o.state;
+}
+
+// ---- CPU baseline helper: step `nWorlds` independent worlds `steps` times on `threads` host threads, one world per
+// thread at a time.  Returns wall seconds of the stepping only. ----
+double orc_batch_step(orc_world** worlds, int32_t nWorlds, float dt, int32_t vi, int32_t pi, int32_t steps, int32_t threads) {
+  auto t0 = std::chrono::steady_clock::now();
+  if (threads <= 1) {
+    for (int i = 0; i < nWorlds; ++i) for (int s = 0; s < steps; ++s) worlds[i]->w.step(dt, vi, pi);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+      pool.emplace_back([=]() { for (int i = t; i < nWorlds; i += threads) for (int s = 0; s < steps; ++s) worlds[i]->w.step(dt, vi, pi); });
+    for (auto& th : pool) th.join();
+  }
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+}  // extern "C"

@@ -1,0 +1,183 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.h header).  PARITY UNPINNED.
+//
+// World / body / fixture / contact / joint object graph, contact manager, contact solver, islands and
+// the TOI sub-stepper; restates
+//   src/dbox/dynamics/b2world.d, b2body.d, b2fixture.d, b2contactmanager.d, b2island.d, b2timestep.d,
+//   src/dbox/dynamics/b2worldcallbacks.d (default filter), dynamics/contacts/b2contact.d, b2contactsolver.d,
+//   src/dbox/dynamics/joints/b2joint.d, b2revolutejoint.d, b2distancejoint.d
+// It keeps the reference's intrusive push-front lists and DFS island order because those define the
+// sequential Gauss-Seidel order the reference results depend on.
+#pragma once
+#include <memory>
+#include <vector>
+#include "orc_collide.h"
+#include "orc_tree.h"
+
+namespace orc {
+
+struct Body; struct Fixture; struct Contact; struct Joint; struct World;
+
+enum BodyType { kStatic = 0, kKinematic = 1, kDynamic = 2 };
+enum BodyFlags { bIsland = 1, bAwake = 2, bAutoSleep = 4, bBullet = 8, bFixedRotation = 0x10, bActive = 0x20, bToi = 0x40 };
+enum ContactFlags { cIsland = 1, cTouching = 2, cEnabled = 4, cFilter = 8, cBulletHit = 0x10, cToi = 0x20 };
+enum JointType { jUnknown, jRevolute, jPrismatic, jDistance, jPulley, jMouse, jGear, jWheel, jWeld, jFriction, jRope, jMotor };
+enum LimitState { kInactiveLimit, kAtLowerLimit, kAtUpperLimit, kEqualLimits };
+
+struct Filter { uint16_t categoryBits = 1, maskBits = 0xFFFF; int16_t groupIndex = 0; };
+struct FixtureProxy { AABB aabb; Fixture* fixture = nullptr; int childIndex = 0; int proxyId = -1; };
+
+struct ContactEdge { Body* other = nullptr; Contact* contact = nullptr; ContactEdge* prev = nullptr; ContactEdge* next = nullptr; };
+struct JointEdge { Body* other = nullptr; Joint* joint = nullptr; JointEdge* prev = nullptr; JointEdge* next = nullptr; };
+
+struct TimeStep { float dt = 0, inv_dt = 0, dtRatio = 0; int velocityIterations = 0, positionIterations = 0; bool warmStarting = false; };
+struct Position { V2 c; float a = 0; };
+struct Velocity { V2 v; float w = 0; };
+struct SolverData { TimeStep step; Position* positions; Velocity* velocities; };
+
+struct Fixture {
+  int id = -1;
+  float density = 0;
+  Fixture* next = nullptr;
+  Body* body = nullptr;
+  Shape shape;
+  float friction = 0.2f, restitution = 0;
+  std::vector<FixtureProxy> proxies;  // sized to childCount at creation, never resized
+  int proxyCount = 0;
+  Filter filter;
+  bool isSensor = false;
+  uint64_t userData = 0;
+};
+
+struct Body {
+  int id = -1;
+  int type = kStatic;
+  uint16_t flags = 0;
+  int islandIndex = 0;
+  Xf xf;
+  Sweep sweep;
+  V2 linearVelocity; float angularVelocity = 0;
+  V2 force; float torque = 0;
+  World* world = nullptr;
+  Body* prev = nullptr; Body* next = nullptr;
+  Fixture* fixtureList = nullptr; int fixtureCount = 0;
+  JointEdge* jointList = nullptr;
+  ContactEdge* contactList = nullptr;
+  float mass = 0, invMass = 0, I = 0, invI = 0;
+  float linearDamping = 0, angularDamping = 0, gravityScale = 1;
+  float sleepTime = 0;
+  uint64_t userData = 0;
+
+  bool isAwake() const { return (flags & bAwake) == bAwake; }
+  bool isActive() const { return (flags & bActive) == bActive; }
+  bool isBullet() const { return (flags & bBullet) == bBullet; }
+  void setAwake(bool flag);                // b2body.d:827-846
+  void synchronizeTransform();             // b2body.d:1143-1147
+  void synchronizeFixtures();              // b2body.d:1129-1141
+  void advance(float alpha);               // b2body.d:1172-1180
+  bool shouldCollide(const Body* other) const;  // b2body.d:1149-1170
+  void resetMassData();                    // b2body.d:555-625
+};
+
+struct Contact {
+  uint32_t flags = cEnabled;
+  Contact* prev = nullptr; Contact* next = nullptr;
+  ContactEdge nodeA, nodeB;
+  Fixture* fixtureA = nullptr; Fixture* fixtureB = nullptr;
+  int indexA = 0, indexB = 0;
+  Manifold manifold;
+  int toiCount = 0;
+  float toi = 0;
+  float friction = 0, restitution = 0, tangentSpeed = 0;
+  bool isTouching() const { return (flags & cTouching) == cTouching; }
+  bool isEnabled() const { return (flags & cEnabled) == cEnabled; }
+  void evaluate(Manifold* m, const Xf& xfA, const Xf& xfB) const;  // the 7 b2*contact.d Evaluate overrides (line 56 each)
+  void update(World* w);                                           // b2contact.d:270-356
+};
+
+struct Joint {
+  int id = -1;
+  int type = jUnknown;
+  Joint* prev = nullptr; Joint* next = nullptr;
+  JointEdge edgeA, edgeB;
+  Body* bodyA = nullptr; Body* bodyB = nullptr;
+  bool islandFlag = false, collideConnected = false;
+  uint64_t userData = 0;
+  virtual ~Joint() {}
+  virtual void initVelocityConstraints(const SolverData& data) = 0;
+  virtual void solveVelocityConstraints(const SolverData& data) = 0;
+  virtual bool solvePositionConstraints(const SolverData& data) = 0;
+};
+
+struct RevoluteJoint : Joint {
+  V2 localAnchorA, localAnchorB; V3 impulse; float motorImpulse = 0;
+  bool enableMotor = false; float maxMotorTorque = 0, motorSpeed = 0;
+  bool enableLimit = false; float referenceAngle = 0, lowerAngle = 0, upperAngle = 0;
+  int indexA = 0, indexB = 0; V2 rA, rB, localCenterA, localCenterB;
+  float invMassA = 0, invMassB = 0, invIA = 0, invIB = 0;
+  M33 mass; float motorMass = 0; int limitState = kInactiveLimit;
+  void initVelocityConstraints(const SolverData& data) override;
+  void solveVelocityConstraints(const SolverData& data) override;
+  bool solvePositionConstraints(const SolverData& data) override;
+};
+
+struct DistanceJoint : Joint {
+  float frequencyHz = 0, dampingRatio = 0, bias = 0;
+  V2 localAnchorA, localAnchorB; float gamma = 0, impulse = 0, length = 0;
+  int indexA = 0, indexB = 0; V2 u, rA, rB, localCenterA, localCenterB;
+  float invMassA = 0, invMassB = 0, invIA = 0, invIB = 0, mass = 0;
+  void initVelocityConstraints(const SolverData& data) override;
+  void solveVelocityConstraints(const SolverData& data) override;
+  bool solvePositionConstraints(const SolverData& data) override;
+};
+
+struct Profile { float step = 0, collide = 0, solve = 0, solveInit = 0, solveVelocity = 0, solvePosition = 0, broadphase = 0, solveTOI = 0; };
+
+struct BodyDef {
+  int type = kStatic; V2 position; float angle = 0; V2 linearVelocity; float angularVelocity = 0;
+  float linearDamping = 0, angularDamping = 0;
+  bool allowSleep = true, awake = true, fixedRotation = false, bullet = false, active = true;
+  float gravityScale = 1.0f; uint64_t userData = 0;
+};
+struct FixtureDef { const Shape* shape = nullptr; float friction = 0.2f, restitution = 0, density = 0; bool isSensor = false; Filter filter; uint64_t userData = 0; };
+
+struct World {
+  explicit World(V2 gravity);
+  ~World();
+  Body* createBody(const BodyDef& def);               // b2world.d:75-99
+  void destroyBody(Body* b);                          // b2world.d:105-191
+  Fixture* createFixture(Body* b, const FixtureDef& def);  // b2body.d:116-155
+  void destroyFixture(Fixture* f);                    // b2body.d:179-247
+  Joint* addJoint(Joint* j);                          // b2world.d:196-261 (takes ownership)
+  void destroyJoint(Joint* j);                        // b2world.d:265-360
+  void step(float dt, int velocityIterations, int positionIterations);  // b2world.d:367-434
+  void clearForces();
+
+  // contact manager (b2contactmanager.d)
+  void addPair(void* proxyUserDataA, void* proxyUserDataB);
+  void findNewContacts();
+  void destroyContact(Contact* c);
+  void collide();
+
+  void solve(const TimeStep& step);
+  void solveTOI(const TimeStep& step);
+
+  // state
+  BroadPhase broadPhase;
+  Contact* contactList = nullptr; int contactCount = 0;
+  Body* bodyList = nullptr; Joint* jointList = nullptr;
+  int bodyCount = 0, jointCount = 0;
+  V2 gravity; bool allowSleep = true;
+  bool newFixture = false, locked = false, clearForcesFlag = true;
+  float inv_dt0 = 0;
+  bool warmStarting = true, continuousPhysics = true, subStepping = false, stepComplete = true;
+  Profile profile;
+
+  // id tables (C API handles)
+  std::vector<Body*> bodiesById; std::vector<Fixture*> fixturesById; std::vector<Joint*> jointsById;
+  // diagnostics for tests
+  int lastIslandCount = 0; int toiEvents = 0;
+  std::vector<std::pair<FixtureProxy*, FixtureProxy*>> lastPairs;  // unique pairs handed to AddPair by the last UpdatePairs
+  std::vector<Contact*> lastSolveOrder;   // contacts in the order islands solved them in the last Solve
+};
+
+}  // namespace orc
