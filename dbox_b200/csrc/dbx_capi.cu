@@ -1,0 +1,235 @@
+// dbx_capi.cu — the extern "C" boundary declared in include/dbox_b200.h.  Plain pointers and sizes only.
+#include <cstring>
+#include <new>
+#include "dbx_world.h"
+
+using namespace dbx;
+
+struct dbx_world { World w; dbx_world(float gx, float gy, int dev, const dbx_caps* caps) : w(gx, gy, dev, caps) {} };
+
+static_assert(sizeof(dbx_body_def) == 72 && sizeof(dbx_shape) == 240 && sizeof(dbx_fixture_def) == 32 && sizeof(dbx_joint_def) == 80, "ABI layout");
+static_assert(sizeof(dbx_body_state) == 116 && sizeof(dbx_manifold) == 64 && sizeof(dbx_contact_rec) == 104 && sizeof(dbx_proxy_rec) == 44, "ABI layout");
+
+#define W_OR_INVALID(w) do { if (!(w) || !(w)->w.ok()) return DBX_E_INVALID; } while (0)
+
+extern "C" {
+
+int32_t dbx_abi_version(void) { return DBX_ABI_VERSION; }
+const char* dbx_last_error(void) { return get_last_error(); }
+int32_t dbx_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+
+// ---- defaults
+void dbx_default_body_def(dbx_body_def* d) {
+  std::memset(d, 0, sizeof(*d));
+  d->type = DBX_STATIC_BODY; d->allowSleep = 1; d->awake = 1; d->active = 1; d->gravityScale = 1.0f;
+}
+void dbx_default_fixture_def(dbx_fixture_def* d) {
+  std::memset(d, 0, sizeof(*d));
+  d->friction = 0.2f; d->categoryBits = 0x0001; d->maskBits = 0xFFFF;
+}
+void dbx_default_joint_def(dbx_joint_def* d, int32_t type) {
+  std::memset(d, 0, sizeof(*d));
+  d->type = type;
+  if (type == DBX_JOINT_DISTANCE) d->length = 1.0f;
+}
+
+// ---- shape helpers (setup time, host): same arithmetic as the reference's shape classes
+void dbx_shape_set_circle(dbx_shape* s, float px, float py, float radius) {
+  std::memset(s, 0, sizeof(*s));
+  s->type = DBX_SHAPE_CIRCLE; s->radius = radius; s->p.x = px; s->p.y = py;
+}
+void dbx_shape_set_edge(dbx_shape* s, dbx_vec2 v1, dbx_vec2 v2) {
+  std::memset(s, 0, sizeof(*s));
+  s->type = DBX_SHAPE_EDGE; s->radius = kPolygonRadius; s->v1 = v1; s->v2 = v2;
+}
+void dbx_shape_set_box(dbx_shape* s, float hx, float hy) {
+  std::memset(s, 0, sizeof(*s));
+  s->type = DBX_SHAPE_POLYGON; s->radius = kPolygonRadius; s->count = 4;
+  s->vertices[0] = dbx_vec2{-hx, -hy}; s->vertices[1] = dbx_vec2{hx, -hy}; s->vertices[2] = dbx_vec2{hx, hy}; s->vertices[3] = dbx_vec2{-hx, hy};
+  s->normals[0] = dbx_vec2{0.0f, -1.0f}; s->normals[1] = dbx_vec2{1.0f, 0.0f}; s->normals[2] = dbx_vec2{0.0f, 1.0f}; s->normals[3] = dbx_vec2{-1.0f, 0.0f};
+}
+void dbx_shape_set_box_at(dbx_shape* s, float hx, float hy, dbx_vec2 center, float angle) {
+  dbx_shape_set_box(s, hx, hy);
+  s->centroid = center;
+  Xf xf; xf.p = V(center.x, center.y); xf.q = rot_from_angle(angle);
+  for (int i = 0; i < 4; ++i) {
+    v2 v = mul(xf, V(s->vertices[i].x, s->vertices[i].y)), n = mul(xf.q, V(s->normals[i].x, s->normals[i].y));
+    s->vertices[i] = dbx_vec2{v.x, v.y}; s->normals[i] = dbx_vec2{n.x, n.y};
+  }
+}
+// b2PolygonShape.Set: weld near-duplicates, gift-wrap the hull, edge normals, area-weighted centroid
+int32_t dbx_shape_set_polygon(dbx_shape* s, const dbx_vec2* pts, int32_t count) {
+  if (count < 3) { dbx_shape_set_box(s, 1.0f, 1.0f); return s->count; }
+  std::memset(s, 0, sizeof(*s));
+  s->type = DBX_SHAPE_POLYGON; s->radius = kPolygonRadius;
+  int n = count < kMaxPolygonVertices ? count : kMaxPolygonVertices;
+  v2 ps[kMaxPolygonVertices];
+  int m = 0;
+  for (int i = 0; i < n; ++i) {
+    v2 v = V(pts[i].x, pts[i].y);
+    bool unique = true;
+    for (int j = 0; j < m; ++j) if (dist2(v, ps[j]) < 0.5f * kLinearSlop) { unique = false; break; }
+    if (unique) ps[m++] = v;
+  }
+  n = m;
+  if (n < 3) { dbx_shape_set_box(s, 1.0f, 1.0f); return s->count; }
+  int i0 = 0; float x0 = ps[0].x;
+  for (int i = 1; i < n; ++i) { float x = ps[i].x; if (x > x0 || (x == x0 && ps[i].y < ps[i0].y)) { i0 = i; x0 = x; } }
+  int hull[kMaxPolygonVertices];
+  int h = 0, ih = i0;
+  for (;;) {
+    hull[h] = ih;
+    int ie = 0;
+    for (int j = 1; j < n; ++j) {
+      if (ie == ih) { ie = j; continue; }
+      v2 r = ps[ie] - ps[hull[h]], v = ps[j] - ps[hull[h]];
+      float c = cross(r, v);
+      if (c < 0.0f) ie = j;
+      if (c == 0.0f && len2(v) > len2(r)) ie = j;
+    }
+    ++h; ih = ie;
+    if (ie == i0) break;
+  }
+  if (h < 3) { dbx_shape_set_box(s, 1.0f, 1.0f); return s->count; }
+  s->count = h;
+  v2 vs[kMaxPolygonVertices];
+  for (int i = 0; i < h; ++i) { vs[i] = ps[hull[i]]; s->vertices[i] = dbx_vec2{vs[i].x, vs[i].y}; }
+  for (int i = 0; i < h; ++i) {
+    v2 e = vs[i + 1 < h ? i + 1 : 0] - vs[i];
+    v2 nn = cross(e, 1.0f);
+    normalize(nn);
+    s->normals[i] = dbx_vec2{nn.x, nn.y};
+  }
+  v2 c = V(0.0f, 0.0f); float area = 0.0f; const float inv3 = 1.0f / 3.0f;
+  for (int i = 0; i < h; ++i) {
+    v2 p1 = V(0.0f, 0.0f), p2 = vs[i], p3 = i + 1 < h ? vs[i + 1] : vs[0];
+    float D = cross(p2 - p1, p3 - p1);
+    float tri = 0.5f * D;
+    area += tri;
+    c += tri * inv3 * (p1 + p2 + p3);
+  }
+  c *= 1.0f / area;
+  s->centroid = dbx_vec2{c.x, c.y};
+  return h;
+}
+void dbx_shape_set_chain(dbx_shape* s, const dbx_vec2* pts, int32_t n, int32_t loop) {
+  std::memset(s, 0, sizeof(*s));
+  s->type = DBX_SHAPE_CHAIN; s->radius = kPolygonRadius; s->chainVertices = pts; s->chainCount = n;
+  if (loop && n >= 3) { s->prevVertex = pts[n - 2]; s->nextVertex = pts[1]; s->hasPrev = 1; s->hasNext = 1; }
+}
+
+// ---- world
+dbx_world* dbx_world_create(float gx, float gy, int32_t device, const dbx_caps* caps) {
+  dbx_world* w = new (std::nothrow) dbx_world(gx, gy, device, caps);
+  if (!w) { set_last_error("out of host memory"); return nullptr; }
+  if (!w->w.ok()) { delete w; return nullptr; }   // no device => no world: there is no CPU path
+  return w;
+}
+void dbx_world_destroy(dbx_world* w) { delete w; }
+int32_t dbx_world_set_flags(dbx_world* w, uint32_t flags) { W_OR_INVALID(w); return w->w.setFlags(flags); }
+uint32_t dbx_world_get_flags(dbx_world* w) { return (w && w->w.ok()) ? w->w.flags() : 0; }
+int32_t dbx_world_set_gravity(dbx_world* w, float gx, float gy) { W_OR_INVALID(w); return w->w.setGravity(gx, gy); }
+
+int32_t dbx_body_create(dbx_world* w, const dbx_body_def* def) { W_OR_INVALID(w); if (!def) return DBX_E_INVALID; return w->w.createBody(*def); }
+int32_t dbx_body_destroy(dbx_world* w, int32_t body) { W_OR_INVALID(w); return w->w.destroyBody(body); }
+int32_t dbx_fixture_create(dbx_world* w, int32_t body, const dbx_fixture_def* def, const dbx_shape* shape) {
+  W_OR_INVALID(w); if (!def || !shape) return DBX_E_INVALID; return w->w.createFixture(body, *def, *shape);
+}
+int32_t dbx_fixture_destroy(dbx_world* w, int32_t fixture) { W_OR_INVALID(w); return w->w.destroyFixture(fixture); }
+int32_t dbx_joint_create(dbx_world* w, const dbx_joint_def* def) { W_OR_INVALID(w); if (!def) return DBX_E_INVALID; return w->w.createJoint(*def); }
+int32_t dbx_joint_destroy(dbx_world* w, int32_t joint) { W_OR_INVALID(w); return w->w.destroyJoint(joint); }
+
+int32_t dbx_world_step(dbx_world* w, float dt, int32_t vi, int32_t pi) { W_OR_INVALID(w); return w->w.step(dt, vi, pi, 1); }
+int32_t dbx_world_step_n(dbx_world* w, float dt, int32_t vi, int32_t pi, int32_t n) { W_OR_INVALID(w); return w->w.step(dt, vi, pi, n); }
+int32_t dbx_world_clear_forces(dbx_world* w) { W_OR_INVALID(w); return w->w.clearForces(); }
+
+// ---- body accessors / mutators (dynamics/b2body.d)
+int32_t dbx_body_get_state(dbx_world* w, int32_t body, dbx_body_state* out) { W_OR_INVALID(w); if (!out) return DBX_E_INVALID; return w->w.getBody(body, out); }
+int32_t dbx_body_set_transform(dbx_world* w, int32_t body, float x, float y, float angle) { W_OR_INVALID(w); return w->w.setTransform(body, x, y, angle); }
+int32_t dbx_body_set_linear_velocity(dbx_world* w, int32_t body, float vx, float vy) {
+  W_OR_INVALID(w); HBody* b = w->w.mutBody(body); if (!b) return DBX_E_INVALID;
+  if (b->st.type == DBX_STATIC_BODY) return 0;
+  if (vx * vx + vy * vy > 0.0f) w->w.wake(*b, true);
+  b->st.v = dbx_vec2{vx, vy}; return 0;
+}
+int32_t dbx_body_set_angular_velocity(dbx_world* w, int32_t body, float omega) {
+  W_OR_INVALID(w); HBody* b = w->w.mutBody(body); if (!b) return DBX_E_INVALID;
+  if (b->st.type == DBX_STATIC_BODY) return 0;
+  if (omega * omega > 0.0f) w->w.wake(*b, true);
+  b->st.w = omega; return 0;
+}
+int32_t dbx_body_apply_force(dbx_world* w, int32_t body, float fx, float fy, float px, float py, int32_t wake) {
+  W_OR_INVALID(w); HBody* b = w->w.mutBody(body); if (!b) return DBX_E_INVALID;
+  if (b->st.type != DBX_DYNAMIC_BODY) return 0;
+  if (wake && (b->st.flags & DBX_BODY_AWAKE) == 0) w->w.wake(*b, true);
+  if (b->st.flags & DBX_BODY_AWAKE) {
+    b->st.force.x += fx; b->st.force.y += fy;
+    b->st.torque += cross(V(px, py) - V(b->st.c.x, b->st.c.y), V(fx, fy));
+  }
+  return 0;
+}
+int32_t dbx_body_apply_torque(dbx_world* w, int32_t body, float torque, int32_t wake) {
+  W_OR_INVALID(w); HBody* b = w->w.mutBody(body); if (!b) return DBX_E_INVALID;
+  if (b->st.type != DBX_DYNAMIC_BODY) return 0;
+  if (wake && (b->st.flags & DBX_BODY_AWAKE) == 0) w->w.wake(*b, true);
+  if (b->st.flags & DBX_BODY_AWAKE) b->st.torque += torque;
+  return 0;
+}
+int32_t dbx_body_apply_linear_impulse(dbx_world* w, int32_t body, float ix, float iy, float px, float py, int32_t wake) {
+  W_OR_INVALID(w); HBody* b = w->w.mutBody(body); if (!b) return DBX_E_INVALID;
+  if (b->st.type != DBX_DYNAMIC_BODY) return 0;
+  if (wake && (b->st.flags & DBX_BODY_AWAKE) == 0) w->w.wake(*b, true);
+  if (b->st.flags & DBX_BODY_AWAKE) {
+    v2 dv = b->st.invMass * V(ix, iy);
+    b->st.v.x += dv.x; b->st.v.y += dv.y;
+    b->st.w += b->st.invI * cross(V(px, py) - V(b->st.c.x, b->st.c.y), V(ix, iy));
+  }
+  return 0;
+}
+int32_t dbx_body_apply_angular_impulse(dbx_world* w, int32_t body, float impulse, int32_t wake) {
+  W_OR_INVALID(w); HBody* b = w->w.mutBody(body); if (!b) return DBX_E_INVALID;
+  if (b->st.type != DBX_DYNAMIC_BODY) return 0;
+  if (wake && (b->st.flags & DBX_BODY_AWAKE) == 0) w->w.wake(*b, true);
+  if (b->st.flags & DBX_BODY_AWAKE) b->st.w += b->st.invI * impulse;
+  return 0;
+}
+int32_t dbx_body_set_awake(dbx_world* w, int32_t body, int32_t flag) {
+  W_OR_INVALID(w); HBody* b = w->w.mutBody(body); if (!b) return DBX_E_INVALID; w->w.wake(*b, flag != 0); return 0;
+}
+int32_t dbx_body_set_bullet(dbx_world* w, int32_t body, int32_t flag) {
+  W_OR_INVALID(w); HBody* b = w->w.mutBody(body); if (!b) return DBX_E_INVALID;
+  if (flag) b->st.flags |= DBX_BODY_BULLET; else b->st.flags &= ~DBX_BODY_BULLET; return 0;
+}
+int32_t dbx_body_set_sleeping_allowed(dbx_world* w, int32_t body, int32_t flag) {
+  W_OR_INVALID(w); HBody* b = w->w.mutBody(body); if (!b) return DBX_E_INVALID;
+  if (flag) b->st.flags |= DBX_BODY_AUTOSLEEP; else { b->st.flags &= ~DBX_BODY_AUTOSLEEP; w->w.wake(*b, true); }
+  return 0;
+}
+
+// ---- bulk state
+int32_t dbx_world_counts(dbx_world* w, dbx_counts* out) { W_OR_INVALID(w); if (!out) return DBX_E_INVALID; return w->w.counts(out); }
+int32_t dbx_world_profile(dbx_world* w, dbx_profile* out) { W_OR_INVALID(w); if (!out) return DBX_E_INVALID; return w->w.profile(out); }
+int32_t dbx_world_read_bodies(dbx_world* w, dbx_body_state* out, int32_t cap) { W_OR_INVALID(w); return w->w.readBodies(out, out ? cap : 0); }
+int32_t dbx_world_write_bodies(dbx_world* w, const dbx_body_state* in, int32_t n) { W_OR_INVALID(w); if (!in && n) return DBX_E_INVALID; return w->w.writeBodies(in, n); }
+int32_t dbx_world_read_contacts(dbx_world* w, dbx_contact_rec* out, int32_t cap) { W_OR_INVALID(w); return w->w.readContacts(out, out ? cap : 0); }
+int32_t dbx_world_write_contacts(dbx_world* w, const dbx_contact_rec* in, int32_t n) { W_OR_INVALID(w); if (!in && n) return DBX_E_INVALID; return w->w.writeContacts(in, n); }
+int32_t dbx_world_read_proxies(dbx_world* w, dbx_proxy_rec* out, int32_t cap) { W_OR_INVALID(w); return w->w.readProxies(out, out ? cap : 0); }
+int32_t dbx_world_write_proxies(dbx_world* w, const dbx_proxy_rec* in, int32_t n) { W_OR_INVALID(w); if (!in && n) return DBX_E_INVALID; return w->w.writeProxies(in, n); }
+int32_t dbx_world_read_joints(dbx_world* w, dbx_joint_state* out, int32_t cap) { W_OR_INVALID(w); return w->w.readJoints(out, out ? cap : 0); }
+int32_t dbx_world_write_joints(dbx_world* w, const dbx_joint_state* in, int32_t n) { W_OR_INVALID(w); if (!in && n) return DBX_E_INVALID; return w->w.writeJoints(in, n); }
+int32_t dbx_world_read_moves(dbx_world* w, int32_t* out, int32_t cap) { W_OR_INVALID(w); return w->w.readMoves(out, out ? cap : 0); }
+int32_t dbx_world_write_moves(dbx_world* w, const int32_t* in, int32_t n) { W_OR_INVALID(w); if (!in && n) return DBX_E_INVALID; return w->w.writeMoves(in, n); }
+int32_t dbx_world_get_inv_dt0(dbx_world* w, float* out) { W_OR_INVALID(w); if (!out) return DBX_E_INVALID; *out = w->w.inv_dt0; return 0; }
+int32_t dbx_world_set_inv_dt0(dbx_world* w, float v) { W_OR_INVALID(w); w->w.inv_dt0 = v; return 0; }
+
+// ---- staged stepping
+int32_t dbx_world_stage_find_new_contacts(dbx_world* w) { W_OR_INVALID(w); return w->w.stageFindNewContacts(); }
+int32_t dbx_world_stage_collide(dbx_world* w) { W_OR_INVALID(w); return w->w.stageCollide(); }
+int32_t dbx_world_read_pairs(dbx_world* w, int32_t* out, int32_t cap) { W_OR_INVALID(w); return w->w.readPairs(out, out ? cap : 0); }
+int32_t dbx_world_debug_set_contact_levels(dbx_world* w, const int32_t* levels, int32_t n) { W_OR_INVALID(w); return w->w.setContactLevels(levels, n); }
+
+// ---- batched independent worlds
+int32_t dbx_world_replicate(dbx_world* w, int32_t copies) { W_OR_INVALID(w); return w->w.replicate(copies); }
+int32_t dbx_world_replica_count(dbx_world* w) { W_OR_INVALID(w); return w->w.replicaCount(); }
+
+}  // extern "C"

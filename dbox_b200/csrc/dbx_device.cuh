@@ -1,0 +1,180 @@
+// dbx_device.cuh — the SoA device world: every array the step pipeline touches, and the device-side header of
+// counters that lets the whole step run without returning to the host.
+//
+// Layout in HBM (one array per field group, float4-packed so a warp's loads are 512 B coalesced transactions):
+//   bodies    (index = body id)      xf, xf0, pos(c,a), pos0(c0,a0,alpha0), vel(v,w), force(f,torque), mass, lc/damping, ...
+//   proxies   (dense slot)           fixture, child, body, shape, refKey, tight AABB, fat AABB, moved flag
+//   contacts  (slot, free-listed)    pair key, ids, fixtures/shapes, flags, manifold (4 x float4), material, colour
+//   joints    (index = joint id)     definition + persistent impulses + per-step temporaries
+//   solver    (colour-sorted)        velocity / position constraint blocks built each step from touching contacts
+// Reference state being replaced: dynamics/b2body.d:1182-1218, b2fixture.d:76-82,504-521, contacts/b2contact.d:441-465,
+// contacts/b2contactsolver.d:32-58,801-814, collision/b2dynamictree.d:31-54.
+#pragma once
+#include "dbx_narrow.cuh"
+
+namespace dbx {
+
+enum { BODY_STATIC = 0, BODY_KINEMATIC = 1, BODY_DYNAMIC = 2 };
+// low 16 bits = b2Body flags (b2body.d:1118-1127); bits 16-17 = body type; bit 20 = slot in use
+enum : uint32_t {
+  BF_ISLAND = 0x0001, BF_AWAKE = 0x0002, BF_AUTOSLEEP = 0x0004, BF_BULLET = 0x0008, BF_FIXEDROT = 0x0010, BF_ACTIVE = 0x0020, BF_TOI = 0x0040,
+  BF_TYPE_SHIFT = 16, BF_TYPE_MASK = 0x30000, BF_ALIVE = 0x100000
+};
+DBX_HD int body_type(uint32_t f) { return (int)((f & BF_TYPE_MASK) >> BF_TYPE_SHIFT); }
+// low bits = b2Contact flags (b2contact.d:242-261); bit 8 = slot alive; bit 9 = either fixture is a sensor
+enum : uint32_t {
+  CF_ISLAND = 0x0001, CF_TOUCHING = 0x0002, CF_ENABLED = 0x0004, CF_FILTER = 0x0008, CF_BULLET_HIT = 0x0010, CF_TOI = 0x0020,
+  CF_ALIVE = 0x0100, CF_SENSOR = 0x0200, CF_SOLVE = 0x0400 /* in an awake island this step */
+};
+enum { FXF_SENSOR = 1 };
+enum { PF_ALIVE = 1, PF_MOVED = 2 };
+enum { JT_REVOLUTE = 1, JT_DISTANCE = 3 };
+enum { LIM_INACTIVE = 0, LIM_LOWER = 1, LIM_UPPER = 2, LIM_EQUAL = 3 };
+
+constexpr int kMaxColours = 256;         // contact colours: 0..63 tracked in per-body bit masks, 64.. = per-body overflow lanes
+constexpr int kMaskColours = 64;
+constexpr int kMaxJointColours = 64;
+constexpr int kSortBlocks = 296;         // 2 CTAs per SM for the colour counting sort
+constexpr int kMaxPosIters = 8;
+constexpr unsigned long long kHashEmpty = ~0ull;
+constexpr unsigned long long kHashTomb = ~0ull - 1;
+
+// device-resident counters and per-step scalars (one cache line group; written by kernels, read back rarely)
+struct Header {
+  int cHigh;          // contact slots in use are [0, cHigh)
+  int nFree;          // entries on the contact free stack
+  int nContacts;      // alive contacts
+  int nMoved;         // entries in the move list
+  int nPairs;         // entries in the candidate pair buffer
+  int nSolve;         // contacts handed to the solver this step
+  int nColours;       // number of contact colours in use this step
+  int nTouching;
+  int nUncoloured;    // worklist sizes of the colouring loop
+  int nUncoloured2;
+  int error;          // sticky DBX_E_* raised on the device (capacity overflow, ...)
+  int nTomb;          // tombstones in the pair hash
+  int nIslands;
+  int nAwake;
+  int toiEvents;
+  int _pad0;
+  unsigned barrier;   // grid barrier ticket counter for the persistent kernels
+  unsigned epoch;     // colouring round stamp
+  unsigned long long toiMin;  // (alpha bits << 32 | contact slot) arg-min for the TOI loop
+  float bounds[4];    // world bounds of fat AABB centres (Morton normalisation), as ordered ints
+  int colourOff[kMaxColours + 1];   // solver order: contacts of colour c are [colourOff[c], colourOff[c+1])
+  int jointColourOff[kMaxJointColours + 1];
+};
+
+struct DevWorld {
+  Header* hdr;
+  // ---- bodies
+  int nBodies;
+  float4* b_xf;      // p.x p.y q.s q.c
+  float4* b_xf0;     // transform at (c0, a0): what b2Body.SynchronizeFixtures recomputes as xf1 (b2body.d:1131-1133)
+  float4* b_pos;     // c.x c.y a  -
+  float4* b_pos0;    // c0.x c0.y a0 alpha0
+  float4* b_vel;     // v.x v.y w  -
+  float4* b_force;   // f.x f.y torque -
+  float4* b_mass;    // invMass invI mass I
+  float4* b_lc;      // localCenter.x localCenter.y linearDamping angularDamping
+  float2* b_gs;      // gravityScale sleepTime
+  uint32_t* b_flags;
+  int* b_wake;       // wake requests raised during Collide (applied when islands are built)
+  int* b_root;       // union-find parent, then island root
+  int* b_islAwake;   // per root: island contains an awake seed body
+  int* b_islMinSleep;// per root: min sleepTime over the island (float bits, non-negative)
+  int* b_posNotOk;   // [kMaxPosIters][nBodies] per root: some constraint still violated after iteration i
+  unsigned long long* b_mask;   // colours used by the touching contacts of a dynamic body
+  unsigned long long* b_claim;  // colouring arbitration word
+  int* b_ovf;        // overflow colour counter (bodies with more than 64 touching contacts)
+  int* b_world;      // replica index (batched independent worlds)
+  // ---- fixtures
+  int nFixtures;
+  int* f_body;
+  float2* f_mat;     // friction restitution
+  uint32_t* f_filter;// categoryBits | maskBits << 16
+  int* f_group;      // groupIndex (low 16, signed) | flags << 16
+  // ---- shapes (de-duplicated geometry pool)
+  int nShapes;
+  const DShape* shapes;
+  // ---- proxies
+  int nProxies;
+  int4* p_ids;       // fixture child body shape
+  int* p_key;        // reference tree-node id: (lo, hi) order of a pair decides fixture A/B (b2broadphase.d:289-290)
+  float4* p_aabb;    // tight swept AABB
+  float4* p_fat;     // persistent fat AABB
+  uint32_t* p_flags;
+  int* moveList; int moveCap;
+  // ---- LBVH over the fat AABBs
+  unsigned long long* bv_key; unsigned long long* bv_keyAlt;
+  int* bv_leaf; int* bv_leafAlt;     // sorted leaf -> proxy slot
+  float4* bv_box;    // [2n-1]: internal nodes 0..n-2, leaves n-1..2n-2
+  int2* bv_child;    // [n-1]
+  int* bv_parent;    // [2n-1]
+  int* bv_visit;     // [n-1]
+  // ---- candidate pairs
+  int2* pairs; int pairCap;   // proxy slots (lo, hi) in reference key order
+  // ---- joints with collideConnected == false, as sorted (bodyLo << 32 | bodyHi)
+  int nJointPairs; const unsigned long long* jp_keys;
+  // ---- contacts
+  int cCap;
+  unsigned long long* c_key;   // (refKeyLo << 32 | refKeyHi)
+  int4* c_ids;       // proxyA proxyB bodyA bodyB   (A/B after the type-registry swap, b2contact.d:387-394)
+  int4* c_fix;       // fixtureA fixtureB shapeA shapeB
+  uint32_t* c_flags;
+  float4* c_m0;      // localNormal.xy localPoint.xy
+  float4* c_m1;      // points[0].localPoint points[1].localPoint
+  float4* c_imp;     // n0 t0 n1 t1
+  uint4* c_mk;       // key0 key1 type pointCount
+  float4* c_mat;     // friction restitution tangentSpeed toi
+  int* c_toiCount;
+  int* c_colour;
+  int* c_free;
+  int* c_work; int* c_work2;   // colouring worklists
+  // pair hash
+  int hCap;          // power of two
+  unsigned long long* h_key; int* h_val;
+  // ---- solver (colour-sorted constraints)
+  int sCap;
+  int* s_contact;    // solver index -> contact slot
+  int* s_hist;       // [kSortBlocks][kMaxColours]
+  int2* s_body;      // bodyA bodyB
+  float4* s_v0;      // normal.xy friction tangentSpeed
+  float4* s_v1;      // invMassA invIA invMassB invIB
+  float4* s_r0;      // point 0: rA.xy rB.xy
+  float4* s_r1;
+  float4* s_q0;      // point 0: normalMass tangentMass velocityBias -
+  float4* s_q1;
+  float4* s_imp;     // n0 t0 n1 t1 (working impulses)
+  float4* s_nm;      // normalMass 2x2: ex.x ex.y ey.x ey.y
+  float4* s_k;       // K 2x2
+  int* s_pc;         // pointCount (possibly reduced to 1 by the block solver) | type << 8 | manifold pointCount << 16
+  float4* s_p0;      // localPoints[0].xy localPoints[1].xy
+  float4* s_p1;      // localNormal.xy localPoint.xy
+  float4* s_p2;      // localCenterA.xy localCenterB.xy
+  float2* s_p3;      // radiusA radiusB
+  int* s_root;       // island root of the constraint
+  // ---- joints
+  int nJoints;
+  int4* j_ids;       // type bodyA bodyB flags(collideConnected | enableLimit<<1 | enableMotor<<2 | alive<<3)
+  float4* j_anchor;  // localAnchorA.xy localAnchorB.xy
+  float4* j_p0;      // revolute: referenceAngle lowerAngle upperAngle maxMotorTorque | distance: length frequencyHz dampingRatio -
+  float4* j_p1;      // revolute: motorSpeed - - -
+  float4* j_imp;     // impulse.xyz motorImpulse   (distance: impulse - - -)
+  int* j_limit;      // limit state
+  int* j_colour;
+  int* j_order;      // colour-sorted joint indices
+  int* j_root;
+  // per-step temporaries (b2revolutejoint.d:654-666, b2distancejoint.d:387-398)
+  float4* j_r;       // rA.xy rB.xy
+  float4* j_lc;      // localCenterA.xy localCenterB.xy
+  float4* j_m;       // invMassA invIA invMassB invIB
+  float4* j_k0;      // revolute mass.ex.xyz motorMass | distance: u.x u.y mass gamma
+  float4* j_k1;      // revolute mass.ey.xyz -        | distance: bias - - -
+  float4* j_k2;      // revolute mass.ez.xyz -
+  // ---- step parameters
+  float dt, inv_dt, dtRatio; int velIters, posIters; int warmStarting; int allowSleep; int continuous; float gx, gy;
+  int nWorlds;
+};
+
+}  // namespace dbx

@@ -1,0 +1,1557 @@
+// dbx_kernels.cu — hand-written CUDA kernels (sm_100a) for dbox's per-step world pipeline.
+//
+// Every kernel is a grid-stride loop over a device-resident count (Header), launched with a fixed grid that is a
+// multiple of the SM count, so a whole step is a fixed launch sequence with no host round trip.  The iteration loops
+// of the constraint solver run inside ONE persistent cooperative kernel (one CTA per SM) with a global barrier per
+// colour.  Nothing here is a dense contraction: the bound is HBM/L2 bandwidth and dependent-launch latency, so the
+// levers are coalesced float4 SoA access, L2-resident constraint blocks and as few barriers as the colouring allows.
+#include <cub/cub.cuh>
+#include "dbx_kernels.cuh"
+
+namespace dbx {
+
+#define GRID_STRIDE(i, n) for (int i = blockIdx.x * blockDim.x + threadIdx.x, _gs = gridDim.x * blockDim.x; i < (n); i += _gs)
+
+// ------------------------------------------------------------------------------------------------ small device utilities
+DBX_D float4 ldcg4(const float4* p) { return __ldcg(p); }
+DBX_D void stcg4(float4* p, float4 v) { __stcg(p, v); }
+
+// 64-bit mix (bijective) for the pair hash and the colouring priorities
+DBX_HD unsigned long long mix64(unsigned long long x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return x;
+}
+DBX_D int hash_find(const DevWorld& W, unsigned long long key) {
+  unsigned mask = (unsigned)W.hCap - 1;
+  unsigned h = (unsigned)mix64(key) & mask;
+  for (int probe = 0; probe < W.hCap; ++probe) {
+    unsigned long long k = W.h_key[h];
+    if (k == key) return W.h_val[h];
+    if (k == kHashEmpty) return -1;
+    h = (h + 1) & mask;
+  }
+  return -1;
+}
+// keys are unique per insertion batch, so a CAS on the key word is enough
+DBX_D bool hash_insert(const DevWorld& W, unsigned long long key, int val) {
+  unsigned mask = (unsigned)W.hCap - 1;
+  unsigned h = (unsigned)mix64(key) & mask;
+  for (int probe = 0; probe < W.hCap; ++probe) {
+    unsigned long long old = atomicCAS(&W.h_key[h], kHashEmpty, key);
+    if (old == kHashEmpty) { W.h_val[h] = val; return true; }
+    h = (h + 1) & mask;
+  }
+  return false;
+}
+DBX_D void hash_remove(const DevWorld& W, unsigned long long key) {
+  unsigned mask = (unsigned)W.hCap - 1;
+  unsigned h = (unsigned)mix64(key) & mask;
+  for (int probe = 0; probe < W.hCap; ++probe) {
+    unsigned long long k = W.h_key[h];
+    if (k == key) { W.h_key[h] = kHashTomb; atomicAdd(&W.hdr->nTomb, 1); return; }
+    if (k == kHashEmpty) return;
+    h = (h + 1) & mask;
+  }
+}
+
+// lock-free union-find; the larger index is always hooked under the smaller, so a component's root is its minimum id
+DBX_D int uf_find(int* parent, int x) {
+  for (;;) {
+    int p = parent[x];
+    if (p == x) return x;
+    int gp = parent[p];
+    if (gp != p) parent[x] = gp;  // path halving (benign race)
+    x = p;
+  }
+}
+DBX_D void uf_unite(int* parent, int a, int b) {
+  for (;;) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) { int t = a; a = b; b = t; }
+    if (atomicCAS(&parent[a], a, b) == a) return;
+  }
+}
+
+// global barrier for the persistent kernels: all CTAs are co-resident (cooperative launch, one per SM)
+DBX_D void grid_barrier(unsigned* counter, unsigned nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned ticket = atomicAdd(counter, 1u);
+    unsigned target = (ticket / nblocks + 1u) * nblocks;
+    while (*((volatile unsigned*)counter) < target) { __nanosleep(20); }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// b2ContactFilter.ShouldCollide (dynamics/b2worldcallbacks.d:52-64)
+DBX_D bool filter_should_collide(const DevWorld& W, int fA, int fB) {
+  short gA = (short)(W.f_group[fA] & 0xFFFF), gB = (short)(W.f_group[fB] & 0xFFFF);
+  if (gA == gB && gA != 0) return gA > 0;
+  uint32_t a = W.f_filter[fA], b = W.f_filter[fB];
+  uint32_t catA = a & 0xFFFF, maskA = a >> 16, catB = b & 0xFFFF, maskB = b >> 16;
+  return (maskA & catB) != 0 && (catA & maskB) != 0;
+}
+// b2Body.ShouldCollide (dynamics/b2body.d:1149-1170): at least one dynamic body, no joint that forbids it
+DBX_D bool body_should_collide(const DevWorld& W, int bA, int bB, uint32_t flA, uint32_t flB) {
+  if (body_type(flA) != BODY_DYNAMIC && body_type(flB) != BODY_DYNAMIC) return false;
+  if (W.nJointPairs > 0) {
+    unsigned long long lo = (unsigned)min(bA, bB), hi = (unsigned)max(bA, bB);
+    unsigned long long k = (lo << 32) | hi;
+    int l = 0, r = W.nJointPairs;
+    while (l < r) { int m = (l + r) >> 1; if (W.jp_keys[m] < k) l = m + 1; else r = m; }
+    if (l < W.nJointPairs && W.jp_keys[l] == k) return false;
+  }
+  return true;
+}
+DBX_D void wake_body_now(const DevWorld& W, int b) {  // b2Body.SetAwake(true) (b2body.d:829-835)
+  uint32_t old = atomicOr(&W.b_flags[b], BF_AWAKE);
+  if (!(old & BF_AWAKE)) W.b_gs[b].y = 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------------ Collide
+// b2ContactManager.Collide (dynamics/b2contactmanager.d:251-317) + b2Contact.Update (contacts/b2contact.d:270-356)
+DBX_D void destroy_contact(const DevWorld& W, int i, uint32_t flags, int bodyA, int bodyB, int pointCount) {
+  // b2ContactManager.Destroy + b2Contact.Destroy: wake both bodies if the manifold had points and no sensor is involved
+  if (pointCount > 0 && !(flags & CF_SENSOR)) { W.b_wake[bodyA] = 1; W.b_wake[bodyB] = 1; }
+  hash_remove(W, W.c_key[i]);
+  W.c_flags[i] = 0;
+  W.c_colour[i] = -1;
+  int slot = atomicAdd(&W.hdr->nFree, 1);
+  W.c_free[slot] = i;
+}
+
+__global__ void __launch_bounds__(256) k_collide(const __grid_constant__ DevWorld W) {
+  const int n = W.hdr->cHigh;
+  GRID_STRIDE(i, n) {
+    uint32_t flags = W.c_flags[i];
+    if (!(flags & CF_ALIVE)) continue;
+    const int4 ids = W.c_ids[i];
+    const int4 fx = W.c_fix[i];
+    const uint32_t flA = W.b_flags[ids.z], flB = W.b_flags[ids.w];
+    uint4 mk = W.c_mk[i];
+    if (flags & CF_FILTER) {
+      if (!body_should_collide(W, ids.w, ids.z, flB, flA) || !filter_should_collide(W, fx.x, fx.y)) {
+        destroy_contact(W, i, flags, ids.z, ids.w, (int)mk.w);
+        continue;
+      }
+      flags &= ~CF_FILTER;
+      W.c_flags[i] = flags;
+    }
+    bool activeA = (flA & BF_AWAKE) && body_type(flA) != BODY_STATIC;
+    bool activeB = (flB & BF_AWAKE) && body_type(flB) != BODY_STATIC;
+    if (!activeA && !activeB) continue;
+    if (!overlap(BX(W.p_fat[ids.x]), BX(W.p_fat[ids.y]))) {
+      destroy_contact(W, i, flags, ids.z, ids.w, (int)mk.w);
+      continue;
+    }
+    // ---- b2Contact.Update
+    flags |= CF_ENABLED;
+    const bool wasTouching = (flags & CF_TOUCHING) != 0;
+    const Xf xfA = XF(W.b_xf[ids.z]), xfB = XF(W.b_xf[ids.w]);
+    const DShape* sA = W.shapes + fx.z;
+    const DShape* sB = W.shapes + fx.w;
+    bool touching;
+    if (flags & CF_SENSOR) {
+      touching = shapes_overlap(sA, xfA, sB, xfB);
+      mk.w = 0;
+      W.c_mk[i] = mk;
+    } else {
+      Manifold m;
+      m.type = (int)mk.z; m.localNormal = V(0, 0); m.localPoint = V(0, 0); m.lp[0] = m.lp[1] = V(0, 0); m.key[0] = m.key[1] = 0;
+      collide_dispatch(m, sA, xfA, sB, xfB);
+      touching = m.pointCount > 0;
+      if (touching) {
+        const float4 oldImp = W.c_imp[i];
+        const int oldCount = (int)mk.w;
+        float4 imp = make_float4(0, 0, 0, 0);
+        // match new points to old ones by feature key and carry the accumulated impulses (b2contact.d:306-324)
+        for (int k = 0; k < m.pointCount; ++k) {
+          float ni = 0.0f, ti = 0.0f;
+          for (int j = 0; j < oldCount; ++j) {
+            uint32_t oldKey = j == 0 ? mk.x : mk.y;
+            if (oldKey == m.key[k]) { ni = j == 0 ? oldImp.x : oldImp.z; ti = j == 0 ? oldImp.y : oldImp.w; break; }
+          }
+          if (k == 0) { imp.x = ni; imp.y = ti; } else { imp.z = ni; imp.w = ti; }
+        }
+        W.c_m0[i] = make_float4(m.localNormal.x, m.localNormal.y, m.localPoint.x, m.localPoint.y);
+        W.c_m1[i] = make_float4(m.lp[0].x, m.lp[0].y, m.lp[1].x, m.lp[1].y);
+        W.c_imp[i] = imp;
+        W.c_mk[i] = make_uint4(m.key[0], m.key[1], (uint32_t)m.type, (uint32_t)m.pointCount);
+      } else {
+        mk.w = 0;
+        W.c_mk[i] = mk;
+      }
+      if (touching != wasTouching) { W.b_wake[ids.z] = 1; W.b_wake[ids.w] = 1; }
+    }
+    flags = touching ? (flags | CF_TOUCHING) : (flags & ~CF_TOUCHING);
+    W.c_flags[i] = flags;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ islands
+// Replaces the DFS of b2World.Solve (dynamics/b2world.d:943-1095) with a union-find over constraint edges.
+__global__ void __launch_bounds__(256) k_island_init(const __grid_constant__ DevWorld W) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) { W.hdr->nSolve = 0; W.hdr->nIslands = 0; W.hdr->nUncoloured = 0; W.hdr->nUncoloured2 = 0; }
+  GRID_STRIDE(b, W.nBodies) {
+    W.b_root[b] = b;
+    W.b_islAwake[b] = 0;
+    W.b_islMinSleep[b] = 0x7f7fffff;  // FLT_MAX bits
+    W.b_mask[b] = 0ull;
+    W.b_ovf[b] = 0;
+    if (W.b_wake[b]) { W.b_wake[b] = 0; wake_body_now(W, b); }
+  }
+  for (int it = 0; it < W.posIters; ++it) { GRID_STRIDE(b, W.nBodies) W.b_posNotOk[it * W.nBodies + b] = 0; }
+}
+
+__global__ void __launch_bounds__(256) k_island_union(const __grid_constant__ DevWorld W) {
+  const int n = W.hdr->cHigh;
+  GRID_STRIDE(i, n) {
+    uint32_t flags = W.c_flags[i];
+    // contacts qualify iff enabled, touching and non-sensor (b2world.d:1016-1030)
+    if ((flags & (CF_ALIVE | CF_TOUCHING | CF_ENABLED | CF_SENSOR)) != (CF_ALIVE | CF_TOUCHING | CF_ENABLED)) continue;
+    int4 ids = W.c_ids[i];
+    if (body_type(W.b_flags[ids.z]) == BODY_STATIC || body_type(W.b_flags[ids.w]) == BODY_STATIC) continue;  // statics end the search (:998-1003)
+    uf_unite(W.b_root, ids.z, ids.w);
+  }
+  GRID_STRIDE(j, W.nJoints) {
+    int4 ids = W.j_ids[j];
+    if (!(ids.w & 8)) continue;
+    uint32_t fa = W.b_flags[ids.y], fb = W.b_flags[ids.z];
+    if (!(fa & BF_ACTIVE) || !(fb & BF_ACTIVE)) continue;                                  // other body must be active (:1058-1062)
+    if (body_type(fa) == BODY_STATIC || body_type(fb) == BODY_STATIC) continue;
+    uf_unite(W.b_root, ids.y, ids.z);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_island_flatten(const __grid_constant__ DevWorld W) {
+  GRID_STRIDE(b, W.nBodies) {
+    uint32_t f = W.b_flags[b];
+    if (!(f & BF_ALIVE)) continue;
+    int r = uf_find(W.b_root, b);
+    W.b_root[b] = r;
+    // seeds: awake, active, non-static (b2world.d:963-979)
+    if ((f & BF_AWAKE) && (f & BF_ACTIVE) && body_type(f) != BODY_STATIC) W.b_islAwake[r] = 1;
+  }
+}
+
+// wake every body of an awake island (b2world.d:996), flag island membership, integrate velocities (b2island.d:82-116)
+__global__ void __launch_bounds__(256) k_island_wake_integrate(const __grid_constant__ DevWorld W) {
+  const float h = W.dt;
+  GRID_STRIDE(b, W.nBodies) {
+    uint32_t f = W.b_flags[b];
+    if (!(f & BF_ALIVE)) continue;
+    int type = body_type(f);
+    bool in = type != BODY_STATIC && (f & BF_ACTIVE) && W.b_islAwake[W.b_root[b]];
+    if (!in) { if (f & BF_ISLAND) W.b_flags[b] = f & ~BF_ISLAND; continue; }
+    if (!(f & BF_AWAKE)) { W.b_gs[b].y = 0.0f; }
+    f |= BF_AWAKE | BF_ISLAND;
+    W.b_flags[b] = f;
+    if (W.b_root[b] == b) atomicAdd(&W.hdr->nIslands, 1);
+    float4 pos = W.b_pos[b];
+    float4 pos0 = W.b_pos0[b];
+    pos0.x = pos.x; pos0.y = pos.y; pos0.z = pos.z;   // c0 = c, a0 = a
+    W.b_pos0[b] = pos0;
+    W.b_xf0[b] = W.b_xf[b];
+    if (type == BODY_DYNAMIC) {
+      float4 vel = W.b_vel[b];
+      const float4 frc = W.b_force[b];
+      const float4 ms = W.b_mass[b];
+      const float4 lc = W.b_lc[b];
+      const float gs = W.b_gs[b].x;
+      v2 v = V(vel.x, vel.y);
+      float w = vel.z;
+      v += h * (gs * V(W.gx, W.gy) + ms.x * V(frc.x, frc.y));
+      w += h * ms.y * frc.z;
+      v *= 1.0f / (1.0f + h * lc.z);
+      w *= 1.0f / (1.0f + h * lc.w);
+      W.b_vel[b] = make_float4(v.x, v.y, w, 0.0f);
+    }
+  }
+}
+
+// mark the contacts the solver takes this step and rebuild the per-body colour masks from the persistent colours
+__global__ void __launch_bounds__(256) k_mark_solve(const __grid_constant__ DevWorld W) {
+  const int n = W.hdr->cHigh;
+  GRID_STRIDE(i, n) {
+    uint32_t flags = W.c_flags[i];
+    if (!(flags & CF_ALIVE)) continue;
+    bool solve = false;
+    int4 ids;
+    if ((flags & (CF_TOUCHING | CF_ENABLED | CF_SENSOR)) == (CF_TOUCHING | CF_ENABLED)) {
+      ids = W.c_ids[i];
+      uint32_t fa = W.b_flags[ids.z], fb = W.b_flags[ids.w];
+      // the contact is in an island iff one of its non-static bodies is (b2world.d:1006-1046)
+      solve = ((fa & BF_ISLAND) && body_type(fa) != BODY_STATIC) || ((fb & BF_ISLAND) && body_type(fb) != BODY_STATIC);
+    }
+    if (!solve) {
+      if (flags & CF_SOLVE) W.c_flags[i] = flags & ~CF_SOLVE;
+      if (!(flags & CF_TOUCHING)) W.c_colour[i] = -1;   // a colour is held only while the contact is touching
+      continue;
+    }
+    if (!(flags & CF_SOLVE)) W.c_flags[i] = flags | CF_SOLVE;
+    int col = W.c_colour[i];
+    uint32_t fa = W.b_flags[ids.z], fb = W.b_flags[ids.w];
+    if (col >= 0 && col < kMaskColours) {
+      if (body_type(fa) == BODY_DYNAMIC) atomicOr(&W.b_mask[ids.z], 1ull << col);
+      if (body_type(fb) == BODY_DYNAMIC) atomicOr(&W.b_mask[ids.w], 1ull << col);
+    } else {
+      W.c_colour[i] = -1;
+      int slot = atomicAdd(&W.hdr->nUncoloured, 1);
+      W.c_work[slot] = i;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ graph colouring
+// New touching contacts take the lowest colour free on both dynamic bodies.  Conflicts between contacts coloured in the
+// same round are arbitrated Jones-Plassmann style: per body the contact with the highest (key-derived) priority wins,
+// so the outcome is independent of thread scheduling.  Static/kinematic bodies are never written by the solver and do
+// not constrain colours.  Runs as one persistent cooperative kernel; rounds loop on the device.
+__global__ void __launch_bounds__(512) k_colour(const __grid_constant__ DevWorld W) {
+  Header* H = W.hdr;
+  const unsigned nb = gridDim.x;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  int* cur = W.c_work; int* nxt = W.c_work2;
+  int n = H->nUncoloured;
+  unsigned epoch = H->epoch;
+  if (epoch > 0xF0000u) {   // the round stamp is 20 bits wide: recycle it long before it wraps
+    for (int b = tid; b < W.nBodies; b += nth) W.b_claim[b] = 0ull;
+    epoch = 0;
+    grid_barrier(&H->barrier, nb);
+  }
+  int guard = 0;
+  while (n > 0 && guard++ < 4096) {
+    ++epoch;
+    // phase 1: claim both bodies
+    for (int k = tid; k < n; k += nth) {
+      int i = cur[k];
+      int4 ids = W.c_ids[i];
+      unsigned long long pr = ((unsigned long long)(epoch & 0xFFFFF) << 44) | (mix64(W.c_key[i]) >> 20);
+      if (body_type(W.b_flags[ids.z]) == BODY_DYNAMIC) atomicMax(&W.b_claim[ids.z], pr);
+      if (body_type(W.b_flags[ids.w]) == BODY_DYNAMIC) atomicMax(&W.b_claim[ids.w], pr);
+    }
+    if (tid == 0) H->nUncoloured2 = 0;
+    grid_barrier(&H->barrier, nb);
+    // phase 2: winners take a colour
+    for (int k = tid; k < n; k += nth) {
+      int i = cur[k];
+      int4 ids = W.c_ids[i];
+      unsigned long long pr = ((unsigned long long)(epoch & 0xFFFFF) << 44) | (mix64(W.c_key[i]) >> 20);
+      bool dynA = body_type(W.b_flags[ids.z]) == BODY_DYNAMIC, dynB = body_type(W.b_flags[ids.w]) == BODY_DYNAMIC;
+      bool win = (!dynA || __ldcg(&W.b_claim[ids.z]) == pr) && (!dynB || __ldcg(&W.b_claim[ids.w]) == pr);
+      if (win) {
+        unsigned long long used = (dynA ? __ldcg(&W.b_mask[ids.z]) : 0ull) | (dynB ? __ldcg(&W.b_mask[ids.w]) : 0ull);
+        int col;
+        if (~used) {
+          col = __ffsll((long long)~used) - 1;
+          if (dynA) __stcg(&W.b_mask[ids.z], __ldcg(&W.b_mask[ids.z]) | (1ull << col));
+          if (dynB) __stcg(&W.b_mask[ids.w], __ldcg(&W.b_mask[ids.w]) | (1ull << col));
+        } else {
+          // more than 64 touching contacts on one body: serialise the surplus on private overflow lanes of that body
+          int oa = dynA ? W.b_ovf[ids.z] : 0, ob = dynB ? W.b_ovf[ids.w] : 0;
+          int o = max(oa, ob);
+          if (dynA) W.b_ovf[ids.z] = o + 1;
+          if (dynB) W.b_ovf[ids.w] = o + 1;
+          col = kMaskColours + o;
+          if (col >= kMaxColours) { col = kMaxColours - 1; H->error = -5; }
+        }
+        W.c_colour[i] = col;
+      } else {
+        int slot = atomicAdd(&H->nUncoloured2, 1);
+        nxt[slot] = i;
+      }
+    }
+    grid_barrier(&H->barrier, nb);
+    n = *((volatile int*)&H->nUncoloured2);
+    int* t = cur; cur = nxt; nxt = t;
+    grid_barrier(&H->barrier, nb);
+  }
+  if (tid == 0) { H->epoch = epoch; H->nUncoloured = 0; }
+}
+
+// ------------------------------------------------------------------------------------------------ colour counting sort
+// One radix digit (the colour) over the contact slots: per-CTA histograms, one scan, scatter.  Output: s_contact in
+// colour order and colourOff[]; the solver then walks one contiguous range per colour.
+__global__ void __launch_bounds__(256) k_sort_hist(const __grid_constant__ DevWorld W) {
+  __shared__ int hist[kMaxColours];
+  for (int c = threadIdx.x; c < kMaxColours; c += blockDim.x) hist[c] = 0;
+  __syncthreads();
+  const int n = W.hdr->cHigh;
+  const int chunk = (n + gridDim.x - 1) / gridDim.x;
+  const int beg = blockIdx.x * chunk, end = min(n, beg + chunk);
+  for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
+    if (W.c_flags[i] & CF_SOLVE) atomicAdd(&hist[W.c_colour[i]], 1);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < kMaxColours; c += blockDim.x) W.s_hist[blockIdx.x * kMaxColours + c] = hist[c];
+}
+__global__ void __launch_bounds__(kMaxColours) k_sort_scan(const __grid_constant__ DevWorld W, int nblocks) {
+  __shared__ int total[kMaxColours];
+  __shared__ int base[kMaxColours + 1];
+  const int c = threadIdx.x;
+  int sum = 0;
+  for (int b = 0; b < nblocks; ++b) { int v = W.s_hist[b * kMaxColours + c]; W.s_hist[b * kMaxColours + c] = sum; sum += v; }
+  total[c] = sum;
+  __syncthreads();
+  if (c == 0) {
+    int acc = 0, ncol = 0;
+    for (int k = 0; k < kMaxColours; ++k) { base[k] = acc; acc += total[k]; if (total[k] > 0) ncol = k + 1; }
+    base[kMaxColours] = acc;
+    W.hdr->nSolve = acc;
+    W.hdr->nColours = ncol;
+    if (acc > W.sCap) W.hdr->error = -5;
+  }
+  __syncthreads();
+  W.hdr->colourOff[c] = base[c];
+  if (c == 0) W.hdr->colourOff[kMaxColours] = base[kMaxColours];
+  for (int b = 0; b < nblocks; ++b) W.s_hist[b * kMaxColours + c] += base[c];
+}
+__global__ void __launch_bounds__(256) k_sort_scatter(const __grid_constant__ DevWorld W) {
+  __shared__ int cursor[kMaxColours];
+  for (int c = threadIdx.x; c < kMaxColours; c += blockDim.x) cursor[c] = W.s_hist[blockIdx.x * kMaxColours + c];
+  __syncthreads();
+  const int n = W.hdr->cHigh;
+  const int chunk = (n + gridDim.x - 1) / gridDim.x;
+  const int beg = blockIdx.x * chunk, end = min(n, beg + chunk);
+  for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
+    if (W.c_flags[i] & CF_SOLVE) {
+      int pos = atomicAdd(&cursor[W.c_colour[i]], 1);
+      if (pos < W.sCap) W.s_contact[pos] = i;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ contact constraints
+// b2ContactSolver ctor + InitializeVelocityConstraints (contacts/b2contactsolver.d:244-450): one thread per solver contact.
+__global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ DevWorld W) {
+  const int n = min(W.hdr->nSolve, W.sCap);
+  GRID_STRIDE(s, n) {
+    const int i = W.s_contact[s];
+    const int4 ids = W.c_ids[i];
+    const int4 fx = W.c_fix[i];
+    const int bA = ids.z, bB = ids.w;
+    const float4 msA = W.b_mass[bA], msB = W.b_mass[bB];
+    const float4 lcA4 = W.b_lc[bA], lcB4 = W.b_lc[bB];
+    const float4 posA = W.b_pos[bA], posB = W.b_pos[bB];
+    const float4 velA = W.b_vel[bA], velB = W.b_vel[bB];
+    const float4 xA = W.b_xf[bA], xB = W.b_xf[bB];
+    const float4 m0 = W.c_m0[i], m1 = W.c_m1[i], cimp = W.c_imp[i], mat = W.c_mat[i];
+    const uint4 mk = W.c_mk[i];
+    const float radiusA = W.shapes[fx.z].radius, radiusB = W.shapes[fx.w].radius;
+    const float mA = msA.x, iA = msA.y, mB = msB.x, iB = msB.y;
+    const v2 localCenterA = V(lcA4.x, lcA4.y), localCenterB = V(lcB4.x, lcB4.y);
+    const v2 cA = V(posA.x, posA.y), cB = V(posB.x, posB.y);
+    const v2 vA = V(velA.x, velA.y), vB = V(velB.x, velB.y);
+    const float wA = velA.z, wB = velB.z;
+    const int pointCount = (int)mk.w, type = (int)mk.z;
+    // xf from (c, a): q is the body's stored rotation (always sin/cos of a), p = c - q * localCenter (:371-375)
+    Xf xfA, xfB;
+    xfA.q = R(xA.z, xA.w); xfB.q = R(xB.z, xB.w);
+    xfA.p = cA - mul(xfA.q, localCenterA);
+    xfB.p = cB - mul(xfB.q, localCenterB);
+    const v2 localNormal = V(m0.x, m0.y), localPoint = V(m0.z, m0.w);
+    const v2 lp0 = V(m1.x, m1.y), lp1 = V(m1.z, m1.w);
+    // b2WorldManifold.Initialize (collision/b2collision.d:123-191)
+    v2 normal, wp[2];
+    if (type == MAN_CIRCLES) {
+      normal = V(1.0f, 0.0f);
+      v2 pointA = mul(xfA, localPoint), pointB = mul(xfB, lp0);
+      if (dist2(pointA, pointB) > kEpsilon * kEpsilon) { normal = pointB - pointA; normalize(normal); }
+      v2 ca = pointA + radiusA * normal, cb = pointB - radiusB * normal;
+      wp[0] = 0.5f * (ca + cb); wp[1] = wp[0];
+    } else if (type == MAN_FACE_A) {
+      normal = mul(xfA.q, localNormal);
+      v2 planePoint = mul(xfA, localPoint);
+      for (int k = 0; k < pointCount; ++k) {
+        v2 clipPoint = mul(xfB, k == 0 ? lp0 : lp1);
+        v2 ca = clipPoint + (radiusA - dot(clipPoint - planePoint, normal)) * normal;
+        v2 cb = clipPoint - radiusB * normal;
+        wp[k] = 0.5f * (ca + cb);
+      }
+    } else {
+      normal = mul(xfB.q, localNormal);
+      v2 planePoint = mul(xfB, localPoint);
+      for (int k = 0; k < pointCount; ++k) {
+        v2 clipPoint = mul(xfA, k == 0 ? lp0 : lp1);
+        v2 cb = clipPoint + (radiusB - dot(clipPoint - planePoint, normal)) * normal;
+        v2 ca = clipPoint - radiusA * normal;
+        wp[k] = 0.5f * (ca + cb);
+      }
+      normal = -normal;
+    }
+    const float friction = mat.x, restitution = mat.y, tangentSpeed = mat.z;
+    const v2 tangent = cross(normal, 1.0f);
+    float4 r[2], q[2];
+    r[1] = make_float4(0, 0, 0, 0); q[1] = make_float4(0, 0, 0, 0);
+    for (int k = 0; k < pointCount; ++k) {
+      v2 rA = wp[k] - cA, rB = wp[k] - cB;
+      float rnA = cross(rA, normal), rnB = cross(rB, normal);
+      float kNormal = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+      float normalMass = kNormal > 0.0f ? 1.0f / kNormal : 0.0f;
+      float rtA = cross(rA, tangent), rtB = cross(rB, tangent);
+      float kTangent = mA + mB + iA * rtA * rtA + iB * rtB * rtB;
+      float tangentMass = kTangent > 0.0f ? 1.0f / kTangent : 0.0f;
+      float velocityBias = 0.0f;
+      float vRel = dot(normal, vB + cross(wB, rB) - vA - cross(wA, rA));
+      if (vRel < -kVelocityThreshold) velocityBias = -restitution * vRel;
+      r[k] = make_float4(rA.x, rA.y, rB.x, rB.y);
+      q[k] = make_float4(normalMass, tangentMass, velocityBias, 0.0f);
+    }
+    int vcCount = pointCount;
+    float4 nm = make_float4(0, 0, 0, 0), K = make_float4(0, 0, 0, 0);
+    if (pointCount == 2) {
+      // block-solver matrix with the reference's conditioning test (:418-448)
+      float rn1A = cross(V(r[0].x, r[0].y), normal), rn1B = cross(V(r[0].z, r[0].w), normal);
+      float rn2A = cross(V(r[1].x, r[1].y), normal), rn2B = cross(V(r[1].z, r[1].w), normal);
+      float k11 = mA + mB + iA * rn1A * rn1A + iB * rn1B * rn1B;
+      float k22 = mA + mB + iA * rn2A * rn2A + iB * rn2B * rn2B;
+      float k12 = mA + mB + iA * rn1A * rn2A + iB * rn1B * rn2B;
+      const float k_maxConditionNumber = 1000.0f;
+      if (k11 * k11 < k_maxConditionNumber * (k11 * k22 - k12 * k12)) {
+        M22 Km; Km.ex = V(k11, k12); Km.ey = V(k12, k22);
+        M22 inv = inverse(Km);
+        K = make_float4(k11, k12, k12, k22);
+        nm = make_float4(inv.ex.x, inv.ex.y, inv.ey.x, inv.ey.y);
+      } else {
+        vcCount = 1;
+      }
+    }
+    // warm-start impulses scaled by dtRatio (:309-313)
+    float4 imp = W.warmStarting ? make_float4(W.dtRatio * cimp.x, W.dtRatio * cimp.y, W.dtRatio * cimp.z, W.dtRatio * cimp.w)
+                                : make_float4(0, 0, 0, 0);
+    if (pointCount < 2) { imp.z = 0.0f; imp.w = 0.0f; }
+    W.s_body[s] = make_int2(bA, bB);
+    W.s_v0[s] = make_float4(normal.x, normal.y, friction, tangentSpeed);
+    W.s_v1[s] = make_float4(mA, iA, mB, iB);
+    W.s_r0[s] = r[0]; W.s_r1[s] = r[1];
+    W.s_q0[s] = q[0]; W.s_q1[s] = q[1];
+    W.s_imp[s] = imp;
+    W.s_nm[s] = nm; W.s_k[s] = K;
+    W.s_pc[s] = vcCount | (type << 8) | (pointCount << 16);
+    W.s_p0[s] = m1;
+    W.s_p1[s] = m0;
+    W.s_p2[s] = make_float4(localCenterA.x, localCenterA.y, localCenterB.x, localCenterB.y);
+    W.s_p3[s] = make_float2(radiusA, radiusB);
+    uint32_t fa = W.b_flags[bA];
+    W.s_root[s] = body_type(fa) != BODY_STATIC ? W.b_root[bA] : W.b_root[bB];
+  }
+}
+
+// velocities of one body pair; only dynamic bodies are ever written (statics/kinematics have zero inverse mass)
+struct BodyVel { v2 vA, vB; float wA, wB; };
+DBX_D BodyVel load_vel(const DevWorld& W, int2 bd) {
+  float4 a = ldcg4(&W.b_vel[bd.x]), b = ldcg4(&W.b_vel[bd.y]);
+  BodyVel r; r.vA = V(a.x, a.y); r.wA = a.z; r.vB = V(b.x, b.y); r.wB = b.z; return r;
+}
+DBX_D void store_vel(const DevWorld& W, int2 bd, const BodyVel& r, float mA, float iA, float mB, float iB) {
+  if (mA != 0.0f || iA != 0.0f) stcg4(&W.b_vel[bd.x], make_float4(r.vA.x, r.vA.y, r.wA, 0.0f));
+  if (mB != 0.0f || iB != 0.0f) stcg4(&W.b_vel[bd.y], make_float4(r.vB.x, r.vB.y, r.wB, 0.0f));
+}
+
+// b2ContactSolver.WarmStart (:452-490)
+DBX_D void contact_warm_start(const DevWorld& W, int s) {
+  const int2 bd = W.s_body[s];
+  const float4 v0 = W.s_v0[s], v1 = W.s_v1[s], imp = W.s_imp[s];
+  const int pointCount = W.s_pc[s] & 0xFF;
+  const float mA = v1.x, iA = v1.y, mB = v1.z, iB = v1.w;
+  BodyVel bv = load_vel(W, bd);
+  const v2 normal = V(v0.x, v0.y), tangent = cross(normal, 1.0f);
+  for (int k = 0; k < pointCount; ++k) {
+    const float4 r = k == 0 ? W.s_r0[s] : W.s_r1[s];
+    const float ni = k == 0 ? imp.x : imp.z, ti = k == 0 ? imp.y : imp.w;
+    v2 P = ni * normal + ti * tangent;
+    bv.wA -= iA * cross(V(r.x, r.y), P);
+    bv.vA -= mA * P;
+    bv.wB += iB * cross(V(r.z, r.w), P);
+    bv.vB += mB * P;
+  }
+  store_vel(W, bd, bv, mA, iA, mB, iB);
+}
+
+// b2ContactSolver.SolveVelocityConstraints (:492-772): friction rows, then 1-point clamp or the 2-point block solver
+DBX_D void contact_solve_velocity(const DevWorld& W, int s) {
+  const int2 bd = W.s_body[s];
+  const float4 v0 = W.s_v0[s], v1 = W.s_v1[s];
+  float4 imp = W.s_imp[s];
+  const int pointCount = W.s_pc[s] & 0xFF;
+  const float mA = v1.x, iA = v1.y, mB = v1.z, iB = v1.w;
+  const float4 r0 = W.s_r0[s], q0 = W.s_q0[s];
+  float4 r1 = make_float4(0, 0, 0, 0), q1 = make_float4(0, 0, 0, 0);
+  if (pointCount == 2) { r1 = W.s_r1[s]; q1 = W.s_q1[s]; }
+  BodyVel bv = load_vel(W, bd);
+  v2 vA = bv.vA, vB = bv.vB; float wA = bv.wA, wB = bv.wB;
+  const v2 normal = V(v0.x, v0.y), tangent = cross(normal, 1.0f);
+  const float friction = v0.z, tangentSpeed = v0.w;
+  for (int k = 0; k < pointCount; ++k) {
+    const float4 r = k == 0 ? r0 : r1;
+    const float tangentMass = k == 0 ? q0.y : q1.y;
+    const v2 rA = V(r.x, r.y), rB = V(r.z, r.w);
+    float ni = k == 0 ? imp.x : imp.z, ti = k == 0 ? imp.y : imp.w;
+    v2 dv = vB + cross(wB, rB) - vA - cross(wA, rA);
+    float vt = dot(dv, tangent) - tangentSpeed;
+    float lambda = tangentMass * (-vt);
+    float maxFriction = friction * ni;
+    float newImpulse = fclampr(ti + lambda, -maxFriction, maxFriction);
+    lambda = newImpulse - ti;
+    if (k == 0) imp.y = newImpulse; else imp.w = newImpulse;
+    v2 P = lambda * tangent;
+    vA -= mA * P; wA -= iA * cross(rA, P);
+    vB += mB * P; wB += iB * cross(rB, P);
+  }
+  if (pointCount == 1) {
+    const v2 rA = V(r0.x, r0.y), rB = V(r0.z, r0.w);
+    v2 dv = vB + cross(wB, rB) - vA - cross(wA, rA);
+    float vn = dot(dv, normal);
+    float lambda = -q0.x * (vn - q0.z);
+    float newImpulse = fmaxr(imp.x + lambda, 0.0f);
+    lambda = newImpulse - imp.x;
+    imp.x = newImpulse;
+    v2 P = lambda * normal;
+    vA -= mA * P; wA -= iA * cross(rA, P);
+    vB += mB * P; wB += iB * cross(rB, P);
+  } else {
+    const float4 nm = W.s_nm[s], K = W.s_k[s];
+    const v2 rA1 = V(r0.x, r0.y), rB1 = V(r0.z, r0.w), rA2 = V(r1.x, r1.y), rB2 = V(r1.z, r1.w);
+    v2 a = V(imp.x, imp.z);
+    v2 dv1 = vB + cross(wB, rB1) - vA - cross(wA, rA1);
+    v2 dv2 = vB + cross(wB, rB2) - vA - cross(wA, rA2);
+    float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
+    v2 b;
+    b.x = vn1 - q0.z;
+    b.y = vn2 - q1.z;
+    M22 Km; Km.ex = V(K.x, K.y); Km.ey = V(K.z, K.w);
+    M22 NM; NM.ex = V(nm.x, nm.y); NM.ey = V(nm.z, nm.w);
+    b -= mul(Km, a);
+    v2 x;
+    bool found = false;
+    // the four LCP cases in the reference's order (:633-765)
+    x = -mul(NM, b);
+    if (x.x >= 0.0f && x.y >= 0.0f) found = true;
+    if (!found) {
+      x.x = -q0.x * b.x; x.y = 0.0f;
+      vn2 = Km.ex.y * x.x + b.y;
+      if (x.x >= 0.0f && vn2 >= 0.0f) found = true;
+    }
+    if (!found) {
+      x.x = 0.0f; x.y = -q1.x * b.y;
+      vn1 = Km.ey.x * x.y + b.x;
+      if (x.y >= 0.0f && vn1 >= 0.0f) found = true;
+    }
+    if (!found) {
+      x.x = 0.0f; x.y = 0.0f;
+      vn1 = b.x; vn2 = b.y;
+      if (vn1 >= 0.0f && vn2 >= 0.0f) found = true;
+    }
+    if (found) {
+      v2 d = x - a;
+      v2 P1 = d.x * normal, P2 = d.y * normal;
+      vA -= mA * (P1 + P2);
+      wA -= iA * (cross(rA1, P1) + cross(rA2, P2));
+      vB += mB * (P1 + P2);
+      wB += iB * (cross(rB1, P1) + cross(rB2, P2));
+      imp.x = x.x; imp.z = x.y;
+    }
+  }
+  W.s_imp[s] = imp;
+  bv.vA = vA; bv.vB = vB; bv.wA = wA; bv.wB = wB;
+  store_vel(W, bd, bv, mA, iA, mB, iB);
+}
+
+// b2ContactSolver.SolvePositionConstraints (:73-149) + b2PositionSolverManifold (:816-868); returns min separation
+DBX_D float contact_solve_position(const DevWorld& W, int s) {
+  const int2 bd = W.s_body[s];
+  const float4 v1 = W.s_v1[s], p0 = W.s_p0[s], p1 = W.s_p1[s], p2 = W.s_p2[s];
+  const float2 p3 = W.s_p3[s];
+  const int pc = W.s_pc[s];
+  const int type = (pc >> 8) & 0xFF, pointCount = pc >> 16;
+  const float mA = v1.x, iA = v1.y, mB = v1.z, iB = v1.w;
+  const v2 localCenterA = V(p2.x, p2.y), localCenterB = V(p2.z, p2.w);
+  const v2 localNormal = V(p1.x, p1.y), localPoint = V(p1.z, p1.w);
+  float4 pa = ldcg4(&W.b_pos[bd.x]), pb = ldcg4(&W.b_pos[bd.y]);
+  v2 cA = V(pa.x, pa.y), cB = V(pb.x, pb.y);
+  float aA = pa.z, aB = pb.z;
+  float minSeparation = 0.0f;
+  for (int j = 0; j < pointCount; ++j) {
+    Xf xfA, xfB;
+    xfA.q = rot_from_angle(aA); xfB.q = rot_from_angle(aB);
+    xfA.p = cA - mul(xfA.q, localCenterA);
+    xfB.p = cB - mul(xfB.q, localCenterB);
+    v2 normal, point; float separation;
+    if (type == MAN_CIRCLES) {
+      v2 pointA = mul(xfA, localPoint), pointB = mul(xfB, V(p0.x, p0.y));
+      normal = pointB - pointA;
+      normalize(normal);
+      point = 0.5f * (pointA + pointB);
+      separation = dot(pointB - pointA, normal) - p3.x - p3.y;
+    } else if (type == MAN_FACE_A) {
+      normal = mul(xfA.q, localNormal);
+      v2 planePoint = mul(xfA, localPoint);
+      v2 clipPoint = mul(xfB, j == 0 ? V(p0.x, p0.y) : V(p0.z, p0.w));
+      separation = dot(clipPoint - planePoint, normal) - p3.x - p3.y;
+      point = clipPoint;
+    } else {
+      normal = mul(xfB.q, localNormal);
+      v2 planePoint = mul(xfB, localPoint);
+      v2 clipPoint = mul(xfA, j == 0 ? V(p0.x, p0.y) : V(p0.z, p0.w));
+      separation = dot(clipPoint - planePoint, normal) - p3.x - p3.y;
+      point = clipPoint;
+      normal = -normal;
+    }
+    v2 rA = point - cA, rB = point - cB;
+    minSeparation = fminr(minSeparation, separation);
+    float C = fclampr(kBaumgarte * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
+    float rnA = cross(rA, normal), rnB = cross(rB, normal);
+    float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+    float impulse = K > 0.0f ? -C / K : 0.0f;
+    v2 P = impulse * normal;
+    cA -= mA * P; aA -= iA * cross(rA, P);
+    cB += mB * P; aB += iB * cross(rB, P);
+  }
+  if (mA != 0.0f || iA != 0.0f) stcg4(&W.b_pos[bd.x], make_float4(cA.x, cA.y, aA, 0.0f));
+  if (mB != 0.0f || iB != 0.0f) stcg4(&W.b_pos[bd.y], make_float4(cB.x, cB.y, aB, 0.0f));
+  return minSeparation;
+}
+
+// ------------------------------------------------------------------------------------------------ joints
+// revolute: dynamics/joints/b2revolutejoint.d:319-636; distance: b2distancejoint.d:211-373
+DBX_D void joint_init(const DevWorld& W, int j) {
+  const int4 ids = W.j_ids[j];
+  const int bA = ids.y, bB = ids.z;
+  const float4 msA = W.b_mass[bA], msB = W.b_mass[bB];
+  const float4 lcA4 = W.b_lc[bA], lcB4 = W.b_lc[bB];
+  const float4 anc = W.j_anchor[j];
+  const float mA = msA.x, iA = msA.y, mB = msB.x, iB = msB.y;
+  const v2 localCenterA = V(lcA4.x, lcA4.y), localCenterB = V(lcB4.x, lcB4.y);
+  const float4 posA = W.b_pos[bA], posB = W.b_pos[bB];
+  const float4 xA = W.b_xf[bA], xB = W.b_xf[bB];
+  float4 velA = ldcg4(&W.b_vel[bA]), velB = ldcg4(&W.b_vel[bB]);
+  v2 vA = V(velA.x, velA.y), vB = V(velB.x, velB.y); float wA = velA.z, wB = velB.z;
+  const float aA = posA.z, aB = posB.z;
+  const Rot qA = R(xA.z, xA.w), qB = R(xB.z, xB.w);  // = b2Rot(aA), b2Rot(aB): positions are not integrated yet
+  const v2 rA = mul(qA, V(anc.x, anc.y) - localCenterA);
+  const v2 rB = mul(qB, V(anc.z, anc.w) - localCenterB);
+  W.j_r[j] = make_float4(rA.x, rA.y, rB.x, rB.y);
+  W.j_lc[j] = make_float4(localCenterA.x, localCenterA.y, localCenterB.x, localCenterB.y);
+  W.j_m[j] = make_float4(mA, iA, mB, iB);
+  W.j_root[j] = body_type(W.b_flags[bA]) != BODY_STATIC ? W.b_root[bA] : W.b_root[bB];
+  float4 imp = W.j_imp[j];
+  if (ids.x == JT_REVOLUTE) {
+    const float4 p0 = W.j_p0[j];
+    const bool enableLimit = (ids.w & 2) != 0, enableMotor = (ids.w & 4) != 0;
+    const bool fixedRotation = (iA + iB == 0.0f);
+    v3 ex, ey, ez;
+    ex.x = mA + mB + rA.y * rA.y * iA + rB.y * rB.y * iB;
+    ey.x = -rA.y * rA.x * iA - rB.y * rB.x * iB;
+    ez.x = -rA.y * iA - rB.y * iB;
+    ex.y = ey.x;
+    ey.y = mA + mB + rA.x * rA.x * iA + rB.x * rB.x * iB;
+    ez.y = rA.x * iA + rB.x * iB;
+    ex.z = ez.x;
+    ey.z = ez.y;
+    ez.z = iA + iB;
+    float motorMass = iA + iB;
+    if (motorMass > 0.0f) motorMass = 1.0f / motorMass;
+    if (!enableMotor || fixedRotation) imp.w = 0.0f;
+    int limitState = W.j_limit[j];
+    if (enableLimit && !fixedRotation) {
+      float jointAngle = aB - aA - p0.x;
+      if (fabsr(p0.z - p0.y) < 2.0f * kAngularSlop) limitState = LIM_EQUAL;
+      else if (jointAngle <= p0.y) { if (limitState != LIM_LOWER) imp.z = 0.0f; limitState = LIM_LOWER; }
+      else if (jointAngle >= p0.z) { if (limitState != LIM_UPPER) imp.z = 0.0f; limitState = LIM_UPPER; }
+      else { limitState = LIM_INACTIVE; imp.z = 0.0f; }
+    } else {
+      limitState = LIM_INACTIVE;
+    }
+    W.j_limit[j] = limitState;
+    if (W.warmStarting) {
+      imp.x *= W.dtRatio; imp.y *= W.dtRatio; imp.z *= W.dtRatio;
+      imp.w *= W.dtRatio;
+      v2 P = V(imp.x, imp.y);
+      vA -= mA * P;
+      wA -= iA * (cross(rA, P) + imp.w + imp.z);
+      vB += mB * P;
+      wB += iB * (cross(rB, P) + imp.w + imp.z);
+    } else {
+      imp = make_float4(0, 0, 0, 0);
+    }
+    W.j_k0[j] = make_float4(ex.x, ex.y, ex.z, motorMass);
+    W.j_k1[j] = make_float4(ey.x, ey.y, ey.z, 0.0f);
+    W.j_k2[j] = make_float4(ez.x, ez.y, ez.z, 0.0f);
+  } else {  // JT_DISTANCE
+    const float4 p0 = W.j_p0[j];
+    const v2 cA = V(posA.x, posA.y), cB = V(posB.x, posB.y);
+    v2 u = cB + rB - cA - rA;
+    float length = len(u);
+    if (length > kLinearSlop) u *= 1.0f / length; else u = V(0.0f, 0.0f);
+    float crAu = cross(rA, u), crBu = cross(rB, u);
+    float invMass = mA + iA * crAu * crAu + mB + iB * crBu * crBu;
+    float mass = invMass != 0.0f ? 1.0f / invMass : 0.0f;
+    float gamma = 0.0f, bias = 0.0f;
+    if (p0.y > 0.0f) {
+      float C = length - p0.x;
+      float omega = 2.0f * kPi * p0.y;
+      float d = 2.0f * mass * p0.z * omega;
+      float k = mass * omega * omega;
+      float h = W.dt;
+      gamma = h * (d + h * k);
+      gamma = gamma != 0.0f ? 1.0f / gamma : 0.0f;
+      bias = C * h * k * gamma;
+      invMass += gamma;
+      mass = invMass != 0.0f ? 1.0f / invMass : 0.0f;
+    }
+    if (W.warmStarting) {
+      imp.x *= W.dtRatio;
+      v2 P = imp.x * u;
+      vA -= mA * P; wA -= iA * cross(rA, P);
+      vB += mB * P; wB += iB * cross(rB, P);
+    } else {
+      imp.x = 0.0f;
+    }
+    W.j_k0[j] = make_float4(u.x, u.y, mass, gamma);
+    W.j_k1[j] = make_float4(bias, 0.0f, 0.0f, 0.0f);
+  }
+  W.j_imp[j] = imp;
+  if (mA != 0.0f || iA != 0.0f) stcg4(&W.b_vel[bA], make_float4(vA.x, vA.y, wA, 0.0f));
+  if (mB != 0.0f || iB != 0.0f) stcg4(&W.b_vel[bB], make_float4(vB.x, vB.y, wB, 0.0f));
+}
+
+DBX_D void joint_solve_velocity(const DevWorld& W, int j) {
+  const int4 ids = W.j_ids[j];
+  const int bA = ids.y, bB = ids.z;
+  const float4 m = W.j_m[j], r = W.j_r[j];
+  const float mA = m.x, iA = m.y, mB = m.z, iB = m.w;
+  const v2 rA = V(r.x, r.y), rB = V(r.z, r.w);
+  float4 velA = ldcg4(&W.b_vel[bA]), velB = ldcg4(&W.b_vel[bB]);
+  v2 vA = V(velA.x, velA.y), vB = V(velB.x, velB.y); float wA = velA.z, wB = velB.z;
+  float4 imp = W.j_imp[j];
+  if (ids.x == JT_REVOLUTE) {
+    const float4 p0 = W.j_p0[j], p1 = W.j_p1[j];
+    const float4 k0 = W.j_k0[j], k1 = W.j_k1[j], k2 = W.j_k2[j];
+    const bool enableLimit = (ids.w & 2) != 0, enableMotor = (ids.w & 4) != 0;
+    const int limitState = W.j_limit[j];
+    const bool fixedRotation = (iA + iB == 0.0f);
+    if (enableMotor && limitState != LIM_EQUAL && !fixedRotation) {
+      float Cdot = wB - wA - p1.x;
+      float impulse = -k0.w * Cdot;
+      float oldImpulse = imp.w;
+      float maxImpulse = W.dt * p0.w;
+      imp.w = fclampr(imp.w + impulse, -maxImpulse, maxImpulse);
+      impulse = imp.w - oldImpulse;
+      wA -= iA * impulse;
+      wB += iB * impulse;
+    }
+    const v3 ex = V3(k0.x, k0.y, k0.z), ey = V3(k1.x, k1.y, k1.z), ez = V3(k2.x, k2.y, k2.z);
+    if (enableLimit && limitState != LIM_INACTIVE && !fixedRotation) {
+      v2 Cdot1 = vB + cross(wB, rB) - vA - cross(wA, rA);
+      float Cdot2 = wB - wA;
+      v3 s = solve33(ex, ey, ez, V3(Cdot1.x, Cdot1.y, Cdot2));
+      v3 impulse = V3(-s.x, -s.y, -s.z);
+      if (limitState == LIM_EQUAL) {
+        imp.x += impulse.x; imp.y += impulse.y; imp.z += impulse.z;
+      } else if (limitState == LIM_LOWER) {
+        float newImpulse = imp.z + impulse.z;
+        if (newImpulse < 0.0f) {
+          v2 rhs = -Cdot1 + imp.z * V(ez.x, ez.y);
+          v2 reduced = solve22(ex.x, ey.x, ex.y, ey.y, rhs);
+          impulse.x = reduced.x; impulse.y = reduced.y; impulse.z = -imp.z;
+          imp.x += reduced.x; imp.y += reduced.y; imp.z = 0.0f;
+        } else { imp.x += impulse.x; imp.y += impulse.y; imp.z += impulse.z; }
+      } else if (limitState == LIM_UPPER) {
+        float newImpulse = imp.z + impulse.z;
+        if (newImpulse > 0.0f) {
+          v2 rhs = -Cdot1 + imp.z * V(ez.x, ez.y);
+          v2 reduced = solve22(ex.x, ey.x, ex.y, ey.y, rhs);
+          impulse.x = reduced.x; impulse.y = reduced.y; impulse.z = -imp.z;
+          imp.x += reduced.x; imp.y += reduced.y; imp.z = 0.0f;
+        } else { imp.x += impulse.x; imp.y += impulse.y; imp.z += impulse.z; }
+      }
+      v2 P = V(impulse.x, impulse.y);
+      vA -= mA * P;
+      wA -= iA * (cross(rA, P) + impulse.z);
+      vB += mB * P;
+      wB += iB * (cross(rB, P) + impulse.z);
+    } else {
+      v2 Cdot = vB + cross(wB, rB) - vA - cross(wA, rA);
+      v2 impulse = solve22(ex.x, ey.x, ex.y, ey.y, -Cdot);
+      imp.x += impulse.x; imp.y += impulse.y;
+      vA -= mA * impulse; wA -= iA * cross(rA, impulse);
+      vB += mB * impulse; wB += iB * cross(rB, impulse);
+    }
+  } else {
+    const float4 k0 = W.j_k0[j], k1 = W.j_k1[j];
+    const v2 u = V(k0.x, k0.y);
+    v2 vpA = vA + cross(wA, rA), vpB = vB + cross(wB, rB);
+    float Cdot = dot(u, vpB - vpA);
+    float impulse = -k0.z * (Cdot + k1.x + k0.w * imp.x);
+    imp.x += impulse;
+    v2 P = impulse * u;
+    vA -= mA * P; wA -= iA * cross(rA, P);
+    vB += mB * P; wB += iB * cross(rB, P);
+  }
+  W.j_imp[j] = imp;
+  if (mA != 0.0f || iA != 0.0f) stcg4(&W.b_vel[bA], make_float4(vA.x, vA.y, wA, 0.0f));
+  if (mB != 0.0f || iB != 0.0f) stcg4(&W.b_vel[bB], make_float4(vB.x, vB.y, wB, 0.0f));
+}
+
+// returns true when the joint is within tolerance
+DBX_D bool joint_solve_position(const DevWorld& W, int j) {
+  const int4 ids = W.j_ids[j];
+  const int bA = ids.y, bB = ids.z;
+  const float4 m = W.j_m[j], lc = W.j_lc[j], anc = W.j_anchor[j];
+  const float mA = m.x, iA = m.y, mB = m.z, iB = m.w;
+  float4 pa = ldcg4(&W.b_pos[bA]), pb = ldcg4(&W.b_pos[bB]);
+  v2 cA = V(pa.x, pa.y), cB = V(pb.x, pb.y); float aA = pa.z, aB = pb.z;
+  bool ok;
+  if (ids.x == JT_REVOLUTE) {
+    const float4 p0 = W.j_p0[j];
+    const float motorMass = W.j_k0[j].w;
+    const bool enableLimit = (ids.w & 2) != 0;
+    const int limitState = W.j_limit[j];
+    float angularError = 0.0f, positionError = 0.0f;
+    const bool fixedRotation = (iA + iB == 0.0f);
+    if (enableLimit && limitState != LIM_INACTIVE && !fixedRotation) {
+      float angle = aB - aA - p0.x;
+      float limitImpulse = 0.0f;
+      if (limitState == LIM_EQUAL) {
+        float C = fclampr(angle - p0.y, -kMaxAngularCorrection, kMaxAngularCorrection);
+        limitImpulse = -motorMass * C;
+        angularError = fabsr(C);
+      } else if (limitState == LIM_LOWER) {
+        float C = angle - p0.y;
+        angularError = -C;
+        C = fclampr(C + kAngularSlop, -kMaxAngularCorrection, 0.0f);
+        limitImpulse = -motorMass * C;
+      } else if (limitState == LIM_UPPER) {
+        float C = angle - p0.z;
+        angularError = C;
+        C = fclampr(C - kAngularSlop, 0.0f, kMaxAngularCorrection);
+        limitImpulse = -motorMass * C;
+      }
+      aA -= iA * limitImpulse;
+      aB += iB * limitImpulse;
+    }
+    {
+      Rot qA = rot_from_angle(aA), qB = rot_from_angle(aB);
+      v2 rA = mul(qA, V(anc.x, anc.y) - V(lc.x, lc.y));
+      v2 rB = mul(qB, V(anc.z, anc.w) - V(lc.z, lc.w));
+      v2 C = cB + rB - cA - rA;
+      positionError = len(C);
+      float k11 = mA + mB + iA * rA.y * rA.y + iB * rB.y * rB.y;
+      float k12 = -iA * rA.x * rA.y - iB * rB.x * rB.y;
+      float k22 = mA + mB + iA * rA.x * rA.x + iB * rB.x * rB.x;
+      v2 impulse = -solve22(k11, k12, k12, k22, C);
+      cA -= mA * impulse; aA -= iA * cross(rA, impulse);
+      cB += mB * impulse; aB += iB * cross(rB, impulse);
+    }
+    ok = positionError <= kLinearSlop && angularError <= kAngularSlop;
+  } else {
+    const float4 p0 = W.j_p0[j];
+    if (p0.y > 0.0f) return true;  // soft joints have no position constraint (b2distancejoint.d:337-341)
+    const float mass = W.j_k0[j].z;
+    Rot qA = rot_from_angle(aA), qB = rot_from_angle(aB);
+    v2 rA = mul(qA, V(anc.x, anc.y) - V(lc.x, lc.y));
+    v2 rB = mul(qB, V(anc.z, anc.w) - V(lc.z, lc.w));
+    v2 u = cB + rB - cA - rA;
+    float length = normalize(u);
+    float C = length - p0.x;
+    C = fclampr(C, -kMaxLinearCorrection, kMaxLinearCorrection);
+    float impulse = -mass * C;
+    v2 P = impulse * u;
+    cA -= mA * P; aA -= iA * cross(rA, P);
+    cB += mB * P; aB += iB * cross(rB, P);
+    ok = fabsr(C) < kLinearSlop;
+  }
+  if (mA != 0.0f || iA != 0.0f) stcg4(&W.b_pos[bA], make_float4(cA.x, cA.y, aA, 0.0f));
+  if (mB != 0.0f || iB != 0.0f) stcg4(&W.b_pos[bB], make_float4(cB.x, cB.y, aB, 0.0f));
+  return ok;
+}
+
+DBX_D bool joint_active(const DevWorld& W, int j) {
+  const int4 ids = W.j_ids[j];
+  if (!(ids.w & 8)) return false;
+  uint32_t fa = W.b_flags[ids.y], fb = W.b_flags[ids.z];
+  if (!(fa & BF_ACTIVE) || !(fb & BF_ACTIVE)) return false;
+  return ((fa & BF_ISLAND) && body_type(fa) != BODY_STATIC) || ((fb & BF_ISLAND) && body_type(fb) != BODY_STATIC);
+}
+
+// ------------------------------------------------------------------------------------------------ the persistent solver
+// b2Island.Solve (dynamics/b2island.d:118-279) for ALL awake islands at once.  Colour c of an iteration is one
+// barrier-delimited phase; within a colour no two constraints touch the same dynamic body, so every read-modify-write
+// of a body is exclusive and the result equals sequential Gauss-Seidel in colour order.
+__global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld W) {
+  Header* H = W.hdr;
+  const unsigned nb = gridDim.x;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const int nColours = H->nColours;
+  const int nJointColours = W.nJoints > 0 ? kMaxJointColours : 0;
+  const int* coff = H->colourOff;
+  const int* joff = H->jointColourOff;
+
+  // contacts warm start (b2island.d:138-141), colour by colour
+  if (W.warmStarting) {
+    for (int c = 0; c < nColours; ++c) {
+      int beg = coff[c], end = coff[c + 1];
+      if (beg == end) continue;
+      for (int s = beg + tid; s < end; s += nth) contact_warm_start(W, s);
+      grid_barrier(&H->barrier, nb);
+    }
+  }
+  // joints: InitVelocityConstraints incl. their warm start (:143-146)
+  for (int c = 0; c < nJointColours; ++c) {
+    int beg = joff[c], end = joff[c + 1];
+    if (beg == end) continue;
+    for (int k = beg + tid; k < end; k += nth) { int j = W.j_order[k]; if (joint_active(W, j)) joint_init(W, j); }
+    grid_barrier(&H->barrier, nb);
+  }
+  // velocity iterations: all joints, then all contacts (:153-161)
+  for (int it = 0; it < W.velIters; ++it) {
+    for (int c = 0; c < nJointColours; ++c) {
+      int beg = joff[c], end = joff[c + 1];
+      if (beg == end) continue;
+      for (int k = beg + tid; k < end; k += nth) { int j = W.j_order[k]; if (joint_active(W, j)) joint_solve_velocity(W, j); }
+      grid_barrier(&H->barrier, nb);
+    }
+    for (int c = 0; c < nColours; ++c) {
+      int beg = coff[c], end = coff[c + 1];
+      if (beg == end) continue;
+      for (int s = beg + tid; s < end; s += nth) contact_solve_velocity(W, s);
+      grid_barrier(&H->barrier, nb);
+    }
+  }
+  // StoreImpulses (:164) + integrate positions (:168-200)
+  {
+    const int n = min(H->nSolve, W.sCap);
+    for (int s = tid; s < n; s += nth) {
+      const int i = W.s_contact[s];
+      const int vcCount = W.s_pc[s] & 0xFF;
+      float4 imp = W.s_imp[s];
+      float4 old = W.c_imp[i];
+      old.x = imp.x; old.y = imp.y;
+      if (vcCount == 2) { old.z = imp.z; old.w = imp.w; }
+      W.c_imp[i] = old;
+    }
+    const float h = W.dt;
+    for (int b = tid; b < W.nBodies; b += nth) {
+      uint32_t f = W.b_flags[b];
+      if ((f & (BF_ALIVE | BF_ISLAND)) != (BF_ALIVE | BF_ISLAND)) continue;
+      float4 pos = ldcg4(&W.b_pos[b]), vel = ldcg4(&W.b_vel[b]);
+      v2 c = V(pos.x, pos.y), v = V(vel.x, vel.y);
+      float a = pos.z, w = vel.z;
+      v2 translation = h * v;
+      if (dot(translation, translation) > kMaxTranslationSquared) { float ratio = kMaxTranslation / len(translation); v *= ratio; }
+      float rotation = h * w;
+      if (rotation * rotation > kMaxRotationSquared) { float ratio = kMaxRotation / fabsr(rotation); w *= ratio; }
+      c += h * v;
+      a += h * w;
+      stcg4(&W.b_pos[b], make_float4(c.x, c.y, a, 0.0f));
+      stcg4(&W.b_vel[b], make_float4(v.x, v.y, w, 0.0f));
+    }
+  }
+  grid_barrier(&H->barrier, nb);
+  // position iterations: contacts then joints, each island stops once all of its constraints are within tolerance (:206-224)
+  for (int it = 0; it < W.posIters; ++it) {
+    int* notOk = W.b_posNotOk + it * W.nBodies;
+    const int* prev = it > 0 ? W.b_posNotOk + (it - 1) * W.nBodies : nullptr;
+    for (int c = 0; c < nColours; ++c) {
+      int beg = coff[c], end = coff[c + 1];
+      if (beg == end) continue;
+      for (int s = beg + tid; s < end; s += nth) {
+        int root = W.s_root[s];
+        if (prev && __ldcg(&prev[root]) == 0) continue;
+        float minSep = contact_solve_position(W, s);
+        if (!(minSep >= -3.0f * kLinearSlop)) notOk[root] = 1;
+      }
+      grid_barrier(&H->barrier, nb);
+    }
+    for (int c = 0; c < nJointColours; ++c) {
+      int beg = joff[c], end = joff[c + 1];
+      if (beg == end) continue;
+      for (int k = beg + tid; k < end; k += nth) {
+        int j = W.j_order[k];
+        if (!joint_active(W, j)) continue;
+        int root = W.j_root[j];
+        if (prev && __ldcg(&prev[root]) == 0) continue;
+        if (!joint_solve_position(W, j)) notOk[root] = 1;
+      }
+      grid_barrier(&H->barrier, nb);
+    }
+  }
+  // write back + SynchronizeTransform (:227-235), sleep bookkeeping (:241-269), ClearForces (b2world.d:443-450)
+  {
+    const float h = W.dt;
+    const float linTolSqr = kLinearSleepTolerance * kLinearSleepTolerance;
+    const float angTolSqr = kAngularSleepTolerance * kAngularSleepTolerance;
+    for (int b = tid; b < W.nBodies; b += nth) {
+      uint32_t f = W.b_flags[b];
+      if ((f & (BF_ALIVE | BF_ISLAND)) != (BF_ALIVE | BF_ISLAND)) continue;
+      float4 pos = ldcg4(&W.b_pos[b]);
+      float4 lc = W.b_lc[b];
+      Xf xf = xf_from_sweep(V(pos.x, pos.y), pos.z, V(lc.x, lc.y));
+      W.b_xf[b] = pack(xf);
+      if (W.allowSleep) {
+        float4 vel = ldcg4(&W.b_vel[b]);
+        float2 gs = W.b_gs[b];
+        if (!(f & BF_AUTOSLEEP) || vel.z * vel.z > angTolSqr || dot(V(vel.x, vel.y), V(vel.x, vel.y)) > linTolSqr) gs.y = 0.0f;
+        else gs.y += h;
+        W.b_gs[b] = gs;
+        atomicMin(&W.b_islMinSleep[W.b_root[b]], __float_as_int(gs.y));
+      }
+    }
+  }
+  grid_barrier(&H->barrier, nb);
+  if (W.allowSleep) {
+    const int* last = W.posIters > 0 ? W.b_posNotOk + (W.posIters - 1) * W.nBodies : nullptr;
+    for (int b = tid; b < W.nBodies; b += nth) {
+      uint32_t f = W.b_flags[b];
+      if ((f & (BF_ALIVE | BF_ISLAND)) != (BF_ALIVE | BF_ISLAND)) continue;
+      int root = W.b_root[b];
+      bool positionSolved = last && __ldcg(&last[root]) == 0;
+      float minSleep = __int_as_float(__ldcg(&W.b_islMinSleep[root]));
+      if (minSleep >= kTimeToSleep && positionSolved) {
+        // b2Body.SetAwake(false) (b2body.d:837-845)
+        W.b_flags[b] = f & ~BF_AWAKE;
+        W.b_gs[b].y = 0.0f;
+        W.b_vel[b] = make_float4(0, 0, 0, 0);
+        W.b_force[b] = make_float4(0, 0, 0, 0);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_clear_forces(const __grid_constant__ DevWorld W) {
+  GRID_STRIDE(b, W.nBodies) W.b_force[b] = make_float4(0, 0, 0, 0);
+}
+
+// ------------------------------------------------------------------------------------------------ SynchronizeFixtures
+// b2Body.SynchronizeFixtures (b2body.d:1129-1141) -> b2Fixture.Synchronize (b2fixture.d:480-502) -> b2DynamicTree.MoveProxy
+// (collision/b2dynamictree.d:140-184): swept tight AABB, fat-box containment test, predictive fattening, move buffer.
+__global__ void __launch_bounds__(256) k_sync_fixtures(const __grid_constant__ DevWorld W) {
+  GRID_STRIDE(p, W.nProxies) {
+    uint32_t pf = W.p_flags[p];
+    if (!(pf & PF_ALIVE)) continue;
+    const int4 ids = W.p_ids[p];
+    const uint32_t bf = W.b_flags[ids.z];
+    if (!(bf & BF_ISLAND) || body_type(bf) == BODY_STATIC) continue;   // b2world.d:1103-1118
+    const Xf xf1 = XF(W.b_xf0[ids.z]), xf2 = XF(W.b_xf[ids.z]);
+    const DShape* s = W.shapes + ids.w;
+    Box aabb = combine(shape_aabb(s, xf1), shape_aabb(s, xf2));
+    W.p_aabb[p] = pack(aabb);
+    Box fat = BX(W.p_fat[p]);
+    if (contains(fat, aabb)) continue;
+    v2 displacement = xf2.p - xf1.p;
+    Box b = aabb;
+    v2 r = V(kAabbExtension, kAabbExtension);
+    b.lo = b.lo - r;
+    b.hi = b.hi + r;
+    v2 d = kAabbMultiplier * displacement;
+    if (d.x < 0.0f) b.lo.x += d.x; else b.hi.x += d.x;
+    if (d.y < 0.0f) b.lo.y += d.y; else b.hi.y += d.y;
+    W.p_fat[p] = pack(b);
+    if (!(pf & PF_MOVED)) {
+      W.p_flags[p] = pf | PF_MOVED;
+      int slot = atomicAdd(&W.hdr->nMoved, 1);
+      if (slot < W.moveCap) W.moveList[slot] = p; else W.hdr->error = -5;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LBVH broadphase
+// Replaces the incremental dynamic tree (collision/b2dynamictree.d:566-915) by a linear BVH rebuilt over the same
+// persistent fat AABBs: Morton keys -> radix sort -> Karras hierarchy -> bottom-up refit.  The pair SET it reports is
+// the one b2BroadPhase.UpdatePairs computes (collision/b2broadphase.d:139-195): for every proxy in the move buffer,
+// all proxies whose fat AABB overlaps its fat AABB, each unordered pair once.
+DBX_D unsigned f2ord(float f) { unsigned u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+DBX_D float ord2f(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+__global__ void k_bounds_init(const __grid_constant__ DevWorld W) {
+  unsigned* b = (unsigned*)W.hdr->bounds;
+  b[0] = b[1] = 0xFFFFFFFFu; b[2] = b[3] = 0u;
+  W.hdr->nPairs = 0;
+}
+__global__ void __launch_bounds__(256) k_bounds(const __grid_constant__ DevWorld W) {
+  float lx = FLT_MAX, ly = FLT_MAX, hx = -FLT_MAX, hy = -FLT_MAX;
+  GRID_STRIDE(p, W.nProxies) {
+    if (!(W.p_flags[p] & PF_ALIVE)) continue;
+    float4 f = W.p_fat[p];
+    float cx = 0.5f * (f.x + f.z), cy = 0.5f * (f.y + f.w);
+    lx = fminf(lx, cx); ly = fminf(ly, cy); hx = fmaxf(hx, cx); hy = fmaxf(hy, cy);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o)); ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o));
+    hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o)); hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o));
+  }
+  if ((threadIdx.x & 31) == 0 && lx <= hx) {
+    unsigned* b = (unsigned*)W.hdr->bounds;
+    atomicMin(&b[0], f2ord(lx)); atomicMin(&b[1], f2ord(ly)); atomicMax(&b[2], f2ord(hx)); atomicMax(&b[3], f2ord(hy));
+  }
+}
+DBX_D unsigned expand_bits15(unsigned v) {  // 15 bits -> every other bit
+  v &= 0x7FFF;
+  v = (v | (v << 8)) & 0x00FF00FF;
+  v = (v | (v << 4)) & 0x0F0F0F0F;
+  v = (v | (v << 2)) & 0x33333333;
+  v = (v | (v << 1)) & 0x55555555;
+  return v;
+}
+__global__ void __launch_bounds__(256) k_morton(const __grid_constant__ DevWorld W) {
+  const unsigned* b = (const unsigned*)W.hdr->bounds;
+  const float lx = ord2f(b[0]), ly = ord2f(b[1]), hx = ord2f(b[2]), hy = ord2f(b[3]);
+  const float sx = hx > lx ? 32767.0f / (hx - lx) : 0.0f, sy = hy > ly ? 32767.0f / (hy - ly) : 0.0f;
+  GRID_STRIDE(p, W.nProxies) {
+    unsigned long long key;
+    if (W.p_flags[p] & PF_ALIVE) {
+      float4 f = W.p_fat[p];
+      float cx = 0.5f * (f.x + f.z), cy = 0.5f * (f.y + f.w);
+      unsigned ix = (unsigned)fminf(fmaxf((cx - lx) * sx, 0.0f), 32767.0f);
+      unsigned iy = (unsigned)fminf(fmaxf((cy - ly) * sy, 0.0f), 32767.0f);
+      unsigned m = expand_bits15(ix) | (expand_bits15(iy) << 1);
+      key = ((unsigned long long)(unsigned)W.b_world[W.p_ids[p].z] << 30) | m;
+    } else {
+      key = (unsigned long long)(unsigned)W.nWorlds << 30;  // dead slots sort last (past every replica) and get an empty box
+    }
+    W.bv_key[p] = key;
+    W.bv_leaf[p] = p;
+  }
+}
+// Karras 2012: each internal node finds its key range from common-prefix lengths
+DBX_D int lbvh_delta(const unsigned long long* keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  unsigned long long a = keys[i], b = keys[j];
+  if (a == b) return 64 + __clz(i ^ j);
+  return __clzll((long long)(a ^ b));
+}
+__global__ void __launch_bounds__(256) k_lbvh_hierarchy(const __grid_constant__ DevWorld W, const unsigned long long* keys) {
+  const int n = W.nProxies;
+  GRID_STRIDE(i, n - 1) {
+    int d = (lbvh_delta(keys, n, i, i + 1) - lbvh_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = lbvh_delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (lbvh_delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1) if (lbvh_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = lbvh_delta(keys, n, i, j);
+    int s = 0;
+    int t = l;
+    do {
+      t = (t + 1) >> 1;
+      if (lbvh_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int left = (min(i, j) == gamma) ? (n - 1 + gamma) : gamma;            // leaves live at [n-1, 2n-1)
+    int right = (max(i, j) == gamma + 1) ? (n - 1 + gamma + 1) : gamma + 1;
+    W.bv_child[i] = make_int2(left, right);
+    W.bv_parent[left] = i;
+    W.bv_parent[right] = i;
+    W.bv_visit[i] = 0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) W.bv_parent[0] = -1;
+}
+__global__ void __launch_bounds__(256) k_lbvh_refit(const __grid_constant__ DevWorld W, const int* leaves) {
+  const int n = W.nProxies;
+  GRID_STRIDE(k, n) {
+    int p = leaves[k];
+    float4 box = (W.p_flags[p] & PF_ALIVE) ? W.p_fat[p] : make_float4(FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX);
+    int node = n - 1 + k;
+    W.bv_box[node] = box;
+    if (n == 1) continue;
+    int parent = W.bv_parent[node];
+    while (parent >= 0) {
+      __threadfence();
+      if (atomicAdd(&W.bv_visit[parent], 1) == 0) break;   // the second child to arrive continues upward
+      int2 ch = W.bv_child[parent];
+      float4 a = __ldcg(&W.bv_box[ch.x]), b = __ldcg(&W.bv_box[ch.y]);
+      float4 u = make_float4(fminf(a.x, b.x), fminf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+      __stcg(&W.bv_box[parent], u);
+      parent = W.bv_parent[parent];
+    }
+  }
+}
+
+// warp-cooperative query: one warp per moved proxy walks the tree with a shared frontier; each lane tests one node
+__global__ void __launch_bounds__(256) k_query(const __grid_constant__ DevWorld W, const int* leaves) {
+  constexpr int kStack = 192;
+  __shared__ int stacks[8][kStack];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n = W.nProxies;
+  const int nMoved = min(W.hdr->nMoved, W.moveCap);
+  int* stack = stacks[wib];
+  for (int mIdx = warp; mIdx < nMoved; mIdx += nwarps) {
+    const int p = W.moveList[mIdx];
+    if (!(W.p_flags[p] & PF_ALIVE)) continue;
+    const Box fat = BX(W.p_fat[p]);
+    const int keyP = W.p_key[p];
+    const int worldP = W.b_world[W.p_ids[p].z];
+    int top = 0;
+    if (lane == 0) stack[0] = (n == 1) ? (n - 1) : 0;
+    top = 1;
+    __syncwarp();
+    while (top > 0) {
+      // pop up to 32 nodes
+      int take = min(top, 32);
+      int node = lane < take ? stack[top - take + lane] : -1;
+      top -= take;
+      __syncwarp();
+      bool hit = false;
+      if (node >= 0) hit = overlap(fat, BX(__ldg(&W.bv_box[node])));
+      bool isLeaf = node >= n - 1;
+      if (hit && isLeaf) {
+        int q = leaves[node - (n - 1)];
+        // each unordered pair once: from the lower-key proxy when both moved (UpdatePairs sorts and dedups the same set)
+        if (q != p && (W.p_flags[q] & PF_ALIVE) && W.b_world[W.p_ids[q].z] == worldP) {
+          int keyQ = W.p_key[q];
+          bool qMoved = (W.p_flags[q] & PF_MOVED) != 0;
+          if (!qMoved || keyP < keyQ) {
+            int slot = atomicAdd(&W.hdr->nPairs, 1);
+            if (slot < W.pairCap) W.pairs[slot] = keyP < keyQ ? make_int2(p, q) : make_int2(q, p);
+            else W.hdr->error = -5;
+          }
+        }
+      }
+      bool push = hit && !isLeaf;
+      unsigned ballot = __ballot_sync(0xffffffffu, push);
+      int offset = __popc(ballot & ((1u << lane) - 1));
+      int total = __popc(ballot);
+      if (top + 2 * total > kStack) { if (lane == 0) W.hdr->error = -5; break; }   // frontier overflow: report, never corrupt
+      if (push) {
+        int2 ch = W.bv_child[node];
+        int base = top + 2 * offset;
+        stack[base] = ch.x; stack[base + 1] = ch.y;
+      }
+      top += 2 * total;
+      __syncwarp();
+    }
+  }
+}
+
+// b2ContactManager.AddPair (dynamics/b2contactmanager.d:52-176) + b2Contact.Create (contacts/b2contact.d:375-400)
+__global__ void __launch_bounds__(256) k_add_pairs(const __grid_constant__ DevWorld W) {
+  const int n = min(W.hdr->nPairs, W.pairCap);
+  GRID_STRIDE(k, n) {
+    const int2 pr = W.pairs[k];
+    const int4 pa = W.p_ids[pr.x], pb = W.p_ids[pr.y];   // fixture child body shape
+    int bodyA = pa.z, bodyB = pb.z;
+    if (bodyA == bodyB) continue;
+    const unsigned long long key = ((unsigned long long)(unsigned)W.p_key[pr.x] << 32) | (unsigned)W.p_key[pr.y];
+    if (hash_find(W, key) >= 0) continue;                 // a contact for this (fixture, child) pair already exists (:75-100)
+    const uint32_t flA = W.b_flags[bodyA], flB = W.b_flags[bodyB];
+    if (!body_should_collide(W, bodyB, bodyA, flB, flA)) continue;
+    if (!filter_should_collide(W, pa.x, pb.x)) continue;
+    // type registry (b2contact.d:425-437): A must be the primary type
+    const int t1 = W.shapes[pa.w].type, t2 = W.shapes[pb.w].type;
+    bool has, primary;
+    if (t1 == SH_EDGE && t2 == SH_EDGE) { has = false; primary = false; }
+    else if (t1 == SH_CIRCLE) { has = true; primary = (t2 == SH_CIRCLE); }
+    else if (t1 == SH_EDGE) { has = true; primary = true; }
+    else { has = true; primary = (t2 != SH_EDGE); }        // polygon vs circle/polygon primary; vs edge swapped
+    if (!has) continue;
+    int proxyA = pr.x, proxyB = pr.y;
+    int4 ia = pa, ib = pb;
+    if (!primary) { int t = proxyA; proxyA = proxyB; proxyB = t; int4 tt = ia; ia = ib; ib = tt; }
+    // slot
+    int slot;
+    int f = atomicSub(&W.hdr->nFree, 1);
+    if (f > 0) slot = W.c_free[f - 1];
+    else { atomicAdd(&W.hdr->nFree, 1); slot = atomicAdd(&W.hdr->cHigh, 1); }
+    if (slot >= W.cCap) { W.hdr->error = -5; atomicSub(&W.hdr->cHigh, 1); continue; }
+    const bool sensor = ((W.f_group[ia.x] >> 16) & FXF_SENSOR) || ((W.f_group[ib.x] >> 16) & FXF_SENSOR);
+    const float2 mA = W.f_mat[ia.x], mB = W.f_mat[ib.x];
+    W.c_key[slot] = key;
+    W.c_ids[slot] = make_int4(proxyA, proxyB, ia.z, ib.z);
+    W.c_fix[slot] = make_int4(ia.x, ib.x, ia.w, ib.w);
+    W.c_flags[slot] = CF_ALIVE | CF_ENABLED | (sensor ? CF_SENSOR : 0);
+    W.c_m0[slot] = make_float4(0, 0, 0, 0);
+    W.c_m1[slot] = make_float4(0, 0, 0, 0);
+    W.c_imp[slot] = make_float4(0, 0, 0, 0);
+    W.c_mk[slot] = make_uint4(0, 0, 0, 0);
+    // b2MixFriction / b2MixRestitution (b2contact.d:32-42)
+    W.c_mat[slot] = make_float4(sqrtf(mA.x * mB.x), mA.y > mB.y ? mA.y : mB.y, 0.0f, 1.0f);
+    W.c_toiCount[slot] = 0;
+    W.c_colour[slot] = -1;
+    if (!hash_insert(W, key, slot)) W.hdr->error = -5;
+    if (!sensor) { wake_body_now(W, ia.z); wake_body_now(W, ib.z); }   // :168-173
+  }
+}
+__global__ void __launch_bounds__(256) k_clear_moves(const __grid_constant__ DevWorld W) {
+  const int nMoved = min(W.hdr->nMoved, W.moveCap);
+  GRID_STRIDE(k, nMoved) { int p = W.moveList[k]; W.p_flags[p] &= ~PF_MOVED; }
+}
+__global__ void k_reset_moves(const __grid_constant__ DevWorld W) { W.hdr->nMoved = 0; }
+
+// ------------------------------------------------------------------------------------------------ maintenance
+__global__ void __launch_bounds__(256) k_hash_clear(const __grid_constant__ DevWorld W) {
+  GRID_STRIDE(i, W.hCap) W.h_key[i] = kHashEmpty;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { W.hdr->nTomb = 0; }
+}
+__global__ void __launch_bounds__(256) k_hash_fill(const __grid_constant__ DevWorld W) {
+  const int n = W.hdr->cHigh;
+  GRID_STRIDE(i, n) if (W.c_flags[i] & CF_ALIVE) { if (!hash_insert(W, W.c_key[i], i)) W.hdr->error = -5; }
+}
+__global__ void __launch_bounds__(256) k_count(const __grid_constant__ DevWorld W) {
+  const int n = W.hdr->cHigh;
+  int alive = 0, touching = 0, awake = 0;
+  GRID_STRIDE(i, n) { uint32_t f = W.c_flags[i]; if (f & CF_ALIVE) { ++alive; if (f & CF_TOUCHING) ++touching; } }
+  GRID_STRIDE(b, W.nBodies) { uint32_t f = W.b_flags[b]; if ((f & BF_ALIVE) && (f & BF_AWAKE) && body_type(f) != BODY_STATIC) ++awake; }
+  for (int o = 16; o > 0; o >>= 1) {
+    alive += __shfl_xor_sync(0xffffffffu, alive, o); touching += __shfl_xor_sync(0xffffffffu, touching, o); awake += __shfl_xor_sync(0xffffffffu, awake, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (alive) atomicAdd(&W.hdr->nContacts, alive);
+    if (touching) atomicAdd(&W.hdr->nTouching, touching);
+    if (awake) atomicAdd(&W.hdr->nAwake, awake);
+  }
+}
+__global__ void k_count_reset(const __grid_constant__ DevWorld W) { W.hdr->nContacts = 0; W.hdr->nTouching = 0; W.hdr->nAwake = 0; }
+__global__ void __launch_bounds__(256) k_set_levels(const __grid_constant__ DevWorld W, const int* levels, int n) {
+  GRID_STRIDE(i, n) W.c_colour[i] = levels[i];
+}
+// after a state import: contact slots [0, n) are all alive, nothing is free
+__global__ void k_import_reset(const __grid_constant__ DevWorld W, int n) { W.hdr->cHigh = n; W.hdr->nFree = 0; }
+
+
+// ------------------------------------------------------------------------------------------------ API-time edits
+// DestroyFixture / DestroyBody / SetActive(false) (b2body.d:211-227, b2world.d:136-145) destroy the matching contacts;
+// CreateJoint / DestroyJoint with collideConnected == false flag them for re-filtering (b2world.d:241-256, 344-359).
+__global__ void __launch_bounds__(256) k_api_contacts(const __grid_constant__ DevWorld W, int body, int fixture, int otherBody, int flagOnly) {
+  const int n = W.hdr->cHigh;
+  GRID_STRIDE(i, n) {
+    uint32_t flags = W.c_flags[i];
+    if (!(flags & CF_ALIVE)) continue;
+    const int4 ids = W.c_ids[i];
+    const int4 fx = W.c_fix[i];
+    bool match;
+    if (fixture >= 0) match = fx.x == fixture || fx.y == fixture;
+    else if (otherBody >= 0) match = (ids.z == body && ids.w == otherBody) || (ids.z == otherBody && ids.w == body);
+    else match = ids.z == body || ids.w == body;
+    if (!match) continue;
+    if (flagOnly) { W.c_flags[i] = flags | CF_FILTER; continue; }
+    const int pointCount = (int)W.c_mk[i].w;
+    if (pointCount > 0 && !(flags & CF_SENSOR)) { wake_body_now(W, ids.z); wake_body_now(W, ids.w); }
+    hash_remove(W, W.c_key[i]);
+    W.c_flags[i] = 0;
+    W.c_colour[i] = -1;
+    int slot = atomicAdd(&W.hdr->nFree, 1);
+    W.c_free[slot] = i;
+  }
+}
+__global__ void k_api_wake(const __grid_constant__ DevWorld W, int a, int b) {
+  if (a >= 0) wake_body_now(W, a);
+  if (b >= 0) wake_body_now(W, b);
+}
+
+// ------------------------------------------------------------------------------------------------ host launchers
+#define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return _e; } while (0)
+
+static cudaError_t launch_coop(const void* fn, const DevWorld& W, const LaunchCfg& L) {
+  CK(cudaMemsetAsync(&W.hdr->barrier, 0, sizeof(unsigned), L.stream));
+  void* args[] = {(void*)&W};
+  return cudaLaunchCooperativeKernel(fn, dim3(L.coopBlocks), dim3(L.coopThreads), args, 0, L.stream);
+}
+
+cudaError_t stage_collide(const DevWorld& W, const LaunchCfg& L) {
+  k_collide<<<L.gridWide, 256, 0, L.stream>>>(W);
+  return cudaGetLastError();
+}
+
+cudaError_t stage_islands_and_integrate(const DevWorld& W, const LaunchCfg& L) {
+  k_island_init<<<L.gridWide, 256, 0, L.stream>>>(W);
+  k_island_union<<<L.gridWide, 256, 0, L.stream>>>(W);
+  k_island_flatten<<<L.gridWide, 256, 0, L.stream>>>(W);
+  k_island_wake_integrate<<<L.gridWide, 256, 0, L.stream>>>(W);
+  return cudaGetLastError();
+}
+
+cudaError_t stage_colour_and_sort(const DevWorld& W, const LaunchCfg& L) {
+  k_mark_solve<<<L.gridWide, 256, 0, L.stream>>>(W);
+  CK(cudaGetLastError());
+  CK(launch_coop((const void*)k_colour, W, L));
+  k_sort_hist<<<kSortBlocks, 256, 0, L.stream>>>(W);
+  k_sort_scan<<<1, kMaxColours, 0, L.stream>>>(W, kSortBlocks);
+  k_sort_scatter<<<kSortBlocks, 256, 0, L.stream>>>(W);
+  return cudaGetLastError();
+}
+
+cudaError_t stage_solve(const DevWorld& W, const LaunchCfg& L) {
+  k_prepare<<<L.gridWide, 256, 0, L.stream>>>(W);
+  CK(cudaGetLastError());
+  return launch_coop((const void*)k_solve, W, L);
+}
+
+cudaError_t stage_sync_fixtures(const DevWorld& W, const LaunchCfg& L) {
+  k_sync_fixtures<<<L.gridWide, 256, 0, L.stream>>>(W);
+  return cudaGetLastError();
+}
+
+size_t cub_temp_bytes(int maxProxies) {
+  size_t bytes = 0;
+  cub::DoubleBuffer<unsigned long long> k(nullptr, nullptr);
+  cub::DoubleBuffer<int> v(nullptr, nullptr);
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, maxProxies, 0, 64);
+  return bytes + 256;
+}
+
+cudaError_t stage_find_new_contacts(const DevWorld& W, const LaunchCfg& L) {
+  const int n = W.nProxies;
+  k_bounds_init<<<1, 1, 0, L.stream>>>(W);
+  if (n > 0) {
+    k_bounds<<<L.gridWide, 256, 0, L.stream>>>(W);
+    k_morton<<<L.gridWide, 256, 0, L.stream>>>(W);
+    cub::DoubleBuffer<unsigned long long> keys(W.bv_key, W.bv_keyAlt);
+    cub::DoubleBuffer<int> vals(W.bv_leaf, W.bv_leafAlt);
+    int worldBits = 1;
+    while ((1 << worldBits) < W.nWorlds + 1) ++worldBits;
+    size_t bytes = L.cubTempBytes;
+    CK(cub::DeviceRadixSort::SortPairs(L.cubTemp, bytes, keys, vals, n, 0, 30 + worldBits + 1, L.stream));
+    const unsigned long long* sk = keys.Current();
+    const int* sl = vals.Current();
+    if (n > 1) k_lbvh_hierarchy<<<L.gridWide, 256, 0, L.stream>>>(W, sk);
+    k_lbvh_refit<<<L.gridWide, 256, 0, L.stream>>>(W, sl);
+    k_query<<<L.gridWide, 256, 0, L.stream>>>(W, sl);
+    k_add_pairs<<<L.gridWide, 256, 0, L.stream>>>(W);
+  }
+  k_clear_moves<<<L.gridWide, 256, 0, L.stream>>>(W);
+  k_reset_moves<<<1, 1, 0, L.stream>>>(W);
+  return cudaGetLastError();
+}
+
+cudaError_t stage_rebuild_hash(const DevWorld& W, const LaunchCfg& L) {
+  k_hash_clear<<<L.gridWide, 256, 0, L.stream>>>(W);
+  k_hash_fill<<<L.gridWide, 256, 0, L.stream>>>(W);
+  return cudaGetLastError();
+}
+
+cudaError_t stage_count(const DevWorld& W, const LaunchCfg& L) {
+  k_count_reset<<<1, 1, 0, L.stream>>>(W);
+  k_count<<<L.gridWide, 256, 0, L.stream>>>(W);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_insert_contacts(const DevWorld& W, const LaunchCfg& L, int n) {
+  k_import_reset<<<1, 1, 0, L.stream>>>(W, n);
+  return stage_rebuild_hash(W, L);
+}
+
+cudaError_t launch_api_contacts(const DevWorld& W, const LaunchCfg& L, int body, int fixture, int otherBody, int flagOnly) {
+  k_api_contacts<<<L.gridWide, 256, 0, L.stream>>>(W, body, fixture, otherBody, flagOnly);
+  return cudaGetLastError();
+}
+cudaError_t launch_api_wake(const DevWorld& W, const LaunchCfg& L, int a, int b) {
+  k_api_wake<<<1, 1, 0, L.stream>>>(W, a, b);
+  return cudaGetLastError();
+}
+cudaError_t launch_clear_forces(const DevWorld& W, const LaunchCfg& L) {
+  k_clear_forces<<<L.gridWide, 256, 0, L.stream>>>(W);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_set_levels(const DevWorld& W, const LaunchCfg& L, const int* d_levels, int n) {
+  k_set_levels<<<L.gridWide, 256, 0, L.stream>>>(W, d_levels, n);
+  return cudaGetLastError();
+}
+
+}  // namespace dbx

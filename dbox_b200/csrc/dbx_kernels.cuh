@@ -1,0 +1,34 @@
+// dbx_kernels.cuh — the step pipeline as CUDA kernels for sm_100a (declared here, defined in dbx_kernels.cu).
+#pragma once
+#include "dbx_device.cuh"
+
+namespace dbx {
+
+struct LaunchCfg {
+  int sms = 148;
+  int gridWide = 148 * 8;   // grid-stride kernels: multiple of the SM count
+  int coopBlocks = 148;     // persistent cooperative kernels: one CTA per SM
+  int coopThreads = 512;
+  cudaStream_t stream = 0;
+  void* cubTemp = nullptr; size_t cubTempBytes = 0;
+};
+
+// stages of b2World.Step (dynamics/b2world.d:367-434); each returns the first CUDA error
+cudaError_t stage_collide(const DevWorld& W, const LaunchCfg& L);                 // b2ContactManager.Collide
+cudaError_t stage_islands_and_integrate(const DevWorld& W, const LaunchCfg& L);   // island discovery + wake + integrate velocities
+cudaError_t stage_colour_and_sort(const DevWorld& W, const LaunchCfg& L);         // graph colouring + colour counting sort
+cudaError_t stage_solve(const DevWorld& W, const LaunchCfg& L);                   // prepare + warm start + iterations + finalize + sleep
+cudaError_t stage_sync_fixtures(const DevWorld& W, const LaunchCfg& L);           // b2Body.SynchronizeFixtures / MoveProxy
+cudaError_t stage_find_new_contacts(const DevWorld& W, const LaunchCfg& L);       // LBVH rebuild + pair query + AddPair
+cudaError_t stage_rebuild_hash(const DevWorld& W, const LaunchCfg& L);
+cudaError_t stage_count(const DevWorld& W, const LaunchCfg& L);                   // refresh hdr->nContacts / nTouching / nAwake
+size_t cub_temp_bytes(int maxProxies);
+
+// helpers used by the state import path
+cudaError_t launch_insert_contacts(const DevWorld& W, const LaunchCfg& L, int n);  // (re)build hash + free list for slots [0,n)
+cudaError_t launch_api_contacts(const DevWorld& W, const LaunchCfg& L, int body, int fixture, int otherBody, int flagOnly);
+cudaError_t launch_api_wake(const DevWorld& W, const LaunchCfg& L, int a, int b);
+cudaError_t launch_clear_forces(const DevWorld& W, const LaunchCfg& L);
+cudaError_t launch_set_levels(const DevWorld& W, const LaunchCfg& L, const int* d_levels, int n);
+
+}  // namespace dbx

@@ -1,0 +1,1038 @@
+// dbx_world.cu — host side of the device world (see dbx_world.h).
+#include "dbx_world.h"
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+namespace dbx {
+
+static thread_local std::string g_lastError;
+void set_last_error(const std::string& s) { g_lastError = s; }
+const char* get_last_error() { return g_lastError.c_str(); }
+
+#define CUDA_OR_FAIL(x, where) do { cudaError_t _e = (x); if (_e != cudaSuccess) return fail(_e, where); } while (0)
+
+int World::fail(cudaError_t e, const char* where) {
+  set_last_error(std::string(where) + ": " + cudaGetErrorString(e));
+  return DBX_E_CUDA;
+}
+
+World::World(float gx, float gy, int device, const dbx_caps* caps) : gx_(gx), gy_(gy) {
+  if (caps) caps_ = *caps;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) { set_last_error("no CUDA device: dbox_b200 has no CPU fallback"); return; }
+  if (device < 0 || device >= ndev) { set_last_error("bad device index"); return; }
+  device_ = device;
+  if (cudaSetDevice(device) != cudaSuccess) { set_last_error("cudaSetDevice failed"); return; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { set_last_error("cudaGetDeviceProperties failed"); return; }
+  if (!prop.cooperativeLaunch) { set_last_error("device lacks cooperative launch"); return; }
+  if (cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking) != cudaSuccess) { set_last_error("stream create failed"); return; }
+  L_.sms = prop.multiProcessorCount;
+  L_.gridWide = L_.sms * 8;
+  L_.coopBlocks = L_.sms;
+  L_.coopThreads = 512;
+  L_.stream = stream_;
+  if (hdr_.reserve(1, false, stream_) != cudaSuccess) { set_last_error("header alloc failed"); return; }
+  for (auto& ev : ev_) cudaEventCreate(&ev);
+  cudaStreamSynchronize(stream_);
+  ok_ = true;
+}
+
+World::~World() {
+  if (!ok_) return;
+  cudaSetDevice(device_);
+  cudaStreamSynchronize(stream_);
+  DevBuf<float4>* f4[] = {&b_xf, &b_xf0, &b_pos, &b_pos0, &b_vel, &b_force, &b_mass, &b_lc, &p_aabb, &p_fat, &bv_box, &c_m0, &c_m1, &c_imp, &c_mat,
+                          &s_v0, &s_v1, &s_r0, &s_r1, &s_q0, &s_q1, &s_imp, &s_nm, &s_k, &s_p0, &s_p1, &s_p2, &j_anchor, &j_p0, &j_p1, &j_imp, &j_r, &j_lc, &j_m, &j_k0, &j_k1, &j_k2};
+  for (auto* b : f4) b->release();
+  DevBuf<int>* i1[] = {&b_wake, &b_root, &b_islAwake, &b_islMinSleep, &b_posNotOk, &b_ovf, &b_world, &f_body, &f_group, &p_key, &moveList, &bv_leaf, &bv_leafAlt,
+                       &bv_parent, &bv_visit, &c_toiCount, &c_colour, &c_free, &c_work, &c_work2, &h_val, &s_contact, &s_hist, &s_pc, &s_root, &j_limit, &j_colour, &j_order, &j_root, &d_levels};
+  for (auto* b : i1) b->release();
+  b_gs.release(); f_mat.release(); s_p3.release(); b_flags.release(); f_filter.release(); p_flags.release(); c_flags.release();
+  b_mask.release(); b_claim.release(); bv_key.release(); bv_keyAlt.release(); jp_keys.release(); c_key.release(); h_key.release();
+  d_shapes.release(); p_ids.release(); c_ids.release(); c_fix.release(); j_ids.release(); bv_child.release(); pairs.release(); s_body.release(); c_mk.release();
+  cubTemp.release(); hdr_.release();
+  for (auto& ev : ev_) cudaEventDestroy(ev);
+  cudaStreamDestroy(stream_);
+}
+
+// ------------------------------------------------------------------------------------------------ reference id order
+// b2DynamicTree hands out node ids from a LIFO free list (collision/b2dynamictree.d:516-564).  Leaves and the internal
+// node created with them always travel through that list in (leaf, parent) blocks, so the id a NEW leaf receives
+// depends only on the history of leaf creations/destructions, not on the tree's shape.  Replaying that history keeps
+// (min, max) proxy-id order — and with it fixture A/B of every contact — identical to the reference.
+int World::allocProxyKey() {
+  int id;
+  if (!keyFree_.empty()) { id = keyFree_.back(); keyFree_.pop_back(); }
+  else { id = keyFresh_; keyFresh_ += (keyLeaves_ >= 1) ? 2 : 1; }
+  ++keyLeaves_;
+  return id;
+}
+void World::freeProxyKey(int key) { keyFree_.push_back(key); --keyLeaves_; }
+
+// ------------------------------------------------------------------------------------------------ shapes (host side)
+int World::internShape(const DShape& s) {
+  std::string k((const char*)&s, sizeof(DShape));
+  auto it = shapeIndex_.find(k);
+  if (it != shapeIndex_.end()) return it->second;
+  int idx = (int)shapes_.size();
+  shapes_.push_back(s);
+  shapeIndex_.emplace(std::move(k), idx);
+  return idx;
+}
+
+void World::buildChildShape(const HShape& hs, int child, DShape* out) const {
+  std::memset(out, 0, sizeof(DShape));
+  const dbx_shape& s = hs.s;
+  out->radius = s.radius;
+  switch (s.type) {
+    case DBX_SHAPE_CIRCLE: out->type = SH_CIRCLE; out->c = V(s.p.x, s.p.y); break;
+    case DBX_SHAPE_EDGE:
+      out->type = SH_EDGE;
+      out->v[0] = V(s.v0.x, s.v0.y); out->v[1] = V(s.v1.x, s.v1.y); out->v[2] = V(s.v2.x, s.v2.y); out->v[3] = V(s.v3.x, s.v3.y);
+      out->flags = (s.hasV0 ? SHF_HAS_V0 : 0) | (s.hasV3 ? SHF_HAS_V3 : 0);
+      break;
+    case DBX_SHAPE_POLYGON:
+      out->type = SH_POLYGON; out->count = s.count; out->c = V(s.centroid.x, s.centroid.y);
+      for (int i = 0; i < s.count; ++i) { out->v[i] = V(s.vertices[i].x, s.vertices[i].y); out->n[i] = V(s.normals[i].x, s.normals[i].y); }
+      break;
+    case DBX_SHAPE_CHAIN: {
+      // b2ChainShape.GetChildEdge (collision/shapes/b2chainshape.d:162-192)
+      const auto& cv = hs.chain;
+      const int cnt = (int)cv.size();
+      out->type = SH_EDGE;
+      out->flags = SHF_CHAIN_CHILD;
+      out->v[1] = V(cv[child].x, cv[child].y);
+      out->v[2] = V(cv[child + 1].x, cv[child + 1].y);
+      if (child > 0) { out->v[0] = V(cv[child - 1].x, cv[child - 1].y); out->flags |= SHF_HAS_V0; }
+      else { out->v[0] = V(s.prevVertex.x, s.prevVertex.y); if (s.hasPrev) out->flags |= SHF_HAS_V0; }
+      if (child < cnt - 2) { out->v[3] = V(cv[child + 2].x, cv[child + 2].y); out->flags |= SHF_HAS_V3; }
+      else { out->v[3] = V(s.nextVertex.x, s.nextVertex.y); if (s.hasNext) out->flags |= SHF_HAS_V3; }
+    } break;
+  }
+}
+
+// Shape.ComputeMass (b2circleshape.d:120-127, b2edgeshape.d:179-186, b2polygonshape.d:376-459, b2chainshape.d:247-254)
+void World::computeMass(const HShape& hs, float density, float* mass, dbx_vec2* center, float* I) const {
+  const dbx_shape& s = hs.s;
+  if (s.type == DBX_SHAPE_CIRCLE) {
+    *mass = density * kPi * s.radius * s.radius;
+    *center = s.p;
+    *I = *mass * (0.5f * s.radius * s.radius + (s.p.x * s.p.x + s.p.y * s.p.y));
+  } else if (s.type == DBX_SHAPE_EDGE) {
+    *mass = 0.0f; center->x = 0.5f * (s.v1.x + s.v2.x); center->y = 0.5f * (s.v1.y + s.v2.y); *I = 0.0f;
+  } else if (s.type == DBX_SHAPE_CHAIN) {
+    *mass = 0.0f; center->x = 0.0f; center->y = 0.0f; *I = 0.0f;
+  } else {
+    const int n = s.count;
+    v2 c = V(0.0f, 0.0f), ref = V(0.0f, 0.0f);
+    float area = 0.0f, inertia = 0.0f;
+    for (int i = 0; i < n; ++i) ref += V(s.vertices[i].x, s.vertices[i].y);
+    ref *= 1.0f / n;
+    const float k_inv3 = 1.0f / 3.0f;
+    for (int i = 0; i < n; ++i) {
+      v2 e1 = V(s.vertices[i].x, s.vertices[i].y) - ref;
+      v2 e2 = i + 1 < n ? V(s.vertices[i + 1].x, s.vertices[i + 1].y) - ref : V(s.vertices[0].x, s.vertices[0].y) - ref;
+      float D = cross(e1, e2);
+      float triangleArea = 0.5f * D;
+      area += triangleArea;
+      c += triangleArea * k_inv3 * (e1 + e2);
+      float intx2 = e1.x * e1.x + e2.x * e1.x + e2.x * e2.x;
+      float inty2 = e1.y * e1.y + e2.y * e1.y + e2.y * e2.y;
+      inertia += (0.25f * k_inv3 * D) * (intx2 + inty2);
+    }
+    *mass = density * area;
+    c *= 1.0f / area;
+    v2 ctr = c + ref;
+    center->x = ctr.x; center->y = ctr.y;
+    *I = density * inertia;
+    *I += *mass * (dot(ctr, ctr) - dot(c, c));
+  }
+}
+
+// b2Body.ResetMassData (dynamics/b2body.d:555-625); fixtures are visited newest first like the reference's list
+void World::resetMassData(HBody& hb) {
+  dbx_body_state& st = hb.st;
+  st.mass = 0.0f; st.invMass = 0.0f; st.I = 0.0f; st.invI = 0.0f;
+  st.localCenter = dbx_vec2{0.0f, 0.0f};
+  if (st.type == DBX_STATIC_BODY || st.type == DBX_KINEMATIC_BODY) {
+    st.c0 = st.p; st.c = st.p; st.a0 = st.a;
+    return;
+  }
+  v2 localCenter = V(0.0f, 0.0f);
+  for (auto it = hb.fixtures.rbegin(); it != hb.fixtures.rend(); ++it) {
+    const HFixture& f = fixtures_[*it];
+    if (f.def.density == 0.0f) continue;
+    float m, I; dbx_vec2 c;
+    computeMass(f.shape, f.def.density, &m, &c, &I);
+    st.mass += m;
+    localCenter += m * V(c.x, c.y);
+    st.I += I;
+  }
+  if (st.mass > 0.0f) { st.invMass = 1.0f / st.mass; localCenter *= st.invMass; }
+  else { st.mass = 1.0f; st.invMass = 1.0f; }
+  if (st.I > 0.0f && (st.flags & DBX_BODY_FIXED_ROTATION) == 0) {
+    st.I -= st.mass * dot(localCenter, localCenter);
+    st.invI = 1.0f / st.I;
+  } else { st.I = 0.0f; st.invI = 0.0f; }
+  v2 oldCenter = V(st.c.x, st.c.y);
+  st.localCenter = dbx_vec2{localCenter.x, localCenter.y};
+  Xf xf; xf.p = V(st.p.x, st.p.y); xf.q = R(st.qs, st.qc);
+  v2 c = mul(xf, localCenter);
+  st.c0 = st.c = dbx_vec2{c.x, c.y};
+  v2 dv = cross(st.w, c - oldCenter);
+  st.v.x += dv.x; st.v.y += dv.y;
+}
+
+void World::wake(HBody& hb, bool flag) {  // b2Body.SetAwake (b2body.d:827-846)
+  dbx_body_state& st = hb.st;
+  if (flag) {
+    if ((st.flags & DBX_BODY_AWAKE) == 0) { st.flags |= DBX_BODY_AWAKE; st.sleepTime = 0.0f; }
+  } else {
+    st.flags &= ~DBX_BODY_AWAKE; st.sleepTime = 0.0f;
+    st.v = dbx_vec2{0, 0}; st.w = 0.0f; st.force = dbx_vec2{0, 0}; st.torque = 0.0f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ lifecycle
+int World::createBody(const dbx_body_def& d) {
+  HBody hb;
+  hb.alive = true;
+  dbx_body_state& st = hb.st;
+  std::memset(&st, 0, sizeof(st));
+  // b2Body ctor (dynamics/b2body.d:1030-1115)
+  st.type = d.type;
+  st.flags = 0;
+  if (d.bullet) st.flags |= DBX_BODY_BULLET;
+  if (d.fixedRotation) st.flags |= DBX_BODY_FIXED_ROTATION;
+  if (d.allowSleep) st.flags |= DBX_BODY_AUTOSLEEP;
+  if (d.awake) st.flags |= DBX_BODY_AWAKE;
+  if (d.active) st.flags |= DBX_BODY_ACTIVE;
+  st.p = d.position;
+  Rot q = rot_from_angle(d.angle);
+  st.qs = q.s; st.qc = q.c;
+  st.c0 = d.position; st.c = d.position; st.a0 = d.angle; st.a = d.angle; st.alpha0 = 0.0f;
+  st.v = d.linearVelocity; st.w = d.angularVelocity;
+  st.linearDamping = d.linearDamping; st.angularDamping = d.angularDamping; st.gravityScale = d.gravityScale;
+  if (d.type == DBX_DYNAMIC_BODY) { st.mass = 1.0f; st.invMass = 1.0f; }
+  hb.xf0 = make_float4(st.p.x, st.p.y, st.qs, st.qc);
+  hb.world = 0;
+  bodies_.push_back(std::move(hb));
+  return (int)bodies_.size() - 1;
+}
+
+int World::createFixture(int b, const dbx_fixture_def& d, const dbx_shape& s) {
+  if (b < 0 || b >= (int)bodies_.size() || !bodies_[b].alive) return DBX_E_INVALID;
+  if ((size_t)b < bodiesSynced_) { int rc = pullBodies(); if (rc < 0) return rc; fullPushBodies_ = true; }
+  HBody& hb = bodies_[b];
+  HFixture f;
+  f.alive = true; f.body = b; f.def = d; f.shape.s = s;
+  if (s.type == DBX_SHAPE_CHAIN) {
+    if (!s.chainVertices || s.chainCount < 2) return DBX_E_INVALID;
+    f.shape.chain.assign(s.chainVertices, s.chainVertices + s.chainCount);
+    f.shape.s.chainVertices = nullptr;
+  }
+  const int fid = (int)fixtures_.size();
+  const int childCount = s.type == DBX_SHAPE_CHAIN ? s.chainCount - 1 : 1;
+  if (hb.st.flags & DBX_BODY_ACTIVE) {
+    // b2Fixture.CreateProxies (b2fixture.d:450-465) -> b2BroadPhase.CreateProxy (b2broadphase.d:78-84)
+    Xf xf; xf.p = V(hb.st.p.x, hb.st.p.y); xf.q = R(hb.st.qs, hb.st.qc);
+    for (int i = 0; i < childCount; ++i) {
+      DShape ds; buildChildShape(f.shape, i, &ds);
+      HProxy p;
+      p.alive = true; p.fixture = fid; p.child = i; p.body = b; p.shape = internShape(ds);
+      Box box = shape_aabb(&ds, xf);
+      p.aabb = pack(box);
+      p.fat = make_float4(box.lo.x - kAabbExtension, box.lo.y - kAabbExtension, box.hi.x + kAabbExtension, box.hi.y + kAabbExtension);
+      p.key = allocProxyKey();
+      p.flags = PF_ALIVE | PF_MOVED;
+      int slot;
+      if (!proxyFree_.empty()) {
+        slot = proxyFree_.back(); proxyFree_.pop_back();
+        if ((size_t)slot < proxiesSynced_) { int rc = pullProxies(); if (rc < 0) return rc; fullPushProxies_ = true; }
+        proxies_[slot] = p;
+      } else { slot = (int)proxies_.size(); proxies_.push_back(p); }
+      f.proxies.push_back(slot);
+      pendingMoves_.push_back(slot);
+    }
+  }
+  fixtures_.push_back(std::move(f));
+  hb.fixtures.push_back(fid);
+  if (d.density > 0.0f) resetMassData(hb);
+  newFixture_ = true;
+  return fid;
+}
+
+int World::destroyContactsWhere(int body, int fixture, int otherBody, bool flagOnly) {
+  int rc = push(); if (rc < 0) return rc;
+  CUDA_OR_FAIL(launch_api_contacts(dw_, L_, body, fixture, otherBody, flagOnly ? 1 : 0), "api_contacts");
+  hostBodiesValid_ = false;
+  return 0;
+}
+
+int World::destroyFixture(int fid) {
+  if (fid < 0 || fid >= (int)fixtures_.size() || !fixtures_[fid].alive) return DBX_E_INVALID;
+  int rc = destroyContactsWhere(-1, fid, -1, false); if (rc < 0) return rc;
+  rc = pullBodies(); if (rc < 0) return rc;
+  rc = pullProxies(); if (rc < 0) return rc;
+  HFixture& f = fixtures_[fid];
+  HBody& hb = bodies_[f.body];
+  for (int slot : f.proxies) {
+    freeProxyKey(proxies_[slot].key);
+    proxies_[slot].alive = false; proxies_[slot].flags = 0;
+    proxyFree_.push_back(slot);
+    pendingMoves_.erase(std::remove(pendingMoves_.begin(), pendingMoves_.end(), slot), pendingMoves_.end());
+  }
+  f.proxies.clear();
+  f.alive = false;
+  hb.fixtures.erase(std::remove(hb.fixtures.begin(), hb.fixtures.end(), fid), hb.fixtures.end());
+  resetMassData(hb);
+  fullPushBodies_ = true; fullPushProxies_ = true;
+  return 0;
+}
+
+int World::destroyBody(int b) {
+  if (b < 0 || b >= (int)bodies_.size() || !bodies_[b].alive) return DBX_E_INVALID;
+  std::vector<int> js = bodies_[b].joints;
+  for (int j : js) destroyJoint(j);
+  int rc = destroyContactsWhere(b, -1, -1, false); if (rc < 0) return rc;
+  rc = pullBodies(); if (rc < 0) return rc;
+  rc = pullProxies(); if (rc < 0) return rc;
+  HBody& hb = bodies_[b];
+  for (auto it = hb.fixtures.rbegin(); it != hb.fixtures.rend(); ++it) {   // newest first (b2world.d:148-167)
+    HFixture& f = fixtures_[*it];
+    for (int slot : f.proxies) {
+      freeProxyKey(proxies_[slot].key);
+      proxies_[slot].alive = false; proxies_[slot].flags = 0;
+      proxyFree_.push_back(slot);
+      pendingMoves_.erase(std::remove(pendingMoves_.begin(), pendingMoves_.end(), slot), pendingMoves_.end());
+    }
+    f.proxies.clear(); f.alive = false;
+  }
+  hb.fixtures.clear();
+  hb.alive = false;
+  hb.st.flags = 0;
+  fullPushBodies_ = true; fullPushProxies_ = true;
+  return 0;
+}
+
+int World::createJoint(const dbx_joint_def& d) {
+  if (d.type != DBX_JOINT_REVOLUTE && d.type != DBX_JOINT_DISTANCE) { set_last_error("joint type not in this build's hot-path scope"); return DBX_E_UNSUPPORTED; }
+  if (d.bodyA < 0 || d.bodyB < 0 || d.bodyA >= (int)bodies_.size() || d.bodyB >= (int)bodies_.size() || !bodies_[d.bodyA].alive || !bodies_[d.bodyB].alive || d.bodyA == d.bodyB) return DBX_E_INVALID;
+  HJoint j; j.alive = true; j.def = d;
+  joints_.push_back(j);
+  const int jid = (int)joints_.size() - 1;
+  bodies_[d.bodyA].joints.push_back(jid);
+  bodies_[d.bodyB].joints.push_back(jid);
+  jointsChanged_ = true;
+  if (!d.collideConnected && bodiesSynced_ > 0 && (size_t)std::max(d.bodyA, d.bodyB) < bodiesSynced_) {
+    int rc = destroyContactsWhere(d.bodyA, -1, d.bodyB, true); if (rc < 0) return rc;   // FlagForFiltering (b2world.d:241-256)
+  }
+  return jid;
+}
+
+int World::destroyJoint(int jid) {
+  if (jid < 0 || jid >= (int)joints_.size() || !joints_[jid].alive) return DBX_E_INVALID;
+  int rc = pullJoints(); if (rc < 0) return rc;
+  HJoint& j = joints_[jid];
+  const int a = j.def.bodyA, b = j.def.bodyB;
+  j.alive = false;
+  auto& ja = bodies_[a].joints; ja.erase(std::remove(ja.begin(), ja.end(), jid), ja.end());
+  auto& jb = bodies_[b].joints; jb.erase(std::remove(jb.begin(), jb.end(), jid), jb.end());
+  jointsChanged_ = true; fullPushJoints_ = true;
+  rc = push(); if (rc < 0) return rc;
+  CUDA_OR_FAIL(launch_api_wake(dw_, L_, a, b), "api_wake");          // b2world.d:297-298
+  hostBodiesValid_ = false;
+  if (!j.def.collideConnected) { rc = destroyContactsWhere(a, -1, b, true); if (rc < 0) return rc; }
+  return 0;
+}
+
+int World::setFlags(uint32_t f) {
+  if ((flags_ & DBX_WORLD_ALLOW_SLEEP) && !(f & DBX_WORLD_ALLOW_SLEEP)) {
+    // b2World.SetAllowSleeping(false) wakes every body (b2world.d:622-640)
+    int rc = pullBodies(); if (rc < 0) return rc;
+    for (auto& hb : bodies_) if (hb.alive) wake(hb, true);
+    fullPushBodies_ = true;
+  }
+  flags_ = f;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ mirroring
+static float4 f4(float a, float b, float c, float d) { return make_float4(a, b, c, d); }
+
+int World::pullBodies() {
+  if (hostBodiesValid_ || bodiesSynced_ == 0) { hostBodiesValid_ = true; return 0; }
+  const size_t n = bodiesSynced_;
+  std::vector<float4> xf(n), xf0(n), pos(n), pos0(n), vel(n), frc(n), ms(n), lc(n);
+  std::vector<float2> gs(n); std::vector<uint32_t> fl(n);
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  CUDA_OR_FAIL(cudaMemcpy(xf.data(), b_xf.p, n * 16, cudaMemcpyDeviceToHost), "pull xf");
+  cudaMemcpy(xf0.data(), b_xf0.p, n * 16, cudaMemcpyDeviceToHost);
+  cudaMemcpy(pos.data(), b_pos.p, n * 16, cudaMemcpyDeviceToHost);
+  cudaMemcpy(pos0.data(), b_pos0.p, n * 16, cudaMemcpyDeviceToHost);
+  cudaMemcpy(vel.data(), b_vel.p, n * 16, cudaMemcpyDeviceToHost);
+  cudaMemcpy(frc.data(), b_force.p, n * 16, cudaMemcpyDeviceToHost);
+  cudaMemcpy(ms.data(), b_mass.p, n * 16, cudaMemcpyDeviceToHost);
+  cudaMemcpy(lc.data(), b_lc.p, n * 16, cudaMemcpyDeviceToHost);
+  cudaMemcpy(gs.data(), b_gs.p, n * 8, cudaMemcpyDeviceToHost);
+  CUDA_OR_FAIL(cudaMemcpy(fl.data(), b_flags.p, n * 4, cudaMemcpyDeviceToHost), "pull flags");
+  for (size_t i = 0; i < n; ++i) {
+    HBody& hb = bodies_[i];
+    if (!hb.alive) continue;
+    dbx_body_state& st = hb.st;
+    st.p = dbx_vec2{xf[i].x, xf[i].y}; st.qs = xf[i].z; st.qc = xf[i].w;
+    hb.xf0 = xf0[i];
+    st.c = dbx_vec2{pos[i].x, pos[i].y}; st.a = pos[i].z;
+    st.c0 = dbx_vec2{pos0[i].x, pos0[i].y}; st.a0 = pos0[i].z; st.alpha0 = pos0[i].w;
+    st.v = dbx_vec2{vel[i].x, vel[i].y}; st.w = vel[i].z;
+    st.force = dbx_vec2{frc[i].x, frc[i].y}; st.torque = frc[i].z;
+    st.invMass = ms[i].x; st.invI = ms[i].y; st.mass = ms[i].z; st.I = ms[i].w;
+    st.localCenter = dbx_vec2{lc[i].x, lc[i].y}; st.linearDamping = lc[i].z; st.angularDamping = lc[i].w;
+    st.gravityScale = gs[i].x; st.sleepTime = gs[i].y;
+    st.flags = fl[i] & 0xFFFF; st.type = body_type(fl[i]);
+  }
+  hostBodiesValid_ = true;
+  return 0;
+}
+
+int World::pullProxies() {
+  if (hostProxiesValid_ || proxiesSynced_ == 0) { hostProxiesValid_ = true; return 0; }
+  const size_t n = proxiesSynced_;
+  std::vector<float4> aabb(n), fat(n); std::vector<uint32_t> fl(n);
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  CUDA_OR_FAIL(cudaMemcpy(aabb.data(), p_aabb.p, n * 16, cudaMemcpyDeviceToHost), "pull aabb");
+  CUDA_OR_FAIL(cudaMemcpy(fat.data(), p_fat.p, n * 16, cudaMemcpyDeviceToHost), "pull fat");
+  CUDA_OR_FAIL(cudaMemcpy(fl.data(), p_flags.p, n * 4, cudaMemcpyDeviceToHost), "pull pflags");
+  for (size_t i = 0; i < n; ++i) { if (!proxies_[i].alive) continue; proxies_[i].aabb = aabb[i]; proxies_[i].fat = fat[i]; proxies_[i].flags = fl[i] & ~PF_MOVED; }
+  hostProxiesValid_ = true;
+  return 0;
+}
+
+int World::pullJoints() {
+  if (hostJointsValid_ || jointsSynced_ == 0) { hostJointsValid_ = true; return 0; }
+  const size_t n = jointsSynced_;
+  std::vector<float4> imp(n); std::vector<int> lim(n);
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  CUDA_OR_FAIL(cudaMemcpy(imp.data(), j_imp.p, n * 16, cudaMemcpyDeviceToHost), "pull jimp");
+  CUDA_OR_FAIL(cudaMemcpy(lim.data(), j_limit.p, n * 4, cudaMemcpyDeviceToHost), "pull jlim");
+  for (size_t i = 0; i < n; ++i) { joints_[i].imp[0] = imp[i].x; joints_[i].imp[1] = imp[i].y; joints_[i].imp[2] = imp[i].z; joints_[i].imp[3] = imp[i].w; joints_[i].limit = lim[i]; }
+  hostJointsValid_ = true;
+  return 0;
+}
+
+// greedy colouring of the joint graph on the host (the joint set only changes through the API)
+int World::recolourJoints() {
+  const int nJ = (int)joints_.size();
+  std::vector<unsigned long long> mask(bodies_.size(), 0ull);
+  std::vector<int> colour(nJ, -1);
+  std::vector<std::vector<int>> byColour(kMaxJointColours);
+  std::vector<unsigned long long> jp;
+  for (int j = 0; j < nJ; ++j) {
+    HJoint& hj = joints_[j];
+    if (!hj.alive) continue;
+    const int a = hj.def.bodyA, b = hj.def.bodyB;
+    const bool dynA = bodies_[a].st.type == DBX_DYNAMIC_BODY, dynB = bodies_[b].st.type == DBX_DYNAMIC_BODY;
+    unsigned long long used = (dynA ? mask[a] : 0ull) | (dynB ? mask[b] : 0ull);
+    if (!~used) { set_last_error("a body has more than 64 joints"); return DBX_E_CAPACITY; }
+    int c = __builtin_ffsll((long long)~used) - 1;
+    if (dynA) mask[a] |= 1ull << c;
+    if (dynB) mask[b] |= 1ull << c;
+    colour[j] = c; hj.colour = c;
+    byColour[c].push_back(j);
+    if (!hj.def.collideConnected) {
+      unsigned long long lo = (unsigned)std::min(a, b), hi = (unsigned)std::max(a, b);
+      jp.push_back((lo << 32) | hi);
+    }
+  }
+  std::vector<int> order; order.reserve(nJ);
+  int off[kMaxJointColours + 1];
+  for (int c = 0; c < kMaxJointColours; ++c) { off[c] = (int)order.size(); order.insert(order.end(), byColour[c].begin(), byColour[c].end()); }
+  off[kMaxJointColours] = (int)order.size();
+  std::sort(jp.begin(), jp.end());
+  jp.erase(std::unique(jp.begin(), jp.end()), jp.end());
+  nJointPairs_ = (int)jp.size();
+  CUDA_OR_FAIL(j_order.reserve(std::max<size_t>(1, order.size()), false, stream_), "j_order");
+  CUDA_OR_FAIL(j_colour.reserve(std::max<size_t>(1, (size_t)nJ), false, stream_), "j_colour");
+  CUDA_OR_FAIL(jp_keys.reserve(std::max<size_t>(1, jp.size()), false, stream_), "jp_keys");
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  if (!order.empty()) CUDA_OR_FAIL(cudaMemcpy(j_order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice), "j_order up");
+  if (nJ) CUDA_OR_FAIL(cudaMemcpy(j_colour.p, colour.data(), (size_t)nJ * 4, cudaMemcpyHostToDevice), "j_colour up");
+  if (!jp.empty()) CUDA_OR_FAIL(cudaMemcpy(jp_keys.p, jp.data(), jp.size() * 8, cudaMemcpyHostToDevice), "jp up");
+  CUDA_OR_FAIL(cudaMemcpy((char*)hdr_.p + offsetof(Header, jointColourOff), off, sizeof(off), cudaMemcpyHostToDevice), "joff up");
+  return 0;
+}
+
+template <class T, class F> static cudaError_t upload_range(DevBuf<T>& buf, size_t from, size_t to, F&& get) {
+  if (to <= from) return cudaSuccess;
+  std::vector<T> tmp(to - from);
+  for (size_t i = from; i < to; ++i) tmp[i - from] = get(i);
+  return cudaMemcpy(buf.p + from, tmp.data(), (to - from) * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+int World::push() {
+  cudaSetDevice(device_);
+  const size_t nB = bodies_.size(), nF = fixtures_.size(), nP = proxies_.size(), nS = shapes_.size(), nJ = joints_.size();
+  const bool anyBody = fullPushBodies_ || nB > bodiesSynced_;
+  const bool anyFix = fullPushFixtures_ || nF > fixturesSynced_;
+  const bool anyProxy = fullPushProxies_ || nP > proxiesSynced_ || !pendingMoves_.empty();
+  const bool anyShape = nS > shapesSynced_;
+  const bool anyJoint = fullPushJoints_ || nJ > jointsSynced_ || jointsChanged_;
+  if (!anyBody && !anyFix && !anyProxy && !anyShape && !anyJoint && dw_.hdr) return 0;
+  if (fullPushBodies_ && !hostBodiesValid_) { int rc = pullBodies(); if (rc < 0) return rc; }
+  if (fullPushProxies_ && !hostProxiesValid_) { int rc = pullProxies(); if (rc < 0) return rc; }
+  if (fullPushJoints_ && !hostJointsValid_) { int rc = pullJoints(); if (rc < 0) return rc; }
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+
+  // ---- capacities
+  const size_t capB = std::max<size_t>(std::max<size_t>(nB, 1), (size_t)caps_.maxBodies);
+  const size_t capP = std::max<size_t>(std::max<size_t>(nP, 1), (size_t)caps_.maxProxies);
+  DevBuf<float4>* bf4[] = {&b_xf, &b_xf0, &b_pos, &b_pos0, &b_vel, &b_force, &b_mass, &b_lc};
+  for (auto* b : bf4) CUDA_OR_FAIL(b->reserve(capB, true, stream_), "body f4");
+  CUDA_OR_FAIL(b_gs.reserve(capB, true, stream_), "b_gs");
+  CUDA_OR_FAIL(b_flags.reserve(capB, true, stream_), "b_flags");
+  DevBuf<int>* bi[] = {&b_wake, &b_root, &b_islAwake, &b_islMinSleep, &b_ovf, &b_world};
+  for (auto* b : bi) CUDA_OR_FAIL(b->reserve(capB, true, stream_), "body int");
+  CUDA_OR_FAIL(b_mask.reserve(capB, true, stream_), "b_mask");
+  CUDA_OR_FAIL(b_claim.reserve(capB, true, stream_), "b_claim");
+  CUDA_OR_FAIL(b_posNotOk.reserve(b_root.cap * (size_t)kMaxPosIters, false, stream_), "b_posNotOk");
+  CUDA_OR_FAIL(f_body.reserve(std::max<size_t>(nF, 1), true, stream_), "f_body");
+  CUDA_OR_FAIL(f_group.reserve(std::max<size_t>(nF, 1), true, stream_), "f_group");
+  CUDA_OR_FAIL(f_mat.reserve(std::max<size_t>(nF, 1), true, stream_), "f_mat");
+  CUDA_OR_FAIL(f_filter.reserve(std::max<size_t>(nF, 1), true, stream_), "f_filter");
+  CUDA_OR_FAIL(d_shapes.reserve(std::max<size_t>(nS, 1), true, stream_), "shapes");
+  CUDA_OR_FAIL(p_ids.reserve(capP, true, stream_), "p_ids");
+  CUDA_OR_FAIL(p_key.reserve(capP, true, stream_), "p_key");
+  CUDA_OR_FAIL(p_aabb.reserve(capP, true, stream_), "p_aabb");
+  CUDA_OR_FAIL(p_fat.reserve(capP, true, stream_), "p_fat");
+  CUDA_OR_FAIL(p_flags.reserve(capP, true, stream_), "p_flags");
+  const size_t pc = p_ids.cap;
+  CUDA_OR_FAIL(moveList.reserve(pc, false, stream_), "moveList");
+  CUDA_OR_FAIL(bv_key.reserve(pc, false, stream_), "bv_key"); CUDA_OR_FAIL(bv_keyAlt.reserve(pc, false, stream_), "bv_keyAlt");
+  CUDA_OR_FAIL(bv_leaf.reserve(pc, false, stream_), "bv_leaf"); CUDA_OR_FAIL(bv_leafAlt.reserve(pc, false, stream_), "bv_leafAlt");
+  CUDA_OR_FAIL(bv_box.reserve(2 * pc, false, stream_), "bv_box"); CUDA_OR_FAIL(bv_child.reserve(pc, false, stream_), "bv_child");
+  CUDA_OR_FAIL(bv_parent.reserve(2 * pc, false, stream_), "bv_parent"); CUDA_OR_FAIL(bv_visit.reserve(pc, false, stream_), "bv_visit");
+  {
+    size_t need = cub_temp_bytes((int)pc);
+    CUDA_OR_FAIL(cubTemp.reserve(need, false, stream_), "cubTemp");
+  }
+  const size_t capC = std::max<size_t>(std::max<size_t>(1024, 8 * pc), (size_t)caps_.maxContacts);
+  const size_t oldCCap = c_key.cap;
+  CUDA_OR_FAIL(c_key.reserve(capC, true, stream_), "c_key");
+  DevBuf<float4>* cf4[] = {&c_m0, &c_m1, &c_imp, &c_mat};
+  for (auto* b : cf4) CUDA_OR_FAIL(b->reserve(capC, true, stream_), "contact f4");
+  CUDA_OR_FAIL(c_ids.reserve(capC, true, stream_), "c_ids"); CUDA_OR_FAIL(c_fix.reserve(capC, true, stream_), "c_fix");
+  CUDA_OR_FAIL(c_flags.reserve(capC, true, stream_), "c_flags"); CUDA_OR_FAIL(c_mk.reserve(capC, true, stream_), "c_mk");
+  DevBuf<int>* ci[] = {&c_toiCount, &c_colour, &c_free, &c_work, &c_work2};
+  for (auto* b : ci) CUDA_OR_FAIL(b->reserve(capC, true, stream_), "contact int");
+  const size_t cc = c_key.cap;
+  bool rehash = false;
+  if (h_key.cap < 4 * cc) {
+    h_key.release(); h_val.release();
+    CUDA_OR_FAIL(h_key.reserve(4 * cc, false, stream_), "h_key"); CUDA_OR_FAIL(h_val.reserve(4 * cc, false, stream_), "h_val");
+    rehash = true;
+  }
+  CUDA_OR_FAIL(pairs.reserve(std::max<size_t>(std::max<size_t>(4096, cc), (size_t)caps_.maxPairs), false, stream_), "pairs");
+  DevBuf<float4>* sf4[] = {&s_v0, &s_v1, &s_r0, &s_r1, &s_q0, &s_q1, &s_imp, &s_nm, &s_k, &s_p0, &s_p1, &s_p2};
+  for (auto* b : sf4) CUDA_OR_FAIL(b->reserve(cc, false, stream_), "solver f4");
+  CUDA_OR_FAIL(s_p3.reserve(cc, false, stream_), "s_p3"); CUDA_OR_FAIL(s_body.reserve(cc, false, stream_), "s_body");
+  CUDA_OR_FAIL(s_contact.reserve(cc, false, stream_), "s_contact"); CUDA_OR_FAIL(s_pc.reserve(cc, false, stream_), "s_pc"); CUDA_OR_FAIL(s_root.reserve(cc, false, stream_), "s_root");
+  CUDA_OR_FAIL(s_hist.reserve((size_t)kSortBlocks * kMaxColours, false, stream_), "s_hist");
+  const size_t capJ = std::max<size_t>(std::max<size_t>(nJ, 1), (size_t)caps_.maxJoints);
+  DevBuf<float4>* jf4[] = {&j_anchor, &j_p0, &j_p1, &j_imp, &j_r, &j_lc, &j_m, &j_k0, &j_k1, &j_k2};
+  for (auto* b : jf4) CUDA_OR_FAIL(b->reserve(capJ, true, stream_), "joint f4");
+  CUDA_OR_FAIL(j_ids.reserve(capJ, true, stream_), "j_ids"); CUDA_OR_FAIL(j_limit.reserve(capJ, true, stream_), "j_limit"); CUDA_OR_FAIL(j_root.reserve(capJ, true, stream_), "j_root");
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  (void)oldCCap;
+
+  // ---- bodies
+  {
+    const size_t from = fullPushBodies_ ? 0 : bodiesSynced_;
+    auto S = [&](size_t i) -> const dbx_body_state& { return bodies_[i].st; };
+    CUDA_OR_FAIL(upload_range(b_xf, from, nB, [&](size_t i) { return f4(S(i).p.x, S(i).p.y, S(i).qs, S(i).qc); }), "up xf");
+    CUDA_OR_FAIL(upload_range(b_xf0, from, nB, [&](size_t i) { return bodies_[i].xf0; }), "up xf0");
+    CUDA_OR_FAIL(upload_range(b_pos, from, nB, [&](size_t i) { return f4(S(i).c.x, S(i).c.y, S(i).a, 0.0f); }), "up pos");
+    CUDA_OR_FAIL(upload_range(b_pos0, from, nB, [&](size_t i) { return f4(S(i).c0.x, S(i).c0.y, S(i).a0, S(i).alpha0); }), "up pos0");
+    CUDA_OR_FAIL(upload_range(b_vel, from, nB, [&](size_t i) { return f4(S(i).v.x, S(i).v.y, S(i).w, 0.0f); }), "up vel");
+    CUDA_OR_FAIL(upload_range(b_force, from, nB, [&](size_t i) { return f4(S(i).force.x, S(i).force.y, S(i).torque, 0.0f); }), "up force");
+    CUDA_OR_FAIL(upload_range(b_mass, from, nB, [&](size_t i) { return f4(S(i).invMass, S(i).invI, S(i).mass, S(i).I); }), "up mass");
+    CUDA_OR_FAIL(upload_range(b_lc, from, nB, [&](size_t i) { return f4(S(i).localCenter.x, S(i).localCenter.y, S(i).linearDamping, S(i).angularDamping); }), "up lc");
+    CUDA_OR_FAIL(upload_range(b_gs, from, nB, [&](size_t i) { return make_float2(S(i).gravityScale, S(i).sleepTime); }), "up gs");
+    CUDA_OR_FAIL(upload_range(b_flags, from, nB, [&](size_t i) {
+      if (!bodies_[i].alive) return (uint32_t)0;
+      return (uint32_t)((S(i).flags & 0xFFFF) | ((uint32_t)S(i).type << BF_TYPE_SHIFT) | BF_ALIVE); }), "up flags");
+    CUDA_OR_FAIL(upload_range(b_world, from, nB, [&](size_t i) { return bodies_[i].world; }), "up world");
+    bodiesSynced_ = nB; fullPushBodies_ = false;
+  }
+  // ---- fixtures, shapes
+  {
+    const size_t from = fullPushFixtures_ ? 0 : fixturesSynced_;
+    CUDA_OR_FAIL(upload_range(f_body, from, nF, [&](size_t i) { return fixtures_[i].body; }), "up f_body");
+    CUDA_OR_FAIL(upload_range(f_mat, from, nF, [&](size_t i) { return make_float2(fixtures_[i].def.friction, fixtures_[i].def.restitution); }), "up f_mat");
+    CUDA_OR_FAIL(upload_range(f_filter, from, nF, [&](size_t i) { return (uint32_t)fixtures_[i].def.categoryBits | ((uint32_t)fixtures_[i].def.maskBits << 16); }), "up f_filter");
+    CUDA_OR_FAIL(upload_range(f_group, from, nF, [&](size_t i) { return (int)((uint32_t)(uint16_t)fixtures_[i].def.groupIndex | ((fixtures_[i].def.isSensor ? FXF_SENSOR : 0u) << 16)); }), "up f_group");
+    fixturesSynced_ = nF; fullPushFixtures_ = false;
+    if (nS > shapesSynced_) CUDA_OR_FAIL(cudaMemcpy(d_shapes.p + shapesSynced_, shapes_.data() + shapesSynced_, (nS - shapesSynced_) * sizeof(DShape), cudaMemcpyHostToDevice), "up shapes");
+    shapesSynced_ = nS;
+  }
+  // ---- proxies + move buffer
+  {
+    const size_t from = fullPushProxies_ ? 0 : proxiesSynced_;
+    CUDA_OR_FAIL(upload_range(p_ids, from, nP, [&](size_t i) { const HProxy& p = proxies_[i]; return make_int4(p.fixture, p.child, p.body, p.shape); }), "up p_ids");
+    CUDA_OR_FAIL(upload_range(p_key, from, nP, [&](size_t i) { return proxies_[i].key; }), "up p_key");
+    CUDA_OR_FAIL(upload_range(p_aabb, from, nP, [&](size_t i) { return proxies_[i].aabb; }), "up p_aabb");
+    CUDA_OR_FAIL(upload_range(p_fat, from, nP, [&](size_t i) { return proxies_[i].fat; }), "up p_fat");
+    CUDA_OR_FAIL(upload_range(p_flags, from, nP, [&](size_t i) { return proxies_[i].alive ? (proxies_[i].flags | PF_ALIVE) : 0u; }), "up p_flags");
+    proxiesSynced_ = nP; fullPushProxies_ = false;
+    if (!pendingMoves_.empty()) {
+      // b2BroadPhase.BufferMove (b2broadphase.d:244-257): the device move list is empty between steps
+      std::vector<int> mv;
+      for (int slot : pendingMoves_) if (proxies_[slot].alive) mv.push_back(slot);
+      std::sort(mv.begin(), mv.end());
+      mv.erase(std::unique(mv.begin(), mv.end()), mv.end());
+      for (int slot : mv) { uint32_t fl = proxies_[slot].flags | PF_ALIVE | PF_MOVED; proxies_[slot].flags = fl & ~PF_MOVED; cudaMemcpy(p_flags.p + slot, &fl, 4, cudaMemcpyHostToDevice); }
+      if (!mv.empty()) CUDA_OR_FAIL(cudaMemcpy(moveList.p, mv.data(), mv.size() * 4, cudaMemcpyHostToDevice), "up moves");
+      int nm = (int)mv.size();
+      CUDA_OR_FAIL(cudaMemcpy((char*)hdr_.p + offsetof(Header, nMoved), &nm, 4, cudaMemcpyHostToDevice), "up nMoved");
+      pendingMoves_.clear();
+    }
+  }
+  // ---- joints
+  {
+    const size_t from = fullPushJoints_ ? 0 : jointsSynced_;
+    CUDA_OR_FAIL(upload_range(j_ids, from, nJ, [&](size_t i) { const HJoint& j = joints_[i];
+      return make_int4(j.def.type, j.def.bodyA, j.def.bodyB, (j.def.collideConnected ? 1 : 0) | (j.def.enableLimit ? 2 : 0) | (j.def.enableMotor ? 4 : 0) | (j.alive ? 8 : 0)); }), "up j_ids");
+    CUDA_OR_FAIL(upload_range(j_anchor, from, nJ, [&](size_t i) { const dbx_joint_def& d = joints_[i].def; return f4(d.localAnchorA.x, d.localAnchorA.y, d.localAnchorB.x, d.localAnchorB.y); }), "up j_anchor");
+    CUDA_OR_FAIL(upload_range(j_p0, from, nJ, [&](size_t i) { const dbx_joint_def& d = joints_[i].def;
+      return d.type == DBX_JOINT_REVOLUTE ? f4(d.referenceAngle, d.lowerAngle, d.upperAngle, d.maxMotorTorque) : f4(d.length, d.frequencyHz, d.dampingRatio, 0.0f); }), "up j_p0");
+    CUDA_OR_FAIL(upload_range(j_p1, from, nJ, [&](size_t i) { return f4(joints_[i].def.motorSpeed, 0, 0, 0); }), "up j_p1");
+    CUDA_OR_FAIL(upload_range(j_imp, from, nJ, [&](size_t i) { const HJoint& j = joints_[i]; return f4(j.imp[0], j.imp[1], j.imp[2], j.imp[3]); }), "up j_imp");
+    CUDA_OR_FAIL(upload_range(j_limit, from, nJ, [&](size_t i) { return joints_[i].limit; }), "up j_limit");
+    jointsSynced_ = nJ; fullPushJoints_ = false;
+    if (jointsChanged_ || !dw_.hdr) { int rc = recolourJoints(); if (rc < 0) return rc; jointsChanged_ = false; }
+  }
+  refreshView();
+  if (rehash) CUDA_OR_FAIL(stage_rebuild_hash(dw_, L_), "rehash");
+  return 0;
+}
+
+void World::refreshView() {
+  DevWorld& w = dw_;
+  w.hdr = hdr_.p;
+  w.nBodies = (int)bodies_.size();
+  w.b_xf = b_xf.p; w.b_xf0 = b_xf0.p; w.b_pos = b_pos.p; w.b_pos0 = b_pos0.p; w.b_vel = b_vel.p; w.b_force = b_force.p; w.b_mass = b_mass.p; w.b_lc = b_lc.p;
+  w.b_gs = b_gs.p; w.b_flags = b_flags.p; w.b_wake = b_wake.p; w.b_root = b_root.p; w.b_islAwake = b_islAwake.p; w.b_islMinSleep = b_islMinSleep.p;
+  w.b_posNotOk = b_posNotOk.p; w.b_mask = b_mask.p; w.b_claim = b_claim.p; w.b_ovf = b_ovf.p; w.b_world = b_world.p;
+  w.nFixtures = (int)fixtures_.size(); w.f_body = f_body.p; w.f_mat = f_mat.p; w.f_filter = f_filter.p; w.f_group = f_group.p;
+  w.nShapes = (int)shapes_.size(); w.shapes = d_shapes.p;
+  w.nProxies = (int)proxies_.size(); w.p_ids = p_ids.p; w.p_key = p_key.p; w.p_aabb = p_aabb.p; w.p_fat = p_fat.p; w.p_flags = p_flags.p;
+  w.moveList = moveList.p; w.moveCap = (int)moveList.cap;
+  w.bv_key = bv_key.p; w.bv_keyAlt = bv_keyAlt.p; w.bv_leaf = bv_leaf.p; w.bv_leafAlt = bv_leafAlt.p; w.bv_box = bv_box.p; w.bv_child = bv_child.p; w.bv_parent = bv_parent.p; w.bv_visit = bv_visit.p;
+  w.pairs = pairs.p; w.pairCap = (int)pairs.cap;
+  w.nJointPairs = nJointPairs_; w.jp_keys = jp_keys.p;
+  w.cCap = (int)c_key.cap; w.c_key = c_key.p; w.c_ids = c_ids.p; w.c_fix = c_fix.p; w.c_flags = c_flags.p; w.c_m0 = c_m0.p; w.c_m1 = c_m1.p; w.c_imp = c_imp.p; w.c_mk = c_mk.p;
+  w.c_mat = c_mat.p; w.c_toiCount = c_toiCount.p; w.c_colour = c_colour.p; w.c_free = c_free.p; w.c_work = c_work.p; w.c_work2 = c_work2.p;
+  w.hCap = (int)h_key.cap; w.h_key = h_key.p; w.h_val = h_val.p;
+  w.sCap = (int)s_contact.cap; w.s_contact = s_contact.p; w.s_hist = s_hist.p; w.s_body = s_body.p; w.s_v0 = s_v0.p; w.s_v1 = s_v1.p; w.s_r0 = s_r0.p; w.s_r1 = s_r1.p;
+  w.s_q0 = s_q0.p; w.s_q1 = s_q1.p; w.s_imp = s_imp.p; w.s_nm = s_nm.p; w.s_k = s_k.p; w.s_pc = s_pc.p; w.s_p0 = s_p0.p; w.s_p1 = s_p1.p; w.s_p2 = s_p2.p; w.s_p3 = s_p3.p; w.s_root = s_root.p;
+  w.nJoints = (int)joints_.size(); w.j_ids = j_ids.p; w.j_anchor = j_anchor.p; w.j_p0 = j_p0.p; w.j_p1 = j_p1.p; w.j_imp = j_imp.p; w.j_limit = j_limit.p; w.j_colour = j_colour.p;
+  w.j_order = j_order.p; w.j_root = j_root.p; w.j_r = j_r.p; w.j_lc = j_lc.p; w.j_m = j_m.p; w.j_k0 = j_k0.p; w.j_k1 = j_k1.p; w.j_k2 = j_k2.p;
+  w.nWorlds = nWorlds_;
+  L_.cubTemp = cubTemp.p; L_.cubTempBytes = cubTemp.cap;
+}
+
+void World::setStepParams(float dt, int vi, int pi) {
+  // b2TimeStep (dynamics/b2world.d:380-396)
+  dw_.dt = dt;
+  dw_.inv_dt = dt > 0.0f ? 1.0f / dt : 0.0f;
+  dw_.dtRatio = inv_dt0 * dt;
+  dw_.velIters = vi; dw_.posIters = std::min(pi, kMaxPosIters);
+  dw_.warmStarting = (flags_ & DBX_WORLD_WARM_STARTING) ? 1 : 0;
+  dw_.allowSleep = (flags_ & DBX_WORLD_ALLOW_SLEEP) ? 1 : 0;
+  dw_.continuous = (flags_ & DBX_WORLD_CONTINUOUS) ? 1 : 0;
+  dw_.gx = gx_; dw_.gy = gy_;
+}
+
+int World::checkDeviceError(bool sync) {
+  if (sync) CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "step sync");
+  int err = 0;
+  CUDA_OR_FAIL(cudaMemcpy(&err, (char*)hdr_.p + offsetof(Header, error), 4, cudaMemcpyDeviceToHost), "read error");
+  if (err != 0) {
+    set_last_error("device pool overflow (contacts / pairs / colours): raise dbx_caps");
+    int zero = 0; cudaMemcpy((char*)hdr_.p + offsetof(Header, error), &zero, 4, cudaMemcpyHostToDevice);
+    return err;
+  }
+  return 0;
+}
+
+// b2World.Step (dynamics/b2world.d:367-434), n times without host round trips in between
+int World::step(float dt, int vi, int pi, int n) {
+  if (!ok_) return DBX_E_NO_DEVICE;
+  cudaSetDevice(device_);
+  for (int k = 0; k < n; ++k) {
+    int rc = push(); if (rc < 0) return rc;
+    if (bodies_.empty()) continue;
+    if (newFixture_) { CUDA_OR_FAIL(stage_find_new_contacts(dw_, L_), "find_new_contacts"); newFixture_ = false; }   // :372-376
+    setStepParams(dt, vi, pi);
+    cudaEventRecord(ev_[0], stream_);
+    CUDA_OR_FAIL(stage_collide(dw_, L_), "collide");
+    cudaEventRecord(ev_[1], stream_);
+    if (stepComplete_ && dt > 0.0f) {
+      CUDA_OR_FAIL(stage_islands_and_integrate(dw_, L_), "islands");
+      CUDA_OR_FAIL(stage_colour_and_sort(dw_, L_), "colour");
+      cudaEventRecord(ev_[2], stream_);
+      CUDA_OR_FAIL(stage_solve(dw_, L_), "solve");
+      cudaEventRecord(ev_[3], stream_);
+      CUDA_OR_FAIL(stage_sync_fixtures(dw_, L_), "sync_fixtures");
+      CUDA_OR_FAIL(stage_find_new_contacts(dw_, L_), "find_new_contacts");
+      cudaEventRecord(ev_[4], stream_);
+    } else {
+      cudaEventRecord(ev_[2], stream_); cudaEventRecord(ev_[3], stream_); cudaEventRecord(ev_[4], stream_);
+    }
+    // TODO(round 2): SolveTOI sub-stepping (b2world.d:1127-1452)
+    cudaEventRecord(ev_[5], stream_);
+    if (dt > 0.0f) inv_dt0 = dw_.inv_dt;
+    if (flags_ & DBX_WORLD_AUTO_CLEAR_FORCES) CUDA_OR_FAIL(launch_clear_forces(dw_, L_), "clear_forces");
+    cudaEventRecord(ev_[6], stream_);
+    evValid_ = true;
+    ++stepCount_;
+    if ((stepCount_ & 63) == 0) CUDA_OR_FAIL(stage_rebuild_hash(dw_, L_), "rehash");
+    hostBodiesValid_ = false; hostProxiesValid_ = false; hostJointsValid_ = false;
+  }
+  return checkDeviceError(true);
+}
+
+int World::clearForces() {
+  int rc = push(); if (rc < 0) return rc;
+  if (bodies_.empty()) return 0;
+  CUDA_OR_FAIL(launch_clear_forces(dw_, L_), "clear_forces");
+  hostBodiesValid_ = false;
+  return 0;
+}
+
+int World::stageFindNewContacts() {
+  int rc = push(); if (rc < 0) return rc;
+  if (bodies_.empty()) return 0;
+  CUDA_OR_FAIL(stage_find_new_contacts(dw_, L_), "find_new_contacts");
+  newFixture_ = false;
+  hostBodiesValid_ = false; hostProxiesValid_ = false;
+  return checkDeviceError(true);
+}
+
+int World::stageCollide() {
+  int rc = push(); if (rc < 0) return rc;
+  if (bodies_.empty()) return 0;
+  setStepParams(0.0f, 0, 0);
+  CUDA_OR_FAIL(stage_collide(dw_, L_), "collide");
+  hostBodiesValid_ = false;
+  return checkDeviceError(true);
+}
+
+// ------------------------------------------------------------------------------------------------ accessors
+int World::getBody(int b, dbx_body_state* out) {
+  if (b < 0 || b >= (int)bodies_.size() || !bodies_[b].alive) return DBX_E_INVALID;
+  int rc = pullBodies(); if (rc < 0) return rc;
+  *out = bodies_[b].st;
+  return 0;
+}
+
+HBody* World::mutBody(int b) {
+  if (b < 0 || b >= (int)bodies_.size() || !bodies_[b].alive) return nullptr;
+  if (pullBodies() < 0) return nullptr;
+  if ((size_t)b < bodiesSynced_) fullPushBodies_ = true;
+  return &bodies_[b];
+}
+
+// b2Body.SetTransform (dynamics/b2body.d:261-285) incl. b2Fixture.Synchronize with xf1 == xf2
+int World::setTransform(int b, float x, float y, float angle) {
+  HBody* hb = mutBody(b);
+  if (!hb) return DBX_E_INVALID;
+  int rc = pullProxies(); if (rc < 0) return rc;
+  dbx_body_state& st = hb->st;
+  Rot q = rot_from_angle(angle);
+  st.qs = q.s; st.qc = q.c; st.p = dbx_vec2{x, y};
+  Xf xf; xf.p = V(x, y); xf.q = q;
+  v2 c = mul(xf, V(st.localCenter.x, st.localCenter.y));
+  st.c = dbx_vec2{c.x, c.y}; st.a = angle; st.c0 = st.c; st.a0 = angle;
+  hb->xf0 = pack(xf);
+  for (auto it = hb->fixtures.rbegin(); it != hb->fixtures.rend(); ++it) {
+    for (int slot : fixtures_[*it].proxies) {
+      HProxy& p = proxies_[slot];
+      Box box = shape_aabb(&shapes_[p.shape], xf);
+      p.aabb = pack(box);
+      if (!contains(BX(p.fat), box)) {   // MoveProxy with zero displacement (b2dynamictree.d:140-184)
+        p.fat = make_float4(box.lo.x - kAabbExtension, box.lo.y - kAabbExtension, box.hi.x + kAabbExtension, box.hi.y + kAabbExtension);
+        pendingMoves_.push_back(slot);
+      }
+      if ((size_t)slot < proxiesSynced_) fullPushProxies_ = true;
+    }
+  }
+  return 0;
+}
+
+int World::counts(dbx_counts* out) {
+  std::memset(out, 0, sizeof(*out));
+  for (auto& b : bodies_) if (b.alive) ++out->bodies;
+  for (auto& f : fixtures_) if (f.alive) ++out->fixtures;
+  for (auto& p : proxies_) if (p.alive) ++out->proxies;
+  for (auto& j : joints_) if (j.alive) ++out->joints;
+  out->moves = (int)pendingMoves_.size();
+  if (!dw_.hdr || bodiesSynced_ == 0) {
+    for (auto& b : bodies_) if (b.alive && (b.st.flags & DBX_BODY_AWAKE) && b.st.type != DBX_STATIC_BODY) ++out->awakeBodies;
+    return 0;
+  }
+  int rc = push(); if (rc < 0) return rc;
+  CUDA_OR_FAIL(stage_count(dw_, L_), "count");
+  Header h;
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  CUDA_OR_FAIL(cudaMemcpy(&h, hdr_.p, sizeof(Header), cudaMemcpyDeviceToHost), "read header");
+  out->contacts = h.nContacts; out->touching = h.nTouching; out->awakeBodies = h.nAwake; out->colours = h.nColours;
+  out->islands = h.nIslands; out->pairs = h.nPairs; out->moves += h.nMoved;
+  return 0;
+}
+
+int World::profile(dbx_profile* out) {
+  std::memset(out, 0, sizeof(*out));
+  if (!evValid_) return 0;
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  float collide = 0, pre = 0, solve = 0, bp = 0, toi = 0, total = 0;
+  cudaEventElapsedTime(&collide, ev_[0], ev_[1]);
+  cudaEventElapsedTime(&pre, ev_[1], ev_[2]);
+  cudaEventElapsedTime(&solve, ev_[2], ev_[3]);
+  cudaEventElapsedTime(&bp, ev_[3], ev_[4]);
+  cudaEventElapsedTime(&toi, ev_[4], ev_[5]);
+  cudaEventElapsedTime(&total, ev_[0], ev_[6]);
+  out->step = total; out->collide = collide; out->solve = pre + solve + bp; out->solveInit = pre; out->solveVelocity = solve;
+  out->solvePosition = 0.0f; out->broadphase = bp; out->solveTOI = toi;
+  return 0;
+}
+
+int World::readBodies(dbx_body_state* out, int cap) {
+  int rc = pullBodies(); if (rc < 0) return rc;
+  const int n = (int)bodies_.size();
+  for (int i = 0; i < n && i < cap; ++i) { if (bodies_[i].alive) out[i] = bodies_[i].st; else std::memset(out + i, 0, sizeof(*out)); }
+  return n;
+}
+
+int World::writeBodies(const dbx_body_state* in, int n) {
+  if (n > (int)bodies_.size()) return DBX_E_INVALID;
+  int rc = pullBodies(); if (rc < 0) return rc;
+  for (int i = 0; i < n; ++i) {
+    if (!bodies_[i].alive) continue;
+    bodies_[i].st = in[i];
+    // xf0 is the transform at (c0, a0) (b2body.d:1131-1133)
+    Xf x0 = xf_from_sweep(V(in[i].c0.x, in[i].c0.y), in[i].a0, V(in[i].localCenter.x, in[i].localCenter.y));
+    if (in[i].a0 == in[i].a && in[i].c0.x == in[i].c.x && in[i].c0.y == in[i].c.y) bodies_[i].xf0 = make_float4(in[i].p.x, in[i].p.y, in[i].qs, in[i].qc);
+    else bodies_[i].xf0 = pack(x0);
+  }
+  fullPushBodies_ = true;
+  return n;
+}
+
+int World::readProxies(dbx_proxy_rec* out, int cap) {
+  int rc = pullProxies(); if (rc < 0) return rc;
+  int n = 0;
+  for (size_t f = 0; f < fixtures_.size(); ++f) {
+    if (!fixtures_[f].alive) continue;
+    for (int slot : fixtures_[f].proxies) {
+      if (n < cap) {
+        const HProxy& p = proxies_[slot];
+        dbx_proxy_rec& o = out[n];
+        o.fixture = p.fixture; o.child = p.child; o.proxyId = p.key;
+        o.aabb.lo = dbx_vec2{p.aabb.x, p.aabb.y}; o.aabb.hi = dbx_vec2{p.aabb.z, p.aabb.w};
+        o.fat.lo = dbx_vec2{p.fat.x, p.fat.y}; o.fat.hi = dbx_vec2{p.fat.z, p.fat.w};
+      }
+      ++n;
+    }
+  }
+  return n;
+}
+
+int World::writeProxies(const dbx_proxy_rec* in, int n) {
+  int rc = pullProxies(); if (rc < 0) return rc;
+  for (int i = 0; i < n; ++i) {
+    const dbx_proxy_rec& r = in[i];
+    if (r.fixture < 0 || r.fixture >= (int)fixtures_.size() || !fixtures_[r.fixture].alive) return DBX_E_INVALID;
+    const auto& ps = fixtures_[r.fixture].proxies;
+    if (r.child < 0 || r.child >= (int)ps.size()) return DBX_E_INVALID;
+    HProxy& p = proxies_[ps[r.child]];
+    p.aabb = make_float4(r.aabb.lo.x, r.aabb.lo.y, r.aabb.hi.x, r.aabb.hi.y);
+    p.fat = make_float4(r.fat.lo.x, r.fat.lo.y, r.fat.hi.x, r.fat.hi.y);
+  }
+  fullPushProxies_ = true;
+  return n;
+}
+
+int World::readJoints(dbx_joint_state* out, int cap) {
+  int rc = pullJoints(); if (rc < 0) return rc;
+  const int n = (int)joints_.size();
+  for (int i = 0; i < n && i < cap; ++i) {
+    std::memset(out + i, 0, sizeof(*out));
+    if (!joints_[i].alive) continue;
+    out[i].type = joints_[i].def.type;
+    out[i].impulse[0] = joints_[i].imp[0]; out[i].impulse[1] = joints_[i].imp[1]; out[i].impulse[2] = joints_[i].imp[2];
+    out[i].motorImpulse = joints_[i].imp[3]; out[i].limitState = joints_[i].limit;
+  }
+  return n;
+}
+
+int World::writeJoints(const dbx_joint_state* in, int n) {
+  if (n > (int)joints_.size()) return DBX_E_INVALID;
+  int rc = pullJoints(); if (rc < 0) return rc;
+  for (int i = 0; i < n; ++i) {
+    joints_[i].imp[0] = in[i].impulse[0]; joints_[i].imp[1] = in[i].impulse[1]; joints_[i].imp[2] = in[i].impulse[2];
+    joints_[i].imp[3] = in[i].motorImpulse; joints_[i].limit = in[i].limitState;
+  }
+  fullPushJoints_ = true;
+  return n;
+}
+
+int World::readMoves(int32_t* out, int cap) {
+  // host-buffered moves (the device move list is empty between steps)
+  int n = 0;
+  std::vector<int> mv = pendingMoves_;
+  std::sort(mv.begin(), mv.end());
+  mv.erase(std::unique(mv.begin(), mv.end()), mv.end());
+  for (int slot : mv) {
+    if (!proxies_[slot].alive) continue;
+    if (n < cap) { out[2 * n] = proxies_[slot].fixture; out[2 * n + 1] = proxies_[slot].child; }
+    ++n;
+  }
+  return n;
+}
+
+int World::writeMoves(const int32_t* in, int n) {
+  pendingMoves_.clear();
+  for (int i = 0; i < n; ++i) {
+    int f = in[2 * i], c = in[2 * i + 1];
+    if (f < 0 || f >= (int)fixtures_.size() || !fixtures_[f].alive || c < 0 || c >= (int)fixtures_[f].proxies.size()) return DBX_E_INVALID;
+    pendingMoves_.push_back(fixtures_[f].proxies[c]);
+  }
+  newFixture_ = false;
+  return n;
+}
+
+int World::readPairs(int32_t* out, int cap) {
+  if (!dw_.hdr) return 0;
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  int n = 0;
+  CUDA_OR_FAIL(cudaMemcpy(&n, (char*)hdr_.p + offsetof(Header, nPairs), 4, cudaMemcpyDeviceToHost), "read nPairs");
+  n = std::min(n, (int)pairs.cap);
+  std::vector<int2> pr(std::max(n, 1));
+  if (n) CUDA_OR_FAIL(cudaMemcpy(pr.data(), pairs.p, (size_t)n * 8, cudaMemcpyDeviceToHost), "read pairs");
+  // reference order: sorted by (proxyIdA, proxyIdB) (b2broadphase.d:166, 312-325)
+  std::sort(pr.begin(), pr.begin() + n, [&](const int2& a, const int2& b) {
+    int ka = proxies_[a.x].key, kb = proxies_[b.x].key;
+    if (ka != kb) return ka < kb;
+    return proxies_[a.y].key < proxies_[b.y].key; });
+  for (int i = 0; i < n && i < cap; ++i) {
+    out[4 * i] = proxies_[pr[i].x].fixture; out[4 * i + 1] = proxies_[pr[i].x].child;
+    out[4 * i + 2] = proxies_[pr[i].y].fixture; out[4 * i + 3] = proxies_[pr[i].y].child;
+  }
+  return n;
+}
+
+int World::readContacts(dbx_contact_rec* out, int cap) {
+  if (!dw_.hdr || bodiesSynced_ == 0) return 0;
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  int high = 0;
+  CUDA_OR_FAIL(cudaMemcpy(&high, (char*)hdr_.p + offsetof(Header, cHigh), 4, cudaMemcpyDeviceToHost), "read cHigh");
+  if (high <= 0) return 0;
+  const size_t n = (size_t)high;
+  std::vector<unsigned long long> key(n); std::vector<int4> ids(n), fix(n); std::vector<uint32_t> fl(n);
+  std::vector<float4> m0(n), m1(n), imp(n), mat(n); std::vector<uint4> mk(n); std::vector<int> tc(n);
+  cudaMemcpy(key.data(), c_key.p, n * 8, cudaMemcpyDeviceToHost);
+  cudaMemcpy(ids.data(), c_ids.p, n * 16, cudaMemcpyDeviceToHost);
+  cudaMemcpy(fix.data(), c_fix.p, n * 16, cudaMemcpyDeviceToHost);
+  cudaMemcpy(fl.data(), c_flags.p, n * 4, cudaMemcpyDeviceToHost);
+  cudaMemcpy(m0.data(), c_m0.p, n * 16, cudaMemcpyDeviceToHost);
+  cudaMemcpy(m1.data(), c_m1.p, n * 16, cudaMemcpyDeviceToHost);
+  cudaMemcpy(imp.data(), c_imp.p, n * 16, cudaMemcpyDeviceToHost);
+  cudaMemcpy(mat.data(), c_mat.p, n * 16, cudaMemcpyDeviceToHost);
+  cudaMemcpy(mk.data(), c_mk.p, n * 16, cudaMemcpyDeviceToHost);
+  CUDA_OR_FAIL(cudaMemcpy(tc.data(), c_toiCount.p, n * 4, cudaMemcpyDeviceToHost), "read contacts");
+  std::vector<int> order;
+  for (size_t i = 0; i < n; ++i) if (fl[i] & CF_ALIVE) order.push_back((int)i);
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });   // deterministic: by reference pair key
+  int cnt = 0;
+  for (int i : order) {
+    if (cnt < cap) {
+      dbx_contact_rec& o = out[cnt];
+      std::memset(&o, 0, sizeof(o));
+      o.fixtureA = fix[i].x; o.fixtureB = fix[i].y;
+      o.childA = proxies_[ids[i].x].child; o.childB = proxies_[ids[i].y].child;
+      o.flags = fl[i] & 0x3F;
+      o.manifold.localNormal = dbx_vec2{m0[i].x, m0[i].y}; o.manifold.localPoint = dbx_vec2{m0[i].z, m0[i].w};
+      o.manifold.points[0].localPoint = dbx_vec2{m1[i].x, m1[i].y}; o.manifold.points[1].localPoint = dbx_vec2{m1[i].z, m1[i].w};
+      o.manifold.points[0].normalImpulse = imp[i].x; o.manifold.points[0].tangentImpulse = imp[i].y;
+      o.manifold.points[1].normalImpulse = imp[i].z; o.manifold.points[1].tangentImpulse = imp[i].w;
+      o.manifold.points[0].key = mk[i].x; o.manifold.points[1].key = mk[i].y;
+      o.manifold.type = (int)mk[i].z; o.manifold.pointCount = (int)mk[i].w;
+      o.friction = mat[i].x; o.restitution = mat[i].y; o.tangentSpeed = mat[i].z; o.toi = mat[i].w; o.toiCount = tc[i];
+    }
+    ++cnt;
+  }
+  return cnt;
+}
+
+int World::writeContacts(const dbx_contact_rec* in, int n) {
+  int rc = push(); if (rc < 0) return rc;
+  if (!dw_.hdr) return DBX_E_INVALID;
+  if ((size_t)n > c_key.cap) { set_last_error("contact capacity"); return DBX_E_CAPACITY; }
+  const size_t m = (size_t)std::max(n, 1);
+  std::vector<unsigned long long> key(m); std::vector<int4> ids(m), fix(m); std::vector<uint32_t> fl(m);
+  std::vector<float4> m0(m), m1(m), imp(m), mat(m); std::vector<uint4> mk(m); std::vector<int> tc(m), col(m, -1);
+  for (int i = 0; i < n; ++i) {
+    const dbx_contact_rec& r = in[i];
+    if (r.fixtureA < 0 || r.fixtureB < 0 || r.fixtureA >= (int)fixtures_.size() || r.fixtureB >= (int)fixtures_.size()) return DBX_E_INVALID;
+    const HFixture& fa = fixtures_[r.fixtureA]; const HFixture& fb = fixtures_[r.fixtureB];
+    if (!fa.alive || !fb.alive || r.childA >= (int)fa.proxies.size() || r.childB >= (int)fb.proxies.size()) return DBX_E_INVALID;
+    const int pa = fa.proxies[r.childA], pb = fb.proxies[r.childB];
+    const unsigned ka = (unsigned)proxies_[pa].key, kb = (unsigned)proxies_[pb].key;
+    key[i] = ((unsigned long long)std::min(ka, kb) << 32) | std::max(ka, kb);
+    ids[i] = make_int4(pa, pb, fa.body, fb.body);
+    fix[i] = make_int4(r.fixtureA, r.fixtureB, proxies_[pa].shape, proxies_[pb].shape);
+    const bool sensor = fa.def.isSensor || fb.def.isSensor;
+    fl[i] = (r.flags & 0x3F) | CF_ALIVE | (sensor ? CF_SENSOR : 0);
+    m0[i] = f4(r.manifold.localNormal.x, r.manifold.localNormal.y, r.manifold.localPoint.x, r.manifold.localPoint.y);
+    m1[i] = f4(r.manifold.points[0].localPoint.x, r.manifold.points[0].localPoint.y, r.manifold.points[1].localPoint.x, r.manifold.points[1].localPoint.y);
+    imp[i] = f4(r.manifold.points[0].normalImpulse, r.manifold.points[0].tangentImpulse, r.manifold.points[1].normalImpulse, r.manifold.points[1].tangentImpulse);
+    mk[i] = make_uint4(r.manifold.points[0].key, r.manifold.points[1].key, (uint32_t)r.manifold.type, (uint32_t)r.manifold.pointCount);
+    mat[i] = f4(r.friction, r.restitution, r.tangentSpeed, r.toi);
+    tc[i] = r.toiCount;
+  }
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  CUDA_OR_FAIL(cudaMemset(c_flags.p, 0, c_flags.cap * 4), "clear contacts");
+  if (n) {
+    cudaMemcpy(c_key.p, key.data(), (size_t)n * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(c_ids.p, ids.data(), (size_t)n * 16, cudaMemcpyHostToDevice);
+    cudaMemcpy(c_fix.p, fix.data(), (size_t)n * 16, cudaMemcpyHostToDevice);
+    cudaMemcpy(c_flags.p, fl.data(), (size_t)n * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(c_m0.p, m0.data(), (size_t)n * 16, cudaMemcpyHostToDevice);
+    cudaMemcpy(c_m1.p, m1.data(), (size_t)n * 16, cudaMemcpyHostToDevice);
+    cudaMemcpy(c_imp.p, imp.data(), (size_t)n * 16, cudaMemcpyHostToDevice);
+    cudaMemcpy(c_mat.p, mat.data(), (size_t)n * 16, cudaMemcpyHostToDevice);
+    cudaMemcpy(c_mk.p, mk.data(), (size_t)n * 16, cudaMemcpyHostToDevice);
+    cudaMemcpy(c_toiCount.p, tc.data(), (size_t)n * 4, cudaMemcpyHostToDevice);
+    CUDA_OR_FAIL(cudaMemcpy(c_colour.p, col.data(), (size_t)n * 4, cudaMemcpyHostToDevice), "write contacts");
+  }
+  CUDA_OR_FAIL(launch_insert_contacts(dw_, L_, n), "insert contacts");
+  return checkDeviceError(true) < 0 ? DBX_E_CAPACITY : n;
+}
+
+int World::setContactLevels(const int32_t* levels, int n) {
+  (void)levels; (void)n;
+  set_last_error("debug contact levels: not wired in this build");
+  return DBX_E_UNSUPPORTED;
+}
+
+int World::replicate(int copies) {
+  (void)copies;
+  set_last_error("replicate: not wired in this build");
+  return DBX_E_UNSUPPORTED;
+}
+
+}  // namespace dbx

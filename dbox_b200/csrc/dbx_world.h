@@ -1,0 +1,157 @@
+// dbx_world.h — host side of the device world: object tables, the reference-compatible id allocators, lazy
+// host<->device mirroring and the per-step launch sequence.  Host code here is setup/boundary work only
+// (b2World.CreateBody / CreateFixture / CreateJoint, mass data, proxy-id order); the step itself never touches it.
+#pragma once
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "../../include/dbox_b200.h"
+#include "dbx_kernels.cuh"
+
+namespace dbx {
+
+template <class T> struct DevBuf {
+  T* p = nullptr; size_t cap = 0;
+  cudaError_t reserve(size_t n, bool keep, cudaStream_t st) {
+    if (n <= cap) return cudaSuccess;
+    size_t ncap = cap ? cap : 64;
+    while (ncap < n) ncap *= 2;
+    T* q = nullptr;
+    cudaError_t e = cudaMalloc((void**)&q, ncap * sizeof(T));
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(q, 0, ncap * sizeof(T), st);
+    if (e != cudaSuccess) return e;
+    if (keep && p && cap) { e = cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st); if (e != cudaSuccess) return e; }
+    if (p) { cudaStreamSynchronize(st); cudaFree(p); }
+    p = q; cap = ncap;
+    return cudaSuccess;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct HShape {            // host copy of a fixture's shape (b2fixture.d:380 clones it)
+  dbx_shape s;
+  std::vector<dbx_vec2> chain;
+};
+struct HFixture {
+  bool alive = false; int body = -1; dbx_fixture_def def{}; HShape shape; std::vector<int> proxies;
+};
+struct HProxy {
+  bool alive = false; int fixture = -1, child = 0, body = -1, shape = -1, key = -1; uint32_t flags = 0; float4 aabb{}, fat{};
+};
+struct HBody {
+  bool alive = false; dbx_body_state st{}; float4 xf0{}; std::vector<int> fixtures, joints; int world = 0;
+};
+struct HJoint {
+  bool alive = false; dbx_joint_def def{}; float imp[4] = {0, 0, 0, 0}; int limit = 0; int colour = -1;
+};
+
+class World {
+ public:
+  World(float gx, float gy, int device, const dbx_caps* caps);
+  ~World();
+  bool ok() const { return ok_; }
+
+  int createBody(const dbx_body_def& d);
+  int destroyBody(int b);
+  int createFixture(int b, const dbx_fixture_def& d, const dbx_shape& s);
+  int destroyFixture(int f);
+  int createJoint(const dbx_joint_def& d);
+  int destroyJoint(int j);
+  int step(float dt, int vi, int pi, int n);
+  int clearForces();
+  int setFlags(uint32_t f);
+  uint32_t flags() const { return flags_; }
+  int setGravity(float gx, float gy) { gx_ = gx; gy_ = gy; return 0; }
+
+  int getBody(int b, dbx_body_state* out);
+  HBody* mutBody(int b);   // pulls, marks dirty; nullptr if invalid
+  int setTransform(int b, float x, float y, float angle);
+  void wake(HBody& hb, bool flag);
+
+  int counts(dbx_counts* out);
+  int profile(dbx_profile* out);
+  int readBodies(dbx_body_state* out, int cap);
+  int writeBodies(const dbx_body_state* in, int n);
+  int readContacts(dbx_contact_rec* out, int cap);
+  int writeContacts(const dbx_contact_rec* in, int n);
+  int readProxies(dbx_proxy_rec* out, int cap);
+  int writeProxies(const dbx_proxy_rec* in, int n);
+  int readJoints(dbx_joint_state* out, int cap);
+  int writeJoints(const dbx_joint_state* in, int n);
+  int readMoves(int32_t* out, int cap);
+  int writeMoves(const int32_t* in, int n);
+  int readPairs(int32_t* out, int cap);
+  int stageFindNewContacts();
+  int stageCollide();
+  int setContactLevels(const int32_t* levels, int n);
+  int replicate(int copies);
+  int replicaCount() const { return nWorlds_; }
+  float inv_dt0 = 0.0f;
+
+ private:
+  int fail(cudaError_t e, const char* where);
+  int push();              // upload pending host-side changes, (re)size device pools
+  int pullBodies();
+  int pullProxies();
+  int pullJoints();
+  int checkDeviceError(bool sync);
+  void refreshView();
+  int allocProxyKey(); void freeProxyKey(int key);
+  int internShape(const DShape& s);
+  void buildChildShape(const HShape& hs, int child, DShape* out) const;
+  void computeMass(const HShape& hs, float density, float* mass, dbx_vec2* center, float* I) const;
+  void resetMassData(HBody& hb);
+  void hostAabb(const DShape& s, const Xf& xf, Box* out) const;
+  int destroyContactsWhere(int body, int fixture, int otherBody, bool flagOnly);
+  int recolourJoints();
+  void setStepParams(float dt, int vi, int pi);
+
+  bool ok_ = false;
+  int device_ = 0;
+  cudaStream_t stream_ = 0;
+  LaunchCfg L_;
+  float gx_, gy_;
+  uint32_t flags_ = DBX_WORLD_DEFAULT_FLAGS;
+  bool newFixture_ = false, stepComplete_ = true;
+  long stepCount_ = 0;
+  int nWorlds_ = 1;
+  dbx_caps caps_{};
+
+  // host tables
+  std::vector<HBody> bodies_; std::vector<HFixture> fixtures_; std::vector<HProxy> proxies_; std::vector<HJoint> joints_;
+  std::vector<DShape> shapes_; std::unordered_map<std::string, int> shapeIndex_;
+  std::vector<int> proxyFree_;
+  // reference leaf-id allocator (collision/b2dynamictree.d:516-564 replayed)
+  std::vector<int> keyFree_; int keyFresh_ = 0; int keyLeaves_ = 0;
+  // mirror state
+  size_t bodiesSynced_ = 0, fixturesSynced_ = 0, proxiesSynced_ = 0, shapesSynced_ = 0, jointsSynced_ = 0;
+  bool hostBodiesValid_ = true, hostProxiesValid_ = true, hostJointsValid_ = true;
+  bool fullPushBodies_ = false, fullPushProxies_ = false, fullPushJoints_ = false, fullPushFixtures_ = false;
+  bool jointsChanged_ = false;
+  std::vector<int> pendingMoves_;   // proxies buffered on the host since the last push (b2broadphase.d:244-257)
+
+  // device
+  DevWorld dw_{};
+  DevBuf<Header> hdr_;
+  DevBuf<float4> b_xf, b_xf0, b_pos, b_pos0, b_vel, b_force, b_mass, b_lc; DevBuf<float2> b_gs; DevBuf<uint32_t> b_flags;
+  DevBuf<int> b_wake, b_root, b_islAwake, b_islMinSleep, b_posNotOk, b_ovf, b_world; DevBuf<unsigned long long> b_mask, b_claim;
+  DevBuf<int> f_body, f_group; DevBuf<float2> f_mat; DevBuf<uint32_t> f_filter;
+  DevBuf<DShape> d_shapes;
+  DevBuf<int4> p_ids; DevBuf<int> p_key, moveList; DevBuf<float4> p_aabb, p_fat; DevBuf<uint32_t> p_flags;
+  DevBuf<unsigned long long> bv_key, bv_keyAlt; DevBuf<int> bv_leaf, bv_leafAlt, bv_parent, bv_visit; DevBuf<float4> bv_box; DevBuf<int2> bv_child;
+  DevBuf<int2> pairs; DevBuf<unsigned long long> jp_keys;
+  DevBuf<unsigned long long> c_key, h_key; DevBuf<int4> c_ids, c_fix; DevBuf<uint32_t> c_flags; DevBuf<float4> c_m0, c_m1, c_imp, c_mat; DevBuf<uint4> c_mk;
+  DevBuf<int> c_toiCount, c_colour, c_free, c_work, c_work2, h_val;
+  DevBuf<int> s_contact, s_hist, s_pc, s_root; DevBuf<int2> s_body; DevBuf<float4> s_v0, s_v1, s_r0, s_r1, s_q0, s_q1, s_imp, s_nm, s_k, s_p0, s_p1, s_p2; DevBuf<float2> s_p3;
+  DevBuf<int4> j_ids; DevBuf<float4> j_anchor, j_p0, j_p1, j_imp, j_r, j_lc, j_m, j_k0, j_k1, j_k2; DevBuf<int> j_limit, j_colour, j_order, j_root;
+  DevBuf<char> cubTemp; DevBuf<int> d_levels;
+  int nJointPairs_ = 0;
+  cudaEvent_t ev_[8]{};
+  bool evValid_ = false;
+};
+
+void set_last_error(const std::string& s);
+const char* get_last_error();
+
+}  // namespace dbx
