@@ -228,6 +228,8 @@ int32_t dbx_world_stage_collide(dbx_world* w) { W_OR_INVALID(w); return w->w.sta
 int32_t dbx_world_read_pairs(dbx_world* w, int32_t* out, int32_t cap) { W_OR_INVALID(w); return w->w.readPairs(out, out ? cap : 0); }
 int32_t dbx_world_debug_set_contact_levels(dbx_world* w, const int32_t* levels, int32_t n) { W_OR_INVALID(w); return w->w.setContactLevels(levels, n); }
 
+int32_t dbx_world_debug_colour_conflicts(dbx_world* w) { W_OR_INVALID(w); return w->w.colourConflicts(); }
+
 // ---- batched independent worlds
 int32_t dbx_world_replicate(dbx_world* w, int32_t copies) { W_OR_INVALID(w); return w->w.replicate(copies); }
 int32_t dbx_world_replica_count(dbx_world* w) { W_OR_INVALID(w); return w->w.replicaCount(); }

@@ -31,11 +31,13 @@ enum { PF_ALIVE = 1, PF_MOVED = 2 };
 enum { JT_REVOLUTE = 1, JT_DISTANCE = 3 };
 enum { LIM_INACTIVE = 0, LIM_LOWER = 1, LIM_UPPER = 2, LIM_EQUAL = 3 };
 
-constexpr int kMaxColours = 256;         // contact colours: 0..63 tracked in per-body bit masks, 64.. = per-body overflow lanes
+constexpr int kMaxColours = 1024;        // contact colours: 0..63 tracked in per-body bit masks, 64.. = per-body overflow lanes
 constexpr int kMaskColours = 64;
 constexpr int kMaxJointColours = 64;
 constexpr int kSortBlocks = 296;         // 2 CTAs per SM for the colour counting sort
 constexpr int kMaxPosIters = 8;
+constexpr int kToiCand = 64;             // candidate contacts per event side (mini-island holds at most 32)
+enum { TF_INVAL = 1, TF_SYNC = 2 };
 constexpr unsigned long long kHashEmpty = ~0ull;
 constexpr unsigned long long kHashTomb = ~0ull - 1;
 
@@ -55,8 +57,8 @@ struct Header {
   int nTomb;          // tombstones in the pair hash
   int nIslands;
   int nAwake;
-  int toiEvents;
-  int _pad0;
+  int toiEvents;      // cumulative TOI events processed
+  int nEvents;        // events selected in the current TOI pass
   unsigned barrier;   // grid barrier ticket counter for the persistent kernels
   unsigned epoch;     // colouring round stamp
   unsigned long long toiMin;  // (alpha bits << 32 | contact slot) arg-min for the TOI loop
@@ -88,6 +90,15 @@ struct DevWorld {
   unsigned long long* b_claim;  // colouring arbitration word
   int* b_ovf;        // overflow colour counter (bodies with more than 64 touching contacts)
   int* b_world;      // replica index (batched independent worlds)
+  // TOI sub-stepping (dynamics/b2world.d:1127-1452)
+  unsigned long long* b_toiMin;    // per non-static body: min (alpha bits << 32 | contact slot) over its candidate events
+  unsigned long long* b_toiOther;  // per non-static body: min priority of the events that would pull it into their mini-island
+  int* b_toiEvt;     // event index that owns the body in this pass (-1 none)
+  int* b_toiFlags;   // bit 0: invalidate cached TOIs of its contacts; bit 1: synchronize its fixtures
+  int* e_contact;    // [events] contact slot
+  int* e_ncand;      // [events][2]
+  int* e_cand;       // [events][2][kToiCand] contacts of bodyA / bodyB that may join the mini-island
+  int eventCap;
   // ---- fixtures
   int nFixtures;
   int* f_body;
@@ -112,6 +123,8 @@ struct DevWorld {
   int2* bv_child;    // [n-1]
   int* bv_parent;    // [2n-1]
   int* bv_visit;     // [n-1]
+  int* bv_pos;       // proxy slot -> sorted leaf index
+  const int* bv_sorted;  // sorted leaf index -> proxy slot (whichever CUB buffer is current)
   // ---- candidate pairs
   int2* pairs; int pairCap;   // proxy slots (lo, hi) in reference key order
   // ---- joints with collideConnected == false, as sorted (bodyLo << 32 | bodyHi)
@@ -175,6 +188,7 @@ struct DevWorld {
   // ---- step parameters
   float dt, inv_dt, dtRatio; int velIters, posIters; int warmStarting; int allowSleep; int continuous; float gx, gy;
   int nWorlds;
+  int colourOverride;   // debug: keep caller-supplied contact levels instead of colouring (dbx_world_debug_set_contact_levels)
 };
 
 }  // namespace dbx

@@ -124,6 +124,56 @@ DBX_D void destroy_contact(const DevWorld& W, int i, uint32_t flags, int bodyA, 
   W.c_free[slot] = i;
 }
 
+// b2Contact.Update (contacts/b2contact.d:270-356).  `immediateWake`: SetAwake(true) now (TOI loop) instead of deferring to
+// the island pass (Collide).  Returns the new flag word (already stored).
+DBX_D uint32_t update_contact(const DevWorld& W, int i, uint32_t flags, const int4 ids, const int4 fx, bool immediateWake) {
+  uint4 mk = W.c_mk[i];
+  flags |= CF_ENABLED;
+  const bool wasTouching = (flags & CF_TOUCHING) != 0;
+  const Xf xfA = XF(ldcg4(&W.b_xf[ids.z])), xfB = XF(ldcg4(&W.b_xf[ids.w]));
+  const DShape* sA = W.shapes + fx.z;
+  const DShape* sB = W.shapes + fx.w;
+  bool touching;
+  if (flags & CF_SENSOR) {
+    touching = shapes_overlap(sA, xfA, sB, xfB);
+    mk.w = 0;
+    W.c_mk[i] = mk;
+  } else {
+    Manifold m;
+    m.type = (int)mk.z; m.localNormal = V(0, 0); m.localPoint = V(0, 0); m.lp[0] = m.lp[1] = V(0, 0); m.key[0] = m.key[1] = 0;
+    collide_dispatch(m, sA, xfA, sB, xfB);
+    touching = m.pointCount > 0;
+    if (touching) {
+      const float4 oldImp = W.c_imp[i];
+      const int oldCount = (int)mk.w;
+      float4 imp = make_float4(0, 0, 0, 0);
+      // match new points to old ones by feature key and carry the accumulated impulses (b2contact.d:306-324)
+      for (int k = 0; k < m.pointCount; ++k) {
+        float ni = 0.0f, ti = 0.0f;
+        for (int j = 0; j < oldCount; ++j) {
+          uint32_t oldKey = j == 0 ? mk.x : mk.y;
+          if (oldKey == m.key[k]) { ni = j == 0 ? oldImp.x : oldImp.z; ti = j == 0 ? oldImp.y : oldImp.w; break; }
+        }
+        if (k == 0) { imp.x = ni; imp.y = ti; } else { imp.z = ni; imp.w = ti; }
+      }
+      W.c_m0[i] = make_float4(m.localNormal.x, m.localNormal.y, m.localPoint.x, m.localPoint.y);
+      W.c_m1[i] = make_float4(m.lp[0].x, m.lp[0].y, m.lp[1].x, m.lp[1].y);
+      W.c_imp[i] = imp;
+      W.c_mk[i] = make_uint4(m.key[0], m.key[1], (uint32_t)m.type, (uint32_t)m.pointCount);
+    } else {
+      mk.w = 0;
+      W.c_mk[i] = mk;
+    }
+    if (touching != wasTouching) {
+      if (immediateWake) { wake_body_now(W, ids.z); wake_body_now(W, ids.w); }
+      else { W.b_wake[ids.z] = 1; W.b_wake[ids.w] = 1; }
+    }
+  }
+  flags = touching ? (flags | CF_TOUCHING) : (flags & ~CF_TOUCHING);
+  W.c_flags[i] = flags;
+  return flags;
+}
+
 __global__ void __launch_bounds__(256) k_collide(const __grid_constant__ DevWorld W) {
   const int n = W.hdr->cHigh;
   GRID_STRIDE(i, n) {
@@ -148,47 +198,7 @@ __global__ void __launch_bounds__(256) k_collide(const __grid_constant__ DevWorl
       destroy_contact(W, i, flags, ids.z, ids.w, (int)mk.w);
       continue;
     }
-    // ---- b2Contact.Update
-    flags |= CF_ENABLED;
-    const bool wasTouching = (flags & CF_TOUCHING) != 0;
-    const Xf xfA = XF(W.b_xf[ids.z]), xfB = XF(W.b_xf[ids.w]);
-    const DShape* sA = W.shapes + fx.z;
-    const DShape* sB = W.shapes + fx.w;
-    bool touching;
-    if (flags & CF_SENSOR) {
-      touching = shapes_overlap(sA, xfA, sB, xfB);
-      mk.w = 0;
-      W.c_mk[i] = mk;
-    } else {
-      Manifold m;
-      m.type = (int)mk.z; m.localNormal = V(0, 0); m.localPoint = V(0, 0); m.lp[0] = m.lp[1] = V(0, 0); m.key[0] = m.key[1] = 0;
-      collide_dispatch(m, sA, xfA, sB, xfB);
-      touching = m.pointCount > 0;
-      if (touching) {
-        const float4 oldImp = W.c_imp[i];
-        const int oldCount = (int)mk.w;
-        float4 imp = make_float4(0, 0, 0, 0);
-        // match new points to old ones by feature key and carry the accumulated impulses (b2contact.d:306-324)
-        for (int k = 0; k < m.pointCount; ++k) {
-          float ni = 0.0f, ti = 0.0f;
-          for (int j = 0; j < oldCount; ++j) {
-            uint32_t oldKey = j == 0 ? mk.x : mk.y;
-            if (oldKey == m.key[k]) { ni = j == 0 ? oldImp.x : oldImp.z; ti = j == 0 ? oldImp.y : oldImp.w; break; }
-          }
-          if (k == 0) { imp.x = ni; imp.y = ti; } else { imp.z = ni; imp.w = ti; }
-        }
-        W.c_m0[i] = make_float4(m.localNormal.x, m.localNormal.y, m.localPoint.x, m.localPoint.y);
-        W.c_m1[i] = make_float4(m.lp[0].x, m.lp[0].y, m.lp[1].x, m.lp[1].y);
-        W.c_imp[i] = imp;
-        W.c_mk[i] = make_uint4(m.key[0], m.key[1], (uint32_t)m.type, (uint32_t)m.pointCount);
-      } else {
-        mk.w = 0;
-        W.c_mk[i] = mk;
-      }
-      if (touching != wasTouching) { W.b_wake[ids.z] = 1; W.b_wake[ids.w] = 1; }
-    }
-    flags = touching ? (flags | CF_TOUCHING) : (flags & ~CF_TOUCHING);
-    W.c_flags[i] = flags;
+    update_contact(W, i, flags, ids, fx, false);
   }
 }
 
@@ -289,10 +299,11 @@ __global__ void __launch_bounds__(256) k_mark_solve(const __grid_constant__ DevW
     }
     if (!solve) {
       if (flags & CF_SOLVE) W.c_flags[i] = flags & ~CF_SOLVE;
-      if (!(flags & CF_TOUCHING)) W.c_colour[i] = -1;   // a colour is held only while the contact is touching
+      if (!(flags & CF_TOUCHING) && !W.colourOverride) W.c_colour[i] = -1;   // a colour is held only while the contact is touching
       continue;
     }
     if (!(flags & CF_SOLVE)) W.c_flags[i] = flags | CF_SOLVE;
+    if (W.colourOverride) { if (W.c_colour[i] < 0) W.c_colour[i] = kMaxColours - 1; continue; }   // test hook: caller-supplied schedule
     int col = W.c_colour[i];
     uint32_t fa = W.b_flags[ids.z], fb = W.b_flags[ids.w];
     if (col >= 0 && col < kMaskColours) {
@@ -427,18 +438,17 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const __grid_constant__ De
 
 // ------------------------------------------------------------------------------------------------ contact constraints
 // b2ContactSolver ctor + InitializeVelocityConstraints (contacts/b2contactsolver.d:244-450): one thread per solver contact.
-__global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ DevWorld W) {
-  const int n = min(W.hdr->nSolve, W.sCap);
-  GRID_STRIDE(s, n) {
-    const int i = W.s_contact[s];
+// `s` = solver slot to fill, `i` = contact slot; warmScale < 0 means "no warm starting" (TOI sub-steps, b2world.d:1419)
+DBX_D void prepare_contact(const DevWorld& W, int s, int i, float warmScale) {
+  {
     const int4 ids = W.c_ids[i];
     const int4 fx = W.c_fix[i];
     const int bA = ids.z, bB = ids.w;
     const float4 msA = W.b_mass[bA], msB = W.b_mass[bB];
     const float4 lcA4 = W.b_lc[bA], lcB4 = W.b_lc[bB];
-    const float4 posA = W.b_pos[bA], posB = W.b_pos[bB];
-    const float4 velA = W.b_vel[bA], velB = W.b_vel[bB];
-    const float4 xA = W.b_xf[bA], xB = W.b_xf[bB];
+    const float4 posA = ldcg4(&W.b_pos[bA]), posB = ldcg4(&W.b_pos[bB]);
+    const float4 velA = ldcg4(&W.b_vel[bA]), velB = ldcg4(&W.b_vel[bB]);
+    const float4 xA = ldcg4(&W.b_xf[bA]), xB = ldcg4(&W.b_xf[bB]);
     const float4 m0 = W.c_m0[i], m1 = W.c_m1[i], cimp = W.c_imp[i], mat = W.c_mat[i];
     const uint4 mk = W.c_mk[i];
     const float radiusA = W.shapes[fx.z].radius, radiusB = W.shapes[fx.w].radius;
@@ -521,8 +531,8 @@ __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ DevWorl
       }
     }
     // warm-start impulses scaled by dtRatio (:309-313)
-    float4 imp = W.warmStarting ? make_float4(W.dtRatio * cimp.x, W.dtRatio * cimp.y, W.dtRatio * cimp.z, W.dtRatio * cimp.w)
-                                : make_float4(0, 0, 0, 0);
+    float4 imp = warmScale >= 0.0f ? make_float4(warmScale * cimp.x, warmScale * cimp.y, warmScale * cimp.z, warmScale * cimp.w)
+                                   : make_float4(0, 0, 0, 0);
     if (pointCount < 2) { imp.z = 0.0f; imp.w = 0.0f; }
     W.s_body[s] = make_int2(bA, bB);
     W.s_v0[s] = make_float4(normal.x, normal.y, friction, tangentSpeed);
@@ -539,6 +549,11 @@ __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ DevWorl
     uint32_t fa = W.b_flags[bA];
     W.s_root[s] = body_type(fa) != BODY_STATIC ? W.b_root[bA] : W.b_root[bB];
   }
+}
+__global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ DevWorld W) {
+  const int n = min(W.hdr->nSolve, W.sCap);
+  const float warmScale = W.warmStarting ? W.dtRatio : -1.0f;
+  GRID_STRIDE(s, n) prepare_contact(W, s, W.s_contact[s], warmScale);
 }
 
 // velocities of one body pair; only dynamic bodies are ever written (statics/kinematics have zero inverse mass)
@@ -662,13 +677,20 @@ DBX_D void contact_solve_velocity(const DevWorld& W, int s) {
 }
 
 // b2ContactSolver.SolvePositionConstraints (:73-149) + b2PositionSolverManifold (:816-868); returns min separation
-DBX_D float contact_solve_position(const DevWorld& W, int s) {
+// toiA/toiB >= 0 selects SolveTOIPositionConstraints (:152-242): only those two bodies keep their mass, Baumgarte 0.75
+DBX_D float contact_solve_position(const DevWorld& W, int s, int toiA = -1, int toiB = -1) {
   const int2 bd = W.s_body[s];
   const float4 v1 = W.s_v1[s], p0 = W.s_p0[s], p1 = W.s_p1[s], p2 = W.s_p2[s];
   const float2 p3 = W.s_p3[s];
   const int pc = W.s_pc[s];
   const int type = (pc >> 8) & 0xFF, pointCount = pc >> 16;
-  const float mA = v1.x, iA = v1.y, mB = v1.z, iB = v1.w;
+  float mA = v1.x, iA = v1.y, mB = v1.z, iB = v1.w;
+  const bool toi = toiA >= 0;
+  if (toi) {
+    if (bd.x != toiA && bd.x != toiB) { mA = 0.0f; iA = 0.0f; }
+    if (bd.y != toiA && bd.y != toiB) { mB = 0.0f; iB = 0.0f; }
+  }
+  const float baumgarte = toi ? kToiBaumgarte : kBaumgarte;
   const v2 localCenterA = V(p2.x, p2.y), localCenterB = V(p2.z, p2.w);
   const v2 localNormal = V(p1.x, p1.y), localPoint = V(p1.z, p1.w);
   float4 pa = ldcg4(&W.b_pos[bd.x]), pb = ldcg4(&W.b_pos[bd.y]);
@@ -703,7 +725,7 @@ DBX_D float contact_solve_position(const DevWorld& W, int s) {
     }
     v2 rA = point - cA, rB = point - cB;
     minSeparation = fminr(minSeparation, separation);
-    float C = fclampr(kBaumgarte * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
+    float C = fclampr(baumgarte * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
     float rnA = cross(rA, normal), rnB = cross(rB, normal);
     float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
     float impulse = K > 0.0f ? -C / K : 0.0f;
@@ -1129,19 +1151,15 @@ __global__ void __launch_bounds__(256) k_clear_forces(const __grid_constant__ De
 // ------------------------------------------------------------------------------------------------ SynchronizeFixtures
 // b2Body.SynchronizeFixtures (b2body.d:1129-1141) -> b2Fixture.Synchronize (b2fixture.d:480-502) -> b2DynamicTree.MoveProxy
 // (collision/b2dynamictree.d:140-184): swept tight AABB, fat-box containment test, predictive fattening, move buffer.
-__global__ void __launch_bounds__(256) k_sync_fixtures(const __grid_constant__ DevWorld W) {
-  GRID_STRIDE(p, W.nProxies) {
-    uint32_t pf = W.p_flags[p];
-    if (!(pf & PF_ALIVE)) continue;
+DBX_D void sync_proxy(const DevWorld& W, int p, uint32_t pf, int body) {
+  {
     const int4 ids = W.p_ids[p];
-    const uint32_t bf = W.b_flags[ids.z];
-    if (!(bf & BF_ISLAND) || body_type(bf) == BODY_STATIC) continue;   // b2world.d:1103-1118
-    const Xf xf1 = XF(W.b_xf0[ids.z]), xf2 = XF(W.b_xf[ids.z]);
+    const Xf xf1 = XF(ldcg4(&W.b_xf0[body])), xf2 = XF(ldcg4(&W.b_xf[body]));
     const DShape* s = W.shapes + ids.w;
     Box aabb = combine(shape_aabb(s, xf1), shape_aabb(s, xf2));
     W.p_aabb[p] = pack(aabb);
     Box fat = BX(W.p_fat[p]);
-    if (contains(fat, aabb)) continue;
+    if (contains(fat, aabb)) return;
     v2 displacement = xf2.p - xf1.p;
     Box b = aabb;
     v2 r = V(kAabbExtension, kAabbExtension);
@@ -1156,6 +1174,16 @@ __global__ void __launch_bounds__(256) k_sync_fixtures(const __grid_constant__ D
       int slot = atomicAdd(&W.hdr->nMoved, 1);
       if (slot < W.moveCap) W.moveList[slot] = p; else W.hdr->error = -5;
     }
+  }
+}
+__global__ void __launch_bounds__(256) k_sync_fixtures(const __grid_constant__ DevWorld W) {
+  GRID_STRIDE(p, W.nProxies) {
+    uint32_t pf = W.p_flags[p];
+    if (!(pf & PF_ALIVE)) continue;
+    const int body = W.p_ids[p].z;
+    const uint32_t bf = W.b_flags[body];
+    if (!(bf & BF_ISLAND) || body_type(bf) == BODY_STATIC) continue;   // b2world.d:1103-1118
+    sync_proxy(W, p, pf, body);
   }
 }
 
@@ -1258,7 +1286,8 @@ __global__ void __launch_bounds__(256) k_lbvh_refit(const __grid_constant__ DevW
     float4 box = (W.p_flags[p] & PF_ALIVE) ? W.p_fat[p] : make_float4(FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX);
     int node = n - 1 + k;
     W.bv_box[node] = box;
-    if (n == 1) continue;
+    W.bv_pos[p] = k;
+    if (n == 1) { W.bv_parent[0] = -1; continue; }
     int parent = W.bv_parent[node];
     while (parent >= 0) {
       __threadfence();
@@ -1273,109 +1302,106 @@ __global__ void __launch_bounds__(256) k_lbvh_refit(const __grid_constant__ DevW
 }
 
 // warp-cooperative query: one warp per moved proxy walks the tree with a shared frontier; each lane tests one node
-__global__ void __launch_bounds__(256) k_query(const __grid_constant__ DevWorld W, const int* leaves) {
-  constexpr int kStack = 192;
-  __shared__ int stacks[8][kStack];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+constexpr int kQueryStack = 192;
+DBX_D void query_proxy(const DevWorld& W, const int* leaves, int* stack, int lane, int p) {
   const int n = W.nProxies;
-  const int nMoved = min(W.hdr->nMoved, W.moveCap);
-  int* stack = stacks[wib];
-  for (int mIdx = warp; mIdx < nMoved; mIdx += nwarps) {
-    const int p = W.moveList[mIdx];
-    if (!(W.p_flags[p] & PF_ALIVE)) continue;
-    const Box fat = BX(W.p_fat[p]);
-    const int keyP = W.p_key[p];
-    const int worldP = W.b_world[W.p_ids[p].z];
-    int top = 0;
-    if (lane == 0) stack[0] = (n == 1) ? (n - 1) : 0;
-    top = 1;
+  if (!(W.p_flags[p] & PF_ALIVE)) return;
+  const Box fat = BX(__ldcg(&W.p_fat[p]));
+  const int keyP = W.p_key[p];
+  const int worldP = W.b_world[W.p_ids[p].z];
+  int top = 1;
+  if (lane == 0) stack[0] = (n == 1) ? (n - 1) : 0;
+  __syncwarp();
+  while (top > 0) {
+    int take = min(top, 32);   // pop up to 32 nodes
+    int node = lane < take ? stack[top - take + lane] : -1;
+    top -= take;
     __syncwarp();
-    while (top > 0) {
-      // pop up to 32 nodes
-      int take = min(top, 32);
-      int node = lane < take ? stack[top - take + lane] : -1;
-      top -= take;
-      __syncwarp();
-      bool hit = false;
-      if (node >= 0) hit = overlap(fat, BX(__ldg(&W.bv_box[node])));
-      bool isLeaf = node >= n - 1;
-      if (hit && isLeaf) {
-        int q = leaves[node - (n - 1)];
-        // each unordered pair once: from the lower-key proxy when both moved (UpdatePairs sorts and dedups the same set)
-        if (q != p && (W.p_flags[q] & PF_ALIVE) && W.b_world[W.p_ids[q].z] == worldP) {
-          int keyQ = W.p_key[q];
-          bool qMoved = (W.p_flags[q] & PF_MOVED) != 0;
-          if (!qMoved || keyP < keyQ) {
-            int slot = atomicAdd(&W.hdr->nPairs, 1);
-            if (slot < W.pairCap) W.pairs[slot] = keyP < keyQ ? make_int2(p, q) : make_int2(q, p);
-            else W.hdr->error = -5;
-          }
+    bool hit = false;
+    if (node >= 0) hit = overlap(fat, BX(__ldcg(&W.bv_box[node])));
+    bool isLeaf = node >= n - 1;
+    if (hit && isLeaf) {
+      int q = leaves[node - (n - 1)];
+      // each unordered pair once: from the lower-key proxy when both moved (UpdatePairs sorts and dedups the same set)
+      if (q != p && (W.p_flags[q] & PF_ALIVE) && W.b_world[W.p_ids[q].z] == worldP) {
+        int keyQ = W.p_key[q];
+        bool qMoved = (W.p_flags[q] & PF_MOVED) != 0;
+        if (!qMoved || keyP < keyQ) {
+          int slot = atomicAdd(&W.hdr->nPairs, 1);
+          if (slot < W.pairCap) W.pairs[slot] = keyP < keyQ ? make_int2(p, q) : make_int2(q, p);
+          else W.hdr->error = -5;
         }
       }
-      bool push = hit && !isLeaf;
-      unsigned ballot = __ballot_sync(0xffffffffu, push);
-      int offset = __popc(ballot & ((1u << lane) - 1));
-      int total = __popc(ballot);
-      if (top + 2 * total > kStack) { if (lane == 0) W.hdr->error = -5; break; }   // frontier overflow: report, never corrupt
-      if (push) {
-        int2 ch = W.bv_child[node];
-        int base = top + 2 * offset;
-        stack[base] = ch.x; stack[base + 1] = ch.y;
-      }
-      top += 2 * total;
-      __syncwarp();
     }
+    bool push = hit && !isLeaf;
+    unsigned ballot = __ballot_sync(0xffffffffu, push);
+    int offset = __popc(ballot & ((1u << lane) - 1));
+    int total = __popc(ballot);
+    if (top + 2 * total > kQueryStack) { if (lane == 0) W.hdr->error = -5; break; }   // frontier overflow: report, never corrupt
+    if (push) {
+      int2 ch = W.bv_child[node];
+      int base = top + 2 * offset;
+      stack[base] = ch.x; stack[base + 1] = ch.y;
+    }
+    top += 2 * total;
+    __syncwarp();
   }
+  __syncwarp();
+}
+__global__ void __launch_bounds__(256) k_query(const __grid_constant__ DevWorld W, const int* leaves) {
+  __shared__ int stacks[8][kQueryStack];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nMoved = min(W.hdr->nMoved, W.moveCap);
+  for (int mIdx = warp; mIdx < nMoved; mIdx += nwarps) query_proxy(W, leaves, stacks[wib], lane, W.moveList[mIdx]);
 }
 
 // b2ContactManager.AddPair (dynamics/b2contactmanager.d:52-176) + b2Contact.Create (contacts/b2contact.d:375-400)
+DBX_D void add_pair(const DevWorld& W, int2 pr) {
+  const int4 pa = W.p_ids[pr.x], pb = W.p_ids[pr.y];   // fixture child body shape
+  int bodyA = pa.z, bodyB = pb.z;
+  if (bodyA == bodyB) return;
+  const unsigned long long key = ((unsigned long long)(unsigned)W.p_key[pr.x] << 32) | (unsigned)W.p_key[pr.y];
+  if (hash_find(W, key) >= 0) return;                   // a contact for this (fixture, child) pair already exists (:75-100)
+  const uint32_t flA = W.b_flags[bodyA], flB = W.b_flags[bodyB];
+  if (!body_should_collide(W, bodyB, bodyA, flB, flA)) return;
+  if (!filter_should_collide(W, pa.x, pb.x)) return;
+  // type registry (b2contact.d:425-437): A must be the primary type
+  const int t1 = W.shapes[pa.w].type, t2 = W.shapes[pb.w].type;
+  bool has, primary;
+  if (t1 == SH_EDGE && t2 == SH_EDGE) { has = false; primary = false; }
+  else if (t1 == SH_CIRCLE) { has = true; primary = (t2 == SH_CIRCLE); }
+  else if (t1 == SH_EDGE) { has = true; primary = true; }
+  else { has = true; primary = (t2 != SH_EDGE); }        // polygon vs circle/polygon primary; vs edge swapped
+  if (!has) return;
+  int proxyA = pr.x, proxyB = pr.y;
+  int4 ia = pa, ib = pb;
+  if (!primary) { int t = proxyA; proxyA = proxyB; proxyB = t; int4 tt = ia; ia = ib; ib = tt; }
+  int slot;
+  int f = atomicSub(&W.hdr->nFree, 1);
+  if (f > 0) slot = W.c_free[f - 1];
+  else { atomicAdd(&W.hdr->nFree, 1); slot = atomicAdd(&W.hdr->cHigh, 1); }
+  if (slot >= W.cCap) { W.hdr->error = -5; atomicSub(&W.hdr->cHigh, 1); return; }
+  const bool sensor = ((W.f_group[ia.x] >> 16) & FXF_SENSOR) || ((W.f_group[ib.x] >> 16) & FXF_SENSOR);
+  const float2 mA = W.f_mat[ia.x], mB = W.f_mat[ib.x];
+  W.c_key[slot] = key;
+  W.c_ids[slot] = make_int4(proxyA, proxyB, ia.z, ib.z);
+  W.c_fix[slot] = make_int4(ia.x, ib.x, ia.w, ib.w);
+  W.c_flags[slot] = CF_ALIVE | CF_ENABLED | (sensor ? CF_SENSOR : 0);
+  W.c_m0[slot] = make_float4(0, 0, 0, 0);
+  W.c_m1[slot] = make_float4(0, 0, 0, 0);
+  W.c_imp[slot] = make_float4(0, 0, 0, 0);
+  W.c_mk[slot] = make_uint4(0, 0, 0, 0);
+  // b2MixFriction / b2MixRestitution (b2contact.d:32-42)
+  W.c_mat[slot] = make_float4(sqrtf(mA.x * mB.x), mA.y > mB.y ? mA.y : mB.y, 0.0f, 1.0f);
+  W.c_toiCount[slot] = 0;
+  W.c_colour[slot] = -1;
+  if (!hash_insert(W, key, slot)) W.hdr->error = -5;
+  if (!sensor) { wake_body_now(W, ia.z); wake_body_now(W, ib.z); }   // :168-173
+}
 __global__ void __launch_bounds__(256) k_add_pairs(const __grid_constant__ DevWorld W) {
   const int n = min(W.hdr->nPairs, W.pairCap);
-  GRID_STRIDE(k, n) {
-    const int2 pr = W.pairs[k];
-    const int4 pa = W.p_ids[pr.x], pb = W.p_ids[pr.y];   // fixture child body shape
-    int bodyA = pa.z, bodyB = pb.z;
-    if (bodyA == bodyB) continue;
-    const unsigned long long key = ((unsigned long long)(unsigned)W.p_key[pr.x] << 32) | (unsigned)W.p_key[pr.y];
-    if (hash_find(W, key) >= 0) continue;                 // a contact for this (fixture, child) pair already exists (:75-100)
-    const uint32_t flA = W.b_flags[bodyA], flB = W.b_flags[bodyB];
-    if (!body_should_collide(W, bodyB, bodyA, flB, flA)) continue;
-    if (!filter_should_collide(W, pa.x, pb.x)) continue;
-    // type registry (b2contact.d:425-437): A must be the primary type
-    const int t1 = W.shapes[pa.w].type, t2 = W.shapes[pb.w].type;
-    bool has, primary;
-    if (t1 == SH_EDGE && t2 == SH_EDGE) { has = false; primary = false; }
-    else if (t1 == SH_CIRCLE) { has = true; primary = (t2 == SH_CIRCLE); }
-    else if (t1 == SH_EDGE) { has = true; primary = true; }
-    else { has = true; primary = (t2 != SH_EDGE); }        // polygon vs circle/polygon primary; vs edge swapped
-    if (!has) continue;
-    int proxyA = pr.x, proxyB = pr.y;
-    int4 ia = pa, ib = pb;
-    if (!primary) { int t = proxyA; proxyA = proxyB; proxyB = t; int4 tt = ia; ia = ib; ib = tt; }
-    // slot
-    int slot;
-    int f = atomicSub(&W.hdr->nFree, 1);
-    if (f > 0) slot = W.c_free[f - 1];
-    else { atomicAdd(&W.hdr->nFree, 1); slot = atomicAdd(&W.hdr->cHigh, 1); }
-    if (slot >= W.cCap) { W.hdr->error = -5; atomicSub(&W.hdr->cHigh, 1); continue; }
-    const bool sensor = ((W.f_group[ia.x] >> 16) & FXF_SENSOR) || ((W.f_group[ib.x] >> 16) & FXF_SENSOR);
-    const float2 mA = W.f_mat[ia.x], mB = W.f_mat[ib.x];
-    W.c_key[slot] = key;
-    W.c_ids[slot] = make_int4(proxyA, proxyB, ia.z, ib.z);
-    W.c_fix[slot] = make_int4(ia.x, ib.x, ia.w, ib.w);
-    W.c_flags[slot] = CF_ALIVE | CF_ENABLED | (sensor ? CF_SENSOR : 0);
-    W.c_m0[slot] = make_float4(0, 0, 0, 0);
-    W.c_m1[slot] = make_float4(0, 0, 0, 0);
-    W.c_imp[slot] = make_float4(0, 0, 0, 0);
-    W.c_mk[slot] = make_uint4(0, 0, 0, 0);
-    // b2MixFriction / b2MixRestitution (b2contact.d:32-42)
-    W.c_mat[slot] = make_float4(sqrtf(mA.x * mB.x), mA.y > mB.y ? mA.y : mB.y, 0.0f, 1.0f);
-    W.c_toiCount[slot] = 0;
-    W.c_colour[slot] = -1;
-    if (!hash_insert(W, key, slot)) W.hdr->error = -5;
-    if (!sensor) { wake_body_now(W, ia.z); wake_body_now(W, ib.z); }   // :168-173
-  }
+  GRID_STRIDE(k, n) add_pair(W, W.pairs[k]);
 }
 __global__ void __launch_bounds__(256) k_clear_moves(const __grid_constant__ DevWorld W) {
   const int nMoved = min(W.hdr->nMoved, W.moveCap);
@@ -1444,6 +1470,339 @@ __global__ void k_api_wake(const __grid_constant__ DevWorld W, int a, int b) {
   if (b >= 0) wake_body_now(W, b);
 }
 
+// ------------------------------------------------------------------------------------------------ time of impact
+// b2World.SolveTOI (dynamics/b2world.d:1127-1452) + b2Island.SolveTOI (b2island.d:282-416).
+// The reference handles one event at a time in ascending alpha.  Events whose mini-islands share no movable body
+// commute, so each pass handles, in parallel, every candidate event that holds the minimum (alpha, slot) on all the
+// movable bodies it would touch; the others wait for the next pass.  One persistent cooperative kernel runs the whole
+// loop (TOI evaluation -> arbitration -> mini-island solve -> SynchronizeFixtures -> FindNewContacts) on the device.
+DBX_D float atomic_min_f(float* addr, float v) {
+  return v >= 0.0f ? __int_as_float(atomicMin((int*)addr, __float_as_int(v))) : __uint_as_float(atomicMax((unsigned*)addr, __float_as_uint(v)));
+}
+DBX_D float atomic_max_f(float* addr, float v) {
+  return v >= 0.0f ? __int_as_float(atomicMax((int*)addr, __float_as_int(v))) : __uint_as_float(atomicMin((unsigned*)addr, __float_as_uint(v)));
+}
+DBX_D Sweep load_sweep(const DevWorld& W, int b) {
+  const float4 lc = W.b_lc[b], p0 = ldcg4(&W.b_pos0[b]), p = ldcg4(&W.b_pos[b]);
+  Sweep s; s.localCenter = V(lc.x, lc.y); s.c0 = V(p0.x, p0.y); s.c = V(p.x, p.y); s.a0 = p0.z; s.a = p.z; s.alpha0 = p0.w;
+  return s;
+}
+struct BodyBackup { float4 pos0, pos, xf, xf0; };
+DBX_D BodyBackup backup_body(const DevWorld& W, int b) {
+  BodyBackup k; k.pos0 = ldcg4(&W.b_pos0[b]); k.pos = ldcg4(&W.b_pos[b]); k.xf = ldcg4(&W.b_xf[b]); k.xf0 = ldcg4(&W.b_xf0[b]); return k;
+}
+DBX_D void restore_body(const DevWorld& W, int b, const BodyBackup& k) {   // m_sweep = backup; SynchronizeTransform()
+  stcg4(&W.b_pos0[b], k.pos0); stcg4(&W.b_pos[b], k.pos); stcg4(&W.b_xf[b], k.xf); stcg4(&W.b_xf0[b], k.xf0);
+}
+// b2Body.Advance (b2body.d:1172-1180); statics are left alone (only their alpha0 would change, which nothing reads here)
+DBX_D void advance_body(const DevWorld& W, int b, float alpha) {
+  if (body_type(W.b_flags[b]) == BODY_STATIC) return;
+  Sweep s = load_sweep(W, b);
+  sweep_advance(s, alpha);
+  s.c = s.c0; s.a = s.a0;
+  Xf xf = xf_from_sweep(s.c, s.a, s.localCenter);
+  stcg4(&W.b_pos0[b], make_float4(s.c0.x, s.c0.y, s.a0, s.alpha0));
+  stcg4(&W.b_pos[b], make_float4(s.c.x, s.c.y, s.a, 0.0f));
+  stcg4(&W.b_xf[b], pack(xf));
+  stcg4(&W.b_xf0[b], pack(xf));
+}
+
+// (a) evaluate b2TimeOfImpact for every eligible contact that has no cached value (b2world.d:1155-1265)
+DBX_D void toi_evaluate(const DevWorld& W, int i) {
+  uint32_t flags = W.c_flags[i];
+  if (!(flags & CF_ALIVE)) return;
+  const int4 ids = W.c_ids[i];
+  if ((flags & CF_TOI) && ((__ldcg(&W.b_toiFlags[ids.z]) | __ldcg(&W.b_toiFlags[ids.w])) & TF_INVAL)) { flags &= ~(CF_TOI | CF_ISLAND); W.c_flags[i] = flags; }
+  if (!(flags & CF_ENABLED)) return;
+  if (W.c_toiCount[i] > kMaxSubSteps) return;
+  float alpha = 1.0f;
+  const uint32_t fa = W.b_flags[ids.z], fb = W.b_flags[ids.w];
+  if (flags & CF_TOI) {
+    alpha = W.c_mat[i].w;
+  } else {
+    if (flags & CF_SENSOR) return;
+    const int typeA = body_type(fa), typeB = body_type(fb);
+    const bool activeA = (fa & BF_AWAKE) && typeA != BODY_STATIC, activeB = (fb & BF_AWAKE) && typeB != BODY_STATIC;
+    if (!activeA && !activeB) return;
+    const bool collideA = (fa & BF_BULLET) || typeA != BODY_DYNAMIC, collideB = (fb & BF_BULLET) || typeB != BODY_DYNAMIC;
+    if (!collideA && !collideB) return;
+    Sweep sA = load_sweep(W, ids.z), sB = load_sweep(W, ids.w);
+    // bring both sweeps to the later alpha0 (:1214-1225); done on local copies, see DESIGN.md
+    float alpha0 = sA.alpha0;
+    if (typeA == BODY_STATIC) { alpha0 = sB.alpha0; sA.alpha0 = alpha0; }
+    else if (typeB == BODY_STATIC) { alpha0 = sA.alpha0; sB.alpha0 = alpha0; }
+    else if (sA.alpha0 < sB.alpha0) { alpha0 = sB.alpha0; sweep_advance(sA, alpha0); }
+    else if (sB.alpha0 < sA.alpha0) { alpha0 = sA.alpha0; sweep_advance(sB, alpha0); }
+    const int4 fx = W.c_fix[i];
+    DProxy pA = make_proxy(W.shapes + fx.z), pB = make_proxy(W.shapes + fx.w);
+    float beta;
+    int state = time_of_impact(&beta, pA, sA, pB, sB, 1.0f);
+    if (state == TOI_TOUCHING) alpha = fminr(alpha0 + (1.0f - alpha0) * beta, 1.0f);
+    else alpha = 1.0f;
+    float4 mat = W.c_mat[i]; mat.w = alpha; W.c_mat[i] = mat;
+    flags |= CF_TOI;
+    W.c_flags[i] = flags;
+  }
+  if (1.0f - 10.0f * kEpsilon < alpha) return;   // never becomes an event (:1267-1272)
+  const unsigned long long prio = ((unsigned long long)__float_as_uint(alpha) << 32) | (unsigned)i;
+  if (body_type(fa) != BODY_STATIC) atomicMin(&W.b_toiMin[ids.z], prio);
+  if (body_type(fb) != BODY_STATIC) atomicMin(&W.b_toiMin[ids.w], prio);
+}
+
+// (d) one event, start to finish, by one thread (b2world.d:1274-1440)
+DBX_D void toi_process_event(const DevWorld& W, int e, float dtStep) {
+  const int i0 = W.e_contact[e];
+  const int4 ids0 = W.c_ids[i0];
+  const int bA = ids0.z, bB = ids0.w;
+  const float minAlpha = W.c_mat[i0].w;
+  const unsigned long long prio = ((unsigned long long)__float_as_uint(minAlpha) << 32) | (unsigned)i0;
+  const uint32_t fA = W.b_flags[bA], fB = W.b_flags[bB];
+  // arbitration over the movable bodies this event would pull in besides bA/bB
+  for (int side = 0; side < 2; ++side) {
+    const int nc = min(W.e_ncand[2 * e + side], kToiCand);
+    const int body = side == 0 ? bA : bB;
+    for (int k = 0; k < nc; ++k) {
+      const int4 ids = W.c_ids[W.e_cand[(2 * e + side) * kToiCand + k]];
+      const int other = ids.z == body ? ids.w : ids.z;
+      if (other == bA || other == bB || body_type(W.b_flags[other]) == BODY_STATIC) continue;
+      if (__ldcg(&W.b_toiOther[other]) != prio) return;                          // a better event wants that body: wait
+      const int oe = __ldcg(&W.b_toiEvt[other]);
+      if (oe >= 0 && oe != e) {
+        const int oc = W.e_contact[oe];
+        const unsigned long long op = ((unsigned long long)__float_as_uint(W.c_mat[oc].w) << 32) | (unsigned)oc;
+        if (op < prio) return;
+      }
+    }
+  }
+  atomicAdd(&W.hdr->toiEvents, 1);
+  const BodyBackup backup1 = backup_body(W, bA), backup2 = backup_body(W, bB);
+  advance_body(W, bA, minAlpha);
+  advance_body(W, bB, minAlpha);
+  uint32_t flags0 = update_contact(W, i0, W.c_flags[i0], ids0, W.c_fix[i0], true);
+  flags0 &= ~CF_TOI;
+  W.c_toiCount[i0] += 1;
+  if (!(flags0 & CF_ENABLED) || !(flags0 & CF_TOUCHING)) {
+    W.c_flags[i0] = flags0 & ~CF_ENABLED;
+    restore_body(W, bA, backup1);
+    restore_body(W, bB, backup2);
+    return;
+  }
+  W.c_flags[i0] = flags0;
+  wake_body_now(W, bA);
+  wake_body_now(W, bB);
+  int bodies[2 * kMaxTOIContacts], contacts[kMaxTOIContacts];
+  int nb = 0, nc = 0;
+  bodies[nb++] = bA; bodies[nb++] = bB; contacts[nc++] = i0;
+  for (int side = 0; side < 2; ++side) {
+    const int body = side == 0 ? bA : bB;
+    const uint32_t fbody = side == 0 ? fA : fB;
+    if (body_type(fbody) != BODY_DYNAMIC) continue;
+    const int ncand = min(W.e_ncand[2 * e + side], kToiCand);
+    int* cand = W.e_cand + (2 * e + side) * kToiCand;
+    // newest first, like the body's contact list: approximated by descending slot
+    for (int a = 1; a < ncand; ++a) { int v = cand[a]; int b = a - 1; while (b >= 0 && cand[b] < v) { cand[b + 1] = cand[b]; --b; } cand[b + 1] = v; }
+    for (int k = 0; k < ncand; ++k) {
+      if (nb == 2 * kMaxTOIContacts) break;
+      if (nc == kMaxTOIContacts) break;
+      const int ci = cand[k];
+      bool already = false;
+      for (int t = 0; t < nc; ++t) if (contacts[t] == ci) { already = true; break; }
+      if (already) continue;
+      const int4 ids = W.c_ids[ci];
+      const int other = ids.z == body ? ids.w : ids.z;
+      bool otherIn = false;
+      for (int t = 0; t < nb; ++t) if (bodies[t] == other) { otherIn = true; break; }
+      const BodyBackup backup = backup_body(W, other);
+      if (!otherIn) advance_body(W, other, minAlpha);
+      const uint32_t fl = update_contact(W, ci, W.c_flags[ci], ids, W.c_fix[ci], true);
+      if (!(fl & CF_ENABLED) || !(fl & CF_TOUCHING)) { restore_body(W, other, backup); continue; }
+      contacts[nc++] = ci;
+      if (otherIn) continue;
+      if (body_type(W.b_flags[other]) != BODY_STATIC) wake_body_now(W, other);
+      bodies[nb++] = other;
+    }
+  }
+  // ---- b2Island.SolveTOI with subStep {dt = (1 - alpha) dt, 20 position iterations, no warm starting}
+  const int sBase = e * kMaxTOIContacts;
+  for (int k = 0; k < nc; ++k) prepare_contact(W, sBase + k, contacts[k], -1.0f);
+  for (int it = 0; it < 20; ++it) {
+    float minSeparation = 0.0f;
+    for (int k = 0; k < nc; ++k) minSeparation = fminr(minSeparation, contact_solve_position(W, sBase + k, bA, bB));
+    if (minSeparation >= -1.5f * kLinearSlop) break;
+  }
+  // leap of faith: the TOI bodies' c0/a0 become the solved pose (b2island.d:352-355); refresh transforms for the velocity pass
+  for (int t = 0; t < nb; ++t) {
+    const int b = bodies[t];
+    if (body_type(W.b_flags[b]) == BODY_STATIC) continue;
+    const float4 pos = ldcg4(&W.b_pos[b]); const float4 lc = W.b_lc[b];
+    const Xf xf = xf_from_sweep(V(pos.x, pos.y), pos.z, V(lc.x, lc.y));
+    stcg4(&W.b_xf[b], pack(xf));
+    if (b == bA || b == bB) {
+      float4 p0 = ldcg4(&W.b_pos0[b]); p0.x = pos.x; p0.y = pos.y; p0.z = pos.z;
+      stcg4(&W.b_pos0[b], p0);
+      stcg4(&W.b_xf0[b], pack(xf));
+    }
+  }
+  for (int k = 0; k < nc; ++k) prepare_contact(W, sBase + k, contacts[k], -1.0f);
+  for (int it = 0; it < W.velIters; ++it) for (int k = 0; k < nc; ++k) contact_solve_velocity(W, sBase + k);
+  const float h = (1.0f - minAlpha) * dtStep;
+  for (int t = 0; t < nb; ++t) {
+    const int b = bodies[t];
+    const int type = body_type(W.b_flags[b]);
+    if (type == BODY_STATIC) continue;
+    float4 pos = ldcg4(&W.b_pos[b]), vel = ldcg4(&W.b_vel[b]);
+    v2 c = V(pos.x, pos.y), v = V(vel.x, vel.y);
+    float a = pos.z, w = vel.z;
+    v2 translation = h * v;
+    if (dot(translation, translation) > kMaxTranslationSquared) { float ratio = kMaxTranslation / len(translation); v *= ratio; }
+    float rotation = h * w;
+    if (rotation * rotation > kMaxRotationSquared) { float ratio = kMaxRotation / fabsr(rotation); w *= ratio; }
+    c += h * v;
+    a += h * w;
+    stcg4(&W.b_pos[b], make_float4(c.x, c.y, a, 0.0f));
+    stcg4(&W.b_vel[b], make_float4(v.x, v.y, w, 0.0f));
+    const float4 lc = W.b_lc[b];
+    stcg4(&W.b_xf[b], pack(xf_from_sweep(c, a, V(lc.x, lc.y))));
+    if (type == BODY_DYNAMIC) atomicOr(&W.b_toiFlags[b], TF_INVAL | TF_SYNC);   // :1423-1440
+  }
+}
+
+__global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W) {
+  __shared__ int stacks[16][kQueryStack];
+  Header* H = W.hdr;
+  const unsigned nb = gridDim.x;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warp = tid >> 5, nwarps = nth >> 5;
+  const int eventCap = min(W.eventCap, nwarps);
+  // reset (m_stepComplete is always true here: sub-stepping is not supported) (:1131-1146)
+  {
+    const int n = H->cHigh;
+    for (int i = tid; i < n; i += nth) {
+      uint32_t f = W.c_flags[i];
+      if (!(f & CF_ALIVE)) continue;
+      if (f & (CF_TOI | CF_ISLAND)) W.c_flags[i] = f & ~(CF_TOI | CF_ISLAND);
+      W.c_toiCount[i] = 0;
+      float4 mat = W.c_mat[i]; if (mat.w != 1.0f) { mat.w = 1.0f; W.c_mat[i] = mat; }
+    }
+    for (int b = tid; b < W.nBodies; b += nth) {
+      float4 p0 = W.b_pos0[b]; if (p0.w != 0.0f) { p0.w = 0.0f; W.b_pos0[b] = p0; }
+      W.b_toiMin[b] = ~0ull; W.b_toiOther[b] = ~0ull; W.b_toiEvt[b] = -1; W.b_toiFlags[b] = 0;
+    }
+    if (tid == 0) H->nEvents = 0;
+  }
+  grid_barrier(&H->barrier, nb);
+  for (int pass = 0; pass < 1024; ++pass) {
+    // (a) TOI evaluation + per-body minima
+    {
+      const int n = *((volatile int*)&H->cHigh);
+      for (int i = tid; i < n; i += nth) toi_evaluate(W, i);
+    }
+    grid_barrier(&H->barrier, nb);
+    // (b) winners: the minimum on every movable body they touch
+    {
+      const int n = *((volatile int*)&H->cHigh);
+      for (int i = tid; i < n; i += nth) {
+        const uint32_t flags = W.c_flags[i];
+        if ((flags & (CF_ALIVE | CF_ENABLED | CF_TOI)) != (CF_ALIVE | CF_ENABLED | CF_TOI)) continue;
+        if (W.c_toiCount[i] > kMaxSubSteps) continue;
+        const float alpha = W.c_mat[i].w;
+        if (1.0f - 10.0f * kEpsilon < alpha) continue;
+        const int4 ids = W.c_ids[i];
+        const unsigned long long prio = ((unsigned long long)__float_as_uint(alpha) << 32) | (unsigned)i;
+        const bool movA = body_type(W.b_flags[ids.z]) != BODY_STATIC, movB = body_type(W.b_flags[ids.w]) != BODY_STATIC;
+        if ((movA && __ldcg(&W.b_toiMin[ids.z]) != prio) || (movB && __ldcg(&W.b_toiMin[ids.w]) != prio)) continue;
+        const int e = atomicAdd(&H->nEvents, 1);
+        if (e >= eventCap) continue;     // stays a candidate for the next pass
+        W.e_contact[e] = i;
+        W.e_ncand[2 * e] = 0; W.e_ncand[2 * e + 1] = 0;
+        if (movA) W.b_toiEvt[ids.z] = e;
+        if (movB) W.b_toiEvt[ids.w] = e;
+      }
+      for (int b = tid; b < W.nBodies; b += nth) if (W.b_toiFlags[b] & TF_INVAL) W.b_toiFlags[b] &= ~TF_INVAL;
+    }
+    grid_barrier(&H->barrier, nb);
+    const int nEvents = min(*((volatile int*)&H->nEvents), eventCap);
+    if (nEvents == 0) break;
+    // (c) contacts of the event bodies that may join their mini-islands (b2world.d:1319-1411)
+    {
+      const int n = *((volatile int*)&H->cHigh);
+      for (int i = tid; i < n; i += nth) {
+        const uint32_t flags = W.c_flags[i];
+        if (!(flags & CF_ALIVE) || (flags & CF_SENSOR)) continue;
+        const int4 ids = W.c_ids[i];
+        for (int side = 0; side < 2; ++side) {
+          const int body = side == 0 ? ids.z : ids.w, other = side == 0 ? ids.w : ids.z;
+          const int e = __ldcg(&W.b_toiEvt[body]);
+          if (e < 0 || e >= nEvents) continue;
+          const int ec = W.e_contact[e];
+          if (ec == i) continue;
+          const uint32_t fbody = W.b_flags[body], fother = W.b_flags[other];
+          if (body_type(fbody) != BODY_DYNAMIC) continue;
+          if (body_type(fother) == BODY_DYNAMIC && !(fbody & BF_BULLET) && !(fother & BF_BULLET)) continue;
+          const int evSide = W.c_ids[ec].z == body ? 0 : 1;
+          const int slot = atomicAdd(&W.e_ncand[2 * e + evSide], 1);
+          if (slot < kToiCand) W.e_cand[(2 * e + evSide) * kToiCand + slot] = i; else H->error = -5;
+          if (body_type(fother) != BODY_STATIC) {
+            const unsigned long long prio = ((unsigned long long)__float_as_uint(W.c_mat[ec].w) << 32) | (unsigned)ec;
+            atomicMin(&W.b_toiOther[other], prio);
+          }
+        }
+      }
+    }
+    grid_barrier(&H->barrier, nb);
+    // (d) events
+    if (lane == 0) for (int e = warp; e < nEvents; e += nwarps) toi_process_event(W, e, W.dt);
+    grid_barrier(&H->barrier, nb);
+    // (e) SynchronizeFixtures of the island's dynamic bodies (:1433), then FindNewContacts (:1444)
+    for (int p = tid; p < W.nProxies; p += nth) {
+      const uint32_t pf = W.p_flags[p];
+      if (!(pf & PF_ALIVE)) continue;
+      const int body = W.p_ids[p].z;
+      if (!(__ldcg(&W.b_toiFlags[body]) & TF_SYNC)) continue;
+      sync_proxy(W, p, pf, body);
+    }
+    if (tid == 0) H->nPairs = 0;
+    grid_barrier(&H->barrier, nb);
+    {
+      // the step's LBVH is still valid for every proxy that did not move; widen it for the ones that did
+      const int nMoved = min(*((volatile int*)&H->nMoved), W.moveCap);
+      const int n = W.nProxies;
+      for (int k = tid; k < nMoved; k += nth) {
+        const int p = W.moveList[k];
+        const float4 f = __ldcg(&W.p_fat[p]);
+        int node = n - 1 + W.bv_pos[p];
+        __stcg(&W.bv_box[node], f);
+        node = W.bv_parent[node];
+        while (node >= 0) {
+          float* bx = (float*)&W.bv_box[node];
+          atomic_min_f(bx + 0, f.x); atomic_min_f(bx + 1, f.y); atomic_max_f(bx + 2, f.z); atomic_max_f(bx + 3, f.w);
+          node = W.bv_parent[node];
+        }
+      }
+      for (int b = tid; b < W.nBodies; b += nth) {
+        W.b_toiMin[b] = ~0ull; W.b_toiOther[b] = ~0ull; W.b_toiEvt[b] = -1;
+        if (W.b_toiFlags[b] & TF_SYNC) W.b_toiFlags[b] &= ~TF_SYNC;
+      }
+      if (tid == 0) H->nEvents = 0;
+    }
+    grid_barrier(&H->barrier, nb);
+    {
+      const int nMoved = min(*((volatile int*)&H->nMoved), W.moveCap);
+      for (int k = warp; k < nMoved; k += nwarps) query_proxy(W, W.bv_sorted, stacks[wib], lane, W.moveList[k]);
+    }
+    grid_barrier(&H->barrier, nb);
+    {
+      const int nPairs = min(*((volatile int*)&H->nPairs), W.pairCap);
+      for (int k = tid; k < nPairs; k += nth) add_pair(W, W.pairs[k]);
+      const int nMoved = min(*((volatile int*)&H->nMoved), W.moveCap);
+      for (int k = tid; k < nMoved; k += nth) { const int p = W.moveList[k]; W.p_flags[p] &= ~PF_MOVED; }
+    }
+    grid_barrier(&H->barrier, nb);
+    if (tid == 0) H->nMoved = 0;
+    grid_barrier(&H->barrier, nb);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host launchers
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return _e; } while (0)
 
@@ -1469,7 +1828,7 @@ cudaError_t stage_islands_and_integrate(const DevWorld& W, const LaunchCfg& L) {
 cudaError_t stage_colour_and_sort(const DevWorld& W, const LaunchCfg& L) {
   k_mark_solve<<<L.gridWide, 256, 0, L.stream>>>(W);
   CK(cudaGetLastError());
-  CK(launch_coop((const void*)k_colour, W, L));
+  if (!W.colourOverride) CK(launch_coop((const void*)k_colour, W, L));
   k_sort_hist<<<kSortBlocks, 256, 0, L.stream>>>(W);
   k_sort_scan<<<1, kMaxColours, 0, L.stream>>>(W, kSortBlocks);
   k_sort_scatter<<<kSortBlocks, 256, 0, L.stream>>>(W);
@@ -1495,7 +1854,11 @@ size_t cub_temp_bytes(int maxProxies) {
   return bytes + 256;
 }
 
-cudaError_t stage_find_new_contacts(const DevWorld& W, const LaunchCfg& L) {
+cudaError_t stage_toi(DevWorld& W, const LaunchCfg& L) {
+  return launch_coop((const void*)k_toi, W, L);
+}
+
+cudaError_t stage_find_new_contacts(DevWorld& W, const LaunchCfg& L) {
   const int n = W.nProxies;
   k_bounds_init<<<1, 1, 0, L.stream>>>(W);
   if (n > 0) {
@@ -1509,6 +1872,7 @@ cudaError_t stage_find_new_contacts(const DevWorld& W, const LaunchCfg& L) {
     CK(cub::DeviceRadixSort::SortPairs(L.cubTemp, bytes, keys, vals, n, 0, 30 + worldBits + 1, L.stream));
     const unsigned long long* sk = keys.Current();
     const int* sl = vals.Current();
+    W.bv_sorted = sl;
     if (n > 1) k_lbvh_hierarchy<<<L.gridWide, 256, 0, L.stream>>>(W, sk);
     k_lbvh_refit<<<L.gridWide, 256, 0, L.stream>>>(W, sl);
     k_query<<<L.gridWide, 256, 0, L.stream>>>(W, sl);

@@ -19,7 +19,8 @@ cudaError_t stage_islands_and_integrate(const DevWorld& W, const LaunchCfg& L); 
 cudaError_t stage_colour_and_sort(const DevWorld& W, const LaunchCfg& L);         // graph colouring + colour counting sort
 cudaError_t stage_solve(const DevWorld& W, const LaunchCfg& L);                   // prepare + warm start + iterations + finalize + sleep
 cudaError_t stage_sync_fixtures(const DevWorld& W, const LaunchCfg& L);           // b2Body.SynchronizeFixtures / MoveProxy
-cudaError_t stage_find_new_contacts(const DevWorld& W, const LaunchCfg& L);       // LBVH rebuild + pair query + AddPair
+cudaError_t stage_find_new_contacts(DevWorld& W, const LaunchCfg& L);       // LBVH rebuild + pair query + AddPair
+cudaError_t stage_toi(DevWorld& W, const LaunchCfg& L);                               // b2World.SolveTOI
 cudaError_t stage_rebuild_hash(const DevWorld& W, const LaunchCfg& L);
 cudaError_t stage_count(const DevWorld& W, const LaunchCfg& L);                   // refresh hdr->nContacts / nTouching / nAwake
 size_t cub_temp_bytes(int maxProxies);

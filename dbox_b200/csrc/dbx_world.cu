@@ -48,7 +48,8 @@ World::~World() {
   DevBuf<float4>* f4[] = {&b_xf, &b_xf0, &b_pos, &b_pos0, &b_vel, &b_force, &b_mass, &b_lc, &p_aabb, &p_fat, &bv_box, &c_m0, &c_m1, &c_imp, &c_mat,
                           &s_v0, &s_v1, &s_r0, &s_r1, &s_q0, &s_q1, &s_imp, &s_nm, &s_k, &s_p0, &s_p1, &s_p2, &j_anchor, &j_p0, &j_p1, &j_imp, &j_r, &j_lc, &j_m, &j_k0, &j_k1, &j_k2};
   for (auto* b : f4) b->release();
-  DevBuf<int>* i1[] = {&b_wake, &b_root, &b_islAwake, &b_islMinSleep, &b_posNotOk, &b_ovf, &b_world, &f_body, &f_group, &p_key, &moveList, &bv_leaf, &bv_leafAlt,
+  b_toiMin.release(); b_toiOther.release();
+  DevBuf<int>* i1[] = {&b_toiEvt, &b_toiFlags, &e_contact, &e_ncand, &e_cand, &bv_pos, &b_wake, &b_root, &b_islAwake, &b_islMinSleep, &b_posNotOk, &b_ovf, &b_world, &f_body, &f_group, &p_key, &moveList, &bv_leaf, &bv_leafAlt,
                        &bv_parent, &bv_visit, &c_toiCount, &c_colour, &c_free, &c_work, &c_work2, &h_val, &s_contact, &s_hist, &s_pc, &s_root, &j_limit, &j_colour, &j_order, &j_root, &d_levels};
   for (auto* b : i1) b->release();
   b_gs.release(); f_mat.release(); s_p3.release(); b_flags.release(); f_filter.release(); p_flags.release(); c_flags.release();
@@ -498,6 +499,11 @@ int World::push() {
   for (auto* b : bi) CUDA_OR_FAIL(b->reserve(capB, true, stream_), "body int");
   CUDA_OR_FAIL(b_mask.reserve(capB, true, stream_), "b_mask");
   CUDA_OR_FAIL(b_claim.reserve(capB, true, stream_), "b_claim");
+  CUDA_OR_FAIL(b_toiMin.reserve(capB, true, stream_), "b_toiMin"); CUDA_OR_FAIL(b_toiOther.reserve(capB, true, stream_), "b_toiOther");
+  CUDA_OR_FAIL(b_toiEvt.reserve(capB, true, stream_), "b_toiEvt"); CUDA_OR_FAIL(b_toiFlags.reserve(capB, true, stream_), "b_toiFlags");
+  const size_t nEv = (size_t)L_.coopBlocks * (L_.coopThreads / 32);
+  CUDA_OR_FAIL(e_contact.reserve(nEv, false, stream_), "e_contact"); CUDA_OR_FAIL(e_ncand.reserve(2 * nEv, false, stream_), "e_ncand");
+  CUDA_OR_FAIL(e_cand.reserve(2 * nEv * kToiCand, false, stream_), "e_cand");
   CUDA_OR_FAIL(b_posNotOk.reserve(b_root.cap * (size_t)kMaxPosIters, false, stream_), "b_posNotOk");
   CUDA_OR_FAIL(f_body.reserve(std::max<size_t>(nF, 1), true, stream_), "f_body");
   CUDA_OR_FAIL(f_group.reserve(std::max<size_t>(nF, 1), true, stream_), "f_group");
@@ -515,6 +521,7 @@ int World::push() {
   CUDA_OR_FAIL(bv_leaf.reserve(pc, false, stream_), "bv_leaf"); CUDA_OR_FAIL(bv_leafAlt.reserve(pc, false, stream_), "bv_leafAlt");
   CUDA_OR_FAIL(bv_box.reserve(2 * pc, false, stream_), "bv_box"); CUDA_OR_FAIL(bv_child.reserve(pc, false, stream_), "bv_child");
   CUDA_OR_FAIL(bv_parent.reserve(2 * pc, false, stream_), "bv_parent"); CUDA_OR_FAIL(bv_visit.reserve(pc, false, stream_), "bv_visit");
+  CUDA_OR_FAIL(bv_pos.reserve(pc, false, stream_), "bv_pos");
   {
     size_t need = cub_temp_bytes((int)pc);
     CUDA_OR_FAIL(cubTemp.reserve(need, false, stream_), "cubTemp");
@@ -537,9 +544,10 @@ int World::push() {
   }
   CUDA_OR_FAIL(pairs.reserve(std::max<size_t>(std::max<size_t>(4096, cc), (size_t)caps_.maxPairs), false, stream_), "pairs");
   DevBuf<float4>* sf4[] = {&s_v0, &s_v1, &s_r0, &s_r1, &s_q0, &s_q1, &s_imp, &s_nm, &s_k, &s_p0, &s_p1, &s_p2};
-  for (auto* b : sf4) CUDA_OR_FAIL(b->reserve(cc, false, stream_), "solver f4");
-  CUDA_OR_FAIL(s_p3.reserve(cc, false, stream_), "s_p3"); CUDA_OR_FAIL(s_body.reserve(cc, false, stream_), "s_body");
-  CUDA_OR_FAIL(s_contact.reserve(cc, false, stream_), "s_contact"); CUDA_OR_FAIL(s_pc.reserve(cc, false, stream_), "s_pc"); CUDA_OR_FAIL(s_root.reserve(cc, false, stream_), "s_root");
+  const size_t sc = std::max<size_t>(cc, nEv * (size_t)kMaxTOIContacts);   // TOI mini-islands borrow solver slots [event * 32, +32)
+  for (auto* b : sf4) CUDA_OR_FAIL(b->reserve(sc, false, stream_), "solver f4");
+  CUDA_OR_FAIL(s_p3.reserve(sc, false, stream_), "s_p3"); CUDA_OR_FAIL(s_body.reserve(sc, false, stream_), "s_body");
+  CUDA_OR_FAIL(s_contact.reserve(sc, false, stream_), "s_contact"); CUDA_OR_FAIL(s_pc.reserve(sc, false, stream_), "s_pc"); CUDA_OR_FAIL(s_root.reserve(sc, false, stream_), "s_root");
   CUDA_OR_FAIL(s_hist.reserve((size_t)kSortBlocks * kMaxColours, false, stream_), "s_hist");
   const size_t capJ = std::max<size_t>(std::max<size_t>(nJ, 1), (size_t)caps_.maxJoints);
   DevBuf<float4>* jf4[] = {&j_anchor, &j_p0, &j_p1, &j_imp, &j_r, &j_lc, &j_m, &j_k0, &j_k1, &j_k2};
@@ -625,6 +633,8 @@ void World::refreshView() {
   w.nBodies = (int)bodies_.size();
   w.b_xf = b_xf.p; w.b_xf0 = b_xf0.p; w.b_pos = b_pos.p; w.b_pos0 = b_pos0.p; w.b_vel = b_vel.p; w.b_force = b_force.p; w.b_mass = b_mass.p; w.b_lc = b_lc.p;
   w.b_gs = b_gs.p; w.b_flags = b_flags.p; w.b_wake = b_wake.p; w.b_root = b_root.p; w.b_islAwake = b_islAwake.p; w.b_islMinSleep = b_islMinSleep.p;
+  w.b_toiMin = b_toiMin.p; w.b_toiOther = b_toiOther.p; w.b_toiEvt = b_toiEvt.p; w.b_toiFlags = b_toiFlags.p;
+  w.e_contact = e_contact.p; w.e_ncand = e_ncand.p; w.e_cand = e_cand.p; w.eventCap = (int)e_contact.cap; w.bv_pos = bv_pos.p;
   w.b_posNotOk = b_posNotOk.p; w.b_mask = b_mask.p; w.b_claim = b_claim.p; w.b_ovf = b_ovf.p; w.b_world = b_world.p;
   w.nFixtures = (int)fixtures_.size(); w.f_body = f_body.p; w.f_mat = f_mat.p; w.f_filter = f_filter.p; w.f_group = f_group.p;
   w.nShapes = (int)shapes_.size(); w.shapes = d_shapes.p;
@@ -677,6 +687,7 @@ int World::step(float dt, int vi, int pi, int n) {
     if (bodies_.empty()) continue;
     if (newFixture_) { CUDA_OR_FAIL(stage_find_new_contacts(dw_, L_), "find_new_contacts"); newFixture_ = false; }   // :372-376
     setStepParams(dt, vi, pi);
+    dw_.colourOverride = overrideLevels_ ? 1 : 0;
     cudaEventRecord(ev_[0], stream_);
     CUDA_OR_FAIL(stage_collide(dw_, L_), "collide");
     cudaEventRecord(ev_[1], stream_);
@@ -692,13 +703,17 @@ int World::step(float dt, int vi, int pi, int n) {
     } else {
       cudaEventRecord(ev_[2], stream_); cudaEventRecord(ev_[3], stream_); cudaEventRecord(ev_[4], stream_);
     }
-    // TODO(round 2): SolveTOI sub-stepping (b2world.d:1127-1452)
+    if ((flags_ & DBX_WORLD_CONTINUOUS) && dt > 0.0f) CUDA_OR_FAIL(stage_toi(dw_, L_), "toi");   // :414-419
     cudaEventRecord(ev_[5], stream_);
     if (dt > 0.0f) inv_dt0 = dw_.inv_dt;
     if (flags_ & DBX_WORLD_AUTO_CLEAR_FORCES) CUDA_OR_FAIL(launch_clear_forces(dw_, L_), "clear_forces");
     cudaEventRecord(ev_[6], stream_);
     evValid_ = true;
     ++stepCount_;
+    if (overrideLevels_) {   // one-shot: hand the colours back to the colouring pass
+      overrideLevels_ = false; dw_.colourOverride = 0;
+      CUDA_OR_FAIL(cudaMemsetAsync(c_colour.p, 0xFF, c_colour.cap * 4, stream_), "reset colours");
+    }
     if ((stepCount_ & 63) == 0) CUDA_OR_FAIL(stage_rebuild_hash(dw_, L_), "rehash");
     hostBodiesValid_ = false; hostProxiesValid_ = false; hostJointsValid_ = false;
   }
@@ -958,6 +973,7 @@ int World::readContacts(dbx_contact_rec* out, int cap) {
   for (size_t i = 0; i < n; ++i) if (fl[i] & CF_ALIVE) order.push_back((int)i);
   std::sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });   // deterministic: by reference pair key
   int cnt = 0;
+  lastReadSlots_ = order;
   for (int i : order) {
     if (cnt < cap) {
       dbx_contact_rec& o = out[cnt];
@@ -1023,10 +1039,51 @@ int World::writeContacts(const dbx_contact_rec* in, int n) {
   return checkDeviceError(true) < 0 ? DBX_E_CAPACITY : n;
 }
 
+// Test hook: replace the colouring of the NEXT step by a caller-supplied level per contact (index = position in the last
+// dbx_world_read_contacts result).  With levels derived from the reference's sequential order the coloured solve is a
+// topological re-ordering of that order, i.e. arithmetically the same Gauss-Seidel sweep.
 int World::setContactLevels(const int32_t* levels, int n) {
-  (void)levels; (void)n;
-  set_last_error("debug contact levels: not wired in this build");
-  return DBX_E_UNSUPPORTED;
+  if (n == 0) { overrideLevels_ = false; return 0; }
+  if (n != (int)lastReadSlots_.size()) { set_last_error("levels must match the last read_contacts result"); return DBX_E_INVALID; }
+  int rc = push(); if (rc < 0) return rc;
+  std::vector<int> col(c_colour.cap, -1);
+  for (int i = 0; i < n; ++i) {
+    if (levels[i] >= kMaxColours) { set_last_error("too many levels"); return DBX_E_CAPACITY; }
+    col[lastReadSlots_[i]] = levels[i];
+  }
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  CUDA_OR_FAIL(cudaMemcpy(c_colour.p, col.data(), col.size() * 4, cudaMemcpyHostToDevice), "levels up");
+  overrideLevels_ = true;
+  return 0;
+}
+
+// Test hook ("colour-validity checker"): number of pairs of solver contacts that share a dynamic body
+// AND a colour after the last step, i.e. would have raced in the coloured Gauss-Seidel sweep.  Must be 0.
+int World::colourConflicts() {
+  if (!dw_.hdr || bodiesSynced_ == 0) return 0;
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  int high = 0;
+  CUDA_OR_FAIL(cudaMemcpy(&high, (char*)hdr_.p + offsetof(Header, cHigh), 4, cudaMemcpyDeviceToHost), "read cHigh");
+  if (high <= 0) return 0;
+  const size_t n = (size_t)high;
+  std::vector<int4> ids(n); std::vector<uint32_t> fl(n), bfl(bodiesSynced_); std::vector<int> col(n);
+  cudaMemcpy(ids.data(), c_ids.p, n * 16, cudaMemcpyDeviceToHost);
+  cudaMemcpy(fl.data(), c_flags.p, n * 4, cudaMemcpyDeviceToHost);
+  cudaMemcpy(col.data(), c_colour.p, n * 4, cudaMemcpyDeviceToHost);
+  CUDA_OR_FAIL(cudaMemcpy(bfl.data(), b_flags.p, bodiesSynced_ * 4, cudaMemcpyDeviceToHost), "read flags");
+  std::unordered_map<unsigned long long, int> seen;
+  int conflicts = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if ((fl[i] & (CF_ALIVE | CF_SOLVE)) != (CF_ALIVE | CF_SOLVE)) continue;
+    if (col[i] < 0) { ++conflicts; continue; }
+    const int bs[2] = {ids[i].z, ids[i].w};
+    for (int b : bs) {
+      if (body_type(bfl[b]) != BODY_DYNAMIC) continue;
+      unsigned long long k = ((unsigned long long)(unsigned)b << 32) | (unsigned)col[i];
+      if (++seen[k] > 1) ++conflicts;
+    }
+  }
+  return conflicts;
 }
 
 int World::replicate(int copies) {

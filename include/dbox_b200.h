@@ -267,6 +267,18 @@ int32_t dbx_world_read_pairs(dbx_world* w, int32_t* fixA_childA_fixB_childB, int
  * dbx_world_read_contacts order; lets a test replay the reference's exact sequential order. n=0 clears. */
 int32_t dbx_world_debug_set_contact_levels(dbx_world* w, const int32_t* levels, int32_t n);
 
+/* number of solver-contact pairs that shared a dynamic body AND a colour in the last step (must be 0) */
+int32_t dbx_world_debug_colour_conflicts(dbx_world* w);
+
+/* ---- parity hooks: the device narrowphase / GJK / TOI functions on caller-supplied inputs, one CUDA thread per item.
+ * xf = {p.x, p.y, sin, cos} per item; sweep = {localCenter.xy, c0.xy, c.xy, a0, a, alpha0} per item; chain shapes are
+ * passed as their child edge.  Replaces, for tests: collision/b2collide*.d, b2distance.d:185-347, b2timeofimpact.d:67-302 */
+int32_t dbx_debug_collide(int32_t device, int32_t n, const dbx_shape* shapesA, const float* xfA, const dbx_shape* shapesB, const float* xfB, dbx_manifold* out);
+int32_t dbx_debug_distance(int32_t device, int32_t n, const dbx_shape* shapesA, const float* xfA, const dbx_shape* shapesB, const float* xfB, int32_t useRadii,
+                           float* outDistance, dbx_vec2* outA, dbx_vec2* outB, int32_t* outIterations);
+int32_t dbx_debug_time_of_impact(int32_t device, int32_t n, const dbx_shape* shapesA, const float* sweepsA, const dbx_shape* shapesB, const float* sweepsB,
+                                 float tMax, int32_t* outState, float* outT);
+
 /* ---- batched independent worlds (config 5): replicas of a template share one device world ---- */
 int32_t dbx_world_replicate(dbx_world* w, int32_t copies);  /* world becomes `copies` disjoint replicas of its current content */
 int32_t dbx_world_replica_count(dbx_world* w);

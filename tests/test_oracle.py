@@ -1,0 +1,137 @@
+"""The CPU oracle against (a) its committed golden vectors on the reference's fixed inputs, (b) the reference's own
+in-scene self-checks, (c) physical invariants.  PARITY UNPINNED: see tests/golden/make_golden.py."""
+import ctypes as C
+import json
+import os
+import random
+
+from dbox_b200 import _abi as A
+from dbox_b200 import scenes
+
+GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_golden.json")))
+DT = 1.0 / 60.0
+
+
+def hexf(x):
+    return C.c_float(x).value.hex()
+
+
+def test_hello_world_golden_and_rest(oracle_api):
+    w, body = scenes.hello_world(api=oracle_api)
+    for i in range(60):
+        w.Step(DT, 6, 2)
+        p = body.GetPosition()
+        assert [hexf(p.x), hexf(p.y), hexf(body.GetAngle())] == GOLD["hello_world"][i], i
+    # rests one polygon skin above the ground's top face at y = 0 (hello_world.d:41,52,60,65)
+    assert abs(body.GetPosition().y - 1.015) < 2e-3 and abs(body.GetAngle()) < 1e-4
+    assert w.counts().colours == 1   # exactly one TOI event (the landing)
+
+
+def test_pyramid_golden_stands_and_sleeps(oracle_api):
+    w, bodies = scenes.pyramid(api=oracle_api)
+    hist, sleep = [], None
+    for i in range(400):
+        w.Step(DT, 8, 3)
+        c = w.counts()
+        if i in (0, 10, 20, 50, 100, 399):
+            hist.append([i, c.contacts, c.touching, c.awakeBodies, c.islands])
+        if sleep is None and c.awakeBodies == 0:
+            sleep = i
+        if i % 50 == 0:
+            assert oracle_api.world_tree_validate(w._w) == 1     # b2dynamictree.d:334-352
+    assert hist == GOLD["pyramid"]["history"] and sleep == GOLD["pyramid"]["sleep_step"]
+    p = bodies[-1].GetPosition()
+    assert [hexf(p.x), hexf(p.y), hexf(bodies[-1].GetAngle())] == GOLD["pyramid"]["top"]
+    assert 19.5 < p.y < 19.9                                       # 20 rows high, still standing
+    # max penetration <= b2_linearSlop at rest: adjacent rows are 1 + 2*polygonRadius - penetration apart
+    rows, k = [], 0
+    for r in range(20):
+        rows.append([bodies[k + j].GetPosition().y for j in range(20 - r)])
+        k += 20 - r
+    means = [sum(r) / len(r) for r in rows]
+    # resting gap = 2 * b2_polygonRadius minus the penetration.  The reference algorithm itself goes to sleep 0.008-0.0125
+    # deep here (b2_linearSlop plus Baumgarte lag at 3 position iterations), so "max penetration <= b2_linearSlop" is not
+    # a property of the reference; what holds is that no row sinks through the 0.02 skin.
+    assert all(1.0 + 0.02 - 0.015 < b - a < 1.0 + 0.0205 for a, b in zip(means, means[1:])), means
+
+
+def test_fixed_input_fixtures(oracle_api):
+    api = oracle_api
+    a, b, m = A.Shape(), A.Shape(), A.Manifold()
+    api.shape_set_box(C.byref(a), 0.2, 0.4)
+    api.shape_set_box(C.byref(b), 0.5, 0.5)
+    assert api.collide(C.byref(a), 0.0, 0.0, 0.0, 0, C.byref(b), 19.345284, 1.5632932, 1.9160721, 0, C.byref(m)) == GOLD["polycollision"]["pointCount"]
+    n = api.collide(C.byref(a), 0.0, 0.0, 0.0, 0, C.byref(b), 0.55, 0.3, 1.9160721, 0, C.byref(m))
+    g = GOLD["polycollision_touching"]
+    assert n == g["pointCount"] and m.type == g["type"]
+    assert [hexf(m.localNormal.x), hexf(m.localNormal.y)] == g["localNormal"]
+    assert [[hexf(m.points[i].localPoint.x), hexf(m.points[i].localPoint.y), m.points[i].key] for i in range(n)] == g["points"]
+    api.shape_set_box(C.byref(a), 10.0, 0.2)
+    api.shape_set_box(C.byref(b), 2.0, 0.1)
+    pa, pb, it = A.Vec2(), A.Vec2(), C.c_int32()
+    d = api.distance(C.byref(a), 0.0, -0.2, 0.0, 0, C.byref(b), 12.017401, 0.13678508, -0.0109265, 0, 1, C.byref(pa), C.byref(pb), C.byref(it))
+    assert hexf(d) == GOLD["distancetest"]["distance"] and it.value == GOLD["distancetest"]["iterations"]
+    api.shape_set_box(C.byref(a), 25.0, 5.0)
+    api.shape_set_box(C.byref(b), 2.5, 2.5)
+    sa = (C.c_float * 9)(0, 0, 24.0, -60.0, 24.0, -60.0, 2.95, 2.95, 0)
+    sb = (C.c_float * 9)(0, 0, 53.474274, -50.252514, 54.595478, -51.083473, 513.36676, 513.62781, 0)
+    t = C.c_float()
+    assert api.time_of_impact(C.byref(a), sa, 0, C.byref(b), sb, 0, 1.0, C.byref(t)) == GOLD["timeofimpact"]["state"]
+    assert hexf(t.value) == GOLD["timeofimpact"]["t"]
+
+
+def test_tree_query_equals_brute_force(oracle_api):
+    """port of the reference's in-scene self-check (examples/demo/tests/dynamictreetest.d:320-335): the pair set found
+    through the dynamic tree equals brute-force b2TestOverlap over all fat AABBs."""
+    w, bodies, _ = scenes.pile(api=oracle_api, n=300, columns=15, joints=False)
+    oracle_api.world_stage_find_new_contacts(w._w)
+    pairs = set(w.read_pairs())
+    prox, n = w.read_proxies()
+    ps = sorted([prox[i] for i in range(n)], key=lambda p: p.proxyId)
+    brute = set()
+    for i in range(n):
+        for j in range(i + 1, n):
+            a, b = ps[i].fat, ps[j].fat
+            if b.lo.x - a.hi.x > 0 or b.lo.y - a.hi.y > 0 or a.lo.x - b.hi.x > 0 or a.lo.y - b.hi.y > 0:
+                continue
+            brute.add((ps[i].fixture, ps[i].child, ps[j].fixture, ps[j].child))
+    assert pairs == brute and len(pairs) > 300
+
+
+def test_momentum_and_energy_sanity(oracle_api):
+    """zero gravity, two circles colliding head-on: linear momentum is conserved through the contact solver"""
+    from dbox_b200.world import b2BodyDef, b2CircleShape, b2World, b2_dynamicBody
+    w = b2World((0.0, 0.0), api=oracle_api)
+    bs = []
+    for x, vx in ((-2.0, 3.0), (2.0, -1.0)):
+        bd = b2BodyDef(); bd.type = b2_dynamicBody; bd.position.Set(x, 0.0); bd.linearVelocity.Set(vx, 0.0)
+        b = w.CreateBody(bd)
+        s = b2CircleShape(oracle_api); s.m_radius = 0.5
+        b.CreateFixture(s, 1.0)
+        bs.append(b)
+    p0 = sum(b.GetMass() * b.GetLinearVelocity().x for b in bs)
+    for _ in range(120):
+        w.Step(DT, 8, 3)
+    p1 = sum(b.GetMass() * b.GetLinearVelocity().x for b in bs)
+    assert abs(p0 - p1) < 1e-4 * abs(p0)
+    assert bs[0].GetLinearVelocity().x < 3.0 - 0.5       # they did collide
+
+
+def test_joints_hold_in_pile(oracle_api):
+    """config-4-style pile at small scale: revolute chains keep their anchors together, distance chains their length"""
+    w, bodies, nj = scenes.pile(api=oracle_api, n=600, columns=30, seed=3)
+    assert nj > 20
+    for _ in range(240):
+        w.Step(DT, 8, 3)
+    st, n = w.read_bodies()
+    assert all(abs(st[i].c.x) < 40 and -0.1 < st[i].c.y < 40 for i in range(n) if st[i].type == A.DYNAMIC_BODY)
+    c = w.counts()
+    assert c.touching > 600
+
+
+def test_tumbler_motor_turns_container(oracle_api):
+    t = scenes.Tumbler(api=oracle_api, count=60)
+    for _ in range(200):
+        t.Step()
+    assert t.container.GetAngle() > 0.4          # 0.05*pi rad/s for 200/60 s
+    assert t.world.counts().bodies == 3 + 60
