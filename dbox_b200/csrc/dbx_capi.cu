@@ -141,6 +141,12 @@ int32_t dbx_joint_destroy(dbx_world* w, int32_t joint) { W_OR_INVALID(w); return
 
 int32_t dbx_world_step(dbx_world* w, float dt, int32_t vi, int32_t pi) { W_OR_INVALID(w); return w->w.step(dt, vi, pi, 1); }
 int32_t dbx_world_step_n(dbx_world* w, float dt, int32_t vi, int32_t pi, int32_t n) { W_OR_INVALID(w); return w->w.step(dt, vi, pi, n); }
+int32_t dbx_world_time_steps(dbx_world* w, float dt, int32_t vi, int32_t pi, int32_t n, int32_t flushL2, float* totalMs, float* stageMs) {
+  W_OR_INVALID(w); return w->w.timeSteps(dt, vi, pi, n, flushL2 != 0, totalMs, stageMs);
+}
+int32_t dbx_world_apply_forces(dbx_world* w, const float* fx_fy_torque_pad, int32_t n) { W_OR_INVALID(w); if (!fx_fy_torque_pad && n) return DBX_E_INVALID; return w->w.applyForces(fx_fy_torque_pad, n); }
+int32_t dbx_world_read_transforms(dbx_world* w, float* out, int32_t n) { W_OR_INVALID(w); if (!out && n) return DBX_E_INVALID; return w->w.readTransforms(out, n); }
+int64_t dbx_world_launch_count(dbx_world* w) { return (w && w->w.ok()) ? (int64_t)w->w.launchCount() : 0; }
 int32_t dbx_world_clear_forces(dbx_world* w) { W_OR_INVALID(w); return w->w.clearForces(); }
 
 // ---- body accessors / mutators (dynamics/b2body.d)

@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(256) k_mark_solve(const __grid_constant__ DevW
     }
     if (!solve) {
       if (flags & CF_SOLVE) W.c_flags[i] = flags & ~CF_SOLVE;
-      if (!(flags & CF_TOUCHING) && !W.colourOverride) W.c_colour[i] = -1;   // a colour is held only while the contact is touching
+      if (!W.colourOverride) W.c_colour[i] = -1;   // a colour is held only while the contact is in the solver (and so in the masks)
       continue;
     }
     if (!(flags & CF_SOLVE)) W.c_flags[i] = flags | CF_SOLVE;
@@ -1144,6 +1144,16 @@ __global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld 
   }
 }
 
+__global__ void __launch_bounds__(256) k_apply_forces(const __grid_constant__ DevWorld W, const float4* forces, int n) {
+  GRID_STRIDE(b, n) {
+    const uint32_t f = W.b_flags[b];
+    if (!(f & BF_ALIVE) || body_type(f) != BODY_DYNAMIC || !(f & BF_AWAKE)) continue;
+    const float4 a = forces[b];
+    float4 cur = W.b_force[b];
+    cur.x += a.x; cur.y += a.y; cur.z += a.z;
+    W.b_force[b] = cur;
+  }
+}
 __global__ void __launch_bounds__(256) k_clear_forces(const __grid_constant__ DevWorld W) {
   GRID_STRIDE(b, W.nBodies) W.b_force[b] = make_float4(0, 0, 0, 0);
 }
@@ -1809,40 +1819,43 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
 static cudaError_t launch_coop(const void* fn, const DevWorld& W, const LaunchCfg& L) {
   CK(cudaMemsetAsync(&W.hdr->barrier, 0, sizeof(unsigned), L.stream));
   void* args[] = {(void*)&W};
+  ++L.launches;
   return cudaLaunchCooperativeKernel(fn, dim3(L.coopBlocks), dim3(L.coopThreads), args, 0, L.stream);
 }
 
 cudaError_t stage_collide(const DevWorld& W, const LaunchCfg& L) {
-  k_collide<<<L.gridWide, 256, 0, L.stream>>>(W);
+  ++L.launches; k_collide<<<L.gridWide, 256, 0, L.stream>>>(W);
   return cudaGetLastError();
 }
 
 cudaError_t stage_islands_and_integrate(const DevWorld& W, const LaunchCfg& L) {
-  k_island_init<<<L.gridWide, 256, 0, L.stream>>>(W);
-  k_island_union<<<L.gridWide, 256, 0, L.stream>>>(W);
-  k_island_flatten<<<L.gridWide, 256, 0, L.stream>>>(W);
-  k_island_wake_integrate<<<L.gridWide, 256, 0, L.stream>>>(W);
+  ++L.launches; k_island_init<<<L.gridWide, 256, 0, L.stream>>>(W);
+  ++L.launches; k_island_union<<<L.gridWide, 256, 0, L.stream>>>(W);
+  ++L.launches; k_island_flatten<<<L.gridWide, 256, 0, L.stream>>>(W);
+  ++L.launches; k_island_wake_integrate<<<L.gridWide, 256, 0, L.stream>>>(W);
   return cudaGetLastError();
 }
 
 cudaError_t stage_colour_and_sort(const DevWorld& W, const LaunchCfg& L) {
-  k_mark_solve<<<L.gridWide, 256, 0, L.stream>>>(W);
+  ++L.launches; k_mark_solve<<<L.gridWide, 256, 0, L.stream>>>(W);
   CK(cudaGetLastError());
   if (!W.colourOverride) CK(launch_coop((const void*)k_colour, W, L));
-  k_sort_hist<<<kSortBlocks, 256, 0, L.stream>>>(W);
-  k_sort_scan<<<1, kMaxColours, 0, L.stream>>>(W, kSortBlocks);
-  k_sort_scatter<<<kSortBlocks, 256, 0, L.stream>>>(W);
+  ++L.launches; k_sort_hist<<<kSortBlocks, 256, 0, L.stream>>>(W);
+  ++L.launches; k_sort_scan<<<1, kMaxColours, 0, L.stream>>>(W, kSortBlocks);
+  ++L.launches; k_sort_scatter<<<kSortBlocks, 256, 0, L.stream>>>(W);
   return cudaGetLastError();
 }
 
+cudaError_t stage_prepare(const DevWorld& W, const LaunchCfg& L) {
+  ++L.launches; k_prepare<<<L.gridWide, 256, 0, L.stream>>>(W);
+  return cudaGetLastError();
+}
 cudaError_t stage_solve(const DevWorld& W, const LaunchCfg& L) {
-  k_prepare<<<L.gridWide, 256, 0, L.stream>>>(W);
-  CK(cudaGetLastError());
   return launch_coop((const void*)k_solve, W, L);
 }
 
 cudaError_t stage_sync_fixtures(const DevWorld& W, const LaunchCfg& L) {
-  k_sync_fixtures<<<L.gridWide, 256, 0, L.stream>>>(W);
+  ++L.launches; k_sync_fixtures<<<L.gridWide, 256, 0, L.stream>>>(W);
   return cudaGetLastError();
 }
 
@@ -1860,10 +1873,10 @@ cudaError_t stage_toi(DevWorld& W, const LaunchCfg& L) {
 
 cudaError_t stage_find_new_contacts(DevWorld& W, const LaunchCfg& L) {
   const int n = W.nProxies;
-  k_bounds_init<<<1, 1, 0, L.stream>>>(W);
+  ++L.launches; k_bounds_init<<<1, 1, 0, L.stream>>>(W);
   if (n > 0) {
-    k_bounds<<<L.gridWide, 256, 0, L.stream>>>(W);
-    k_morton<<<L.gridWide, 256, 0, L.stream>>>(W);
+    ++L.launches; k_bounds<<<L.gridWide, 256, 0, L.stream>>>(W);
+    ++L.launches; k_morton<<<L.gridWide, 256, 0, L.stream>>>(W);
     cub::DoubleBuffer<unsigned long long> keys(W.bv_key, W.bv_keyAlt);
     cub::DoubleBuffer<int> vals(W.bv_leaf, W.bv_leafAlt);
     int worldBits = 1;
@@ -1873,48 +1886,52 @@ cudaError_t stage_find_new_contacts(DevWorld& W, const LaunchCfg& L) {
     const unsigned long long* sk = keys.Current();
     const int* sl = vals.Current();
     W.bv_sorted = sl;
-    if (n > 1) k_lbvh_hierarchy<<<L.gridWide, 256, 0, L.stream>>>(W, sk);
-    k_lbvh_refit<<<L.gridWide, 256, 0, L.stream>>>(W, sl);
-    k_query<<<L.gridWide, 256, 0, L.stream>>>(W, sl);
-    k_add_pairs<<<L.gridWide, 256, 0, L.stream>>>(W);
+    if (n > 1) ++L.launches; k_lbvh_hierarchy<<<L.gridWide, 256, 0, L.stream>>>(W, sk);
+    ++L.launches; k_lbvh_refit<<<L.gridWide, 256, 0, L.stream>>>(W, sl);
+    ++L.launches; k_query<<<L.gridWide, 256, 0, L.stream>>>(W, sl);
+    ++L.launches; k_add_pairs<<<L.gridWide, 256, 0, L.stream>>>(W);
   }
-  k_clear_moves<<<L.gridWide, 256, 0, L.stream>>>(W);
-  k_reset_moves<<<1, 1, 0, L.stream>>>(W);
+  ++L.launches; k_clear_moves<<<L.gridWide, 256, 0, L.stream>>>(W);
+  ++L.launches; k_reset_moves<<<1, 1, 0, L.stream>>>(W);
   return cudaGetLastError();
 }
 
 cudaError_t stage_rebuild_hash(const DevWorld& W, const LaunchCfg& L) {
-  k_hash_clear<<<L.gridWide, 256, 0, L.stream>>>(W);
-  k_hash_fill<<<L.gridWide, 256, 0, L.stream>>>(W);
+  ++L.launches; k_hash_clear<<<L.gridWide, 256, 0, L.stream>>>(W);
+  ++L.launches; k_hash_fill<<<L.gridWide, 256, 0, L.stream>>>(W);
   return cudaGetLastError();
 }
 
 cudaError_t stage_count(const DevWorld& W, const LaunchCfg& L) {
-  k_count_reset<<<1, 1, 0, L.stream>>>(W);
-  k_count<<<L.gridWide, 256, 0, L.stream>>>(W);
+  ++L.launches; k_count_reset<<<1, 1, 0, L.stream>>>(W);
+  ++L.launches; k_count<<<L.gridWide, 256, 0, L.stream>>>(W);
   return cudaGetLastError();
 }
 
 cudaError_t launch_insert_contacts(const DevWorld& W, const LaunchCfg& L, int n) {
-  k_import_reset<<<1, 1, 0, L.stream>>>(W, n);
+  ++L.launches; k_import_reset<<<1, 1, 0, L.stream>>>(W, n);
   return stage_rebuild_hash(W, L);
 }
 
 cudaError_t launch_api_contacts(const DevWorld& W, const LaunchCfg& L, int body, int fixture, int otherBody, int flagOnly) {
-  k_api_contacts<<<L.gridWide, 256, 0, L.stream>>>(W, body, fixture, otherBody, flagOnly);
+  ++L.launches; k_api_contacts<<<L.gridWide, 256, 0, L.stream>>>(W, body, fixture, otherBody, flagOnly);
   return cudaGetLastError();
 }
 cudaError_t launch_api_wake(const DevWorld& W, const LaunchCfg& L, int a, int b) {
-  k_api_wake<<<1, 1, 0, L.stream>>>(W, a, b);
+  ++L.launches; k_api_wake<<<1, 1, 0, L.stream>>>(W, a, b);
+  return cudaGetLastError();
+}
+cudaError_t launch_apply_forces(const DevWorld& W, const LaunchCfg& L, const float4* forces, int n) {
+  ++L.launches; k_apply_forces<<<L.gridWide, 256, 0, L.stream>>>(W, forces, n);
   return cudaGetLastError();
 }
 cudaError_t launch_clear_forces(const DevWorld& W, const LaunchCfg& L) {
-  k_clear_forces<<<L.gridWide, 256, 0, L.stream>>>(W);
+  ++L.launches; k_clear_forces<<<L.gridWide, 256, 0, L.stream>>>(W);
   return cudaGetLastError();
 }
 
 cudaError_t launch_set_levels(const DevWorld& W, const LaunchCfg& L, const int* d_levels, int n) {
-  k_set_levels<<<L.gridWide, 256, 0, L.stream>>>(W, d_levels, n);
+  ++L.launches; k_set_levels<<<L.gridWide, 256, 0, L.stream>>>(W, d_levels, n);
   return cudaGetLastError();
 }
 

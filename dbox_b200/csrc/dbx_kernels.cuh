@@ -11,13 +11,15 @@ struct LaunchCfg {
   int coopThreads = 512;
   cudaStream_t stream = 0;
   void* cubTemp = nullptr; size_t cubTempBytes = 0;
+  mutable long launches = 0;   // kernels of this library launched so far (CUB's radix-sort kernels are not counted)
 };
 
 // stages of b2World.Step (dynamics/b2world.d:367-434); each returns the first CUDA error
 cudaError_t stage_collide(const DevWorld& W, const LaunchCfg& L);                 // b2ContactManager.Collide
 cudaError_t stage_islands_and_integrate(const DevWorld& W, const LaunchCfg& L);   // island discovery + wake + integrate velocities
 cudaError_t stage_colour_and_sort(const DevWorld& W, const LaunchCfg& L);         // graph colouring + colour counting sort
-cudaError_t stage_solve(const DevWorld& W, const LaunchCfg& L);                   // prepare + warm start + iterations + finalize + sleep
+cudaError_t stage_prepare(const DevWorld& W, const LaunchCfg& L);                 // contact constraint setup
+cudaError_t stage_solve(const DevWorld& W, const LaunchCfg& L);                   // warm start + iterations + finalize + sleep (one persistent kernel)
 cudaError_t stage_sync_fixtures(const DevWorld& W, const LaunchCfg& L);           // b2Body.SynchronizeFixtures / MoveProxy
 cudaError_t stage_find_new_contacts(DevWorld& W, const LaunchCfg& L);       // LBVH rebuild + pair query + AddPair
 cudaError_t stage_toi(DevWorld& W, const LaunchCfg& L);                               // b2World.SolveTOI
@@ -29,6 +31,7 @@ size_t cub_temp_bytes(int maxProxies);
 cudaError_t launch_insert_contacts(const DevWorld& W, const LaunchCfg& L, int n);  // (re)build hash + free list for slots [0,n)
 cudaError_t launch_api_contacts(const DevWorld& W, const LaunchCfg& L, int body, int fixture, int otherBody, int flagOnly);
 cudaError_t launch_api_wake(const DevWorld& W, const LaunchCfg& L, int a, int b);
+cudaError_t launch_apply_forces(const DevWorld& W, const LaunchCfg& L, const float4* forces, int n);
 cudaError_t launch_clear_forces(const DevWorld& W, const LaunchCfg& L);
 cudaError_t launch_set_levels(const DevWorld& W, const LaunchCfg& L, const int* d_levels, int n);
 

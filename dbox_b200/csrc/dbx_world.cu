@@ -678,46 +678,99 @@ int World::checkDeviceError(bool sync) {
   return 0;
 }
 
-// b2World.Step (dynamics/b2world.d:367-434), n times without host round trips in between
+// one b2World.Step (dynamics/b2world.d:367-434) enqueued on the world's stream; no host synchronisation
+int World::enqueueStep(float dt, int vi, int pi, bool fineEvents) {
+  int rc = push(); if (rc < 0) return rc;
+  if (bodies_.empty()) return 0;
+  if (newFixture_) { CUDA_OR_FAIL(stage_find_new_contacts(dw_, L_), "find_new_contacts"); newFixture_ = false; }   // :372-376
+  setStepParams(dt, vi, pi);
+  dw_.colourOverride = overrideLevels_ ? 1 : 0;
+  auto mark = [&](int i) { if (fineEvents || i == 0 || i == 1 || i == 3 || i == 5 || i == 7 || i == 8 || i == 9) cudaEventRecord(ev_[i], stream_); };
+  mark(0);
+  CUDA_OR_FAIL(stage_collide(dw_, L_), "collide");
+  mark(1);
+  if (stepComplete_ && dt > 0.0f) {
+    CUDA_OR_FAIL(stage_islands_and_integrate(dw_, L_), "islands");
+    mark(2);
+    CUDA_OR_FAIL(stage_colour_and_sort(dw_, L_), "colour");
+    mark(3);
+    CUDA_OR_FAIL(stage_prepare(dw_, L_), "prepare");
+    mark(4);
+    CUDA_OR_FAIL(stage_solve(dw_, L_), "solve");
+    mark(5);
+    CUDA_OR_FAIL(stage_sync_fixtures(dw_, L_), "sync_fixtures");
+    mark(6);
+    CUDA_OR_FAIL(stage_find_new_contacts(dw_, L_), "find_new_contacts");
+    mark(7);
+  } else {
+    for (int i = 2; i <= 7; ++i) cudaEventRecord(ev_[i], stream_);
+  }
+  if ((flags_ & DBX_WORLD_CONTINUOUS) && dt > 0.0f) CUDA_OR_FAIL(stage_toi(dw_, L_), "toi");   // :414-419
+  mark(8);
+  if (dt > 0.0f) inv_dt0 = dw_.inv_dt;
+  if (flags_ & DBX_WORLD_AUTO_CLEAR_FORCES) CUDA_OR_FAIL(launch_clear_forces(dw_, L_), "clear_forces");
+  mark(9);
+  evValid_ = true; evFine_ = fineEvents;
+  ++stepCount_;
+  if (overrideLevels_) {   // one-shot: hand the colours back to the colouring pass
+    overrideLevels_ = false; dw_.colourOverride = 0;
+    CUDA_OR_FAIL(cudaMemsetAsync(c_colour.p, 0xFF, c_colour.cap * 4, stream_), "reset colours");
+  }
+  if ((stepCount_ & 63) == 0) CUDA_OR_FAIL(stage_rebuild_hash(dw_, L_), "rehash");
+  hostBodiesValid_ = false; hostProxiesValid_ = false; hostJointsValid_ = false;
+  return 0;
+}
+
+// n steps without host round trips in between; one synchronisation at the end
 int World::step(float dt, int vi, int pi, int n) {
   if (!ok_) return DBX_E_NO_DEVICE;
   cudaSetDevice(device_);
-  for (int k = 0; k < n; ++k) {
-    int rc = push(); if (rc < 0) return rc;
-    if (bodies_.empty()) continue;
-    if (newFixture_) { CUDA_OR_FAIL(stage_find_new_contacts(dw_, L_), "find_new_contacts"); newFixture_ = false; }   // :372-376
-    setStepParams(dt, vi, pi);
-    dw_.colourOverride = overrideLevels_ ? 1 : 0;
-    cudaEventRecord(ev_[0], stream_);
-    CUDA_OR_FAIL(stage_collide(dw_, L_), "collide");
-    cudaEventRecord(ev_[1], stream_);
-    if (stepComplete_ && dt > 0.0f) {
-      CUDA_OR_FAIL(stage_islands_and_integrate(dw_, L_), "islands");
-      CUDA_OR_FAIL(stage_colour_and_sort(dw_, L_), "colour");
-      cudaEventRecord(ev_[2], stream_);
-      CUDA_OR_FAIL(stage_solve(dw_, L_), "solve");
-      cudaEventRecord(ev_[3], stream_);
-      CUDA_OR_FAIL(stage_sync_fixtures(dw_, L_), "sync_fixtures");
-      CUDA_OR_FAIL(stage_find_new_contacts(dw_, L_), "find_new_contacts");
-      cudaEventRecord(ev_[4], stream_);
-    } else {
-      cudaEventRecord(ev_[2], stream_); cudaEventRecord(ev_[3], stream_); cudaEventRecord(ev_[4], stream_);
-    }
-    if ((flags_ & DBX_WORLD_CONTINUOUS) && dt > 0.0f) CUDA_OR_FAIL(stage_toi(dw_, L_), "toi");   // :414-419
-    cudaEventRecord(ev_[5], stream_);
-    if (dt > 0.0f) inv_dt0 = dw_.inv_dt;
-    if (flags_ & DBX_WORLD_AUTO_CLEAR_FORCES) CUDA_OR_FAIL(launch_clear_forces(dw_, L_), "clear_forces");
-    cudaEventRecord(ev_[6], stream_);
-    evValid_ = true;
-    ++stepCount_;
-    if (overrideLevels_) {   // one-shot: hand the colours back to the colouring pass
-      overrideLevels_ = false; dw_.colourOverride = 0;
-      CUDA_OR_FAIL(cudaMemsetAsync(c_colour.p, 0xFF, c_colour.cap * 4, stream_), "reset colours");
-    }
-    if ((stepCount_ & 63) == 0) CUDA_OR_FAIL(stage_rebuild_hash(dw_, L_), "rehash");
-    hostBodiesValid_ = false; hostProxiesValid_ = false; hostJointsValid_ = false;
-  }
+  for (int k = 0; k < n; ++k) { int rc = enqueueStep(dt, vi, pi, false); if (rc < 0) return rc; }
   return checkDeviceError(true);
+}
+
+// Benchmark helper: n steps, each bracketed by CUDA events ON THE WORLD'S STREAM; optionally a >L2-sized buffer is
+// overwritten between steps (outside the timed brackets) so no step starts with the previous step's lines in L2.
+// totalMs = sum of the per-step brackets; stageMs[9] = average per step of
+// {collide, islands+integrate, colour+sort, prepare, solve, sync_fixtures, find_new_contacts, toi, clear_forces}.
+int World::timeSteps(float dt, int vi, int pi, int n, bool flushL2, float* totalMs, float* stageMs) {
+  if (!ok_) return DBX_E_NO_DEVICE;
+  cudaSetDevice(device_);
+  const size_t flushBytes = 256u << 20;
+  if (flushL2) CUDA_OR_FAIL(flushBuf_.reserve(flushBytes, false, stream_), "flush buffer");
+  double total = 0.0, stage[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = 0; k < n; ++k) {
+    int rc = enqueueStep(dt, vi, pi, true); if (rc < 0) return rc;
+    if (bodies_.empty()) continue;
+    if (flushL2) CUDA_OR_FAIL(cudaMemsetAsync(flushBuf_.p, k & 0xFF, flushBytes, stream_), "l2 flush");
+    CUDA_OR_FAIL(cudaEventSynchronize(ev_[9]), "event sync");
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, ev_[0], ev_[9]);
+    total += ms;
+    for (int i = 0; i < 9; ++i) { float t = 0.0f; cudaEventElapsedTime(&t, ev_[i], ev_[i + 1]); stage[i] += t; }
+  }
+  if (totalMs) *totalMs = (float)total;
+  if (stageMs) for (int i = 0; i < 9; ++i) stageMs[i] = n > 0 ? (float)(stage[i] / n) : 0.0f;
+  return checkDeviceError(true);
+}
+
+// RL-style per-step I/O: add (fx, fy, torque) to every awake dynamic body (b2Body.ApplyForceToCenter + ApplyTorque with
+// wake = false, b2body.d:390-431) from a host buffer, and read all body transforms back into a host buffer.
+int World::applyForces(const float* f4, int n) {
+  int rc = push(); if (rc < 0) return rc;
+  if (n > (int)bodies_.size()) return DBX_E_INVALID;
+  CUDA_OR_FAIL(ioBuf_.reserve(std::max<size_t>(bodies_.size(), 1), false, stream_), "io buffer");
+  CUDA_OR_FAIL(cudaMemcpyAsync(ioBuf_.p, f4, (size_t)n * 16, cudaMemcpyHostToDevice, stream_), "forces h2d");
+  CUDA_OR_FAIL(launch_apply_forces(dw_, L_, ioBuf_.p, n), "apply_forces");
+  hostBodiesValid_ = false;
+  return n;
+}
+int World::readTransforms(float* out, int n) {
+  int rc = push(); if (rc < 0) return rc;
+  if (n > (int)bodies_.size()) return DBX_E_INVALID;
+  CUDA_OR_FAIL(cudaMemcpyAsync(out, b_xf.p, (size_t)n * 16, cudaMemcpyDeviceToHost, stream_), "xf d2h");
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  return n;
 }
 
 int World::clearForces() {
@@ -815,11 +868,11 @@ int World::profile(dbx_profile* out) {
   CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
   float collide = 0, pre = 0, solve = 0, bp = 0, toi = 0, total = 0;
   cudaEventElapsedTime(&collide, ev_[0], ev_[1]);
-  cudaEventElapsedTime(&pre, ev_[1], ev_[2]);
-  cudaEventElapsedTime(&solve, ev_[2], ev_[3]);
-  cudaEventElapsedTime(&bp, ev_[3], ev_[4]);
-  cudaEventElapsedTime(&toi, ev_[4], ev_[5]);
-  cudaEventElapsedTime(&total, ev_[0], ev_[6]);
+  cudaEventElapsedTime(&pre, ev_[1], ev_[3]);
+  cudaEventElapsedTime(&solve, ev_[3], ev_[5]);
+  cudaEventElapsedTime(&bp, ev_[5], ev_[7]);
+  cudaEventElapsedTime(&toi, ev_[7], ev_[8]);
+  cudaEventElapsedTime(&total, ev_[0], ev_[9]);
   out->step = total; out->collide = collide; out->solve = pre + solve + bp; out->solveInit = pre; out->solveVelocity = solve;
   out->solvePosition = 0.0f; out->broadphase = bp; out->solveTOI = toi;
   return 0;

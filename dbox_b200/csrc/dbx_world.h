@@ -59,6 +59,11 @@ class World {
   int createJoint(const dbx_joint_def& d);
   int destroyJoint(int j);
   int step(float dt, int vi, int pi, int n);
+  int enqueueStep(float dt, int vi, int pi, bool fineEvents);
+  int timeSteps(float dt, int vi, int pi, int n, bool flushL2, float* totalMs, float* stageMs);
+  int applyForces(const float* f4, int n);
+  int readTransforms(float* out, int n);
+  long launchCount() const { return L_.launches; }
   int clearForces();
   int setFlags(uint32_t f);
   uint32_t flags() const { return flags_; }
@@ -149,8 +154,9 @@ class World {
   DevBuf<int4> j_ids; DevBuf<float4> j_anchor, j_p0, j_p1, j_imp, j_r, j_lc, j_m, j_k0, j_k1, j_k2; DevBuf<int> j_limit, j_colour, j_order, j_root;
   DevBuf<char> cubTemp; DevBuf<int> d_levels;
   int nJointPairs_ = 0;
-  cudaEvent_t ev_[8]{};
-  bool evValid_ = false;
+  cudaEvent_t ev_[10]{};
+  bool evValid_ = false, evFine_ = false;
+  DevBuf<char> flushBuf_; DevBuf<float4> ioBuf_;
   bool overrideLevels_ = false;
   std::vector<int> lastReadSlots_;
 };

@@ -230,6 +230,16 @@ int32_t dbx_world_step(dbx_world* w, float dt, int32_t velocityIterations, int32
 int32_t dbx_world_step_n(dbx_world* w, float dt, int32_t velocityIterations, int32_t positionIterations, int32_t n);
 int32_t dbx_world_clear_forces(dbx_world* w);                          /* b2world.d:443-450 */
 
+/* measurement + bulk per-step I/O (RL loops): n steps each bracketed by CUDA events on the world's stream, optional >L2
+ * flush between steps (untimed); stageMs[9] = average ms of {collide, islands, colour+sort, prepare, solve, sync_fixtures,
+ * find_new_contacts, toi, clear_forces}.  apply_forces adds (fx, fy, torque, -) per body like b2Body.ApplyForceToCenter /
+ * ApplyTorque with wake=false (b2body.d:390-431); read_transforms returns (p.x, p.y, sin, cos) per body. */
+int32_t dbx_world_time_steps(dbx_world* w, float dt, int32_t velocityIterations, int32_t positionIterations, int32_t n, int32_t flushL2,
+                             float* totalMs, float* stageMs);
+int32_t dbx_world_apply_forces(dbx_world* w, const float* fx_fy_torque_pad, int32_t n);
+int32_t dbx_world_read_transforms(dbx_world* w, float* out, int32_t n);
+int64_t dbx_world_launch_count(dbx_world* w);   /* kernels of this library launched so far on this world */
+
 /* ---- body accessors / mutators: dynamics/b2body.d ---- */
 int32_t dbx_body_get_state(dbx_world* w, int32_t body, dbx_body_state* out);
 int32_t dbx_body_set_transform(dbx_world* w, int32_t body, float x, float y, float angle);   /* b2body.d:261-285 */

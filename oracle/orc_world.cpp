@@ -6,9 +6,9 @@
 
 namespace orc {
 
-static float nowMs() {
+static double nowMs() {
   using namespace std::chrono;
-  return duration<float, std::milli>(steady_clock::now().time_since_epoch()).count();
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
 // ------------------------------------------------------------------ Body
@@ -756,7 +756,7 @@ struct Island {
 
   // b2island.d:75-280
   void solve(Profile* profile, const TimeStep& step, V2 gravity, bool allowSleep) {
-    float t0 = nowMs();
+    double t0 = nowMs();
     float h = step.dt;
     int bodyCount = (int)bodies.size();
     positions.resize(bodyCount); velocities.resize(bodyCount);
@@ -780,13 +780,13 @@ struct Island {
     contactSolver.initializeVelocityConstraints();
     if (step.warmStarting) contactSolver.warmStart();
     for (Joint* j : joints) j->initVelocityConstraints(solverData);
-    float t1 = nowMs(); profile->solveInit = t1 - t0;
+    double t1 = nowMs(); profile->solveInit = (float)(t1 - t0);
     for (int i = 0; i < step.velocityIterations; ++i) {
       for (Joint* j : joints) j->solveVelocityConstraints(solverData);
       contactSolver.solveVelocityConstraints();
     }
     contactSolver.storeImpulses();
-    float t2 = nowMs(); profile->solveVelocity = t2 - t1;
+    double t2 = nowMs(); profile->solveVelocity = (float)(t2 - t1);
     for (int i = 0; i < bodyCount; ++i) {
       V2 c = positions[i].c; float a = positions[i].a;
       V2 v = velocities[i].v; float w = velocities[i].w;
@@ -818,7 +818,7 @@ struct Island {
       b->linearVelocity = velocities[i].v; b->angularVelocity = velocities[i].w;
       b->synchronizeTransform();
     }
-    profile->solvePosition = nowMs() - t2;
+    profile->solvePosition = (float)(nowMs() - t2);
     if (allowSleep) {
       float minSleepTime = kMaxFloat;
       const float linTolSqr = kLinearSleepTolerance * kLinearSleepTolerance;
@@ -941,14 +941,14 @@ void World::solve(const TimeStep& step) {
     profile.solveInit += p.solveInit; profile.solveVelocity += p.solveVelocity; profile.solvePosition += p.solvePosition;
     for (Body* b : island.bodies) if (b->type == kStatic) b->flags &= ~bIsland;
   }
-  float t0 = nowMs();
+  double t0 = nowMs();
   for (Body* b = bodyList; b; b = b->next) {
     if ((b->flags & bIsland) == 0) continue;
     if (b->type == kStatic) continue;
     b->synchronizeFixtures();
   }
   findNewContacts();
-  profile.broadphase = nowMs() - t0;
+  profile.broadphase = (float)(nowMs() - t0);
 }
 
 // ------------------------------------------------------------------ World::solveTOI (b2world.d:1127-1452)
@@ -1066,7 +1066,7 @@ void World::solveTOI(const TimeStep& step) {
 
 // ------------------------------------------------------------------ World::step (b2world.d:367-434)
 void World::step(float dt, int velocityIterations, int positionIterations) {
-  float t0 = nowMs();
+  double t0 = nowMs();
   if (newFixture) { findNewContacts(); newFixture = false; }
   locked = true;
   TimeStep step;
@@ -1076,13 +1076,13 @@ void World::step(float dt, int velocityIterations, int positionIterations) {
   step.inv_dt = dt > 0.0f ? 1.0f / dt : 0.0f;
   step.dtRatio = inv_dt0 * dt;
   step.warmStarting = warmStarting;
-  { float t = nowMs(); collide(); profile.collide = nowMs() - t; }
-  if (stepComplete && step.dt > 0.0f) { float t = nowMs(); solve(step); profile.solve = nowMs() - t; }
-  if (continuousPhysics && step.dt > 0.0f) { float t = nowMs(); solveTOI(step); profile.solveTOI = nowMs() - t; }
+  { double t = nowMs(); collide(); profile.collide = (float)(nowMs() - t); }
+  if (stepComplete && step.dt > 0.0f) { double t = nowMs(); solve(step); profile.solve = (float)(nowMs() - t); }
+  if (continuousPhysics && step.dt > 0.0f) { double t = nowMs(); solveTOI(step); profile.solveTOI = (float)(nowMs() - t); }
   if (step.dt > 0.0f) inv_dt0 = step.inv_dt;
   if (clearForcesFlag) clearForces();
   locked = false;
-  profile.step = nowMs() - t0;
+  profile.step = (float)(nowMs() - t0);
 }
 
 void World::clearForces() {
