@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's headline metric on B200: body-steps/s of the 100k-body pile at 8 velocity / 3 position
+iterations (config 4), one world per GPU.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA path through the C ABI)
+  python bench.py --impl reference --gpus N ...            # the reference algorithm's CPU path (oracle port) on host cores
+
+A "step" is one b2World.Step of the settled pile.  `value` is timed with CUDA events on the world's own stream with
+all state resident in HBM; `e2e` drives the same steps through the public API with host buffers (per-step H2D of a
+force array from pinned memory and D2H of all body transforms).  A single large world does not shard:
+with N > 1 every rank steps its own replica of the pile ("replicas only", weak scaling, no data-path collective; NCCL
+only reduces the timing).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
+UNIT = "body-steps/s"
+DT, VEL_ITERS, POS_ITERS = 1.0 / 60.0, 8, 3
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def algorithmic_bytes_solve(ct, nb, n_rev, n_dist, iv, ip):
+    """compulsory traffic of what the persistent solve kernel does in one launch: contact warm start
+    (128), Iv velocity iterations (212 each), store impulses (32), Ip position iterations (136 each) per solver contact;
+    integrate positions (48), write-back + transform (64) and sleep bookkeeping (24) per awake body; joints: prep + Iv*vel +
+    Ip*pos (revolute 200/164/120, distance 150/116/112)."""
+    contact = (128 + 212 * iv + 32 + 136 * ip) * ct
+    body = (48 + 64 + 24) * nb
+    joints = n_rev * (200 + 164 * iv + 120 * ip) + n_dist * (150 + 116 * iv + 112 * ip)
+    return contact + body + joints
+
+
+def run_cpu_port(n_bodies, columns, settle, steps, warmup, threads=1, replicas=1):
+    """the reference algorithm's CPU path (oracle/liborc.so, a C++ restatement of dbox): one world per thread"""
+    from oracle import orc
+    from dbox_b200 import scenes
+    api = orc.api()
+    worlds = []
+    for r in range(replicas):
+        w, _, _ = scenes.pile(api=api, n=n_bodies, columns=columns, seed=12345 + r)
+        w.SetAllowSleeping(False)
+        worlds.append(w)
+    arr = (C.c_void_p * replicas)(*[w._w for w in worlds])
+    api.batch_step(arr, replicas, DT, VEL_ITERS, POS_ITERS, settle + warmup, threads)
+    secs = api.batch_step(arr, replicas, DT, VEL_ITERS, POS_ITERS, steps, threads)
+    c = worlds[0].counts()
+    return replicas * n_bodies * steps / secs, secs, c
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bodies", type=int, default=100000)
+    ap.add_argument("--columns", type=int, default=1000)
+    ap.add_argument("--settle", type=int, default=600, help="untimed steps that let the pile settle before warm-up (SURVEY.md 8(d))")
+    ap.add_argument("--no-l2-flush", action="store_true")
+    ap.add_argument("--cpu-bodies", type=int, default=10000, help="bounded CPU sample: same generator and pile depth, fewer columns")
+    ap.add_argument("--cpu-steps", type=int, default=60)
+    ap.add_argument("--cpu-settle", type=int, default=240)
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--save-state", default=None, help="write the settled world state here (profiling runs reload it instead of settling)")
+    ap.add_argument("--load-state", default=None)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = max(args.gpus, world_size)
+    W = max(args.warmup, 3)
+    K = args.steps
+    rows = (args.bodies + args.columns - 1) // args.columns
+    cpu_cols = max(1, args.cpu_bodies // rows)
+    cpu_bodies = cpu_cols * rows
+    cores = os.cpu_count() or 1
+    config = {"workload": "C4: %d-body box/circle pile with revolute + distance joint chains, 60 Hz, %dv/%dp, sleeping off, one world per GPU"
+                          % (args.bodies, VEL_ITERS, POS_ITERS),
+              "bodies": args.bodies, "columns": args.columns, "settle_steps": args.settle,
+              "parallelism": "replicas only (a single world does not shard); %d independent world(s)" % n_gpus,
+              "l2": "256 MiB buffer overwritten between timed steps (outside the event brackets)" if not args.no_l2_flush else "no flush"}
+
+    # ------------------------------------------------------------------ reference arm: the CPU path on host cores
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        threads = max(1, min(n_gpus, cores))
+        steps = max(1, min(K, args.cpu_steps))
+        t0 = time.time()
+        value, secs, c = run_cpu_port(cpu_bodies, cpu_cols, args.cpu_settle, steps, W, threads=threads, replicas=threads)
+        sample = ("%d replica(s) of a %d-body pile (same generator, same %d-row depth, %d columns), %d settle + %d warm-up + %d timed steps, "
+                  "one world per thread" % (threads, cpu_bodies, rows, cpu_cols, args.cpu_settle, W, steps))
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": W,
+                "ms_per_step": 1e3 * secs / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "wall_s": time.time() - t0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------ our arm: CUDA path through the C ABI
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: dbox_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world_size, device_id=torch.device("cuda", local_rank))
+    from dbox_b200 import _abi as A
+    from dbox_b200 import lib, scenes
+    api = lib.api()
+
+    world, bodies, n_joints = scenes.pile(api=api, n=args.bodies, columns=args.columns, seed=12345 + rank, device=local_rank)
+    world.SetAllowSleeping(False)
+    n_rev = sum(1 for j in world._joints.values() if True)  # refined below from the scene definition
+    if args.load_state:
+        from dbox_b200 import state
+        state.load(world, args.load_state)
+    world.StepN(DT, VEL_ITERS, POS_ITERS, args.settle)
+    if args.save_state and rank == 0:
+        from dbox_b200 import state
+        state.save(world, args.save_state)
+
+    tot = C.c_float()
+    stage = (C.c_float * 9)()
+    flush = 0 if args.no_l2_flush else 1
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up (untimed)
+    rc = api.world_time_steps(world._w, DT, VEL_ITERS, POS_ITERS, W, flush, C.byref(tot), stage)
+    assert rc >= 0, api.last_error()
+    launches0 = api.world_launch_count(world._w)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t_wall = time.time()
+    rc = api.world_time_steps(world._w, DT, VEL_ITERS, POS_ITERS, K, flush, C.byref(tot), stage)
+    assert rc >= 0, api.last_error()
+    barrier()
+    wall = time.time() - t_wall
+    clocks = sampler.stop()
+    launches = api.world_launch_count(world._w) - launches0
+    dev_ms = torch.tensor([tot.value], dtype=torch.float64, device="cuda")
+    if world_size > 1:
+        dist.all_reduce(dev_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(dev_ms.item())
+    counts = world.counts()
+    stage_ms = [float(x) for x in stage]
+
+    # ---- e2e: same steps through the public API with host buffers (pinned), H2D + D2H inside the timed region
+    n = args.bodies + 1
+    forces = torch.zeros((n, 4), dtype=torch.float32).pin_memory()
+    xf_out = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+    Ke = min(K, 100)
+    for _ in range(3):
+        api.world_apply_forces(world._w, forces.data_ptr(), n); world.Step(DT, VEL_ITERS, POS_ITERS); api.world_read_transforms(world._w, xf_out.data_ptr(), n)
+    barrier()
+    t0 = time.time()
+    for _ in range(Ke):
+        assert api.world_apply_forces(world._w, forces.data_ptr(), n) == n
+        world.Step(DT, VEL_ITERS, POS_ITERS)
+        assert api.world_read_transforms(world._w, xf_out.data_ptr(), n) == n
+    barrier()
+    e2e_s = torch.tensor([time.time() - t0], dtype=torch.float64, device="cuda")
+    if world_size > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = n_gpus * args.bodies * Ke / float(e2e_s.item())
+
+    if rank == 0:
+        value = n_gpus * args.bodies * K / (total_ms / 1e3)
+        peak, peak_src = peaks()
+        # joints of the scene: revolute chains on every 10th column, distance chains on every 10th row (dbox_b200/scenes.py)
+        js, nj = world.read_joints()
+        n_rev = sum(1 for i in range(nj) if js[i].type == A.JOINT_REVOLUTE)
+        n_dist = sum(1 for i in range(nj) if js[i].type == A.JOINT_DISTANCE)
+        solve_ms = stage_ms[4]
+        alg = algorithmic_bytes_solve(counts.touching, counts.awakeBodies, n_rev, n_dist, VEL_ITERS, POS_ITERS)
+        achieved = alg / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_solve_traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
+                "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config, "steps_per_s_per_world": K / (total_ms / 1e3),
+                "counts": {"contacts": counts.contacts, "touching": counts.touching, "awake_bodies": counts.awakeBodies, "joints": counts.joints,
+                           "colours": counts.colours, "islands": counts.islands},
+                "stage_ms": dict(zip(["collide", "islands", "colour_sort", "prepare", "solve", "sync_fixtures", "find_new_contacts", "toi", "clear_forces"], stage_ms)),
+                "roofline": {"bound": "hbm", "kernel": "k_solve (persistent coloured Gauss-Seidel: warm start + %d velocity + %d position iterations + write-back)" % (VEL_ITERS, POS_ITERS),
+                             "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                             "algorithmic_bytes_per_launch": alg, "kernel_ms": solve_ms, "traffic": traffic},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n, "steps": Ke},
+                "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall}
+        if n_gpus == 1 and not args.skip_cpu_baseline:
+            t0 = time.time()
+            v, secs, c = run_cpu_port(cpu_bodies, cpu_cols, args.cpu_settle, args.cpu_steps, 3)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": "%d-body pile (same generator, same %d-row depth, %d columns), %d settle + %d timed steps, single thread, %.1f s"
+                                              % (cpu_bodies, rows, cpu_cols, args.cpu_settle, args.cpu_steps, time.time() - t0)}
+        print(json.dumps(line), flush=True)
+    if world_size > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
