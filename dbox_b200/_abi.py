@@ -176,6 +176,9 @@ PROTOTYPES = {
     "debug_collide": (c_i32, [c_i32, c_i32, P(Shape), P(c_f32), P(Shape), P(c_f32), P(Manifold)]),
     "debug_distance": (c_i32, [c_i32, c_i32, P(Shape), P(c_f32), P(Shape), P(c_f32), c_i32, P(c_f32), P(Vec2), P(Vec2), P(c_i32)]),
     "debug_time_of_impact": (c_i32, [c_i32, c_i32, P(Shape), P(c_f32), P(Shape), P(c_f32), c_f32, P(c_i32), P(c_f32)]),
+    "world_debug_phase_times": (c_i32, [W, P(C.c_uint64), c_i32]),
+    "world_debug_header": (c_i32, [W, C.c_void_p, c_i32]),
+    "debug_barrier_us": (c_f32, [c_i32, c_i32, c_i32, c_i32]),
     "world_replicate": (c_i32, [W, c_i32]),
     "world_replica_count": (c_i32, [W]),
 }

@@ -236,6 +236,10 @@ int32_t dbx_world_debug_set_contact_levels(dbx_world* w, const int32_t* levels, 
 
 int32_t dbx_world_debug_colour_conflicts(dbx_world* w) { W_OR_INVALID(w); return w->w.colourConflicts(); }
 
+int32_t dbx_world_debug_phase_times(dbx_world* w, uint64_t* out, int32_t cap) { W_OR_INVALID(w); return w->w.phaseTimes((unsigned long long*)out, cap); }
+
+int32_t dbx_world_debug_header(dbx_world* w, void* out, int32_t bytes) { W_OR_INVALID(w); return w->w.readHeader(out, bytes); }
+
 // ---- batched independent worlds
 int32_t dbx_world_replicate(dbx_world* w, int32_t copies) { W_OR_INVALID(w); return w->w.replicate(copies); }
 int32_t dbx_world_replica_count(dbx_world* w) { W_OR_INVALID(w); return w->w.replicaCount(); }

@@ -87,7 +87,42 @@ int finish(const char* what) {
 }
 }  // namespace
 
+__global__ void k_dbg_barrier(unsigned* counter, int iters) {
+  const unsigned nb = gridDim.x;
+  for (int i = 0; i < iters; ++i) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      unsigned ticket = atomicAdd(counter, 1u);
+      unsigned target = (ticket / nb + 1u) * nb;
+      while (*((volatile unsigned*)counter) < target) { }
+      __threadfence();
+    }
+    __syncthreads();
+  }
+}
+
 extern "C" {
+
+/* microbenchmark: average microseconds per grid barrier of `blocks` co-resident CTAs (design input for the persistent solver) */
+float dbx_debug_barrier_us(int32_t device, int32_t blocks, int32_t threads, int32_t iters) {
+  if (dev_ok(device) < 0) return -1.0f;
+  Tmp<unsigned> ctr; if (ctr.alloc(1) != cudaSuccess) return -1.0f;
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaMemset(ctr.p, 0, 4);
+    void* args[] = {(void*)&ctr.p, (void*)&iters};
+    cudaEventRecord(a);
+    if (cudaLaunchCooperativeKernel((const void*)k_dbg_barrier, dim3(blocks), dim3(threads), args, 0, 0) != cudaSuccess) return -1.0f;
+    cudaEventRecord(b);
+    if (cudaEventSynchronize(b) != cudaSuccess) return -1.0f;
+    float ms = 0; cudaEventElapsedTime(&ms, a, b);
+    best = ms < best ? ms : best;
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  return best * 1000.0f / iters;
+}
 
 int32_t dbx_debug_collide(int32_t device, int32_t n, const dbx_shape* shapesA, const float* xfA, const dbx_shape* shapesB, const float* xfB, dbx_manifold* out) {
   int rc = dev_ok(device); if (rc < 0) return rc;

@@ -188,6 +188,7 @@ struct DevWorld {
   // ---- step parameters
   float dt, inv_dt, dtRatio; int velIters, posIters; int warmStarting; int allowSleep; int continuous; float gx, gy;
   int nWorlds;
+  unsigned long long* phaseTimes; int phaseCap;   // debug: globaltimer stamp after every barrier of k_solve (null = off)
   int colourOverride;   // debug: keep caller-supplied contact levels instead of colouring (dbx_world_debug_set_contact_levels)
 };
 

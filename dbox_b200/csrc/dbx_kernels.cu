@@ -10,6 +10,8 @@
 
 namespace dbx {
 
+cudaError_t stage_rebuild_hash(const DevWorld& W, const LaunchCfg& L);
+
 #define GRID_STRIDE(i, n) for (int i = blockIdx.x * blockDim.x + threadIdx.x, _gs = gridDim.x * blockDim.x; i < (n); i += _gs)
 
 // ------------------------------------------------------------------------------------------------ small device utilities
@@ -81,7 +83,7 @@ DBX_D void grid_barrier(unsigned* counter, unsigned nblocks) {
     __threadfence();
     unsigned ticket = atomicAdd(counter, 1u);
     unsigned target = (ticket / nblocks + 1u) * nblocks;
-    while (*((volatile unsigned*)counter) < target) { __nanosleep(20); }
+    while (*((volatile unsigned*)counter) < target) { }
     __threadfence();
   }
   __syncthreads();
@@ -387,6 +389,7 @@ __global__ void __launch_bounds__(512) k_colour(const __grid_constant__ DevWorld
 // ------------------------------------------------------------------------------------------------ colour counting sort
 // One radix digit (the colour) over the contact slots: per-CTA histograms, one scan, scatter.  Output: s_contact in
 // colour order and colourOff[]; the solver then walks one contiguous range per colour.
+// s_hist is colour-major: s_hist[c * kSortBlocks + block]
 __global__ void __launch_bounds__(256) k_sort_hist(const __grid_constant__ DevWorld W) {
   __shared__ int hist[kMaxColours];
   for (int c = threadIdx.x; c < kMaxColours; c += blockDim.x) hist[c] = 0;
@@ -398,32 +401,58 @@ __global__ void __launch_bounds__(256) k_sort_hist(const __grid_constant__ DevWo
     if (W.c_flags[i] & CF_SOLVE) atomicAdd(&hist[W.c_colour[i]], 1);
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < kMaxColours; c += blockDim.x) W.s_hist[blockIdx.x * kMaxColours + c] = hist[c];
+  for (int c = threadIdx.x; c < kMaxColours; c += blockDim.x) W.s_hist[c * kSortBlocks + blockIdx.x] = hist[c];
 }
-__global__ void __launch_bounds__(kMaxColours) k_sort_scan(const __grid_constant__ DevWorld W, int nblocks) {
-  __shared__ int total[kMaxColours];
-  __shared__ int base[kMaxColours + 1];
-  const int c = threadIdx.x;
-  int sum = 0;
-  for (int b = 0; b < nblocks; ++b) { int v = W.s_hist[b * kMaxColours + c]; W.s_hist[b * kMaxColours + c] = sum; sum += v; }
-  total[c] = sum;
+// one warp per colour: exclusive prefix over the per-CTA counts (coalesced, shuffle scan); total -> colourOff[c] (temporarily)
+__global__ void __launch_bounds__(256) k_sort_scan_blocks(const __grid_constant__ DevWorld W) {
+  const int lane = threadIdx.x & 31;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= kMaxColours) return;
+  int* row = W.s_hist + c * kSortBlocks;
+  int carry = 0;
+  for (int b0 = 0; b0 < kSortBlocks; b0 += 32) {
+    const int b = b0 + lane;
+    const int v = b < kSortBlocks ? row[b] : 0;
+    int x = v;
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (b < kSortBlocks) row[b] = carry + x - v;
+    carry += __shfl_sync(0xffffffffu, x, 31);
+  }
+  if (lane == 0) W.hdr->colourOff[c] = carry;
+}
+// one CTA: exclusive prefix over the colour totals -> colourOff[], nSolve, nColours
+__global__ void __launch_bounds__(kMaxColours) k_sort_scan_colours(const __grid_constant__ DevWorld W) {
+  __shared__ int warpSum[32];
+  __shared__ int lastColour;
+  const int c = threadIdx.x, lane = c & 31, wid = c >> 5;
+  if (c == 0) lastColour = 0;
+  const int v = W.hdr->colourOff[c];
+  int x = v;
+  for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) warpSum[wid] = x;
   __syncthreads();
-  if (c == 0) {
-    int acc = 0, ncol = 0;
-    for (int k = 0; k < kMaxColours; ++k) { base[k] = acc; acc += total[k]; if (total[k] > 0) ncol = k + 1; }
-    base[kMaxColours] = acc;
-    W.hdr->nSolve = acc;
-    W.hdr->nColours = ncol;
-    if (acc > W.sCap) W.hdr->error = -5;
+  if (wid == 0) {
+    int w = warpSum[lane];
+    int y = w;
+    for (int o = 1; o < 32; o <<= 1) { int z = __shfl_up_sync(0xffffffffu, y, o); if (lane >= o) y += z; }
+    warpSum[lane] = y - w;
   }
   __syncthreads();
-  W.hdr->colourOff[c] = base[c];
-  if (c == 0) W.hdr->colourOff[kMaxColours] = base[kMaxColours];
-  for (int b = 0; b < nblocks; ++b) W.s_hist[b * kMaxColours + c] += base[c];
+  const int excl = warpSum[wid] + x - v;
+  if (v > 0) atomicMax(&lastColour, c + 1);
+  __syncthreads();
+  W.hdr->colourOff[c] = excl;
+  if (c == kMaxColours - 1) {
+    const int total = excl + v;
+    W.hdr->colourOff[kMaxColours] = total;
+    W.hdr->nSolve = total;
+    if (total > W.sCap) W.hdr->error = -5;
+  }
+  if (c == 0) W.hdr->nColours = lastColour;
 }
 __global__ void __launch_bounds__(256) k_sort_scatter(const __grid_constant__ DevWorld W) {
   __shared__ int cursor[kMaxColours];
-  for (int c = threadIdx.x; c < kMaxColours; c += blockDim.x) cursor[c] = W.s_hist[blockIdx.x * kMaxColours + c];
+  for (int c = threadIdx.x; c < kMaxColours; c += blockDim.x) cursor[c] = W.s_hist[c * kSortBlocks + blockIdx.x] + W.hdr->colourOff[c];
   __syncthreads();
   const int n = W.hdr->cHigh;
   const int chunk = (n + gridDim.x - 1) / gridDim.x;
@@ -588,15 +617,22 @@ DBX_D void contact_warm_start(const DevWorld& W, int s) {
 }
 
 // b2ContactSolver.SolveVelocityConstraints (:492-772): friction rows, then 1-point clamp or the 2-point block solver
-DBX_D void contact_solve_velocity(const DevWorld& W, int s) {
-  const int2 bd = W.s_body[s];
-  const float4 v0 = W.s_v0[s], v1 = W.s_v1[s];
-  float4 imp = W.s_imp[s];
-  const int pointCount = W.s_pc[s] & 0xFF;
+// constraint block of one solver contact, loadable ahead of the barrier that precedes its colour (only s_imp ever changes,
+// and only through the thread that owns the slot)
+struct VC { int2 bd; int pc; float4 v0, v1, r0, r1, q0, q1, imp, nm, K; };
+DBX_D void vc_load(const DevWorld& W, int s, VC& c) {
+  c.bd = W.s_body[s]; c.pc = W.s_pc[s];
+  c.v0 = W.s_v0[s]; c.v1 = W.s_v1[s]; c.r0 = W.s_r0[s]; c.q0 = W.s_q0[s]; c.imp = W.s_imp[s];
+  c.r1 = W.s_r1[s]; c.q1 = W.s_q1[s]; c.nm = W.s_nm[s]; c.K = W.s_k[s];
+}
+DBX_D void contact_solve_velocity(const DevWorld& W, int s, const VC& c) {
+  const int2 bd = c.bd;
+  const float4 v0 = c.v0, v1 = c.v1;
+  float4 imp = c.imp;
+  const int pointCount = c.pc & 0xFF;
   const float mA = v1.x, iA = v1.y, mB = v1.z, iB = v1.w;
-  const float4 r0 = W.s_r0[s], q0 = W.s_q0[s];
-  float4 r1 = make_float4(0, 0, 0, 0), q1 = make_float4(0, 0, 0, 0);
-  if (pointCount == 2) { r1 = W.s_r1[s]; q1 = W.s_q1[s]; }
+  const float4 r0 = c.r0, q0 = c.q0;
+  const float4 r1 = c.r1, q1 = c.q1;
   BodyVel bv = load_vel(W, bd);
   v2 vA = bv.vA, vB = bv.vB; float wA = bv.wA, wB = bv.wB;
   const v2 normal = V(v0.x, v0.y), tangent = cross(normal, 1.0f);
@@ -629,7 +665,7 @@ DBX_D void contact_solve_velocity(const DevWorld& W, int s) {
     vA -= mA * P; wA -= iA * cross(rA, P);
     vB += mB * P; wB += iB * cross(rB, P);
   } else {
-    const float4 nm = W.s_nm[s], K = W.s_k[s];
+    const float4 nm = c.nm, K = c.K;
     const v2 rA1 = V(r0.x, r0.y), rB1 = V(r0.z, r0.w), rA2 = V(r1.x, r1.y), rB2 = V(r1.z, r1.w);
     v2 a = V(imp.x, imp.z);
     v2 dv1 = vB + cross(wB, rB1) - vA - cross(wA, rA1);
@@ -675,6 +711,8 @@ DBX_D void contact_solve_velocity(const DevWorld& W, int s) {
   bv.vA = vA; bv.vB = vB; bv.wA = wA; bv.wB = wB;
   store_vel(W, bd, bv, mA, iA, mB, iB);
 }
+
+DBX_D void contact_solve_velocity(const DevWorld& W, int s) { VC c; vc_load(W, s, c); contact_solve_velocity(W, s, c); }
 
 // b2ContactSolver.SolvePositionConstraints (:73-149) + b2PositionSolverManifold (:816-868); returns min separation
 // toiA/toiB >= 0 selects SolveTOIPositionConstraints (:152-242): only those two bodies keep their mass, Baumgarte 0.75
@@ -740,7 +778,9 @@ DBX_D float contact_solve_position(const DevWorld& W, int s, int toiA = -1, int 
 
 // ------------------------------------------------------------------------------------------------ joints
 // revolute: dynamics/joints/b2revolutejoint.d:319-636; distance: b2distancejoint.d:211-373
+DBX_D bool joint_active(const DevWorld& W, int j);
 DBX_D void joint_init(const DevWorld& W, int j) {
+  if (!joint_active(W, j)) { W.j_root[j] = -1; return; }   // later phases only look at j_root
   const int4 ids = W.j_ids[j];
   const int bA = ids.y, bB = ids.z;
   const float4 msA = W.b_mass[bA], msB = W.b_mass[bB];
@@ -1012,6 +1052,9 @@ __global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld 
   const int nJointColours = W.nJoints > 0 ? kMaxJointColours : 0;
   const int* coff = H->colourOff;
   const int* joff = H->jointColourOff;
+  int phaseIdx = 0;
+#define PHASE_MARK() do { if (W.phaseTimes && tid == 0 && phaseIdx < W.phaseCap) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); W.phaseTimes[phaseIdx++] = t_; } } while (0)
+  PHASE_MARK();
 
   // contacts warm start (b2island.d:138-141), colour by colour
   if (W.warmStarting) {
@@ -1019,29 +1062,43 @@ __global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld 
       int beg = coff[c], end = coff[c + 1];
       if (beg == end) continue;
       for (int s = beg + tid; s < end; s += nth) contact_warm_start(W, s);
-      grid_barrier(&H->barrier, nb);
+      grid_barrier(&H->barrier, nb); PHASE_MARK();
     }
   }
   // joints: InitVelocityConstraints incl. their warm start (:143-146)
   for (int c = 0; c < nJointColours; ++c) {
     int beg = joff[c], end = joff[c + 1];
     if (beg == end) continue;
-    for (int k = beg + tid; k < end; k += nth) { int j = W.j_order[k]; if (joint_active(W, j)) joint_init(W, j); }
-    grid_barrier(&H->barrier, nb);
+    for (int k = beg + tid; k < end; k += nth) joint_init(W, k);
+    grid_barrier(&H->barrier, nb); PHASE_MARK();
   }
   // velocity iterations: all joints, then all contacts (:153-161)
+  VC pre; int preS = -1;
   for (int it = 0; it < W.velIters; ++it) {
     for (int c = 0; c < nJointColours; ++c) {
       int beg = joff[c], end = joff[c + 1];
       if (beg == end) continue;
-      for (int k = beg + tid; k < end; k += nth) { int j = W.j_order[k]; if (joint_active(W, j)) joint_solve_velocity(W, j); }
-      grid_barrier(&H->barrier, nb);
+      for (int k = beg + tid; k < end; k += nth) if (W.j_root[k] >= 0) joint_solve_velocity(W, k);
+      grid_barrier(&H->barrier, nb); PHASE_MARK();
     }
     for (int c = 0; c < nColours; ++c) {
       int beg = coff[c], end = coff[c + 1];
       if (beg == end) continue;
-      for (int s = beg + tid; s < end; s += nth) contact_solve_velocity(W, s);
-      grid_barrier(&H->barrier, nb);
+      // the first item of this colour was fetched before the previous barrier; fetch the next colour's before this one
+      int s = beg + tid;
+      if (s < end) {
+        if (preS != s) vc_load(W, s, pre);
+        contact_solve_velocity(W, s, pre);
+        for (s += nth; s < end; s += nth) contact_solve_velocity(W, s);
+      }
+      {
+        int cn = c + 1;
+        while (cn < nColours && coff[cn] == coff[cn + 1]) ++cn;
+        if (cn >= nColours) { cn = 0; while (cn < nColours && coff[cn] == coff[cn + 1]) ++cn; }
+        preS = -1;
+        if (cn < nColours && (cn > c || it + 1 < W.velIters)) { int sn = coff[cn] + tid; if (sn < coff[cn + 1]) { vc_load(W, sn, pre); preS = sn; } }
+      }
+      grid_barrier(&H->barrier, nb); PHASE_MARK();
     }
   }
   // StoreImpulses (:164) + integrate positions (:168-200)
@@ -1073,7 +1130,7 @@ __global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld 
       stcg4(&W.b_vel[b], make_float4(v.x, v.y, w, 0.0f));
     }
   }
-  grid_barrier(&H->barrier, nb);
+  grid_barrier(&H->barrier, nb); PHASE_MARK();
   // position iterations: contacts then joints, each island stops once all of its constraints are within tolerance (:206-224)
   for (int it = 0; it < W.posIters; ++it) {
     int* notOk = W.b_posNotOk + it * W.nBodies;
@@ -1087,19 +1144,19 @@ __global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld 
         float minSep = contact_solve_position(W, s);
         if (!(minSep >= -3.0f * kLinearSlop)) notOk[root] = 1;
       }
-      grid_barrier(&H->barrier, nb);
+      grid_barrier(&H->barrier, nb); PHASE_MARK();
     }
     for (int c = 0; c < nJointColours; ++c) {
       int beg = joff[c], end = joff[c + 1];
       if (beg == end) continue;
       for (int k = beg + tid; k < end; k += nth) {
-        int j = W.j_order[k];
-        if (!joint_active(W, j)) continue;
+        const int j = k;
         int root = W.j_root[j];
+        if (root < 0) continue;
         if (prev && __ldcg(&prev[root]) == 0) continue;
         if (!joint_solve_position(W, j)) notOk[root] = 1;
       }
-      grid_barrier(&H->barrier, nb);
+      grid_barrier(&H->barrier, nb); PHASE_MARK();
     }
   }
   // write back + SynchronizeTransform (:227-235), sleep bookkeeping (:241-269), ClearForces (b2world.d:443-450)
@@ -1124,7 +1181,7 @@ __global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld 
       }
     }
   }
-  grid_barrier(&H->barrier, nb);
+  grid_barrier(&H->barrier, nb); PHASE_MARK();
   if (W.allowSleep) {
     const int* last = W.posIters > 0 ? W.b_posNotOk + (W.posIters - 1) * W.nBodies : nullptr;
     for (int b = tid; b < W.nBodies; b += nth) {
@@ -1144,6 +1201,7 @@ __global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld 
   }
 }
 
+#undef PHASE_MARK
 __global__ void __launch_bounds__(256) k_apply_forces(const __grid_constant__ DevWorld W, const float4* forces, int n) {
   GRID_STRIDE(b, n) {
     const uint32_t f = W.b_flags[b];
@@ -1450,6 +1508,49 @@ __global__ void __launch_bounds__(256) k_set_levels(const __grid_constant__ DevW
 __global__ void k_import_reset(const __grid_constant__ DevWorld W, int n) { W.hdr->cHigh = n; W.hdr->nFree = 0; }
 
 
+// ------------------------------------------------------------------------------------------------ contact compaction
+// Contact slots are handed out by atomics, so after a while neighbours in space are strangers in memory.  Every few
+// dozen steps the alive contacts are re-packed in reference pair-key order (= proxy creation order = spatial order for
+// scenes built in a sweep), which restores coalescing for Collide, the island pass and constraint setup.
+__global__ void __launch_bounds__(256) k_compact_keys(const __grid_constant__ DevWorld W, int n, unsigned long long* keys, int* vals) {
+  GRID_STRIDE(i, n) { keys[i] = (W.c_flags[i] & CF_ALIVE) ? W.c_key[i] : ~0ull; vals[i] = i; }
+}
+template <class T> __global__ void __launch_bounds__(256) k_gather(const T* __restrict__ src, T* __restrict__ dst, const int* __restrict__ perm, int n) {
+  GRID_STRIDE(i, n) dst[i] = src[perm[i]];
+}
+__global__ void k_compact_finish(const __grid_constant__ DevWorld W, int nAlive, int oldHigh) {
+  GRID_STRIDE(i, oldHigh) if (i >= nAlive) { W.c_flags[i] = 0; W.c_colour[i] = -1; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { W.hdr->cHigh = nAlive; W.hdr->nFree = 0; }
+}
+template <class T> static cudaError_t permute_array(const LaunchCfg& L, T* arr, void* scratch, const int* perm, int n) {
+  ++L.launches; k_gather<T><<<L.gridWide, 256, 0, L.stream>>>(arr, (T*)scratch, perm, n);
+  return cudaMemcpyAsync(arr, scratch, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, L.stream);
+}
+// `high` = current hdr->cHigh, `nAlive` = alive contacts (both read back by the caller); scratch >= 16 * high bytes
+cudaError_t stage_compact_contacts(DevWorld& W, const LaunchCfg& L, int high, int nAlive, void* scratch, unsigned long long* keyA, unsigned long long* keyB, int* valA, int* valB) {
+  if (high <= 0) return cudaSuccess;
+  ++L.launches; k_compact_keys<<<L.gridWide, 256, 0, L.stream>>>(W, high, keyA, valA);
+  cub::DoubleBuffer<unsigned long long> keys(keyA, keyB);
+  cub::DoubleBuffer<int> vals(valA, valB);
+  size_t bytes = L.cubTempBytes;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(L.cubTemp, bytes, keys, vals, high, 0, 64, L.stream);
+  if (e != cudaSuccess) return e;
+  const int* perm = vals.Current();
+  if ((e = permute_array(L, W.c_key, scratch, perm, high)) != cudaSuccess) return e;
+  if ((e = permute_array(L, W.c_ids, scratch, perm, high)) != cudaSuccess) return e;
+  if ((e = permute_array(L, W.c_fix, scratch, perm, high)) != cudaSuccess) return e;
+  if ((e = permute_array(L, W.c_flags, scratch, perm, high)) != cudaSuccess) return e;
+  if ((e = permute_array(L, W.c_m0, scratch, perm, high)) != cudaSuccess) return e;
+  if ((e = permute_array(L, W.c_m1, scratch, perm, high)) != cudaSuccess) return e;
+  if ((e = permute_array(L, W.c_imp, scratch, perm, high)) != cudaSuccess) return e;
+  if ((e = permute_array(L, W.c_mk, scratch, perm, high)) != cudaSuccess) return e;
+  if ((e = permute_array(L, W.c_mat, scratch, perm, high)) != cudaSuccess) return e;
+  if ((e = permute_array(L, W.c_toiCount, scratch, perm, high)) != cudaSuccess) return e;
+  if ((e = permute_array(L, W.c_colour, scratch, perm, high)) != cudaSuccess) return e;
+  ++L.launches; k_compact_finish<<<L.gridWide, 256, 0, L.stream>>>(W, nAlive, high);
+  return stage_rebuild_hash(W, L);
+}
+
 // ------------------------------------------------------------------------------------------------ API-time edits
 // DestroyFixture / DestroyBody / SetActive(false) (b2body.d:211-227, b2world.d:136-145) destroy the matching contacts;
 // CreateJoint / DestroyJoint with collideConnected == false flag them for re-filtering (b2world.d:241-256, 344-359).
@@ -1515,6 +1616,25 @@ DBX_D void advance_body(const DevWorld& W, int b, float alpha) {
   stcg4(&W.b_pos[b], make_float4(s.c.x, s.c.y, s.a, 0.0f));
   stcg4(&W.b_xf[b], pack(xf));
   stcg4(&W.b_xf0[b], pack(xf));
+}
+
+// Between rebuilds the LBVH stays a valid acceleration structure if every moved proxy's new fat box is merged into its
+// leaf and all ancestors (boxes only ever grow until the next rebuild); the reported pair set does not depend on it.
+DBX_D void lbvh_enlarge(const DevWorld& W, int p) {
+  const int n = W.nProxies;
+  const float4 f = __ldcg(&W.p_fat[p]);
+  int node = n - 1 + W.bv_pos[p];
+  __stcg(&W.bv_box[node], f);
+  node = W.bv_parent[node];
+  while (node >= 0) {
+    float* bx = (float*)&W.bv_box[node];
+    atomic_min_f(bx + 0, f.x); atomic_min_f(bx + 1, f.y); atomic_max_f(bx + 2, f.z); atomic_max_f(bx + 3, f.w);
+    node = W.bv_parent[node];
+  }
+}
+__global__ void __launch_bounds__(256) k_lbvh_enlarge(const __grid_constant__ DevWorld W) {
+  const int nMoved = min(W.hdr->nMoved, W.moveCap);
+  GRID_STRIDE(k, nMoved) lbvh_enlarge(W, W.moveList[k]);
 }
 
 // (a) evaluate b2TimeOfImpact for every eligible contact that has no cached value (b2world.d:1155-1265)
@@ -1776,19 +1896,7 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
     {
       // the step's LBVH is still valid for every proxy that did not move; widen it for the ones that did
       const int nMoved = min(*((volatile int*)&H->nMoved), W.moveCap);
-      const int n = W.nProxies;
-      for (int k = tid; k < nMoved; k += nth) {
-        const int p = W.moveList[k];
-        const float4 f = __ldcg(&W.p_fat[p]);
-        int node = n - 1 + W.bv_pos[p];
-        __stcg(&W.bv_box[node], f);
-        node = W.bv_parent[node];
-        while (node >= 0) {
-          float* bx = (float*)&W.bv_box[node];
-          atomic_min_f(bx + 0, f.x); atomic_min_f(bx + 1, f.y); atomic_max_f(bx + 2, f.z); atomic_max_f(bx + 3, f.w);
-          node = W.bv_parent[node];
-        }
-      }
+      for (int k = tid; k < nMoved; k += nth) lbvh_enlarge(W, W.moveList[k]);
       for (int b = tid; b < W.nBodies; b += nth) {
         W.b_toiMin[b] = ~0ull; W.b_toiOther[b] = ~0ull; W.b_toiEvt[b] = -1;
         if (W.b_toiFlags[b] & TF_SYNC) W.b_toiFlags[b] &= ~TF_SYNC;
@@ -1841,7 +1949,8 @@ cudaError_t stage_colour_and_sort(const DevWorld& W, const LaunchCfg& L) {
   CK(cudaGetLastError());
   if (!W.colourOverride) CK(launch_coop((const void*)k_colour, W, L));
   ++L.launches; k_sort_hist<<<kSortBlocks, 256, 0, L.stream>>>(W);
-  ++L.launches; k_sort_scan<<<1, kMaxColours, 0, L.stream>>>(W, kSortBlocks);
+  ++L.launches; k_sort_scan_blocks<<<kMaxColours / 8, 256, 0, L.stream>>>(W);
+  ++L.launches; k_sort_scan_colours<<<1, kMaxColours, 0, L.stream>>>(W);
   ++L.launches; k_sort_scatter<<<kSortBlocks, 256, 0, L.stream>>>(W);
   return cudaGetLastError();
 }
@@ -1871,10 +1980,14 @@ cudaError_t stage_toi(DevWorld& W, const LaunchCfg& L) {
   return launch_coop((const void*)k_toi, W, L);
 }
 
-cudaError_t stage_find_new_contacts(DevWorld& W, const LaunchCfg& L) {
+cudaError_t stage_find_new_contacts(DevWorld& W, const LaunchCfg& L, bool rebuild) {
   const int n = W.nProxies;
   ++L.launches; k_bounds_init<<<1, 1, 0, L.stream>>>(W);
-  if (n > 0) {
+  if (n > 0 && !rebuild) {
+    ++L.launches; k_lbvh_enlarge<<<L.gridWide, 256, 0, L.stream>>>(W);
+    ++L.launches; k_query<<<L.gridWide, 256, 0, L.stream>>>(W, W.bv_sorted);
+    ++L.launches; k_add_pairs<<<L.gridWide, 256, 0, L.stream>>>(W);
+  } else if (n > 0) {
     ++L.launches; k_bounds<<<L.gridWide, 256, 0, L.stream>>>(W);
     ++L.launches; k_morton<<<L.gridWide, 256, 0, L.stream>>>(W);
     cub::DoubleBuffer<unsigned long long> keys(W.bv_key, W.bv_keyAlt);

@@ -414,13 +414,13 @@ int World::pullProxies() {
 }
 
 int World::pullJoints() {
-  if (hostJointsValid_ || jointsSynced_ == 0) { hostJointsValid_ = true; return 0; }
-  const size_t n = jointsSynced_;
+  const size_t n = jointAt_.size();
+  if (hostJointsValid_ || n == 0 || !dw_.hdr) { hostJointsValid_ = true; return 0; }
   std::vector<float4> imp(n); std::vector<int> lim(n);
   CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
   CUDA_OR_FAIL(cudaMemcpy(imp.data(), j_imp.p, n * 16, cudaMemcpyDeviceToHost), "pull jimp");
   CUDA_OR_FAIL(cudaMemcpy(lim.data(), j_limit.p, n * 4, cudaMemcpyDeviceToHost), "pull jlim");
-  for (size_t i = 0; i < n; ++i) { joints_[i].imp[0] = imp[i].x; joints_[i].imp[1] = imp[i].y; joints_[i].imp[2] = imp[i].z; joints_[i].imp[3] = imp[i].w; joints_[i].limit = lim[i]; }
+  for (size_t k = 0; k < n; ++k) { HJoint& j = joints_[jointAt_[k]]; j.imp[0] = imp[k].x; j.imp[1] = imp[k].y; j.imp[2] = imp[k].z; j.imp[3] = imp[k].w; j.limit = lim[k]; }
   hostJointsValid_ = true;
   return 0;
 }
@@ -449,19 +449,16 @@ int World::recolourJoints() {
       jp.push_back((lo << 32) | hi);
     }
   }
-  std::vector<int> order; order.reserve(nJ);
+  jointAt_.clear(); jointPos_.assign(nJ, -1);
   int off[kMaxJointColours + 1];
-  for (int c = 0; c < kMaxJointColours; ++c) { off[c] = (int)order.size(); order.insert(order.end(), byColour[c].begin(), byColour[c].end()); }
-  off[kMaxJointColours] = (int)order.size();
+  for (int c = 0; c < kMaxJointColours; ++c) { off[c] = (int)jointAt_.size(); jointAt_.insert(jointAt_.end(), byColour[c].begin(), byColour[c].end()); }
+  off[kMaxJointColours] = (int)jointAt_.size();
+  for (size_t k = 0; k < jointAt_.size(); ++k) jointPos_[jointAt_[k]] = (int)k;
   std::sort(jp.begin(), jp.end());
   jp.erase(std::unique(jp.begin(), jp.end()), jp.end());
   nJointPairs_ = (int)jp.size();
-  CUDA_OR_FAIL(j_order.reserve(std::max<size_t>(1, order.size()), false, stream_), "j_order");
-  CUDA_OR_FAIL(j_colour.reserve(std::max<size_t>(1, (size_t)nJ), false, stream_), "j_colour");
   CUDA_OR_FAIL(jp_keys.reserve(std::max<size_t>(1, jp.size()), false, stream_), "jp_keys");
   CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
-  if (!order.empty()) CUDA_OR_FAIL(cudaMemcpy(j_order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice), "j_order up");
-  if (nJ) CUDA_OR_FAIL(cudaMemcpy(j_colour.p, colour.data(), (size_t)nJ * 4, cudaMemcpyHostToDevice), "j_colour up");
   if (!jp.empty()) CUDA_OR_FAIL(cudaMemcpy(jp_keys.p, jp.data(), jp.size() * 8, cudaMemcpyHostToDevice), "jp up");
   CUDA_OR_FAIL(cudaMemcpy((char*)hdr_.p + offsetof(Header, jointColourOff), off, sizeof(off), cudaMemcpyHostToDevice), "joff up");
   return 0;
@@ -485,7 +482,7 @@ int World::push() {
   if (!anyBody && !anyFix && !anyProxy && !anyShape && !anyJoint && dw_.hdr) return 0;
   if (fullPushBodies_ && !hostBodiesValid_) { int rc = pullBodies(); if (rc < 0) return rc; }
   if (fullPushProxies_ && !hostProxiesValid_) { int rc = pullProxies(); if (rc < 0) return rc; }
-  if (fullPushJoints_ && !hostJointsValid_) { int rc = pullJoints(); if (rc < 0) return rc; }
+  if (anyJoint && !hostJointsValid_) { int rc = pullJoints(); if (rc < 0) return rc; }
   CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
 
   // ---- capacities
@@ -594,6 +591,7 @@ int World::push() {
     CUDA_OR_FAIL(upload_range(p_aabb, from, nP, [&](size_t i) { return proxies_[i].aabb; }), "up p_aabb");
     CUDA_OR_FAIL(upload_range(p_fat, from, nP, [&](size_t i) { return proxies_[i].fat; }), "up p_fat");
     CUDA_OR_FAIL(upload_range(p_flags, from, nP, [&](size_t i) { return proxies_[i].alive ? (proxies_[i].flags | PF_ALIVE) : 0u; }), "up p_flags");
+    if (fullPushProxies_ || nP > proxiesSynced_) treeValid_ = false;   // the proxy set (or its boxes) changed under the tree
     proxiesSynced_ = nP; fullPushProxies_ = false;
     if (!pendingMoves_.empty()) {
       // b2BroadPhase.BufferMove (b2broadphase.d:244-257): the device move list is empty between steps
@@ -608,19 +606,21 @@ int World::push() {
       pendingMoves_.clear();
     }
   }
-  // ---- joints
-  {
-    const size_t from = fullPushJoints_ ? 0 : jointsSynced_;
-    CUDA_OR_FAIL(upload_range(j_ids, from, nJ, [&](size_t i) { const HJoint& j = joints_[i];
-      return make_int4(j.def.type, j.def.bodyA, j.def.bodyB, (j.def.collideConnected ? 1 : 0) | (j.def.enableLimit ? 2 : 0) | (j.def.enableMotor ? 4 : 0) | (j.alive ? 8 : 0)); }), "up j_ids");
-    CUDA_OR_FAIL(upload_range(j_anchor, from, nJ, [&](size_t i) { const dbx_joint_def& d = joints_[i].def; return f4(d.localAnchorA.x, d.localAnchorA.y, d.localAnchorB.x, d.localAnchorB.y); }), "up j_anchor");
-    CUDA_OR_FAIL(upload_range(j_p0, from, nJ, [&](size_t i) { const dbx_joint_def& d = joints_[i].def;
+  // ---- joints: the device arrays hold the alive joints in colour order (slot k = joint jointAt_[k]), so every colour is a
+  // contiguous, coalesced range for the solver; any change of the joint set re-colours and re-uploads all of them
+  if (anyJoint || !dw_.hdr) {
+    int rc = recolourJoints(); if (rc < 0) return rc;
+    const size_t nD = jointAt_.size();
+    auto J = [&](size_t k) -> const HJoint& { return joints_[jointAt_[k]]; };
+    CUDA_OR_FAIL(upload_range(j_ids, 0, nD, [&](size_t k) { const HJoint& j = J(k);
+      return make_int4(j.def.type, j.def.bodyA, j.def.bodyB, (j.def.collideConnected ? 1 : 0) | (j.def.enableLimit ? 2 : 0) | (j.def.enableMotor ? 4 : 0) | 8); }), "up j_ids");
+    CUDA_OR_FAIL(upload_range(j_anchor, 0, nD, [&](size_t k) { const dbx_joint_def& d = J(k).def; return f4(d.localAnchorA.x, d.localAnchorA.y, d.localAnchorB.x, d.localAnchorB.y); }), "up j_anchor");
+    CUDA_OR_FAIL(upload_range(j_p0, 0, nD, [&](size_t k) { const dbx_joint_def& d = J(k).def;
       return d.type == DBX_JOINT_REVOLUTE ? f4(d.referenceAngle, d.lowerAngle, d.upperAngle, d.maxMotorTorque) : f4(d.length, d.frequencyHz, d.dampingRatio, 0.0f); }), "up j_p0");
-    CUDA_OR_FAIL(upload_range(j_p1, from, nJ, [&](size_t i) { return f4(joints_[i].def.motorSpeed, 0, 0, 0); }), "up j_p1");
-    CUDA_OR_FAIL(upload_range(j_imp, from, nJ, [&](size_t i) { const HJoint& j = joints_[i]; return f4(j.imp[0], j.imp[1], j.imp[2], j.imp[3]); }), "up j_imp");
-    CUDA_OR_FAIL(upload_range(j_limit, from, nJ, [&](size_t i) { return joints_[i].limit; }), "up j_limit");
-    jointsSynced_ = nJ; fullPushJoints_ = false;
-    if (jointsChanged_ || !dw_.hdr) { int rc = recolourJoints(); if (rc < 0) return rc; jointsChanged_ = false; }
+    CUDA_OR_FAIL(upload_range(j_p1, 0, nD, [&](size_t k) { return f4(J(k).def.motorSpeed, 0, 0, 0); }), "up j_p1");
+    CUDA_OR_FAIL(upload_range(j_imp, 0, nD, [&](size_t k) { const HJoint& j = J(k); return f4(j.imp[0], j.imp[1], j.imp[2], j.imp[3]); }), "up j_imp");
+    CUDA_OR_FAIL(upload_range(j_limit, 0, nD, [&](size_t k) { return J(k).limit; }), "up j_limit");
+    jointsSynced_ = nJ; fullPushJoints_ = false; jointsChanged_ = false;
   }
   refreshView();
   if (rehash) CUDA_OR_FAIL(stage_rebuild_hash(dw_, L_), "rehash");
@@ -648,9 +648,10 @@ void World::refreshView() {
   w.hCap = (int)h_key.cap; w.h_key = h_key.p; w.h_val = h_val.p;
   w.sCap = (int)s_contact.cap; w.s_contact = s_contact.p; w.s_hist = s_hist.p; w.s_body = s_body.p; w.s_v0 = s_v0.p; w.s_v1 = s_v1.p; w.s_r0 = s_r0.p; w.s_r1 = s_r1.p;
   w.s_q0 = s_q0.p; w.s_q1 = s_q1.p; w.s_imp = s_imp.p; w.s_nm = s_nm.p; w.s_k = s_k.p; w.s_pc = s_pc.p; w.s_p0 = s_p0.p; w.s_p1 = s_p1.p; w.s_p2 = s_p2.p; w.s_p3 = s_p3.p; w.s_root = s_root.p;
-  w.nJoints = (int)joints_.size(); w.j_ids = j_ids.p; w.j_anchor = j_anchor.p; w.j_p0 = j_p0.p; w.j_p1 = j_p1.p; w.j_imp = j_imp.p; w.j_limit = j_limit.p; w.j_colour = j_colour.p;
+  w.nJoints = (int)jointAt_.size(); w.j_ids = j_ids.p; w.j_anchor = j_anchor.p; w.j_p0 = j_p0.p; w.j_p1 = j_p1.p; w.j_imp = j_imp.p; w.j_limit = j_limit.p; w.j_colour = j_colour.p;
   w.j_order = j_order.p; w.j_root = j_root.p; w.j_r = j_r.p; w.j_lc = j_lc.p; w.j_m = j_m.p; w.j_k0 = j_k0.p; w.j_k1 = j_k1.p; w.j_k2 = j_k2.p;
   w.nWorlds = nWorlds_;
+  w.phaseTimes = phaseBuf_.p; w.phaseCap = phaseBuf_.p ? (int)phaseBuf_.cap : 0;
   L_.cubTemp = cubTemp.p; L_.cubTempBytes = cubTemp.cap;
 }
 
@@ -678,11 +679,21 @@ int World::checkDeviceError(bool sync) {
   return 0;
 }
 
+// b2ContactManager.FindNewContacts.  The LBVH is rebuilt when the proxy set changed or every kRebuildPeriod calls; in
+// between it is widened for the moved proxies (lbvh_enlarge), which keeps the pair set exact at a fraction of the cost.
+int World::findNewContacts() {
+  constexpr int kRebuildPeriod = 8;
+  const bool rebuild = !treeValid_ || sinceRebuild_ >= kRebuildPeriod;
+  CUDA_OR_FAIL(stage_find_new_contacts(dw_, L_, rebuild), "find_new_contacts");
+  if (rebuild) { treeValid_ = true; sinceRebuild_ = 0; } else ++sinceRebuild_;
+  return 0;
+}
+
 // one b2World.Step (dynamics/b2world.d:367-434) enqueued on the world's stream; no host synchronisation
 int World::enqueueStep(float dt, int vi, int pi, bool fineEvents) {
   int rc = push(); if (rc < 0) return rc;
   if (bodies_.empty()) return 0;
-  if (newFixture_) { CUDA_OR_FAIL(stage_find_new_contacts(dw_, L_), "find_new_contacts"); newFixture_ = false; }   // :372-376
+  if (newFixture_) { int rf = findNewContacts(); if (rf < 0) return rf; newFixture_ = false; }   // :372-376
   setStepParams(dt, vi, pi);
   dw_.colourOverride = overrideLevels_ ? 1 : 0;
   auto mark = [&](int i) { if (fineEvents || i == 0 || i == 1 || i == 3 || i == 5 || i == 7 || i == 8 || i == 9) cudaEventRecord(ev_[i], stream_); };
@@ -700,7 +711,7 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents) {
     mark(5);
     CUDA_OR_FAIL(stage_sync_fixtures(dw_, L_), "sync_fixtures");
     mark(6);
-    CUDA_OR_FAIL(stage_find_new_contacts(dw_, L_), "find_new_contacts");
+    { int rf = findNewContacts(); if (rf < 0) return rf; }
     mark(7);
   } else {
     for (int i = 2; i <= 7; ++i) cudaEventRecord(ev_[i], stream_);
@@ -716,7 +727,7 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents) {
     overrideLevels_ = false; dw_.colourOverride = 0;
     CUDA_OR_FAIL(cudaMemsetAsync(c_colour.p, 0xFF, c_colour.cap * 4, stream_), "reset colours");
   }
-  if ((stepCount_ & 63) == 0) CUDA_OR_FAIL(stage_rebuild_hash(dw_, L_), "rehash");
+  if ((stepCount_ & 63) == 0) { int rc2 = compactContacts(); if (rc2 < 0) return rc2; }
   hostBodiesValid_ = false; hostProxiesValid_ = false; hostJointsValid_ = false;
   return 0;
 }
@@ -784,7 +795,7 @@ int World::clearForces() {
 int World::stageFindNewContacts() {
   int rc = push(); if (rc < 0) return rc;
   if (bodies_.empty()) return 0;
-  CUDA_OR_FAIL(stage_find_new_contacts(dw_, L_), "find_new_contacts");
+  { int rf = findNewContacts(); if (rf < 0) return rf; }
   newFixture_ = false;
   hostBodiesValid_ = false; hostProxiesValid_ = false;
   return checkDeviceError(true);
@@ -1137,6 +1148,38 @@ int World::colourConflicts() {
     }
   }
   return conflicts;
+}
+
+// every 64 steps: re-pack the contact slots in pair-key order and rebuild the pair hash without tombstones (one host
+// round trip to learn the slot count; amortised to a few microseconds per step)
+int World::compactContacts() {
+  CUDA_OR_FAIL(stage_count(dw_, L_), "count");
+  Header h;
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  CUDA_OR_FAIL(cudaMemcpy(&h, hdr_.p, sizeof(Header), cudaMemcpyDeviceToHost), "read header");
+  if (h.cHigh <= 0) return 0;
+  const size_t n = (size_t)h.cHigh;
+  CUDA_OR_FAIL(cmpKeyA_.reserve(n, false, stream_), "cmp"); CUDA_OR_FAIL(cmpKeyB_.reserve(n, false, stream_), "cmp");
+  CUDA_OR_FAIL(cmpValA_.reserve(n, false, stream_), "cmp"); CUDA_OR_FAIL(cmpValB_.reserve(n, false, stream_), "cmp");
+  size_t need = cub_temp_bytes((int)n);
+  if (need > cubTemp.cap) { CUDA_OR_FAIL(cubTemp.reserve(need, false, stream_), "cubTemp"); L_.cubTemp = cubTemp.p; L_.cubTempBytes = cubTemp.cap; }
+  // s_v0 (16 B per solver slot, sCap >= cCap) is free between steps and serves as the gather scratch
+  CUDA_OR_FAIL(stage_compact_contacts(dw_, L_, h.cHigh, h.nContacts, s_v0.p, cmpKeyA_.p, cmpKeyB_.p, cmpValA_.p, cmpValB_.p), "compact");
+  return 0;
+}
+
+int World::phaseTimes(unsigned long long* out, int cap) {
+  const int kCap = 4096;
+  if (!phaseBuf_.p) {
+    CUDA_OR_FAIL(phaseBuf_.reserve(kCap, false, stream_), "phase buffer");
+    dw_.phaseTimes = phaseBuf_.p; dw_.phaseCap = kCap;
+    return 0;   // enabled; stamps are available after the next step
+  }
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  const int n = std::min(cap, kCap);
+  CUDA_OR_FAIL(cudaMemcpy(out, phaseBuf_.p, (size_t)n * 8, cudaMemcpyDeviceToHost), "phase read");
+  CUDA_OR_FAIL(cudaMemset(phaseBuf_.p, 0, (size_t)kCap * 8), "phase clear");
+  return n;
 }
 
 int World::replicate(int copies) {

@@ -91,6 +91,8 @@ class World {
   int stageCollide();
   int setContactLevels(const int32_t* levels, int n);
   int colourConflicts();
+  int readHeader(void* out, int bytes) { cudaStreamSynchronize(stream_); int n = bytes < (int)sizeof(Header) ? bytes : (int)sizeof(Header); return cudaMemcpy(out, hdr_.p, n, cudaMemcpyDeviceToHost) == cudaSuccess ? n : DBX_E_CUDA; }
+  int phaseTimes(unsigned long long* out, int cap);   // debug: enable + fetch the last step's k_solve barrier stamps
   int replicate(int copies);
   int replicaCount() const { return nWorlds_; }
   float inv_dt0 = 0.0f;
@@ -111,6 +113,8 @@ class World {
   void hostAabb(const DShape& s, const Xf& xf, Box* out) const;
   int destroyContactsWhere(int body, int fixture, int otherBody, bool flagOnly);
   int recolourJoints();
+  int findNewContacts();
+  int compactContacts();
   void setStepParams(float dt, int vi, int pi);
 
   bool ok_ = false;
@@ -128,6 +132,7 @@ class World {
   std::vector<HBody> bodies_; std::vector<HFixture> fixtures_; std::vector<HProxy> proxies_; std::vector<HJoint> joints_;
   std::vector<DShape> shapes_; std::unordered_map<std::string, int> shapeIndex_;
   std::vector<int> proxyFree_;
+  std::vector<int> jointAt_, jointPos_;   // device joint slot <-> joint id (device arrays are colour-sorted)
   // reference leaf-id allocator (collision/b2dynamictree.d:516-564 replayed)
   std::vector<int> keyFree_; int keyFresh_ = 0; int keyLeaves_ = 0;
   // mirror state
@@ -153,11 +158,13 @@ class World {
   DevBuf<int> s_contact, s_hist, s_pc, s_root; DevBuf<int2> s_body; DevBuf<float4> s_v0, s_v1, s_r0, s_r1, s_q0, s_q1, s_imp, s_nm, s_k, s_p0, s_p1, s_p2; DevBuf<float2> s_p3;
   DevBuf<int4> j_ids; DevBuf<float4> j_anchor, j_p0, j_p1, j_imp, j_r, j_lc, j_m, j_k0, j_k1, j_k2; DevBuf<int> j_limit, j_colour, j_order, j_root;
   DevBuf<char> cubTemp; DevBuf<int> d_levels;
+  DevBuf<unsigned long long> cmpKeyA_, cmpKeyB_; DevBuf<int> cmpValA_, cmpValB_;
   int nJointPairs_ = 0;
   cudaEvent_t ev_[10]{};
   bool evValid_ = false, evFine_ = false;
-  DevBuf<char> flushBuf_; DevBuf<float4> ioBuf_;
+  DevBuf<char> flushBuf_; DevBuf<float4> ioBuf_; DevBuf<unsigned long long> phaseBuf_;
   bool overrideLevels_ = false;
+  bool treeValid_ = false; int sinceRebuild_ = 0;
   std::vector<int> lastReadSlots_;
 };
 

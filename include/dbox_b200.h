@@ -289,6 +289,11 @@ int32_t dbx_debug_distance(int32_t device, int32_t n, const dbx_shape* shapesA, 
 int32_t dbx_debug_time_of_impact(int32_t device, int32_t n, const dbx_shape* shapesA, const float* sweepsA, const dbx_shape* shapesB, const float* sweepsB,
                                  float tMax, int32_t* outState, float* outT);
 
+/* first call enables %globaltimer stamps after every barrier of the persistent solve kernel; later calls return the last step's stamps (ns) */
+int32_t dbx_world_debug_phase_times(dbx_world* w, uint64_t* out, int32_t cap);
+int32_t dbx_world_debug_header(dbx_world* w, void* out, int32_t bytes); /* raw copy of the device-side counter block (debug) */
+float dbx_debug_barrier_us(int32_t device, int32_t blocks, int32_t threads, int32_t iters); /* grid-barrier latency microbenchmark */
+
 /* ---- batched independent worlds (config 5): replicas of a template share one device world ---- */
 int32_t dbx_world_replicate(dbx_world* w, int32_t copies);  /* world becomes `copies` disjoint replicas of its current content */
 int32_t dbx_world_replica_count(dbx_world* w);
