@@ -87,16 +87,34 @@ int finish(const char* what) {
 }
 }  // namespace
 
-__global__ void k_dbg_barrier(unsigned* counter, int iters) {
+__global__ void k_dbg_barrier(unsigned* counter, int iters, int mode, float4* scratch) {
   const unsigned nb = gridDim.x;
+  unsigned* flag = counter + 64;   // separate 128 B line
+  unsigned gen = 0;
   for (int i = 0; i < iters; ++i) {
+    if (scratch) __stcg(&scratch[blockIdx.x * blockDim.x + threadIdx.x], make_float4(i, 0, 0, 0));   // stores in flight, like the solver
     __syncthreads();
     if (threadIdx.x == 0) {
-      __threadfence();
-      unsigned ticket = atomicAdd(counter, 1u);
-      unsigned target = (ticket / nb + 1u) * nb;
-      while (*((volatile unsigned*)counter) < target) { }
-      __threadfence();
+      if (mode == 0) {
+        __threadfence();
+        unsigned ticket = atomicAdd(counter, 1u);
+        unsigned target = (ticket / nb + 1u) * nb;
+        while (*((volatile unsigned*)counter) < target) { }
+        __threadfence();
+      } else if (mode == 1) {
+        ++gen;
+        __threadfence();
+        unsigned ticket = atomicAdd(counter, 1u);
+        if (ticket == gen * nb - 1u) { *((volatile unsigned*)flag) = gen; }
+        else { while (*((volatile unsigned*)flag) < gen) { } }
+        __threadfence();
+      } else {
+        ++gen;
+        unsigned ticket;
+        asm volatile("atom.add.release.gpu.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(counter) : "memory");
+        if (ticket == gen * nb - 1u) { asm volatile("st.release.gpu.u32 [%0], %1;" :: "l"(flag), "r"(gen) : "memory"); }
+        else { unsigned v; do { asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory"); } while (v < gen); }
+      }
     }
     __syncthreads();
   }
@@ -106,13 +124,16 @@ extern "C" {
 
 /* microbenchmark: average microseconds per grid barrier of `blocks` co-resident CTAs (design input for the persistent solver) */
 float dbx_debug_barrier_us(int32_t device, int32_t blocks, int32_t threads, int32_t iters) {
+  int mode = iters / 100000; iters = iters % 100000; int withStores = mode / 10; mode = mode % 10;
+  Tmp<float4> scr; if (withStores && scr.alloc((size_t)blocks * threads) != cudaSuccess) return -1.0f;
+  float4* scrp = withStores ? scr.p : nullptr;
   if (dev_ok(device) < 0) return -1.0f;
-  Tmp<unsigned> ctr; if (ctr.alloc(1) != cudaSuccess) return -1.0f;
+  Tmp<unsigned> ctr; if (ctr.alloc(256) != cudaSuccess) return -1.0f;
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   float best = 1e30f;
   for (int rep = 0; rep < 3; ++rep) {
-    cudaMemset(ctr.p, 0, 4);
-    void* args[] = {(void*)&ctr.p, (void*)&iters};
+    cudaMemset(ctr.p, 0, 1024);
+    void* args[] = {(void*)&ctr.p, (void*)&iters, (void*)&mode, (void*)&scrp};
     cudaEventRecord(a);
     if (cudaLaunchCooperativeKernel((const void*)k_dbg_barrier, dim3(blocks), dim3(threads), args, 0, 0) != cudaSuccess) return -1.0f;
     cudaEventRecord(b);
