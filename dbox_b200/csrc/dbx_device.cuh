@@ -36,6 +36,7 @@ constexpr int kMaskColours = 64;
 constexpr int kMaxJointColours = 64;
 constexpr int kSortBlocks = 296;         // 2 CTAs per SM for the colour counting sort
 constexpr int kMaxPosIters = 8;
+constexpr int kTailContacts = 1024;       // tail colours holding at most this many constraints share one CTA-local phase
 constexpr int kToiCand = 64;             // candidate contacts per event side (mini-island holds at most 32)
 enum { TF_INVAL = 1, TF_SYNC = 2 };
 constexpr unsigned long long kHashEmpty = ~0ull;
@@ -59,6 +60,8 @@ struct Header {
   int nAwake;
   int toiEvents;      // cumulative TOI events processed
   int nEvents;        // events selected in the current TOI pass
+  int tailStart;      // first colour of the tail that k_solve runs inside one CTA
+  int _pad1;
   unsigned barrier;   // grid barrier ticket counter for the persistent kernels
   unsigned epoch;     // colouring round stamp
   unsigned long long toiMin;  // (alpha bits << 32 | contact slot) arg-min for the TOI loop
@@ -189,6 +192,9 @@ struct DevWorld {
   float dt, inv_dt, dtRatio; int velIters, posIters; int warmStarting; int allowSleep; int continuous; float gx, gy;
   int nWorlds;
   unsigned long long* phaseTimes; int phaseCap;   // debug: globaltimer stamp after every barrier of k_solve (null = off)
+  int dbgFlags;         // experiments only (DBX_DEBUG env): bit 0 = joint velocity phases do no work
+  int nJointColours;    // joint colours in use (host-side greedy colouring)
+  int jointBlocks;      // CTAs of the persistent solver dedicated to joint phases
   int colourOverride;   // debug: keep caller-supplied contact levels instead of colouring (dbx_world_debug_set_contact_levels)
 };
 

@@ -440,7 +440,16 @@ __global__ void __launch_bounds__(kMaxColours) k_sort_scan_colours(const __grid_
   __syncthreads();
   const int excl = warpSum[wid] + x - v;
   if (v > 0) atomicMax(&lastColour, c + 1);
+  __shared__ int tot[kMaxColours];
+  tot[c] = v;
   __syncthreads();
+  if (c == 0) {
+    // tail = the longest suffix of colours holding at most kTailContacts constraints in total
+    int t = lastColour, acc = 0;
+    while (t > 0 && acc + tot[t - 1] <= kTailContacts) { acc += tot[t - 1]; --t; }
+    if (lastColour - t < 2 && t > 0) t = lastColour;   // a single small colour gains nothing from the CTA-local path
+    W.hdr->tailStart = W.colourOverride ? lastColour : t;
+  }
   W.hdr->colourOff[c] = excl;
   if (c == kMaxColours - 1) {
     const int total = excl + v;
@@ -1049,28 +1058,61 @@ __global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld 
   const unsigned nb = gridDim.x;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   const int nColours = H->nColours;
-  const int nJointColours = W.nJoints > 0 ? kMaxJointColours : 0;
-  const int* coff = H->colourOff;
-  const int* joff = H->jointColourOff;
+  const int nJointColours = W.nJoints > 0 ? min(W.nJointColours, kMaxJointColours) : 0;
+  // colour offsets live in shared memory: every barrier invalidates L1, and a phase must not start with an L2 round trip
+  // (let alone 64 of them over empty joint colours) just to learn its own range
+  __shared__ int coff[kMaxColours + 1];
+  __shared__ int joff[kMaxJointColours + 1];
+  for (int c = threadIdx.x; c <= nColours; c += blockDim.x) coff[c] = H->colourOff[c];
+  for (int c = threadIdx.x; c <= kMaxJointColours; c += blockDim.x) joff[c] = H->jointColourOff[c];
+  __syncthreads();
+  // Role split: the first JB CTAs only ever run joint code, the others only contact code, so the two large code paths never
+  // evict each other from an SM's instruction cache (measured: +4.4 us on every joint->contact switch otherwise).
+  const int JB = (W.nJoints > 0 && (int)nb >= 8) ? min(max(W.jointBlocks, 1), (int)nb / 2) : 0;
+  const bool jointRole = JB == 0 || (int)blockIdx.x < JB;
+  const bool contactRole = JB == 0 || (int)blockIdx.x >= JB;
+  const int jtid = tid, jnth = JB == 0 ? nth : JB * blockDim.x;
+  const int ctid = JB == 0 ? tid : tid - JB * blockDim.x, cnth = JB == 0 ? nth : nth - JB * blockDim.x;
+  // Tail colours (together at most kTailContacts constraints) run inside ONE CTA with CTA-scope barriers: a colour with a
+  // few hundred constraints is not worth a 1.7 us global barrier per pass.
+  const int T = min(H->tailStart, nColours);
+  const bool tailBlock = blockIdx.x == nb - 1;
   int phaseIdx = 0;
 #define PHASE_MARK() do { if (W.phaseTimes && tid == 0 && phaseIdx < W.phaseCap) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); W.phaseTimes[phaseIdx++] = t_; } } while (0)
   PHASE_MARK();
+  // debug window (DBX_DEBUG bit 1): per-CTA arrival / release stamps of 8 consecutive barriers starting at phase (flags >> 8)
+  const bool dbgWin = (W.dbgFlags & 2) && W.phaseTimes != nullptr;
+  const int dbgP0 = W.dbgFlags >> 8;
+  int barIdx = 0;
+#define GB() do { \
+    if (dbgWin && threadIdx.x == 0 && barIdx >= dbgP0 && barIdx < dbgP0 + 8) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); W.phaseTimes[512 + ((barIdx - dbgP0) * nb + blockIdx.x) * 2] = t_; } \
+    grid_barrier(&H->barrier, nb); \
+    if (dbgWin && threadIdx.x == 0 && barIdx >= dbgP0 && barIdx < dbgP0 + 8) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); W.phaseTimes[512 + ((barIdx - dbgP0) * nb + blockIdx.x) * 2 + 1] = t_; } \
+    ++barIdx; PHASE_MARK(); } while (0)
+  const bool haveTail = T < nColours && coff[T] < coff[nColours];
 
   // contacts warm start (b2island.d:138-141), colour by colour
   if (W.warmStarting) {
-    for (int c = 0; c < nColours; ++c) {
+    for (int c = 0; c < T; ++c) {
       int beg = coff[c], end = coff[c + 1];
       if (beg == end) continue;
-      for (int s = beg + tid; s < end; s += nth) contact_warm_start(W, s);
-      grid_barrier(&H->barrier, nb); PHASE_MARK();
+      if (contactRole) for (int s = beg + ctid; s < end; s += cnth) contact_warm_start(W, s);
+      GB();
+    }
+    if (haveTail) {
+      if (tailBlock) for (int c = T; c < nColours; ++c) {
+        for (int s = coff[c] + threadIdx.x; s < coff[c + 1]; s += blockDim.x) contact_warm_start(W, s);
+        __syncthreads();
+      }
+      GB();
     }
   }
   // joints: InitVelocityConstraints incl. their warm start (:143-146)
   for (int c = 0; c < nJointColours; ++c) {
     int beg = joff[c], end = joff[c + 1];
     if (beg == end) continue;
-    for (int k = beg + tid; k < end; k += nth) joint_init(W, k);
-    grid_barrier(&H->barrier, nb); PHASE_MARK();
+    if (jointRole) for (int k = beg + jtid; k < end; k += jnth) joint_init(W, k);
+    GB();
   }
   // velocity iterations: all joints, then all contacts (:153-161)
   VC pre; int preS = -1;
@@ -1078,27 +1120,34 @@ __global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld 
     for (int c = 0; c < nJointColours; ++c) {
       int beg = joff[c], end = joff[c + 1];
       if (beg == end) continue;
-      for (int k = beg + tid; k < end; k += nth) if (W.j_root[k] >= 0) joint_solve_velocity(W, k);
-      grid_barrier(&H->barrier, nb); PHASE_MARK();
+      if (jointRole && !(W.dbgFlags & 1)) for (int k = beg + jtid; k < end; k += jnth) if (W.j_root[k] >= 0) joint_solve_velocity(W, k);
+      GB();
     }
-    for (int c = 0; c < nColours; ++c) {
+    for (int c = 0; c < T; ++c) {
       int beg = coff[c], end = coff[c + 1];
       if (beg == end) continue;
-      // the first item of this colour was fetched before the previous barrier; fetch the next colour's before this one
-      int s = beg + tid;
-      if (s < end) {
-        if (preS != s) vc_load(W, s, pre);
-        contact_solve_velocity(W, s, pre);
-        for (s += nth; s < end; s += nth) contact_solve_velocity(W, s);
-      }
-      {
+      if (contactRole) {
+        // the first item of this colour was fetched before the previous barrier; fetch the next colour's before this one
+        int s = beg + ctid;
+        if (s < end) {
+          if (preS != s) vc_load(W, s, pre);
+          contact_solve_velocity(W, s, pre);
+          for (s += cnth; s < end; s += cnth) contact_solve_velocity(W, s);
+        }
         int cn = c + 1;
-        while (cn < nColours && coff[cn] == coff[cn + 1]) ++cn;
-        if (cn >= nColours) { cn = 0; while (cn < nColours && coff[cn] == coff[cn + 1]) ++cn; }
+        while (cn < T && coff[cn] == coff[cn + 1]) ++cn;
+        if (cn >= T) { cn = 0; while (cn < T && coff[cn] == coff[cn + 1]) ++cn; }
         preS = -1;
-        if (cn < nColours && (cn > c || it + 1 < W.velIters)) { int sn = coff[cn] + tid; if (sn < coff[cn + 1]) { vc_load(W, sn, pre); preS = sn; } }
+        if (cn < T && (cn > c || it + 1 < W.velIters)) { int sn = coff[cn] + ctid; if (sn < coff[cn + 1]) { vc_load(W, sn, pre); preS = sn; } }
       }
-      grid_barrier(&H->barrier, nb); PHASE_MARK();
+      GB();
+    }
+    if (haveTail) {
+      if (tailBlock) for (int c = T; c < nColours; ++c) {
+        for (int s = coff[c] + threadIdx.x; s < coff[c + 1]; s += blockDim.x) contact_solve_velocity(W, s);
+        __syncthreads();
+      }
+      GB();
     }
   }
   // StoreImpulses (:164) + integrate positions (:168-200)
@@ -1130,33 +1179,45 @@ __global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld 
       stcg4(&W.b_vel[b], make_float4(v.x, v.y, w, 0.0f));
     }
   }
-  grid_barrier(&H->barrier, nb); PHASE_MARK();
+  GB();
   // position iterations: contacts then joints, each island stops once all of its constraints are within tolerance (:206-224)
   for (int it = 0; it < W.posIters; ++it) {
     int* notOk = W.b_posNotOk + it * W.nBodies;
     const int* prev = it > 0 ? W.b_posNotOk + (it - 1) * W.nBodies : nullptr;
-    for (int c = 0; c < nColours; ++c) {
+    for (int c = 0; c < T; ++c) {
       int beg = coff[c], end = coff[c + 1];
       if (beg == end) continue;
-      for (int s = beg + tid; s < end; s += nth) {
+      if (contactRole) for (int s = beg + ctid; s < end; s += cnth) {
         int root = W.s_root[s];
         if (prev && __ldcg(&prev[root]) == 0) continue;
         float minSep = contact_solve_position(W, s);
         if (!(minSep >= -3.0f * kLinearSlop)) notOk[root] = 1;
       }
-      grid_barrier(&H->barrier, nb); PHASE_MARK();
+      GB();
+    }
+    if (haveTail) {
+      if (tailBlock) for (int c = T; c < nColours; ++c) {
+        for (int s = coff[c] + threadIdx.x; s < coff[c + 1]; s += blockDim.x) {
+          int root = W.s_root[s];
+          if (prev && __ldcg(&prev[root]) == 0) continue;
+          float minSep = contact_solve_position(W, s);
+          if (!(minSep >= -3.0f * kLinearSlop)) notOk[root] = 1;
+        }
+        __syncthreads();
+      }
+      GB();
     }
     for (int c = 0; c < nJointColours; ++c) {
       int beg = joff[c], end = joff[c + 1];
       if (beg == end) continue;
-      for (int k = beg + tid; k < end; k += nth) {
+      if (jointRole) for (int k = beg + jtid; k < end; k += jnth) {
         const int j = k;
         int root = W.j_root[j];
         if (root < 0) continue;
         if (prev && __ldcg(&prev[root]) == 0) continue;
         if (!joint_solve_position(W, j)) notOk[root] = 1;
       }
-      grid_barrier(&H->barrier, nb); PHASE_MARK();
+      GB();
     }
   }
   // write back + SynchronizeTransform (:227-235), sleep bookkeeping (:241-269), ClearForces (b2world.d:443-450)
@@ -1181,7 +1242,7 @@ __global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld 
       }
     }
   }
-  grid_barrier(&H->barrier, nb); PHASE_MARK();
+  GB();
   if (W.allowSleep) {
     const int* last = W.posIters > 0 ? W.b_posNotOk + (W.posIters - 1) * W.nBodies : nullptr;
     for (int b = tid; b < W.nBodies; b += nth) {
@@ -1201,6 +1262,7 @@ __global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld 
   }
 }
 
+#undef GB
 #undef PHASE_MARK
 __global__ void __launch_bounds__(256) k_apply_forces(const __grid_constant__ DevWorld W, const float4* forces, int n) {
   GRID_STRIDE(b, n) {

@@ -2,6 +2,7 @@
 #include "dbx_world.h"
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -454,6 +455,10 @@ int World::recolourJoints() {
   for (int c = 0; c < kMaxJointColours; ++c) { off[c] = (int)jointAt_.size(); jointAt_.insert(jointAt_.end(), byColour[c].begin(), byColour[c].end()); }
   off[kMaxJointColours] = (int)jointAt_.size();
   for (size_t k = 0; k < jointAt_.size(); ++k) jointPos_[jointAt_[k]] = (int)k;
+  size_t maxPerColour = 0;
+  nJointColours_ = 0;
+  for (int c = 0; c < kMaxJointColours; ++c) { maxPerColour = std::max(maxPerColour, byColour[c].size()); if (!byColour[c].empty()) nJointColours_ = c + 1; }
+  jointBlocks_ = (int)std::min<size_t>((maxPerColour + L_.coopThreads - 1) / L_.coopThreads, (size_t)L_.coopBlocks / 4);
   std::sort(jp.begin(), jp.end());
   jp.erase(std::unique(jp.begin(), jp.end()), jp.end());
   nJointPairs_ = (int)jp.size();
@@ -651,6 +656,8 @@ void World::refreshView() {
   w.nJoints = (int)jointAt_.size(); w.j_ids = j_ids.p; w.j_anchor = j_anchor.p; w.j_p0 = j_p0.p; w.j_p1 = j_p1.p; w.j_imp = j_imp.p; w.j_limit = j_limit.p; w.j_colour = j_colour.p;
   w.j_order = j_order.p; w.j_root = j_root.p; w.j_r = j_r.p; w.j_lc = j_lc.p; w.j_m = j_m.p; w.j_k0 = j_k0.p; w.j_k1 = j_k1.p; w.j_k2 = j_k2.p;
   w.nWorlds = nWorlds_;
+  w.jointBlocks = jointBlocks_; w.nJointColours = nJointColours_;
+  { const char* e = getenv("DBX_DEBUG"); w.dbgFlags = e ? atoi(e) : 0; }
   w.phaseTimes = phaseBuf_.p; w.phaseCap = phaseBuf_.p ? (int)phaseBuf_.cap : 0;
   L_.cubTemp = cubTemp.p; L_.cubTempBytes = cubTemp.cap;
 }

@@ -159,7 +159,7 @@ class World {
   DevBuf<int4> j_ids; DevBuf<float4> j_anchor, j_p0, j_p1, j_imp, j_r, j_lc, j_m, j_k0, j_k1, j_k2; DevBuf<int> j_limit, j_colour, j_order, j_root;
   DevBuf<char> cubTemp; DevBuf<int> d_levels;
   DevBuf<unsigned long long> cmpKeyA_, cmpKeyB_; DevBuf<int> cmpValA_, cmpValB_;
-  int nJointPairs_ = 0;
+  int nJointPairs_ = 0; int jointBlocks_ = 0, nJointColours_ = 0;
   cudaEvent_t ev_[10]{};
   bool evValid_ = false, evFine_ = false;
   DevBuf<char> flushBuf_; DevBuf<float4> ioBuf_; DevBuf<unsigned long long> phaseBuf_;
