@@ -191,6 +191,7 @@ struct DevWorld {
   // ---- step parameters
   float dt, inv_dt, dtRatio; int velIters, posIters; int warmStarting; int allowSleep; int continuous; float gx, gy;
   int nWorlds;
+  int keyStride;        // reference-key stride between replicas (0 when not replicated)
   unsigned long long* phaseTimes; int phaseCap;   // debug: globaltimer stamp after every barrier of k_solve (null = off)
   int dbgFlags;         // experiments only (DBX_DEBUG env): bit 0 = joint velocity phases do no work
   int nJointColours;    // joint colours in use (host-side greedy colouring)

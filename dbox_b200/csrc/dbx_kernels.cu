@@ -243,8 +243,11 @@ __global__ void __launch_bounds__(256) k_island_flatten(const __grid_constant__ 
   GRID_STRIDE(b, W.nBodies) {
     uint32_t f = W.b_flags[b];
     if (!(f & BF_ALIVE)) continue;
-    int r = uf_find(W.b_root, b);
-    W.b_root[b] = r;
+    // read-only walk: a compressing find here could let another thread's late path-halving store overwrite this body's
+    // final root with an intermediate ancestor (observed as a body dropping out of its island)
+    int r = b;
+    for (;;) { int p = __ldcg(&W.b_root[r]); if (p == r) break; r = p; }
+    __stcg(&W.b_root[b], r);
     // seeds: awake, active, non-static (b2world.d:963-979)
     if ((f & BF_AWAKE) && (f & BF_ACTIVE) && body_type(f) != BODY_STATIC) W.b_islAwake[r] = 1;
   }
@@ -324,6 +327,12 @@ __global__ void __launch_bounds__(256) k_mark_solve(const __grid_constant__ DevW
 // same round are arbitrated Jones-Plassmann style: per body the contact with the highest (key-derived) priority wins,
 // so the outcome is independent of thread scheduling.  Static/kinematic bodies are never written by the solver and do
 // not constrain colours.  Runs as one persistent cooperative kernel; rounds loop on the device.
+// pair key with the replica offset removed, so that every replica of a batched world arbitrates (and hence colours) alike
+DBX_D unsigned long long local_key(const DevWorld& W, unsigned long long key, int body) {
+  if (W.keyStride == 0) return key;
+  const unsigned long long o = (unsigned long long)(unsigned)(W.b_world[body] * W.keyStride);
+  return key - (o << 32) - o;
+}
 __global__ void __launch_bounds__(512) k_colour(const __grid_constant__ DevWorld W) {
   Header* H = W.hdr;
   const unsigned nb = gridDim.x;
@@ -343,7 +352,7 @@ __global__ void __launch_bounds__(512) k_colour(const __grid_constant__ DevWorld
     for (int k = tid; k < n; k += nth) {
       int i = cur[k];
       int4 ids = W.c_ids[i];
-      unsigned long long pr = ((unsigned long long)(epoch & 0xFFFFF) << 44) | (mix64(W.c_key[i]) >> 20);
+      unsigned long long pr = ((unsigned long long)(epoch & 0xFFFFF) << 44) | (mix64(local_key(W, W.c_key[i], ids.z)) >> 20);
       if (body_type(W.b_flags[ids.z]) == BODY_DYNAMIC) atomicMax(&W.b_claim[ids.z], pr);
       if (body_type(W.b_flags[ids.w]) == BODY_DYNAMIC) atomicMax(&W.b_claim[ids.w], pr);
     }
@@ -353,7 +362,7 @@ __global__ void __launch_bounds__(512) k_colour(const __grid_constant__ DevWorld
     for (int k = tid; k < n; k += nth) {
       int i = cur[k];
       int4 ids = W.c_ids[i];
-      unsigned long long pr = ((unsigned long long)(epoch & 0xFFFFF) << 44) | (mix64(W.c_key[i]) >> 20);
+      unsigned long long pr = ((unsigned long long)(epoch & 0xFFFFF) << 44) | (mix64(local_key(W, W.c_key[i], ids.z)) >> 20);
       bool dynA = body_type(W.b_flags[ids.z]) == BODY_DYNAMIC, dynB = body_type(W.b_flags[ids.w]) == BODY_DYNAMIC;
       bool win = (!dynA || __ldcg(&W.b_claim[ids.z]) == pr) && (!dynB || __ldcg(&W.b_claim[ids.w]) == pr);
       if (win) {
@@ -1613,6 +1622,38 @@ cudaError_t stage_compact_contacts(DevWorld& W, const LaunchCfg& L, int high, in
   return stage_rebuild_hash(W, L);
 }
 
+// ------------------------------------------------------------------------------------------------ replicas
+// dbx_world_replicate: replica r > 0 of every body / fixture / proxy is a copy of replica 0 with its indices shifted.
+__global__ void __launch_bounds__(256) k_replicate(const __grid_constant__ DevWorld W, int nB, int nF, int nP, int nMoved, int keyStride, int copies) {
+  GRID_STRIDE(idx, nB * copies) {
+    const int r = idx / nB, b = idx - r * nB;
+    if (r > 0) {
+      W.b_xf[idx] = W.b_xf[b]; W.b_xf0[idx] = W.b_xf0[b]; W.b_pos[idx] = W.b_pos[b]; W.b_pos0[idx] = W.b_pos0[b]; W.b_vel[idx] = W.b_vel[b];
+      W.b_force[idx] = W.b_force[b]; W.b_mass[idx] = W.b_mass[b]; W.b_lc[idx] = W.b_lc[b]; W.b_gs[idx] = W.b_gs[b]; W.b_flags[idx] = W.b_flags[b];
+    }
+    W.b_world[idx] = r;
+  }
+  GRID_STRIDE(idx, nF * copies) {
+    const int r = idx / nF, f = idx - r * nF;
+    if (r > 0) { W.f_body[idx] = W.f_body[f] + r * nB; W.f_mat[idx] = W.f_mat[f]; W.f_filter[idx] = W.f_filter[f]; W.f_group[idx] = W.f_group[f]; }
+  }
+  GRID_STRIDE(idx, nP * copies) {
+    const int r = idx / nP, p = idx - r * nP;
+    if (r > 0) {
+      int4 ids = W.p_ids[p];
+      ids.x += r * nF; ids.z += r * nB;
+      W.p_ids[idx] = ids;
+      W.p_key[idx] = W.p_key[p] + r * keyStride;
+      W.p_aabb[idx] = W.p_aabb[p]; W.p_fat[idx] = W.p_fat[p]; W.p_flags[idx] = W.p_flags[p];
+    }
+  }
+  GRID_STRIDE(idx, nMoved * copies) {
+    const int r = idx / nMoved, k = idx - r * nMoved;
+    if (r > 0) W.moveList[idx] = W.moveList[k] + r * nP;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { W.hdr->nMoved = nMoved * copies; if (nMoved * copies > W.moveCap) W.hdr->error = -5; }
+}
+
 // ------------------------------------------------------------------------------------------------ API-time edits
 // DestroyFixture / DestroyBody / SetActive(false) (b2body.d:211-227, b2world.d:136-145) destroy the matching contacts;
 // CreateJoint / DestroyJoint with collideConnected == false flag them for re-filtering (b2world.d:241-256, 344-359).
@@ -1699,6 +1740,12 @@ __global__ void __launch_bounds__(256) k_lbvh_enlarge(const __grid_constant__ De
   GRID_STRIDE(k, nMoved) lbvh_enlarge(W, W.moveList[k]);
 }
 
+// event priority: earlier alpha first; exact ties on a shared body are broken by a hash of the replica-local pair key, so
+// the choice does not depend on slot numbers (which atomics hand out in a run-dependent order)
+DBX_D unsigned long long toi_prio(const DevWorld& W, float alpha, int contact, int bodyOfContact) {
+  return ((unsigned long long)__float_as_uint(alpha) << 32) | (unsigned)(mix64(local_key(W, W.c_key[contact], bodyOfContact)) >> 32);
+}
+
 // (a) evaluate b2TimeOfImpact for every eligible contact that has no cached value (b2world.d:1155-1265)
 DBX_D void toi_evaluate(const DevWorld& W, int i) {
   uint32_t flags = W.c_flags[i];
@@ -1736,7 +1783,7 @@ DBX_D void toi_evaluate(const DevWorld& W, int i) {
     W.c_flags[i] = flags;
   }
   if (1.0f - 10.0f * kEpsilon < alpha) return;   // never becomes an event (:1267-1272)
-  const unsigned long long prio = ((unsigned long long)__float_as_uint(alpha) << 32) | (unsigned)i;
+  const unsigned long long prio = toi_prio(W, alpha, i, ids.z);
   if (body_type(fa) != BODY_STATIC) atomicMin(&W.b_toiMin[ids.z], prio);
   if (body_type(fb) != BODY_STATIC) atomicMin(&W.b_toiMin[ids.w], prio);
 }
@@ -1747,7 +1794,7 @@ DBX_D void toi_process_event(const DevWorld& W, int e, float dtStep) {
   const int4 ids0 = W.c_ids[i0];
   const int bA = ids0.z, bB = ids0.w;
   const float minAlpha = W.c_mat[i0].w;
-  const unsigned long long prio = ((unsigned long long)__float_as_uint(minAlpha) << 32) | (unsigned)i0;
+  const unsigned long long prio = toi_prio(W, minAlpha, i0, bA);
   const uint32_t fA = W.b_flags[bA], fB = W.b_flags[bB];
   // arbitration over the movable bodies this event would pull in besides bA/bB
   for (int side = 0; side < 2; ++side) {
@@ -1761,7 +1808,7 @@ DBX_D void toi_process_event(const DevWorld& W, int e, float dtStep) {
       const int oe = __ldcg(&W.b_toiEvt[other]);
       if (oe >= 0 && oe != e) {
         const int oc = W.e_contact[oe];
-        const unsigned long long op = ((unsigned long long)__float_as_uint(W.c_mat[oc].w) << 32) | (unsigned)oc;
+        const unsigned long long op = toi_prio(W, W.c_mat[oc].w, oc, W.c_ids[oc].z);
         if (op < prio) return;
       }
     }
@@ -1791,8 +1838,13 @@ DBX_D void toi_process_event(const DevWorld& W, int e, float dtStep) {
     if (body_type(fbody) != BODY_DYNAMIC) continue;
     const int ncand = min(W.e_ncand[2 * e + side], kToiCand);
     int* cand = W.e_cand + (2 * e + side) * kToiCand;
-    // newest first, like the body's contact list: approximated by descending slot
-    for (int a = 1; a < ncand; ++a) { int v = cand[a]; int b = a - 1; while (b >= 0 && cand[b] < v) { cand[b + 1] = cand[b]; --b; } cand[b + 1] = v; }
+    // newest first, like the body's contact list: approximated by descending (replica-local) pair key
+    for (int a = 1; a < ncand; ++a) {
+      const int v = cand[a]; const unsigned long long kv = local_key(W, W.c_key[v], body);
+      int b = a - 1;
+      while (b >= 0 && local_key(W, W.c_key[cand[b]], body) < kv) { cand[b + 1] = cand[b]; --b; }
+      cand[b + 1] = v;
+    }
     for (int k = 0; k < ncand; ++k) {
       if (nb == 2 * kMaxTOIContacts) break;
       if (nc == kMaxTOIContacts) break;
@@ -1866,6 +1918,9 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warp = tid >> 5, nwarps = nth >> 5;
   const int eventCap = min(W.eventCap, nwarps);
+  int tmark = 0;
+#define TMARK() do { if (W.phaseTimes && tid == 0 && tmark < 64) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); W.phaseTimes[3000 + tmark++] = t_; } } while (0)
+  TMARK();
   // reset (m_stepComplete is always true here: sub-stepping is not supported) (:1131-1146)
   {
     const int n = H->cHigh;
@@ -1882,14 +1937,14 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
     }
     if (tid == 0) H->nEvents = 0;
   }
-  grid_barrier(&H->barrier, nb);
+  grid_barrier(&H->barrier, nb); TMARK();
   for (int pass = 0; pass < 1024; ++pass) {
     // (a) TOI evaluation + per-body minima
     {
       const int n = *((volatile int*)&H->cHigh);
       for (int i = tid; i < n; i += nth) toi_evaluate(W, i);
     }
-    grid_barrier(&H->barrier, nb);
+    grid_barrier(&H->barrier, nb); TMARK();
     // (b) winners: the minimum on every movable body they touch
     {
       const int n = *((volatile int*)&H->cHigh);
@@ -1900,7 +1955,7 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
         const float alpha = W.c_mat[i].w;
         if (1.0f - 10.0f * kEpsilon < alpha) continue;
         const int4 ids = W.c_ids[i];
-        const unsigned long long prio = ((unsigned long long)__float_as_uint(alpha) << 32) | (unsigned)i;
+        const unsigned long long prio = toi_prio(W, alpha, i, ids.z);
         const bool movA = body_type(W.b_flags[ids.z]) != BODY_STATIC, movB = body_type(W.b_flags[ids.w]) != BODY_STATIC;
         if ((movA && __ldcg(&W.b_toiMin[ids.z]) != prio) || (movB && __ldcg(&W.b_toiMin[ids.w]) != prio)) continue;
         const int e = atomicAdd(&H->nEvents, 1);
@@ -1912,7 +1967,7 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
       }
       for (int b = tid; b < W.nBodies; b += nth) if (W.b_toiFlags[b] & TF_INVAL) W.b_toiFlags[b] &= ~TF_INVAL;
     }
-    grid_barrier(&H->barrier, nb);
+    grid_barrier(&H->barrier, nb); TMARK();
     const int nEvents = min(*((volatile int*)&H->nEvents), eventCap);
     if (nEvents == 0) break;
     // (c) contacts of the event bodies that may join their mini-islands (b2world.d:1319-1411)
@@ -1935,16 +1990,16 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
           const int slot = atomicAdd(&W.e_ncand[2 * e + evSide], 1);
           if (slot < kToiCand) W.e_cand[(2 * e + evSide) * kToiCand + slot] = i; else H->error = -5;
           if (body_type(fother) != BODY_STATIC) {
-            const unsigned long long prio = ((unsigned long long)__float_as_uint(W.c_mat[ec].w) << 32) | (unsigned)ec;
+            const unsigned long long prio = toi_prio(W, W.c_mat[ec].w, ec, W.c_ids[ec].z);
             atomicMin(&W.b_toiOther[other], prio);
           }
         }
       }
     }
-    grid_barrier(&H->barrier, nb);
+    grid_barrier(&H->barrier, nb); TMARK();
     // (d) events
     if (lane == 0) for (int e = warp; e < nEvents; e += nwarps) toi_process_event(W, e, W.dt);
-    grid_barrier(&H->barrier, nb);
+    grid_barrier(&H->barrier, nb); TMARK();
     // (e) SynchronizeFixtures of the island's dynamic bodies (:1433), then FindNewContacts (:1444)
     for (int p = tid; p < W.nProxies; p += nth) {
       const uint32_t pf = W.p_flags[p];
@@ -1954,7 +2009,7 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
       sync_proxy(W, p, pf, body);
     }
     if (tid == 0) H->nPairs = 0;
-    grid_barrier(&H->barrier, nb);
+    grid_barrier(&H->barrier, nb); TMARK();
     {
       // the step's LBVH is still valid for every proxy that did not move; widen it for the ones that did
       const int nMoved = min(*((volatile int*)&H->nMoved), W.moveCap);
@@ -1965,24 +2020,25 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
       }
       if (tid == 0) H->nEvents = 0;
     }
-    grid_barrier(&H->barrier, nb);
+    grid_barrier(&H->barrier, nb); TMARK();
     {
       const int nMoved = min(*((volatile int*)&H->nMoved), W.moveCap);
       for (int k = warp; k < nMoved; k += nwarps) query_proxy(W, W.bv_sorted, stacks[wib], lane, W.moveList[k]);
     }
-    grid_barrier(&H->barrier, nb);
+    grid_barrier(&H->barrier, nb); TMARK();
     {
       const int nPairs = min(*((volatile int*)&H->nPairs), W.pairCap);
       for (int k = tid; k < nPairs; k += nth) add_pair(W, W.pairs[k]);
       const int nMoved = min(*((volatile int*)&H->nMoved), W.moveCap);
       for (int k = tid; k < nMoved; k += nth) { const int p = W.moveList[k]; W.p_flags[p] &= ~PF_MOVED; }
     }
-    grid_barrier(&H->barrier, nb);
+    grid_barrier(&H->barrier, nb); TMARK();
     if (tid == 0) H->nMoved = 0;
-    grid_barrier(&H->barrier, nb);
+    grid_barrier(&H->barrier, nb); TMARK();
   }
 }
 
+#undef TMARK
 // ------------------------------------------------------------------------------------------------ host launchers
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return _e; } while (0)
 
@@ -2105,6 +2161,10 @@ cudaError_t launch_clear_forces(const DevWorld& W, const LaunchCfg& L) {
   return cudaGetLastError();
 }
 
+cudaError_t launch_replicate(const DevWorld& W, const LaunchCfg& L, int nB, int nF, int nP, int nMoved, int keyStride, int copies) {
+  ++L.launches; k_replicate<<<L.gridWide, 256, 0, L.stream>>>(W, nB, nF, nP, nMoved, keyStride, copies);
+  return cudaGetLastError();
+}
 cudaError_t launch_set_levels(const DevWorld& W, const LaunchCfg& L, const int* d_levels, int n) {
   ++L.launches; k_set_levels<<<L.gridWide, 256, 0, L.stream>>>(W, d_levels, n);
   return cudaGetLastError();

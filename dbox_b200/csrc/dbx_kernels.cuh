@@ -34,6 +34,7 @@ cudaError_t launch_api_contacts(const DevWorld& W, const LaunchCfg& L, int body,
 cudaError_t launch_api_wake(const DevWorld& W, const LaunchCfg& L, int a, int b);
 cudaError_t launch_apply_forces(const DevWorld& W, const LaunchCfg& L, const float4* forces, int n);
 cudaError_t launch_clear_forces(const DevWorld& W, const LaunchCfg& L);
+cudaError_t launch_replicate(const DevWorld& W, const LaunchCfg& L, int nB, int nF, int nP, int nMoved, int keyStride, int copies);
 cudaError_t launch_set_levels(const DevWorld& W, const LaunchCfg& L, const int* d_levels, int n);
 
 }  // namespace dbx

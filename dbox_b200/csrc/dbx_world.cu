@@ -201,6 +201,7 @@ void World::wake(HBody& hb, bool flag) {  // b2Body.SetAwake (b2body.d:827-846)
 
 // ------------------------------------------------------------------------------------------------ lifecycle
 int World::createBody(const dbx_body_def& d) {
+  if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
   HBody hb;
   hb.alive = true;
   dbx_body_state& st = hb.st;
@@ -227,6 +228,7 @@ int World::createBody(const dbx_body_def& d) {
 }
 
 int World::createFixture(int b, const dbx_fixture_def& d, const dbx_shape& s) {
+  if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
   if (b < 0 || b >= (int)bodies_.size() || !bodies_[b].alive) return DBX_E_INVALID;
   if ((size_t)b < bodiesSynced_) { int rc = pullBodies(); if (rc < 0) return rc; fullPushBodies_ = true; }
   HBody& hb = bodies_[b];
@@ -276,6 +278,7 @@ int World::destroyContactsWhere(int body, int fixture, int otherBody, bool flagO
 }
 
 int World::destroyFixture(int fid) {
+  if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
   if (fid < 0 || fid >= (int)fixtures_.size() || !fixtures_[fid].alive) return DBX_E_INVALID;
   int rc = destroyContactsWhere(-1, fid, -1, false); if (rc < 0) return rc;
   rc = pullBodies(); if (rc < 0) return rc;
@@ -297,6 +300,7 @@ int World::destroyFixture(int fid) {
 }
 
 int World::destroyBody(int b) {
+  if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
   if (b < 0 || b >= (int)bodies_.size() || !bodies_[b].alive) return DBX_E_INVALID;
   std::vector<int> js = bodies_[b].joints;
   for (int j : js) destroyJoint(j);
@@ -322,6 +326,7 @@ int World::destroyBody(int b) {
 }
 
 int World::createJoint(const dbx_joint_def& d) {
+  if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
   if (d.type != DBX_JOINT_REVOLUTE && d.type != DBX_JOINT_DISTANCE) { set_last_error("joint type not in this build's hot-path scope"); return DBX_E_UNSUPPORTED; }
   if (d.bodyA < 0 || d.bodyB < 0 || d.bodyA >= (int)bodies_.size() || d.bodyB >= (int)bodies_.size() || !bodies_[d.bodyA].alive || !bodies_[d.bodyB].alive || d.bodyA == d.bodyB) return DBX_E_INVALID;
   HJoint j; j.alive = true; j.def = d;
@@ -337,6 +342,7 @@ int World::createJoint(const dbx_joint_def& d) {
 }
 
 int World::destroyJoint(int jid) {
+  if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
   if (jid < 0 || jid >= (int)joints_.size() || !joints_[jid].alive) return DBX_E_INVALID;
   int rc = pullJoints(); if (rc < 0) return rc;
   HJoint& j = joints_[jid];
@@ -476,21 +482,11 @@ template <class T, class F> static cudaError_t upload_range(DevBuf<T>& buf, size
   return cudaMemcpy(buf.p + from, tmp.data(), (to - from) * sizeof(T), cudaMemcpyHostToDevice);
 }
 
-int World::push() {
-  cudaSetDevice(device_);
-  const size_t nB = bodies_.size(), nF = fixtures_.size(), nP = proxies_.size(), nS = shapes_.size(), nJ = joints_.size();
-  const bool anyBody = fullPushBodies_ || nB > bodiesSynced_;
-  const bool anyFix = fullPushFixtures_ || nF > fixturesSynced_;
-  const bool anyProxy = fullPushProxies_ || nP > proxiesSynced_ || !pendingMoves_.empty();
-  const bool anyShape = nS > shapesSynced_;
-  const bool anyJoint = fullPushJoints_ || nJ > jointsSynced_ || jointsChanged_;
-  if (!anyBody && !anyFix && !anyProxy && !anyShape && !anyJoint && dw_.hdr) return 0;
-  if (fullPushBodies_ && !hostBodiesValid_) { int rc = pullBodies(); if (rc < 0) return rc; }
-  if (fullPushProxies_ && !hostProxiesValid_) { int rc = pullProxies(); if (rc < 0) return rc; }
-  if (anyJoint && !hostJointsValid_) { int rc = pullJoints(); if (rc < 0) return rc; }
-  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
-
+// (re)size every device pool for the current object counts (times the replica count)
+int World::reserveDevice(bool& rehash) {
   // ---- capacities
+  const size_t W_ = (size_t)nWorlds_;
+  const size_t nB = bodies_.size() * W_, nF = fixtures_.size() * W_, nP = proxies_.size() * W_, nS = shapes_.size(), nJ = joints_.size() * W_;
   const size_t capB = std::max<size_t>(std::max<size_t>(nB, 1), (size_t)caps_.maxBodies);
   const size_t capP = std::max<size_t>(std::max<size_t>(nP, 1), (size_t)caps_.maxProxies);
   DevBuf<float4>* bf4[] = {&b_xf, &b_xf0, &b_pos, &b_pos0, &b_vel, &b_force, &b_mass, &b_lc};
@@ -518,7 +514,7 @@ int World::push() {
   CUDA_OR_FAIL(p_fat.reserve(capP, true, stream_), "p_fat");
   CUDA_OR_FAIL(p_flags.reserve(capP, true, stream_), "p_flags");
   const size_t pc = p_ids.cap;
-  CUDA_OR_FAIL(moveList.reserve(pc, false, stream_), "moveList");
+  CUDA_OR_FAIL(moveList.reserve(pc, true, stream_), "moveList");   // keep: pending moves may be waiting (replicate)
   CUDA_OR_FAIL(bv_key.reserve(pc, false, stream_), "bv_key"); CUDA_OR_FAIL(bv_keyAlt.reserve(pc, false, stream_), "bv_keyAlt");
   CUDA_OR_FAIL(bv_leaf.reserve(pc, false, stream_), "bv_leaf"); CUDA_OR_FAIL(bv_leafAlt.reserve(pc, false, stream_), "bv_leafAlt");
   CUDA_OR_FAIL(bv_box.reserve(2 * pc, false, stream_), "bv_box"); CUDA_OR_FAIL(bv_child.reserve(pc, false, stream_), "bv_child");
@@ -538,10 +534,11 @@ int World::push() {
   DevBuf<int>* ci[] = {&c_toiCount, &c_colour, &c_free, &c_work, &c_work2};
   for (auto* b : ci) CUDA_OR_FAIL(b->reserve(capC, true, stream_), "contact int");
   const size_t cc = c_key.cap;
-  bool rehash = false;
-  if (h_key.cap < 4 * cc) {
+  size_t hc = 1024;
+  while (hc < 2 * cc) hc <<= 1;            // power of two (the probe sequence masks), load factor <= 0.5
+  if (h_key.cap < hc) {
     h_key.release(); h_val.release();
-    CUDA_OR_FAIL(h_key.reserve(4 * cc, false, stream_), "h_key"); CUDA_OR_FAIL(h_val.reserve(4 * cc, false, stream_), "h_val");
+    CUDA_OR_FAIL(h_key.reserve(hc, false, stream_), "h_key"); CUDA_OR_FAIL(h_val.reserve(hc, false, stream_), "h_val");
     rehash = true;
   }
   CUDA_OR_FAIL(pairs.reserve(std::max<size_t>(std::max<size_t>(4096, cc), (size_t)caps_.maxPairs), false, stream_), "pairs");
@@ -557,6 +554,27 @@ int World::push() {
   CUDA_OR_FAIL(j_ids.reserve(capJ, true, stream_), "j_ids"); CUDA_OR_FAIL(j_limit.reserve(capJ, true, stream_), "j_limit"); CUDA_OR_FAIL(j_root.reserve(capJ, true, stream_), "j_root");
   CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
   (void)oldCCap;
+
+  return 0;
+}
+
+int World::push() {
+  cudaSetDevice(device_);
+  if (replicated_) return 0;   // nothing on the host can be newer than the device any more
+  const size_t nB = bodies_.size(), nF = fixtures_.size(), nP = proxies_.size(), nS = shapes_.size(), nJ = joints_.size();
+  const bool anyBody = fullPushBodies_ || nB > bodiesSynced_;
+  const bool anyFix = fullPushFixtures_ || nF > fixturesSynced_;
+  const bool anyProxy = fullPushProxies_ || nP > proxiesSynced_ || !pendingMoves_.empty();
+  const bool anyShape = nS > shapesSynced_;
+  const bool anyJoint = fullPushJoints_ || nJ > jointsSynced_ || jointsChanged_;
+  if (!anyBody && !anyFix && !anyProxy && !anyShape && !anyJoint && dw_.hdr) return 0;
+  if (fullPushBodies_ && !hostBodiesValid_) { int rc = pullBodies(); if (rc < 0) return rc; }
+  if (fullPushProxies_ && !hostProxiesValid_) { int rc = pullProxies(); if (rc < 0) return rc; }
+  if (anyJoint && !hostJointsValid_) { int rc = pullJoints(); if (rc < 0) return rc; }
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+
+  bool rehash = false;
+  { int rcap = reserveDevice(rehash); if (rcap < 0) return rcap; }
 
   // ---- bodies
   {
@@ -635,15 +653,15 @@ int World::push() {
 void World::refreshView() {
   DevWorld& w = dw_;
   w.hdr = hdr_.p;
-  w.nBodies = (int)bodies_.size();
+  w.nBodies = (int)bodies_.size() * nWorlds_;
   w.b_xf = b_xf.p; w.b_xf0 = b_xf0.p; w.b_pos = b_pos.p; w.b_pos0 = b_pos0.p; w.b_vel = b_vel.p; w.b_force = b_force.p; w.b_mass = b_mass.p; w.b_lc = b_lc.p;
   w.b_gs = b_gs.p; w.b_flags = b_flags.p; w.b_wake = b_wake.p; w.b_root = b_root.p; w.b_islAwake = b_islAwake.p; w.b_islMinSleep = b_islMinSleep.p;
   w.b_toiMin = b_toiMin.p; w.b_toiOther = b_toiOther.p; w.b_toiEvt = b_toiEvt.p; w.b_toiFlags = b_toiFlags.p;
   w.e_contact = e_contact.p; w.e_ncand = e_ncand.p; w.e_cand = e_cand.p; w.eventCap = (int)e_contact.cap; w.bv_pos = bv_pos.p;
   w.b_posNotOk = b_posNotOk.p; w.b_mask = b_mask.p; w.b_claim = b_claim.p; w.b_ovf = b_ovf.p; w.b_world = b_world.p;
-  w.nFixtures = (int)fixtures_.size(); w.f_body = f_body.p; w.f_mat = f_mat.p; w.f_filter = f_filter.p; w.f_group = f_group.p;
+  w.nFixtures = (int)fixtures_.size() * nWorlds_; w.f_body = f_body.p; w.f_mat = f_mat.p; w.f_filter = f_filter.p; w.f_group = f_group.p;
   w.nShapes = (int)shapes_.size(); w.shapes = d_shapes.p;
-  w.nProxies = (int)proxies_.size(); w.p_ids = p_ids.p; w.p_key = p_key.p; w.p_aabb = p_aabb.p; w.p_fat = p_fat.p; w.p_flags = p_flags.p;
+  w.nProxies = (int)proxies_.size() * nWorlds_; w.p_ids = p_ids.p; w.p_key = p_key.p; w.p_aabb = p_aabb.p; w.p_fat = p_fat.p; w.p_flags = p_flags.p;
   w.moveList = moveList.p; w.moveCap = (int)moveList.cap;
   w.bv_key = bv_key.p; w.bv_keyAlt = bv_keyAlt.p; w.bv_leaf = bv_leaf.p; w.bv_leafAlt = bv_leafAlt.p; w.bv_box = bv_box.p; w.bv_child = bv_child.p; w.bv_parent = bv_parent.p; w.bv_visit = bv_visit.p;
   w.pairs = pairs.p; w.pairCap = (int)pairs.cap;
@@ -653,9 +671,9 @@ void World::refreshView() {
   w.hCap = (int)h_key.cap; w.h_key = h_key.p; w.h_val = h_val.p;
   w.sCap = (int)s_contact.cap; w.s_contact = s_contact.p; w.s_hist = s_hist.p; w.s_body = s_body.p; w.s_v0 = s_v0.p; w.s_v1 = s_v1.p; w.s_r0 = s_r0.p; w.s_r1 = s_r1.p;
   w.s_q0 = s_q0.p; w.s_q1 = s_q1.p; w.s_imp = s_imp.p; w.s_nm = s_nm.p; w.s_k = s_k.p; w.s_pc = s_pc.p; w.s_p0 = s_p0.p; w.s_p1 = s_p1.p; w.s_p2 = s_p2.p; w.s_p3 = s_p3.p; w.s_root = s_root.p;
-  w.nJoints = (int)jointAt_.size(); w.j_ids = j_ids.p; w.j_anchor = j_anchor.p; w.j_p0 = j_p0.p; w.j_p1 = j_p1.p; w.j_imp = j_imp.p; w.j_limit = j_limit.p; w.j_colour = j_colour.p;
+  w.nJoints = (int)jointAt_.size() * nWorlds_; w.j_ids = j_ids.p; w.j_anchor = j_anchor.p; w.j_p0 = j_p0.p; w.j_p1 = j_p1.p; w.j_imp = j_imp.p; w.j_limit = j_limit.p; w.j_colour = j_colour.p;
   w.j_order = j_order.p; w.j_root = j_root.p; w.j_r = j_r.p; w.j_lc = j_lc.p; w.j_m = j_m.p; w.j_k0 = j_k0.p; w.j_k1 = j_k1.p; w.j_k2 = j_k2.p;
-  w.nWorlds = nWorlds_;
+  w.nWorlds = nWorlds_; w.keyStride = keyStride_;
   w.jointBlocks = jointBlocks_; w.nJointColours = nJointColours_;
   { const char* e = getenv("DBX_DEBUG"); w.dbgFlags = e ? atoi(e) : 0; }
   w.phaseTimes = phaseBuf_.p; w.phaseCap = phaseBuf_.p ? (int)phaseBuf_.cap : 0;
@@ -776,8 +794,8 @@ int World::timeSteps(float dt, int vi, int pi, int n, bool flushL2, float* total
 // wake = false, b2body.d:390-431) from a host buffer, and read all body transforms back into a host buffer.
 int World::applyForces(const float* f4, int n) {
   int rc = push(); if (rc < 0) return rc;
-  if (n > (int)bodies_.size()) return DBX_E_INVALID;
-  CUDA_OR_FAIL(ioBuf_.reserve(std::max<size_t>(bodies_.size(), 1), false, stream_), "io buffer");
+  if (n > (int)bodies_.size() * nWorlds_) return DBX_E_INVALID;
+  CUDA_OR_FAIL(ioBuf_.reserve(std::max<size_t>(bodies_.size() * (size_t)nWorlds_, 1), false, stream_), "io buffer");
   CUDA_OR_FAIL(cudaMemcpyAsync(ioBuf_.p, f4, (size_t)n * 16, cudaMemcpyHostToDevice, stream_), "forces h2d");
   CUDA_OR_FAIL(launch_apply_forces(dw_, L_, ioBuf_.p, n), "apply_forces");
   hostBodiesValid_ = false;
@@ -785,7 +803,7 @@ int World::applyForces(const float* f4, int n) {
 }
 int World::readTransforms(float* out, int n) {
   int rc = push(); if (rc < 0) return rc;
-  if (n > (int)bodies_.size()) return DBX_E_INVALID;
+  if (n > (int)bodies_.size() * nWorlds_) return DBX_E_INVALID;
   CUDA_OR_FAIL(cudaMemcpyAsync(out, b_xf.p, (size_t)n * 16, cudaMemcpyDeviceToHost, stream_), "xf d2h");
   CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
   return n;
@@ -818,7 +836,36 @@ int World::stageCollide() {
 }
 
 // ------------------------------------------------------------------------------------------------ accessors
+// body states straight from the device arrays (replicated worlds have no per-replica host mirror)
+int World::readBodiesDevice(int from, int count, dbx_body_state* out) {
+  const size_t n = (size_t)count;
+  std::vector<float4> xf(n), pos(n), pos0(n), vel(n), frc(n), ms(n), lc(n); std::vector<float2> gs(n); std::vector<uint32_t> fl(n);
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  cudaMemcpy(xf.data(), b_xf.p + from, n * 16, cudaMemcpyDeviceToHost); cudaMemcpy(pos.data(), b_pos.p + from, n * 16, cudaMemcpyDeviceToHost);
+  cudaMemcpy(pos0.data(), b_pos0.p + from, n * 16, cudaMemcpyDeviceToHost); cudaMemcpy(vel.data(), b_vel.p + from, n * 16, cudaMemcpyDeviceToHost);
+  cudaMemcpy(frc.data(), b_force.p + from, n * 16, cudaMemcpyDeviceToHost); cudaMemcpy(ms.data(), b_mass.p + from, n * 16, cudaMemcpyDeviceToHost);
+  cudaMemcpy(lc.data(), b_lc.p + from, n * 16, cudaMemcpyDeviceToHost); cudaMemcpy(gs.data(), b_gs.p + from, n * 8, cudaMemcpyDeviceToHost);
+  CUDA_OR_FAIL(cudaMemcpy(fl.data(), b_flags.p + from, n * 4, cudaMemcpyDeviceToHost), "read bodies");
+  for (size_t i = 0; i < n; ++i) {
+    dbx_body_state& st = out[i];
+    st.p = dbx_vec2{xf[i].x, xf[i].y}; st.qs = xf[i].z; st.qc = xf[i].w;
+    st.c = dbx_vec2{pos[i].x, pos[i].y}; st.a = pos[i].z;
+    st.c0 = dbx_vec2{pos0[i].x, pos0[i].y}; st.a0 = pos0[i].z; st.alpha0 = pos0[i].w;
+    st.v = dbx_vec2{vel[i].x, vel[i].y}; st.w = vel[i].z;
+    st.force = dbx_vec2{frc[i].x, frc[i].y}; st.torque = frc[i].z;
+    st.invMass = ms[i].x; st.invI = ms[i].y; st.mass = ms[i].z; st.I = ms[i].w;
+    st.localCenter = dbx_vec2{lc[i].x, lc[i].y}; st.linearDamping = lc[i].z; st.angularDamping = lc[i].w;
+    st.gravityScale = gs[i].x; st.sleepTime = gs[i].y;
+    st.flags = fl[i] & 0xFFFF; st.type = body_type(fl[i]);
+  }
+  return count;
+}
+
 int World::getBody(int b, dbx_body_state* out) {
+  if (replicated_) {
+    if (b < 0 || b >= (int)bodies_.size() * nWorlds_ || !bodies_[b % (int)bodies_.size()].alive) return DBX_E_INVALID;
+    int rc = readBodiesDevice(b, 1, out); return rc < 0 ? rc : 0;
+  }
   if (b < 0 || b >= (int)bodies_.size() || !bodies_[b].alive) return DBX_E_INVALID;
   int rc = pullBodies(); if (rc < 0) return rc;
   *out = bodies_[b].st;
@@ -826,6 +873,7 @@ int World::getBody(int b, dbx_body_state* out) {
 }
 
 HBody* World::mutBody(int b) {
+  if (replicated_) return nullptr;
   if (b < 0 || b >= (int)bodies_.size() || !bodies_[b].alive) return nullptr;
   if (pullBodies() < 0) return nullptr;
   if ((size_t)b < bodiesSynced_) fullPushBodies_ = true;
@@ -834,6 +882,7 @@ HBody* World::mutBody(int b) {
 
 // b2Body.SetTransform (dynamics/b2body.d:261-285) incl. b2Fixture.Synchronize with xf1 == xf2
 int World::setTransform(int b, float x, float y, float angle) {
+  if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
   HBody* hb = mutBody(b);
   if (!hb) return DBX_E_INVALID;
   int rc = pullProxies(); if (rc < 0) return rc;
@@ -865,6 +914,7 @@ int World::counts(dbx_counts* out) {
   for (auto& f : fixtures_) if (f.alive) ++out->fixtures;
   for (auto& p : proxies_) if (p.alive) ++out->proxies;
   for (auto& j : joints_) if (j.alive) ++out->joints;
+  out->bodies *= nWorlds_; out->fixtures *= nWorlds_; out->proxies *= nWorlds_; out->joints *= nWorlds_;
   out->moves = (int)pendingMoves_.size();
   if (!dw_.hdr || bodiesSynced_ == 0) {
     for (auto& b : bodies_) if (b.alive && (b.st.flags & DBX_BODY_AWAKE) && b.st.type != DBX_STATIC_BODY) ++out->awakeBodies;
@@ -897,6 +947,11 @@ int World::profile(dbx_profile* out) {
 }
 
 int World::readBodies(dbx_body_state* out, int cap) {
+  if (replicated_) {
+    const int n = (int)bodies_.size() * nWorlds_;
+    if (cap > 0) { int rc = readBodiesDevice(0, std::min(cap, n), out); if (rc < 0) return rc; }
+    return n;
+  }
   int rc = pullBodies(); if (rc < 0) return rc;
   const int n = (int)bodies_.size();
   for (int i = 0; i < n && i < cap; ++i) { if (bodies_[i].alive) out[i] = bodies_[i].st; else std::memset(out + i, 0, sizeof(*out)); }
@@ -904,6 +959,7 @@ int World::readBodies(dbx_body_state* out, int cap) {
 }
 
 int World::writeBodies(const dbx_body_state* in, int n) {
+  if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
   if (n > (int)bodies_.size()) return DBX_E_INVALID;
   int rc = pullBodies(); if (rc < 0) return rc;
   for (int i = 0; i < n; ++i) {
@@ -938,6 +994,7 @@ int World::readProxies(dbx_proxy_rec* out, int cap) {
 }
 
 int World::writeProxies(const dbx_proxy_rec* in, int n) {
+  if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
   int rc = pullProxies(); if (rc < 0) return rc;
   for (int i = 0; i < n; ++i) {
     const dbx_proxy_rec& r = in[i];
@@ -966,6 +1023,7 @@ int World::readJoints(dbx_joint_state* out, int cap) {
 }
 
 int World::writeJoints(const dbx_joint_state* in, int n) {
+  if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
   if (n > (int)joints_.size()) return DBX_E_INVALID;
   int rc = pullJoints(); if (rc < 0) return rc;
   for (int i = 0; i < n; ++i) {
@@ -991,6 +1049,7 @@ int World::readMoves(int32_t* out, int cap) {
 }
 
 int World::writeMoves(const int32_t* in, int n) {
+  if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
   pendingMoves_.clear();
   for (int i = 0; i < n; ++i) {
     int f = in[2 * i], c = in[2 * i + 1];
@@ -1050,7 +1109,7 @@ int World::readContacts(dbx_contact_rec* out, int cap) {
       dbx_contact_rec& o = out[cnt];
       std::memset(&o, 0, sizeof(o));
       o.fixtureA = fix[i].x; o.fixtureB = fix[i].y;
-      o.childA = proxies_[ids[i].x].child; o.childB = proxies_[ids[i].y].child;
+      o.childA = proxies_[ids[i].x % (int)proxies_.size()].child; o.childB = proxies_[ids[i].y % (int)proxies_.size()].child;
       o.flags = fl[i] & 0x3F;
       o.manifold.localNormal = dbx_vec2{m0[i].x, m0[i].y}; o.manifold.localPoint = dbx_vec2{m0[i].z, m0[i].w};
       o.manifold.points[0].localPoint = dbx_vec2{m1[i].x, m1[i].y}; o.manifold.points[1].localPoint = dbx_vec2{m1[i].z, m1[i].w};
@@ -1066,6 +1125,7 @@ int World::readContacts(dbx_contact_rec* out, int cap) {
 }
 
 int World::writeContacts(const dbx_contact_rec* in, int n) {
+  if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
   int rc = push(); if (rc < 0) return rc;
   if (!dw_.hdr) return DBX_E_INVALID;
   if ((size_t)n > c_key.cap) { set_last_error("contact capacity"); return DBX_E_CAPACITY; }
@@ -1189,10 +1249,73 @@ int World::phaseTimes(unsigned long long* out, int cap) {
   return n;
 }
 
+// Batched independent worlds (BASELINE config 5): the world's current content becomes replica 0 of `copies` disjoint
+// replicas living in the SAME device arrays (replica r owns bodies [r*nB, (r+1)*nB) etc.).  Replicas never interact: the
+// replica index is part of the Morton key and of the pair test, islands cannot span replicas, and colouring priorities
+// use replica-local pair keys, so all replicas evolve bit-identically until something perturbs one of them.
 int World::replicate(int copies) {
-  (void)copies;
-  set_last_error("replicate: not wired in this build");
-  return DBX_E_UNSUPPORTED;
+  if (copies < 1) return DBX_E_INVALID;
+  if (replicated_ || stepCount_ > 0) { set_last_error("replicate: call once, before the first step"); return DBX_E_INVALID; }
+  if (copies == 1) return 0;
+  int rc = push(); if (rc < 0) return rc;
+  const int nB = (int)bodies_.size(), nF = (int)fixtures_.size(), nP = (int)proxies_.size(), nJ = (int)jointAt_.size();
+  if ((long long)nB * copies > 0x3fffffffLL || (long long)keyFresh_ * copies > 0x7fffffffLL) { set_last_error("replicate: too many replicas"); return DBX_E_CAPACITY; }
+  int nMoved = 0;
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  CUDA_OR_FAIL(cudaMemcpy(&nMoved, (char*)hdr_.p + offsetof(Header, nMoved), 4, cudaMemcpyDeviceToHost), "read nMoved");
+  nWorlds_ = copies;
+  bool rehash = false;
+  rc = reserveDevice(rehash); if (rc < 0) return rc;
+  refreshView();
+  if (rehash) CUDA_OR_FAIL(stage_rebuild_hash(dw_, L_), "rehash");
+  keyStride_ = keyFresh_;
+  dw_.keyStride = keyStride_;
+  CUDA_OR_FAIL(launch_replicate(dw_, L_, nB, nF, nP, nMoved, keyStride_, copies), "replicate");
+  // joints: colour-major layout across replicas so that every colour stays one contiguous range
+  if (nJ > 0) {
+    std::vector<int> off(kMaxJointColours + 1, 0);
+    { int c = 0; for (int k = 0; k < nJ; ++k) { while (c < joints_[jointAt_[k]].colour) off[++c] = k; } while (c < kMaxJointColours) off[++c] = nJ; }
+    const size_t nD = (size_t)nJ * copies;
+    std::vector<int4> ids(nD); std::vector<float4> anc(nD), p0(nD), p1(nD), imp(nD); std::vector<int> lim(nD);
+    int newOff[kMaxJointColours + 1];
+    for (int c = 0; c <= kMaxJointColours; ++c) newOff[c] = off[c] * copies;
+    for (int c = 0; c < kMaxJointColours; ++c) {
+      const int cnt = off[c + 1] - off[c];
+      for (int r = 0; r < copies; ++r) for (int k = 0; k < cnt; ++k) {
+        const HJoint& j = joints_[jointAt_[off[c] + k]];
+        const size_t d = (size_t)newOff[c] + (size_t)r * cnt + k;
+        const dbx_joint_def& jd = j.def;
+        ids[d] = make_int4(jd.type, jd.bodyA + r * nB, jd.bodyB + r * nB, (jd.collideConnected ? 1 : 0) | (jd.enableLimit ? 2 : 0) | (jd.enableMotor ? 4 : 0) | 8);
+        anc[d] = make_float4(jd.localAnchorA.x, jd.localAnchorA.y, jd.localAnchorB.x, jd.localAnchorB.y);
+        p0[d] = jd.type == DBX_JOINT_REVOLUTE ? make_float4(jd.referenceAngle, jd.lowerAngle, jd.upperAngle, jd.maxMotorTorque) : make_float4(jd.length, jd.frequencyHz, jd.dampingRatio, 0.0f);
+        p1[d] = make_float4(jd.motorSpeed, 0, 0, 0);
+        imp[d] = make_float4(j.imp[0], j.imp[1], j.imp[2], j.imp[3]);
+        lim[d] = j.limit;
+      }
+    }
+    CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+    cudaMemcpy(j_ids.p, ids.data(), nD * 16, cudaMemcpyHostToDevice); cudaMemcpy(j_anchor.p, anc.data(), nD * 16, cudaMemcpyHostToDevice);
+    cudaMemcpy(j_p0.p, p0.data(), nD * 16, cudaMemcpyHostToDevice); cudaMemcpy(j_p1.p, p1.data(), nD * 16, cudaMemcpyHostToDevice);
+    cudaMemcpy(j_imp.p, imp.data(), nD * 16, cudaMemcpyHostToDevice);
+    CUDA_OR_FAIL(cudaMemcpy(j_limit.p, lim.data(), nD * 4, cudaMemcpyHostToDevice), "joints up");
+    CUDA_OR_FAIL(cudaMemcpy((char*)hdr_.p + offsetof(Header, jointColourOff), newOff, sizeof(newOff), cudaMemcpyHostToDevice), "joff up");
+    // joints that forbid collisions between their bodies, per replica (stays sorted: body ids grow with the replica index)
+    if (nJointPairs_ > 0) {
+      std::vector<unsigned long long> base(nJointPairs_), all((size_t)nJointPairs_ * copies);
+      CUDA_OR_FAIL(cudaMemcpy(base.data(), jp_keys.p, (size_t)nJointPairs_ * 8, cudaMemcpyDeviceToHost), "jp down");
+      for (int r = 0; r < copies; ++r) for (int k = 0; k < nJointPairs_; ++k)
+        all[(size_t)r * nJointPairs_ + k] = base[k] + (((unsigned long long)(unsigned)(r * nB)) << 32) + (unsigned)(r * nB);
+      CUDA_OR_FAIL(jp_keys.reserve(all.size(), false, stream_), "jp_keys");
+      CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+      CUDA_OR_FAIL(cudaMemcpy(jp_keys.p, all.data(), all.size() * 8, cudaMemcpyHostToDevice), "jp up");
+      nJointPairs_ *= copies;
+    }
+    jointBlocks_ = (int)std::min<size_t>(((size_t)jointBlocks_ * L_.coopThreads * copies + L_.coopThreads - 1) / L_.coopThreads, (size_t)L_.coopBlocks / 4);
+  }
+  replicated_ = true;
+  treeValid_ = false;
+  refreshView();
+  return checkDeviceError(true);
 }
 
 }  // namespace dbx

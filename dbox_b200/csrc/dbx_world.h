@@ -16,6 +16,7 @@ template <class T> struct DevBuf {
     if (n <= cap) return cudaSuccess;
     size_t ncap = cap ? cap : 64;
     while (ncap < n) ncap *= 2;
+    if (n > (1u << 22)) ncap = n;   // very large pools (replicated worlds): no power-of-two slack
     T* q = nullptr;
     cudaError_t e = cudaMalloc((void**)&q, ncap * sizeof(T));
     if (e != cudaSuccess) return e;
@@ -70,6 +71,7 @@ class World {
   int setGravity(float gx, float gy) { gx_ = gx; gy_ = gy; return 0; }
 
   int getBody(int b, dbx_body_state* out);
+  int readBodiesDevice(int from, int count, dbx_body_state* out);
   HBody* mutBody(int b);   // pulls, marks dirty; nullptr if invalid
   int setTransform(int b, float x, float y, float angle);
   void wake(HBody& hb, bool flag);
@@ -113,6 +115,7 @@ class World {
   void hostAabb(const DShape& s, const Xf& xf, Box* out) const;
   int destroyContactsWhere(int body, int fixture, int otherBody, bool flagOnly);
   int recolourJoints();
+  int reserveDevice(bool& rehash);
   int findNewContacts();
   int compactContacts();
   void setStepParams(float dt, int vi, int pi);
@@ -125,7 +128,7 @@ class World {
   uint32_t flags_ = DBX_WORLD_DEFAULT_FLAGS;
   bool newFixture_ = false, stepComplete_ = true;
   long stepCount_ = 0;
-  int nWorlds_ = 1;
+  int nWorlds_ = 1; bool replicated_ = false; int keyStride_ = 0;
   dbx_caps caps_{};
 
   // host tables

@@ -414,6 +414,11 @@ class b2World:
     def Step(self, dt, velocityIterations, positionIterations):
         self._ck(self._api.world_step(self._w, dt, velocityIterations, positionIterations))
 
+    def Replicate(self, copies):
+        """dbx_world_replicate: this world's content becomes replica 0 of `copies` independent replicas stepped together
+        (BASELINE config 5, batched RL-style worlds).  Body id of replica r = r * bodies_per_replica + local id."""
+        self._ck(self._api.world_replicate(self._w, copies))
+
     def StepN(self, dt, velocityIterations, positionIterations, n):
         self._ck(self._api.world_step_n(self._w, dt, velocityIterations, positionIterations, n))
 

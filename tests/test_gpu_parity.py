@@ -233,3 +233,30 @@ def test_pyramid_long_horizon_invariants(gpu_api, oracle_api):
             continue
         assert abs(sg[i].c.y - so[i].c.y) < 0.01, (i, sg[i].c.y, so[i].c.y)   # 2 * b2_linearSlop: stacked resting depths add up
         assert abs(sg[i].a) < 0.05 and abs(sg[i].a - so[i].a) < 0.05, (i, sg[i].a, so[i].a)
+
+
+def test_replicated_worlds_match_single_world(gpu_api, oracle_api):
+    """config 5 (batched independent worlds): 16 replicas of the Pyramid inside one device world evolve exactly like the
+    single world (replica-local colouring priorities => bit-identical), never interact, and all fall asleep."""
+    single, _ = scenes.pyramid(api=gpu_api)
+    batch, _ = scenes.pyramid(api=gpu_api)
+    copies = 16
+    batch.Replicate(copies)
+    assert gpu_api.world_replica_count(batch._w) == copies
+    nb = single.counts().bodies
+    assert batch.counts().bodies == nb * copies
+    for k in range(6):
+        single.StepN(DT, 8, 3, 50)
+        batch.StepN(DT, 8, 3, 50)
+        cs, cb = single.counts(), batch.counts()
+        assert cb.contacts == cs.contacts * copies and cb.touching == cs.touching * copies, (k, cs.contacts, cb.contacts)
+        assert cb.awakeBodies == cs.awakeBodies * copies
+        assert gpu_api.world_debug_colour_conflicts(batch._w) == 0
+        ss, _ = single.read_bodies()
+        sb, n = batch.read_bodies()
+        assert n == nb * copies
+        for r in (0, 5, copies - 1):
+            for i in range(nb):
+                a, b = ss[i], sb[r * nb + i]
+                assert (a.c.x, a.c.y, a.a, a.v.x, a.v.y, a.w) == (b.c.x, b.c.y, b.a, b.v.x, b.v.y, b.w), (k, r, i)
+    assert batch.counts().awakeBodies == 0

@@ -31,3 +31,6 @@ if int(os.environ.get("DBX_DEBUG","0")) & 2:
         rel=[(buf[512+(ph*148+b)*2+1]-base)/1000. for b in range(148)]
         ja=arr[:17]; ca=arr[17:]
         print("bar %d: joint-blk arrive %.2f..%.2f  contact-blk arrive %.2f..%.2f (median %.2f) | release %.2f..%.2f" % (p0+ph, min(ja), max(ja), min(ca), max(ca), sorted(ca)[len(ca)//2], min(rel), max(rel)))
+
+tt=[buf[3000+i] for i in range(64) if buf[3000+i]]
+print("toi marks (us):", " ".join("%.1f" % ((tt[i+1]-tt[i])/1000.) for i in range(len(tt)-1)))
