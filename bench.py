@@ -115,6 +115,84 @@ def run_cpu_port(n_bodies, columns, settle, steps, warmup, threads=1, replicas=1
     return replicas * n_bodies * steps / secs, secs, c
 
 
+def run_cpu_pyramids(worlds, settle, steps, threads):
+    """C5 on the host: `worlds` independent Pyramid worlds, one world per thread at a time (oracle port of the reference)"""
+    from oracle import orc
+    from dbox_b200 import scenes
+    api = orc.api()
+    ws = []
+    for r in range(worlds):
+        w, _ = scenes.pyramid(api=api)
+        w.SetAllowSleeping(False)
+        ws.append(w)
+    arr = (C.c_void_p * worlds)(*[w._w for w in ws])
+    api.batch_step(arr, worlds, DT, VEL_ITERS, POS_ITERS, settle, threads)
+    secs = api.batch_step(arr, worlds, DT, VEL_ITERS, POS_ITERS, steps, threads)
+    return worlds * steps / secs, secs
+
+
+def bench_batched(api, args, rank, world_size, local_rank, barrier, dist, torch):
+    """C5: args.worlds independent Pyramid worlds (strong scaling: the batch is partitioned across the ranks, no data-path
+    collective), all replicas of a rank inside one device world (dbx_world_replicate).  Returns rank 0's report."""
+    from dbox_b200 import _abi as A
+    from dbox_b200 import scenes
+    per = args.worlds // world_size + (1 if rank < args.worlds % world_size else 0)
+    caps = A.Caps()
+    caps.maxContacts = int(per * 640)
+    w, _ = scenes.pyramid(api=api, caps=caps, device=local_rank)
+    w.SetAllowSleeping(False)
+    w.Replicate(per)
+    nb = w.counts().bodies
+    w.StepN(DT, VEL_ITERS, POS_ITERS, args.batch_settle)
+    tot = C.c_float(); stage = (C.c_float * 9)()
+    flush = 0 if args.no_l2_flush else 1
+    assert api.world_time_steps(w._w, DT, VEL_ITERS, POS_ITERS, 3, flush, C.byref(tot), stage) >= 0, api.last_error()
+    K = args.batch_steps
+    l0 = api.world_launch_count(w._w)
+    barrier()
+    assert api.world_time_steps(w._w, DT, VEL_ITERS, POS_ITERS, K, flush, C.byref(tot), stage) >= 0, api.last_error()
+    barrier()
+    launches = api.world_launch_count(w._w) - l0
+    ms = torch.tensor([tot.value], dtype=torch.float64, device="cuda")
+    if world_size > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    # e2e: RL-style loop, per step H2D of one force/torque record per body and D2H of every body transform
+    forces = torch.zeros((nb, 4), dtype=torch.float32).pin_memory()
+    xf_out = torch.empty((nb, 4), dtype=torch.float32).pin_memory()
+    Ke = min(K, 30)
+    for _ in range(2):
+        api.world_apply_forces(w._w, forces.data_ptr(), nb); w.Step(DT, VEL_ITERS, POS_ITERS); api.world_read_transforms(w._w, xf_out.data_ptr(), nb)
+    barrier()
+    t0 = time.time()
+    for _ in range(Ke):
+        assert api.world_apply_forces(w._w, forces.data_ptr(), nb) == nb
+        w.Step(DT, VEL_ITERS, POS_ITERS)
+        assert api.world_read_transforms(w._w, xf_out.data_ptr(), nb) == nb
+    barrier()
+    es = torch.tensor([time.time() - t0], dtype=torch.float64, device="cuda")
+    if world_size > 1:
+        dist.all_reduce(es, op=dist.ReduceOp.MAX)
+    c = w.counts()
+    stage_ms = [float(x) for x in stage]
+    out = {"workload": "C5: %d independent Pyramid worlds (20-row, 211 bodies each), 60 Hz, %dv/%dp, sleeping off, partitioned over %d GPU(s)"
+                       % (args.worlds, VEL_ITERS, POS_ITERS, world_size),
+           "value": args.worlds * K / (total_ms / 1e3), "unit": "world-steps/s", "scaling": "strong", "worlds": args.worlds,
+           "worlds_per_gpu": per, "steps": K, "settle_steps": args.batch_settle, "ms_per_step": total_ms / K,
+           "body_steps_per_s": args.worlds * K * (nb / per) / (total_ms / 1e3),
+           "counts_rank0": {"bodies": nb, "contacts": c.contacts, "touching": c.touching, "colours": c.colours},
+           "stage_ms": dict(zip(["collide", "islands", "colour_sort", "prepare", "solve", "sync_fixtures", "find_new_contacts", "toi", "clear_forces"], stage_ms)),
+           "e2e": {"value": args.worlds * Ke / float(es.item()), "unit": "world-steps/s", "h2d_bytes_per_step": 16 * nb, "d2h_bytes_per_step": 16 * nb, "steps": Ke},
+           "gpu_launches": int(launches)}
+    alg = algorithmic_bytes_solve(c.touching, c.awakeBodies, 0, 0, VEL_ITERS, POS_ITERS)
+    peak, peak_src = peaks()
+    ach = alg / (stage_ms[4] * 1e-3) / 1e9 if stage_ms[4] > 0 else 0.0
+    out["roofline"] = {"bound": "hbm", "kernel": "k_solve", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
+                       "algorithmic_bytes_per_launch": alg, "kernel_ms": stage_ms[4], "traffic": None}
+    w.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -129,6 +207,10 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=60)
     ap.add_argument("--cpu-settle", type=int, default=240)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--worlds", type=int, default=65536, help="C5: independent Pyramid worlds in the batched leg (0 = skip the leg)")
+    ap.add_argument("--batch-steps", type=int, default=100)
+    ap.add_argument("--batch-settle", type=int, default=60)
+    ap.add_argument("--cpu-worlds-per-thread", type=int, default=2)
     ap.add_argument("--save-state", default=None, help="write the settled world state here (profiling runs reload it instead of settling)")
     ap.add_argument("--load-state", default=None)
     args = ap.parse_args()
@@ -165,6 +247,12 @@ def main():
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0, "wall_s": time.time() - t0}
+        if args.worlds > 0:
+            nw = cores * args.cpu_worlds_per_thread
+            bsteps = min(args.batch_steps, 100)
+            v, secs = run_cpu_pyramids(nw, args.batch_settle, bsteps, cores)
+            line["batched"] = {"workload": "C5 sample: %d Pyramid worlds, one world per host thread at a time" % nw, "value": v, "unit": "world-steps/s",
+                               "cores": cores, "kind": "port", "steps": bsteps, "settle_steps": args.batch_settle, "seconds": secs}
         print(json.dumps(line), flush=True)
         return 0
 
@@ -183,7 +271,6 @@ def main():
 
     world, bodies, n_joints = scenes.pile(api=api, n=args.bodies, columns=args.columns, seed=12345 + rank, device=local_rank)
     world.SetAllowSleeping(False)
-    n_rev = sum(1 for j in world._joints.values() if True)  # refined below from the scene definition
     if args.load_state:
         from dbox_b200 import state
         state.load(world, args.load_state)
@@ -242,13 +329,17 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = n_gpus * args.bodies * Ke / float(e2e_s.item())
 
+    js, nj = world.read_joints()
+    n_rev = sum(1 for i in range(nj) if js[i].type == A.JOINT_REVOLUTE)
+    n_dist = sum(1 for i in range(nj) if js[i].type == A.JOINT_DISTANCE)
+    world.close()      # free the pile's device buffers before the batched leg
+    batched = None
+    if args.worlds > 0:
+        batched = bench_batched(api, args, rank, world_size, local_rank, barrier, dist, torch)
+
     if rank == 0:
         value = n_gpus * args.bodies * K / (total_ms / 1e3)
         peak, peak_src = peaks()
-        # joints of the scene: revolute chains on every 10th column, distance chains on every 10th row (dbox_b200/scenes.py)
-        js, nj = world.read_joints()
-        n_rev = sum(1 for i in range(nj) if js[i].type == A.JOINT_REVOLUTE)
-        n_dist = sum(1 for i in range(nj) if js[i].type == A.JOINT_DISTANCE)
         solve_ms = stage_ms[4]
         alg = algorithmic_bytes_solve(counts.touching, counts.awakeBodies, n_rev, n_dist, VEL_ITERS, POS_ITERS)
         achieved = alg / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
@@ -268,7 +359,15 @@ def main():
                              "algorithmic_bytes_per_launch": alg, "kernel_ms": solve_ms, "traffic": traffic},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n, "steps": Ke},
                 "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall}
+        if batched is not None:
+            line["batched"] = batched
         if n_gpus == 1 and not args.skip_cpu_baseline:
+            if batched is not None:
+                nw = cores * args.cpu_worlds_per_thread
+                v, secs = run_cpu_pyramids(nw, args.batch_settle, min(args.batch_steps, 100), cores)
+                batched["cpu_baseline"] = {"value": v, "unit": "world-steps/s", "cores": cores, "kind": "port",
+                                           "sample": "%d Pyramid worlds, %d settle + %d timed steps, one world per host thread at a time, %.1f s"
+                                                     % (nw, args.batch_settle, min(args.batch_steps, 100), secs)}
             t0 = time.time()
             v, secs, c = run_cpu_port(cpu_bodies, cpu_cols, args.cpu_settle, args.cpu_steps, 3)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",

@@ -126,6 +126,7 @@ struct DevWorld {
   int2* bv_child;    // [n-1]
   int* bv_parent;    // [2n-1]
   int* bv_visit;     // [n-1]
+  int2* bv_wr;       // [n-1] replica-index range of the leaves under an internal node
   int* bv_pos;       // proxy slot -> sorted leaf index
   const int* bv_sorted;  // sorted leaf index -> proxy slot (whichever CUB buffer is current)
   // ---- candidate pairs

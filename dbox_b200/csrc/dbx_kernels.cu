@@ -1412,6 +1412,7 @@ __global__ void __launch_bounds__(256) k_lbvh_hierarchy(const __grid_constant__ 
     int left = (min(i, j) == gamma) ? (n - 1 + gamma) : gamma;            // leaves live at [n-1, 2n-1)
     int right = (max(i, j) == gamma + 1) ? (n - 1 + gamma + 1) : gamma + 1;
     W.bv_child[i] = make_int2(left, right);
+    W.bv_wr[i] = make_int2((int)(keys[min(i, j)] >> 30), (int)(keys[max(i, j)] >> 30));   // replica range under this node
     W.bv_parent[left] = i;
     W.bv_parent[right] = i;
     W.bv_visit[i] = 0;
@@ -1457,8 +1458,12 @@ DBX_D void query_proxy(const DevWorld& W, const int* leaves, int* stack, int lan
     top -= take;
     __syncwarp();
     bool hit = false;
-    if (node >= 0) hit = overlap(fat, BX(__ldcg(&W.bv_box[node])));
     bool isLeaf = node >= n - 1;
+    if (node >= 0) {
+      hit = overlap(fat, BX(__ldcg(&W.bv_box[node])));
+      // replicas share coordinates: without this test every query would descend into every replica's subtree
+      if (hit && !isLeaf && W.nWorlds > 1) { const int2 wr = W.bv_wr[node]; hit = worldP >= wr.x && worldP <= wr.y; }
+    }
     if (hit && isLeaf) {
       int q = leaves[node - (n - 1)];
       // each unordered pair once: from the lower-key proxy when both moved (UpdatePairs sorts and dedups the same set)
@@ -1917,7 +1922,7 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
   const unsigned nb = gridDim.x;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warp = tid >> 5, nwarps = nth >> 5;
-  const int eventCap = min(W.eventCap, nwarps);
+  const int eventCap = W.eventCap;
   int tmark = 0;
 #define TMARK() do { if (W.phaseTimes && tid == 0 && tmark < 64) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); W.phaseTimes[3000 + tmark++] = t_; } } while (0)
   TMARK();
@@ -1998,7 +2003,9 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
     }
     grid_barrier(&H->barrier, nb); TMARK();
     // (d) events
-    if (lane == 0) for (int e = warp; e < nEvents; e += nwarps) toi_process_event(W, e, W.dt);
+    // one thread per event: a pass with few events (one big world) gives each its own warp, a pass with many (batched
+    // worlds) fills the lanes
+    for (int e = lane * nwarps + warp; e < nEvents; e += nth) toi_process_event(W, e, W.dt);
     grid_barrier(&H->barrier, nb); TMARK();
     // (e) SynchronizeFixtures of the island's dynamic bodies (:1433), then FindNewContacts (:1444)
     for (int p = tid; p < W.nProxies; p += nth) {

@@ -55,7 +55,7 @@ World::~World() {
   for (auto* b : i1) b->release();
   b_gs.release(); f_mat.release(); s_p3.release(); b_flags.release(); f_filter.release(); p_flags.release(); c_flags.release();
   b_mask.release(); b_claim.release(); bv_key.release(); bv_keyAlt.release(); jp_keys.release(); c_key.release(); h_key.release();
-  d_shapes.release(); p_ids.release(); c_ids.release(); c_fix.release(); j_ids.release(); bv_child.release(); pairs.release(); s_body.release(); c_mk.release();
+  d_shapes.release(); p_ids.release(); c_ids.release(); c_fix.release(); j_ids.release(); bv_child.release(); bv_wr.release(); pairs.release(); s_body.release(); c_mk.release();
   cubTemp.release(); hdr_.release();
   for (auto& ev : ev_) cudaEventDestroy(ev);
   cudaStreamDestroy(stream_);
@@ -499,7 +499,9 @@ int World::reserveDevice(bool& rehash) {
   CUDA_OR_FAIL(b_claim.reserve(capB, true, stream_), "b_claim");
   CUDA_OR_FAIL(b_toiMin.reserve(capB, true, stream_), "b_toiMin"); CUDA_OR_FAIL(b_toiOther.reserve(capB, true, stream_), "b_toiOther");
   CUDA_OR_FAIL(b_toiEvt.reserve(capB, true, stream_), "b_toiEvt"); CUDA_OR_FAIL(b_toiFlags.reserve(capB, true, stream_), "b_toiFlags");
-  const size_t nEv = (size_t)L_.coopBlocks * (L_.coopThreads / 32);
+  // TOI events handled per pass of k_toi: at least one per resident warp, more for batched worlds (events of different
+  // worlds are always independent); the surplus of a pass simply waits for the next one
+  const size_t nEv = std::min<size_t>(std::max<size_t>((size_t)L_.coopBlocks * (L_.coopThreads / 32), capB / 16), (size_t)1 << 18);
   CUDA_OR_FAIL(e_contact.reserve(nEv, false, stream_), "e_contact"); CUDA_OR_FAIL(e_ncand.reserve(2 * nEv, false, stream_), "e_ncand");
   CUDA_OR_FAIL(e_cand.reserve(2 * nEv * kToiCand, false, stream_), "e_cand");
   CUDA_OR_FAIL(b_posNotOk.reserve(b_root.cap * (size_t)kMaxPosIters, false, stream_), "b_posNotOk");
@@ -517,7 +519,7 @@ int World::reserveDevice(bool& rehash) {
   CUDA_OR_FAIL(moveList.reserve(pc, true, stream_), "moveList");   // keep: pending moves may be waiting (replicate)
   CUDA_OR_FAIL(bv_key.reserve(pc, false, stream_), "bv_key"); CUDA_OR_FAIL(bv_keyAlt.reserve(pc, false, stream_), "bv_keyAlt");
   CUDA_OR_FAIL(bv_leaf.reserve(pc, false, stream_), "bv_leaf"); CUDA_OR_FAIL(bv_leafAlt.reserve(pc, false, stream_), "bv_leafAlt");
-  CUDA_OR_FAIL(bv_box.reserve(2 * pc, false, stream_), "bv_box"); CUDA_OR_FAIL(bv_child.reserve(pc, false, stream_), "bv_child");
+  CUDA_OR_FAIL(bv_box.reserve(2 * pc, false, stream_), "bv_box"); CUDA_OR_FAIL(bv_child.reserve(pc, false, stream_), "bv_child"); CUDA_OR_FAIL(bv_wr.reserve(pc, false, stream_), "bv_wr");
   CUDA_OR_FAIL(bv_parent.reserve(2 * pc, false, stream_), "bv_parent"); CUDA_OR_FAIL(bv_visit.reserve(pc, false, stream_), "bv_visit");
   CUDA_OR_FAIL(bv_pos.reserve(pc, false, stream_), "bv_pos");
   {
@@ -663,7 +665,7 @@ void World::refreshView() {
   w.nShapes = (int)shapes_.size(); w.shapes = d_shapes.p;
   w.nProxies = (int)proxies_.size() * nWorlds_; w.p_ids = p_ids.p; w.p_key = p_key.p; w.p_aabb = p_aabb.p; w.p_fat = p_fat.p; w.p_flags = p_flags.p;
   w.moveList = moveList.p; w.moveCap = (int)moveList.cap;
-  w.bv_key = bv_key.p; w.bv_keyAlt = bv_keyAlt.p; w.bv_leaf = bv_leaf.p; w.bv_leafAlt = bv_leafAlt.p; w.bv_box = bv_box.p; w.bv_child = bv_child.p; w.bv_parent = bv_parent.p; w.bv_visit = bv_visit.p;
+  w.bv_key = bv_key.p; w.bv_keyAlt = bv_keyAlt.p; w.bv_leaf = bv_leaf.p; w.bv_leafAlt = bv_leafAlt.p; w.bv_box = bv_box.p; w.bv_child = bv_child.p; w.bv_wr = bv_wr.p; w.bv_parent = bv_parent.p; w.bv_visit = bv_visit.p;
   w.pairs = pairs.p; w.pairCap = (int)pairs.cap;
   w.nJointPairs = nJointPairs_; w.jp_keys = jp_keys.p;
   w.cCap = (int)c_key.cap; w.c_key = c_key.p; w.c_ids = c_ids.p; w.c_fix = c_fix.p; w.c_flags = c_flags.p; w.c_m0 = c_m0.p; w.c_m1 = c_m1.p; w.c_imp = c_imp.p; w.c_mk = c_mk.p;

@@ -154,7 +154,7 @@ class World {
   DevBuf<int> f_body, f_group; DevBuf<float2> f_mat; DevBuf<uint32_t> f_filter;
   DevBuf<DShape> d_shapes;
   DevBuf<int4> p_ids; DevBuf<int> p_key, moveList; DevBuf<float4> p_aabb, p_fat; DevBuf<uint32_t> p_flags;
-  DevBuf<unsigned long long> bv_key, bv_keyAlt; DevBuf<int> bv_leaf, bv_leafAlt, bv_parent, bv_visit; DevBuf<float4> bv_box; DevBuf<int2> bv_child;
+  DevBuf<unsigned long long> bv_key, bv_keyAlt; DevBuf<int> bv_leaf, bv_leafAlt, bv_parent, bv_visit; DevBuf<float4> bv_box; DevBuf<int2> bv_child, bv_wr;
   DevBuf<int2> pairs; DevBuf<unsigned long long> jp_keys;
   DevBuf<unsigned long long> c_key, h_key; DevBuf<int4> c_ids, c_fix; DevBuf<uint32_t> c_flags; DevBuf<float4> c_m0, c_m1, c_imp, c_mat; DevBuf<uint4> c_mk;
   DevBuf<int> c_toiCount, c_colour, c_free, c_work, c_work2, h_val;
