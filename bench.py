@@ -131,65 +131,62 @@ def run_cpu_pyramids(worlds, settle, steps, threads):
     return worlds * steps / secs, secs
 
 
-def bench_batched(api, args, rank, world_size, local_rank, barrier, dist, torch):
+def bench_batched(api, args, rank, world_size, local_rank, barrier, torch):
     """C5: args.worlds independent Pyramid worlds (strong scaling: the batch is partitioned across the ranks, no data-path
-    collective), all replicas of a rank inside one device world (dbx_world_replicate).  Returns rank 0's report."""
-    from dbox_b200 import _abi as A
+    collective; only the final statistics are reduced), each rank's share as replicas inside one device world.  Every
+    world gets its own random initial velocities (the RL reset), so the worlds do not evolve in lockstep."""
+    import numpy as np
     from dbox_b200 import scenes
-    per = args.worlds // world_size + (1 if rank < args.worlds % world_size else 0)
-    caps = A.Caps()
-    caps.maxContacts = int(per * 640)
-    w, _ = scenes.pyramid(api=api, caps=caps, device=local_rank)
-    w.SetAllowSleeping(False)
-    w.Replicate(per)
-    nb = w.counts().bodies
-    w.StepN(DT, VEL_ITERS, POS_ITERS, args.batch_settle)
-    tot = C.c_float(); stage = (C.c_float * 9)()
-    flush = 0 if args.no_l2_flush else 1
-    assert api.world_time_steps(w._w, DT, VEL_ITERS, POS_ITERS, 3, flush, C.byref(tot), stage) >= 0, api.last_error()
+    from dbox_b200.batch import WorldBatch, reduce_stats
+    batch = WorldBatch(scenes.pyramid, args.worlds, rank, world_size, device=local_rank, api=api, contacts_per_world=700)
+    batch.world.SetAllowSleeping(False)
+    nb = batch.n_bodies
+    rng = np.random.RandomState(777 + batch.first)
+    vel = np.zeros((nb, 4), np.float32)
+    vel[:, 0] = rng.uniform(-0.5, 0.5, nb); vel[:, 1] = rng.uniform(-0.5, 0.5, nb); vel[:, 2] = rng.uniform(-0.5, 0.5, nb)
+    batch.set_states(vel=vel)
+    del vel
+    batch.step(DT, VEL_ITERS, POS_ITERS, args.batch_settle)
+    flush = not args.no_l2_flush
+    batch.time_steps(DT, VEL_ITERS, POS_ITERS, 3, flush)
     K = args.batch_steps
-    l0 = api.world_launch_count(w._w)
+    l0 = api.world_launch_count(batch.world._w)
     barrier()
-    assert api.world_time_steps(w._w, DT, VEL_ITERS, POS_ITERS, K, flush, C.byref(tot), stage) >= 0, api.last_error()
+    ms, stage_ms = batch.time_steps(DT, VEL_ITERS, POS_ITERS, K, flush)
     barrier()
-    launches = api.world_launch_count(w._w) - l0
-    ms = torch.tensor([tot.value], dtype=torch.float64, device="cuda")
-    if world_size > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms.item())
+    launches = api.world_launch_count(batch.world._w) - l0
     # e2e: RL-style loop, per step H2D of one force/torque record per body and D2H of every body transform
     forces = torch.zeros((nb, 4), dtype=torch.float32).pin_memory()
     xf_out = torch.empty((nb, 4), dtype=torch.float32).pin_memory()
     Ke = min(K, 30)
     for _ in range(2):
-        api.world_apply_forces(w._w, forces.data_ptr(), nb); w.Step(DT, VEL_ITERS, POS_ITERS); api.world_read_transforms(w._w, xf_out.data_ptr(), nb)
+        batch.apply_forces(forces.data_ptr()); batch.step(DT, VEL_ITERS, POS_ITERS); batch.read_transforms(xf_out.data_ptr())
     barrier()
     t0 = time.time()
     for _ in range(Ke):
-        assert api.world_apply_forces(w._w, forces.data_ptr(), nb) == nb
-        w.Step(DT, VEL_ITERS, POS_ITERS)
-        assert api.world_read_transforms(w._w, xf_out.data_ptr(), nb) == nb
+        batch.apply_forces(forces.data_ptr())
+        batch.step(DT, VEL_ITERS, POS_ITERS)
+        batch.read_transforms(xf_out.data_ptr())
     barrier()
-    es = torch.tensor([time.time() - t0], dtype=torch.float64, device="cuda")
-    if world_size > 1:
-        dist.all_reduce(es, op=dist.ReduceOp.MAX)
-    c = w.counts()
-    stage_ms = [float(x) for x in stage]
-    out = {"workload": "C5: %d independent Pyramid worlds (20-row, 211 bodies each), 60 Hz, %dv/%dp, sleeping off, partitioned over %d GPU(s)"
-                       % (args.worlds, VEL_ITERS, POS_ITERS, world_size),
-           "value": args.worlds * K / (total_ms / 1e3), "unit": "world-steps/s", "scaling": "strong", "worlds": args.worlds,
-           "worlds_per_gpu": per, "steps": K, "settle_steps": args.batch_settle, "ms_per_step": total_ms / K,
-           "body_steps_per_s": args.worlds * K * (nb / per) / (total_ms / 1e3),
-           "counts_rank0": {"bodies": nb, "contacts": c.contacts, "touching": c.touching, "colours": c.colours},
-           "stage_ms": dict(zip(["collide", "islands", "colour_sort", "prepare", "solve", "sync_fixtures", "find_new_contacts", "toi", "clear_forces"], stage_ms)),
-           "e2e": {"value": args.worlds * Ke / float(es.item()), "unit": "world-steps/s", "h2d_bytes_per_step": 16 * nb, "d2h_bytes_per_step": 16 * nb, "steps": Ke},
-           "gpu_launches": int(launches)}
-    alg = algorithmic_bytes_solve(c.touching, c.awakeBodies, 0, 0, VEL_ITERS, POS_ITERS)
+    local = batch.stats()
+    local.update(ms=ms, seconds=time.time() - t0, launches=launches)
+    tot = reduce_stats(local)          # the only collective of the batched path: final statistics (NCCL)
+    out = {"workload": "C5: %d independent Pyramid worlds (20-row, %d bodies each, per-world random initial velocities), 60 Hz, %dv/%dp, "
+                       "sleeping off, partitioned over %d GPU(s)" % (args.worlds, batch.bodies_per_world, VEL_ITERS, POS_ITERS, world_size),
+           "value": args.worlds * K / (tot["ms"] / 1e3), "unit": "world-steps/s", "scaling": "strong", "worlds": args.worlds,
+           "worlds_rank0": batch.count, "steps": K, "settle_steps": args.batch_settle, "ms_per_step": tot["ms"] / K,
+           "body_steps_per_s": tot["bodies"] * K / (tot["ms"] / 1e3),
+           "counts": {"bodies": int(tot["bodies"]), "contacts": int(tot["contacts"]), "touching": int(tot["touching"])},
+           "stage_ms_rank0": dict(zip(["collide", "islands", "colour_sort", "prepare", "solve", "sync_fixtures", "find_new_contacts", "toi", "clear_forces"], stage_ms)),
+           "e2e": {"value": args.worlds * Ke / tot["seconds"], "unit": "world-steps/s", "h2d_bytes_per_step": 16 * int(tot["bodies"]),
+                   "d2h_bytes_per_step": 16 * int(tot["bodies"]), "steps": Ke},
+           "gpu_launches": int(tot["launches"])}
+    alg = algorithmic_bytes_solve(local["touching"], local["awake_bodies"], 0, 0, VEL_ITERS, POS_ITERS)
     peak, peak_src = peaks()
     ach = alg / (stage_ms[4] * 1e-3) / 1e9 if stage_ms[4] > 0 else 0.0
-    out["roofline"] = {"bound": "hbm", "kernel": "k_solve", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
+    out["roofline"] = {"bound": "hbm", "kernel": "k_solve (rank 0)", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
                        "algorithmic_bytes_per_launch": alg, "kernel_ms": stage_ms[4], "traffic": None}
-    w.close()
+    batch.close()
     return out
 
 
@@ -335,7 +332,7 @@ def main():
     world.close()      # free the pile's device buffers before the batched leg
     batched = None
     if args.worlds > 0:
-        batched = bench_batched(api, args, rank, world_size, local_rank, barrier, dist, torch)
+        batched = bench_batched(api, args, rank, world_size, local_rank, barrier, torch)
 
     if rank == 0:
         value = n_gpus * args.bodies * K / (total_ms / 1e3)

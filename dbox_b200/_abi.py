@@ -141,6 +141,7 @@ PROTOTYPES = {
     "world_clear_forces": (c_i32, [W]),
     "world_time_steps": (c_i32, [W, c_f32, c_i32, c_i32, c_i32, c_i32, P(c_f32), P(c_f32)]),
     "world_apply_forces": (c_i32, [W, C.c_void_p, c_i32]),
+    "world_set_body_states": (c_i32, [W, C.c_void_p, C.c_void_p, C.c_void_p, c_i32]),
     "world_read_transforms": (c_i32, [W, C.c_void_p, c_i32]),
     "world_launch_count": (C.c_int64, [W]),
     "body_get_state": (c_i32, [W, c_i32, P(BodyState)]),

@@ -144,6 +144,9 @@ int32_t dbx_world_step_n(dbx_world* w, float dt, int32_t vi, int32_t pi, int32_t
 int32_t dbx_world_time_steps(dbx_world* w, float dt, int32_t vi, int32_t pi, int32_t n, int32_t flushL2, float* totalMs, float* stageMs) {
   W_OR_INVALID(w); return w->w.timeSteps(dt, vi, pi, n, flushL2 != 0, totalMs, stageMs);
 }
+int32_t dbx_world_set_body_states(dbx_world* w, const int32_t* ids, const float* x_y_angle_pad, const float* vx_vy_w_pad, int32_t n) {
+  W_OR_INVALID(w); return w->w.setBodyStates(ids, x_y_angle_pad, vx_vy_w_pad, n);
+}
 int32_t dbx_world_apply_forces(dbx_world* w, const float* fx_fy_torque_pad, int32_t n) { W_OR_INVALID(w); if (!fx_fy_torque_pad && n) return DBX_E_INVALID; return w->w.applyForces(fx_fy_torque_pad, n); }
 int32_t dbx_world_read_transforms(dbx_world* w, float* out, int32_t n) { W_OR_INVALID(w); if (!out && n) return DBX_E_INVALID; return w->w.readTransforms(out, n); }
 int64_t dbx_world_launch_count(dbx_world* w) { return (w && w->w.ok()) ? (int64_t)w->w.launchCount() : 0; }

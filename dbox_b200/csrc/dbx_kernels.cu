@@ -1689,6 +1689,45 @@ __global__ void k_api_wake(const __grid_constant__ DevWorld W, int a, int b) {
   if (b >= 0) wake_body_now(W, b);
 }
 
+// Bulk b2Body.SetTransform + SetLinearVelocity + SetAngularVelocity (dynamics/b2body.d:261-285, 296-326) for n bodies of a
+// (possibly replicated) world: the reset call of a batched-worlds loop.  Pass 1 writes the body state and tags the body,
+// pass 2 runs b2Fixture.Synchronize(xf, xf) (zero displacement) for the proxies of tagged bodies, pass 3 removes the tags.
+__global__ void __launch_bounds__(256) k_api_set_states(const __grid_constant__ DevWorld W, const int* ids, const float4* pose, const float4* vel, int n) {
+  GRID_STRIDE(k, n) {
+    const int b = ids ? ids[k] : k;
+    if (b < 0 || b >= W.nBodies) continue;
+    const uint32_t f = W.b_flags[b];
+    if (!(f & BF_ALIVE)) continue;
+    if (pose) {
+      const float4 ps = pose[k];
+      Xf xf; xf.p = V(ps.x, ps.y); xf.q = rot_from_angle(ps.z);
+      const float4 lc = W.b_lc[b];
+      const v2 c = mul(xf, V(lc.x, lc.y));
+      W.b_xf[b] = pack(xf); W.b_xf0[b] = pack(xf);
+      W.b_pos[b] = make_float4(c.x, c.y, ps.z, 0.0f);
+      W.b_pos0[b] = make_float4(c.x, c.y, ps.z, W.b_pos0[b].w);
+      W.b_toiFlags[b] = TF_SYNC;
+    }
+    if (vel && body_type(f) != BODY_STATIC) {
+      const float4 v = vel[k];
+      if (v.x * v.x + v.y * v.y > 0.0f || v.z * v.z > 0.0f) wake_body_now(W, b);
+      W.b_vel[b] = make_float4(v.x, v.y, v.z, 0.0f);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_api_sync_tagged(const __grid_constant__ DevWorld W) {
+  GRID_STRIDE(p, W.nProxies) {
+    const uint32_t pf = W.p_flags[p];
+    if (!(pf & PF_ALIVE)) continue;
+    const int body = W.p_ids[p].z;
+    if (!(W.b_toiFlags[body] & TF_SYNC)) continue;
+    sync_proxy(W, p, pf, body);
+  }
+}
+__global__ void __launch_bounds__(256) k_api_untag(const __grid_constant__ DevWorld W, const int* ids, int n) {
+  GRID_STRIDE(k, n) { const int b = ids ? ids[k] : k; if (b >= 0 && b < W.nBodies) W.b_toiFlags[b] = 0; }
+}
+
 // ------------------------------------------------------------------------------------------------ time of impact
 // b2World.SolveTOI (dynamics/b2world.d:1127-1452) + b2Island.SolveTOI (b2island.d:282-416).
 // The reference handles one event at a time in ascending alpha.  Events whose mini-islands share no movable body
@@ -2157,6 +2196,14 @@ cudaError_t launch_api_contacts(const DevWorld& W, const LaunchCfg& L, int body,
 }
 cudaError_t launch_api_wake(const DevWorld& W, const LaunchCfg& L, int a, int b) {
   ++L.launches; k_api_wake<<<1, 1, 0, L.stream>>>(W, a, b);
+  return cudaGetLastError();
+}
+cudaError_t launch_set_states(const DevWorld& W, const LaunchCfg& L, const int* ids, const float4* pose, const float4* vel, int n) {
+  ++L.launches; k_api_set_states<<<L.gridWide, 256, 0, L.stream>>>(W, ids, pose, vel, n);
+  if (pose) {
+    ++L.launches; k_api_sync_tagged<<<L.gridWide, 256, 0, L.stream>>>(W);
+    ++L.launches; k_api_untag<<<L.gridWide, 256, 0, L.stream>>>(W, ids, n);
+  }
   return cudaGetLastError();
 }
 cudaError_t launch_apply_forces(const DevWorld& W, const LaunchCfg& L, const float4* forces, int n) {

@@ -803,6 +803,22 @@ int World::applyForces(const float* f4, int n) {
   hostBodiesValid_ = false;
   return n;
 }
+// bulk SetTransform / SetLinearVelocity / SetAngularVelocity from host arrays (either may be null); ids null = bodies 0..n-1
+int World::setBodyStates(const int* ids, const float* pose4, const float* vel4, int n) {
+  int rc = push(); if (rc < 0) return rc;
+  const size_t nAll = bodies_.size() * (size_t)nWorlds_;
+  if (n < 0 || (size_t)n > nAll || (!pose4 && !vel4)) return DBX_E_INVALID;
+  if (n == 0) return 0;
+  CUDA_OR_FAIL(ioBuf_.reserve(std::max<size_t>(nAll, 1), false, stream_), "io buffer");
+  CUDA_OR_FAIL(ioBuf2_.reserve(std::max<size_t>(nAll, 1), false, stream_), "io buffer");
+  CUDA_OR_FAIL(ioIds_.reserve(std::max<size_t>(nAll, 1), false, stream_), "io ids");
+  if (ids) CUDA_OR_FAIL(cudaMemcpyAsync(ioIds_.p, ids, (size_t)n * 4, cudaMemcpyHostToDevice, stream_), "ids h2d");
+  if (pose4) CUDA_OR_FAIL(cudaMemcpyAsync(ioBuf_.p, pose4, (size_t)n * 16, cudaMemcpyHostToDevice, stream_), "pose h2d");
+  if (vel4) CUDA_OR_FAIL(cudaMemcpyAsync(ioBuf2_.p, vel4, (size_t)n * 16, cudaMemcpyHostToDevice, stream_), "vel h2d");
+  CUDA_OR_FAIL(launch_set_states(dw_, L_, ids ? ioIds_.p : nullptr, pose4 ? ioBuf_.p : nullptr, vel4 ? ioBuf2_.p : nullptr, n), "set_states");
+  hostBodiesValid_ = false; hostProxiesValid_ = false;
+  return n;
+}
 int World::readTransforms(float* out, int n) {
   int rc = push(); if (rc < 0) return rc;
   if (n > (int)bodies_.size() * nWorlds_) return DBX_E_INVALID;

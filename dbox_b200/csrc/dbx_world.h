@@ -63,6 +63,7 @@ class World {
   int enqueueStep(float dt, int vi, int pi, bool fineEvents);
   int timeSteps(float dt, int vi, int pi, int n, bool flushL2, float* totalMs, float* stageMs);
   int applyForces(const float* f4, int n);
+  int setBodyStates(const int* ids, const float* pose4, const float* vel4, int n);
   int readTransforms(float* out, int n);
   long launchCount() const { return L_.launches; }
   int clearForces();
@@ -165,7 +166,7 @@ class World {
   int nJointPairs_ = 0; int jointBlocks_ = 0, nJointColours_ = 0;
   cudaEvent_t ev_[10]{};
   bool evValid_ = false, evFine_ = false;
-  DevBuf<char> flushBuf_; DevBuf<float4> ioBuf_; DevBuf<unsigned long long> phaseBuf_;
+  DevBuf<char> flushBuf_; DevBuf<float4> ioBuf_, ioBuf2_; DevBuf<int> ioIds_; DevBuf<unsigned long long> phaseBuf_;
   bool overrideLevels_ = false;
   bool treeValid_ = false; int sinceRebuild_ = 0;
   std::vector<int> lastReadSlots_;

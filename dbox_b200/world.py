@@ -419,6 +419,21 @@ class b2World:
         (BASELINE config 5, batched RL-style worlds).  Body id of replica r = r * bodies_per_replica + local id."""
         self._ck(self._api.world_replicate(self._w, copies))
 
+    def SetBodyStates(self, ids=None, pose=None, vel=None):
+        """bulk b2Body.SetTransform / SetLinearVelocity / SetAngularVelocity (b2body.d:261-326) from numpy arrays:
+        pose[n,4] = (x, y, angle, -), vel[n,4] = (vx, vy, w, -), ids[n] int32 (None = bodies 0..n-1); also valid on a
+        replicated world, where body r * bodies_per_replica + b is body b of replica r"""
+        import numpy as np
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float32) for a in (pose, vel)]
+        n = next(a.shape[0] for a in arrs if a is not None)
+        idp = None
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.int32); n = ids.shape[0]; idp = ids.ctypes.data
+        for a in arrs:
+            assert a is None or a.shape == (n, 4)
+        self._ck(self._api.world_set_body_states(self._w, idp, None if arrs[0] is None else arrs[0].ctypes.data,
+                                                 None if arrs[1] is None else arrs[1].ctypes.data, n))
+
     def StepN(self, dt, velocityIterations, positionIterations, n):
         self._ck(self._api.world_step_n(self._w, dt, velocityIterations, positionIterations, n))
 

@@ -237,6 +237,11 @@ int32_t dbx_world_clear_forces(dbx_world* w);                          /* b2worl
 int32_t dbx_world_time_steps(dbx_world* w, float dt, int32_t velocityIterations, int32_t positionIterations, int32_t n, int32_t flushL2,
                              float* totalMs, float* stageMs);
 int32_t dbx_world_apply_forces(dbx_world* w, const float* fx_fy_torque_pad, int32_t n);
+/* Bulk b2Body.SetTransform (dynamics/b2body.d:261-285: pose, sweep c0 = c, b2Fixture.Synchronize with zero displacement)
+ * and SetLinearVelocity / SetAngularVelocity (:296-326: a non-zero velocity wakes the body) for n bodies from host arrays
+ * of 4 floats per body; either array may be NULL (that part is left alone); ids NULL = bodies 0..n-1.  Works on replicated
+ * worlds (body r*B+b is body b of replica r): the reset / randomisation call of a batched-worlds loop.  Returns n. */
+int32_t dbx_world_set_body_states(dbx_world* w, const int32_t* ids, const float* x_y_angle_pad, const float* vx_vy_w_pad, int32_t n);
 int32_t dbx_world_read_transforms(dbx_world* w, float* out, int32_t n);
 int64_t dbx_world_launch_count(dbx_world* w);   /* kernels of this library launched so far on this world */
 

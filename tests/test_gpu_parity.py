@@ -260,3 +260,70 @@ def test_replicated_worlds_match_single_world(gpu_api, oracle_api):
                 a, b = ss[i], sb[r * nb + i]
                 assert (a.c.x, a.c.y, a.a, a.v.x, a.v.y, a.w) == (b.c.x, b.c.y, b.a, b.v.x, b.v.y, b.w), (k, r, i)
     assert batch.counts().awakeBodies == 0
+
+
+def _perturbation(nb, seed):
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    pose = np.zeros((nb, 4), np.float32)
+    vel = np.zeros((nb, 4), np.float32)
+    vel[:, 0] = rng.uniform(-2, 2, nb); vel[:, 1] = rng.uniform(-1, 1, nb); vel[:, 2] = rng.uniform(-1, 1, nb)
+    return rng, pose, vel
+
+
+def test_bulk_set_body_states_equals_per_body_calls(gpu_api):
+    """dbx_world_set_body_states == b2Body.SetTransform + SetLinearVelocity + SetAngularVelocity per body (b2body.d:261-326)"""
+    import numpy as np
+    a, bodies_a = scenes.pyramid(api=gpu_api)
+    b, bodies_b = scenes.pyramid(api=gpu_api)
+    a.StepN(DT, 8, 3, 5); b.StepN(DT, 8, 3, 5)
+    sa, n = a.read_bodies()
+    rng = np.random.RandomState(3)
+    ids = np.array(sorted(rng.choice(np.arange(2, n), 40, replace=False)), np.int32)
+    pose = np.zeros((len(ids), 4), np.float32); vel = np.zeros((len(ids), 4), np.float32)
+    for k, i in enumerate(ids):
+        pose[k, :3] = (sa[i].p.x + rng.uniform(-0.3, 0.3), sa[i].p.y + rng.uniform(0, 0.5), rng.uniform(-0.2, 0.2))
+        vel[k, :3] = (rng.uniform(-3, 3), rng.uniform(-3, 3), rng.uniform(-2, 2))
+    a.SetBodyStates(ids, pose, vel)
+    by_id = {bd.id: bd for bd in bodies_b}
+    for k, i in enumerate(ids):
+        bd = by_id[int(i)]
+        bd.SetTransform((float(pose[k, 0]), float(pose[k, 1])), float(pose[k, 2]))
+        bd.SetLinearVelocity((float(vel[k, 0]), float(vel[k, 1])))
+        bd.SetAngularVelocity(float(vel[k, 2]))
+    for step in range(30):
+        a.Step(DT, 8, 3); b.Step(DT, 8, 3)
+        ca, cb = a.counts(), b.counts()
+        assert (ca.contacts, ca.touching, ca.awakeBodies) == (cb.contacts, cb.touching, cb.awakeBodies), step
+    sa, _ = a.read_bodies(); sb, _ = b.read_bodies()
+    for i in range(n):
+        assert (sa[i].c.x, sa[i].c.y, sa[i].a, sa[i].v.x, sa[i].v.y, sa[i].w) == (sb[i].c.x, sb[i].c.y, sb[i].a, sb[i].v.x, sb[i].v.y, sb[i].w), i
+
+
+def test_divergent_replicas_match_separately_built_worlds(gpu_api):
+    """batched worlds that are randomised per replica (the RL reset) evolve exactly like the same world built alone"""
+    import numpy as np
+    copies = 6
+    batch, _ = scenes.pyramid(api=gpu_api)
+    batch.Replicate(copies)
+    nb = batch.counts().bodies // copies
+    vel_all = np.zeros((nb * copies, 4), np.float32)
+    singles = []
+    for r in range(copies):
+        rng, pose, vel = _perturbation(nb, 100 + r)
+        vel[:2] = 0                                  # the two static bodies
+        vel_all[r * nb:(r + 1) * nb] = vel
+        w, _ = scenes.pyramid(api=gpu_api)
+        w.SetBodyStates(None, None, vel)
+        singles.append(w)
+    batch.SetBodyStates(None, None, vel_all)
+    for k in range(4):
+        batch.StepN(DT, 8, 3, 40)
+        sb, n = batch.read_bodies()
+        for r, w in enumerate(singles):
+            w.StepN(DT, 8, 3, 40)
+            ss, _ = w.read_bodies()
+            for i in range(nb):
+                a, b = ss[i], sb[r * nb + i]
+                assert (a.c.x, a.c.y, a.a, a.v.x, a.v.y, a.w) == (b.c.x, b.c.y, b.a, b.v.x, b.v.y, b.w), (k, r, i)
+    assert gpu_api.world_debug_colour_conflicts(batch._w) == 0
