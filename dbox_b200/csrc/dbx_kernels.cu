@@ -7,112 +7,12 @@
 // levers are coalesced float4 SoA access, L2-resident constraint blocks and as few barriers as the colouring allows.
 #include <cub/cub.cuh>
 #include "dbx_kernels.cuh"
+#include "dbx_solver.cuh"
 
 namespace dbx {
 
 cudaError_t stage_rebuild_hash(const DevWorld& W, const LaunchCfg& L);
 
-#define GRID_STRIDE(i, n) for (int i = blockIdx.x * blockDim.x + threadIdx.x, _gs = gridDim.x * blockDim.x; i < (n); i += _gs)
-
-// ------------------------------------------------------------------------------------------------ small device utilities
-DBX_D float4 ldcg4(const float4* p) { return __ldcg(p); }
-DBX_D void stcg4(float4* p, float4 v) { __stcg(p, v); }
-
-// 64-bit mix (bijective) for the pair hash and the colouring priorities
-DBX_HD unsigned long long mix64(unsigned long long x) {
-  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
-  return x;
-}
-DBX_D int hash_find(const DevWorld& W, unsigned long long key) {
-  unsigned mask = (unsigned)W.hCap - 1;
-  unsigned h = (unsigned)mix64(key) & mask;
-  for (int probe = 0; probe < W.hCap; ++probe) {
-    unsigned long long k = W.h_key[h];
-    if (k == key) return W.h_val[h];
-    if (k == kHashEmpty) return -1;
-    h = (h + 1) & mask;
-  }
-  return -1;
-}
-// keys are unique per insertion batch, so a CAS on the key word is enough
-DBX_D bool hash_insert(const DevWorld& W, unsigned long long key, int val) {
-  unsigned mask = (unsigned)W.hCap - 1;
-  unsigned h = (unsigned)mix64(key) & mask;
-  for (int probe = 0; probe < W.hCap; ++probe) {
-    unsigned long long old = atomicCAS(&W.h_key[h], kHashEmpty, key);
-    if (old == kHashEmpty) { W.h_val[h] = val; return true; }
-    h = (h + 1) & mask;
-  }
-  return false;
-}
-DBX_D void hash_remove(const DevWorld& W, unsigned long long key) {
-  unsigned mask = (unsigned)W.hCap - 1;
-  unsigned h = (unsigned)mix64(key) & mask;
-  for (int probe = 0; probe < W.hCap; ++probe) {
-    unsigned long long k = W.h_key[h];
-    if (k == key) { W.h_key[h] = kHashTomb; atomicAdd(&W.hdr->nTomb, 1); return; }
-    if (k == kHashEmpty) return;
-    h = (h + 1) & mask;
-  }
-}
-
-// lock-free union-find; the larger index is always hooked under the smaller, so a component's root is its minimum id
-DBX_D int uf_find(int* parent, int x) {
-  for (;;) {
-    int p = parent[x];
-    if (p == x) return x;
-    int gp = parent[p];
-    if (gp != p) parent[x] = gp;  // path halving (benign race)
-    x = p;
-  }
-}
-DBX_D void uf_unite(int* parent, int a, int b) {
-  for (;;) {
-    a = uf_find(parent, a);
-    b = uf_find(parent, b);
-    if (a == b) return;
-    if (a < b) { int t = a; a = b; b = t; }
-    if (atomicCAS(&parent[a], a, b) == a) return;
-  }
-}
-
-// global barrier for the persistent kernels: all CTAs are co-resident (cooperative launch, one per SM)
-DBX_D void grid_barrier(unsigned* counter, unsigned nblocks) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    unsigned ticket = atomicAdd(counter, 1u);
-    unsigned target = (ticket / nblocks + 1u) * nblocks;
-    while (*((volatile unsigned*)counter) < target) { }
-    __threadfence();
-  }
-  __syncthreads();
-}
-
-// b2ContactFilter.ShouldCollide (dynamics/b2worldcallbacks.d:52-64)
-DBX_D bool filter_should_collide(const DevWorld& W, int fA, int fB) {
-  short gA = (short)(W.f_group[fA] & 0xFFFF), gB = (short)(W.f_group[fB] & 0xFFFF);
-  if (gA == gB && gA != 0) return gA > 0;
-  uint32_t a = W.f_filter[fA], b = W.f_filter[fB];
-  uint32_t catA = a & 0xFFFF, maskA = a >> 16, catB = b & 0xFFFF, maskB = b >> 16;
-  return (maskA & catB) != 0 && (catA & maskB) != 0;
-}
-// b2Body.ShouldCollide (dynamics/b2body.d:1149-1170): at least one dynamic body, no joint that forbids it
-DBX_D bool body_should_collide(const DevWorld& W, int bA, int bB, uint32_t flA, uint32_t flB) {
-  if (body_type(flA) != BODY_DYNAMIC && body_type(flB) != BODY_DYNAMIC) return false;
-  if (W.nJointPairs > 0) {
-    unsigned long long lo = (unsigned)min(bA, bB), hi = (unsigned)max(bA, bB);
-    unsigned long long k = (lo << 32) | hi;
-    int l = 0, r = W.nJointPairs;
-    while (l < r) { int m = (l + r) >> 1; if (W.jp_keys[m] < k) l = m + 1; else r = m; }
-    if (l < W.nJointPairs && W.jp_keys[l] == k) return false;
-  }
-  return true;
-}
-DBX_D void wake_body_now(const DevWorld& W, int b) {  // b2Body.SetAwake(true) (b2body.d:829-835)
-  uint32_t old = atomicOr(&W.b_flags[b], BF_AWAKE);
-  if (!(old & BF_AWAKE)) W.b_gs[b].y = 0.0f;
-}
 
 // ------------------------------------------------------------------------------------------------ Collide
 // b2ContactManager.Collide (dynamics/b2contactmanager.d:251-317) + b2Contact.Update (contacts/b2contact.d:270-356)
@@ -483,796 +383,6 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const __grid_constant__ De
   }
 }
 
-// ------------------------------------------------------------------------------------------------ contact constraints
-// b2ContactSolver ctor + InitializeVelocityConstraints (contacts/b2contactsolver.d:244-450): one thread per solver contact.
-// `s` = solver slot to fill, `i` = contact slot; warmScale < 0 means "no warm starting" (TOI sub-steps, b2world.d:1419)
-DBX_D void prepare_contact(const DevWorld& W, int s, int i, float warmScale) {
-  {
-    const int4 ids = W.c_ids[i];
-    const int4 fx = W.c_fix[i];
-    const int bA = ids.z, bB = ids.w;
-    const float4 msA = W.b_mass[bA], msB = W.b_mass[bB];
-    const float4 lcA4 = W.b_lc[bA], lcB4 = W.b_lc[bB];
-    const float4 posA = ldcg4(&W.b_pos[bA]), posB = ldcg4(&W.b_pos[bB]);
-    const float4 velA = ldcg4(&W.b_vel[bA]), velB = ldcg4(&W.b_vel[bB]);
-    const float4 xA = ldcg4(&W.b_xf[bA]), xB = ldcg4(&W.b_xf[bB]);
-    const float4 m0 = W.c_m0[i], m1 = W.c_m1[i], cimp = W.c_imp[i], mat = W.c_mat[i];
-    const uint4 mk = W.c_mk[i];
-    const float radiusA = W.shapes[fx.z].radius, radiusB = W.shapes[fx.w].radius;
-    const float mA = msA.x, iA = msA.y, mB = msB.x, iB = msB.y;
-    const v2 localCenterA = V(lcA4.x, lcA4.y), localCenterB = V(lcB4.x, lcB4.y);
-    const v2 cA = V(posA.x, posA.y), cB = V(posB.x, posB.y);
-    const v2 vA = V(velA.x, velA.y), vB = V(velB.x, velB.y);
-    const float wA = velA.z, wB = velB.z;
-    const int pointCount = (int)mk.w, type = (int)mk.z;
-    // xf from (c, a): q is the body's stored rotation (always sin/cos of a), p = c - q * localCenter (:371-375)
-    Xf xfA, xfB;
-    xfA.q = R(xA.z, xA.w); xfB.q = R(xB.z, xB.w);
-    xfA.p = cA - mul(xfA.q, localCenterA);
-    xfB.p = cB - mul(xfB.q, localCenterB);
-    const v2 localNormal = V(m0.x, m0.y), localPoint = V(m0.z, m0.w);
-    const v2 lp0 = V(m1.x, m1.y), lp1 = V(m1.z, m1.w);
-    // b2WorldManifold.Initialize (collision/b2collision.d:123-191)
-    v2 normal, wp[2];
-    if (type == MAN_CIRCLES) {
-      normal = V(1.0f, 0.0f);
-      v2 pointA = mul(xfA, localPoint), pointB = mul(xfB, lp0);
-      if (dist2(pointA, pointB) > kEpsilon * kEpsilon) { normal = pointB - pointA; normalize(normal); }
-      v2 ca = pointA + radiusA * normal, cb = pointB - radiusB * normal;
-      wp[0] = 0.5f * (ca + cb); wp[1] = wp[0];
-    } else if (type == MAN_FACE_A) {
-      normal = mul(xfA.q, localNormal);
-      v2 planePoint = mul(xfA, localPoint);
-      for (int k = 0; k < pointCount; ++k) {
-        v2 clipPoint = mul(xfB, k == 0 ? lp0 : lp1);
-        v2 ca = clipPoint + (radiusA - dot(clipPoint - planePoint, normal)) * normal;
-        v2 cb = clipPoint - radiusB * normal;
-        wp[k] = 0.5f * (ca + cb);
-      }
-    } else {
-      normal = mul(xfB.q, localNormal);
-      v2 planePoint = mul(xfB, localPoint);
-      for (int k = 0; k < pointCount; ++k) {
-        v2 clipPoint = mul(xfA, k == 0 ? lp0 : lp1);
-        v2 cb = clipPoint + (radiusB - dot(clipPoint - planePoint, normal)) * normal;
-        v2 ca = clipPoint - radiusA * normal;
-        wp[k] = 0.5f * (ca + cb);
-      }
-      normal = -normal;
-    }
-    const float friction = mat.x, restitution = mat.y, tangentSpeed = mat.z;
-    const v2 tangent = cross(normal, 1.0f);
-    float4 r[2], q[2];
-    r[1] = make_float4(0, 0, 0, 0); q[1] = make_float4(0, 0, 0, 0);
-    for (int k = 0; k < pointCount; ++k) {
-      v2 rA = wp[k] - cA, rB = wp[k] - cB;
-      float rnA = cross(rA, normal), rnB = cross(rB, normal);
-      float kNormal = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
-      float normalMass = kNormal > 0.0f ? 1.0f / kNormal : 0.0f;
-      float rtA = cross(rA, tangent), rtB = cross(rB, tangent);
-      float kTangent = mA + mB + iA * rtA * rtA + iB * rtB * rtB;
-      float tangentMass = kTangent > 0.0f ? 1.0f / kTangent : 0.0f;
-      float velocityBias = 0.0f;
-      float vRel = dot(normal, vB + cross(wB, rB) - vA - cross(wA, rA));
-      if (vRel < -kVelocityThreshold) velocityBias = -restitution * vRel;
-      r[k] = make_float4(rA.x, rA.y, rB.x, rB.y);
-      q[k] = make_float4(normalMass, tangentMass, velocityBias, 0.0f);
-    }
-    int vcCount = pointCount;
-    float4 nm = make_float4(0, 0, 0, 0), K = make_float4(0, 0, 0, 0);
-    if (pointCount == 2) {
-      // block-solver matrix with the reference's conditioning test (:418-448)
-      float rn1A = cross(V(r[0].x, r[0].y), normal), rn1B = cross(V(r[0].z, r[0].w), normal);
-      float rn2A = cross(V(r[1].x, r[1].y), normal), rn2B = cross(V(r[1].z, r[1].w), normal);
-      float k11 = mA + mB + iA * rn1A * rn1A + iB * rn1B * rn1B;
-      float k22 = mA + mB + iA * rn2A * rn2A + iB * rn2B * rn2B;
-      float k12 = mA + mB + iA * rn1A * rn2A + iB * rn1B * rn2B;
-      const float k_maxConditionNumber = 1000.0f;
-      if (k11 * k11 < k_maxConditionNumber * (k11 * k22 - k12 * k12)) {
-        M22 Km; Km.ex = V(k11, k12); Km.ey = V(k12, k22);
-        M22 inv = inverse(Km);
-        K = make_float4(k11, k12, k12, k22);
-        nm = make_float4(inv.ex.x, inv.ex.y, inv.ey.x, inv.ey.y);
-      } else {
-        vcCount = 1;
-      }
-    }
-    // warm-start impulses scaled by dtRatio (:309-313)
-    float4 imp = warmScale >= 0.0f ? make_float4(warmScale * cimp.x, warmScale * cimp.y, warmScale * cimp.z, warmScale * cimp.w)
-                                   : make_float4(0, 0, 0, 0);
-    if (pointCount < 2) { imp.z = 0.0f; imp.w = 0.0f; }
-    W.s_body[s] = make_int2(bA, bB);
-    W.s_v0[s] = make_float4(normal.x, normal.y, friction, tangentSpeed);
-    W.s_v1[s] = make_float4(mA, iA, mB, iB);
-    W.s_r0[s] = r[0]; W.s_r1[s] = r[1];
-    W.s_q0[s] = q[0]; W.s_q1[s] = q[1];
-    W.s_imp[s] = imp;
-    W.s_nm[s] = nm; W.s_k[s] = K;
-    W.s_pc[s] = vcCount | (type << 8) | (pointCount << 16);
-    W.s_p0[s] = m1;
-    W.s_p1[s] = m0;
-    W.s_p2[s] = make_float4(localCenterA.x, localCenterA.y, localCenterB.x, localCenterB.y);
-    W.s_p3[s] = make_float2(radiusA, radiusB);
-    uint32_t fa = W.b_flags[bA];
-    W.s_root[s] = body_type(fa) != BODY_STATIC ? W.b_root[bA] : W.b_root[bB];
-  }
-}
-__global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ DevWorld W) {
-  const int n = min(W.hdr->nSolve, W.sCap);
-  const float warmScale = W.warmStarting ? W.dtRatio : -1.0f;
-  GRID_STRIDE(s, n) prepare_contact(W, s, W.s_contact[s], warmScale);
-}
-
-// velocities of one body pair; only dynamic bodies are ever written (statics/kinematics have zero inverse mass)
-struct BodyVel { v2 vA, vB; float wA, wB; };
-DBX_D BodyVel load_vel(const DevWorld& W, int2 bd) {
-  float4 a = ldcg4(&W.b_vel[bd.x]), b = ldcg4(&W.b_vel[bd.y]);
-  BodyVel r; r.vA = V(a.x, a.y); r.wA = a.z; r.vB = V(b.x, b.y); r.wB = b.z; return r;
-}
-DBX_D void store_vel(const DevWorld& W, int2 bd, const BodyVel& r, float mA, float iA, float mB, float iB) {
-  if (mA != 0.0f || iA != 0.0f) stcg4(&W.b_vel[bd.x], make_float4(r.vA.x, r.vA.y, r.wA, 0.0f));
-  if (mB != 0.0f || iB != 0.0f) stcg4(&W.b_vel[bd.y], make_float4(r.vB.x, r.vB.y, r.wB, 0.0f));
-}
-
-// b2ContactSolver.WarmStart (:452-490)
-DBX_D void contact_warm_start(const DevWorld& W, int s) {
-  const int2 bd = W.s_body[s];
-  const float4 v0 = W.s_v0[s], v1 = W.s_v1[s], imp = W.s_imp[s];
-  const int pointCount = W.s_pc[s] & 0xFF;
-  const float mA = v1.x, iA = v1.y, mB = v1.z, iB = v1.w;
-  BodyVel bv = load_vel(W, bd);
-  const v2 normal = V(v0.x, v0.y), tangent = cross(normal, 1.0f);
-  for (int k = 0; k < pointCount; ++k) {
-    const float4 r = k == 0 ? W.s_r0[s] : W.s_r1[s];
-    const float ni = k == 0 ? imp.x : imp.z, ti = k == 0 ? imp.y : imp.w;
-    v2 P = ni * normal + ti * tangent;
-    bv.wA -= iA * cross(V(r.x, r.y), P);
-    bv.vA -= mA * P;
-    bv.wB += iB * cross(V(r.z, r.w), P);
-    bv.vB += mB * P;
-  }
-  store_vel(W, bd, bv, mA, iA, mB, iB);
-}
-
-// b2ContactSolver.SolveVelocityConstraints (:492-772): friction rows, then 1-point clamp or the 2-point block solver
-// constraint block of one solver contact, loadable ahead of the barrier that precedes its colour (only s_imp ever changes,
-// and only through the thread that owns the slot)
-struct VC { int2 bd; int pc; float4 v0, v1, r0, r1, q0, q1, imp, nm, K; };
-DBX_D void vc_load(const DevWorld& W, int s, VC& c) {
-  c.bd = W.s_body[s]; c.pc = W.s_pc[s];
-  c.v0 = W.s_v0[s]; c.v1 = W.s_v1[s]; c.r0 = W.s_r0[s]; c.q0 = W.s_q0[s]; c.imp = W.s_imp[s];
-  c.r1 = W.s_r1[s]; c.q1 = W.s_q1[s]; c.nm = W.s_nm[s]; c.K = W.s_k[s];
-}
-DBX_D void contact_solve_velocity(const DevWorld& W, int s, const VC& c) {
-  const int2 bd = c.bd;
-  const float4 v0 = c.v0, v1 = c.v1;
-  float4 imp = c.imp;
-  const int pointCount = c.pc & 0xFF;
-  const float mA = v1.x, iA = v1.y, mB = v1.z, iB = v1.w;
-  const float4 r0 = c.r0, q0 = c.q0;
-  const float4 r1 = c.r1, q1 = c.q1;
-  BodyVel bv = load_vel(W, bd);
-  v2 vA = bv.vA, vB = bv.vB; float wA = bv.wA, wB = bv.wB;
-  const v2 normal = V(v0.x, v0.y), tangent = cross(normal, 1.0f);
-  const float friction = v0.z, tangentSpeed = v0.w;
-  for (int k = 0; k < pointCount; ++k) {
-    const float4 r = k == 0 ? r0 : r1;
-    const float tangentMass = k == 0 ? q0.y : q1.y;
-    const v2 rA = V(r.x, r.y), rB = V(r.z, r.w);
-    float ni = k == 0 ? imp.x : imp.z, ti = k == 0 ? imp.y : imp.w;
-    v2 dv = vB + cross(wB, rB) - vA - cross(wA, rA);
-    float vt = dot(dv, tangent) - tangentSpeed;
-    float lambda = tangentMass * (-vt);
-    float maxFriction = friction * ni;
-    float newImpulse = fclampr(ti + lambda, -maxFriction, maxFriction);
-    lambda = newImpulse - ti;
-    if (k == 0) imp.y = newImpulse; else imp.w = newImpulse;
-    v2 P = lambda * tangent;
-    vA -= mA * P; wA -= iA * cross(rA, P);
-    vB += mB * P; wB += iB * cross(rB, P);
-  }
-  if (pointCount == 1) {
-    const v2 rA = V(r0.x, r0.y), rB = V(r0.z, r0.w);
-    v2 dv = vB + cross(wB, rB) - vA - cross(wA, rA);
-    float vn = dot(dv, normal);
-    float lambda = -q0.x * (vn - q0.z);
-    float newImpulse = fmaxr(imp.x + lambda, 0.0f);
-    lambda = newImpulse - imp.x;
-    imp.x = newImpulse;
-    v2 P = lambda * normal;
-    vA -= mA * P; wA -= iA * cross(rA, P);
-    vB += mB * P; wB += iB * cross(rB, P);
-  } else {
-    const float4 nm = c.nm, K = c.K;
-    const v2 rA1 = V(r0.x, r0.y), rB1 = V(r0.z, r0.w), rA2 = V(r1.x, r1.y), rB2 = V(r1.z, r1.w);
-    v2 a = V(imp.x, imp.z);
-    v2 dv1 = vB + cross(wB, rB1) - vA - cross(wA, rA1);
-    v2 dv2 = vB + cross(wB, rB2) - vA - cross(wA, rA2);
-    float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
-    v2 b;
-    b.x = vn1 - q0.z;
-    b.y = vn2 - q1.z;
-    M22 Km; Km.ex = V(K.x, K.y); Km.ey = V(K.z, K.w);
-    M22 NM; NM.ex = V(nm.x, nm.y); NM.ey = V(nm.z, nm.w);
-    b -= mul(Km, a);
-    v2 x;
-    bool found = false;
-    // the four LCP cases in the reference's order (:633-765)
-    x = -mul(NM, b);
-    if (x.x >= 0.0f && x.y >= 0.0f) found = true;
-    if (!found) {
-      x.x = -q0.x * b.x; x.y = 0.0f;
-      vn2 = Km.ex.y * x.x + b.y;
-      if (x.x >= 0.0f && vn2 >= 0.0f) found = true;
-    }
-    if (!found) {
-      x.x = 0.0f; x.y = -q1.x * b.y;
-      vn1 = Km.ey.x * x.y + b.x;
-      if (x.y >= 0.0f && vn1 >= 0.0f) found = true;
-    }
-    if (!found) {
-      x.x = 0.0f; x.y = 0.0f;
-      vn1 = b.x; vn2 = b.y;
-      if (vn1 >= 0.0f && vn2 >= 0.0f) found = true;
-    }
-    if (found) {
-      v2 d = x - a;
-      v2 P1 = d.x * normal, P2 = d.y * normal;
-      vA -= mA * (P1 + P2);
-      wA -= iA * (cross(rA1, P1) + cross(rA2, P2));
-      vB += mB * (P1 + P2);
-      wB += iB * (cross(rB1, P1) + cross(rB2, P2));
-      imp.x = x.x; imp.z = x.y;
-    }
-  }
-  W.s_imp[s] = imp;
-  bv.vA = vA; bv.vB = vB; bv.wA = wA; bv.wB = wB;
-  store_vel(W, bd, bv, mA, iA, mB, iB);
-}
-
-DBX_D void contact_solve_velocity(const DevWorld& W, int s) { VC c; vc_load(W, s, c); contact_solve_velocity(W, s, c); }
-
-// b2ContactSolver.SolvePositionConstraints (:73-149) + b2PositionSolverManifold (:816-868); returns min separation
-// toiA/toiB >= 0 selects SolveTOIPositionConstraints (:152-242): only those two bodies keep their mass, Baumgarte 0.75
-DBX_D float contact_solve_position(const DevWorld& W, int s, int toiA = -1, int toiB = -1) {
-  const int2 bd = W.s_body[s];
-  const float4 v1 = W.s_v1[s], p0 = W.s_p0[s], p1 = W.s_p1[s], p2 = W.s_p2[s];
-  const float2 p3 = W.s_p3[s];
-  const int pc = W.s_pc[s];
-  const int type = (pc >> 8) & 0xFF, pointCount = pc >> 16;
-  float mA = v1.x, iA = v1.y, mB = v1.z, iB = v1.w;
-  const bool toi = toiA >= 0;
-  if (toi) {
-    if (bd.x != toiA && bd.x != toiB) { mA = 0.0f; iA = 0.0f; }
-    if (bd.y != toiA && bd.y != toiB) { mB = 0.0f; iB = 0.0f; }
-  }
-  const float baumgarte = toi ? kToiBaumgarte : kBaumgarte;
-  const v2 localCenterA = V(p2.x, p2.y), localCenterB = V(p2.z, p2.w);
-  const v2 localNormal = V(p1.x, p1.y), localPoint = V(p1.z, p1.w);
-  float4 pa = ldcg4(&W.b_pos[bd.x]), pb = ldcg4(&W.b_pos[bd.y]);
-  v2 cA = V(pa.x, pa.y), cB = V(pb.x, pb.y);
-  float aA = pa.z, aB = pb.z;
-  float minSeparation = 0.0f;
-  for (int j = 0; j < pointCount; ++j) {
-    Xf xfA, xfB;
-    xfA.q = rot_from_angle(aA); xfB.q = rot_from_angle(aB);
-    xfA.p = cA - mul(xfA.q, localCenterA);
-    xfB.p = cB - mul(xfB.q, localCenterB);
-    v2 normal, point; float separation;
-    if (type == MAN_CIRCLES) {
-      v2 pointA = mul(xfA, localPoint), pointB = mul(xfB, V(p0.x, p0.y));
-      normal = pointB - pointA;
-      normalize(normal);
-      point = 0.5f * (pointA + pointB);
-      separation = dot(pointB - pointA, normal) - p3.x - p3.y;
-    } else if (type == MAN_FACE_A) {
-      normal = mul(xfA.q, localNormal);
-      v2 planePoint = mul(xfA, localPoint);
-      v2 clipPoint = mul(xfB, j == 0 ? V(p0.x, p0.y) : V(p0.z, p0.w));
-      separation = dot(clipPoint - planePoint, normal) - p3.x - p3.y;
-      point = clipPoint;
-    } else {
-      normal = mul(xfB.q, localNormal);
-      v2 planePoint = mul(xfB, localPoint);
-      v2 clipPoint = mul(xfA, j == 0 ? V(p0.x, p0.y) : V(p0.z, p0.w));
-      separation = dot(clipPoint - planePoint, normal) - p3.x - p3.y;
-      point = clipPoint;
-      normal = -normal;
-    }
-    v2 rA = point - cA, rB = point - cB;
-    minSeparation = fminr(minSeparation, separation);
-    float C = fclampr(baumgarte * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
-    float rnA = cross(rA, normal), rnB = cross(rB, normal);
-    float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
-    float impulse = K > 0.0f ? -C / K : 0.0f;
-    v2 P = impulse * normal;
-    cA -= mA * P; aA -= iA * cross(rA, P);
-    cB += mB * P; aB += iB * cross(rB, P);
-  }
-  if (mA != 0.0f || iA != 0.0f) stcg4(&W.b_pos[bd.x], make_float4(cA.x, cA.y, aA, 0.0f));
-  if (mB != 0.0f || iB != 0.0f) stcg4(&W.b_pos[bd.y], make_float4(cB.x, cB.y, aB, 0.0f));
-  return minSeparation;
-}
-
-// ------------------------------------------------------------------------------------------------ joints
-// revolute: dynamics/joints/b2revolutejoint.d:319-636; distance: b2distancejoint.d:211-373
-DBX_D bool joint_active(const DevWorld& W, int j);
-DBX_D void joint_init(const DevWorld& W, int j) {
-  if (!joint_active(W, j)) { W.j_root[j] = -1; return; }   // later phases only look at j_root
-  const int4 ids = W.j_ids[j];
-  const int bA = ids.y, bB = ids.z;
-  const float4 msA = W.b_mass[bA], msB = W.b_mass[bB];
-  const float4 lcA4 = W.b_lc[bA], lcB4 = W.b_lc[bB];
-  const float4 anc = W.j_anchor[j];
-  const float mA = msA.x, iA = msA.y, mB = msB.x, iB = msB.y;
-  const v2 localCenterA = V(lcA4.x, lcA4.y), localCenterB = V(lcB4.x, lcB4.y);
-  const float4 posA = W.b_pos[bA], posB = W.b_pos[bB];
-  const float4 xA = W.b_xf[bA], xB = W.b_xf[bB];
-  float4 velA = ldcg4(&W.b_vel[bA]), velB = ldcg4(&W.b_vel[bB]);
-  v2 vA = V(velA.x, velA.y), vB = V(velB.x, velB.y); float wA = velA.z, wB = velB.z;
-  const float aA = posA.z, aB = posB.z;
-  const Rot qA = R(xA.z, xA.w), qB = R(xB.z, xB.w);  // = b2Rot(aA), b2Rot(aB): positions are not integrated yet
-  const v2 rA = mul(qA, V(anc.x, anc.y) - localCenterA);
-  const v2 rB = mul(qB, V(anc.z, anc.w) - localCenterB);
-  W.j_r[j] = make_float4(rA.x, rA.y, rB.x, rB.y);
-  W.j_lc[j] = make_float4(localCenterA.x, localCenterA.y, localCenterB.x, localCenterB.y);
-  W.j_m[j] = make_float4(mA, iA, mB, iB);
-  W.j_root[j] = body_type(W.b_flags[bA]) != BODY_STATIC ? W.b_root[bA] : W.b_root[bB];
-  float4 imp = W.j_imp[j];
-  if (ids.x == JT_REVOLUTE) {
-    const float4 p0 = W.j_p0[j];
-    const bool enableLimit = (ids.w & 2) != 0, enableMotor = (ids.w & 4) != 0;
-    const bool fixedRotation = (iA + iB == 0.0f);
-    v3 ex, ey, ez;
-    ex.x = mA + mB + rA.y * rA.y * iA + rB.y * rB.y * iB;
-    ey.x = -rA.y * rA.x * iA - rB.y * rB.x * iB;
-    ez.x = -rA.y * iA - rB.y * iB;
-    ex.y = ey.x;
-    ey.y = mA + mB + rA.x * rA.x * iA + rB.x * rB.x * iB;
-    ez.y = rA.x * iA + rB.x * iB;
-    ex.z = ez.x;
-    ey.z = ez.y;
-    ez.z = iA + iB;
-    float motorMass = iA + iB;
-    if (motorMass > 0.0f) motorMass = 1.0f / motorMass;
-    if (!enableMotor || fixedRotation) imp.w = 0.0f;
-    int limitState = W.j_limit[j];
-    if (enableLimit && !fixedRotation) {
-      float jointAngle = aB - aA - p0.x;
-      if (fabsr(p0.z - p0.y) < 2.0f * kAngularSlop) limitState = LIM_EQUAL;
-      else if (jointAngle <= p0.y) { if (limitState != LIM_LOWER) imp.z = 0.0f; limitState = LIM_LOWER; }
-      else if (jointAngle >= p0.z) { if (limitState != LIM_UPPER) imp.z = 0.0f; limitState = LIM_UPPER; }
-      else { limitState = LIM_INACTIVE; imp.z = 0.0f; }
-    } else {
-      limitState = LIM_INACTIVE;
-    }
-    W.j_limit[j] = limitState;
-    if (W.warmStarting) {
-      imp.x *= W.dtRatio; imp.y *= W.dtRatio; imp.z *= W.dtRatio;
-      imp.w *= W.dtRatio;
-      v2 P = V(imp.x, imp.y);
-      vA -= mA * P;
-      wA -= iA * (cross(rA, P) + imp.w + imp.z);
-      vB += mB * P;
-      wB += iB * (cross(rB, P) + imp.w + imp.z);
-    } else {
-      imp = make_float4(0, 0, 0, 0);
-    }
-    W.j_k0[j] = make_float4(ex.x, ex.y, ex.z, motorMass);
-    W.j_k1[j] = make_float4(ey.x, ey.y, ey.z, 0.0f);
-    W.j_k2[j] = make_float4(ez.x, ez.y, ez.z, 0.0f);
-  } else {  // JT_DISTANCE
-    const float4 p0 = W.j_p0[j];
-    const v2 cA = V(posA.x, posA.y), cB = V(posB.x, posB.y);
-    v2 u = cB + rB - cA - rA;
-    float length = len(u);
-    if (length > kLinearSlop) u *= 1.0f / length; else u = V(0.0f, 0.0f);
-    float crAu = cross(rA, u), crBu = cross(rB, u);
-    float invMass = mA + iA * crAu * crAu + mB + iB * crBu * crBu;
-    float mass = invMass != 0.0f ? 1.0f / invMass : 0.0f;
-    float gamma = 0.0f, bias = 0.0f;
-    if (p0.y > 0.0f) {
-      float C = length - p0.x;
-      float omega = 2.0f * kPi * p0.y;
-      float d = 2.0f * mass * p0.z * omega;
-      float k = mass * omega * omega;
-      float h = W.dt;
-      gamma = h * (d + h * k);
-      gamma = gamma != 0.0f ? 1.0f / gamma : 0.0f;
-      bias = C * h * k * gamma;
-      invMass += gamma;
-      mass = invMass != 0.0f ? 1.0f / invMass : 0.0f;
-    }
-    if (W.warmStarting) {
-      imp.x *= W.dtRatio;
-      v2 P = imp.x * u;
-      vA -= mA * P; wA -= iA * cross(rA, P);
-      vB += mB * P; wB += iB * cross(rB, P);
-    } else {
-      imp.x = 0.0f;
-    }
-    W.j_k0[j] = make_float4(u.x, u.y, mass, gamma);
-    W.j_k1[j] = make_float4(bias, 0.0f, 0.0f, 0.0f);
-  }
-  W.j_imp[j] = imp;
-  if (mA != 0.0f || iA != 0.0f) stcg4(&W.b_vel[bA], make_float4(vA.x, vA.y, wA, 0.0f));
-  if (mB != 0.0f || iB != 0.0f) stcg4(&W.b_vel[bB], make_float4(vB.x, vB.y, wB, 0.0f));
-}
-
-DBX_D void joint_solve_velocity(const DevWorld& W, int j) {
-  const int4 ids = W.j_ids[j];
-  const int bA = ids.y, bB = ids.z;
-  const float4 m = W.j_m[j], r = W.j_r[j];
-  const float mA = m.x, iA = m.y, mB = m.z, iB = m.w;
-  const v2 rA = V(r.x, r.y), rB = V(r.z, r.w);
-  float4 velA = ldcg4(&W.b_vel[bA]), velB = ldcg4(&W.b_vel[bB]);
-  v2 vA = V(velA.x, velA.y), vB = V(velB.x, velB.y); float wA = velA.z, wB = velB.z;
-  float4 imp = W.j_imp[j];
-  if (ids.x == JT_REVOLUTE) {
-    const float4 p0 = W.j_p0[j], p1 = W.j_p1[j];
-    const float4 k0 = W.j_k0[j], k1 = W.j_k1[j], k2 = W.j_k2[j];
-    const bool enableLimit = (ids.w & 2) != 0, enableMotor = (ids.w & 4) != 0;
-    const int limitState = W.j_limit[j];
-    const bool fixedRotation = (iA + iB == 0.0f);
-    if (enableMotor && limitState != LIM_EQUAL && !fixedRotation) {
-      float Cdot = wB - wA - p1.x;
-      float impulse = -k0.w * Cdot;
-      float oldImpulse = imp.w;
-      float maxImpulse = W.dt * p0.w;
-      imp.w = fclampr(imp.w + impulse, -maxImpulse, maxImpulse);
-      impulse = imp.w - oldImpulse;
-      wA -= iA * impulse;
-      wB += iB * impulse;
-    }
-    const v3 ex = V3(k0.x, k0.y, k0.z), ey = V3(k1.x, k1.y, k1.z), ez = V3(k2.x, k2.y, k2.z);
-    if (enableLimit && limitState != LIM_INACTIVE && !fixedRotation) {
-      v2 Cdot1 = vB + cross(wB, rB) - vA - cross(wA, rA);
-      float Cdot2 = wB - wA;
-      v3 s = solve33(ex, ey, ez, V3(Cdot1.x, Cdot1.y, Cdot2));
-      v3 impulse = V3(-s.x, -s.y, -s.z);
-      if (limitState == LIM_EQUAL) {
-        imp.x += impulse.x; imp.y += impulse.y; imp.z += impulse.z;
-      } else if (limitState == LIM_LOWER) {
-        float newImpulse = imp.z + impulse.z;
-        if (newImpulse < 0.0f) {
-          v2 rhs = -Cdot1 + imp.z * V(ez.x, ez.y);
-          v2 reduced = solve22(ex.x, ey.x, ex.y, ey.y, rhs);
-          impulse.x = reduced.x; impulse.y = reduced.y; impulse.z = -imp.z;
-          imp.x += reduced.x; imp.y += reduced.y; imp.z = 0.0f;
-        } else { imp.x += impulse.x; imp.y += impulse.y; imp.z += impulse.z; }
-      } else if (limitState == LIM_UPPER) {
-        float newImpulse = imp.z + impulse.z;
-        if (newImpulse > 0.0f) {
-          v2 rhs = -Cdot1 + imp.z * V(ez.x, ez.y);
-          v2 reduced = solve22(ex.x, ey.x, ex.y, ey.y, rhs);
-          impulse.x = reduced.x; impulse.y = reduced.y; impulse.z = -imp.z;
-          imp.x += reduced.x; imp.y += reduced.y; imp.z = 0.0f;
-        } else { imp.x += impulse.x; imp.y += impulse.y; imp.z += impulse.z; }
-      }
-      v2 P = V(impulse.x, impulse.y);
-      vA -= mA * P;
-      wA -= iA * (cross(rA, P) + impulse.z);
-      vB += mB * P;
-      wB += iB * (cross(rB, P) + impulse.z);
-    } else {
-      v2 Cdot = vB + cross(wB, rB) - vA - cross(wA, rA);
-      v2 impulse = solve22(ex.x, ey.x, ex.y, ey.y, -Cdot);
-      imp.x += impulse.x; imp.y += impulse.y;
-      vA -= mA * impulse; wA -= iA * cross(rA, impulse);
-      vB += mB * impulse; wB += iB * cross(rB, impulse);
-    }
-  } else {
-    const float4 k0 = W.j_k0[j], k1 = W.j_k1[j];
-    const v2 u = V(k0.x, k0.y);
-    v2 vpA = vA + cross(wA, rA), vpB = vB + cross(wB, rB);
-    float Cdot = dot(u, vpB - vpA);
-    float impulse = -k0.z * (Cdot + k1.x + k0.w * imp.x);
-    imp.x += impulse;
-    v2 P = impulse * u;
-    vA -= mA * P; wA -= iA * cross(rA, P);
-    vB += mB * P; wB += iB * cross(rB, P);
-  }
-  W.j_imp[j] = imp;
-  if (mA != 0.0f || iA != 0.0f) stcg4(&W.b_vel[bA], make_float4(vA.x, vA.y, wA, 0.0f));
-  if (mB != 0.0f || iB != 0.0f) stcg4(&W.b_vel[bB], make_float4(vB.x, vB.y, wB, 0.0f));
-}
-
-// returns true when the joint is within tolerance
-DBX_D bool joint_solve_position(const DevWorld& W, int j) {
-  const int4 ids = W.j_ids[j];
-  const int bA = ids.y, bB = ids.z;
-  const float4 m = W.j_m[j], lc = W.j_lc[j], anc = W.j_anchor[j];
-  const float mA = m.x, iA = m.y, mB = m.z, iB = m.w;
-  float4 pa = ldcg4(&W.b_pos[bA]), pb = ldcg4(&W.b_pos[bB]);
-  v2 cA = V(pa.x, pa.y), cB = V(pb.x, pb.y); float aA = pa.z, aB = pb.z;
-  bool ok;
-  if (ids.x == JT_REVOLUTE) {
-    const float4 p0 = W.j_p0[j];
-    const float motorMass = W.j_k0[j].w;
-    const bool enableLimit = (ids.w & 2) != 0;
-    const int limitState = W.j_limit[j];
-    float angularError = 0.0f, positionError = 0.0f;
-    const bool fixedRotation = (iA + iB == 0.0f);
-    if (enableLimit && limitState != LIM_INACTIVE && !fixedRotation) {
-      float angle = aB - aA - p0.x;
-      float limitImpulse = 0.0f;
-      if (limitState == LIM_EQUAL) {
-        float C = fclampr(angle - p0.y, -kMaxAngularCorrection, kMaxAngularCorrection);
-        limitImpulse = -motorMass * C;
-        angularError = fabsr(C);
-      } else if (limitState == LIM_LOWER) {
-        float C = angle - p0.y;
-        angularError = -C;
-        C = fclampr(C + kAngularSlop, -kMaxAngularCorrection, 0.0f);
-        limitImpulse = -motorMass * C;
-      } else if (limitState == LIM_UPPER) {
-        float C = angle - p0.z;
-        angularError = C;
-        C = fclampr(C - kAngularSlop, 0.0f, kMaxAngularCorrection);
-        limitImpulse = -motorMass * C;
-      }
-      aA -= iA * limitImpulse;
-      aB += iB * limitImpulse;
-    }
-    {
-      Rot qA = rot_from_angle(aA), qB = rot_from_angle(aB);
-      v2 rA = mul(qA, V(anc.x, anc.y) - V(lc.x, lc.y));
-      v2 rB = mul(qB, V(anc.z, anc.w) - V(lc.z, lc.w));
-      v2 C = cB + rB - cA - rA;
-      positionError = len(C);
-      float k11 = mA + mB + iA * rA.y * rA.y + iB * rB.y * rB.y;
-      float k12 = -iA * rA.x * rA.y - iB * rB.x * rB.y;
-      float k22 = mA + mB + iA * rA.x * rA.x + iB * rB.x * rB.x;
-      v2 impulse = -solve22(k11, k12, k12, k22, C);
-      cA -= mA * impulse; aA -= iA * cross(rA, impulse);
-      cB += mB * impulse; aB += iB * cross(rB, impulse);
-    }
-    ok = positionError <= kLinearSlop && angularError <= kAngularSlop;
-  } else {
-    const float4 p0 = W.j_p0[j];
-    if (p0.y > 0.0f) return true;  // soft joints have no position constraint (b2distancejoint.d:337-341)
-    const float mass = W.j_k0[j].z;
-    Rot qA = rot_from_angle(aA), qB = rot_from_angle(aB);
-    v2 rA = mul(qA, V(anc.x, anc.y) - V(lc.x, lc.y));
-    v2 rB = mul(qB, V(anc.z, anc.w) - V(lc.z, lc.w));
-    v2 u = cB + rB - cA - rA;
-    float length = normalize(u);
-    float C = length - p0.x;
-    C = fclampr(C, -kMaxLinearCorrection, kMaxLinearCorrection);
-    float impulse = -mass * C;
-    v2 P = impulse * u;
-    cA -= mA * P; aA -= iA * cross(rA, P);
-    cB += mB * P; aB += iB * cross(rB, P);
-    ok = fabsr(C) < kLinearSlop;
-  }
-  if (mA != 0.0f || iA != 0.0f) stcg4(&W.b_pos[bA], make_float4(cA.x, cA.y, aA, 0.0f));
-  if (mB != 0.0f || iB != 0.0f) stcg4(&W.b_pos[bB], make_float4(cB.x, cB.y, aB, 0.0f));
-  return ok;
-}
-
-DBX_D bool joint_active(const DevWorld& W, int j) {
-  const int4 ids = W.j_ids[j];
-  if (!(ids.w & 8)) return false;
-  uint32_t fa = W.b_flags[ids.y], fb = W.b_flags[ids.z];
-  if (!(fa & BF_ACTIVE) || !(fb & BF_ACTIVE)) return false;
-  return ((fa & BF_ISLAND) && body_type(fa) != BODY_STATIC) || ((fb & BF_ISLAND) && body_type(fb) != BODY_STATIC);
-}
-
-// ------------------------------------------------------------------------------------------------ the persistent solver
-// b2Island.Solve (dynamics/b2island.d:118-279) for ALL awake islands at once.  Colour c of an iteration is one
-// barrier-delimited phase; within a colour no two constraints touch the same dynamic body, so every read-modify-write
-// of a body is exclusive and the result equals sequential Gauss-Seidel in colour order.
-__global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld W) {
-  Header* H = W.hdr;
-  const unsigned nb = gridDim.x;
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-  const int nColours = H->nColours;
-  const int nJointColours = W.nJoints > 0 ? min(W.nJointColours, kMaxJointColours) : 0;
-  // colour offsets live in shared memory: every barrier invalidates L1, and a phase must not start with an L2 round trip
-  // (let alone 64 of them over empty joint colours) just to learn its own range
-  __shared__ int coff[kMaxColours + 1];
-  __shared__ int joff[kMaxJointColours + 1];
-  for (int c = threadIdx.x; c <= nColours; c += blockDim.x) coff[c] = H->colourOff[c];
-  for (int c = threadIdx.x; c <= kMaxJointColours; c += blockDim.x) joff[c] = H->jointColourOff[c];
-  __syncthreads();
-  // Role split: the first JB CTAs only ever run joint code, the others only contact code, so the two large code paths never
-  // evict each other from an SM's instruction cache (measured: +4.4 us on every joint->contact switch otherwise).
-  const int JB = (W.nJoints > 0 && (int)nb >= 8) ? min(max(W.jointBlocks, 1), (int)nb / 2) : 0;
-  const bool jointRole = JB == 0 || (int)blockIdx.x < JB;
-  const bool contactRole = JB == 0 || (int)blockIdx.x >= JB;
-  const int jtid = tid, jnth = JB == 0 ? nth : JB * blockDim.x;
-  const int ctid = JB == 0 ? tid : tid - JB * blockDim.x, cnth = JB == 0 ? nth : nth - JB * blockDim.x;
-  // Tail colours (together at most kTailContacts constraints) run inside ONE CTA with CTA-scope barriers: a colour with a
-  // few hundred constraints is not worth a 1.7 us global barrier per pass.
-  const int T = min(H->tailStart, nColours);
-  const bool tailBlock = blockIdx.x == nb - 1;
-  int phaseIdx = 0;
-#define PHASE_MARK() do { if (W.phaseTimes && tid == 0 && phaseIdx < W.phaseCap) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); W.phaseTimes[phaseIdx++] = t_; } } while (0)
-  PHASE_MARK();
-  // debug window (DBX_DEBUG bit 1): per-CTA arrival / release stamps of 8 consecutive barriers starting at phase (flags >> 8)
-  const bool dbgWin = (W.dbgFlags & 2) && W.phaseTimes != nullptr;
-  const int dbgP0 = W.dbgFlags >> 8;
-  int barIdx = 0;
-#define GB() do { \
-    if (dbgWin && threadIdx.x == 0 && barIdx >= dbgP0 && barIdx < dbgP0 + 8) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); W.phaseTimes[512 + ((barIdx - dbgP0) * nb + blockIdx.x) * 2] = t_; } \
-    grid_barrier(&H->barrier, nb); \
-    if (dbgWin && threadIdx.x == 0 && barIdx >= dbgP0 && barIdx < dbgP0 + 8) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); W.phaseTimes[512 + ((barIdx - dbgP0) * nb + blockIdx.x) * 2 + 1] = t_; } \
-    ++barIdx; PHASE_MARK(); } while (0)
-  const bool haveTail = T < nColours && coff[T] < coff[nColours];
-
-  // contacts warm start (b2island.d:138-141), colour by colour
-  if (W.warmStarting) {
-    for (int c = 0; c < T; ++c) {
-      int beg = coff[c], end = coff[c + 1];
-      if (beg == end) continue;
-      if (contactRole) for (int s = beg + ctid; s < end; s += cnth) contact_warm_start(W, s);
-      GB();
-    }
-    if (haveTail) {
-      if (tailBlock) for (int c = T; c < nColours; ++c) {
-        for (int s = coff[c] + threadIdx.x; s < coff[c + 1]; s += blockDim.x) contact_warm_start(W, s);
-        __syncthreads();
-      }
-      GB();
-    }
-  }
-  // joints: InitVelocityConstraints incl. their warm start (:143-146)
-  for (int c = 0; c < nJointColours; ++c) {
-    int beg = joff[c], end = joff[c + 1];
-    if (beg == end) continue;
-    if (jointRole) for (int k = beg + jtid; k < end; k += jnth) joint_init(W, k);
-    GB();
-  }
-  // velocity iterations: all joints, then all contacts (:153-161)
-  VC pre; int preS = -1;
-  for (int it = 0; it < W.velIters; ++it) {
-    for (int c = 0; c < nJointColours; ++c) {
-      int beg = joff[c], end = joff[c + 1];
-      if (beg == end) continue;
-      if (jointRole && !(W.dbgFlags & 1)) for (int k = beg + jtid; k < end; k += jnth) if (W.j_root[k] >= 0) joint_solve_velocity(W, k);
-      GB();
-    }
-    for (int c = 0; c < T; ++c) {
-      int beg = coff[c], end = coff[c + 1];
-      if (beg == end) continue;
-      if (contactRole) {
-        // the first item of this colour was fetched before the previous barrier; fetch the next colour's before this one
-        int s = beg + ctid;
-        if (s < end) {
-          if (preS != s) vc_load(W, s, pre);
-          contact_solve_velocity(W, s, pre);
-          for (s += cnth; s < end; s += cnth) contact_solve_velocity(W, s);
-        }
-        int cn = c + 1;
-        while (cn < T && coff[cn] == coff[cn + 1]) ++cn;
-        if (cn >= T) { cn = 0; while (cn < T && coff[cn] == coff[cn + 1]) ++cn; }
-        preS = -1;
-        if (cn < T && (cn > c || it + 1 < W.velIters)) { int sn = coff[cn] + ctid; if (sn < coff[cn + 1]) { vc_load(W, sn, pre); preS = sn; } }
-      }
-      GB();
-    }
-    if (haveTail) {
-      if (tailBlock) for (int c = T; c < nColours; ++c) {
-        for (int s = coff[c] + threadIdx.x; s < coff[c + 1]; s += blockDim.x) contact_solve_velocity(W, s);
-        __syncthreads();
-      }
-      GB();
-    }
-  }
-  // StoreImpulses (:164) + integrate positions (:168-200)
-  {
-    const int n = min(H->nSolve, W.sCap);
-    for (int s = tid; s < n; s += nth) {
-      const int i = W.s_contact[s];
-      const int vcCount = W.s_pc[s] & 0xFF;
-      float4 imp = W.s_imp[s];
-      float4 old = W.c_imp[i];
-      old.x = imp.x; old.y = imp.y;
-      if (vcCount == 2) { old.z = imp.z; old.w = imp.w; }
-      W.c_imp[i] = old;
-    }
-    const float h = W.dt;
-    for (int b = tid; b < W.nBodies; b += nth) {
-      uint32_t f = W.b_flags[b];
-      if ((f & (BF_ALIVE | BF_ISLAND)) != (BF_ALIVE | BF_ISLAND)) continue;
-      float4 pos = ldcg4(&W.b_pos[b]), vel = ldcg4(&W.b_vel[b]);
-      v2 c = V(pos.x, pos.y), v = V(vel.x, vel.y);
-      float a = pos.z, w = vel.z;
-      v2 translation = h * v;
-      if (dot(translation, translation) > kMaxTranslationSquared) { float ratio = kMaxTranslation / len(translation); v *= ratio; }
-      float rotation = h * w;
-      if (rotation * rotation > kMaxRotationSquared) { float ratio = kMaxRotation / fabsr(rotation); w *= ratio; }
-      c += h * v;
-      a += h * w;
-      stcg4(&W.b_pos[b], make_float4(c.x, c.y, a, 0.0f));
-      stcg4(&W.b_vel[b], make_float4(v.x, v.y, w, 0.0f));
-    }
-  }
-  GB();
-  // position iterations: contacts then joints, each island stops once all of its constraints are within tolerance (:206-224)
-  for (int it = 0; it < W.posIters; ++it) {
-    int* notOk = W.b_posNotOk + it * W.nBodies;
-    const int* prev = it > 0 ? W.b_posNotOk + (it - 1) * W.nBodies : nullptr;
-    for (int c = 0; c < T; ++c) {
-      int beg = coff[c], end = coff[c + 1];
-      if (beg == end) continue;
-      if (contactRole) for (int s = beg + ctid; s < end; s += cnth) {
-        int root = W.s_root[s];
-        if (prev && __ldcg(&prev[root]) == 0) continue;
-        float minSep = contact_solve_position(W, s);
-        if (!(minSep >= -3.0f * kLinearSlop)) notOk[root] = 1;
-      }
-      GB();
-    }
-    if (haveTail) {
-      if (tailBlock) for (int c = T; c < nColours; ++c) {
-        for (int s = coff[c] + threadIdx.x; s < coff[c + 1]; s += blockDim.x) {
-          int root = W.s_root[s];
-          if (prev && __ldcg(&prev[root]) == 0) continue;
-          float minSep = contact_solve_position(W, s);
-          if (!(minSep >= -3.0f * kLinearSlop)) notOk[root] = 1;
-        }
-        __syncthreads();
-      }
-      GB();
-    }
-    for (int c = 0; c < nJointColours; ++c) {
-      int beg = joff[c], end = joff[c + 1];
-      if (beg == end) continue;
-      if (jointRole) for (int k = beg + jtid; k < end; k += jnth) {
-        const int j = k;
-        int root = W.j_root[j];
-        if (root < 0) continue;
-        if (prev && __ldcg(&prev[root]) == 0) continue;
-        if (!joint_solve_position(W, j)) notOk[root] = 1;
-      }
-      GB();
-    }
-  }
-  // write back + SynchronizeTransform (:227-235), sleep bookkeeping (:241-269), ClearForces (b2world.d:443-450)
-  {
-    const float h = W.dt;
-    const float linTolSqr = kLinearSleepTolerance * kLinearSleepTolerance;
-    const float angTolSqr = kAngularSleepTolerance * kAngularSleepTolerance;
-    for (int b = tid; b < W.nBodies; b += nth) {
-      uint32_t f = W.b_flags[b];
-      if ((f & (BF_ALIVE | BF_ISLAND)) != (BF_ALIVE | BF_ISLAND)) continue;
-      float4 pos = ldcg4(&W.b_pos[b]);
-      float4 lc = W.b_lc[b];
-      Xf xf = xf_from_sweep(V(pos.x, pos.y), pos.z, V(lc.x, lc.y));
-      W.b_xf[b] = pack(xf);
-      if (W.allowSleep) {
-        float4 vel = ldcg4(&W.b_vel[b]);
-        float2 gs = W.b_gs[b];
-        if (!(f & BF_AUTOSLEEP) || vel.z * vel.z > angTolSqr || dot(V(vel.x, vel.y), V(vel.x, vel.y)) > linTolSqr) gs.y = 0.0f;
-        else gs.y += h;
-        W.b_gs[b] = gs;
-        atomicMin(&W.b_islMinSleep[W.b_root[b]], __float_as_int(gs.y));
-      }
-    }
-  }
-  GB();
-  if (W.allowSleep) {
-    const int* last = W.posIters > 0 ? W.b_posNotOk + (W.posIters - 1) * W.nBodies : nullptr;
-    for (int b = tid; b < W.nBodies; b += nth) {
-      uint32_t f = W.b_flags[b];
-      if ((f & (BF_ALIVE | BF_ISLAND)) != (BF_ALIVE | BF_ISLAND)) continue;
-      int root = W.b_root[b];
-      bool positionSolved = last && __ldcg(&last[root]) == 0;
-      float minSleep = __int_as_float(__ldcg(&W.b_islMinSleep[root]));
-      if (minSleep >= kTimeToSleep && positionSolved) {
-        // b2Body.SetAwake(false) (b2body.d:837-845)
-        W.b_flags[b] = f & ~BF_AWAKE;
-        W.b_gs[b].y = 0.0f;
-        W.b_vel[b] = make_float4(0, 0, 0, 0);
-        W.b_force[b] = make_float4(0, 0, 0, 0);
-      }
-    }
-  }
-}
-
-#undef GB
-#undef PHASE_MARK
 __global__ void __launch_bounds__(256) k_apply_forces(const __grid_constant__ DevWorld W, const float4* forces, int n) {
   GRID_STRIDE(b, n) {
     const uint32_t f = W.b_flags[b];
@@ -1774,6 +884,9 @@ DBX_D void lbvh_enlarge(const DevWorld& W, int p) {
   __stcg(&W.bv_box[node], f);
   node = W.bv_parent[node];
   while (node >= 0) {
+    // boxes only grow and a parent contains its children, so the first ancestor that already contains f ends the walk
+    const float4 cur = __ldcg(&W.bv_box[node]);
+    if (cur.x <= f.x && cur.y <= f.y && cur.z >= f.z && cur.w >= f.w) break;
     float* bx = (float*)&W.bv_box[node];
     atomic_min_f(bx + 0, f.x); atomic_min_f(bx + 1, f.y); atomic_max_f(bx + 2, f.z); atomic_max_f(bx + 3, f.w);
     node = W.bv_parent[node];
@@ -1790,46 +903,67 @@ DBX_D unsigned long long toi_prio(const DevWorld& W, float alpha, int contact, i
   return ((unsigned long long)__float_as_uint(alpha) << 32) | (unsigned)(mix64(local_key(W, W.c_key[contact], bodyOfContact)) >> 32);
 }
 
-// (a) evaluate b2TimeOfImpact for every eligible contact that has no cached value (b2world.d:1155-1265)
-DBX_D void toi_evaluate(const DevWorld& W, int i) {
-  uint32_t flags = W.c_flags[i];
-  if (!(flags & CF_ALIVE)) return;
-  const int4 ids = W.c_ids[i];
-  if ((flags & CF_TOI) && ((__ldcg(&W.b_toiFlags[ids.z]) | __ldcg(&W.b_toiFlags[ids.w])) & TF_INVAL)) { flags &= ~(CF_TOI | CF_ISLAND); W.c_flags[i] = flags; }
-  if (!(flags & CF_ENABLED)) return;
-  if (W.c_toiCount[i] > kMaxSubSteps) return;
-  float alpha = 1.0f;
-  const uint32_t fa = W.b_flags[ids.z], fb = W.b_flags[ids.w];
-  if (flags & CF_TOI) {
-    alpha = W.c_mat[i].w;
-  } else {
-    if (flags & CF_SENSOR) return;
-    const int typeA = body_type(fa), typeB = body_type(fb);
-    const bool activeA = (fa & BF_AWAKE) && typeA != BODY_STATIC, activeB = (fb & BF_AWAKE) && typeB != BODY_STATIC;
-    if (!activeA && !activeB) return;
-    const bool collideA = (fa & BF_BULLET) || typeA != BODY_DYNAMIC, collideB = (fb & BF_BULLET) || typeB != BODY_DYNAMIC;
-    if (!collideA && !collideB) return;
-    Sweep sA = load_sweep(W, ids.z), sB = load_sweep(W, ids.w);
-    // bring both sweeps to the later alpha0 (:1214-1225); done on local copies, see DESIGN.md
-    float alpha0 = sA.alpha0;
-    if (typeA == BODY_STATIC) { alpha0 = sB.alpha0; sA.alpha0 = alpha0; }
-    else if (typeB == BODY_STATIC) { alpha0 = sA.alpha0; sB.alpha0 = alpha0; }
-    else if (sA.alpha0 < sB.alpha0) { alpha0 = sB.alpha0; sweep_advance(sA, alpha0); }
-    else if (sB.alpha0 < sA.alpha0) { alpha0 = sA.alpha0; sweep_advance(sB, alpha0); }
-    const int4 fx = W.c_fix[i];
-    DProxy pA = make_proxy(W.shapes + fx.z), pB = make_proxy(W.shapes + fx.w);
-    float beta;
-    int state = time_of_impact(&beta, pA, sA, pB, sB, 1.0f);
-    if (state == TOI_TOUCHING) alpha = fminr(alpha0 + (1.0f - alpha0) * beta, 1.0f);
-    else alpha = 1.0f;
-    float4 mat = W.c_mat[i]; mat.w = alpha; W.c_mat[i] = mat;
-    flags |= CF_TOI;
-    W.c_flags[i] = flags;
-  }
+// (a) evaluate b2TimeOfImpact for every eligible contact that has no cached value (b2world.d:1155-1265), in two halves so
+// that a warp can gather the few contacts that need the long computation and run them on full lanes:
+// toi_classify = the cheap filters (returns true when b2TimeOfImpact must run), toi_compute = the computation.
+DBX_D void toi_publish(const DevWorld& W, int i, const int4 ids, uint32_t fa, uint32_t fb, float alpha) {
   if (1.0f - 10.0f * kEpsilon < alpha) return;   // never becomes an event (:1267-1272)
   const unsigned long long prio = toi_prio(W, alpha, i, ids.z);
   if (body_type(fa) != BODY_STATIC) atomicMin(&W.b_toiMin[ids.z], prio);
   if (body_type(fb) != BODY_STATIC) atomicMin(&W.b_toiMin[ids.w], prio);
+}
+DBX_D bool toi_classify(const DevWorld& W, int i) {
+  uint32_t flags = W.c_flags[i];
+  if (!(flags & CF_ALIVE)) return false;
+  const int4 ids = W.c_ids[i];
+  if ((flags & CF_TOI) && ((__ldcg(&W.b_toiFlags[ids.z]) | __ldcg(&W.b_toiFlags[ids.w])) & TF_INVAL)) { flags &= ~(CF_TOI | CF_ISLAND); W.c_flags[i] = flags; }
+  if (!(flags & CF_ENABLED)) return false;
+  if (W.c_toiCount[i] > kMaxSubSteps) return false;
+  const uint32_t fa = W.b_flags[ids.z], fb = W.b_flags[ids.w];
+  if (flags & CF_TOI) { toi_publish(W, i, ids, fa, fb, W.c_mat[i].w); return false; }
+  if (flags & CF_SENSOR) return false;
+  const int typeA = body_type(fa), typeB = body_type(fb);
+  const bool activeA = (fa & BF_AWAKE) && typeA != BODY_STATIC, activeB = (fb & BF_AWAKE) && typeB != BODY_STATIC;
+  if (!activeA && !activeB) return false;
+  const bool collideA = (fa & BF_BULLET) || typeA != BODY_DYNAMIC, collideB = (fb & BF_BULLET) || typeB != BODY_DYNAMIC;
+  return collideA || collideB;
+}
+DBX_D void toi_compute(const DevWorld& W, int i) {
+  const int4 ids = W.c_ids[i];
+  const uint32_t fa = W.b_flags[ids.z], fb = W.b_flags[ids.w];
+  const int typeA = body_type(fa), typeB = body_type(fb);
+  Sweep sA = load_sweep(W, ids.z), sB = load_sweep(W, ids.w);
+  // bring both sweeps to the later alpha0 (:1214-1225); done on local copies, see DESIGN.md
+  float alpha0 = sA.alpha0;
+  if (typeA == BODY_STATIC) { alpha0 = sB.alpha0; sA.alpha0 = alpha0; }
+  else if (typeB == BODY_STATIC) { alpha0 = sA.alpha0; sB.alpha0 = alpha0; }
+  else if (sA.alpha0 < sB.alpha0) { alpha0 = sB.alpha0; sweep_advance(sA, alpha0); }
+  else if (sB.alpha0 < sA.alpha0) { alpha0 = sA.alpha0; sweep_advance(sB, alpha0); }
+  const int4 fx = W.c_fix[i];
+  DProxy pA = make_proxy(W.shapes + fx.z), pB = make_proxy(W.shapes + fx.w);
+  float beta;
+  float alpha = 1.0f;
+  int state = time_of_impact(&beta, pA, sA, pB, sB, 1.0f);
+  if (state == TOI_TOUCHING) alpha = fminr(alpha0 + (1.0f - alpha0) * beta, 1.0f);
+  float4 mat = W.c_mat[i]; mat.w = alpha; W.c_mat[i] = mat;
+  W.c_flags[i] |= CF_TOI;
+  toi_publish(W, i, ids, fa, fb, alpha);
+}
+// one warp: scan contacts [.., n) in strides of the whole grid, queue the ones that need b2TimeOfImpact in `q` (>= 64 ints of
+// shared memory private to the warp) and run them 32 at a time
+DBX_D void toi_evaluate_all(const DevWorld& W, int n, int warp, int nwarps, int lane, int* q) {
+  int qn = 0;
+  for (int base = warp * 32; base < n; base += nwarps * 32) {
+    const int i = base + lane;
+    const bool need = i < n && toi_classify(W, i);
+    const unsigned m = __ballot_sync(0xffffffffu, need);
+    if (need) q[qn + __popc(m & ((1u << lane) - 1u))] = i;
+    qn += __popc(m);
+    __syncwarp();
+    if (qn >= 32) { qn -= 32; toi_compute(W, q[qn + lane]); __syncwarp(); }
+  }
+  if (lane < qn) toi_compute(W, q[lane]);
+  __syncwarp();
 }
 
 // (d) one event, start to finish, by one thread (b2world.d:1274-1440)
@@ -1986,7 +1120,10 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
     // (a) TOI evaluation + per-body minima
     {
       const int n = *((volatile int*)&H->cHigh);
-      for (int i = tid; i < n; i += nth) toi_evaluate(W, i);
+      // few contacts per thread (one big world): evaluate in place, every chain on its own warp; many (batched worlds):
+      // gather the eligible ones so that b2TimeOfImpact runs on full warps
+      if (n <= 8 * nth) { for (int i = tid; i < n; i += nth) if (toi_classify(W, i)) toi_compute(W, i); }
+      else toi_evaluate_all(W, n, warp, nwarps, lane, stacks[wib]);
     }
     grid_barrier(&H->barrier, nb); TMARK();
     // (b) winners: the minimum on every movable body they touch
@@ -2119,13 +1256,6 @@ cudaError_t stage_colour_and_sort(const DevWorld& W, const LaunchCfg& L) {
   return cudaGetLastError();
 }
 
-cudaError_t stage_prepare(const DevWorld& W, const LaunchCfg& L) {
-  ++L.launches; k_prepare<<<L.gridWide, 256, 0, L.stream>>>(W);
-  return cudaGetLastError();
-}
-cudaError_t stage_solve(const DevWorld& W, const LaunchCfg& L) {
-  return launch_coop((const void*)k_solve, W, L);
-}
 
 cudaError_t stage_sync_fixtures(const DevWorld& W, const LaunchCfg& L) {
   ++L.launches; k_sync_fixtures<<<L.gridWide, 256, 0, L.stream>>>(W);

@@ -1,0 +1,244 @@
+// dbx_solve.cu — constraint setup and the persistent coloured Gauss-Seidel island solver (sm_100a).
+// Separate translation unit so that fused multiply-add can be enabled for it alone (csrc/Makefile, SOLVER_FMAD): nothing
+// in here has to be bit-identical to the reference (feature keys, manifolds and the pair set come from dbx_kernels.cu).
+// Default is un-contracted: FMA bought 1.5 % and cost the bit-identity between the solver's own code paths.
+#include "dbx_solver.cuh"
+
+namespace dbx {
+
+__global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ DevWorld W) {
+  const int n = min(W.hdr->nSolve, W.sCap);
+  const float warmScale = W.warmStarting ? W.dtRatio : -1.0f;
+  GRID_STRIDE(s, n) prepare_contact(W, s, W.s_contact[s], warmScale);
+}
+
+// ------------------------------------------------------------------------------------------------ the persistent solver
+// b2Island.Solve (dynamics/b2island.d:118-279) for ALL awake islands at once.  Colour c of an iteration is one
+// barrier-delimited phase; within a colour no two constraints touch the same dynamic body, so every read-modify-write
+// of a body is exclusive and the result equals sequential Gauss-Seidel in colour order.
+__global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld W) {
+  Header* H = W.hdr;
+  const unsigned nb = gridDim.x;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const int nColours = H->nColours;
+  const int nJointColours = W.nJoints > 0 ? min(W.nJointColours, kMaxJointColours) : 0;
+  // colour offsets live in shared memory: every barrier invalidates L1, and a phase must not start with an L2 round trip
+  // (let alone 64 of them over empty joint colours) just to learn its own range
+  __shared__ int coff[kMaxColours + 1];
+  __shared__ int joff[kMaxJointColours + 1];
+  for (int c = threadIdx.x; c <= nColours; c += blockDim.x) coff[c] = H->colourOff[c];
+  for (int c = threadIdx.x; c <= kMaxJointColours; c += blockDim.x) joff[c] = H->jointColourOff[c];
+  __syncthreads();
+  // Role split: the first JB CTAs only ever run joint code, the others only contact code, so the two large code paths never
+  // evict each other from an SM's instruction cache (measured: +4.4 us on every joint->contact switch otherwise).
+  const int JB = (W.nJoints > 0 && (int)nb >= 8) ? min(max(W.jointBlocks, 1), (int)nb / 2) : 0;
+  const bool jointRole = JB == 0 || (int)blockIdx.x < JB;
+  const bool contactRole = JB == 0 || (int)blockIdx.x >= JB;
+  const int jtid = tid, jnth = JB == 0 ? nth : JB * blockDim.x;
+  const int ctid = JB == 0 ? tid : tid - JB * blockDim.x, cnth = JB == 0 ? nth : nth - JB * blockDim.x;
+  // Tail colours (together at most kTailContacts constraints) run inside ONE CTA with CTA-scope barriers: a colour with a
+  // few hundred constraints is not worth a 1.7 us global barrier per pass.
+  const int T = min(H->tailStart, nColours);
+  const bool tailBlock = blockIdx.x == nb - 1;
+  int phaseIdx = 0;
+#define PHASE_MARK() do { if (W.phaseTimes && tid == 0 && phaseIdx < W.phaseCap) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); W.phaseTimes[phaseIdx++] = t_; } } while (0)
+  PHASE_MARK();
+  // debug window (DBX_DEBUG bit 1): per-CTA arrival / release stamps of 8 consecutive barriers starting at phase (flags >> 8)
+  const bool dbgWin = (W.dbgFlags & 2) && W.phaseTimes != nullptr;
+  const int dbgP0 = W.dbgFlags >> 8;
+  int barIdx = 0;
+#define GB() do { \
+    if (dbgWin && threadIdx.x == 0 && barIdx >= dbgP0 && barIdx < dbgP0 + 8) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); W.phaseTimes[512 + ((barIdx - dbgP0) * nb + blockIdx.x) * 2] = t_; } \
+    grid_barrier(&H->barrier, nb); \
+    if (dbgWin && threadIdx.x == 0 && barIdx >= dbgP0 && barIdx < dbgP0 + 8) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); W.phaseTimes[512 + ((barIdx - dbgP0) * nb + blockIdx.x) * 2 + 1] = t_; } \
+    ++barIdx; PHASE_MARK(); } while (0)
+  const bool haveTail = T < nColours && coff[T] < coff[nColours];
+
+  // contacts warm start (b2island.d:138-141), colour by colour
+  if (W.warmStarting) {
+    for (int c = 0; c < T; ++c) {
+      int beg = coff[c], end = coff[c + 1];
+      if (beg == end) continue;
+      if (contactRole) for (int s = beg + ctid; s < end; s += cnth) contact_warm_start(W, s);
+      GB();
+    }
+    if (haveTail) {
+      if (tailBlock) for (int c = T; c < nColours; ++c) {
+        for (int s = coff[c] + threadIdx.x; s < coff[c + 1]; s += blockDim.x) contact_warm_start(W, s);
+        __syncthreads();
+      }
+      GB();
+    }
+  }
+  // joints: InitVelocityConstraints incl. their warm start (:143-146)
+  for (int c = 0; c < nJointColours; ++c) {
+    int beg = joff[c], end = joff[c + 1];
+    if (beg == end) continue;
+    if (jointRole) for (int k = beg + jtid; k < end; k += jnth) joint_init(W, k);
+    GB();
+  }
+  // velocity iterations: all joints, then all contacts (:153-161)
+  VC pre; int preS = -1;
+  for (int it = 0; it < W.velIters; ++it) {
+    for (int c = 0; c < nJointColours; ++c) {
+      int beg = joff[c], end = joff[c + 1];
+      if (beg == end) continue;
+      if (jointRole && !(W.dbgFlags & 1)) for (int k = beg + jtid; k < end; k += jnth) if (W.j_root[k] >= 0) joint_solve_velocity(W, k);
+      GB();
+    }
+    for (int c = 0; c < T; ++c) {
+      int beg = coff[c], end = coff[c + 1];
+      if (beg == end) continue;
+      if (contactRole) {
+        // the first item of this colour was fetched before the previous barrier; fetch the next colour's before this one
+        int s = beg + ctid;
+        if (s < end) {
+          if (preS != s) vc_load(W, s, pre);
+          contact_solve_velocity(W, s, pre);
+          for (s += cnth; s < end; s += cnth) contact_solve_velocity(W, s);
+        }
+        int cn = c + 1;
+        while (cn < T && coff[cn] == coff[cn + 1]) ++cn;
+        if (cn >= T) { cn = 0; while (cn < T && coff[cn] == coff[cn + 1]) ++cn; }
+        preS = -1;
+        if (cn < T && (cn > c || it + 1 < W.velIters)) { int sn = coff[cn] + ctid; if (sn < coff[cn + 1]) { vc_load(W, sn, pre); preS = sn; } }
+      }
+      GB();
+    }
+    if (haveTail) {
+      if (tailBlock) for (int c = T; c < nColours; ++c) {
+        for (int s = coff[c] + threadIdx.x; s < coff[c + 1]; s += blockDim.x) contact_solve_velocity(W, s);
+        __syncthreads();
+      }
+      GB();
+    }
+  }
+  // StoreImpulses (:164) + integrate positions (:168-200)
+  {
+    const int n = min(H->nSolve, W.sCap);
+    for (int s = tid; s < n; s += nth) {
+      const int i = W.s_contact[s];
+      const int vcCount = W.s_pc[s] & 0xFF;
+      float4 imp = W.s_imp[s];
+      float4 old = W.c_imp[i];
+      old.x = imp.x; old.y = imp.y;
+      if (vcCount == 2) { old.z = imp.z; old.w = imp.w; }
+      W.c_imp[i] = old;
+    }
+    const float h = W.dt;
+    for (int b = tid; b < W.nBodies; b += nth) {
+      uint32_t f = W.b_flags[b];
+      if ((f & (BF_ALIVE | BF_ISLAND)) != (BF_ALIVE | BF_ISLAND)) continue;
+      float4 pos = ldcg4(&W.b_pos[b]), vel = ldcg4(&W.b_vel[b]);
+      v2 c = V(pos.x, pos.y), v = V(vel.x, vel.y);
+      float a = pos.z, w = vel.z;
+      v2 translation = h * v;
+      if (dot(translation, translation) > kMaxTranslationSquared) { float ratio = kMaxTranslation / len(translation); v *= ratio; }
+      float rotation = h * w;
+      if (rotation * rotation > kMaxRotationSquared) { float ratio = kMaxRotation / fabsr(rotation); w *= ratio; }
+      c += h * v;
+      a += h * w;
+      stcg4(&W.b_pos[b], make_float4(c.x, c.y, a, 0.0f));
+      stcg4(&W.b_vel[b], make_float4(v.x, v.y, w, 0.0f));
+    }
+  }
+  GB();
+  // position iterations: contacts then joints, each island stops once all of its constraints are within tolerance (:206-224)
+  for (int it = 0; it < W.posIters; ++it) {
+    int* notOk = W.b_posNotOk + it * W.nBodies;
+    const int* prev = it > 0 ? W.b_posNotOk + (it - 1) * W.nBodies : nullptr;
+    for (int c = 0; c < T; ++c) {
+      int beg = coff[c], end = coff[c + 1];
+      if (beg == end) continue;
+      if (contactRole) for (int s = beg + ctid; s < end; s += cnth) {
+        int root = W.s_root[s];
+        if (prev && __ldcg(&prev[root]) == 0) continue;
+        float minSep = contact_solve_position(W, s);
+        if (!(minSep >= -3.0f * kLinearSlop)) notOk[root] = 1;
+      }
+      GB();
+    }
+    if (haveTail) {
+      if (tailBlock) for (int c = T; c < nColours; ++c) {
+        for (int s = coff[c] + threadIdx.x; s < coff[c + 1]; s += blockDim.x) {
+          int root = W.s_root[s];
+          if (prev && __ldcg(&prev[root]) == 0) continue;
+          float minSep = contact_solve_position(W, s);
+          if (!(minSep >= -3.0f * kLinearSlop)) notOk[root] = 1;
+        }
+        __syncthreads();
+      }
+      GB();
+    }
+    for (int c = 0; c < nJointColours; ++c) {
+      int beg = joff[c], end = joff[c + 1];
+      if (beg == end) continue;
+      if (jointRole) for (int k = beg + jtid; k < end; k += jnth) {
+        const int j = k;
+        int root = W.j_root[j];
+        if (root < 0) continue;
+        if (prev && __ldcg(&prev[root]) == 0) continue;
+        if (!joint_solve_position(W, j)) notOk[root] = 1;
+      }
+      GB();
+    }
+  }
+  // write back + SynchronizeTransform (:227-235), sleep bookkeeping (:241-269), ClearForces (b2world.d:443-450)
+  {
+    const float h = W.dt;
+    const float linTolSqr = kLinearSleepTolerance * kLinearSleepTolerance;
+    const float angTolSqr = kAngularSleepTolerance * kAngularSleepTolerance;
+    for (int b = tid; b < W.nBodies; b += nth) {
+      uint32_t f = W.b_flags[b];
+      if ((f & (BF_ALIVE | BF_ISLAND)) != (BF_ALIVE | BF_ISLAND)) continue;
+      float4 pos = ldcg4(&W.b_pos[b]);
+      float4 lc = W.b_lc[b];
+      Xf xf = xf_from_sweep(V(pos.x, pos.y), pos.z, V(lc.x, lc.y));
+      W.b_xf[b] = pack(xf);
+      if (W.allowSleep) {
+        float4 vel = ldcg4(&W.b_vel[b]);
+        float2 gs = W.b_gs[b];
+        if (!(f & BF_AUTOSLEEP) || vel.z * vel.z > angTolSqr || dot(V(vel.x, vel.y), V(vel.x, vel.y)) > linTolSqr) gs.y = 0.0f;
+        else gs.y += h;
+        W.b_gs[b] = gs;
+        atomicMin(&W.b_islMinSleep[W.b_root[b]], __float_as_int(gs.y));
+      }
+    }
+  }
+  GB();
+  if (W.allowSleep) {
+    const int* last = W.posIters > 0 ? W.b_posNotOk + (W.posIters - 1) * W.nBodies : nullptr;
+    for (int b = tid; b < W.nBodies; b += nth) {
+      uint32_t f = W.b_flags[b];
+      if ((f & (BF_ALIVE | BF_ISLAND)) != (BF_ALIVE | BF_ISLAND)) continue;
+      int root = W.b_root[b];
+      bool positionSolved = last && __ldcg(&last[root]) == 0;
+      float minSleep = __int_as_float(__ldcg(&W.b_islMinSleep[root]));
+      if (minSleep >= kTimeToSleep && positionSolved) {
+        // b2Body.SetAwake(false) (b2body.d:837-845)
+        W.b_flags[b] = f & ~BF_AWAKE;
+        W.b_gs[b].y = 0.0f;
+        W.b_vel[b] = make_float4(0, 0, 0, 0);
+        W.b_force[b] = make_float4(0, 0, 0, 0);
+      }
+    }
+  }
+}
+
+#undef GB
+#undef PHASE_MARK
+
+#define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return _e; } while (0)
+
+cudaError_t stage_prepare(const DevWorld& W, const LaunchCfg& L) {
+  ++L.launches; k_prepare<<<L.gridWide, 256, 0, L.stream>>>(W);
+  return cudaGetLastError();
+}
+cudaError_t stage_solve(const DevWorld& W, const LaunchCfg& L) {
+  CK(cudaMemsetAsync(&W.hdr->barrier, 0, sizeof(unsigned), L.stream));
+  void* args[] = {(void*)&W};
+  ++L.launches;
+  return cudaLaunchCooperativeKernel((const void*)k_solve, dim3(L.coopBlocks), dim3(L.coopThreads), args, 0, L.stream);
+}
+
+}  // namespace dbx
