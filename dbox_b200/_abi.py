@@ -86,6 +86,13 @@ class ProxyRec(C.Structure):
     _fields_ = [("fixture", c_i32), ("child", c_i32), ("proxyId", c_i32), ("aabb", AABB), ("fat", AABB)]
 
 
+class ContactEvent(C.Structure):
+    _fields_ = [(n, c_i32) for n in ("type", "phase", "stepsAgo", "fixtureA", "fixtureB", "childA", "childB", "bodyA", "bodyB")]
+
+
+CONTACT_BEGIN, CONTACT_END = 1, 2
+
+
 class JointState(C.Structure):
     _fields_ = [("type", c_i32), ("impulse", c_f32 * 3), ("motorImpulse", c_f32), ("limitState", c_i32)]
 
@@ -106,7 +113,7 @@ class Caps(C.Structure):
 # sizes the header implies (checked by tests/test_abi.py and by the library's own static_asserts)
 EXPECTED_SIZES = {"Vec2": 8, "AABB": 16, "BodyDef": 72, "Shape": 240, "FixtureDef": 32, "JointDef": 80, "BodyState": 116,
                   "ManifoldPoint": 20, "Manifold": 64, "ContactRec": 104, "ProxyRec": 44, "JointState": 24, "Counts": 44,
-                  "Profile": 32, "Caps": 20}
+                  "Profile": 32, "Caps": 20, "ContactEvent": 36}
 
 P = C.POINTER
 W = C.c_void_p
@@ -182,6 +189,8 @@ PROTOTYPES = {
     "debug_barrier_us": (c_f32, [c_i32, c_i32, c_i32, c_i32]),
     "world_replicate": (c_i32, [W, c_i32]),
     "world_replica_count": (c_i32, [W]),
+    "world_enable_contact_events": (c_i32, [W, c_i32]),
+    "world_poll_contact_events": (c_i32, [W, P(ContactEvent), c_i32]),
 }
 
 

@@ -8,7 +8,7 @@ using namespace dbx;
 struct dbx_world { World w; dbx_world(float gx, float gy, int dev, const dbx_caps* caps) : w(gx, gy, dev, caps) {} };
 
 static_assert(sizeof(dbx_body_def) == 72 && sizeof(dbx_shape) == 240 && sizeof(dbx_fixture_def) == 32 && sizeof(dbx_joint_def) == 80, "ABI layout");
-static_assert(sizeof(dbx_body_state) == 116 && sizeof(dbx_manifold) == 64 && sizeof(dbx_contact_rec) == 104 && sizeof(dbx_proxy_rec) == 44, "ABI layout");
+static_assert(sizeof(dbx_body_state) == 116 && sizeof(dbx_manifold) == 64 && sizeof(dbx_contact_rec) == 104 && sizeof(dbx_proxy_rec) == 44 && sizeof(dbx_contact_event) == 36, "ABI layout");
 
 #define W_OR_INVALID(w) do { if (!(w) || !(w)->w.ok()) return DBX_E_INVALID; } while (0)
 
@@ -246,5 +246,7 @@ int32_t dbx_world_debug_header(dbx_world* w, void* out, int32_t bytes) { W_OR_IN
 // ---- batched independent worlds
 int32_t dbx_world_replicate(dbx_world* w, int32_t copies) { W_OR_INVALID(w); return w->w.replicate(copies); }
 int32_t dbx_world_replica_count(dbx_world* w) { W_OR_INVALID(w); return w->w.replicaCount(); }
+int32_t dbx_world_enable_contact_events(dbx_world* w, int32_t capacity) { W_OR_INVALID(w); return w->w.enableContactEvents(capacity); }
+int32_t dbx_world_poll_contact_events(dbx_world* w, dbx_contact_event* out, int32_t cap) { W_OR_INVALID(w); return w->w.pollContactEvents(out, cap); }
 
 }  // extern "C"

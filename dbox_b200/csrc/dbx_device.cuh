@@ -61,7 +61,7 @@ struct Header {
   int toiEvents;      // cumulative TOI events processed
   int nEvents;        // events selected in the current TOI pass
   int tailStart;      // first colour of the tail that k_solve runs inside one CTA
-  int _pad1;
+  int nCtEvents;      // contact begin/end events recorded since the last poll (may exceed evCap: the surplus is lost and reported)
   unsigned barrier;   // grid barrier ticket counter for the persistent kernels
   unsigned epoch;     // colouring round stamp
   unsigned long long toiMin;  // (alpha bits << 32 | contact slot) arg-min for the TOI loop
@@ -126,6 +126,10 @@ struct DevWorld {
   int2* bv_child;    // [n-1]
   int* bv_parent;    // [2n-1]
   int* bv_visit;     // [n-1]
+  int4* ev_a;        // [evCap] contact events: (type | phase << 8 | step << 16, fixtureA, fixtureB, childA | childB << 16)
+  int4* ev_b;        //         (bodyA, bodyB, pair key lo, pair key hi)
+  int evCap;         // 0 = contact events off
+  int stepIndex;     // low 16 bits stamp the events of this step
   int2* bv_wr;       // [n-1] replica-index range of the leaves under an internal node
   int* bv_pos;       // proxy slot -> sorted leaf index
   const int* bv_sorted;  // sorted leaf index -> proxy slot (whichever CUB buffer is current)

@@ -16,7 +16,21 @@ cudaError_t stage_rebuild_hash(const DevWorld& W, const LaunchCfg& L);
 
 // ------------------------------------------------------------------------------------------------ Collide
 // b2ContactManager.Collide (dynamics/b2contactmanager.d:251-317) + b2Contact.Update (contacts/b2contact.d:270-356)
+// b2ContactListener.BeginContact / EndContact (b2worldcallbacks.d:87-95), deferred: the call sites of the reference
+// (b2contact.d:338-346, b2contactmanager.d:60-63) append a record here and the host polls them after the step.
+// phase: 1 = Collide, 2 = TOI sub-steps, 3 = destroyed through the API after that step.
+enum { EV_BEGIN = 1, EV_END = 2 };
+DBX_D void emit_contact_event(const DevWorld& W, int type, int phase, int i, const int4 ids, const int4 fx) {
+  if (W.evCap == 0) return;
+  const int k = atomicAdd(&W.hdr->nCtEvents, 1);
+  if (k >= W.evCap) return;
+  const unsigned long long key = W.c_key[i];
+  const int childA = W.p_ids[ids.x].y, childB = W.p_ids[ids.y].y;
+  W.ev_a[k] = make_int4(type | (phase << 8) | ((W.stepIndex & 0xFFFF) << 16), fx.x, fx.y, (childA & 0xFFFF) | (childB << 16));
+  W.ev_b[k] = make_int4(ids.z, ids.w, (int)(unsigned)(key & 0xFFFFFFFFull), (int)(unsigned)(key >> 32));
+}
 DBX_D void destroy_contact(const DevWorld& W, int i, uint32_t flags, int bodyA, int bodyB, int pointCount) {
+  if (flags & CF_TOUCHING) emit_contact_event(W, EV_END, 1, i, W.c_ids[i], W.c_fix[i]);
   // b2ContactManager.Destroy + b2Contact.Destroy: wake both bodies if the manifold had points and no sensor is involved
   if (pointCount > 0 && !(flags & CF_SENSOR)) { W.b_wake[bodyA] = 1; W.b_wake[bodyB] = 1; }
   hash_remove(W, W.c_key[i]);
@@ -71,6 +85,7 @@ DBX_D uint32_t update_contact(const DevWorld& W, int i, uint32_t flags, const in
       else { W.b_wake[ids.z] = 1; W.b_wake[ids.w] = 1; }
     }
   }
+  if (touching != wasTouching) emit_contact_event(W, touching ? EV_BEGIN : EV_END, immediateWake ? 2 : 1, i, ids, fx);
   flags = touching ? (flags | CF_TOUCHING) : (flags & ~CF_TOUCHING);
   W.c_flags[i] = flags;
   return flags;
@@ -552,8 +567,14 @@ __global__ void __launch_bounds__(256) k_lbvh_refit(const __grid_constant__ DevW
 }
 
 // warp-cooperative query: one warp per moved proxy walks the tree with a shared frontier; each lane tests one node
-constexpr int kQueryStack = 192;
-DBX_D void query_proxy(const DevWorld& W, const int* leaves, int* stack, int lane, int p) {
+// The frontier is a LIFO in shared memory popped 32 nodes at a time (32 interleaved depth-first walks: it holds about
+// 32 x depth nodes for a box that overlaps everything, e.g. a wall of a rotating container).  When it gets within
+// kQueryReserve of its capacity the walk degrades to one node at a time, a plain depth-first walk whose stack grows by
+// at most one per level, so any tree up to kQueryReserve deep is traversed whatever the query box is.
+constexpr int kQueryStack = 1024;      // k_query: 8 warps x 4 KB
+constexpr int kQueryStackToi = 256;    // k_toi: 16 warps x 1 KB
+constexpr int kQueryReserve = 96;
+DBX_D void query_proxy(const DevWorld& W, const int* leaves, int* stack, int cap, int lane, int p) {
   const int n = W.nProxies;
   if (!(W.p_flags[p] & PF_ALIVE)) return;
   const Box fat = BX(__ldcg(&W.p_fat[p]));
@@ -563,7 +584,7 @@ DBX_D void query_proxy(const DevWorld& W, const int* leaves, int* stack, int lan
   if (lane == 0) stack[0] = (n == 1) ? (n - 1) : 0;
   __syncwarp();
   while (top > 0) {
-    int take = min(top, 32);   // pop up to 32 nodes
+    int take = (top + 32 <= cap - kQueryReserve) ? min(top, 32) : 1;   // pop up to 32 nodes; one when nearly full
     int node = lane < take ? stack[top - take + lane] : -1;
     top -= take;
     __syncwarp();
@@ -591,7 +612,7 @@ DBX_D void query_proxy(const DevWorld& W, const int* leaves, int* stack, int lan
     unsigned ballot = __ballot_sync(0xffffffffu, push);
     int offset = __popc(ballot & ((1u << lane) - 1));
     int total = __popc(ballot);
-    if (top + 2 * total > kQueryStack) { if (lane == 0) W.hdr->error = -5; break; }   // frontier overflow: report, never corrupt
+    if (top + 2 * total > cap) { if (lane == 0) W.hdr->error = -5; break; }   // tree deeper than kQueryReserve: report, never corrupt
     if (push) {
       int2 ch = W.bv_child[node];
       int base = top + 2 * offset;
@@ -607,7 +628,7 @@ __global__ void __launch_bounds__(256) k_query(const __grid_constant__ DevWorld 
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const int nMoved = min(W.hdr->nMoved, W.moveCap);
-  for (int mIdx = warp; mIdx < nMoved; mIdx += nwarps) query_proxy(W, leaves, stacks[wib], lane, W.moveList[mIdx]);
+  for (int mIdx = warp; mIdx < nMoved; mIdx += nwarps) query_proxy(W, leaves, stacks[wib], kQueryStack, lane, W.moveList[mIdx]);
 }
 
 // b2ContactManager.AddPair (dynamics/b2contactmanager.d:52-176) + b2Contact.Create (contacts/b2contact.d:375-400)
@@ -787,6 +808,7 @@ __global__ void __launch_bounds__(256) k_api_contacts(const __grid_constant__ De
     if (flagOnly) { W.c_flags[i] = flags | CF_FILTER; continue; }
     const int pointCount = (int)W.c_mk[i].w;
     if (pointCount > 0 && !(flags & CF_SENSOR)) { wake_body_now(W, ids.z); wake_body_now(W, ids.w); }
+    if (flags & CF_TOUCHING) emit_contact_event(W, EV_END, 3, i, ids, fx);
     hash_remove(W, W.c_key[i]);
     W.c_flags[i] = 0;
     W.c_colour[i] = -1;
@@ -1090,7 +1112,7 @@ DBX_D void toi_process_event(const DevWorld& W, int e, float dtStep) {
 }
 
 __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W) {
-  __shared__ int stacks[16][kQueryStack];
+  __shared__ int stacks[16][kQueryStackToi];
   Header* H = W.hdr;
   const unsigned nb = gridDim.x;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
@@ -1206,7 +1228,7 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
     grid_barrier(&H->barrier, nb); TMARK();
     {
       const int nMoved = min(*((volatile int*)&H->nMoved), W.moveCap);
-      for (int k = warp; k < nMoved; k += nwarps) query_proxy(W, W.bv_sorted, stacks[wib], lane, W.moveList[k]);
+      for (int k = warp; k < nMoved; k += nwarps) query_proxy(W, W.bv_sorted, stacks[wib], kQueryStackToi, lane, W.moveList[k]);
     }
     grid_barrier(&H->barrier, nb); TMARK();
     {

@@ -26,13 +26,18 @@ DBX_D int hash_find(const DevWorld& W, unsigned long long key) {
   }
   return -1;
 }
-// keys are unique per insertion batch, so a CAS on the key word is enough
+// Keys are unique per insertion batch and the caller has already looked the key up (it is not in the table), so a CAS on
+// the key word is enough and the first tombstone on the probe path can be recycled: without that a scene that keeps
+// creating and destroying contacts fills the table with tombstones between two rebuilds.
 DBX_D bool hash_insert(const DevWorld& W, unsigned long long key, int val) {
   unsigned mask = (unsigned)W.hCap - 1;
   unsigned h = (unsigned)mix64(key) & mask;
   for (int probe = 0; probe < W.hCap; ++probe) {
-    unsigned long long old = atomicCAS(&W.h_key[h], kHashEmpty, key);
-    if (old == kHashEmpty) { W.h_val[h] = val; return true; }
+    unsigned long long cur = W.h_key[h];
+    if (cur == kHashEmpty || cur == kHashTomb) {
+      unsigned long long old = atomicCAS(&W.h_key[h], cur, key);
+      if (old == cur) { W.h_val[h] = val; if (cur == kHashTomb) atomicSub(&W.hdr->nTomb, 1); return true; }
+    }
     h = (h + 1) & mask;
   }
   return false;

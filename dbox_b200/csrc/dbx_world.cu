@@ -46,6 +46,8 @@ World::~World() {
   if (!ok_) return;
   cudaSetDevice(device_);
   cudaStreamSynchronize(stream_);
+  if (wm_) cudaFreeHost(wm_);
+  if (wmEv_) cudaEventDestroy(wmEv_);
   DevBuf<float4>* f4[] = {&b_xf, &b_xf0, &b_pos, &b_pos0, &b_vel, &b_force, &b_mass, &b_lc, &p_aabb, &p_fat, &bv_box, &c_m0, &c_m1, &c_imp, &c_mat,
                           &s_v0, &s_v1, &s_r0, &s_r1, &s_q0, &s_q1, &s_imp, &s_nm, &s_k, &s_p0, &s_p1, &s_p2, &j_anchor, &j_p0, &j_p1, &j_imp, &j_r, &j_lc, &j_m, &j_k0, &j_k1, &j_k2};
   for (auto* b : f4) b->release();
@@ -526,7 +528,7 @@ int World::reserveDevice(bool& rehash) {
     size_t need = cub_temp_bytes((int)pc);
     CUDA_OR_FAIL(cubTemp.reserve(need, false, stream_), "cubTemp");
   }
-  const size_t capC = std::max<size_t>(std::max<size_t>(1024, 8 * pc), (size_t)caps_.maxContacts);
+  const size_t capC = std::max<size_t>(std::max<size_t>(std::max<size_t>(1024, 8 * pc), (size_t)caps_.maxContacts), contactFloor_);
   const size_t oldCCap = c_key.cap;
   CUDA_OR_FAIL(c_key.reserve(capC, true, stream_), "c_key");
   DevBuf<float4>* cf4[] = {&c_m0, &c_m1, &c_imp, &c_mat};
@@ -692,6 +694,7 @@ void World::setStepParams(float dt, int vi, int pi) {
   dw_.allowSleep = (flags_ & DBX_WORLD_ALLOW_SLEEP) ? 1 : 0;
   dw_.continuous = (flags_ & DBX_WORLD_CONTINUOUS) ? 1 : 0;
   dw_.gx = gx_; dw_.gy = gy_;
+  dw_.stepIndex = (stepCount_ + 1) & 0xFFFF;
 }
 
 int World::checkDeviceError(bool sync) {
@@ -716,10 +719,24 @@ int World::findNewContacts() {
   return 0;
 }
 
+int World::growContactsIfNeeded() {
+  if (!wmPending_ || cudaEventQuery(wmEv_) != cudaSuccess) return 0;
+  wmPending_ = false;
+  const size_t high = (size_t)std::max(wm_[0], 0);          // Header::cHigh
+  if (2 * high <= c_key.cap) return 0;
+  contactFloor_ = 2 * c_key.cap;
+  bool rehash = false;
+  int rc = reserveDevice(rehash); if (rc < 0) return rc;
+  refreshView();
+  if (rehash) CUDA_OR_FAIL(stage_rebuild_hash(dw_, L_), "rehash");
+  return 0;
+}
+
 // one b2World.Step (dynamics/b2world.d:367-434) enqueued on the world's stream; no host synchronisation
 int World::enqueueStep(float dt, int vi, int pi, bool fineEvents) {
   int rc = push(); if (rc < 0) return rc;
   if (bodies_.empty()) return 0;
+  rc = growContactsIfNeeded(); if (rc < 0) return rc;
   if (newFixture_) { int rf = findNewContacts(); if (rf < 0) return rf; newFixture_ = false; }   // :372-376
   setStepParams(dt, vi, pi);
   dw_.colourOverride = overrideLevels_ ? 1 : 0;
@@ -755,6 +772,12 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents) {
     CUDA_OR_FAIL(cudaMemsetAsync(c_colour.p, 0xFF, c_colour.cap * 4, stream_), "reset colours");
   }
   if ((stepCount_ & 63) == 0) { int rc2 = compactContacts(); if (rc2 < 0) return rc2; }
+  if ((stepCount_ & 7) == 0 && !wmPending_) {
+    if (!wm_) { CUDA_OR_FAIL(cudaMallocHost((void**)&wm_, 64), "watermark"); CUDA_OR_FAIL(cudaEventCreateWithFlags(&wmEv_, cudaEventDisableTiming), "watermark"); }
+    CUDA_OR_FAIL(cudaMemcpyAsync(wm_, hdr_.p, 64, cudaMemcpyDeviceToHost, stream_), "watermark");
+    CUDA_OR_FAIL(cudaEventRecord(wmEv_, stream_), "watermark");
+    wmPending_ = true;
+  }
   hostBodiesValid_ = false; hostProxiesValid_ = false; hostJointsValid_ = false;
   return 0;
 }
@@ -818,6 +841,50 @@ int World::setBodyStates(const int* ids, const float* pose4, const float* vel4, 
   CUDA_OR_FAIL(launch_set_states(dw_, L_, ids ? ioIds_.p : nullptr, pose4 ? ioBuf_.p : nullptr, vel4 ? ioBuf2_.p : nullptr, n), "set_states");
   hostBodiesValid_ = false; hostProxiesValid_ = false;
   return n;
+}
+// b2World.SetContactListener (dynamics/b2world.d:62-66), deferred form: capacity > 0 turns recording on, 0 off
+int World::enableContactEvents(int capacity) {
+  if (capacity < 0) return DBX_E_INVALID;
+  int rc = push(); if (rc < 0) return rc;
+  if (capacity > 0) { CUDA_OR_FAIL(ev_a_.reserve((size_t)capacity, false, stream_), "events"); CUDA_OR_FAIL(ev_b_.reserve((size_t)capacity, false, stream_), "events"); }
+  dw_.ev_a = ev_a_.p; dw_.ev_b = ev_b_.p; dw_.evCap = capacity > 0 ? (int)std::min(ev_a_.cap, ev_b_.cap) : 0;
+  if (dw_.hdr) { int zero = 0; CUDA_OR_FAIL(cudaMemcpyAsync((char*)hdr_.p + offsetof(Header, nCtEvents), &zero, 4, cudaMemcpyHostToDevice, stream_), "events reset"); CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync"); }
+  return dw_.evCap;
+}
+// events since the last poll in (step, phase, pair key, type) order; the device order is whatever the atomics gave
+int World::pollContactEvents(dbx_contact_event* out, int cap) {
+  if (dw_.evCap == 0 || !dw_.hdr) return 0;
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  int n = 0;
+  CUDA_OR_FAIL(cudaMemcpy(&n, (char*)hdr_.p + offsetof(Header, nCtEvents), 4, cudaMemcpyDeviceToHost), "events count");
+  if (!out || cap <= 0) return n;
+  const int have = std::min(n, dw_.evCap);
+  std::vector<int4> a((size_t)have), b((size_t)have);
+  if (have > 0) { CUDA_OR_FAIL(cudaMemcpy(a.data(), ev_a_.p, (size_t)have * 16, cudaMemcpyDeviceToHost), "events"); CUDA_OR_FAIL(cudaMemcpy(b.data(), ev_b_.p, (size_t)have * 16, cudaMemcpyDeviceToHost), "events"); }
+  int zero = 0; CUDA_OR_FAIL(cudaMemcpy((char*)hdr_.p + offsetof(Header, nCtEvents), &zero, 4, cudaMemcpyHostToDevice), "events reset");
+  if (n > dw_.evCap) { set_last_error("contact event buffer overflow: events were lost, raise the capacity of dbx_world_enable_contact_events"); return DBX_E_CAPACITY; }
+  // steps are stamped with 16 bits: order them relative to the current step so that a wrap does not reorder
+  const int cur = stepCount_ & 0xFFFF;
+  std::vector<int> order((size_t)have);
+  for (int i = 0; i < have; ++i) order[i] = i;
+  auto age = [&](int i) { return (cur - ((a[i].x >> 16) & 0xFFFF)) & 0xFFFF; };
+  auto key = [&](int i) { return ((unsigned long long)(unsigned)b[i].w << 32) | (unsigned)b[i].z; };
+  std::sort(order.begin(), order.end(), [&](int x, int y) {
+    if (age(x) != age(y)) return age(x) > age(y);
+    const int px = (a[x].x >> 8) & 0xFF, py = (a[y].x >> 8) & 0xFF;
+    if (px != py) return px < py;
+    if (key(x) != key(y)) return key(x) < key(y);
+    return (a[x].x & 0xFF) < (a[y].x & 0xFF);
+  });
+  const int m = std::min(have, cap);
+  for (int k = 0; k < m; ++k) {
+    const int i = order[k];
+    dbx_contact_event& e = out[k];
+    e.type = a[i].x & 0xFF; e.phase = (a[i].x >> 8) & 0xFF; e.stepsAgo = age(i);
+    e.fixtureA = a[i].y; e.fixtureB = a[i].z; e.childA = a[i].w & 0xFFFF; e.childB = (a[i].w >> 16) & 0xFFFF;
+    e.bodyA = b[i].x; e.bodyB = b[i].y;
+  }
+  return have;
 }
 int World::readTransforms(float* out, int n) {
   int rc = push(); if (rc < 0) return rc;
@@ -1215,11 +1282,12 @@ int World::colourConflicts() {
   CUDA_OR_FAIL(cudaMemcpy(&high, (char*)hdr_.p + offsetof(Header, cHigh), 4, cudaMemcpyDeviceToHost), "read cHigh");
   if (high <= 0) return 0;
   const size_t n = (size_t)high;
-  std::vector<int4> ids(n); std::vector<uint32_t> fl(n), bfl(bodiesSynced_); std::vector<int> col(n);
+  const size_t nb = replicated_ ? bodies_.size() * (size_t)nWorlds_ : bodiesSynced_;
+  std::vector<int4> ids(n); std::vector<uint32_t> fl(n), bfl(nb); std::vector<int> col(n);
   cudaMemcpy(ids.data(), c_ids.p, n * 16, cudaMemcpyDeviceToHost);
   cudaMemcpy(fl.data(), c_flags.p, n * 4, cudaMemcpyDeviceToHost);
   cudaMemcpy(col.data(), c_colour.p, n * 4, cudaMemcpyDeviceToHost);
-  CUDA_OR_FAIL(cudaMemcpy(bfl.data(), b_flags.p, bodiesSynced_ * 4, cudaMemcpyDeviceToHost), "read flags");
+  CUDA_OR_FAIL(cudaMemcpy(bfl.data(), b_flags.p, nb * 4, cudaMemcpyDeviceToHost), "read flags");
   std::unordered_map<unsigned long long, int> seen;
   int conflicts = 0;
   for (size_t i = 0; i < n; ++i) {
@@ -1227,7 +1295,7 @@ int World::colourConflicts() {
     if (col[i] < 0) { ++conflicts; continue; }
     const int bs[2] = {ids[i].z, ids[i].w};
     for (int b : bs) {
-      if (body_type(bfl[b]) != BODY_DYNAMIC) continue;
+      if ((size_t)b >= nb || body_type(bfl[b]) != BODY_DYNAMIC) continue;
       unsigned long long k = ((unsigned long long)(unsigned)b << 32) | (unsigned)col[i];
       if (++seen[k] > 1) ++conflicts;
     }

@@ -64,6 +64,8 @@ class World {
   int timeSteps(float dt, int vi, int pi, int n, bool flushL2, float* totalMs, float* stageMs);
   int applyForces(const float* f4, int n);
   int setBodyStates(const int* ids, const float* pose4, const float* vel4, int n);
+  int enableContactEvents(int capacity);
+  int pollContactEvents(dbx_contact_event* out, int cap);
   int readTransforms(float* out, int n);
   long launchCount() const { return L_.launches; }
   int clearForces();
@@ -166,9 +168,13 @@ class World {
   int nJointPairs_ = 0; int jointBlocks_ = 0, nJointColours_ = 0;
   cudaEvent_t ev_[10]{};
   bool evValid_ = false, evFine_ = false;
-  DevBuf<char> flushBuf_; DevBuf<float4> ioBuf_, ioBuf2_; DevBuf<int> ioIds_; DevBuf<unsigned long long> phaseBuf_;
+  DevBuf<char> flushBuf_; DevBuf<float4> ioBuf_, ioBuf2_; DevBuf<int> ioIds_; DevBuf<int4> ev_a_, ev_b_; DevBuf<unsigned long long> phaseBuf_;
   bool overrideLevels_ = false;
   bool treeValid_ = false; int sinceRebuild_ = 0;
+  // contact-pool watermark: every 8th step the header is copied to pinned memory without waiting; a later step looks at
+  // the copy that has landed and doubles the pool before it can overflow
+  int* wm_ = nullptr; cudaEvent_t wmEv_ = nullptr; bool wmPending_ = false; size_t contactFloor_ = 0;
+  int growContactsIfNeeded();
   std::vector<int> lastReadSlots_;
 };
 

@@ -352,6 +352,37 @@ class b2Body:
         self.world._ck(self.world._api.body_set_sleeping_allowed(self.world._w, self.id, int(flag)))
 
 
+class b2ContactListener:
+    """b2worldcallbacks.d:87-128.  BeginContact / EndContact are delivered right after b2World.Step returns; PreSolve /
+    PostSolve are not (include/dbox_b200.h, "contact listener, deferred")."""
+
+    def BeginContact(self, contact):
+        pass
+
+    def EndContact(self, contact):
+        pass
+
+
+class b2ContactView:
+    """what a deferred listener call sees of a b2Contact: its fixtures and child indices (b2contact.d:108-135)"""
+
+    def __init__(self, world, ev):
+        self.world, self.event = world, ev
+        self.fixtureA_id, self.fixtureB_id, self.childA, self.childB, self.bodyA_id, self.bodyB_id = ev[3:9]
+
+    def GetFixtureA(self):
+        return self.world._fixtures.get(self.fixtureA_id)
+
+    def GetFixtureB(self):
+        return self.world._fixtures.get(self.fixtureB_id)
+
+    def GetChildIndexA(self):
+        return self.childA
+
+    def GetChildIndexB(self):
+        return self.childB
+
+
 class b2World:
     """dynamics/b2world.d:34-1591 — construction, factories, Step, toggles and bulk state access."""
 
@@ -413,6 +444,33 @@ class b2World:
     # stepping ----------------------------------------------------------------------------------------------
     def Step(self, dt, velocityIterations, positionIterations):
         self._ck(self._api.world_step(self._w, dt, velocityIterations, positionIterations))
+        if getattr(self, "_listener", None) is not None:
+            self._deliver_contact_events()
+
+    # contact listener (b2world.d:62-66, b2worldcallbacks.d:87-128), deferred: see include/dbox_b200.h ------------
+    def SetContactListener(self, listener, capacity=1 << 16):
+        self._listener = listener
+        self._ck(self._api.world_enable_contact_events(self._w, capacity if listener is not None else 0))
+
+    def EnableContactEvents(self, capacity=1 << 16):
+        return self._ck(self._api.world_enable_contact_events(self._w, capacity))
+
+    def PollContactEvents(self):
+        """events since the last poll as (type, phase, stepsAgo, fixtureA, fixtureB, childA, childB, bodyA, bodyB) tuples"""
+        n = self._ck(self._api.world_poll_contact_events(self._w, None, 0))
+        if n == 0:
+            return []
+        buf = (A.ContactEvent * n)()
+        n = self._ck(self._api.world_poll_contact_events(self._w, buf, n))
+        return [tuple(getattr(buf[i], f) for f, _ in A.ContactEvent._fields_) for i in range(n)]
+
+    def _deliver_contact_events(self):
+        for ev in self.PollContactEvents():
+            c = b2ContactView(self, ev)
+            if ev[0] == A.CONTACT_BEGIN:
+                self._listener.BeginContact(c)
+            else:
+                self._listener.EndContact(c)
 
     def Replicate(self, copies):
         """dbx_world_replicate: this world's content becomes replica 0 of `copies` independent replicas stepped together

@@ -303,6 +303,31 @@ float dbx_debug_barrier_us(int32_t device, int32_t blocks, int32_t threads, int3
 int32_t dbx_world_replicate(dbx_world* w, int32_t copies);  /* world becomes `copies` disjoint replicas of its current content */
 int32_t dbx_world_replica_count(dbx_world* w);
 
+/* ---- contact listener, deferred ------------------------------------------------------------
+ * b2World.SetContactListener (dynamics/b2world.d:62-66) + b2ContactListener.BeginContact / EndContact
+ * (dynamics/b2worldcallbacks.d:87-95).  The reference calls the listener in the middle of the step, from b2Contact.Update
+ * (contacts/b2contact.d:338-346; also inside the TOI loop, dynamics/b2world.d:1295,1379) and from b2ContactManager.Destroy
+ * (dynamics/b2contactmanager.d:60-63).  Device code cannot call back into the host, so the same call sites append records
+ * to a device buffer and the host shim delivers them right after dbx_world_step returns: same events, same fixtures,
+ * later in time.  Consequences: a listener cannot change the step it is told about (PreSolve's SetEnabled(false) /
+ * friction edits are NOT supported -- such programs stay on the CPU path); PostSolve's impulses are the normal/tangent
+ * impulses dbx_world_read_contacts returns.  Events are ordered (step, phase, pair key, type); phase 1 = Collide,
+ * 2 = TOI sub-steps, 3 = contact destroyed by an API call after that step (DestroyBody / DestroyFixture / CreateJoint). */
+typedef struct dbx_contact_event {
+  int32_t type;               /* DBX_CONTACT_BEGIN / DBX_CONTACT_END */
+  int32_t phase;
+  int32_t stepsAgo;           /* 0 = the step that just ran */
+  int32_t fixtureA, fixtureB; /* in the contact's A/B order (b2contact.d:375-400) */
+  int32_t childA, childB;
+  int32_t bodyA, bodyB;
+} dbx_contact_event;
+enum { DBX_CONTACT_BEGIN = 1, DBX_CONTACT_END = 2 };
+/* capacity > 0: start recording (at most `capacity` events between two polls), 0: stop.  Returns the capacity in use. */
+int32_t dbx_world_enable_contact_events(dbx_world* w, int32_t capacity);
+/* Copies the events recorded since the last poll (sorted) and clears the buffer; returns their number, or
+ * DBX_E_CAPACITY if more than `capacity` were produced (the surplus is lost).  out == NULL: returns the count only. */
+int32_t dbx_world_poll_contact_events(dbx_world* w, dbx_contact_event* out, int32_t cap);
+
 #ifdef __cplusplus
 }
 #endif

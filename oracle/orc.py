@@ -55,6 +55,8 @@ def api():
             "distance": (f32, [P(A.Shape), f32, f32, f32, i32, P(A.Shape), f32, f32, f32, i32, i32, P(A.Vec2), P(A.Vec2), P(i32)]),
             "time_of_impact": (i32, [P(A.Shape), P(f32), i32, P(A.Shape), P(f32), i32, f32, P(f32)]),
             "batch_step": (C.c_double, [P(W), i32, f32, i32, i32, i32, i32]),
+            "world_enable_contact_events": (i32, [W, i32]),
+            "world_poll_contact_events": (i32, [W, P(A.ContactEvent), i32]),
         }
         for name, (res, args) in extra.items():
             fn = getattr(lib, "orc_" + name)

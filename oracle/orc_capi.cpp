@@ -270,6 +270,22 @@ int32_t orc_world_read_contacts(orc_world* w, dbx_contact_rec* out, int32_t cap)
   for (Contact* c = w->w.contactList; c; c = c->next) { if (n < cap) fillContact(c, out + n); ++n; }
   return n;
 }
+// the listener call log since the last poll, in the reference's CALL order (the CUDA library returns the same events sorted)
+int32_t orc_world_enable_contact_events(orc_world* w, int32_t capacity) {
+  w->w.recordContactEvents = capacity > 0; w->w.contactEvents.clear(); return capacity;
+}
+int32_t orc_world_poll_contact_events(orc_world* w, dbx_contact_event* out, int32_t cap) {
+  const int n = (int)w->w.contactEvents.size();
+  if (!out || cap <= 0) return n;
+  for (int i = 0; i < n && i < cap; ++i) {
+    const World::ContactEvt& e = w->w.contactEvents[i];
+    out[i].type = e.type; out[i].phase = e.phase; out[i].stepsAgo = w->w.stepCount - e.step;
+    out[i].fixtureA = e.fixtureA; out[i].fixtureB = e.fixtureB; out[i].childA = e.childA; out[i].childB = e.childB;
+    out[i].bodyA = e.bodyA; out[i].bodyB = e.bodyB;
+  }
+  w->w.contactEvents.clear();
+  return n;
+}
 // contacts in the order the islands solved them during the last Step (sequential Gauss-Seidel order)
 int32_t orc_world_read_solve_order(orc_world* w, int32_t* fixA_childA_fixB_childB, int32_t cap) {
   int n = 0;

@@ -106,7 +106,7 @@ void Contact::evaluate(Manifold* m, const Xf& xfA, const Xf& xfB) const {
   else if (tA == kChain && tB == kPolygon) { Shape e; sA.childEdge(&e, indexA); collideEdgeAndPolygon(m, e, xfA, sB, xfB); } // b2chainandpolygoncontact.d:56-66
 }
 
-void Contact::update(World*) {
+void Contact::update(World* w) {
   Manifold oldManifold = manifold;
   flags |= cEnabled;
   bool touching = false;
@@ -138,7 +138,14 @@ void Contact::update(World*) {
     if (touching != wasTouching) { bodyA->setAwake(true); bodyB->setAwake(true); }
   }
   if (touching) flags |= cTouching; else flags &= ~cTouching;
-  // listener callbacks (BeginContact/EndContact/PreSolve) are the default no-ops here (b2worldcallbacks.d:87-128)
+  // listener callbacks (b2contact.d:338-355): BeginContact / EndContact are logged, PreSolve is the default no-op
+  if (w && wasTouching == false && touching == true) w->logContactEvent(1, this);
+  if (w && wasTouching == true && touching == false) w->logContactEvent(2, this);
+}
+
+void World::logContactEvent(int type, const Contact* c) {
+  if (!recordContactEvents) return;
+  contactEvents.push_back({type, evPhase, stepCount + (evPhase == 3 ? 0 : 1), c->fixtureA->id, c->indexA, c->fixtureB->id, c->indexB, c->fixtureA->body->id, c->fixtureB->body->id});
 }
 
 // b2contact.d:375-400 + ctor :208-239
@@ -384,6 +391,7 @@ void World::findNewContacts() {
 void World::destroyContact(Contact* c) {
   Fixture* fixtureA = c->fixtureA; Fixture* fixtureB = c->fixtureB;
   Body* bodyA = fixtureA->body; Body* bodyB = fixtureB->body;
+  if (c->isTouching()) logContactEvent(2, c);   // b2contactmanager.d:60-63
   if (c->prev) c->prev->next = c->next;
   if (c->next) c->next->prev = c->prev;
   if (c == contactList) contactList = c->next;
@@ -1076,9 +1084,12 @@ void World::step(float dt, int velocityIterations, int positionIterations) {
   step.inv_dt = dt > 0.0f ? 1.0f / dt : 0.0f;
   step.dtRatio = inv_dt0 * dt;
   step.warmStarting = warmStarting;
+  evPhase = 1;
   { double t = nowMs(); collide(); profile.collide = (float)(nowMs() - t); }
   if (stepComplete && step.dt > 0.0f) { double t = nowMs(); solve(step); profile.solve = (float)(nowMs() - t); }
+  evPhase = 2;
   if (continuousPhysics && step.dt > 0.0f) { double t = nowMs(); solveTOI(step); profile.solveTOI = (float)(nowMs() - t); }
+  evPhase = 3; ++stepCount;
   if (step.dt > 0.0f) inv_dt0 = step.inv_dt;
   if (clearForcesFlag) clearForces();
   locked = false;

@@ -176,6 +176,11 @@ struct World {
   std::vector<Body*> bodiesById; std::vector<Fixture*> fixturesById; std::vector<Joint*> jointsById;
   // diagnostics for tests
   int lastIslandCount = 0; int toiEvents = 0;
+  // b2ContactListener.BeginContact / EndContact call log, in the reference's call order (b2contact.d:338-346,
+  // b2contactmanager.d:60-63); phase 1 = Collide, 2 = SolveTOI, 3 = API call between steps
+  struct ContactEvt { int type, phase, step, fixtureA, childA, fixtureB, childB, bodyA, bodyB; };
+  std::vector<ContactEvt> contactEvents; bool recordContactEvents = false; int evPhase = 3; int stepCount = 0;
+  void logContactEvent(int type, const Contact* c);
   std::vector<std::pair<FixtureProxy*, FixtureProxy*>> lastPairs;  // unique pairs handed to AddPair by the last UpdatePairs
   std::vector<Contact*> lastSolveOrder;   // contacts in the order islands solved them in the last Solve
 };

@@ -327,3 +327,94 @@ def test_divergent_replicas_match_separately_built_worlds(gpu_api):
                 a, b = ss[i], sb[r * nb + i]
                 assert (a.c.x, a.c.y, a.a, a.v.x, a.v.y, a.w) == (b.c.x, b.c.y, b.a, b.v.x, b.v.y, b.w), (k, r, i)
     assert gpu_api.world_debug_colour_conflicts(batch._w) == 0
+
+
+def _event_key(ev):
+    # (type, phase, stepsAgo, fixtureA, fixtureB, childA, childB, bodyA, bodyB) -> order-free identity of one callback
+    return (ev[0], ev[1], ev[3], ev[4], ev[5], ev[6], ev[7], ev[8])
+
+
+def test_contact_events_match_reference_callbacks(gpu_api, oracle_api):
+    """b2ContactListener.BeginContact / EndContact (b2contact.d:338-346, b2contactmanager.d:60-63): per step, the deferred
+    device events are exactly the callbacks the reference makes (same fixtures in the same A/B order, Collide vs TOI)."""
+    g, gb = scenes.pyramid(api=gpu_api, count=8)
+    o, ob = scenes.pyramid(api=oracle_api, count=8)
+    g.EnableContactEvents(4096); o.EnableContactEvents(4096)
+    total = 0
+    for step in range(23):      # free fall and the first impacts: later a marginal contact may flicker on one side only
+        g.Step(DT, 8, 3); o.Step(DT, 8, 3)
+        eg, eo = g.PollContactEvents(), o.PollContactEvents()
+        assert sorted(map(_event_key, eg)) == sorted(map(_event_key, eo)), step
+        assert all(e[2] == 0 for e in eg)
+        keys = [(e[1], ) for e in eg]
+        assert keys == sorted(keys)                       # delivered in (phase, pair key, type) order
+        total += len(eg)
+    assert total > 30
+    # the balance of begins and ends is the number of touching contacts
+    g2, _ = scenes.pyramid(api=gpu_api, count=8)
+    g2.EnableContactEvents(1 << 14)
+    balance = 0
+    for step in range(150):
+        g2.Step(DT, 8, 3)
+        for e in g2.PollContactEvents():
+            balance += 1 if e[0] == 1 else -1
+    assert balance == g2.counts().touching
+
+
+def test_contact_events_on_destroy_and_listener_delivery(gpu_api):
+    """DestroyBody ends its touching contacts (b2world.d:128-137 -> b2contactmanager.d:60-63); the Python mirror of
+    b2ContactListener receives the deferred calls right after Step"""
+    from dbox_b200.world import b2ContactListener
+
+    class Log(b2ContactListener):
+        def __init__(self):
+            self.begin, self.end = [], []
+
+        def BeginContact(self, c):
+            self.begin.append((c.GetFixtureA().id, c.GetFixtureB().id))
+
+        def EndContact(self, c):
+            self.end.append((c.GetFixtureA().id, c.GetFixtureB().id))
+
+    w, box = scenes.hello_world(api=gpu_api)
+    log = Log()
+    w.SetContactListener(log)
+    for _ in range(90):
+        w.Step(DT, 6, 2)
+    assert len(log.begin) == 1 and log.end == []
+    w.DestroyBody(box)
+    ev = w.PollContactEvents()
+    assert len(ev) == 1 and ev[0][0] == 2 and ev[0][1] == 3 and (ev[0][3], ev[0][4]) == log.begin[0]
+    # overflow is reported, not silent
+    p, _ = scenes.pyramid(api=gpu_api, count=10)
+    p.EnableContactEvents(4)
+    for _ in range(40):
+        p.Step(DT, 8, 3)
+    with pytest.raises(Exception):
+        p.PollContactEvents()
+
+
+def test_tumbler_invariants(gpu_api, oracle_api):
+    """config 3 (tumbler.d:40-97): a motor-driven container (one dynamic body touched by hundreds of contacts -> overflow
+    colour lanes), one new body per step (host mirror pushes while stepping, contact pool grows on its own), boxes and
+    circles.  Chaotic, so judged by invariants against the oracle: nothing leaks out, the container follows the motor,
+    contact populations agree."""
+    n, steps = 300, 500
+    tg = scenes.Tumbler(api=gpu_api, count=n)
+    to = scenes.Tumbler(api=oracle_api, count=n)
+    for _ in range(steps):
+        tg.Step(); to.Step()
+    assert tg.m_count == to.m_count == n
+    for t in (tg, to):
+        inside = sum(1 for b in t.bodies if abs(b.GetPosition().x) < 10.6 and -0.6 < b.GetPosition().y < 20.6)
+        assert inside == n
+    assert abs(tg.container.GetAngle() - to.container.GetAngle()) < 1e-3
+    assert abs(tg.container.GetAngularVelocity() - to.container.GetAngularVelocity()) < 1e-3
+    cg, co = tg.world.counts(), to.world.counts()
+    assert cg.bodies == co.bodies and cg.joints == co.joints == 1
+    assert abs(cg.contacts - co.contacts) < 0.15 * co.contacts, (cg.contacts, co.contacts)
+    assert abs(cg.touching - co.touching) < 0.15 * co.touching, (cg.touching, co.touching)
+    assert gpu_api.world_debug_colour_conflicts(tg.world._w) == 0
+    mg = sum(b.GetPosition().y for b in tg.bodies) / n
+    mo = sum(b.GetPosition().y for b in to.bodies) / n
+    assert abs(mg - mo) < 0.5, (mg, mo)

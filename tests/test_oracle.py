@@ -135,3 +135,21 @@ def test_tumbler_motor_turns_container(oracle_api):
         t.Step()
     assert t.container.GetAngle() > 0.4          # 0.05*pi rad/s for 200/60 s
     assert t.world.counts().bodies == 3 + 60
+
+
+def test_oracle_contact_event_log_balances(oracle_api):
+    """the oracle's BeginContact/EndContact call log (b2contact.d:338-346, b2contactmanager.d:60-63): begins minus ends is
+    the number of touching contacts, and destroying a resting body ends its contacts in the API phase"""
+    from dbox_b200 import scenes
+    w, bodies = scenes.pyramid(api=oracle_api, count=6)
+    w.EnableContactEvents(1 << 14)
+    balance = 0
+    for _ in range(120):
+        w.Step(1.0 / 60.0, 8, 3)
+        for e in w.PollContactEvents():
+            assert e[2] == 0 and e[1] in (1, 2)
+            balance += 1 if e[0] == 1 else -1
+    assert balance == w.counts().touching > 0
+    w.DestroyBody(bodies[-1])
+    ev = w.PollContactEvents()
+    assert ev and all(e[0] == 2 and e[1] == 3 for e in ev)

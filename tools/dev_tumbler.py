@@ -12,7 +12,10 @@ for k in range(steps):
     try:
         t.Step(spawn_per_step=spawn)
     except Exception as e:
-        print("step", k, "FAILED", e); break
+        print("step", k, "FAILED", e)
+        hb = (C.c_int32 * 64)(); ga.world_debug_header(t.world._w, hb, 256)
+        names = "cHigh nFree nContacts nMoved nPairs nSolve nColours nTouching nUncoloured nUncoloured2 error nTomb nIslands nAwake toiEvents nEvents tailStart nCtEvents".split()
+        print({n: hb[i] for i, n in enumerate(names)}); break
     if (k + 1) % 200 == 0:
         c = t.world.counts()
         print("step %d bodies %d contacts %d touching %d colours %d  %.2f ms/step wall" % (k + 1, c.bodies, c.contacts, c.touching, c.colours, 1e3 * (time.time() - t0) / (k + 1)), flush=True)
