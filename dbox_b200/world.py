@@ -284,6 +284,12 @@ class b2Body:
         self.world._fixtures[fid] = f
         return f
 
+    def DestroyFixture(self, fixture):
+        """b2body.d:172-254"""
+        self.world._ck(self.world._api.fixture_destroy(self.world._w, fixture.id))
+        self.fixtures.remove(fixture)
+        self.world._fixtures.pop(fixture.id, None)
+
     def GetPosition(self):
         s = self._state()
         return b2Vec2(s.p.x, s.p.y)

@@ -1,0 +1,215 @@
+"""Feature-by-feature parity of the CUDA path (through the C ABI) against the oracle: each scene exercises one part of the
+step pipeline in a configuration where the Gauss-Seidel order cannot matter (one constraint per body, or islands of one
+body), so the two sides must agree to float rounding, not just statistically."""
+import math
+
+import pytest
+
+from dbox_b200 import _abi as A
+from dbox_b200 import scenes
+from dbox_b200.world import (b2BodyDef, b2ChainShape, b2CircleShape, b2DistanceJointDef, b2EdgeShape, b2FixtureDef,
+                             b2PolygonShape, b2RevoluteJointDef, b2World, b2_dynamicBody, b2_kinematicBody)
+
+pytestmark = pytest.mark.gpu
+DT = 1.0 / 60.0
+
+
+def both(gpu_api, oracle_api, build, steps, vi=8, pi=3, tol_p=2e-5, tol_v=2e-4, each=None):
+    """build(api) -> (world, [bodies to compare]); step both sides and compare positions / velocities every step"""
+    wg, bg = build(gpu_api)
+    wo, bo = build(oracle_api)
+    for k in range(steps):
+        wg.Step(DT, vi, pi); wo.Step(DT, vi, pi)
+        if each:
+            each(k, wg, wo)
+        for i, (g, o) in enumerate(zip(bg, bo)):
+            pg, po = g.GetPosition(), o.GetPosition()
+            scale = max(1.0, abs(po.x), abs(po.y))
+            assert abs(pg.x - po.x) <= tol_p * scale and abs(pg.y - po.y) <= tol_p * scale, (k, i, (pg.x, pg.y), (po.x, po.y))
+            assert abs(g.GetAngle() - o.GetAngle()) <= tol_p * max(1.0, abs(o.GetAngle())), (k, i, g.GetAngle(), o.GetAngle())
+            vg, vo = g.GetLinearVelocity(), o.GetLinearVelocity()
+            vs = max(1.0, abs(vo.x), abs(vo.y))
+            assert abs(vg.x - vo.x) <= tol_v * vs and abs(vg.y - vo.y) <= tol_v * vs, (k, i, (vg.x, vg.y), (vo.x, vo.y))
+            assert abs(g.GetAngularVelocity() - o.GetAngularVelocity()) <= tol_v * max(1.0, abs(o.GetAngularVelocity())), (k, i)
+    return wg, wo, bg, bo
+
+
+def _ground(world, api):
+    g = world.CreateBody(b2BodyDef())
+    e = b2EdgeShape(api)
+    e.Set((-40.0, 0.0), (40.0, 0.0))
+    g.CreateFixture(e, 0.0)
+    return g
+
+
+def _dyn(world, x, y, angle=0.0, **kw):
+    bd = b2BodyDef()
+    bd.type = b2_dynamicBody
+    bd.position.Set(x, y)
+    bd.angle = angle
+    for k, v in kw.items():
+        setattr(bd, k, v)
+    return world.CreateBody(bd)
+
+
+def test_revolute_joint_limit_and_motor(gpu_api, oracle_api):
+    """b2RevoluteJoint (joints/b2revolutejoint.d:130-495): point constraint + limit (3x3 block, all limit states) + motor"""
+    def build(api):
+        w = b2World((0.0, -10.0), api=api)
+        g = _ground(w, api)
+        out = []
+        for k, (limit, motor) in enumerate(((False, False), (True, False), (False, True), (True, True))):
+            b = _dyn(w, 6.0 * k - 9.0, 8.0)
+            s = b2PolygonShape(api); s.SetAsBox(0.25, 1.5)
+            b.CreateFixture(s, 2.0)
+            jd = b2RevoluteJointDef()
+            jd.Initialize(g, b, (6.0 * k - 9.0, 9.5))
+            jd.enableLimit, jd.lowerAngle, jd.upperAngle = limit, -0.3, 0.45
+            jd.enableMotor, jd.motorSpeed, jd.maxMotorTorque = motor, 1.5, 40.0
+            w.CreateJoint(jd)
+            b.SetAngularVelocity(2.0 - k)
+            out.append(b)
+        return w, out
+    wg, wo, _, _ = both(gpu_api, oracle_api, build, 240)
+    jg, n = wg.read_joints(); jo, _ = wo.read_joints()
+    for i in range(n):
+        assert jg[i].limitState == jo[i].limitState
+        for a, b in zip(list(jg[i].impulse) + [jg[i].motorImpulse], list(jo[i].impulse) + [jo[i].motorImpulse]):
+            assert abs(a - b) <= 2e-3 * max(1.0, abs(b)), (i, a, b)
+
+
+def test_distance_joint_rigid_and_spring(gpu_api, oracle_api):
+    """b2DistanceJoint (joints/b2distancejoint.d:113-330): rigid rod and soft spring (frequency / damping ratio)"""
+    def build(api):
+        w = b2World((0.0, -10.0), api=api)
+        g = _ground(w, api)
+        out = []
+        for k, (hz, zeta) in enumerate(((0.0, 0.0), (2.0, 0.1), (4.0, 0.7))):
+            b = _dyn(w, 8.0 * k - 8.0 + 1.0, 6.0)
+            c = b2CircleShape(api); c.m_radius = 0.5
+            b.CreateFixture(c, 1.0)
+            jd = b2DistanceJointDef()
+            jd.Initialize(g, b, (8.0 * k - 8.0, 10.0), (8.0 * k - 8.0 + 1.0, 6.0))
+            jd.frequencyHz, jd.dampingRatio = hz, zeta
+            w.CreateJoint(jd)
+            out.append(b)
+        return w, out
+    both(gpu_api, oracle_api, build, 240)
+
+
+def test_shapes_on_chain_ground(gpu_api, oracle_api):
+    """circle / polygon against chain children with ghost vertices (b2chainshape.d:162-192, b2collideedge.d), circle-circle,
+    polygon-circle; every body is its own island, so order cannot matter"""
+    def build(api):
+        w = b2World((0.0, -10.0), api=api)
+        g = w.CreateBody(b2BodyDef())
+        ch = b2ChainShape(api)
+        ch.CreateChain([(-20.0, 2.0), (-12.0, 0.0), (-4.0, 0.5), (4.0, 0.0), (12.0, 1.0), (20.0, 0.0)])
+        g.CreateFixture(ch, 0.0)
+        out = []
+        for k in range(8):
+            x = -17.0 + 4.6 * k
+            b = _dyn(w, x, 4.0 + 0.3 * k, angle=0.2 * k)
+            if k % 3 == 0:
+                s = b2CircleShape(api); s.m_radius = 0.4 + 0.05 * k
+            elif k % 3 == 1:
+                s = b2PolygonShape(api); s.SetAsBox(0.5, 0.3 + 0.05 * k)
+            else:
+                s = b2PolygonShape(api); s.Set([(-0.5, -0.4), (0.6, -0.3), (0.4, 0.5), (-0.2, 0.7), (-0.6, 0.2)])
+            fd = b2FixtureDef(); fd.shape = s; fd.density = 1.0 + 0.2 * k; fd.friction = 0.1 * k; fd.restitution = 0.1 * (k % 4)
+            b.CreateFixture(fd)
+            out.append(b)
+        # a circle resting on a circle that is pinned by being static
+        pin = w.CreateBody(b2BodyDef()); pc = b2CircleShape(api); pc.m_radius = 1.0; pc.m_p = (0.0, 12.0); pin.CreateFixture(pc, 0.0)
+        top = _dyn(w, 0.05, 14.0); tc = b2CircleShape(api); tc.m_radius = 0.5; top.CreateFixture(tc, 1.0)
+        out.append(top)
+        return w, out
+    both(gpu_api, oracle_api, build, 120, tol_p=1e-4, tol_v=1e-3)     # beyond that a tumbling polygon amplifies 1-ulp sin/cos differences
+
+
+def test_sensor_and_filters(gpu_api, oracle_api):
+    """sensors overlap without response (b2contact.d:283-292), category/mask and group filtering
+    (b2worldcallbacks.d:52-64): same contacts, same touching flags, same trajectories, same begin/end events"""
+    def build(api):
+        w = b2World((0.0, -10.0), api=api)
+        g = _ground(w, api)
+        zone = w.CreateBody(b2BodyDef())
+        zs = b2PolygonShape(api); zs.SetAsBox(3.0, 1.0, (0.0, 3.0), 0.0)
+        fd = b2FixtureDef(); fd.shape = zs; fd.isSensor = True
+        zone.CreateFixture(fd)
+        out = []
+        for k in range(6):
+            b = _dyn(w, -5.0 + 2.0 * k, 6.0 + 0.5 * k)
+            s = b2PolygonShape(api); s.SetAsBox(0.4, 0.4)
+            fd = b2FixtureDef(); fd.shape = s; fd.density = 1.0
+            if k == 1:
+                fd.filter.maskBits = 0x0000              # collides with nothing: falls through the ground
+            if k in (2, 3):
+                fd.filter.groupIndex = -7                # never collide with each other
+            if k == 4:
+                fd.filter.categoryBits = 0x0004; fd.filter.maskBits = 0xFFFF
+            b.CreateFixture(fd)
+            out.append(b)
+        out[3].SetTransform((out[2].GetPosition().x + 0.2, 9.0), 0.0)     # k=3 lands on k=2's spot: same negative group
+        w.EnableContactEvents(4096)
+        return w, out
+
+    def each(k, wg, wo):
+        key = lambda e: (e[0], e[1], e[3], e[4])
+        assert sorted(map(key, wg.PollContactEvents())) == sorted(map(key, wo.PollContactEvents())), k
+        cg, co = wg.counts(), wo.counts()
+        assert (cg.contacts, cg.touching) == (co.contacts, co.touching), k
+    both(gpu_api, oracle_api, build, 150, each=each)
+
+
+def test_bullet_does_not_tunnel(gpu_api, oracle_api):
+    """continuous collision of a bullet against a thin dynamic wall and of a fast non-bullet against a static one
+    (b2world.d:1127-1452): same TOI events, same outcome"""
+    def build(api):
+        w = b2World((0.0, 0.0), api=api)
+        wall = w.CreateBody(b2BodyDef()); ws = b2PolygonShape(api); ws.SetAsBox(0.05, 5.0, (10.0, 0.0), 0.0); wall.CreateFixture(ws, 0.0)
+        plate = _dyn(w, -10.0, 0.0); ps = b2PolygonShape(api); ps.SetAsBox(0.05, 3.0); plate.CreateFixture(ps, 20.0)
+        fast = _dyn(w, 0.0, 1.0); fs = b2PolygonShape(api); fs.SetAsBox(0.1, 0.1); fast.CreateFixture(fs, 1.0)
+        fast.SetLinearVelocity((300.0, 0.0))
+        bullet = _dyn(w, 0.0, -1.0, bullet=True); bs = b2CircleShape(api); bs.m_radius = 0.1; bullet.CreateFixture(bs, 1.0)
+        bullet.SetLinearVelocity((-400.0, 0.0))
+        return w, [plate, fast, bullet]
+    wg, wo, bg, bo = both(gpu_api, oracle_api, build, 30, tol_p=1e-4, tol_v=1e-3)
+    assert bg[1].GetPosition().x < 10.0 and bg[2].GetPosition().x > -10.5     # neither went through
+
+
+def test_kinematic_platform_and_destroy_calls(gpu_api, oracle_api):
+    """kinematic body driving a box (b2island.d integrates it, zero inverse mass), then DestroyJoint / DestroyFixture /
+    DestroyBody between steps (b2world.d:105-359, b2body.d:172-254): wake-ups and contact removal as in the reference"""
+    def build(api):
+        w = b2World((0.0, -10.0), api=api)
+        g = _ground(w, api)
+        bd = b2BodyDef(); bd.type = b2_kinematicBody; bd.position.Set(0.0, 2.0)
+        plat = w.CreateBody(bd); s = b2PolygonShape(api); s.SetAsBox(3.0, 0.25); plat.CreateFixture(s, 0.0)
+        plat.SetLinearVelocity((1.0, 0.0))
+        rider = _dyn(w, 0.0, 3.0); rs = b2PolygonShape(api); rs.SetAsBox(0.5, 0.5)
+        fd = b2FixtureDef(); fd.shape = rs; fd.density = 1.0; fd.friction = 0.8
+        rider.CreateFixture(fd)
+        hang = _dyn(w, 8.0, 6.0); hs = b2CircleShape(api); hs.m_radius = 0.5; hang.CreateFixture(hs, 1.0)
+        jd = b2DistanceJointDef(); jd.Initialize(g, hang, (8.0, 10.0), (8.0, 6.0))
+        w.joint = w.CreateJoint(jd)
+        two = _dyn(w, -8.0, 1.0); a = b2PolygonShape(api); a.SetAsBox(0.5, 0.5); two.CreateFixture(a, 1.0)
+        b2 = b2PolygonShape(api); b2.SetAsBox(0.3, 0.3, (0.0, 0.8), 0.0)     # rides on top: one ground contact only
+        w.extra = two.CreateFixture(b2, 1.0)
+        w.plat, w.two = plat, two
+        return w, [plat, rider, hang, two]
+
+    def each(k, wg, wo):
+        for w in (wg, wo):
+            if k == 60:
+                w.DestroyJoint(w.joint)
+            if k == 90:
+                w.two.DestroyFixture(w.extra)
+            if k == 120:
+                w.DestroyBody(w.plat)
+    wg, wo = None, None
+
+    def build2(api):
+        w, out = build(api)
+        return w, out[1:]                                       # the platform gets destroyed: compare the others
+    both(gpu_api, oracle_api, build2, 180, each=each, tol_p=1e-4, tol_v=1e-3)

@@ -406,8 +406,12 @@ def test_tumbler_invariants(gpu_api, oracle_api):
         tg.Step(); to.Step()
     assert tg.m_count == to.m_count == n
     for t in (tg, to):
-        inside = sum(1 for b in t.bodies if abs(b.GetPosition().x) < 10.6 and -0.6 < b.GetPosition().y < 20.6)
-        assert inside == n
+        c = t.container._state()
+        for b in t.bodies:
+            p = b.GetPosition()
+            dx, dy = p.x - c.p.x, p.y - c.p.y
+            lx, ly = c.qc * dx + c.qs * dy, -c.qs * dx + c.qc * dy          # container frame
+            assert abs(lx) < 10.6 and abs(ly) < 10.6, (b.id, lx, ly)
     assert abs(tg.container.GetAngle() - to.container.GetAngle()) < 1e-3
     assert abs(tg.container.GetAngularVelocity() - to.container.GetAngularVelocity()) < 1e-3
     cg, co = tg.world.counts(), to.world.counts()
