@@ -79,6 +79,7 @@ struct DevWorld {
   float4* b_pos;     // c.x c.y a  -
   float4* b_pos0;    // c0.x c0.y a0 alpha0
   float4* b_vel;     // v.x v.y w  -
+  unsigned long long* b_acc;   // [3 * nBodies] contact warm-start velocity deltas (x, y, w) in 32.32 fixed point, zero between steps
   float4* b_force;   // f.x f.y torque -
   float4* b_mass;    // invMass invI mass I
   float4* b_lc;      // localCenter.x localCenter.y linearDamping angularDamping

@@ -54,21 +54,18 @@ __global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld 
     ++barIdx; PHASE_MARK(); } while (0)
   const bool haveTail = T < nColours && coff[T] < coff[nColours];
 
-  // contacts warm start (b2island.d:138-141), colour by colour
+  // contacts warm start (b2island.d:138-141): fold the per-body accumulators k_prepare filled into the velocities
   if (W.warmStarting) {
-    for (int c = 0; c < T; ++c) {
-      int beg = coff[c], end = coff[c + 1];
-      if (beg == end) continue;
-      if (contactRole) for (int s = beg + ctid; s < end; s += cnth) contact_warm_start(W, s);
-      GB();
+    const float k = 1.0f / 4294967296.0f;
+    for (int b = tid; b < W.nBodies; b += nth) {
+      const long long ax = (long long)__ldcg(&W.b_acc[3 * b]), ay = (long long)__ldcg(&W.b_acc[3 * b + 1]), aw = (long long)__ldcg(&W.b_acc[3 * b + 2]);
+      if ((ax | ay | aw) == 0) continue;
+      float4 vel = ldcg4(&W.b_vel[b]);
+      vel.x += (float)ax * k; vel.y += (float)ay * k; vel.z += (float)aw * k;
+      stcg4(&W.b_vel[b], vel);
+      __stcg(&W.b_acc[3 * b], 0ull); __stcg(&W.b_acc[3 * b + 1], 0ull); __stcg(&W.b_acc[3 * b + 2], 0ull);
     }
-    if (haveTail) {
-      if (tailBlock) for (int c = T; c < nColours; ++c) {
-        for (int s = coff[c] + threadIdx.x; s < coff[c + 1]; s += blockDim.x) contact_warm_start(W, s);
-        __syncthreads();
-      }
-      GB();
-    }
+    GB();
   }
   // joints: InitVelocityConstraints incl. their warm start (:143-146)
   for (int c = 0; c < nJointColours; ++c) {

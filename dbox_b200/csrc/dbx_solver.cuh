@@ -8,6 +8,12 @@ namespace dbx {
 // ------------------------------------------------------------------------------------------------ contact constraints
 // b2ContactSolver ctor + InitializeVelocityConstraints (contacts/b2contactsolver.d:244-450): one thread per solver contact.
 // `s` = solver slot to fill, `i` = contact slot; warmScale < 0 means "no warm starting" (TOI sub-steps, b2world.d:1419)
+DBX_D void acc_add(const DevWorld& W, int b, float x, float y, float w) {
+  const float k = 4294967296.0f;   // 2^32: scaling a float by a power of two is exact
+  atomicAdd(&W.b_acc[3 * b + 0], (unsigned long long)__float2ll_rn(x * k));
+  atomicAdd(&W.b_acc[3 * b + 1], (unsigned long long)__float2ll_rn(y * k));
+  atomicAdd(&W.b_acc[3 * b + 2], (unsigned long long)__float2ll_rn(w * k));
+}
 DBX_D void prepare_contact(const DevWorld& W, int s, int i, float warmScale) {
   {
     const int4 ids = W.c_ids[i];
@@ -103,6 +109,21 @@ DBX_D void prepare_contact(const DevWorld& W, int s, int i, float warmScale) {
     float4 imp = warmScale >= 0.0f ? make_float4(warmScale * cimp.x, warmScale * cimp.y, warmScale * cimp.z, warmScale * cimp.w)
                                    : make_float4(0, 0, 0, 0);
     if (pointCount < 2) { imp.z = 0.0f; imp.w = 0.0f; }
+    // b2ContactSolver.WarmStart (:452-489), order-free: the reference adds each contact's impulse to its two bodies one
+    // contact after the other; here every contact adds its velocity delta to a per-body 32.32 fixed-point accumulator
+    // (integer atomics commute, so the sum does not depend on the schedule) and k_solve folds the accumulators into the
+    // velocities in one pass.  That replaces one barrier-delimited phase per colour by a single one.
+    if (warmScale >= 0.0f && (imp.x != 0.0f || imp.y != 0.0f || imp.z != 0.0f || imp.w != 0.0f)) {
+      v2 P = V(0.0f, 0.0f); float LA = 0.0f, LB = 0.0f;
+      for (int k = 0; k < pointCount; ++k) {
+        const v2 Pk = (k == 0 ? imp.x : imp.z) * normal + (k == 0 ? imp.y : imp.w) * tangent;
+        P += Pk;
+        LA += cross(V(r[k].x, r[k].y), Pk);
+        LB += cross(V(r[k].z, r[k].w), Pk);
+      }
+      if (mA != 0.0f || iA != 0.0f) acc_add(W, bA, -(mA * P.x), -(mA * P.y), -(iA * LA));
+      if (mB != 0.0f || iB != 0.0f) acc_add(W, bB, mB * P.x, mB * P.y, iB * LB);
+    }
     W.s_body[s] = make_int2(bA, bB);
     W.s_v0[s] = make_float4(normal.x, normal.y, friction, tangentSpeed);
     W.s_v1[s] = make_float4(mA, iA, mB, iB);
@@ -132,25 +153,6 @@ DBX_D void store_vel(const DevWorld& W, int2 bd, const BodyVel& r, float mA, flo
 }
 
 // b2ContactSolver.WarmStart (:452-490)
-DBX_D void contact_warm_start(const DevWorld& W, int s) {
-  const int2 bd = W.s_body[s];
-  const float4 v0 = W.s_v0[s], v1 = W.s_v1[s], imp = W.s_imp[s];
-  const int pointCount = W.s_pc[s] & 0xFF;
-  const float mA = v1.x, iA = v1.y, mB = v1.z, iB = v1.w;
-  BodyVel bv = load_vel(W, bd);
-  const v2 normal = V(v0.x, v0.y), tangent = cross(normal, 1.0f);
-  for (int k = 0; k < pointCount; ++k) {
-    const float4 r = k == 0 ? W.s_r0[s] : W.s_r1[s];
-    const float ni = k == 0 ? imp.x : imp.z, ti = k == 0 ? imp.y : imp.w;
-    v2 P = ni * normal + ti * tangent;
-    bv.wA -= iA * cross(V(r.x, r.y), P);
-    bv.vA -= mA * P;
-    bv.wB += iB * cross(V(r.z, r.w), P);
-    bv.vB += mB * P;
-  }
-  store_vel(W, bd, bv, mA, iA, mB, iB);
-}
-
 // b2ContactSolver.SolveVelocityConstraints (:492-772): friction rows, then 1-point clamp or the 2-point block solver
 // constraint block of one solver contact, loadable ahead of the barrier that precedes its colour (only s_imp ever changes,
 // and only through the thread that owns the slot)

@@ -51,7 +51,7 @@ World::~World() {
   DevBuf<float4>* f4[] = {&b_xf, &b_xf0, &b_pos, &b_pos0, &b_vel, &b_force, &b_mass, &b_lc, &p_aabb, &p_fat, &bv_box, &c_m0, &c_m1, &c_imp, &c_mat,
                           &s_v0, &s_v1, &s_r0, &s_r1, &s_q0, &s_q1, &s_imp, &s_nm, &s_k, &s_p0, &s_p1, &s_p2, &j_anchor, &j_p0, &j_p1, &j_imp, &j_r, &j_lc, &j_m, &j_k0, &j_k1, &j_k2};
   for (auto* b : f4) b->release();
-  b_toiMin.release(); b_toiOther.release();
+  b_toiMin.release(); b_toiOther.release(); b_acc.release();
   DevBuf<int>* i1[] = {&b_toiEvt, &b_toiFlags, &e_contact, &e_ncand, &e_cand, &bv_pos, &b_wake, &b_root, &b_islAwake, &b_islMinSleep, &b_posNotOk, &b_ovf, &b_world, &f_body, &f_group, &p_key, &moveList, &bv_leaf, &bv_leafAlt,
                        &bv_parent, &bv_visit, &c_toiCount, &c_colour, &c_free, &c_work, &c_work2, &h_val, &s_contact, &s_hist, &s_pc, &s_root, &j_limit, &j_colour, &j_order, &j_root, &d_levels};
   for (auto* b : i1) b->release();
@@ -499,6 +499,7 @@ int World::reserveDevice(bool& rehash) {
   for (auto* b : bi) CUDA_OR_FAIL(b->reserve(capB, true, stream_), "body int");
   CUDA_OR_FAIL(b_mask.reserve(capB, true, stream_), "b_mask");
   CUDA_OR_FAIL(b_claim.reserve(capB, true, stream_), "b_claim");
+  CUDA_OR_FAIL(b_acc.reserve(3 * capB, false, stream_), "b_acc");
   CUDA_OR_FAIL(b_toiMin.reserve(capB, true, stream_), "b_toiMin"); CUDA_OR_FAIL(b_toiOther.reserve(capB, true, stream_), "b_toiOther");
   CUDA_OR_FAIL(b_toiEvt.reserve(capB, true, stream_), "b_toiEvt"); CUDA_OR_FAIL(b_toiFlags.reserve(capB, true, stream_), "b_toiFlags");
   // TOI events handled per pass of k_toi: at least one per resident warp, more for batched worlds (events of different
@@ -660,7 +661,7 @@ void World::refreshView() {
   w.nBodies = (int)bodies_.size() * nWorlds_;
   w.b_xf = b_xf.p; w.b_xf0 = b_xf0.p; w.b_pos = b_pos.p; w.b_pos0 = b_pos0.p; w.b_vel = b_vel.p; w.b_force = b_force.p; w.b_mass = b_mass.p; w.b_lc = b_lc.p;
   w.b_gs = b_gs.p; w.b_flags = b_flags.p; w.b_wake = b_wake.p; w.b_root = b_root.p; w.b_islAwake = b_islAwake.p; w.b_islMinSleep = b_islMinSleep.p;
-  w.b_toiMin = b_toiMin.p; w.b_toiOther = b_toiOther.p; w.b_toiEvt = b_toiEvt.p; w.b_toiFlags = b_toiFlags.p;
+  w.b_acc = b_acc.p; w.b_toiMin = b_toiMin.p; w.b_toiOther = b_toiOther.p; w.b_toiEvt = b_toiEvt.p; w.b_toiFlags = b_toiFlags.p;
   w.e_contact = e_contact.p; w.e_ncand = e_ncand.p; w.e_cand = e_cand.p; w.eventCap = (int)e_contact.cap; w.bv_pos = bv_pos.p;
   w.b_posNotOk = b_posNotOk.p; w.b_mask = b_mask.p; w.b_claim = b_claim.p; w.b_ovf = b_ovf.p; w.b_world = b_world.p;
   w.nFixtures = (int)fixtures_.size() * nWorlds_; w.f_body = f_body.p; w.f_mat = f_mat.p; w.f_filter = f_filter.p; w.f_group = f_group.p;

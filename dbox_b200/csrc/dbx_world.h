@@ -152,7 +152,7 @@ class World {
   DevWorld dw_{};
   DevBuf<Header> hdr_;
   DevBuf<float4> b_xf, b_xf0, b_pos, b_pos0, b_vel, b_force, b_mass, b_lc; DevBuf<float2> b_gs; DevBuf<uint32_t> b_flags;
-  DevBuf<unsigned long long> b_toiMin, b_toiOther; DevBuf<int> b_toiEvt, b_toiFlags, e_contact, e_ncand, e_cand, bv_pos;
+  DevBuf<unsigned long long> b_toiMin, b_toiOther, b_acc; DevBuf<int> b_toiEvt, b_toiFlags, e_contact, e_ncand, e_cand, bv_pos;
   DevBuf<int> b_wake, b_root, b_islAwake, b_islMinSleep, b_posNotOk, b_ovf, b_world; DevBuf<unsigned long long> b_mask, b_claim;
   DevBuf<int> f_body, f_group; DevBuf<float2> f_mat; DevBuf<uint32_t> f_filter;
   DevBuf<DShape> d_shapes;
