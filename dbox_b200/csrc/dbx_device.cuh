@@ -24,7 +24,8 @@ DBX_HD int body_type(uint32_t f) { return (int)((f & BF_TYPE_MASK) >> BF_TYPE_SH
 // low bits = b2Contact flags (b2contact.d:242-261); bit 8 = slot alive; bit 9 = either fixture is a sensor
 enum : uint32_t {
   CF_ISLAND = 0x0001, CF_TOUCHING = 0x0002, CF_ENABLED = 0x0004, CF_FILTER = 0x0008, CF_BULLET_HIT = 0x0010, CF_TOI = 0x0020,
-  CF_ALIVE = 0x0100, CF_SENSOR = 0x0200, CF_SOLVE = 0x0400 /* in an awake island this step */
+  CF_ALIVE = 0x0100, CF_SENSOR = 0x0200, CF_SOLVE = 0x0400 /* in an awake island this step */,
+  CF_FRESH = 0x0800 /* created by this step's FindNewContacts: the overlapped TOI pre-evaluation must not look at it */
 };
 enum { FXF_SENSOR = 1 };
 enum { PF_ALIVE = 1, PF_MOVED = 2 };
@@ -130,6 +131,10 @@ struct DevWorld {
   int4* ev_a;        // [evCap] contact events: (type | phase << 8 | step << 16, fixtureA, fixtureB, childA | childB << 16)
   int4* ev_b;        //         (bodyA, bodyB, pair key lo, pair key hi)
   int evCap;         // 0 = contact events off
+  int toiReset;      // k_toi: the per-body TOI scratch may be dirty (first step, bodies added) -> full reset phase
+  int toiClearMoves; // k_toi also empties the move buffer FindNewContacts left (saves two launches)
+  int toiClearForces;// k_toi also runs ClearForces (b2world.d:443-450) in its final body pass
+  int toiPre;        // k_toi: k_toi_pre already did the first evaluation of the contacts that existed before FindNewContacts
   int stepIndex;     // low 16 bits stamp the events of this step
   int2* bv_wr;       // [n-1] replica-index range of the leaves under an internal node
   int* bv_pos;       // proxy slot -> sorted leaf index
@@ -138,6 +143,7 @@ struct DevWorld {
   int2* pairs; int pairCap;   // proxy slots (lo, hi) in reference key order
   // ---- joints with collideConnected == false, as sorted (bodyLo << 32 | bodyHi)
   int nJointPairs; const unsigned long long* jp_keys;
+  const uint32_t* jp_bits;   // one bit per body: set if some joint forbids a collision of that body (skips the search above)
   // ---- contacts
   int cCap;
   unsigned long long* c_key;   // (refKeyLo << 32 | refKeyHi)

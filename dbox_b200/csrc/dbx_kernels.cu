@@ -91,11 +91,12 @@ DBX_D uint32_t update_contact(const DevWorld& W, int i, uint32_t flags, const in
   return flags;
 }
 
-__global__ void __launch_bounds__(256) k_collide(const __grid_constant__ DevWorld W) {
+__global__ void __launch_bounds__(256, 4) k_collide(const __grid_constant__ DevWorld W) {
   const int n = W.hdr->cHigh;
   GRID_STRIDE(i, n) {
     uint32_t flags = W.c_flags[i];
     if (!(flags & CF_ALIVE)) continue;
+    if (flags & CF_FRESH) { flags &= ~CF_FRESH; W.c_flags[i] = flags; }
     const int4 ids = W.c_ids[i];
     const int4 fx = W.c_fix[i];
     const uint32_t flA = W.b_flags[ids.z], flB = W.b_flags[ids.w];
@@ -590,6 +591,9 @@ DBX_D void query_proxy(const DevWorld& W, const int* leaves, int* stack, int cap
     __syncwarp();
     bool hit = false;
     bool isLeaf = node >= n - 1;
+    // the children are fetched together with the box, not after the overlap test: one L2 round trip per level, not two
+    int2 ch = make_int2(-1, -1);
+    if (node >= 0 && !isLeaf) ch = W.bv_child[node];
     if (node >= 0) {
       hit = overlap(fat, BX(__ldcg(&W.bv_box[node])));
       // replicas share coordinates: without this test every query would descend into every replica's subtree
@@ -614,7 +618,6 @@ DBX_D void query_proxy(const DevWorld& W, const int* leaves, int* stack, int cap
     int total = __popc(ballot);
     if (top + 2 * total > cap) { if (lane == 0) W.hdr->error = -5; break; }   // tree deeper than kQueryReserve: report, never corrupt
     if (push) {
-      int2 ch = W.bv_child[node];
       int base = top + 2 * offset;
       stack[base] = ch.x; stack[base + 1] = ch.y;
     }
@@ -662,7 +665,7 @@ DBX_D void add_pair(const DevWorld& W, int2 pr) {
   W.c_key[slot] = key;
   W.c_ids[slot] = make_int4(proxyA, proxyB, ia.z, ib.z);
   W.c_fix[slot] = make_int4(ia.x, ib.x, ia.w, ib.w);
-  W.c_flags[slot] = CF_ALIVE | CF_ENABLED | (sensor ? CF_SENSOR : 0);
+  W.c_flags[slot] = CF_ALIVE | CF_ENABLED | CF_FRESH | (sensor ? CF_SENSOR : 0);
   W.c_m0[slot] = make_float4(0, 0, 0, 0);
   W.c_m1[slot] = make_float4(0, 0, 0, 0);
   W.c_imp[slot] = make_float4(0, 0, 0, 0);
@@ -915,6 +918,7 @@ DBX_D void lbvh_enlarge(const DevWorld& W, int p) {
   }
 }
 __global__ void __launch_bounds__(256) k_lbvh_enlarge(const __grid_constant__ DevWorld W) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) W.hdr->nPairs = 0;   // first kernel of a FindNewContacts without rebuild
   const int nMoved = min(W.hdr->nMoved, W.moveCap);
   GRID_STRIDE(k, nMoved) lbvh_enlarge(W, W.moveList[k]);
 }
@@ -934,9 +938,16 @@ DBX_D void toi_publish(const DevWorld& W, int i, const int4 ids, uint32_t fa, ui
   if (body_type(fa) != BODY_STATIC) atomicMin(&W.b_toiMin[ids.z], prio);
   if (body_type(fb) != BODY_STATIC) atomicMin(&W.b_toiMin[ids.w], prio);
 }
-DBX_D bool toi_classify(const DevWorld& W, int i) {
+// `first`: this is the step's first look at the contact, which doubles as the reset of b2world.d:1131-1146 (m_stepComplete
+// is always true here: sub-stepping is not supported) -- forget the cached TOI, the island flag and the sub-step count
+DBX_D bool toi_classify(const DevWorld& W, int i, bool first) {
   uint32_t flags = W.c_flags[i];
   if (!(flags & CF_ALIVE)) return false;
+  if (first) {
+    if (flags & CF_FRESH) return false;
+    if (flags & (CF_TOI | CF_ISLAND)) { flags &= ~(CF_TOI | CF_ISLAND); W.c_flags[i] = flags; }
+    if (W.c_toiCount[i] != 0) W.c_toiCount[i] = 0;
+  }
   const int4 ids = W.c_ids[i];
   if ((flags & CF_TOI) && ((__ldcg(&W.b_toiFlags[ids.z]) | __ldcg(&W.b_toiFlags[ids.w])) & TF_INVAL)) { flags &= ~(CF_TOI | CF_ISLAND); W.c_flags[i] = flags; }
   if (!(flags & CF_ENABLED)) return false;
@@ -973,11 +984,11 @@ DBX_D void toi_compute(const DevWorld& W, int i) {
 }
 // one warp: scan contacts [.., n) in strides of the whole grid, queue the ones that need b2TimeOfImpact in `q` (>= 64 ints of
 // shared memory private to the warp) and run them 32 at a time
-DBX_D void toi_evaluate_all(const DevWorld& W, int n, int warp, int nwarps, int lane, int* q) {
+DBX_D void toi_evaluate_all(const DevWorld& W, int n, int warp, int nwarps, int lane, int* q, bool first) {
   int qn = 0;
   for (int base = warp * 32; base < n; base += nwarps * 32) {
     const int i = base + lane;
-    const bool need = i < n && toi_classify(W, i);
+    const bool need = i < n && toi_classify(W, i, first);
     const unsigned m = __ballot_sync(0xffffffffu, need);
     if (need) q[qn + __popc(m & ((1u << lane) - 1u))] = i;
     qn += __popc(m);
@@ -1121,33 +1132,33 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
   int tmark = 0;
 #define TMARK() do { if (W.phaseTimes && tid == 0 && tmark < 64) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); W.phaseTimes[3000 + tmark++] = t_; } } while (0)
   TMARK();
-  // reset (m_stepComplete is always true here: sub-stepping is not supported) (:1131-1146)
-  {
-    const int n = H->cHigh;
-    for (int i = tid; i < n; i += nth) {
-      uint32_t f = W.c_flags[i];
-      if (!(f & CF_ALIVE)) continue;
-      if (f & (CF_TOI | CF_ISLAND)) W.c_flags[i] = f & ~(CF_TOI | CF_ISLAND);
-      W.c_toiCount[i] = 0;
-      float4 mat = W.c_mat[i]; if (mat.w != 1.0f) { mat.w = 1.0f; W.c_mat[i] = mat; }
-    }
+  // The per-body TOI scratch is left clean by the previous launch (see the end of this kernel) and the per-contact part
+  // of the reset (:1131-1146) rides on the first classification; only a world whose scratch may be dirty (first step,
+  // bodies added since) pays for a reset phase.
+  if (W.toiReset) {
     for (int b = tid; b < W.nBodies; b += nth) {
       float4 p0 = W.b_pos0[b]; if (p0.w != 0.0f) { p0.w = 0.0f; W.b_pos0[b] = p0; }
       W.b_toiMin[b] = ~0ull; W.b_toiOther[b] = ~0ull; W.b_toiEvt[b] = -1; W.b_toiFlags[b] = 0;
     }
     if (tid == 0) H->nEvents = 0;
+    grid_barrier(&H->barrier, nb); TMARK();
   }
-  grid_barrier(&H->barrier, nb); TMARK();
+  if (W.toiClearMoves) {   // tail of the step's FindNewContacts (b2broadphase.d:190-191): forget the move buffer
+    const int nMoved = min(H->nMoved, W.moveCap);
+    for (int k = tid; k < nMoved; k += nth) { const int p = W.moveList[k]; W.p_flags[p] &= ~PF_MOVED; }
+  }
   for (int pass = 0; pass < 1024; ++pass) {
     // (a) TOI evaluation + per-body minima
     {
       const int n = *((volatile int*)&H->cHigh);
       // few contacts per thread (one big world): evaluate in place, every chain on its own warp; many (batched worlds):
       // gather the eligible ones so that b2TimeOfImpact runs on full warps
-      if (n <= 8 * nth) { for (int i = tid; i < n; i += nth) if (toi_classify(W, i)) toi_compute(W, i); }
-      else toi_evaluate_all(W, n, warp, nwarps, lane, stacks[wib]);
+      const bool first = pass == 0 && !W.toiPre;
+      if (n <= 8 * nth) { for (int i = tid; i < n; i += nth) if (toi_classify(W, i, first)) toi_compute(W, i); }
+      else toi_evaluate_all(W, n, warp, nwarps, lane, stacks[wib], first);
     }
     grid_barrier(&H->barrier, nb); TMARK();
+    if (pass == 0 && W.toiClearMoves && tid == 0) H->nMoved = 0;   // every CTA has read it; next used three barriers on
     // (b) winners: the minimum on every movable body they touch
     {
       const int n = *((volatile int*)&H->cHigh);
@@ -1241,6 +1252,28 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
     if (tid == 0) H->nMoved = 0;
     grid_barrier(&H->barrier, nb); TMARK();
   }
+  // leave the per-body scratch clean for the next step (every CTA is past the last arbitration phase here)
+  for (int b = tid; b < W.nBodies; b += nth) {
+    if (W.b_toiMin[b] != ~0ull) W.b_toiMin[b] = ~0ull;
+    if (W.b_toiOther[b] != ~0ull) W.b_toiOther[b] = ~0ull;
+    if (W.b_toiEvt[b] != -1) W.b_toiEvt[b] = -1;
+    if (W.b_toiFlags[b] != 0) W.b_toiFlags[b] = 0;
+    float4 p0 = W.b_pos0[b]; if (p0.w != 0.0f) { p0.w = 0.0f; W.b_pos0[b] = p0; }
+    if (W.toiClearForces) W.b_force[b] = make_float4(0, 0, 0, 0);
+  }
+  if (tid == 0) H->nEvents = 0;
+}
+
+// The first TOI evaluation of the step for the contacts that exist before FindNewContacts, as a plain kernel on a second
+// stream: it depends only on the solver's output, so it runs beside SynchronizeFixtures and the broadphase instead of
+// after them.  Contacts created meanwhile carry CF_FRESH and are left to k_toi.
+__global__ void __launch_bounds__(256) k_toi_pre(const __grid_constant__ DevWorld W) {
+  __shared__ int queue[8][64];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warp = tid >> 5, nwarps = nth >> 5;
+  const int n = W.hdr->cHigh;
+  if (n <= 8 * nth) { for (int i = tid; i < n; i += nth) if (toi_classify(W, i, true)) toi_compute(W, i); }
+  else toi_evaluate_all(W, n, warp, nwarps, lane, queue[wib], true);
 }
 
 #undef TMARK
@@ -1295,10 +1328,14 @@ size_t cub_temp_bytes(int maxProxies) {
 cudaError_t stage_toi(DevWorld& W, const LaunchCfg& L) {
   return launch_coop((const void*)k_toi, W, L);
 }
+cudaError_t stage_toi_pre(const DevWorld& W, const LaunchCfg& L, cudaStream_t aux) {
+  ++L.launches; k_toi_pre<<<L.gridWide / 2, 256, 0, aux>>>(W);
+  return cudaGetLastError();
+}
 
-cudaError_t stage_find_new_contacts(DevWorld& W, const LaunchCfg& L, bool rebuild) {
+cudaError_t stage_find_new_contacts(DevWorld& W, const LaunchCfg& L, bool rebuild, bool deferClear) {
   const int n = W.nProxies;
-  ++L.launches; k_bounds_init<<<1, 1, 0, L.stream>>>(W);
+  if (n == 0 || rebuild) { ++L.launches; k_bounds_init<<<1, 1, 0, L.stream>>>(W); }
   if (n > 0 && !rebuild) {
     ++L.launches; k_lbvh_enlarge<<<L.gridWide, 256, 0, L.stream>>>(W);
     ++L.launches; k_query<<<L.gridWide, 256, 0, L.stream>>>(W, W.bv_sorted);
@@ -1320,8 +1357,10 @@ cudaError_t stage_find_new_contacts(DevWorld& W, const LaunchCfg& L, bool rebuil
     ++L.launches; k_query<<<L.gridWide, 256, 0, L.stream>>>(W, sl);
     ++L.launches; k_add_pairs<<<L.gridWide, 256, 0, L.stream>>>(W);
   }
-  ++L.launches; k_clear_moves<<<L.gridWide, 256, 0, L.stream>>>(W);
-  ++L.launches; k_reset_moves<<<1, 1, 0, L.stream>>>(W);
+  if (!deferClear) {   // otherwise k_toi, which follows, empties the move buffer
+    ++L.launches; k_clear_moves<<<L.gridWide, 256, 0, L.stream>>>(W);
+    ++L.launches; k_reset_moves<<<1, 1, 0, L.stream>>>(W);
+  }
   return cudaGetLastError();
 }
 

@@ -21,8 +21,9 @@ cudaError_t stage_colour_and_sort(const DevWorld& W, const LaunchCfg& L);       
 cudaError_t stage_prepare(const DevWorld& W, const LaunchCfg& L);                 // contact constraint setup
 cudaError_t stage_solve(const DevWorld& W, const LaunchCfg& L);                   // warm start + iterations + finalize + sleep (one persistent kernel)
 cudaError_t stage_sync_fixtures(const DevWorld& W, const LaunchCfg& L);           // b2Body.SynchronizeFixtures / MoveProxy
-cudaError_t stage_find_new_contacts(DevWorld& W, const LaunchCfg& L, bool rebuild);       // LBVH rebuild + pair query + AddPair
-cudaError_t stage_toi(DevWorld& W, const LaunchCfg& L);                               // b2World.SolveTOI
+cudaError_t stage_find_new_contacts(DevWorld& W, const LaunchCfg& L, bool rebuild, bool deferClear);       // LBVH rebuild + pair query + AddPair
+cudaError_t stage_toi(DevWorld& W, const LaunchCfg& L);
+cudaError_t stage_toi_pre(const DevWorld& W, const LaunchCfg& L, cudaStream_t aux);                               // b2World.SolveTOI
 cudaError_t stage_rebuild_hash(const DevWorld& W, const LaunchCfg& L);
 cudaError_t stage_compact_contacts(DevWorld& W, const LaunchCfg& L, int high, int nAlive, void* scratch, unsigned long long* keyA, unsigned long long* keyB, int* valA, int* valB);
 cudaError_t stage_count(const DevWorld& W, const LaunchCfg& L);                   // refresh hdr->nContacts / nTouching / nAwake

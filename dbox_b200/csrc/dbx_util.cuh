@@ -108,7 +108,7 @@ DBX_D bool filter_should_collide(const DevWorld& W, int fA, int fB) {
 // b2Body.ShouldCollide (dynamics/b2body.d:1149-1170): at least one dynamic body, no joint that forbids it
 DBX_D bool body_should_collide(const DevWorld& W, int bA, int bB, uint32_t flA, uint32_t flB) {
   if (body_type(flA) != BODY_DYNAMIC && body_type(flB) != BODY_DYNAMIC) return false;
-  if (W.nJointPairs > 0) {
+  if (W.nJointPairs > 0 && ((W.jp_bits[bA >> 5] >> (bA & 31)) & (W.jp_bits[bB >> 5] >> (bB & 31)) & 1u)) {
     unsigned long long lo = (unsigned)min(bA, bB), hi = (unsigned)max(bA, bB);
     unsigned long long k = (lo << 32) | hi;
     int l = 0, r = W.nJointPairs;

@@ -46,12 +46,13 @@ World::~World() {
   if (!ok_) return;
   cudaSetDevice(device_);
   cudaStreamSynchronize(stream_);
+  if (aux_) { cudaStreamSynchronize(aux_); cudaStreamDestroy(aux_); cudaEventDestroy(evFork_); cudaEventDestroy(evJoin_); }
   if (wm_) cudaFreeHost(wm_);
   if (wmEv_) cudaEventDestroy(wmEv_);
   DevBuf<float4>* f4[] = {&b_xf, &b_xf0, &b_pos, &b_pos0, &b_vel, &b_force, &b_mass, &b_lc, &p_aabb, &p_fat, &bv_box, &c_m0, &c_m1, &c_imp, &c_mat,
                           &s_v0, &s_v1, &s_r0, &s_r1, &s_q0, &s_q1, &s_imp, &s_nm, &s_k, &s_p0, &s_p1, &s_p2, &j_anchor, &j_p0, &j_p1, &j_imp, &j_r, &j_lc, &j_m, &j_k0, &j_k1, &j_k2};
   for (auto* b : f4) b->release();
-  b_toiMin.release(); b_toiOther.release(); b_acc.release();
+  b_toiMin.release(); b_toiOther.release(); b_acc.release(); jp_bits.release();
   DevBuf<int>* i1[] = {&b_toiEvt, &b_toiFlags, &e_contact, &e_ncand, &e_cand, &bv_pos, &b_wake, &b_root, &b_islAwake, &b_islMinSleep, &b_posNotOk, &b_ovf, &b_world, &f_body, &f_group, &p_key, &moveList, &bv_leaf, &bv_leafAlt,
                        &bv_parent, &bv_visit, &c_toiCount, &c_colour, &c_free, &c_work, &c_work2, &h_val, &s_contact, &s_hist, &s_pc, &s_root, &j_limit, &j_colour, &j_order, &j_root, &d_levels};
   for (auto* b : i1) b->release();
@@ -474,6 +475,24 @@ int World::recolourJoints() {
   CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
   if (!jp.empty()) CUDA_OR_FAIL(cudaMemcpy(jp_keys.p, jp.data(), jp.size() * 8, cudaMemcpyHostToDevice), "jp up");
   CUDA_OR_FAIL(cudaMemcpy((char*)hdr_.p + offsetof(Header, jointColourOff), off, sizeof(off), cudaMemcpyHostToDevice), "joff up");
+  return uploadJointBits(jp);
+}
+
+// one bit per body that appears in the sorted joint-pair list: b2Body.ShouldCollide only searches the list for those
+int World::uploadJointBits(const std::vector<unsigned long long>& keys) {
+  const size_t nb = bodies_.size() * (size_t)nWorlds_;
+  if (&keys != &jpHost_) jpHost_ = keys;
+  jpBitsBodies_ = nb;
+  std::vector<uint32_t> bits((nb + 31) / 32 + 1, 0u);
+  for (unsigned long long k : keys) {
+    const size_t a = (size_t)(k >> 32), b = (size_t)(k & 0xFFFFFFFFull);
+    if (a < nb) bits[a >> 5] |= 1u << (a & 31);
+    if (b < nb) bits[b >> 5] |= 1u << (b & 31);
+  }
+  CUDA_OR_FAIL(jp_bits.reserve(bits.size(), false, stream_), "jp_bits");
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  CUDA_OR_FAIL(cudaMemcpy(jp_bits.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice), "jp bits up");
+  dw_.jp_bits = jp_bits.p;
   return 0;
 }
 
@@ -649,6 +668,8 @@ int World::push() {
     CUDA_OR_FAIL(upload_range(j_imp, 0, nD, [&](size_t k) { const HJoint& j = J(k); return f4(j.imp[0], j.imp[1], j.imp[2], j.imp[3]); }), "up j_imp");
     CUDA_OR_FAIL(upload_range(j_limit, 0, nD, [&](size_t k) { return J(k).limit; }), "up j_limit");
     jointsSynced_ = nJ; fullPushJoints_ = false; jointsChanged_ = false;
+  } else if (nJointPairs_ > 0 && nB > jpBitsBodies_) {
+    int rc = uploadJointBits(jpHost_); if (rc < 0) return rc;     // bodies were added: the bit array must cover them
   }
   refreshView();
   if (rehash) CUDA_OR_FAIL(stage_rebuild_hash(dw_, L_), "rehash");
@@ -670,7 +691,7 @@ void World::refreshView() {
   w.moveList = moveList.p; w.moveCap = (int)moveList.cap;
   w.bv_key = bv_key.p; w.bv_keyAlt = bv_keyAlt.p; w.bv_leaf = bv_leaf.p; w.bv_leafAlt = bv_leafAlt.p; w.bv_box = bv_box.p; w.bv_child = bv_child.p; w.bv_wr = bv_wr.p; w.bv_parent = bv_parent.p; w.bv_visit = bv_visit.p;
   w.pairs = pairs.p; w.pairCap = (int)pairs.cap;
-  w.nJointPairs = nJointPairs_; w.jp_keys = jp_keys.p;
+  w.nJointPairs = nJointPairs_; w.jp_keys = jp_keys.p; w.jp_bits = jp_bits.p;
   w.cCap = (int)c_key.cap; w.c_key = c_key.p; w.c_ids = c_ids.p; w.c_fix = c_fix.p; w.c_flags = c_flags.p; w.c_m0 = c_m0.p; w.c_m1 = c_m1.p; w.c_imp = c_imp.p; w.c_mk = c_mk.p;
   w.c_mat = c_mat.p; w.c_toiCount = c_toiCount.p; w.c_colour = c_colour.p; w.c_free = c_free.p; w.c_work = c_work.p; w.c_work2 = c_work2.p;
   w.hCap = (int)h_key.cap; w.h_key = h_key.p; w.h_val = h_val.p;
@@ -712,10 +733,10 @@ int World::checkDeviceError(bool sync) {
 
 // b2ContactManager.FindNewContacts.  The LBVH is rebuilt when the proxy set changed or every kRebuildPeriod calls; in
 // between it is widened for the moved proxies (lbvh_enlarge), which keeps the pair set exact at a fraction of the cost.
-int World::findNewContacts() {
+int World::findNewContacts(bool deferClear) {
   constexpr int kRebuildPeriod = 8;
   const bool rebuild = !treeValid_ || sinceRebuild_ >= kRebuildPeriod;
-  CUDA_OR_FAIL(stage_find_new_contacts(dw_, L_, rebuild), "find_new_contacts");
+  CUDA_OR_FAIL(stage_find_new_contacts(dw_, L_, rebuild, deferClear), "find_new_contacts");
   if (rebuild) { treeValid_ = true; sinceRebuild_ = 0; } else ++sinceRebuild_;
   return 0;
 }
@@ -741,6 +762,11 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents) {
   if (newFixture_) { int rf = findNewContacts(); if (rf < 0) return rf; newFixture_ = false; }   // :372-376
   setStepParams(dt, vi, pi);
   dw_.colourOverride = overrideLevels_ ? 1 : 0;
+  // TOI: the kernel leaves its per-body scratch clean; a world that has not run it yet, or has grown since, resets first.
+  // When the scratch is clean the first TOI evaluation is forked onto a second stream right after the solver.
+  const bool continuous = (flags_ & DBX_WORLD_CONTINUOUS) && dt > 0.0f;
+  const bool toiScratchDirty = !toiClean_ || toiBodies_ != bodies_.size() * (size_t)nWorlds_;
+  const bool toiPre = continuous && !toiScratchDirty && stepComplete_ && !overrideLevels_ && !(dw_.dbgFlags & 8);
   auto mark = [&](int i) { if (fineEvents || i == 0 || i == 1 || i == 3 || i == 5 || i == 7 || i == 8 || i == 9) cudaEventRecord(ev_[i], stream_); };
   mark(0);
   CUDA_OR_FAIL(stage_collide(dw_, L_), "collide");
@@ -754,17 +780,35 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents) {
     mark(4);
     CUDA_OR_FAIL(stage_solve(dw_, L_), "solve");
     mark(5);
+    if (toiPre) {
+      if (!aux_) {
+        CUDA_OR_FAIL(cudaStreamCreateWithFlags(&aux_, cudaStreamNonBlocking), "aux stream");
+        CUDA_OR_FAIL(cudaEventCreateWithFlags(&evFork_, cudaEventDisableTiming), "fork event");
+        CUDA_OR_FAIL(cudaEventCreateWithFlags(&evJoin_, cudaEventDisableTiming), "join event");
+      }
+      CUDA_OR_FAIL(cudaEventRecord(evFork_, stream_), "fork");
+      CUDA_OR_FAIL(cudaStreamWaitEvent(aux_, evFork_, 0), "fork wait");
+      CUDA_OR_FAIL(stage_toi_pre(dw_, L_, aux_), "toi_pre");
+      CUDA_OR_FAIL(cudaEventRecord(evJoin_, aux_), "join");
+    }
     CUDA_OR_FAIL(stage_sync_fixtures(dw_, L_), "sync_fixtures");
     mark(6);
-    { int rf = findNewContacts(); if (rf < 0) return rf; }
+    { int rf = findNewContacts(continuous); if (rf < 0) return rf; }
     mark(7);
   } else {
     for (int i = 2; i <= 7; ++i) cudaEventRecord(ev_[i], stream_);
   }
-  if ((flags_ & DBX_WORLD_CONTINUOUS) && dt > 0.0f) CUDA_OR_FAIL(stage_toi(dw_, L_), "toi");   // :414-419
+  if (toiPre) CUDA_OR_FAIL(cudaStreamWaitEvent(stream_, evJoin_, 0), "join wait");
+  if (continuous) {   // :414-419
+    dw_.toiReset = toiScratchDirty ? 1 : 0; dw_.toiPre = toiPre ? 1 : 0;
+    dw_.toiClearMoves = (stepComplete_ && dt > 0.0f) ? 1 : 0;      // this step's FindNewContacts left its move buffer to us
+    dw_.toiClearForces = (flags_ & DBX_WORLD_AUTO_CLEAR_FORCES) ? 1 : 0;
+    CUDA_OR_FAIL(stage_toi(dw_, L_), "toi");
+    toiClean_ = true; toiBodies_ = bodies_.size() * (size_t)nWorlds_;
+  }
   mark(8);
   if (dt > 0.0f) inv_dt0 = dw_.inv_dt;
-  if (flags_ & DBX_WORLD_AUTO_CLEAR_FORCES) CUDA_OR_FAIL(launch_clear_forces(dw_, L_), "clear_forces");
+  if ((flags_ & DBX_WORLD_AUTO_CLEAR_FORCES) && !continuous) CUDA_OR_FAIL(launch_clear_forces(dw_, L_), "clear_forces");   // else k_toi did it
   mark(9);
   evValid_ = true; evFine_ = fineEvents;
   ++stepCount_;
@@ -802,14 +846,14 @@ int World::timeSteps(float dt, int vi, int pi, int n, bool flushL2, float* total
   if (flushL2) CUDA_OR_FAIL(flushBuf_.reserve(flushBytes, false, stream_), "flush buffer");
   double total = 0.0, stage[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int k = 0; k < n; ++k) {
-    int rc = enqueueStep(dt, vi, pi, true); if (rc < 0) return rc;
+    int rc = enqueueStep(dt, vi, pi, stageMs != nullptr); if (rc < 0) return rc;
     if (bodies_.empty()) continue;
     if (flushL2) CUDA_OR_FAIL(cudaMemsetAsync(flushBuf_.p, k & 0xFF, flushBytes, stream_), "l2 flush");
     CUDA_OR_FAIL(cudaEventSynchronize(ev_[9]), "event sync");
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, ev_[0], ev_[9]);
     total += ms;
-    for (int i = 0; i < 9; ++i) { float t = 0.0f; cudaEventElapsedTime(&t, ev_[i], ev_[i + 1]); stage[i] += t; }
+    if (stageMs) for (int i = 0; i < 9; ++i) { float t = 0.0f; cudaEventElapsedTime(&t, ev_[i], ev_[i + 1]); stage[i] += t; }
   }
   if (totalMs) *totalMs = (float)total;
   if (stageMs) for (int i = 0; i < 9; ++i) stageMs[i] = n > 0 ? (float)(stage[i] / n) : 0.0f;
@@ -1396,6 +1440,7 @@ int World::replicate(int copies) {
       CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
       CUDA_OR_FAIL(cudaMemcpy(jp_keys.p, all.data(), all.size() * 8, cudaMemcpyHostToDevice), "jp up");
       nJointPairs_ *= copies;
+      { int rb = uploadJointBits(all); if (rb < 0) return rb; }
     }
     jointBlocks_ = (int)std::min<size_t>(((size_t)jointBlocks_ * L_.coopThreads * copies + L_.coopThreads - 1) / L_.coopThreads, (size_t)L_.coopBlocks / 4);
   }

@@ -119,7 +119,7 @@ class World {
   int destroyContactsWhere(int body, int fixture, int otherBody, bool flagOnly);
   int recolourJoints();
   int reserveDevice(bool& rehash);
-  int findNewContacts();
+  int findNewContacts(bool deferClear = false);
   int compactContacts();
   void setStepParams(float dt, int vi, int pi);
 
@@ -158,7 +158,9 @@ class World {
   DevBuf<DShape> d_shapes;
   DevBuf<int4> p_ids; DevBuf<int> p_key, moveList; DevBuf<float4> p_aabb, p_fat; DevBuf<uint32_t> p_flags;
   DevBuf<unsigned long long> bv_key, bv_keyAlt; DevBuf<int> bv_leaf, bv_leafAlt, bv_parent, bv_visit; DevBuf<float4> bv_box; DevBuf<int2> bv_child, bv_wr;
-  DevBuf<int2> pairs; DevBuf<unsigned long long> jp_keys;
+  DevBuf<int2> pairs; DevBuf<unsigned long long> jp_keys; DevBuf<uint32_t> jp_bits;
+  int uploadJointBits(const std::vector<unsigned long long>& keys);
+  std::vector<unsigned long long> jpHost_; size_t jpBitsBodies_ = 0;
   DevBuf<unsigned long long> c_key, h_key; DevBuf<int4> c_ids, c_fix; DevBuf<uint32_t> c_flags; DevBuf<float4> c_m0, c_m1, c_imp, c_mat; DevBuf<uint4> c_mk;
   DevBuf<int> c_toiCount, c_colour, c_free, c_work, c_work2, h_val;
   DevBuf<int> s_contact, s_hist, s_pc, s_root; DevBuf<int2> s_body; DevBuf<float4> s_v0, s_v1, s_r0, s_r1, s_q0, s_q1, s_imp, s_nm, s_k, s_p0, s_p1, s_p2; DevBuf<float2> s_p3;
@@ -175,6 +177,8 @@ class World {
   // the copy that has landed and doubles the pool before it can overflow
   int* wm_ = nullptr; cudaEvent_t wmEv_ = nullptr; bool wmPending_ = false; size_t contactFloor_ = 0;
   int growContactsIfNeeded();
+  // second stream for the overlapped TOI pre-evaluation (fork after the solver, join before k_toi)
+  cudaStream_t aux_ = nullptr; cudaEvent_t evFork_ = nullptr, evJoin_ = nullptr; bool toiClean_ = false; size_t toiBodies_ = 0;
   std::vector<int> lastReadSlots_;
 };
 
