@@ -65,7 +65,8 @@ struct Header {
   int nCtEvents;      // contact begin/end events recorded since the last poll (may exceed evCap: the surplus is lost and reported)
   unsigned barrier;   // grid barrier ticket counter for the persistent kernels
   unsigned epoch;     // colouring round stamp
-  unsigned long long toiMin;  // (alpha bits << 32 | contact slot) arg-min for the TOI loop
+  int nFresh;         // contacts created by the current FindNewContacts, listed in c_work for k_toi's first pass
+  int _pad2;
   float bounds[4];    // world bounds of fat AABB centres (Morton normalisation), as ordered ints
   int colourOff[kMaxColours + 1];   // solver order: contacts of colour c are [colourOff[c], colourOff[c+1])
   int jointColourOff[kMaxJointColours + 1];
@@ -134,6 +135,7 @@ struct DevWorld {
   int toiReset;      // k_toi: the per-body TOI scratch may be dirty (first step, bodies added) -> full reset phase
   int toiClearMoves; // k_toi also empties the move buffer FindNewContacts left (saves two launches)
   int toiClearForces;// k_toi also runs ClearForces (b2world.d:443-450) in its final body pass
+  int toiMode;       // k_toi: 1 = only the first evaluation, launched as a plain kernel on the second stream (no grid barrier is reached)
   int toiPre;        // k_toi: k_toi_pre already did the first evaluation of the contacts that existed before FindNewContacts
   int stepIndex;     // low 16 bits stamp the events of this step
   int2* bv_wr;       // [n-1] replica-index range of the leaves under an internal node

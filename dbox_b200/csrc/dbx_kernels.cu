@@ -463,7 +463,7 @@ DBX_D float ord2f(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 
 __global__ void k_bounds_init(const __grid_constant__ DevWorld W) {
   unsigned* b = (unsigned*)W.hdr->bounds;
   b[0] = b[1] = 0xFFFFFFFFu; b[2] = b[3] = 0u;
-  W.hdr->nPairs = 0;
+  W.hdr->nPairs = 0; W.hdr->nFresh = 0;
 }
 __global__ void __launch_bounds__(256) k_bounds(const __grid_constant__ DevWorld W) {
   float lx = FLT_MAX, ly = FLT_MAX, hx = -FLT_MAX, hy = -FLT_MAX;
@@ -666,6 +666,7 @@ DBX_D void add_pair(const DevWorld& W, int2 pr) {
   W.c_ids[slot] = make_int4(proxyA, proxyB, ia.z, ib.z);
   W.c_fix[slot] = make_int4(ia.x, ib.x, ia.w, ib.w);
   W.c_flags[slot] = CF_ALIVE | CF_ENABLED | CF_FRESH | (sensor ? CF_SENSOR : 0);
+  { const int k = atomicAdd(&W.hdr->nFresh, 1); if (k < W.cCap) W.c_work[k] = slot; }   // c_work is idle between the colouring pass and the next step
   W.c_m0[slot] = make_float4(0, 0, 0, 0);
   W.c_m1[slot] = make_float4(0, 0, 0, 0);
   W.c_imp[slot] = make_float4(0, 0, 0, 0);
@@ -918,7 +919,7 @@ DBX_D void lbvh_enlarge(const DevWorld& W, int p) {
   }
 }
 __global__ void __launch_bounds__(256) k_lbvh_enlarge(const __grid_constant__ DevWorld W) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) W.hdr->nPairs = 0;   // first kernel of a FindNewContacts without rebuild
+  if (blockIdx.x == 0 && threadIdx.x == 0) { W.hdr->nPairs = 0; W.hdr->nFresh = 0; }   // first kernel of a FindNewContacts without rebuild
   const int nMoved = min(W.hdr->nMoved, W.moveCap);
   GRID_STRIDE(k, nMoved) lbvh_enlarge(W, W.moveList[k]);
 }
@@ -1143,7 +1144,7 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
     if (tid == 0) H->nEvents = 0;
     grid_barrier(&H->barrier, nb); TMARK();
   }
-  if (W.toiClearMoves) {   // tail of the step's FindNewContacts (b2broadphase.d:190-191): forget the move buffer
+  if (W.toiClearMoves && W.toiMode == 0) {   // tail of the step's FindNewContacts (b2broadphase.d:190-191): forget the move buffer
     const int nMoved = min(H->nMoved, W.moveCap);
     for (int k = tid; k < nMoved; k += nth) { const int p = W.moveList[k]; W.p_flags[p] &= ~PF_MOVED; }
   }
@@ -1153,10 +1154,20 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
       const int n = *((volatile int*)&H->cHigh);
       // few contacts per thread (one big world): evaluate in place, every chain on its own warp; many (batched worlds):
       // gather the eligible ones so that b2TimeOfImpact runs on full warps
-      const bool first = pass == 0 && !W.toiPre;
-      if (n <= 8 * nth) { for (int i = tid; i < n; i += nth) if (toi_classify(W, i, first)) toi_compute(W, i); }
+      const bool first = pass == 0 && (!W.toiPre || W.toiMode == 1);
+      const int nFresh = *((volatile int*)&H->nFresh);
+      if (pass == 0 && W.toiPre && W.toiMode == 0 && nFresh <= W.cCap) {
+        // k_toi_pre has evaluated and published everything except the contacts FindNewContacts created meanwhile
+        // (one per warp while they last: a b2TimeOfImpact chain is long and divergent)
+        const int stride = nFresh * 32 <= nth ? 32 : 1;
+        if (tid % stride == 0) for (int k = tid / stride; k < nFresh; k += nth / stride) { const int i = W.c_work[k]; if (toi_classify(W, i, false)) toi_compute(W, i); }
+      } else if (n <= 8 * nth) { for (int i = tid; i < n; i += nth) if (toi_classify(W, i, first)) toi_compute(W, i); }
       else toi_evaluate_all(W, n, warp, nwarps, lane, stacks[wib], first);
     }
+    // The overlapped first evaluation is this same kernel (same code, warm instruction caches) launched as a plain grid
+    // on the second stream: it stops here, before any grid barrier.  Contacts FindNewContacts creates meanwhile carry
+    // CF_FRESH and are left to the real launch.
+    if (W.toiMode == 1) return;
     grid_barrier(&H->barrier, nb); TMARK();
     if (pass == 0 && W.toiClearMoves && tid == 0) H->nMoved = 0;   // every CTA has read it; next used three barriers on
     // (b) winners: the minimum on every movable body they touch
@@ -1264,18 +1275,6 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
   if (tid == 0) H->nEvents = 0;
 }
 
-// The first TOI evaluation of the step for the contacts that exist before FindNewContacts, as a plain kernel on a second
-// stream: it depends only on the solver's output, so it runs beside SynchronizeFixtures and the broadphase instead of
-// after them.  Contacts created meanwhile carry CF_FRESH and are left to k_toi.
-__global__ void __launch_bounds__(256) k_toi_pre(const __grid_constant__ DevWorld W) {
-  __shared__ int queue[8][64];
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warp = tid >> 5, nwarps = nth >> 5;
-  const int n = W.hdr->cHigh;
-  if (n <= 8 * nth) { for (int i = tid; i < n; i += nth) if (toi_classify(W, i, true)) toi_compute(W, i); }
-  else toi_evaluate_all(W, n, warp, nwarps, lane, queue[wib], true);
-}
-
 #undef TMARK
 // ------------------------------------------------------------------------------------------------ host launchers
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return _e; } while (0)
@@ -1329,7 +1328,11 @@ cudaError_t stage_toi(DevWorld& W, const LaunchCfg& L) {
   return launch_coop((const void*)k_toi, W, L);
 }
 cudaError_t stage_toi_pre(const DevWorld& W, const LaunchCfg& L, cudaStream_t aux) {
-  ++L.launches; k_toi_pre<<<L.gridWide / 2, 256, 0, aux>>>(W);
+  DevWorld P = W;
+  P.toiMode = 1; P.toiReset = 0; P.toiPre = 0; P.phaseTimes = nullptr;
+  // three quarters of the SMs: at 125 registers x 512 threads a CTA owns a whole register file, and the broadphase kernels this
+  // overlaps with need somewhere to run
+  ++L.launches; k_toi<<<(3 * L.coopBlocks + 3) / 4, L.coopThreads, 0, aux>>>(P);
   return cudaGetLastError();
 }
 

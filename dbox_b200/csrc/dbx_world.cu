@@ -800,7 +800,7 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents) {
   }
   if (toiPre) CUDA_OR_FAIL(cudaStreamWaitEvent(stream_, evJoin_, 0), "join wait");
   if (continuous) {   // :414-419
-    dw_.toiReset = toiScratchDirty ? 1 : 0; dw_.toiPre = toiPre ? 1 : 0;
+    dw_.toiReset = toiScratchDirty ? 1 : 0; dw_.toiPre = toiPre ? 1 : 0; dw_.toiMode = 0;
     dw_.toiClearMoves = (stepComplete_ && dt > 0.0f) ? 1 : 0;      // this step's FindNewContacts left its move buffer to us
     dw_.toiClearForces = (flags_ & DBX_WORLD_AUTO_CLEAR_FORCES) ? 1 : 0;
     CUDA_OR_FAIL(stage_toi(dw_, L_), "toi");
