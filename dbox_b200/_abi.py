@@ -15,7 +15,8 @@ BODY_ISLAND, BODY_AWAKE, BODY_AUTOSLEEP, BODY_BULLET, BODY_FIXED_ROTATION, BODY_
 CONTACT_ISLAND, CONTACT_TOUCHING, CONTACT_ENABLED, CONTACT_FILTER, CONTACT_BULLET_HIT, CONTACT_TOI = 1, 2, 4, 8, 0x10, 0x20
 SHAPE_CIRCLE, SHAPE_EDGE, SHAPE_POLYGON, SHAPE_CHAIN = 0, 1, 2, 3
 MANIFOLD_CIRCLES, MANIFOLD_FACE_A, MANIFOLD_FACE_B = 0, 1, 2
-JOINT_REVOLUTE, JOINT_DISTANCE = 1, 3
+JOINT_REVOLUTE, JOINT_PRISMATIC, JOINT_DISTANCE, JOINT_PULLEY, JOINT_MOUSE, JOINT_GEAR = 1, 2, 3, 4, 5, 6
+JOINT_WHEEL, JOINT_WELD, JOINT_FRICTION, JOINT_ROPE, JOINT_MOTOR = 7, 8, 9, 10, 11
 WORLD_ALLOW_SLEEP, WORLD_WARM_STARTING, WORLD_CONTINUOUS, WORLD_SUB_STEPPING, WORLD_AUTO_CLEAR_FORCES = 1, 2, 4, 8, 0x10
 WORLD_DEFAULT_FLAGS = 0x17
 
@@ -58,7 +59,12 @@ class JointDef(C.Structure):
                 ("localAnchorA", Vec2), ("localAnchorB", Vec2), ("referenceAngle", c_f32), ("enableLimit", c_i32),
                 ("lowerAngle", c_f32), ("upperAngle", c_f32), ("enableMotor", c_i32), ("motorSpeed", c_f32),
                 ("maxMotorTorque", c_f32), ("length", c_f32), ("frequencyHz", c_f32), ("dampingRatio", c_f32),
-                ("userData", c_u64)]
+                ("userData", c_u64),
+                ("localAxisA", Vec2), ("lowerTranslation", c_f32), ("upperTranslation", c_f32), ("maxMotorForce", c_f32),
+                ("maxLength", c_f32), ("maxForce", c_f32), ("maxTorque", c_f32), ("linearOffset", Vec2),
+                ("angularOffset", c_f32), ("correctionFactor", c_f32), ("target", Vec2), ("groundAnchorA", Vec2),
+                ("groundAnchorB", Vec2), ("lengthA", c_f32), ("lengthB", c_f32), ("ratio", c_f32), ("joint1", c_i32),
+                ("joint2", c_i32), ("_pad", c_i32)]
 
 
 class BodyState(C.Structure):
@@ -111,7 +117,7 @@ class Caps(C.Structure):
 
 
 # sizes the header implies (checked by tests/test_abi.py and by the library's own static_asserts)
-EXPECTED_SIZES = {"Vec2": 8, "AABB": 16, "BodyDef": 72, "Shape": 240, "FixtureDef": 32, "JointDef": 80, "BodyState": 116,
+EXPECTED_SIZES = {"Vec2": 8, "AABB": 16, "BodyDef": 72, "Shape": 240, "FixtureDef": 32, "JointDef": 176, "BodyState": 116,
                   "ManifoldPoint": 20, "Manifold": 64, "ContactRec": 104, "ProxyRec": 44, "JointState": 24, "Counts": 44,
                   "Profile": 32, "Caps": 20, "ContactEvent": 36}
 
@@ -143,6 +149,7 @@ PROTOTYPES = {
     "fixture_destroy": (c_i32, [W, c_i32]),
     "joint_create": (c_i32, [W, P(JointDef)]),
     "joint_destroy": (c_i32, [W, c_i32]),
+    "joint_set_target": (c_i32, [W, c_i32, c_f32, c_f32]),
     "world_step": (c_i32, [W, c_f32, c_i32, c_i32]),
     "world_step_n": (c_i32, [W, c_f32, c_i32, c_i32, c_i32]),
     "world_clear_forces": (c_i32, [W]),

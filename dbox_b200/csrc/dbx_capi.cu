@@ -7,7 +7,7 @@ using namespace dbx;
 
 struct dbx_world { World w; dbx_world(float gx, float gy, int dev, const dbx_caps* caps) : w(gx, gy, dev, caps) {} };
 
-static_assert(sizeof(dbx_body_def) == 72 && sizeof(dbx_shape) == 240 && sizeof(dbx_fixture_def) == 32 && sizeof(dbx_joint_def) == 80, "ABI layout");
+static_assert(sizeof(dbx_body_def) == 72 && sizeof(dbx_shape) == 240 && sizeof(dbx_fixture_def) == 32 && sizeof(dbx_joint_def) == 176, "ABI layout");
 static_assert(sizeof(dbx_body_state) == 116 && sizeof(dbx_manifold) == 64 && sizeof(dbx_contact_rec) == 104 && sizeof(dbx_proxy_rec) == 44 && sizeof(dbx_contact_event) == 36, "ABI layout");
 
 #define W_OR_INVALID(w) do { if (!(w) || !(w)->w.ok()) return DBX_E_INVALID; } while (0)
@@ -30,7 +30,17 @@ void dbx_default_fixture_def(dbx_fixture_def* d) {
 void dbx_default_joint_def(dbx_joint_def* d, int32_t type) {
   std::memset(d, 0, sizeof(*d));
   d->type = type;
-  if (type == DBX_JOINT_DISTANCE) d->length = 1.0f;
+  // the defaults of the reference's def structs
+  if (type == DBX_JOINT_DISTANCE) d->length = 1.0f;                                              // b2distancejoint.d:43-52
+  if (type == DBX_JOINT_PRISMATIC || type == DBX_JOINT_WHEEL) d->localAxisA = dbx_vec2{1.0f, 0.0f}; // b2prismaticjoint.d:46, b2wheeljoint.d:46
+  if (type == DBX_JOINT_WHEEL) { d->frequencyHz = 2.0f; d->dampingRatio = 0.7f; }                // b2wheeljoint.d:50-52
+  if (type == DBX_JOINT_MOUSE) { d->frequencyHz = 5.0f; d->dampingRatio = 0.7f; }                // b2mousejoint.d:43-46
+  if (type == DBX_JOINT_MOTOR) { d->maxForce = 1.0f; d->maxTorque = 1.0f; d->correctionFactor = 0.3f; }   // b2motorjoint.d:43-49
+  if (type == DBX_JOINT_ROPE) { d->localAnchorA = dbx_vec2{-1.0f, 0.0f}; d->localAnchorB = dbx_vec2{1.0f, 0.0f}; }   // b2ropejoint.d:47-50
+  if (type == DBX_JOINT_PULLEY) {                                                                // b2pulleyjoint.d:47-57
+    d->groundAnchorA = dbx_vec2{-1.0f, 1.0f}; d->groundAnchorB = dbx_vec2{1.0f, 1.0f};
+    d->localAnchorA = dbx_vec2{-1.0f, 0.0f}; d->localAnchorB = dbx_vec2{1.0f, 0.0f}; d->ratio = 1.0f; d->collideConnected = 1;
+  }
 }
 
 // ---- shape helpers (setup time, host): same arithmetic as the reference's shape classes
@@ -138,6 +148,7 @@ int32_t dbx_fixture_create(dbx_world* w, int32_t body, const dbx_fixture_def* de
 int32_t dbx_fixture_destroy(dbx_world* w, int32_t fixture) { W_OR_INVALID(w); return w->w.destroyFixture(fixture); }
 int32_t dbx_joint_create(dbx_world* w, const dbx_joint_def* def) { W_OR_INVALID(w); if (!def) return DBX_E_INVALID; return w->w.createJoint(*def); }
 int32_t dbx_joint_destroy(dbx_world* w, int32_t joint) { W_OR_INVALID(w); return w->w.destroyJoint(joint); }
+int32_t dbx_joint_set_target(dbx_world* w, int32_t joint, float x, float y) { W_OR_INVALID(w); return w->w.setJointTarget(joint, x, y); }
 
 int32_t dbx_world_step(dbx_world* w, float dt, int32_t vi, int32_t pi) { W_OR_INVALID(w); return w->w.step(dt, vi, pi, 1); }
 int32_t dbx_world_step_n(dbx_world* w, float dt, int32_t vi, int32_t pi, int32_t n) { W_OR_INVALID(w); return w->w.step(dt, vi, pi, n); }

@@ -2,6 +2,7 @@
 // Included by dbx_solve.cu (the persistent island solver) and by dbx_kernels.cu (TOI mini-islands).
 #pragma once
 #include "dbx_util.cuh"
+#include "dbx_joints2.cuh"
 
 namespace dbx {
 
@@ -338,7 +339,12 @@ DBX_D void joint_init(const DevWorld& W, int j) {
   W.j_m[j] = make_float4(mA, iA, mB, iB);
   W.j_root[j] = body_type(W.b_flags[bA]) != BODY_STATIC ? W.b_root[bA] : W.b_root[bB];
   float4 imp = W.j_imp[j];
-  if (ids.x == JT_REVOLUTE) {
+  if (ids.x != JT_REVOLUTE && ids.x != JT_DISTANCE) {
+    JCtx c; c.mA = mA; c.iA = iA; c.mB = mB; c.iB = iB; c.rA = rA; c.rB = rB; c.cA = V(posA.x, posA.y); c.cB = V(posB.x, posB.y);
+    c.aA = aA; c.aB = aB; c.qA = qA; c.qB = qB; c.vA = vA; c.vB = vB; c.wA = wA; c.wB = wB; c.imp = imp;
+    joint2_init(W, j, ids.x, ids.w, bB, c);
+    vA = c.vA; vB = c.vB; wA = c.wA; wB = c.wB; imp = c.imp;
+  } else if (ids.x == JT_REVOLUTE) {
     const float4 p0 = W.j_p0[j];
     const bool enableLimit = (ids.w & 2) != 0, enableMotor = (ids.w & 4) != 0;
     const bool fixedRotation = (iA + iB == 0.0f);
@@ -427,7 +433,11 @@ DBX_D void joint_solve_velocity(const DevWorld& W, int j) {
   float4 velA = ldcg4(&W.b_vel[bA]), velB = ldcg4(&W.b_vel[bB]);
   v2 vA = V(velA.x, velA.y), vB = V(velB.x, velB.y); float wA = velA.z, wB = velB.z;
   float4 imp = W.j_imp[j];
-  if (ids.x == JT_REVOLUTE) {
+  if (ids.x != JT_REVOLUTE && ids.x != JT_DISTANCE) {
+    JCtx c; c.mA = mA; c.iA = iA; c.mB = mB; c.iB = iB; c.rA = rA; c.rB = rB; c.vA = vA; c.vB = vB; c.wA = wA; c.wB = wB; c.imp = imp;
+    joint2_solve_velocity(W, j, ids.x, ids.w, c);
+    vA = c.vA; vB = c.vB; wA = c.wA; wB = c.wB; imp = c.imp;
+  } else if (ids.x == JT_REVOLUTE) {
     const float4 p0 = W.j_p0[j], p1 = W.j_p1[j];
     const float4 k0 = W.j_k0[j], k1 = W.j_k1[j], k2 = W.j_k2[j];
     const bool enableLimit = (ids.w & 2) != 0, enableMotor = (ids.w & 4) != 0;
@@ -505,7 +515,11 @@ DBX_D bool joint_solve_position(const DevWorld& W, int j) {
   float4 pa = ldcg4(&W.b_pos[bA]), pb = ldcg4(&W.b_pos[bB]);
   v2 cA = V(pa.x, pa.y), cB = V(pb.x, pb.y); float aA = pa.z, aB = pb.z;
   bool ok;
-  if (ids.x == JT_REVOLUTE) {
+  if (ids.x != JT_REVOLUTE && ids.x != JT_DISTANCE) {
+    const Rot qA = rot_from_angle(aA), qB = rot_from_angle(aB);
+    const v2 rA = mul(qA, V(anc.x, anc.y) - V(lc.x, lc.y)), rB = mul(qB, V(anc.z, anc.w) - V(lc.z, lc.w));
+    ok = joint2_solve_position(W, j, ids.x, ids.w, mA, iA, mB, iB, rA, rB, qA, cA, aA, cB, aB);
+  } else if (ids.x == JT_REVOLUTE) {
     const float4 p0 = W.j_p0[j];
     const float motorMass = W.j_k0[j].w;
     const bool enableLimit = (ids.w & 2) != 0;

@@ -50,7 +50,7 @@ World::~World() {
   if (wm_) cudaFreeHost(wm_);
   if (wmEv_) cudaEventDestroy(wmEv_);
   DevBuf<float4>* f4[] = {&b_xf, &b_xf0, &b_pos, &b_pos0, &b_vel, &b_force, &b_mass, &b_lc, &p_aabb, &p_fat, &bv_box, &c_m0, &c_m1, &c_imp, &c_mat,
-                          &s_v0, &s_v1, &s_r0, &s_r1, &s_q0, &s_q1, &s_imp, &s_nm, &s_k, &s_p0, &s_p1, &s_p2, &j_anchor, &j_p0, &j_p1, &j_imp, &j_r, &j_lc, &j_m, &j_k0, &j_k1, &j_k2};
+                          &s_v0, &s_v1, &s_r0, &s_r1, &s_q0, &s_q1, &s_imp, &s_nm, &s_k, &s_p0, &s_p1, &s_p2, &j_anchor, &j_p0, &j_p1, &j_imp, &j_r, &j_lc, &j_m, &j_k0, &j_k1, &j_k2, &j_k3};
   for (auto* b : f4) b->release();
   b_toiMin.release(); b_toiOther.release(); b_acc.release(); jp_bits.release();
   DevBuf<int>* i1[] = {&b_toiEvt, &b_toiFlags, &e_contact, &e_ncand, &e_cand, &bv_pos, &b_wake, &b_root, &b_islAwake, &b_islMinSleep, &b_posNotOk, &b_ovf, &b_world, &f_body, &f_group, &p_key, &moveList, &bv_leaf, &bv_leafAlt,
@@ -330,9 +330,22 @@ int World::destroyBody(int b) {
 
 int World::createJoint(const dbx_joint_def& d) {
   if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
-  if (d.type != DBX_JOINT_REVOLUTE && d.type != DBX_JOINT_DISTANCE) { set_last_error("joint type not in this build's hot-path scope"); return DBX_E_UNSUPPORTED; }
+  if (d.type < DBX_JOINT_REVOLUTE || d.type > DBX_JOINT_MOTOR || d.type == DBX_JOINT_GEAR) { set_last_error("gear joints are not built yet"); return DBX_E_UNSUPPORTED; }
   if (d.bodyA < 0 || d.bodyB < 0 || d.bodyA >= (int)bodies_.size() || d.bodyB >= (int)bodies_.size() || !bodies_[d.bodyA].alive || !bodies_[d.bodyB].alive || d.bodyA == d.bodyB) return DBX_E_INVALID;
+  if (d.type == DBX_JOINT_PULLEY && d.ratio == 0.0f) return DBX_E_INVALID;   // b2pulleyjoint.d:118
   HJoint j; j.alive = true; j.def = d;
+  if (d.type == DBX_JOINT_PRISMATIC) {       // b2prismaticjoint.d:173-174: the axis is stored normalised
+    v2 ax = V(d.localAxisA.x, d.localAxisA.y); normalize(ax);
+    j.def.localAxisA = dbx_vec2{ax.x, ax.y};
+  } else if (d.type == DBX_JOINT_MOTOR) {    // b2motorjoint.d:230-231: rA = qA * (-localCenterA), i.e. anchors at the body origins
+    j.def.localAnchorA = dbx_vec2{0.0f, 0.0f}; j.def.localAnchorB = dbx_vec2{0.0f, 0.0f};
+  } else if (d.type == DBX_JOINT_MOUSE) {    // b2mousejoint.d:70-71: localAnchorB = b2MulT(bodyB.GetTransform(), target)
+    int rcp = pullBodies(); if (rcp < 0) return rcp;
+    const dbx_body_state& st = bodies_[d.bodyB].st;
+    Xf xf; xf.p = V(st.p.x, st.p.y); xf.q = R(st.qs, st.qc);
+    const v2 la = mulT(xf, V(d.target.x, d.target.y));
+    j.def.localAnchorB = dbx_vec2{la.x, la.y};
+  }
   joints_.push_back(j);
   const int jid = (int)joints_.size() - 1;
   bodies_[d.bodyA].joints.push_back(jid);
@@ -436,6 +449,37 @@ int World::pullJoints() {
 }
 
 // greedy colouring of the joint graph on the host (the joint set only changes through the API)
+// parameter packing of the device joint record (which = 0: j_p0, 1: j_p1); the kernels' side is dbx_solver.cuh / dbx_joints2.cuh
+float4 World::jointParams(const dbx_joint_def& d, int which) {
+  auto f = [](float a, float b, float c, float e) { return make_float4(a, b, c, e); };
+  switch (d.type) {
+    case DBX_JOINT_REVOLUTE:  return which == 0 ? f(d.referenceAngle, d.lowerAngle, d.upperAngle, d.maxMotorTorque) : f(d.motorSpeed, 0, 0, 0);
+    case DBX_JOINT_DISTANCE:  return which == 0 ? f(d.length, d.frequencyHz, d.dampingRatio, 0) : f(0, 0, 0, 0);
+    case DBX_JOINT_PRISMATIC: return which == 0 ? f(d.localAxisA.x, d.localAxisA.y, d.referenceAngle, d.maxMotorForce) : f(d.motorSpeed, d.lowerTranslation, d.upperTranslation, 0);
+    case DBX_JOINT_WELD:      return which == 0 ? f(d.referenceAngle, d.frequencyHz, d.dampingRatio, 0) : f(0, 0, 0, 0);
+    case DBX_JOINT_WHEEL:     return which == 0 ? f(d.localAxisA.x, d.localAxisA.y, d.maxMotorTorque, d.motorSpeed) : f(d.frequencyHz, d.dampingRatio, 0, 0);
+    case DBX_JOINT_ROPE:      return which == 0 ? f(d.maxLength, 0, 0, 0) : f(0, 0, 0, 0);
+    case DBX_JOINT_FRICTION:  return which == 0 ? f(d.maxForce, d.maxTorque, 0, 0) : f(0, 0, 0, 0);
+    case DBX_JOINT_MOTOR:     return which == 0 ? f(d.linearOffset.x, d.linearOffset.y, d.angularOffset, d.correctionFactor) : f(d.maxForce, d.maxTorque, 0, 0);
+    case DBX_JOINT_MOUSE:     return which == 0 ? f(d.target.x, d.target.y, d.maxForce, d.frequencyHz) : f(d.dampingRatio, 0, 0, 0);
+    case DBX_JOINT_PULLEY:    return which == 0 ? f(d.groundAnchorA.x, d.groundAnchorA.y, d.groundAnchorB.x, d.groundAnchorB.y) : f(d.lengthA, d.lengthB, d.ratio, d.lengthA + d.ratio * d.lengthB);
+    default:                  return f(0, 0, 0, 0);
+  }
+}
+
+// b2MouseJoint.SetTarget (b2mousejoint.d:112-120): wakes bodyB, moves the target
+int World::setJointTarget(int jid, float x, float y) {
+  if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
+  if (jid < 0 || jid >= (int)joints_.size() || !joints_[jid].alive || joints_[jid].def.type != DBX_JOINT_MOUSE) return DBX_E_INVALID;
+  int rc = pullJoints(); if (rc < 0) return rc;
+  joints_[jid].def.target = dbx_vec2{x, y};
+  fullPushJoints_ = true;
+  rc = push(); if (rc < 0) return rc;
+  CUDA_OR_FAIL(launch_api_wake(dw_, L_, joints_[jid].def.bodyB, -1), "api_wake");
+  hostBodiesValid_ = false;
+  return 0;
+}
+
 int World::recolourJoints() {
   const int nJ = (int)joints_.size();
   std::vector<unsigned long long> mask(bodies_.size(), 0ull);
@@ -573,7 +617,7 @@ int World::reserveDevice(bool& rehash) {
   CUDA_OR_FAIL(s_contact.reserve(sc, false, stream_), "s_contact"); CUDA_OR_FAIL(s_pc.reserve(sc, false, stream_), "s_pc"); CUDA_OR_FAIL(s_root.reserve(sc, false, stream_), "s_root");
   CUDA_OR_FAIL(s_hist.reserve((size_t)kSortBlocks * kMaxColours, false, stream_), "s_hist");
   const size_t capJ = std::max<size_t>(std::max<size_t>(nJ, 1), (size_t)caps_.maxJoints);
-  DevBuf<float4>* jf4[] = {&j_anchor, &j_p0, &j_p1, &j_imp, &j_r, &j_lc, &j_m, &j_k0, &j_k1, &j_k2};
+  DevBuf<float4>* jf4[] = {&j_anchor, &j_p0, &j_p1, &j_imp, &j_r, &j_lc, &j_m, &j_k0, &j_k1, &j_k2, &j_k3};
   for (auto* b : jf4) CUDA_OR_FAIL(b->reserve(capJ, true, stream_), "joint f4");
   CUDA_OR_FAIL(j_ids.reserve(capJ, true, stream_), "j_ids"); CUDA_OR_FAIL(j_limit.reserve(capJ, true, stream_), "j_limit"); CUDA_OR_FAIL(j_root.reserve(capJ, true, stream_), "j_root");
   CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
@@ -662,9 +706,8 @@ int World::push() {
     CUDA_OR_FAIL(upload_range(j_ids, 0, nD, [&](size_t k) { const HJoint& j = J(k);
       return make_int4(j.def.type, j.def.bodyA, j.def.bodyB, (j.def.collideConnected ? 1 : 0) | (j.def.enableLimit ? 2 : 0) | (j.def.enableMotor ? 4 : 0) | 8); }), "up j_ids");
     CUDA_OR_FAIL(upload_range(j_anchor, 0, nD, [&](size_t k) { const dbx_joint_def& d = J(k).def; return f4(d.localAnchorA.x, d.localAnchorA.y, d.localAnchorB.x, d.localAnchorB.y); }), "up j_anchor");
-    CUDA_OR_FAIL(upload_range(j_p0, 0, nD, [&](size_t k) { const dbx_joint_def& d = J(k).def;
-      return d.type == DBX_JOINT_REVOLUTE ? f4(d.referenceAngle, d.lowerAngle, d.upperAngle, d.maxMotorTorque) : f4(d.length, d.frequencyHz, d.dampingRatio, 0.0f); }), "up j_p0");
-    CUDA_OR_FAIL(upload_range(j_p1, 0, nD, [&](size_t k) { return f4(J(k).def.motorSpeed, 0, 0, 0); }), "up j_p1");
+    CUDA_OR_FAIL(upload_range(j_p0, 0, nD, [&](size_t k) { return jointParams(J(k).def, 0); }), "up j_p0");
+    CUDA_OR_FAIL(upload_range(j_p1, 0, nD, [&](size_t k) { return jointParams(J(k).def, 1); }), "up j_p1");
     CUDA_OR_FAIL(upload_range(j_imp, 0, nD, [&](size_t k) { const HJoint& j = J(k); return f4(j.imp[0], j.imp[1], j.imp[2], j.imp[3]); }), "up j_imp");
     CUDA_OR_FAIL(upload_range(j_limit, 0, nD, [&](size_t k) { return J(k).limit; }), "up j_limit");
     jointsSynced_ = nJ; fullPushJoints_ = false; jointsChanged_ = false;
@@ -698,7 +741,7 @@ void World::refreshView() {
   w.sCap = (int)s_contact.cap; w.s_contact = s_contact.p; w.s_hist = s_hist.p; w.s_body = s_body.p; w.s_v0 = s_v0.p; w.s_v1 = s_v1.p; w.s_r0 = s_r0.p; w.s_r1 = s_r1.p;
   w.s_q0 = s_q0.p; w.s_q1 = s_q1.p; w.s_imp = s_imp.p; w.s_nm = s_nm.p; w.s_k = s_k.p; w.s_pc = s_pc.p; w.s_p0 = s_p0.p; w.s_p1 = s_p1.p; w.s_p2 = s_p2.p; w.s_p3 = s_p3.p; w.s_root = s_root.p;
   w.nJoints = (int)jointAt_.size() * nWorlds_; w.j_ids = j_ids.p; w.j_anchor = j_anchor.p; w.j_p0 = j_p0.p; w.j_p1 = j_p1.p; w.j_imp = j_imp.p; w.j_limit = j_limit.p; w.j_colour = j_colour.p;
-  w.j_order = j_order.p; w.j_root = j_root.p; w.j_r = j_r.p; w.j_lc = j_lc.p; w.j_m = j_m.p; w.j_k0 = j_k0.p; w.j_k1 = j_k1.p; w.j_k2 = j_k2.p;
+  w.j_order = j_order.p; w.j_root = j_root.p; w.j_r = j_r.p; w.j_lc = j_lc.p; w.j_m = j_m.p; w.j_k0 = j_k0.p; w.j_k1 = j_k1.p; w.j_k2 = j_k2.p; w.j_k3 = j_k3.p;
   w.nWorlds = nWorlds_; w.keyStride = keyStride_;
   w.jointBlocks = jointBlocks_; w.nJointColours = nJointColours_;
   { const char* e = getenv("DBX_DEBUG"); w.dbgFlags = e ? atoi(e) : 0; }
@@ -1418,8 +1461,8 @@ int World::replicate(int copies) {
         const dbx_joint_def& jd = j.def;
         ids[d] = make_int4(jd.type, jd.bodyA + r * nB, jd.bodyB + r * nB, (jd.collideConnected ? 1 : 0) | (jd.enableLimit ? 2 : 0) | (jd.enableMotor ? 4 : 0) | 8);
         anc[d] = make_float4(jd.localAnchorA.x, jd.localAnchorA.y, jd.localAnchorB.x, jd.localAnchorB.y);
-        p0[d] = jd.type == DBX_JOINT_REVOLUTE ? make_float4(jd.referenceAngle, jd.lowerAngle, jd.upperAngle, jd.maxMotorTorque) : make_float4(jd.length, jd.frequencyHz, jd.dampingRatio, 0.0f);
-        p1[d] = make_float4(jd.motorSpeed, 0, 0, 0);
+        p0[d] = jointParams(jd, 0);
+        p1[d] = jointParams(jd, 1);
         imp[d] = make_float4(j.imp[0], j.imp[1], j.imp[2], j.imp[3]);
         lim[d] = j.limit;
       }

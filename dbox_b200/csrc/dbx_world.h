@@ -59,6 +59,7 @@ class World {
   int destroyFixture(int f);
   int createJoint(const dbx_joint_def& d);
   int destroyJoint(int j);
+  int setJointTarget(int j, float x, float y);
   int step(float dt, int vi, int pi, int n);
   int enqueueStep(float dt, int vi, int pi, bool fineEvents);
   int timeSteps(float dt, int vi, int pi, int n, bool flushL2, float* totalMs, float* stageMs);
@@ -118,6 +119,7 @@ class World {
   void hostAabb(const DShape& s, const Xf& xf, Box* out) const;
   int destroyContactsWhere(int body, int fixture, int otherBody, bool flagOnly);
   int recolourJoints();
+  static float4 jointParams(const dbx_joint_def& d, int which);
   int reserveDevice(bool& rehash);
   int findNewContacts(bool deferClear = false);
   int compactContacts();
@@ -164,7 +166,7 @@ class World {
   DevBuf<unsigned long long> c_key, h_key; DevBuf<int4> c_ids, c_fix; DevBuf<uint32_t> c_flags; DevBuf<float4> c_m0, c_m1, c_imp, c_mat; DevBuf<uint4> c_mk;
   DevBuf<int> c_toiCount, c_colour, c_free, c_work, c_work2, h_val;
   DevBuf<int> s_contact, s_hist, s_pc, s_root; DevBuf<int2> s_body; DevBuf<float4> s_v0, s_v1, s_r0, s_r1, s_q0, s_q1, s_imp, s_nm, s_k, s_p0, s_p1, s_p2; DevBuf<float2> s_p3;
-  DevBuf<int4> j_ids; DevBuf<float4> j_anchor, j_p0, j_p1, j_imp, j_r, j_lc, j_m, j_k0, j_k1, j_k2; DevBuf<int> j_limit, j_colour, j_order, j_root;
+  DevBuf<int4> j_ids; DevBuf<float4> j_anchor, j_p0, j_p1, j_imp, j_r, j_lc, j_m, j_k0, j_k1, j_k2, j_k3; DevBuf<int> j_limit, j_colour, j_order, j_root;
   DevBuf<char> cubTemp; DevBuf<int> d_levels;
   DevBuf<unsigned long long> cmpKeyA_, cmpKeyB_; DevBuf<int> cmpValA_, cmpValB_;
   int nJointPairs_ = 0; int jointBlocks_ = 0, nJointColours_ = 0;

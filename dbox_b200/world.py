@@ -241,6 +241,186 @@ class b2DistanceJointDef(b2JointDef):
         return d
 
 
+class _AnchoredDef(b2JointDef):
+    """shared by the second-wave joint defs: head of dbx_joint_def + localAnchorA/B"""
+
+    def __init__(self):
+        super().__init__()
+        self.localAnchorA, self.localAnchorB = b2Vec2(), b2Vec2()
+
+    def _head(self):
+        d = A.JointDef()
+        d.type, d.bodyA, d.bodyB, d.collideConnected = self.type, self.bodyA.id, self.bodyB.id, int(self.collideConnected)
+        d.localAnchorA, d.localAnchorB, d.userData = _v(self.localAnchorA), _v(self.localAnchorB), self.userData
+        return d
+
+    def _anchor(self, bA, bB, anchor):
+        self.bodyA, self.bodyB = bA, bB
+        self.localAnchorA, self.localAnchorB = bA.GetLocalPoint(anchor), bB.GetLocalPoint(anchor)
+
+
+class b2PrismaticJointDef(_AnchoredDef):
+    """dynamics/joints/b2prismaticjoint.d:39-113"""
+    type = A.JOINT_PRISMATIC
+
+    def __init__(self):
+        super().__init__()
+        self.localAxisA = b2Vec2(1.0, 0.0)
+        self.referenceAngle = self.lowerTranslation = self.upperTranslation = self.maxMotorForce = self.motorSpeed = 0.0
+        self.enableLimit = self.enableMotor = False
+
+    def Initialize(self, bA, bB, anchor, axis):
+        self._anchor(bA, bB, anchor)
+        self.localAxisA = bA.GetLocalVector(axis)
+        self.referenceAngle = _f32(bB.GetAngle() - bA.GetAngle())
+
+    def _pod(self):
+        d = self._head()
+        d.localAxisA, d.referenceAngle, d.enableLimit, d.enableMotor = _v(self.localAxisA), self.referenceAngle, int(self.enableLimit), int(self.enableMotor)
+        d.lowerTranslation, d.upperTranslation, d.maxMotorForce, d.motorSpeed = self.lowerTranslation, self.upperTranslation, self.maxMotorForce, self.motorSpeed
+        return d
+
+
+class b2WeldJointDef(_AnchoredDef):
+    """dynamics/joints/b2weldjoint.d:38-80"""
+    type = A.JOINT_WELD
+
+    def __init__(self):
+        super().__init__()
+        self.referenceAngle = self.frequencyHz = self.dampingRatio = 0.0
+
+    def Initialize(self, bA, bB, anchor):
+        self._anchor(bA, bB, anchor)
+        self.referenceAngle = _f32(bB.GetAngle() - bA.GetAngle())
+
+    def _pod(self):
+        d = self._head()
+        d.referenceAngle, d.frequencyHz, d.dampingRatio = self.referenceAngle, self.frequencyHz, self.dampingRatio
+        return d
+
+
+class b2WheelJointDef(_AnchoredDef):
+    """dynamics/joints/b2wheeljoint.d:39-92"""
+    type = A.JOINT_WHEEL
+
+    def __init__(self):
+        super().__init__()
+        self.localAxisA = b2Vec2(1.0, 0.0)
+        self.enableMotor = False
+        self.maxMotorTorque = self.motorSpeed = 0.0
+        self.frequencyHz, self.dampingRatio = 2.0, 0.7
+
+    def Initialize(self, bA, bB, anchor, axis):
+        self._anchor(bA, bB, anchor)
+        self.localAxisA = bA.GetLocalVector(axis)
+
+    def _pod(self):
+        d = self._head()
+        d.localAxisA, d.enableMotor, d.maxMotorTorque, d.motorSpeed = _v(self.localAxisA), int(self.enableMotor), self.maxMotorTorque, self.motorSpeed
+        d.frequencyHz, d.dampingRatio = self.frequencyHz, self.dampingRatio
+        return d
+
+
+class b2RopeJointDef(_AnchoredDef):
+    """dynamics/joints/b2ropejoint.d:40-66"""
+    type = A.JOINT_ROPE
+
+    def __init__(self):
+        super().__init__()
+        self.localAnchorA, self.localAnchorB, self.maxLength = b2Vec2(-1.0, 0.0), b2Vec2(1.0, 0.0), 0.0
+
+    def _pod(self):
+        d = self._head()
+        d.maxLength = self.maxLength
+        return d
+
+
+class b2FrictionJointDef(_AnchoredDef):
+    """dynamics/joints/b2frictionjoint.d:36-72"""
+    type = A.JOINT_FRICTION
+
+    def __init__(self):
+        super().__init__()
+        self.maxForce = self.maxTorque = 0.0
+
+    def Initialize(self, bA, bB, anchor):
+        self._anchor(bA, bB, anchor)
+
+    def _pod(self):
+        d = self._head()
+        d.maxForce, d.maxTorque = self.maxForce, self.maxTorque
+        return d
+
+
+class b2MotorJointDef(_AnchoredDef):
+    """dynamics/joints/b2motorjoint.d:36-80"""
+    type = A.JOINT_MOTOR
+
+    def __init__(self):
+        super().__init__()
+        self.linearOffset, self.angularOffset, self.maxForce, self.maxTorque, self.correctionFactor = b2Vec2(), 0.0, 1.0, 1.0, 0.3
+
+    def Initialize(self, bA, bB):
+        self.bodyA, self.bodyB = bA, bB
+        self.linearOffset = bA.GetLocalPoint(bB.GetPosition())
+        self.angularOffset = _f32(bB.GetAngle() - bA.GetAngle())
+
+    def _pod(self):
+        d = self._head()
+        d.linearOffset, d.angularOffset, d.maxForce, d.maxTorque, d.correctionFactor = _v(self.linearOffset), self.angularOffset, self.maxForce, self.maxTorque, self.correctionFactor
+        return d
+
+
+class b2MouseJointDef(_AnchoredDef):
+    """dynamics/joints/b2mousejoint.d:36-66"""
+    type = A.JOINT_MOUSE
+
+    def __init__(self):
+        super().__init__()
+        self.target, self.maxForce, self.frequencyHz, self.dampingRatio = b2Vec2(), 0.0, 5.0, 0.7
+
+    def _pod(self):
+        d = self._head()
+        d.target, d.maxForce, d.frequencyHz, d.dampingRatio = _v(self.target), self.maxForce, self.frequencyHz, self.dampingRatio
+        return d
+
+
+class b2PulleyJointDef(_AnchoredDef):
+    """dynamics/joints/b2pulleyjoint.d:41-100"""
+    type = A.JOINT_PULLEY
+
+    def __init__(self):
+        super().__init__()
+        self.groundAnchorA, self.groundAnchorB = b2Vec2(-1.0, 1.0), b2Vec2(1.0, 1.0)
+        self.localAnchorA, self.localAnchorB = b2Vec2(-1.0, 0.0), b2Vec2(1.0, 0.0)
+        self.lengthA = self.lengthB = 0.0
+        self.ratio = 1.0
+        self.collideConnected = True
+
+    def Initialize(self, bA, bB, groundA, groundB, anchorA, anchorB, ratio):
+        self.bodyA, self.bodyB = bA, bB
+        self.groundAnchorA, self.groundAnchorB = _pt(groundA), _pt(groundB)
+        self.localAnchorA, self.localAnchorB = bA.GetLocalPoint(anchorA), bB.GetLocalPoint(anchorB)
+        a, ga, b, gb = _v(anchorA), _v(groundA), _v(anchorB), _v(groundB)
+        self.lengthA = _len32(_f32(a.x - ga.x), _f32(a.y - ga.y))
+        self.lengthB = _len32(_f32(b.x - gb.x), _f32(b.y - gb.y))
+        self.ratio = ratio
+
+    def _pod(self):
+        d = self._head()
+        d.groundAnchorA, d.groundAnchorB, d.lengthA, d.lengthB, d.ratio = _v(self.groundAnchorA), _v(self.groundAnchorB), self.lengthA, self.lengthB, self.ratio
+        return d
+
+
+def _pt(p):
+    v = _v(p)
+    return b2Vec2(v.x, v.y)
+
+
+def _len32(dx, dy):
+    return _f32(math.sqrt(_f32(_f32(dx * dx) + _f32(dy * dy))))
+
+
 def _f32(x):
     return C.c_float(x).value
 
@@ -322,6 +502,13 @@ class b2Body:
         x = _f32(_f32(s.qc * px) + _f32(s.qs * py))
         y = _f32(_f32(-s.qs * px) + _f32(s.qc * py))
         return b2Vec2(x, y)
+
+    def GetLocalVector(self, worldVector):
+        """b2body.d GetLocalVector = b2MulT(m_xf.q, v) (common/b2math.d:640-643), evaluated in fp32."""
+        s = self._state()
+        vx, vy = worldVector
+        vx, vy = _f32(vx), _f32(vy)
+        return b2Vec2(_f32(_f32(s.qc * vx) + _f32(s.qs * vy)), _f32(_f32(-s.qs * vx) + _f32(s.qc * vy)))
 
     def SetTransform(self, position, angle):
         x, y = position
@@ -442,6 +629,11 @@ class b2World:
         j = b2Joint(self, jid, jointDef.bodyA, jointDef.bodyB)
         self._joints[jid] = j
         return j
+
+    def SetMouseTarget(self, joint, target):
+        """b2MouseJoint.SetTarget (b2mousejoint.d:112-120)"""
+        x, y = target
+        self._ck(self._api.joint_set_target(self._w, joint.id, x, y))
 
     def DestroyJoint(self, joint):
         self._ck(self._api.joint_destroy(self._w, joint.id))

@@ -129,9 +129,28 @@ typedef struct {
   float lowerAngle, upperAngle;
   int32_t enableMotor;
   float motorSpeed, maxMotorTorque;
-  /* distance */
+  /* distance (frequencyHz / dampingRatio also: weld, wheel, mouse) */
   float length, frequencyHz, dampingRatio;
   uint64_t userData;
+  /* ---- second-wave joints; a def only reads the fields of its own type (+ the common head above) ------------------
+   * prismatic b2prismaticjoint.d:39-113 (localAxisA, referenceAngle, enableLimit, lower/upperTranslation, enableMotor,
+   *   maxMotorForce, motorSpeed) · wheel b2wheeljoint.d:39-92 (localAxisA, enableMotor, maxMotorTorque, motorSpeed,
+   *   frequencyHz, dampingRatio) · weld b2weldjoint.d:38-80 (referenceAngle, frequencyHz, dampingRatio) ·
+   * rope b2ropejoint.d:40-66 (maxLength) · friction b2frictionjoint.d:36-72 (maxForce, maxTorque) ·
+   * motor b2motorjoint.d:36-80 (linearOffset, angularOffset, maxForce, maxTorque, correctionFactor; anchors unused) ·
+   * mouse b2mousejoint.d:36-66 (target, maxForce, frequencyHz, dampingRatio; bodyA is only a placeholder) ·
+   * pulley b2pulleyjoint.d:41-100 (groundAnchorA/B, lengthA, lengthB, ratio) */
+  dbx_vec2 localAxisA;
+  float lowerTranslation, upperTranslation, maxMotorForce;
+  float maxLength;
+  float maxForce, maxTorque;
+  dbx_vec2 linearOffset;
+  float angularOffset, correctionFactor;
+  dbx_vec2 target;
+  dbx_vec2 groundAnchorA, groundAnchorB;
+  float lengthA, lengthB, ratio;
+  int32_t joint1, joint2;     /* gear (not built) */
+  int32_t _pad;
 } dbx_joint_def;
 
 /* full per-body state (dynamics/b2body.d:1182-1218) */
@@ -223,6 +242,7 @@ int32_t dbx_fixture_create(dbx_world* w, int32_t body, const dbx_fixture_def* de
 int32_t dbx_fixture_destroy(dbx_world* w, int32_t fixture);                                       /* b2body.d:179-247 */
 int32_t dbx_joint_create(dbx_world* w, const dbx_joint_def* def);                                 /* b2world.d:196-261 */
 int32_t dbx_joint_destroy(dbx_world* w, int32_t joint);                                           /* b2world.d:265-360 */
+int32_t dbx_joint_set_target(dbx_world* w, int32_t joint, float x, float y);                       /* b2MouseJoint.SetTarget b2mousejoint.d:112-120 (wakes bodyB) */
 
 /* ---- the hot path: dynamics/b2world.d:367-434 (Collide -> Solve -> SolveTOI -> ClearForces) ---- */
 int32_t dbx_world_step(dbx_world* w, float dt, int32_t velocityIterations, int32_t positionIterations);

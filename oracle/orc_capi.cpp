@@ -138,12 +138,64 @@ int32_t orc_joint_create(orc_world* w, const dbx_joint_def* d) {
     dj->localAnchorA = v2(d->localAnchorA); dj->localAnchorB = v2(d->localAnchorB); dj->length = d->length;
     dj->frequencyHz = d->frequencyHz; dj->dampingRatio = d->dampingRatio;
     j = dj;
+  } else if (d->type == jRope) {             // b2ropejoint.d:86-99
+    RopeJoint* r = new RopeJoint();
+    r->localAnchorA = v2(d->localAnchorA); r->localAnchorB = v2(d->localAnchorB); r->maxLength = d->maxLength;
+    j = r;
+  } else if (d->type == jWeld) {             // b2weldjoint.d:89-102
+    WeldJoint* r = new WeldJoint();
+    r->localAnchorA = v2(d->localAnchorA); r->localAnchorB = v2(d->localAnchorB); r->referenceAngle = d->referenceAngle;
+    r->frequencyHz = d->frequencyHz; r->dampingRatio = d->dampingRatio;
+    j = r;
+  } else if (d->type == jFriction) {         // b2frictionjoint.d:81-94
+    FrictionJoint* r = new FrictionJoint();
+    r->localAnchorA = v2(d->localAnchorA); r->localAnchorB = v2(d->localAnchorB); r->maxForce = d->maxForce; r->maxTorque = d->maxTorque;
+    j = r;
+  } else if (d->type == jMotor) {            // b2motorjoint.d:90-104
+    MotorJoint* r = new MotorJoint();
+    r->linearOffset = v2(d->linearOffset); r->angularOffset = d->angularOffset; r->maxForce = d->maxForce; r->maxTorque = d->maxTorque;
+    r->correctionFactor = d->correctionFactor;
+    j = r;
+  } else if (d->type == jMouse) {            // b2mousejoint.d:62-82
+    MouseJoint* r = new MouseJoint();
+    r->targetA = v2(d->target);
+    r->localAnchorB = mulT(B[d->bodyB]->xf, r->targetA);
+    r->maxForce = d->maxForce; r->frequencyHz = d->frequencyHz; r->dampingRatio = d->dampingRatio;
+    j = r;
+  } else if (d->type == jPrismatic) {        // b2prismaticjoint.d:166-190
+    PrismaticJoint* r = new PrismaticJoint();
+    r->localAnchorA = v2(d->localAnchorA); r->localAnchorB = v2(d->localAnchorB);
+    r->localXAxisA = v2(d->localAxisA); r->localXAxisA.normalize(); r->localYAxisA = cross(1.0f, r->localXAxisA);
+    r->referenceAngle = d->referenceAngle; r->lowerTranslation = d->lowerTranslation; r->upperTranslation = d->upperTranslation;
+    r->maxMotorForce = d->maxMotorForce; r->motorSpeed = d->motorSpeed; r->enableLimit = d->enableLimit != 0; r->enableMotor = d->enableMotor != 0;
+    j = r;
+  } else if (d->type == jWheel) {            // b2wheeljoint.d:108-135
+    WheelJoint* r = new WheelJoint();
+    r->localAnchorA = v2(d->localAnchorA); r->localAnchorB = v2(d->localAnchorB);
+    r->localXAxisA = v2(d->localAxisA); r->localYAxisA = cross(1.0f, r->localXAxisA);
+    r->maxMotorTorque = d->maxMotorTorque; r->motorSpeed = d->motorSpeed; r->enableMotor = d->enableMotor != 0;
+    r->frequencyHz = d->frequencyHz; r->dampingRatio = d->dampingRatio;
+    j = r;
+  } else if (d->type == jPulley) {           // b2pulleyjoint.d:107-123
+    PulleyJoint* r = new PulleyJoint();
+    r->localAnchorA = v2(d->localAnchorA); r->localAnchorB = v2(d->localAnchorB);
+    r->groundAnchorA = v2(d->groundAnchorA); r->groundAnchorB = v2(d->groundAnchorB);
+    r->lengthA = d->lengthA; r->lengthB = d->lengthB; r->ratio = d->ratio; r->constant = d->lengthA + r->ratio * d->lengthB;
+    j = r;
   } else {
     return DBX_E_UNSUPPORTED;
   }
   j->type = d->type; j->bodyA = B[d->bodyA]; j->bodyB = B[d->bodyB]; j->collideConnected = d->collideConnected != 0; j->userData = d->userData;
   Joint* r = w->w.addJoint(j);
   return r ? r->id : DBX_E_LOCKED;
+}
+// b2MouseJoint.SetTarget (b2mousejoint.d:112-120)
+int32_t orc_joint_set_target(orc_world* w, int32_t joint, float x, float y) {
+  if (joint < 0 || joint >= (int)w->w.jointsById.size() || !w->w.jointsById[joint] || w->w.jointsById[joint]->type != jMouse) return DBX_E_INVALID;
+  MouseJoint* m = (MouseJoint*)w->w.jointsById[joint];
+  if (m->bodyB->isAwake() == false) m->bodyB->setAwake(true);
+  m->targetA = V2(x, y);
+  return 0;
 }
 int32_t orc_joint_destroy(orc_world* w, int32_t joint) {
   if (joint < 0 || joint >= (int)w->w.jointsById.size() || !w->w.jointsById[joint]) return DBX_E_INVALID;
@@ -320,6 +372,14 @@ int32_t orc_world_read_joints(orc_world* w, dbx_joint_state* out, int32_t cap) {
     o->type = j->type;
     if (j->type == jRevolute) { auto* r = (RevoluteJoint*)j; o->impulse[0] = r->impulse.x; o->impulse[1] = r->impulse.y; o->impulse[2] = r->impulse.z; o->motorImpulse = r->motorImpulse; o->limitState = r->limitState; }
     else if (j->type == jDistance) { auto* d = (DistanceJoint*)j; o->impulse[0] = d->impulse; }
+    else if (j->type == jRope) { auto* d = (RopeJoint*)j; o->impulse[0] = d->impulse; o->limitState = d->state; }
+    else if (j->type == jWeld) { auto* d = (WeldJoint*)j; o->impulse[0] = d->impulse.x; o->impulse[1] = d->impulse.y; o->impulse[2] = d->impulse.z; }
+    else if (j->type == jFriction) { auto* d = (FrictionJoint*)j; o->impulse[0] = d->linearImpulse.x; o->impulse[1] = d->linearImpulse.y; o->impulse[2] = d->angularImpulse; }
+    else if (j->type == jMotor) { auto* d = (MotorJoint*)j; o->impulse[0] = d->linearImpulse.x; o->impulse[1] = d->linearImpulse.y; o->impulse[2] = d->angularImpulse; }
+    else if (j->type == jMouse) { auto* d = (MouseJoint*)j; o->impulse[0] = d->impulse.x; o->impulse[1] = d->impulse.y; }
+    else if (j->type == jPrismatic) { auto* d = (PrismaticJoint*)j; o->impulse[0] = d->impulse.x; o->impulse[1] = d->impulse.y; o->impulse[2] = d->impulse.z; o->motorImpulse = d->motorImpulse; o->limitState = d->limitState; }
+    else if (j->type == jWheel) { auto* d = (WheelJoint*)j; o->impulse[0] = d->impulse; o->impulse[1] = d->springImpulse; o->motorImpulse = d->motorImpulse; }
+    else if (j->type == jPulley) { auto* d = (PulleyJoint*)j; o->impulse[0] = d->impulse; }
   }
   return n;
 }

@@ -130,6 +130,55 @@ struct DistanceJoint : Joint {
   bool solvePositionConstraints(const SolverData& data) override;
 };
 
+// ---- second-wave joints, restated in orc_joints.cpp
+#define ORC_JOINT_HOOKS \
+  void initVelocityConstraints(const SolverData& data) override; \
+  void solveVelocityConstraints(const SolverData& data) override; \
+  bool solvePositionConstraints(const SolverData& data) override;
+struct JointCommon : Joint {   // the solver-temp block every reference joint repeats
+  int indexA = 0, indexB = 0; V2 rA, rB, localCenterA, localCenterB;
+  float invMassA = 0, invMassB = 0, invIA = 0, invIB = 0;
+  V2 localAnchorA, localAnchorB;
+  void loadBodies();
+};
+struct RopeJoint : JointCommon {        // b2ropejoint.d
+  float maxLength = 0, length = 0, impulse = 0, mass = 0; V2 u; int state = kInactiveLimit;
+  ORC_JOINT_HOOKS
+};
+struct WeldJoint : JointCommon {        // b2weldjoint.d
+  float frequencyHz = 0, dampingRatio = 0, bias = 0, referenceAngle = 0, gamma = 0; V3 impulse; M33 mass;
+  ORC_JOINT_HOOKS
+};
+struct FrictionJoint : JointCommon {    // b2frictionjoint.d
+  V2 linearImpulse; float angularImpulse = 0, maxForce = 0, maxTorque = 0; M22 linearMass; float angularMass = 0;
+  ORC_JOINT_HOOKS
+};
+struct MotorJoint : JointCommon {       // b2motorjoint.d (no anchors: rA = -qA*lcA, rB = -qB*lcB)
+  V2 linearOffset; float angularOffset = 0; V2 linearImpulse; float angularImpulse = 0, maxForce = 0, maxTorque = 0, correctionFactor = 0;
+  V2 linearError; float angularError = 0; M22 linearMass; float angularMass = 0;
+  ORC_JOINT_HOOKS
+};
+struct MouseJoint : JointCommon {       // b2mousejoint.d (drives bodyB only)
+  V2 targetA; float frequencyHz = 0, dampingRatio = 0, beta = 0; V2 impulse; float maxForce = 0, gamma = 0; M22 mass; V2 C;
+  ORC_JOINT_HOOKS
+};
+struct PrismaticJoint : JointCommon {   // b2prismaticjoint.d
+  V2 localXAxisA, localYAxisA; float referenceAngle = 0; V3 impulse; float motorImpulse = 0, lowerTranslation = 0, upperTranslation = 0;
+  float maxMotorForce = 0, motorSpeed = 0; bool enableLimit = false, enableMotor = false; int limitState = kInactiveLimit;
+  V2 axis, perp; float s1 = 0, s2 = 0, a1 = 0, a2 = 0; M33 K; float motorMass = 0;
+  ORC_JOINT_HOOKS
+};
+struct WheelJoint : JointCommon {       // b2wheeljoint.d
+  float frequencyHz = 0, dampingRatio = 0; V2 localXAxisA, localYAxisA; float impulse = 0, motorImpulse = 0, springImpulse = 0;
+  float maxMotorTorque = 0, motorSpeed = 0; bool enableMotor = false;
+  V2 ax, ay; float sAx = 0, sBx = 0, sAy = 0, sBy = 0, mass = 0, motorMass = 0, springMass = 0, bias = 0, gamma = 0;
+  ORC_JOINT_HOOKS
+};
+struct PulleyJoint : JointCommon {      // b2pulleyjoint.d
+  V2 groundAnchorA, groundAnchorB; float lengthA = 0, lengthB = 0, constant = 0, ratio = 1, impulse = 0; V2 uA, uB; float mass = 0;
+  ORC_JOINT_HOOKS
+};
+
 struct Profile { float step = 0, collide = 0, solve = 0, solveInit = 0, solveVelocity = 0, solvePosition = 0, broadphase = 0, solveTOI = 0; };
 
 struct BodyDef {

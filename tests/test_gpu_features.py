@@ -213,3 +213,121 @@ def test_kinematic_platform_and_destroy_calls(gpu_api, oracle_api):
         w, out = build(api)
         return w, out[1:]                                       # the platform gets destroyed: compare the others
     both(gpu_api, oracle_api, build2, 180, each=each, tol_p=1e-4, tol_v=1e-3)
+
+
+def _box_body(w, api, x, y, hx=0.5, hy=0.5, density=1.0, **kw):
+    b = _dyn(w, x, y, **kw)
+    s = b2PolygonShape(api); s.SetAsBox(hx, hy)
+    b.CreateFixture(s, density)
+    return b
+
+
+def test_second_wave_joints_one_each(gpu_api, oracle_api):
+    """prismatic (limit + motor), weld (rigid and soft), wheel (spring + motor), rope, friction, motor,
+    mouse (with SetTarget) and pulley, one joint per island so the Gauss-Seidel order cannot matter: the CUDA hooks must
+    track the oracle's restatement of the reference hooks to float rounding, impulses and limit states included"""
+    from dbox_b200.world import (b2PrismaticJointDef, b2WeldJointDef, b2WheelJointDef, b2RopeJointDef, b2FrictionJointDef,
+                                 b2MotorJointDef, b2MouseJointDef, b2PulleyJointDef, b2Vec2)
+
+    def build(api):
+        w = b2World((0.0, -10.0), api=api)
+        g = w.CreateBody(b2BodyDef())
+        out = []
+        # prismatic: slanted axis, limits, motor pushing against the upper limit
+        a = _box_body(w, api, 0.0, 5.0, angle=0.1)
+        jd = b2PrismaticJointDef(); jd.Initialize(g, a, (0.0, 5.0), (0.6, 0.8))
+        jd.enableLimit, jd.lowerTranslation, jd.upperTranslation = True, -2.0, 1.0
+        jd.enableMotor, jd.motorSpeed, jd.maxMotorForce = True, 2.0, 60.0
+        w.CreateJoint(jd); out.append(a)
+        # prismatic without limit or motor
+        a2 = _box_body(w, api, 3.0, 5.0)
+        jd = b2PrismaticJointDef(); jd.Initialize(g, a2, (3.0, 6.0), (1.0, 0.3)); w.CreateJoint(jd); out.append(a2)
+        # weld rigid (off-centre anchor) and soft
+        b = _box_body(w, api, 6.0, 5.0)
+        jd = b2WeldJointDef(); jd.Initialize(g, b, (7.5, 6.0)); w.CreateJoint(jd); out.append(b)
+        b2 = _box_body(w, api, 10.0, 5.0)
+        jd = b2WeldJointDef(); jd.Initialize(g, b2, (11.5, 5.0)); jd.frequencyHz, jd.dampingRatio = 3.0, 0.3; w.CreateJoint(jd); out.append(b2)
+        # wheel: suspension spring + motor
+        c = _dyn(w, 14.0, 5.0); cs = b2CircleShape(api); cs.m_radius = 0.5; c.CreateFixture(cs, 1.0)
+        jd = b2WheelJointDef(); jd.Initialize(g, c, (14.0, 5.0), (0.0, 1.0))
+        jd.enableMotor, jd.motorSpeed, jd.maxMotorTorque, jd.frequencyHz, jd.dampingRatio = True, -3.0, 5.0, 4.0, 0.5
+        w.CreateJoint(jd); out.append(c)
+        # wheel without spring
+        c2 = _box_body(w, api, 17.0, 5.0)
+        jd = b2WheelJointDef(); jd.Initialize(g, c2, (17.0, 5.0), (0.3, 1.0)); jd.frequencyHz = 0.0; w.CreateJoint(jd); out.append(c2)
+        # rope: slack at first, then taut
+        d = _box_body(w, api, 20.0, 7.0)
+        jd = b2RopeJointDef(); jd.bodyA, jd.bodyB = g, d
+        jd.localAnchorA, jd.localAnchorB, jd.maxLength = b2Vec2(21.0, 8.0), b2Vec2(0.5, 0.5), 3.0
+        w.CreateJoint(jd); d.SetLinearVelocity((2.0, 0.0)); out.append(d)
+        # friction: saturated
+        e = _box_body(w, api, 24.0, 5.0)
+        jd = b2FrictionJointDef(); jd.Initialize(g, e, (24.0, 5.0)); jd.maxForce, jd.maxTorque = 6.0, 0.5
+        w.CreateJoint(jd); e.SetAngularVelocity(3.0); out.append(e)
+        # motor: holds an offset pose against gravity with a soft correction
+        f = _box_body(w, api, 28.0, 5.0)
+        jd = b2MotorJointDef(); jd.Initialize(g, f); jd.maxForce, jd.maxTorque = 40.0, 20.0
+        jd.linearOffset = b2Vec2(28.5, 5.5); jd.angularOffset = 0.4
+        w.CreateJoint(jd); out.append(f)
+        # mouse
+        m = _box_body(w, api, 32.0, 5.0)
+        jd = b2MouseJointDef(); jd.bodyA, jd.bodyB = g, m; jd.target = b2Vec2(32.3, 5.4); jd.maxForce = 200.0
+        w.mouse = w.CreateJoint(jd); out.append(m)
+        # pulley with ratio
+        p1 = _box_body(w, api, 36.0, 5.0); p2 = _box_body(w, api, 39.0, 5.0, density=1.6)
+        jd = b2PulleyJointDef(); jd.Initialize(p1, p2, (36.0, 10.0), (39.0, 10.0), (36.0, 5.5), (39.0, 5.5), 1.5)
+        w.CreateJoint(jd); out += [p1, p2]
+        return w, out
+
+    def each(k, wg, wo):
+        if k == 60:
+            for w in (wg, wo):
+                w.SetMouseTarget(w.mouse, (33.0, 6.5))
+    wg, wo, _, _ = both(gpu_api, oracle_api, build, 200, each=each, tol_p=1e-4, tol_v=1e-3)
+    jg, n = wg.read_joints(); jo, _ = wo.read_joints()
+    assert n == 11
+    for i in range(n):
+        assert jg[i].type == jo[i].type and jg[i].limitState == jo[i].limitState, i
+        for a, b in zip(list(jg[i].impulse) + [jg[i].motorImpulse], list(jo[i].impulse) + [jo[i].motorImpulse]):
+            assert abs(a - b) <= 5e-3 * max(1.0, abs(b)), (i, jg[i].type, a, b)
+
+
+def test_joint_scene_with_contacts(gpu_api, oracle_api):
+    """a small car (two wheel joints with springs, motor on the rear wheel) on a chain-shape track, a weld-joint beam and a
+    prismatic elevator carrying a box: joints and contacts in the same islands.  Order now matters, so this is judged like
+    the long-horizon scenes: same outcome within a loose tolerance"""
+    from dbox_b200.world import b2PrismaticJointDef, b2WeldJointDef, b2WheelJointDef
+
+    def build(api):
+        w = b2World((0.0, -10.0), api=api)
+        g = w.CreateBody(b2BodyDef())
+        ch = b2ChainShape(api); ch.CreateChain([(-20.0, 0.0), (20.0, 0.0), (40.0, 2.0), (60.0, 2.0)])
+        fd = b2FixtureDef(); fd.shape = ch; fd.friction = 0.9
+        g.CreateFixture(fd)
+        chassis = _box_body(w, api, 0.0, 1.0, hx=1.5, hy=0.25)
+        wheels = []
+        for x in (-1.0, 1.0):
+            wb = _dyn(w, x, 0.45); cs = b2CircleShape(api); cs.m_radius = 0.4
+            fd = b2FixtureDef(); fd.shape = cs; fd.density = 1.0; fd.friction = 0.9
+            wb.CreateFixture(fd)
+            jd = b2WheelJointDef(); jd.Initialize(chassis, wb, (x, 0.45), (0.0, 1.0))
+            jd.frequencyHz, jd.dampingRatio = 4.0, 0.7
+            if x < 0:
+                jd.enableMotor, jd.motorSpeed, jd.maxMotorTorque = True, -8.0, 20.0
+            w.CreateJoint(jd); wheels.append(wb)
+        lift = _box_body(w, api, -10.0, 1.0, hx=1.0, hy=0.2)
+        jd = b2PrismaticJointDef(); jd.Initialize(g, lift, (-10.0, 1.0), (0.0, 1.0))
+        jd.enableLimit, jd.lowerTranslation, jd.upperTranslation = True, 0.0, 4.0
+        jd.enableMotor, jd.motorSpeed, jd.maxMotorForce = True, 1.0, 500.0
+        w.CreateJoint(jd)
+        cargo = _box_body(w, api, -10.0, 1.7)
+        return w, [chassis, lift, cargo] + wheels
+    wg, bg = build(gpu_api); wo, bo = build(oracle_api)
+    for k in range(240):
+        wg.Step(DT, 8, 3); wo.Step(DT, 8, 3)
+    for i, (g_, o_) in enumerate(zip(bg, bo)):
+        pg, po = g_.GetPosition(), o_.GetPosition()
+        assert abs(pg.x - po.x) < 0.05 and abs(pg.y - po.y) < 0.05, (i, (pg.x, pg.y), (po.x, po.y))
+    assert bg[0].GetPosition().x > 5.0                       # the car drove off
+    assert abs(bg[1].GetPosition().y - 5.0) < 0.05           # the lift reached its upper limit with the cargo on it
+    assert bg[2].GetPosition().y > 5.5
