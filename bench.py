@@ -207,7 +207,8 @@ def main():
     ap.add_argument("--worlds", type=int, default=65536, help="C5: independent Pyramid worlds in the batched leg (0 = skip the leg)")
     ap.add_argument("--batch-steps", type=int, default=100)
     ap.add_argument("--batch-settle", type=int, default=60)
-    ap.add_argument("--cpu-worlds-per-thread", type=int, default=2)
+    ap.add_argument("--cpu-batch-steps", type=int, default=400)
+    ap.add_argument("--cpu-worlds-per-thread", type=int, default=32)
     ap.add_argument("--save-state", default=None, help="write the settled world state here (profiling runs reload it instead of settling)")
     ap.add_argument("--load-state", default=None)
     args = ap.parse_args()
@@ -246,7 +247,7 @@ def main():
                 "gpu_launches": 0, "wall_s": time.time() - t0}
         if args.worlds > 0:
             nw = cores * args.cpu_worlds_per_thread
-            bsteps = min(args.batch_steps, 100)
+            bsteps = args.cpu_batch_steps
             v, secs = run_cpu_pyramids(nw, args.batch_settle, bsteps, cores)
             line["batched"] = {"workload": "C5 sample: %d Pyramid worlds, one world per host thread at a time" % nw, "value": v, "unit": "world-steps/s",
                                "cores": cores, "kind": "port", "steps": bsteps, "settle_steps": args.batch_settle, "seconds": secs}
@@ -361,10 +362,10 @@ def main():
         if n_gpus == 1 and not args.skip_cpu_baseline:
             if batched is not None:
                 nw = cores * args.cpu_worlds_per_thread
-                v, secs = run_cpu_pyramids(nw, args.batch_settle, min(args.batch_steps, 100), cores)
+                v, secs = run_cpu_pyramids(nw, args.batch_settle, args.cpu_batch_steps, cores)
                 batched["cpu_baseline"] = {"value": v, "unit": "world-steps/s", "cores": cores, "kind": "port",
                                            "sample": "%d Pyramid worlds, %d settle + %d timed steps, one world per host thread at a time, %.1f s"
-                                                     % (nw, args.batch_settle, min(args.batch_steps, 100), secs)}
+                                                     % (nw, args.batch_settle, args.cpu_batch_steps, secs)}
             t0 = time.time()
             v, secs, c = run_cpu_port(cpu_bodies, cpu_cols, args.cpu_settle, args.cpu_steps, 3)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",

@@ -257,6 +257,10 @@ int32_t dbx_world_debug_header(dbx_world* w, void* out, int32_t bytes) { W_OR_IN
 // ---- batched independent worlds
 int32_t dbx_world_replicate(dbx_world* w, int32_t copies) { W_OR_INVALID(w); return w->w.replicate(copies); }
 int32_t dbx_world_replica_count(dbx_world* w) { W_OR_INVALID(w); return w->w.replicaCount(); }
+int32_t dbx_world_raycast_closest(dbx_world* w, const dbx_ray* rays, int32_t n, dbx_ray_hit* out) { W_OR_INVALID(w); return w->w.rayCastClosest(rays, n, out); }
+int32_t dbx_world_query_aabb(dbx_world* w, const dbx_aabb* boxes, int32_t n, int32_t capPerQuery, int32_t* counts, int32_t* fixture_child) {
+  W_OR_INVALID(w); return w->w.queryAabb(boxes, n, capPerQuery, counts, fixture_child);
+}
 int32_t dbx_world_enable_contact_events(dbx_world* w, int32_t capacity) { W_OR_INVALID(w); return w->w.enableContactEvents(capacity); }
 int32_t dbx_world_poll_contact_events(dbx_world* w, dbx_contact_event* out, int32_t cap) { W_OR_INVALID(w); return w->w.pollContactEvents(out, cap); }
 

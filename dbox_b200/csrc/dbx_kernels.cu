@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) k_island_union(const __grid_constant__ De
     if ((flags & (CF_ALIVE | CF_TOUCHING | CF_ENABLED | CF_SENSOR)) != (CF_ALIVE | CF_TOUCHING | CF_ENABLED)) continue;
     int4 ids = W.c_ids[i];
     if (body_type(W.b_flags[ids.z]) == BODY_STATIC || body_type(W.b_flags[ids.w]) == BODY_STATIC) continue;  // statics end the search (:998-1003)
-    uf_unite(W.b_root, ids.z, ids.w);
+    uf_unite(W.b_root, ids.z, ids.w, W.nWorlds == 1);
   }
   GRID_STRIDE(j, W.nJoints) {
     int4 ids = W.j_ids[j];
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) k_island_union(const __grid_constant__ De
     uint32_t fa = W.b_flags[ids.y], fb = W.b_flags[ids.z];
     if (!(fa & BF_ACTIVE) || !(fb & BF_ACTIVE)) continue;                                  // other body must be active (:1058-1062)
     if (body_type(fa) == BODY_STATIC || body_type(fb) == BODY_STATIC) continue;
-    uf_unite(W.b_root, ids.y, ids.z);
+    uf_unite(W.b_root, ids.y, ids.z, W.nWorlds == 1);
   }
 }
 
@@ -632,6 +632,147 @@ __global__ void __launch_bounds__(256) k_query(const __grid_constant__ DevWorld 
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const int nMoved = min(W.hdr->nMoved, W.moveCap);
   for (int mIdx = warp; mIdx < nMoved; mIdx += nwarps) query_proxy(W, leaves, stacks[wib], kQueryStack, lane, W.moveList[mIdx]);
+}
+
+// ------------------------------------------------------------------------------------------------ world queries
+// b2World.RayCast / QueryAABB on the LBVH (dynamics/b2world.d:563-587), batched: one thread per ray / per box.
+// b2Shape.RayCast: circle b2circleshape.d:67-94, edge (and chain children) b2edgeshape.d:96-150, polygon b2polygonshape.d:279-332
+DBX_D bool shape_raycast(const DShape* S, Xf xf, v2 P1, v2 P2, float maxFraction, float* fraction, v2* normalOut) {
+  if (S->type == SH_CIRCLE) {
+    const v2 position = xf.p + mul(xf.q, S->c);
+    const v2 s = P1 - position;
+    const float b = dot(s, s) - S->radius * S->radius;
+    const v2 r = P2 - P1;
+    const float c = dot(s, r);
+    const float rr = dot(r, r);
+    const float sigma = c * c - rr * b;
+    if (sigma < 0.0f || rr < kEpsilon) return false;
+    float a = -(c + sqrtf(sigma));
+    if (0.0f <= a && a <= maxFraction * rr) {
+      a /= rr;
+      *fraction = a;
+      v2 n = s + a * r;
+      normalize(n);
+      *normalOut = n;
+      return true;
+    }
+    return false;
+  }
+  const v2 p1 = mulT(xf.q, P1 - xf.p), p2 = mulT(xf.q, P2 - xf.p);
+  const v2 d = p2 - p1;
+  if (S->type == SH_EDGE) {
+    const v2 v1 = S->v[1], v2_ = S->v[2];
+    const v2 e = v2_ - v1;
+    v2 normal = V(e.y, -e.x);
+    normalize(normal);
+    const float numerator = dot(normal, v1 - p1);
+    const float denominator = dot(normal, d);
+    if (denominator == 0.0f) return false;
+    const float t = numerator / denominator;
+    if (t < 0.0f || maxFraction < t) return false;
+    const v2 q = p1 + t * d;
+    const v2 r = v2_ - v1;
+    const float rr = dot(r, r);
+    if (rr == 0.0f) return false;
+    const float sc = dot(q - v1, r) / rr;
+    if (sc < 0.0f || 1.0f < sc) return false;
+    *fraction = t;
+    *normalOut = numerator > 0.0f ? -mul(xf.q, normal) : mul(xf.q, normal);
+    return true;
+  }
+  float lower = 0.0f, upper = maxFraction;
+  int index = -1;
+  for (int i = 0; i < S->count; ++i) {
+    const float numerator = dot(S->n[i], S->v[i] - p1);
+    const float denominator = dot(S->n[i], d);
+    if (denominator == 0.0f) {
+      if (numerator < 0.0f) return false;
+    } else {
+      if (denominator < 0.0f && numerator < lower * denominator) { lower = numerator / denominator; index = i; }
+      else if (denominator > 0.0f && numerator < upper * denominator) upper = numerator / denominator;
+    }
+    if (upper < lower) return false;
+  }
+  if (index >= 0) { *fraction = lower; *normalOut = mul(xf.q, S->n[index]); return true; }
+  return false;
+}
+
+constexpr int kRayStack = 96;
+// out: 8 floats per ray = (fixture, child, fraction, point.x, point.y, normal.x, normal.y, -) with ints stored bitwise
+__global__ void __launch_bounds__(128) k_raycast(const __grid_constant__ DevWorld W, const int* leaves, const float4* rays, int nRays, float4* out) {
+  const int n = W.nProxies;
+  GRID_STRIDE(k, nRays) {
+    const float4 ry = rays[k];
+    const v2 p1 = V(ry.x, ry.y), p2 = V(ry.z, ry.w);
+    int bestFixture = -1, bestChild = 0, bestKey = 0x7fffffff;
+    float maxFraction = 1.0f;
+    v2 bestNormal = V(0.0f, 0.0f);
+    v2 r = p2 - p1;
+    if (n > 0 && dot(r, r) > 0.0f) {
+      normalize(r);
+      const v2 v = cross(1.0f, r), abs_v = V(fabsr(v.x), fabsr(v.y));
+      int stack[kRayStack];
+      int top = 0;
+      stack[top++] = (n == 1) ? (n - 1) : 0;
+      while (top > 0) {
+        const int node = stack[--top];
+        const float4 bx = __ldcg(&W.bv_box[node]);
+        const v2 t = p1 + maxFraction * (p2 - p1);
+        const v2 slo = vmin(p1, t), shi = vmax(p1, t);
+        if (bx.z < slo.x || bx.w < slo.y || shi.x < bx.x || shi.y < bx.y) continue;       // b2TestOverlap(node.aabb, segmentAABB)
+        const v2 c = 0.5f * V(bx.x + bx.z, bx.y + bx.w), h = 0.5f * V(bx.z - bx.x, bx.w - bx.y);
+        const float separation = fabsr(dot(v, p1 - c)) - dot(abs_v, h);
+        if (separation > 0.0f) continue;
+        if (node >= n - 1) {
+          const int q = leaves[node - (n - 1)];
+          if (!(W.p_flags[q] & PF_ALIVE)) continue;
+          const int4 ids = W.p_ids[q];   // fixture child body shape
+          float fraction; v2 normal;
+          if (!shape_raycast(W.shapes + ids.w, XF(W.b_xf[ids.z]), p1, p2, maxFraction, &fraction, &normal)) continue;
+          const int key = W.p_key[q];
+          if (fraction < maxFraction || bestFixture < 0 || key < bestKey) {
+            bestFixture = ids.x; bestChild = ids.y; bestKey = key; bestNormal = normal; maxFraction = fraction;
+          }
+        } else {
+          if (top + 2 > kRayStack) { W.hdr->error = -5; break; }
+          const int2 ch = W.bv_child[node];
+          stack[top++] = ch.x; stack[top++] = ch.y;
+        }
+      }
+    }
+    const v2 point = (1.0f - maxFraction) * p1 + maxFraction * p2;
+    out[2 * k] = make_float4(__int_as_float(bestFixture), __int_as_float(bestChild), maxFraction, point.x);
+    out[2 * k + 1] = make_float4(point.y, bestNormal.x, bestNormal.y, 0.0f);
+  }
+}
+// counts[k] = number of proxies whose fat box overlaps boxes[k]; the first capPer of them as (fixture, child) in out
+__global__ void __launch_bounds__(128) k_query_aabb(const __grid_constant__ DevWorld W, const int* leaves, const float4* boxes, int nBoxes, int capPer, int* counts, int2* out) {
+  const int n = W.nProxies;
+  GRID_STRIDE(k, nBoxes) {
+    const Box box = BX(boxes[k]);
+    int count = 0;
+    if (n > 0) {
+      int stack[kRayStack];
+      int top = 0;
+      stack[top++] = (n == 1) ? (n - 1) : 0;
+      while (top > 0) {
+        const int node = stack[--top];
+        if (!overlap(BX(__ldcg(&W.bv_box[node])), box)) continue;
+        if (node >= n - 1) {
+          const int q = leaves[node - (n - 1)];
+          if (!(W.p_flags[q] & PF_ALIVE) || !overlap(BX(W.p_fat[q]), box)) continue;   // the leaf box may be wider than the fat box
+          const int4 ids = W.p_ids[q];
+          if (count < capPer) out[(size_t)k * capPer + count] = make_int2(ids.x, ids.y);
+          ++count;
+        } else {
+          if (top + 2 > kRayStack) { W.hdr->error = -5; break; }
+          const int2 ch = W.bv_child[node];
+          stack[top++] = ch.x; stack[top++] = ch.y;
+        }
+      }
+    }
+    counts[k] = count;
+  }
 }
 
 // b2ContactManager.AddPair (dynamics/b2contactmanager.d:52-176) + b2Contact.Create (contacts/b2contact.d:375-400)
@@ -1333,6 +1474,34 @@ cudaError_t stage_toi_pre(const DevWorld& W, const LaunchCfg& L, cudaStream_t au
   // three quarters of the SMs: at 125 registers x 512 threads a CTA owns a whole register file, and the broadphase kernels this
   // overlaps with need somewhere to run
   ++L.launches; k_toi<<<(3 * L.coopBlocks + 3) / 4, L.coopThreads, 0, aux>>>(P);
+  return cudaGetLastError();
+}
+
+// (re)build the LBVH alone, or widen it for the proxies in the move buffer: what a world query needs before it can run
+cudaError_t stage_refresh_tree(DevWorld& W, const LaunchCfg& L, bool rebuild) {
+  const int n = W.nProxies;
+  if (n == 0) return cudaSuccess;
+  if (!rebuild) { ++L.launches; k_lbvh_enlarge<<<L.gridWide, 256, 0, L.stream>>>(W); return cudaGetLastError(); }
+  ++L.launches; k_bounds_init<<<1, 1, 0, L.stream>>>(W);
+  ++L.launches; k_bounds<<<L.gridWide, 256, 0, L.stream>>>(W);
+  ++L.launches; k_morton<<<L.gridWide, 256, 0, L.stream>>>(W);
+  cub::DoubleBuffer<unsigned long long> keys(W.bv_key, W.bv_keyAlt);
+  cub::DoubleBuffer<int> vals(W.bv_leaf, W.bv_leafAlt);
+  int worldBits = 1;
+  while ((1 << worldBits) < W.nWorlds + 1) ++worldBits;
+  size_t bytes = L.cubTempBytes;
+  CK(cub::DeviceRadixSort::SortPairs(L.cubTemp, bytes, keys, vals, n, 0, 30 + worldBits + 1, L.stream));
+  W.bv_sorted = vals.Current();
+  ++L.launches; k_lbvh_hierarchy<<<L.gridWide, 256, 0, L.stream>>>(W, keys.Current());
+  ++L.launches; k_lbvh_refit<<<L.gridWide, 256, 0, L.stream>>>(W, W.bv_sorted);
+  return cudaGetLastError();
+}
+cudaError_t launch_raycast(const DevWorld& W, const LaunchCfg& L, const float4* rays, int n, float4* out) {
+  ++L.launches; k_raycast<<<(n + 127) / 128, 128, 0, L.stream>>>(W, W.bv_sorted, rays, n, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_query_aabb(const DevWorld& W, const LaunchCfg& L, const float4* boxes, int n, int capPer, int* counts, int2* out) {
+  ++L.launches; k_query_aabb<<<(n + 127) / 128, 128, 0, L.stream>>>(W, W.bv_sorted, boxes, n, capPer, counts, out);
   return cudaGetLastError();
 }
 

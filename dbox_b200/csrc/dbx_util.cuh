@@ -56,7 +56,8 @@ DBX_D void hash_remove(const DevWorld& W, unsigned long long key) {
 // lock-free union-find.  Roots are hooked by a bijective hash of the body id (smaller hash wins), not by the id itself:
 // a stack of consecutively numbered bodies would otherwise hook into one chain as deep as the stack, and the dependent
 // loads of walking it are what the island pass costs.  A component's root is still a pure function of its member set.
-DBX_D unsigned uf_rank(int x) { return (unsigned)x * 0x9E3779B1u; }
+// (Batched worlds keep id order: their islands are small, and hashing only scatters the accesses over a 50 MB array.)
+DBX_D unsigned uf_rank(int x, bool hashed) { return hashed ? (unsigned)x * 0x9E3779B1u : (unsigned)x; }
 DBX_D int uf_find(int* parent, int x) {
   for (;;) {
     int p = parent[x];
@@ -66,7 +67,7 @@ DBX_D int uf_find(int* parent, int x) {
     x = p;
   }
 }
-DBX_D void uf_unite(int* parent, int a, int b) {
+DBX_D void uf_unite(int* parent, int a, int b, bool hashed) {
   const int a0 = a, b0 = b;
   for (;;) {
     // both root walks in lock-step: two independent loads in flight per hop instead of one
@@ -76,7 +77,7 @@ DBX_D void uf_unite(int* parent, int a, int b) {
       a = pa; b = pb;
     }
     if (a == b) break;
-    if (uf_rank(a) < uf_rank(b)) { int t = a; a = b; b = t; }
+    if (uf_rank(a, hashed) < uf_rank(b, hashed)) { int t = a; a = b; b = t; }
     if (atomicCAS(&parent[a], a, b) == a) { a = b; break; }
   }
   // shortcut the two starting points to the root just found (always one of their ancestors)

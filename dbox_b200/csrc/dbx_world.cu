@@ -809,7 +809,9 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents) {
   // When the scratch is clean the first TOI evaluation is forked onto a second stream right after the solver.
   const bool continuous = (flags_ & DBX_WORLD_CONTINUOUS) && dt > 0.0f;
   const bool toiScratchDirty = !toiClean_ || toiBodies_ != bodies_.size() * (size_t)nWorlds_;
-  const bool toiPre = continuous && !toiScratchDirty && stepComplete_ && !overrideLevels_ && !(dw_.dbgFlags & 8);
+  // (a world big enough to fill the machine gains nothing from the overlap: the two streams just take SMs from each other)
+  const bool toiPre = continuous && !toiScratchDirty && stepComplete_ && !overrideLevels_ && !(dw_.dbgFlags & 8) &&
+                      bodies_.size() * (size_t)nWorlds_ <= ((size_t)1 << 21);
   auto mark = [&](int i) { if (fineEvents || i == 0 || i == 1 || i == 3 || i == 5 || i == 7 || i == 8 || i == 9) cudaEventRecord(ev_[i], stream_); };
   mark(0);
   CUDA_OR_FAIL(stage_collide(dw_, L_), "collide");
@@ -930,6 +932,57 @@ int World::setBodyStates(const int* ids, const float* pose4, const float* vel4, 
   hostBodiesValid_ = false; hostProxiesValid_ = false;
   return n;
 }
+// world queries (b2world.d:563-587) see the world as it is now: pending host edits are pushed, and the LBVH is rebuilt if
+// the proxy set changed under it, otherwise widened for whatever is in the move buffer
+int World::refreshTreeForQuery() {
+  if (replicated_) { set_last_error("world queries on a replicated world are not built (replicas share coordinates)"); return DBX_E_UNSUPPORTED; }
+  int rc = push(); if (rc < 0) return rc;
+  if (proxies_.empty()) return 0;
+  const bool rebuild = !treeValid_;
+  CUDA_OR_FAIL(stage_refresh_tree(dw_, L_, rebuild), "refresh tree");
+  if (rebuild) { treeValid_ = true; sinceRebuild_ = 0; }
+  return 0;
+}
+int World::rayCastClosest(const dbx_ray* rays, int n, dbx_ray_hit* out) {
+  if (n < 0 || (n > 0 && (!rays || !out))) return DBX_E_INVALID;
+  if (n == 0) return 0;
+  int rc = refreshTreeForQuery(); if (rc < 0) return rc;
+  CUDA_OR_FAIL(qIn_.reserve((size_t)n, false, stream_), "rays"); CUDA_OR_FAIL(qOut_.reserve(2 * (size_t)n, false, stream_), "hits");
+  CUDA_OR_FAIL(cudaMemcpyAsync(qIn_.p, rays, (size_t)n * 16, cudaMemcpyHostToDevice, stream_), "rays h2d");
+  CUDA_OR_FAIL(launch_raycast(dw_, L_, qIn_.p, n, qOut_.p), "raycast");
+  std::vector<float4> h(2 * (size_t)n);
+  CUDA_OR_FAIL(cudaMemcpyAsync(h.data(), qOut_.p, h.size() * 16, cudaMemcpyDeviceToHost, stream_), "hits d2h");
+  rc = checkDeviceError(true); if (rc < 0) return DBX_E_CAPACITY;
+  for (int k = 0; k < n; ++k) {
+    const float4 a = h[2 * k], b = h[2 * k + 1];
+    dbx_ray_hit& o = out[k];
+    std::memcpy(&o.fixture, &a.x, 4); std::memcpy(&o.child, &a.y, 4);
+    o.fraction = a.z; o.point = dbx_vec2{a.w, b.x}; o.normal = dbx_vec2{b.y, b.z};
+    if (o.fixture < 0) { o.fraction = 1.0f; o.point = dbx_vec2{0, 0}; o.normal = dbx_vec2{0, 0}; o.child = 0; }
+  }
+  return n;
+}
+int World::queryAabb(const dbx_aabb* boxes, int n, int capPer, int32_t* counts, int32_t* fixtureChild) {
+  if (n < 0 || capPer < 0 || (n > 0 && (!boxes || !counts)) || (n > 0 && capPer > 0 && !fixtureChild)) return DBX_E_INVALID;
+  if (n == 0) return 0;
+  int rc = refreshTreeForQuery(); if (rc < 0) return rc;
+  const size_t np = (size_t)n * (size_t)std::max(capPer, 1);
+  CUDA_OR_FAIL(qIn_.reserve((size_t)n, false, stream_), "boxes"); CUDA_OR_FAIL(qCount_.reserve((size_t)n, false, stream_), "counts"); CUDA_OR_FAIL(qPairs_.reserve(np, false, stream_), "pairs");
+  CUDA_OR_FAIL(cudaMemcpyAsync(qIn_.p, boxes, (size_t)n * 16, cudaMemcpyHostToDevice, stream_), "boxes h2d");
+  CUDA_OR_FAIL(launch_query_aabb(dw_, L_, qIn_.p, n, capPer, qCount_.p, qPairs_.p), "query_aabb");
+  std::vector<int2> hp(np);
+  CUDA_OR_FAIL(cudaMemcpyAsync(counts, qCount_.p, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_), "counts d2h");
+  CUDA_OR_FAIL(cudaMemcpyAsync(hp.data(), qPairs_.p, np * 8, cudaMemcpyDeviceToHost, stream_), "pairs d2h");
+  rc = checkDeviceError(true); if (rc < 0) return DBX_E_CAPACITY;
+  for (int k = 0; k < n && capPer > 0; ++k) {   // traversal order means nothing: report sorted by (fixture, child)
+    const int m = std::min(counts[k], capPer);
+    int2* b = hp.data() + (size_t)k * capPer;
+    std::sort(b, b + m, [](const int2& x, const int2& y) { return x.x != y.x ? x.x < y.x : x.y < y.y; });
+    for (int i = 0; i < m; ++i) { fixtureChild[2 * ((size_t)k * capPer + i)] = b[i].x; fixtureChild[2 * ((size_t)k * capPer + i) + 1] = b[i].y; }
+  }
+  return n;
+}
+
 // b2World.SetContactListener (dynamics/b2world.d:62-66), deferred form: capacity > 0 turns recording on, 0 off
 int World::enableContactEvents(int capacity) {
   if (capacity < 0) return DBX_E_INVALID;

@@ -65,6 +65,9 @@ class World {
   int timeSteps(float dt, int vi, int pi, int n, bool flushL2, float* totalMs, float* stageMs);
   int applyForces(const float* f4, int n);
   int setBodyStates(const int* ids, const float* pose4, const float* vel4, int n);
+  int rayCastClosest(const dbx_ray* rays, int n, dbx_ray_hit* out);
+  int queryAabb(const dbx_aabb* boxes, int n, int capPer, int32_t* counts, int32_t* fixtureChild);
+  int refreshTreeForQuery();
   int enableContactEvents(int capacity);
   int pollContactEvents(dbx_contact_event* out, int cap);
   int readTransforms(float* out, int n);
@@ -172,7 +175,7 @@ class World {
   int nJointPairs_ = 0; int jointBlocks_ = 0, nJointColours_ = 0;
   cudaEvent_t ev_[10]{};
   bool evValid_ = false, evFine_ = false;
-  DevBuf<char> flushBuf_; DevBuf<float4> ioBuf_, ioBuf2_; DevBuf<int> ioIds_; DevBuf<int4> ev_a_, ev_b_; DevBuf<unsigned long long> phaseBuf_;
+  DevBuf<char> flushBuf_; DevBuf<float4> ioBuf_, ioBuf2_; DevBuf<int> ioIds_; DevBuf<int4> ev_a_, ev_b_; DevBuf<float4> qIn_, qOut_; DevBuf<int> qCount_; DevBuf<int2> qPairs_; DevBuf<unsigned long long> phaseBuf_;
   bool overrideLevels_ = false;
   bool treeValid_ = false; int sinceRebuild_ = 0;
   // contact-pool watermark: every 8th step the header is copied to pinned memory without waiting; a later step looks at

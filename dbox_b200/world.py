@@ -645,6 +645,35 @@ class b2World:
         if getattr(self, "_listener", None) is not None:
             self._deliver_contact_events()
 
+    # world queries, batched (b2world.d:563-587; include/dbox_b200.h "world queries") --------------------------
+    def RayCastClosest(self, rays):
+        """rays: iterable of ((x1, y1), (x2, y2)); returns [(fixture_id | -1, child, fraction, (px, py), (nx, ny))]"""
+        rays = list(rays)
+        n = len(rays)
+        buf = (A.Ray * max(n, 1))()
+        for k, (a, b) in enumerate(rays):
+            buf[k].p1, buf[k].p2 = _v(a), _v(b)
+        out = (A.RayHit * max(n, 1))()
+        self._ck(self._api.world_raycast_closest(self._w, buf, n, out))
+        return [(out[k].fixture, out[k].child, out[k].fraction, (out[k].point.x, out[k].point.y), (out[k].normal.x, out[k].normal.y)) for k in range(n)]
+
+    def QueryAABB(self, boxes, cap=64):
+        """boxes: iterable of ((lox, loy), (hix, hiy)); returns one sorted list of (fixture_id, child) per box"""
+        boxes = list(boxes)
+        n = len(boxes)
+        buf = (A.AABB * max(n, 1))()
+        for k, (lo, hi) in enumerate(boxes):
+            buf[k].lo, buf[k].hi = _v(lo), _v(hi)
+        counts = (C.c_int32 * max(n, 1))()
+        pairs = (C.c_int32 * (2 * max(n, 1) * cap))()
+        self._ck(self._api.world_query_aabb(self._w, buf, n, cap, counts, pairs))
+        out = []
+        for k in range(n):
+            if counts[k] > cap:
+                raise RuntimeError("QueryAABB: %d hits, cap %d" % (counts[k], cap))
+            out.append([(pairs[2 * (k * cap + i)], pairs[2 * (k * cap + i) + 1]) for i in range(counts[k])])
+        return out
+
     # contact listener (b2world.d:62-66, b2worldcallbacks.d:87-128), deferred: see include/dbox_b200.h ------------
     def SetContactListener(self, listener, capacity=1 << 16):
         self._listener = listener

@@ -323,6 +323,20 @@ float dbx_debug_barrier_us(int32_t device, int32_t blocks, int32_t threads, int3
 int32_t dbx_world_replicate(dbx_world* w, int32_t copies);  /* world becomes `copies` disjoint replicas of its current content */
 int32_t dbx_world_replica_count(dbx_world* w);
 
+/* ---- world queries on the device tree, batched ---------------------------------------------
+ * b2World.RayCast (dynamics/b2world.d:577-587; wrapper :1605-1624; b2DynamicTree.RayCast collision/b2dynamictree.d:237-331;
+ * b2Shape.RayCast b2circleshape.d:67-94, b2edgeshape.d:96-150, b2polygonshape.d:279-332, b2chainshape.d:204-223) and
+ * b2World.QueryAABB (b2world.d:563-570, b2dynamictree.d:203-235).  The reference hands one ray / one box to a user
+ * callback; here a whole batch goes to the device (one thread per ray, one warp per box) and the answers come back in
+ * arrays.  raycast_closest is the callback that returns `fraction` (the testbed's RayCastClosestCallback): the nearest
+ * hit along p1 -> p2, fixture = -1 for a miss.  query_aabb reports the (fixture, child) pairs whose FAT proxy box overlaps,
+ * as the reference does, sorted by (fixture, child); counts[k] may exceed capPerQuery (the surplus is dropped).
+ * Both see the world as it is after the last step / edit. */
+typedef struct dbx_ray { dbx_vec2 p1, p2; } dbx_ray;
+typedef struct dbx_ray_hit { int32_t fixture, child; float fraction; dbx_vec2 point, normal; } dbx_ray_hit;
+int32_t dbx_world_raycast_closest(dbx_world* w, const dbx_ray* rays, int32_t n, dbx_ray_hit* out);
+int32_t dbx_world_query_aabb(dbx_world* w, const dbx_aabb* boxes, int32_t n, int32_t capPerQuery, int32_t* counts, int32_t* fixture_child);
+
 /* ---- contact listener, deferred ------------------------------------------------------------
  * b2World.SetContactListener (dynamics/b2world.d:62-66) + b2ContactListener.BeginContact / EndContact
  * (dynamics/b2worldcallbacks.d:87-95).  The reference calls the listener in the middle of the step, from b2Contact.Update

@@ -322,6 +322,42 @@ int32_t orc_world_read_contacts(orc_world* w, dbx_contact_rec* out, int32_t cap)
   for (Contact* c = w->w.contactList; c; c = c->next) { if (n < cap) fillContact(c, out + n); ++n; }
   return n;
 }
+// b2World.RayCast (b2world.d:577-587, wrapper :1605-1624) with the callback that returns `fraction` (closest hit)
+int32_t orc_world_raycast_closest(orc_world* w, const dbx_ray* rays, int32_t n, dbx_ray_hit* out) {
+  for (int k = 0; k < n; ++k) {
+    dbx_ray_hit& h = out[k];
+    h.fixture = -1; h.child = 0; h.fraction = 1.0f; h.point = dbx_vec2{0, 0}; h.normal = dbx_vec2{0, 0};
+    V2 P1 = v2(rays[k].p1), P2 = v2(rays[k].p2);
+    if ((P2 - P1).len2() <= 0.0f) continue;
+    w->w.broadPhase.tree().rayCast([&](V2 p1, V2 p2, float maxFraction, int proxyId) -> float {
+      FixtureProxy* proxy = (FixtureProxy*)w->w.broadPhase.userData(proxyId);
+      Fixture* f = proxy->fixture;
+      float fraction; V2 normal;
+      bool hit = f->shape.rayCast(&fraction, &normal, p1, p2, maxFraction, f->body->xf, proxy->childIndex);
+      if (!hit) return maxFraction;
+      V2 point = (1.0f - fraction) * p1 + fraction * p2;
+      h.fixture = f->id; h.child = proxy->childIndex; h.fraction = fraction; h.point = d2(point); h.normal = d2(normal);
+      return fraction;
+    }, P1, P2, 1.0f);
+  }
+  return n;
+}
+// b2World.QueryAABB (b2world.d:563-570): fixtures whose FAT proxy box overlaps; reported here sorted by (fixture, child)
+int32_t orc_world_query_aabb(orc_world* w, const dbx_aabb* boxes, int32_t n, int32_t capPerQuery, int32_t* counts, int32_t* fixture_child) {
+  for (int k = 0; k < n; ++k) {
+    AABB box; box.lo = v2(boxes[k].lo); box.hi = v2(boxes[k].hi);
+    std::vector<std::pair<int, int>> hits;
+    w->w.broadPhase.tree().query([&](int proxyId) {
+      FixtureProxy* proxy = (FixtureProxy*)w->w.broadPhase.userData(proxyId);
+      hits.push_back({proxy->fixture->id, proxy->childIndex});
+      return true;
+    }, box);
+    std::sort(hits.begin(), hits.end());
+    counts[k] = (int)hits.size();
+    for (int i = 0; i < (int)hits.size() && i < capPerQuery; ++i) { fixture_child[2 * ((size_t)k * capPerQuery + i)] = hits[i].first; fixture_child[2 * ((size_t)k * capPerQuery + i) + 1] = hits[i].second; }
+  }
+  return n;
+}
 // the listener call log since the last poll, in the reference's CALL order (the CUDA library returns the same events sorted)
 int32_t orc_world_enable_contact_events(orc_world* w, int32_t capacity) {
   w->w.recordContactEvents = capacity > 0; w->w.contactEvents.clear(); return capacity;

@@ -1132,4 +1132,74 @@ void timeOfImpact(TOIOutput* output, const TOIInput* input) {
   }
 }
 
+static bool rayCastEdge(float* fraction, V2* normalOut, V2 P1, V2 P2, float maxFraction, const Xf& xf, V2 v1, V2 v2) {
+  V2 p1 = mulT(xf.q, P1 - xf.p);
+  V2 p2 = mulT(xf.q, P2 - xf.p);
+  V2 d = p2 - p1;
+  V2 e = v2 - v1;
+  V2 normal(e.y, -e.x);
+  normal.normalize();
+  float numerator = dot(normal, v1 - p1);
+  float denominator = dot(normal, d);
+  if (denominator == 0.0f) return false;
+  float t = numerator / denominator;
+  if (t < 0.0f || maxFraction < t) return false;
+  V2 q = p1 + t * d;
+  V2 r = v2 - v1;
+  float rr = dot(r, r);
+  if (rr == 0.0f) return false;
+  float s = dot(q - v1, r) / rr;
+  if (s < 0.0f || 1.0f < s) return false;
+  *fraction = t;
+  *normalOut = numerator > 0.0f ? -mul(xf.q, normal) : mul(xf.q, normal);
+  return true;
+}
+
+bool Shape::rayCast(float* fraction, V2* normalOut, V2 P1, V2 P2, float maxFraction, const Xf& xf, int child) const {
+  if (type == kCircle) {
+    V2 position = xf.p + mul(xf.q, p);
+    V2 s = P1 - position;
+    float b = dot(s, s) - radius * radius;
+    V2 r = P2 - P1;
+    float c = dot(s, r);
+    float rr = dot(r, r);
+    float sigma = c * c - rr * b;
+    if (sigma < 0.0f || rr < kEpsilon) return false;
+    float a = -(c + sqrtf(sigma));
+    if (0.0f <= a && a <= maxFraction * rr) {
+      a /= rr;
+      *fraction = a;
+      *normalOut = s + a * r;
+      normalOut->normalize();
+      return true;
+    }
+    return false;
+  }
+  if (type == kEdge) return rayCastEdge(fraction, normalOut, P1, P2, maxFraction, xf, v1, v2);
+  if (type == kChain) {
+    int i1 = child, i2 = child + 1;
+    if (i2 == (int)chain.size()) i2 = 0;
+    return rayCastEdge(fraction, normalOut, P1, P2, maxFraction, xf, chain[i1], chain[i2]);
+  }
+  // polygon
+  V2 p1 = mulT(xf.q, P1 - xf.p);
+  V2 p2 = mulT(xf.q, P2 - xf.p);
+  V2 d = p2 - p1;
+  float lower = 0.0f, upper = maxFraction;
+  int index = -1;
+  for (int i = 0; i < count; ++i) {
+    float numerator = dot(normals[i], verts[i] - p1);
+    float denominator = dot(normals[i], d);
+    if (denominator == 0.0f) {
+      if (numerator < 0.0f) return false;
+    } else {
+      if (denominator < 0.0f && numerator < lower * denominator) { lower = numerator / denominator; index = i; }
+      else if (denominator > 0.0f && numerator < upper * denominator) upper = numerator / denominator;
+    }
+    if (upper < lower) return false;
+  }
+  if (index >= 0) { *fraction = lower; *normalOut = mul(xf.q, normals[index]); return true; }
+  return false;
+}
+
 }  // namespace orc

@@ -46,6 +46,8 @@ struct Shape {
   void childEdge(Shape* e, int index) const;               // b2chainshape.d:162-192
   void computeAABB(AABB* out, const Xf& xf, int child) const;
   void computeMass(MassData* md, float density) const;
+  // b2Shape.RayCast (b2circleshape.d:67-94, b2edgeshape.d:96-150, b2polygonshape.d:279-332, b2chainshape.d:204-223)
+  bool rayCast(float* fraction, V2* normal, V2 p1, V2 p2, float maxFraction, const Xf& xf, int child) const;
 };
 
 // b2collision.d:38-114

@@ -77,6 +77,38 @@ class DynamicTree {
       }
     }
   }
+  // b2dynamictree.d:237-331.  cb(p1, p2, maxFraction, nodeId) -> 0: stop, < 0: ignore, else new maxFraction
+  template <class F> void rayCast(F&& cb, V2 p1, V2 p2, float maxFraction) const {
+    V2 r = p2 - p1;
+    r.normalize();
+    V2 v = cross(1.0f, r);
+    V2 abs_v = absv(v);
+    AABB segmentAABB;
+    { V2 t = p1 + maxFraction * (p2 - p1); segmentAABB.lo = minv(p1, t); segmentAABB.hi = maxv(p1, t); }
+    std::vector<int> stack;
+    stack.reserve(256);
+    stack.push_back(root_);
+    while (!stack.empty()) {
+      int nodeId = stack.back();
+      stack.pop_back();
+      if (nodeId == kNullNode) continue;
+      const TreeNode* node = &nodes_[nodeId];
+      if (overlap(node->aabb, segmentAABB) == false) continue;
+      V2 c = 0.5f * (node->aabb.lo + node->aabb.hi);
+      V2 h = 0.5f * (node->aabb.hi - node->aabb.lo);
+      float separation = absT(dot(v, p1 - c)) - dot(abs_v, h);
+      if (separation > 0.0f) continue;
+      if (node->isLeaf()) {
+        float value = cb(p1, p2, maxFraction, nodeId);
+        if (value == 0.0f) return;
+        if (value > 0.0f) {
+          maxFraction = value;
+          V2 t = p1 + maxFraction * (p2 - p1);
+          segmentAABB.lo = minv(p1, t); segmentAABB.hi = maxv(p1, t);
+        }
+      } else { stack.push_back(node->child1); stack.push_back(node->child2); }
+    }
+  }
   int height() const { return root_ == kNullNode ? 0 : nodes_[root_].height; }
 
   // b2dynamictree.d:334-352, 939-1011 (Validate) — structural self-check used by the oracle's own tests.

@@ -331,3 +331,72 @@ def test_joint_scene_with_contacts(gpu_api, oracle_api):
     assert bg[0].GetPosition().x > 5.0                       # the car drove off
     assert abs(bg[1].GetPosition().y - 5.0) < 0.05           # the lift reached its upper limit with the cargo on it
     assert bg[2].GetPosition().y > 5.5
+
+
+def _query_scene(api):
+    w = b2World((0.0, -10.0), api=api)
+    g = w.CreateBody(b2BodyDef())
+    ch = b2ChainShape(api); ch.CreateChain([(-30.0, 0.0), (-10.0, 1.0), (10.0, 0.0), (30.0, 2.0)])
+    g.CreateFixture(ch, 0.0)
+    e = b2EdgeShape(api); e.Set((-30.0, 0.0), (-30.0, 20.0)); g.CreateFixture(e, 0.0)
+    import random
+    rng = random.Random(5)
+    bodies = []
+    for k in range(60):
+        b = _dyn(w, rng.uniform(-25, 25), rng.uniform(2, 18), angle=rng.uniform(-3, 3))
+        t = k % 3
+        if t == 0:
+            s = b2CircleShape(api); s.m_radius = rng.uniform(0.3, 1.0)
+        elif t == 1:
+            s = b2PolygonShape(api); s.SetAsBox(rng.uniform(0.3, 1.2), rng.uniform(0.3, 1.2))
+        else:
+            s = b2PolygonShape(api); s.Set([(-0.7, -0.5), (0.8, -0.4), (0.5, 0.6), (-0.3, 0.9), (-0.8, 0.2)])
+        b.CreateFixture(s, 1.0)
+        bodies.append(b)
+    return w, bodies
+
+
+def test_raycast_and_query_match_reference(gpu_api, oracle_api):
+    """b2World.RayCast (closest-hit callback) and b2World.QueryAABB (b2world.d:563-587) on the LBVH against the oracle's
+    dynamic tree + b2Shape.RayCast restatements: same fixture / child, fraction and normal to float rounding, same
+    fat-box overlap sets; before the first step, after stepping, and after an edit without a step"""
+    import random
+    wg, bg = _query_scene(gpu_api); wo, bo = _query_scene(oracle_api)
+    rng = random.Random(11)
+    rays = [((rng.uniform(-35, 35), rng.uniform(-2, 25)), (rng.uniform(-35, 35), rng.uniform(-2, 25))) for _ in range(400)]
+    rays += [((0.0, 30.0), (0.0, -5.0)), ((-40.0, 5.0), (40.0, 5.0)), ((3.0, 3.0), (3.0, 3.0))]      # incl. a zero-length ray
+    boxes = [((x, y), (x + rng.uniform(0.1, 8), y + rng.uniform(0.1, 8))) for x, y in
+             [(rng.uniform(-32, 28), rng.uniform(-2, 20)) for _ in range(120)]] + [((-100.0, -100.0), (100.0, 100.0))]
+
+    def compare(tag, tol_f, tol_p, exact):
+        hg, ho = wg.RayCastClosest(rays), wo.RayCastClosest(rays)
+        hits = other = 0
+        for k, (a, b) in enumerate(zip(hg, ho)):
+            if (a[0], a[1]) != (b[0], b[1]):
+                assert not exact, (tag, k, a, b)
+                other += 1
+                continue
+            if b[0] >= 0:
+                hits += 1
+                close = abs(a[2] - b[2]) <= tol_f * max(1.0, abs(b[2])) and abs(a[3][0] - b[3][0]) <= tol_p and abs(a[3][1] - b[3][1]) <= tol_p
+                if exact:
+                    assert close and abs(a[4][0] - b[4][0]) <= tol_p and abs(a[4][1] - b[4][1]) <= tol_p, (tag, k, a, b)
+                elif not close:
+                    other += 1
+        assert hits > 100 and other <= 12, (tag, hits, other)          # 3 % of the rays may see a body that tumbled differently
+        qg, qo = wg.QueryAABB(boxes, cap=128), wo.QueryAABB(boxes, cap=128)
+        if exact:
+            assert qg == qo, tag
+        else:
+            assert sum(1 for x, y in zip(qg, qo) if x != y) <= 3, tag
+        assert len(qg[-1]) == 60 + 3 + 1
+
+    compare("before the first step", 1e-5, 2e-4, True)       # identical worlds: identical answers
+    for _ in range(40):
+        wg.Step(DT, 8, 3); wo.Step(DT, 8, 3)
+    compare("after 40 steps", 5e-3, 5e-2, False)              # chaotic scene: the two worlds now differ by the Gauss-Seidel order
+    for w, bs in ((wg, bg), (wo, bo)):
+        bs[7].SetTransform((0.0, 25.0), 0.3)
+        w.DestroyBody(bs[9])
+    hg, ho = wg.RayCastClosest([((0.0, 30.0), (0.0, 20.0))]), wo.RayCastClosest([((0.0, 30.0), (0.0, 20.0))])
+    assert hg[0][0] == ho[0][0] == bg[7].fixtures[0].id
