@@ -92,6 +92,14 @@ class ProxyRec(C.Structure):
     _fields_ = [("fixture", c_i32), ("child", c_i32), ("proxyId", c_i32), ("aabb", AABB), ("fat", AABB)]
 
 
+class ContactPatch(C.Structure):
+    _fields_ = [("fixtureA", c_i32), ("childA", c_i32), ("fixtureB", c_i32), ("childB", c_i32), ("mask", c_i32), ("enabled", c_i32),
+                ("friction", c_f32), ("restitution", c_f32), ("tangentSpeed", c_f32)]
+
+
+PATCH_ENABLED, PATCH_FRICTION, PATCH_RESTITUTION, PATCH_TANGENT_SPEED = 1, 2, 4, 8
+
+
 class Ray(C.Structure):
     _fields_ = [("p1", Vec2), ("p2", Vec2)]
 
@@ -127,7 +135,7 @@ class Caps(C.Structure):
 # sizes the header implies (checked by tests/test_abi.py and by the library's own static_asserts)
 EXPECTED_SIZES = {"Vec2": 8, "AABB": 16, "BodyDef": 72, "Shape": 240, "FixtureDef": 32, "JointDef": 176, "BodyState": 116,
                   "ManifoldPoint": 20, "Manifold": 64, "ContactRec": 104, "ProxyRec": 44, "JointState": 24, "Counts": 44,
-                  "Profile": 32, "Caps": 20, "ContactEvent": 36, "Ray": 16, "RayHit": 28}
+                  "Profile": 32, "Caps": 20, "ContactEvent": 36, "Ray": 16, "RayHit": 28, "ContactPatch": 36}
 
 P = C.POINTER
 W = C.c_void_p
@@ -204,6 +212,9 @@ PROTOTYPES = {
     "debug_barrier_us": (c_f32, [c_i32, c_i32, c_i32, c_i32]),
     "world_replicate": (c_i32, [W, c_i32]),
     "world_replica_count": (c_i32, [W]),
+    "world_step_begin": (c_i32, [W, c_f32, c_i32, c_i32]),
+    "world_step_end": (c_i32, [W]),
+    "world_patch_contacts": (c_i32, [W, P(ContactPatch), c_i32]),
     "world_raycast_closest": (c_i32, [W, P(Ray), c_i32, P(RayHit)]),
     "world_query_aabb": (c_i32, [W, P(AABB), c_i32, c_i32, P(c_i32), P(c_i32)]),
     "world_enable_contact_events": (c_i32, [W, c_i32]),

@@ -8,7 +8,7 @@ using namespace dbx;
 struct dbx_world { World w; dbx_world(float gx, float gy, int dev, const dbx_caps* caps) : w(gx, gy, dev, caps) {} };
 
 static_assert(sizeof(dbx_body_def) == 72 && sizeof(dbx_shape) == 240 && sizeof(dbx_fixture_def) == 32 && sizeof(dbx_joint_def) == 176, "ABI layout");
-static_assert(sizeof(dbx_body_state) == 116 && sizeof(dbx_manifold) == 64 && sizeof(dbx_contact_rec) == 104 && sizeof(dbx_proxy_rec) == 44 && sizeof(dbx_contact_event) == 36, "ABI layout");
+static_assert(sizeof(dbx_body_state) == 116 && sizeof(dbx_manifold) == 64 && sizeof(dbx_contact_rec) == 104 && sizeof(dbx_proxy_rec) == 44 && sizeof(dbx_contact_event) == 36 && sizeof(dbx_contact_patch) == 36, "ABI layout");
 
 #define W_OR_INVALID(w) do { if (!(w) || !(w)->w.ok()) return DBX_E_INVALID; } while (0)
 
@@ -257,6 +257,9 @@ int32_t dbx_world_debug_header(dbx_world* w, void* out, int32_t bytes) { W_OR_IN
 // ---- batched independent worlds
 int32_t dbx_world_replicate(dbx_world* w, int32_t copies) { W_OR_INVALID(w); return w->w.replicate(copies); }
 int32_t dbx_world_replica_count(dbx_world* w) { W_OR_INVALID(w); return w->w.replicaCount(); }
+int32_t dbx_world_step_begin(dbx_world* w, float dt, int32_t vi, int32_t pi) { W_OR_INVALID(w); return w->w.stepBegin(dt, vi, pi); }
+int32_t dbx_world_step_end(dbx_world* w) { W_OR_INVALID(w); return w->w.stepEnd(); }
+int32_t dbx_world_patch_contacts(dbx_world* w, const dbx_contact_patch* patches, int32_t n) { W_OR_INVALID(w); return w->w.patchContacts(patches, n); }
 int32_t dbx_world_raycast_closest(dbx_world* w, const dbx_ray* rays, int32_t n, dbx_ray_hit* out) { W_OR_INVALID(w); return w->w.rayCastClosest(rays, n, out); }
 int32_t dbx_world_query_aabb(dbx_world* w, const dbx_aabb* boxes, int32_t n, int32_t capPerQuery, int32_t* counts, int32_t* fixture_child) {
   W_OR_INVALID(w); return w->w.queryAabb(boxes, n, capPerQuery, counts, fixture_child);

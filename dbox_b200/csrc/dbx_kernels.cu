@@ -961,6 +961,23 @@ __global__ void __launch_bounds__(256) k_api_contacts(const __grid_constant__ De
     W.c_free[slot] = i;
   }
 }
+// mask bits: 1 enabled, 2 friction, 4 restitution, 8 tangentSpeed; bit 8 carries the `enabled` value
+__global__ void __launch_bounds__(256) k_patch_contacts(const __grid_constant__ DevWorld W, const unsigned long long* keys, const float4* vals, const int* masks, int n) {
+  GRID_STRIDE(k, n) {
+    const int i = hash_find(W, keys[k]);
+    if (i < 0) continue;
+    const int m = masks[k];
+    if (m & 1) { uint32_t f = W.c_flags[i]; W.c_flags[i] = (m & 0x100) ? (f | CF_ENABLED) : (f & ~CF_ENABLED); }
+    if (m & 14) {
+      float4 mat = W.c_mat[i];
+      const float4 v = vals[k];
+      if (m & 2) mat.x = v.x;
+      if (m & 4) mat.y = v.y;
+      if (m & 8) mat.z = v.z;
+      W.c_mat[i] = mat;
+    }
+  }
+}
 __global__ void k_api_wake(const __grid_constant__ DevWorld W, int a, int b) {
   if (a >= 0) wake_body_now(W, a);
   if (b >= 0) wake_body_now(W, b);
@@ -1555,6 +1572,10 @@ cudaError_t launch_insert_contacts(const DevWorld& W, const LaunchCfg& L, int n)
 
 cudaError_t launch_api_contacts(const DevWorld& W, const LaunchCfg& L, int body, int fixture, int otherBody, int flagOnly) {
   ++L.launches; k_api_contacts<<<L.gridWide, 256, 0, L.stream>>>(W, body, fixture, otherBody, flagOnly);
+  return cudaGetLastError();
+}
+cudaError_t launch_patch_contacts(const DevWorld& W, const LaunchCfg& L, const unsigned long long* keys, const float4* vals, const int* masks, int n) {
+  ++L.launches; k_patch_contacts<<<(n + 255) / 256, 256, 0, L.stream>>>(W, keys, vals, masks, n);
   return cudaGetLastError();
 }
 cudaError_t launch_api_wake(const DevWorld& W, const LaunchCfg& L, int a, int b) {

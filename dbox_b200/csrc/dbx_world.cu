@@ -798,12 +798,17 @@ int World::growContactsIfNeeded() {
 }
 
 // one b2World.Step (dynamics/b2world.d:367-434) enqueued on the world's stream; no host synchronisation
-int World::enqueueStep(float dt, int vi, int pi, bool fineEvents) {
-  int rc = push(); if (rc < 0) return rc;
-  if (bodies_.empty()) return 0;
-  rc = growContactsIfNeeded(); if (rc < 0) return rc;
-  if (newFixture_) { int rf = findNewContacts(); if (rf < 0) return rf; newFixture_ = false; }   // :372-376
-  setStepParams(dt, vi, pi);
+// `halves`: 1 = up to and including Collide, 2 = everything after it, 3 = the whole step.  The split exists for
+// b2ContactListener.PreSolve (b2contact.d:348-355): dbx_world_step_begin / patch_contacts / step_end.
+int World::enqueueStep(float dt, int vi, int pi, bool fineEvents, int halves) {
+  int rc = 0;
+  if (halves & 1) {
+    rc = push(); if (rc < 0) return rc;
+    if (bodies_.empty()) return 0;
+    rc = growContactsIfNeeded(); if (rc < 0) return rc;
+    if (newFixture_) { int rf = findNewContacts(); if (rf < 0) return rf; newFixture_ = false; }   // :372-376
+    setStepParams(dt, vi, pi);
+  } else if (bodies_.empty()) return 0;
   dw_.colourOverride = overrideLevels_ ? 1 : 0;
   // TOI: the kernel leaves its per-body scratch clean; a world that has not run it yet, or has grown since, resets first.
   // When the scratch is clean the first TOI evaluation is forked onto a second stream right after the solver.
@@ -813,9 +818,12 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents) {
   const bool toiPre = continuous && !toiScratchDirty && stepComplete_ && !overrideLevels_ && !(dw_.dbgFlags & 8) &&
                       bodies_.size() * (size_t)nWorlds_ <= ((size_t)1 << 21);
   auto mark = [&](int i) { if (fineEvents || i == 0 || i == 1 || i == 3 || i == 5 || i == 7 || i == 8 || i == 9) cudaEventRecord(ev_[i], stream_); };
-  mark(0);
-  CUDA_OR_FAIL(stage_collide(dw_, L_), "collide");
-  mark(1);
+  if (halves & 1) {
+    mark(0);
+    CUDA_OR_FAIL(stage_collide(dw_, L_), "collide");
+    mark(1);
+  }
+  if (!(halves & 2)) { hostBodiesValid_ = false; return 0; }
   if (stepComplete_ && dt > 0.0f) {
     CUDA_OR_FAIL(stage_islands_and_integrate(dw_, L_), "islands");
     mark(2);
@@ -873,6 +881,51 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents) {
 }
 
 // n steps without host round trips in between; one synchronisation at the end
+// b2World.Step cut at the point where the reference calls PreSolve: begin = FindNewContacts-if-needed + Collide; the host
+// may then read the contacts, poll the begin/end events and patch contacts; end = Solve, SolveTOI, ClearForces
+int World::stepBegin(float dt, int vi, int pi) {
+  if (!ok_) return DBX_E_NO_DEVICE;
+  cudaSetDevice(device_);
+  if (midStep_) { set_last_error("step_begin: the previous step was not ended"); return DBX_E_INVALID; }
+  stepDt_ = dt; stepVi_ = vi; stepPi_ = pi;
+  int rc = enqueueStep(dt, vi, pi, false, 1); if (rc < 0) return rc;
+  midStep_ = true;
+  return checkDeviceError(true);
+}
+int World::stepEnd() {
+  if (!ok_) return DBX_E_NO_DEVICE;
+  cudaSetDevice(device_);
+  if (!midStep_) { set_last_error("step_end without step_begin"); return DBX_E_INVALID; }
+  midStep_ = false;
+  int rc = enqueueStep(stepDt_, stepVi_, stepPi_, false, 2); if (rc < 0) return rc;
+  return checkDeviceError(true);
+}
+// b2Contact.SetEnabled / SetFriction / SetRestitution / SetTangentSpeed (contacts/b2contact.d:137-205) from PreSolve
+int World::patchContacts(const dbx_contact_patch* in, int n) {
+  if (n < 0 || (n > 0 && !in)) return DBX_E_INVALID;
+  if (n == 0 || !dw_.hdr) return 0;
+  std::vector<unsigned long long> keys((size_t)n); std::vector<float4> vals((size_t)n); std::vector<int> masks((size_t)n);
+  for (int k = 0; k < n; ++k) {
+    const dbx_contact_patch& c = in[k];
+    auto proxyKey = [&](int f, int child) -> int {
+      if (f < 0 || f >= (int)fixtures_.size() || !fixtures_[f].alive || child < 0 || child >= (int)fixtures_[f].proxies.size()) return -1;
+      return proxies_[fixtures_[f].proxies[child]].key;
+    };
+    const int ka = proxyKey(c.fixtureA, c.childA), kb = proxyKey(c.fixtureB, c.childB);
+    if (ka < 0 || kb < 0) return DBX_E_INVALID;
+    keys[k] = ((unsigned long long)(unsigned)std::min(ka, kb) << 32) | (unsigned)std::max(ka, kb);
+    masks[k] = c.mask | (c.enabled ? 0x100 : 0);
+    vals[k] = make_float4(c.friction, c.restitution, c.tangentSpeed, 0.0f);
+  }
+  CUDA_OR_FAIL(patchKeys_.reserve((size_t)n, false, stream_), "patch"); CUDA_OR_FAIL(qIn_.reserve((size_t)n, false, stream_), "patch"); CUDA_OR_FAIL(qCount_.reserve((size_t)n, false, stream_), "patch");
+  CUDA_OR_FAIL(cudaMemcpyAsync(patchKeys_.p, keys.data(), (size_t)n * 8, cudaMemcpyHostToDevice, stream_), "patch h2d");
+  CUDA_OR_FAIL(cudaMemcpyAsync(qIn_.p, vals.data(), (size_t)n * 16, cudaMemcpyHostToDevice, stream_), "patch h2d");
+  CUDA_OR_FAIL(cudaMemcpyAsync(qCount_.p, masks.data(), (size_t)n * 4, cudaMemcpyHostToDevice, stream_), "patch h2d");
+  CUDA_OR_FAIL(launch_patch_contacts(dw_, L_, patchKeys_.p, qIn_.p, qCount_.p, n), "patch_contacts");
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");     // the host vectors go away
+  return n;
+}
+
 int World::step(float dt, int vi, int pi, int n) {
   if (!ok_) return DBX_E_NO_DEVICE;
   cudaSetDevice(device_);

@@ -645,6 +645,34 @@ class b2World:
         if getattr(self, "_listener", None) is not None:
             self._deliver_contact_events()
 
+    # PreSolve: the step cut after Collide (include/dbox_b200.h "PreSolve") ---------------------------------
+    def StepWithPreSolve(self, dt, velocityIterations, positionIterations, pre_solve):
+        """pre_solve(contact_rec) is called for every touching non-sensor contact after Collide and may return a dict with any
+        of enabled / friction / restitution / tangentSpeed (what a b2ContactListener.PreSolve would set on the contact)"""
+        self._ck(self._api.world_step_begin(self._w, dt, velocityIterations, positionIterations))
+        recs, n = self.read_contacts()
+        patches = []
+        for i in range(n):
+            r = recs[i]
+            if not (r.flags & A.CONTACT_TOUCHING) or r.manifold.pointCount == 0:      # PreSolve skips sensors (b2contact.d:352)
+                continue
+            ch = pre_solve(r)
+            if not ch:
+                continue
+            p = A.ContactPatch()
+            p.fixtureA, p.childA, p.fixtureB, p.childB = r.fixtureA, r.childA, r.fixtureB, r.childB
+            for name, bit in (("enabled", A.PATCH_ENABLED), ("friction", A.PATCH_FRICTION), ("restitution", A.PATCH_RESTITUTION), ("tangentSpeed", A.PATCH_TANGENT_SPEED)):
+                if name in ch:
+                    p.mask |= bit
+                    setattr(p, name, int(ch[name]) if name == "enabled" else float(ch[name]))
+            patches.append(p)
+        if patches:
+            arr = (A.ContactPatch * len(patches))(*patches)
+            self._ck(self._api.world_patch_contacts(self._w, arr, len(patches)))
+        self._ck(self._api.world_step_end(self._w))
+        if getattr(self, "_listener", None) is not None:
+            self._deliver_contact_events()
+
     # world queries, batched (b2world.d:563-587; include/dbox_b200.h "world queries") --------------------------
     def RayCastClosest(self, rays):
         """rays: iterable of ((x1, y1), (x2, y2)); returns [(fixture_id | -1, child, fraction, (px, py), (nx, ny))]"""

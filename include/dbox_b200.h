@@ -362,6 +362,27 @@ int32_t dbx_world_enable_contact_events(dbx_world* w, int32_t capacity);
  * DBX_E_CAPACITY if more than `capacity` were produced (the surplus is lost).  out == NULL: returns the count only. */
 int32_t dbx_world_poll_contact_events(dbx_world* w, dbx_contact_event* out, int32_t cap);
 
+/* ---- PreSolve: the step cut where the reference calls it ---------------------------------------------------------------
+ * b2ContactListener.PreSolve runs inside b2Contact.Update for every touching non-sensor contact (contacts/b2contact.d:348-355)
+ * and may call b2Contact.SetEnabled(false) (this step only: Update re-enables, :272), SetFriction, SetRestitution,
+ * SetTangentSpeed (:137-205).  A shim that has a PreSolve listener steps like this:
+ *     dbx_world_step_begin(w, dt, vi, pi);          // FindNewContacts-if-needed + Collide (b2world.d:372-399)
+ *     dbx_world_read_contacts(...)                  // touching, non-sensor contacts -> listener.PreSolve(contact, oldManifold = none)
+ *     dbx_world_patch_contacts(w, patches, n);      // what the listener changed
+ *     dbx_world_step_end(w);                        // Solve, SolveTOI, ClearForces (b2world.d:401-431)
+ * and is bit-identical to dbx_world_step when nothing is patched.  Not covered: the Update calls inside the TOI loop
+ * (b2world.d:1295,1379) and the old manifold argument. */
+typedef struct dbx_contact_patch {
+  int32_t fixtureA, childA, fixtureB, childB;   /* either order */
+  int32_t mask;                                 /* DBX_PATCH_* of the fields to apply */
+  int32_t enabled;
+  float friction, restitution, tangentSpeed;
+} dbx_contact_patch;
+enum { DBX_PATCH_ENABLED = 1, DBX_PATCH_FRICTION = 2, DBX_PATCH_RESTITUTION = 4, DBX_PATCH_TANGENT_SPEED = 8 };
+int32_t dbx_world_step_begin(dbx_world* w, float dt, int32_t velocityIterations, int32_t positionIterations);
+int32_t dbx_world_patch_contacts(dbx_world* w, const dbx_contact_patch* patches, int32_t n);   /* unknown pairs are ignored */
+int32_t dbx_world_step_end(dbx_world* w);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,9 @@ def api():
             "distance": (f32, [P(A.Shape), f32, f32, f32, i32, P(A.Shape), f32, f32, f32, i32, i32, P(A.Vec2), P(A.Vec2), P(i32)]),
             "time_of_impact": (i32, [P(A.Shape), P(f32), i32, P(A.Shape), P(f32), i32, f32, P(f32)]),
             "batch_step": (C.c_double, [P(W), i32, f32, i32, i32, i32, i32]),
+            "world_step_begin": (i32, [W, f32, i32, i32]),
+            "world_step_end": (i32, [W]),
+            "world_patch_contacts": (i32, [W, P(A.ContactPatch), i32]),
             "world_raycast_closest": (i32, [W, P(A.Ray), i32, P(A.RayHit)]),
             "world_query_aabb": (i32, [W, P(A.AABB), i32, i32, P(i32), P(i32)]),
             "joint_set_target": (i32, [W, i32, f32, f32]),

@@ -322,6 +322,34 @@ int32_t orc_world_read_contacts(orc_world* w, dbx_contact_rec* out, int32_t cap)
   for (Contact* c = w->w.contactList; c; c = c->next) { if (n < cap) fillContact(c, out + n); ++n; }
   return n;
 }
+// the step cut at PreSolve (see include/dbox_b200.h)
+int32_t orc_world_step_begin(orc_world* w, float dt, int32_t vi, int32_t pi) {
+  if (w->w.midStep) return DBX_E_INVALID;
+  w->w.pendDt = dt; w->w.pendVi = vi; w->w.pendPi = pi; w->w.midStep = true;
+  w->w.stepHalves(dt, vi, pi, 1);
+  return 0;
+}
+int32_t orc_world_step_end(orc_world* w) {
+  if (!w->w.midStep) return DBX_E_INVALID;
+  w->w.midStep = false;
+  w->w.stepHalves(w->w.pendDt, w->w.pendVi, w->w.pendPi, 2);
+  return 0;
+}
+int32_t orc_world_patch_contacts(orc_world* w, const dbx_contact_patch* p, int32_t n) {
+  for (int k = 0; k < n; ++k) {
+    for (Contact* c = w->w.contactList; c; c = c->next) {
+      const bool same = c->fixtureA->id == p[k].fixtureA && c->indexA == p[k].childA && c->fixtureB->id == p[k].fixtureB && c->indexB == p[k].childB;
+      const bool swapped = c->fixtureA->id == p[k].fixtureB && c->indexA == p[k].childB && c->fixtureB->id == p[k].fixtureA && c->indexB == p[k].childA;
+      if (!same && !swapped) continue;
+      if (p[k].mask & DBX_PATCH_ENABLED) { if (p[k].enabled) c->flags |= cEnabled; else c->flags &= ~cEnabled; }   // b2contact.d:137-147
+      if (p[k].mask & DBX_PATCH_FRICTION) c->friction = p[k].friction;
+      if (p[k].mask & DBX_PATCH_RESTITUTION) c->restitution = p[k].restitution;
+      if (p[k].mask & DBX_PATCH_TANGENT_SPEED) c->tangentSpeed = p[k].tangentSpeed;
+      break;
+    }
+  }
+  return n;
+}
 // b2World.RayCast (b2world.d:577-587, wrapper :1605-1624) with the callback that returns `fraction` (closest hit)
 int32_t orc_world_raycast_closest(orc_world* w, const dbx_ray* rays, int32_t n, dbx_ray_hit* out) {
   for (int k = 0; k < n; ++k) {

@@ -1073,9 +1073,12 @@ void World::solveTOI(const TimeStep& step) {
 }
 
 // ------------------------------------------------------------------ World::step (b2world.d:367-434)
-void World::step(float dt, int velocityIterations, int positionIterations) {
+// b2World.Step (b2world.d:367-434) cut after Collide, which is where PreSolve edits land (b2contact.d:348-355); halves = 3 is the
+// plain step
+void World::step(float dt, int velocityIterations, int positionIterations) { stepHalves(dt, velocityIterations, positionIterations, 3); }
+void World::stepHalves(float dt, int velocityIterations, int positionIterations, int halves) {
   double t0 = nowMs();
-  if (newFixture) { findNewContacts(); newFixture = false; }
+  if (halves & 1) { if (newFixture) { findNewContacts(); newFixture = false; } }
   locked = true;
   TimeStep step;
   step.dt = dt;
@@ -1085,7 +1088,8 @@ void World::step(float dt, int velocityIterations, int positionIterations) {
   step.dtRatio = inv_dt0 * dt;
   step.warmStarting = warmStarting;
   evPhase = 1;
-  { double t = nowMs(); collide(); profile.collide = (float)(nowMs() - t); }
+  if (halves & 1) { double t = nowMs(); collide(); profile.collide = (float)(nowMs() - t); }
+  if (!(halves & 2)) { locked = false; return; }
   if (stepComplete && step.dt > 0.0f) { double t = nowMs(); solve(step); profile.solve = (float)(nowMs() - t); }
   evPhase = 2;
   if (continuousPhysics && step.dt > 0.0f) { double t = nowMs(); solveTOI(step); profile.solveTOI = (float)(nowMs() - t); }

@@ -199,6 +199,8 @@ struct World {
   Joint* addJoint(Joint* j);                          // b2world.d:196-261 (takes ownership)
   void destroyJoint(Joint* j);                        // b2world.d:265-360
   void step(float dt, int velocityIterations, int positionIterations);  // b2world.d:367-434
+  void stepHalves(float dt, int velocityIterations, int positionIterations, int halves);
+  float pendDt = 0; int pendVi = 0, pendPi = 0; bool midStep = false;
   void clearForces();
 
   // contact manager (b2contactmanager.d)

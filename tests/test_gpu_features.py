@@ -400,3 +400,55 @@ def test_raycast_and_query_match_reference(gpu_api, oracle_api):
         w.DestroyBody(bs[9])
     hg, ho = wg.RayCastClosest([((0.0, 30.0), (0.0, 20.0))]), wo.RayCastClosest([((0.0, 30.0), (0.0, 20.0))])
     assert hg[0][0] == ho[0][0] == bg[7].fixtures[0].id
+
+
+def test_pre_solve_split_step(gpu_api, oracle_api):
+    """b2ContactListener.PreSolve (b2contact.d:348-355) through the step cut after Collide: a one-way platform
+    (SetEnabled(false) while the box comes from below), a conveyor (SetTangentSpeed) and a per-contact friction override;
+    and the split step without patches is bit-identical to the plain step"""
+    def build(api):
+        w = b2World((0.0, -10.0), api=api)
+        # the TOI loop's own Update calls cannot be intercepted (include/dbox_b200.h): a one-way platform needs discrete stepping
+        w.SetContinuousPhysics(False)
+        g = _ground(w, api)
+        plat = w.CreateBody(b2BodyDef()); ps = b2PolygonShape(api); ps.SetAsBox(3.0, 0.25, (0.0, 6.0), 0.0)
+        w.platform_fixture = plat.CreateFixture(ps, 0.0).id
+        up = _box_body(w, api, 0.0, 3.0); up.SetLinearVelocity((0.0, 14.0))          # shot upwards through the platform
+        belt = w.CreateBody(b2BodyDef()); bs = b2PolygonShape(api); bs.SetAsBox(4.0, 0.25, (12.0, 2.0), 0.0)
+        w.belt_fixture = belt.CreateFixture(bs, 0.0).id
+        rider = _box_body(w, api, 10.0, 2.8)
+        ice = _box_body(w, api, -12.0, 0.55); ice.SetLinearVelocity((6.0, 0.0))       # friction overridden to 0 against the ground
+        w.ice_fixture = ice.fixtures[0].id
+        w.up = up
+        return w, [up, rider, ice]
+
+    def pre_solve_for(w):
+        def pre_solve(c):
+            fx = (c.fixtureA, c.fixtureB)
+            if w.platform_fixture in fx:
+                return {"enabled": w.up.GetLinearVelocity().y <= 0.0}                # solid only for a box coming down
+            if w.belt_fixture in fx:
+                return {"tangentSpeed": 2.0 if c.fixtureA == w.belt_fixture else -2.0}
+            if w.ice_fixture in fx:
+                return {"friction": 0.0}
+            return None
+        return pre_solve
+    wg, bg = build(gpu_api); wo, bo = build(oracle_api)
+    fg, fo = pre_solve_for(wg), pre_solve_for(wo)
+    for k in range(150):
+        wg.StepWithPreSolve(DT, 8, 3, fg); wo.StepWithPreSolve(DT, 8, 3, fo)
+        for i, (a, b) in enumerate(zip(bg, bo)):
+            pa, pb = a.GetPosition(), b.GetPosition()
+            assert abs(pa.x - pb.x) < 2e-4 * max(1.0, abs(pb.x)) and abs(pa.y - pb.y) < 2e-4 * max(1.0, abs(pb.y)), (k, i, (pa.x, pa.y), (pb.x, pb.y))
+    up, rider, ice = bg
+    assert 6.7 < up.GetPosition().y < 6.85                    # went up through the platform, landed on top of it
+    assert rider.GetPosition().x > 10.5                       # carried by the conveyor
+    assert ice.GetLinearVelocity().x > 5.9                    # no friction against the ground
+    # no patches: same bits as dbx_world_step
+    a, _ = scenes.pyramid(api=gpu_api, count=8); b, _ = scenes.pyramid(api=gpu_api, count=8)
+    for k in range(60):
+        a.Step(DT, 8, 3)
+        b.StepWithPreSolve(DT, 8, 3, lambda c: None)
+    sa, n = a.read_bodies(); sb, _ = b.read_bodies()
+    for i in range(n):
+        assert (sa[i].c.x, sa[i].c.y, sa[i].a, sa[i].v.x, sa[i].v.y, sa[i].w) == (sb[i].c.x, sb[i].c.y, sb[i].a, sb[i].v.x, sb[i].v.y, sb[i].w), i
