@@ -202,7 +202,9 @@ struct DevWorld {
   float4* j_k0;      // revolute mass.ex.xyz motorMass | distance: u.x u.y mass gamma
   float4* j_k1;      // revolute mass.ey.xyz -        | distance: bias - - -
   float4* j_k2;      // revolute mass.ez.xyz -
-  float4* j_k3;      // prismatic / wheel (dbx_joints2.cuh)
+  float4* j_k3;      // prismatic / wheel / gear (dbx_joints2.cuh)
+  float4* j_p2;      // gear: referenceAngleA referenceAngleB ratio constant
+  int4* j_ids2;      // gear: bodyC bodyD typeA typeB
   // ---- step parameters
   float dt, inv_dt, dtRatio; int velIters, posIters; int warmStarting; int allowSleep; int continuous; float gx, gy;
   int nWorlds;

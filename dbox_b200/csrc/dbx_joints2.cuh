@@ -9,7 +9,7 @@
 
 namespace dbx {
 
-enum { JT_PRISMATIC = 2, JT_PULLEY = 4, JT_MOUSE = 5, JT_GEAR = 6, JT_WHEEL = 7, JT_WELD = 8, JT_FRICTION = 9, JT_ROPE = 10, JT_MOTOR = 11 };
+enum { JT_REVOLUTE_ = 1, JT_PRISMATIC = 2, JT_PULLEY = 4, JT_MOUSE = 5, JT_GEAR = 6, JT_WHEEL = 7, JT_WELD = 8, JT_FRICTION = 9, JT_ROPE = 10, JT_MOTOR = 11 };
 
 struct JCtx {
   float mA, iA, mB, iB;
@@ -63,6 +63,99 @@ DBX_D void weld_k(const float mA, const float iA, const float mB, const float iB
   ex.z = ez.x;
   ey.z = ez.y;
   ez.z = iA + iB;
+}
+
+// ------------------------------------------------------------------------------------------------ gear (b2gearjoint.d:245-500)
+// bodies A, B (the joint's own pair) move through JCtx; C, D (the other ends of joint1 / joint2) are handled here.
+// p0 = (localAnchorC, localAnchorD), p1 = (localAxisC, localAxisD), p2 = (referenceAngleA, referenceAngleB, ratio, constant)
+// k0 = (JvAC, JvBD), k1 = (JwA, JwB, JwC, JwD), k2.x = mass, k3 = (mC, iC, mD, iD)
+struct GearJ { v2 JvAC, JvBD; float JwA, JwB, JwC, JwD, mass; };
+DBX_D GearJ gear_jacobian(int typeA, int typeB, float ratio, float4 p0, float4 p1, Rot qC, Rot qD, v2 rA, v2 rB, v2 lcC, v2 lcD,
+                          float mA, float iA, float mB, float iB, float mC, float iC, float mD, float iD) {
+  GearJ g; g.mass = 0.0f;
+  if (typeA == JT_REVOLUTE_) { g.JvAC = V(0.0f, 0.0f); g.JwA = 1.0f; g.JwC = 1.0f; g.mass += iA + iC; }
+  else {
+    const v2 u = mul(qC, V(p1.x, p1.y));
+    const v2 rC = mul(qC, V(p0.x, p0.y) - lcC);
+    g.JvAC = u; g.JwC = cross(rC, u); g.JwA = cross(rA, u);
+    g.mass += mC + mA + iC * g.JwC * g.JwC + iA * g.JwA * g.JwA;
+  }
+  if (typeB == JT_REVOLUTE_) { g.JvBD = V(0.0f, 0.0f); g.JwB = ratio; g.JwD = ratio; g.mass += ratio * ratio * (iB + iD); }
+  else {
+    const v2 u = mul(qD, V(p1.z, p1.w));
+    const v2 rD = mul(qD, V(p0.z, p0.w) - lcD);
+    g.JvBD = ratio * u; g.JwD = ratio * cross(rD, u); g.JwB = ratio * cross(rB, u);
+    g.mass += ratio * ratio * (mD + mB) + iD * g.JwD * g.JwD + iB * g.JwB * g.JwB;
+  }
+  return g;
+}
+DBX_D void gear_init(const DevWorld& W, int j, JCtx& c) {
+  const int4 id2 = W.j_ids2[j];
+  const int bC = id2.x, bD = id2.y;
+  const float4 p0 = W.j_p0[j], p1 = W.j_p1[j], p2 = W.j_p2[j];
+  const float4 msC = W.b_mass[bC], msD = W.b_mass[bD], xC = W.b_xf[bC], xD = W.b_xf[bD], lcC4 = W.b_lc[bC], lcD4 = W.b_lc[bD];
+  float4 velC = ldcg4(&W.b_vel[bC]), velD = ldcg4(&W.b_vel[bD]);
+  const float mC = msC.x, iC = msC.y, mD = msD.x, iD = msD.y;
+  GearJ g = gear_jacobian(id2.z, id2.w, p2.z, p0, p1, R(xC.z, xC.w), R(xD.z, xD.w), c.rA, c.rB, V(lcC4.x, lcC4.y), V(lcD4.x, lcD4.y),
+                          c.mA, c.iA, c.mB, c.iB, mC, iC, mD, iD);
+  g.mass = g.mass > 0.0f ? 1.0f / g.mass : 0.0f;
+  W.j_k0[j] = make_float4(g.JvAC.x, g.JvAC.y, g.JvBD.x, g.JvBD.y);
+  W.j_k1[j] = make_float4(g.JwA, g.JwB, g.JwC, g.JwD);
+  W.j_k2[j] = make_float4(g.mass, 0.0f, 0.0f, 0.0f);
+  W.j_k3[j] = make_float4(mC, iC, mD, iD);
+  if (W.warmStarting) {
+    const float imp = c.imp.x;     // the reference does not scale the gear impulse by dtRatio (b2gearjoint.d:329-339)
+    c.vA += (c.mA * imp) * g.JvAC; c.wA += c.iA * imp * g.JwA;
+    c.vB += (c.mB * imp) * g.JvBD; c.wB += c.iB * imp * g.JwB;
+    if (mC != 0.0f || iC != 0.0f) { v2 vC = V(velC.x, velC.y) - (mC * imp) * g.JvAC; stcg4(&W.b_vel[bC], make_float4(vC.x, vC.y, velC.z - iC * imp * g.JwC, 0.0f)); }
+    if (mD != 0.0f || iD != 0.0f) { v2 vD = V(velD.x, velD.y) - (mD * imp) * g.JvBD; stcg4(&W.b_vel[bD], make_float4(vD.x, vD.y, velD.z - iD * imp * g.JwD, 0.0f)); }
+  } else c.imp.x = 0.0f;
+}
+DBX_D void gear_solve_velocity(const DevWorld& W, int j, JCtx& c) {
+  const int4 id2 = W.j_ids2[j];
+  const int bC = id2.x, bD = id2.y;
+  const float4 k0 = W.j_k0[j], k1 = W.j_k1[j], k3 = W.j_k3[j];
+  const float mass = W.j_k2[j].x;
+  const v2 JvAC = V(k0.x, k0.y), JvBD = V(k0.z, k0.w);
+  const float4 velC = ldcg4(&W.b_vel[bC]), velD = ldcg4(&W.b_vel[bD]);
+  v2 vC = V(velC.x, velC.y), vD = V(velD.x, velD.y); float wC = velC.z, wD = velD.z;
+  float Cdot = dot(JvAC, c.vA - vC) + dot(JvBD, c.vB - vD);
+  Cdot += (k1.x * c.wA - k1.z * wC) + (k1.y * c.wB - k1.w * wD);
+  const float impulse = -mass * Cdot;
+  c.imp.x += impulse;
+  c.vA += (c.mA * impulse) * JvAC; c.wA += c.iA * impulse * k1.x;
+  c.vB += (c.mB * impulse) * JvBD; c.wB += c.iB * impulse * k1.y;
+  vC -= (k3.x * impulse) * JvAC; wC -= k3.y * impulse * k1.z;
+  vD -= (k3.z * impulse) * JvBD; wD -= k3.w * impulse * k1.w;
+  if (k3.x != 0.0f || k3.y != 0.0f) stcg4(&W.b_vel[bC], make_float4(vC.x, vC.y, wC, 0.0f));
+  if (k3.z != 0.0f || k3.w != 0.0f) stcg4(&W.b_vel[bD], make_float4(vD.x, vD.y, wD, 0.0f));
+}
+DBX_D bool gear_solve_position(const DevWorld& W, int j, float mA, float iA, float mB, float iB, v2 rA, v2 rB, v2& cA, float& aA, v2& cB, float& aB) {
+  const int4 id2 = W.j_ids2[j];
+  const int bC = id2.x, bD = id2.y;
+  const float4 p0 = W.j_p0[j], p1 = W.j_p1[j], p2 = W.j_p2[j], k3 = W.j_k3[j];
+  const float4 lcC4 = W.b_lc[bC], lcD4 = W.b_lc[bD];
+  const v2 lcC = V(lcC4.x, lcC4.y), lcD = V(lcD4.x, lcD4.y);
+  float4 pc = ldcg4(&W.b_pos[bC]), pd = ldcg4(&W.b_pos[bD]);
+  v2 cC = V(pc.x, pc.y), cD = V(pd.x, pd.y); float aC = pc.z, aD = pd.z;
+  const Rot qC = rot_from_angle(aC), qD = rot_from_angle(aD);
+  const float ratio = p2.z;
+  const GearJ g = gear_jacobian(id2.z, id2.w, ratio, p0, p1, qC, qD, rA, rB, lcC, lcD, mA, iA, mB, iB, k3.x, k3.y, k3.z, k3.w);
+  float coordinateA, coordinateB;
+  if (id2.z == JT_REVOLUTE_) coordinateA = aA - aC - p2.x;
+  else { const v2 pC = V(p0.x, p0.y) - lcC; const v2 pA = mulT(qC, rA + (cA - cC)); coordinateA = dot(pA - pC, V(p1.x, p1.y)); }
+  if (id2.w == JT_REVOLUTE_) coordinateB = aB - aD - p2.y;
+  else { const v2 pD = V(p0.z, p0.w) - lcD; const v2 pB = mulT(qD, rB + (cB - cD)); coordinateB = dot(pB - pD, V(p1.z, p1.w)); }
+  const float C = (coordinateA + ratio * coordinateB) - p2.w;
+  float impulse = 0.0f;
+  if (g.mass > 0.0f) impulse = -C / g.mass;
+  cA += mA * impulse * g.JvAC; aA += iA * impulse * g.JwA;
+  cB += mB * impulse * g.JvBD; aB += iB * impulse * g.JwB;
+  cC -= k3.x * impulse * g.JvAC; aC -= k3.y * impulse * g.JwC;
+  cD -= k3.z * impulse * g.JvBD; aD -= k3.w * impulse * g.JwD;
+  if (k3.x != 0.0f || k3.y != 0.0f) stcg4(&W.b_pos[bC], make_float4(cC.x, cC.y, aC, 0.0f));
+  if (k3.z != 0.0f || k3.w != 0.0f) stcg4(&W.b_pos[bD], make_float4(cD.x, cD.y, aD, 0.0f));
+  return true;     // linearError stays 0 in the reference (b2gearjoint.d:393, 499)
 }
 
 // ------------------------------------------------------------------------------------------------ InitVelocityConstraints
@@ -239,6 +332,8 @@ DBX_D void joint2_init(const DevWorld& W, int j, int type, int flags, int bB, JC
       const float LB = imp.x * sBy + imp.y * k1.y + imp.w;
       japply(c, P, LA, LB);
     } else imp = make_float4(0, 0, 0, 0);
+  } else if (type == JT_GEAR) {
+    gear_init(W, j, c);
   } else if (type == JT_PULLEY) {            // b2pulleyjoint.d:238-326; p0 = (groundA, groundB), p1 = (lengthA, lengthB, ratio, constant)
     v2 uA = c.cA + c.rA - V(p0.x, p0.y), uB = c.cB + c.rB - V(p0.z, p0.w);
     const float lengthA = len(uA), lengthB = len(uB);
@@ -396,6 +491,8 @@ DBX_D void joint2_solve_velocity(const DevWorld& W, int j, int type, int flags, 
       imp.x += impulse;
       japply(c, impulse * ay, impulse * sAy, impulse * sBy);
     }
+  } else if (type == JT_GEAR) {
+    gear_solve_velocity(W, j, c);
   } else if (type == JT_PULLEY) {            // b2pulleyjoint.d:329-354
     const v2 uA = V(k0.x, k0.y), uB = V(k0.z, k0.w);
     const v2 vpA = c.vA + cross(c.wA, c.rA), vpB = c.vB + cross(c.wB, c.rB);
@@ -530,6 +627,7 @@ DBX_D bool joint2_solve_position(const DevWorld& W, int j, int type, int flags, 
     cB += mB * PB; aB += iB * cross(rB, PB);
     return linearError < kLinearSlop;
   }
+  if (type == JT_GEAR) return gear_solve_position(W, j, mA, iA, mB, iB, rA, rB, cA, aA, cB, aB);
   return true;                               // friction, motor, mouse: no position correction
 }
 

@@ -50,8 +50,9 @@ World::~World() {
   if (wm_) cudaFreeHost(wm_);
   if (wmEv_) cudaEventDestroy(wmEv_);
   DevBuf<float4>* f4[] = {&b_xf, &b_xf0, &b_pos, &b_pos0, &b_vel, &b_force, &b_mass, &b_lc, &p_aabb, &p_fat, &bv_box, &c_m0, &c_m1, &c_imp, &c_mat,
-                          &s_v0, &s_v1, &s_r0, &s_r1, &s_q0, &s_q1, &s_imp, &s_nm, &s_k, &s_p0, &s_p1, &s_p2, &j_anchor, &j_p0, &j_p1, &j_imp, &j_r, &j_lc, &j_m, &j_k0, &j_k1, &j_k2, &j_k3};
+                          &s_v0, &s_v1, &s_r0, &s_r1, &s_q0, &s_q1, &s_imp, &s_nm, &s_k, &s_p0, &s_p1, &s_p2, &j_anchor, &j_p0, &j_p1, &j_imp, &j_r, &j_lc, &j_m, &j_k0, &j_k1, &j_k2, &j_k3, &j_p2};
   for (auto* b : f4) b->release();
+  j_ids2.release();
   b_toiMin.release(); b_toiOther.release(); b_acc.release(); jp_bits.release();
   DevBuf<int>* i1[] = {&b_toiEvt, &b_toiFlags, &e_contact, &e_ncand, &e_cand, &bv_pos, &b_wake, &b_root, &b_islAwake, &b_islMinSleep, &b_posNotOk, &b_ovf, &b_world, &f_body, &f_group, &p_key, &moveList, &bv_leaf, &bv_leafAlt,
                        &bv_parent, &bv_visit, &c_toiCount, &c_colour, &c_free, &c_work, &c_work2, &h_val, &s_contact, &s_hist, &s_pc, &s_root, &j_limit, &j_colour, &j_order, &j_root, &d_levels};
@@ -330,7 +331,8 @@ int World::destroyBody(int b) {
 
 int World::createJoint(const dbx_joint_def& d) {
   if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
-  if (d.type < DBX_JOINT_REVOLUTE || d.type > DBX_JOINT_MOTOR || d.type == DBX_JOINT_GEAR) { set_last_error("gear joints are not built yet"); return DBX_E_UNSUPPORTED; }
+  if (d.type < DBX_JOINT_REVOLUTE || d.type > DBX_JOINT_MOTOR) return DBX_E_INVALID;
+  if (d.type == DBX_JOINT_GEAR) return createGearJoint(d);
   if (d.bodyA < 0 || d.bodyB < 0 || d.bodyA >= (int)bodies_.size() || d.bodyB >= (int)bodies_.size() || !bodies_[d.bodyA].alive || !bodies_[d.bodyB].alive || d.bodyA == d.bodyB) return DBX_E_INVALID;
   if (d.type == DBX_JOINT_PULLEY && d.ratio == 0.0f) return DBX_E_INVALID;   // b2pulleyjoint.d:118
   HJoint j; j.alive = true; j.def = d;
@@ -353,6 +355,46 @@ int World::createJoint(const dbx_joint_def& d) {
   jointsChanged_ = true;
   if (!d.collideConnected && bodiesSynced_ > 0 && (size_t)std::max(d.bodyA, d.bodyB) < bodiesSynced_) {
     int rc = destroyContactsWhere(d.bodyA, -1, d.bodyB, true); if (rc < 0) return rc;   // FlagForFiltering (b2world.d:241-256)
+  }
+  return jid;
+}
+
+// b2GearJoint (b2gearjoint.d:84-160): bodies A / B are the second bodies of joint1 / joint2, C / D their first bodies; the
+// anchors, axes and reference angles are copied from those joints and the constant is measured on the current pose.
+// The record travels in otherwise unused fields of the joint def: groundAnchorA/B = localAnchorC/D, localAxisA = localAxisC,
+// linearOffset = localAxisD, referenceAngle / angularOffset = referenceAngleA / B, lengthA = constant.
+int World::createGearJoint(const dbx_joint_def& d) {
+  const int nJ = (int)joints_.size();
+  if (d.joint1 < 0 || d.joint2 < 0 || d.joint1 >= nJ || d.joint2 >= nJ || !joints_[d.joint1].alive || !joints_[d.joint2].alive || d.joint1 == d.joint2) return DBX_E_INVALID;
+  const dbx_joint_def& j1 = joints_[d.joint1].def; const dbx_joint_def& j2 = joints_[d.joint2].def;
+  auto ok = [](int t) { return t == DBX_JOINT_REVOLUTE || t == DBX_JOINT_PRISMATIC; };
+  if (!ok(j1.type) || !ok(j2.type)) { set_last_error("gear: joint1 / joint2 must be revolute or prismatic"); return DBX_E_INVALID; }
+  int rc = pullBodies(); if (rc < 0) return rc;
+  HJoint j; j.alive = true; j.def = d;
+  j.typeA = j1.type; j.typeB = j2.type; j.bodyC = j1.bodyA; j.bodyD = j2.bodyA;
+  j.def.bodyA = j1.bodyB; j.def.bodyB = j2.bodyB;
+  if (j.def.bodyA == j.def.bodyB) return DBX_E_INVALID;
+  auto pose = [&](int b, Xf* xf, float* a) { const dbx_body_state& st = bodies_[b].st; xf->p = V(st.p.x, st.p.y); xf->q = R(st.qs, st.qc); *a = st.a; };
+  auto coordinate = [&](const dbx_joint_def& jj, int bFar, int bNear, dbx_vec2* ancFar, dbx_vec2* ancNear, dbx_vec2* axisFar, float* ref) -> float {
+    Xf xfN, xfF; float aN, aF;
+    pose(bNear, &xfN, &aN); pose(bFar, &xfF, &aF);
+    *ancFar = jj.localAnchorA; *ancNear = jj.localAnchorB; *ref = jj.referenceAngle;
+    if (jj.type == DBX_JOINT_REVOLUTE) { *axisFar = dbx_vec2{0.0f, 0.0f}; return aN - aF - jj.referenceAngle; }
+    *axisFar = jj.localAxisA;      // stored normalised at creation
+    const v2 pF = V(jj.localAnchorA.x, jj.localAnchorA.y);
+    const v2 pN = mulT(xfF.q, mul(xfN.q, V(jj.localAnchorB.x, jj.localAnchorB.y)) + (xfN.p - xfF.p));
+    return dot(pN - pF, V(jj.localAxisA.x, jj.localAxisA.y));
+  };
+  const float coordinateA = coordinate(j1, j.bodyC, j.def.bodyA, &j.def.groundAnchorA, &j.def.localAnchorA, &j.def.localAxisA, &j.def.referenceAngle);
+  const float coordinateB = coordinate(j2, j.bodyD, j.def.bodyB, &j.def.groundAnchorB, &j.def.localAnchorB, &j.def.linearOffset, &j.def.angularOffset);
+  j.def.lengthA = coordinateA + d.ratio * coordinateB;
+  joints_.push_back(j);
+  const int jid = (int)joints_.size() - 1;
+  bodies_[j.def.bodyA].joints.push_back(jid);
+  bodies_[j.def.bodyB].joints.push_back(jid);
+  jointsChanged_ = true;
+  if (!d.collideConnected && bodiesSynced_ > 0 && (size_t)std::max(j.def.bodyA, j.def.bodyB) < bodiesSynced_) {
+    rc = destroyContactsWhere(j.def.bodyA, -1, j.def.bodyB, true); if (rc < 0) return rc;
   }
   return jid;
 }
@@ -452,6 +494,7 @@ int World::pullJoints() {
 // parameter packing of the device joint record (which = 0: j_p0, 1: j_p1); the kernels' side is dbx_solver.cuh / dbx_joints2.cuh
 float4 World::jointParams(const dbx_joint_def& d, int which) {
   auto f = [](float a, float b, float c, float e) { return make_float4(a, b, c, e); };
+  if (which == 2 && d.type != DBX_JOINT_GEAR) return f(0, 0, 0, 0);
   switch (d.type) {
     case DBX_JOINT_REVOLUTE:  return which == 0 ? f(d.referenceAngle, d.lowerAngle, d.upperAngle, d.maxMotorTorque) : f(d.motorSpeed, 0, 0, 0);
     case DBX_JOINT_DISTANCE:  return which == 0 ? f(d.length, d.frequencyHz, d.dampingRatio, 0) : f(0, 0, 0, 0);
@@ -462,6 +505,9 @@ float4 World::jointParams(const dbx_joint_def& d, int which) {
     case DBX_JOINT_FRICTION:  return which == 0 ? f(d.maxForce, d.maxTorque, 0, 0) : f(0, 0, 0, 0);
     case DBX_JOINT_MOTOR:     return which == 0 ? f(d.linearOffset.x, d.linearOffset.y, d.angularOffset, d.correctionFactor) : f(d.maxForce, d.maxTorque, 0, 0);
     case DBX_JOINT_MOUSE:     return which == 0 ? f(d.target.x, d.target.y, d.maxForce, d.frequencyHz) : f(d.dampingRatio, 0, 0, 0);
+    case DBX_JOINT_GEAR:      return which == 0 ? f(d.groundAnchorA.x, d.groundAnchorA.y, d.groundAnchorB.x, d.groundAnchorB.y)
+                                   : which == 1 ? f(d.localAxisA.x, d.localAxisA.y, d.linearOffset.x, d.linearOffset.y)
+                                                : f(d.referenceAngle, d.angularOffset, d.ratio, d.lengthA);
     case DBX_JOINT_PULLEY:    return which == 0 ? f(d.groundAnchorA.x, d.groundAnchorA.y, d.groundAnchorB.x, d.groundAnchorB.y) : f(d.lengthA, d.lengthB, d.ratio, d.lengthA + d.ratio * d.lengthB);
     default:                  return f(0, 0, 0, 0);
   }
@@ -492,10 +538,16 @@ int World::recolourJoints() {
     const int a = hj.def.bodyA, b = hj.def.bodyB;
     const bool dynA = bodies_[a].st.type == DBX_DYNAMIC_BODY, dynB = bodies_[b].st.type == DBX_DYNAMIC_BODY;
     unsigned long long used = (dynA ? mask[a] : 0ull) | (dynB ? mask[b] : 0ull);
+    // a gear joint also writes the far bodies of joint1 / joint2
+    const bool dynC = hj.bodyC >= 0 && bodies_[hj.bodyC].st.type == DBX_DYNAMIC_BODY, dynD = hj.bodyD >= 0 && bodies_[hj.bodyD].st.type == DBX_DYNAMIC_BODY;
+    if (dynC) used |= mask[hj.bodyC];
+    if (dynD) used |= mask[hj.bodyD];
     if (!~used) { set_last_error("a body has more than 64 joints"); return DBX_E_CAPACITY; }
     int c = __builtin_ffsll((long long)~used) - 1;
     if (dynA) mask[a] |= 1ull << c;
     if (dynB) mask[b] |= 1ull << c;
+    if (dynC) mask[hj.bodyC] |= 1ull << c;
+    if (dynD) mask[hj.bodyD] |= 1ull << c;
     colour[j] = c; hj.colour = c;
     byColour[c].push_back(j);
     if (!hj.def.collideConnected) {
@@ -617,7 +669,8 @@ int World::reserveDevice(bool& rehash) {
   CUDA_OR_FAIL(s_contact.reserve(sc, false, stream_), "s_contact"); CUDA_OR_FAIL(s_pc.reserve(sc, false, stream_), "s_pc"); CUDA_OR_FAIL(s_root.reserve(sc, false, stream_), "s_root");
   CUDA_OR_FAIL(s_hist.reserve((size_t)kSortBlocks * kMaxColours, false, stream_), "s_hist");
   const size_t capJ = std::max<size_t>(std::max<size_t>(nJ, 1), (size_t)caps_.maxJoints);
-  DevBuf<float4>* jf4[] = {&j_anchor, &j_p0, &j_p1, &j_imp, &j_r, &j_lc, &j_m, &j_k0, &j_k1, &j_k2, &j_k3};
+  DevBuf<float4>* jf4[] = {&j_anchor, &j_p0, &j_p1, &j_imp, &j_r, &j_lc, &j_m, &j_k0, &j_k1, &j_k2, &j_k3, &j_p2};
+  CUDA_OR_FAIL(j_ids2.reserve(capJ, true, stream_), "j_ids2");
   for (auto* b : jf4) CUDA_OR_FAIL(b->reserve(capJ, true, stream_), "joint f4");
   CUDA_OR_FAIL(j_ids.reserve(capJ, true, stream_), "j_ids"); CUDA_OR_FAIL(j_limit.reserve(capJ, true, stream_), "j_limit"); CUDA_OR_FAIL(j_root.reserve(capJ, true, stream_), "j_root");
   CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
@@ -708,6 +761,8 @@ int World::push() {
     CUDA_OR_FAIL(upload_range(j_anchor, 0, nD, [&](size_t k) { const dbx_joint_def& d = J(k).def; return f4(d.localAnchorA.x, d.localAnchorA.y, d.localAnchorB.x, d.localAnchorB.y); }), "up j_anchor");
     CUDA_OR_FAIL(upload_range(j_p0, 0, nD, [&](size_t k) { return jointParams(J(k).def, 0); }), "up j_p0");
     CUDA_OR_FAIL(upload_range(j_p1, 0, nD, [&](size_t k) { return jointParams(J(k).def, 1); }), "up j_p1");
+    CUDA_OR_FAIL(upload_range(j_p2, 0, nD, [&](size_t k) { return jointParams(J(k).def, 2); }), "up j_p2");
+    CUDA_OR_FAIL(upload_range(j_ids2, 0, nD, [&](size_t k) { const HJoint& j = J(k); return make_int4(j.bodyC, j.bodyD, j.typeA, j.typeB); }), "up j_ids2");
     CUDA_OR_FAIL(upload_range(j_imp, 0, nD, [&](size_t k) { const HJoint& j = J(k); return f4(j.imp[0], j.imp[1], j.imp[2], j.imp[3]); }), "up j_imp");
     CUDA_OR_FAIL(upload_range(j_limit, 0, nD, [&](size_t k) { return J(k).limit; }), "up j_limit");
     jointsSynced_ = nJ; fullPushJoints_ = false; jointsChanged_ = false;
@@ -741,7 +796,7 @@ void World::refreshView() {
   w.sCap = (int)s_contact.cap; w.s_contact = s_contact.p; w.s_hist = s_hist.p; w.s_body = s_body.p; w.s_v0 = s_v0.p; w.s_v1 = s_v1.p; w.s_r0 = s_r0.p; w.s_r1 = s_r1.p;
   w.s_q0 = s_q0.p; w.s_q1 = s_q1.p; w.s_imp = s_imp.p; w.s_nm = s_nm.p; w.s_k = s_k.p; w.s_pc = s_pc.p; w.s_p0 = s_p0.p; w.s_p1 = s_p1.p; w.s_p2 = s_p2.p; w.s_p3 = s_p3.p; w.s_root = s_root.p;
   w.nJoints = (int)jointAt_.size() * nWorlds_; w.j_ids = j_ids.p; w.j_anchor = j_anchor.p; w.j_p0 = j_p0.p; w.j_p1 = j_p1.p; w.j_imp = j_imp.p; w.j_limit = j_limit.p; w.j_colour = j_colour.p;
-  w.j_order = j_order.p; w.j_root = j_root.p; w.j_r = j_r.p; w.j_lc = j_lc.p; w.j_m = j_m.p; w.j_k0 = j_k0.p; w.j_k1 = j_k1.p; w.j_k2 = j_k2.p; w.j_k3 = j_k3.p;
+  w.j_order = j_order.p; w.j_root = j_root.p; w.j_r = j_r.p; w.j_lc = j_lc.p; w.j_m = j_m.p; w.j_k0 = j_k0.p; w.j_k1 = j_k1.p; w.j_k2 = j_k2.p; w.j_k3 = j_k3.p; w.j_p2 = j_p2.p; w.j_ids2 = j_ids2.p;
   w.nWorlds = nWorlds_; w.keyStride = keyStride_;
   w.jointBlocks = jointBlocks_; w.nJointColours = nJointColours_;
   { const char* e = getenv("DBX_DEBUG"); w.dbgFlags = e ? atoi(e) : 0; }
@@ -1556,7 +1611,7 @@ int World::replicate(int copies) {
     std::vector<int> off(kMaxJointColours + 1, 0);
     { int c = 0; for (int k = 0; k < nJ; ++k) { while (c < joints_[jointAt_[k]].colour) off[++c] = k; } while (c < kMaxJointColours) off[++c] = nJ; }
     const size_t nD = (size_t)nJ * copies;
-    std::vector<int4> ids(nD); std::vector<float4> anc(nD), p0(nD), p1(nD), imp(nD); std::vector<int> lim(nD);
+    std::vector<int4> ids(nD), id2(nD); std::vector<float4> anc(nD), p0(nD), p1(nD), p2(nD), imp(nD); std::vector<int> lim(nD);
     int newOff[kMaxJointColours + 1];
     for (int c = 0; c <= kMaxJointColours; ++c) newOff[c] = off[c] * copies;
     for (int c = 0; c < kMaxJointColours; ++c) {
@@ -1569,6 +1624,8 @@ int World::replicate(int copies) {
         anc[d] = make_float4(jd.localAnchorA.x, jd.localAnchorA.y, jd.localAnchorB.x, jd.localAnchorB.y);
         p0[d] = jointParams(jd, 0);
         p1[d] = jointParams(jd, 1);
+        p2[d] = jointParams(jd, 2);
+        id2[d] = make_int4(j.bodyC >= 0 ? j.bodyC + r * nB : -1, j.bodyD >= 0 ? j.bodyD + r * nB : -1, j.typeA, j.typeB);
         imp[d] = make_float4(j.imp[0], j.imp[1], j.imp[2], j.imp[3]);
         lim[d] = j.limit;
       }
@@ -1576,6 +1633,7 @@ int World::replicate(int copies) {
     CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
     cudaMemcpy(j_ids.p, ids.data(), nD * 16, cudaMemcpyHostToDevice); cudaMemcpy(j_anchor.p, anc.data(), nD * 16, cudaMemcpyHostToDevice);
     cudaMemcpy(j_p0.p, p0.data(), nD * 16, cudaMemcpyHostToDevice); cudaMemcpy(j_p1.p, p1.data(), nD * 16, cudaMemcpyHostToDevice);
+    cudaMemcpy(j_p2.p, p2.data(), nD * 16, cudaMemcpyHostToDevice); cudaMemcpy(j_ids2.p, id2.data(), nD * 16, cudaMemcpyHostToDevice);
     cudaMemcpy(j_imp.p, imp.data(), nD * 16, cudaMemcpyHostToDevice);
     CUDA_OR_FAIL(cudaMemcpy(j_limit.p, lim.data(), nD * 4, cudaMemcpyHostToDevice), "joints up");
     CUDA_OR_FAIL(cudaMemcpy((char*)hdr_.p + offsetof(Header, jointColourOff), newOff, sizeof(newOff), cudaMemcpyHostToDevice), "joff up");

@@ -45,6 +45,7 @@ struct HBody {
 };
 struct HJoint {
   bool alive = false; dbx_joint_def def{}; float imp[4] = {0, 0, 0, 0}; int limit = 0; int colour = -1;
+  int bodyC = -1, bodyD = -1, typeA = 0, typeB = 0;   // gear only: the far ends and kinds of joint1 / joint2
 };
 
 class World {
@@ -58,6 +59,7 @@ class World {
   int createFixture(int b, const dbx_fixture_def& d, const dbx_shape& s);
   int destroyFixture(int f);
   int createJoint(const dbx_joint_def& d);
+  int createGearJoint(const dbx_joint_def& d);
   int destroyJoint(int j);
   int setJointTarget(int j, float x, float y);
   int step(float dt, int vi, int pi, int n);
@@ -172,7 +174,7 @@ class World {
   DevBuf<unsigned long long> c_key, h_key; DevBuf<int4> c_ids, c_fix; DevBuf<uint32_t> c_flags; DevBuf<float4> c_m0, c_m1, c_imp, c_mat; DevBuf<uint4> c_mk;
   DevBuf<int> c_toiCount, c_colour, c_free, c_work, c_work2, h_val;
   DevBuf<int> s_contact, s_hist, s_pc, s_root; DevBuf<int2> s_body; DevBuf<float4> s_v0, s_v1, s_r0, s_r1, s_q0, s_q1, s_imp, s_nm, s_k, s_p0, s_p1, s_p2; DevBuf<float2> s_p3;
-  DevBuf<int4> j_ids; DevBuf<float4> j_anchor, j_p0, j_p1, j_imp, j_r, j_lc, j_m, j_k0, j_k1, j_k2, j_k3; DevBuf<int> j_limit, j_colour, j_order, j_root;
+  DevBuf<int4> j_ids; DevBuf<float4> j_anchor, j_p0, j_p1, j_imp, j_r, j_lc, j_m, j_k0, j_k1, j_k2, j_k3, j_p2; DevBuf<int4> j_ids2; DevBuf<int> j_limit, j_colour, j_order, j_root;
   DevBuf<char> cubTemp; DevBuf<int> d_levels;
   DevBuf<unsigned long long> cmpKeyA_, cmpKeyB_; DevBuf<int> cmpValA_, cmpValB_;
   int nJointPairs_ = 0; int jointBlocks_ = 0, nJointColours_ = 0;

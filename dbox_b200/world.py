@@ -412,6 +412,23 @@ class b2PulleyJointDef(_AnchoredDef):
         return d
 
 
+class b2GearJointDef(b2JointDef):
+    """dynamics/joints/b2gearjoint.d:36-58: joint1 / joint2 are revolute or prismatic b2Joint handles of this world"""
+    type = A.JOINT_GEAR
+
+    def __init__(self):
+        super().__init__()
+        self.joint1 = self.joint2 = None
+        self.ratio = 1.0
+
+    def _pod(self):
+        d = A.JointDef()
+        d.type, d.collideConnected, d.userData = self.type, int(self.collideConnected), self.userData
+        d.bodyA, d.bodyB = self.joint1.bodyB.id, self.joint2.bodyB.id
+        d.joint1, d.joint2, d.ratio = self.joint1.id, self.joint2.id, self.ratio
+        return d
+
+
 def _pt(p):
     v = _v(p)
     return b2Vec2(v.x, v.y)
@@ -626,6 +643,8 @@ class b2World:
     def CreateJoint(self, jointDef):
         pod = jointDef._pod()
         jid = self._ck(self._api.joint_create(self._w, C.byref(pod)))
+        if jointDef.bodyA is None and getattr(jointDef, "joint1", None) is not None:     # gear: bodies come from the two joints
+            jointDef.bodyA, jointDef.bodyB = jointDef.joint1.bodyB, jointDef.joint2.bodyB
         j = b2Joint(self, jid, jointDef.bodyA, jointDef.bodyB)
         self._joints[jid] = j
         return j

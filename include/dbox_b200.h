@@ -149,7 +149,7 @@ typedef struct {
   dbx_vec2 target;
   dbx_vec2 groundAnchorA, groundAnchorB;
   float lengthA, lengthB, ratio;
-  int32_t joint1, joint2;     /* gear (not built) */
+  int32_t joint1, joint2;     /* gear b2gearjoint.d:36-58: ids of two revolute / prismatic joints (+ ratio); bodyA / bodyB are derived */
   int32_t _pad;
 } dbx_joint_def;
 

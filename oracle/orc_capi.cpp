@@ -182,6 +182,45 @@ int32_t orc_joint_create(orc_world* w, const dbx_joint_def* d) {
     r->groundAnchorA = v2(d->groundAnchorA); r->groundAnchorB = v2(d->groundAnchorB);
     r->lengthA = d->lengthA; r->lengthB = d->lengthB; r->ratio = d->ratio; r->constant = d->lengthA + r->ratio * d->lengthB;
     j = r;
+  } else if (d->type == jGear) {             // b2gearjoint.d:84-160
+    auto& J = w->w.jointsById;
+    if (d->joint1 < 0 || d->joint2 < 0 || d->joint1 >= (int)J.size() || d->joint2 >= (int)J.size() || !J[d->joint1] || !J[d->joint2]) return DBX_E_INVALID;
+    Joint* j1 = J[d->joint1]; Joint* j2 = J[d->joint2];
+    if ((j1->type != jRevolute && j1->type != jPrismatic) || (j2->type != jRevolute && j2->type != jPrismatic)) return DBX_E_INVALID;
+    GearJoint* g = new GearJoint();
+    g->typeA = j1->type; g->typeB = j2->type;
+    float coordinateA, coordinateB;
+    g->bodyC = j1->bodyA; Body* bA = j1->bodyB;
+    Xf xfA = bA->xf; float aA = bA->sweep.a; Xf xfC = g->bodyC->xf; float aC = g->bodyC->sweep.a;
+    if (g->typeA == jRevolute) {
+      RevoluteJoint* r = (RevoluteJoint*)j1;
+      g->localAnchorC = r->localAnchorA; g->localAnchorA = r->localAnchorB; g->referenceAngleA = r->referenceAngle; g->localAxisC = V2(0, 0);
+      coordinateA = aA - aC - g->referenceAngleA;
+    } else {
+      PrismaticJoint* pj = (PrismaticJoint*)j1;
+      g->localAnchorC = pj->localAnchorA; g->localAnchorA = pj->localAnchorB; g->referenceAngleA = pj->referenceAngle; g->localAxisC = pj->localXAxisA;
+      V2 pC = g->localAnchorC;
+      V2 pA = mulT(xfC.q, mul(xfA.q, g->localAnchorA) + (xfA.p - xfC.p));
+      coordinateA = dot(pA - pC, g->localAxisC);
+    }
+    g->bodyD = j2->bodyA; Body* bB = j2->bodyB;
+    Xf xfB = bB->xf; float aB = bB->sweep.a; Xf xfD = g->bodyD->xf; float aD = g->bodyD->sweep.a;
+    if (g->typeB == jRevolute) {
+      RevoluteJoint* r = (RevoluteJoint*)j2;
+      g->localAnchorD = r->localAnchorA; g->localAnchorB = r->localAnchorB; g->referenceAngleB = r->referenceAngle; g->localAxisD = V2(0, 0);
+      coordinateB = aB - aD - g->referenceAngleB;
+    } else {
+      PrismaticJoint* pj = (PrismaticJoint*)j2;
+      g->localAnchorD = pj->localAnchorA; g->localAnchorB = pj->localAnchorB; g->referenceAngleB = pj->referenceAngle; g->localAxisD = pj->localXAxisA;
+      V2 pD = g->localAnchorD;
+      V2 pB = mulT(xfD.q, mul(xfB.q, g->localAnchorB) + (xfB.p - xfD.p));
+      coordinateB = dot(pB - pD, g->localAxisD);
+    }
+    g->ratio = d->ratio;
+    g->constant = coordinateA + g->ratio * coordinateB;
+    g->type = d->type; g->bodyA = bA; g->bodyB = bB; g->collideConnected = d->collideConnected != 0; g->userData = d->userData;
+    Joint* r = w->w.addJoint(g);
+    return r ? r->id : DBX_E_LOCKED;
   } else {
     return DBX_E_UNSUPPORTED;
   }
@@ -444,6 +483,7 @@ int32_t orc_world_read_joints(orc_world* w, dbx_joint_state* out, int32_t cap) {
     else if (j->type == jPrismatic) { auto* d = (PrismaticJoint*)j; o->impulse[0] = d->impulse.x; o->impulse[1] = d->impulse.y; o->impulse[2] = d->impulse.z; o->motorImpulse = d->motorImpulse; o->limitState = d->limitState; }
     else if (j->type == jWheel) { auto* d = (WheelJoint*)j; o->impulse[0] = d->impulse; o->impulse[1] = d->springImpulse; o->motorImpulse = d->motorImpulse; }
     else if (j->type == jPulley) { auto* d = (PulleyJoint*)j; o->impulse[0] = d->impulse; }
+    else if (j->type == jGear) { auto* d = (GearJoint*)j; o->impulse[0] = d->impulse; }
   }
   return n;
 }

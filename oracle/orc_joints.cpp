@@ -639,4 +639,112 @@ bool PulleyJoint::solvePositionConstraints(const SolverData& data) {
   return linearError < kLinearSlop;
 }
 
+// ------------------------------------------------------------------ gear (b2gearjoint.d:245-500)
+void GearJoint::initVelocityConstraints(const SolverData& data) {
+  indexA = bodyA->islandIndex; indexB = bodyB->islandIndex; indexC = bodyC->islandIndex; indexD = bodyD->islandIndex;
+  lcA = bodyA->sweep.localCenter; lcB = bodyB->sweep.localCenter; lcC = bodyC->sweep.localCenter; lcD = bodyD->sweep.localCenter;
+  mA = bodyA->invMass; mB = bodyB->invMass; mC = bodyC->invMass; mD = bodyD->invMass;
+  iA = bodyA->invI; iB = bodyB->invI; iC = bodyC->invI; iD = bodyD->invI;
+  float aA = data.positions[indexA].a; V2 vA = data.velocities[indexA].v; float wA = data.velocities[indexA].w;
+  float aB = data.positions[indexB].a; V2 vB = data.velocities[indexB].v; float wB = data.velocities[indexB].w;
+  float aC = data.positions[indexC].a; V2 vC = data.velocities[indexC].v; float wC = data.velocities[indexC].w;
+  float aD = data.positions[indexD].a; V2 vD = data.velocities[indexD].v; float wD = data.velocities[indexD].w;
+  Rot qA(aA), qB(aB), qC(aC), qD(aD);
+  mass = 0.0f;
+  if (typeA == jRevolute) {
+    JvAC = V2(0, 0); JwA = 1.0f; JwC = 1.0f;
+    mass += iA + iC;
+  } else {
+    V2 u = mul(qC, localAxisC);
+    V2 rC = mul(qC, localAnchorC - lcC);
+    V2 rA = mul(qA, localAnchorA - lcA);
+    JvAC = u; JwC = cross(rC, u); JwA = cross(rA, u);
+    mass += mC + mA + iC * JwC * JwC + iA * JwA * JwA;
+  }
+  if (typeB == jRevolute) {
+    JvBD = V2(0, 0); JwB = ratio; JwD = ratio;
+    mass += ratio * ratio * (iB + iD);
+  } else {
+    V2 u = mul(qD, localAxisD);
+    V2 rD = mul(qD, localAnchorD - lcD);
+    V2 rB = mul(qB, localAnchorB - lcB);
+    JvBD = ratio * u; JwD = ratio * cross(rD, u); JwB = ratio * cross(rB, u);
+    mass += ratio * ratio * (mD + mB) + iD * JwD * JwD + iB * JwB * JwB;
+  }
+  mass = mass > 0.0f ? 1.0f / mass : 0.0f;
+  if (data.step.warmStarting) {
+    vA += (mA * impulse) * JvAC; wA += iA * impulse * JwA;
+    vB += (mB * impulse) * JvBD; wB += iB * impulse * JwB;
+    vC -= (mC * impulse) * JvAC; wC -= iC * impulse * JwC;
+    vD -= (mD * impulse) * JvBD; wD -= iD * impulse * JwD;
+  } else impulse = 0.0f;
+  data.velocities[indexA].v = vA; data.velocities[indexA].w = wA; data.velocities[indexB].v = vB; data.velocities[indexB].w = wB;
+  data.velocities[indexC].v = vC; data.velocities[indexC].w = wC; data.velocities[indexD].v = vD; data.velocities[indexD].w = wD;
+}
+void GearJoint::solveVelocityConstraints(const SolverData& data) {
+  V2 vA = data.velocities[indexA].v; float wA = data.velocities[indexA].w;
+  V2 vB = data.velocities[indexB].v; float wB = data.velocities[indexB].w;
+  V2 vC = data.velocities[indexC].v; float wC = data.velocities[indexC].w;
+  V2 vD = data.velocities[indexD].v; float wD = data.velocities[indexD].w;
+  float Cdot = dot(JvAC, vA - vC) + dot(JvBD, vB - vD);
+  Cdot += (JwA * wA - JwC * wC) + (JwB * wB - JwD * wD);
+  float imp = -mass * Cdot;
+  impulse += imp;
+  vA += (mA * imp) * JvAC; wA += iA * imp * JwA;
+  vB += (mB * imp) * JvBD; wB += iB * imp * JwB;
+  vC -= (mC * imp) * JvAC; wC -= iC * imp * JwC;
+  vD -= (mD * imp) * JvBD; wD -= iD * imp * JwD;
+  data.velocities[indexA].v = vA; data.velocities[indexA].w = wA; data.velocities[indexB].v = vB; data.velocities[indexB].w = wB;
+  data.velocities[indexC].v = vC; data.velocities[indexC].w = wC; data.velocities[indexD].v = vD; data.velocities[indexD].w = wD;
+}
+bool GearJoint::solvePositionConstraints(const SolverData& data) {
+  V2 cA = data.positions[indexA].c; float aA = data.positions[indexA].a;
+  V2 cB = data.positions[indexB].c; float aB = data.positions[indexB].a;
+  V2 cC = data.positions[indexC].c; float aC = data.positions[indexC].a;
+  V2 cD = data.positions[indexD].c; float aD = data.positions[indexD].a;
+  Rot qA(aA), qB(aB), qC(aC), qD(aD);
+  float linearError = 0.0f;
+  float coordinateA, coordinateB;
+  V2 JvAC_, JvBD_; float JwA_, JwB_, JwC_, JwD_;
+  float m = 0.0f;
+  if (typeA == jRevolute) {
+    JvAC_ = V2(0, 0); JwA_ = 1.0f; JwC_ = 1.0f;
+    m += iA + iC;
+    coordinateA = aA - aC - referenceAngleA;
+  } else {
+    V2 u = mul(qC, localAxisC);
+    V2 rC = mul(qC, localAnchorC - lcC);
+    V2 rA = mul(qA, localAnchorA - lcA);
+    JvAC_ = u; JwC_ = cross(rC, u); JwA_ = cross(rA, u);
+    m += mC + mA + iC * JwC_ * JwC_ + iA * JwA_ * JwA_;
+    V2 pC = localAnchorC - lcC;
+    V2 pA = mulT(qC, rA + (cA - cC));
+    coordinateA = dot(pA - pC, localAxisC);
+  }
+  if (typeB == jRevolute) {
+    JvBD_ = V2(0, 0); JwB_ = ratio; JwD_ = ratio;
+    m += ratio * ratio * (iB + iD);
+    coordinateB = aB - aD - referenceAngleB;
+  } else {
+    V2 u = mul(qD, localAxisD);
+    V2 rD = mul(qD, localAnchorD - lcD);
+    V2 rB = mul(qB, localAnchorB - lcB);
+    JvBD_ = ratio * u; JwD_ = ratio * cross(rD, u); JwB_ = ratio * cross(rB, u);
+    m += ratio * ratio * (mD + mB) + iD * JwD_ * JwD_ + iB * JwB_ * JwB_;
+    V2 pD = localAnchorD - lcD;
+    V2 pB = mulT(qD, rB + (cB - cD));
+    coordinateB = dot(pB - pD, localAxisD);
+  }
+  float C = (coordinateA + ratio * coordinateB) - constant;
+  float imp = 0.0f;
+  if (m > 0.0f) imp = -C / m;
+  cA += mA * imp * JvAC_; aA += iA * imp * JwA_;
+  cB += mB * imp * JvBD_; aB += iB * imp * JwB_;
+  cC -= mC * imp * JvAC_; aC -= iC * imp * JwC_;
+  cD -= mD * imp * JvBD_; aD -= iD * imp * JwD_;
+  data.positions[indexA].c = cA; data.positions[indexA].a = aA; data.positions[indexB].c = cB; data.positions[indexB].a = aB;
+  data.positions[indexC].c = cC; data.positions[indexC].a = aC; data.positions[indexD].c = cD; data.positions[indexD].a = aD;
+  return linearError < kLinearSlop;
+}
+
 }  // namespace orc

@@ -179,6 +179,16 @@ struct PulleyJoint : JointCommon {      // b2pulleyjoint.d
   ORC_JOINT_HOOKS
 };
 
+struct GearJoint : Joint {             // b2gearjoint.d (four bodies: A, B driven through joint1 / joint2 against C, D)
+  int typeA = 0, typeB = 0; Body* bodyC = nullptr; Body* bodyD = nullptr;
+  V2 localAnchorA, localAnchorB, localAnchorC, localAnchorD, localAxisC, localAxisD;
+  float referenceAngleA = 0, referenceAngleB = 0, constant = 0, ratio = 1, impulse = 0;
+  int indexA = 0, indexB = 0, indexC = 0, indexD = 0; V2 lcA, lcB, lcC, lcD;
+  float mA = 0, mB = 0, mC = 0, mD = 0, iA = 0, iB = 0, iC = 0, iD = 0;
+  V2 JvAC, JvBD; float JwA = 0, JwB = 0, JwC = 0, JwD = 0, mass = 0;
+  ORC_JOINT_HOOKS
+};
+
 struct Profile { float step = 0, collide = 0, solve = 0, solveInit = 0, solveVelocity = 0, solvePosition = 0, broadphase = 0, solveTOI = 0; };
 
 struct BodyDef {

@@ -452,3 +452,38 @@ def test_pre_solve_split_step(gpu_api, oracle_api):
     sa, n = a.read_bodies(); sb, _ = b.read_bodies()
     for i in range(n):
         assert (sa[i].c.x, sa[i].c.y, sa[i].a, sa[i].v.x, sa[i].v.y, sa[i].w) == (sb[i].c.x, sb[i].c.y, sb[i].a, sb[i].v.x, sb[i].v.y, sb[i].w), i
+
+
+def test_gear_joint(gpu_api, oracle_api):
+    """b2GearJoint (b2gearjoint.d): revolute-revolute with a ratio and revolute-prismatic, the Gears demo layout.  The gear
+    shares its island with joint1 and joint2, so the order of the three joints matters: loose tolerance against the oracle,
+    tight tolerance on the constraint itself (coordinateA + ratio * coordinateB stays what it was at creation)"""
+    from dbox_b200.world import b2GearJointDef, b2PrismaticJointDef
+
+    def build(api):
+        w = b2World((0.0, -10.0), api=api)
+        g = w.CreateBody(b2BodyDef())
+        b1 = _dyn(w, 0.0, 12.0); c1 = b2CircleShape(api); c1.m_radius = 1.0; b1.CreateFixture(c1, 5.0)
+        jd = b2RevoluteJointDef(); jd.Initialize(g, b1, (0.0, 12.0)); j1 = w.CreateJoint(jd)
+        b2 = _dyn(w, 3.0, 12.0); c2 = b2CircleShape(api); c2.m_radius = 2.0; b2.CreateFixture(c2, 5.0)
+        jd = b2RevoluteJointDef(); jd.Initialize(g, b2, (3.0, 12.0)); j2 = w.CreateJoint(jd)
+        b3 = _box_body(w, api, 5.5, 12.0, hx=0.5, hy=5.0, density=5.0)
+        jd = b2PrismaticJointDef(); jd.Initialize(g, b3, (5.5, 12.0), (0.0, 1.0))
+        jd.enableLimit, jd.lowerTranslation, jd.upperTranslation = True, -5.0, 5.0
+        j3 = w.CreateJoint(jd)
+        gd = b2GearJointDef(); gd.joint1, gd.joint2, gd.ratio = j1, j2, 2.0; w.gear1 = w.CreateJoint(gd)
+        gd = b2GearJointDef(); gd.joint1, gd.joint2, gd.ratio = j2, j3, -1.0 / 2.0; w.gear2 = w.CreateJoint(gd)
+        b1.SetAngularVelocity(1.0)
+        return w, [b1, b2, b3]
+    wg, bg = build(gpu_api); wo, bo = build(oracle_api)
+    for k in range(180):
+        wg.Step(DT, 8, 3); wo.Step(DT, 8, 3)
+        for i, (a, b) in enumerate(zip(bg, bo)):
+            assert abs(a.GetAngle() - b.GetAngle()) < 5e-3 and abs(a.GetPosition().y - b.GetPosition().y) < 5e-3, (k, i, a.GetAngle(), b.GetAngle())
+        a1, a2, y3 = bg[0].GetAngle(), bg[1].GetAngle(), bg[2].GetPosition().y - 12.0
+        assert abs(a1 + 2.0 * a2) < 2e-2 and abs(a2 - 0.5 * y3) < 2e-2, (k, a1, a2, y3)
+    assert abs(bg[2].GetPosition().y - 12.0) > 0.5                  # the weight of the bar drives the whole train
+    jg, n = wg.read_joints(); jo, _ = wo.read_joints()
+    assert jg[3].type == jo[3].type == A.JOINT_GEAR
+    for i in (3, 4):
+        assert abs(jg[i].impulse[0] - jo[i].impulse[0]) < 0.05 * max(1.0, abs(jo[i].impulse[0])), (i, jg[i].impulse[0], jo[i].impulse[0])
