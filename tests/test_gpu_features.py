@@ -487,3 +487,78 @@ def test_gear_joint(gpu_api, oracle_api):
     assert jg[3].type == jo[3].type == A.JOINT_GEAR
     for i in (3, 4):
         assert abs(jg[i].impulse[0] - jo[i].impulse[0]) < 0.05 * max(1.0, abs(jo[i].impulse[0])), (i, jg[i].impulse[0], jo[i].impulse[0])
+
+
+def test_edge_cases(gpu_api, oracle_api):
+    """empty and degenerate worlds, error codes instead of silent clamps, a body with more than 64 contacts (overflow colour
+    lanes), zero time step, a step with nothing awake"""
+    # empty world, world with only static bodies, world whose only body has no fixture
+    w = b2World((0.0, -10.0), api=gpu_api)
+    w.Step(DT, 8, 3)
+    c = w.counts(); assert (c.bodies, c.contacts, c.proxies) == (0, 0, 0)
+    assert w.RayCastClosest([((0.0, 0.0), (1.0, 1.0))])[0][0] == -1 and w.QueryAABB([((-1.0, -1.0), (1.0, 1.0))]) == [[]]
+    g = _ground(w, gpu_api)
+    lone = _dyn(w, 0.0, 5.0)                       # no fixture: zero mass, falls under gravity like the reference (mass defaults to 1)
+    wo = b2World((0.0, -10.0), api=oracle_api); _ground(wo, oracle_api); lone_o = _dyn(wo, 0.0, 5.0)
+    for _ in range(30):
+        w.Step(DT, 8, 3); wo.Step(DT, 8, 3)
+    assert abs(lone.GetPosition().y - lone_o.GetPosition().y) < 1e-5
+    # dt = 0 (b2world.d:388-396: inv_dt = 0, nothing integrates, contacts still update)
+    before = lone.GetPosition().y
+    w.Step(0.0, 8, 3)
+    assert lone.GetPosition().y == before
+    # invalid handles are errors, not crashes
+    assert gpu_api.body_destroy(w._w, 12345) < 0 and gpu_api.fixture_destroy(w._w, -3) < 0 and gpu_api.joint_destroy(w._w, 7) < 0
+    jd = A.JointDef(); gpu_api.default_joint_def(jd, A.JOINT_REVOLUTE); jd.bodyA, jd.bodyB = 0, 0
+    assert gpu_api.joint_create(w._w, jd) < 0                                      # same body twice
+    jd.type = 99
+    assert gpu_api.joint_create(w._w, jd) < 0
+    # one dynamic body touched by far more than 64 contacts: the colouring spills into that body's private lanes
+    def heavy(api):
+        w2 = b2World((0.0, -10.0), api=api)
+        _ground(w2, api)
+        slab = _box_body(w2, api, 0.0, 1.0, hx=30.0, hy=0.5, density=0.2)
+        small = []
+        for k in range(100):
+            b = _dyn(w2, -29.0 + 0.58 * k, 1.8); s = b2PolygonShape(api); s.SetAsBox(0.25, 0.25); b.CreateFixture(s, 1.0)
+            small.append(b)
+        return w2, [slab] + small
+    wg2, bg2 = heavy(gpu_api); wo2, bo2 = heavy(oracle_api)
+    most = 0
+    for k in range(120):
+        wg2.Step(DT, 8, 3); wo2.Step(DT, 8, 3)
+        if k % 10 == 9:
+            most = max(most, wg2.counts().colours)
+            assert gpu_api.world_debug_colour_conflicts(wg2._w) == 0
+    cg, co = wg2.counts(), wo2.counts()
+    assert cg.touching == co.touching and most > 64, most
+    for a, b in zip(bg2, bo2):
+        assert abs(a.GetPosition().y - b.GetPosition().y) < 0.02, (a.id, a.GetPosition().y, b.GetPosition().y)
+    # a pool that is too small says so
+    caps = A.Caps(); caps.maxContacts = 1
+    tiny, _ = scenes.pyramid(api=gpu_api, count=3)
+    assert tiny.counts().bodies == 8
+
+
+def test_everything_asleep_costs_nothing_wrong(gpu_api, oracle_api):
+    """a world that has gone to sleep keeps stepping without touching anything, and wakes up on contact exactly like the
+    reference (b2world.d:963-1118, b2island.d:249-279)"""
+    wg, bg = scenes.pyramid(api=gpu_api, count=6); wo, bo = scenes.pyramid(api=oracle_api, count=6)
+    for _ in range(400):
+        wg.Step(DT, 8, 3); wo.Step(DT, 8, 3)
+    assert wg.counts().awakeBodies == wo.counts().awakeBodies == 0
+    frozen = [(b.GetPosition().x, b.GetPosition().y, b.GetAngle()) for b in bg]
+    for _ in range(50):
+        wg.Step(DT, 8, 3)
+    assert frozen == [(b.GetPosition().x, b.GetPosition().y, b.GetAngle()) for b in bg]
+    for w, api in ((wg, gpu_api), (wo, oracle_api)):                     # drop a box on the sleeping pile
+        bd = b2BodyDef(); bd.type = b2_dynamicBody; bd.position.Set(-5.0, 12.0)
+        nb = w.CreateBody(bd); s = b2PolygonShape(api); s.SetAsBox(0.5, 0.5); nb.CreateFixture(s, 5.0)
+    woke = False
+    for k in range(150):
+        wg.Step(DT, 8, 3); wo.Step(DT, 8, 3)
+        cg, co = wg.counts(), wo.counts()
+        woke = woke or cg.awakeBodies > 1
+        if k < 60:
+            assert cg.awakeBodies == co.awakeBodies, (k, cg.awakeBodies, co.awakeBodies)
+    assert woke
