@@ -422,3 +422,29 @@ def test_tumbler_invariants(gpu_api, oracle_api):
     mg = sum(b.GetPosition().y for b in tg.bodies) / n
     mo = sum(b.GetPosition().y for b in to.bodies) / n
     assert abs(mg - mo) < 0.5, (mg, mo)
+
+
+def test_world_batch_api(gpu_api):
+    """dbox_b200.batch.WorldBatch (what bench.py's batched leg drives): partitioned share, bulk reset / act / observe calls"""
+    import numpy as np
+    import ctypes as C
+    from dbox_b200.batch import WorldBatch, partition
+    total = 10
+    first, count = partition(total, 1, 3)
+    b = WorldBatch(lambda **kw: scenes.pyramid(count=6, **kw), total, rank=1, world_size=3, api=gpu_api, contacts_per_world=200)
+    assert (b.first, b.count) == (first, count) == (4, 3) and b.n_bodies == b.bodies_per_world * 3
+    vel = np.zeros((b.n_bodies, 4), np.float32); vel[:, 0] = 0.1
+    b.set_states(vel=vel)
+    forces = np.zeros((b.n_bodies, 4), np.float32)
+    xf = np.zeros((b.n_bodies, 4), np.float32)
+    for _ in range(20):
+        b.apply_forces(forces.ctypes.data)
+        b.step(DT, 8, 3)
+        b.read_transforms(xf.ctypes.data)
+    ms, stages = b.time_steps(DT, 8, 3, 5, flush_l2=False)
+    assert ms > 0 and len(stages) == 9
+    st = b.stats()
+    assert st["worlds"] == 3 and st["bodies"] == b.n_bodies and st["contacts"] > 0
+    per = b.bodies_per_world
+    assert np.allclose(xf[:per], xf[per:2 * per]) and np.allclose(xf[:per], xf[2 * per:])      # same reset -> same worlds
+    b.close()
