@@ -66,7 +66,7 @@ struct Header {
   unsigned barrier;   // grid barrier ticket counter for the persistent kernels
   unsigned epoch;     // colouring round stamp
   int nFresh;         // contacts created by the current FindNewContacts, listed in c_work for k_toi's first pass
-  int _pad2;
+  int maxColour;      // largest colour ever handed out (monotonic): bounds the key width of the world-major sort
   float bounds[4];    // world bounds of fat AABB centres (Morton normalisation), as ordered ints
   int colourOff[kMaxColours + 1];   // solver order: contacts of colour c are [colourOff[c], colourOff[c+1])
   int jointColourOff[kMaxJointColours + 1];
@@ -132,6 +132,11 @@ struct DevWorld {
   int4* ev_a;        // [evCap] contact events: (type | phase << 8 | step << 16, fixtureA, fixtureB, childA | childB << 16)
   int4* ev_b;        //         (bodyA, bodyB, pair key lo, pair key hi)
   int evCap;         // 0 = contact events off
+  // world-local solve (batched replicas without joints): solver slots sorted by (replica, colour) instead of colour alone
+  const unsigned* sw_key;   // [nSolve] sorted (replica << swColourBits | colour)
+  int swColourBits;
+  int* w_start;             // [nWorlds] first solver slot of a replica
+  int* w_end;               // [nWorlds] one past its last
   int toiReset;      // k_toi: the per-body TOI scratch may be dirty (first step, bodies added) -> full reset phase
   int toiClearMoves; // k_toi also empties the move buffer FindNewContacts left (saves two launches)
   int toiClearForces;// k_toi also runs ClearForces (b2world.d:443-450) in its final body pass

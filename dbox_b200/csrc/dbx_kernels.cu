@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256, 4) k_collide(const __grid_constant__ DevW
 // ------------------------------------------------------------------------------------------------ islands
 // Replaces the DFS of b2World.Solve (dynamics/b2world.d:943-1095) with a union-find over constraint edges.
 __global__ void __launch_bounds__(256) k_island_init(const __grid_constant__ DevWorld W) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) { W.hdr->nSolve = 0; W.hdr->nIslands = 0; W.hdr->nUncoloured = 0; W.hdr->nUncoloured2 = 0; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { W.hdr->nSolve = 0; W.hdr->nColours = 0; W.hdr->nIslands = 0; W.hdr->nUncoloured = 0; W.hdr->nUncoloured2 = 0; }
   GRID_STRIDE(b, W.nBodies) {
     W.b_root[b] = b;
     W.b_islAwake[b] = 0;
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) k_island_union(const __grid_constant__ De
     if ((flags & (CF_ALIVE | CF_TOUCHING | CF_ENABLED | CF_SENSOR)) != (CF_ALIVE | CF_TOUCHING | CF_ENABLED)) continue;
     int4 ids = W.c_ids[i];
     if (body_type(W.b_flags[ids.z]) == BODY_STATIC || body_type(W.b_flags[ids.w]) == BODY_STATIC) continue;  // statics end the search (:998-1003)
-    uf_unite(W.b_root, ids.z, ids.w, W.nWorlds == 1);
+    if (W.nWorlds == 1) uf_unite(W.b_root, ids.z, ids.w, true); else uf_unite_small(W.b_root, ids.z, ids.w);
   }
   GRID_STRIDE(j, W.nJoints) {
     int4 ids = W.j_ids[j];
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) k_island_union(const __grid_constant__ De
     uint32_t fa = W.b_flags[ids.y], fb = W.b_flags[ids.z];
     if (!(fa & BF_ACTIVE) || !(fb & BF_ACTIVE)) continue;                                  // other body must be active (:1058-1062)
     if (body_type(fa) == BODY_STATIC || body_type(fb) == BODY_STATIC) continue;
-    uf_unite(W.b_root, ids.y, ids.z, W.nWorlds == 1);
+    if (W.nWorlds == 1) uf_unite(W.b_root, ids.y, ids.z, true); else uf_unite_small(W.b_root, ids.y, ids.z);
   }
 }
 
@@ -298,6 +298,7 @@ __global__ void __launch_bounds__(512) k_colour(const __grid_constant__ DevWorld
           if (col >= kMaxColours) { col = kMaxColours - 1; H->error = -5; }
         }
         W.c_colour[i] = col;
+        if (col > *((volatile int*)&H->maxColour)) atomicMax(&H->maxColour, col);
       } else {
         int slot = atomicAdd(&H->nUncoloured2, 1);
         nxt[slot] = i;
@@ -1455,6 +1456,68 @@ cudaError_t stage_islands_and_integrate(const DevWorld& W, const LaunchCfg& L) {
   ++L.launches; k_island_flatten<<<L.gridWide, 256, 0, L.stream>>>(W);
   ++L.launches; k_island_wake_integrate<<<L.gridWide, 256, 0, L.stream>>>(W);
   return cudaGetLastError();
+}
+
+// ---- world-major solver order for the world-local solver (dbx_solve.cu): key = replica << 10 | colour over every contact
+// slot (slots not in the solver sort to the end), CUB radix sort, then the slot range of every replica
+// The sort key keeps only `colourBits` of the colour when the host knows (from the last header it saw) that no colour
+// needs more: fewer radix passes.  A colour that does not fit raises the sticky error instead of corrupting the order.
+__global__ void __launch_bounds__(256) k_world_keys(const __grid_constant__ DevWorld W, unsigned* keys, int* vals, int n, int colourBits) {
+  const int high = W.hdr->cHigh;
+  int count = 0, maxc = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && high > n) W.hdr->error = -5;
+  GRID_STRIDE(i, n) {
+    unsigned key = (unsigned)W.nWorlds << colourBits;
+    if (i < high && (W.c_flags[i] & CF_SOLVE)) {
+      const int4 ids = W.c_ids[i];
+      const int c = W.c_colour[i];
+      if (c >= (1 << colourBits)) W.hdr->error = -5;
+      key = ((unsigned)W.b_world[ids.z] << colourBits) | (unsigned)(c & ((1 << colourBits) - 1));
+      ++count; maxc = max(maxc, c + 1);
+    }
+    keys[i] = key; vals[i] = i;
+  }
+  for (int o = 16; o > 0; o >>= 1) { count += __shfl_xor_sync(0xffffffffu, count, o); maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, o)); }
+  if ((threadIdx.x & 31) == 0 && count > 0) { atomicAdd(&W.hdr->nSolve, count); atomicMax(&W.hdr->nColours, maxc); }
+}
+__global__ void __launch_bounds__(256) k_world_ranges(const __grid_constant__ DevWorld W, const unsigned* keys, int colourBits) {
+  const int n = min(W.hdr->nSolve, W.sCap);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && W.hdr->nSolve > W.sCap) W.hdr->error = -5;
+  GRID_STRIDE(s, n) {
+    const int w = (int)(keys[s] >> colourBits);
+    if (s == 0 || (int)(keys[s - 1] >> colourBits) != w) W.w_start[w] = s;
+    if (s == n - 1 || (int)(keys[s + 1] >> colourBits) != w) W.w_end[w] = s + 1;
+  }
+}
+cudaError_t launch_mark_and_colour(const DevWorld& W, const LaunchCfg& L) {
+  ++L.launches; k_mark_solve<<<L.gridWide, 256, 0, L.stream>>>(W);
+  CK(cudaGetLastError());
+  if (!W.colourOverride) CK(launch_coop((const void*)k_colour, W, L));
+  return cudaGetLastError();
+}
+// keysA/B, valsA/B: n entries each; on return W.s_contact / W.sw_key point at the sorted buffers
+cudaError_t stage_colour_and_sort_worlds(DevWorld& W, const LaunchCfg& L, unsigned* keysA, unsigned* keysB, int* valsA, int* valsB, int n, int colourBits) {
+  CK(cudaMemsetAsync(W.w_start, 0, (size_t)W.nWorlds * 4, L.stream));
+  CK(cudaMemsetAsync(W.w_end, 0, (size_t)W.nWorlds * 4, L.stream));
+  ++L.launches; k_world_keys<<<L.gridWide, 256, 0, L.stream>>>(W, keysA, valsA, n, colourBits);
+  cub::DoubleBuffer<unsigned> keys(keysA, keysB);
+  cub::DoubleBuffer<int> vals(valsA, valsB);
+  int worldBits = 1;
+  while ((1 << worldBits) < W.nWorlds + 1) ++worldBits;
+  size_t bytes = L.cubTempBytes;
+  CK(cub::DeviceRadixSort::SortPairs(L.cubTemp, bytes, keys, vals, n, 0, colourBits + worldBits, L.stream));
+  W.s_contact = vals.Current();
+  W.sw_key = keys.Current();
+  W.swColourBits = colourBits;
+  ++L.launches; k_world_ranges<<<L.gridWide, 256, 0, L.stream>>>(W, keys.Current(), colourBits);
+  return cudaGetLastError();
+}
+size_t cub_temp_bytes_u32(int n) {
+  size_t bytes = 0;
+  cub::DoubleBuffer<unsigned> k(nullptr, nullptr);
+  cub::DoubleBuffer<int> v(nullptr, nullptr);
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, n, 0, 32);
+  return bytes + 256;
 }
 
 cudaError_t stage_colour_and_sort(const DevWorld& W, const LaunchCfg& L) {

@@ -17,7 +17,11 @@ struct LaunchCfg {
 // stages of b2World.Step (dynamics/b2world.d:367-434); each returns the first CUDA error
 cudaError_t stage_collide(const DevWorld& W, const LaunchCfg& L);                 // b2ContactManager.Collide
 cudaError_t stage_islands_and_integrate(const DevWorld& W, const LaunchCfg& L);   // island discovery + wake + integrate velocities
-cudaError_t stage_colour_and_sort(const DevWorld& W, const LaunchCfg& L);         // graph colouring + colour counting sort
+cudaError_t stage_colour_and_sort(const DevWorld& W, const LaunchCfg& L);
+cudaError_t stage_colour_and_sort_worlds(DevWorld& W, const LaunchCfg& L, unsigned* keysA, unsigned* keysB, int* valsA, int* valsB, int n, int colourBits);
+cudaError_t launch_mark_and_colour(const DevWorld& W, const LaunchCfg& L);
+cudaError_t stage_solve_worlds(const DevWorld& W, const LaunchCfg& L, int bodiesPerWorld);
+size_t cub_temp_bytes_u32(int n);         // graph colouring + colour counting sort
 cudaError_t stage_prepare(const DevWorld& W, const LaunchCfg& L);                 // contact constraint setup
 cudaError_t stage_solve(const DevWorld& W, const LaunchCfg& L);                   // warm start + iterations + finalize + sleep (one persistent kernel)
 cudaError_t stage_sync_fixtures(const DevWorld& W, const LaunchCfg& L);           // b2Body.SynchronizeFixtures / MoveProxy

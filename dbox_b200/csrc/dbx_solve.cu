@@ -225,8 +225,145 @@ __global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld 
 #undef GB
 #undef PHASE_MARK
 
+// ------------------------------------------------------------------------------------------------ world-local solver
+// Batched replicas (dbx_world_replicate) are thousands of small, independent constraint graphs.  Running them through
+// k_solve means one grid barrier per colour for ALL of them and every row streamed from HBM on every iteration.  Here one
+// CTA takes one replica at a time and runs the whole of b2Island.Solve for it -- warm-start fold, velocity iterations,
+// integration, position iterations with the per-island early-out, write-back and sleep -- with __syncthreads() between
+// colours: a replica's rows (tens of kB) stay in L1/L2 for all eleven passes and no CTA ever waits for another.
+// Same row functions, same colour order, same arithmetic as k_solve: results are bit-identical (tests compare a replica
+// with the same world stepped alone through k_solve).  Solver slots arrive sorted by (replica, colour); joints are not
+// handled here (worlds with joints take the k_solve path).
+constexpr int kWorldMaxColours = 256;
+__global__ void __launch_bounds__(128) k_solve_worlds(const __grid_constant__ DevWorld W, int bodiesPerWorld) {
+  __shared__ int cstart[kWorldMaxColours + 1];
+  __shared__ int ncol;
+  const int t = threadIdx.x, B = blockDim.x;
+  for (int w = blockIdx.x; w < W.nWorlds; w += gridDim.x) {
+    const int beg = W.w_start[w], end = W.w_end[w];
+    // (a replica with no solver contact -- asleep, or in free fall -- has beg == end: only the body loops do anything)
+    const int b0 = w * bodiesPerWorld, b1 = b0 + bodiesPerWorld;
+    // colour boundaries of this replica's slot range (sorted by colour): the slots where the colour changes, in order
+    if (t == 0) ncol = 0;
+    __syncthreads();
+    for (int s = beg + t; s < end; s += B) {
+      const unsigned cm = (1u << W.swColourBits) - 1u;
+      const int c = (int)(W.sw_key[s] & cm);
+      if (s == beg || c != (int)(W.sw_key[s - 1] & cm)) { const int k = atomicAdd(&ncol, 1); if (k < kWorldMaxColours) cstart[k] = s; }
+    }
+    __syncthreads();
+    const int nc = min(ncol, kWorldMaxColours);
+    if (ncol > kWorldMaxColours && t == 0) W.hdr->error = -5;
+    if (t == 0) {                                  // a handful of entries: insertion sort
+      for (int a = 1; a < nc; ++a) { const int v = cstart[a]; int b = a - 1; while (b >= 0 && cstart[b] > v) { cstart[b + 1] = cstart[b]; --b; } cstart[b + 1] = v; }
+      cstart[nc] = end;
+    }
+    __syncthreads();
+    // contact warm start: fold the accumulators (see k_solve)
+    if (W.warmStarting) {
+      const float k = 1.0f / 4294967296.0f;
+      for (int b = b0 + t; b < b1; b += B) {
+        const long long ax = (long long)__ldcg(&W.b_acc[3 * b]), ay = (long long)__ldcg(&W.b_acc[3 * b + 1]), aw = (long long)__ldcg(&W.b_acc[3 * b + 2]);
+        if ((ax | ay | aw) == 0) continue;
+        float4 vel = ldcg4(&W.b_vel[b]);
+        vel.x += (float)ax * k; vel.y += (float)ay * k; vel.z += (float)aw * k;
+        stcg4(&W.b_vel[b], vel);
+        __stcg(&W.b_acc[3 * b], 0ull); __stcg(&W.b_acc[3 * b + 1], 0ull); __stcg(&W.b_acc[3 * b + 2], 0ull);
+      }
+      __syncthreads();
+    }
+    for (int it = 0; it < W.velIters; ++it)
+      for (int c = 0; c < nc; ++c) {
+        for (int s = cstart[c] + t; s < cstart[c + 1]; s += B) contact_solve_velocity(W, s);
+        __syncthreads();
+      }
+    // StoreImpulses + integrate positions
+    for (int s = beg + t; s < end; s += B) {
+      const int i = W.s_contact[s];
+      const int vcCount = W.s_pc[s] & 0xFF;
+      const float4 imp = W.s_imp[s];
+      float4 old = W.c_imp[i];
+      old.x = imp.x; old.y = imp.y;
+      if (vcCount == 2) { old.z = imp.z; old.w = imp.w; }
+      W.c_imp[i] = old;
+    }
+    const float h = W.dt;
+    for (int b = b0 + t; b < b1; b += B) {
+      const uint32_t f = W.b_flags[b];
+      if ((f & (BF_ALIVE | BF_ISLAND)) != (BF_ALIVE | BF_ISLAND)) continue;
+      float4 pos = ldcg4(&W.b_pos[b]), vel = ldcg4(&W.b_vel[b]);
+      v2 c = V(pos.x, pos.y), v = V(vel.x, vel.y);
+      float a = pos.z, wv = vel.z;
+      v2 translation = h * v;
+      if (dot(translation, translation) > kMaxTranslationSquared) { float ratio = kMaxTranslation / len(translation); v *= ratio; }
+      float rotation = h * wv;
+      if (rotation * rotation > kMaxRotationSquared) { float ratio = kMaxRotation / fabsr(rotation); wv *= ratio; }
+      c += h * v;
+      a += h * wv;
+      stcg4(&W.b_pos[b], make_float4(c.x, c.y, a, 0.0f));
+      stcg4(&W.b_vel[b], make_float4(v.x, v.y, wv, 0.0f));
+    }
+    __syncthreads();
+    for (int it = 0; it < W.posIters; ++it) {
+      int* notOk = W.b_posNotOk + it * W.nBodies;
+      const int* prev = it > 0 ? W.b_posNotOk + (it - 1) * W.nBodies : nullptr;
+      for (int c = 0; c < nc; ++c) {
+        for (int s = cstart[c] + t; s < cstart[c + 1]; s += B) {
+          const int root = W.s_root[s];
+          if (prev && __ldcg(&prev[root]) == 0) continue;
+          const float minSep = contact_solve_position(W, s);
+          if (!(minSep >= -3.0f * kLinearSlop)) __stcg(&notOk[root], 1);
+        }
+        __syncthreads();
+      }
+    }
+    // write back + SynchronizeTransform, sleep bookkeeping
+    {
+      const float linTolSqr = kLinearSleepTolerance * kLinearSleepTolerance;
+      const float angTolSqr = kAngularSleepTolerance * kAngularSleepTolerance;
+      for (int b = b0 + t; b < b1; b += B) {
+        const uint32_t f = W.b_flags[b];
+        if ((f & (BF_ALIVE | BF_ISLAND)) != (BF_ALIVE | BF_ISLAND)) continue;
+        const float4 pos = ldcg4(&W.b_pos[b]);
+        const float4 lc = W.b_lc[b];
+        W.b_xf[b] = pack(xf_from_sweep(V(pos.x, pos.y), pos.z, V(lc.x, lc.y)));
+        if (W.allowSleep) {
+          const float4 vel = ldcg4(&W.b_vel[b]);
+          float2 gs = W.b_gs[b];
+          if (!(f & BF_AUTOSLEEP) || vel.z * vel.z > angTolSqr || dot(V(vel.x, vel.y), V(vel.x, vel.y)) > linTolSqr) gs.y = 0.0f;
+          else gs.y += h;
+          W.b_gs[b] = gs;
+          atomicMin(&W.b_islMinSleep[W.b_root[b]], __float_as_int(gs.y));
+        }
+      }
+    }
+    __syncthreads();
+    if (W.allowSleep) {
+      const int* last = W.posIters > 0 ? W.b_posNotOk + (W.posIters - 1) * W.nBodies : nullptr;
+      for (int b = b0 + t; b < b1; b += B) {
+        const uint32_t f = W.b_flags[b];
+        if ((f & (BF_ALIVE | BF_ISLAND)) != (BF_ALIVE | BF_ISLAND)) continue;
+        const int root = W.b_root[b];
+        const bool positionSolved = last && __ldcg(&last[root]) == 0;
+        const float minSleep = __int_as_float(__ldcg(&W.b_islMinSleep[root]));
+        if (minSleep >= kTimeToSleep && positionSolved) {
+          W.b_flags[b] = f & ~BF_AWAKE;
+          W.b_gs[b].y = 0.0f;
+          W.b_vel[b] = make_float4(0, 0, 0, 0);
+          W.b_force[b] = make_float4(0, 0, 0, 0);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return _e; } while (0)
 
+cudaError_t stage_solve_worlds(const DevWorld& W, const LaunchCfg& L, int bodiesPerWorld) {
+  const int grid = W.nWorlds < L.coopBlocks * 8 ? W.nWorlds : L.coopBlocks * 8;
+  ++L.launches; k_solve_worlds<<<grid, 128, 0, L.stream>>>(W, bodiesPerWorld);
+  return cudaGetLastError();
+}
 cudaError_t stage_prepare(const DevWorld& W, const LaunchCfg& L) {
   ++L.launches; k_prepare<<<L.gridWide, 256, 0, L.stream>>>(W);
   return cudaGetLastError();

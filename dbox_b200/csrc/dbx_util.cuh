@@ -56,7 +56,6 @@ DBX_D void hash_remove(const DevWorld& W, unsigned long long key) {
 // lock-free union-find.  Roots are hooked by a bijective hash of the body id (smaller hash wins), not by the id itself:
 // a stack of consecutively numbered bodies would otherwise hook into one chain as deep as the stack, and the dependent
 // loads of walking it are what the island pass costs.  A component's root is still a pure function of its member set.
-// (Batched worlds keep id order: their islands are small, and hashing only scatters the accesses over a 50 MB array.)
 DBX_D unsigned uf_rank(int x, bool hashed) { return hashed ? (unsigned)x * 0x9E3779B1u : (unsigned)x; }
 DBX_D int uf_find(int* parent, int x) {
   for (;;) {
@@ -65,6 +64,16 @@ DBX_D int uf_find(int* parent, int x) {
     int gp = parent[p];
     if (gp != p) parent[x] = gp;  // path halving (benign race)
     x = p;
+  }
+}
+// plain variant (finds with path halving, one after the other): better for the thousands of small islands of batched worlds
+DBX_D void uf_unite_small(int* parent, int a, int b) {
+  for (;;) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (uf_rank(a, true) < uf_rank(b, true)) { int t = a; a = b; b = t; }
+    if (atomicCAS(&parent[a], a, b) == a) return;
   }
 }
 DBX_D void uf_unite(int* parent, int a, int b, bool hashed) {

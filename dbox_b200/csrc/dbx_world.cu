@@ -882,11 +882,37 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents, int halves) {
   if (stepComplete_ && dt > 0.0f) {
     CUDA_OR_FAIL(stage_islands_and_integrate(dw_, L_), "islands");
     mark(2);
-    CUDA_OR_FAIL(stage_colour_and_sort(dw_, L_), "colour");
+    // batched replicas without joints: solver slots in (replica, colour) order and one CTA per replica (k_solve_worlds)
+    const bool worldsPath = replicated_ && jointAt_.empty() && !overrideLevels_ && !(dw_.dbgFlags & 16);
+    if (worldsPath) {
+      // Sort exactly the slots in use, with exactly the key bits the colours need.  Both numbers are device-side facts
+      // (cHigh: final since the last FindNewContacts; maxColour: monotonic, so a stale read is still an upper bound for
+      // what existed then -- it is read AFTER this step's colouring): one small D2H copy and a stream sync per step,
+      // ~20 us against a step of tens of milliseconds.
+      CUDA_OR_FAIL(launch_mark_and_colour(dw_, L_), "colour");
+      if (!wm_) { CUDA_OR_FAIL(cudaMallocHost((void**)&wm_, 256), "watermark"); CUDA_OR_FAIL(cudaEventCreateWithFlags(&wmEv_, cudaEventDisableTiming), "watermark"); }
+      CUDA_OR_FAIL(cudaMemcpyAsync(wm_ + 16, hdr_.p, 64 + 32, cudaMemcpyDeviceToHost, stream_), "header peek");
+      CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "header peek");
+      const size_t n = std::min(c_key.cap, (size_t)std::max(wm_[16 + 0], 1));                       // Header::cHigh
+      const int maxColour = std::max(wm_[16 + (int)(offsetof(Header, maxColour) / 4)], 0);
+      int colourBits = 1;
+      while ((1 << colourBits) <= maxColour && colourBits < 10) ++colourBits;
+      CUDA_OR_FAIL(swKeyA_.reserve(n, false, stream_), "world keys"); CUDA_OR_FAIL(swKeyB_.reserve(n, false, stream_), "world keys");
+      CUDA_OR_FAIL(swValA_.reserve(n, false, stream_), "world vals"); CUDA_OR_FAIL(swValB_.reserve(n, false, stream_), "world vals");
+      CUDA_OR_FAIL(wStart_.reserve((size_t)nWorlds_, false, stream_), "world ranges"); CUDA_OR_FAIL(wEnd_.reserve((size_t)nWorlds_, false, stream_), "world ranges");
+      const size_t need = cub_temp_bytes_u32((int)n);
+      if (need > cubTemp.cap) { CUDA_OR_FAIL(cubTemp.reserve(need, false, stream_), "cubTemp"); L_.cubTemp = cubTemp.p; L_.cubTempBytes = cubTemp.cap; }
+      dw_.w_start = wStart_.p; dw_.w_end = wEnd_.p;
+      CUDA_OR_FAIL(stage_colour_and_sort_worlds(dw_, L_, swKeyA_.p, swKeyB_.p, swValA_.p, swValB_.p, (int)n, colourBits), "colour (worlds)");
+    } else {
+      dw_.s_contact = s_contact.p;
+      CUDA_OR_FAIL(stage_colour_and_sort(dw_, L_), "colour");
+    }
     mark(3);
     CUDA_OR_FAIL(stage_prepare(dw_, L_), "prepare");
     mark(4);
-    CUDA_OR_FAIL(stage_solve(dw_, L_), "solve");
+    if (worldsPath) CUDA_OR_FAIL(stage_solve_worlds(dw_, L_, (int)bodies_.size()), "solve (worlds)");
+    else CUDA_OR_FAIL(stage_solve(dw_, L_), "solve");
     mark(5);
     if (toiPre) {
       if (!aux_) {
@@ -926,7 +952,7 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents, int halves) {
   }
   if ((stepCount_ & 63) == 0) { int rc2 = compactContacts(); if (rc2 < 0) return rc2; }
   if ((stepCount_ & 7) == 0 && !wmPending_) {
-    if (!wm_) { CUDA_OR_FAIL(cudaMallocHost((void**)&wm_, 64), "watermark"); CUDA_OR_FAIL(cudaEventCreateWithFlags(&wmEv_, cudaEventDisableTiming), "watermark"); }
+    if (!wm_) { CUDA_OR_FAIL(cudaMallocHost((void**)&wm_, 256), "watermark"); CUDA_OR_FAIL(cudaEventCreateWithFlags(&wmEv_, cudaEventDisableTiming), "watermark"); }
     CUDA_OR_FAIL(cudaMemcpyAsync(wm_, hdr_.p, 64, cudaMemcpyDeviceToHost, stream_), "watermark");
     CUDA_OR_FAIL(cudaEventRecord(wmEv_, stream_), "watermark");
     wmPending_ = true;

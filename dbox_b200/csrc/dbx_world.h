@@ -180,7 +180,8 @@ class World {
   int nJointPairs_ = 0; int jointBlocks_ = 0, nJointColours_ = 0;
   cudaEvent_t ev_[10]{};
   bool evValid_ = false, evFine_ = false;
-  DevBuf<char> flushBuf_; DevBuf<float4> ioBuf_, ioBuf2_; DevBuf<int> ioIds_; DevBuf<int4> ev_a_, ev_b_; DevBuf<unsigned long long> patchKeys_; bool midStep_ = false; float stepDt_ = 0; int stepVi_ = 0, stepPi_ = 0; DevBuf<float4> qIn_, qOut_; DevBuf<int> qCount_; DevBuf<int2> qPairs_; DevBuf<unsigned long long> phaseBuf_;
+  DevBuf<char> flushBuf_; DevBuf<float4> ioBuf_, ioBuf2_; DevBuf<int> ioIds_; DevBuf<unsigned> swKeyA_, swKeyB_; DevBuf<int> swValA_, swValB_, wStart_, wEnd_;
+  DevBuf<int4> ev_a_, ev_b_; DevBuf<unsigned long long> patchKeys_; bool midStep_ = false; float stepDt_ = 0; int stepVi_ = 0, stepPi_ = 0; DevBuf<float4> qIn_, qOut_; DevBuf<int> qCount_; DevBuf<int2> qPairs_; DevBuf<unsigned long long> phaseBuf_;
   bool overrideLevels_ = false;
   bool treeValid_ = false; int sinceRebuild_ = 0;
   // contact-pool watermark: every 8th step the header is copied to pinned memory without waiting; a later step looks at
