@@ -235,7 +235,10 @@ __global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld 
 // with the same world stepped alone through k_solve).  Solver slots arrive sorted by (replica, colour); joints are not
 // handled here (worlds with joints take the k_solve path).
 constexpr int kWorldMaxColours = 256;
-__global__ void __launch_bounds__(128) k_solve_worlds(const __grid_constant__ DevWorld W, int bodiesPerWorld) {
+// kLocal: the replica's body velocities and positions live in shared memory for the duration of its solve (loaded once,
+// written back once); otherwise (a replica too big for shared memory) they stay in the global arrays.
+template <bool kLocal> __global__ void __launch_bounds__(128) k_solve_worlds(const __grid_constant__ DevWorld W, int bodiesPerWorld) {
+  extern __shared__ float4 sBodies[];              // kLocal: [bodiesPerWorld] velocities, then [bodiesPerWorld] positions
   __shared__ int cstart[kWorldMaxColours + 1];
   __shared__ int ncol;
   const int t = threadIdx.x, B = blockDim.x;
@@ -243,6 +246,8 @@ __global__ void __launch_bounds__(128) k_solve_worlds(const __grid_constant__ De
     const int beg = W.w_start[w], end = W.w_end[w];
     // (a replica with no solver contact -- asleep, or in free fall -- has beg == end: only the body loops do anything)
     const int b0 = w * bodiesPerWorld, b1 = b0 + bodiesPerWorld;
+    BodyView bvw; bvw.vel = sBodies; bvw.pos = sBodies + bodiesPerWorld; bvw.off = b0;
+    const BodyView* view = kLocal ? &bvw : nullptr;
     // colour boundaries of this replica's slot range (sorted by colour): the slots where the colour changes, in order
     if (t == 0) ncol = 0;
     __syncthreads();
@@ -259,22 +264,26 @@ __global__ void __launch_bounds__(128) k_solve_worlds(const __grid_constant__ De
       cstart[nc] = end;
     }
     __syncthreads();
-    // contact warm start: fold the accumulators (see k_solve)
-    if (W.warmStarting) {
+    // bodies in (kLocal); the contact warm start is folded in on the way (see k_solve)
+    {
       const float k = 1.0f / 4294967296.0f;
       for (int b = b0 + t; b < b1; b += B) {
-        const long long ax = (long long)__ldcg(&W.b_acc[3 * b]), ay = (long long)__ldcg(&W.b_acc[3 * b + 1]), aw = (long long)__ldcg(&W.b_acc[3 * b + 2]);
-        if ((ax | ay | aw) == 0) continue;
         float4 vel = ldcg4(&W.b_vel[b]);
-        vel.x += (float)ax * k; vel.y += (float)ay * k; vel.z += (float)aw * k;
-        stcg4(&W.b_vel[b], vel);
-        __stcg(&W.b_acc[3 * b], 0ull); __stcg(&W.b_acc[3 * b + 1], 0ull); __stcg(&W.b_acc[3 * b + 2], 0ull);
+        if (W.warmStarting) {
+          const long long ax = (long long)__ldcg(&W.b_acc[3 * b]), ay = (long long)__ldcg(&W.b_acc[3 * b + 1]), aw = (long long)__ldcg(&W.b_acc[3 * b + 2]);
+          if ((ax | ay | aw) != 0) {
+            vel.x += (float)ax * k; vel.y += (float)ay * k; vel.z += (float)aw * k;
+            __stcg(&W.b_acc[3 * b], 0ull); __stcg(&W.b_acc[3 * b + 1], 0ull); __stcg(&W.b_acc[3 * b + 2], 0ull);
+            if (!kLocal) stcg4(&W.b_vel[b], vel);
+          }
+        }
+        if (kLocal) { bvw.vel[b - b0] = vel; bvw.pos[b - b0] = ldcg4(&W.b_pos[b]); }
       }
       __syncthreads();
     }
     for (int it = 0; it < W.velIters; ++it)
       for (int c = 0; c < nc; ++c) {
-        for (int s = cstart[c] + t; s < cstart[c + 1]; s += B) contact_solve_velocity(W, s);
+        for (int s = cstart[c] + t; s < cstart[c + 1]; s += B) contact_solve_velocity(W, s, view);
         __syncthreads();
       }
     // StoreImpulses + integrate positions
@@ -291,7 +300,7 @@ __global__ void __launch_bounds__(128) k_solve_worlds(const __grid_constant__ De
     for (int b = b0 + t; b < b1; b += B) {
       const uint32_t f = W.b_flags[b];
       if ((f & (BF_ALIVE | BF_ISLAND)) != (BF_ALIVE | BF_ISLAND)) continue;
-      float4 pos = ldcg4(&W.b_pos[b]), vel = ldcg4(&W.b_vel[b]);
+      float4 pos = kLocal ? bvw.pos[b - b0] : ldcg4(&W.b_pos[b]), vel = kLocal ? bvw.vel[b - b0] : ldcg4(&W.b_vel[b]);
       v2 c = V(pos.x, pos.y), v = V(vel.x, vel.y);
       float a = pos.z, wv = vel.z;
       v2 translation = h * v;
@@ -300,8 +309,8 @@ __global__ void __launch_bounds__(128) k_solve_worlds(const __grid_constant__ De
       if (rotation * rotation > kMaxRotationSquared) { float ratio = kMaxRotation / fabsr(rotation); wv *= ratio; }
       c += h * v;
       a += h * wv;
-      stcg4(&W.b_pos[b], make_float4(c.x, c.y, a, 0.0f));
-      stcg4(&W.b_vel[b], make_float4(v.x, v.y, wv, 0.0f));
+      if (kLocal) { bvw.pos[b - b0] = make_float4(c.x, c.y, a, 0.0f); bvw.vel[b - b0] = make_float4(v.x, v.y, wv, 0.0f); }
+      else { stcg4(&W.b_pos[b], make_float4(c.x, c.y, a, 0.0f)); stcg4(&W.b_vel[b], make_float4(v.x, v.y, wv, 0.0f)); }
     }
     __syncthreads();
     for (int it = 0; it < W.posIters; ++it) {
@@ -311,7 +320,7 @@ __global__ void __launch_bounds__(128) k_solve_worlds(const __grid_constant__ De
         for (int s = cstart[c] + t; s < cstart[c + 1]; s += B) {
           const int root = W.s_root[s];
           if (prev && __ldcg(&prev[root]) == 0) continue;
-          const float minSep = contact_solve_position(W, s);
+          const float minSep = contact_solve_position(W, s, -1, -1, view);
           if (!(minSep >= -3.0f * kLinearSlop)) __stcg(&notOk[root], 1);
         }
         __syncthreads();
@@ -324,11 +333,12 @@ __global__ void __launch_bounds__(128) k_solve_worlds(const __grid_constant__ De
       for (int b = b0 + t; b < b1; b += B) {
         const uint32_t f = W.b_flags[b];
         if ((f & (BF_ALIVE | BF_ISLAND)) != (BF_ALIVE | BF_ISLAND)) continue;
-        const float4 pos = ldcg4(&W.b_pos[b]);
+        const float4 pos = kLocal ? bvw.pos[b - b0] : ldcg4(&W.b_pos[b]);
+        const float4 vel = kLocal ? bvw.vel[b - b0] : ldcg4(&W.b_vel[b]);
+        if (kLocal) { stcg4(&W.b_pos[b], pos); stcg4(&W.b_vel[b], vel); }
         const float4 lc = W.b_lc[b];
         W.b_xf[b] = pack(xf_from_sweep(V(pos.x, pos.y), pos.z, V(lc.x, lc.y)));
         if (W.allowSleep) {
-          const float4 vel = ldcg4(&W.b_vel[b]);
           float2 gs = W.b_gs[b];
           if (!(f & BF_AUTOSLEEP) || vel.z * vel.z > angTolSqr || dot(V(vel.x, vel.y), V(vel.x, vel.y)) > linTolSqr) gs.y = 0.0f;
           else gs.y += h;
@@ -361,7 +371,10 @@ __global__ void __launch_bounds__(128) k_solve_worlds(const __grid_constant__ De
 
 cudaError_t stage_solve_worlds(const DevWorld& W, const LaunchCfg& L, int bodiesPerWorld) {
   const int grid = W.nWorlds < L.coopBlocks * 8 ? W.nWorlds : L.coopBlocks * 8;
-  ++L.launches; k_solve_worlds<<<grid, 128, 0, L.stream>>>(W, bodiesPerWorld);
+  const size_t smem = (size_t)bodiesPerWorld * 32;
+  ++L.launches;
+  if (smem <= 40 * 1024) k_solve_worlds<true><<<grid, 128, smem, L.stream>>>(W, bodiesPerWorld);
+  else k_solve_worlds<false><<<grid, 128, 0, L.stream>>>(W, bodiesPerWorld);
   return cudaGetLastError();
 }
 cudaError_t stage_prepare(const DevWorld& W, const LaunchCfg& L) {

@@ -144,11 +144,21 @@ DBX_D void prepare_contact(const DevWorld& W, int s, int i, float warmScale) {
 
 // velocities of one body pair; only dynamic bodies are ever written (statics/kinematics have zero inverse mass)
 struct BodyVel { v2 vA, vB; float wA, wB; };
-DBX_D BodyVel load_vel(const DevWorld& W, int2 bd) {
-  float4 a = ldcg4(&W.b_vel[bd.x]), b = ldcg4(&W.b_vel[bd.y]);
+// Optional CTA-local copy of a replica's bodies (k_solve_worlds): vel / pos point into shared memory and hold bodies
+// [off, off + n); a null view means the global arrays (through L2).
+struct BodyView { float4* vel; float4* pos; int off; };
+DBX_D BodyVel load_vel(const DevWorld& W, int2 bd, const BodyView* view = nullptr) {
+  float4 a, b;
+  if (view) { a = view->vel[bd.x - view->off]; b = view->vel[bd.y - view->off]; }
+  else { a = ldcg4(&W.b_vel[bd.x]); b = ldcg4(&W.b_vel[bd.y]); }
   BodyVel r; r.vA = V(a.x, a.y); r.wA = a.z; r.vB = V(b.x, b.y); r.wB = b.z; return r;
 }
-DBX_D void store_vel(const DevWorld& W, int2 bd, const BodyVel& r, float mA, float iA, float mB, float iB) {
+DBX_D void store_vel(const DevWorld& W, int2 bd, const BodyVel& r, float mA, float iA, float mB, float iB, const BodyView* view = nullptr) {
+  if (view) {
+    if (mA != 0.0f || iA != 0.0f) view->vel[bd.x - view->off] = make_float4(r.vA.x, r.vA.y, r.wA, 0.0f);
+    if (mB != 0.0f || iB != 0.0f) view->vel[bd.y - view->off] = make_float4(r.vB.x, r.vB.y, r.wB, 0.0f);
+    return;
+  }
   if (mA != 0.0f || iA != 0.0f) stcg4(&W.b_vel[bd.x], make_float4(r.vA.x, r.vA.y, r.wA, 0.0f));
   if (mB != 0.0f || iB != 0.0f) stcg4(&W.b_vel[bd.y], make_float4(r.vB.x, r.vB.y, r.wB, 0.0f));
 }
@@ -163,7 +173,7 @@ DBX_D void vc_load(const DevWorld& W, int s, VC& c) {
   c.v0 = W.s_v0[s]; c.v1 = W.s_v1[s]; c.r0 = W.s_r0[s]; c.q0 = W.s_q0[s]; c.imp = W.s_imp[s];
   c.r1 = W.s_r1[s]; c.q1 = W.s_q1[s]; c.nm = W.s_nm[s]; c.K = W.s_k[s];
 }
-DBX_D void contact_solve_velocity(const DevWorld& W, int s, const VC& c) {
+DBX_D void contact_solve_velocity(const DevWorld& W, int s, const VC& c, const BodyView* view = nullptr) {
   const int2 bd = c.bd;
   const float4 v0 = c.v0, v1 = c.v1;
   float4 imp = c.imp;
@@ -171,7 +181,7 @@ DBX_D void contact_solve_velocity(const DevWorld& W, int s, const VC& c) {
   const float mA = v1.x, iA = v1.y, mB = v1.z, iB = v1.w;
   const float4 r0 = c.r0, q0 = c.q0;
   const float4 r1 = c.r1, q1 = c.q1;
-  BodyVel bv = load_vel(W, bd);
+  BodyVel bv = load_vel(W, bd, view);
   v2 vA = bv.vA, vB = bv.vB; float wA = bv.wA, wB = bv.wB;
   const v2 normal = V(v0.x, v0.y), tangent = cross(normal, 1.0f);
   const float friction = v0.z, tangentSpeed = v0.w;
@@ -247,14 +257,14 @@ DBX_D void contact_solve_velocity(const DevWorld& W, int s, const VC& c) {
   }
   W.s_imp[s] = imp;
   bv.vA = vA; bv.vB = vB; bv.wA = wA; bv.wB = wB;
-  store_vel(W, bd, bv, mA, iA, mB, iB);
+  store_vel(W, bd, bv, mA, iA, mB, iB, view);
 }
 
-DBX_D void contact_solve_velocity(const DevWorld& W, int s) { VC c; vc_load(W, s, c); contact_solve_velocity(W, s, c); }
+DBX_D void contact_solve_velocity(const DevWorld& W, int s, const BodyView* view = nullptr) { VC c; vc_load(W, s, c); contact_solve_velocity(W, s, c, view); }
 
 // b2ContactSolver.SolvePositionConstraints (:73-149) + b2PositionSolverManifold (:816-868); returns min separation
 // toiA/toiB >= 0 selects SolveTOIPositionConstraints (:152-242): only those two bodies keep their mass, Baumgarte 0.75
-DBX_D float contact_solve_position(const DevWorld& W, int s, int toiA = -1, int toiB = -1) {
+DBX_D float contact_solve_position(const DevWorld& W, int s, int toiA = -1, int toiB = -1, const BodyView* view = nullptr) {
   const int2 bd = W.s_body[s];
   const float4 v1 = W.s_v1[s], p0 = W.s_p0[s], p1 = W.s_p1[s], p2 = W.s_p2[s];
   const float2 p3 = W.s_p3[s];
@@ -269,7 +279,9 @@ DBX_D float contact_solve_position(const DevWorld& W, int s, int toiA = -1, int 
   const float baumgarte = toi ? kToiBaumgarte : kBaumgarte;
   const v2 localCenterA = V(p2.x, p2.y), localCenterB = V(p2.z, p2.w);
   const v2 localNormal = V(p1.x, p1.y), localPoint = V(p1.z, p1.w);
-  float4 pa = ldcg4(&W.b_pos[bd.x]), pb = ldcg4(&W.b_pos[bd.y]);
+  float4 pa, pb;
+  if (view) { pa = view->pos[bd.x - view->off]; pb = view->pos[bd.y - view->off]; }
+  else { pa = ldcg4(&W.b_pos[bd.x]); pb = ldcg4(&W.b_pos[bd.y]); }
   v2 cA = V(pa.x, pa.y), cB = V(pb.x, pb.y);
   float aA = pa.z, aB = pb.z;
   float minSeparation = 0.0f;
@@ -308,6 +320,11 @@ DBX_D float contact_solve_position(const DevWorld& W, int s, int toiA = -1, int 
     v2 P = impulse * normal;
     cA -= mA * P; aA -= iA * cross(rA, P);
     cB += mB * P; aB += iB * cross(rB, P);
+  }
+  if (view) {
+    if (mA != 0.0f || iA != 0.0f) view->pos[bd.x - view->off] = make_float4(cA.x, cA.y, aA, 0.0f);
+    if (mB != 0.0f || iB != 0.0f) view->pos[bd.y - view->off] = make_float4(cB.x, cB.y, aB, 0.0f);
+    return minSeparation;
   }
   if (mA != 0.0f || iA != 0.0f) stcg4(&W.b_pos[bd.x], make_float4(cA.x, cA.y, aA, 0.0f));
   if (mB != 0.0f || iB != 0.0f) stcg4(&W.b_pos[bd.y], make_float4(cB.x, cB.y, aB, 0.0f));
