@@ -70,6 +70,7 @@ struct Header {
   float bounds[4];    // world bounds of fat AABB centres (Morton normalisation), as ordered ints
   int colourOff[kMaxColours + 1];   // solver order: contacts of colour c are [colourOff[c], colourOff[c+1])
   int jointColourOff[kMaxJointColours + 1];
+  int nToi;           // entries of c_toiList: contacts the TOI pass can ever care about this step (listed by k_collide)
 };
 
 struct DevWorld {
@@ -162,6 +163,7 @@ struct DevWorld {
   float4* c_imp;     // n0 t0 n1 t1
   uint4* c_mk;       // key0 key1 type pointCount
   float4* c_mat;     // friction restitution tangentSpeed toi
+  int* c_toiList;    // [cCap] see Header::nToi
   int* c_toiCount;
   int* c_colour;
   int* c_free;

@@ -111,11 +111,17 @@ __global__ void __launch_bounds__(256, 4) k_collide(const __grid_constant__ DevW
     }
     bool activeA = (flA & BF_AWAKE) && body_type(flA) != BODY_STATIC;
     bool activeB = (flB & BF_AWAKE) && body_type(flB) != BODY_STATIC;
-    if (!activeA && !activeB) continue;
+    // Contacts the TOI pass can ever look at this step (b2world.d:1165-1199: not a sensor, and one side is a bullet or not
+    // dynamic) are a few per cent of all contacts: list them here, where every contact and both body flag words are in
+    // registers anyway, so that k_toi never has to scan the whole contact pool.
+    const bool toiKind = W.continuous && !(flags & CF_SENSOR) &&
+                         ((flA & BF_BULLET) || body_type(flA) != BODY_DYNAMIC || (flB & BF_BULLET) || body_type(flB) != BODY_DYNAMIC);
+    if (!activeA && !activeB) { if (toiKind) W.c_toiList[atomicAdd(&W.hdr->nToi, 1)] = i; continue; }
     if (!overlap(BX(W.p_fat[ids.x]), BX(W.p_fat[ids.y]))) {
       destroy_contact(W, i, flags, ids.z, ids.w, (int)mk.w);
       continue;
     }
+    if (toiKind) W.c_toiList[atomicAdd(&W.hdr->nToi, 1)] = i;
     update_contact(W, i, flags, ids, fx, false);
   }
 }
@@ -1104,7 +1110,7 @@ DBX_D bool toi_classify(const DevWorld& W, int i, bool first) {
   uint32_t flags = W.c_flags[i];
   if (!(flags & CF_ALIVE)) return false;
   if (first) {
-    if (flags & CF_FRESH) return false;
+    if ((flags & CF_FRESH) && W.toiMode == 1) return false;   // the overlapped launch must not look at a contact still being built
     if (flags & (CF_TOI | CF_ISLAND)) { flags &= ~(CF_TOI | CF_ISLAND); W.c_flags[i] = flags; }
     if (W.c_toiCount[i] != 0) W.c_toiCount[i] = 0;
   }
@@ -1144,11 +1150,14 @@ DBX_D void toi_compute(const DevWorld& W, int i) {
 }
 // one warp: scan contacts [.., n) in strides of the whole grid, queue the ones that need b2TimeOfImpact in `q` (>= 64 ints of
 // shared memory private to the warp) and run them 32 at a time
-DBX_D void toi_evaluate_all(const DevWorld& W, int n, int warp, int nwarps, int lane, int* q, bool first) {
+// the k-th contact the TOI pass looks at: k_collide's list first, then the contacts created since (k_add_pairs' list)
+DBX_D int toi_slot(const DevWorld& W, int k, int nList) { return k < nList ? W.c_toiList[k] : W.c_work[k - nList]; }
+DBX_D void toi_evaluate_all(const DevWorld& W, int n, int nList, int warp, int nwarps, int lane, int* q, bool first) {
   int qn = 0;
   for (int base = warp * 32; base < n; base += nwarps * 32) {
-    const int i = base + lane;
-    const bool need = i < n && toi_classify(W, i, first);
+    const int k = base + lane;
+    const int i = k < n ? toi_slot(W, k, nList) : 0;
+    const bool need = k < n && toi_classify(W, i, first);
     const unsigned m = __ballot_sync(0xffffffffu, need);
     if (need) q[qn + __popc(m & ((1u << lane) - 1u))] = i;
     qn += __popc(m);
@@ -1310,18 +1319,19 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
   for (int pass = 0; pass < 1024; ++pass) {
     // (a) TOI evaluation + per-body minima
     {
-      const int n = *((volatile int*)&H->cHigh);
       // few contacts per thread (one big world): evaluate in place, every chain on its own warp; many (batched worlds):
       // gather the eligible ones so that b2TimeOfImpact runs on full warps
       const bool first = pass == 0 && (!W.toiPre || W.toiMode == 1);
-      const int nFresh = *((volatile int*)&H->nFresh);
+      const int nFresh = min(*((volatile int*)&H->nFresh), W.cCap);
+      const int nList = min(*((volatile int*)&H->nToi), W.cCap);
+      const int n = nList + (W.toiMode == 1 ? 0 : nFresh);     // the overlapped first evaluation leaves the fresh ones alone
       if (pass == 0 && W.toiPre && W.toiMode == 0 && nFresh <= W.cCap) {
         // k_toi_pre has evaluated and published everything except the contacts FindNewContacts created meanwhile
         // (one per warp while they last: a b2TimeOfImpact chain is long and divergent)
         const int stride = nFresh * 32 <= nth ? 32 : 1;
         if (tid % stride == 0) for (int k = tid / stride; k < nFresh; k += nth / stride) { const int i = W.c_work[k]; if (toi_classify(W, i, false)) toi_compute(W, i); }
-      } else if (n <= 8 * nth) { for (int i = tid; i < n; i += nth) if (toi_classify(W, i, first)) toi_compute(W, i); }
-      else toi_evaluate_all(W, n, warp, nwarps, lane, stacks[wib], first);
+      } else if (n <= 8 * nth) { for (int k = tid; k < n; k += nth) { const int i = toi_slot(W, k, nList); if (toi_classify(W, i, first)) toi_compute(W, i); } }
+      else toi_evaluate_all(W, n, nList, warp, nwarps, lane, stacks[wib], first);
     }
     // The overlapped first evaluation is this same kernel (same code, warm instruction caches) launched as a plain grid
     // on the second stream: it stops here, before any grid barrier.  Contacts FindNewContacts creates meanwhile carry
@@ -1331,8 +1341,10 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
     if (pass == 0 && W.toiClearMoves && tid == 0) H->nMoved = 0;   // every CTA has read it; next used three barriers on
     // (b) winners: the minimum on every movable body they touch
     {
-      const int n = *((volatile int*)&H->cHigh);
-      for (int i = tid; i < n; i += nth) {
+      const int nList = min(*((volatile int*)&H->nToi), W.cCap);
+      const int n = nList + min(*((volatile int*)&H->nFresh), W.cCap);
+      for (int k = tid; k < n; k += nth) {
+        const int i = toi_slot(W, k, nList);
         const uint32_t flags = W.c_flags[i];
         if ((flags & (CF_ALIVE | CF_ENABLED | CF_TOI)) != (CF_ALIVE | CF_ENABLED | CF_TOI)) continue;
         if (W.c_toiCount[i] > kMaxSubSteps) continue;
@@ -1356,8 +1368,10 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
     if (nEvents == 0) break;
     // (c) contacts of the event bodies that may join their mini-islands (b2world.d:1319-1411)
     {
-      const int n = *((volatile int*)&H->cHigh);
-      for (int i = tid; i < n; i += nth) {
+      const int nList = min(*((volatile int*)&H->nToi), W.cCap);
+      const int n = nList + min(*((volatile int*)&H->nFresh), W.cCap);
+      for (int k = tid; k < n; k += nth) {
+        const int i = toi_slot(W, k, nList);
         const uint32_t flags = W.c_flags[i];
         if (!(flags & CF_ALIVE) || (flags & CF_SENSOR)) continue;
         const int4 ids = W.c_ids[i];
@@ -1446,6 +1460,7 @@ static cudaError_t launch_coop(const void* fn, const DevWorld& W, const LaunchCf
 }
 
 cudaError_t stage_collide(const DevWorld& W, const LaunchCfg& L) {
+  CK(cudaMemsetAsync(&W.hdr->nToi, 0, sizeof(int), L.stream));
   ++L.launches; k_collide<<<L.gridWide, 256, 0, L.stream>>>(W);
   return cudaGetLastError();
 }

@@ -55,7 +55,7 @@ World::~World() {
   j_ids2.release();
   b_toiMin.release(); b_toiOther.release(); b_acc.release(); jp_bits.release();
   DevBuf<int>* i1[] = {&b_toiEvt, &b_toiFlags, &e_contact, &e_ncand, &e_cand, &bv_pos, &b_wake, &b_root, &b_islAwake, &b_islMinSleep, &b_posNotOk, &b_ovf, &b_world, &f_body, &f_group, &p_key, &moveList, &bv_leaf, &bv_leafAlt,
-                       &bv_parent, &bv_visit, &c_toiCount, &c_colour, &c_free, &c_work, &c_work2, &h_val, &s_contact, &s_hist, &s_pc, &s_root, &j_limit, &j_colour, &j_order, &j_root, &d_levels};
+                       &bv_parent, &bv_visit, &c_toiList, &c_toiCount, &c_colour, &c_free, &c_work, &c_work2, &h_val, &s_contact, &s_hist, &s_pc, &s_root, &j_limit, &j_colour, &j_order, &j_root, &d_levels};
   for (auto* b : i1) b->release();
   b_gs.release(); f_mat.release(); s_p3.release(); b_flags.release(); f_filter.release(); p_flags.release(); c_flags.release();
   b_mask.release(); b_claim.release(); bv_key.release(); bv_keyAlt.release(); jp_keys.release(); c_key.release(); h_key.release();
@@ -652,6 +652,7 @@ int World::reserveDevice(bool& rehash) {
   CUDA_OR_FAIL(c_ids.reserve(capC, true, stream_), "c_ids"); CUDA_OR_FAIL(c_fix.reserve(capC, true, stream_), "c_fix");
   CUDA_OR_FAIL(c_flags.reserve(capC, true, stream_), "c_flags"); CUDA_OR_FAIL(c_mk.reserve(capC, true, stream_), "c_mk");
   DevBuf<int>* ci[] = {&c_toiCount, &c_colour, &c_free, &c_work, &c_work2};
+  CUDA_OR_FAIL(c_toiList.reserve(capC, false, stream_), "c_toiList");
   for (auto* b : ci) CUDA_OR_FAIL(b->reserve(capC, true, stream_), "contact int");
   const size_t cc = c_key.cap;
   size_t hc = 1024;
@@ -791,7 +792,7 @@ void World::refreshView() {
   w.pairs = pairs.p; w.pairCap = (int)pairs.cap;
   w.nJointPairs = nJointPairs_; w.jp_keys = jp_keys.p; w.jp_bits = jp_bits.p;
   w.cCap = (int)c_key.cap; w.c_key = c_key.p; w.c_ids = c_ids.p; w.c_fix = c_fix.p; w.c_flags = c_flags.p; w.c_m0 = c_m0.p; w.c_m1 = c_m1.p; w.c_imp = c_imp.p; w.c_mk = c_mk.p;
-  w.c_mat = c_mat.p; w.c_toiCount = c_toiCount.p; w.c_colour = c_colour.p; w.c_free = c_free.p; w.c_work = c_work.p; w.c_work2 = c_work2.p;
+  w.c_mat = c_mat.p; w.c_toiList = c_toiList.p; w.c_toiCount = c_toiCount.p; w.c_colour = c_colour.p; w.c_free = c_free.p; w.c_work = c_work.p; w.c_work2 = c_work2.p;
   w.hCap = (int)h_key.cap; w.h_key = h_key.p; w.h_val = h_val.p;
   w.sCap = (int)s_contact.cap; w.s_contact = s_contact.p; w.s_hist = s_hist.p; w.s_body = s_body.p; w.s_v0 = s_v0.p; w.s_v1 = s_v1.p; w.s_r0 = s_r0.p; w.s_r1 = s_r1.p;
   w.s_q0 = s_q0.p; w.s_q1 = s_q1.p; w.s_imp = s_imp.p; w.s_nm = s_nm.p; w.s_k = s_k.p; w.s_pc = s_pc.p; w.s_p0 = s_p0.p; w.s_p1 = s_p1.p; w.s_p2 = s_p2.p; w.s_p3 = s_p3.p; w.s_root = s_root.p;
