@@ -181,11 +181,21 @@ def bench_batched(api, args, rank, world_size, local_rank, barrier, torch):
            "e2e": {"value": args.worlds * Ke / tot["seconds"], "unit": "world-steps/s", "h2d_bytes_per_step": 16 * int(tot["bodies"]),
                    "d2h_bytes_per_step": 16 * int(tot["bodies"]), "steps": Ke},
            "gpu_launches": int(tot["launches"])}
-    alg = algorithmic_bytes_solve(local["touching"], local["awake_bodies"], 0, 0, VEL_ITERS, POS_ITERS)
+    # k_solve_worlds (one CTA per replica, rows and bodies stay on chip between passes): compulsory HBM traffic is the rows
+    # once (216 B), the impulses (16 + 32 B) and the sort entries (8 B) per solver contact, and 156 B per awake body
+    # (velocity, position, transform, flags, sleep time in and out); DESIGN.md 7.2
+    alg = 272 * local["touching"] + 156 * local["awake_bodies"]
     peak, peak_src = peaks()
     ach = alg / (stage_ms[4] * 1e-3) / 1e9 if stage_ms[4] > 0 else 0.0
-    out["roofline"] = {"bound": "hbm", "kernel": "k_solve (rank 0)", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
-                       "algorithmic_bytes_per_launch": alg, "kernel_ms": stage_ms[4], "traffic": None}
+    traffic = None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_solve_worlds_traffic.json")))
+        traffic = int(t["dram_bytes_per_launch"] * local["touching"] / t["touching"])      # scaled from the profiled batch size
+    except Exception:
+        pass
+    out["roofline"] = {"bound": "hbm", "kernel": "k_solve_worlds (rank 0)", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                       "frac": ach / peak, "algorithmic_bytes_per_launch": alg, "kernel_ms": stage_ms[4], "traffic": traffic,
+                       "limiter": "instruction issue: 58 % of peak issue slots, 15 % of DRAM throughput (profiles/r01e_ncu_batched8192_summary.txt)"}
     batch.close()
     return out
 
