@@ -1445,23 +1445,25 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
     float4 p0 = W.b_pos0[b]; if (p0.w != 0.0f) { p0.w = 0.0f; W.b_pos0[b] = p0; }
     if (W.toiClearForces) W.b_force[b] = make_float4(0, 0, 0, 0);
   }
-  if (tid == 0) H->nEvents = 0;
+  if (tid == 0) { H->nEvents = 0; H->nToi = 0; }
 }
 
 #undef TMARK
 // ------------------------------------------------------------------------------------------------ host launchers
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return _e; } while (0)
 
+// The barrier is a ticket counter: a barrier is complete when the counter reaches the next multiple of the CTA count, so
+// it needs no reset between launches as long as every launch uses the same grid and leaves it on a multiple (all do).
+// It is zeroed every 4096 launches, long before 2^32 tickets.
 static cudaError_t launch_coop(const void* fn, const DevWorld& W, const LaunchCfg& L) {
-  CK(cudaMemsetAsync(&W.hdr->barrier, 0, sizeof(unsigned), L.stream));
+  if ((L.coopLaunches++ & 4095) == 0) CK(cudaMemsetAsync(&W.hdr->barrier, 0, sizeof(unsigned), L.stream));
   void* args[] = {(void*)&W};
   ++L.launches;
   return cudaLaunchCooperativeKernel(fn, dim3(L.coopBlocks), dim3(L.coopThreads), args, 0, L.stream);
 }
 
 cudaError_t stage_collide(const DevWorld& W, const LaunchCfg& L) {
-  CK(cudaMemsetAsync(&W.hdr->nToi, 0, sizeof(int), L.stream));
-  ++L.launches; k_collide<<<L.gridWide, 256, 0, L.stream>>>(W);
+  ++L.launches; k_collide<<<L.gridWide, 256, 0, L.stream>>>(W);   // appends to the TOI list; k_toi empties it on its way out
   return cudaGetLastError();
 }
 

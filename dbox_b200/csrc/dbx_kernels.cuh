@@ -11,6 +11,7 @@ struct LaunchCfg {
   int coopThreads = 512;
   cudaStream_t stream = 0;
   void* cubTemp = nullptr; size_t cubTempBytes = 0;
+  mutable long coopLaunches = 0;
   mutable long launches = 0;   // kernels of this library launched so far (CUB's radix-sort kernels are not counted)
 };
 

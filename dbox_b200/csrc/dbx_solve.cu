@@ -382,7 +382,7 @@ cudaError_t stage_prepare(const DevWorld& W, const LaunchCfg& L) {
   return cudaGetLastError();
 }
 cudaError_t stage_solve(const DevWorld& W, const LaunchCfg& L) {
-  CK(cudaMemsetAsync(&W.hdr->barrier, 0, sizeof(unsigned), L.stream));
+  if ((L.coopLaunches++ & 4095) == 0) CK(cudaMemsetAsync(&W.hdr->barrier, 0, sizeof(unsigned), L.stream));   // see launch_coop
   void* args[] = {(void*)&W};
   ++L.launches;
   return cudaLaunchCooperativeKernel((const void*)k_solve, dim3(L.coopBlocks), dim3(L.coopThreads), args, 0, L.stream);
