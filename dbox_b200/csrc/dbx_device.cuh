@@ -151,6 +151,8 @@ struct DevWorld {
   int2* pairs; int pairCap;   // proxy slots (lo, hi) in reference key order
   // ---- joints with collideConnected == false, as sorted (bodyLo << 32 | bodyHi)
   int nJointPairs; const unsigned long long* jp_keys;
+  const unsigned long long* b_jmask;   // per body: all colours up to its highest joint colour (contacts there must stay above)
+  int unifiedColours;                  // joint colour c and contact colour c share a solver phase (see k_solve)
   const uint32_t* jp_bits;   // one bit per body: set if some joint forbids a collision of that body (skips the search above)
   // ---- contacts
   int cCap;

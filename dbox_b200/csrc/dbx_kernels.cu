@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) k_island_init(const __grid_constant__ Dev
     W.b_root[b] = b;
     W.b_islAwake[b] = 0;
     W.b_islMinSleep[b] = 0x7f7fffff;  // FLT_MAX bits
-    W.b_mask[b] = 0ull;
+    W.b_mask[b] = W.unifiedColours ? W.b_jmask[b] : 0ull;   // colours its joints occupy (and everything below them)
     W.b_ovf[b] = 0;
     if (W.b_wake[b]) { W.b_wake[b] = 0; wake_body_now(W, b); }
   }
@@ -233,6 +233,9 @@ __global__ void __launch_bounds__(256) k_mark_solve(const __grid_constant__ DevW
     if (W.colourOverride) { if (W.c_colour[i] < 0) W.c_colour[i] = kMaxColours - 1; continue; }   // test hook: caller-supplied schedule
     int col = W.c_colour[i];
     uint32_t fa = W.b_flags[ids.z], fb = W.b_flags[ids.w];
+    // a colour kept from an earlier step is void if a joint has since claimed it (or a higher one) on either body
+    if (W.unifiedColours && col >= 0 && col < kMaskColours &&
+        ((((body_type(fa) == BODY_DYNAMIC ? W.b_jmask[ids.z] : 0ull) | (body_type(fb) == BODY_DYNAMIC ? W.b_jmask[ids.w] : 0ull)) >> col) & 1ull)) col = -1;
     if (col >= 0 && col < kMaskColours) {
       if (body_type(fa) == BODY_DYNAMIC) atomicOr(&W.b_mask[ids.z], 1ull << col);
       if (body_type(fb) == BODY_DYNAMIC) atomicOr(&W.b_mask[ids.w], 1ull << col);

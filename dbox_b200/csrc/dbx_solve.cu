@@ -74,33 +74,41 @@ __global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld 
     if (jointRole) for (int k = beg + jtid; k < end; k += jnth) joint_init(W, k);
     GB();
   }
-  // velocity iterations: all joints, then all contacts (:153-161)
+  // velocity iterations: all joints, then all contacts (:153-161).  With unified colours (W.unifiedColours: contacts on a
+  // jointed body only take colours above that body's joint colours, k_mark_solve / k_colour) joint colour c and contact
+  // colour c share one phase -- every body still sees its joints before its contacts -- which saves the joint colours'
+  // barriers in every pass; otherwise (colour override hook) joint colours run as phases of their own first.
+  const bool unified = W.unifiedColours != 0;
+  const int nPhases = unified ? max(T, nJointColours) : nJointColours + T;
   VC pre; int preS = -1;
   for (int it = 0; it < W.velIters; ++it) {
-    for (int c = 0; c < nJointColours; ++c) {
-      int beg = joff[c], end = joff[c + 1];
-      if (beg == end) continue;
-      if (jointRole && !(W.dbgFlags & 1)) for (int k = beg + jtid; k < end; k += jnth) if (W.j_root[k] >= 0) joint_solve_velocity(W, k);
-      GB();
-    }
-    for (int c = 0; c < T; ++c) {
-      int beg = coff[c], end = coff[c + 1];
-      if (beg == end) continue;
-      if (contactRole) {
-        // the first item of this colour was fetched before the previous barrier; fetch the next colour's before this one
-        int s = beg + ctid;
-        if (s < end) {
-          if (preS != s) vc_load(W, s, pre);
-          contact_solve_velocity(W, s, pre);
-          for (s += cnth; s < end; s += cnth) contact_solve_velocity(W, s);
-        }
-        int cn = c + 1;
-        while (cn < T && coff[cn] == coff[cn + 1]) ++cn;
-        if (cn >= T) { cn = 0; while (cn < T && coff[cn] == coff[cn + 1]) ++cn; }
-        preS = -1;
-        if (cn < T && (cn > c || it + 1 < W.velIters)) { int sn = coff[cn] + ctid; if (sn < coff[cn + 1]) { vc_load(W, sn, pre); preS = sn; } }
+    for (int p = 0; p < nPhases; ++p) {
+      const int jc = unified ? (p < nJointColours ? p : -1) : (p < nJointColours ? p : -1);
+      const int c = unified ? (p < T ? p : -1) : (p >= nJointColours ? p - nJointColours : -1);
+      bool any = false;
+      if (jc >= 0 && joff[jc] != joff[jc + 1]) {
+        any = true;
+        if (jointRole && !(W.dbgFlags & 1)) for (int k = joff[jc] + jtid; k < joff[jc + 1]; k += jnth) if (W.j_root[k] >= 0) joint_solve_velocity(W, k);
       }
-      GB();
+      if (c >= 0 && coff[c] != coff[c + 1]) {
+        any = true;
+        const int beg = coff[c], end = coff[c + 1];
+        if (contactRole) {
+          // the first item of this colour was fetched before the previous barrier; fetch the next colour's before this one
+          int s = beg + ctid;
+          if (s < end) {
+            if (preS != s) vc_load(W, s, pre);
+            contact_solve_velocity(W, s, pre);
+            for (s += cnth; s < end; s += cnth) contact_solve_velocity(W, s);
+          }
+          int cn = c + 1;
+          while (cn < T && coff[cn] == coff[cn + 1]) ++cn;
+          if (cn >= T) { cn = 0; while (cn < T && coff[cn] == coff[cn + 1]) ++cn; }
+          preS = -1;
+          if (cn < T && (cn > c || it + 1 < W.velIters)) { int sn = coff[cn] + ctid; if (sn < coff[cn + 1]) { vc_load(W, sn, pre); preS = sn; } }
+        }
+      }
+      if (any) GB();
     }
     if (haveTail) {
       if (tailBlock) for (int c = T; c < nColours; ++c) {
@@ -140,44 +148,52 @@ __global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld 
     }
   }
   GB();
-  // position iterations: contacts then joints, each island stops once all of its constraints are within tolerance (:206-224)
+  // position iterations: contacts then joints, each island stops once all of its constraints are within tolerance
+  // (:206-224).  Unified colours run from the highest colour down, so that every body again sees its contacts (higher
+  // colours) before its joints; slot q of the pass is the tail colours, a contact colour, a joint colour or both.
   for (int it = 0; it < W.posIters; ++it) {
     int* notOk = W.b_posNotOk + it * W.nBodies;
     const int* prev = it > 0 ? W.b_posNotOk + (it - 1) * W.nBodies : nullptr;
-    for (int c = 0; c < T; ++c) {
-      int beg = coff[c], end = coff[c + 1];
-      if (beg == end) continue;
-      if (contactRole) for (int s = beg + ctid; s < end; s += cnth) {
-        int root = W.s_root[s];
-        if (prev && __ldcg(&prev[root]) == 0) continue;
-        float minSep = contact_solve_position(W, s);
-        if (!(minSep >= -3.0f * kLinearSlop)) notOk[root] = 1;
+    for (int q = 0; q <= nPhases; ++q) {
+      bool tail; int c, jc;
+      if (unified) { tail = q == 0; const int p = nPhases - q; c = (!tail && p < T) ? p : -1; jc = (!tail && p < nJointColours) ? p : -1; }
+      else { tail = q == T; c = q < T ? q : -1; jc = q > T ? q - T - 1 : -1; }
+      if (tail) {
+        if (haveTail) {
+          if (tailBlock) for (int k = 0; k < nColours - T; ++k) {
+            const int tc = unified ? nColours - 1 - k : T + k;
+            for (int s = coff[tc] + threadIdx.x; s < coff[tc + 1]; s += blockDim.x) {
+              int root = W.s_root[s];
+              if (prev && __ldcg(&prev[root]) == 0) continue;
+              float minSep = contact_solve_position(W, s);
+              if (!(minSep >= -3.0f * kLinearSlop)) notOk[root] = 1;
+            }
+            __syncthreads();
+          }
+          GB();
+        }
+        continue;
       }
-      GB();
-    }
-    if (haveTail) {
-      if (tailBlock) for (int c = T; c < nColours; ++c) {
-        for (int s = coff[c] + threadIdx.x; s < coff[c + 1]; s += blockDim.x) {
+      bool any = false;
+      if (c >= 0 && coff[c] != coff[c + 1]) {
+        any = true;
+        if (contactRole) for (int s = coff[c] + ctid; s < coff[c + 1]; s += cnth) {
           int root = W.s_root[s];
           if (prev && __ldcg(&prev[root]) == 0) continue;
           float minSep = contact_solve_position(W, s);
           if (!(minSep >= -3.0f * kLinearSlop)) notOk[root] = 1;
         }
-        __syncthreads();
       }
-      GB();
-    }
-    for (int c = 0; c < nJointColours; ++c) {
-      int beg = joff[c], end = joff[c + 1];
-      if (beg == end) continue;
-      if (jointRole) for (int k = beg + jtid; k < end; k += jnth) {
-        const int j = k;
-        int root = W.j_root[j];
-        if (root < 0) continue;
-        if (prev && __ldcg(&prev[root]) == 0) continue;
-        if (!joint_solve_position(W, j)) notOk[root] = 1;
+      if (jc >= 0 && joff[jc] != joff[jc + 1]) {
+        any = true;
+        if (jointRole) for (int k = joff[jc] + jtid; k < joff[jc + 1]; k += jnth) {
+          int root = W.j_root[k];
+          if (root < 0) continue;
+          if (prev && __ldcg(&prev[root]) == 0) continue;
+          if (!joint_solve_position(W, k)) notOk[root] = 1;
+        }
       }
-      GB();
+      if (any) GB();
     }
   }
   // write back + SynchronizeTransform (:227-235), sleep bookkeeping (:241-269), ClearForces (b2world.d:443-450)

@@ -53,7 +53,7 @@ World::~World() {
                           &s_v0, &s_v1, &s_r0, &s_r1, &s_q0, &s_q1, &s_imp, &s_nm, &s_k, &s_p0, &s_p1, &s_p2, &j_anchor, &j_p0, &j_p1, &j_imp, &j_r, &j_lc, &j_m, &j_k0, &j_k1, &j_k2, &j_k3, &j_p2};
   for (auto* b : f4) b->release();
   j_ids2.release();
-  b_toiMin.release(); b_toiOther.release(); b_acc.release(); jp_bits.release();
+  b_toiMin.release(); b_toiOther.release(); b_acc.release(); jp_bits.release(); b_jmask.release();
   DevBuf<int>* i1[] = {&b_toiEvt, &b_toiFlags, &e_contact, &e_ncand, &e_cand, &bv_pos, &b_wake, &b_root, &b_islAwake, &b_islMinSleep, &b_posNotOk, &b_ovf, &b_world, &f_body, &f_group, &p_key, &moveList, &bv_leaf, &bv_leafAlt,
                        &bv_parent, &bv_visit, &c_toiList, &c_toiCount, &c_colour, &c_free, &c_work, &c_work2, &h_val, &s_contact, &s_hist, &s_pc, &s_root, &j_limit, &j_colour, &j_order, &j_root, &d_levels};
   for (auto* b : i1) b->release();
@@ -564,6 +564,17 @@ int World::recolourJoints() {
   nJointColours_ = 0;
   for (int c = 0; c < kMaxJointColours; ++c) { maxPerColour = std::max(maxPerColour, byColour[c].size()); if (!byColour[c].empty()) nJointColours_ = c + 1; }
   jointBlocks_ = (int)std::min<size_t>((maxPerColour + L_.coopThreads - 1) / L_.coopThreads, (size_t)L_.coopBlocks / 4);
+  // per body: every colour up to its highest joint colour is closed to its contacts (k_mark_solve / k_colour), so that a
+  // body's joints always come before its contacts when joint colour c and contact colour c share a solver phase
+  jmaskHost_.assign(bodies_.size(), 0ull);
+  for (int j = 0; j < nJ; ++j) {
+    const HJoint& hj = joints_[j];
+    if (!hj.alive) continue;
+    const unsigned long long m = hj.colour >= 63 ? ~0ull : ((1ull << (hj.colour + 1)) - 1ull);
+    const int bs[4] = {hj.def.bodyA, hj.def.bodyB, hj.bodyC, hj.bodyD};
+    for (int b : bs) if (b >= 0 && bodies_[b].st.type == DBX_DYNAMIC_BODY) jmaskHost_[b] |= m;
+  }
+  { int rm = uploadJointMasks(); if (rm < 0) return rm; }
   std::sort(jp.begin(), jp.end());
   jp.erase(std::unique(jp.begin(), jp.end()), jp.end());
   nJointPairs_ = (int)jp.size();
@@ -572,6 +583,18 @@ int World::recolourJoints() {
   if (!jp.empty()) CUDA_OR_FAIL(cudaMemcpy(jp_keys.p, jp.data(), jp.size() * 8, cudaMemcpyHostToDevice), "jp up");
   CUDA_OR_FAIL(cudaMemcpy((char*)hdr_.p + offsetof(Header, jointColourOff), off, sizeof(off), cudaMemcpyHostToDevice), "joff up");
   return uploadJointBits(jp);
+}
+
+int World::uploadJointMasks() {
+  const size_t nb = bodies_.size() * (size_t)nWorlds_;
+  std::vector<unsigned long long> all(std::max<size_t>(nb, 1), 0ull);
+  for (size_t r = 0; r < (size_t)nWorlds_; ++r) for (size_t b = 0; b < jmaskHost_.size() && b < bodies_.size(); ++b) all[r * bodies_.size() + b] = jmaskHost_[b];
+  jmaskBodies_ = nb;
+  CUDA_OR_FAIL(b_jmask.reserve(all.size(), false, stream_), "b_jmask");
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  CUDA_OR_FAIL(cudaMemcpy(b_jmask.p, all.data(), all.size() * 8, cudaMemcpyHostToDevice), "jmask up");
+  dw_.b_jmask = b_jmask.p;
+  return 0;
 }
 
 // one bit per body that appears in the sorted joint-pair list: b2Body.ShouldCollide only searches the list for those
@@ -767,8 +790,9 @@ int World::push() {
     CUDA_OR_FAIL(upload_range(j_imp, 0, nD, [&](size_t k) { const HJoint& j = J(k); return f4(j.imp[0], j.imp[1], j.imp[2], j.imp[3]); }), "up j_imp");
     CUDA_OR_FAIL(upload_range(j_limit, 0, nD, [&](size_t k) { return J(k).limit; }), "up j_limit");
     jointsSynced_ = nJ; fullPushJoints_ = false; jointsChanged_ = false;
-  } else if (nJointPairs_ > 0 && nB > jpBitsBodies_) {
-    int rc = uploadJointBits(jpHost_); if (rc < 0) return rc;     // bodies were added: the bit array must cover them
+  } else {
+    if (nJointPairs_ > 0 && nB > jpBitsBodies_) { int rc = uploadJointBits(jpHost_); if (rc < 0) return rc; }   // bodies were added: the bit array must cover them
+    if (nB > jmaskBodies_) { jmaskHost_.resize(nB, 0ull); int rc = uploadJointMasks(); if (rc < 0) return rc; }
   }
   refreshView();
   if (rehash) CUDA_OR_FAIL(stage_rebuild_hash(dw_, L_), "rehash");
@@ -790,7 +814,7 @@ void World::refreshView() {
   w.moveList = moveList.p; w.moveCap = (int)moveList.cap;
   w.bv_key = bv_key.p; w.bv_keyAlt = bv_keyAlt.p; w.bv_leaf = bv_leaf.p; w.bv_leafAlt = bv_leafAlt.p; w.bv_box = bv_box.p; w.bv_child = bv_child.p; w.bv_wr = bv_wr.p; w.bv_parent = bv_parent.p; w.bv_visit = bv_visit.p;
   w.pairs = pairs.p; w.pairCap = (int)pairs.cap;
-  w.nJointPairs = nJointPairs_; w.jp_keys = jp_keys.p; w.jp_bits = jp_bits.p;
+  w.nJointPairs = nJointPairs_; w.jp_keys = jp_keys.p; w.jp_bits = jp_bits.p; w.b_jmask = b_jmask.p;
   w.cCap = (int)c_key.cap; w.c_key = c_key.p; w.c_ids = c_ids.p; w.c_fix = c_fix.p; w.c_flags = c_flags.p; w.c_m0 = c_m0.p; w.c_m1 = c_m1.p; w.c_imp = c_imp.p; w.c_mk = c_mk.p;
   w.c_mat = c_mat.p; w.c_toiList = c_toiList.p; w.c_toiCount = c_toiCount.p; w.c_colour = c_colour.p; w.c_free = c_free.p; w.c_work = c_work.p; w.c_work2 = c_work2.p;
   w.hCap = (int)h_key.cap; w.h_key = h_key.p; w.h_val = h_val.p;
@@ -866,6 +890,7 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents, int halves) {
     setStepParams(dt, vi, pi);
   } else if (bodies_.empty()) return 0;
   dw_.colourOverride = overrideLevels_ ? 1 : 0;
+  dw_.unifiedColours = (!overrideLevels_ && !jointAt_.empty() && !(dw_.dbgFlags & 32)) ? 1 : 0;
   // TOI: the kernel leaves its per-body scratch clean; a world that has not run it yet, or has grown since, resets first.
   // When the scratch is clean the first TOI evaluation is forked onto a second stream right after the solver.
   const bool continuous = (flags_ & DBX_WORLD_CONTINUOUS) && dt > 0.0f;
@@ -1566,6 +1591,13 @@ int World::colourConflicts() {
   CUDA_OR_FAIL(cudaMemcpy(bfl.data(), b_flags.p, nb * 4, cudaMemcpyDeviceToHost), "read flags");
   std::unordered_map<unsigned long long, int> seen;
   int conflicts = 0;
+  // unified phases: a joint occupies its colour on its dynamic bodies, and their contacts must sit above it
+  std::vector<int> maxJoint(nb, -1);
+  if (!replicated_) for (const HJoint& hj : joints_) {
+    if (!hj.alive) continue;
+    const int bs[4] = {hj.def.bodyA, hj.def.bodyB, hj.bodyC, hj.bodyD};
+    for (int b : bs) if (b >= 0 && (size_t)b < nb && body_type(bfl[b]) == BODY_DYNAMIC) maxJoint[b] = std::max(maxJoint[b], hj.colour);
+  }
   for (size_t i = 0; i < n; ++i) {
     if ((fl[i] & (CF_ALIVE | CF_SOLVE)) != (CF_ALIVE | CF_SOLVE)) continue;
     if (col[i] < 0) { ++conflicts; continue; }
@@ -1574,6 +1606,7 @@ int World::colourConflicts() {
       if ((size_t)b >= nb || body_type(bfl[b]) != BODY_DYNAMIC) continue;
       unsigned long long k = ((unsigned long long)(unsigned)b << 32) | (unsigned)col[i];
       if (++seen[k] > 1) ++conflicts;
+      if (col[i] <= maxJoint[b]) ++conflicts;
     }
   }
   return conflicts;
@@ -1676,6 +1709,7 @@ int World::replicate(int copies) {
       nJointPairs_ *= copies;
       { int rb = uploadJointBits(all); if (rb < 0) return rb; }
     }
+    { int rm = uploadJointMasks(); if (rm < 0) return rm; }
     jointBlocks_ = (int)std::min<size_t>(((size_t)jointBlocks_ * L_.coopThreads * copies + L_.coopThreads - 1) / L_.coopThreads, (size_t)L_.coopBlocks / 4);
   }
   replicated_ = true;

@@ -171,6 +171,8 @@ class World {
   DevBuf<int2> pairs; DevBuf<unsigned long long> jp_keys; DevBuf<uint32_t> jp_bits;
   int uploadJointBits(const std::vector<unsigned long long>& keys);
   std::vector<unsigned long long> jpHost_; size_t jpBitsBodies_ = 0;
+  DevBuf<unsigned long long> b_jmask; std::vector<unsigned long long> jmaskHost_; size_t jmaskBodies_ = 0;
+  int uploadJointMasks();
   DevBuf<unsigned long long> c_key, h_key; DevBuf<int4> c_ids, c_fix; DevBuf<uint32_t> c_flags; DevBuf<float4> c_m0, c_m1, c_imp, c_mat; DevBuf<uint4> c_mk;
   DevBuf<int> c_toiList, c_toiCount, c_colour, c_free, c_work, c_work2, h_val;
   DevBuf<int> s_contact, s_hist, s_pc, s_root; DevBuf<int2> s_body; DevBuf<float4> s_v0, s_v1, s_r0, s_r1, s_q0, s_q1, s_imp, s_nm, s_k, s_p0, s_p1, s_p2; DevBuf<float2> s_p3;
