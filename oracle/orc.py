@@ -61,6 +61,8 @@ def api():
             "world_raycast_closest": (i32, [W, P(A.Ray), i32, P(A.RayHit)]),
             "world_query_aabb": (i32, [W, P(A.AABB), i32, i32, P(i32), P(i32)]),
             "joint_set_target": (i32, [W, i32, f32, f32]),
+            "body_set_type": (i32, [W, i32, i32]),
+            "body_set_active": (i32, [W, i32, i32]),
             "world_enable_contact_events": (i32, [W, i32]),
             "world_poll_contact_events": (i32, [W, P(A.ContactEvent), i32]),
         }

@@ -228,6 +228,14 @@ int32_t orc_joint_create(orc_world* w, const dbx_joint_def* d) {
   Joint* r = w->w.addJoint(j);
   return r ? r->id : DBX_E_LOCKED;
 }
+int32_t orc_body_set_type(orc_world* w, int32_t body, int32_t type) {
+  if (body < 0 || body >= (int)w->w.bodiesById.size() || !w->w.bodiesById[body] || type < 0 || type > 2) return DBX_E_INVALID;
+  w->w.setBodyType(w->w.bodiesById[body], type); return 0;
+}
+int32_t orc_body_set_active(orc_world* w, int32_t body, int32_t flag) {
+  if (body < 0 || body >= (int)w->w.bodiesById.size() || !w->w.bodiesById[body]) return DBX_E_INVALID;
+  w->w.setBodyActive(w->w.bodiesById[body], flag != 0); return 0;
+}
 // b2MouseJoint.SetTarget (b2mousejoint.d:112-120)
 int32_t orc_joint_set_target(orc_world* w, int32_t joint, float x, float y) {
   if (joint < 0 || joint >= (int)w->w.jointsById.size() || !w->w.jointsById[joint] || w->w.jointsById[joint]->type != jMouse) return DBX_E_INVALID;

@@ -268,6 +268,51 @@ void World::destroyFixture(Fixture* fixture) {
   b->resetMassData();
 }
 
+// b2Body.SetType (b2body.d:867-914)
+void World::setBodyType(Body* b, int type) {
+  if (locked) return;
+  if (b->type == type) return;
+  b->type = type;
+  b->resetMassData();
+  if (b->type == kStatic) {
+    b->linearVelocity = V2(0, 0); b->angularVelocity = 0.0f;
+    b->sweep.a0 = b->sweep.a; b->sweep.c0 = b->sweep.c;
+    b->synchronizeFixtures();
+  }
+  b->setAwake(true);
+  b->force = V2(0, 0); b->torque = 0.0f;
+  ContactEdge* ce = b->contactList;
+  while (ce) { ContactEdge* ce0 = ce; ce = ce->next; destroyContact(ce0->contact); }
+  b->contactList = nullptr;
+  for (Fixture* f = b->fixtureList; f; f = f->next)
+    for (int i = 0; i < f->proxyCount; ++i) broadPhase.touchProxy(f->proxies[i].proxyId);
+}
+// b2Body.SetActive (b2body.d:718-775)
+void World::setBodyActive(Body* b, bool flag) {
+  if (flag == ((b->flags & bActive) == bActive)) return;
+  if (flag) {
+    b->flags |= bActive;
+    for (Fixture* f = b->fixtureList; f; f = f->next) {
+      f->proxyCount = f->shape.childCount();
+      for (int i = 0; i < f->proxyCount; ++i) {
+        FixtureProxy* proxy = &f->proxies[i];
+        f->shape.computeAABB(&proxy->aabb, b->xf, i);
+        proxy->proxyId = broadPhase.createProxy(proxy->aabb, proxy);
+        proxy->fixture = f; proxy->childIndex = i;
+      }
+    }
+  } else {
+    b->flags &= ~bActive;
+    for (Fixture* f = b->fixtureList; f; f = f->next) {
+      for (int i = 0; i < f->proxyCount; ++i) { broadPhase.destroyProxy(f->proxies[i].proxyId); f->proxies[i].proxyId = -1; }
+      f->proxyCount = 0;
+    }
+    ContactEdge* ce = b->contactList;
+    while (ce) { ContactEdge* ce0 = ce; ce = ce->next; destroyContact(ce0->contact); }
+    b->contactList = nullptr;
+  }
+}
+
 void World::destroyBody(Body* b) {
   if (locked) return;
   JointEdge* je = b->jointList;

@@ -204,6 +204,8 @@ struct World {
   ~World();
   Body* createBody(const BodyDef& def);               // b2world.d:75-99
   void destroyBody(Body* b);                          // b2world.d:105-191
+  void setBodyType(Body* b, int type);                // b2body.d:867-914
+  void setBodyActive(Body* b, bool flag);             // b2body.d:718-775
   Fixture* createFixture(Body* b, const FixtureDef& def);  // b2body.d:116-155
   void destroyFixture(Fixture* f);                    // b2body.d:179-247
   Joint* addJoint(Joint* j);                          // b2world.d:196-261 (takes ownership)
