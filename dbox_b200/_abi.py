@@ -185,6 +185,8 @@ PROTOTYPES = {
     "body_set_awake": (c_i32, [W, c_i32, c_i32]),
     "body_set_bullet": (c_i32, [W, c_i32, c_i32]),
     "body_set_sleeping_allowed": (c_i32, [W, c_i32, c_i32]),
+    "body_set_type": (c_i32, [W, c_i32, c_i32]),
+    "body_set_active": (c_i32, [W, c_i32, c_i32]),
     "world_counts": (c_i32, [W, P(Counts)]),
     "world_profile": (c_i32, [W, P(Profile)]),
     "world_read_bodies": (c_i32, [W, P(BodyState), c_i32]),

@@ -220,6 +220,8 @@ int32_t dbx_body_set_bullet(dbx_world* w, int32_t body, int32_t flag) {
   W_OR_INVALID(w); HBody* b = w->w.mutBody(body); if (!b) return DBX_E_INVALID;
   if (flag) b->st.flags |= DBX_BODY_BULLET; else b->st.flags &= ~DBX_BODY_BULLET; return 0;
 }
+int32_t dbx_body_set_type(dbx_world* w, int32_t body, int32_t type) { W_OR_INVALID(w); return w->w.setBodyType(body, type); }
+int32_t dbx_body_set_active(dbx_world* w, int32_t body, int32_t flag) { W_OR_INVALID(w); return w->w.setBodyActive(body, flag != 0); }
 int32_t dbx_body_set_sleeping_allowed(dbx_world* w, int32_t body, int32_t flag) {
   W_OR_INVALID(w); HBody* b = w->w.mutBody(body); if (!b) return DBX_E_INVALID;
   if (flag) b->st.flags |= DBX_BODY_AUTOSLEEP; else { b->st.flags &= ~DBX_BODY_AUTOSLEEP; w->w.wake(*b, true); }

@@ -245,33 +245,101 @@ int World::createFixture(int b, const dbx_fixture_def& d, const dbx_shape& s) {
   }
   const int fid = (int)fixtures_.size();
   const int childCount = s.type == DBX_SHAPE_CHAIN ? s.chainCount - 1 : 1;
-  if (hb.st.flags & DBX_BODY_ACTIVE) {
-    // b2Fixture.CreateProxies (b2fixture.d:450-465) -> b2BroadPhase.CreateProxy (b2broadphase.d:78-84)
-    Xf xf; xf.p = V(hb.st.p.x, hb.st.p.y); xf.q = R(hb.st.qs, hb.st.qc);
-    for (int i = 0; i < childCount; ++i) {
-      DShape ds; buildChildShape(f.shape, i, &ds);
-      HProxy p;
-      p.alive = true; p.fixture = fid; p.child = i; p.body = b; p.shape = internShape(ds);
-      Box box = shape_aabb(&ds, xf);
-      p.aabb = pack(box);
-      p.fat = make_float4(box.lo.x - kAabbExtension, box.lo.y - kAabbExtension, box.hi.x + kAabbExtension, box.hi.y + kAabbExtension);
-      p.key = allocProxyKey();
-      p.flags = PF_ALIVE | PF_MOVED;
-      int slot;
-      if (!proxyFree_.empty()) {
-        slot = proxyFree_.back(); proxyFree_.pop_back();
-        if ((size_t)slot < proxiesSynced_) { int rc = pullProxies(); if (rc < 0) return rc; fullPushProxies_ = true; }
-        proxies_[slot] = p;
-      } else { slot = (int)proxies_.size(); proxies_.push_back(p); }
-      f.proxies.push_back(slot);
-      pendingMoves_.push_back(slot);
-    }
-  }
+  (void)childCount;
   fixtures_.push_back(std::move(f));
   hb.fixtures.push_back(fid);
-  if (d.density > 0.0f) resetMassData(hb);
+  if (hb.st.flags & DBX_BODY_ACTIVE) { int rc = createProxiesFor(fid); if (rc < 0) return rc; }
+  if (d.density > 0.0f) resetMassData(bodies_[b]);
   newFixture_ = true;
   return fid;
+}
+
+// b2Fixture.CreateProxies (b2fixture.d:450-465) -> b2BroadPhase.CreateProxy (b2broadphase.d:78-84)
+int World::createProxiesFor(int fid) {
+  HFixture& f = fixtures_[fid];
+  const int b = f.body;
+  const HBody& hb = bodies_[b];
+  const int childCount = f.shape.s.type == DBX_SHAPE_CHAIN ? (int)f.shape.chain.size() - 1 : 1;
+  Xf xf; xf.p = V(hb.st.p.x, hb.st.p.y); xf.q = R(hb.st.qs, hb.st.qc);
+  for (int i = 0; i < childCount; ++i) {
+    DShape ds; buildChildShape(f.shape, i, &ds);
+    HProxy p;
+    p.alive = true; p.fixture = fid; p.child = i; p.body = b; p.shape = internShape(ds);
+    Box box = shape_aabb(&ds, xf);
+    p.aabb = pack(box);
+    p.fat = make_float4(box.lo.x - kAabbExtension, box.lo.y - kAabbExtension, box.hi.x + kAabbExtension, box.hi.y + kAabbExtension);
+    p.key = allocProxyKey();
+    p.flags = PF_ALIVE | PF_MOVED;
+    int slot;
+    if (!proxyFree_.empty()) {
+      slot = proxyFree_.back(); proxyFree_.pop_back();
+      if ((size_t)slot < proxiesSynced_) { int rc = pullProxies(); if (rc < 0) return rc; fullPushProxies_ = true; }
+      proxies_[slot] = p;
+    } else { slot = (int)proxies_.size(); proxies_.push_back(p); }
+    f.proxies.push_back(slot);
+    pendingMoves_.push_back(slot);
+  }
+  return 0;
+}
+
+// b2Body.SetType (dynamics/b2body.d:867-914)
+int World::setBodyType(int b, int type) {
+  if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
+  if (b < 0 || b >= (int)bodies_.size() || !bodies_[b].alive || type < DBX_STATIC_BODY || type > DBX_DYNAMIC_BODY) return DBX_E_INVALID;
+  if (bodies_[b].st.type == type) return 0;
+  int rc = destroyContactsWhere(b, -1, -1, false); if (rc < 0) return rc;     // :896-903 (ends touching contacts, wakes the other bodies)
+  HBody* hb = mutBody(b); if (!hb) return DBX_E_INVALID;
+  rc = pullProxies(); if (rc < 0) return rc;
+  dbx_body_state& st = hb->st;
+  st.type = type;
+  resetMassData(*hb);
+  if (type == DBX_STATIC_BODY) {
+    st.v = dbx_vec2{0, 0}; st.w = 0.0f; st.a0 = st.a; st.c0 = st.c;
+    Xf xf; xf.p = V(st.p.x, st.p.y); xf.q = R(st.qs, st.qc);
+    hb->xf0 = pack(xf);
+    for (auto it = hb->fixtures.rbegin(); it != hb->fixtures.rend(); ++it) for (int slot : fixtures_[*it].proxies) {     // SynchronizeFixtures with xf1 == xf2
+      HProxy& p = proxies_[slot];
+      Box box = shape_aabb(&shapes_[p.shape], xf);
+      p.aabb = pack(box);
+      if (!contains(BX(p.fat), box)) { p.fat = make_float4(box.lo.x - kAabbExtension, box.lo.y - kAabbExtension, box.hi.x + kAabbExtension, box.hi.y + kAabbExtension); pendingMoves_.push_back(slot); }
+    }
+  }
+  wake(*hb, true);
+  st.force = dbx_vec2{0, 0}; st.torque = 0.0f;
+  for (auto it = hb->fixtures.rbegin(); it != hb->fixtures.rend(); ++it) for (int slot : fixtures_[*it].proxies) pendingMoves_.push_back(slot);   // TouchProxy (:905-913)
+  fullPushProxies_ = true;
+  if (!hb->joints.empty()) jointsChanged_ = true;      // joint colouring looks at body types
+  return 0;
+}
+
+// b2Body.SetActive (dynamics/b2body.d:718-775)
+int World::setBodyActive(int b, bool flag) {
+  if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
+  if (b < 0 || b >= (int)bodies_.size() || !bodies_[b].alive) return DBX_E_INVALID;
+  if (flag == ((bodies_[b].st.flags & DBX_BODY_ACTIVE) != 0)) return 0;
+  int rc = 0;
+  if (!flag) { rc = destroyContactsWhere(b, -1, -1, false); if (rc < 0) return rc; }
+  HBody* hb = mutBody(b); if (!hb) return DBX_E_INVALID;
+  rc = pullProxies(); if (rc < 0) return rc;
+  if (flag) {
+    hb->st.flags |= DBX_BODY_ACTIVE;
+    const std::vector<int> fx(hb->fixtures.rbegin(), hb->fixtures.rend());      // m_fixtureList order: newest first
+    for (int fid : fx) { rc = createProxiesFor(fid); if (rc < 0) return rc; }
+  } else {
+    hb->st.flags &= ~DBX_BODY_ACTIVE;
+    for (auto it = hb->fixtures.rbegin(); it != hb->fixtures.rend(); ++it) {
+      HFixture& f = fixtures_[*it];
+      for (int slot : f.proxies) {
+        freeProxyKey(proxies_[slot].key);
+        proxies_[slot].alive = false; proxies_[slot].flags = 0;
+        proxyFree_.push_back(slot);
+        pendingMoves_.erase(std::remove(pendingMoves_.begin(), pendingMoves_.end(), slot), pendingMoves_.end());
+      }
+      f.proxies.clear();
+    }
+  }
+  fullPushBodies_ = true; fullPushProxies_ = true;
+  return 0;
 }
 
 int World::destroyContactsWhere(int body, int fixture, int otherBody, bool flagOnly) {
@@ -710,6 +778,7 @@ int World::push() {
   const bool anyBody = fullPushBodies_ || nB > bodiesSynced_;
   const bool anyFix = fullPushFixtures_ || nF > fixturesSynced_;
   const bool anyProxy = fullPushProxies_ || nP > proxiesSynced_ || !pendingMoves_.empty();
+  const size_t proxiesKnown = proxiesSynced_;      // proxies the device had before this push
   const bool anyShape = nS > shapesSynced_;
   const bool anyJoint = fullPushJoints_ || nJ > jointsSynced_ || jointsChanged_;
   if (!anyBody && !anyFix && !anyProxy && !anyShape && !anyJoint && dw_.hdr) return 0;
@@ -762,14 +831,27 @@ int World::push() {
     if (fullPushProxies_ || nP > proxiesSynced_) treeValid_ = false;   // the proxy set (or its boxes) changed under the tree
     proxiesSynced_ = nP; fullPushProxies_ = false;
     if (!pendingMoves_.empty()) {
-      // b2BroadPhase.BufferMove (b2broadphase.d:244-257): the device move list is empty between steps
-      std::vector<int> mv;
-      for (int slot : pendingMoves_) if (proxies_[slot].alive) mv.push_back(slot);
-      std::sort(mv.begin(), mv.end());
-      mv.erase(std::unique(mv.begin(), mv.end()), mv.end());
-      for (int slot : mv) { uint32_t fl = proxies_[slot].flags | PF_ALIVE | PF_MOVED; proxies_[slot].flags = fl & ~PF_MOVED; cudaMemcpy(p_flags.p + slot, &fl, 4, cudaMemcpyHostToDevice); }
-      if (!mv.empty()) CUDA_OR_FAIL(cudaMemcpy(moveList.p, mv.data(), mv.size() * 4, cudaMemcpyHostToDevice), "up moves");
-      int nm = (int)mv.size();
+      // b2BroadPhase.BufferMove (b2broadphase.d:244-257).  The device move list is empty right after a step; several
+      // pushes may happen before the next one (every API call that edits contacts pushes), so later moves are appended
+      // behind the ones already uploaded, each proxy at most once.
+      CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+      int onDevice = 0;      // includes moves the device buffered itself (dbx_world_set_body_states)
+      CUDA_OR_FAIL(cudaMemcpy(&onDevice, (char*)hdr_.p + offsetof(Header, nMoved), 4, cudaMemcpyDeviceToHost), "read nMoved");
+      std::vector<int> cand, mv;
+      for (int slot : pendingMoves_) if (proxies_[slot].alive && !movesUploaded_.count(slot)) cand.push_back(slot);
+      std::sort(cand.begin(), cand.end());
+      cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+      for (int slot : cand) {      // already in the device list (flagged there)?  only possible for proxies the device knows
+        uint32_t fl = 0;
+        if ((size_t)slot < proxiesKnown && onDevice > (int)movesOnDevice_.size()) cudaMemcpy(&fl, p_flags.p + slot, 4, cudaMemcpyDeviceToHost);
+        if (!(fl & PF_MOVED)) mv.push_back(slot);
+      }
+      for (int slot : mv) { uint32_t fl = proxies_[slot].flags | PF_ALIVE | PF_MOVED; proxies_[slot].flags = fl & ~PF_MOVED; cudaMemcpy(p_flags.p + slot, &fl, 4, cudaMemcpyHostToDevice); movesUploaded_.insert(slot); }
+      // a full proxy push rewrites p_flags from the host copy, which does not carry PF_MOVED: restore it for the earlier moves
+      for (int slot : movesOnDevice_) if (proxies_[slot].alive) { uint32_t fl = proxies_[slot].flags | PF_ALIVE | PF_MOVED; cudaMemcpy(p_flags.p + slot, &fl, 4, cudaMemcpyHostToDevice); }
+      if (!mv.empty()) CUDA_OR_FAIL(cudaMemcpy(moveList.p + onDevice, mv.data(), mv.size() * 4, cudaMemcpyHostToDevice), "up moves");
+      movesOnDevice_.insert(movesOnDevice_.end(), mv.begin(), mv.end());
+      int nm = onDevice + (int)mv.size();
       CUDA_OR_FAIL(cudaMemcpy((char*)hdr_.p + offsetof(Header, nMoved), &nm, 4, cudaMemcpyHostToDevice), "up nMoved");
       pendingMoves_.clear();
     }
@@ -857,6 +939,7 @@ int World::checkDeviceError(bool sync) {
 // b2ContactManager.FindNewContacts.  The LBVH is rebuilt when the proxy set changed or every kRebuildPeriod calls; in
 // between it is widened for the moved proxies (lbvh_enlarge), which keeps the pair set exact at a fraction of the cost.
 int World::findNewContacts(bool deferClear) {
+  movesOnDevice_.clear(); movesUploaded_.clear();      // this call consumes the move buffer
   constexpr int kRebuildPeriod = 8;
   const bool rebuild = !treeValid_ || sinceRebuild_ >= kRebuildPeriod;
   CUDA_OR_FAIL(stage_find_new_contacts(dw_, L_, rebuild, deferClear), "find_new_contacts");

@@ -4,6 +4,7 @@
 #pragma once
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 #include "../../include/dbox_b200.h"
 #include "dbx_kernels.cuh"
@@ -86,6 +87,9 @@ class World {
   int readBodiesDevice(int from, int count, dbx_body_state* out);
   HBody* mutBody(int b);   // pulls, marks dirty; nullptr if invalid
   int setTransform(int b, float x, float y, float angle);
+  int setBodyType(int b, int type);
+  int setBodyActive(int b, bool flag);
+  int createProxiesFor(int fid);
   void wake(HBody& hb, bool flag);
 
   int counts(dbx_counts* out);
@@ -156,6 +160,7 @@ class World {
   bool hostBodiesValid_ = true, hostProxiesValid_ = true, hostJointsValid_ = true;
   bool fullPushBodies_ = false, fullPushProxies_ = false, fullPushJoints_ = false, fullPushFixtures_ = false;
   bool jointsChanged_ = false;
+  std::vector<int> movesOnDevice_; std::unordered_set<int> movesUploaded_;   // host moves already in the device move list since the last FindNewContacts
   std::vector<int> pendingMoves_;   // proxies buffered on the host since the last push (b2broadphase.d:244-257)
 
   // device

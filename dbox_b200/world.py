@@ -520,6 +520,14 @@ class b2Body:
         y = _f32(_f32(-s.qs * px) + _f32(s.qc * py))
         return b2Vec2(x, y)
 
+    def SetType(self, type):
+        """b2body.d:867-914"""
+        self.world._ck(self.world._api.body_set_type(self.world._w, self.id, type))
+
+    def SetActive(self, flag):
+        """b2body.d:718-775"""
+        self.world._ck(self.world._api.body_set_active(self.world._w, self.id, int(flag)))
+
     def GetLocalVector(self, worldVector):
         """b2body.d GetLocalVector = b2MulT(m_xf.q, v) (common/b2math.d:640-643), evaluated in fp32."""
         s = self._state()

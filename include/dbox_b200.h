@@ -277,6 +277,8 @@ int32_t dbx_body_apply_angular_impulse(dbx_world* w, int32_t body, float impulse
 int32_t dbx_body_set_awake(dbx_world* w, int32_t body, int32_t flag);                       /* :827-846 */
 int32_t dbx_body_set_bullet(dbx_world* w, int32_t body, int32_t flag);                      /* :784-794 */
 int32_t dbx_body_set_sleeping_allowed(dbx_world* w, int32_t body, int32_t flag);            /* :804-815 */
+int32_t dbx_body_set_type(dbx_world* w, int32_t body, int32_t type);                           /* :867-914: mass reset, contacts destroyed, proxies touched */
+int32_t dbx_body_set_active(dbx_world* w, int32_t body, int32_t flag);                         /* :718-775: proxies created / destroyed, contacts destroyed */
 
 /* ---- bulk state access (one D2H / H2D copy each; also the checkpoint / parity-injection path) ---- */
 int32_t dbx_world_counts(dbx_world* w, dbx_counts* out);

@@ -562,3 +562,44 @@ def test_everything_asleep_costs_nothing_wrong(gpu_api, oracle_api):
         if k < 60:
             assert cg.awakeBodies == co.awakeBodies, (k, cg.awakeBodies, co.awakeBodies)
     assert woke
+
+
+def test_set_type_and_set_active(gpu_api, oracle_api):
+    """b2Body.SetType (b2body.d:867-914: mass reset, contacts destroyed, proxies touched) and SetActive (:718-775: proxies
+    destroyed / re-created in fixture-list order, contacts destroyed) between steps, against the oracle: same contact and
+    proxy populations, same A/B order of the contacts that come back, same trajectories"""
+    from dbox_b200.world import b2_staticBody
+
+    def build(api):
+        w = b2World((0.0, -10.0), api=api)
+        _ground(w, api)
+        out = [_box_body(w, api, -6.0 + 3.0 * k, 0.52 + 0.0 * k) for k in range(5)]       # five boxes resting on the ground
+        tops = [_box_body(w, api, -6.0 + 3.0 * k, 1.55) for k in range(5)]                # one box on each
+        return w, out + tops
+    wg, bg = build(gpu_api); wo, bo = build(oracle_api)
+
+    def edit(k):
+        for w, bs in ((wg, bg), (wo, bo)):
+            if k == 40:
+                bs[0].SetType(b2_staticBody)            # a resting box becomes part of the scenery
+                bs[6].SetActive(False)                  # the box on top of #1 disappears from the simulation
+            if k == 70:
+                bs[0].SetType(b2_dynamicBody)
+                bs[6].SetTransform((-3.0, 4.0), 0.3)
+                bs[6].SetActive(True)                   # and comes back higher up
+                bs[2].SetType(b2_kinematicBody); bs[2].SetLinearVelocity((0.5, 0.0))
+    for k in range(160):
+        edit(k)
+        wg.Step(DT, 8, 3); wo.Step(DT, 8, 3)
+        cg, co = wg.counts(), wo.counts()
+        assert (cg.contacts, cg.touching, cg.proxies) == (co.contacts, co.touching, co.proxies), (k, cg.contacts, co.contacts, cg.touching, co.touching, cg.proxies, co.proxies)
+        for i, (a, b) in enumerate(zip(bg, bo)):
+            if i == 6 and 40 <= k < 70:
+                continue                                # inactive: frozen on both sides
+            pa, pb = a.GetPosition(), b.GetPosition()
+            tol = 1e-3 if k < 100 else 3e-2          # after that the tilted box lands on a stack: Gauss-Seidel order shows
+            assert abs(pa.x - pb.x) < tol and abs(pa.y - pb.y) < tol, (k, i, (pa.x, pa.y), (pb.x, pb.y))
+    from tests.parity import contacts_by_key
+    kg, _, _ = contacts_by_key(wg); ko, _, _ = contacts_by_key(wo)
+    assert set(kg) == set(ko)                                               # same (fixtureA, childA, fixtureB, childB) keys: same A/B order
+    assert bg[2].GetPosition().x > 0.5                                      # the kinematic box carried its passenger along
