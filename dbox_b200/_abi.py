@@ -214,6 +214,8 @@ PROTOTYPES = {
     "debug_barrier_us": (c_f32, [c_i32, c_i32, c_i32, c_i32]),
     "world_replicate": (c_i32, [W, c_i32]),
     "world_replica_count": (c_i32, [W]),
+    "world_export_state": (C.c_int64, [W, C.c_void_p, C.c_int64]),
+    "world_import_state": (c_i32, [W, C.c_void_p, C.c_int64]),
     "world_step_begin": (c_i32, [W, c_f32, c_i32, c_i32]),
     "world_step_end": (c_i32, [W]),
     "world_patch_contacts": (c_i32, [W, P(ContactPatch), c_i32]),

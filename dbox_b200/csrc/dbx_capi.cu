@@ -259,6 +259,50 @@ int32_t dbx_world_debug_header(dbx_world* w, void* out, int32_t bytes) { W_OR_IN
 // ---- batched independent worlds
 int32_t dbx_world_replicate(dbx_world* w, int32_t copies) { W_OR_INVALID(w); return w->w.replicate(copies); }
 int32_t dbx_world_replica_count(dbx_world* w) { W_OR_INVALID(w); return w->w.replicaCount(); }
+// ---- snapshot / restore (SURVEY.md 5 "checkpoint / resume"; the reference only has b2World.Dump, dynamics/b2world.d:796-855)
+// blob = { magic, version, nb, np, nc, nj, nm, inv_dt0 } + bodies + proxies + contacts + joints + moves + contact colours
+namespace { struct SnapHead { uint32_t magic, version; int32_t nb, np, nc, nj, nm; float inv_dt0; }; constexpr uint32_t kSnapMagic = 0x58424431u; }
+int64_t dbx_world_export_state(dbx_world* w, void* buf, int64_t cap) {
+  W_OR_INVALID(w);
+  World& W = w->w;
+  SnapHead h{kSnapMagic, 1, 0, 0, 0, 0, 0, 0.0f};
+  h.nb = W.readBodies(nullptr, 0); h.np = W.readProxies(nullptr, 0); h.nc = W.readContacts(nullptr, 0); h.nj = W.readJoints(nullptr, 0); h.nm = W.readMoves(nullptr, 0);
+  if (h.nb < 0 || h.np < 0 || h.nc < 0 || h.nj < 0 || h.nm < 0) return DBX_E_CUDA;
+  h.inv_dt0 = W.inv_dt0;
+  const int64_t need = (int64_t)sizeof(SnapHead) + (int64_t)h.nb * sizeof(dbx_body_state) + (int64_t)h.np * sizeof(dbx_proxy_rec) + (int64_t)h.nc * sizeof(dbx_contact_rec) +
+                       (int64_t)h.nj * sizeof(dbx_joint_state) + (int64_t)h.nm * 8 + (int64_t)h.nc * 4;
+  if (!buf || cap < need) return need;            // size query
+  char* p = (char*)buf;
+  std::memcpy(p, &h, sizeof(h)); p += sizeof(h);
+  if (W.readBodies((dbx_body_state*)p, h.nb) != h.nb) return DBX_E_CUDA; p += (size_t)h.nb * sizeof(dbx_body_state);
+  if (W.readProxies((dbx_proxy_rec*)p, h.np) != h.np) return DBX_E_CUDA; p += (size_t)h.np * sizeof(dbx_proxy_rec);
+  if (W.readContacts((dbx_contact_rec*)p, h.nc) != h.nc) return DBX_E_CUDA; p += (size_t)h.nc * sizeof(dbx_contact_rec);
+  if (W.readJoints((dbx_joint_state*)p, h.nj) != h.nj) return DBX_E_CUDA; p += (size_t)h.nj * sizeof(dbx_joint_state);
+  if (W.readMoves((int32_t*)p, h.nm) != h.nm) return DBX_E_CUDA; p += (size_t)h.nm * 8;
+  if (W.readContactColours((int32_t*)p, h.nc) != h.nc) return DBX_E_CUDA;      // same order as the contact records above
+  return need;
+}
+int32_t dbx_world_import_state(dbx_world* w, const void* buf, int64_t n) {
+  W_OR_INVALID(w);
+  World& W = w->w;
+  if (!buf || n < (int64_t)sizeof(SnapHead)) return DBX_E_INVALID;
+  SnapHead h; std::memcpy(&h, buf, sizeof(h));
+  if (h.magic != kSnapMagic || h.version != 1) { set_last_error("import_state: not a dbox_b200 snapshot"); return DBX_E_INVALID; }
+  const int64_t need = (int64_t)sizeof(SnapHead) + (int64_t)h.nb * sizeof(dbx_body_state) + (int64_t)h.np * sizeof(dbx_proxy_rec) + (int64_t)h.nc * sizeof(dbx_contact_rec) +
+                       (int64_t)h.nj * sizeof(dbx_joint_state) + (int64_t)h.nm * 8 + (int64_t)h.nc * 4;
+  if (n < need) return DBX_E_INVALID;
+  const char* p = (const char*)buf + sizeof(SnapHead);
+  int rc = W.writeBodies((const dbx_body_state*)p, h.nb); if (rc != h.nb) return rc < 0 ? rc : DBX_E_INVALID; p += (size_t)h.nb * sizeof(dbx_body_state);
+  rc = W.writeProxies((const dbx_proxy_rec*)p, h.np); if (rc != h.np) return rc < 0 ? rc : DBX_E_INVALID; p += (size_t)h.np * sizeof(dbx_proxy_rec);
+  const dbx_contact_rec* cons = (const dbx_contact_rec*)p; p += (size_t)h.nc * sizeof(dbx_contact_rec);
+  if (h.nj > 0) { rc = W.writeJoints((const dbx_joint_state*)p, h.nj); if (rc != h.nj) return rc < 0 ? rc : DBX_E_INVALID; }
+  p += (size_t)h.nj * sizeof(dbx_joint_state);
+  rc = W.writeContacts(cons, h.nc); if (rc != h.nc) return rc < 0 ? rc : DBX_E_INVALID;
+  rc = W.writeMoves((const int32_t*)p, h.nm); if (rc != h.nm) return rc < 0 ? rc : DBX_E_INVALID; p += (size_t)h.nm * 8;
+  rc = W.writeContactColours((const int32_t*)p, h.nc); if (rc != h.nc) return rc < 0 ? rc : DBX_E_INVALID;
+  W.inv_dt0 = h.inv_dt0;
+  return 0;
+}
 int32_t dbx_world_step_begin(dbx_world* w, float dt, int32_t vi, int32_t pi) { W_OR_INVALID(w); return w->w.stepBegin(dt, vi, pi); }
 int32_t dbx_world_step_end(dbx_world* w) { W_OR_INVALID(w); return w->w.stepEnd(); }
 int32_t dbx_world_patch_contacts(dbx_world* w, const dbx_contact_patch* patches, int32_t n) { W_OR_INVALID(w); return w->w.patchContacts(patches, n); }

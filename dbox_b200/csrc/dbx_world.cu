@@ -1507,6 +1507,7 @@ int World::readMoves(int32_t* out, int cap) {
   // host-buffered moves (the device move list is empty between steps)
   int n = 0;
   std::vector<int> mv = pendingMoves_;
+  mv.insert(mv.end(), movesOnDevice_.begin(), movesOnDevice_.end());      // already uploaded by an earlier push, not yet consumed
   std::sort(mv.begin(), mv.end());
   mv.erase(std::unique(mv.begin(), mv.end()), mv.end());
   for (int slot : mv) {
@@ -1593,6 +1594,26 @@ int World::readContacts(dbx_contact_rec* out, int cap) {
   return cnt;
 }
 
+// the persistent colours of the contacts (solver schedule): part of a snapshot, so that a restored world runs the same
+// Gauss-Seidel order as the one it was taken from
+int World::readContactColours(int32_t* out, int cap) {
+  const int n = (int)lastReadSlots_.size();
+  if (n == 0 || !out) return n;
+  int high = 0;
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  CUDA_OR_FAIL(cudaMemcpy(&high, (char*)hdr_.p + offsetof(Header, cHigh), 4, cudaMemcpyDeviceToHost), "read cHigh");
+  std::vector<int> col((size_t)std::max(high, 1));
+  CUDA_OR_FAIL(cudaMemcpy(col.data(), c_colour.p, (size_t)high * 4, cudaMemcpyDeviceToHost), "read colours");
+  for (int k = 0; k < n && k < cap; ++k) out[k] = lastReadSlots_[k] < high ? col[lastReadSlots_[k]] : -1;
+  return n;
+}
+int World::writeContactColours(const int32_t* in, int n) {
+  if (n <= 0) return 0;
+  if ((size_t)n > c_colour.cap) return DBX_E_INVALID;
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  CUDA_OR_FAIL(cudaMemcpy(c_colour.p, in, (size_t)n * 4, cudaMemcpyHostToDevice), "write colours");   // writeContacts put record k in slot k
+  return n;
+}
 int World::writeContacts(const dbx_contact_rec* in, int n) {
   if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
   int rc = push(); if (rc < 0) return rc;

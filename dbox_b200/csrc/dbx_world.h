@@ -98,6 +98,8 @@ class World {
   int writeBodies(const dbx_body_state* in, int n);
   int readContacts(dbx_contact_rec* out, int cap);
   int writeContacts(const dbx_contact_rec* in, int n);
+  int readContactColours(int32_t* out, int cap);      // in the order of the last readContacts
+  int writeContactColours(const int32_t* in, int n);  // for the records of the last writeContacts
   int readProxies(dbx_proxy_rec* out, int cap);
   int writeProxies(const dbx_proxy_rec* in, int n);
   int readJoints(dbx_joint_state* out, int cap);

@@ -325,6 +325,15 @@ float dbx_debug_barrier_us(int32_t device, int32_t blocks, int32_t threads, int3
 int32_t dbx_world_replicate(dbx_world* w, int32_t copies);  /* world becomes `copies` disjoint replicas of its current content */
 int32_t dbx_world_replica_count(dbx_world* w);
 
+/* ---- snapshot / restore ---------------------------------------------------------------------------------------------
+ * The reference can only Dump() D source text that rebuilds a scene (dynamics/b2world.d:796-855).  Here the dynamic state of
+ * a world -- body states, proxy boxes (tight + fat), the contact cache with manifolds, impulses and solver colours, joint
+ * impulses, the pending move buffer, inv_dt0 -- goes to / comes from one flat buffer.  The scene itself (bodies, fixtures, joints) is not
+ * in the blob: import into a world built the same way.  export returns the bytes needed (call with buf = NULL to size it);
+ * stepping an imported world continues bit for bit where the exported one would have. */
+int64_t dbx_world_export_state(dbx_world* w, void* buf, int64_t cap);
+int32_t dbx_world_import_state(dbx_world* w, const void* buf, int64_t n);
+
 /* ---- world queries on the device tree, batched ---------------------------------------------
  * b2World.RayCast (dynamics/b2world.d:577-587; wrapper :1605-1624; b2DynamicTree.RayCast collision/b2dynamictree.d:237-331;
  * b2Shape.RayCast b2circleshape.d:67-94, b2edgeshape.d:96-150, b2polygonshape.d:279-332, b2chainshape.d:204-223) and

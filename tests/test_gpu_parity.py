@@ -448,3 +448,23 @@ def test_world_batch_api(gpu_api):
     per = b.bodies_per_world
     assert np.allclose(xf[:per], xf[per:2 * per]) and np.allclose(xf[:per], xf[2 * per:])      # same reset -> same worlds
     b.close()
+
+
+def test_export_import_state_continues_bit_for_bit(gpu_api):
+    """dbx_world_export_state / import_state: a world restored from a snapshot steps exactly like the one it was taken from"""
+    a, _ = scenes.pyramid(api=gpu_api, count=10)
+    a.StepN(DT, 8, 3, 45)
+    need = gpu_api.world_export_state(a._w, None, 0)
+    assert need > 0
+    buf = (C.c_char * need)()
+    assert gpu_api.world_export_state(a._w, buf, need) == need
+    b, _ = scenes.pyramid(api=gpu_api, count=10)
+    assert gpu_api.world_import_state(b._w, buf, need) == 0
+    assert gpu_api.world_import_state(b._w, buf, 10) < 0            # truncated blob
+    for k in range(5):
+        a.StepN(DT, 8, 3, 20); b.StepN(DT, 8, 3, 20)
+        sa, n = a.read_bodies(); sb, _ = b.read_bodies()
+        ca, cb = a.counts(), b.counts()
+        assert (ca.contacts, ca.touching, ca.awakeBodies) == (cb.contacts, cb.touching, cb.awakeBodies)
+        for i in range(n):
+            assert (sa[i].c.x, sa[i].c.y, sa[i].a, sa[i].v.x, sa[i].v.y, sa[i].w) == (sb[i].c.x, sb[i].c.y, sb[i].a, sb[i].v.x, sb[i].v.y, sb[i].w), (k, i)
