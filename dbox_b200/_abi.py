@@ -185,6 +185,17 @@ PROTOTYPES = {
     "body_set_awake": (c_i32, [W, c_i32, c_i32]),
     "body_set_bullet": (c_i32, [W, c_i32, c_i32]),
     "body_set_sleeping_allowed": (c_i32, [W, c_i32, c_i32]),
+    "body_set_mass_data": (c_i32, [W, c_i32, c_f32, c_f32, c_f32, c_f32]),
+    "body_reset_mass_data": (c_i32, [W, c_i32]),
+    "body_set_fixed_rotation": (c_i32, [W, c_i32, c_i32]),
+    "body_set_linear_damping": (c_i32, [W, c_i32, c_f32]),
+    "body_set_angular_damping": (c_i32, [W, c_i32, c_f32]),
+    "body_set_gravity_scale": (c_i32, [W, c_i32, c_f32]),
+    "fixture_set_filter": (c_i32, [W, c_i32, c_i32, c_i32, c_i32]),
+    "fixture_set_sensor": (c_i32, [W, c_i32, c_i32]),
+    "fixture_set_friction": (c_i32, [W, c_i32, c_f32]),
+    "fixture_set_restitution": (c_i32, [W, c_i32, c_f32]),
+    "fixture_set_density": (c_i32, [W, c_i32, c_f32]),
     "body_set_type": (c_i32, [W, c_i32, c_i32]),
     "body_set_active": (c_i32, [W, c_i32, c_i32]),
     "world_counts": (c_i32, [W, P(Counts)]),

@@ -222,6 +222,17 @@ int32_t dbx_body_set_bullet(dbx_world* w, int32_t body, int32_t flag) {
 }
 int32_t dbx_body_set_type(dbx_world* w, int32_t body, int32_t type) { W_OR_INVALID(w); return w->w.setBodyType(body, type); }
 int32_t dbx_body_set_active(dbx_world* w, int32_t body, int32_t flag) { W_OR_INVALID(w); return w->w.setBodyActive(body, flag != 0); }
+int32_t dbx_body_set_mass_data(dbx_world* w, int32_t body, float mass, float cx, float cy, float I) { W_OR_INVALID(w); return w->w.setMassData(body, mass, cx, cy, I); }
+int32_t dbx_body_reset_mass_data(dbx_world* w, int32_t body) { W_OR_INVALID(w); return w->w.resetMass(body); }
+int32_t dbx_body_set_fixed_rotation(dbx_world* w, int32_t body, int32_t flag) { W_OR_INVALID(w); return w->w.setFixedRotation(body, flag != 0); }
+int32_t dbx_body_set_linear_damping(dbx_world* w, int32_t body, float d) { W_OR_INVALID(w); return w->w.setBodyScalars(body, &d, nullptr, nullptr); }
+int32_t dbx_body_set_angular_damping(dbx_world* w, int32_t body, float d) { W_OR_INVALID(w); return w->w.setBodyScalars(body, nullptr, &d, nullptr); }
+int32_t dbx_body_set_gravity_scale(dbx_world* w, int32_t body, float s) { W_OR_INVALID(w); return w->w.setBodyScalars(body, nullptr, nullptr, &s); }
+int32_t dbx_fixture_set_filter(dbx_world* w, int32_t fixture, int32_t categoryBits, int32_t maskBits, int32_t groupIndex) { W_OR_INVALID(w); return w->w.setFixtureFilter(fixture, categoryBits, maskBits, groupIndex); }
+int32_t dbx_fixture_set_sensor(dbx_world* w, int32_t fixture, int32_t flag) { W_OR_INVALID(w); return w->w.setFixtureSensor(fixture, flag != 0); }
+int32_t dbx_fixture_set_friction(dbx_world* w, int32_t fixture, float v) { W_OR_INVALID(w); return w->w.setFixtureMaterial(fixture, &v, nullptr, nullptr); }
+int32_t dbx_fixture_set_restitution(dbx_world* w, int32_t fixture, float v) { W_OR_INVALID(w); return w->w.setFixtureMaterial(fixture, nullptr, &v, nullptr); }
+int32_t dbx_fixture_set_density(dbx_world* w, int32_t fixture, float v) { W_OR_INVALID(w); return w->w.setFixtureMaterial(fixture, nullptr, nullptr, &v); }
 int32_t dbx_body_set_sleeping_allowed(dbx_world* w, int32_t body, int32_t flag) {
   W_OR_INVALID(w); HBody* b = w->w.mutBody(body); if (!b) return DBX_E_INVALID;
   if (flag) b->st.flags |= DBX_BODY_AUTOSLEEP; else { b->st.flags &= ~DBX_BODY_AUTOSLEEP; w->w.wake(*b, true); }

@@ -988,6 +988,18 @@ __global__ void __launch_bounds__(256) k_patch_contacts(const __grid_constant__ 
     }
   }
 }
+// b2Fixture.SetSensor: the contacts of that fixture re-derive their cached sensor bit from the two fixtures
+__global__ void __launch_bounds__(256) k_api_resensor(const __grid_constant__ DevWorld W, int fixture) {
+  const int n = W.hdr->cHigh;
+  GRID_STRIDE(i, n) {
+    const uint32_t flags = W.c_flags[i];
+    if (!(flags & CF_ALIVE)) continue;
+    const int4 fx = W.c_fix[i];
+    if (fx.x != fixture && fx.y != fixture) continue;
+    const bool sensor = ((W.f_group[fx.x] >> 16) & FXF_SENSOR) || ((W.f_group[fx.y] >> 16) & FXF_SENSOR);
+    W.c_flags[i] = sensor ? (flags | CF_SENSOR) : (flags & ~CF_SENSOR);
+  }
+}
 __global__ void k_api_wake(const __grid_constant__ DevWorld W, int a, int b) {
   if (a >= 0) wake_body_now(W, a);
   if (b >= 0) wake_body_now(W, b);
@@ -1659,6 +1671,10 @@ cudaError_t launch_api_contacts(const DevWorld& W, const LaunchCfg& L, int body,
 }
 cudaError_t launch_patch_contacts(const DevWorld& W, const LaunchCfg& L, const unsigned long long* keys, const float4* vals, const int* masks, int n) {
   ++L.launches; k_patch_contacts<<<(n + 255) / 256, 256, 0, L.stream>>>(W, keys, vals, masks, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_api_resensor(const DevWorld& W, const LaunchCfg& L, int fixture) {
+  ++L.launches; k_api_resensor<<<L.gridWide, 256, 0, L.stream>>>(W, fixture);
   return cudaGetLastError();
 }
 cudaError_t launch_api_wake(const DevWorld& W, const LaunchCfg& L, int a, int b) {

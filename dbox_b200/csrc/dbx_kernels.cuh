@@ -27,6 +27,7 @@ cudaError_t stage_prepare(const DevWorld& W, const LaunchCfg& L);               
 cudaError_t stage_solve(const DevWorld& W, const LaunchCfg& L);                   // warm start + iterations + finalize + sleep (one persistent kernel)
 cudaError_t stage_sync_fixtures(const DevWorld& W, const LaunchCfg& L);           // b2Body.SynchronizeFixtures / MoveProxy
 cudaError_t stage_find_new_contacts(DevWorld& W, const LaunchCfg& L, bool rebuild, bool deferClear);       // LBVH rebuild + pair query + AddPair
+cudaError_t launch_api_resensor(const DevWorld& W, const LaunchCfg& L, int fixture);
 cudaError_t launch_patch_contacts(const DevWorld& W, const LaunchCfg& L, const unsigned long long* keys, const float4* vals, const int* masks, int n);
 cudaError_t stage_refresh_tree(DevWorld& W, const LaunchCfg& L, bool rebuild);
 cudaError_t launch_raycast(const DevWorld& W, const LaunchCfg& L, const float4* rays, int n, float4* out);

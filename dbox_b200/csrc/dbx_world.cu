@@ -312,6 +312,84 @@ int World::setBodyType(int b, int type) {
   return 0;
 }
 
+// b2Body.SetMassData (dynamics/b2body.d:502-540)
+int World::setMassData(int b, float mass, float cx, float cy, float I) {
+  if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
+  HBody* hb = mutBody(b); if (!hb) return DBX_E_INVALID;
+  dbx_body_state& st = hb->st;
+  if (st.type != DBX_DYNAMIC_BODY) return 0;
+  st.invMass = 0.0f; st.I = 0.0f; st.invI = 0.0f;
+  st.mass = mass;
+  if (st.mass <= 0.0f) st.mass = 1.0f;
+  st.invMass = 1.0f / st.mass;
+  if (I > 0.0f && (st.flags & DBX_BODY_FIXED_ROTATION) == 0) { st.I = I - st.mass * (cx * cx + cy * cy); st.invI = 1.0f / st.I; }
+  const v2 oldCenter = V(st.c.x, st.c.y);
+  st.localCenter = dbx_vec2{cx, cy};
+  Xf xf; xf.p = V(st.p.x, st.p.y); xf.q = R(st.qs, st.qc);
+  const v2 c = mul(xf, V(cx, cy));
+  st.c0 = st.c = dbx_vec2{c.x, c.y};
+  const v2 dv = cross(st.w, c - oldCenter);
+  st.v.x += dv.x; st.v.y += dv.y;
+  return 0;
+}
+int World::resetMass(int b) {                         // b2Body.ResetMassData (b2body.d:555-625)
+  if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
+  HBody* hb = mutBody(b); if (!hb) return DBX_E_INVALID;
+  resetMassData(*hb);
+  return 0;
+}
+int World::setFixedRotation(int b, bool flag) {       // b2body.d:924-945
+  if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
+  HBody* hb = mutBody(b); if (!hb) return DBX_E_INVALID;
+  if (flag == ((hb->st.flags & DBX_BODY_FIXED_ROTATION) != 0)) return 0;
+  if (flag) hb->st.flags |= DBX_BODY_FIXED_ROTATION; else hb->st.flags &= ~DBX_BODY_FIXED_ROTATION;
+  hb->st.w = 0.0f;
+  resetMassData(*hb);
+  return 0;
+}
+int World::setBodyScalars(int b, const float* linearDamping, const float* angularDamping, const float* gravityScale) {   // b2body.d:653-690
+  if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
+  HBody* hb = mutBody(b); if (!hb) return DBX_E_INVALID;
+  if (linearDamping) hb->st.linearDamping = *linearDamping;
+  if (angularDamping) hb->st.angularDamping = *angularDamping;
+  if (gravityScale) hb->st.gravityScale = *gravityScale;
+  return 0;
+}
+// b2Fixture.SetFilterData + Refilter (dynamics/b2fixture.d:131-178): flag the fixture's contacts, touch its proxies
+int World::setFixtureFilter(int f, int category, int mask, int group) {
+  if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
+  if (f < 0 || f >= (int)fixtures_.size() || !fixtures_[f].alive) return DBX_E_INVALID;
+  fixtures_[f].def.categoryBits = (uint16_t)category; fixtures_[f].def.maskBits = (uint16_t)mask; fixtures_[f].def.groupIndex = (int16_t)group;
+  fullPushFixtures_ = true;
+  int rc = destroyContactsWhere(-1, f, -1, true); if (rc < 0) return rc;       // FlagForFiltering (pushes the new filter first)
+  for (int slot : fixtures_[f].proxies) pendingMoves_.push_back(slot);          // TouchProxy
+  return 0;
+}
+// b2Fixture.SetSensor (b2fixture.d:108-115); contacts cache the sensor bit, so the fixture's contacts are re-flagged
+int World::setFixtureSensor(int f, bool flag) {
+  if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
+  if (f < 0 || f >= (int)fixtures_.size() || !fixtures_[f].alive) return DBX_E_INVALID;
+  if (flag == (fixtures_[f].def.isSensor != 0)) return 0;
+  HBody* hb = mutBody(fixtures_[f].body); if (!hb) return DBX_E_INVALID;
+  wake(*hb, true);
+  fixtures_[f].def.isSensor = flag ? 1 : 0;
+  fullPushFixtures_ = true;
+  int rc = push(); if (rc < 0) return rc;
+  CUDA_OR_FAIL(launch_api_resensor(dw_, L_, f), "resensor");
+  return 0;
+}
+// b2Fixture.SetFriction / SetRestitution / SetDensity (b2fixture.d:225-262): existing contacts keep their mixed values,
+// the density only counts at the next ResetMassData
+int World::setFixtureMaterial(int f, const float* friction, const float* restitution, const float* density) {
+  if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }
+  if (f < 0 || f >= (int)fixtures_.size() || !fixtures_[f].alive) return DBX_E_INVALID;
+  if (friction) fixtures_[f].def.friction = *friction;
+  if (restitution) fixtures_[f].def.restitution = *restitution;
+  if (density) fixtures_[f].def.density = *density;
+  fullPushFixtures_ = true;
+  return 0;
+}
+
 // b2Body.SetActive (dynamics/b2body.d:718-775)
 int World::setBodyActive(int b, bool flag) {
   if (replicated_) { set_last_error("world is replicated: topology and per-body mutation are frozen"); return DBX_E_UNSUPPORTED; }

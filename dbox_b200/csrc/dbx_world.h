@@ -89,6 +89,13 @@ class World {
   int setTransform(int b, float x, float y, float angle);
   int setBodyType(int b, int type);
   int setBodyActive(int b, bool flag);
+  int setMassData(int b, float mass, float cx, float cy, float I);
+  int resetMass(int b);
+  int setFixedRotation(int b, bool flag);
+  int setBodyScalars(int b, const float* linearDamping, const float* angularDamping, const float* gravityScale);
+  int setFixtureFilter(int f, int category, int mask, int group);
+  int setFixtureSensor(int f, bool flag);
+  int setFixtureMaterial(int f, const float* friction, const float* restitution, const float* density);
   int createProxiesFor(int fid);
   void wake(HBody& hb, bool flag);
 

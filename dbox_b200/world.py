@@ -449,6 +449,27 @@ class b2Fixture:
     def GetBody(self):
         return self.body
 
+    # b2fixture.d:108-262
+    def SetFilterData(self, categoryBits=0x0001, maskBits=0xFFFF, groupIndex=0):
+        w = self.body.world
+        w._ck(w._api.fixture_set_filter(w._w, self.id, categoryBits, maskBits, groupIndex))
+
+    def SetSensor(self, flag):
+        w = self.body.world
+        w._ck(w._api.fixture_set_sensor(w._w, self.id, int(flag)))
+
+    def SetFriction(self, v):
+        w = self.body.world
+        w._ck(w._api.fixture_set_friction(w._w, self.id, v))
+
+    def SetRestitution(self, v):
+        w = self.body.world
+        w._ck(w._api.fixture_set_restitution(w._w, self.id, v))
+
+    def SetDensity(self, v):
+        w = self.body.world
+        w._ck(w._api.fixture_set_density(w._w, self.id, v))
+
 
 class b2Joint:
     def __init__(self, world, jid, bodyA, bodyB):
@@ -519,6 +540,26 @@ class b2Body:
         x = _f32(_f32(s.qc * px) + _f32(s.qs * py))
         y = _f32(_f32(-s.qs * px) + _f32(s.qc * py))
         return b2Vec2(x, y)
+
+    def SetMassData(self, mass, center, I):
+        """b2body.d:502-540"""
+        cx, cy = center
+        self.world._ck(self.world._api.body_set_mass_data(self.world._w, self.id, mass, cx, cy, I))
+
+    def ResetMassData(self):
+        self.world._ck(self.world._api.body_reset_mass_data(self.world._w, self.id))
+
+    def SetFixedRotation(self, flag):
+        self.world._ck(self.world._api.body_set_fixed_rotation(self.world._w, self.id, int(flag)))
+
+    def SetLinearDamping(self, d):
+        self.world._ck(self.world._api.body_set_linear_damping(self.world._w, self.id, d))
+
+    def SetAngularDamping(self, d):
+        self.world._ck(self.world._api.body_set_angular_damping(self.world._w, self.id, d))
+
+    def SetGravityScale(self, s):
+        self.world._ck(self.world._api.body_set_gravity_scale(self.world._w, self.id, s))
 
     def SetType(self, type):
         """b2body.d:867-914"""

@@ -277,6 +277,20 @@ int32_t dbx_body_apply_angular_impulse(dbx_world* w, int32_t body, float impulse
 int32_t dbx_body_set_awake(dbx_world* w, int32_t body, int32_t flag);                       /* :827-846 */
 int32_t dbx_body_set_bullet(dbx_world* w, int32_t body, int32_t flag);                      /* :784-794 */
 int32_t dbx_body_set_sleeping_allowed(dbx_world* w, int32_t body, int32_t flag);            /* :804-815 */
+int32_t dbx_body_set_mass_data(dbx_world* w, int32_t body, float mass, float centerX, float centerY, float I); /* :502-540 */
+int32_t dbx_body_reset_mass_data(dbx_world* w, int32_t body);                                  /* :555-625 */
+int32_t dbx_body_set_fixed_rotation(dbx_world* w, int32_t body, int32_t flag);                 /* :924-945 */
+int32_t dbx_body_set_linear_damping(dbx_world* w, int32_t body, float damping);                /* :653-656 */
+int32_t dbx_body_set_angular_damping(dbx_world* w, int32_t body, float damping);               /* :665-668 */
+int32_t dbx_body_set_gravity_scale(dbx_world* w, int32_t body, float scale);                   /* :677-680 */
+/* fixture mutators (dynamics/b2fixture.d): SetFilterData + Refilter :131-178 (contacts flagged for filtering, proxies touched),
+ * SetSensor :108-115 (wakes the body), SetFriction / SetRestitution :225-249 (existing contacts keep their mixed values),
+ * SetDensity :257-262 (counts at the next ResetMassData) */
+int32_t dbx_fixture_set_filter(dbx_world* w, int32_t fixture, int32_t categoryBits, int32_t maskBits, int32_t groupIndex);
+int32_t dbx_fixture_set_sensor(dbx_world* w, int32_t fixture, int32_t flag);
+int32_t dbx_fixture_set_friction(dbx_world* w, int32_t fixture, float friction);
+int32_t dbx_fixture_set_restitution(dbx_world* w, int32_t fixture, float restitution);
+int32_t dbx_fixture_set_density(dbx_world* w, int32_t fixture, float density);
 int32_t dbx_body_set_type(dbx_world* w, int32_t body, int32_t type);                           /* :867-914: mass reset, contacts destroyed, proxies touched */
 int32_t dbx_body_set_active(dbx_world* w, int32_t body, int32_t flag);                         /* :718-775: proxies created / destroyed, contacts destroyed */
 

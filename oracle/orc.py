@@ -62,6 +62,11 @@ def api():
             "world_query_aabb": (i32, [W, P(A.AABB), i32, i32, P(i32), P(i32)]),
             "joint_set_target": (i32, [W, i32, f32, f32]),
             "body_set_type": (i32, [W, i32, i32]),
+            "body_set_mass_data": (i32, [W, i32, f32, f32, f32, f32]), "body_reset_mass_data": (i32, [W, i32]),
+            "body_set_fixed_rotation": (i32, [W, i32, i32]), "body_set_linear_damping": (i32, [W, i32, f32]),
+            "body_set_angular_damping": (i32, [W, i32, f32]), "body_set_gravity_scale": (i32, [W, i32, f32]),
+            "fixture_set_filter": (i32, [W, i32, i32, i32, i32]), "fixture_set_sensor": (i32, [W, i32, i32]),
+            "fixture_set_friction": (i32, [W, i32, f32]), "fixture_set_restitution": (i32, [W, i32, f32]), "fixture_set_density": (i32, [W, i32, f32]),
             "body_set_active": (i32, [W, i32, i32]),
             "world_enable_contact_events": (i32, [W, i32]),
             "world_poll_contact_events": (i32, [W, P(A.ContactEvent), i32]),

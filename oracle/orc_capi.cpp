@@ -228,6 +228,53 @@ int32_t orc_joint_create(orc_world* w, const dbx_joint_def* d) {
   Joint* r = w->w.addJoint(j);
   return r ? r->id : DBX_E_LOCKED;
 }
+static Body* bodyAt(orc_world* w, int32_t body) { return (body >= 0 && body < (int)w->w.bodiesById.size()) ? w->w.bodiesById[body] : nullptr; }
+static Fixture* fixtureAt(orc_world* w, int32_t f) { return (f >= 0 && f < (int)w->w.fixturesById.size()) ? w->w.fixturesById[f] : nullptr; }
+// b2Body.SetMassData (b2body.d:502-540)
+int32_t orc_body_set_mass_data(orc_world* w, int32_t body, float mass, float cx, float cy, float I) {
+  Body* b = bodyAt(w, body); if (!b) return DBX_E_INVALID;
+  if (w->w.locked || b->type != kDynamic) return 0;
+  b->invMass = 0.0f; b->I = 0.0f; b->invI = 0.0f;
+  b->mass = mass;
+  if (b->mass <= 0.0f) b->mass = 1.0f;
+  b->invMass = 1.0f / b->mass;
+  V2 center(cx, cy);
+  if (I > 0.0f && (b->flags & bFixedRotation) == 0) { b->I = I - b->mass * dot(center, center); b->invI = 1.0f / b->I; }
+  V2 oldCenter = b->sweep.c;
+  b->sweep.localCenter = center;
+  b->sweep.c0 = b->sweep.c = mul(b->xf, b->sweep.localCenter);
+  b->linearVelocity += cross(b->angularVelocity, b->sweep.c - oldCenter);
+  return 0;
+}
+int32_t orc_body_reset_mass_data(orc_world* w, int32_t body) { Body* b = bodyAt(w, body); if (!b) return DBX_E_INVALID; b->resetMassData(); return 0; }
+int32_t orc_body_set_fixed_rotation(orc_world* w, int32_t body, int32_t flag) {      // b2body.d:924-945
+  Body* b = bodyAt(w, body); if (!b) return DBX_E_INVALID;
+  bool status = (b->flags & bFixedRotation) == bFixedRotation;
+  if (status == (flag != 0)) return 0;
+  if (flag) b->flags |= bFixedRotation; else b->flags &= ~bFixedRotation;
+  b->angularVelocity = 0.0f;
+  b->resetMassData();
+  return 0;
+}
+int32_t orc_body_set_linear_damping(orc_world* w, int32_t body, float d) { Body* b = bodyAt(w, body); if (!b) return DBX_E_INVALID; b->linearDamping = d; return 0; }
+int32_t orc_body_set_angular_damping(orc_world* w, int32_t body, float d) { Body* b = bodyAt(w, body); if (!b) return DBX_E_INVALID; b->angularDamping = d; return 0; }
+int32_t orc_body_set_gravity_scale(orc_world* w, int32_t body, float s) { Body* b = bodyAt(w, body); if (!b) return DBX_E_INVALID; b->gravityScale = s; return 0; }
+// b2Fixture.SetFilterData + Refilter (b2fixture.d:131-178)
+int32_t orc_fixture_set_filter(orc_world* w, int32_t fixture, int32_t cat, int32_t mask, int32_t group) {
+  Fixture* f = fixtureAt(w, fixture); if (!f) return DBX_E_INVALID;
+  f->filter.categoryBits = (uint16_t)cat; f->filter.maskBits = (uint16_t)mask; f->filter.groupIndex = (int16_t)group;
+  for (ContactEdge* e = f->body->contactList; e; e = e->next) { Contact* c = e->contact; if (c->fixtureA == f || c->fixtureB == f) c->flags |= cFilter; }
+  for (int i = 0; i < f->proxyCount; ++i) w->w.broadPhase.touchProxy(f->proxies[i].proxyId);
+  return 0;
+}
+int32_t orc_fixture_set_sensor(orc_world* w, int32_t fixture, int32_t flag) {        // b2fixture.d:108-115
+  Fixture* f = fixtureAt(w, fixture); if (!f) return DBX_E_INVALID;
+  if ((flag != 0) != f->isSensor) { f->body->setAwake(true); f->isSensor = flag != 0; }
+  return 0;
+}
+int32_t orc_fixture_set_friction(orc_world* w, int32_t fixture, float v) { Fixture* f = fixtureAt(w, fixture); if (!f) return DBX_E_INVALID; f->friction = v; return 0; }
+int32_t orc_fixture_set_restitution(orc_world* w, int32_t fixture, float v) { Fixture* f = fixtureAt(w, fixture); if (!f) return DBX_E_INVALID; f->restitution = v; return 0; }
+int32_t orc_fixture_set_density(orc_world* w, int32_t fixture, float v) { Fixture* f = fixtureAt(w, fixture); if (!f) return DBX_E_INVALID; f->density = v; return 0; }
 int32_t orc_body_set_type(orc_world* w, int32_t body, int32_t type) {
   if (body < 0 || body >= (int)w->w.bodiesById.size() || !w->w.bodiesById[body] || type < 0 || type > 2) return DBX_E_INVALID;
   w->w.setBodyType(w->w.bodiesById[body], type); return 0;

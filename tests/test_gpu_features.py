@@ -603,3 +603,41 @@ def test_set_type_and_set_active(gpu_api, oracle_api):
     kg, _, _ = contacts_by_key(wg); ko, _, _ = contacts_by_key(wo)
     assert set(kg) == set(ko)                                               # same (fixtureA, childA, fixtureB, childB) keys: same A/B order
     assert bg[2].GetPosition().x > 0.5                                      # the kinematic box carried its passenger along
+
+
+def test_body_and_fixture_mutators(gpu_api, oracle_api):
+    """b2Fixture.SetFilterData / SetSensor / SetFriction / SetRestitution / SetDensity (b2fixture.d:108-262) and b2Body.SetMassData /
+    ResetMassData / SetFixedRotation / Set*Damping / SetGravityScale (b2body.d:502-690, 924-945) between steps"""
+    def build(api):
+        w = b2World((0.0, -10.0), api=api)
+        _ground(w, api)
+        bs = [_box_body(w, api, -8.0 + 4.0 * k, 0.52) for k in range(5)]
+        tops = [_box_body(w, api, -8.0 + 4.0 * k, 1.55) for k in range(5)]
+        return w, bs + tops
+
+    def edit(k, bs):
+        if k == 30:
+            bs[5].fixtures[0].SetFilterData(0x0002, 0x0000, 0)       # top box 0 stops colliding: falls through everything
+            bs[1].fixtures[0].SetSensor(True)                         # bottom box 1 becomes a sensor: falls through the ground, its passenger lands
+            bs[7].SetGravityScale(-0.5); bs[7].SetLinearDamping(0.4)  # top box 2 floats away, damped
+            bs[8].SetMassData(3.0, (0.2, 0.0), 2.0)                   # top box 3 gets an off-centre mass
+            bs[9].SetFixedRotation(True); bs[9].SetAngularDamping(0.2)
+            bs[4].fixtures[0].SetFriction(0.0); bs[4].fixtures[0].SetRestitution(0.5)
+        if k == 60:
+            bs[5].SetTransform((-8.0, 4.0), 0.0); bs[5].SetLinearVelocity((0.0, 0.0))
+            bs[5].fixtures[0].SetFilterData()                         # collides again: lands back on its box
+            bs[3].fixtures[0].SetDensity(4.0); bs[3].ResetMassData()
+            bs[3].ApplyLinearImpulse((6.0, 0.0), (bs[3].GetPosition().x, bs[3].GetPosition().y + 0.4))
+    wg, bg = build(gpu_api); wo, bo = build(oracle_api)
+    for k in range(120):
+        edit(k, bg); edit(k, bo)
+        wg.Step(DT, 8, 3); wo.Step(DT, 8, 3)
+        cg, co = wg.counts(), wo.counts()
+        # touching contacts exactly; the AABB-level cache may drop a pair of a fast-falling body one step apart
+        assert cg.touching == co.touching and abs(cg.contacts - co.contacts) <= 2, (k, cg.contacts, co.contacts, cg.touching, co.touching)
+        for i, (a, b) in enumerate(zip(bg, bo)):
+            pa, pb = a.GetPosition(), b.GetPosition()
+            tol = 2e-3 * max(1.0, abs(pb.x), abs(pb.y))
+            assert abs(pa.x - pb.x) < tol and abs(pa.y - pb.y) < tol and abs(a.GetAngle() - b.GetAngle()) < 5e-3, (k, i, (pa.x, pa.y), (pb.x, pb.y))
+    assert 1.4 < bg[5].GetPosition().y < 1.7 and bg[1].GetPosition().y < 0.0 and bg[7].GetPosition().y > 2.0
+    assert abs(bg[8].GetMass() - 3.0) < 1e-6 and abs(bg[3].GetMass() - 4.0) < 1e-5
