@@ -115,6 +115,15 @@ class ContactEvent(C.Structure):
 CONTACT_BEGIN, CONTACT_END = 1, 2
 
 
+class WorldManifold(C.Structure):
+    _fields_ = [("normal", Vec2), ("points", Vec2 * 2), ("separations", c_f32 * 2), ("pointCount", c_i32), ("_pad", c_i32)]
+
+
+class PostSolve(C.Structure):
+    _fields_ = [("fixtureA", c_i32), ("fixtureB", c_i32), ("childA", c_i32), ("childB", c_i32), ("phase", c_i32), ("count", c_i32),
+                ("normalImpulses", c_f32 * 2), ("tangentImpulses", c_f32 * 2)]
+
+
 class JointState(C.Structure):
     _fields_ = [("type", c_i32), ("impulse", c_f32 * 3), ("motorImpulse", c_f32), ("limitState", c_i32)]
 
@@ -135,7 +144,8 @@ class Caps(C.Structure):
 # sizes the header implies (checked by tests/test_abi.py and by the library's own static_asserts)
 EXPECTED_SIZES = {"Vec2": 8, "AABB": 16, "BodyDef": 72, "Shape": 240, "FixtureDef": 32, "JointDef": 176, "BodyState": 116,
                   "ManifoldPoint": 20, "Manifold": 64, "ContactRec": 104, "ProxyRec": 44, "JointState": 24, "Counts": 44,
-                  "Profile": 32, "Caps": 20, "ContactEvent": 36, "Ray": 16, "RayHit": 28, "ContactPatch": 36}
+                  "Profile": 32, "Caps": 20, "ContactEvent": 36, "Ray": 16, "RayHit": 28, "ContactPatch": 36,
+                  "WorldManifold": 40, "PostSolve": 40}
 
 P = C.POINTER
 W = C.c_void_p
@@ -234,6 +244,12 @@ PROTOTYPES = {
     "world_query_aabb": (c_i32, [W, P(AABB), c_i32, c_i32, P(c_i32), P(c_i32)]),
     "world_enable_contact_events": (c_i32, [W, c_i32]),
     "world_poll_contact_events": (c_i32, [W, P(ContactEvent), c_i32]),
+    "world_test_points": (c_i32, [W, P(c_i32), P(Vec2), c_i32, P(c_i32)]),
+    "world_raycast_all": (c_i32, [W, P(Ray), c_i32, c_i32, P(c_i32), P(RayHit)]),
+    "world_shift_origin": (c_i32, [W, c_f32, c_f32]),
+    "world_read_world_manifolds": (c_i32, [W, P(WorldManifold), c_i32]),
+    "world_enable_post_solve": (c_i32, [W, c_i32]),
+    "world_read_post_solve": (c_i32, [W, P(PostSolve), c_i32]),
 }
 
 

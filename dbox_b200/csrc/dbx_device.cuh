@@ -71,6 +71,7 @@ struct Header {
   int colourOff[kMaxColours + 1];   // solver order: contacts of colour c are [colourOff[c], colourOff[c+1])
   int jointColourOff[kMaxJointColours + 1];
   int nToi;           // entries of c_toiList: contacts the TOI pass can ever care about this step (listed by k_collide)
+  int nPostSolve;     // PostSolve records of the current step (may exceed psCap: the surplus is lost and reported)
 };
 
 struct DevWorld {
@@ -133,6 +134,10 @@ struct DevWorld {
   int4* ev_a;        // [evCap] contact events: (type | phase << 8 | step << 16, fixtureA, fixtureB, childA | childB << 16)
   int4* ev_b;        //         (bodyA, bodyB, pair key lo, pair key hi)
   int evCap;         // 0 = contact events off
+  int4* ps_a;        // [psCap] PostSolve records: (fixtureA, fixtureB, childA | childB << 16, count | phase << 8)
+  float4* ps_b;      //         (normalImpulse0, tangentImpulse0, normalImpulse1, tangentImpulse1)
+  unsigned long long* ps_key;   //  pair key
+  int psCap;         // 0 = PostSolve recording off
   // world-local solve (batched replicas without joints): solver slots sorted by (replica, colour) instead of colour alone
   const unsigned* sw_key;   // [nSolve] sorted (replica << swColourBits | colour)
   int swColourBits;

@@ -29,6 +29,20 @@ DBX_D void emit_contact_event(const DevWorld& W, int type, int phase, int i, con
   W.ev_a[k] = make_int4(type | (phase << 8) | ((W.stepIndex & 0xFFFF) << 16), fx.x, fx.y, (childA & 0xFFFF) | (childB << 16));
   W.ev_b[k] = make_int4(ids.z, ids.w, (int)(unsigned)(key & 0xFFFFFFFFull), (int)(unsigned)(key >> 32));
 }
+// b2Island.Report (dynamics/b2island.d:438-462), deferred: one record per contact of the island that was just solved, carrying
+// the b2ContactImpulse the listener's PostSolve would have been given.  s = solver slot, i = contact slot.
+DBX_D void emit_post_solve(const DevWorld& W, int phase, int s, int i) {
+  const int k = atomicAdd(&W.hdr->nPostSolve, 1);
+  if (k >= W.psCap) return;
+  const int4 ids = W.c_ids[i], fx = W.c_fix[i];
+  const int childA = W.p_ids[ids.x].y, childB = W.p_ids[ids.y].y;
+  const int count = W.s_pc[s] & 0xFF;
+  float4 imp = W.s_imp[s];
+  if (count < 2) { imp.z = 0.0f; imp.w = 0.0f; }
+  W.ps_a[k] = make_int4(fx.x, fx.y, (childA & 0xFFFF) | (childB << 16), count | (phase << 8));
+  W.ps_b[k] = imp;
+  W.ps_key[k] = W.c_key[i];
+}
 DBX_D void destroy_contact(const DevWorld& W, int i, uint32_t flags, int bodyA, int bodyB, int pointCount) {
   if (flags & CF_TOUCHING) emit_contact_event(W, EV_END, 1, i, W.c_ids[i], W.c_fix[i]);
   // b2ContactManager.Destroy + b2Contact.Destroy: wake both bodies if the manifold had points and no sensor is involved
@@ -785,6 +799,151 @@ __global__ void __launch_bounds__(128) k_query_aabb(const __grid_constant__ DevW
   }
 }
 
+// b2World.RayCast with a callback that returns 1 (every fixture on the ray, no clipping): the ray keeps its full length
+// (b2dynamictree.d:303-316 with value == maxFraction == 1), each hit is one record of two float4 as in k_raycast
+__global__ void __launch_bounds__(128) k_raycast_all(const __grid_constant__ DevWorld W, const int* leaves, const float4* rays, int nRays, int capPer, int* counts, float4* out) {
+  const int n = W.nProxies;
+  GRID_STRIDE(k, nRays) {
+    const float4 ry = rays[k];
+    const v2 p1 = V(ry.x, ry.y), p2 = V(ry.z, ry.w);
+    int count = 0;
+    v2 r = p2 - p1;
+    if (n > 0 && dot(r, r) > 0.0f) {
+      normalize(r);
+      const v2 v = cross(1.0f, r), abs_v = V(fabsr(v.x), fabsr(v.y));
+      const v2 slo = vmin(p1, p2), shi = vmax(p1, p2);
+      int stack[kRayStack];
+      int top = 0;
+      stack[top++] = (n == 1) ? (n - 1) : 0;
+      while (top > 0) {
+        const int node = stack[--top];
+        const float4 bx = __ldcg(&W.bv_box[node]);
+        if (bx.z < slo.x || bx.w < slo.y || shi.x < bx.x || shi.y < bx.y) continue;
+        const v2 c = 0.5f * V(bx.x + bx.z, bx.y + bx.w), h = 0.5f * V(bx.z - bx.x, bx.w - bx.y);
+        const float separation = fabsr(dot(v, p1 - c)) - dot(abs_v, h);
+        if (separation > 0.0f) continue;
+        if (node >= n - 1) {
+          const int q = leaves[node - (n - 1)];
+          if (!(W.p_flags[q] & PF_ALIVE)) continue;
+          const int4 ids = W.p_ids[q];   // fixture child body shape
+          float fraction; v2 normal;
+          if (!shape_raycast(W.shapes + ids.w, XF(W.b_xf[ids.z]), p1, p2, 1.0f, &fraction, &normal)) continue;
+          if (count < capPer) {
+            const v2 point = (1.0f - fraction) * p1 + fraction * p2;
+            float4* o = out + 2 * ((size_t)k * capPer + count);
+            o[0] = make_float4(__int_as_float(ids.x), __int_as_float(ids.y), fraction, point.x);
+            o[1] = make_float4(point.y, normal.x, normal.y, 0.0f);
+          }
+          ++count;
+        } else {
+          if (top + 2 > kRayStack) { W.hdr->error = -5; break; }
+          const int2 ch = W.bv_child[node];
+          stack[top++] = ch.x; stack[top++] = ch.y;
+        }
+      }
+    }
+    counts[k] = count;
+  }
+}
+// b2Shape.TestPoint: polygon b2polygonshape.d:265-279, circle b2circleshape.d:60-65; an edge (and so a chain child) contains
+// no point (b2edgeshape.d:84-87, b2chainshape.d:196-199)
+DBX_D bool shape_test_point(const DShape* S, Xf xf, v2 p) {
+  if (S->type == SH_CIRCLE) {
+    const v2 center = xf.p + mul(xf.q, S->c);
+    const v2 d = p - center;
+    return dot(d, d) <= S->radius * S->radius;
+  }
+  if (S->type != SH_POLYGON) return false;
+  const v2 pLocal = mulT(xf.q, p - xf.p);
+  for (int i = 0; i < S->count; ++i) {
+    const float d = dot(S->n[i], pLocal - S->v[i]);
+    if (d > 0.0f) return false;
+  }
+  return true;
+}
+// b2Fixture.TestPoint (b2fixture.d:209-212), batched: q = (point.x, point.y, shape index | -1, body index), one thread each
+__global__ void __launch_bounds__(128) k_test_points(const __grid_constant__ DevWorld W, const float4* q, int n, int* inside) {
+  GRID_STRIDE(k, n) {
+    const float4 t = q[k];
+    const int shape = __float_as_int(t.z), body = __float_as_int(t.w);
+    inside[k] = (shape >= 0 && shape < W.nShapes && body >= 0 && body < W.nBodies) ? (shape_test_point(W.shapes + shape, XF(W.b_xf[body]), V(t.x, t.y)) ? 1 : 0) : 0;
+  }
+}
+// b2World.ShiftOrigin (dynamics/b2world.d:758-780): bodies (m_xf.p, m_sweep.c0, m_sweep.c) and the tree's boxes
+// (b2dynamictree.d:503-511: the persistent fat AABBs; b2FixtureProxy.aabb is left as it is there, and here).  xf0 is this
+// library's cached transform at (c0, a0) and moves with c0.  The LBVH is rebuilt by the host before its next use.
+__global__ void __launch_bounds__(256) k_shift_origin(const __grid_constant__ DevWorld W, float ox, float oy) {
+  GRID_STRIDE(b, W.nBodies) {
+    if (!(W.b_flags[b] & BF_ALIVE)) continue;
+    float4 xf = W.b_xf[b], xf0 = W.b_xf0[b], pos = W.b_pos[b], pos0 = W.b_pos0[b];
+    xf.x -= ox; xf.y -= oy; xf0.x -= ox; xf0.y -= oy; pos.x -= ox; pos.y -= oy; pos0.x -= ox; pos0.y -= oy;
+    W.b_xf[b] = xf; W.b_xf0[b] = xf0; W.b_pos[b] = pos; W.b_pos0[b] = pos0;
+  }
+  GRID_STRIDE(p, W.nProxies) {
+    if (!(W.p_flags[p] & PF_ALIVE)) continue;
+    float4 fat = W.p_fat[p];
+    fat.x -= ox; fat.y -= oy; fat.z -= ox; fat.w -= oy;
+    W.p_fat[p] = fat;
+  }
+}
+// b2Contact.GetWorldManifold (contacts/b2contact.d:77-91) -> b2WorldManifold.Initialize (collision/b2collision.d:123-191) for the
+// contact slots [0, high): out[2i] = (normal.xy, separations), out[2i+1] = (points[0], points[1]); untouched for dead slots
+__global__ void __launch_bounds__(256) k_world_manifolds(const __grid_constant__ DevWorld W, int high, float4* out) {
+  GRID_STRIDE(i, high) {
+    float4 o0 = make_float4(0, 0, 0, 0), o1 = make_float4(0, 0, 0, 0);
+    const uint32_t fl = W.c_flags[i];
+    const uint4 mk = W.c_mk[i];
+    const int pointCount = (int)mk.w, type = (int)mk.z;
+    if ((fl & CF_ALIVE) && pointCount > 0) {
+      const int4 ids = W.c_ids[i], fx = W.c_fix[i];
+      const Xf xfA = XF(W.b_xf[ids.z]), xfB = XF(W.b_xf[ids.w]);
+      const float radiusA = W.shapes[fx.z].radius, radiusB = W.shapes[fx.w].radius;
+      const float4 m0 = W.c_m0[i], m1 = W.c_m1[i];
+      const v2 localNormal = V(m0.x, m0.y), localPoint = V(m0.z, m0.w);
+      const v2 lp[2] = {V(m1.x, m1.y), V(m1.z, m1.w)};
+      v2 normal = V(0.0f, 0.0f), wp[2] = {V(0.0f, 0.0f), V(0.0f, 0.0f)};
+      float sep[2] = {0.0f, 0.0f};
+      if (type == MAN_CIRCLES) {
+        normal = V(1.0f, 0.0f);
+        const v2 pointA = mul(xfA, localPoint), pointB = mul(xfB, lp[0]);
+        if (dist2(pointA, pointB) > kEpsilon * kEpsilon) { normal = pointB - pointA; normalize(normal); }
+        const v2 cA = pointA + radiusA * normal, cB = pointB - radiusB * normal;
+        wp[0] = 0.5f * (cA + cB);
+        sep[0] = dot(cB - cA, normal);
+      } else if (type == MAN_FACE_A) {
+        normal = mul(xfA.q, localNormal);
+        const v2 planePoint = mul(xfA, localPoint);
+        for (int k = 0; k < pointCount && k < 2; ++k) {
+          const v2 clipPoint = mul(xfB, lp[k]);
+          const v2 cA = clipPoint + (radiusA - dot(clipPoint - planePoint, normal)) * normal;
+          const v2 cB = clipPoint - radiusB * normal;
+          wp[k] = 0.5f * (cA + cB);
+          sep[k] = dot(cB - cA, normal);
+        }
+      } else if (type == MAN_FACE_B) {
+        normal = mul(xfB.q, localNormal);
+        const v2 planePoint = mul(xfB, localPoint);
+        for (int k = 0; k < pointCount && k < 2; ++k) {
+          const v2 clipPoint = mul(xfA, lp[k]);
+          const v2 cB = clipPoint + (radiusB - dot(clipPoint - planePoint, normal)) * normal;
+          const v2 cA = clipPoint - radiusA * normal;
+          wp[k] = 0.5f * (cA + cB);
+          sep[k] = dot(cA - cB, normal);
+        }
+        normal = -normal;
+      }
+      o0 = make_float4(normal.x, normal.y, sep[0], sep[1]);
+      o1 = make_float4(wp[0].x, wp[0].y, wp[1].x, wp[1].y);
+    }
+    out[2 * (size_t)i] = o0; out[2 * (size_t)i + 1] = o1;
+  }
+}
+// PostSolve records of the island solve that just ran (b2island.d:239): one per solver contact
+__global__ void __launch_bounds__(256) k_post_solve(const __grid_constant__ DevWorld W) {
+  const int n = min(W.hdr->nSolve, W.sCap);
+  GRID_STRIDE(s, n) emit_post_solve(W, 1, s, W.s_contact[s]);
+}
+
 // b2ContactManager.AddPair (dynamics/b2contactmanager.d:52-176) + b2Contact.Create (contacts/b2contact.d:375-400)
 DBX_D void add_pair(const DevWorld& W, int2 pr) {
   const int4 pa = W.p_ids[pr.x], pb = W.p_ids[pr.y];   // fixture child body shape
@@ -1284,6 +1443,7 @@ DBX_D void toi_process_event(const DevWorld& W, int e, float dtStep) {
   }
   for (int k = 0; k < nc; ++k) prepare_contact(W, sBase + k, contacts[k], -1.0f);
   for (int it = 0; it < W.velIters; ++it) for (int k = 0; k < nc; ++k) contact_solve_velocity(W, sBase + k);
+  if (W.psCap > 0) for (int k = 0; k < nc; ++k) emit_post_solve(W, 2, sBase + k, contacts[k]);   // island.Report (b2island.d:414)
   const float h = (1.0f - minAlpha) * dtStep;
   for (int t = 0; t < nb; ++t) {
     const int b = bodies[t];
@@ -1614,6 +1774,27 @@ cudaError_t launch_raycast(const DevWorld& W, const LaunchCfg& L, const float4* 
 }
 cudaError_t launch_query_aabb(const DevWorld& W, const LaunchCfg& L, const float4* boxes, int n, int capPer, int* counts, int2* out) {
   ++L.launches; k_query_aabb<<<(n + 127) / 128, 128, 0, L.stream>>>(W, W.bv_sorted, boxes, n, capPer, counts, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_raycast_all(const DevWorld& W, const LaunchCfg& L, const float4* rays, int n, int capPer, int* counts, float4* out) {
+  ++L.launches; k_raycast_all<<<(n + 127) / 128, 128, 0, L.stream>>>(W, W.bv_sorted, rays, n, capPer, counts, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_test_points(const DevWorld& W, const LaunchCfg& L, const float4* q, int n, int* inside) {
+  ++L.launches; k_test_points<<<(n + 127) / 128, 128, 0, L.stream>>>(W, q, n, inside);
+  return cudaGetLastError();
+}
+cudaError_t launch_shift_origin(const DevWorld& W, const LaunchCfg& L, float ox, float oy) {
+  ++L.launches; k_shift_origin<<<L.gridWide, 256, 0, L.stream>>>(W, ox, oy);
+  return cudaGetLastError();
+}
+cudaError_t launch_world_manifolds(const DevWorld& W, const LaunchCfg& L, int high, float4* out) {
+  ++L.launches; k_world_manifolds<<<L.gridWide, 256, 0, L.stream>>>(W, high, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_post_solve(const DevWorld& W, const LaunchCfg& L) {
+  ++L.launches; k_post_solve<<<L.gridWide, 256, 0, L.stream>>>(W);
   return cudaGetLastError();
 }
 

@@ -32,6 +32,11 @@ cudaError_t launch_patch_contacts(const DevWorld& W, const LaunchCfg& L, const u
 cudaError_t stage_refresh_tree(DevWorld& W, const LaunchCfg& L, bool rebuild);
 cudaError_t launch_raycast(const DevWorld& W, const LaunchCfg& L, const float4* rays, int n, float4* out);
 cudaError_t launch_query_aabb(const DevWorld& W, const LaunchCfg& L, const float4* boxes, int n, int capPer, int* counts, int2* out);
+cudaError_t launch_raycast_all(const DevWorld& W, const LaunchCfg& L, const float4* rays, int n, int capPer, int* counts, float4* out);
+cudaError_t launch_test_points(const DevWorld& W, const LaunchCfg& L, const float4* q, int n, int* inside);
+cudaError_t launch_shift_origin(const DevWorld& W, const LaunchCfg& L, float ox, float oy);
+cudaError_t launch_world_manifolds(const DevWorld& W, const LaunchCfg& L, int high, float4* out);
+cudaError_t launch_post_solve(const DevWorld& W, const LaunchCfg& L);
 cudaError_t stage_toi(DevWorld& W, const LaunchCfg& L);
 cudaError_t stage_toi_pre(const DevWorld& W, const LaunchCfg& L, cudaStream_t aux);                               // b2World.SolveTOI
 cudaError_t stage_rebuild_hash(const DevWorld& W, const LaunchCfg& L);

@@ -60,6 +60,7 @@ World::~World() {
   b_gs.release(); f_mat.release(); s_p3.release(); b_flags.release(); f_filter.release(); p_flags.release(); c_flags.release();
   b_mask.release(); b_claim.release(); bv_key.release(); bv_keyAlt.release(); jp_keys.release(); c_key.release(); h_key.release();
   d_shapes.release(); p_ids.release(); c_ids.release(); c_fix.release(); j_ids.release(); bv_child.release(); bv_wr.release(); pairs.release(); s_body.release(); c_mk.release();
+  ps_a_.release(); ps_b_.release(); ps_key_.release(); ev_a_.release(); ev_b_.release(); qIn_.release(); qOut_.release(); qCount_.release(); qPairs_.release();
   cubTemp.release(); hdr_.release();
   for (auto& ev : ev_) cudaEventDestroy(ev);
   cudaStreamDestroy(stream_);
@@ -1066,6 +1067,7 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents, int halves) {
     mark(1);
   }
   if (!(halves & 2)) { hostBodiesValid_ = false; return 0; }
+  if (dw_.psCap > 0) CUDA_OR_FAIL(cudaMemsetAsync((char*)hdr_.p + offsetof(Header, nPostSolve), 0, 4, stream_), "post-solve reset");
   if (stepComplete_ && dt > 0.0f) {
     CUDA_OR_FAIL(stage_islands_and_integrate(dw_, L_), "islands");
     mark(2);
@@ -1100,6 +1102,7 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents, int halves) {
     mark(4);
     if (worldsPath) CUDA_OR_FAIL(stage_solve_worlds(dw_, L_, (int)bodies_.size()), "solve (worlds)");
     else CUDA_OR_FAIL(stage_solve(dw_, L_), "solve");
+    if (dw_.psCap > 0) CUDA_OR_FAIL(launch_post_solve(dw_, L_), "post_solve");   // island.Report (b2island.d:239); before k_toi reuses the rows
     mark(5);
     if (toiPre) {
       if (!aux_) {
@@ -1300,6 +1303,163 @@ int World::queryAabb(const dbx_aabb* boxes, int n, int capPer, int32_t* counts, 
     int2* b = hp.data() + (size_t)k * capPer;
     std::sort(b, b + m, [](const int2& x, const int2& y) { return x.x != y.x ? x.x < y.x : x.y < y.y; });
     for (int i = 0; i < m; ++i) { fixtureChild[2 * ((size_t)k * capPer + i)] = b[i].x; fixtureChild[2 * ((size_t)k * capPer + i) + 1] = b[i].y; }
+  }
+  return n;
+}
+
+// b2World.RayCast with the "report everything" callback (see include/dbox_b200.h): all hits per ray, sorted by (fraction, fixture, child)
+int World::rayCastAll(const dbx_ray* rays, int n, int capPer, int32_t* counts, dbx_ray_hit* hits) {
+  if (n < 0 || capPer < 0 || (n > 0 && (!rays || !counts)) || (n > 0 && capPer > 0 && !hits)) return DBX_E_INVALID;
+  if (n == 0) return 0;
+  int rc = refreshTreeForQuery(); if (rc < 0) return rc;
+  const size_t nh = (size_t)n * (size_t)std::max(capPer, 1);
+  CUDA_OR_FAIL(qIn_.reserve((size_t)n, false, stream_), "rays"); CUDA_OR_FAIL(qCount_.reserve((size_t)n, false, stream_), "counts"); CUDA_OR_FAIL(qOut_.reserve(2 * nh, false, stream_), "hits");
+  CUDA_OR_FAIL(cudaMemcpyAsync(qIn_.p, rays, (size_t)n * 16, cudaMemcpyHostToDevice, stream_), "rays h2d");
+  if (proxies_.empty()) { for (int k = 0; k < n; ++k) counts[k] = 0; return n; }
+  CUDA_OR_FAIL(launch_raycast_all(dw_, L_, qIn_.p, n, capPer, qCount_.p, qOut_.p), "raycast_all");
+  std::vector<float4> h(2 * nh);
+  CUDA_OR_FAIL(cudaMemcpyAsync(counts, qCount_.p, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_), "counts d2h");
+  CUDA_OR_FAIL(cudaMemcpyAsync(h.data(), qOut_.p, h.size() * 16, cudaMemcpyDeviceToHost, stream_), "hits d2h");
+  rc = checkDeviceError(true); if (rc < 0) return DBX_E_CAPACITY;
+  std::vector<dbx_ray_hit> tmp;
+  for (int k = 0; k < n && capPer > 0; ++k) {
+    const int m = std::min(counts[k], capPer);
+    tmp.resize((size_t)m);
+    for (int i = 0; i < m; ++i) {
+      const float4 a = h[2 * ((size_t)k * capPer + i)], b = h[2 * ((size_t)k * capPer + i) + 1];
+      dbx_ray_hit& o = tmp[i];
+      std::memcpy(&o.fixture, &a.x, 4); std::memcpy(&o.child, &a.y, 4);
+      o.fraction = a.z; o.point = dbx_vec2{a.w, b.x}; o.normal = dbx_vec2{b.y, b.z};
+    }
+    std::sort(tmp.begin(), tmp.end(), [](const dbx_ray_hit& x, const dbx_ray_hit& y) {
+      return x.fraction != y.fraction ? x.fraction < y.fraction : x.fixture != y.fixture ? x.fixture < y.fixture : x.child < y.child; });
+    for (int i = 0; i < m; ++i) hits[(size_t)k * capPer + i] = tmp[i];
+  }
+  return n;
+}
+// b2Fixture.TestPoint (b2fixture.d:209-212), batched.  The fixture's geometry record is the one its proxy uses; a fixture
+// without proxies (inactive body) gets its record interned here.  Chains (and edges) contain no point.
+int World::testPoints(const int32_t* fixtures, const dbx_vec2* points, int n, int32_t* inside) {
+  if (n < 0 || (n > 0 && (!fixtures || !points || !inside))) return DBX_E_INVALID;
+  if (n == 0) return 0;
+  if (replicated_) { set_last_error("world queries on a replicated world are not built (replicas share coordinates)"); return DBX_E_UNSUPPORTED; }
+  std::vector<float4> q((size_t)n);
+  for (int k = 0; k < n; ++k) {
+    const int f = fixtures[k];
+    if (f < 0 || f >= (int)fixtures_.size() || !fixtures_[f].alive) return DBX_E_INVALID;
+    const HFixture& hf = fixtures_[f];
+    int shape = -1;
+    if (hf.shape.s.type == DBX_SHAPE_CIRCLE || hf.shape.s.type == DBX_SHAPE_POLYGON) {
+      if (!hf.proxies.empty()) shape = proxies_[hf.proxies[0]].shape;
+      else { DShape ds; buildChildShape(hf.shape, 0, &ds); shape = internShape(ds); }
+    }
+    float fs, fb; std::memcpy(&fs, &shape, 4); std::memcpy(&fb, &hf.body, 4);
+    q[k] = make_float4(points[k].x, points[k].y, fs, fb);
+  }
+  int rc = push(); if (rc < 0) return rc;
+  CUDA_OR_FAIL(qIn_.reserve((size_t)n, false, stream_), "points"); CUDA_OR_FAIL(qCount_.reserve((size_t)n, false, stream_), "inside");
+  CUDA_OR_FAIL(cudaMemcpyAsync(qIn_.p, q.data(), (size_t)n * 16, cudaMemcpyHostToDevice, stream_), "points h2d");
+  CUDA_OR_FAIL(launch_test_points(dw_, L_, qIn_.p, n, qCount_.p), "test_points");
+  CUDA_OR_FAIL(cudaMemcpyAsync(inside, qCount_.p, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_), "inside d2h");
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  return n;
+}
+// b2World.ShiftOrigin (b2world.d:758-780).  Joint anchors kept in world coordinates live in the host definitions (mouse target
+// b2mousejoint.d:174-177, pulley ground anchors b2pulleyjoint.d:227-231) and are re-uploaded with the impulses pulled first.
+int World::shiftOrigin(float x, float y) {
+  if (midStep_) return DBX_E_INVALID;
+  int rc = push(); if (rc < 0) return rc;
+  if (bodies_.empty()) return 0;
+  bool anyJoint = false;
+  for (const HJoint& j : joints_) if (j.alive && (j.def.type == DBX_JOINT_MOUSE || j.def.type == DBX_JOINT_PULLEY)) anyJoint = true;
+  if (anyJoint) {
+    if (replicated_) { set_last_error("world is replicated: joints with world-space anchors cannot be shifted"); return DBX_E_UNSUPPORTED; }
+    rc = pullJoints(); if (rc < 0) return rc;
+    for (HJoint& j : joints_) {
+      if (!j.alive) continue;
+      if (j.def.type == DBX_JOINT_MOUSE) { j.def.target.x -= x; j.def.target.y -= y; }
+      else if (j.def.type == DBX_JOINT_PULLEY) { j.def.groundAnchorA.x -= x; j.def.groundAnchorA.y -= y; j.def.groundAnchorB.x -= x; j.def.groundAnchorB.y -= y; }
+    }
+    fullPushJoints_ = true;
+  }
+  CUDA_OR_FAIL(launch_shift_origin(dw_, L_, x, y), "shift_origin");
+  treeValid_ = false;                       // the LBVH boxes are stale: rebuilt before the next pair query / world query
+  hostBodiesValid_ = false; hostProxiesValid_ = false;
+  if (anyJoint) { rc = push(); if (rc < 0) return rc; }
+  return 0;
+}
+// b2Contact.GetWorldManifold for every contact, in readContacts order (ascending reference pair key)
+int World::readWorldManifolds(dbx_world_manifold* out, int cap) {
+  if (!dw_.hdr || bodiesSynced_ == 0) return 0;
+  int rc = push(); if (rc < 0) return rc;
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  int high = 0;
+  CUDA_OR_FAIL(cudaMemcpy(&high, (char*)hdr_.p + offsetof(Header, cHigh), 4, cudaMemcpyDeviceToHost), "read cHigh");
+  if (high <= 0) return 0;
+  const size_t n = (size_t)high;
+  CUDA_OR_FAIL(qOut_.reserve(2 * n, false, stream_), "world manifolds");
+  CUDA_OR_FAIL(launch_world_manifolds(dw_, L_, high, qOut_.p), "world_manifolds");
+  std::vector<float4> wm(2 * n); std::vector<unsigned long long> key(n); std::vector<uint32_t> fl(n); std::vector<uint4> mk(n);
+  CUDA_OR_FAIL(cudaMemcpyAsync(wm.data(), qOut_.p, 2 * n * 16, cudaMemcpyDeviceToHost, stream_), "world manifolds d2h");
+  CUDA_OR_FAIL(cudaMemcpyAsync(key.data(), c_key.p, n * 8, cudaMemcpyDeviceToHost, stream_), "keys d2h");
+  CUDA_OR_FAIL(cudaMemcpyAsync(fl.data(), c_flags.p, n * 4, cudaMemcpyDeviceToHost, stream_), "flags d2h");
+  CUDA_OR_FAIL(cudaMemcpyAsync(mk.data(), c_mk.p, n * 16, cudaMemcpyDeviceToHost, stream_), "mk d2h");
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  std::vector<int> order;
+  for (size_t i = 0; i < n; ++i) if (fl[i] & CF_ALIVE) order.push_back((int)i);
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+  int cnt = 0;
+  for (int i : order) {
+    if (cnt < cap) {
+      dbx_world_manifold& o = out[cnt];
+      const float4 a = wm[2 * (size_t)i], b = wm[2 * (size_t)i + 1];
+      o.normal = dbx_vec2{a.x, a.y}; o.separations[0] = a.z; o.separations[1] = a.w;
+      o.points[0] = dbx_vec2{b.x, b.y}; o.points[1] = dbx_vec2{b.z, b.w};
+      o.pointCount = (int)mk[i].w; o._pad = 0;
+    }
+    ++cnt;
+  }
+  return cnt;
+}
+// b2ContactListener.PostSolve, deferred (see include/dbox_b200.h): capacity > 0 turns recording on, 0 off
+int World::enablePostSolve(int capacity) {
+  if (capacity < 0) return DBX_E_INVALID;
+  int rc = push(); if (rc < 0) return rc;
+  if (capacity > 0) {
+    CUDA_OR_FAIL(ps_a_.reserve((size_t)capacity, false, stream_), "post-solve"); CUDA_OR_FAIL(ps_b_.reserve((size_t)capacity, false, stream_), "post-solve");
+    CUDA_OR_FAIL(ps_key_.reserve((size_t)capacity, false, stream_), "post-solve");
+  }
+  dw_.ps_a = ps_a_.p; dw_.ps_b = ps_b_.p; dw_.ps_key = ps_key_.p;
+  dw_.psCap = capacity > 0 ? (int)std::min(ps_a_.cap, std::min(ps_b_.cap, ps_key_.cap)) : 0;
+  if (dw_.hdr) { CUDA_OR_FAIL(cudaMemsetAsync((char*)hdr_.p + offsetof(Header, nPostSolve), 0, 4, stream_), "post-solve reset"); CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync"); }
+  return dw_.psCap;
+}
+int World::readPostSolve(dbx_post_solve* out, int cap) {
+  if (dw_.psCap == 0 || !dw_.hdr) return 0;
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  int n = 0;
+  CUDA_OR_FAIL(cudaMemcpy(&n, (char*)hdr_.p + offsetof(Header, nPostSolve), 4, cudaMemcpyDeviceToHost), "post-solve count");
+  if (n > dw_.psCap) { set_last_error("post-solve buffer overflow: " + std::to_string(n) + " records, capacity " + std::to_string(dw_.psCap)); return DBX_E_CAPACITY; }
+  if (!out || cap <= 0 || n == 0) return n;
+  std::vector<int4> a((size_t)n); std::vector<float4> b((size_t)n); std::vector<unsigned long long> key((size_t)n);
+  CUDA_OR_FAIL(cudaMemcpy(a.data(), ps_a_.p, (size_t)n * 16, cudaMemcpyDeviceToHost), "post-solve d2h");
+  CUDA_OR_FAIL(cudaMemcpy(b.data(), ps_b_.p, (size_t)n * 16, cudaMemcpyDeviceToHost), "post-solve d2h");
+  CUDA_OR_FAIL(cudaMemcpy(key.data(), ps_key_.p, (size_t)n * 8, cudaMemcpyDeviceToHost), "post-solve d2h");
+  std::vector<int> order((size_t)n);
+  for (int i = 0; i < n; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int x, int y) {
+    const int px = (a[x].w >> 8) & 0xFF, py = (a[y].w >> 8) & 0xFF;
+    if (px != py) return px < py;
+    // the island solve's records arrive in solver-slot order (meaningless): by key; TOI sub-steps: by key, then arrival
+    if (key[x] != key[y]) return key[x] < key[y];
+    return x < y;
+  });
+  for (int k = 0; k < n && k < cap; ++k) {
+    const int i = order[k];
+    dbx_post_solve& o = out[k];
+    o.fixtureA = a[i].x; o.fixtureB = a[i].y; o.childA = a[i].z & 0xFFFF; o.childB = (a[i].z >> 16) & 0xFFFF;
+    o.count = a[i].w & 0xFF; o.phase = (a[i].w >> 8) & 0xFF;
+    o.normalImpulses[0] = b[i].x; o.tangentImpulses[0] = b[i].y; o.normalImpulses[1] = b[i].z; o.tangentImpulses[1] = b[i].w;
   }
   return n;
 }

@@ -74,6 +74,12 @@ class World {
   int rayCastClosest(const dbx_ray* rays, int n, dbx_ray_hit* out);
   int queryAabb(const dbx_aabb* boxes, int n, int capPer, int32_t* counts, int32_t* fixtureChild);
   int refreshTreeForQuery();
+  int rayCastAll(const dbx_ray* rays, int n, int capPer, int32_t* counts, dbx_ray_hit* hits);
+  int testPoints(const int32_t* fixtures, const dbx_vec2* points, int n, int32_t* inside);
+  int shiftOrigin(float x, float y);
+  int readWorldManifolds(dbx_world_manifold* out, int cap);
+  int enablePostSolve(int capacity);
+  int readPostSolve(dbx_post_solve* out, int cap);
   int enableContactEvents(int capacity);
   int pollContactEvents(dbx_contact_event* out, int cap);
   int readTransforms(float* out, int n);
@@ -198,6 +204,7 @@ class World {
   bool evValid_ = false, evFine_ = false;
   DevBuf<char> flushBuf_; DevBuf<float4> ioBuf_, ioBuf2_; DevBuf<int> ioIds_; DevBuf<unsigned> swKeyA_, swKeyB_; DevBuf<int> swValA_, swValB_, wStart_, wEnd_;
   DevBuf<int4> ev_a_, ev_b_; DevBuf<unsigned long long> patchKeys_; bool midStep_ = false; float stepDt_ = 0; int stepVi_ = 0, stepPi_ = 0; DevBuf<float4> qIn_, qOut_; DevBuf<int> qCount_; DevBuf<int2> qPairs_; DevBuf<unsigned long long> phaseBuf_;
+  DevBuf<int4> ps_a_; DevBuf<float4> ps_b_; DevBuf<unsigned long long> ps_key_;
   bool overrideLevels_ = false;
   bool treeValid_ = false; int sinceRebuild_ = 0;
   // contact-pool watermark: every 8th step the header is copied to pinned memory without waiting; a later step looks at

@@ -470,6 +470,10 @@ class b2Fixture:
         w = self.body.world
         w._ck(w._api.fixture_set_density(w._w, self.id, v))
 
+    def TestPoint(self, p):
+        """b2fixture.d:209-212"""
+        return self.body.world.TestPoints([(self, p)])[0]
+
 
 class b2Joint:
     def __init__(self, world, jid, bodyA, bodyB):
@@ -612,14 +616,19 @@ class b2Body:
 
 
 class b2ContactListener:
-    """b2worldcallbacks.d:87-128.  BeginContact / EndContact are delivered right after b2World.Step returns; PreSolve /
-    PostSolve are not (include/dbox_b200.h, "contact listener, deferred")."""
+    """b2worldcallbacks.d:87-128.  BeginContact / EndContact / PostSolve are delivered right after b2World.Step returns
+    (include/dbox_b200.h, "contact listener, deferred"); PreSolve goes through b2World.StepWithPreSolve."""
 
     def BeginContact(self, contact):
         pass
 
     def EndContact(self, contact):
         pass
+
+    post_solve = False      # set True (or override PostSolve and set it) to have the step record b2ContactImpulse per contact
+
+    def PostSolve(self, contact, impulse):
+        """impulse = (count, normalImpulses, tangentImpulses) as b2ContactImpulse (b2worldcallbacks.d:73-79)"""
 
 
 class b2ContactView:
@@ -770,10 +779,62 @@ class b2World:
             out.append([(pairs[2 * (k * cap + i)], pairs[2 * (k * cap + i) + 1]) for i in range(counts[k])])
         return out
 
+    def RayCastAll(self, rays, cap=64):
+        """the RayCast callback that returns 1: per ray every (fixture_id, child, fraction, (px, py), (nx, ny)) hit, nearest first"""
+        rays = list(rays)
+        n = len(rays)
+        buf = (A.Ray * max(n, 1))()
+        for k, (a, b) in enumerate(rays):
+            buf[k].p1, buf[k].p2 = _v(a), _v(b)
+        counts = (C.c_int32 * max(n, 1))()
+        hits = (A.RayHit * (max(n, 1) * cap))()
+        self._ck(self._api.world_raycast_all(self._w, buf, n, cap, counts, hits))
+        out = []
+        for k in range(n):
+            if counts[k] > cap:
+                raise RuntimeError("RayCastAll: %d hits, cap %d" % (counts[k], cap))
+            out.append([(h.fixture, h.child, h.fraction, (h.point.x, h.point.y), (h.normal.x, h.normal.y)) for h in hits[k * cap:k * cap + counts[k]]])
+        return out
+
+    def TestPoints(self, fixture_points):
+        """b2Fixture.TestPoint for a batch of (fixture | fixture id, (x, y)) pairs -> [bool]"""
+        fp = list(fixture_points)
+        n = len(fp)
+        ids = (C.c_int32 * max(n, 1))(*[f if isinstance(f, int) else f.id for f, _ in fp])
+        pts = (A.Vec2 * max(n, 1))(*[_v(p) for _, p in fp])
+        out = (C.c_int32 * max(n, 1))()
+        self._ck(self._api.world_test_points(self._w, ids, pts, n, out))
+        return [bool(out[k]) for k in range(n)]
+
+    def ShiftOrigin(self, newOrigin):
+        """b2world.d:758-780"""
+        x, y = newOrigin
+        self._ck(self._api.world_shift_origin(self._w, x, y))
+
+    def GetWorldManifolds(self):
+        """b2Contact.GetWorldManifold for every contact, in read_contacts order: [(pointCount, normal, points, separations)]"""
+        n = self._ck(self._api.world_read_world_manifolds(self._w, None, 0))
+        buf = (A.WorldManifold * max(n, 1))()
+        n = self._ck(self._api.world_read_world_manifolds(self._w, buf, n))
+        return [(m.pointCount, (m.normal.x, m.normal.y), [(m.points[i].x, m.points[i].y) for i in range(2)], [m.separations[i] for i in range(2)]) for m in buf[:n]]
+
     # contact listener (b2world.d:62-66, b2worldcallbacks.d:87-128), deferred: see include/dbox_b200.h ------------
     def SetContactListener(self, listener, capacity=1 << 16):
         self._listener = listener
         self._ck(self._api.world_enable_contact_events(self._w, capacity if listener is not None else 0))
+        self._ck(self._api.world_enable_post_solve(self._w, capacity if (listener is not None and listener.post_solve) else 0))
+
+    def EnablePostSolve(self, capacity=1 << 16):
+        return self._ck(self._api.world_enable_post_solve(self._w, capacity))
+
+    def ReadPostSolve(self):
+        """PostSolve records of the last step: (phase, fixtureA, childA, fixtureB, childB, count, normalImpulses, tangentImpulses)"""
+        n = self._ck(self._api.world_read_post_solve(self._w, None, 0))
+        if n == 0:
+            return []
+        buf = (A.PostSolve * n)()
+        n = self._ck(self._api.world_read_post_solve(self._w, buf, n))
+        return [(r.phase, r.fixtureA, r.childA, r.fixtureB, r.childB, r.count, tuple(r.normalImpulses), tuple(r.tangentImpulses)) for r in buf[:n]]
 
     def EnableContactEvents(self, capacity=1 << 16):
         return self._ck(self._api.world_enable_contact_events(self._w, capacity))
@@ -794,6 +855,10 @@ class b2World:
                 self._listener.BeginContact(c)
             else:
                 self._listener.EndContact(c)
+        if self._listener.post_solve:
+            for r in self.ReadPostSolve():
+                c = b2ContactView(self, (0, r[0], 0, r[1], r[3], r[2], r[4], -1, -1))
+                self._listener.PostSolve(c, (r[5], r[6], r[7]))
 
     def Replicate(self, copies):
         """dbx_world_replicate: this world's content becomes replica 0 of `copies` independent replicas stepped together

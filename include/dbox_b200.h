@@ -408,6 +408,38 @@ int32_t dbx_world_step_begin(dbx_world* w, float dt, int32_t velocityIterations,
 int32_t dbx_world_patch_contacts(dbx_world* w, const dbx_contact_patch* patches, int32_t n);   /* unknown pairs are ignored */
 int32_t dbx_world_step_end(dbx_world* w);
 
+/* ---- more queries, accessors and world edits either side of the step ---------------------- */
+/* b2Fixture.TestPoint (dynamics/b2fixture.d:209-212) -> b2Shape.TestPoint (polygon b2polygonshape.d:265-279, circle
+ * b2circleshape.d:60-65; edges and chains contain no point, b2edgeshape.d:84-87, b2chainshape.d:196-199): n (fixture, point)
+ * pairs, one device thread each, against the bodies' current transforms; inside[k] = 1 / 0.  The testbed's mouse pick
+ * (QueryAABB over a small box, then TestPoint: demos/tests/test.d MouseDown) is dbx_world_query_aabb + this call. */
+int32_t dbx_world_test_points(dbx_world* w, const int32_t* fixtures, const dbx_vec2* points, int32_t n, int32_t* inside);
+/* b2World.RayCast with the callback that returns 1 ("report every fixture on the ray, do not clip": the testbed's
+ * RayCastMultipleCallback, demos/tests/raycast.d): every (fixture, child) the ray p1 -> p2 hits, with fraction, point and
+ * normal, sorted by (fraction, fixture, child); counts[k] may exceed capPerRay (the surplus is dropped).  The callback that
+ * returns 0 (any hit) is counts[k] > 0. */
+int32_t dbx_world_raycast_all(dbx_world* w, const dbx_ray* rays, int32_t n, int32_t capPerRay, int32_t* counts, dbx_ray_hit* hits);
+/* b2World.ShiftOrigin (dynamics/b2world.d:758-780): body transforms and sweeps, joint anchors kept in world coordinates
+ * (b2mousejoint.d:174-177, b2pulleyjoint.d:227-231) and the broadphase boxes (b2dynamictree.d:503-511) all move by -newOrigin,
+ * on the device; the pair cache, manifolds and impulses are local quantities and stay. */
+int32_t dbx_world_shift_origin(dbx_world* w, float newOriginX, float newOriginY);
+/* b2Contact.GetWorldManifold (contacts/b2contact.d:77-91) -> b2WorldManifold.Initialize (collision/b2collision.d:123-191) for
+ * every contact, computed on the device from the bodies' current transforms; records come in dbx_world_read_contacts order. */
+typedef struct dbx_world_manifold { dbx_vec2 normal; dbx_vec2 points[2]; float separations[2]; int32_t pointCount; int32_t _pad; } dbx_world_manifold;
+int32_t dbx_world_read_world_manifolds(dbx_world* w, dbx_world_manifold* out, int32_t cap);
+/* b2ContactListener.PostSolve (dynamics/b2worldcallbacks.d:120-128), deferred like Begin/EndContact: b2Island.Report
+ * (dynamics/b2island.d:438-462) runs once per island solve (:239) and once per TOI sub-step (:414) and hands every contact of
+ * that island its b2ContactImpulse.  With recording on, the same call sites append one record per contact; read returns the
+ * records of the LAST step sorted by (phase, pair key, order of arrival): phase 1 = the island solve, 2 = TOI sub-steps
+ * (a contact may appear several times there). */
+typedef struct dbx_post_solve {
+  int32_t fixtureA, fixtureB, childA, childB;
+  int32_t phase, count;                         /* b2ContactImpulse.count = the constraint's point count */
+  float normalImpulses[2], tangentImpulses[2];
+} dbx_post_solve;
+int32_t dbx_world_enable_post_solve(dbx_world* w, int32_t capacity);   /* > 0: record (at most `capacity` per step), 0: stop */
+int32_t dbx_world_read_post_solve(dbx_world* w, dbx_post_solve* out, int32_t cap);   /* out == NULL: the count only */
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,12 @@ def api():
             "body_set_active": (i32, [W, i32, i32]),
             "world_enable_contact_events": (i32, [W, i32]),
             "world_poll_contact_events": (i32, [W, P(A.ContactEvent), i32]),
+            "world_test_points": (i32, [W, P(i32), P(A.Vec2), i32, P(i32)]),
+            "world_raycast_all": (i32, [W, P(A.Ray), i32, i32, P(i32), P(A.RayHit)]),
+            "world_shift_origin": (i32, [W, f32, f32]),
+            "world_read_world_manifolds": (i32, [W, P(A.WorldManifold), i32]),
+            "world_enable_post_solve": (i32, [W, i32]),
+            "world_read_post_solve": (i32, [W, P(A.PostSolve), i32]),
         }
         for name, (res, args) in extra.items():
             fn = getattr(lib, "orc_" + name)

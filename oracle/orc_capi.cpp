@@ -480,6 +480,75 @@ int32_t orc_world_query_aabb(orc_world* w, const dbx_aabb* boxes, int32_t n, int
   }
   return n;
 }
+// b2World.RayCast with the callback that returns 1 (report every fixture, keep the full ray): sorted by (fraction, fixture, child)
+int32_t orc_world_raycast_all(orc_world* w, const dbx_ray* rays, int32_t n, int32_t capPerRay, int32_t* counts, dbx_ray_hit* hits) {
+  for (int k = 0; k < n; ++k) {
+    std::vector<dbx_ray_hit> found;
+    V2 P1 = v2(rays[k].p1), P2 = v2(rays[k].p2);
+    if ((P2 - P1).len2() > 0.0f) {
+      w->w.broadPhase.tree().rayCast([&](V2 p1, V2 p2, float maxFraction, int proxyId) -> float {
+        FixtureProxy* proxy = (FixtureProxy*)w->w.broadPhase.userData(proxyId);
+        Fixture* f = proxy->fixture;
+        float fraction; V2 normal;
+        bool hit = f->shape.rayCast(&fraction, &normal, p1, p2, maxFraction, f->body->xf, proxy->childIndex);
+        if (!hit) return maxFraction;
+        V2 point = (1.0f - fraction) * p1 + fraction * p2;
+        dbx_ray_hit h; h.fixture = f->id; h.child = proxy->childIndex; h.fraction = fraction; h.point = d2(point); h.normal = d2(normal);
+        found.push_back(h);
+        return 1.0f;
+      }, P1, P2, 1.0f);
+    }
+    std::sort(found.begin(), found.end(), [](const dbx_ray_hit& x, const dbx_ray_hit& y) {
+      return x.fraction != y.fraction ? x.fraction < y.fraction : x.fixture != y.fixture ? x.fixture < y.fixture : x.child < y.child; });
+    counts[k] = (int)found.size();
+    for (int i = 0; i < (int)found.size() && i < capPerRay; ++i) hits[(size_t)k * capPerRay + i] = found[i];
+  }
+  return n;
+}
+// b2Fixture.TestPoint (b2fixture.d:209-212)
+int32_t orc_world_test_points(orc_world* w, const int32_t* fixtures, const dbx_vec2* points, int32_t n, int32_t* inside) {
+  for (int k = 0; k < n; ++k) {
+    const int id = fixtures[k];
+    if (id < 0 || id >= (int)w->w.fixturesById.size() || !w->w.fixturesById[id]) return DBX_E_INVALID;
+    const Fixture* f = w->w.fixturesById[id];
+    inside[k] = f->shape.testPoint(f->body->xf, v2(points[k])) ? 1 : 0;
+  }
+  return n;
+}
+int32_t orc_world_shift_origin(orc_world* w, float x, float y) { w->w.shiftOrigin(V2(x, y)); return 0; }
+// b2Contact.GetWorldManifold (contacts/b2contact.d:77-91) for every contact, in orc_world_read_contacts order
+int32_t orc_world_read_world_manifolds(orc_world* w, dbx_world_manifold* out, int32_t cap) {
+  int n = 0;
+  for (Contact* c = w->w.contactList; c; c = c->next) {
+    if (n < cap) {
+      WorldManifold wm;
+      const Shape& sa = c->fixtureA->shape; const Shape& sb = c->fixtureB->shape;
+      wm.initialize(&c->manifold, c->fixtureA->body->xf, sa.radius, c->fixtureB->body->xf, sb.radius);
+      dbx_world_manifold& o = out[n];
+      std::memset(&o, 0, sizeof(o));
+      o.pointCount = c->manifold.pointCount;
+      if (o.pointCount > 0) {
+        o.normal = d2(wm.normal);
+        for (int i = 0; i < o.pointCount && i < 2; ++i) { o.points[i] = d2(wm.points[i]); o.separations[i] = wm.separations[i]; }
+      }
+    }
+    ++n;
+  }
+  return n;
+}
+// the PostSolve call log of the last step, in the reference's CALL order
+int32_t orc_world_enable_post_solve(orc_world* w, int32_t capacity) { w->w.recordPostSolve = capacity > 0; w->w.postSolveLog.clear(); return capacity; }
+int32_t orc_world_read_post_solve(orc_world* w, dbx_post_solve* out, int32_t cap) {
+  const int n = (int)w->w.postSolveLog.size();
+  if (!out || cap <= 0) return n;
+  for (int i = 0; i < n && i < cap; ++i) {
+    const World::PostSolveRec& r = w->w.postSolveLog[i];
+    dbx_post_solve& o = out[i];
+    o.fixtureA = r.fixtureA; o.fixtureB = r.fixtureB; o.childA = r.childA; o.childB = r.childB; o.phase = r.phase; o.count = r.count;
+    for (int j = 0; j < 2; ++j) { o.normalImpulses[j] = r.normalImpulses[j]; o.tangentImpulses[j] = r.tangentImpulses[j]; }
+  }
+  return n;
+}
 // the listener call log since the last poll, in the reference's CALL order (the CUDA library returns the same events sorted)
 int32_t orc_world_enable_contact_events(orc_world* w, int32_t capacity) {
   w->w.recordContactEvents = capacity > 0; w->w.contactEvents.clear(); return capacity;

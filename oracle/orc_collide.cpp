@@ -1155,6 +1155,21 @@ static bool rayCastEdge(float* fraction, V2* normalOut, V2 P1, V2 P2, float maxF
   return true;
 }
 
+bool Shape::testPoint(const Xf& xf, V2 pt) const {
+  if (type == kCircle) {
+    V2 center = xf.p + mul(xf.q, p);
+    V2 d = pt - center;
+    return dot(d, d) <= radius * radius;
+  }
+  if (type != kPolygon) return false;
+  V2 pLocal = mulT(xf.q, pt - xf.p);
+  for (int i = 0; i < count; ++i) {
+    float d = dot(normals[i], pLocal - verts[i]);
+    if (d > 0.0f) return false;
+  }
+  return true;
+}
+
 bool Shape::rayCast(float* fraction, V2* normalOut, V2 P1, V2 P2, float maxFraction, const Xf& xf, int child) const {
   if (type == kCircle) {
     V2 position = xf.p + mul(xf.q, p);

@@ -48,6 +48,8 @@ struct Shape {
   void computeMass(MassData* md, float density) const;
   // b2Shape.RayCast (b2circleshape.d:67-94, b2edgeshape.d:96-150, b2polygonshape.d:279-332, b2chainshape.d:204-223)
   bool rayCast(float* fraction, V2* normal, V2 p1, V2 p2, float maxFraction, const Xf& xf, int child) const;
+  // b2Shape.TestPoint (b2circleshape.d:60-65, b2polygonshape.d:265-279; false for edges b2edgeshape.d:84-87 and chains b2chainshape.d:196-199)
+  bool testPoint(const Xf& xf, V2 pt) const;
 };
 
 // b2collision.d:38-114

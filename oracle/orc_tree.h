@@ -60,6 +60,8 @@ class DynamicTree {
   }
   void* userData(int id) const { return nodes_[id].userData; }
   const AABB& fatAABB(int id) const { return nodes_[id].aabb; }
+  // b2dynamictree.d:503-511: every pool node, in use or not
+  void shiftOrigin(V2 newOrigin) { for (auto& n : nodes_) { n.aabb.lo -= newOrigin; n.aabb.hi -= newOrigin; } }
   void setFatAABB(int id, const AABB& a) { nodes_[id].aabb = a; }  // state import only (tests)
 
   template <class F> void query(F&& cb, const AABB& aabb) const {

@@ -806,6 +806,20 @@ struct Island {
   void add(Body* b) { b->islandIndex = (int)bodies.size(); bodies.push_back(b); }
   void add(Contact* c) { contacts.push_back(c); }
   void add(Joint* j) { joints.push_back(j); }
+  // b2island.d:438-462: hand every contact of the island its b2ContactImpulse (here: append to the world's call log)
+  std::vector<World::PostSolveRec>* postSolveLog = nullptr; int reportPhase = 1;
+  void report(const ContactVelocityConstraint* constraints) {
+    if (postSolveLog == nullptr) return;
+    for (size_t i = 0; i < contacts.size(); ++i) {
+      const Contact* c = contacts[i];
+      const ContactVelocityConstraint* vc = constraints + i;
+      World::PostSolveRec r{};
+      r.phase = reportPhase; r.fixtureA = c->fixtureA->id; r.childA = c->indexA; r.fixtureB = c->fixtureB->id; r.childB = c->indexB;
+      r.count = vc->pointCount;
+      for (int j = 0; j < vc->pointCount; ++j) { r.normalImpulses[j] = vc->points[j].normalImpulse; r.tangentImpulses[j] = vc->points[j].tangentImpulse; }
+      postSolveLog->push_back(r);
+    }
+  }
 
   // b2island.d:75-280
   void solve(Profile* profile, const TimeStep& step, V2 gravity, bool allowSleep) {
@@ -872,6 +886,7 @@ struct Island {
       b->synchronizeTransform();
     }
     profile->solvePosition = (float)(nowMs() - t2);
+    report(contactSolver.vcs.data());            // b2island.d:239
     if (allowSleep) {
       float minSleepTime = kMaxFloat;
       const float linTolSqr = kLinearSleepTolerance * kLinearSleepTolerance;
@@ -937,6 +952,7 @@ struct Island {
       b->linearVelocity = v; b->angularVelocity = w;
       b->synchronizeTransform();
     }
+    report(contactSolver.vcs.data());            // b2island.d:414
   }
 };
 }  // namespace
@@ -945,6 +961,7 @@ struct Island {
 void World::solve(const TimeStep& step) {
   profile.solveInit = 0.0f; profile.solveVelocity = 0.0f; profile.solvePosition = 0.0f;
   Island island(bodyCount, contactCount);
+  if (recordPostSolve) { island.postSolveLog = &postSolveLog; island.reportPhase = 1; }
   for (Body* b = bodyList; b; b = b->next) b->flags &= ~bIsland;
   for (Contact* c = contactList; c; c = c->next) c->flags &= ~cIsland;
   for (Joint* j = jointList; j; j = j->next) j->islandFlag = false;
@@ -1007,6 +1024,7 @@ void World::solve(const TimeStep& step) {
 // ------------------------------------------------------------------ World::solveTOI (b2world.d:1127-1452)
 void World::solveTOI(const TimeStep& step) {
   Island island(2 * kMaxTOIContacts, kMaxTOIContacts);
+  if (recordPostSolve) { island.postSolveLog = &postSolveLog; island.reportPhase = 2; }
   if (stepComplete) {
     for (Body* b = bodyList; b; b = b->next) { b->flags &= ~bIsland; b->sweep.alpha0 = 0.0f; }
     for (Contact* c = contactList; c; c = c->next) { c->flags &= ~(cToi | cIsland); c->toiCount = 0; c->toi = 1.0f; }
@@ -1135,6 +1153,7 @@ void World::stepHalves(float dt, int velocityIterations, int positionIterations,
   evPhase = 1;
   if (halves & 1) { double t = nowMs(); collide(); profile.collide = (float)(nowMs() - t); }
   if (!(halves & 2)) { locked = false; return; }
+  postSolveLog.clear();
   if (stepComplete && step.dt > 0.0f) { double t = nowMs(); solve(step); profile.solve = (float)(nowMs() - t); }
   evPhase = 2;
   if (continuousPhysics && step.dt > 0.0f) { double t = nowMs(); solveTOI(step); profile.solveTOI = (float)(nowMs() - t); }
@@ -1143,6 +1162,22 @@ void World::stepHalves(float dt, int velocityIterations, int positionIterations,
   if (clearForcesFlag) clearForces();
   locked = false;
   profile.step = (float)(nowMs() - t0);
+}
+
+// b2world.d:758-780
+void World::shiftOrigin(V2 newOrigin) {
+  if (locked) return;
+  for (Body* b = bodyList; b; b = b->next) {
+    b->xf.p -= newOrigin;
+    b->sweep.c0 -= newOrigin;
+    b->sweep.c -= newOrigin;
+  }
+  for (Joint* j = jointList; j; j = j->next) {
+    // b2Joint.ShiftOrigin is a no-op except b2mousejoint.d:174-177 and b2pulleyjoint.d:227-231
+    if (j->type == jMouse) static_cast<MouseJoint*>(j)->targetA -= newOrigin;
+    else if (j->type == jPulley) { PulleyJoint* pj = static_cast<PulleyJoint*>(j); pj->groundAnchorA -= newOrigin; pj->groundAnchorB -= newOrigin; }
+  }
+  broadPhase.tree().shiftOrigin(newOrigin);          // b2broadphase.d:237-240
 }
 
 void World::clearForces() {

@@ -244,6 +244,10 @@ struct World {
   struct ContactEvt { int type, phase, step, fixtureA, childA, fixtureB, childB, bodyA, bodyB; };
   std::vector<ContactEvt> contactEvents; bool recordContactEvents = false; int evPhase = 3; int stepCount = 0;
   void logContactEvent(int type, const Contact* c);
+  // b2ContactListener.PostSolve call log of the last step (b2Island.Report, b2island.d:438-462; call sites :239 and :414)
+  struct PostSolveRec { int phase, fixtureA, childA, fixtureB, childB, count; float normalImpulses[2], tangentImpulses[2]; };
+  std::vector<PostSolveRec> postSolveLog; bool recordPostSolve = false;
+  void shiftOrigin(V2 newOrigin);                     // b2world.d:758-780
   std::vector<std::pair<FixtureProxy*, FixtureProxy*>> lastPairs;  // unique pairs handed to AddPair by the last UpdatePairs
   std::vector<Contact*> lastSolveOrder;   // contacts in the order islands solved them in the last Solve
 };

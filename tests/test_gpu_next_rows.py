@@ -1,0 +1,241 @@
+"""SURVEY.md 8(f) rows through the C ABI against the oracle: b2Fixture.TestPoint, the report-everything RayCast callback,
+b2Contact.GetWorldManifold, b2World.ShiftOrigin and b2ContactListener.PostSolve.  Where the two sides hold the same state
+(before the first step, or after the oracle's state was transplanted into the device world) the answers must be identical;
+where they stepped separately the scenes are order-free, so they agree to float rounding."""
+import random
+
+import pytest
+
+from dbox_b200 import scenes
+from dbox_b200.world import (b2BodyDef, b2CircleShape, b2EdgeShape, b2MouseJointDef, b2PolygonShape, b2PulleyJointDef, b2World,
+                             b2_dynamicBody)
+from tests.parity import contact_key, transplant
+from tests.test_gpu_features import _dyn, _ground, _query_scene, both
+
+pytestmark = pytest.mark.gpu
+DT = 1.0 / 60.0
+
+
+def _same_state_pair(gpu_api, oracle_api, steps):
+    """the query scene stepped by the oracle, its state copied into a device world built the same way"""
+    wo, bo = _query_scene(oracle_api)
+    wg, bg = _query_scene(gpu_api)
+    for _ in range(steps):
+        wo.Step(DT, 8, 3)
+    if steps:
+        transplant(wo, wg)
+    return wg, bg, wo, bo
+
+
+@pytest.mark.parametrize("steps", [0, 45])
+def test_test_point_matches_reference(gpu_api, oracle_api, steps):
+    """b2Fixture.TestPoint (b2fixture.d:209-212; polygon b2polygonshape.d:265-279, circle b2circleshape.d:60-65, never inside an
+    edge or a chain) on identical states: identical answers, including points on and next to the boundary"""
+    wg, bg, wo, bo = _same_state_pair(gpu_api, oracle_api, steps)
+    rng = random.Random(3)
+    queries_g, queries_o = [], []
+    for b_g, b_o in zip(bg, bo):
+        p = b_o.GetPosition()
+        for _ in range(40):
+            q = (p.x + rng.uniform(-1.5, 1.5), p.y + rng.uniform(-1.5, 1.5))
+            queries_g.append((b_g.fixtures[0], q)); queries_o.append((b_o.fixtures[0], q))
+        queries_g.append((b_g.fixtures[0], (p.x, p.y))); queries_o.append((b_o.fixtures[0], (p.x, p.y)))
+    # the ground's chain (fixture 0) and edge (fixture 1) never contain a point
+    for fid in (0, 1):
+        for q in ((0.0, 0.5), (-30.0, 10.0), (-10.0, 1.0)):
+            queries_g.append((fid, q)); queries_o.append((fid, q))
+    ins_g, ins_o = wg.TestPoints(queries_g), wo.TestPoints(queries_o)
+    assert ins_g == ins_o
+    assert 300 < sum(ins_o) < len(ins_o) - 300          # the sample really straddles the shapes
+    assert not any(ins_g[-6:])
+    assert bg[0].fixtures[0].TestPoint(tuple(bo[0].GetPosition())) is True
+    with pytest.raises(RuntimeError):
+        wg.TestPoints([(10 ** 6, (0.0, 0.0))])
+
+
+@pytest.mark.parametrize("steps", [0, 45])
+def test_raycast_all_matches_reference(gpu_api, oracle_api, steps):
+    """b2World.RayCast with a callback that returns 1 (every fixture along the whole ray, b2world.d:577-587 and the wrapper
+    :1605-1624): same hit lists (fixture, child), fractions / points / normals to float rounding"""
+    wg, bg, wo, bo = _same_state_pair(gpu_api, oracle_api, steps)
+    rng = random.Random(17)
+    rays = [((rng.uniform(-35, 35), rng.uniform(-2, 25)), (rng.uniform(-35, 35), rng.uniform(-2, 25))) for _ in range(300)]
+    rays += [((-40.0, 3.0), (40.0, 3.0)), ((0.0, 30.0), (0.0, -5.0)), ((3.0, 3.0), (3.0, 3.0)), ((-31.0, 10.0), (-29.0, 10.0))]
+    hg, ho = wg.RayCastAll(rays, cap=96), wo.RayCastAll(rays, cap=96)
+    multi = 0
+    for k, (a, b) in enumerate(zip(hg, ho)):
+        assert [(h[0], h[1]) for h in a] == [(h[0], h[1]) for h in b], (k, a, b)
+        multi += len(b) > 1
+        for x, y in zip(a, b):
+            assert abs(x[2] - y[2]) <= 1e-6 and max(abs(x[3][0] - y[3][0]), abs(x[3][1] - y[3][1])) <= 1e-4, (k, x, y)
+            assert max(abs(x[4][0] - y[4][0]), abs(x[4][1] - y[4][1])) <= 1e-5, (k, x, y)
+        # the closest-hit query is the head of the list
+        if b:
+            c = wg.RayCastClosest([rays[k]])[0]
+            assert abs(c[2] - a[0][2]) <= 1e-6
+    assert multi > 40 and hg[-2] == []                  # a zero-length ray hits nothing
+    assert len(hg[-1]) == 1 and hg[-1][0][0] == 1       # the vertical edge fixture
+    # the surplus over cap is counted, not stored
+    with pytest.raises(RuntimeError):
+        wg.RayCastAll([((-40.0, 3.0), (40.0, 3.0)), ((-40.0, 1.5), (40.0, 1.5))], cap=1)
+
+
+def test_world_manifolds_match_reference(gpu_api, oracle_api):
+    """b2Contact.GetWorldManifold (b2contact.d:77-91) -> b2WorldManifold.Initialize (b2collision.d:123-191): normal, points and
+    separations of every contact, computed on the device, against the oracle on the same state"""
+    wg, bg, wo, bo = _same_state_pair(gpu_api, oracle_api, 90)
+    rg, ng = wg.read_contacts(); ro, no = wo.read_contacts()
+    mg, mo = wg.GetWorldManifolds(), wo.GetWorldManifolds()
+    assert ng == no == len(mg) == len(mo) and ng > 60
+    by_key = {contact_key(ro[i]): mo[i] for i in range(no)}
+    touching = types = 0
+    seen_types = set()
+    for i in range(ng):
+        a, b = mg[i], by_key[contact_key(rg[i])]
+        assert a[0] == b[0]
+        if a[0] == 0:
+            continue
+        touching += 1
+        seen_types.add(rg[i].manifold.type)
+        assert max(abs(a[1][0] - b[1][0]), abs(a[1][1] - b[1][1])) <= 1e-6, (i, a, b)
+        for k in range(a[0]):
+            assert max(abs(a[2][k][0] - b[2][k][0]), abs(a[2][k][1] - b[2][k][1])) <= 2e-5, (i, a, b)
+            assert abs(a[3][k] - b[3][k]) <= 2e-6, (i, a, b)
+            assert a[3][k] < 0.25                           # (evaluated at the post-step transforms, so not exactly inside the skin)
+    assert touching > 40 and len(seen_types) == 3           # circles, faceA and faceB manifolds all present
+    # an empty world has none
+    assert b2World((0.0, -10.0), api=gpu_api).GetWorldManifolds() == []
+
+
+def _shift_scene(api):
+    """order-free: separate boxes and circles resting on the ground, a pulley pair hanging from two ground anchors, a body on
+    a mouse joint: one constraint row per body"""
+    w = b2World((0.0, -10.0), api=api)
+    g = _ground(w, api)
+    out = []
+    for k in range(8):
+        b = _dyn(w, -20.0 + 3.0 * k, 0.6 + 0.05 * k)
+        if k % 2:
+            s = b2CircleShape(api); s.m_radius = 0.5
+        else:
+            s = b2PolygonShape(api); s.SetAsBox(0.5, 0.5)
+        b.CreateFixture(s, 1.0)
+        out.append(b)
+    pa, pb = _dyn(w, 10.0, 6.0), _dyn(w, 14.0, 6.0)
+    for b in (pa, pb):
+        s = b2PolygonShape(api); s.SetAsBox(0.5, 0.5); b.CreateFixture(s, 1.0 if b is pa else 1.3)
+    pj = b2PulleyJointDef(); pj.Initialize(pa, pb, (10.0, 12.0), (14.0, 12.0), (10.0, 6.5), (14.0, 6.5), 1.0)
+    w.CreateJoint(pj)
+    m = _dyn(w, 22.0, 8.0)
+    s = b2CircleShape(api); s.m_radius = 0.4; m.CreateFixture(s, 1.0)
+    md = b2MouseJointDef(); md.bodyA, md.bodyB = g, m
+    md.target.Set(22.0, 8.0); md.maxForce = 1000.0
+    w.CreateJoint(md)
+    return w, out + [pa, pb, m]
+
+
+def test_shift_origin_matches_reference(gpu_api, oracle_api):
+    """b2World.ShiftOrigin (b2world.d:758-780): bodies, world-space joint anchors (mouse target, pulley ground anchors) and the
+    broadphase boxes move; contacts, impulses and the pair cache do not notice"""
+    origin = (100.0, -37.5)
+    state = {}
+
+    def each(k, wg, wo):
+        if k == 39:
+            state["contacts"] = (wg.counts().contacts, wo.counts().contacts)
+            for w in (wg, wo):
+                w.EnableContactEvents(1024); w.PollContactEvents()
+                w.ShiftOrigin(origin)
+            pg, n = wg.read_proxies(); po, m = wo.read_proxies()
+            assert n == m
+            fat = {(po[i].fixture, po[i].child): po[i].fat for i in range(m)}
+            for i in range(n):                                   # the tree's boxes moved by the same float subtraction
+                f = fat[(pg[i].fixture, pg[i].child)]
+                assert (pg[i].fat.lo.x, pg[i].fat.lo.y, pg[i].fat.hi.x, pg[i].fat.hi.y) == (f.lo.x, f.lo.y, f.hi.x, f.hi.y)
+    wg, wo, bg, bo = both(gpu_api, oracle_api, _shift_scene, 120, each=each, tol_p=3e-5)
+    assert abs(bo[0].GetPosition().x - (-20.0 - origin[0])) < 1e-3 and abs(bo[0].GetPosition().y - (0.5 + 0.01 - origin[1])) < 2e-2
+    assert state["contacts"] == (wg.counts().contacts, wo.counts().contacts) and state["contacts"][0] >= 8
+    assert wg.PollContactEvents() == wo.PollContactEvents() == []     # nothing began or ended because of the shift
+    # queries see the shifted world
+    hit = wg.RayCastClosest([((-20.0 - origin[0], 10.0 - origin[1]), (-20.0 - origin[0], -5.0 - origin[1]))])[0]
+    assert hit[0] == bg[0].fixtures[0].id
+    assert wg.RayCastClosest([((-20.0, 10.0), (-20.0, -5.0))])[0][0] == -1
+
+
+def _impact_scene(api):
+    """order-free PostSolve scene: separate resting bodies (island solve) and two bullets flying at a thin wall (TOI sub-steps)"""
+    w = b2World((0.0, -10.0), api=api)
+    g = _ground(w, api)
+    wall = b2EdgeShape(api); wall.Set((10.0, 0.0), (10.0, 20.0)); g.CreateFixture(wall, 0.0)
+    out = []
+    for k in range(6):
+        b = _dyn(w, -20.0 + 3.0 * k, 0.55)
+        if k % 2:
+            s = b2CircleShape(api); s.m_radius = 0.5
+        else:
+            s = b2PolygonShape(api); s.SetAsBox(0.5, 0.5)
+        b.CreateFixture(s, 1.0 + 0.1 * k)
+        out.append(b)
+    for k in range(2):
+        b = _dyn(w, 0.0, 5.0 + 6.0 * k, bullet=True, gravityScale=0.0)
+        s = b2CircleShape(api); s.m_radius = 0.25; b.CreateFixture(s, 1.0)
+        b.SetLinearVelocity((300.0 + 50.0 * k, 0.0))
+        out.append(b)
+    return w, out
+
+
+def test_post_solve_records_match_reference(gpu_api, oracle_api):
+    """b2ContactListener.PostSolve (b2worldcallbacks.d:120-128) through b2Island.Report (b2island.d:438-462): one record per
+    contact of every solved island (phase 1, :239) and of every TOI mini-island (phase 2, :414) with the constraint's impulses"""
+    seen = {1: 0, 2: 0}
+
+    def each(k, wg, wo):
+        rg, ro = wg.ReadPostSolve(), sorted(wo.ReadPostSolve(), key=lambda r: (r[0], r[1:5]))
+        rg = sorted(rg, key=lambda r: (r[0], r[1:5]))
+        assert [r[:6] for r in rg] == [r[:6] for r in ro], (k, rg, ro)
+        for a, b in zip(rg, ro):
+            seen[a[0]] += 1
+            for j in range(a[5]):
+                assert abs(a[6][j] - b[6][j]) <= 2e-4 * max(1.0, abs(b[6][j])), (k, a, b)
+                assert abs(a[7][j] - b[7][j]) <= 2e-4 * max(1.0, abs(b[7][j])), (k, a, b)
+            assert a[6][1] == 0.0 or a[5] == 2
+
+    def build(api):
+        w, out = _impact_scene(api)
+        assert w.EnablePostSolve(4096) >= 4096
+        return w, out
+    both(gpu_api, oracle_api, build, 60, each=each)
+    assert seen[1] > 200 and seen[2] >= 2
+    # records are per step: a step without touching contacts leaves none; switching off stops recording
+    w = b2World((0.0, -10.0), api=gpu_api)
+    b = _dyn(w, 0.0, 50.0); s = b2CircleShape(gpu_api); s.m_radius = 0.5; b.CreateFixture(s, 1.0)
+    w.EnablePostSolve(16); w.Step(DT, 8, 3)
+    assert w.ReadPostSolve() == []
+
+
+def test_post_solve_listener_on_pyramid(gpu_api, oracle_api):
+    """the deferred listener delivers PostSolve after Step: on the pyramid the same contacts are reported as in the oracle's
+    call log while the contact sets still agree, and the normal impulses carry the pile's weight"""
+    from dbox_b200.world import b2ContactListener
+
+    class L(b2ContactListener):
+        post_solve = True
+
+        def __init__(self):
+            self.calls = []
+
+        def PostSolve(self, contact, impulse):
+            self.calls.append(((contact.fixtureA_id, contact.childA, contact.fixtureB_id, contact.childB), impulse))
+    wg, _ = scenes.pyramid(api=gpu_api, count=12)
+    wo, _ = scenes.pyramid(api=oracle_api, count=12)
+    lst = L()
+    wg.SetContactListener(lst, capacity=1 << 14)
+    wo.EnablePostSolve(1 << 14)
+    for k in range(40):
+        lst.calls = []
+        wg.Step(DT, 8, 3); wo.Step(DT, 8, 3)
+        ro = wo.ReadPostSolve()
+        assert sorted(c[0] for c in lst.calls) == sorted((r[1], r[2], r[3], r[4]) for r in ro), k
+    total_g = sum(sum(c[1][1][:c[1][0]]) for c in lst.calls)
+    total_o = sum(sum(r[6][:r[5]]) for r in ro)
+    assert total_o > 0 and abs(total_g - total_o) <= 0.02 * total_o
