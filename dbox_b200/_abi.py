@@ -97,7 +97,8 @@ class ContactPatch(C.Structure):
                 ("friction", c_f32), ("restitution", c_f32), ("tangentSpeed", c_f32)]
 
 
-PATCH_ENABLED, PATCH_FRICTION, PATCH_RESTITUTION, PATCH_TANGENT_SPEED = 1, 2, 4, 8
+PATCH_ENABLED, PATCH_FRICTION, PATCH_RESTITUTION, PATCH_TANGENT_SPEED, PATCH_DESTROY = 1, 2, 4, 8, 16
+FILTER_LOG, FILTER_REPLACES_DEFAULT = 1, 2
 
 
 class Ray(C.Structure):
@@ -250,6 +251,8 @@ PROTOTYPES = {
     "world_read_world_manifolds": (c_i32, [W, P(WorldManifold), c_i32]),
     "world_enable_post_solve": (c_i32, [W, c_i32]),
     "world_read_post_solve": (c_i32, [W, P(PostSolve), c_i32]),
+    "world_set_user_filter": (c_i32, [W, c_i32]),
+    "world_poll_new_contacts": (c_i32, [W, P(c_i32), c_i32]),
 }
 
 

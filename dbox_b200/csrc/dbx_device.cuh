@@ -25,7 +25,8 @@ DBX_HD int body_type(uint32_t f) { return (int)((f & BF_TYPE_MASK) >> BF_TYPE_SH
 enum : uint32_t {
   CF_ISLAND = 0x0001, CF_TOUCHING = 0x0002, CF_ENABLED = 0x0004, CF_FILTER = 0x0008, CF_BULLET_HIT = 0x0010, CF_TOI = 0x0020,
   CF_ALIVE = 0x0100, CF_SENSOR = 0x0200, CF_SOLVE = 0x0400 /* in an awake island this step */,
-  CF_FRESH = 0x0800 /* created by this step's FindNewContacts: the overlapped TOI pre-evaluation must not look at it */
+  CF_FRESH = 0x0800 /* created by this step's FindNewContacts: the overlapped TOI pre-evaluation must not look at it */,
+  CF_NEW = 0x1000 /* created since the host last polled the new-contact list (user contact filter, deferred) */
 };
 enum { FXF_SENSOR = 1 };
 enum { PF_ALIVE = 1, PF_MOVED = 2 };
@@ -72,6 +73,7 @@ struct Header {
   int jointColourOff[kMaxJointColours + 1];
   int nToi;           // entries of c_toiList: contacts the TOI pass can ever care about this step (listed by k_collide)
   int nPostSolve;     // PostSolve records of the current step (may exceed psCap: the surplus is lost and reported)
+  int nNewContacts;   // scratch counter of k_list_new_contacts
 };
 
 struct DevWorld {
@@ -138,6 +140,7 @@ struct DevWorld {
   float4* ps_b;      //         (normalImpulse0, tangentImpulse0, normalImpulse1, tangentImpulse1)
   unsigned long long* ps_key;   //  pair key
   int psCap;         // 0 = PostSolve recording off
+  int userFilter;    // DBX_FILTER_* (user b2ContactFilter, deferred): bit 0 tag new contacts, bit 1 skip the default filter
   // world-local solve (batched replicas without joints): solver slots sorted by (replica, colour) instead of colour alone
   const unsigned* sw_key;   // [nSolve] sorted (replica << swColourBits | colour)
   int swColourBits;

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256, 4) k_collide(const __grid_constant__ DevW
     const uint32_t flA = W.b_flags[ids.z], flB = W.b_flags[ids.w];
     uint4 mk = W.c_mk[i];
     if (flags & CF_FILTER) {
-      if (!body_should_collide(W, ids.w, ids.z, flB, flA) || !filter_should_collide(W, fx.x, fx.y)) {
+      if (!body_should_collide(W, ids.w, ids.z, flB, flA) || (!(W.userFilter & 2) && !filter_should_collide(W, fx.x, fx.y))) {
         destroy_contact(W, i, flags, ids.z, ids.w, (int)mk.w);
         continue;
       }
@@ -953,7 +953,7 @@ DBX_D void add_pair(const DevWorld& W, int2 pr) {
   if (hash_find(W, key) >= 0) return;                   // a contact for this (fixture, child) pair already exists (:75-100)
   const uint32_t flA = W.b_flags[bodyA], flB = W.b_flags[bodyB];
   if (!body_should_collide(W, bodyB, bodyA, flB, flA)) return;
-  if (!filter_should_collide(W, pa.x, pb.x)) return;
+  if (!(W.userFilter & 2) && !filter_should_collide(W, pa.x, pb.x)) return;   // bit 1: the user's filter replaces the default one
   // type registry (b2contact.d:425-437): A must be the primary type
   const int t1 = W.shapes[pa.w].type, t2 = W.shapes[pb.w].type;
   bool has, primary;
@@ -975,7 +975,7 @@ DBX_D void add_pair(const DevWorld& W, int2 pr) {
   W.c_key[slot] = key;
   W.c_ids[slot] = make_int4(proxyA, proxyB, ia.z, ib.z);
   W.c_fix[slot] = make_int4(ia.x, ib.x, ia.w, ib.w);
-  W.c_flags[slot] = CF_ALIVE | CF_ENABLED | CF_FRESH | (sensor ? CF_SENSOR : 0);
+  W.c_flags[slot] = CF_ALIVE | CF_ENABLED | CF_FRESH | (sensor ? CF_SENSOR : 0) | ((W.userFilter & 1) ? CF_NEW : 0);
   { const int k = atomicAdd(&W.hdr->nFresh, 1); if (k < W.cCap) W.c_work[k] = slot; }   // c_work is idle between the colouring pass and the next step
   W.c_m0[slot] = make_float4(0, 0, 0, 0);
   W.c_m1[slot] = make_float4(0, 0, 0, 0);
@@ -1136,6 +1136,18 @@ __global__ void __launch_bounds__(256) k_patch_contacts(const __grid_constant__ 
     const int i = hash_find(W, keys[k]);
     if (i < 0) continue;
     const int m = masks[k];
+    if (m & 16) {   // vetoed by the user's b2ContactFilter: b2ContactManager.Destroy (b2contactmanager.d:183-246)
+      const uint32_t flags = W.c_flags[i];
+      const int4 ids = W.c_ids[i];
+      if ((int)W.c_mk[i].w > 0 && !(flags & CF_SENSOR)) { wake_body_now(W, ids.z); wake_body_now(W, ids.w); }
+      if (flags & CF_TOUCHING) emit_contact_event(W, EV_END, 3, i, ids, W.c_fix[i]);
+      hash_remove(W, W.c_key[i]);
+      W.c_flags[i] = 0;
+      W.c_colour[i] = -1;
+      const int slot = atomicAdd(&W.hdr->nFree, 1);
+      W.c_free[slot] = i;
+      continue;
+    }
     if (m & 1) { uint32_t f = W.c_flags[i]; W.c_flags[i] = (m & 0x100) ? (f | CF_ENABLED) : (f & ~CF_ENABLED); }
     if (m & 14) {
       float4 mat = W.c_mat[i];
@@ -1145,6 +1157,20 @@ __global__ void __launch_bounds__(256) k_patch_contacts(const __grid_constant__ 
       if (m & 8) mat.z = v.z;
       W.c_mat[i] = mat;
     }
+  }
+}
+// user contact filter, deferred: list (and untag unless `peek`) the contacts created since the last poll
+__global__ void __launch_bounds__(256) k_list_new_contacts(const __grid_constant__ DevWorld W, int4* out, unsigned long long* keys, int cap, int peek) {
+  const int n = W.hdr->cHigh;
+  GRID_STRIDE(i, n) {
+    const uint32_t flags = W.c_flags[i];
+    if ((flags & (CF_ALIVE | CF_NEW)) != (CF_ALIVE | CF_NEW)) continue;
+    const int k = atomicAdd(&W.hdr->nNewContacts, 1);
+    if (peek || k >= cap) continue;
+    W.c_flags[i] = flags & ~CF_NEW;
+    const int4 ids = W.c_ids[i], fx = W.c_fix[i];
+    out[k] = make_int4(fx.x, W.p_ids[ids.x].y, fx.y, W.p_ids[ids.y].y);
+    keys[k] = W.c_key[i];
   }
 }
 // b2Fixture.SetSensor: the contacts of that fixture re-derive their cached sensor bit from the two fixtures
@@ -1852,6 +1878,10 @@ cudaError_t launch_api_contacts(const DevWorld& W, const LaunchCfg& L, int body,
 }
 cudaError_t launch_patch_contacts(const DevWorld& W, const LaunchCfg& L, const unsigned long long* keys, const float4* vals, const int* masks, int n) {
   ++L.launches; k_patch_contacts<<<(n + 255) / 256, 256, 0, L.stream>>>(W, keys, vals, masks, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_list_new_contacts(const DevWorld& W, const LaunchCfg& L, int4* out, unsigned long long* keys, int cap, int peek) {
+  ++L.launches; k_list_new_contacts<<<L.gridWide, 256, 0, L.stream>>>(W, out, keys, cap, peek);
   return cudaGetLastError();
 }
 cudaError_t launch_api_resensor(const DevWorld& W, const LaunchCfg& L, int fixture) {

@@ -37,6 +37,7 @@ cudaError_t launch_test_points(const DevWorld& W, const LaunchCfg& L, const floa
 cudaError_t launch_shift_origin(const DevWorld& W, const LaunchCfg& L, float ox, float oy);
 cudaError_t launch_world_manifolds(const DevWorld& W, const LaunchCfg& L, int high, float4* out);
 cudaError_t launch_post_solve(const DevWorld& W, const LaunchCfg& L);
+cudaError_t launch_list_new_contacts(const DevWorld& W, const LaunchCfg& L, int4* out, unsigned long long* keys, int cap, int peek);
 cudaError_t stage_toi(DevWorld& W, const LaunchCfg& L);
 cudaError_t stage_toi_pre(const DevWorld& W, const LaunchCfg& L, cudaStream_t aux);                               // b2World.SolveTOI
 cudaError_t stage_rebuild_hash(const DevWorld& W, const LaunchCfg& L);

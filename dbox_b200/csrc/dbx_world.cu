@@ -1176,6 +1176,7 @@ int World::patchContacts(const dbx_contact_patch* in, int n) {
   if (n < 0 || (n > 0 && !in)) return DBX_E_INVALID;
   if (n == 0 || !dw_.hdr) return 0;
   std::vector<unsigned long long> keys((size_t)n); std::vector<float4> vals((size_t)n); std::vector<int> masks((size_t)n);
+  std::unordered_set<unsigned long long> destroyed;
   for (int k = 0; k < n; ++k) {
     const dbx_contact_patch& c = in[k];
     auto proxyKey = [&](int f, int child) -> int {
@@ -1186,6 +1187,7 @@ int World::patchContacts(const dbx_contact_patch* in, int n) {
     if (ka < 0 || kb < 0) return DBX_E_INVALID;
     keys[k] = ((unsigned long long)(unsigned)std::min(ka, kb) << 32) | (unsigned)std::max(ka, kb);
     masks[k] = c.mask | (c.enabled ? 0x100 : 0);
+    if ((c.mask & DBX_PATCH_DESTROY) && !destroyed.insert(keys[k]).second) masks[k] = 0;   // the same pair twice: destroy once
     vals[k] = make_float4(c.friction, c.restitution, c.tangentSpeed, 0.0f);
   }
   CUDA_OR_FAIL(patchKeys_.reserve((size_t)n, false, stream_), "patch"); CUDA_OR_FAIL(qIn_.reserve((size_t)n, false, stream_), "patch"); CUDA_OR_FAIL(qCount_.reserve((size_t)n, false, stream_), "patch");
@@ -1461,6 +1463,40 @@ int World::readPostSolve(dbx_post_solve* out, int cap) {
     o.count = a[i].w & 0xFF; o.phase = (a[i].w >> 8) & 0xFF;
     o.normalImpulses[0] = b[i].x; o.tangentImpulses[0] = b[i].y; o.normalImpulses[1] = b[i].z; o.tangentImpulses[1] = b[i].w;
   }
+  return n;
+}
+
+// user b2ContactFilter, deferred (see include/dbox_b200.h)
+int World::setUserFilter(int mode) {
+  if (mode < 0 || mode > 3) return DBX_E_INVALID;
+  dw_.userFilter = mode;
+  return 0;
+}
+int World::pollNewContacts(int32_t* out, int cap) {
+  if (!dw_.hdr || bodiesSynced_ == 0) return 0;
+  int rc = push(); if (rc < 0) return rc;
+  if (newFixture_) { int rf = findNewContacts(); if (rf < 0) return rf; newFixture_ = false; }   // pairs of fixtures added since the last step
+  const bool peek = !out || cap <= 0;
+  int high = 0;
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  CUDA_OR_FAIL(cudaMemcpy(&high, (char*)hdr_.p + offsetof(Header, cHigh), 4, cudaMemcpyDeviceToHost), "read cHigh");
+  if (high <= 0) return 0;
+  const size_t room = peek ? 1 : (size_t)cap;
+  CUDA_OR_FAIL(qPairs_.reserve(2 * room, false, stream_), "new contacts"); CUDA_OR_FAIL(patchKeys_.reserve(room, false, stream_), "new contacts");
+  CUDA_OR_FAIL(cudaMemsetAsync((char*)hdr_.p + offsetof(Header, nNewContacts), 0, 4, stream_), "new contacts reset");
+  CUDA_OR_FAIL(launch_list_new_contacts(dw_, L_, (int4*)qPairs_.p, patchKeys_.p, peek ? 0 : cap, peek ? 1 : 0), "list_new_contacts");
+  int n = 0;
+  CUDA_OR_FAIL(cudaMemcpyAsync(&n, (char*)hdr_.p + offsetof(Header, nNewContacts), 4, cudaMemcpyDeviceToHost, stream_), "new contacts count");
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  if (peek || n == 0) return n;
+  const int m = std::min(n, cap);            // the surplus stays tagged for the next poll
+  std::vector<int4> rec((size_t)m); std::vector<unsigned long long> key((size_t)m);
+  CUDA_OR_FAIL(cudaMemcpy(rec.data(), qPairs_.p, (size_t)m * 16, cudaMemcpyDeviceToHost), "new contacts d2h");
+  CUDA_OR_FAIL(cudaMemcpy(key.data(), patchKeys_.p, (size_t)m * 8, cudaMemcpyDeviceToHost), "new contacts d2h");
+  std::vector<int> order((size_t)m);
+  for (int i = 0; i < m; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+  for (int k = 0; k < m; ++k) { const int4 r = rec[order[k]]; out[4 * k] = r.x; out[4 * k + 1] = r.y; out[4 * k + 2] = r.z; out[4 * k + 3] = r.w; }
   return n;
 }
 

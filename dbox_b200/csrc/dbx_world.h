@@ -80,6 +80,8 @@ class World {
   int readWorldManifolds(dbx_world_manifold* out, int cap);
   int enablePostSolve(int capacity);
   int readPostSolve(dbx_post_solve* out, int cap);
+  int setUserFilter(int mode);
+  int pollNewContacts(int32_t* out, int cap);
   int enableContactEvents(int capacity);
   int pollContactEvents(dbx_contact_event* out, int cap);
   int readTransforms(float* out, int n);

@@ -452,7 +452,9 @@ class b2Fixture:
     # b2fixture.d:108-262
     def SetFilterData(self, categoryBits=0x0001, maskBits=0xFFFF, groupIndex=0):
         w = self.body.world
+        self.filter = (categoryBits, maskBits, groupIndex)
         w._ck(w._api.fixture_set_filter(w._w, self.id, categoryBits, maskBits, groupIndex))
+        w._refilter_user(self)
 
     def SetSensor(self, flag):
         w = self.body.world
@@ -502,6 +504,7 @@ class b2Body:
         pod = fd._pod()
         fid = self.world._ck(self.world._api.fixture_create(self.world._w, self.id, C.byref(pod), C.byref(shape._pod)))
         f = b2Fixture(self, fid)
+        f.filter = (fd.filter.categoryBits, fd.filter.maskBits, fd.filter.groupIndex)
         self.fixtures.append(f)
         self.world._fixtures[fid] = f
         return f
@@ -631,6 +634,18 @@ class b2ContactListener:
         """impulse = (count, normalImpulses, tangentImpulses) as b2ContactImpulse (b2worldcallbacks.d:73-79)"""
 
 
+class b2ContactFilter:
+    """b2worldcallbacks.d:36-66.  Subclass and override ShouldCollide; the base implementation is the default category / mask /
+    group rule, so an override can call super().ShouldCollide(a, b) like the reference's subclasses do."""
+
+    def ShouldCollide(self, fixtureA, fixtureB):
+        catA, maskA, groupA = fixtureA.filter
+        catB, maskB, groupB = fixtureB.filter
+        if groupA == groupB and groupA != 0:
+            return groupA > 0
+        return (maskA & catB) != 0 and (catA & maskB) != 0
+
+
 class b2ContactView:
     """what a deferred listener call sees of a b2Contact: its fixtures and child indices (b2contact.d:108-135)"""
 
@@ -704,6 +719,7 @@ class b2World:
         if jointDef.bodyA is None and getattr(jointDef, "joint1", None) is not None:     # gear: bodies come from the two joints
             jointDef.bodyA, jointDef.bodyB = jointDef.joint1.bodyB, jointDef.joint2.bodyB
         j = b2Joint(self, jid, jointDef.bodyA, jointDef.bodyB)
+        j.type, j.collideConnected = jointDef.type, bool(jointDef.collideConnected)
         self._joints[jid] = j
         return j
 
@@ -716,9 +732,58 @@ class b2World:
         self._ck(self._api.joint_destroy(self._w, joint.id))
         self._joints.pop(joint.id, None)
 
+    # user contact filter (b2world.d:52-56), deferred: see include/dbox_b200.h "user contact filter" ---------------
+    def SetContactFilter(self, contact_filter, replaces_default=True):
+        """contact_filter: a b2ContactFilter (None = back to the default rule).  replaces_default: the device leaves the
+        category / mask / group test to the filter object (whose base class implements it)."""
+        self._filter = contact_filter
+        if self._api.prefix == "dbx_":
+            mode = 0 if contact_filter is None else (A.FILTER_LOG | (A.FILTER_REPLACES_DEFAULT if replaces_default else 0))
+            self._ck(self._api.world_set_user_filter(self._w, mode))
+        else:       # the oracle calls the filter where the reference does
+            if contact_filter is None:
+                self._filter_cb = None
+                self._ck(self._api.world_set_contact_filter(self._w, None))
+            else:
+                proto = C.CFUNCTYPE(C.c_int, C.c_int, C.c_int, C.c_int)
+                self._filter_cb = proto(lambda fa, fb, default: int(bool(self._filter.ShouldCollide(self._fixtures[fa], self._fixtures[fb]))))
+                self._ck(self._api.world_set_contact_filter(self._w, C.cast(self._filter_cb, C.c_void_p)))
+
+    def _veto(self, pairs):
+        if not pairs:
+            return
+        arr = (A.ContactPatch * len(pairs))()
+        for k, (fa, ca, fb, cb) in enumerate(pairs):
+            arr[k].fixtureA, arr[k].childA, arr[k].fixtureB, arr[k].childB, arr[k].mask = fa, ca, fb, cb, A.PATCH_DESTROY
+        self._ck(self._api.world_patch_contacts(self._w, arr, len(pairs)))
+
+    def _apply_user_filter(self):
+        """ask the user's filter about every contact the broadphase created since the last poll; destroy what it rejects"""
+        if getattr(self, "_filter", None) is None or self._api.prefix != "dbx_":
+            return
+        n = self._ck(self._api.world_poll_new_contacts(self._w, None, 0))
+        if n == 0:
+            return
+        buf = (C.c_int32 * (4 * n))()
+        n = min(n, self._ck(self._api.world_poll_new_contacts(self._w, buf, n)))
+        self._veto([tuple(buf[4 * k:4 * k + 4]) for k in range(n)
+                    if not self._filter.ShouldCollide(self._fixtures[buf[4 * k]], self._fixtures[buf[4 * k + 2]])])
+
+    def _refilter_user(self, fixture):
+        """b2Fixture.Refilter (b2fixture.d:140-178) flags the fixture's contacts; the reference's next Collide asks the filter
+        about each (b2contactmanager.d:264-284).  Deferred form: ask now, destroy what is rejected."""
+        if getattr(self, "_filter", None) is None or self._api.prefix != "dbx_":
+            return
+        recs, n = self.read_contacts()
+        self._veto([(recs[i].fixtureA, recs[i].childA, recs[i].fixtureB, recs[i].childB) for i in range(n)
+                    if fixture.id in (recs[i].fixtureA, recs[i].fixtureB)
+                    and not self._filter.ShouldCollide(self._fixtures[recs[i].fixtureA], self._fixtures[recs[i].fixtureB])])
+
     # stepping ----------------------------------------------------------------------------------------------
     def Step(self, dt, velocityIterations, positionIterations):
+        self._apply_user_filter()          # pairs of fixtures created since the last step (b2world.d:372-376 runs the broadphase first)
         self._ck(self._api.world_step(self._w, dt, velocityIterations, positionIterations))
+        self._apply_user_filter()          # pairs the step's FindNewContacts found
         if getattr(self, "_listener", None) is not None:
             self._deliver_contact_events()
 

@@ -403,7 +403,8 @@ typedef struct dbx_contact_patch {
   int32_t enabled;
   float friction, restitution, tangentSpeed;
 } dbx_contact_patch;
-enum { DBX_PATCH_ENABLED = 1, DBX_PATCH_FRICTION = 2, DBX_PATCH_RESTITUTION = 4, DBX_PATCH_TANGENT_SPEED = 8 };
+enum { DBX_PATCH_ENABLED = 1, DBX_PATCH_FRICTION = 2, DBX_PATCH_RESTITUTION = 4, DBX_PATCH_TANGENT_SPEED = 8,
+       DBX_PATCH_DESTROY = 16 /* the user's b2ContactFilter said no: see "user contact filter" below */ };
 int32_t dbx_world_step_begin(dbx_world* w, float dt, int32_t velocityIterations, int32_t positionIterations);
 int32_t dbx_world_patch_contacts(dbx_world* w, const dbx_contact_patch* patches, int32_t n);   /* unknown pairs are ignored */
 int32_t dbx_world_step_end(dbx_world* w);
@@ -439,6 +440,24 @@ typedef struct dbx_post_solve {
 } dbx_post_solve;
 int32_t dbx_world_enable_post_solve(dbx_world* w, int32_t capacity);   /* > 0: record (at most `capacity` per step), 0: stop */
 int32_t dbx_world_read_post_solve(dbx_world* w, dbx_post_solve* out, int32_t cap);   /* out == NULL: the count only */
+
+/* ---- user contact filter, deferred ------------------------------------------------------------
+ * b2World.SetContactFilter (dynamics/b2world.d:52-56) + b2ContactFilter.ShouldCollide (dynamics/b2worldcallbacks.d:55-66).
+ * The reference asks the filter when the broadphase reports a new pair (b2contactmanager.d:110-114: no contact is created on
+ * "no") and when a contact flagged by Refilter is visited by Collide (:274-281: the contact is destroyed on "no").  Device
+ * code cannot call the filter, so with logging on every contact the broadphase creates is also listed; the shim polls the
+ * list after the step (and after any call that runs the broadphase), asks the user's filter and destroys what it rejects
+ * with dbx_world_patch_contacts(mask = DBX_PATCH_DESTROY) before the next Collide can evaluate it -- such a contact never
+ * touches, never reaches the solver and raises no Begin/EndContact.  Refilter: the shim walks the fixture's contacts
+ * (dbx_world_read_contacts) at SetFilterData time and vetoes the same way.  Not covered: contacts the TOI sub-steps create
+ * and use inside the same step.
+ * mode: 0 = off; DBX_FILTER_LOG = list new contacts; | DBX_FILTER_REPLACES_DEFAULT = the device skips the category / mask /
+ * group test (b2worldcallbacks.d:40-52), because the user's ShouldCollide does not call the default one. */
+enum { DBX_FILTER_LOG = 1, DBX_FILTER_REPLACES_DEFAULT = 2 };
+int32_t dbx_world_set_user_filter(dbx_world* w, int32_t mode);
+/* contacts created since the last poll as (fixtureA, childA, fixtureB, childB), ascending pair key; returns their number
+ * (out == NULL: the count only, nothing is consumed) */
+int32_t dbx_world_poll_new_contacts(dbx_world* w, int32_t* fixA_childA_fixB_childB, int32_t cap);
 
 #ifdef __cplusplus
 }

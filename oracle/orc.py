@@ -76,6 +76,7 @@ def api():
             "world_read_world_manifolds": (i32, [W, P(A.WorldManifold), i32]),
             "world_enable_post_solve": (i32, [W, i32]),
             "world_read_post_solve": (i32, [W, P(A.PostSolve), i32]),
+            "world_set_contact_filter": (i32, [W, C.c_void_p]),
         }
         for name, (res, args) in extra.items():
             fn = getattr(lib, "orc_" + name)

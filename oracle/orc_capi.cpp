@@ -536,6 +536,8 @@ int32_t orc_world_read_world_manifolds(orc_world* w, dbx_world_manifold* out, in
   }
   return n;
 }
+// b2World.SetContactFilter with a C callback standing in for the user's b2ContactFilter subclass (tests)
+int32_t orc_world_set_contact_filter(orc_world* w, int (*cb)(int, int, int)) { w->w.userFilter = cb; return 0; }
 // the PostSolve call log of the last step, in the reference's CALL order
 int32_t orc_world_enable_post_solve(orc_world* w, int32_t capacity) { w->w.recordPostSolve = capacity > 0; w->w.postSolveLog.clear(); return capacity; }
 int32_t orc_world_read_post_solve(orc_world* w, dbx_post_solve* out, int32_t cap) {

@@ -409,7 +409,7 @@ void World::addPair(void* udA, void* udB) {
     }
   }
   if (bodyB->shouldCollide(bodyA) == false) return;
-  if (defaultShouldCollide(fixtureA, fixtureB) == false) return;
+  if ((userFilter ? userFilter(fixtureA->id, fixtureB->id, defaultShouldCollide(fixtureA, fixtureB)) != 0 : defaultShouldCollide(fixtureA, fixtureB)) == false) return;
   Contact* c = createContact(fixtureA, indexA, fixtureB, indexB);
   if (c == nullptr) return;
   fixtureA = c->fixtureA; fixtureB = c->fixtureB;
@@ -463,7 +463,7 @@ void World::collide() {
     Body* bodyA = fixtureA->body; Body* bodyB = fixtureB->body;
     if (c->flags & cFilter) {
       if (bodyB->shouldCollide(bodyA) == false) { Contact* n = c; c = n->next; destroyContact(n); continue; }
-      if (defaultShouldCollide(fixtureA, fixtureB) == false) { Contact* n = c; c = n->next; destroyContact(n); continue; }
+      if ((userFilter ? userFilter(fixtureA->id, fixtureB->id, defaultShouldCollide(fixtureA, fixtureB)) != 0 : defaultShouldCollide(fixtureA, fixtureB)) == false) { Contact* n = c; c = n->next; destroyContact(n); continue; }
       c->flags &= ~cFilter;
     }
     bool activeA = bodyA->isAwake() && bodyA->type != kStatic;

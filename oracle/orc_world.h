@@ -248,6 +248,10 @@ struct World {
   struct PostSolveRec { int phase, fixtureA, childA, fixtureB, childB, count; float normalImpulses[2], tangentImpulses[2]; };
   std::vector<PostSolveRec> postSolveLog; bool recordPostSolve = false;
   void shiftOrigin(V2 newOrigin);                     // b2world.d:758-780
+  // b2World.SetContactFilter (b2world.d:52-56): a user b2ContactFilter.ShouldCollide (b2worldcallbacks.d:55-66) REPLACES the
+  // default one at both call sites (b2contactmanager.d:110-114, 274-281); callback(fixtureA id, fixtureB id, default answer)
+  typedef int (*UserFilter)(int fixtureA, int fixtureB, int defaultAnswer);
+  UserFilter userFilter = nullptr;
   std::vector<std::pair<FixtureProxy*, FixtureProxy*>> lastPairs;  // unique pairs handed to AddPair by the last UpdatePairs
   std::vector<Contact*> lastSolveOrder;   // contacts in the order islands solved them in the last Solve
 };

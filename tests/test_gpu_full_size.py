@@ -1,0 +1,128 @@
+"""BASELINE config 4 at its FULL size (100 000-body pile with joint chains) through size-independent properties: the oracle
+cannot step a world this big in seconds, so what is checked is what must hold whatever the size --
+* the broadphase + pair cache are exact: after a step every pair of proxies whose persistent fat AABBs overlap (different
+  bodies, not vetoed by a joint: b2body.d:476-500, b2contactmanager.d:52-176) owns a contact, and after the next Collide no
+  contact is left whose fat boxes do not overlap (b2contactmanager.d:299-308).  The checker is an independent numpy / k-d tree
+  sweep over the proxy boxes read back through the ABI;
+* the solver schedule is a proper colouring (no two constraints of a colour share a dynamic body);
+* replay is exact: a snapshot taken mid-run, restored and stepped again reproduces the run bit for bit;
+* the state stays finite and inside the container."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from dbox_b200 import _abi as A
+from dbox_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+DT = 1.0 / 60.0
+
+
+def _np(buf, n, typ):
+    return np.frombuffer(buf, dtype=np.uint8, count=n * C.sizeof(typ)).reshape(n, C.sizeof(typ))
+
+
+def _proxy_arrays(world):
+    buf, n = world.read_proxies()
+    raw = _np(buf, n, A.ProxyRec)
+    ids = raw[:, :12].copy().view(np.int32)          # fixture child proxyId
+    fat = raw[:, 28:44].copy().view(np.float32)      # lo.x lo.y hi.x hi.y
+    return ids[:, 0], ids[:, 1], fat
+
+
+def _contact_pairs(world):
+    buf, n = world.read_contacts()
+    ids = _np(buf, n, A.ContactRec)[:, :16].copy().view(np.int32)   # fixtureA fixtureB childA childB
+    return ids
+
+
+def _overlapping_fat_pairs(fat):
+    """indices (i < j) of boxes that overlap (b2TestOverlap: touching edges count), by an independent method"""
+    from scipy.spatial import cKDTree
+    ext = np.maximum(fat[:, 2] - fat[:, 0], fat[:, 3] - fat[:, 1])
+    small = np.nonzero(ext < 4.0)[0]
+    big = np.nonzero(ext >= 4.0)[0]
+    c = 0.5 * (fat[small, :2] + fat[small, 2:])
+    r = float(np.sqrt(2.0) * ext[small].max()) + 1e-3
+    cand = cKDTree(c).query_pairs(r, output_type="ndarray")
+    i, j = small[cand[:, 0]], small[cand[:, 1]]
+
+    def ov(a, b):
+        return (fat[a, 0] <= fat[b, 2]) & (fat[b, 0] <= fat[a, 2]) & (fat[a, 1] <= fat[b, 3]) & (fat[b, 1] <= fat[a, 3])
+    m = ov(i, j)
+    pairs = [np.stack([i[m], j[m]], 1)]
+    allidx = np.arange(fat.shape[0])
+    for b in big:
+        hit = allidx[ov(np.full(allidx.shape, b), allidx) & (allidx != b)]
+        hit = hit[(ext[hit] < 4.0) | (hit > b)]       # big-big pairs once
+        pairs.append(np.stack([np.full(hit.shape, b), hit], 1))
+    p = np.concatenate(pairs, 0)
+    return np.stack([p.min(1), p.max(1)], 1)
+
+
+def _key(a, b):
+    lo, hi = np.minimum(a, b), np.maximum(a, b)
+    return lo.astype(np.int64) * (1 << 32) + hi.astype(np.int64)
+
+
+def test_pile_100k_full_size_properties(gpu_api):
+    n, columns = 100000, 1000
+    w, bodies, njoints = scenes.pile(api=gpu_api, n=n, columns=columns)
+    assert njoints > 15000
+    w.SetAllowSleeping(False)
+    w.StepN(DT, 8, 3, 25)
+    cnt = w.counts()
+    assert cnt.bodies == n + 1 and cnt.contacts > 2 * n and cnt.touching > n and cnt.awakeBodies == n
+    assert w._api.world_debug_colour_conflicts(w._w) == 0
+
+    # ---- broadphase / pair-cache exactness at full size
+    fix, child, fat = _proxy_arrays(w)
+    assert fat.shape[0] == cnt.proxies and np.isfinite(fat).all()
+    fix_body = np.full(int(fix.max()) + 1, -1, np.int64)
+    for f in w._fixtures.values():
+        fix_body[f.id] = f.body.id
+    body = fix_body[fix]
+    ov = _overlapping_fat_pairs(fat)
+    bi, bj = body[ov[:, 0]], body[ov[:, 1]]
+    veto = np.array(sorted(_key(np.array([j.bodyA.id]), np.array([j.bodyB.id]))[0] for j in w._joints.values() if not j.collideConnected), np.int64)
+    assert veto.size > 5000
+    keep = (bi != bj) & ~np.isin(_key(bi, bj), veto)
+    # proxies are identified by (fixture, child); child < 2^12 here
+    pid = fix.astype(np.int64) * 4096 + child
+    expected = np.unique(_key(pid[ov[keep, 0]], pid[ov[keep, 1]]))
+    c = _contact_pairs(w)
+    have = np.unique(_key(c[:, 0].astype(np.int64) * 4096 + c[:, 2], c[:, 1].astype(np.int64) * 4096 + c[:, 3]))
+    assert have.size == c.shape[0] == cnt.contacts            # one contact per proxy pair
+    missing = np.setdiff1d(expected, have)
+    assert missing.size == 0, "overlapping proxy pairs without a contact: %d of %d" % (missing.size, expected.size)
+    stale = np.setdiff1d(have, expected)
+    assert stale.size < 0.05 * have.size                       # boxes that drifted apart during the last step: gone after Collide
+    assert w._api.world_stage_collide(w._w) >= 0
+    c2 = _contact_pairs(w)
+    have2 = np.unique(_key(c2[:, 0].astype(np.int64) * 4096 + c2[:, 2], c2[:, 1].astype(np.int64) * 4096 + c2[:, 3]))
+    assert np.array_equal(have2, expected), (have2.size, expected.size)
+
+    # ---- exact replay from a snapshot
+    need = gpu_api.world_export_state(w._w, None, 0)
+    blob = (C.c_char * need)()
+    assert gpu_api.world_export_state(w._w, blob, need) == need
+    w.StepN(DT, 8, 3, 12)
+    buf, nb = w.read_bodies()
+    first = _np(buf, nb, A.BodyState).copy()
+    counts1 = w.counts()
+    assert gpu_api.world_import_state(w._w, blob, need) == 0
+    w.StepN(DT, 8, 3, 12)
+    buf, nb2 = w.read_bodies()
+    second = _np(buf, nb2, A.BodyState)
+    counts2 = w.counts()
+    assert nb == nb2 and np.array_equal(first, second)
+    assert (counts1.contacts, counts1.touching) == (counts2.contacts, counts2.touching)
+
+    # ---- the state is finite and inside the container
+    st = np.frombuffer(second.tobytes(), dtype=np.float32).reshape(nb, -1)
+    assert np.isfinite(st).all()
+    half_w = 1.05 * columns * 0.5 + 5.0
+    px, py = st[1:, 2], st[1:, 3]                             # BodyState.p of the dynamic bodies (body 0 is the ground)
+    assert px.min() > -half_w - 0.6 and px.max() < half_w + 0.6 and py.min() > 0.3
+    assert w._api.world_debug_colour_conflicts(w._w) == 0

@@ -7,7 +7,7 @@ import random
 import pytest
 
 from dbox_b200 import scenes
-from dbox_b200.world import (b2BodyDef, b2CircleShape, b2EdgeShape, b2MouseJointDef, b2PolygonShape, b2PulleyJointDef, b2World,
+from dbox_b200.world import (b2BodyDef, b2CircleShape, b2EdgeShape, b2FixtureDef, b2MouseJointDef, b2PolygonShape, b2PulleyJointDef, b2World,
                              b2_dynamicBody)
 from tests.parity import contact_key, transplant
 from tests.test_gpu_features import _dyn, _ground, _query_scene, both
@@ -239,3 +239,79 @@ def test_post_solve_listener_on_pyramid(gpu_api, oracle_api):
     total_g = sum(sum(c[1][1][:c[1][0]]) for c in lst.calls)
     total_o = sum(sum(r[6][:r[5]]) for r in ro)
     assert total_o > 0 and abs(total_g - total_o) <= 0.02 * total_o
+
+
+def _filter_scene(api, contact_filter, replaces_default):
+    """boxes dropped on top of each other in three loose columns; the user's filter decides which of them see each other"""
+    w = b2World((0.0, -10.0), api=api)
+    g = _ground(w, api)
+    w.SetContactFilter(contact_filter, replaces_default=replaces_default)
+    out = []
+    for k in range(12):
+        b = _dyn(w, -6.0 + 6.0 * (k % 3) + 0.05 * (k // 3), 0.6 + 1.3 * (k // 3))
+        s = b2PolygonShape(api); s.SetAsBox(0.5, 0.5)
+        fd = b2FixtureDef(); fd.shape, fd.density = s, 1.0
+        if k % 3 == 2:
+            fd.filter.maskBits = 0x0000          # the default rule would let these fall through everything, ground included
+        b.CreateFixture(fd)
+        out.append(b)
+    return w, out, g
+
+
+def test_user_contact_filter_matches_reference(gpu_api, oracle_api):
+    """b2World.SetContactFilter + b2ContactFilter.ShouldCollide (b2world.d:52-56, b2worldcallbacks.d:36-66; call sites
+    b2contactmanager.d:110-114 and :274-281), deferred on the device side: the pairs a user filter rejects never touch, never
+    reach the solver and raise no events; a filter that overrides the default rule can also allow what the masks forbid; after a
+    Refilter the filter is asked again"""
+    from dbox_b200.world import b2ContactFilter
+
+    class F(b2ContactFilter):
+        """dynamic boxes ignore each other (whatever their masks say) and always collide with the ground body"""
+        def __init__(self):
+            self.solid = False
+            self.asked = 0
+
+        def ShouldCollide(self, fa, fb):
+            self.asked += 1
+            if fa.body.id == 0 or fb.body.id == 0:
+                return True
+            return self.solid and super().ShouldCollide(fa, fb)
+    fg, fo = F(), F()
+    wg, bg, _ = _filter_scene(gpu_api, fg, True)
+    wo, bo, _ = _filter_scene(oracle_api, fo, True)
+    wg.EnableContactEvents(4096); wo.EnableContactEvents(4096)
+
+    def check(k, tol):
+        for i, (a, b) in enumerate(zip(bg, bo)):
+            pa, pb = a.GetPosition(), b.GetPosition()
+            assert abs(pa.x - pb.x) <= tol and abs(pa.y - pb.y) <= tol and abs(a.GetAngle() - b.GetAngle()) <= tol, (k, i, (pa.x, pa.y), (pb.x, pb.y))
+    for k in range(150):
+        wg.Step(DT, 8, 3); wo.Step(DT, 8, 3)
+        check(k, 2e-4)
+        cg, co = wg.counts(), wo.counts()
+        assert (cg.contacts, cg.touching) == (co.contacts, co.touching), k
+        eg = sorted(e[:1] + e[3:] for e in wg.PollContactEvents()); eo = sorted(e[:1] + e[3:] for e in wo.PollContactEvents())
+        assert eg == eo, (k, eg, eo)
+    # every box lies on the ground, also the ones whose mask is 0: all twelve passed through each other
+    assert all(abs(b.GetPosition().y - 0.5) < 0.02 for b in bg)
+    assert wg.counts().contacts == 12 and fg.asked >= 12
+    rg, n = wg.read_contacts()
+    assert all(0 in (wg._fixtures[rg[i].fixtureA].body.id, wg._fixtures[rg[i].fixtureB].body.id) for i in range(n))
+    # Refilter: boxes become solid to each other where the masks allow it (columns 0 and 1); lift them and let them stack
+    for f, bodies, w in ((fg, bg, wg), (fo, bo, wo)):
+        f.solid = True
+        for k, b in enumerate(bodies):
+            b.SetTransform((-6.0 + 6.0 * (k % 3), 0.6 + 1.3 * (k // 3)), 0.0)
+            b.SetAwake(True)
+            b.fixtures[0].SetFilterData(*b.fixtures[0].filter)
+    for k in range(150):
+        wg.Step(DT, 8, 3); wo.Step(DT, 8, 3)
+        cg, co = wg.counts(), wo.counts()
+        assert (cg.contacts, cg.touching) == (co.contacts, co.touching), k
+    check("stacked", 5e-3)                                   # four-high stacks: the Gauss-Seidel order now matters a little
+    ys = sorted(b.GetPosition().y for k, b in enumerate(bg) if k % 3 == 0)
+    assert [round(y) for y in ys] == [0, 2, 3, 4] or all(abs(ys[i] - (0.5 + 1.0 * i)) < 0.1 for i in range(4))
+    assert all(abs(b.GetPosition().y - 0.5) < 0.02 for k, b in enumerate(bg) if k % 3 == 2)     # mask 0: still only the ground
+    # switching the filter off hands the decision back to the default rule
+    wg.SetContactFilter(None)
+    assert gpu_api.world_poll_new_contacts(wg._w, None, 0) == 0
