@@ -112,6 +112,9 @@ def run_cpu_port(n_bodies, columns, settle, steps, warmup, threads=1, replicas=1
     api.batch_step(arr, replicas, DT, VEL_ITERS, POS_ITERS, settle + warmup, threads)
     secs = api.batch_step(arr, replicas, DT, VEL_ITERS, POS_ITERS, steps, threads)
     c = worlds[0].counts()
+    # the reference's own b2Profile split (b2timestep.d:37-47) for the last timed step: where the CPU time goes
+    p = worlds[0].GetProfile()
+    c.profile_ms = {k: round(float(getattr(p, k)), 4) for k in ("step", "collide", "solve", "solveInit", "solveVelocity", "solvePosition", "broadphase", "solveTOI")}
     return replicas * n_bodies * steps / secs, secs, c
 
 
@@ -252,7 +255,7 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": W,
                 "ms_per_step": 1e3 * secs / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "b2Profile_ms_last_step": c.profile_ms},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0, "wall_s": time.time() - t0}
         if args.worlds > 0:
@@ -380,7 +383,8 @@ def main():
             v, secs, c = run_cpu_port(cpu_bodies, cpu_cols, args.cpu_settle, args.cpu_steps, 3)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": "%d-body pile (same generator, same %d-row depth, %d columns), %d settle + %d timed steps, single thread, %.1f s"
-                                              % (cpu_bodies, rows, cpu_cols, args.cpu_settle, args.cpu_steps, time.time() - t0)}
+                                              % (cpu_bodies, rows, cpu_cols, args.cpu_settle, args.cpu_steps, time.time() - t0),
+                                    "b2Profile_ms_last_step": c.profile_ms}
         print(json.dumps(line), flush=True)
     if world_size > 1:
         dist.barrier()

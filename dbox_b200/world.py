@@ -709,7 +709,24 @@ class b2World:
         self._bodies[bid] = b
         return b
 
+    def SetDestructionListener(self, listener):
+        """b2world.d:44-48; listener.SayGoodbye(joint | fixture) (b2worldcallbacks.d:34-49)"""
+        self._destruction = listener
+
     def DestroyBody(self, body):
+        """b2world.d:105-191: the joints attached to the body (newest first, like its joint list) and its fixtures go with it,
+        each announced to the destruction listener first.  Host-side bookkeeping of the shim: the library destroys the same
+        objects inside dbx_body_destroy."""
+        lst = getattr(self, "_destruction", None)
+        attached = [j for j in self._joints.values() if body in (j.bodyA, j.bodyB) or body in getattr(j, "extra_bodies", ())]
+        for j in sorted(attached, key=lambda j: -j.id):
+            if lst is not None:
+                lst.SayGoodbye(j)
+            self._joints.pop(j.id, None)
+        for f in reversed(body.fixtures):
+            if lst is not None:
+                lst.SayGoodbye(f)
+            self._fixtures.pop(f.id, None)
         self._ck(self._api.body_destroy(self._w, body.id))
         self._bodies.pop(body.id, None)
 

@@ -153,3 +153,54 @@ def test_oracle_contact_event_log_balances(oracle_api):
     w.DestroyBody(bodies[-1])
     ev = w.PollContactEvents()
     assert ev and all(e[0] == 2 and e[1] == 3 for e in ev)
+
+
+def test_shift_origin_is_a_translation(oracle_api):
+    """b2World.ShiftOrigin (b2world.d:758-780) restated: a pyramid shifted by (64, -32) -- exactly representable, and small
+    enough that the coordinates keep their low bits -- evolves like the unshifted one, translated; the tree stays valid"""
+    a, ba = scenes.pyramid(api=oracle_api, count=8)
+    b, bb = scenes.pyramid(api=oracle_api, count=8)
+    for _ in range(30):
+        a.Step(DT, 8, 3); b.Step(DT, 8, 3)
+    b.ShiftOrigin((64.0, -32.0))
+    assert oracle_api.world_tree_validate(b._w) == 1
+    for _ in range(60):
+        a.Step(DT, 8, 3); b.Step(DT, 8, 3)
+    ca, cb = a.counts(), b.counts()
+    assert (ca.contacts, ca.touching) == (cb.contacts, cb.touching)
+    for x, y in zip(ba, bb):
+        px, py = x.GetPosition(), y.GetPosition()
+        assert abs(px.x - 64.0 - py.x) < 2e-3 and abs(px.y + 32.0 - py.y) < 2e-3
+
+
+def test_post_solve_log_carries_the_weight(oracle_api):
+    """b2Island.Report (b2island.d:438-462) restated: at rest, the normal impulses reported for the contacts with the ground
+    add up to the weight of the pyramid times the time step"""
+    w, bodies = scenes.pyramid(api=oracle_api, count=6)
+    w.SetAllowSleeping(False)
+    w.EnablePostSolve(1 << 12)
+    for _ in range(240):
+        w.Step(DT, 8, 3)
+    recs = w.ReadPostSolve()
+    assert recs and all(r[0] == 1 for r in recs)
+    ground = [r for r in recs if 0 in (w._fixtures[r[1]].body.id, w._fixtures[r[3]].body.id) or 1 in (w._fixtures[r[1]].body.id, w._fixtures[r[3]].body.id)]
+    total = sum(sum(r[6][:r[5]]) for r in ground)
+    weight = 21 * 5.0 * 1.0 * 10.0 * DT            # 21 boxes, density 5, area 1, g = 10
+    assert abs(total - weight) < 0.02 * weight, (total, weight)
+
+
+def test_test_point_and_world_manifold_fixed_inputs(oracle_api):
+    """b2Shape.TestPoint (b2polygonshape.d:265-279, b2circleshape.d:60-65) and b2WorldManifold.Initialize (b2collision.d:123-191)
+    on hand-checkable inputs: a unit box on the ground"""
+    w, body = scenes.hello_world(api=oracle_api)
+    for _ in range(90):
+        w.Step(DT, 6, 2)
+    f = body.fixtures[0]
+    y = body.GetPosition().y
+    assert f.TestPoint((0.0, y)) and f.TestPoint((0.99, y + 0.99)) and not f.TestPoint((1.01, y)) and not f.TestPoint((0.0, y + 1.01))
+    wm = w.GetWorldManifolds()
+    assert len(wm) == 1 and wm[0][0] == 2
+    n, pts, sep = wm[0][1], wm[0][2], wm[0][3]
+    assert abs(abs(n[1]) - 1.0) < 1e-6 and abs(n[0]) < 1e-6            # vertical normal, A -> B
+    assert sorted(round(p[0], 3) for p in pts) == [-1.0, 1.0]            # the box's two bottom corners
+    assert all(-0.011 < s < 0.0 for s in sep)                            # resting inside the 2 * b2_polygonRadius skin
