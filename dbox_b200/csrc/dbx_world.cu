@@ -998,7 +998,8 @@ void World::setStepParams(float dt, int vi, int pi) {
   dw_.velIters = vi; dw_.posIters = std::min(pi, kMaxPosIters);
   dw_.warmStarting = (flags_ & DBX_WORLD_WARM_STARTING) ? 1 : 0;
   dw_.allowSleep = (flags_ & DBX_WORLD_ALLOW_SLEEP) ? 1 : 0;
-  dw_.continuous = (flags_ & DBX_WORLD_CONTINUOUS) ? 1 : 0;
+  // k_collide lists TOI candidates only for a step whose SolveTOI will run and consume (and empty) the list (b2world.d:414-419)
+  dw_.continuous = ((flags_ & DBX_WORLD_CONTINUOUS) && dt > 0.0f) ? 1 : 0;
   dw_.gx = gx_; dw_.gy = gy_;
   dw_.stepIndex = (stepCount_ + 1) & 0xFFFF;
 }
