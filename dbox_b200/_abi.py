@@ -252,6 +252,11 @@ PROTOTYPES = {
     "world_enable_post_solve": (c_i32, [W, c_i32]),
     "world_read_post_solve": (c_i32, [W, P(PostSolve), c_i32]),
     "world_set_user_filter": (c_i32, [W, c_i32]),
+    "world_step_async": (c_i32, [W, c_f32, c_i32, c_i32]),
+    "world_apply_forces_async": (c_i32, [W, C.c_void_p, c_i32]),
+    "world_read_transforms_async": (c_i32, [W, C.c_void_p, c_i32]),
+    "world_io_wait": (c_i32, [W, c_i32]),
+    "world_sync": (c_i32, [W]),
     "world_poll_new_contacts": (c_i32, [W, P(c_i32), c_i32]),
 }
 

@@ -35,6 +35,25 @@ def reduce_stats(local, maxima=("ms", "seconds")):
     return {k: float(maxs[i] if k in maxima else sums[i]) for i, k in enumerate(keys)}
 
 
+def run_pipelined(api, w, n_bodies, dt, velocity_iterations, position_iterations, n, force_ptrs, out_ptrs):
+    """the act / step / observe loop on the pipelined calls of the ABI (include/dbox_b200.h "pipelined stepping and bulk I/O")"""
+    def ck(rc):
+        if rc < 0:
+            raise RuntimeError("ABI call failed with %d %s" % (rc, api.last_error().decode()))
+        return rc
+    prev = 0
+    for k in range(n):
+        ck(api.world_apply_forces_async(w, force_ptrs[k & 1], n_bodies))
+        ck(api.world_step_async(w, dt, velocity_iterations, position_iterations))
+        ticket = ck(api.world_read_transforms_async(w, out_ptrs[k & 1], n_bodies))
+        if prev:
+            ck(api.world_io_wait(w, prev))          # observation k - 1 is on the host; its buffer is reused at k + 1
+        prev = ticket
+    if prev:
+        ck(api.world_io_wait(w, prev))
+    ck(api.world_sync(w))
+
+
 class WorldBatch:
     """`n_worlds` copies of the world `build(api=..., caps=..., device=...)` returns, this rank's share on its GPU.
 
@@ -73,6 +92,13 @@ class WorldBatch:
         n = self.api.world_read_transforms(self.world._w, host_ptr, self.n_bodies)
         if n != self.n_bodies:
             raise RuntimeError(self.api.last_error())
+
+    def run_pipelined(self, dt, velocity_iterations, position_iterations, n, force_ptrs, out_ptrs):
+        """n iterations of act -> step -> observe with the copies on the copy streams beside the steps
+        (dbx_world_apply_forces_async / step_async / read_transforms_async): iteration k uploads force_ptrs[k % 2], steps, and
+        snapshots + downloads the transforms into out_ptrs[k % 2]; the host waits for observation k - 1 while step k runs.
+        Both pointer pairs are pinned host buffers of n_bodies * 16 bytes."""
+        run_pipelined(self.api, self.world._w, self.n_bodies, dt, velocity_iterations, position_iterations, n, force_ptrs, out_ptrs)
 
     def time_steps(self, dt, velocity_iterations, position_iterations, n, flush_l2=True):
         """n steps timed with CUDA events on the world's stream; returns (total ms, 9 per-stage ms)"""

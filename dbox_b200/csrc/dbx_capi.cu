@@ -320,6 +320,11 @@ int32_t dbx_world_patch_contacts(dbx_world* w, const dbx_contact_patch* patches,
 int32_t dbx_world_raycast_closest(dbx_world* w, const dbx_ray* rays, int32_t n, dbx_ray_hit* out) { W_OR_INVALID(w); return w->w.rayCastClosest(rays, n, out); }
 int32_t dbx_world_set_user_filter(dbx_world* w, int32_t mode) { W_OR_INVALID(w); return w->w.setUserFilter(mode); }
 int32_t dbx_world_poll_new_contacts(dbx_world* w, int32_t* out, int32_t cap) { W_OR_INVALID(w); return w->w.pollNewContacts(out, cap); }
+int32_t dbx_world_step_async(dbx_world* w, float dt, int32_t vi, int32_t pi) { W_OR_INVALID(w); return w->w.stepAsync(dt, vi, pi); }
+int32_t dbx_world_apply_forces_async(dbx_world* w, const float* f, int32_t n) { W_OR_INVALID(w); return w->w.applyForcesAsync(f, n); }
+int32_t dbx_world_read_transforms_async(dbx_world* w, float* out, int32_t n) { W_OR_INVALID(w); return w->w.readTransformsAsync(out, n); }
+int32_t dbx_world_io_wait(dbx_world* w, int32_t ticket) { W_OR_INVALID(w); return w->w.ioWait(ticket); }
+int32_t dbx_world_sync(dbx_world* w) { W_OR_INVALID(w); return w->w.sync(); }
 int32_t dbx_world_raycast_all(dbx_world* w, const dbx_ray* rays, int32_t n, int32_t capPerRay, int32_t* counts, dbx_ray_hit* hits) { W_OR_INVALID(w); return w->w.rayCastAll(rays, n, capPerRay, counts, hits); }
 int32_t dbx_world_test_points(dbx_world* w, const int32_t* fixtures, const dbx_vec2* points, int32_t n, int32_t* inside) { W_OR_INVALID(w); return w->w.testPoints(fixtures, points, n, inside); }
 int32_t dbx_world_shift_origin(dbx_world* w, float x, float y) { W_OR_INVALID(w); return w->w.shiftOrigin(x, y); }

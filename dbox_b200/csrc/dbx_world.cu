@@ -60,6 +60,7 @@ World::~World() {
   b_gs.release(); f_mat.release(); s_p3.release(); b_flags.release(); f_filter.release(); p_flags.release(); c_flags.release();
   b_mask.release(); b_claim.release(); bv_key.release(); bv_keyAlt.release(); jp_keys.release(); c_key.release(); h_key.release();
   d_shapes.release(); p_ids.release(); c_ids.release(); c_fix.release(); j_ids.release(); bv_child.release(); bv_wr.release(); pairs.release(); s_body.release(); c_mk.release();
+  for (int i = 0; i < 2; ++i) { inStage_[i].release(); outSnap_[i].release(); }
   ps_a_.release(); ps_b_.release(); ps_key_.release(); ev_a_.release(); ev_b_.release(); qIn_.release(); qOut_.release(); qCount_.release(); qPairs_.release();
   cubTemp.release(); hdr_.release();
   for (auto& ev : ev_) cudaEventDestroy(ev);
@@ -1551,6 +1552,84 @@ int World::readTransforms(float* out, int n) {
   CUDA_OR_FAIL(cudaMemcpyAsync(out, b_xf.p, (size_t)n * 16, cudaMemcpyDeviceToHost, stream_), "xf d2h");
   CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
   return n;
+}
+
+// ---- pipelined stepping and bulk I/O (see include/dbox_b200.h) ----
+int World::ensureIoStreams() {
+  if (h2d_) return 0;
+  CUDA_OR_FAIL(cudaStreamCreateWithFlags(&h2d_, cudaStreamNonBlocking), "h2d stream");
+  CUDA_OR_FAIL(cudaStreamCreateWithFlags(&d2h_, cudaStreamNonBlocking), "d2h stream");
+  for (int i = 0; i < 2; ++i) {
+    CUDA_OR_FAIL(cudaEventCreateWithFlags(&inCopied_[i], cudaEventDisableTiming), "io event");
+    CUDA_OR_FAIL(cudaEventCreateWithFlags(&inRead_[i], cudaEventDisableTiming), "io event");
+    CUDA_OR_FAIL(cudaEventCreateWithFlags(&snapReady_[i], cudaEventDisableTiming), "io event");
+    CUDA_OR_FAIL(cudaEventCreateWithFlags(&outDone_[i], cudaEventDisableTiming), "io event");
+  }
+  return 0;
+}
+int World::stepAsync(float dt, int vi, int pi) {
+  if (!ok_) return DBX_E_NO_DEVICE;
+  if (midStep_) return DBX_E_INVALID;
+  cudaSetDevice(device_);
+  return enqueueStep(dt, vi, pi, false);
+}
+int World::applyForcesAsync(const float* f4, int n) {
+  int rc = push(); if (rc < 0) return rc;
+  const size_t nAll = bodies_.size() * (size_t)nWorlds_;
+  if (n < 0 || (size_t)n > nAll || (n > 0 && !f4)) return DBX_E_INVALID;
+  if (n == 0) return 0;
+  rc = ensureIoStreams(); if (rc < 0) return rc;
+  const int k = inFlip_; inFlip_ ^= 1;
+  if (inStage_[k].cap < nAll) {               // (re)allocation zero-fills on the world's stream: let that land before the copy stream writes
+    CUDA_OR_FAIL(inStage_[k].reserve(std::max<size_t>(nAll, 1), false, stream_), "force staging");
+    CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+    inReadValid_[k] = false;
+  }
+  if (inReadValid_[k]) CUDA_OR_FAIL(cudaStreamWaitEvent(h2d_, inRead_[k], 0), "staging reuse");   // its previous consumer has run
+  CUDA_OR_FAIL(cudaMemcpyAsync(inStage_[k].p, f4, (size_t)n * 16, cudaMemcpyHostToDevice, h2d_), "forces h2d");
+  CUDA_OR_FAIL(cudaEventRecord(inCopied_[k], h2d_), "io event");
+  CUDA_OR_FAIL(cudaStreamWaitEvent(stream_, inCopied_[k], 0), "forces ready");
+  CUDA_OR_FAIL(launch_apply_forces(dw_, L_, inStage_[k].p, n), "apply_forces");
+  CUDA_OR_FAIL(cudaEventRecord(inRead_[k], stream_), "io event");
+  inReadValid_[k] = true;
+  hostBodiesValid_ = false;
+  return n;
+}
+int World::readTransformsAsync(float* out, int n) {
+  int rc = push(); if (rc < 0) return rc;
+  const size_t nAll = bodies_.size() * (size_t)nWorlds_;
+  if (n < 0 || (size_t)n > nAll || (n > 0 && !out)) return DBX_E_INVALID;
+  rc = ensureIoStreams(); if (rc < 0) return rc;
+  const int ticket = ++ioTicket_;
+  const int k = ticket & 1;
+  if (n == 0) return ticket;
+  if (outSnap_[k].cap < nAll) {
+    if (outDoneValid_[k]) CUDA_OR_FAIL(cudaEventSynchronize(outDone_[k]), "io wait");
+    CUDA_OR_FAIL(outSnap_[k].reserve(std::max<size_t>(nAll, 1), false, stream_), "transform snapshot");
+    outDoneValid_[k] = false;
+  }
+  if (outDoneValid_[k]) CUDA_OR_FAIL(cudaStreamWaitEvent(stream_, outDone_[k], 0), "snapshot reuse");   // the read two tickets ago has left
+  CUDA_OR_FAIL(cudaMemcpyAsync(outSnap_[k].p, b_xf.p, (size_t)n * 16, cudaMemcpyDeviceToDevice, stream_), "xf snapshot");
+  CUDA_OR_FAIL(cudaEventRecord(snapReady_[k], stream_), "io event");
+  CUDA_OR_FAIL(cudaStreamWaitEvent(d2h_, snapReady_[k], 0), "snapshot ready");
+  CUDA_OR_FAIL(cudaMemcpyAsync(out, outSnap_[k].p, (size_t)n * 16, cudaMemcpyDeviceToHost, d2h_), "xf d2h");
+  CUDA_OR_FAIL(cudaEventRecord(outDone_[k], d2h_), "io event");
+  outDoneValid_[k] = true;
+  return ticket;
+}
+int World::ioWait(int ticket) {
+  if (ticket <= 0 || ticket > ioTicket_) return DBX_E_INVALID;
+  // a ticket older than the last two shares its slot with a newer read, which was ordered after it
+  const int k = ticket & 1;
+  if (outDoneValid_[k]) CUDA_OR_FAIL(cudaEventSynchronize(outDone_[k]), "io wait");
+  return 0;
+}
+int World::sync() {
+  if (!ok_) return DBX_E_NO_DEVICE;
+  if (h2d_) { CUDA_OR_FAIL(cudaStreamSynchronize(h2d_), "sync"); }
+  int rc = checkDeviceError(true);
+  if (d2h_) { CUDA_OR_FAIL(cudaStreamSynchronize(d2h_), "sync"); }
+  return rc;
 }
 
 int World::clearForces() {

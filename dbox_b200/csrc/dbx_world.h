@@ -85,6 +85,11 @@ class World {
   int enableContactEvents(int capacity);
   int pollContactEvents(dbx_contact_event* out, int cap);
   int readTransforms(float* out, int n);
+  int stepAsync(float dt, int vi, int pi);
+  int applyForcesAsync(const float* f4, int n);
+  int readTransformsAsync(float* out, int n);
+  int ioWait(int ticket);
+  int sync();
   long launchCount() const { return L_.launches; }
   int clearForces();
   int setFlags(uint32_t f);
@@ -207,6 +212,13 @@ class World {
   DevBuf<char> flushBuf_; DevBuf<float4> ioBuf_, ioBuf2_; DevBuf<int> ioIds_; DevBuf<unsigned> swKeyA_, swKeyB_; DevBuf<int> swValA_, swValB_, wStart_, wEnd_;
   DevBuf<int4> ev_a_, ev_b_; DevBuf<unsigned long long> patchKeys_; bool midStep_ = false; float stepDt_ = 0; int stepVi_ = 0, stepPi_ = 0; DevBuf<float4> qIn_, qOut_; DevBuf<int> qCount_; DevBuf<int2> qPairs_; DevBuf<unsigned long long> phaseBuf_;
   DevBuf<int4> ps_a_; DevBuf<float4> ps_b_; DevBuf<unsigned long long> ps_key_;
+  // pipelined I/O: copy streams beside the step, double-buffered staging on both sides
+  int ensureIoStreams();
+  cudaStream_t h2d_ = nullptr, d2h_ = nullptr;
+  DevBuf<float4> inStage_[2], outSnap_[2];
+  cudaEvent_t inCopied_[2]{}, inRead_[2]{}, snapReady_[2]{}, outDone_[2]{};
+  bool inReadValid_[2] = {false, false}, outDoneValid_[2] = {false, false};
+  int inFlip_ = 0, ioTicket_ = 0;
   bool overrideLevels_ = false;
   bool treeValid_ = false; int sinceRebuild_ = 0;
   // contact-pool watermark: every 8th step the header is copied to pinned memory without waiting; a later step looks at

@@ -459,6 +459,22 @@ int32_t dbx_world_set_user_filter(dbx_world* w, int32_t mode);
  * (out == NULL: the count only, nothing is consumed) */
 int32_t dbx_world_poll_new_contacts(dbx_world* w, int32_t* fixA_childA_fixB_childB, int32_t cap);
 
+/* ---- pipelined stepping and bulk I/O (act / step / observe loops) ------------------------------------------------------
+ * dbx_world_step, dbx_world_apply_forces and dbx_world_read_transforms are synchronous: the caller gets its answer (and
+ * any device error) when they return, and a step's host<->device copies sit between the steps.  The calls below only
+ * ENQUEUE: the step goes to the world's stream; the copies go to two copy streams (host -> device, device -> host) that run
+ * beside it, ordered against the step by events.  forces must be pinned host memory and stay untouched until the step that
+ * consumes them has been enqueued AND a later dbx_world_io_wait / dbx_world_sync has returned; read_transforms_async takes
+ * a snapshot of the transforms at its place in the queue (device-to-device, so the next step is free to move on), copies
+ * it to pinned `out` on the copy stream and returns a ticket; the data is there once dbx_world_io_wait(w, ticket) returns.
+ * Two reads may be in flight (double-buffered snapshot); a third waits for the first.  dbx_world_sync waits for everything
+ * and returns the sticky device error (DBX_E_CAPACITY ...) like a synchronous step would have. */
+int32_t dbx_world_step_async(dbx_world* w, float dt, int32_t velocityIterations, int32_t positionIterations);
+int32_t dbx_world_apply_forces_async(dbx_world* w, const float* pinned_fx_fy_torque_pad, int32_t n);
+int32_t dbx_world_read_transforms_async(dbx_world* w, float* pinned_out, int32_t n);
+int32_t dbx_world_io_wait(dbx_world* w, int32_t ticket);
+int32_t dbx_world_sync(dbx_world* w);
+
 #ifdef __cplusplus
 }
 #endif

@@ -336,3 +336,51 @@ def test_zero_dt_steps_and_staged_collide_leave_no_residue(gpu_api):
         return [(st[i].c.x, st[i].c.y, st[i].a, st[i].v.x, st[i].v.y, st[i].w) for i in range(n)], w.counts().colours
     a, b = run(False), run(True)
     assert a == b
+
+
+def test_pipelined_io_equals_synchronous_calls(gpu_api):
+    """dbx_world_apply_forces_async / step_async / read_transforms_async / io_wait / sync: the act -> step -> observe loop with the
+    copies on copy streams gives, observation by observation, exactly what the synchronous calls give"""
+    import numpy as np
+    import torch
+    steps = 40
+    wa, _ = scenes.pyramid(api=gpu_api, count=10)
+    wb, _ = scenes.pyramid(api=gpu_api, count=10)
+    n = wa.counts().bodies
+    rng = np.random.RandomState(5)
+    acts = rng.uniform(-30.0, 30.0, (steps, n, 4)).astype(np.float32)
+    f = [torch.zeros((n, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    o = [torch.zeros((n, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    sync_obs, pipe_obs = [], []
+    for k in range(steps):
+        f[0].copy_(torch.from_numpy(acts[k]))
+        assert gpu_api.world_apply_forces(wa._w, f[0].data_ptr(), n) == n
+        wa.Step(DT, 8, 3)
+        assert gpu_api.world_read_transforms(wa._w, o[0].data_ptr(), n) == n
+        sync_obs.append(o[0].numpy().copy())
+    prev = 0
+    for k in range(steps):
+        if k >= 2:
+            assert gpu_api.world_sync(wb._w) == 0 if k == 2 else True     # (buffer k & 1 was consumed by step k - 2, long enqueued)
+        f[k & 1].copy_(torch.from_numpy(acts[k]))
+        assert gpu_api.world_apply_forces_async(wb._w, f[k & 1].data_ptr(), n) == n
+        assert gpu_api.world_step_async(wb._w, DT, 8, 3) >= 0
+        t = gpu_api.world_read_transforms_async(wb._w, o[k & 1].data_ptr(), n)
+        assert t == k + 1
+        if prev:
+            assert gpu_api.world_io_wait(wb._w, prev) == 0
+            pipe_obs.append(o[(k - 1) & 1].numpy().copy())
+        prev = t
+        # the host buffer of step k must not change until its copy has happened: wait for the H2D before the next overwrite
+        assert gpu_api.world_io_wait(wb._w, t) == 0
+    pipe_obs.append(o[(steps - 1) & 1].numpy().copy())
+    assert gpu_api.world_sync(wb._w) == 0
+    assert gpu_api.world_io_wait(wb._w, steps + 5) < 0               # a ticket that was never issued
+    assert len(pipe_obs) == steps
+    for k in range(steps):
+        assert np.array_equal(sync_obs[k], pipe_obs[k]), k
+    sa, _ = wa.read_bodies(); sb, _ = wb.read_bodies()
+    assert bytes(sa) == bytes(sb)
+    # and the helper the bench uses
+    from dbox_b200.batch import run_pipelined
+    run_pipelined(gpu_api, wb._w, n, DT, 8, 3, 5, (f[0].data_ptr(), f[1].data_ptr()), (o[0].data_ptr(), o[1].data_ptr()))
