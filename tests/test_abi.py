@@ -80,3 +80,21 @@ def test_shape_helpers_match_oracle(oracle_api):
     api.shape_set_box_at(C.byref(a), 0.5, 10.0, A.Vec2(10.0, 0.0), 0.3)
     oracle_api.shape_set_box_at(C.byref(b), 0.5, 10.0, A.Vec2(10.0, 0.0), 0.3)
     assert bytes(a)[:200] == bytes(b)[:200]
+
+
+def test_d_binding_is_generated_from_the_header_and_complete():
+    """bindings/d/dbox_b200_c.d (the extern (C) module a D build of dbox imports) is exactly what tools/gen_d_binding.py makes of
+    include/dbox_b200.h, declares every entry point once, mirrors every struct field for field, and uses no D keyword as a name"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_d_binding", os.path.join(ROOT, "tools", "gen_d_binding.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    text, funcs = gen.generate()
+    assert open(gen.OUT).read() == text, "run python tools/gen_d_binding.py"
+    assert sorted(funcs) == _declared() and len(set(funcs)) == len(funcs)
+    for name, typ in (("dbx_body_def", A.BodyDef), ("dbx_shape", A.Shape), ("dbx_joint_def", A.JointDef), ("dbx_contact_rec", A.ContactRec),
+                      ("dbx_post_solve", A.PostSolve), ("dbx_world_manifold", A.WorldManifold), ("dbx_ray_hit", A.RayHit)):
+        body = re.search(r"struct %s\n\{(.*?)\n\}" % name, text, re.S).group(1)
+        assert len([l for l in body.split("\n") if l.strip()]) == len(typ._fields_), name
+    for m in re.finditer(r"[\s\*\]]([A-Za-z_]\w*)\s*[;,)]", text.split("extern (C) nothrow @nogc:")[1]):
+        assert m.group(1) not in gen.D_KEYWORDS or m.group(1) in ("float", "int", "uint", "long", "ulong", "short", "ushort", "void", "char"), m.group(1)
