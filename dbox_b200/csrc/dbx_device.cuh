@@ -28,6 +28,9 @@ enum : uint32_t {
   CF_FRESH = 0x0800 /* created by this step's FindNewContacts: the overlapped TOI pre-evaluation must not look at it */,
   CF_NEW = 0x1000 /* created since the host last polled the new-contact list (user contact filter, deferred) */
 };
+// what a kernel stores in Header::error: DBX_E_CAPACITY (-5) in the low bits, the pool that overflowed above (host: checkDeviceError)
+enum { E_CONTACTS = -5 - 16 * 1, E_PAIRS = -5 - 16 * 2, E_MOVES = -5 - 16 * 3, E_COLOURS = -5 - 16 * 4, E_SOLVER_ROWS = -5 - 16 * 5,
+       E_HASH = -5 - 16 * 6, E_QUERY_STACK = -5 - 16 * 7, E_TOI_CANDIDATES = -5 - 16 * 8 };
 enum { FXF_SENSOR = 1 };
 enum { PF_ALIVE = 1, PF_MOVED = 2 };
 enum { JT_REVOLUTE = 1, JT_DISTANCE = 3 };

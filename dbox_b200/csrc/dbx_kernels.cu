@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(512) k_colour(const __grid_constant__ DevWorld
           if (dynA) W.b_ovf[ids.z] = o + 1;
           if (dynB) W.b_ovf[ids.w] = o + 1;
           col = kMaskColours + o;
-          if (col >= kMaxColours) { col = kMaxColours - 1; H->error = -5; }
+          if (col >= kMaxColours) { col = kMaxColours - 1; H->error = E_COLOURS; }
         }
         W.c_colour[i] = col;
         if (col > *((volatile int*)&H->maxColour)) atomicMax(&H->maxColour, col);
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(kMaxColours) k_sort_scan_colours(const __grid_
     const int total = excl + v;
     W.hdr->colourOff[kMaxColours] = total;
     W.hdr->nSolve = total;
-    if (total > W.sCap) W.hdr->error = -5;
+    if (total > W.sCap) W.hdr->error = E_SOLVER_ROWS;
   }
   if (c == 0) W.hdr->nColours = lastColour;
 }
@@ -461,7 +461,7 @@ DBX_D void sync_proxy(const DevWorld& W, int p, uint32_t pf, int body) {
     if (!(pf & PF_MOVED)) {
       W.p_flags[p] = pf | PF_MOVED;
       int slot = atomicAdd(&W.hdr->nMoved, 1);
-      if (slot < W.moveCap) W.moveList[slot] = p; else W.hdr->error = -5;
+      if (slot < W.moveCap) W.moveList[slot] = p; else W.hdr->error = E_MOVES;
     }
   }
 }
@@ -632,7 +632,7 @@ DBX_D void query_proxy(const DevWorld& W, const int* leaves, int* stack, int cap
         if (!qMoved || keyP < keyQ) {
           int slot = atomicAdd(&W.hdr->nPairs, 1);
           if (slot < W.pairCap) W.pairs[slot] = keyP < keyQ ? make_int2(p, q) : make_int2(q, p);
-          else W.hdr->error = -5;
+          else W.hdr->error = E_PAIRS;
         }
       }
     }
@@ -640,7 +640,7 @@ DBX_D void query_proxy(const DevWorld& W, const int* leaves, int* stack, int cap
     unsigned ballot = __ballot_sync(0xffffffffu, push);
     int offset = __popc(ballot & ((1u << lane) - 1));
     int total = __popc(ballot);
-    if (top + 2 * total > cap) { if (lane == 0) W.hdr->error = -5; break; }   // tree deeper than kQueryReserve: report, never corrupt
+    if (top + 2 * total > cap) { if (lane == 0) W.hdr->error = E_QUERY_STACK; break; }   // tree deeper than kQueryReserve: report, never corrupt
     if (push) {
       int base = top + 2 * offset;
       stack[base] = ch.x; stack[base + 1] = ch.y;
@@ -758,7 +758,7 @@ __global__ void __launch_bounds__(128) k_raycast(const __grid_constant__ DevWorl
             bestFixture = ids.x; bestChild = ids.y; bestKey = key; bestNormal = normal; maxFraction = fraction;
           }
         } else {
-          if (top + 2 > kRayStack) { W.hdr->error = -5; break; }
+          if (top + 2 > kRayStack) { W.hdr->error = E_QUERY_STACK; break; }
           const int2 ch = W.bv_child[node];
           stack[top++] = ch.x; stack[top++] = ch.y;
         }
@@ -789,7 +789,7 @@ __global__ void __launch_bounds__(128) k_query_aabb(const __grid_constant__ DevW
           if (count < capPer) out[(size_t)k * capPer + count] = make_int2(ids.x, ids.y);
           ++count;
         } else {
-          if (top + 2 > kRayStack) { W.hdr->error = -5; break; }
+          if (top + 2 > kRayStack) { W.hdr->error = E_QUERY_STACK; break; }
           const int2 ch = W.bv_child[node];
           stack[top++] = ch.x; stack[top++] = ch.y;
         }
@@ -836,7 +836,7 @@ __global__ void __launch_bounds__(128) k_raycast_all(const __grid_constant__ Dev
           }
           ++count;
         } else {
-          if (top + 2 > kRayStack) { W.hdr->error = -5; break; }
+          if (top + 2 > kRayStack) { W.hdr->error = E_QUERY_STACK; break; }
           const int2 ch = W.bv_child[node];
           stack[top++] = ch.x; stack[top++] = ch.y;
         }
@@ -969,7 +969,7 @@ DBX_D void add_pair(const DevWorld& W, int2 pr) {
   int f = atomicSub(&W.hdr->nFree, 1);
   if (f > 0) slot = W.c_free[f - 1];
   else { atomicAdd(&W.hdr->nFree, 1); slot = atomicAdd(&W.hdr->cHigh, 1); }
-  if (slot >= W.cCap) { W.hdr->error = -5; atomicSub(&W.hdr->cHigh, 1); return; }
+  if (slot >= W.cCap) { W.hdr->error = E_CONTACTS; atomicSub(&W.hdr->cHigh, 1); return; }
   const bool sensor = ((W.f_group[ia.x] >> 16) & FXF_SENSOR) || ((W.f_group[ib.x] >> 16) & FXF_SENSOR);
   const float2 mA = W.f_mat[ia.x], mB = W.f_mat[ib.x];
   W.c_key[slot] = key;
@@ -985,7 +985,7 @@ DBX_D void add_pair(const DevWorld& W, int2 pr) {
   W.c_mat[slot] = make_float4(sqrtf(mA.x * mB.x), mA.y > mB.y ? mA.y : mB.y, 0.0f, 1.0f);
   W.c_toiCount[slot] = 0;
   W.c_colour[slot] = -1;
-  if (!hash_insert(W, key, slot)) W.hdr->error = -5;
+  if (!hash_insert(W, key, slot)) W.hdr->error = E_HASH;
   if (!sensor) { wake_body_now(W, ia.z); wake_body_now(W, ib.z); }   // :168-173
 }
 __global__ void __launch_bounds__(256) k_add_pairs(const __grid_constant__ DevWorld W) {
@@ -1005,7 +1005,7 @@ __global__ void __launch_bounds__(256) k_hash_clear(const __grid_constant__ DevW
 }
 __global__ void __launch_bounds__(256) k_hash_fill(const __grid_constant__ DevWorld W) {
   const int n = W.hdr->cHigh;
-  GRID_STRIDE(i, n) if (W.c_flags[i] & CF_ALIVE) { if (!hash_insert(W, W.c_key[i], i)) W.hdr->error = -5; }
+  GRID_STRIDE(i, n) if (W.c_flags[i] & CF_ALIVE) { if (!hash_insert(W, W.c_key[i], i)) W.hdr->error = E_HASH; }
 }
 __global__ void __launch_bounds__(256) k_count(const __grid_constant__ DevWorld W) {
   const int n = W.hdr->cHigh;
@@ -1101,7 +1101,7 @@ __global__ void __launch_bounds__(256) k_replicate(const __grid_constant__ DevWo
     const int r = idx / nMoved, k = idx - r * nMoved;
     if (r > 0) W.moveList[idx] = W.moveList[k] + r * nP;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) { W.hdr->nMoved = nMoved * copies; if (nMoved * copies > W.moveCap) W.hdr->error = -5; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { W.hdr->nMoved = nMoved * copies; if (nMoved * copies > W.moveCap) W.hdr->error = E_MOVES; }
 }
 
 // ------------------------------------------------------------------------------------------------ API-time edits
@@ -1587,7 +1587,7 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
           if (body_type(fother) == BODY_DYNAMIC && !(fbody & BF_BULLET) && !(fother & BF_BULLET)) continue;
           const int evSide = W.c_ids[ec].z == body ? 0 : 1;
           const int slot = atomicAdd(&W.e_ncand[2 * e + evSide], 1);
-          if (slot < kToiCand) W.e_cand[(2 * e + evSide) * kToiCand + slot] = i; else H->error = -5;
+          if (slot < kToiCand) W.e_cand[(2 * e + evSide) * kToiCand + slot] = i; else H->error = E_TOI_CANDIDATES;
           if (body_type(fother) != BODY_STATIC) {
             const unsigned long long prio = toi_prio(W, W.c_mat[ec].w, ec, W.c_ids[ec].z);
             atomicMin(&W.b_toiOther[other], prio);
@@ -1683,13 +1683,13 @@ cudaError_t stage_islands_and_integrate(const DevWorld& W, const LaunchCfg& L) {
 __global__ void __launch_bounds__(256) k_world_keys(const __grid_constant__ DevWorld W, unsigned* keys, int* vals, int n, int colourBits) {
   const int high = W.hdr->cHigh;
   int count = 0, maxc = 0;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && high > n) W.hdr->error = -5;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && high > n) W.hdr->error = E_SOLVER_ROWS;
   GRID_STRIDE(i, n) {
     unsigned key = (unsigned)W.nWorlds << colourBits;
     if (i < high && (W.c_flags[i] & CF_SOLVE)) {
       const int4 ids = W.c_ids[i];
       const int c = W.c_colour[i];
-      if (c >= (1 << colourBits)) W.hdr->error = -5;
+      if (c >= (1 << colourBits)) W.hdr->error = E_COLOURS;
       key = ((unsigned)W.b_world[ids.z] << colourBits) | (unsigned)(c & ((1 << colourBits) - 1));
       ++count; maxc = max(maxc, c + 1);
     }
@@ -1700,7 +1700,7 @@ __global__ void __launch_bounds__(256) k_world_keys(const __grid_constant__ DevW
 }
 __global__ void __launch_bounds__(256) k_world_ranges(const __grid_constant__ DevWorld W, const unsigned* keys, int colourBits) {
   const int n = min(W.hdr->nSolve, W.sCap);
-  if (blockIdx.x == 0 && threadIdx.x == 0 && W.hdr->nSolve > W.sCap) W.hdr->error = -5;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && W.hdr->nSolve > W.sCap) W.hdr->error = E_SOLVER_ROWS;
   GRID_STRIDE(s, n) {
     const int w = (int)(keys[s] >> colourBits);
     if (s == 0 || (int)(keys[s - 1] >> colourBits) != w) W.w_start[w] = s;

@@ -274,7 +274,7 @@ template <bool kLocal> __global__ void __launch_bounds__(128) k_solve_worlds(con
     }
     __syncthreads();
     const int nc = min(ncol, kWorldMaxColours);
-    if (ncol > kWorldMaxColours && t == 0) W.hdr->error = -5;
+    if (ncol > kWorldMaxColours && t == 0) W.hdr->error = E_COLOURS;
     if (t == 0) {                                  // a handful of entries: insertion sort
       for (int a = 1; a < nc; ++a) { const int v = cstart[a]; int b = a - 1; while (b >= 0 && cstart[b] > v) { cstart[b + 1] = cstart[b]; --b; } cstart[b + 1] = v; }
       cstart[nc] = end;

@@ -1010,7 +1010,13 @@ int World::checkDeviceError(bool sync) {
   int err = 0;
   CUDA_OR_FAIL(cudaMemcpy(&err, (char*)hdr_.p + offsetof(Header, error), 4, cudaMemcpyDeviceToHost), "read error");
   if (err != 0) {
-    set_last_error("device pool overflow (contacts / pairs / colours): raise dbx_caps");
+    static const char* const what[] = {"a device pool", "the contact pool (dbx_caps.maxContacts)", "the candidate pair buffer (dbx_caps.maxPairs)",
+        "the move buffer (dbx_caps.maxProxies)", "the constraint colours (more than 1024 constraints on one body)", "the solver rows (dbx_caps.maxContacts)",
+        "the pair hash (dbx_caps.maxContacts)", "a tree traversal stack (LBVH deeper than the query reserve)",
+        "the TOI candidate list (more than 64 non-dynamic / bullet contacts on one body of a TOI event)"};
+    const int site = err <= -5 ? ((-err - 5) / 16) : 0;
+    set_last_error(std::string("device pool overflow: ") + what[site >= 0 && site < 9 ? site : 0] + "; see dbx_caps");
+    err = (err <= -5) ? DBX_E_CAPACITY : err;
     int zero = 0; cudaMemcpy((char*)hdr_.p + offsetof(Header, error), &zero, 4, cudaMemcpyHostToDevice);
     return err;
   }

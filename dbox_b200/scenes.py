@@ -107,12 +107,14 @@ class Tumbler:
         self.bodies = []
 
     def Step(self, dt=1.0 / 60.0, vi=8, pi=3, spawn_per_step=1):
+        """tumbler.d:78-97: one new body per step at the container's centre; spawn_per_step > 1 (grow a big scene in fewer
+        steps) lays the extra bodies out side by side, half a unit apart, instead of on top of each other"""
         self.world.Step(dt, vi, pi)
-        for _ in range(spawn_per_step):
+        for k in range(spawn_per_step):
             if self.m_count < self.count:
                 bd = b2BodyDef()
                 bd.type = b2_dynamicBody
-                bd.position.Set(0.0, 10.0 * self.scale)
+                bd.position.Set(f32(0.5 * (k - 0.5 * (spawn_per_step - 1))), 10.0 * self.scale)
                 body = self.world.CreateBody(bd)
                 if self.mixed and (self.m_count & 1):
                     shape = b2CircleShape(self.world._api)

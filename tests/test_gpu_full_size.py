@@ -126,3 +126,69 @@ def test_pile_100k_full_size_properties(gpu_api):
     px, py = st[1:, 2], st[1:, 3]                             # BodyState.p of the dynamic bodies (body 0 is the ground)
     assert px.min() > -half_w - 0.6 and px.max() < half_w + 0.6 and py.min() > 0.3
     assert w._api.world_debug_colour_conflicts(w._w) == 0
+
+
+def test_batched_65536_pyramids_full_size_properties(gpu_api):
+    """BASELINE config 5 at its full size on one GPU: 65,536 Pyramid worlds (13.9 M bodies) as replicas of one device world.
+    Size-independent properties: worlds that start identical stay identical BIT FOR BIT (every replica equals replica 0, which
+    tests/test_gpu_parity.py compares with a world stepped alone), the populations are exact multiples of one world's, the
+    solver schedule is a proper colouring, and worlds that are then pushed apart diverge without touching their neighbours"""
+    worlds = 65536
+    single, _ = scenes.pyramid(api=gpu_api)
+    caps = A.Caps(); caps.maxContacts = worlds * 700
+    batch, _ = scenes.pyramid(api=gpu_api, caps=caps)
+    nb = batch.counts().bodies
+    batch.Replicate(worlds)
+    assert gpu_api.world_replica_count(batch._w) == worlds
+    single.StepN(DT, 8, 3, 40); batch.StepN(DT, 8, 3, 40)
+    cs, cb = single.counts(), batch.counts()
+    assert cb.bodies == nb * worlds
+    assert (cb.contacts, cb.touching, cb.awakeBodies) == (cs.contacts * worlds, cs.touching * worlds, cs.awakeBodies * worlds)
+    assert gpu_api.world_debug_colour_conflicts(batch._w) == 0
+    xf = np.empty((nb * worlds, 4), np.float32)
+    assert gpu_api.world_read_transforms(batch._w, xf.ctypes.data, nb * worlds) == nb * worlds
+    xf = xf.reshape(worlds, nb, 4).view(np.uint32)
+    assert (xf == xf[0]).all()
+    one = np.empty((nb, 4), np.float32)
+    assert gpu_api.world_read_transforms(single._w, one.ctypes.data, nb) == nb
+    assert np.array_equal(one.view(np.uint32), xf[0])
+    # push every 4096th world: it diverges, the worlds next to it do not
+    vel = np.zeros((worlds // 4096, 4), np.float32); vel[:, 0] = 3.0
+    ids = (np.arange(worlds // 4096, dtype=np.int32) * 4096 * nb + nb - 1)          # the top box of those worlds
+    batch.SetBodyStates(ids=ids, vel=vel)
+    batch.StepN(DT, 8, 3, 20)
+    xf2 = np.empty((nb * worlds, 4), np.float32)
+    assert gpu_api.world_read_transforms(batch._w, xf2.ctypes.data, nb * worlds) == nb * worlds
+    xf2 = xf2.reshape(worlds, nb, 4).view(np.uint32)
+    same = (xf2 == xf2[1]).all(axis=(1, 2))
+    assert not same[::4096].any() and same.sum() == worlds - worlds // 4096
+    batch.close(); single.close()
+
+
+def test_tumbler_20k_full_size_invariants(gpu_api):
+    """BASELINE config 3 at its full size: the Tumbler grown to 20,000 bodies (container x5); bodies are added
+    while the world runs (the reference adds one per step; here 16 side by side so that the scene is full after 1,250 steps).
+    The container is ONE dynamic body under hundreds of contacts (overflow colour lanes).  Invariants: nothing leaks out of the
+    container, the schedule stays a proper colouring, the motor keeps its speed, populations are sane, the state is finite"""
+    n = 20000
+    caps = A.Caps(); caps.maxContacts = 1 << 19          # bodies are born on top of each other: more than the default 8 contacts per proxy early on
+    t = scenes.Tumbler(api=gpu_api, count=n, scale=5.0, caps=caps)
+    steps = 0
+    while t.m_count < n:
+        t.Step(spawn_per_step=16); steps += 1
+    for _ in range(150):
+        t.Step(); steps += 1
+    w = t.world
+    cnt = w.counts()
+    assert cnt.bodies == n + 3 and cnt.joints == 1 and cnt.contacts > n and cnt.touching > n // 2
+    assert gpu_api.world_debug_colour_conflicts(w._w) == 0
+    buf, nb = w.read_bodies()
+    st = np.frombuffer(buf, dtype=np.float32, count=nb * 29).reshape(nb, 29)
+    assert np.isfinite(st).all()
+    c = t.container._state()
+    p = st[3:, 2:4]                                               # the spawned bodies (ids 0-2: demo body, ground, container)
+    dx, dy = p[:, 0] - c.p.x, p[:, 1] - c.p.y
+    lx, ly = c.qc * dx + c.qs * dy, -c.qs * dx + c.qc * dy        # container frame
+    assert np.abs(lx).max() < 53.0 and np.abs(ly).max() < 53.0
+    assert abs(t.container.GetAngularVelocity() - 0.05 * np.pi) < 2e-3
+    assert abs(t.container.GetAngle() - steps * DT * 0.05 * np.pi) < 0.05
