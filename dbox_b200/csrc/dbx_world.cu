@@ -1038,8 +1038,11 @@ int World::growContactsIfNeeded() {
   if (!wmPending_ || cudaEventQuery(wmEv_) != cudaSuccess) return 0;
   wmPending_ = false;
   const size_t high = (size_t)std::max(wm_[0], 0);          // Header::cHigh
-  if (2 * high <= c_key.cap) return 0;
-  contactFloor_ = 2 * c_key.cap;
+  // a small pool is watched more closely and grown by more: a scene that is just being filled (bodies born on top of each
+  // other, tumbler.d:78-97) can double its contacts within a few steps, and the memory at stake is nothing
+  const size_t factor = c_key.cap <= 65536 ? 4 : 2;
+  if (factor * high <= c_key.cap) return 0;
+  contactFloor_ = factor * c_key.cap;
   bool rehash = false;
   int rc = reserveDevice(rehash); if (rc < 0) return rc;
   refreshView();
@@ -1149,7 +1152,7 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents, int halves) {
     CUDA_OR_FAIL(cudaMemsetAsync(c_colour.p, 0xFF, c_colour.cap * 4, stream_), "reset colours");
   }
   if ((stepCount_ & 63) == 0) { int rc2 = compactContacts(); if (rc2 < 0) return rc2; }
-  if ((stepCount_ & 7) == 0 && !wmPending_) {
+  if ((stepCount_ & (c_key.cap <= 65536 ? 1 : 7)) == 0 && !wmPending_) {
     if (!wm_) { CUDA_OR_FAIL(cudaMallocHost((void**)&wm_, 256), "watermark"); CUDA_OR_FAIL(cudaEventCreateWithFlags(&wmEv_, cudaEventDisableTiming), "watermark"); }
     CUDA_OR_FAIL(cudaMemcpyAsync(wm_, hdr_.p, 64, cudaMemcpyDeviceToHost, stream_), "watermark");
     CUDA_OR_FAIL(cudaEventRecord(wmEv_, stream_), "watermark");

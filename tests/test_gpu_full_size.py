@@ -171,8 +171,7 @@ def test_tumbler_20k_full_size_invariants(gpu_api):
     The container is ONE dynamic body under hundreds of contacts (overflow colour lanes).  Invariants: nothing leaks out of the
     container, the schedule stays a proper colouring, the motor keeps its speed, populations are sane, the state is finite"""
     n = 20000
-    caps = A.Caps(); caps.maxContacts = 1 << 19          # bodies are born on top of each other: more than the default 8 contacts per proxy early on
-    t = scenes.Tumbler(api=gpu_api, count=n, scale=5.0, caps=caps)
+    t = scenes.Tumbler(api=gpu_api, count=n, scale=5.0)          # default pools: the contact pool grows by its watermark while the scene fills
     steps = 0
     while t.m_count < n:
         t.Step(spawn_per_step=16); steps += 1
