@@ -1480,6 +1480,7 @@ int World::readPostSolve(dbx_post_solve* out, int cap) {
 // user b2ContactFilter, deferred (see include/dbox_b200.h)
 int World::setUserFilter(int mode) {
   if (mode < 0 || mode > 3) return DBX_E_INVALID;
+  if (replicated_ && mode != 0) { set_last_error("world is replicated: per-contact vetoes address fixtures of the template world only"); return DBX_E_UNSUPPORTED; }
   dw_.userFilter = mode;
   return 0;
 }
