@@ -384,3 +384,30 @@ def test_pipelined_io_equals_synchronous_calls(gpu_api):
     # and the helper the bench uses
     from dbox_b200.batch import run_pipelined
     run_pipelined(gpu_api, wb._w, n, DT, 8, 3, 5, (f[0].data_ptr(), f[1].data_ptr()), (o[0].data_ptr(), o[1].data_ptr()))
+
+
+def test_world_queries_against_committed_goldens(gpu_api):
+    """the CUDA path against the committed fixture tests/golden/oracle_golden.json ("queries", made by tests/golden/make_golden.py
+    from the oracle): on the identical, not yet stepped scene the fixtures / children hit, the AABB query sets and the TestPoint
+    answers are equal, fractions and normals agree to float rounding; after 60 steps the resting scene gives the same hit lists"""
+    import importlib.util
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = json.load(open(os.path.join(here, "golden", "oracle_golden.json")))["queries"]
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    got = json.loads(json.dumps(mg.queries_golden(gpu_api)))
+    fh = float.fromhex
+    g0, w0 = got["initial"], gold["initial"]
+    assert g0["inside"] == w0["inside"] and g0["boxes"] == w0["boxes"] and g0["world_manifolds"] == w0["world_manifolds"] == []
+    for a, b in zip(g0["closest"], w0["closest"]):
+        assert a[:2] == b[:2] and all(abs(fh(x) - fh(y)) <= 1e-6 for x, y in zip(a[2:], b[2:])), (a, b)
+    for ha, hb in zip(g0["all"], w0["all"]):
+        assert [h[:2] for h in ha] == [h[:2] for h in hb]
+        assert all(abs(fh(x[2]) - fh(y[2])) <= 1e-6 for x, y in zip(ha, hb))
+    g1, w1 = got["after60"], gold["after60"]
+    assert [[h[:2] for h in hits] for hits in g1["all"]] == [[h[:2] for h in hits] for hits in w1["all"]]
+    assert g1["boxes"] == w1["boxes"] and len(g1["world_manifolds"]) == len(w1["world_manifolds"])
+    assert sum(a != b for a, b in zip(g1["inside"], w1["inside"])) <= 2          # sample points next to an edge of a body at rest

@@ -204,3 +204,16 @@ def test_test_point_and_world_manifold_fixed_inputs(oracle_api):
     assert abs(abs(n[1]) - 1.0) < 1e-6 and abs(n[0]) < 1e-6            # vertical normal, A -> B
     assert sorted(round(p[0], 3) for p in pts) == [-1.0, 1.0]            # the box's two bottom corners
     assert all(-0.011 < s < 0.0 for s in sep)                            # resting inside the 2 * b2_polygonRadius skin
+
+
+def test_world_query_goldens(oracle_api):
+    """ray casts (closest hit and every hit), AABB queries, TestPoint and world manifolds of the oracle on a fixed scene, before the
+    first step and after 60: frozen in tests/golden/oracle_golden.json so that the checker itself cannot drift"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    got = mg.queries_golden(oracle_api)
+    assert json.loads(json.dumps(got)) == GOLD["queries"]
+    assert "1" in GOLD["queries"]["initial"]["inside"] and "0" in GOLD["queries"]["initial"]["inside"]
+    assert len(GOLD["queries"]["after60"]["world_manifolds"]) >= 9
