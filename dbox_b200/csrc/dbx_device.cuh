@@ -77,6 +77,9 @@ struct Header {
   int nToi;           // entries of c_toiList: contacts the TOI pass can ever care about this step (listed by k_collide)
   int nPostSolve;     // PostSolve records of the current step (may exceed psCap: the surplus is lost and reported)
   int nNewContacts;   // scratch counter of k_list_new_contacts
+  int stepIncomplete; // sub-stepping (b2World.SetSubStepping): k_toi stopped after one solved TOI event; the next Step resumes
+  int toiSolved;      // TOI mini-islands solved by the current k_toi launch (sub-stepping stops at the first)
+  unsigned long long toiGlobalMin;   // sub-stepping: smallest event priority of the current pass (the ONE event to handle)
 };
 
 struct DevWorld {
@@ -154,6 +157,8 @@ struct DevWorld {
   int toiClearForces;// k_toi also runs ClearForces (b2world.d:443-450) in its final body pass
   int toiMode;       // k_toi: 1 = only the first evaluation, launched as a plain kernel on the second stream (no grid barrier is reached)
   int toiPre;        // k_toi: k_toi_pre already did the first evaluation of the contacts that existed before FindNewContacts
+  int subStep;       // b2World.SetSubStepping(true): handle ONE TOI event per Step (dynamics/b2world.d:1441-1446)
+  int toiResume;     // the previous Step left SolveTOI unfinished (m_stepComplete == false): no reset of the TOI state (:1131-1146)
   int stepIndex;     // low 16 bits stamp the events of this step
   int2* bv_wr;       // [n-1] replica-index range of the leaves under an internal node
   int* bv_pos;       // proxy slot -> sorted leaf index

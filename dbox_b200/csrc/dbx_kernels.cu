@@ -1303,9 +1303,10 @@ DBX_D void toi_publish(const DevWorld& W, int i, const int4 ids, uint32_t fa, ui
   const unsigned long long prio = toi_prio(W, alpha, i, ids.z);
   if (body_type(fa) != BODY_STATIC) atomicMin(&W.b_toiMin[ids.z], prio);
   if (body_type(fb) != BODY_STATIC) atomicMin(&W.b_toiMin[ids.w], prio);
+  if (W.subStep) atomicMin(&W.hdr->toiGlobalMin, prio);
 }
-// `first`: this is the step's first look at the contact, which doubles as the reset of b2world.d:1131-1146 (m_stepComplete
-// is always true here: sub-stepping is not supported) -- forget the cached TOI, the island flag and the sub-step count
+// `first`: this is the step's first look at the contact, which doubles as the reset of b2world.d:1131-1146 (skipped when a
+// sub-stepped world resumes an unfinished SolveTOI, W.toiResume) -- forget the cached TOI, the island flag and the sub-step count
 DBX_D bool toi_classify(const DevWorld& W, int i, bool first) {
   uint32_t flags = W.c_flags[i];
   if (!(flags & CF_ALIVE)) return false;
@@ -1407,6 +1408,7 @@ DBX_D void toi_process_event(const DevWorld& W, int e, float dtStep) {
     return;
   }
   W.c_flags[i0] = flags0;
+  atomicAdd(&W.hdr->toiSolved, 1);
   wake_body_now(W, bA);
   wake_body_now(W, bB);
   int bodies[2 * kMaxTOIContacts], contacts[kMaxTOIContacts];
@@ -1507,8 +1509,8 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
   // bodies added since) pays for a reset phase.
   if (W.toiReset) {
     for (int b = tid; b < W.nBodies; b += nth) {
-      float4 p0 = W.b_pos0[b]; if (p0.w != 0.0f) { p0.w = 0.0f; W.b_pos0[b] = p0; }
-      W.b_toiMin[b] = ~0ull; W.b_toiOther[b] = ~0ull; W.b_toiEvt[b] = -1; W.b_toiFlags[b] = 0;
+      if (!W.toiResume) { float4 p0 = W.b_pos0[b]; if (p0.w != 0.0f) { p0.w = 0.0f; W.b_pos0[b] = p0; } }
+      W.b_toiMin[b] = ~0ull; W.b_toiOther[b] = ~0ull; W.b_toiEvt[b] = -1; W.b_toiFlags[b] = W.toiResume ? (W.b_toiFlags[b] & TF_INVAL) : 0;
     }
     if (tid == 0) H->nEvents = 0;
     grid_barrier(&H->barrier, nb); TMARK();
@@ -1517,12 +1519,13 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
     const int nMoved = min(H->nMoved, W.moveCap);
     for (int k = tid; k < nMoved; k += nth) { const int p = W.moveList[k]; W.p_flags[p] &= ~PF_MOVED; }
   }
+  bool incomplete = false;
   for (int pass = 0; pass < 1024; ++pass) {
     // (a) TOI evaluation + per-body minima
     {
       // few contacts per thread (one big world): evaluate in place, every chain on its own warp; many (batched worlds):
       // gather the eligible ones so that b2TimeOfImpact runs on full warps
-      const bool first = pass == 0 && (!W.toiPre || W.toiMode == 1);
+      const bool first = pass == 0 && (!W.toiPre || W.toiMode == 1) && !W.toiResume;
       const int nFresh = min(*((volatile int*)&H->nFresh), W.cCap);
       const int nList = min(*((volatile int*)&H->nToi), W.cCap);
       const int n = nList + (W.toiMode == 1 ? 0 : nFresh);     // the overlapped first evaluation leaves the fresh ones alone
@@ -1555,6 +1558,7 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
         const unsigned long long prio = toi_prio(W, alpha, i, ids.z);
         const bool movA = body_type(W.b_flags[ids.z]) != BODY_STATIC, movB = body_type(W.b_flags[ids.w]) != BODY_STATIC;
         if ((movA && __ldcg(&W.b_toiMin[ids.z]) != prio) || (movB && __ldcg(&W.b_toiMin[ids.w]) != prio)) continue;
+        if (W.subStep && __ldcg(&H->toiGlobalMin) != prio) continue;     // one event per Step: the earliest of all
         const int e = atomicAdd(&H->nEvents, 1);
         if (e >= eventCap) continue;     // stays a candidate for the next pass
         W.e_contact[e] = i;
@@ -1619,7 +1623,7 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
         W.b_toiMin[b] = ~0ull; W.b_toiOther[b] = ~0ull; W.b_toiEvt[b] = -1;
         if (W.b_toiFlags[b] & TF_SYNC) W.b_toiFlags[b] &= ~TF_SYNC;
       }
-      if (tid == 0) H->nEvents = 0;
+      if (tid == 0) { H->nEvents = 0; H->toiGlobalMin = ~0ull; }
     }
     grid_barrier(&H->barrier, nb); TMARK();
     {
@@ -1635,18 +1639,24 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
     }
     grid_barrier(&H->barrier, nb); TMARK();
     if (tid == 0) H->nMoved = 0;
+    const bool stopHere = W.subStep && *((volatile int*)&H->toiSolved) > 0;   // b2world.d:1441-1446: m_stepComplete = false; break
     grid_barrier(&H->barrier, nb); TMARK();
+    if (stopHere) { incomplete = true; break; }
   }
-  // leave the per-body scratch clean for the next step (every CTA is past the last arbitration phase here)
+  // leave the per-body scratch clean for the next step (every CTA is past the last arbitration phase here); a sub-stepped
+  // world that stopped after one event keeps what the resumed SolveTOI needs: the sweeps' alpha0 and the pending invalidations
   for (int b = tid; b < W.nBodies; b += nth) {
     if (W.b_toiMin[b] != ~0ull) W.b_toiMin[b] = ~0ull;
     if (W.b_toiOther[b] != ~0ull) W.b_toiOther[b] = ~0ull;
     if (W.b_toiEvt[b] != -1) W.b_toiEvt[b] = -1;
-    if (W.b_toiFlags[b] != 0) W.b_toiFlags[b] = 0;
-    float4 p0 = W.b_pos0[b]; if (p0.w != 0.0f) { p0.w = 0.0f; W.b_pos0[b] = p0; }
+    if (incomplete) { const int f = W.b_toiFlags[b]; if (f & ~TF_INVAL) W.b_toiFlags[b] = f & TF_INVAL; }
+    else {
+      if (W.b_toiFlags[b] != 0) W.b_toiFlags[b] = 0;
+      float4 p0 = W.b_pos0[b]; if (p0.w != 0.0f) { p0.w = 0.0f; W.b_pos0[b] = p0; }
+    }
     if (W.toiClearForces) W.b_force[b] = make_float4(0, 0, 0, 0);
   }
-  if (tid == 0) { H->nEvents = 0; H->nToi = 0; }
+  if (tid == 0) { H->nEvents = 0; H->nToi = 0; H->nFresh = 0; H->stepIncomplete = incomplete ? 1 : 0; H->toiSolved = 0; H->toiGlobalMin = ~0ull; }
 }
 
 #undef TMARK

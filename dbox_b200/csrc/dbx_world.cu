@@ -565,6 +565,7 @@ int World::destroyJoint(int jid) {
 }
 
 int World::setFlags(uint32_t f) {
+  if ((f & DBX_WORLD_SUB_STEPPING) && replicated_) { set_last_error("sub-stepping a replicated world is not built (one TOI event per Step would be one over ALL replicas)"); return DBX_E_UNSUPPORTED; }
   if ((flags_ & DBX_WORLD_ALLOW_SLEEP) && !(f & DBX_WORLD_ALLOW_SLEEP)) {
     // b2World.SetAllowSleeping(false) wakes every body (b2world.d:622-640)
     int rc = pullBodies(); if (rc < 0) return rc;
@@ -1069,7 +1070,8 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents, int halves) {
   const bool continuous = (flags_ & DBX_WORLD_CONTINUOUS) && dt > 0.0f;
   const bool toiScratchDirty = !toiClean_ || toiBodies_ != bodies_.size() * (size_t)nWorlds_;
   // (a world big enough to fill the machine gains nothing from the overlap: the two streams just take SMs from each other)
-  const bool toiPre = continuous && !toiScratchDirty && stepComplete_ && !overrideLevels_ && !(dw_.dbgFlags & 8) &&
+  const bool subStepping = (flags_ & DBX_WORLD_SUB_STEPPING) != 0;
+  const bool toiPre = continuous && !toiScratchDirty && stepComplete_ && !subStepping && !overrideLevels_ && !(dw_.dbgFlags & 8) &&
                       bodies_.size() * (size_t)nWorlds_ <= ((size_t)1 << 21);
   auto mark = [&](int i) { if (fineEvents || i == 0 || i == 1 || i == 3 || i == 5 || i == 7 || i == 8 || i == 9) cudaEventRecord(ev_[i], stream_); };
   if (halves & 1) {
@@ -1136,12 +1138,21 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents, int halves) {
   if (toiPre) CUDA_OR_FAIL(cudaStreamWaitEvent(stream_, evJoin_, 0), "join wait");
   if (continuous) {   // :414-419
     dw_.toiReset = toiScratchDirty ? 1 : 0; dw_.toiPre = toiPre ? 1 : 0; dw_.toiMode = 0;
+    // b2World.SetSubStepping (b2world.d:1441-1446): one TOI event per Step; a Step that follows an unfinished one resumes (:1131)
+    dw_.subStep = subStepping ? 1 : 0; dw_.toiResume = stepComplete_ ? 0 : 1;
+    if (subStepping) CUDA_OR_FAIL(cudaMemsetAsync((char*)hdr_.p + offsetof(Header, toiGlobalMin), 0xFF, 8, stream_), "toi min reset");
     dw_.toiClearMoves = (stepComplete_ && dt > 0.0f) ? 1 : 0;      // this step's FindNewContacts left its move buffer to us
     dw_.toiClearForces = (flags_ & DBX_WORLD_AUTO_CLEAR_FORCES) ? 1 : 0;
     CUDA_OR_FAIL(stage_toi(dw_, L_), "toi");
     toiClean_ = true; toiBodies_ = bodies_.size() * (size_t)nWorlds_;
   }
   mark(8);
+  if (continuous && (subStepping || !stepComplete_)) {
+    int inc = 0;
+    CUDA_OR_FAIL(cudaMemcpyAsync(&inc, (char*)hdr_.p + offsetof(Header, stepIncomplete), 4, cudaMemcpyDeviceToHost, stream_), "step complete?");
+    CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+    stepComplete_ = inc == 0;
+  }
   if (dt > 0.0f) inv_dt0 = dw_.inv_dt;
   if ((flags_ & DBX_WORLD_AUTO_CLEAR_FORCES) && !continuous) CUDA_OR_FAIL(launch_clear_forces(dw_, L_), "clear_forces");   // else k_toi did it
   mark(9);

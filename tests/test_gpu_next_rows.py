@@ -162,7 +162,7 @@ def test_shift_origin_matches_reference(gpu_api, oracle_api):
     assert wg.RayCastClosest([((-20.0, 10.0), (-20.0, -5.0))])[0][0] == -1
 
 
-def _impact_scene(api):
+def _impact_scene(api, bullets=2):
     """order-free PostSolve scene: separate resting bodies (island solve) and two bullets flying at a thin wall (TOI sub-steps)"""
     w = b2World((0.0, -10.0), api=api)
     g = _ground(w, api)
@@ -176,10 +176,12 @@ def _impact_scene(api):
             s = b2PolygonShape(api); s.SetAsBox(0.5, 0.5)
         b.CreateFixture(s, 1.0 + 0.1 * k)
         out.append(b)
-    for k in range(2):
-        b = _dyn(w, 0.0, 5.0 + 6.0 * k, bullet=True, gravityScale=0.0)
+    for k in range(bullets):
+        b = _dyn(w, 0.0, 5.0 + (6.0 if bullets == 2 else 2.0) * k, bullet=True, gravityScale=0.0)
         s = b2CircleShape(api); s.m_radius = 0.25; b.CreateFixture(s, 1.0)
-        b.SetLinearVelocity((300.0 + 50.0 * k, 0.0))
+        # two bullets: far above b2_maxTranslation per step (both are clamped to 2 m / step); six: distinct speeds below the clamp,
+        # so that their times of impact differ and the order of the TOI events is not a tie-break
+        b.SetLinearVelocity((300.0 + 50.0 * k, 0.0) if bullets == 2 else (100.0 + 3.0 * k, 0.0))
         out.append(b)
     return w, out
 
@@ -411,3 +413,36 @@ def test_world_queries_against_committed_goldens(gpu_api):
     assert [[h[:2] for h in hits] for hits in g1["all"]] == [[h[:2] for h in hits] for hits in w1["all"]]
     assert g1["boxes"] == w1["boxes"] and len(g1["world_manifolds"]) == len(w1["world_manifolds"])
     assert sum(a != b for a, b in zip(g1["inside"], w1["inside"])) <= 2          # sample points next to an edge of a body at rest
+
+
+def test_sub_stepping_matches_reference(gpu_api, oracle_api):
+    """b2World.SetSubStepping(true) (b2world.d:1127-1146, 1441-1446): SolveTOI handles ONE event per Step and leaves
+    m_stepComplete false; the following Steps run Collide and resume SolveTOI (no Solve) until no event is left.  Bullets hitting
+    a wall and boxes landing: event by event the same states as the oracle; switching sub-stepping off finishes the step"""
+    def build(api):
+        w, out = _impact_scene(api, bullets=6)
+        w.SetSubStepping(True)
+        return w, out
+    seen = {"events": [], "stalls": 0}
+
+    def each(k, wg, wo):
+        # (counts.colours on the oracle side is its cumulative TOI event count)
+        prev = seen["events"][-1] if seen["events"] else 0
+        seen["events"].append(wo.counts().colours)
+        pg, po = wg.read_bodies()[0], wo.read_bodies()[0]
+        if seen["events"][-1] > prev:       # a Step that handled an event: the same bodies sit at the same point of their sweeps
+            assert all(abs(pg[i].alpha0 - po[i].alpha0) < 1e-5 for i in range(1, 13)), (k, [pg[i].alpha0 for i in range(13)], [po[i].alpha0 for i in range(13)])
+            seen["stalls"] += 1
+    wg, wo, bg, bo = both(gpu_api, oracle_api, build, 90, each=each)
+    ev = seen["events"]
+    assert ev[-1] >= 6 and all(b - a <= 1 for a, b in zip(ev, ev[1:]))       # never more than one event per Step
+    assert seen["stalls"] >= 6                                                # Steps that ended with SolveTOI unfinished
+    for w in (wg, wo):
+        w.SetSubStepping(False)
+    for k in range(30):
+        wg.Step(DT, 8, 3); wo.Step(DT, 8, 3)
+    for g, o in zip(bg, bo):
+        pg, po = g.GetPosition(), o.GetPosition()
+        assert abs(pg.x - po.x) < 1e-3 and abs(pg.y - po.y) < 1e-3
+    sg, so = wg.read_bodies()[0], wo.read_bodies()[0]
+    assert all(sg[i].alpha0 == 0.0 == so[i].alpha0 for i in range(1, 13))
