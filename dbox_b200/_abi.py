@@ -99,6 +99,7 @@ class ContactPatch(C.Structure):
 
 PATCH_ENABLED, PATCH_FRICTION, PATCH_RESTITUTION, PATCH_TANGENT_SPEED, PATCH_DESTROY = 1, 2, 4, 8, 16
 FILTER_LOG, FILTER_REPLACES_DEFAULT = 1, 2
+JP_MOTOR_SPEED, JP_MAX_MOTOR, JP_ENABLE_MOTOR, JP_ENABLE_LIMIT, JP_LIMITS, JP_SPRING, JP_LENGTH, JP_MAX_FORCE, JP_OFFSETS, JP_CORRECTION = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
 
 
 class Ray(C.Structure):
@@ -252,6 +253,8 @@ PROTOTYPES = {
     "world_enable_post_solve": (c_i32, [W, c_i32]),
     "world_read_post_solve": (c_i32, [W, P(PostSolve), c_i32]),
     "world_set_user_filter": (c_i32, [W, c_i32]),
+    "joint_set_params": (c_i32, [W, c_i32, P(JointDef), c_u32]),
+    "world_set_motor_speeds": (c_i32, [W, P(c_i32), P(c_f32), c_i32]),
     "world_step_async": (c_i32, [W, c_f32, c_i32, c_i32]),
     "world_apply_forces_async": (c_i32, [W, C.c_void_p, c_i32]),
     "world_read_transforms_async": (c_i32, [W, C.c_void_p, c_i32]),

@@ -1185,6 +1185,18 @@ __global__ void __launch_bounds__(256) k_api_resensor(const __grid_constant__ De
     W.c_flags[i] = sensor ? (flags | CF_SENSOR) : (flags & ~CF_SENSOR);
   }
 }
+// bulk b2RevoluteJoint / b2PrismaticJoint / b2WheelJoint.SetMotorSpeed: slots index the (colour-sorted) device joint arrays
+__global__ void __launch_bounds__(256) k_api_motor_speeds(const __grid_constant__ DevWorld W, const int* slots, const float* speeds, int n) {
+  GRID_STRIDE(k, n) {
+    const int j = slots[k];
+    if (j < 0 || j >= W.nJoints) continue;
+    const int4 ids = W.j_ids[j];
+    if (ids.x == JT_REVOLUTE || ids.x == 2 /* prismatic */) { float4 p = W.j_p1[j]; p.x = speeds[k]; W.j_p1[j] = p; }
+    else if (ids.x == 7 /* wheel */) { float4 p = W.j_p0[j]; p.w = speeds[k]; W.j_p0[j] = p; }
+    else continue;
+    wake_body_now(W, ids.y); wake_body_now(W, ids.z);          // m_bodyA.SetAwake(true); m_bodyB.SetAwake(true)
+  }
+}
 __global__ void k_api_wake(const __grid_constant__ DevWorld W, int a, int b) {
   if (a >= 0) wake_body_now(W, a);
   if (b >= 0) wake_body_now(W, b);
@@ -1896,6 +1908,10 @@ cudaError_t launch_list_new_contacts(const DevWorld& W, const LaunchCfg& L, int4
 }
 cudaError_t launch_api_resensor(const DevWorld& W, const LaunchCfg& L, int fixture) {
   ++L.launches; k_api_resensor<<<L.gridWide, 256, 0, L.stream>>>(W, fixture);
+  return cudaGetLastError();
+}
+cudaError_t launch_set_motor_speeds(const DevWorld& W, const LaunchCfg& L, const int* slots, const float* speeds, int n) {
+  ++L.launches; k_api_motor_speeds<<<(n + 255) / 256, 256, 0, L.stream>>>(W, slots, speeds, n);
   return cudaGetLastError();
 }
 cudaError_t launch_api_wake(const DevWorld& W, const LaunchCfg& L, int a, int b) {

@@ -675,6 +675,82 @@ int World::setJointTarget(int jid, float x, float y) {
   return 0;
 }
 
+// the joint classes' setters (see include/dbox_b200.h "joint parameters at run time")
+int World::setJointParams(int jid, const dbx_joint_def& d, uint32_t mask) {
+  if (replicated_) { set_last_error("world is replicated: use dbx_world_set_motor_speeds"); return DBX_E_UNSUPPORTED; }
+  if (jid < 0 || jid >= (int)joints_.size() || !joints_[jid].alive || joints_[jid].def.type != d.type) return DBX_E_INVALID;
+  int rc = push(); if (rc < 0) return rc;              // the joint is on the device, in its colour slot
+  rc = pullJoints(); if (rc < 0) return rc;
+  HJoint& j = joints_[jid];
+  dbx_joint_def& o = j.def;
+  const int t = o.type;
+  const bool motorised = t == DBX_JOINT_REVOLUTE || t == DBX_JOINT_PRISMATIC || t == DBX_JOINT_WHEEL;
+  bool wakeBoth = false, zeroLimitImpulse = false;
+  if ((mask & DBX_JP_MOTOR_SPEED) && motorised) { o.motorSpeed = d.motorSpeed; wakeBoth = true; }
+  if ((mask & DBX_JP_MAX_MOTOR) && motorised) { if (t == DBX_JOINT_PRISMATIC) o.maxMotorForce = d.maxMotorForce; else o.maxMotorTorque = d.maxMotorTorque; wakeBoth = true; }
+  if ((mask & DBX_JP_ENABLE_MOTOR) && motorised) { o.enableMotor = d.enableMotor ? 1 : 0; wakeBoth = true; }
+  if ((mask & DBX_JP_ENABLE_LIMIT) && (t == DBX_JOINT_REVOLUTE || t == DBX_JOINT_PRISMATIC) && (d.enableLimit != 0) != (o.enableLimit != 0)) {
+    o.enableLimit = d.enableLimit ? 1 : 0; wakeBoth = true; zeroLimitImpulse = true;
+  }
+  if (mask & DBX_JP_LIMITS) {
+    if (t == DBX_JOINT_REVOLUTE && (d.lowerAngle != o.lowerAngle || d.upperAngle != o.upperAngle)) {
+      if (!(d.lowerAngle <= d.upperAngle)) return DBX_E_INVALID;
+      o.lowerAngle = d.lowerAngle; o.upperAngle = d.upperAngle; wakeBoth = true; zeroLimitImpulse = true;
+    } else if (t == DBX_JOINT_PRISMATIC && (d.lowerTranslation != o.lowerTranslation || d.upperTranslation != o.upperTranslation)) {
+      if (!(d.lowerTranslation <= d.upperTranslation)) return DBX_E_INVALID;
+      o.lowerTranslation = d.lowerTranslation; o.upperTranslation = d.upperTranslation; wakeBoth = true; zeroLimitImpulse = true;
+    }
+  }
+  if ((mask & DBX_JP_SPRING) && (t == DBX_JOINT_DISTANCE || t == DBX_JOINT_WELD || t == DBX_JOINT_WHEEL || t == DBX_JOINT_MOUSE)) { o.frequencyHz = d.frequencyHz; o.dampingRatio = d.dampingRatio; }
+  if (mask & DBX_JP_LENGTH) { if (t == DBX_JOINT_DISTANCE) o.length = d.length; else if (t == DBX_JOINT_ROPE) o.maxLength = d.maxLength; }
+  if ((mask & DBX_JP_MAX_FORCE) && (t == DBX_JOINT_FRICTION || t == DBX_JOINT_MOTOR || t == DBX_JOINT_MOUSE)) { o.maxForce = d.maxForce; if (t != DBX_JOINT_MOUSE) o.maxTorque = d.maxTorque; }
+  if ((mask & DBX_JP_OFFSETS) && t == DBX_JOINT_MOTOR && (d.linearOffset.x != o.linearOffset.x || d.linearOffset.y != o.linearOffset.y || d.angularOffset != o.angularOffset)) {
+    o.linearOffset = d.linearOffset; o.angularOffset = d.angularOffset; wakeBoth = true;
+  }
+  if ((mask & DBX_JP_CORRECTION) && t == DBX_JOINT_MOTOR) o.correctionFactor = d.correctionFactor;
+  if (zeroLimitImpulse) j.imp[2] = 0.0f;               // m_impulse.z = 0 (b2revolutejoint.d:236,252; b2prismaticjoint.d likewise)
+  // patch the one record where it lives
+  const int slot = jointPos_[jid];
+  const int4 ids = make_int4(o.type, o.bodyA, o.bodyB, (o.collideConnected ? 1 : 0) | (o.enableLimit ? 2 : 0) | (o.enableMotor ? 4 : 0) | 8);
+  const float4 p0 = jointParams(o, 0), p1 = jointParams(o, 1), imp = make_float4(j.imp[0], j.imp[1], j.imp[2], j.imp[3]);
+  CUDA_OR_FAIL(cudaMemcpyAsync(j_ids.p + slot, &ids, 16, cudaMemcpyHostToDevice, stream_), "joint patch");
+  CUDA_OR_FAIL(cudaMemcpyAsync(j_p0.p + slot, &p0, 16, cudaMemcpyHostToDevice, stream_), "joint patch");
+  CUDA_OR_FAIL(cudaMemcpyAsync(j_p1.p + slot, &p1, 16, cudaMemcpyHostToDevice, stream_), "joint patch");
+  if (zeroLimitImpulse) CUDA_OR_FAIL(cudaMemcpyAsync(j_imp.p + slot, &imp, 16, cudaMemcpyHostToDevice, stream_), "joint patch");
+  if (wakeBoth) { CUDA_OR_FAIL(launch_api_wake(dw_, L_, o.bodyA, o.bodyB), "api_wake"); hostBodiesValid_ = false; }
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");      // the host temporaries go away
+  return 0;
+}
+int World::setMotorSpeeds(const int32_t* joints, const float* speeds, int n) {
+  if (n < 0 || (n > 0 && (!joints || !speeds))) return DBX_E_INVALID;
+  if (n == 0) return 0;
+  int rc = push(); if (rc < 0) return rc;
+  // device layout: colour-major; inside a colour replica-major (World::replicate): colour c of the template occupies slots
+  // [first[c], first[c] + count[c]) and, replicated, [first[c] * R + r * count[c], ...) for replica r
+  const int nId = (int)joints_.size();
+  std::vector<int> first(kMaxJointColours + 1, 0), count(kMaxJointColours + 1, 0);
+  for (size_t k = 0; k < jointAt_.size(); ++k) { const int c = std::min(std::max(joints_[jointAt_[k]].colour, 0), kMaxJointColours); if (count[c]++ == 0) first[c] = (int)k; }
+  std::vector<int> slots((size_t)n);
+  for (int k = 0; k < n; ++k) {
+    const int g = joints[k];
+    if (g < 0 || nId == 0) return DBX_E_INVALID;
+    const int r = replicated_ ? g / nId : 0, local = replicated_ ? g % nId : g;
+    if (r >= nWorlds_ || local >= nId || !joints_[local].alive) return DBX_E_INVALID;
+    const int t = joints_[local].def.type;
+    if (t != DBX_JOINT_REVOLUTE && t != DBX_JOINT_PRISMATIC && t != DBX_JOINT_WHEEL) return DBX_E_INVALID;
+    const int c = std::min(std::max(joints_[local].colour, 0), kMaxJointColours), sl = jointPos_[local];
+    slots[k] = replicated_ ? first[c] * nWorlds_ + r * count[c] + (sl - first[c]) : sl;
+    if (r == 0) joints_[local].def.motorSpeed = speeds[k];     // the host definition follows (replica 0 = the template)
+  }
+  CUDA_OR_FAIL(ioIds_.reserve((size_t)n, false, stream_), "io ids"); CUDA_OR_FAIL(qIn_.reserve(((size_t)n + 3) / 4, false, stream_), "io");
+  CUDA_OR_FAIL(cudaMemcpyAsync(ioIds_.p, slots.data(), (size_t)n * 4, cudaMemcpyHostToDevice, stream_), "slots h2d");
+  CUDA_OR_FAIL(cudaMemcpyAsync(qIn_.p, speeds, (size_t)n * 4, cudaMemcpyHostToDevice, stream_), "speeds h2d");
+  CUDA_OR_FAIL(launch_set_motor_speeds(dw_, L_, ioIds_.p, (const float*)qIn_.p, n), "motor_speeds");
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  hostBodiesValid_ = false;
+  return n;
+}
+
 int World::recolourJoints() {
   const int nJ = (int)joints_.size();
   std::vector<unsigned long long> mask(bodies_.size(), 0ull);

@@ -63,6 +63,8 @@ class World {
   int createGearJoint(const dbx_joint_def& d);
   int destroyJoint(int j);
   int setJointTarget(int j, float x, float y);
+  int setJointParams(int j, const dbx_joint_def& d, uint32_t mask);
+  int setMotorSpeeds(const int32_t* joints, const float* speeds, int n);
   int step(float dt, int vi, int pi, int n);
   int enqueueStep(float dt, int vi, int pi, bool fineEvents, int halves = 3);
   int stepBegin(float dt, int vi, int pi);

@@ -478,8 +478,86 @@ class b2Fixture:
 
 
 class b2Joint:
+    """handle of a joint; the run-time setters of the reference's joint classes forward to dbx_joint_set_params (the joint keeps
+    the POD it was created from, so a setter only changes its own fields)"""
+
     def __init__(self, world, jid, bodyA, bodyB):
         self.world, self.id, self.bodyA, self.bodyB = world, jid, bodyA, bodyB
+        self._pod = None
+
+    def _set(self, mask, **fields):
+        for k, v in fields.items():
+            setattr(self._pod, k, v)
+        self.world._ck(self.world._api.joint_set_params(self.world._w, self.id, C.byref(self._pod), mask))
+
+    # b2revolutejoint.d:216-300, b2prismaticjoint.d:250-330, b2wheeljoint.d:170-230
+    def SetMotorSpeed(self, speed):
+        self._set(A.JP_MOTOR_SPEED, motorSpeed=speed)
+
+    def EnableMotor(self, flag):
+        self._set(A.JP_ENABLE_MOTOR, enableMotor=int(flag))
+
+    def SetMaxMotorTorque(self, torque):
+        self._set(A.JP_MAX_MOTOR, maxMotorTorque=torque)
+
+    def SetMaxMotorForce(self, force):
+        self._set(A.JP_MAX_MOTOR, maxMotorForce=force)
+
+    def EnableLimit(self, flag):
+        self._set(A.JP_ENABLE_LIMIT, enableLimit=int(flag))
+
+    def SetLimits(self, lower, upper):
+        if self._pod.type == A.JOINT_PRISMATIC:
+            self._set(A.JP_LIMITS, lowerTranslation=lower, upperTranslation=upper)
+        else:
+            self._set(A.JP_LIMITS, lowerAngle=lower, upperAngle=upper)
+
+    # springs and lengths: b2distancejoint.d, b2weldjoint.d, b2wheeljoint.d, b2mousejoint.d, b2ropejoint.d
+    def SetFrequency(self, hz):
+        self._set(A.JP_SPRING, frequencyHz=hz)
+
+    def SetDampingRatio(self, ratio):
+        self._set(A.JP_SPRING, dampingRatio=ratio)
+
+    def SetLength(self, length):
+        self._set(A.JP_LENGTH, length=length)
+
+    def SetMaxLength(self, length):
+        self._set(A.JP_LENGTH, maxLength=length)
+
+    # b2frictionjoint.d, b2motorjoint.d, b2mousejoint.d
+    def SetMaxForce(self, force):
+        self._set(A.JP_MAX_FORCE, maxForce=force)
+
+    def SetMaxTorque(self, torque):
+        self._set(A.JP_MAX_FORCE, maxTorque=torque)
+
+    def SetLinearOffset(self, offset):
+        self._set(A.JP_OFFSETS, linearOffset=_v(offset))
+
+    def SetAngularOffset(self, angle):
+        self._set(A.JP_OFFSETS, angularOffset=angle)
+
+    def SetCorrectionFactor(self, factor):
+        self._set(A.JP_CORRECTION, correctionFactor=factor)
+
+    # accessors computed in the shim from body states and the joint's accumulated impulses (b2revolutejoint.d:140-214)
+    def _state(self):
+        js, n = self.world.read_joints()
+        return js[sorted(self.world._joints).index(self.id)]
+
+    def GetJointAngle(self):
+        return C.c_float(C.c_float(self.bodyB.GetAngle() - self.bodyA.GetAngle()).value - self._pod.referenceAngle).value
+
+    def GetJointSpeed(self):
+        return self.bodyB.GetAngularVelocity() - self.bodyA.GetAngularVelocity()
+
+    def GetMotorTorque(self, inv_dt):
+        return inv_dt * self._state().motorImpulse
+
+    def GetReactionForce(self, inv_dt):
+        st = self._state()
+        return (inv_dt * st.impulse[0], inv_dt * st.impulse[1])
 
 
 class b2Body:
@@ -737,8 +815,17 @@ class b2World:
             jointDef.bodyA, jointDef.bodyB = jointDef.joint1.bodyB, jointDef.joint2.bodyB
         j = b2Joint(self, jid, jointDef.bodyA, jointDef.bodyB)
         j.type, j.collideConnected = jointDef.type, bool(jointDef.collideConnected)
+        j._pod = pod
         self._joints[jid] = j
         return j
+
+    def SetMotorSpeeds(self, joints, speeds):
+        """bulk SetMotorSpeed (dbx_world_set_motor_speeds): joints = b2Joint handles or (replicated worlds) global joint indices"""
+        ids = [j if isinstance(j, int) else j.id for j in joints]
+        n = len(ids)
+        a = (C.c_int32 * max(n, 1))(*ids)
+        v = (C.c_float * max(n, 1))(*speeds)
+        self._ck(self._api.world_set_motor_speeds(self._w, a, v, n))
 
     def SetMouseTarget(self, joint, target):
         """b2MouseJoint.SetTarget (b2mousejoint.d:112-120)"""

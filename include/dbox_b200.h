@@ -475,6 +475,28 @@ int32_t dbx_world_read_transforms_async(dbx_world* w, float* pinned_out, int32_t
 int32_t dbx_world_io_wait(dbx_world* w, int32_t ticket);
 int32_t dbx_world_sync(dbx_world* w);
 
+/* ---- joint parameters at run time -----------------------------------------------------------------
+ * The setters of the joint classes: b2RevoluteJoint.EnableLimit / SetLimits / EnableMotor / SetMotorSpeed / SetMaxMotorTorque
+ * (joints/b2revolutejoint.d:216-300), the same five of b2PrismaticJoint (b2prismaticjoint.d:250-330), b2WheelJoint.EnableMotor /
+ * SetMotorSpeed / SetMaxMotorTorque / SetSpringFrequencyHz / SetSpringDampingRatio (b2wheeljoint.d:170-230), b2DistanceJoint.SetLength /
+ * SetFrequency / SetDampingRatio, b2WeldJoint.SetFrequency / SetDampingRatio, b2RopeJoint.SetMaxLength, b2FrictionJoint / b2MouseJoint /
+ * b2MotorJoint.SetMaxForce / SetMaxTorque, b2MotorJoint.SetLinearOffset / SetAngularOffset / SetCorrectionFactor.
+ * `def` carries the new values in the fields of the joint's own type; `mask` says which groups to take.  Side effects as in the
+ * reference: the motor groups wake both bodies; the limit groups, when they change something, wake both bodies and zero the limit
+ * impulse; the motor joint's offsets wake both bodies when they change; the other groups wake nobody.  One joint's record is patched
+ * in place on the device (no re-upload of the joint set). */
+enum {
+  DBX_JP_MOTOR_SPEED = 1, DBX_JP_MAX_MOTOR = 2 /* maxMotorTorque | maxMotorForce */, DBX_JP_ENABLE_MOTOR = 4, DBX_JP_ENABLE_LIMIT = 8,
+  DBX_JP_LIMITS = 16 /* lower / upper angle | translation */, DBX_JP_SPRING = 32 /* frequencyHz, dampingRatio */,
+  DBX_JP_LENGTH = 64 /* distance length | rope maxLength */, DBX_JP_MAX_FORCE = 128 /* maxForce, maxTorque */,
+  DBX_JP_OFFSETS = 256 /* motor joint: linearOffset, angularOffset */, DBX_JP_CORRECTION = 512
+};
+int32_t dbx_joint_set_params(dbx_world* w, int32_t joint, const dbx_joint_def* def, uint32_t mask);
+/* Bulk SetMotorSpeed for n revolute / prismatic / wheel joints from host arrays (the actuation call of a control loop), on the
+ * device; wakes the bodies of every joint named, like the setter.  Works on replicated worlds: joint r * J + j is joint j of
+ * replica r (J = joints per replica). */
+int32_t dbx_world_set_motor_speeds(dbx_world* w, const int32_t* joints, const float* speeds, int32_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,8 @@ def api():
             "world_enable_post_solve": (i32, [W, i32]),
             "world_read_post_solve": (i32, [W, P(A.PostSolve), i32]),
             "world_set_contact_filter": (i32, [W, C.c_void_p]),
+            "joint_set_params": (i32, [W, i32, P(A.JointDef), C.c_uint32]),
+            "world_set_motor_speeds": (i32, [W, P(i32), P(f32), i32]),
         }
         for name, (res, args) in extra.items():
             fn = getattr(lib, "orc_" + name)

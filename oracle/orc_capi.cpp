@@ -536,6 +536,70 @@ int32_t orc_world_read_world_manifolds(orc_world* w, dbx_world_manifold* out, in
   }
   return n;
 }
+// the joint classes' setters, grouped by `mask` as in include/dbox_b200.h; side effects as in the reference:
+// b2revolutejoint.d:216-300, b2prismaticjoint.d:250-330, b2wheeljoint.d:170-230, b2motorjoint.d:110-170
+int32_t orc_joint_set_params(orc_world* w, int32_t joint, const dbx_joint_def* d, uint32_t mask) {
+  auto& J = w->w.jointsById;
+  if (joint < 0 || joint >= (int)J.size() || !J[joint] || J[joint]->type != d->type) return DBX_E_INVALID;
+  Joint* j = J[joint];
+  auto wake = [&]() { j->bodyA->setAwake(true); j->bodyB->setAwake(true); };
+  if (j->type == jRevolute) {
+    RevoluteJoint* r = (RevoluteJoint*)j;
+    if (mask & DBX_JP_MOTOR_SPEED) { wake(); r->motorSpeed = d->motorSpeed; }
+    if (mask & DBX_JP_MAX_MOTOR) { wake(); r->maxMotorTorque = d->maxMotorTorque; }
+    if (mask & DBX_JP_ENABLE_MOTOR) { wake(); r->enableMotor = d->enableMotor != 0; }
+    if ((mask & DBX_JP_ENABLE_LIMIT) && (d->enableLimit != 0) != r->enableLimit) { wake(); r->enableLimit = d->enableLimit != 0; r->impulse.z = 0.0f; }
+    if ((mask & DBX_JP_LIMITS) && (d->lowerAngle != r->lowerAngle || d->upperAngle != r->upperAngle)) { wake(); r->impulse.z = 0.0f; r->lowerAngle = d->lowerAngle; r->upperAngle = d->upperAngle; }
+  } else if (j->type == jPrismatic) {
+    PrismaticJoint* r = (PrismaticJoint*)j;
+    if (mask & DBX_JP_MOTOR_SPEED) { wake(); r->motorSpeed = d->motorSpeed; }
+    if (mask & DBX_JP_MAX_MOTOR) { wake(); r->maxMotorForce = d->maxMotorForce; }
+    if (mask & DBX_JP_ENABLE_MOTOR) { wake(); r->enableMotor = d->enableMotor != 0; }
+    if ((mask & DBX_JP_ENABLE_LIMIT) && (d->enableLimit != 0) != r->enableLimit) { wake(); r->enableLimit = d->enableLimit != 0; r->impulse.z = 0.0f; }
+    if ((mask & DBX_JP_LIMITS) && (d->lowerTranslation != r->lowerTranslation || d->upperTranslation != r->upperTranslation)) { wake(); r->lowerTranslation = d->lowerTranslation; r->upperTranslation = d->upperTranslation; r->impulse.z = 0.0f; }
+  } else if (j->type == jWheel) {
+    WheelJoint* r = (WheelJoint*)j;
+    if (mask & DBX_JP_MOTOR_SPEED) { wake(); r->motorSpeed = d->motorSpeed; }
+    if (mask & DBX_JP_MAX_MOTOR) { wake(); r->maxMotorTorque = d->maxMotorTorque; }
+    if (mask & DBX_JP_ENABLE_MOTOR) { wake(); r->enableMotor = d->enableMotor != 0; }
+    if (mask & DBX_JP_SPRING) { r->frequencyHz = d->frequencyHz; r->dampingRatio = d->dampingRatio; }
+  } else if (j->type == jDistance) {
+    DistanceJoint* r = (DistanceJoint*)j;
+    if (mask & DBX_JP_LENGTH) r->length = d->length;
+    if (mask & DBX_JP_SPRING) { r->frequencyHz = d->frequencyHz; r->dampingRatio = d->dampingRatio; }
+  } else if (j->type == jWeld) {
+    WeldJoint* r = (WeldJoint*)j;
+    if (mask & DBX_JP_SPRING) { r->frequencyHz = d->frequencyHz; r->dampingRatio = d->dampingRatio; }
+  } else if (j->type == jRope) {
+    if (mask & DBX_JP_LENGTH) ((RopeJoint*)j)->maxLength = d->maxLength;
+  } else if (j->type == jFriction) {
+    FrictionJoint* r = (FrictionJoint*)j;
+    if (mask & DBX_JP_MAX_FORCE) { r->maxForce = d->maxForce; r->maxTorque = d->maxTorque; }
+  } else if (j->type == jMouse) {
+    MouseJoint* r = (MouseJoint*)j;
+    if (mask & DBX_JP_MAX_FORCE) r->maxForce = d->maxForce;
+    if (mask & DBX_JP_SPRING) { r->frequencyHz = d->frequencyHz; r->dampingRatio = d->dampingRatio; }
+  } else if (j->type == jMotor) {
+    MotorJoint* r = (MotorJoint*)j;
+    if (mask & DBX_JP_MAX_FORCE) { r->maxForce = d->maxForce; r->maxTorque = d->maxTorque; }
+    if ((mask & DBX_JP_OFFSETS) && (d->linearOffset.x != r->linearOffset.x || d->linearOffset.y != r->linearOffset.y || d->angularOffset != r->angularOffset)) {
+      wake(); r->linearOffset = v2(d->linearOffset); r->angularOffset = d->angularOffset;
+    }
+    if (mask & DBX_JP_CORRECTION) r->correctionFactor = d->correctionFactor;
+  }
+  return 0;
+}
+int32_t orc_world_set_motor_speeds(orc_world* w, const int32_t* joints, const float* speeds, int32_t n) {
+  for (int k = 0; k < n; ++k) {
+    dbx_joint_def d{};
+    auto& J = w->w.jointsById;
+    if (joints[k] < 0 || joints[k] >= (int)J.size() || !J[joints[k]]) return DBX_E_INVALID;
+    d.type = J[joints[k]]->type; d.motorSpeed = speeds[k];
+    if (d.type != jRevolute && d.type != jPrismatic && d.type != jWheel) return DBX_E_INVALID;
+    int rc = orc_joint_set_params(w, joints[k], &d, DBX_JP_MOTOR_SPEED); if (rc < 0) return rc;
+  }
+  return n;
+}
 // b2World.SetContactFilter with a C callback standing in for the user's b2ContactFilter subclass (tests)
 int32_t orc_world_set_contact_filter(orc_world* w, int (*cb)(int, int, int)) { w->w.userFilter = cb; return 0; }
 // the PostSolve call log of the last step, in the reference's CALL order

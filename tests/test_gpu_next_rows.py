@@ -446,3 +446,125 @@ def test_sub_stepping_matches_reference(gpu_api, oracle_api):
         assert abs(pg.x - po.x) < 1e-3 and abs(pg.y - po.y) < 1e-3
     sg, so = wg.read_bodies()[0], wo.read_bodies()[0]
     assert all(sg[i].alpha0 == 0.0 == so[i].alpha0 for i in range(1, 13))
+
+
+def _actuated_scene(api):
+    """independent mechanisms far from each other (no contacts between them): a revolute arm with motor and limit, a prismatic
+    slider with motor and limit, a distance spring, a wheel joint with a motor, a motor joint, a rope"""
+    from dbox_b200.world import (b2DistanceJointDef, b2MotorJointDef, b2PrismaticJointDef, b2RevoluteJointDef, b2RopeJointDef,
+                                 b2WheelJointDef)
+    from tests.test_gpu_features import _box_body
+    w = b2World((0.0, -10.0), api=api)
+    g = w.CreateBody(b2BodyDef())
+    arm = _box_body(w, api, -30.0, 10.0, hx=2.0, hy=0.25)
+    rd = b2RevoluteJointDef(); rd.Initialize(g, arm, (-32.0, 10.0))
+    rd.enableMotor, rd.motorSpeed, rd.maxMotorTorque = True, 0.0, 2000.0
+    rd.enableLimit, rd.lowerAngle, rd.upperAngle = False, -0.5, 0.75
+    rev = w.CreateJoint(rd)
+    sl = _box_body(w, api, -15.0, 10.0)
+    pd = b2PrismaticJointDef(); pd.Initialize(g, sl, (-15.0, 10.0), (1.0, 0.0))
+    pd.enableMotor, pd.motorSpeed, pd.maxMotorForce = True, 0.0, 500.0
+    pd.enableLimit, pd.lowerTranslation, pd.upperTranslation = True, -1.0, 1.0
+    pri = w.CreateJoint(pd)
+    bob = _box_body(w, api, 0.0, 8.0)
+    dd = b2DistanceJointDef(); dd.Initialize(g, bob, (0.0, 12.0), (0.0, 8.0)); dd.frequencyHz, dd.dampingRatio = 2.0, 0.3
+    dist = w.CreateJoint(dd)
+    chassis = _box_body(w, api, 15.0, 10.0, hx=1.0, hy=0.25, gravityScale=0.0)
+    wheel = _dyn(w, 15.0, 9.0, gravityScale=0.0)
+    s = b2CircleShape(api); s.m_radius = 0.4; wheel.CreateFixture(s, 1.0)
+    wd = b2WheelJointDef(); wd.Initialize(chassis, wheel, (15.0, 9.0), (0.0, 1.0))
+    wd.enableMotor, wd.motorSpeed, wd.maxMotorTorque, wd.frequencyHz, wd.dampingRatio = True, 0.0, 50.0, 4.0, 0.7
+    whl = w.CreateJoint(wd)
+    hold = w.CreateJoint(_pin(b2RevoluteJointDef, g, chassis, (15.0, 10.0)))
+    mover = _box_body(w, api, 30.0, 10.0, gravityScale=0.0)
+    md = b2MotorJointDef(); md.Initialize(g, mover); md.maxForce, md.maxTorque = 500.0, 500.0
+    mot = w.CreateJoint(md)
+    weight = _box_body(w, api, 45.0, 8.0)
+    pd2 = b2RopeJointDef(); pd2.bodyA, pd2.bodyB = g, weight
+    pd2.localAnchorA.Set(45.0, 12.0); pd2.localAnchorB.Set(0.0, 0.0); pd2.maxLength = 4.5
+    rope = w.CreateJoint(pd2)
+    return w, [arm, sl, bob, chassis, wheel, mover, weight], dict(rev=rev, pri=pri, dist=dist, whl=whl, mot=mot, rope=rope, hold=hold)
+
+
+def _pin(cls, a, b, anchor):
+    d = cls(); d.Initialize(a, b, anchor)
+    return d
+
+
+def test_joint_setters_match_reference(gpu_api, oracle_api):
+    """the run-time setters of the joint classes (dbx_joint_set_params): motor speed / torque / on-off, limits on-off and range
+    (with the limit impulse reset and the wake-ups of b2revolutejoint.d:216-300, b2prismaticjoint.d:250-330), spring frequency,
+    rest length, rope length, motor-joint offsets -- each mechanism alone in its island, so both sides agree to float rounding"""
+    js = {}
+
+    def build(api):
+        w, bodies, joints = _actuated_scene(api)
+        w.SetAllowSleeping(False)          # (SetLength / SetMaxLength / SetFrequency wake nobody, in the reference as here)
+        js[api.prefix] = joints
+        return w, bodies
+
+    def each(k, wg, wo):
+        for joints in js.values():
+            if k == 20:
+                joints["rev"].SetMotorSpeed(1.5); joints["pri"].SetMotorSpeed(2.0); joints["whl"].SetMotorSpeed(-6.0)
+                joints["mot"].SetLinearOffset((1.0, 0.5)); joints["mot"].SetAngularOffset(0.4)
+            if k == 50:
+                joints["rev"].EnableLimit(True); joints["pri"].SetLimits(-0.5, 0.25); joints["dist"].SetLength(3.0)
+                joints["dist"].SetFrequency(4.0); joints["rope"].SetMaxLength(3.5); joints["whl"].SetMaxMotorTorque(5.0)
+            if k == 90:
+                joints["rev"].SetLimits(-1.0, 0.2); joints["rev"].SetMotorSpeed(-2.0); joints["pri"].EnableMotor(False)
+                joints["whl"].EnableMotor(False); joints["mot"].SetMaxForce(50.0); joints["mot"].SetLinearOffset((-1.0, 0.0))
+                joints["pri"].SetMaxMotorForce(10.0)
+    wg, wo, bg, bo = both(gpu_api, oracle_api, build, 150, each=each, tol_p=5e-5, tol_v=5e-4)
+    # the setters did something: the arm sits at its new upper limit, the slider was driven to its limit and then let go
+    assert abs(js["dbx_"]["rev"].GetJointAngle() - js["orc_"]["rev"].GetJointAngle()) < 1e-4
+    assert -1.08 < js["dbx_"]["rev"].GetJointAngle() < 0.21
+    assert abs(bg[2].GetPosition().y - bo[2].GetPosition().y) < 1e-3 and bg[6].GetPosition().y > 12.0 - 3.6, (bg[2].GetPosition().y, bg[6].GetPosition().y)
+    jg, jo = wg.read_joints()[0], wo.read_joints()[0]
+    for i in range(7):
+        assert jg[i].limitState == jo[i].limitState, i
+        assert all(abs(jg[i].impulse[c] - jo[i].impulse[c]) <= 2e-3 * max(1.0, abs(jo[i].impulse[c])) for c in range(3)), (i, list(jg[i].impulse), list(jo[i].impulse))
+
+
+def test_motor_speed_wakes_and_bulk_setter(gpu_api, oracle_api):
+    """SetMotorSpeed wakes both bodies (b2revolutejoint.d:262-267): an arm that fell asleep on its motor starts to turn; the bulk
+    call (dbx_world_set_motor_speeds) does the same for many joints at once, also per replica of a replicated world"""
+    from dbox_b200.world import b2RevoluteJointDef
+    from tests.test_gpu_features import _box_body
+
+    def build(api, n=4):
+        w = b2World((0.0, -10.0), api=api)
+        g = w.CreateBody(b2BodyDef())
+        arms, joints = [], []
+        for k in range(n):
+            arm = _box_body(w, api, 10.0 * k, 10.0, hx=1.0, hy=0.2)
+            rd = b2RevoluteJointDef(); rd.Initialize(g, arm, (10.0 * k, 10.0))
+            rd.enableMotor, rd.motorSpeed, rd.maxMotorTorque = True, 0.0, 1e4
+            joints.append(w.CreateJoint(rd)); arms.append(arm)
+        return w, arms, joints
+    wg, ag, jg = build(gpu_api); wo, ao, jo = build(oracle_api)
+    for _ in range(60):
+        wg.Step(DT, 8, 3); wo.Step(DT, 8, 3)
+    assert wg.counts().awakeBodies == wo.counts().awakeBodies == 0          # held by their motors, asleep
+    jg[1].SetMotorSpeed(1.0); jo[1].SetMotorSpeed(1.0)
+    wg.SetMotorSpeeds(jg[2:], [2.0, -3.0]); wo.SetMotorSpeeds(jo[2:], [2.0, -3.0])
+    assert wg.counts().awakeBodies == wo.counts().awakeBodies == 3
+    for _ in range(30):
+        wg.Step(DT, 8, 3); wo.Step(DT, 8, 3)
+    for k, want in enumerate((0.0, 1.0, 2.0, -3.0)):
+        assert abs(ag[k].GetAngularVelocity() - want) < 1e-3 and abs(ag[k].GetAngle() - ao[k].GetAngle()) < 1e-4, k
+    with pytest.raises(RuntimeError):
+        wg.SetMotorSpeeds([10 ** 6], [1.0])
+    # replicated: joint r * J + j is joint j of replica r
+    wr, ar, jr = build(gpu_api, n=3)
+    wr.SetAllowSleeping(False)
+    wr.Replicate(5)
+    nb = 4                                                                 # bodies per replica: ground + 3 arms
+    wr.SetMotorSpeeds([0 * 3 + 1, 2 * 3 + 0, 4 * 3 + 2], [1.0, -2.0, 4.0])
+    wr.StepN(DT, 8, 3, 20)
+    st, n = wr.read_bodies()
+    assert n == 5 * nb
+    got = {(r, j): st[r * nb + 1 + j].w for r in range(5) for j in range(3)}
+    for key, w_ in got.items():
+        want = {(0, 1): 1.0, (2, 0): -2.0, (4, 2): 4.0}.get(key, 0.0)
+        assert abs(w_ - want) < 1e-3, (key, w_)
