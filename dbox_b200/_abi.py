@@ -253,6 +253,7 @@ PROTOTYPES = {
     "world_enable_post_solve": (c_i32, [W, c_i32]),
     "world_read_post_solve": (c_i32, [W, P(PostSolve), c_i32]),
     "world_set_user_filter": (c_i32, [W, c_i32]),
+    "world_tree_stats": (c_i32, [W, P(c_i32), P(c_i32), P(c_f32)]),
     "joint_set_params": (c_i32, [W, c_i32, P(JointDef), c_u32]),
     "world_set_motor_speeds": (c_i32, [W, P(c_i32), P(c_f32), c_i32]),
     "world_step_async": (c_i32, [W, c_f32, c_i32, c_i32]),

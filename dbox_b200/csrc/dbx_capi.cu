@@ -327,6 +327,7 @@ int32_t dbx_world_io_wait(dbx_world* w, int32_t ticket) { W_OR_INVALID(w); retur
 int32_t dbx_world_sync(dbx_world* w) { W_OR_INVALID(w); return w->w.sync(); }
 int32_t dbx_joint_set_params(dbx_world* w, int32_t joint, const dbx_joint_def* def, uint32_t mask) { W_OR_INVALID(w); if (!def) return DBX_E_INVALID; return w->w.setJointParams(joint, *def, mask); }
 int32_t dbx_world_set_motor_speeds(dbx_world* w, const int32_t* joints, const float* speeds, int32_t n) { W_OR_INVALID(w); return w->w.setMotorSpeeds(joints, speeds, n); }
+int32_t dbx_world_tree_stats(dbx_world* w, int32_t* height, int32_t* maxBalance, float* quality) { W_OR_INVALID(w); return w->w.treeStats(height, maxBalance, quality); }
 int32_t dbx_world_raycast_all(dbx_world* w, const dbx_ray* rays, int32_t n, int32_t capPerRay, int32_t* counts, dbx_ray_hit* hits) { W_OR_INVALID(w); return w->w.rayCastAll(rays, n, capPerRay, counts, hits); }
 int32_t dbx_world_test_points(dbx_world* w, const int32_t* fixtures, const dbx_vec2* points, int32_t n, int32_t* inside) { W_OR_INVALID(w); return w->w.testPoints(fixtures, points, n, inside); }
 int32_t dbx_world_shift_origin(dbx_world* w, float x, float y) { W_OR_INVALID(w); return w->w.shiftOrigin(x, y); }

@@ -1407,6 +1407,43 @@ int World::queryAabb(const dbx_aabb* boxes, int n, int capPer, int32_t* counts, 
   return n;
 }
 
+// b2World.GetTreeHeight / GetTreeBalance / GetTreeQuality for the LBVH (diagnostics; the tree comes down once)
+int World::treeStats(int32_t* height, int32_t* maxBalance, float* quality) {
+  if (height) *height = 0; if (maxBalance) *maxBalance = 0; if (quality) *quality = 0.0f;
+  int rc = refreshTreeForQuery(); if (rc < 0) return rc;
+  const int n = (int)proxies_.size() * nWorlds_;
+  if (n == 0) return 0;
+  std::vector<float4> box((size_t)2 * n - 1); std::vector<int2> child((size_t)std::max(n - 1, 1));
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  CUDA_OR_FAIL(cudaMemcpy(box.data(), bv_box.p, box.size() * 16, cudaMemcpyDeviceToHost), "tree d2h");
+  if (n > 1) CUDA_OR_FAIL(cudaMemcpy(child.data(), bv_child.p, (size_t)(n - 1) * 8, cudaMemcpyDeviceToHost), "tree d2h");
+  auto perimeter = [](const float4& b) { return 2.0f * ((b.z - b.x) + (b.w - b.y)); };
+  // internal nodes 0 .. n-2 (root 0), leaves n-1 .. 2n-2; heights by an explicit post-order walk
+  std::vector<int> h((size_t)2 * n - 1, 0), stack;
+  std::vector<char> seen((size_t)2 * n - 1, 0);
+  int balance = 0;
+  double total = 0.0;
+  const int root = n == 1 ? 0 : 0;
+  if (n == 1) { total = perimeter(box[0]); }
+  else {
+    stack.push_back(root);
+    while (!stack.empty()) {
+      const int v = stack.back();
+      if (v >= n - 1) { h[v] = 0; total += perimeter(box[v]); stack.pop_back(); continue; }
+      if (!seen[v]) { seen[v] = 1; stack.push_back(child[v].x); stack.push_back(child[v].y); continue; }
+      stack.pop_back();
+      const int a = h[child[v].x], b = h[child[v].y];
+      h[v] = 1 + std::max(a, b);
+      if (h[v] > 1) balance = std::max(balance, std::abs(a - b));
+      total += perimeter(box[v]);
+    }
+  }
+  if (height) *height = h[root];
+  if (maxBalance) *maxBalance = balance;
+  const float rootP = perimeter(box[root]);
+  if (quality) *quality = rootP > 0.0f ? (float)(total / rootP) : 0.0f;
+  return 0;
+}
 // b2World.RayCast with the "report everything" callback (see include/dbox_b200.h): all hits per ray, sorted by (fraction, fixture, child)
 int World::rayCastAll(const dbx_ray* rays, int n, int capPer, int32_t* counts, dbx_ray_hit* hits) {
   if (n < 0 || capPer < 0 || (n > 0 && (!rays || !counts)) || (n > 0 && capPer > 0 && !hits)) return DBX_E_INVALID;

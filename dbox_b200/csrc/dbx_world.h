@@ -76,6 +76,7 @@ class World {
   int rayCastClosest(const dbx_ray* rays, int n, dbx_ray_hit* out);
   int queryAabb(const dbx_aabb* boxes, int n, int capPer, int32_t* counts, int32_t* fixtureChild);
   int refreshTreeForQuery();
+  int treeStats(int32_t* height, int32_t* maxBalance, float* quality);
   int rayCastAll(const dbx_ray* rays, int n, int capPer, int32_t* counts, dbx_ray_hit* hits);
   int testPoints(const int32_t* fixtures, const dbx_vec2* points, int n, int32_t* inside);
   int shiftOrigin(float x, float y);

@@ -1081,6 +1081,14 @@ class b2World:
         self._ck(self._api.world_counts(self._w, C.byref(c)))
         return c
 
+    def GetTreeStats(self):
+        """(GetTreeHeight, GetTreeBalance, GetTreeQuality) of the broadphase tree (b2world.d:694-716); the CUDA library reports its LBVH"""
+        if self._api.prefix != "dbx_":
+            return (self._api.world_tree_height(self._w), None, None)
+        h, b, q = C.c_int32(), C.c_int32(), C.c_float()
+        self._ck(self._api.world_tree_stats(self._w, C.byref(h), C.byref(b), C.byref(q)))
+        return (h.value, b.value, q.value)
+
     def GetBodyCount(self):
         return self.counts().bodies
 

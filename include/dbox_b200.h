@@ -497,6 +497,13 @@ int32_t dbx_joint_set_params(dbx_world* w, int32_t joint, const dbx_joint_def* d
  * replica r (J = joints per replica). */
 int32_t dbx_world_set_motor_speeds(dbx_world* w, const int32_t* joints, const float* speeds, int32_t n);
 
+/* b2World.GetTreeHeight / GetTreeBalance / GetTreeQuality (dynamics/b2world.d:694-716 -> collision/b2dynamictree.d:354-419), the
+ * diagnostics some demos print (tiles.d:118-120) -- of THIS library's broadphase tree, the LBVH over the fat AABBs (rebuilt or
+ * widened as for a world query), so the numbers describe a different tree than the reference's incremental one: height = edges
+ * on the longest root-to-leaf path, balance = largest height difference between the two children of a node, quality = sum of
+ * all node perimeters / root perimeter.  "Should not be called often" there; here it costs one download of the tree. */
+int32_t dbx_world_tree_stats(dbx_world* w, int32_t* height, int32_t* maxBalance, float* quality);
+
 #ifdef __cplusplus
 }
 #endif

@@ -568,3 +568,21 @@ def test_motor_speed_wakes_and_bulk_setter(gpu_api, oracle_api):
     for key, w_ in got.items():
         want = {(0, 1): 1.0, (2, 0): -2.0, (4, 2): 4.0}.get(key, 0.0)
         assert abs(w_ - want) < 1e-3, (key, w_)
+
+
+def test_tree_stats_of_the_lbvh(gpu_api, oracle_api):
+    """b2World.GetTreeHeight / GetTreeBalance / GetTreeQuality (b2world.d:694-716): reported for this library's LBVH -- a valid
+    binary tree over the same leaves as the reference's dynamic tree: height between log2(n) and n - 1, quality >= 1"""
+    import math
+    wg, _ = scenes.pyramid(api=gpu_api)
+    wo, _ = scenes.pyramid(api=oracle_api)
+    for _ in range(10):
+        wg.Step(DT, 8, 3); wo.Step(DT, 8, 3)
+    h, bal, q = wg.GetTreeStats()
+    n = wg.counts().proxies
+    assert n == 211 and math.ceil(math.log2(n)) <= h <= n - 1 and 0 <= bal < h and q >= 1.0
+    ho = wo.GetTreeStats()[0]
+    assert math.ceil(math.log2(n)) <= ho <= n - 1                        # the reference's own tree, for scale
+    assert h <= 4 * ho
+    e = b2World((0.0, -10.0), api=gpu_api)
+    assert e.GetTreeStats() == (0, 0, 0.0)
