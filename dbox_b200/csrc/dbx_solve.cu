@@ -248,8 +248,8 @@ __global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld 
 // integration, position iterations with the per-island early-out, write-back and sleep -- with __syncthreads() between
 // colours: a replica's rows (tens of kB) stay in L1/L2 for all eleven passes and no CTA ever waits for another.
 // Same row functions, same colour order, same arithmetic as k_solve: results are bit-identical (tests compare a replica
-// with the same world stepped alone through k_solve).  Solver slots arrive sorted by (replica, colour); joints are not
-// handled here (worlds with joints take the k_solve path).
+// with the same world stepped alone through k_solve).  Solver slots arrive sorted by (replica, colour); a replica's joints
+// are solved here too, from the global body arrays (see nJC below).
 constexpr int kWorldMaxColours = 256;
 // kLocal: the replica's body velocities and positions live in shared memory for the duration of its solve (loaded once,
 // written back once); otherwise (a replica too big for shared memory) they stay in the global arrays.
@@ -257,7 +257,16 @@ template <bool kLocal> __global__ void __launch_bounds__(128) k_solve_worlds(con
   extern __shared__ float4 sBodies[];              // kLocal: [bodiesPerWorld] velocities, then [bodiesPerWorld] positions
   __shared__ int cstart[kWorldMaxColours + 1];
   __shared__ int ncol;
+  __shared__ int joff[kMaxJointColours + 1];
   const int t = threadIdx.x, B = blockDim.x;
+  // Joints (replicas of a jointed template, e.g. articulated robots): the device joint arrays are colour-major and, inside a
+  // colour, replica-major (World::replicate), so replica w's joints of colour c are [joff[c] + w * cnt, + cnt) with
+  // cnt = (joff[c + 1] - joff[c]) / nWorlds.  Order as in b2Island.Solve: velocity passes joints then contacts (:153-161), position
+  // passes contacts then joints (:206-216); the position colours run downwards like k_solve's unified phases, so that a replica
+  // stays bit-identical to the same world stepped alone.  Joint code reads and writes the global body arrays (kLocal is off).
+  const int nJC = (!kLocal && W.nJoints > 0) ? min(W.nJointColours, kMaxJointColours) : 0;
+  for (int c = t; c <= kMaxJointColours; c += B) joff[c] = W.hdr->jointColourOff[c];
+  __syncthreads();
   for (int w = blockIdx.x; w < W.nWorlds; w += gridDim.x) {
     const int beg = W.w_start[w], end = W.w_end[w];
     // (a replica with no solver contact -- asleep, or in free fall -- has beg == end: only the body loops do anything)
@@ -297,11 +306,25 @@ template <bool kLocal> __global__ void __launch_bounds__(128) k_solve_worlds(con
       }
       __syncthreads();
     }
-    for (int it = 0; it < W.velIters; ++it)
+    // joints: InitVelocityConstraints incl. their warm start (b2island.d:143-146), colour by colour
+    for (int c = 0; c < nJC; ++c) {
+      const int cnt = (joff[c + 1] - joff[c]) / W.nWorlds;
+      if (cnt == 0) continue;
+      for (int k = joff[c] + w * cnt + t; k < joff[c] + (w + 1) * cnt; k += B) joint_init(W, k);
+      __syncthreads();
+    }
+    for (int it = 0; it < W.velIters; ++it) {
+      for (int c = 0; c < nJC; ++c) {
+        const int cnt = (joff[c + 1] - joff[c]) / W.nWorlds;
+        if (cnt == 0) continue;
+        for (int k = joff[c] + w * cnt + t; k < joff[c] + (w + 1) * cnt; k += B) if (W.j_root[k] >= 0) joint_solve_velocity(W, k);
+        __syncthreads();
+      }
       for (int c = 0; c < nc; ++c) {
         for (int s = cstart[c] + t; s < cstart[c + 1]; s += B) contact_solve_velocity(W, s, view);
         __syncthreads();
       }
+    }
     // StoreImpulses + integrate positions
     for (int s = beg + t; s < end; s += B) {
       const int i = W.s_contact[s];
@@ -332,12 +355,24 @@ template <bool kLocal> __global__ void __launch_bounds__(128) k_solve_worlds(con
     for (int it = 0; it < W.posIters; ++it) {
       int* notOk = W.b_posNotOk + it * W.nBodies;
       const int* prev = it > 0 ? W.b_posNotOk + (it - 1) * W.nBodies : nullptr;
-      for (int c = 0; c < nc; ++c) {
+      for (int q = 0; q < nc; ++q) {
+        const int c = nJC > 0 ? nc - 1 - q : q;        // jointed worlds: downwards, like k_solve's unified phases
         for (int s = cstart[c] + t; s < cstart[c + 1]; s += B) {
           const int root = W.s_root[s];
           if (prev && __ldcg(&prev[root]) == 0) continue;
           const float minSep = contact_solve_position(W, s, -1, -1, view);
           if (!(minSep >= -3.0f * kLinearSlop)) __stcg(&notOk[root], 1);
+        }
+        __syncthreads();
+      }
+      for (int c = nJC - 1; c >= 0; --c) {
+        const int cnt = (joff[c + 1] - joff[c]) / W.nWorlds;
+        if (cnt == 0) continue;
+        for (int k = joff[c] + w * cnt + t; k < joff[c] + (w + 1) * cnt; k += B) {
+          const int root = W.j_root[k];
+          if (root < 0) continue;
+          if (prev && __ldcg(&prev[root]) == 0) continue;
+          if (!joint_solve_position(W, k)) __stcg(&notOk[root], 1);
         }
         __syncthreads();
       }
@@ -389,7 +424,7 @@ cudaError_t stage_solve_worlds(const DevWorld& W, const LaunchCfg& L, int bodies
   const int grid = W.nWorlds < L.coopBlocks * 8 ? W.nWorlds : L.coopBlocks * 8;
   const size_t smem = (size_t)bodiesPerWorld * 32;
   ++L.launches;
-  if (smem <= 40 * 1024) k_solve_worlds<true><<<grid, 128, smem, L.stream>>>(W, bodiesPerWorld);
+  if (smem <= 40 * 1024 && W.nJoints == 0) k_solve_worlds<true><<<grid, 128, smem, L.stream>>>(W, bodiesPerWorld);
   else k_solve_worlds<false><<<grid, 128, 0, L.stream>>>(W, bodiesPerWorld);
   return cudaGetLastError();
 }

@@ -1161,7 +1161,13 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents, int halves) {
     CUDA_OR_FAIL(stage_islands_and_integrate(dw_, L_), "islands");
     mark(2);
     // batched replicas without joints: solver slots in (replica, colour) order and one CTA per replica (k_solve_worlds)
-    const bool worldsPath = replicated_ && jointAt_.empty() && !overrideLevels_ && !(dw_.dbgFlags & 16);
+    // One CTA per replica pays off when a replica has enough constraints to keep a CTA busy between its block barriers (the
+    // Pyramid: 212 bodies, ~400 contacts); replicas of a tiny world (a dozen bodies) are better served by the global solver,
+    // whose every phase spans all replicas at once.  Measured on 4,096 replicas of a jointed mechanism repeated u times per world:
+    // u = 24 (193 bodies, 192 contacts, 96 joints per world) 1.25 ms per step here against 1.67 ms through the global solver;
+    // u = 7 (57 bodies) 0.74 against 0.60 ms; 16,384 replicas of u = 1 (9 bodies) 1.74 against 0.44 ms.
+    const bool bigEnough = bodies_.size() >= 128 || (dw_.dbgFlags & 1024);
+    const bool worldsPath = replicated_ && bigEnough && (jointAt_.empty() || !(dw_.dbgFlags & 512)) && !overrideLevels_ && !(dw_.dbgFlags & 16);
     if (worldsPath) {
       // Sort exactly the slots in use, with exactly the key bits the colours need.  Both numbers are device-side facts
       // (cHigh: final since the last FindNewContacts; maxColour: monotonic, so a stale read is still an upper bound for

@@ -586,3 +586,58 @@ def test_tree_stats_of_the_lbvh(gpu_api, oracle_api):
     assert h <= 4 * ho
     e = b2World((0.0, -10.0), api=gpu_api)
     assert e.GetTreeStats() == (0, 0, 0.0)
+
+
+def _crawler_scene(api, units=1, **kw):
+    """a jointed mechanism with contacts, `units` times side by side: a four-link chain with motorised revolute joints lying on
+    the ground next to a short stack of loose boxes, and a pendulum on a distance joint that knocks into the stack"""
+    from dbox_b200.world import b2DistanceJointDef, b2RevoluteJointDef
+    from tests.test_gpu_features import _box_body
+    w = b2World((0.0, -10.0), api=api, **kw)
+    g = w.CreateBody(b2BodyDef())
+    e = b2EdgeShape(api); e.Set((-40.0, 0.0), (40.0 + 30.0 * units, 0.0)); g.CreateFixture(e, 0.0)
+    bodies, joints = [], []
+    for u in range(units):
+        x0 = 30.0 * u
+        links = [_box_body(w, api, x0 - 4.0 + 2.0 * k, 0.3, hx=0.9, hy=0.25, density=2.0) for k in range(4)]
+        for k in range(3):
+            rd = b2RevoluteJointDef(); rd.Initialize(links[k], links[k + 1], (x0 - 3.0 + 2.0 * k, 0.3))
+            rd.enableMotor, rd.motorSpeed, rd.maxMotorTorque = True, (0.8 if k % 2 == 0 else -0.8), 400.0
+            rd.enableLimit, rd.lowerAngle, rd.upperAngle = True, -0.6, 0.6
+            joints.append(w.CreateJoint(rd))
+        boxes = [_box_body(w, api, x0 + 6.0, 0.5 + 1.01 * k) for k in range(3)]
+        bob = _box_body(w, api, x0 + 9.0, 4.0, hx=0.4, hy=0.4, density=3.0)
+        dd = b2DistanceJointDef(); dd.Initialize(g, bob, (x0 + 6.5, 6.0), (x0 + 9.0, 4.0))
+        joints.append(w.CreateJoint(dd))
+        bodies += links + boxes + [bob]
+    return w, bodies, joints
+
+
+def test_jointed_replicas_match_single_world(gpu_api):
+    """batched worlds WITH joints (articulated mechanisms): the world-local solver runs the joint colours inside the replica's CTA;
+    every replica evolves bit for bit like the same world stepped alone through the global solver, and per-replica motor commands
+    make exactly the commanded replicas diverge"""
+    single, bs, js = _crawler_scene(gpu_api, units=16)         # 129 bodies: above the size where replicas get a CTA each
+    batch, bb, jb = _crawler_scene(gpu_api, units=16)
+    copies = 12
+    nb, nj = single.counts().bodies, len(js)
+    batch.Replicate(copies)
+    for k in range(6):
+        single.StepN(DT, 8, 3, 25); batch.StepN(DT, 8, 3, 25)
+        cs, cb = single.counts(), batch.counts()
+        assert (cb.contacts, cb.touching, cb.awakeBodies) == (cs.contacts * copies, cs.touching * copies, cs.awakeBodies * copies), k
+        assert gpu_api.world_debug_colour_conflicts(batch._w) == 0
+        ss, _ = single.read_bodies(); sb, n = batch.read_bodies()
+        assert n == nb * copies
+        for r in (0, 5, copies - 1):
+            for i in range(nb):
+                a, b = ss[i], sb[r * nb + i]
+                assert (a.c.x, a.c.y, a.a, a.v.x, a.v.y, a.w) == (b.c.x, b.c.y, b.a, b.v.x, b.v.y, b.w), (k, r, i)
+    assert abs(bs[0].GetAngle()) + abs(bs[3].GetAngle()) > 0.05            # the chain really moved
+    # command replica 7 alone: its chain reverses, the others carry on identically
+    batch.SetMotorSpeeds([7 * nj + 0, 7 * nj + 1, 7 * nj + 2], [-1.5, 1.5, -1.5])
+    single.StepN(DT, 8, 3, 40); batch.StepN(DT, 8, 3, 40)
+    ss, _ = single.read_bodies(); sb, n = batch.read_bodies()
+    for r in range(copies):
+        same = all((ss[i].c.x, ss[i].c.y, ss[i].a) == (sb[r * nb + i].c.x, sb[r * nb + i].c.y, sb[r * nb + i].a) for i in range(nb))
+        assert same == (r != 7), r
