@@ -1934,6 +1934,9 @@ int World::writeBodies(const dbx_body_state* in, int n) {
     else bodies_[i].xf0 = pack(x0);
   }
   fullPushBodies_ = true;
+  // the written sweeps may carry an alpha0 from somebody else's unfinished bookkeeping (the reference leaves alpha0 as the last
+  // SolveTOI set it and resets it when the next one starts, b2world.d:1131-1137): have the next k_toi start from its reset phase
+  toiClean_ = false;
   return n;
 }
 

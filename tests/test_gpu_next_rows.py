@@ -2,13 +2,15 @@
 b2Contact.GetWorldManifold, b2World.ShiftOrigin and b2ContactListener.PostSolve.  Where the two sides hold the same state
 (before the first step, or after the oracle's state was transplanted into the device world) the answers must be identical;
 where they stepped separately the scenes are order-free, so they agree to float rounding."""
+import math
 import random
 
 import pytest
 
+from dbox_b200 import _abi as A
 from dbox_b200 import scenes
 from dbox_b200.world import (b2BodyDef, b2CircleShape, b2EdgeShape, b2FixtureDef, b2MouseJointDef, b2PolygonShape, b2PulleyJointDef, b2World,
-                             b2_dynamicBody)
+                             b2_dynamicBody, b2_kinematicBody)
 from tests.parity import contact_key, transplant
 from tests.test_gpu_features import _dyn, _ground, _query_scene, both
 
@@ -641,3 +643,93 @@ def test_jointed_replicas_match_single_world(gpu_api):
     for r in range(copies):
         same = all((ss[i].c.x, ss[i].c.y, ss[i].a) == (sb[r * nb + i].c.x, sb[r * nb + i].c.y, sb[r * nb + i].a) for i in range(nb))
         assert same == (r != 7), r
+
+
+def _random_scene(api, seed, continuous):
+    """a random mixed scene: sloped chain ground and walls, circles / boxes / convex polygons / two-fixture compounds with random
+    materials, a kinematic paddle, and a few joints on bodies of their own (so that no two joints share a body)"""
+    from dbox_b200.world import b2ChainShape, b2PrismaticJointDef, b2RevoluteJointDef
+    rng = random.Random(seed)
+    w = b2World((0.0, -10.0), api=api)
+    w.SetContinuousPhysics(continuous)
+    g = w.CreateBody(b2BodyDef())
+    ch = b2ChainShape(api)
+    ch.CreateChain([(-22.0, 6.0), (-20.0, 0.0)] + [(-16.0 + 4.0 * k, rng.uniform(-0.6, 0.6)) for k in range(9)] + [(20.0, 0.0), (22.0, 6.0)])
+    g.CreateFixture(ch, 0.0)
+    bodies = []
+    for k in range(70):
+        b = _dyn(w, rng.uniform(-17.0, 17.0), rng.uniform(1.0, 14.0), angle=rng.uniform(-3.0, 3.0))
+        kind = rng.randrange(4)
+        fd = b2FixtureDef()
+        fd.density, fd.friction, fd.restitution = rng.uniform(0.5, 3.0), rng.uniform(0.0, 0.9), rng.choice((0.0, 0.0, 0.2, 0.6))
+        if kind == 0:
+            s = b2CircleShape(api); s.m_radius = rng.uniform(0.25, 0.8)
+        elif kind == 1:
+            s = b2PolygonShape(api); s.SetAsBox(rng.uniform(0.25, 1.0), rng.uniform(0.25, 1.0))
+        else:
+            nv = rng.randint(3, 8)
+            s = b2PolygonShape(api)
+            s.Set([(rng.uniform(0.3, 0.9) * math.cos(2.0 * math.pi * (i + rng.uniform(0.0, 0.6)) / nv),
+                    rng.uniform(0.3, 0.9) * math.sin(2.0 * math.pi * (i + rng.uniform(0.0, 0.6)) / nv)) for i in range(nv)])
+        fd.shape = s
+        b.CreateFixture(fd)
+        if kind == 3:
+            s2 = b2CircleShape(api); s2.m_radius = 0.3; s2.m_p.Set(0.7, 0.0)
+            fd.shape = s2
+            b.CreateFixture(fd)
+        b.SetLinearVelocity((rng.uniform(-3.0, 3.0), rng.uniform(-3.0, 1.0)))
+        bodies.append(b)
+    bd = b2BodyDef(); bd.type = b2_kinematicBody; bd.position.Set(0.0, 3.0)
+    paddle = w.CreateBody(bd)
+    s = b2PolygonShape(api); s.SetAsBox(3.0, 0.2); paddle.CreateFixture(s, 0.0)
+    paddle.SetAngularVelocity(0.7)
+    for k in range(3):
+        a = _dyn(w, -15.0 + 12.0 * k, 16.0)
+        s = b2PolygonShape(api); s.SetAsBox(1.5, 0.2); a.CreateFixture(s, 1.0)
+        if k % 2 == 0:
+            jd = b2RevoluteJointDef(); jd.Initialize(g, a, (-15.0 + 12.0 * k, 16.0))
+            jd.enableMotor, jd.motorSpeed, jd.maxMotorTorque = True, 1.0, 100.0
+        else:
+            jd = b2PrismaticJointDef(); jd.Initialize(g, a, (-15.0 + 12.0 * k, 16.0), (1.0, 0.0))
+            jd.enableLimit, jd.lowerTranslation, jd.upperTranslation = True, -2.0, 2.0
+        w.CreateJoint(jd)
+        bodies.append(a)
+    return w, bodies
+
+
+@pytest.mark.parametrize("seed", list(range(1, 17)))
+def test_random_scenes_single_step_sequential_order(gpu_api, oracle_api, seed):
+    """differential test over random mixed scenes: from the oracle's state (transplanted), with the oracle's own Gauss-Seidel order
+    injected as the level schedule, one step of the CUDA path reproduces the oracle's step -- contact set, touching flags, manifold
+    types and feature keys exactly, body states to float rounding -- at several moments of the scene's life"""
+    from tests import parity as P
+    continuous = seed % 2 == 0
+    wo, _ = _random_scene(oracle_api, seed, continuous)
+    wg, _ = _random_scene(gpu_api, seed, continuous)
+    fixture_body = {f.id: f.body.id for f in wg._fixtures.values()}
+    body_dynamic = {b.id: False for b in wg._bodies.values()}
+    st, n = wg.read_bodies()
+    for i in range(n):
+        body_dynamic[i] = st[i].type == A.DYNAMIC_BODY
+    worst = (0.0, 0.0)
+    for presteps in (3, 25, 60, 60):
+        for _ in range(presteps):
+            wo.Step(DT, 8, 3)
+        P.transplant(wo, wg)
+        wo.Step(DT, 8, 3)
+        levels, m, nlev = P.sequential_levels(oracle_api, wo, wg, fixture_body, body_dynamic)
+        assert gpu_api.world_debug_set_contact_levels(wg._w, levels, m) == 0, gpu_api.last_error()
+        wg.Step(DT, 8, 3)
+        so, n = wo.read_bodies(); sg, _ = wg.read_bodies()
+        ep, ev = P.body_state_errors(so, sg, n)
+        worst = (max(worst[0], ep), max(worst[1], ev))
+        co, _, no = P.contacts_by_key(wo); cg, _, ng = P.contacts_by_key(wg)
+        assert set(co) == set(cg), (seed, presteps, set(co) ^ set(cg))
+        for k, ro in co.items():
+            rg = cg[k]
+            assert (ro.flags & A.CONTACT_TOUCHING) == (rg.flags & A.CONTACT_TOUCHING), (seed, presteps, k)
+            if ro.flags & A.CONTACT_TOUCHING:
+                assert ro.manifold.pointCount == rg.manifold.pointCount and ro.manifold.type == rg.manifold.type, (seed, presteps, k)
+                for j in range(ro.manifold.pointCount):
+                    assert ro.manifold.points[j].key == rg.manifold.points[j].key, (seed, presteps, k)
+    assert worst[0] < 5e-5 and worst[1] < 5e-4, (seed, worst)
