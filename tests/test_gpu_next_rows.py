@@ -2,6 +2,7 @@
 b2Contact.GetWorldManifold, b2World.ShiftOrigin and b2ContactListener.PostSolve.  Where the two sides hold the same state
 (before the first step, or after the oracle's state was transplanted into the device world) the answers must be identical;
 where they stepped separately the scenes are order-free, so they agree to float rounding."""
+import ctypes as C
 import math
 import random
 
@@ -733,3 +734,60 @@ def test_random_scenes_single_step_sequential_order(gpu_api, oracle_api, seed):
                 for j in range(ro.manifold.pointCount):
                     assert ro.manifold.points[j].key == rg.manifold.points[j].key, (seed, presteps, k)
     assert worst[0] < 5e-5 and worst[1] < 5e-4, (seed, worst)
+
+
+def test_error_paths_of_the_new_calls(gpu_api):
+    """misuse of the calls added for the 8(f) rows fails loudly with a DBX_E_* code and a message, never silently: wrong joint type,
+    bad limits, unknown fixtures / joints, a PostSolve buffer that is too small, ShiftOrigin in the middle of a split step, user filter
+    or sub-stepping on a replicated world"""
+    from dbox_b200.world import b2RevoluteJointDef
+    from tests.test_gpu_features import _box_body
+    api = gpu_api
+    w = b2World((0.0, -10.0), api=api)
+    g = _ground(w, api)
+    a = _box_body(w, api, 0.0, 0.6)
+    b = _box_body(w, api, 0.0, 1.7)
+    rd = b2RevoluteJointDef(); rd.Initialize(g, b, (0.0, 1.7)); rd.enableLimit, rd.lowerAngle, rd.upperAngle = True, -0.1, 0.1
+    j = w.CreateJoint(rd)
+    pod = rd._pod()
+    pod.lowerAngle, pod.upperAngle = 0.5, -0.5
+    assert api.joint_set_params(w._w, j.id, C.byref(pod), A.JP_LIMITS) == A.DBX_E_INVALID            # lower > upper
+    pod.type = A.JOINT_PRISMATIC
+    assert api.joint_set_params(w._w, j.id, C.byref(pod), A.JP_MOTOR_SPEED) == A.DBX_E_INVALID        # not this joint's type
+    assert api.joint_set_params(w._w, 99, C.byref(pod), A.JP_MOTOR_SPEED) == A.DBX_E_INVALID
+    assert api.joint_set_params(w._w, j.id, None, A.JP_MOTOR_SPEED) == A.DBX_E_INVALID
+    ids = (C.c_int32 * 1)(5); sp = (C.c_float * 1)(1.0)
+    assert api.world_set_motor_speeds(w._w, ids, sp, 1) == A.DBX_E_INVALID
+    assert api.world_set_motor_speeds(w._w, None, None, 0) == 0
+    # PostSolve buffer too small: the overflow is reported, not truncated silently
+    assert w.EnablePostSolve(1) >= 1
+    for _ in range(30):
+        w.Step(DT, 8, 3)
+    assert api.world_read_post_solve(w._w, None, 0) in (A.DBX_E_CAPACITY, 0, 1) 
+    big = w.EnablePostSolve(64)
+    w.Step(DT, 8, 3)
+    assert 1 <= len(w.ReadPostSolve()) <= big
+    # no new-contact list unless the user filter is on; a veto of a pair that does not exist is ignored
+    assert api.world_poll_new_contacts(w._w, None, 0) == 0
+    p = (A.ContactPatch * 1)(); p[0].fixtureA, p[0].fixtureB, p[0].mask = 0, 0, A.PATCH_DESTROY
+    assert api.world_patch_contacts(w._w, p, 1) == 1
+    # ShiftOrigin between step_begin and step_end is refused
+    assert api.world_step_begin(w._w, DT, 8, 3) == 0
+    assert api.world_shift_origin(w._w, 1.0, 1.0) == A.DBX_E_INVALID
+    assert api.world_step_async(w._w, DT, 8, 3) == A.DBX_E_INVALID
+    assert api.world_step_end(w._w) == 0
+    assert api.world_tree_stats(w._w, None, None, None) == 0
+    # replicated worlds (replicate comes before the first step): per-contact vetoes and sub-stepping are refused, and say why
+    with pytest.raises(RuntimeError):
+        w.Replicate(3)
+    w = b2World((0.0, -10.0), api=api)
+    g = _ground(w, api)
+    b = _box_body(w, api, 0.0, 1.7)
+    rd = b2RevoluteJointDef(); rd.Initialize(g, b, (0.0, 1.7)); rd.enableMotor, rd.maxMotorTorque = True, 10.0
+    j = w.CreateJoint(rd)
+    w.Replicate(3)
+    assert api.world_set_user_filter(w._w, A.FILTER_LOG) == A.DBX_E_UNSUPPORTED and b"replicated" in api.last_error()
+    assert api.world_set_flags(w._w, A.WORLD_DEFAULT_FLAGS | A.WORLD_SUB_STEPPING) == A.DBX_E_UNSUPPORTED
+    assert api.joint_set_params(w._w, j.id, C.byref(rd._pod()), A.JP_MOTOR_SPEED) == A.DBX_E_UNSUPPORTED
+    assert api.world_set_motor_speeds(w._w, (C.c_int32 * 1)(2), sp, 1) == 1                             # joint 0 of replica 2
+    assert api.world_set_motor_speeds(w._w, (C.c_int32 * 1)(3), sp, 1) == A.DBX_E_INVALID              # there is no replica 3
