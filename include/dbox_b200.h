@@ -68,7 +68,8 @@ enum {
   DBX_JOINT_ROPE = 10, DBX_JOINT_MOTOR = 11
 };
 /* world toggles: dynamics/b2world.d:622-753 (SetAllowSleeping / SetWarmStarting / SetContinuousPhysics /
- * SetSubStepping / SetAutoClearForces) */
+ * SetSubStepping / SetAutoClearForces).  Sub-stepping: one TOI event per Step, the following Steps run Collide and resume
+ * SolveTOI without Solve until no event is left (b2world.d:1127-1146, 1441-1446); not available on replicated worlds. */
 enum {
   DBX_WORLD_ALLOW_SLEEP = 0x01, DBX_WORLD_WARM_STARTING = 0x02, DBX_WORLD_CONTINUOUS = 0x04,
   DBX_WORLD_SUB_STEPPING = 0x08, DBX_WORLD_AUTO_CLEAR_FORCES = 0x10,
@@ -368,9 +369,9 @@ int32_t dbx_world_query_aabb(dbx_world* w, const dbx_aabb* boxes, int32_t n, int
  * (contacts/b2contact.d:338-346; also inside the TOI loop, dynamics/b2world.d:1295,1379) and from b2ContactManager.Destroy
  * (dynamics/b2contactmanager.d:60-63).  Device code cannot call back into the host, so the same call sites append records
  * to a device buffer and the host shim delivers them right after dbx_world_step returns: same events, same fixtures,
- * later in time.  Consequences: a listener cannot change the step it is told about (PreSolve's SetEnabled(false) /
- * friction edits are NOT supported -- such programs stay on the CPU path); PostSolve's impulses are the normal/tangent
- * impulses dbx_world_read_contacts returns.  Events are ordered (step, phase, pair key, type); phase 1 = Collide,
+ * later in time.  Consequence: a listener cannot change the step it is told about through THESE calls; PreSolve's
+ * SetEnabled(false) / friction edits go through the split step below (dbx_world_step_begin / patch_contacts / step_end),
+ * PostSolve's impulses through dbx_world_enable_post_solve / dbx_world_read_post_solve.  Events are ordered (step, phase, pair key, type); phase 1 = Collide,
  * 2 = TOI sub-steps, 3 = contact destroyed by an API call after that step (DestroyBody / DestroyFixture / CreateJoint). */
 typedef struct dbx_contact_event {
   int32_t type;               /* DBX_CONTACT_BEGIN / DBX_CONTACT_END */
