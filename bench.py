@@ -118,6 +118,52 @@ def run_cpu_port(n_bodies, columns, settle, steps, warmup, threads=1, replicas=1
     return replicas * n_bodies * steps / secs, secs, c
 
 
+def run_cpu_pile_from_snapshot(n_bodies, columns, snap, steps, warmup, replicas=1):
+    """The reference algorithm's CPU path on the REAL headline configuration: the oracle builds the same n_bodies pile, takes
+    over the settled state the device produced (dbox_b200.state.apply -> orc_world_write_*: bodies, fat AABBs, contact cache with
+    impulses, joint impulses) and steps it single-threaded.  No CPU settle (600 oracle steps of this world take ~10 minutes)."""
+    from oracle import orc
+    from dbox_b200 import scenes, state
+    api = orc.api()
+    worlds = []
+    for _ in range(replicas):             # N > 1: one world per host thread, like our arm's one world per GPU
+        w, _, _ = scenes.pile(api=api, n=n_bodies, columns=columns, seed=12345)
+        w.SetAllowSleeping(False)
+        state.apply(w, snap)
+        worlds.append(w)
+    arr = (C.c_void_p * replicas)(*[w._w for w in worlds])
+    if warmup > 0:
+        api.batch_step(arr, replicas, DT, VEL_ITERS, POS_ITERS, warmup, replicas)
+    secs = api.batch_step(arr, replicas, DT, VEL_ITERS, POS_ITERS, steps, replicas)
+    c = worlds[0].counts()
+    p = worlds[0].GetProfile()
+    c.profile_ms = {k: round(float(getattr(p, k)), 4) for k in ("step", "collide", "solve", "solveInit", "solveVelocity", "solvePosition", "broadphase", "solveTOI")}
+    for w in worlds:
+        w.close()
+    return replicas * n_bodies * steps / secs, secs, c
+
+
+def settled_pile_snapshot(args, device=0):
+    """settle the headline pile on the device and return its state as ABI records (the reference arm's starting point)"""
+    from dbox_b200 import lib, scenes, state
+    api = lib.api()
+    if api.device_count() < 1:
+        return None
+    world, _, _ = scenes.pile(api=api, n=args.bodies, columns=args.columns, seed=12345, device=device)
+    world.SetAllowSleeping(False)
+    world.StepN(DT, VEL_ITERS, POS_ITERS, args.settle)
+    snap = state.capture(world)
+    world.close()
+    return snap
+
+
+def probe_d_toolchain():
+    """is there a D compiler on this box?  (None in the build image; recorded with every reference line.)"""
+    import shutil
+    found = {t: shutil.which(t) for t in ("dmd", "ldc2", "gdc", "dub")}
+    return {k: v for k, v in found.items() if v} or None
+
+
 def run_cpu_pyramids(worlds, settle, steps, threads):
     """C5 on the host: `worlds` independent Pyramid worlds, one world per thread at a time (oracle port of the reference)"""
     from oracle import orc
@@ -226,7 +272,8 @@ def main():
     ap.add_argument("--settle", type=int, default=600, help="untimed steps that let the pile settle before warm-up (SURVEY.md 8(d))")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--cpu-bodies", type=int, default=10000, help="bounded CPU sample: same generator and pile depth, fewer columns")
-    ap.add_argument("--cpu-steps", type=int, default=60)
+    ap.add_argument("--cpu-steps", type=int, default=8, help="timed CPU steps of the full pile (each takes seconds: SolveTOI rescans the contact list per event)")
+    ap.add_argument("--cpu-warmup", type=int, default=1)
     ap.add_argument("--cpu-settle", type=int, default=240)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--worlds", type=int, default=65536, help="C5: independent Pyramid worlds in the batched leg (0 = skip the leg)")
@@ -258,18 +305,36 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        threads = max(1, min(n_gpus, cores))
-        steps = max(1, min(K, args.cpu_steps))
         t0 = time.time()
-        value, secs, c = run_cpu_port(cpu_bodies, cpu_cols, args.cpu_settle, steps, W, threads=threads, replicas=threads)
-        sample = ("%d replica(s) of a %d-body pile (same generator, same %d-row depth, %d columns), %d settle + %d warm-up + %d timed steps, "
-                  "one world per thread" % (threads, cpu_bodies, rows, cpu_cols, args.cpu_settle, W, steps))
-        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": W,
+        steps = max(1, min(K, args.cpu_steps))
+        snap = None
+        try:
+            snap = settled_pile_snapshot(args, local_rank)
+        except Exception as e:      # no usable device: fall back to a CPU-settled sample and say so
+            print("reference arm: device settle unavailable (%s)" % e, file=sys.stderr)
+        if snap is not None:
+            # same config as our arm: the 100,000-body pile in the state 600 settle steps left it in (settled on the device,
+            # transplanted through orc_world_write_*), then timed on one host core -- the reference is single-threaded per world
+            threads, same_config = max(1, min(n_gpus, cores)), True
+            value, secs, c = run_cpu_pile_from_snapshot(args.bodies, args.columns, snap, steps, args.cpu_warmup, replicas=threads)
+            sample = ("%d replica(s) of the full %d-body pile, settled %d steps on the device and transplanted into the CPU port (orc_world_write_*), "
+                      "%d warm-up + %d timed steps, one world per host thread (the reference is single-threaded per world); ours steps one such world per GPU"
+                      % (threads, args.bodies, args.settle, args.cpu_warmup, steps))
+        else:
+            threads, same_config = 1, False
+            steps = max(1, min(K, 60))
+            value, secs, c = run_cpu_port(cpu_bodies, cpu_cols, args.cpu_settle, steps, W, threads=1, replicas=1)
+            config = dict(config, bodies=cpu_bodies, columns=cpu_cols, settle_steps=args.cpu_settle,
+                          workload=config["workload"].replace("%d-body" % args.bodies, "%d-body (REDUCED: no device to settle the full pile)" % cpu_bodies))
+            sample = ("%d-body pile (same generator, same %d-row depth, %d columns), %d settle + %d warm-up + %d timed steps on the CPU, single thread"
+                      % (cpu_bodies, rows, cpu_cols, args.cpu_settle, W, steps))
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": args.cpu_warmup,
                 "ms_per_step": 1e3 * secs / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": config,
+                "data": "synthetic", "config": config, "same_config": same_config,
+                "counts": {"contacts": c.contacts, "touching": c.touching, "awake_bodies": c.awakeBodies, "joints": c.joints},
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "b2Profile_ms_last_step": c.profile_ms},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0, "wall_s": time.time() - t0}
+                "gpu_launches": 0, "d_toolchain": probe_d_toolchain(), "wall_s": time.time() - t0}
         if args.worlds > 0:
             nw = cores * args.cpu_worlds_per_thread
             bsteps = args.cpu_batch_steps
@@ -301,6 +366,10 @@ def main():
     if args.save_state and rank == 0:
         from dbox_b200 import state
         state.save(world, args.save_state)
+    cpu_snap = None
+    if rank == 0 and n_gpus == 1 and not args.skip_cpu_baseline:
+        from dbox_b200 import state
+        cpu_snap = state.capture(world)      # the settled pile: the CPU baseline below steps exactly this world
 
     tot = C.c_float()
     stage = (C.c_float * 9)()
@@ -407,10 +476,11 @@ def main():
                                            "sample": "%d Pyramid worlds, %d settle + %d timed steps, one world per host thread at a time, %.1f s"
                                                      % (nw, args.batch_settle, args.cpu_batch_steps, secs)}
             t0 = time.time()
-            v, secs, c = run_cpu_port(cpu_bodies, cpu_cols, args.cpu_settle, args.cpu_steps, 3)
+            csteps = max(1, min(args.cpu_steps, 3))
+            v, secs, c = run_cpu_pile_from_snapshot(args.bodies, args.columns, cpu_snap, csteps, args.cpu_warmup)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": "%d-body pile (same generator, same %d-row depth, %d columns), %d settle + %d timed steps, single thread, %.1f s"
-                                              % (cpu_bodies, rows, cpu_cols, args.cpu_settle, args.cpu_steps, time.time() - t0),
+                                    "sample": "the full %d-body pile in the settled state this run timed (transplanted into the CPU port through orc_world_write_*), "
+                                              "%d warm-up + %d timed steps, single thread, %.1f s" % (args.bodies, args.cpu_warmup, csteps, time.time() - t0),
                                     "b2Profile_ms_last_step": c.profile_ms}
         print(json.dumps(line), flush=True)
     if world_size > 1:

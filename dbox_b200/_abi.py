@@ -228,6 +228,7 @@ PROTOTYPES = {
     "world_stage_collide": (c_i32, [W]),
     "world_read_pairs": (c_i32, [W, P(c_i32), c_i32]),
     "world_debug_set_contact_levels": (c_i32, [W, P(c_i32), c_i32]),
+    "world_debug_read_solve_order": (c_i32, [W, P(c_i32), c_i32, P(c_i32), c_i32, P(c_i32)]),
     "world_debug_colour_conflicts": (c_i32, [W]),
     "debug_collide": (c_i32, [c_i32, c_i32, P(Shape), P(c_f32), P(Shape), P(c_f32), P(Manifold)]),
     "debug_distance": (c_i32, [c_i32, c_i32, P(Shape), P(c_f32), P(Shape), P(c_f32), c_i32, P(c_f32), P(Vec2), P(Vec2), P(c_i32)]),

@@ -260,6 +260,7 @@ int32_t dbx_world_stage_find_new_contacts(dbx_world* w) { W_OR_INVALID(w); retur
 int32_t dbx_world_stage_collide(dbx_world* w) { W_OR_INVALID(w); return w->w.stageCollide(); }
 int32_t dbx_world_read_pairs(dbx_world* w, int32_t* out, int32_t cap) { W_OR_INVALID(w); return w->w.readPairs(out, out ? cap : 0); }
 int32_t dbx_world_debug_set_contact_levels(dbx_world* w, const int32_t* levels, int32_t n) { W_OR_INVALID(w); return w->w.setContactLevels(levels, n); }
+int32_t dbx_world_debug_read_solve_order(dbx_world* w, int32_t* cc, int32_t capC, int32_t* jc, int32_t capJ, int32_t* info3) { W_OR_INVALID(w); return w->w.readSolveOrder(cc, capC, jc, capJ, info3); }
 
 int32_t dbx_world_debug_colour_conflicts(dbx_world* w) { W_OR_INVALID(w); return w->w.colourConflicts(); }
 
@@ -301,7 +302,19 @@ int32_t dbx_world_import_state(dbx_world* w, const void* buf, int64_t n) {
   if (h.magic != kSnapMagic || h.version != 1) { set_last_error("import_state: not a dbox_b200 snapshot"); return DBX_E_INVALID; }
   const int64_t need = (int64_t)sizeof(SnapHead) + (int64_t)h.nb * sizeof(dbx_body_state) + (int64_t)h.np * sizeof(dbx_proxy_rec) + (int64_t)h.nc * sizeof(dbx_contact_rec) +
                        (int64_t)h.nj * sizeof(dbx_joint_state) + (int64_t)h.nm * 8 + (int64_t)h.nc * 4;
-  if (n < need) return DBX_E_INVALID;
+  // the header is untrusted input: every count must be non-negative, the blob exactly as long as its counts say (anything else
+  // is a truncated or foreign buffer), and the counts must be those of THIS world's topology -- the scene is not in the blob, so
+  // a snapshot of another scene would otherwise restore half a world
+  if (h.nb < 0 || h.np < 0 || h.nc < 0 || h.nj < 0 || h.nm < 0) { set_last_error("import_state: negative record count"); return DBX_E_INVALID; }
+  if (n != need) { set_last_error("import_state: blob length does not match its header"); return DBX_E_INVALID; }
+  {
+    const int nb = W.readBodies(nullptr, 0), np = W.readProxies(nullptr, 0), nj = W.readJoints(nullptr, 0);
+    if (nb < 0 || np < 0 || nj < 0) return DBX_E_CUDA;
+    if (h.nb != nb || h.np != np || h.nj != nj) {
+      set_last_error("import_state: snapshot of a different scene (bodies / proxies / joints do not match this world)"); return DBX_E_INVALID;
+    }
+    if (h.nm > np) { set_last_error("import_state: more moves than proxies"); return DBX_E_INVALID; }
+  }
   const char* p = (const char*)buf + sizeof(SnapHead);
   int rc = W.writeBodies((const dbx_body_state*)p, h.nb); if (rc != h.nb) return rc < 0 ? rc : DBX_E_INVALID; p += (size_t)h.nb * sizeof(dbx_body_state);
   rc = W.writeProxies((const dbx_proxy_rec*)p, h.np); if (rc != h.np) return rc < 0 ? rc : DBX_E_INVALID; p += (size_t)h.np * sizeof(dbx_proxy_rec);

@@ -1678,8 +1678,11 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
 // The barrier is a ticket counter: a barrier is complete when the counter reaches the next multiple of the CTA count, so
 // it needs no reset between launches as long as every launch uses the same grid and leaves it on a multiple (all do).
 // It is zeroed every 4096 launches, long before 2^32 tickets.
+// The barrier word only ever counts up inside a launch and is a multiple of the CTA count between launches.  Worst case per
+// launch is kMaxColours phases x 11 passes x 148 CTAs = 1.7 M tickets (k_toi: 1024 passes x ~10 barriers x 148 = 1.5 M), so a
+// reset every 1024 cooperative launches keeps it below 2^31 with room to spare; grid_barrier compares wrap-safely as well.
 static cudaError_t launch_coop(const void* fn, const DevWorld& W, const LaunchCfg& L) {
-  if ((L.coopLaunches++ & 4095) == 0) CK(cudaMemsetAsync(&W.hdr->barrier, 0, sizeof(unsigned), L.stream));
+  if ((L.coopLaunches++ & 1023) == 0) CK(cudaMemsetAsync(&W.hdr->barrier, 0, sizeof(unsigned), L.stream));
   void* args[] = {(void*)&W};
   ++L.launches;
   return cudaLaunchCooperativeKernel(fn, dim3(L.coopBlocks), dim3(L.coopThreads), args, 0, L.stream);

@@ -433,7 +433,7 @@ cudaError_t stage_prepare(const DevWorld& W, const LaunchCfg& L) {
   return cudaGetLastError();
 }
 cudaError_t stage_solve(const DevWorld& W, const LaunchCfg& L) {
-  if ((L.coopLaunches++ & 4095) == 0) CK(cudaMemsetAsync(&W.hdr->barrier, 0, sizeof(unsigned), L.stream));   // see launch_coop
+  if ((L.coopLaunches++ & 1023) == 0) CK(cudaMemsetAsync(&W.hdr->barrier, 0, sizeof(unsigned), L.stream));   // see launch_coop
   void* args[] = {(void*)&W};
   ++L.launches;
   return cudaLaunchCooperativeKernel((const void*)k_solve, dim3(L.coopBlocks), dim3(L.coopThreads), args, 0, L.stream);

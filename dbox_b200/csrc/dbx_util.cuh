@@ -101,7 +101,7 @@ DBX_D void grid_barrier(unsigned* counter, unsigned nblocks) {
     __threadfence();
     unsigned ticket = atomicAdd(counter, 1u);
     unsigned target = (ticket / nblocks + 1u) * nblocks;
-    while (*((volatile unsigned*)counter) < target) { }
+    while ((int)(*((volatile unsigned*)counter) - target) < 0) { }   // wrap-safe: the distance to the target is always < 2^31
     __threadfence();
   }
   __syncthreads();

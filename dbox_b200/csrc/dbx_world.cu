@@ -1141,6 +1141,7 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents, int halves) {
   } else if (bodies_.empty()) return 0;
   dw_.colourOverride = overrideLevels_ ? 1 : 0;
   dw_.unifiedColours = (!overrideLevels_ && !jointAt_.empty() && !(dw_.dbgFlags & 32)) ? 1 : 0;
+  lastUnified_ = dw_.unifiedColours != 0;
   // TOI: the kernel leaves its per-body scratch clean; a world that has not run it yet, or has grown since, resets first.
   // When the scratch is clean the first TOI evaluation is forked onto a second stream right after the solver.
   const bool continuous = (flags_ & DBX_WORLD_CONTINUOUS) && dt > 0.0f;
@@ -1306,6 +1307,7 @@ int World::patchContacts(const dbx_contact_patch* in, int n) {
 int World::step(float dt, int vi, int pi, int n) {
   if (!ok_) return DBX_E_NO_DEVICE;
   cudaSetDevice(device_);
+  if (midStep_) { set_last_error("step: a split step is open (step_begin without step_end)"); return DBX_E_INVALID; }
   for (int k = 0; k < n; ++k) { int rc = enqueueStep(dt, vi, pi, false); if (rc < 0) return rc; }
   return checkDeviceError(true);
 }
@@ -1317,6 +1319,7 @@ int World::step(float dt, int vi, int pi, int n) {
 int World::timeSteps(float dt, int vi, int pi, int n, bool flushL2, float* totalMs, float* stageMs) {
   if (!ok_) return DBX_E_NO_DEVICE;
   cudaSetDevice(device_);
+  if (midStep_) { set_last_error("time_steps: a split step is open (step_begin without step_end)"); return DBX_E_INVALID; }
   const size_t flushBytes = 256u << 20;
   if (flushL2) CUDA_OR_FAIL(flushBuf_.reserve(flushBytes, false, stream_), "flush buffer");
   double total = 0.0, stage[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -2173,6 +2176,20 @@ int World::setContactLevels(const int32_t* levels, int n) {
   CUDA_OR_FAIL(cudaMemcpy(c_colour.p, col.data(), col.size() * 4, cudaMemcpyHostToDevice), "levels up");
   overrideLevels_ = true;
   return 0;
+}
+
+// Test hook: the schedule the last step ran (see include/dbox_b200.h).  Contact colours are persistent device state
+// (c_colour, valid while the contact is in the solver); joint colours and the unified-phase switch live on the host.
+int World::readSolveOrder(int32_t* contactColours, int capC, int32_t* jointColours, int capJ, int32_t* info3) {
+  const int n = readContactColours(contactColours, capC);
+  if (n < 0) return n;
+  for (int j = 0; j < (int)joints_.size() && j < capJ; ++j) jointColours[j] = joints_[j].alive ? joints_[j].colour : -1;
+  if (info3) {
+    int nc = 0;
+    if (dw_.hdr) CUDA_OR_FAIL(cudaMemcpy(&nc, (char*)hdr_.p + offsetof(Header, nColours), 4, cudaMemcpyDeviceToHost), "read nColours");
+    info3[0] = lastUnified_ ? 1 : 0; info3[1] = nc; info3[2] = jointAt_.empty() ? 0 : nJointColours_;
+  }
+  return n;
 }
 
 // Test hook ("colour-validity checker"): number of pairs of solver contacts that share a dynamic body

@@ -133,6 +133,7 @@ class World {
   int stageFindNewContacts();
   int stageCollide();
   int setContactLevels(const int32_t* levels, int n);
+  int readSolveOrder(int32_t* contactColours, int capC, int32_t* jointColours, int capJ, int32_t* info3);
   int colourConflicts();
   int readHeader(void* out, int bytes) { cudaStreamSynchronize(stream_); int n = bytes < (int)sizeof(Header) ? bytes : (int)sizeof(Header); return cudaMemcpy(out, hdr_.p, n, cudaMemcpyDeviceToHost) == cudaSuccess ? n : DBX_E_CUDA; }
   int phaseTimes(unsigned long long* out, int cap);   // debug: enable + fetch the last step's k_solve barrier stamps
@@ -223,6 +224,7 @@ class World {
   bool inReadValid_[2] = {false, false}, outDoneValid_[2] = {false, false};
   int inFlip_ = 0, ioTicket_ = 0;
   bool overrideLevels_ = false;
+  bool lastUnified_ = false;   // the last step ran joint colour c and contact colour c in one phase
   bool treeValid_ = false; int sinceRebuild_ = 0;
   // contact-pool watermark: every 8th step the header is copied to pinned memory without waiting; a later step looks at
   // the copy that has landed and doubles the pool before it can overflow

@@ -39,3 +39,40 @@ def load(world, path):
     flat = (C.c_int32 * max(2 * len(moves), 2))(*[x for m in moves for x in m])
     assert api.world_write_moves(w, flat, len(moves)) == len(moves)
     api.world_set_inv_dt0(w, blob["inv_dt0"])
+
+
+def capture(src):
+    """The dynamic state of world `src` as the ABI's bulk records (ctypes arrays + counts)."""
+    bodies, nb = src.read_bodies()
+    prox, npx = src.read_proxies()
+    joints, nj = src.read_joints()
+    cons, nc = src.read_contacts()
+    return {"bodies": bodies, "nb": nb, "proxies": prox, "np": npx, "joints": joints, "nj": nj, "contacts": cons, "nc": nc,
+            "moves": src.read_moves(), "inv_dt0": src.get_inv_dt0()}
+
+
+def apply(dst, snap):
+    """Write a `capture` into world `dst` (the same scene built on it).  Works with any library that exports the ABI's
+    write_* calls -- the CUDA library, or the CPU oracle in tests / bench.py's reference arm."""
+    api, w = dst._api, dst._w
+    rc = api.world_write_bodies(w, snap["bodies"], snap["nb"])
+    assert rc == snap["nb"], ("write_bodies", rc, snap["nb"])
+    rc = api.world_write_proxies(w, snap["proxies"], snap["np"])
+    assert rc == snap["np"], ("write_proxies", rc, snap["np"])
+    if snap["nj"]:
+        rc = api.world_write_joints(w, snap["joints"], snap["nj"])
+        assert rc == snap["nj"], ("write_joints", rc, snap["nj"])
+    rc = api.world_write_contacts(w, snap["contacts"], snap["nc"])
+    assert rc == snap["nc"], ("write_contacts", rc, snap["nc"])
+    moves = snap["moves"]
+    flat = (C.c_int32 * max(2 * len(moves), 2))(*[x for m in moves for x in m])
+    rc = api.world_write_moves(w, flat, len(moves))
+    assert rc == len(moves), ("write_moves", rc, len(moves))
+    api.world_set_inv_dt0(w, snap["inv_dt0"])
+    return {"bodies": snap["nb"], "proxies": snap["np"], "joints": snap["nj"], "contacts": snap["nc"], "moves": len(moves)}
+
+
+def transplant(src, dst):
+    """Copy the dynamic state of world `src` into world `dst` (the same scene built on both): bodies, proxies (tight + fat
+    AABBs), joints' accumulated impulses, the contact cache (manifolds, impulses, flags), the pending move buffer, inv_dt0."""
+    return apply(dst, capture(src))

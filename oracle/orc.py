@@ -22,6 +22,8 @@ _REQUIRED = [
     "body_set_sleeping_allowed", "world_counts", "world_profile", "world_read_bodies", "world_read_contacts",
     "world_read_proxies", "world_read_joints", "world_read_moves", "world_get_inv_dt0", "world_stage_find_new_contacts",
     "world_stage_collide", "world_read_pairs",
+    # state import: the mirror of dbx_world_write_* (transplant a device-resident world into the oracle)
+    "world_write_bodies", "world_write_proxies", "world_write_contacts", "world_write_joints", "world_write_moves", "world_set_inv_dt0",
 ]
 
 
@@ -48,6 +50,7 @@ def api():
             "shape_mass": (None, [P(A.Shape), f32, P(f32), P(A.Vec2), P(f32)]),
             "shape_aabb": (None, [P(A.Shape), f32, f32, f32, i32, P(A.AABB)]),
             "world_read_solve_order": (i32, [W, P(i32), i32]),
+            "world_read_joint_solve_order": (i32, [W, P(i32), i32]),
             "world_tree_height": (i32, [W]),
             "world_tree_validate": (i32, [W]),
             "collide": (i32, [P(A.Shape), f32, f32, f32, i32, P(A.Shape), f32, f32, f32, i32, P(A.Manifold)]),
@@ -79,6 +82,7 @@ def api():
             "world_set_contact_filter": (i32, [W, C.c_void_p]),
             "joint_set_params": (i32, [W, i32, P(A.JointDef), C.c_uint32]),
             "world_set_motor_speeds": (i32, [W, P(i32), P(f32), i32]),
+            "world_debug_set_solve_order": (i32, [W, P(i32), P(i32), i32, P(i32), i32, i32]),
         }
         for name, (res, args) in extra.items():
             fn = getattr(lib, "orc_" + name)

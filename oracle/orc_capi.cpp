@@ -640,6 +640,11 @@ int32_t orc_world_read_solve_order(orc_world* w, int32_t* fixA_childA_fixB_child
   }
   return n;
 }
+int32_t orc_world_read_joint_solve_order(orc_world* w, int32_t* jointIds, int32_t cap) {
+  int n = 0;
+  for (int id : w->w.lastJointOrder) { if (n < cap) jointIds[n] = id; ++n; }
+  return n;
+}
 int32_t orc_world_read_proxies(orc_world* w, dbx_proxy_rec* out, int32_t cap) {
   int n = 0;
   for (Fixture* f : w->w.fixturesById) {
@@ -694,6 +699,114 @@ int32_t orc_world_read_pairs(orc_world* w, int32_t* out, int32_t cap) {
     ++n;
   }
   return n;
+}
+// ------------------------------------------------------------------------------------------------ state import
+// Mirror of dbx_world_write_* (include/dbox_b200.h): lets a test / bench.py transplant a device-resident world (same scene
+// built on both sides) into the oracle, e.g. the settled 100,000-body pile the oracle would need ten minutes to settle itself.
+// No reference counterpart: the records are the persistent state of b2Body (b2body.d:1182-1218), the tree's fat AABBs
+// (b2dynamictree.d:146-180), b2Contact (b2contact.d:441-465), the joints' accumulated impulses and the move buffer
+// (b2broadphase.d:244-257).
+int32_t orc_world_write_bodies(orc_world* w, const dbx_body_state* in, int32_t n) {
+  auto& B = w->w.bodiesById;
+  if (n > (int)B.size()) return DBX_E_INVALID;
+  for (int i = 0; i < n; ++i) {
+    Body* b = B[i]; if (!b) continue;
+    const dbx_body_state& s = in[i];
+    if (s.type != b->type) return DBX_E_INVALID;
+    b->flags = (uint16_t)(s.flags & 0x7F);
+    b->xf.p = v2(s.p); b->xf.q.s = s.qs; b->xf.q.c = s.qc;
+    b->sweep.localCenter = v2(s.localCenter); b->sweep.c0 = v2(s.c0); b->sweep.c = v2(s.c);
+    b->sweep.a0 = s.a0; b->sweep.a = s.a; b->sweep.alpha0 = s.alpha0;
+    b->linearVelocity = v2(s.v); b->angularVelocity = s.w; b->force = v2(s.force); b->torque = s.torque;
+    b->mass = s.mass; b->invMass = s.invMass; b->I = s.I; b->invI = s.invI;
+    b->linearDamping = s.linearDamping; b->angularDamping = s.angularDamping; b->gravityScale = s.gravityScale; b->sleepTime = s.sleepTime;
+  }
+  return n;
+}
+int32_t orc_world_write_proxies(orc_world* w, const dbx_proxy_rec* in, int32_t n) {
+  for (int i = 0; i < n; ++i) {
+    const dbx_proxy_rec& r = in[i];
+    Fixture* f = fixtureAt(w, r.fixture);
+    if (!f || r.child < 0 || r.child >= f->proxyCount) return DBX_E_INVALID;
+    FixtureProxy& p = f->proxies[r.child];
+    if (p.proxyId != r.proxyId) return DBX_E_INVALID;     // both sides must have lived the same history of proxy creations (b2dynamictree.d:516-564)
+    p.aabb.lo = v2(r.aabb.lo); p.aabb.hi = v2(r.aabb.hi);
+    AABB fat; fat.lo = v2(r.fat.lo); fat.hi = v2(r.fat.hi);
+    w->w.broadPhase.importFatAABB(p.proxyId, fat);
+  }
+  return n;
+}
+int32_t orc_world_write_contacts(orc_world* w, const dbx_contact_rec* in, int32_t n) {
+  w->w.clearContacts();
+  for (int i = 0; i < n; ++i) {
+    const dbx_contact_rec& r = in[i];
+    Fixture* fA = fixtureAt(w, r.fixtureA); Fixture* fB = fixtureAt(w, r.fixtureB);
+    if (!fA || !fB || r.childA < 0 || r.childB < 0 || r.childA >= fA->proxyCount || r.childB >= fB->proxyCount) return DBX_E_INVALID;
+    Contact* c = w->w.importContact(fA, r.childA, fB, r.childB);
+    c->flags = r.flags & 0x3F;
+    for (int k = 0; k < 2; ++k) {
+      c->manifold.points[k].localPoint = v2(r.manifold.points[k].localPoint);
+      c->manifold.points[k].normalImpulse = r.manifold.points[k].normalImpulse;
+      c->manifold.points[k].tangentImpulse = r.manifold.points[k].tangentImpulse;
+      c->manifold.points[k].id.key = r.manifold.points[k].key;
+    }
+    c->manifold.localNormal = v2(r.manifold.localNormal); c->manifold.localPoint = v2(r.manifold.localPoint);
+    c->manifold.type = r.manifold.type; c->manifold.pointCount = r.manifold.pointCount;
+    c->friction = r.friction; c->restitution = r.restitution; c->tangentSpeed = r.tangentSpeed; c->toiCount = r.toiCount; c->toi = r.toi;
+  }
+  return n;
+}
+int32_t orc_world_write_joints(orc_world* w, const dbx_joint_state* in, int32_t n) {
+  auto& J = w->w.jointsById;
+  if (n > (int)J.size()) return DBX_E_INVALID;
+  for (int i = 0; i < n; ++i) {
+    Joint* j = J[i]; if (!j) continue;
+    const dbx_joint_state* o = in + i;
+    if (o->type != j->type) return DBX_E_INVALID;
+    if (j->type == jRevolute) { auto* r = (RevoluteJoint*)j; r->impulse.x = o->impulse[0]; r->impulse.y = o->impulse[1]; r->impulse.z = o->impulse[2]; r->motorImpulse = o->motorImpulse; r->limitState = o->limitState; }
+    else if (j->type == jDistance) { auto* d = (DistanceJoint*)j; d->impulse = o->impulse[0]; }
+    else if (j->type == jRope) { auto* d = (RopeJoint*)j; d->impulse = o->impulse[0]; d->state = o->limitState; }
+    else if (j->type == jWeld) { auto* d = (WeldJoint*)j; d->impulse.x = o->impulse[0]; d->impulse.y = o->impulse[1]; d->impulse.z = o->impulse[2]; }
+    else if (j->type == jFriction) { auto* d = (FrictionJoint*)j; d->linearImpulse.x = o->impulse[0]; d->linearImpulse.y = o->impulse[1]; d->angularImpulse = o->impulse[2]; }
+    else if (j->type == jMotor) { auto* d = (MotorJoint*)j; d->linearImpulse.x = o->impulse[0]; d->linearImpulse.y = o->impulse[1]; d->angularImpulse = o->impulse[2]; }
+    else if (j->type == jMouse) { auto* d = (MouseJoint*)j; d->impulse.x = o->impulse[0]; d->impulse.y = o->impulse[1]; }
+    else if (j->type == jPrismatic) { auto* d = (PrismaticJoint*)j; d->impulse.x = o->impulse[0]; d->impulse.y = o->impulse[1]; d->impulse.z = o->impulse[2]; d->motorImpulse = o->motorImpulse; d->limitState = o->limitState; }
+    else if (j->type == jWheel) { auto* d = (WheelJoint*)j; d->impulse = o->impulse[0]; d->springImpulse = o->impulse[1]; d->motorImpulse = o->motorImpulse; }
+    else if (j->type == jPulley) { auto* d = (PulleyJoint*)j; d->impulse = o->impulse[0]; }
+    else if (j->type == jGear) { auto* d = (GearJoint*)j; d->impulse = o->impulse[0]; }
+  }
+  return n;
+}
+int32_t orc_world_write_moves(orc_world* w, const int32_t* fc, int32_t n) {
+  std::vector<int> ids;
+  for (int i = 0; i < n; ++i) {
+    Fixture* f = fixtureAt(w, fc[2 * i]);
+    if (!f || fc[2 * i + 1] < 0 || fc[2 * i + 1] >= f->proxyCount) return DBX_E_INVALID;
+    ids.push_back(f->proxies[fc[2 * i + 1]].proxyId);
+  }
+  w->w.broadPhase.importMoveBuffer(ids);
+  w->w.newFixture = false;
+  return n;
+}
+int32_t orc_world_set_inv_dt0(orc_world* w, float v) { w->w.inv_dt0 = v; return 0; }
+// Test hook (orc_world.h, World::orderOverride): the NEXT Solve walks every island's contacts by ascending rank[i] (contact i
+// identified by keys4[4 i ..] = fixtureA, childA, fixtureB, childB) and its joints by ascending jointRank[joint id]; contacts
+// that are not listed go last.  reversePosition != 0: position iterations walk the same arrays backwards.
+int32_t orc_world_debug_set_solve_order(orc_world* w, const int32_t* keys4, const int32_t* rank, int32_t n, const int32_t* jointRank, int32_t nj, int32_t reversePosition) {
+  struct K { int a, b, c, d; bool operator<(const K& o) const { return a != o.a ? a < o.a : b != o.b ? b < o.b : c != o.c ? c < o.c : d < o.d; } };
+  std::vector<std::pair<K, int>> tab((size_t)n);
+  for (int i = 0; i < n; ++i) tab[i] = {K{keys4[4 * i], keys4[4 * i + 1], keys4[4 * i + 2], keys4[4 * i + 3]}, rank[i]};
+  std::sort(tab.begin(), tab.end(), [](const std::pair<K, int>& x, const std::pair<K, int>& y) { return x.first < y.first; });
+  int found = 0;
+  for (Contact* c = w->w.contactList; c; c = c->next) {
+    const K k{c->fixtureA->id, c->indexA, c->fixtureB->id, c->indexB};
+    auto it = std::lower_bound(tab.begin(), tab.end(), k, [](const std::pair<K, int>& x, const K& y) { return x.first < y; });
+    if (it != tab.end() && !(k < it->first)) { c->orderRank = it->second; ++found; } else c->orderRank = 0x7fffffff;
+  }
+  auto& J = w->w.jointsById;
+  for (int i = 0; i < (int)J.size(); ++i) if (J[i]) J[i]->orderRank = i < nj ? jointRank[i] : 0x7fffffff;
+  w->w.orderOverride = true; w->w.orderReversePosition = reversePosition != 0;
+  return found;
 }
 int32_t orc_world_get_inv_dt0(orc_world* w, float* out) { *out = w->w.inv_dt0; return 0; }
 int32_t orc_world_stage_find_new_contacts(orc_world* w) { w->w.findNewContacts(); w->w.newFixture = false; return 0; }

@@ -62,7 +62,9 @@ class DynamicTree {
   const AABB& fatAABB(int id) const { return nodes_[id].aabb; }
   // b2dynamictree.d:503-511: every pool node, in use or not
   void shiftOrigin(V2 newOrigin) { for (auto& n : nodes_) { n.aabb.lo -= newOrigin; n.aabb.hi -= newOrigin; } }
-  void setFatAABB(int id, const AABB& a) { nodes_[id].aabb = a; }  // state import only (tests)
+  // state import only (tests, bench transplant): give leaf `id` exactly this fat AABB and re-link it so that every ancestor
+  // contains its children again (remove + insert, like MoveProxy :140-184 without the extension / displacement rule)
+  void importFatAABB(int id, const AABB& a) { removeLeaf(id); nodes_[id].aabb = a; insertLeaf(id); }
 
   template <class F> void query(F&& cb, const AABB& aabb) const {
     std::vector<int> stack;
@@ -314,6 +316,8 @@ class BroadPhase {
   int treeHeight() const { return tree_.height(); }
   DynamicTree& tree() { return tree_; }
   const std::vector<int>& moveBuffer() const { return moveBuffer_; }
+  void importMoveBuffer(const std::vector<int>& ids) { moveBuffer_ = ids; }   // state import only
+  void importFatAABB(int id, const AABB& a) { tree_.importFatAABB(id, a); }
   const std::vector<Pair>& lastPairs() const { return pairBuffer_; }  // sorted, with duplicates (diagnostics)
 
   template <class F> void updatePairs(F&& addPair) {

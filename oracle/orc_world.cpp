@@ -432,6 +432,32 @@ void World::findNewContacts() {
   broadPhase.updatePairs([this](void* a, void* b) { addPair(a, b); });
 }
 
+// State import (tests, bench transplant; no reference counterpart): link a contact exactly as recorded -- fixture A/B as
+// given (the record already carries the type-registry order of b2contact.d:375-400), no filter test, no wake-up -- with
+// the same push-front list surgery as AddPair (b2contactmanager.d:134-166).
+Contact* World::importContact(Fixture* fA, int iA, Fixture* fB, int iB) {
+  Contact* c = new Contact();
+  c->fixtureA = fA; c->indexA = iA; c->fixtureB = fB; c->indexB = iB;
+  Body* bodyA = fA->body; Body* bodyB = fB->body;
+  c->prev = nullptr; c->next = contactList;
+  if (contactList) contactList->prev = c;
+  contactList = c;
+  c->nodeA.contact = c; c->nodeA.other = bodyB; c->nodeA.prev = nullptr; c->nodeA.next = bodyA->contactList;
+  if (bodyA->contactList) bodyA->contactList->prev = &c->nodeA;
+  bodyA->contactList = &c->nodeA;
+  c->nodeB.contact = c; c->nodeB.other = bodyA; c->nodeB.prev = nullptr; c->nodeB.next = bodyB->contactList;
+  if (bodyB->contactList) bodyB->contactList->prev = &c->nodeB;
+  bodyB->contactList = &c->nodeB;
+  ++contactCount;
+  return c;
+}
+void World::clearContacts() {
+  while (contactList) { Contact* c = contactList; contactList = c->next; delete c; }
+  contactCount = 0;
+  for (Body* b = bodyList; b; b = b->next) b->contactList = nullptr;
+  lastSolveOrder.clear();
+}
+
 // b2contactmanager.d:183-246 + b2contact.d:402-423
 void World::destroyContact(Contact* c) {
   Fixture* fixtureA = c->fixtureA; Fixture* fixtureB = c->fixtureB;
@@ -751,9 +777,10 @@ struct ContactSolver {
   }
 
   // b2contactsolver.d:73-149 (toi=false) and :152-242 (toi=true)
-  bool solvePositionImpl(bool toi, int toiIndexA, int toiIndexB) {
+  bool solvePositionImpl(bool toi, int toiIndexA, int toiIndexB, bool reverse = false) {
     float minSeparation = 0.0f;
-    for (int i = 0; i < count; ++i) {
+    for (int k = 0; k < count; ++k) {
+      const int i = reverse ? count - 1 - k : k;      // reverse: World::orderReversePosition (test hook)
       ContactPositionConstraint* pc = &pcs[i];
       int indexA = pc->indexA, indexB = pc->indexB;
       V2 localCenterA = pc->localCenterA, localCenterB = pc->localCenterB;
@@ -822,7 +849,7 @@ struct Island {
   }
 
   // b2island.d:75-280
-  void solve(Profile* profile, const TimeStep& step, V2 gravity, bool allowSleep) {
+  void solve(Profile* profile, const TimeStep& step, V2 gravity, bool allowSleep, bool reversePosition = false) {
     double t0 = nowMs();
     float h = step.dt;
     int bodyCount = (int)bodies.size();
@@ -874,9 +901,10 @@ struct Island {
     }
     bool positionSolved = false;
     for (int i = 0; i < step.positionIterations; ++i) {
-      bool contactsOkay = contactSolver.solvePositionImpl(false, 0, 0);
+      bool contactsOkay = contactSolver.solvePositionImpl(false, 0, 0, reversePosition);
       bool jointsOkay = true;
-      for (Joint* j : joints) { bool jointOkay = j->solvePositionConstraints(solverData); jointsOkay = jointsOkay && jointOkay; }
+      if (!reversePosition) for (Joint* j : joints) { bool jointOkay = j->solvePositionConstraints(solverData); jointsOkay = jointsOkay && jointOkay; }
+      else for (size_t k = joints.size(); k-- > 0;) { bool jointOkay = joints[k]->solvePositionConstraints(solverData); jointsOkay = jointsOkay && jointOkay; }
       if (contactsOkay && jointsOkay) { positionSolved = true; break; }
     }
     for (int i = 0; i < bodyCount; ++i) {
@@ -966,7 +994,7 @@ void World::solve(const TimeStep& step) {
   for (Contact* c = contactList; c; c = c->next) c->flags &= ~cIsland;
   for (Joint* j = jointList; j; j = j->next) j->islandFlag = false;
   lastIslandCount = 0;
-  lastSolveOrder.clear();
+  lastSolveOrder.clear(); lastJointOrder.clear();
   std::vector<Body*> stack(bodyCount);
   for (Body* seed = bodyList; seed; seed = seed->next) {
     if (seed->flags & bIsland) continue;
@@ -1004,13 +1032,19 @@ void World::solve(const TimeStep& step) {
         other->flags |= bIsland;
       }
     }
+    if (orderOverride) {   // test hook (orc_world.h): caller-supplied Gauss-Seidel order instead of DFS order
+      std::stable_sort(island.contacts.begin(), island.contacts.end(), [](const Contact* a, const Contact* b) { return a->orderRank < b->orderRank; });
+      std::stable_sort(island.joints.begin(), island.joints.end(), [](const Joint* a, const Joint* b) { return a->orderRank < b->orderRank; });
+    }
     Profile p;
-    island.solve(&p, step, gravity, allowSleep);
+    island.solve(&p, step, gravity, allowSleep, orderOverride && orderReversePosition);
     ++lastIslandCount;
     lastSolveOrder.insert(lastSolveOrder.end(), island.contacts.begin(), island.contacts.end());
+    for (Joint* j : island.joints) lastJointOrder.push_back(j->id);
     profile.solveInit += p.solveInit; profile.solveVelocity += p.solveVelocity; profile.solvePosition += p.solvePosition;
     for (Body* b : island.bodies) if (b->type == kStatic) b->flags &= ~bIsland;
   }
+  orderOverride = false;
   double t0 = nowMs();
   for (Body* b = bodyList; b; b = b->next) {
     if ((b->flags & bIsland) == 0) continue;

@@ -88,6 +88,7 @@ struct Contact {
   int toiCount = 0;
   float toi = 0;
   float friction = 0, restitution = 0, tangentSpeed = 0;
+  int orderRank = 0x7fffffff;   // test hook (World::orderOverride): position in the caller-supplied Gauss-Seidel order
   bool isTouching() const { return (flags & cTouching) == cTouching; }
   bool isEnabled() const { return (flags & cEnabled) == cEnabled; }
   void evaluate(Manifold* m, const Xf& xfA, const Xf& xfB) const;  // the 7 b2*contact.d Evaluate overrides (line 56 each)
@@ -102,6 +103,7 @@ struct Joint {
   Body* bodyA = nullptr; Body* bodyB = nullptr;
   bool islandFlag = false, collideConnected = false;
   uint64_t userData = 0;
+  int orderRank = 0x7fffffff;   // test hook, see Contact::orderRank
   virtual ~Joint() {}
   virtual void initVelocityConstraints(const SolverData& data) = 0;
   virtual void solveVelocityConstraints(const SolverData& data) = 0;
@@ -254,6 +256,16 @@ struct World {
   UserFilter userFilter = nullptr;
   std::vector<std::pair<FixtureProxy*, FixtureProxy*>> lastPairs;  // unique pairs handed to AddPair by the last UpdatePairs
   std::vector<Contact*> lastSolveOrder;   // contacts in the order islands solved them in the last Solve
+  std::vector<int> lastJointOrder;        // joint ids, likewise
+  // Test hook: solve every island's contacts / joints in a caller-supplied order instead of DFS order (one-shot, consumed by
+  // the next Solve).  A coloured Gauss-Seidel sweep is a topological re-ordering of SOME sequential sweep; handing that sweep
+  // to the oracle lets a test compare the device solver with the sequential algorithm at sizes where the DFS order would
+  // need more levels than the device's level override holds.  orderReversePosition: the position iterations walk the same
+  // arrays backwards (the device's unified joint/contact phases run the position colours downwards).
+  bool orderOverride = false, orderReversePosition = false;
+  // state import (tests, bench transplant): a contact exactly as recorded, no filtering, no Evaluate
+  Contact* importContact(Fixture* fA, int iA, Fixture* fB, int iB);
+  void clearContacts();
 };
 
 }  // namespace orc

@@ -8,21 +8,10 @@ from dbox_b200 import _abi as A
 
 def transplant(wo, wg):
     """Copy bodies, proxies (tight + fat AABBs), contacts (manifolds + impulses + flags), joints, the pending move
-    buffer and inv_dt0 from oracle world `wo` into GPU world `wg` (same scene built on both)."""
-    bodies, nb = wo.read_bodies()
-    assert wg._api.world_write_bodies(wg._w, bodies, nb) == nb
-    prox, np_ = wo.read_proxies()
-    assert wg._api.world_write_proxies(wg._w, prox, np_) == np_
-    joints, nj = wo.read_joints()
-    if nj:
-        assert wg._api.world_write_joints(wg._w, joints, nj) == nj
-    cons, nc = wo.read_contacts()
-    rc = wg._api.world_write_contacts(wg._w, cons, nc)
-    assert rc == nc, (rc, nc, wg._api.last_error())
-    moves = wo.read_moves()
-    flat = (C.c_int32 * max(2 * len(moves), 2))(*[x for m in moves for x in m])
-    assert wg._api.world_write_moves(wg._w, flat, len(moves)) == len(moves)
-    wg._api.world_set_inv_dt0(wg._w, wo.get_inv_dt0())
+    buffer and inv_dt0 from world `wo` into world `wg` (same scene built on both); either direction between the oracle
+    and the CUDA library."""
+    from dbox_b200 import state
+    return state.transplant(wo, wg)
 
 
 def contact_key(r):
@@ -80,3 +69,27 @@ def body_state_errors(so, sg, n, skip_static=True):
 
 def f32(x):
     return C.c_float(x).value
+
+
+def hand_device_order_to_oracle(oracle_api, wg, wo):
+    """Give the oracle the Gauss-Seidel schedule the device's LAST step ran (dbx_world_debug_read_solve_order): contacts by
+    ascending solver colour, joints by ascending joint colour, position iterations backwards when the device ran unified
+    joint / contact phases.  Within a colour no two constraints share a dynamic body, so the oracle's sequential sweep in that
+    order is arithmetically the sweep the device ran.  Call between the device's step and the oracle's; returns
+    (contacts the oracle found, info = [unified, contact colours, joint colours])."""
+    recs, n = wg.read_contacts()
+    nj = wg.read_joints()[1]
+    cc = (C.c_int32 * max(n, 1))()
+    jc = (C.c_int32 * max(nj, 1))()
+    info = (C.c_int32 * 3)()
+    rc = wg._api.world_debug_read_solve_order(wg._w, cc, n, jc, nj, info)
+    assert rc == n, (rc, n)
+    keys = (C.c_int32 * max(4 * n, 4))()
+    rank = (C.c_int32 * max(n, 1))()
+    for i in range(n):
+        r = recs[i]
+        keys[4 * i], keys[4 * i + 1], keys[4 * i + 2], keys[4 * i + 3] = r.fixtureA, r.childA, r.fixtureB, r.childB
+        rank[i] = cc[i] if cc[i] >= 0 else 0x7fffffff
+    jr = (C.c_int32 * max(nj, 1))(*[(jc[j] if jc[j] >= 0 else 0x7fffffff) for j in range(nj)])
+    found = oracle_api.world_debug_set_solve_order(wo._w, keys, rank, n, jr, nj, int(info[0]))
+    return found, list(info)

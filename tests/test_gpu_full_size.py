@@ -191,3 +191,96 @@ def test_tumbler_20k_full_size_invariants(gpu_api):
     assert np.abs(lx).max() < 53.0 and np.abs(ly).max() < 53.0
     assert abs(t.container.GetAngularVelocity() - 0.05 * np.pi) < 2e-3
     assert abs(t.container.GetAngle() - steps * DT * 0.05 * np.pi) < 0.05
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Config 4 at full size against the oracle, one step: the settled 100,000-body device world is transplanted into the CPU
+# oracle (orc_world_write_*), both step once from the identical state, the oracle walking its constraints in the schedule
+# the device's colouring produced (parity.hand_device_order_to_oracle; the DFS order of a 100k-body island would need far
+# more levels than the device's level override holds, so the order travels device -> oracle here, and oracle -> device in
+# tests/test_gpu_parity.py at sizes where it fits).  north_star tolerances: contact set / feature keys exact, manifolds
+# 1e-5, velocities and impulses 1e-4 relative.
+def _recs(buf, n, typ):
+    return np.frombuffer(buf, dtype=np.dtype(typ), count=n)
+
+
+def _ckey(r):
+    return ((r["fixtureA"].astype(np.int64) * 64 + r["childA"]) << 32) | (r["fixtureB"].astype(np.int64) * 64 + r["childB"])
+
+
+def _rel(a, b, floor):
+    return np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), floor)
+
+
+def _compare_step(wg, wo, label):
+    """both worlds have just stepped once from the same state; returns the measured worst errors"""
+    bg, nb = wg.read_bodies(); bo, nbo = wo.read_bodies()
+    assert nb == nbo
+    G, O = _recs(bg, nb, A.BodyState), _recs(bo, nb, A.BodyState)
+    dyn = O["type"] != A.STATIC_BODY
+    ep = max(float(_rel(G[f][k][dyn], O[f][k][dyn], 1.0).max()) for f, k in (("c", "x"), ("c", "y")))
+    ep = max(ep, float(_rel(G["a"][dyn], O["a"][dyn], 1.0).max()))
+    ev = max(float(_rel(G["v"]["x"][dyn], O["v"]["x"][dyn], 1.0).max()), float(_rel(G["v"]["y"][dyn], O["v"]["y"][dyn], 1.0).max()),
+             float(_rel(G["w"][dyn], O["w"][dyn], 1.0).max()))
+    assert np.array_equal(G["flags"][dyn] & 0x2, O["flags"][dyn] & 0x2), "awake flags differ"
+    cg, ng = wg.read_contacts(); co, no = wo.read_contacts()
+    CG, CO = _recs(cg, ng, A.ContactRec), _recs(co, no, A.ContactRec)
+    kg, ko = _ckey(CG), _ckey(CO)
+    ig, io = np.argsort(kg), np.argsort(ko)
+    assert ng == no and np.array_equal(kg[ig], ko[io]), "%s: contact sets differ (%d vs %d)" % (label, ng, no)
+    CG, CO = CG[ig], CO[io]
+    assert np.array_equal(CG["flags"] & 0x6, CO["flags"] & 0x6), "touching / enabled flags differ"
+    mg, mo = CG["manifold"], CO["manifold"]
+    assert np.array_equal(mg["pointCount"], mo["pointCount"]) and np.array_equal(mg["type"], mo["type"])
+    em = ei = 0.0
+    for k in range(2):
+        live = mo["pointCount"] > k
+        assert np.array_equal(mg["points"]["key"][:, k][live], mo["points"]["key"][:, k][live]), "feature keys differ"
+        for ax in ("x", "y"):
+            em = max(em, float(_rel(mg["points"]["localPoint"][ax][:, k][live], mo["points"]["localPoint"][ax][:, k][live], 1.0).max()))
+        for f in ("normalImpulse", "tangentImpulse"):
+            ei = max(ei, float(_rel(mg["points"][f][:, k][live], mo["points"][f][:, k][live], 1.0).max()))
+    touching = mo["pointCount"] > 0
+    for f in ("localNormal", "localPoint"):
+        for ax in ("x", "y"):
+            em = max(em, float(_rel(mg[f][ax][touching], mo[f][ax][touching], 1.0).max()))
+    jg, nj = wg.read_joints(); jo, njo = wo.read_joints()
+    assert nj == njo
+    JG, JO = _recs(jg, nj, A.JointState), _recs(jo, nj, A.JointState)
+    ej = float(_rel(JG["impulse"], JO["impulse"], 1.0).max()) if nj else 0.0
+    assert np.array_equal(JG["limitState"], JO["limitState"])
+    return {"pos": ep, "vel": ev, "manifold": em, "contact_impulse": ei, "joint_impulse": ej, "contacts": int(ng),
+            "touching": int(touching.sum()), "joints": int(nj)}
+
+
+@pytest.mark.parametrize("n,columns,settle", [(3000, 100, 300), (100000, 1000, 600)])
+def test_pile_single_step_matches_oracle(gpu_api, oracle_api, n, columns, settle):
+    from dbox_b200 import state
+    from tests.parity import hand_device_order_to_oracle
+    wg, _, nj = scenes.pile(api=gpu_api, n=n, columns=columns)
+    wo, _, _ = scenes.pile(api=oracle_api, n=n, columns=columns)
+    wg.SetAllowSleeping(False); wo.SetAllowSleeping(False)
+    wg.StepN(DT, 8, 3, settle)
+    snap = state.capture(wg)
+    assert snap["nb"] == n + 1 and snap["nj"] == nj
+    report = {}
+    for continuous in (False, True):
+        for w in (wg, wo):
+            w.SetContinuousPhysics(continuous)
+            state.apply(w, snap)
+        assert oracle_api.world_tree_validate(wo._w) == 1
+        wg.Step(DT, 8, 3)
+        found, info = hand_device_order_to_oracle(oracle_api, wg, wo)
+        wo.Step(DT, 8, 3)
+        cg, co = wg.counts(), wo.counts()
+        assert found > 0
+        assert cg.islands == co.islands, ("island count", cg.islands, co.islands)          # row a14
+        assert cg.touching == co.touching and cg.contacts == co.contacts
+        r = _compare_step(wg, wo, "continuous=%s" % continuous)
+        r.update(order_found=found, unified=info[0], colours=info[1], joint_colours=info[2], islands=cg.islands)
+        report[continuous] = r
+        print("pile %d single step vs oracle, continuous=%s: %s" % (n, continuous, r))
+        # north_star: manifolds 1e-5, velocities / impulses 1e-4 relative (floor 1.0 = the unit scale of the scene)
+        assert r["manifold"] < 1e-5 and r["pos"] < 1e-5, r
+        assert r["vel"] < 1e-4 and r["contact_impulse"] < 1e-4 and r["joint_impulse"] < 1e-4, r
+    wg.close(); wo.close()

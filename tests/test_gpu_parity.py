@@ -461,6 +461,18 @@ def test_export_import_state_continues_bit_for_bit(gpu_api):
     b, _ = scenes.pyramid(api=gpu_api, count=10)
     assert gpu_api.world_import_state(b._w, buf, need) == 0
     assert gpu_api.world_import_state(b._w, buf, 10) < 0            # truncated blob
+    assert gpu_api.world_import_state(b._w, buf, need - 4) == A.DBX_E_INVALID      # length must match the header exactly
+    # a hostile header: negative counts, or the counts of another scene, are refused before anything is written
+    import struct
+    for off, val in ((8, -1), (12, -5), (16, -1), (24, -2), (8, 3)):
+        bad = (C.c_char * need).from_buffer_copy(buf)
+        struct.pack_into("<i", bad, off, val)
+        assert gpu_api.world_import_state(b._w, bad, need) == A.DBX_E_INVALID, (off, val)
+    c, _ = scenes.pyramid(api=gpu_api, count=6)
+    assert gpu_api.world_import_state(c._w, buf, need) == A.DBX_E_INVALID          # snapshot of a different scene
+    c.close()
+    sb0, n0 = b.read_bodies(); sa0, _ = a.read_bodies()
+    assert all((sa0[i].c.x, sa0[i].c.y) == (sb0[i].c.x, sb0[i].c.y) for i in range(n0))    # the refused imports changed nothing
     for k in range(5):
         a.StepN(DT, 8, 3, 20); b.StepN(DT, 8, 3, 20)
         sa, n = a.read_bodies(); sb, _ = b.read_bodies()
