@@ -116,7 +116,9 @@ DBX_D void prepare_contact(const DevWorld& W, int s, int i, float warmScale) {
     // velocities in one pass.  That replaces one barrier-delimited phase per colour by a single one.
     if (warmScale >= 0.0f && (imp.x != 0.0f || imp.y != 0.0f || imp.z != 0.0f || imp.w != 0.0f)) {
       v2 P = V(0.0f, 0.0f); float LA = 0.0f, LB = 0.0f;
-      for (int k = 0; k < pointCount; ++k) {
+      // over the VELOCITY constraint's points: when the conditioning test above drops the block solver, the reference's
+      // vc.pointCount becomes 1 (:444-446) and WarmStart (:459) no longer applies the second point's impulse
+      for (int k = 0; k < vcCount; ++k) {
         const v2 Pk = (k == 0 ? imp.x : imp.z) * normal + (k == 0 ? imp.y : imp.w) * tangent;
         P += Pk;
         LA += cross(V(r[k].x, r[k].y), Pk);
