@@ -42,6 +42,8 @@ constexpr int kMaxJointColours = 64;
 constexpr int kSortBlocks = 296;         // 2 CTAs per SM for the colour counting sort
 constexpr int kMaxPosIters = 8;
 constexpr int kTailContacts = 1024;       // tail colours holding at most this many constraints share one CTA-local phase
+constexpr int kTileColours = 64;         // tile solver: colours a tile walks locally (higher ones, the overflow lanes, run as global phases)
+enum { XF_FOREIGN = 1 /* moved by the left neighbour's boundary rows */, XF_OWNB = 2 /* by this tile's own boundary rows */, XF_G = 4 /* by global rows */ };
 constexpr int kToiCand = 64;             // candidate contacts per event side (mini-island holds at most 32)
 enum { TF_INVAL = 1, TF_SYNC = 2 };
 constexpr unsigned long long kHashEmpty = ~0ull;
@@ -80,6 +82,7 @@ struct Header {
   int stepIncomplete; // sub-stepping (b2World.SetSubStepping): k_toi stopped after one solved TOI event; the next Step resumes
   int toiSolved;      // TOI mini-islands solved by the current k_toi launch (sub-stepping stops at the first)
   unsigned long long toiGlobalMin;   // sub-stepping: smallest event priority of the current pass (the ONE event to handle)
+  int nTileB, nTileG; // tile solver: boundary / global constraints (contacts + joints) of this step
 };
 
 struct DevWorld {
@@ -239,6 +242,18 @@ struct DevWorld {
   int nJointColours;    // joint colours in use (host-side greedy colouring)
   int jointBlocks;      // CTAs of the persistent solver dedicated to joint phases
   int colourOverride;   // debug: keep caller-supplied contact levels instead of colouring (dbx_world_debug_set_contact_levels)
+  // ---- tile solver (dbx_tiles.cu): dynamic bodies in x order cut into nTiles tiles of tileBodies; constraints by (class, tile, colour)
+  int tiled;            // this step's rows / joints carry body references (dbx_solver.cuh, BodyView) and k_solve_tiles runs them
+  int nTiles, tileBodies, nTileBodies;
+  int* b_tslot;         // body -> position in tile order (-1: not a dynamic body)
+  int* t_body;          // position in tile order -> body
+  int* b_tclaim;        // per body: lowest boundary straddled by one of its constraints (0x7fffffff at rest)
+  int* b_xflag;         // per body: XF_* (0 at rest)
+  int* c_tkey; int2* c_bref;     // per contact slot: bin and body references of this step
+  int* c_tcol; int* j_tcol;      // boundary constraints: the local colour their tile gave them (k_solve_tiles), -1 otherwise
+  int* j_tkey; int2* j_bref;     // per joint slot likewise
+  int* t_off; int* t_cur;        // [bins + 1] solver-slot offsets per bin, [bins] histogram / scatter cursors
+  int* tj_off; int* tj_cur; int* tj_order;   // joints: offsets, cursors, joint slots in bin order
 };
 
 }  // namespace dbx

@@ -25,6 +25,11 @@ cudaError_t stage_solve_worlds(const DevWorld& W, const LaunchCfg& L, int bodies
 size_t cub_temp_bytes_u32(int n);         // graph colouring + colour counting sort
 cudaError_t stage_prepare(const DevWorld& W, const LaunchCfg& L);                 // contact constraint setup
 cudaError_t stage_solve(const DevWorld& W, const LaunchCfg& L);                   // warm start + iterations + finalize + sleep (one persistent kernel)
+// tile solver (dbx_tiles.cu)
+cudaError_t stage_tile_assign(const DevWorld& W, const LaunchCfg& L, unsigned* keysA, unsigned* keysB, int* valsA, int* valsB);
+cudaError_t stage_colour_and_sort_tiles(const DevWorld& W, const LaunchCfg& L);
+cudaError_t stage_solve_tiles(const DevWorld& W, const LaunchCfg& L);
+size_t tile_smem_bytes(int tileBodies);
 cudaError_t stage_sync_fixtures(const DevWorld& W, const LaunchCfg& L);           // b2Body.SynchronizeFixtures / MoveProxy
 cudaError_t stage_find_new_contacts(DevWorld& W, const LaunchCfg& L, bool rebuild, bool deferClear);       // LBVH rebuild + pair query + AddPair
 cudaError_t launch_api_resensor(const DevWorld& W, const LaunchCfg& L, int fixture);

@@ -9,7 +9,11 @@ namespace dbx {
 __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ DevWorld W) {
   const int n = min(W.hdr->nSolve, W.sCap);
   const float warmScale = W.warmStarting ? W.dtRatio : -1.0f;
-  GRID_STRIDE(s, n) prepare_contact(W, s, W.s_contact[s], warmScale);
+  GRID_STRIDE(s, n) {
+    const int i = W.s_contact[s];
+    prepare_contact(W, s, i, warmScale);
+    if (W.tiled) W.s_body[s] = W.c_bref[i];     // tile solver: how the row reaches its two bodies (dbx_solver.cuh, BodyView)
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ the persistent solver
@@ -272,7 +276,7 @@ template <bool kLocal> __global__ void __launch_bounds__(128) k_solve_worlds(con
     // (a replica with no solver contact -- asleep, or in free fall -- has beg == end: only the body loops do anything)
     const int b0 = w * bodiesPerWorld, b1 = b0 + bodiesPerWorld;
     BodyView bvw; bvw.vel = sBodies; bvw.pos = sBodies + bodiesPerWorld; bvw.off = b0;
-    const BodyView* view = kLocal ? &bvw : nullptr;
+    const BodyView view = kLocal ? bvw : BodyView();
     // colour boundaries of this replica's slot range (sorted by colour): the slots where the colour changes, in order
     if (t == 0) ncol = 0;
     __syncthreads();

@@ -146,23 +146,35 @@ DBX_D void prepare_contact(const DevWorld& W, int s, int i, float warmScale) {
 
 // velocities of one body pair; only dynamic bodies are ever written (statics/kinematics have zero inverse mass)
 struct BodyVel { v2 vA, vB; float wA, wB; };
-// Optional CTA-local copy of a replica's bodies (k_solve_worlds): vel / pos point into shared memory and hold bodies
-// [off, off + n); a null view means the global arrays (through L2).
-struct BodyView { float4* vel; float4* pos; int off; };
-DBX_D BodyVel load_vel(const DevWorld& W, int2 bd, const BodyView* view = nullptr) {
-  float4 a, b;
-  if (view) { a = view->vel[bd.x - view->off]; b = view->vel[bd.y - view->off]; }
-  else { a = ldcg4(&W.b_vel[bd.x]); b = ldcg4(&W.b_vel[bd.y]); }
+// Optional CTA-local copy of bodies: vel / pos point into shared memory.  A body reference `ref` in a solver row or joint is
+//   * a plain body id (>= 0) when there is no view (k_solve, TOI mini-islands: the global arrays through L2), or with the
+//     world-local view of k_solve_worlds (the replica's bodies [off, off + n) live in shared memory);
+//   * with the tile view of k_solve_tiles: ref >= 0 is the body's position in tile order, owned by THIS CTA (shared memory at
+//     ref - off); ref < 0 carries a body id in its low 31 bits and means "not mine": a static / kinematic body, or a body of
+//     another tile that is currently published in the global arrays.
+struct BodyView { float4* vel = nullptr; float4* pos = nullptr; int off = 0; };   // passed by value; vel == nullptr: no view
+constexpr int kRefGlobal = (int)0x80000000;
+DBX_D float4 ld_vel(const DevWorld& W, BodyView view, int ref) {
+  if (view.vel && ref >= 0) return view.vel[ref - view.off];
+  return ldcg4(&W.b_vel[ref & 0x7fffffff]);
+}
+DBX_D void st_vel(const DevWorld& W, BodyView view, int ref, float4 v) {
+  if (view.vel && ref >= 0) view.vel[ref - view.off] = v; else stcg4(&W.b_vel[ref & 0x7fffffff], v);
+}
+DBX_D float4 ld_pos(const DevWorld& W, BodyView view, int ref) {
+  if (view.vel && ref >= 0) return view.pos[ref - view.off];
+  return ldcg4(&W.b_pos[ref & 0x7fffffff]);
+}
+DBX_D void st_pos(const DevWorld& W, BodyView view, int ref, float4 v) {
+  if (view.vel && ref >= 0) view.pos[ref - view.off] = v; else stcg4(&W.b_pos[ref & 0x7fffffff], v);
+}
+DBX_D BodyVel load_vel(const DevWorld& W, int2 bd, BodyView view = BodyView()) {
+  const float4 a = ld_vel(W, view, bd.x), b = ld_vel(W, view, bd.y);
   BodyVel r; r.vA = V(a.x, a.y); r.wA = a.z; r.vB = V(b.x, b.y); r.wB = b.z; return r;
 }
-DBX_D void store_vel(const DevWorld& W, int2 bd, const BodyVel& r, float mA, float iA, float mB, float iB, const BodyView* view = nullptr) {
-  if (view) {
-    if (mA != 0.0f || iA != 0.0f) view->vel[bd.x - view->off] = make_float4(r.vA.x, r.vA.y, r.wA, 0.0f);
-    if (mB != 0.0f || iB != 0.0f) view->vel[bd.y - view->off] = make_float4(r.vB.x, r.vB.y, r.wB, 0.0f);
-    return;
-  }
-  if (mA != 0.0f || iA != 0.0f) stcg4(&W.b_vel[bd.x], make_float4(r.vA.x, r.vA.y, r.wA, 0.0f));
-  if (mB != 0.0f || iB != 0.0f) stcg4(&W.b_vel[bd.y], make_float4(r.vB.x, r.vB.y, r.wB, 0.0f));
+DBX_D void store_vel(const DevWorld& W, int2 bd, const BodyVel& r, float mA, float iA, float mB, float iB, BodyView view = BodyView()) {
+  if (mA != 0.0f || iA != 0.0f) st_vel(W, view, bd.x, make_float4(r.vA.x, r.vA.y, r.wA, 0.0f));
+  if (mB != 0.0f || iB != 0.0f) st_vel(W, view, bd.y, make_float4(r.vB.x, r.vB.y, r.wB, 0.0f));
 }
 
 // b2ContactSolver.WarmStart (:452-490)
@@ -175,7 +187,7 @@ DBX_D void vc_load(const DevWorld& W, int s, VC& c) {
   c.v0 = W.s_v0[s]; c.v1 = W.s_v1[s]; c.r0 = W.s_r0[s]; c.q0 = W.s_q0[s]; c.imp = W.s_imp[s];
   c.r1 = W.s_r1[s]; c.q1 = W.s_q1[s]; c.nm = W.s_nm[s]; c.K = W.s_k[s];
 }
-DBX_D void contact_solve_velocity(const DevWorld& W, int s, const VC& c, const BodyView* view = nullptr) {
+DBX_D void contact_solve_velocity(const DevWorld& W, int s, const VC& c, BodyView view = BodyView()) {
   const int2 bd = c.bd;
   const float4 v0 = c.v0, v1 = c.v1;
   float4 imp = c.imp;
@@ -262,11 +274,11 @@ DBX_D void contact_solve_velocity(const DevWorld& W, int s, const VC& c, const B
   store_vel(W, bd, bv, mA, iA, mB, iB, view);
 }
 
-DBX_D void contact_solve_velocity(const DevWorld& W, int s, const BodyView* view = nullptr) { VC c; vc_load(W, s, c); contact_solve_velocity(W, s, c, view); }
+DBX_D void contact_solve_velocity(const DevWorld& W, int s, BodyView view = BodyView()) { VC c; vc_load(W, s, c); contact_solve_velocity(W, s, c, view); }
 
 // b2ContactSolver.SolvePositionConstraints (:73-149) + b2PositionSolverManifold (:816-868); returns min separation
 // toiA/toiB >= 0 selects SolveTOIPositionConstraints (:152-242): only those two bodies keep their mass, Baumgarte 0.75
-DBX_D float contact_solve_position(const DevWorld& W, int s, int toiA = -1, int toiB = -1, const BodyView* view = nullptr) {
+DBX_D float contact_solve_position(const DevWorld& W, int s, int toiA = -1, int toiB = -1, BodyView view = BodyView()) {
   const int2 bd = W.s_body[s];
   const float4 v1 = W.s_v1[s], p0 = W.s_p0[s], p1 = W.s_p1[s], p2 = W.s_p2[s];
   const float2 p3 = W.s_p3[s];
@@ -281,9 +293,7 @@ DBX_D float contact_solve_position(const DevWorld& W, int s, int toiA = -1, int 
   const float baumgarte = toi ? kToiBaumgarte : kBaumgarte;
   const v2 localCenterA = V(p2.x, p2.y), localCenterB = V(p2.z, p2.w);
   const v2 localNormal = V(p1.x, p1.y), localPoint = V(p1.z, p1.w);
-  float4 pa, pb;
-  if (view) { pa = view->pos[bd.x - view->off]; pb = view->pos[bd.y - view->off]; }
-  else { pa = ldcg4(&W.b_pos[bd.x]); pb = ldcg4(&W.b_pos[bd.y]); }
+  const float4 pa = ld_pos(W, view, bd.x), pb = ld_pos(W, view, bd.y);
   v2 cA = V(pa.x, pa.y), cB = V(pb.x, pb.y);
   float aA = pa.z, aB = pb.z;
   float minSeparation = 0.0f;
@@ -323,23 +333,19 @@ DBX_D float contact_solve_position(const DevWorld& W, int s, int toiA = -1, int 
     cA -= mA * P; aA -= iA * cross(rA, P);
     cB += mB * P; aB += iB * cross(rB, P);
   }
-  if (view) {
-    if (mA != 0.0f || iA != 0.0f) view->pos[bd.x - view->off] = make_float4(cA.x, cA.y, aA, 0.0f);
-    if (mB != 0.0f || iB != 0.0f) view->pos[bd.y - view->off] = make_float4(cB.x, cB.y, aB, 0.0f);
-    return minSeparation;
-  }
-  if (mA != 0.0f || iA != 0.0f) stcg4(&W.b_pos[bd.x], make_float4(cA.x, cA.y, aA, 0.0f));
-  if (mB != 0.0f || iB != 0.0f) stcg4(&W.b_pos[bd.y], make_float4(cB.x, cB.y, aB, 0.0f));
+  if (mA != 0.0f || iA != 0.0f) st_pos(W, view, bd.x, make_float4(cA.x, cA.y, aA, 0.0f));
+  if (mB != 0.0f || iB != 0.0f) st_pos(W, view, bd.y, make_float4(cB.x, cB.y, aB, 0.0f));
   return minSeparation;
 }
 
 // ------------------------------------------------------------------------------------------------ joints
 // revolute: dynamics/joints/b2revolutejoint.d:319-636; distance: b2distancejoint.d:211-373
 DBX_D bool joint_active(const DevWorld& W, int j);
-DBX_D void joint_init(const DevWorld& W, int j) {
+DBX_D void joint_init(const DevWorld& W, int j, BodyView view = BodyView()) {
   if (!joint_active(W, j)) { W.j_root[j] = -1; return; }   // later phases only look at j_root
   const int4 ids = W.j_ids[j];
   const int bA = ids.y, bB = ids.z;
+  const int2 jb = view.vel ? W.j_bref[j] : make_int2(bA, bB);   // how this joint's two bodies are reached (see BodyView)
   const float4 msA = W.b_mass[bA], msB = W.b_mass[bB];
   const float4 lcA4 = W.b_lc[bA], lcB4 = W.b_lc[bB];
   const float4 anc = W.j_anchor[j];
@@ -347,7 +353,7 @@ DBX_D void joint_init(const DevWorld& W, int j) {
   const v2 localCenterA = V(lcA4.x, lcA4.y), localCenterB = V(lcB4.x, lcB4.y);
   const float4 posA = W.b_pos[bA], posB = W.b_pos[bB];
   const float4 xA = W.b_xf[bA], xB = W.b_xf[bB];
-  float4 velA = ldcg4(&W.b_vel[bA]), velB = ldcg4(&W.b_vel[bB]);
+  float4 velA = ld_vel(W, view, jb.x), velB = ld_vel(W, view, jb.y);
   v2 vA = V(velA.x, velA.y), vB = V(velB.x, velB.y); float wA = velA.z, wB = velB.z;
   const float aA = posA.z, aB = posB.z;
   const Rot qA = R(xA.z, xA.w), qB = R(xB.z, xB.w);  // = b2Rot(aA), b2Rot(aB): positions are not integrated yet
@@ -439,17 +445,18 @@ DBX_D void joint_init(const DevWorld& W, int j) {
     W.j_k1[j] = make_float4(bias, 0.0f, 0.0f, 0.0f);
   }
   W.j_imp[j] = imp;
-  if (mA != 0.0f || iA != 0.0f) stcg4(&W.b_vel[bA], make_float4(vA.x, vA.y, wA, 0.0f));
-  if (mB != 0.0f || iB != 0.0f) stcg4(&W.b_vel[bB], make_float4(vB.x, vB.y, wB, 0.0f));
+  if (mA != 0.0f || iA != 0.0f) st_vel(W, view, jb.x, make_float4(vA.x, vA.y, wA, 0.0f));
+  if (mB != 0.0f || iB != 0.0f) st_vel(W, view, jb.y, make_float4(vB.x, vB.y, wB, 0.0f));
 }
 
-DBX_D void joint_solve_velocity(const DevWorld& W, int j) {
+DBX_D void joint_solve_velocity(const DevWorld& W, int j, BodyView view = BodyView()) {
   const int4 ids = W.j_ids[j];
   const int bA = ids.y, bB = ids.z;
+  const int2 jb = view.vel ? W.j_bref[j] : make_int2(bA, bB);   // how this joint's two bodies are reached (see BodyView)
   const float4 m = W.j_m[j], r = W.j_r[j];
   const float mA = m.x, iA = m.y, mB = m.z, iB = m.w;
   const v2 rA = V(r.x, r.y), rB = V(r.z, r.w);
-  float4 velA = ldcg4(&W.b_vel[bA]), velB = ldcg4(&W.b_vel[bB]);
+  float4 velA = ld_vel(W, view, jb.x), velB = ld_vel(W, view, jb.y);
   v2 vA = V(velA.x, velA.y), vB = V(velB.x, velB.y); float wA = velA.z, wB = velB.z;
   float4 imp = W.j_imp[j];
   if (ids.x != JT_REVOLUTE && ids.x != JT_DISTANCE) {
@@ -521,17 +528,18 @@ DBX_D void joint_solve_velocity(const DevWorld& W, int j) {
     vB += mB * P; wB += iB * cross(rB, P);
   }
   W.j_imp[j] = imp;
-  if (mA != 0.0f || iA != 0.0f) stcg4(&W.b_vel[bA], make_float4(vA.x, vA.y, wA, 0.0f));
-  if (mB != 0.0f || iB != 0.0f) stcg4(&W.b_vel[bB], make_float4(vB.x, vB.y, wB, 0.0f));
+  if (mA != 0.0f || iA != 0.0f) st_vel(W, view, jb.x, make_float4(vA.x, vA.y, wA, 0.0f));
+  if (mB != 0.0f || iB != 0.0f) st_vel(W, view, jb.y, make_float4(vB.x, vB.y, wB, 0.0f));
 }
 
 // returns true when the joint is within tolerance
-DBX_D bool joint_solve_position(const DevWorld& W, int j) {
+DBX_D bool joint_solve_position(const DevWorld& W, int j, BodyView view = BodyView()) {
   const int4 ids = W.j_ids[j];
   const int bA = ids.y, bB = ids.z;
+  const int2 jb = view.vel ? W.j_bref[j] : make_int2(bA, bB);   // how this joint's two bodies are reached (see BodyView)
   const float4 m = W.j_m[j], lc = W.j_lc[j], anc = W.j_anchor[j];
   const float mA = m.x, iA = m.y, mB = m.z, iB = m.w;
-  float4 pa = ldcg4(&W.b_pos[bA]), pb = ldcg4(&W.b_pos[bB]);
+  float4 pa = ld_pos(W, view, jb.x), pb = ld_pos(W, view, jb.y);
   v2 cA = V(pa.x, pa.y), cB = V(pb.x, pb.y); float aA = pa.z, aB = pb.z;
   bool ok;
   if (ids.x != JT_REVOLUTE && ids.x != JT_DISTANCE) {
@@ -597,8 +605,8 @@ DBX_D bool joint_solve_position(const DevWorld& W, int j) {
     cB += mB * P; aB += iB * cross(rB, P);
     ok = fabsr(C) < kLinearSlop;
   }
-  if (mA != 0.0f || iA != 0.0f) stcg4(&W.b_pos[bA], make_float4(cA.x, cA.y, aA, 0.0f));
-  if (mB != 0.0f || iB != 0.0f) stcg4(&W.b_pos[bB], make_float4(cB.x, cB.y, aB, 0.0f));
+  if (mA != 0.0f || iA != 0.0f) st_pos(W, view, jb.x, make_float4(cA.x, cA.y, aA, 0.0f));
+  if (mB != 0.0f || iB != 0.0f) st_pos(W, view, jb.y, make_float4(cB.x, cB.y, aB, 0.0f));
   return ok;
 }
 

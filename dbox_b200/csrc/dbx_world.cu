@@ -939,6 +939,7 @@ int World::push() {
   const bool anyShape = nS > shapesSynced_;
   const bool anyJoint = fullPushJoints_ || nJ > jointsSynced_ || jointsChanged_;
   if (!anyBody && !anyFix && !anyProxy && !anyShape && !anyJoint && dw_.hdr) return 0;
+  if (anyBody) tilesDirty_ = true;       // body set or body types may have changed: the tile solver re-counts and re-sorts
   if (fullPushBodies_ && !hostBodiesValid_) { int rc = pullBodies(); if (rc < 0) return rc; }
   if (fullPushProxies_ && !hostProxiesValid_) { int rc = pullProxies(); if (rc < 0) return rc; }
   if (anyJoint && !hostJointsValid_) { int rc = pullJoints(); if (rc < 0) return rc; }
@@ -1127,6 +1128,52 @@ int World::growContactsIfNeeded() {
   return 0;
 }
 
+// Tile solver set-up (dbx_tiles.cu).  Worth it for a single big world: the dynamic bodies are counted (when the body set may
+// have changed), cut into at most one tile per CTA of at least 256 bodies, and re-sorted along x every 16 steps -- any
+// assignment is VALID (it only decides which constraints are local, boundary or global), a fresh one keeps the tiles compact.
+int World::prepareTiles() {
+  constexpr int kTileMinBodies = 2048, kTileMinPerTile = 256, kTileMaxPerTile = 4800, kTileSortPeriod = 16;
+  if (replicated_ || overrideLevels_ || (dw_.dbgFlags & 64)) return 0;
+  if (tilesDirty_) {
+    int n = 0;
+    for (const HBody& hb : bodies_) if (hb.alive && hb.st.type == DBX_DYNAMIC_BODY) ++n;
+    nDynamic_ = n; tilesDirty_ = false; tilesValid_ = false;
+  }
+  if (nDynamic_ < kTileMinBodies) return 0;
+  const int P = std::max(1, std::min(L_.coopBlocks, nDynamic_ / kTileMinPerTile));
+  const int T = (nDynamic_ + P - 1) / P;
+  if (T > kTileMaxPerTile) return 0;
+  const size_t capB = b_root.cap, capC = c_key.cap, capJ = std::max<size_t>(j_ids.cap, 1);
+  const size_t nBins = (size_t)2 * P * kTileColours + kMaxColours + 1;
+  DevBuf<int>* perBody[] = {&b_tslot_, &t_body_, &b_tclaim_, &b_xflag_, &tValA_, &tValB_};
+  for (auto* b : perBody) CUDA_OR_FAIL(b->reserve(capB, false, stream_), "tile bodies");
+  CUDA_OR_FAIL(tKeyA_.reserve(capB, false, stream_), "tile keys"); CUDA_OR_FAIL(tKeyB_.reserve(capB, false, stream_), "tile keys");
+  if (tileBodyCap_ != b_tclaim_.cap) {       // fresh buffers: claims at rest, no exchange flags, tiles to be assigned
+    CUDA_OR_FAIL(cudaMemsetAsync(b_tclaim_.p, 0x7F, b_tclaim_.cap * 4, stream_), "claims");
+    CUDA_OR_FAIL(cudaMemsetAsync(b_xflag_.p, 0, b_xflag_.cap * 4, stream_), "xflags");
+    tileBodyCap_ = b_tclaim_.cap; tilesValid_ = false;
+  }
+  CUDA_OR_FAIL(c_tkey_.reserve(capC, false, stream_), "tile contact keys"); CUDA_OR_FAIL(c_bref_.reserve(capC, false, stream_), "tile contact refs");
+  CUDA_OR_FAIL(j_tkey_.reserve(capJ, false, stream_), "tile joint keys"); CUDA_OR_FAIL(j_bref_.reserve(capJ, false, stream_), "tile joint refs");
+  CUDA_OR_FAIL(tj_order_.reserve(capJ, false, stream_), "tile joint order");
+  CUDA_OR_FAIL(c_tcol_.reserve(capC, false, stream_), "tile contact colours"); CUDA_OR_FAIL(j_tcol_.reserve(capJ, false, stream_), "tile joint colours");
+  DevBuf<int>* bins[] = {&t_off_, &t_cur_, &tj_off_, &tj_cur_};
+  for (auto* b : bins) CUDA_OR_FAIL(b->reserve(nBins, false, stream_), "tile bins");
+  const size_t need = cub_temp_bytes_u32((int)capB);
+  if (need > cubTemp.cap) { CUDA_OR_FAIL(cubTemp.reserve(need, false, stream_), "cubTemp"); L_.cubTemp = cubTemp.p; L_.cubTempBytes = cubTemp.cap; }
+  DevWorld& w = dw_;
+  if (w.nTiles != P || w.tileBodies != T || w.nTileBodies != nDynamic_) tilesValid_ = false;
+  w.nTiles = P; w.tileBodies = T; w.nTileBodies = nDynamic_;
+  w.b_tslot = b_tslot_.p; w.t_body = t_body_.p; w.b_tclaim = b_tclaim_.p; w.b_xflag = b_xflag_.p;
+  w.c_tkey = c_tkey_.p; w.c_bref = c_bref_.p; w.j_tkey = j_tkey_.p; w.j_bref = j_bref_.p; w.c_tcol = c_tcol_.p; w.j_tcol = j_tcol_.p;
+  w.t_off = t_off_.p; w.t_cur = t_cur_.p; w.tj_off = tj_off_.p; w.tj_cur = tj_cur_.p; w.tj_order = tj_order_.p;
+  if (!tilesValid_ || sinceTileSort_ >= kTileSortPeriod) {
+    CUDA_OR_FAIL(stage_tile_assign(w, L_, tKeyA_.p, tKeyB_.p, tValA_.p, tValB_.p), "tile assign");
+    tilesValid_ = true; sinceTileSort_ = 0;
+  } else ++sinceTileSort_;
+  return P;
+}
+
 // one b2World.Step (dynamics/b2world.d:367-434) enqueued on the world's stream; no host synchronisation
 // `halves`: 1 = up to and including Collide, 2 = everything after it, 3 = the whole step.  The split exists for
 // b2ContactListener.PreSolve (b2contact.d:348-355): dbx_world_step_begin / patch_contacts / step_end.
@@ -1169,6 +1216,8 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents, int halves) {
     // u = 7 (57 bodies) 0.74 against 0.60 ms; 16,384 replicas of u = 1 (9 bodies) 1.74 against 0.44 ms.
     const bool bigEnough = bodies_.size() >= 128 || (dw_.dbgFlags & 1024);
     const bool worldsPath = replicated_ && bigEnough && (jointAt_.empty() || !(dw_.dbgFlags & 512)) && !overrideLevels_ && !(dw_.dbgFlags & 16);
+    bool tilesPath = false;
+    dw_.tiled = 0;
     if (worldsPath) {
       // Sort exactly the slots in use, with exactly the key bits the colours need.  Both numbers are device-side facts
       // (cHigh: final since the last FindNewContacts; maxColour: monotonic, so a stale read is still an upper bound for
@@ -1191,13 +1240,20 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents, int halves) {
       CUDA_OR_FAIL(stage_colour_and_sort_worlds(dw_, L_, swKeyA_.p, swKeyB_.p, swValA_.p, swValB_.p, (int)n, colourBits), "colour (worlds)");
     } else {
       dw_.s_contact = s_contact.p;
-      CUDA_OR_FAIL(stage_colour_and_sort(dw_, L_), "colour");
+      const int tp = prepareTiles(); if (tp < 0) return tp;
+      tilesPath = tp > 0;
+      dw_.tiled = tilesPath ? 1 : 0;
+      if (tilesPath) CUDA_OR_FAIL(stage_colour_and_sort_tiles(dw_, L_), "colour (tiles)");
+      else CUDA_OR_FAIL(stage_colour_and_sort(dw_, L_), "colour");
     }
+    lastTiled_ = tilesPath;
     mark(3);
     CUDA_OR_FAIL(stage_prepare(dw_, L_), "prepare");
     mark(4);
     if (worldsPath) CUDA_OR_FAIL(stage_solve_worlds(dw_, L_, (int)bodies_.size()), "solve (worlds)");
+    else if (tilesPath) CUDA_OR_FAIL(stage_solve_tiles(dw_, L_), "solve (tiles)");
     else CUDA_OR_FAIL(stage_solve(dw_, L_), "solve");
+    dw_.tiled = 0;        // the TOI sub-steps that follow build their own rows with plain body ids
     if (dw_.psCap > 0) CUDA_OR_FAIL(launch_post_solve(dw_, L_), "post_solve");   // island.Report (b2island.d:239); before k_toi reuses the rows
     mark(5);
     if (toiPre) {
@@ -2178,16 +2234,56 @@ int World::setContactLevels(const int32_t* levels, int n) {
   return 0;
 }
 
-// Test hook: the schedule the last step ran (see include/dbox_b200.h).  Contact colours are persistent device state
-// (c_colour, valid while the contact is in the solver); joint colours and the unified-phase switch live on the host.
-int World::readSolveOrder(int32_t* contactColours, int capC, int32_t* jointColours, int capJ, int32_t* info3) {
-  const int n = readContactColours(contactColours, capC);
-  if (n < 0) return n;
-  for (int j = 0; j < (int)joints_.size() && j < capJ; ++j) jointColours[j] = joints_[j].alive ? joints_[j].colour : -1;
-  if (info3) {
+// Test hook: the schedule the last step ran (see include/dbox_b200.h), as ONE rank space over joints and contacts.
+// k_solve: phase = colour, joints of a colour before its contacts (they never share a dynamic body).  k_solve_tiles: class
+// (local / boundary / global) above the colour.  Contact colours and bins are persistent device state, joint colours live on
+// the host.
+int World::readSolveOrder(int32_t* contactRank, int capC, int32_t* jointRank, int capJ, int32_t* info4) {
+  const int n = (int)lastReadSlots_.size();
+  if (!lastTiled_ && !lastUnified_ && !jointAt_.empty()) {
+    set_last_error("read_solve_order: joints solved as phases of their own (level override / DBX_DEBUG 32) have no merged order"); return DBX_E_UNSUPPORTED;
+  }
+  std::vector<int> col((size_t)std::max(n, 1));
+  if (n > 0) { const int rc = readContactColours(col.data(), n); if (rc < 0) return rc; }
+  const int P = dw_.nTiles;
+  auto classOfBin = [&](int bin) { return bin >= 2 * P * kTileColours ? 2 : bin / (P * kTileColours); };
+  std::vector<int> cls((size_t)std::max(n, 1), 0);
+  if (lastTiled_ && n > 0) {
+    int high = 0;
+    CUDA_OR_FAIL(cudaMemcpy(&high, (char*)hdr_.p + offsetof(Header, cHigh), 4, cudaMemcpyDeviceToHost), "read cHigh");
+    std::vector<int> key((size_t)std::max(high, 1)), tcol((size_t)std::max(high, 1));
+    CUDA_OR_FAIL(cudaMemcpy(key.data(), c_tkey_.p, (size_t)high * 4, cudaMemcpyDeviceToHost), "read tile keys");
+    CUDA_OR_FAIL(cudaMemcpy(tcol.data(), c_tcol_.p, (size_t)high * 4, cudaMemcpyDeviceToHost), "read tile colours");
+    for (int k = 0; k < n; ++k) if (lastReadSlots_[k] < high && col[k] >= 0) {
+      cls[k] = classOfBin(key[lastReadSlots_[k]]);
+      if (cls[k] == 1 && tcol[lastReadSlots_[k]] >= 0) col[k] = tcol[lastReadSlots_[k]];     // boundary rows run in their tile's own colouring
+    }
+  }
+  for (int k = 0; k < n && k < capC; ++k) contactRank[k] = col[k] < 0 ? -1 : ((((cls[k] << 12) | col[k]) << 1) | 1);
+  if (capJ > 0 && jointRank) {
+    std::vector<int> jkey, jtcol;
+    if (lastTiled_ && !jointAt_.empty()) {
+      jkey.resize(jointAt_.size()); jtcol.resize(jointAt_.size());
+      CUDA_OR_FAIL(cudaMemcpy(jkey.data(), j_tkey_.p, jkey.size() * 4, cudaMemcpyDeviceToHost), "read tile joint keys");
+      CUDA_OR_FAIL(cudaMemcpy(jtcol.data(), j_tcol_.p, jtcol.size() * 4, cudaMemcpyDeviceToHost), "read tile joint colours");
+    }
+    for (int j = 0; j < (int)joints_.size() && j < capJ; ++j) {
+      jointRank[j] = -1;
+      if (!joints_[j].alive) continue;
+      int c = 0, colour = joints_[j].colour;
+      if (lastTiled_) {
+        const int bin = jkey[jointPos_[j]]; if (bin < 0) continue;
+        c = classOfBin(bin);
+        if (c == 1 && jtcol[jointPos_[j]] >= 0) colour = jtcol[jointPos_[j]];
+      }
+      jointRank[j] = ((c << 12) | colour) << 1;
+    }
+  }
+  if (info4) {
     int nc = 0;
     if (dw_.hdr) CUDA_OR_FAIL(cudaMemcpy(&nc, (char*)hdr_.p + offsetof(Header, nColours), 4, cudaMemcpyDeviceToHost), "read nColours");
-    info3[0] = lastUnified_ ? 1 : 0; info3[1] = nc; info3[2] = jointAt_.empty() ? 0 : nJointColours_;
+    info4[0] = (lastTiled_ || lastUnified_) ? 1 : 0;     // position passes walk the order backwards
+    info4[1] = nc; info4[2] = jointAt_.empty() ? 0 : nJointColours_; info4[3] = lastTiled_ ? P : 0;
   }
   return n;
 }

@@ -133,7 +133,7 @@ class World {
   int stageFindNewContacts();
   int stageCollide();
   int setContactLevels(const int32_t* levels, int n);
-  int readSolveOrder(int32_t* contactColours, int capC, int32_t* jointColours, int capJ, int32_t* info3);
+  int readSolveOrder(int32_t* contactRank, int capC, int32_t* jointRank, int capJ, int32_t* info4);
   int colourConflicts();
   int readHeader(void* out, int bytes) { cudaStreamSynchronize(stream_); int n = bytes < (int)sizeof(Header) ? bytes : (int)sizeof(Header); return cudaMemcpy(out, hdr_.p, n, cudaMemcpyDeviceToHost) == cudaSuccess ? n : DBX_E_CUDA; }
   int phaseTimes(unsigned long long* out, int cap);   // debug: enable + fetch the last step's k_solve barrier stamps
@@ -233,6 +233,11 @@ class World {
   // second stream for the overlapped TOI pre-evaluation (fork after the solver, join before k_toi)
   cudaStream_t aux_ = nullptr; cudaEvent_t evFork_ = nullptr, evJoin_ = nullptr; bool toiClean_ = false; size_t toiBodies_ = 0;
   std::vector<int> lastReadSlots_;
+  // tile solver (dbx_tiles.cu): dynamic bodies of a big single world in x order, cut into one tile per CTA
+  int prepareTiles();            // > 0: this step runs the tile solver (buffers sized, tiles assigned, dw_ filled in)
+  DevBuf<int> b_tslot_, t_body_, b_tclaim_, b_xflag_, c_tkey_, j_tkey_, c_tcol_, j_tcol_, t_off_, t_cur_, tj_off_, tj_cur_, tj_order_, tValA_, tValB_;
+  DevBuf<int2> c_bref_, j_bref_; DevBuf<unsigned> tKeyA_, tKeyB_;
+  bool tilesDirty_ = true, tilesValid_ = false, lastTiled_ = false; int sinceTileSort_ = 0, nDynamic_ = 0; size_t tileBodyCap_ = 0;
 };
 
 void set_last_error(const std::string& s);

@@ -319,12 +319,13 @@ int32_t dbx_world_read_pairs(dbx_world* w, int32_t* fixA_childA_fixB_childB, int
  * dbx_world_read_contacts order; lets a test replay the reference's exact sequential order. n=0 clears. */
 int32_t dbx_world_debug_set_contact_levels(dbx_world* w, const int32_t* levels, int32_t n);
 
-/* the Gauss-Seidel schedule the LAST step actually ran, for handing it to a sequential checker: contactColours[i] = solver
- * colour of contact rec i of the last dbx_world_read_contacts order (-1 = not in the solver), jointColours[j] = colour of joint
- * id j; info[0] = 1 if joint colour c and contact colour c shared a phase (position passes then ran the colours downwards),
- * info[1] = number of contact colours, info[2] = number of joint colours.  Velocity passes run the colours upwards, a body's
- * joints before its contacts (dynamics/b2island.d:153-161); position passes its contacts before its joints (:206-216). */
-int32_t dbx_world_debug_read_solve_order(dbx_world* w, int32_t* contactColours, int32_t capContacts, int32_t* jointColours, int32_t capJoints, int32_t* info3);
+/* the Gauss-Seidel schedule the LAST step actually ran, for handing it to a sequential checker.  Joints and contacts share ONE
+ * rank space: contactRank[i] for contact rec i of the last dbx_world_read_contacts order, jointRank[j] for joint id j (-1 = not
+ * in the solver); a velocity pass walks the constraints by ascending rank (equal ranks never share a dynamic body; a body's
+ * joints come before its contacts, dynamics/b2island.d:153-161).  info[0] = 1: position passes walk the same order backwards
+ * (a body's contacts before its joints, :206-216); info[1] = contact colours, info[2] = joint colours, info[3] = tiles of the
+ * tile solver (0: the grid-phase solver ran). */
+int32_t dbx_world_debug_read_solve_order(dbx_world* w, int32_t* contactRank, int32_t capContacts, int32_t* jointRank, int32_t capJoints, int32_t* info4);
 
 /* number of solver-contact pairs that shared a dynamic body AND a colour in the last step (must be 0) */
 int32_t dbx_world_debug_colour_conflicts(dbx_world* w);

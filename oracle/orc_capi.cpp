@@ -789,10 +789,11 @@ int32_t orc_world_write_moves(orc_world* w, const int32_t* fc, int32_t n) {
   return n;
 }
 int32_t orc_world_set_inv_dt0(orc_world* w, float v) { w->w.inv_dt0 = v; return 0; }
-// Test hook (orc_world.h, World::orderOverride): the NEXT Solve walks every island's contacts by ascending rank[i] (contact i
-// identified by keys4[4 i ..] = fixtureA, childA, fixtureB, childB) and its joints by ascending jointRank[joint id]; contacts
-// that are not listed go last.  reversePosition != 0: position iterations walk the same arrays backwards.
-int32_t orc_world_debug_set_solve_order(orc_world* w, const int32_t* keys4, const int32_t* rank, int32_t n, const int32_t* jointRank, int32_t nj, int32_t reversePosition) {
+// Test hook (orc_world.h, World::orderOverride): the NEXT Solve walks every island's joints and contacts as ONE sequence by
+// ascending rank -- rank[i] for contact i (identified by keys4[4 i ..] = fixtureA, childA, fixtureB, childB), jointRank[joint id]
+// for a joint; at equal rank joints go first; contacts that are not listed go last.  Position iterations walk the same sequence
+// forwards (positionMode 0), backwards (1), or its contacts and then its joints (2, the reference's own split).
+int32_t orc_world_debug_set_solve_order(orc_world* w, const int32_t* keys4, const int32_t* rank, int32_t n, const int32_t* jointRank, int32_t nj, int32_t positionMode) {
   struct K { int a, b, c, d; bool operator<(const K& o) const { return a != o.a ? a < o.a : b != o.b ? b < o.b : c != o.c ? c < o.c : d < o.d; } };
   std::vector<std::pair<K, int>> tab((size_t)n);
   for (int i = 0; i < n; ++i) tab[i] = {K{keys4[4 * i], keys4[4 * i + 1], keys4[4 * i + 2], keys4[4 * i + 3]}, rank[i]};
@@ -805,7 +806,7 @@ int32_t orc_world_debug_set_solve_order(orc_world* w, const int32_t* keys4, cons
   }
   auto& J = w->w.jointsById;
   for (int i = 0; i < (int)J.size(); ++i) if (J[i]) J[i]->orderRank = i < nj ? jointRank[i] : 0x7fffffff;
-  w->w.orderOverride = true; w->w.orderReversePosition = reversePosition != 0;
+  w->w.orderOverride = true; w->w.orderPositionMode = positionMode;
   return found;
 }
 int32_t orc_world_get_inv_dt0(orc_world* w, float* out) { *out = w->w.inv_dt0; return 0; }

@@ -676,8 +676,10 @@ struct ContactSolver {
   }
 
   // b2contactsolver.d:492-772
-  void solveVelocityConstraints() {
-    for (int i = 0; i < count; ++i) {
+  void solveVelocityConstraints() { solveVelocityRange(0, count); }
+  // constraints [i0, i1) of the loop above (:492-772); a single constraint at a time serves the merged-order test hook
+  void solveVelocityRange(int i0, int i1) {
+    for (int i = i0; i < i1; ++i) {
       ContactVelocityConstraint* vc = &vcs[i];
       int indexA = vc->indexA, indexB = vc->indexB;
       float mA = vc->invMassA, iA = vc->invIA, mB = vc->invMassB, iB = vc->invIB;
@@ -777,10 +779,13 @@ struct ContactSolver {
   }
 
   // b2contactsolver.d:73-149 (toi=false) and :152-242 (toi=true)
-  bool solvePositionImpl(bool toi, int toiIndexA, int toiIndexB, bool reverse = false) {
-    float minSeparation = 0.0f;
-    for (int k = 0; k < count; ++k) {
-      const int i = reverse ? count - 1 - k : k;      // reverse: World::orderReversePosition (test hook)
+  bool solvePositionImpl(bool toi, int toiIndexA, int toiIndexB) {
+    const float minSeparation = solvePositionRange(toi, toiIndexA, toiIndexB, 0, count, 0.0f);
+    return minSeparation >= (toi ? -1.5f : -3.0f) * kLinearSlop;
+  }
+  // constraints [i0, i1) of SolvePositionConstraints (:73-149) / SolveTOIPositionConstraints (:152-242); carries the running minimum
+  float solvePositionRange(bool toi, int toiIndexA, int toiIndexB, int i0, int i1, float minSeparation) {
+    for (int i = i0; i < i1; ++i) {
       ContactPositionConstraint* pc = &pcs[i];
       int indexA = pc->indexA, indexB = pc->indexB;
       V2 localCenterA = pc->localCenterA, localCenterB = pc->localCenterB;
@@ -819,7 +824,7 @@ struct ContactSolver {
       positions[indexA].c = cA; positions[indexA].a = aA;
       positions[indexB].c = cB; positions[indexB].a = aB;
     }
-    return minSeparation >= (toi ? -1.5f : -3.0f) * kLinearSlop;
+    return minSeparation;
   }
 };
 
@@ -849,7 +854,10 @@ struct Island {
   }
 
   // b2island.d:75-280
-  void solve(Profile* profile, const TimeStep& step, V2 gravity, bool allowSleep, bool reversePosition = false) {
+  // seq != nullptr: test hook (World::orderOverride) -- one merged Gauss-Seidel order over joints (entry ~index) and contacts
+  // (entry index), walked forwards by the velocity passes and, with reversePosition, backwards by the position passes, instead
+  // of "all joints, then all contacts" (:153-161) / "all contacts, then all joints" (:206-216)
+  void solve(Profile* profile, const TimeStep& step, V2 gravity, bool allowSleep, const std::vector<int>* seq = nullptr, int positionMode = 0) {
     double t0 = nowMs();
     float h = step.dt;
     int bodyCount = (int)bodies.size();
@@ -873,9 +881,14 @@ struct Island {
     ContactSolver contactSolver(step, contacts.data(), (int)contacts.size(), positions.data(), velocities.data());
     contactSolver.initializeVelocityConstraints();
     if (step.warmStarting) contactSolver.warmStart();
-    for (Joint* j : joints) j->initVelocityConstraints(solverData);
+    if (seq) { for (int e : *seq) if (e < 0) joints[~e]->initVelocityConstraints(solverData); }
+    else for (Joint* j : joints) j->initVelocityConstraints(solverData);
     double t1 = nowMs(); profile->solveInit = (float)(t1 - t0);
     for (int i = 0; i < step.velocityIterations; ++i) {
+      if (seq) {
+        for (int e : *seq) { if (e < 0) joints[~e]->solveVelocityConstraints(solverData); else contactSolver.solveVelocityRange(e, e + 1); }
+        continue;
+      }
       for (Joint* j : joints) j->solveVelocityConstraints(solverData);
       contactSolver.solveVelocityConstraints();
     }
@@ -901,10 +914,23 @@ struct Island {
     }
     bool positionSolved = false;
     for (int i = 0; i < step.positionIterations; ++i) {
-      bool contactsOkay = contactSolver.solvePositionImpl(false, 0, 0, reversePosition);
-      bool jointsOkay = true;
-      if (!reversePosition) for (Joint* j : joints) { bool jointOkay = j->solvePositionConstraints(solverData); jointsOkay = jointsOkay && jointOkay; }
-      else for (size_t k = joints.size(); k-- > 0;) { bool jointOkay = joints[k]->solvePositionConstraints(solverData); jointsOkay = jointsOkay && jointOkay; }
+      bool contactsOkay, jointsOkay = true;
+      if (seq) {
+        float minSeparation = 0.0f;
+        const int m = (int)seq->size();
+        // positionMode 0: the sequence forwards; 1: backwards; 2: its contacts, then its joints (the reference's own split, :206-216)
+        for (int pass = 0; pass < (positionMode == 2 ? 2 : 1); ++pass)
+          for (int k = 0; k < m; ++k) {
+            const int e = (*seq)[positionMode == 1 ? m - 1 - k : k];
+            if (positionMode == 2 && (e < 0) != (pass == 1)) continue;
+            if (e < 0) { bool jointOkay = joints[~e]->solvePositionConstraints(solverData); jointsOkay = jointsOkay && jointOkay; }
+            else minSeparation = contactSolver.solvePositionRange(false, 0, 0, e, e + 1, minSeparation);
+          }
+        contactsOkay = minSeparation >= -3.0f * kLinearSlop;
+      } else {
+        contactsOkay = contactSolver.solvePositionImpl(false, 0, 0);
+        for (Joint* j : joints) { bool jointOkay = j->solvePositionConstraints(solverData); jointsOkay = jointsOkay && jointOkay; }
+      }
       if (contactsOkay && jointsOkay) { positionSolved = true; break; }
     }
     for (int i = 0; i < bodyCount; ++i) {
@@ -1032,12 +1058,20 @@ void World::solve(const TimeStep& step) {
         other->flags |= bIsland;
       }
     }
-    if (orderOverride) {   // test hook (orc_world.h): caller-supplied Gauss-Seidel order instead of DFS order
+    std::vector<int> seq;
+    if (orderOverride) {   // test hook (orc_world.h): caller-supplied Gauss-Seidel order instead of DFS order, joints and contacts merged
+      // the arrays themselves go into rank order too: the contacts' warm start (:138-141) walks the contact array
       std::stable_sort(island.contacts.begin(), island.contacts.end(), [](const Contact* a, const Contact* b) { return a->orderRank < b->orderRank; });
       std::stable_sort(island.joints.begin(), island.joints.end(), [](const Joint* a, const Joint* b) { return a->orderRank < b->orderRank; });
+      const int nc = (int)island.contacts.size(), nj = (int)island.joints.size();
+      seq.resize((size_t)nc + nj);
+      for (int k = 0; k < nj; ++k) seq[k] = ~k;
+      for (int k = 0; k < nc; ++k) seq[nj + k] = k;
+      auto rank = [&](int e) { return e < 0 ? island.joints[~e]->orderRank : island.contacts[e]->orderRank; };
+      std::stable_sort(seq.begin(), seq.end(), [&](int a, int b) { return rank(a) < rank(b); });
     }
     Profile p;
-    island.solve(&p, step, gravity, allowSleep, orderOverride && orderReversePosition);
+    island.solve(&p, step, gravity, allowSleep, orderOverride ? &seq : nullptr, orderPositionMode);
     ++lastIslandCount;
     lastSolveOrder.insert(lastSolveOrder.end(), island.contacts.begin(), island.contacts.end());
     for (Joint* j : island.joints) lastJointOrder.push_back(j->id);

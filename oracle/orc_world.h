@@ -260,9 +260,11 @@ struct World {
   // Test hook: solve every island's contacts / joints in a caller-supplied order instead of DFS order (one-shot, consumed by
   // the next Solve).  A coloured Gauss-Seidel sweep is a topological re-ordering of SOME sequential sweep; handing that sweep
   // to the oracle lets a test compare the device solver with the sequential algorithm at sizes where the DFS order would
-  // need more levels than the device's level override holds.  orderReversePosition: the position iterations walk the same
-  // arrays backwards (the device's unified joint/contact phases run the position colours downwards).
-  bool orderOverride = false, orderReversePosition = false;
+  // need more levels than the device's level override holds.  Contact::orderRank and Joint::orderRank live in ONE rank space:
+  // the island walks joints and contacts merged by rank (ties: joints first, then island order).  orderPositionMode: the
+  // position iterations walk the same sequence forwards (0), backwards (1: the device runs its position phases downwards), or
+  // its contacts and then its joints (2: the reference's own split).
+  bool orderOverride = false; int orderPositionMode = 0;
   // state import (tests, bench transplant): a contact exactly as recorded, no filtering, no Evaluate
   Contact* importContact(Fixture* fA, int iA, Fixture* fB, int iB);
   void clearContacts();

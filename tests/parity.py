@@ -72,24 +72,26 @@ def f32(x):
 
 
 def hand_device_order_to_oracle(oracle_api, wg, wo):
-    """Give the oracle the Gauss-Seidel schedule the device's LAST step ran (dbx_world_debug_read_solve_order): contacts by
-    ascending solver colour, joints by ascending joint colour, position iterations backwards when the device ran unified
-    joint / contact phases.  Within a colour no two constraints share a dynamic body, so the oracle's sequential sweep in that
-    order is arithmetically the sweep the device ran.  Call between the device's step and the oracle's; returns
-    (contacts the oracle found, info = [unified, contact colours, joint colours])."""
+    """Give the oracle the Gauss-Seidel schedule the device's LAST step ran (dbx_world_debug_read_solve_order): joints and
+    contacts in one rank space (phase by phase; the tile solver's local / boundary / global classes above the colours), position
+    iterations walking it backwards.  Within a rank no two constraints share a dynamic body, so the oracle's sequential sweep
+    in that order is arithmetically the sweep the device ran.  Call between the device's step and the oracle's; returns
+    (contacts the oracle found, info = [position passes backwards, contact colours, joint colours, tiles])."""
     recs, n = wg.read_contacts()
     nj = wg.read_joints()[1]
-    cc = (C.c_int32 * max(n, 1))()
-    jc = (C.c_int32 * max(nj, 1))()
-    info = (C.c_int32 * 3)()
-    rc = wg._api.world_debug_read_solve_order(wg._w, cc, n, jc, nj, info)
-    assert rc == n, (rc, n)
+    cr = (C.c_int32 * max(n, 1))()
+    jr = (C.c_int32 * max(nj, 1))()
+    info = (C.c_int32 * 4)()
+    rc = wg._api.world_debug_read_solve_order(wg._w, cr, n, jr, nj, info)
+    assert rc == n, (rc, n, wg._api.last_error())
     keys = (C.c_int32 * max(4 * n, 4))()
-    rank = (C.c_int32 * max(n, 1))()
     for i in range(n):
         r = recs[i]
         keys[4 * i], keys[4 * i + 1], keys[4 * i + 2], keys[4 * i + 3] = r.fixtureA, r.childA, r.fixtureB, r.childB
-        rank[i] = cc[i] if cc[i] >= 0 else 0x7fffffff
-    jr = (C.c_int32 * max(nj, 1))(*[(jc[j] if jc[j] >= 0 else 0x7fffffff) for j in range(nj)])
-    found = oracle_api.world_debug_set_solve_order(wo._w, keys, rank, n, jr, nj, int(info[0]))
+        if cr[i] < 0:
+            cr[i] = 0x7fffffff
+    for j in range(nj):
+        if jr[j] < 0:
+            jr[j] = 0x7fffffff
+    found = oracle_api.world_debug_set_solve_order(wo._w, keys, cr, n, jr, nj, 1 if info[0] else 0)
     return found, list(info)

@@ -241,14 +241,14 @@ def test_state_import_round_trip_and_ordered_step(oracle_api):
     wa.Step(1.0 / 60.0, 8, 3)
     n = api.world_read_solve_order(wa._w, None, 0)
     keys = (C.c_int32 * (4 * n))(); api.world_read_solve_order(wa._w, keys, n)
-    rank = (C.c_int32 * n)(*range(n))
     nj = wa.counts().joints
+    rank = (C.c_int32 * n)(*range(nj, nj + n))      # one rank space: the joints (ranks 0 .. nj-1) before every contact
     m = api.world_read_joint_solve_order(wa._w, None, 0)
     jo = (C.c_int32 * m)(); api.world_read_joint_solve_order(wa._w, jo, m)
     jr = (C.c_int32 * nj)(*([0x7fffffff] * nj))
     for k in range(m):
         jr[jo[k]] = k
-    assert api.world_debug_set_solve_order(wb._w, keys, rank, n, jr, nj, 0) == n
+    assert api.world_debug_set_solve_order(wb._w, keys, rank, n, jr, nj, 2) == n    # 2: position passes contacts, then joints (b2island.d:206-216)
     wb.Step(1.0 / 60.0, 8, 3)
     a, na = wa.read_bodies(); b, nb = wb.read_bodies()
     assert bytes(a)[:na * C.sizeof(A.BodyState)] == bytes(b)[:nb * C.sizeof(A.BodyState)]

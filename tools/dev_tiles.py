@@ -1,0 +1,32 @@
+"""dev: phase stamps of k_solve_tiles on the 100k pile (CTA 0 and the middle CTA) + class sizes"""
+import sys, os, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dbox_b200 import scenes, lib
+ga = lib.api()
+n = int(os.environ.get("N", "100000")); cols = int(os.environ.get("COLS", "1000"))
+w, b, nj = scenes.pile(api=ga, n=n, columns=cols, joints=os.environ.get('NOJ') is None)
+w.SetAllowSleeping(False)
+w.StepN(1 / 60., 8, 3, int(os.environ.get("SETTLE", "400")))
+buf = (C.c_uint64 * 4096)()
+ga.world_debug_phase_times(w._w, buf, 4096)
+w.StepN(1 / 60., 8, 3, 3)
+m = ga.world_debug_phase_times(w._w, buf, 4096)
+for base, name in ((0, "CTA 0"), (1024, "middle CTA")):
+    ts = [buf[base + i] for i in range(1000) if buf[base + i]]
+    d = [(ts[i + 1] - ts[i]) / 1000. for i in range(len(ts) - 1)]
+    print(name, "marks", len(ts), "total us %.1f" % sum(d))
+    print("  load %.1f" % d[0] if d else "")
+    rest = d[1:]
+    # forward sweeps: 4 intervals each (L, publish+GB, B, GB+readback)
+    for k in range(0, min(len(rest), 4 * 9), 4):
+        print("  sweep %d: L %.1f  pub+GB %.1f  B %.1f  GB+rb %.1f" % tuple([k // 4] + rest[k:k + 4]) if len(rest) >= k + 4 else rest[k:])
+for base, name in ((2048, "CTA 0"), (2048 + 128, "middle CTA")):
+    print(name, "velocity pass 4, per local colour: (colour, items, cycles own item, cycles waiting at the barrier)")
+    print("  ", [(int(buf[base + 4 * k + 3]), int(buf[base + 4 * k + 2]), int(buf[base + 4 * k]), int(buf[base + 4 * k + 1])) for k in range(12)])
+hb = (C.c_int32 * 2400)()
+ga.world_debug_header(w._w, hb, 9600)
+c = w.counts()
+print("colours", c.colours, "touching", c.touching, "tail ints of header (.., nTileB, nTileG):", list(hb[1120:1140]))
+tot = C.c_float(); st = (C.c_float * 9)()
+ga.world_time_steps(w._w, 1 / 60., 8, 3, 50, 1, C.byref(tot), st)
+print("ms/step %.4f" % (tot.value / 50), "stages", ["%.3f" % x for x in st])
