@@ -277,6 +277,7 @@ namespace { struct SnapHead { uint32_t magic, version; int32_t nb, np, nc, nj, n
 int64_t dbx_world_export_state(dbx_world* w, void* buf, int64_t cap) {
   W_OR_INVALID(w);
   World& W = w->w;
+  W.resetSolverSchedule();      // the tile assignment is re-derived from the state the blob holds, here and in whoever imports it
   SnapHead h{kSnapMagic, 1, 0, 0, 0, 0, 0, 0.0f};
   h.nb = W.readBodies(nullptr, 0); h.np = W.readProxies(nullptr, 0); h.nc = W.readContacts(nullptr, 0); h.nj = W.readJoints(nullptr, 0); h.nm = W.readMoves(nullptr, 0);
   if (h.nb < 0 || h.np < 0 || h.nc < 0 || h.nj < 0 || h.nm < 0) return DBX_E_CUDA;
@@ -325,6 +326,7 @@ int32_t dbx_world_import_state(dbx_world* w, const void* buf, int64_t n) {
   rc = W.writeMoves((const int32_t*)p, h.nm); if (rc != h.nm) return rc < 0 ? rc : DBX_E_INVALID; p += (size_t)h.nm * 8;
   rc = W.writeContactColours((const int32_t*)p, h.nc); if (rc != h.nc) return rc < 0 ? rc : DBX_E_INVALID;
   W.inv_dt0 = h.inv_dt0;
+  W.resetSolverSchedule();
   return 0;
 }
 int32_t dbx_world_step_begin(dbx_world* w, float dt, int32_t vi, int32_t pi) { W_OR_INVALID(w); return w->w.stepBegin(dt, vi, pi); }

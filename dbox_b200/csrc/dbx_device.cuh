@@ -254,6 +254,7 @@ struct DevWorld {
   int* j_tkey; int2* j_bref;     // per joint slot likewise
   int* t_off; int* t_cur;        // [bins + 1] solver-slot offsets per bin, [bins] histogram / scatter cursors
   int* tj_off; int* tj_cur; int* tj_order;   // joints: offsets, cursors, joint slots in bin order
+  int* t_flag;          // [2 nTiles] k_solve_tiles' neighbour handshakes: passes published / boundary passes done, per tile
 };
 
 }  // namespace dbx

@@ -8,6 +8,7 @@
 #include <cub/cub.cuh>
 #include "dbx_kernels.cuh"
 #include "dbx_solver.cuh"
+#include "dbx_colour.cuh"
 
 namespace dbx {
 
@@ -224,116 +225,8 @@ __global__ void __launch_bounds__(256) k_island_wake_integrate(const __grid_cons
   }
 }
 
-// mark the contacts the solver takes this step and rebuild the per-body colour masks from the persistent colours
-__global__ void __launch_bounds__(256) k_mark_solve(const __grid_constant__ DevWorld W) {
-  const int n = W.hdr->cHigh;
-  GRID_STRIDE(i, n) {
-    uint32_t flags = W.c_flags[i];
-    if (!(flags & CF_ALIVE)) continue;
-    bool solve = false;
-    int4 ids;
-    if ((flags & (CF_TOUCHING | CF_ENABLED | CF_SENSOR)) == (CF_TOUCHING | CF_ENABLED)) {
-      ids = W.c_ids[i];
-      uint32_t fa = W.b_flags[ids.z], fb = W.b_flags[ids.w];
-      // the contact is in an island iff one of its non-static bodies is (b2world.d:1006-1046)
-      solve = ((fa & BF_ISLAND) && body_type(fa) != BODY_STATIC) || ((fb & BF_ISLAND) && body_type(fb) != BODY_STATIC);
-    }
-    if (!solve) {
-      if (flags & CF_SOLVE) W.c_flags[i] = flags & ~CF_SOLVE;
-      if (!W.colourOverride) W.c_colour[i] = -1;   // a colour is held only while the contact is in the solver (and so in the masks)
-      continue;
-    }
-    if (!(flags & CF_SOLVE)) W.c_flags[i] = flags | CF_SOLVE;
-    if (W.colourOverride) { if (W.c_colour[i] < 0) W.c_colour[i] = kMaxColours - 1; continue; }   // test hook: caller-supplied schedule
-    int col = W.c_colour[i];
-    uint32_t fa = W.b_flags[ids.z], fb = W.b_flags[ids.w];
-    // a colour kept from an earlier step is void if a joint has since claimed it (or a higher one) on either body
-    if (W.unifiedColours && col >= 0 && col < kMaskColours &&
-        ((((body_type(fa) == BODY_DYNAMIC ? W.b_jmask[ids.z] : 0ull) | (body_type(fb) == BODY_DYNAMIC ? W.b_jmask[ids.w] : 0ull)) >> col) & 1ull)) col = -1;
-    if (col >= 0 && col < kMaskColours) {
-      if (body_type(fa) == BODY_DYNAMIC) atomicOr(&W.b_mask[ids.z], 1ull << col);
-      if (body_type(fb) == BODY_DYNAMIC) atomicOr(&W.b_mask[ids.w], 1ull << col);
-    } else {
-      W.c_colour[i] = -1;
-      int slot = atomicAdd(&W.hdr->nUncoloured, 1);
-      W.c_work[slot] = i;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ graph colouring
-// New touching contacts take the lowest colour free on both dynamic bodies.  Conflicts between contacts coloured in the
-// same round are arbitrated Jones-Plassmann style: per body the contact with the highest (key-derived) priority wins,
-// so the outcome is independent of thread scheduling.  Static/kinematic bodies are never written by the solver and do
-// not constrain colours.  Runs as one persistent cooperative kernel; rounds loop on the device.
-// pair key with the replica offset removed, so that every replica of a batched world arbitrates (and hence colours) alike
-DBX_D unsigned long long local_key(const DevWorld& W, unsigned long long key, int body) {
-  if (W.keyStride == 0) return key;
-  const unsigned long long o = (unsigned long long)(unsigned)(W.b_world[body] * W.keyStride);
-  return key - (o << 32) - o;
-}
-__global__ void __launch_bounds__(512) k_colour(const __grid_constant__ DevWorld W) {
-  Header* H = W.hdr;
-  const unsigned nb = gridDim.x;
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-  int* cur = W.c_work; int* nxt = W.c_work2;
-  int n = H->nUncoloured;
-  unsigned epoch = H->epoch;
-  if (epoch > 0xF0000u) {   // the round stamp is 20 bits wide: recycle it long before it wraps
-    for (int b = tid; b < W.nBodies; b += nth) W.b_claim[b] = 0ull;
-    epoch = 0;
-    grid_barrier(&H->barrier, nb);
-  }
-  int guard = 0;
-  while (n > 0 && guard++ < 4096) {
-    ++epoch;
-    // phase 1: claim both bodies
-    for (int k = tid; k < n; k += nth) {
-      int i = cur[k];
-      int4 ids = W.c_ids[i];
-      unsigned long long pr = ((unsigned long long)(epoch & 0xFFFFF) << 44) | (mix64(local_key(W, W.c_key[i], ids.z)) >> 20);
-      if (body_type(W.b_flags[ids.z]) == BODY_DYNAMIC) atomicMax(&W.b_claim[ids.z], pr);
-      if (body_type(W.b_flags[ids.w]) == BODY_DYNAMIC) atomicMax(&W.b_claim[ids.w], pr);
-    }
-    if (tid == 0) H->nUncoloured2 = 0;
-    grid_barrier(&H->barrier, nb);
-    // phase 2: winners take a colour
-    for (int k = tid; k < n; k += nth) {
-      int i = cur[k];
-      int4 ids = W.c_ids[i];
-      unsigned long long pr = ((unsigned long long)(epoch & 0xFFFFF) << 44) | (mix64(local_key(W, W.c_key[i], ids.z)) >> 20);
-      bool dynA = body_type(W.b_flags[ids.z]) == BODY_DYNAMIC, dynB = body_type(W.b_flags[ids.w]) == BODY_DYNAMIC;
-      bool win = (!dynA || __ldcg(&W.b_claim[ids.z]) == pr) && (!dynB || __ldcg(&W.b_claim[ids.w]) == pr);
-      if (win) {
-        unsigned long long used = (dynA ? __ldcg(&W.b_mask[ids.z]) : 0ull) | (dynB ? __ldcg(&W.b_mask[ids.w]) : 0ull);
-        int col;
-        if (~used) {
-          col = __ffsll((long long)~used) - 1;
-          if (dynA) __stcg(&W.b_mask[ids.z], __ldcg(&W.b_mask[ids.z]) | (1ull << col));
-          if (dynB) __stcg(&W.b_mask[ids.w], __ldcg(&W.b_mask[ids.w]) | (1ull << col));
-        } else {
-          // more than 64 touching contacts on one body: serialise the surplus on private overflow lanes of that body
-          int oa = dynA ? W.b_ovf[ids.z] : 0, ob = dynB ? W.b_ovf[ids.w] : 0;
-          int o = max(oa, ob);
-          if (dynA) W.b_ovf[ids.z] = o + 1;
-          if (dynB) W.b_ovf[ids.w] = o + 1;
-          col = kMaskColours + o;
-          if (col >= kMaxColours) { col = kMaxColours - 1; H->error = E_COLOURS; }
-        }
-        W.c_colour[i] = col;
-        if (col > *((volatile int*)&H->maxColour)) atomicMax(&H->maxColour, col);
-      } else {
-        int slot = atomicAdd(&H->nUncoloured2, 1);
-        nxt[slot] = i;
-      }
-    }
-    grid_barrier(&H->barrier, nb);
-    n = *((volatile int*)&H->nUncoloured2);
-    int* t = cur; cur = nxt; nxt = t;
-    grid_barrier(&H->barrier, nb);
-  }
-  if (tid == 0) { H->epoch = epoch; H->nUncoloured = 0; }
-}
+__global__ void __launch_bounds__(256) k_mark_solve(const __grid_constant__ DevWorld W) { mark_solve_body(W); }
+__global__ void __launch_bounds__(512) k_colour(const __grid_constant__ DevWorld W) { colour_body(W); }
 
 // ------------------------------------------------------------------------------------------------ colour counting sort
 // One radix digit (the colour) over the contact slots: per-CTA histograms, one scan, scatter.  Output: s_contact in

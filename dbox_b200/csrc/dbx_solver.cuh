@@ -187,7 +187,8 @@ DBX_D void vc_load(const DevWorld& W, int s, VC& c) {
   c.v0 = W.s_v0[s]; c.v1 = W.s_v1[s]; c.r0 = W.s_r0[s]; c.q0 = W.s_q0[s]; c.imp = W.s_imp[s];
   c.r1 = W.s_r1[s]; c.q1 = W.s_q1[s]; c.nm = W.s_nm[s]; c.K = W.s_k[s];
 }
-DBX_D void contact_solve_velocity(const DevWorld& W, int s, const VC& c, BodyView view = BodyView()) {
+// the row itself: reads and writes the two bodies' velocities, returns the row's new accumulated impulses (n0 t0 n1 t1)
+DBX_D float4 contact_velocity_row(const DevWorld& W, const VC& c, BodyView view = BodyView()) {
   const int2 bd = c.bd;
   const float4 v0 = c.v0, v1 = c.v1;
   float4 imp = c.imp;
@@ -269,20 +270,26 @@ DBX_D void contact_solve_velocity(const DevWorld& W, int s, const VC& c, BodyVie
       imp.x = x.x; imp.z = x.y;
     }
   }
-  W.s_imp[s] = imp;
   bv.vA = vA; bv.vB = vB; bv.wA = wA; bv.wB = wB;
   store_vel(W, bd, bv, mA, iA, mB, iB, view);
+  return imp;
 }
-
+DBX_D void contact_solve_velocity(const DevWorld& W, int s, const VC& c, BodyView view = BodyView()) { W.s_imp[s] = contact_velocity_row(W, c, view); }
 DBX_D void contact_solve_velocity(const DevWorld& W, int s, BodyView view = BodyView()) { VC c; vc_load(W, s, c); contact_solve_velocity(W, s, c, view); }
 
 // b2ContactSolver.SolvePositionConstraints (:73-149) + b2PositionSolverManifold (:816-868); returns min separation
 // toiA/toiB >= 0 selects SolveTOIPositionConstraints (:152-242): only those two bodies keep their mass, Baumgarte 0.75
-DBX_D float contact_solve_position(const DevWorld& W, int s, int toiA = -1, int toiB = -1, BodyView view = BodyView()) {
-  const int2 bd = W.s_body[s];
-  const float4 v1 = W.s_v1[s], p0 = W.s_p0[s], p1 = W.s_p1[s], p2 = W.s_p2[s];
-  const float2 p3 = W.s_p3[s];
-  const int pc = W.s_pc[s];
+// position constraint block of one solver contact (b2ContactPositionConstraint, :801-814)
+struct PCn { int2 bd; int pc; float4 v1, p0, p1, p2; float2 p3; };
+DBX_D void pcn_load(const DevWorld& W, int s, PCn& c) {
+  c.bd = W.s_body[s]; c.pc = W.s_pc[s];
+  c.v1 = W.s_v1[s]; c.p0 = W.s_p0[s]; c.p1 = W.s_p1[s]; c.p2 = W.s_p2[s]; c.p3 = W.s_p3[s];
+}
+DBX_D float contact_position_row(const DevWorld& W, const PCn& c, int toiA = -1, int toiB = -1, BodyView view = BodyView()) {
+  const int2 bd = c.bd;
+  const float4 v1 = c.v1, p0 = c.p0, p1 = c.p1, p2 = c.p2;
+  const float2 p3 = c.p3;
+  const int pc = c.pc;
   const int type = (pc >> 8) & 0xFF, pointCount = pc >> 16;
   float mA = v1.x, iA = v1.y, mB = v1.z, iB = v1.w;
   const bool toi = toiA >= 0;
@@ -336,6 +343,10 @@ DBX_D float contact_solve_position(const DevWorld& W, int s, int toiA = -1, int 
   if (mA != 0.0f || iA != 0.0f) st_pos(W, view, bd.x, make_float4(cA.x, cA.y, aA, 0.0f));
   if (mB != 0.0f || iB != 0.0f) st_pos(W, view, bd.y, make_float4(cB.x, cB.y, aB, 0.0f));
   return minSeparation;
+}
+DBX_D float contact_solve_position(const DevWorld& W, int s, int toiA = -1, int toiB = -1, BodyView view = BodyView()) {
+  PCn c; pcn_load(W, s, c);
+  return contact_position_row(W, c, toiA, toiB, view);
 }
 
 // ------------------------------------------------------------------------------------------------ joints

@@ -45,135 +45,62 @@ __global__ void __launch_bounds__(256) k_tile_slots(const __grid_constant__ DevW
   }
 }
 
-// ------------------------------------------------------------------------------------------------ classification (every step)
-struct TileEnds { int sA, sB, tA, tB; };
-DBX_D TileEnds tile_ends(const DevWorld& W, int bA, int bB) {
-  TileEnds e; e.sA = W.b_tslot[bA]; e.sB = W.b_tslot[bB];
-  e.tA = e.sA >= 0 ? e.sA / W.tileBodies : -1; e.tB = e.sB >= 0 ? e.sB / W.tileBodies : -1;
-  return e;
-}
-// pass 1: every body learns the lowest boundary any of its tile-crossing constraints straddles; the bins are emptied
-__global__ void __launch_bounds__(256) k_tile_claim(const __grid_constant__ DevWorld W) {
-  const int nBins = 2 * W.nTiles * kTileColours + kMaxColours;
-  GRID_STRIDE(k, nBins) { W.t_cur[k] = 0; W.tj_cur[k] = 0; }
-  const int n = W.hdr->cHigh;
-  GRID_STRIDE(i, n) {
-    if (!(W.c_flags[i] & CF_SOLVE)) continue;
-    const int4 ids = W.c_ids[i];
-    const TileEnds e = tile_ends(W, ids.z, ids.w);
-    if (e.tA < 0 || e.tB < 0 || e.tA == e.tB) continue;
-    const int lo = min(e.tA, e.tB), hi = max(e.tA, e.tB);
-    if (hi - lo == 1) { atomicMin(&W.b_tclaim[ids.z], lo); atomicMin(&W.b_tclaim[ids.w], lo); }
-  }
-  GRID_STRIDE(j, W.nJoints) {
-    if (!joint_active(W, j)) continue;
-    const int4 ids = W.j_ids[j];
-    if (ids.x == JT_GEAR) continue;
-    const TileEnds e = tile_ends(W, ids.y, ids.z);
-    if (e.tA < 0 || e.tB < 0 || e.tA == e.tB) continue;
-    const int lo = min(e.tA, e.tB), hi = max(e.tA, e.tB);
-    if (hi - lo == 1) { atomicMin(&W.b_tclaim[ids.y], lo); atomicMin(&W.b_tclaim[ids.z], lo); }
-  }
-}
-// class, owner tile and the two body references of a constraint between bodies bA, bB with colour `col`; returns the bin
-DBX_D int tile_classify(const DevWorld& W, int bA, int bB, int col, bool forceGlobal, int2* bref) {
-  const int P = W.nTiles;
-  const TileEnds e = tile_ends(W, bA, bB);
-  int cls, owner = 0;
-  if (forceGlobal || col >= kTileColours || (e.tA < 0 && e.tB < 0)) cls = 2;
-  else if (e.tA < 0 || e.tB < 0 || e.tA == e.tB) { cls = 0; owner = e.tA >= 0 ? e.tA : e.tB; }
-  else {
-    const int lo = min(e.tA, e.tB), hi = max(e.tA, e.tB);
-    if (hi - lo == 1 && W.b_tclaim[bA] == lo && W.b_tclaim[bB] == lo) { cls = 1; owner = lo; } else cls = 2;
-  }
-  if (cls == 2) {
-    if (e.sA >= 0) atomicOr(&W.b_xflag[bA], XF_G);
-    if (e.sB >= 0) atomicOr(&W.b_xflag[bB], XF_G);
-    *bref = make_int2(bA | kRefGlobal, bB | kRefGlobal);
-    return 2 * P * kTileColours + min(col, kMaxColours - 1);
-  }
-  if (cls == 1) {
-    atomicOr(&W.b_xflag[bA], e.tA == owner ? XF_OWNB : XF_FOREIGN);
-    atomicOr(&W.b_xflag[bB], e.tB == owner ? XF_OWNB : XF_FOREIGN);
-  }
-  *bref = make_int2(e.tA == owner ? e.sA : (bA | kRefGlobal), e.tB == owner ? e.sB : (bB | kRefGlobal));
-  return (cls * P + owner) * kTileColours + col;
-}
-// pass 2: bin and body references per solver contact / active joint; histogram of the bins
-__global__ void __launch_bounds__(256) k_tile_key(const __grid_constant__ DevWorld W) {
-  // joint slots are colour-major (World::recolourJoints): the colour of slot j is the range of jointColourOff it falls into
-  __shared__ int sjoff[kMaxJointColours + 1];
-  for (int c = threadIdx.x; c <= kMaxJointColours; c += blockDim.x) sjoff[c] = W.hdr->jointColourOff[c];
-  __syncthreads();
-  const int n = W.hdr->cHigh;
-  GRID_STRIDE(i, n) {
-    if (!(W.c_flags[i] & CF_SOLVE)) continue;
-    const int4 ids = W.c_ids[i];
-    int2 br;
-    const int bin = tile_classify(W, ids.z, ids.w, W.c_colour[i], false, &br);
-    W.c_tkey[i] = bin; W.c_bref[i] = br; W.c_tcol[i] = -1;
-    atomicAdd(&W.t_cur[bin], 1);
-  }
-  GRID_STRIDE(j, W.nJoints) {
-    if (!joint_active(W, j)) { W.j_tkey[j] = -1; W.j_root[j] = -1; continue; }
-    const int4 ids = W.j_ids[j];
-    int2 br;
-    int lo = 0, hi = kMaxJointColours;          // largest c with sjoff[c] <= j
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (sjoff[mid] <= j) lo = mid; else hi = mid - 1; }
-    const int bin = tile_classify(W, ids.y, ids.z, lo, ids.x == JT_GEAR, &br);
-    if (ids.x == JT_GEAR) {   // the far bodies of joint1 / joint2 are written too (b2gearjoint.d:352-386)
-      const int4 id2 = W.j_ids2[j];
-      if (W.b_tslot[id2.x] >= 0) atomicOr(&W.b_xflag[id2.x], XF_G);
-      if (W.b_tslot[id2.y] >= 0) atomicOr(&W.b_xflag[id2.y], XF_G);
-    }
-    W.j_tkey[j] = bin; W.j_bref[j] = br; W.j_tcol[j] = -1;
-    atomicAdd(&W.tj_cur[bin], 1);
-  }
-}
-// one CTA: exclusive scan of both histograms -> offsets; totals and class sizes into the header; cursors back to zero
+// (classification of the constraints: dbx_tilekey.cuh, called from k_mark_solve / k_colour)
+// one CTA: exclusive scan of both histograms -> offsets, 1024 bins per round (coalesced, warp shuffles); totals and class sizes
+// into the header; cursors back to zero for the scatter; handshake flags of k_solve_tiles back to zero
 __global__ void __launch_bounds__(1024) k_tile_scan(const __grid_constant__ DevWorld W) {
-  __shared__ int part[2][1024];
-  __shared__ int stats[4];     // B constraints, G constraints, highest colour in use + 1
+  __shared__ int wsum[2][32];
+  __shared__ int carry[2];
+  __shared__ int stats[4];
   const int P = W.nTiles, nBins = 2 * P * kTileColours + kMaxColours;
-  const int t = threadIdx.x, per = (nBins + 1023) / 1024;
-  const int beg = min(t * per, nBins), end = min(beg + per, nBins);
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   if (t < 4) stats[t] = 0;
-  int sc = 0, sj = 0, nb = 0, ng = 0, maxc = 0;
-  for (int k = beg; k < end; ++k) {
-    const int c = W.t_cur[k], j = W.tj_cur[k];
-    sc += c; sj += j;
+  if (t < 2) carry[t] = 0;
+  __syncthreads();
+  int nb = 0, ng = 0, maxc = 0;
+  for (int base = 0; base < nBins; base += 1024) {
+    const int k = base + t;
+    const int c = k < nBins ? W.t_cur[k] : 0, j = k < nBins ? W.tj_cur[k] : 0;
     if (c + j > 0) {
       const int col = k < 2 * P * kTileColours ? k % kTileColours : k - 2 * P * kTileColours;
       maxc = max(maxc, col + 1);
       if (k >= 2 * P * kTileColours) ng += c + j; else if (k >= P * kTileColours) nb += c + j;
     }
+    int x = c, y = j;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, x, o), b = __shfl_up_sync(0xffffffffu, y, o);
+      if (lane >= o) { x += a; y += b; }
+    }
+    if (lane == 31) { wsum[0][wid] = x; wsum[1][wid] = y; }
+    __syncthreads();
+    if (wid == 0) {
+      const int v0 = wsum[0][lane], v1 = wsum[1][lane];
+      int p = v0, q = v1;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, p, o), b = __shfl_up_sync(0xffffffffu, q, o);
+        if (lane >= o) { p += a; q += b; }
+      }
+      wsum[0][lane] = p - v0; wsum[1][lane] = q - v1;          // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    const int oc = carry[0] + wsum[0][wid] + x - c, oj = carry[1] + wsum[1][wid] + y - j;
+    if (k < nBins) { W.t_off[k] = oc; W.tj_off[k] = oj; W.t_cur[k] = 0; W.tj_cur[k] = 0; }
+    __syncthreads();
+    if (t == 1023) { carry[0] = oc + c; carry[1] = oj + j; }
+    __syncthreads();
   }
-  part[0][t] = sc; part[1][t] = sj;
-  __syncthreads();
   if (nb) atomicAdd(&stats[0], nb);
   if (ng) atomicAdd(&stats[1], ng);
   if (maxc) atomicMax(&stats[2], maxc);
-  // Hillis-Steele over the 1024 partial sums (two arrays at once)
-  for (int o = 1; o < 1024; o <<= 1) {
-    const int a = t >= o ? part[0][t - o] : 0, b = t >= o ? part[1][t - o] : 0;
-    __syncthreads();
-    part[0][t] += a; part[1][t] += b;
-    __syncthreads();
-  }
-  int oc = part[0][t] - sc, oj = part[1][t] - sj;
-  for (int k = beg; k < end; ++k) {
-    const int c = W.t_cur[k], j = W.tj_cur[k];
-    W.t_off[k] = oc; W.tj_off[k] = oj; oc += c; oj += j;
-    W.t_cur[k] = 0; W.tj_cur[k] = 0;
-  }
-  if (t == 1023) {
-    const int total = part[0][1023];
-    W.t_off[nBins] = total; W.tj_off[nBins] = part[1][1023];
+  for (int k = t; k < 2 * P; k += 1024) W.t_flag[k] = 0;
+  __syncthreads();
+  if (t == 0) {
+    const int total = carry[0];
+    W.t_off[nBins] = total; W.tj_off[nBins] = carry[1];
     W.hdr->nSolve = total;
     if (total > W.sCap) W.hdr->error = E_SOLVER_ROWS;
+    W.hdr->nTileB = stats[0]; W.hdr->nTileG = stats[1]; W.hdr->nColours = stats[2]; W.hdr->tailStart = stats[2];
   }
-  __syncthreads();
-  if (t == 0) { W.hdr->nTileB = stats[0]; W.hdr->nTileG = stats[1]; W.hdr->nColours = stats[2]; W.hdr->tailStart = stats[2]; }
 }
 __global__ void __launch_bounds__(256) k_tile_scatter(const __grid_constant__ DevWorld W) {
   const int n = W.hdr->cHigh;
@@ -195,8 +122,9 @@ enum { TM_INIT = 0, TM_VEL = 1, TM_POS = 2 };
 constexpr int kTileBMax = 1024;      // boundary constraints one CTA re-colours locally (more: it walks them by global colour)
 constexpr int kTileBColours = 32;
 
-// one constraint of a phase: item >= 0 is a contact row (solver slot), item < 0 a joint (~joint slot).  Deliberately not
-// inlined: the kernel below reaches it from its local, boundary and global loops and should hold ONE copy of the row code.
+// A constraint that works on rows in the GLOBAL arrays: item >= 0 is a contact row (solver slot), item < 0 a joint
+// (~joint slot).  Boundary and global phases, all joints, and the local rows of a tile too big for shared memory come here;
+// deliberately not inlined, so the kernel holds one copy of this code.
 __device__ __noinline__ void tile_item(const DevWorld& W, BodyView view, int mode, int item, int* notOk, const int* prev) {
   if (item >= 0) {
     if (mode == TM_VEL) contact_solve_velocity(W, item, view);
@@ -218,7 +146,7 @@ __device__ __noinline__ void tile_item(const DevWorld& W, BodyView view, int mod
     }
   }
 }
-// pull the row a thread will need in its NEXT phase from L2 into L1 while it works on the current one (rows are read-only
+// pull a row the thread will need in its NEXT phase from L2 into L1 while it works on the current one (rows are read-only
 // during the solve except for s_imp, which only the owning thread writes)
 DBX_D void pf(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 DBX_D void tile_prefetch_row(const DevWorld& W, int mode, int s) {
@@ -229,13 +157,33 @@ DBX_D void tile_prefetch_row(const DevWorld& W, int mode, int s) {
     pf(&W.s_p0[s]); pf(&W.s_p1[s]); pf(&W.s_p2[s]); pf(&W.s_p3[s]); pf(&W.s_root[s]);
   }
 }
+// ---- TMA: contiguous pieces of the row arrays go to shared memory as bulk asynchronous copies that complete on an mbarrier
+DBX_D unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+DBX_D void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+DBX_D void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DBX_D void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile("{\n\t.reg .pred P1;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+               ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+DBX_D void bulk_g2s(void* dstSmem, const void* srcGlobal, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 __global__ void __launch_bounds__(512) k_solve_tiles(const __grid_constant__ DevWorld W) {
-  extern __shared__ float4 sm4[];                 // [T] velocities, [T] positions, then [T] body ids, [T] exchange flags
+  // dynamic shared memory: the tile's bodies [T] and as many of its local rows as fit [R]
+  //   float4 vel[T] pos[T] | a0..a5[R] (velocity: v0 r0 r1 q0 q1 imp; position: p0 p1 p2 p3) | float2 mass[T] | int2 bd[R] | int body[T] flag[T] | int pc[R]
+  extern __shared__ float4 sm4[];
   __shared__ int offL[kTileColours + 1], joffL[kTileColours + 1], offB[kTileColours + 1], joffB[kTileColours + 1];
   __shared__ int offG[kMaxColours + 1], joffG[kTileColours + 1];
   __shared__ int phL[kTileColours], nPhL;          // the local colours that hold anything, in order
-  __shared__ int sBItem[kTileBMax], sBOff[kTileBColours + 1], nPhB, bDirect;
+  __shared__ int sBItem[kTileBMax], sBOff[kTileBColours + 1], sBCnt[kTileBColours], nPhB, bDirect;
+  __shared__ unsigned long long rowBar;             // mbarrier of the row staging copies
   Header* H = W.hdr;
   const unsigned nb = gridDim.x;
   const int lt = threadIdx.x, ln = blockDim.x;
@@ -243,8 +191,13 @@ __global__ void __launch_bounds__(512) k_solve_tiles(const __grid_constant__ Dev
   const int P = W.nTiles, T = W.tileBodies;
   const int tile = blockIdx.x;
   const int s0 = tile * T, n = tile < P ? max(0, min(T, W.nTileBodies - s0)) : 0;
+  unsigned dynBytes; asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dynBytes));
+  const int R = (int)(((long long)dynBytes - 48ll * T) / 108) & ~1;
   float4* sVel = sm4; float4* sPos = sm4 + T;
-  int* sBody = (int*)(sm4 + 2 * T); int* sFlag = sBody + T;
+  float4* ra0 = sm4 + 2 * T; float4* ra1 = ra0 + R; float4* ra2 = ra1 + R; float4* ra3 = ra2 + R; float4* ra4 = ra3 + R; float4* ra5 = ra4 + R;
+  float2* sMass = (float2*)(ra5 + R);
+  int2* rbd = (int2*)(sMass + T);
+  int* sBody = (int*)(rbd + R); int* sFlag = sBody + T; int* rpc = sFlag + T;
   BodyView view; view.vel = sVel; view.pos = sPos; view.off = s0;
   const BodyView noView;
   {
@@ -257,9 +210,11 @@ __global__ void __launch_bounds__(512) k_solve_tiles(const __grid_constant__ Dev
       joffG[c] = W.tj_off[baseG + c];
     }
     for (int c = lt; c <= kMaxColours; c += ln) offG[c] = W.t_off[baseG + c];
+    if (lt == 0) mbar_init(&rowBar, 1);
   }
   const int nColours = H->nColours;
   const int nG = H->nTileG, nCross = H->nTileB + nG;      // uniform over the grid
+  for (int k = gt; k < 2 * P * kTileColours + kMaxColours; k += gn) { W.t_cur[k] = 0; W.tj_cur[k] = 0; }   // the next step's histogram starts from zero
   const int nLoc = min(nColours, kTileColours);
 #define GB() grid_barrier(&H->barrier, nb)
   // debug (dbx_world_debug_phase_times): %globaltimer stamps of CTA 0 at [0 ..) and of the middle CTA at [1024 ..)
@@ -269,75 +224,95 @@ __global__ void __launch_bounds__(512) k_solve_tiles(const __grid_constant__ Dev
 #define MARK() do { if (marking && markIdx < 1000) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); W.phaseTimes[markBase + markIdx++] = t_; } } while (0)
   MARK();
   __syncthreads();
+  MARK();
+  const int rs0 = offL[0], nRows = offL[kTileColours] - rs0;        // the tile's local rows: one contiguous piece of the row arrays
+  const bool rowsLocal = nRows > 0 && nRows <= R;                   // they fit: they live in shared memory for the whole solve
   if (lt == 0) {
     int k = 0;
     for (int c = 0; c < nLoc; ++c) if (offL[c] != offL[c + 1] || joffL[c] != joffL[c + 1]) phL[k++] = c;
     nPhL = k;
   }
-  // Boundary constraints: the global colouring spreads a boundary's ~150 rows over every colour in use (ten phases of a
-  // dozen rows each); among themselves they need three or four.  Re-colour them greedily, joints first and in ascending global
-  // colour (so a body still meets its joints before its contacts), and walk them through an index list in that order.
+  // Boundary constraints: the global colouring spreads a boundary's ~150 rows over every colour in use (ten phases of a dozen
+  // rows each); among themselves they need three or four.  Re-colour them here: Jones-Plassmann rounds in shared memory, an
+  // item takes the lowest colour free on both bodies once it holds the smallest priority on both (priority = joints before
+  // contacts, then a hash of the item -- so a body still meets its joints first and the outcome does not depend on scheduling).
   {
     const int nBJ = joffB[kTileColours] - joffB[0], nBC = offB[kTileColours] - offB[0], nB = nBJ + nBC;
-    int2* sRef = (int2*)sm4;                          // scratch in the body area (the bodies come in afterwards)
-    unsigned* sMask = (unsigned*)(sRef + kTileBMax);  // [2T] local colours in use per own / neighbour body
-    const bool fits = nB <= kTileBMax;              // (tile_smem_bytes leaves room for this scratch whatever T is)
+    unsigned* sMask = (unsigned*)sm4;                 // scratch in the body / row area (both are filled afterwards)
+    unsigned* sClaim = sMask + 2 * T;                 // [2T] each: own tile's bodies [0, T), the right-hand neighbour's [T, 2T)
+    const bool fits = nB <= kTileBMax && (size_t)16 * T <= (size_t)dynBytes;
     if (lt == 0) { bDirect = fits ? 0 : 1; nPhB = 0; }
+    if (lt < kTileBColours) sBCnt[lt] = 0;
     if (fits && nB > 0) {
-      for (int k = lt; k < 2 * T; k += ln) sMask[k] = 0u;
-      for (int k = lt; k < nB; k += ln) {
-        int item; int2 br;
-        if (k < nBJ) { const int j = W.tj_order[joffB[0] + k]; item = ~j; br = W.j_bref[j]; }
-        else { const int s = offB[0] + (k - nBJ); item = s; br = W.c_bref[W.s_contact[s]]; }
-        sBItem[k] = item;
-        // index of each body in the mask array: own tile [0, T), the right-hand neighbour's [T, 2T), -1 for a body nobody moves
-        int ia = -1, ib = -1;
-        if (br.x >= 0) ia = br.x - s0; else { const int sl = W.b_tslot[br.x & 0x7fffffff]; if (sl >= 0) ia = sl - s0; }
-        if (br.y >= 0) ib = br.y - s0; else { const int sl = W.b_tslot[br.y & 0x7fffffff]; if (sl >= 0) ib = sl - s0; }
-        sRef[k] = make_int2(ia, ib);
+      for (int k = lt; k < 2 * T; k += ln) { sMask[k] = 0u; sClaim[k] = 0xFFFFFFFFu; }
+      // every thread keeps at most two items in registers (nB <= 1024 = 2 x 512)
+      int item[2], ia[2], ib[2], lc[2]; unsigned pr[2];
+      for (int u = 0; u < 2; ++u) {
+        const int k = lt + u * ln;
+        item[u] = 0; ia[u] = ib[u] = -1; lc[u] = k < nB ? -1 : 0; pr[u] = 0xFFFFFFFFu;
+        if (k >= nB) continue;
+        int2 br;
+        if (k < nBJ) { const int j = W.tj_order[joffB[0] + k]; item[u] = ~j; br = W.j_bref[j]; pr[u] = ((unsigned)(mix64((unsigned long long)j + 1ull) >> 33)) & 0x7FFFFC00u; }
+        else {
+          // (the hash is of the pair key, not of the slot: slots inside a bin come out of an atomic scatter in any order)
+          const int s = offB[0] + (k - nBJ), i = W.s_contact[s]; item[u] = s; br = W.c_bref[i];
+          pr[u] = 0x80000000u | (((unsigned)(mix64(W.c_key[i]) >> 33)) & 0x7FFFFC00u);
+        }
+        pr[u] |= (unsigned)k;                        // unique (two pair keys with equal hash bits: practically never)
+        // index of each body in the scratch: own tile [0, T), the neighbour's [T, 2T), -1 for a body nobody moves
+        if (br.x >= 0) ia[u] = br.x - s0; else { const int sl = W.b_tslot[br.x & 0x7fffffff]; if (sl >= 0) ia[u] = sl - s0; }
+        if (br.y >= 0) ib[u] = br.y - s0; else { const int sl = W.b_tslot[br.y & 0x7fffffff]; if (sl >= 0) ib[u] = sl - s0; }
       }
+      __syncthreads();
+      for (int round = 0; round < 4096; ++round) {
+        int open = 0;
+        for (int u = 0; u < 2; ++u) if (lc[u] < 0) { ++open; if (ia[u] >= 0) atomicMin(&sClaim[ia[u]], pr[u]); if (ib[u] >= 0) atomicMin(&sClaim[ib[u]], pr[u]); }
+        if (__syncthreads_count(open) == 0) break;
+        bool won[2] = {false, false};
+        for (int u = 0; u < 2; ++u) if (lc[u] < 0 && (ia[u] < 0 || sClaim[ia[u]] == pr[u]) && (ib[u] < 0 || sClaim[ib[u]] == pr[u])) {
+          const unsigned used = (ia[u] >= 0 ? sMask[ia[u]] : 0u) | (ib[u] >= 0 ? sMask[ib[u]] : 0u);
+          won[u] = true;
+          if (!~used) { bDirect = 1; lc[u] = 0; continue; }       // more than 32 boundary rows on one body: walk them by global colour
+          lc[u] = __ffs((int)~used) - 1;
+          if (ia[u] >= 0) sMask[ia[u]] |= 1u << lc[u];
+          if (ib[u] >= 0) sMask[ib[u]] |= 1u << lc[u];
+        }
+        __syncthreads();
+        for (int u = 0; u < 2; ++u) if (won[u]) { if (ia[u] >= 0) sClaim[ia[u]] = 0xFFFFFFFFu; if (ib[u] >= 0) sClaim[ib[u]] = 0xFFFFFFFFu; }
+        __syncthreads();
+      }
+      // counting sort of the items by local colour (the order inside a colour is free)
+      for (int u = 0; u < 2; ++u) if (lt + u * ln < nB) atomicAdd(&sBCnt[lc[u]], 1);
       __syncthreads();
       if (lt == 0) {
-        int count[kTileBColours];
-        for (int c = 0; c < kTileBColours; ++c) count[c] = 0;
-        bool ok = true;
-        for (int k = 0; k < nB && ok; ++k) {
-          const int2 r = sRef[k];
-          const unsigned used = (r.x >= 0 ? sMask[r.x] : 0u) | (r.y >= 0 ? sMask[r.y] : 0u);
-          if (!~used) { ok = false; break; }
-          const int lc = __ffs((int)~used) - 1;
-          if (r.x >= 0) sMask[r.x] |= 1u << lc;
-          if (r.y >= 0) sMask[r.y] |= 1u << lc;
-          sRef[k].x = lc;                             // (the mask indices are not needed any more)
-          ++count[lc];
-        }
-        if (!ok) bDirect = 1;
-        else {
-          int acc = 0, np = 0;
-          for (int c = 0; c < kTileBColours; ++c) { sBOff[c] = acc; acc += count[c]; if (count[c]) np = c + 1; count[c] = sBOff[c]; }
-          for (int c = np; c <= kTileBColours; ++c) sBOff[c] = acc;
-          nPhB = np;
-          // stable counting sort of the items by local colour, in place via the scratch: sRef[k].y <- destination
-          for (int k = 0; k < nB; ++k) sRef[k].y = count[sRef[k].x]++;
-        }
+        int acc = 0, np = 0;
+        for (int c = 0; c < kTileBColours; ++c) { const int v = sBCnt[c]; sBOff[c] = acc; sBCnt[c] = acc; acc += v; if (v) np = c + 1; }
+        sBOff[kTileBColours] = acc;
+        nPhB = np;
       }
       __syncthreads();
-      if (!bDirect) {
-        int item = 0, dst = -1, lc = 0;
-        // (every thread keeps at most two items: nB <= 1024 = 2 x 512)
-        int item2 = 0, dst2 = -1, lc2 = 0;
-        if (lt < nB) { item = sBItem[lt]; dst = sRef[lt].y; lc = sRef[lt].x; }
-        if (lt + ln < nB) { item2 = sBItem[lt + ln]; dst2 = sRef[lt + ln].y; lc2 = sRef[lt + ln].x; }
-        __syncthreads();
-        if (dst >= 0) { sBItem[dst] = item; if (item >= 0) W.c_tcol[W.s_contact[item]] = lc; else W.j_tcol[~item] = lc; }
-        if (dst2 >= 0) { sBItem[dst2] = item2; if (item2 >= 0) W.c_tcol[W.s_contact[item2]] = lc2; else W.j_tcol[~item2] = lc2; }
+      if (!bDirect) for (int u = 0; u < 2; ++u) if (lt + u * ln < nB) {
+        sBItem[atomicAdd(&sBCnt[lc[u]], 1)] = item[u];
+        if (item[u] >= 0) W.c_tcol[W.s_contact[item[u]]] = lc[u]; else W.j_tcol[~item[u]] = lc[u];    // for dbx_world_debug_read_solve_order
       }
     }
     __syncthreads();
   }
   const bool bLocal = bDirect == 0;
+  MARK();
 
-  // bodies in: velocities with the contacts' warm start folded in (see k_solve), positions, ids, exchange flags
+  // the tile's local rows into shared memory: the six float4 arrays as TMA bulk copies, the two narrow ones by hand
+  if (rowsLocal) {
+    if (lt == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the scratch above was written through the generic proxy
+      const unsigned bytes = (unsigned)nRows * 16u;
+      mbar_expect_tx(&rowBar, 6u * bytes);
+      bulk_g2s(ra0, W.s_v0 + rs0, bytes, &rowBar); bulk_g2s(ra1, W.s_r0 + rs0, bytes, &rowBar); bulk_g2s(ra2, W.s_r1 + rs0, bytes, &rowBar);
+      bulk_g2s(ra3, W.s_q0 + rs0, bytes, &rowBar); bulk_g2s(ra4, W.s_q1 + rs0, bytes, &rowBar); bulk_g2s(ra5, W.s_imp + rs0, bytes, &rowBar);
+    }
+    for (int k = lt; k < nRows; k += ln) { rbd[k] = W.s_body[rs0 + k]; rpc[k] = W.s_pc[rs0 + k]; }
+  }
+  // bodies in: velocities with the contacts' warm start folded in (see k_solve), positions, inverse masses, ids, exchange flags
   {
     const float k = 1.0f / 4294967296.0f;
     for (int i = lt; i < n; i += ln) {
@@ -350,32 +325,63 @@ __global__ void __launch_bounds__(512) k_solve_tiles(const __grid_constant__ Dev
           __stcg(&W.b_acc[3 * b], 0ull); __stcg(&W.b_acc[3 * b + 1], 0ull); __stcg(&W.b_acc[3 * b + 2], 0ull);
         }
       }
-      sVel[i] = vel; sPos[i] = ldcg4(&W.b_pos[b]);
+      const float4 ms = W.b_mass[b];
+      sVel[i] = vel; sPos[i] = ldcg4(&W.b_pos[b]); sMass[i] = make_float2(ms.x, ms.y);
       sBody[i] = b; sFlag[i] = W.b_xflag[b];
     }
     __syncthreads();
   }
   MARK();
+  if (rowsLocal) mbar_wait(&rowBar, 0);
+  MARK();
 
-  int sweepNo = 0;
   // ---- the phases of one class
-  // local colour `c` of this tile: joints, then rows; the thread's row of the NEXT non-empty colour is prefetched meanwhile
-  auto local_phase = [&](int mode, int k, int kNext, int* notOk, const int* prev) {
-    const int c = phL[k];
-    const int jb = joffL[c], nj = joffL[c + 1] - jb, beg = offL[c], total = nj + (offL[c + 1] - beg);
-    if (mode == TM_INIT && nj == 0) return;
-    if (kNext >= 0 && mode != TM_INIT) {
-      const int cn = phL[kNext];
-      const int sn = offL[cn] + lt - (joffL[cn + 1] - joffL[cn]);
-      if (sn >= offL[cn] && sn < offL[cn + 1]) tile_prefetch_row(W, mode, sn);
+  int sweepNo = 0;
+  // local colours of this tile, upwards or downwards: joints first, then rows -- from shared memory when they fit
+  auto local_phases = [&](int mode, bool backwards, int* notOk, const int* prev) {
+    for (int kk = 0; kk < nPhL; ++kk) {
+      const int k = backwards ? nPhL - 1 - kk : kk;
+      const int c = phL[k];
+      const int jb = joffL[c], nj = joffL[c + 1] - jb, beg = offL[c], nr = offL[c + 1] - beg;
+      if (mode == TM_INIT && nj == 0) continue;
+      const bool fine = marking && sweepNo == 4 && kk < 16;       // debug: clock stamps of one velocity pass at [2048 + 4 kk ..)
+      long long c0 = 0, c1 = 0;
+      if (fine) c0 = clock64();
+      for (int q = lt; q < nj; q += ln) tile_item(W, view, mode, ~W.tj_order[jb + q], notOk, prev);
+      if (mode != TM_INIT) {
+        if (rowsLocal) {
+          // (row q of the colour belongs to thread q - nj, as in the global layout, so a jointed colour spreads over all warps)
+          for (int q = lt - nj; q < nr; q += ln) {
+            if (q < 0) continue;
+            const int x = beg - rs0 + q;
+            const int2 bd = rbd[x];
+            const float2 mA = bd.x >= 0 ? sMass[bd.x - s0] : make_float2(0.0f, 0.0f), mB = bd.y >= 0 ? sMass[bd.y - s0] : make_float2(0.0f, 0.0f);
+            if (mode == TM_VEL) {
+              VC v; v.bd = bd; v.pc = rpc[x]; v.v0 = ra0[x]; v.v1 = make_float4(mA.x, mA.y, mB.x, mB.y); v.r0 = ra1[x]; v.r1 = ra2[x]; v.q0 = ra3[x]; v.q1 = ra4[x]; v.imp = ra5[x];
+              if ((v.pc & 0xFF) == 2) { v.nm = W.s_nm[beg + q]; v.K = W.s_k[beg + q]; }      // (the block solver's matrices stay in L2: no room; fetching them a phase ahead into registers was measured slower)
+              ra5[x] = contact_velocity_row(W, v, view);
+            } else {
+              const int root = W.s_root[beg + q];
+              if (prev && __ldcg(&prev[root]) == 0) continue;
+              PCn p; p.bd = bd; p.pc = rpc[x]; p.v1 = make_float4(mA.x, mA.y, mB.x, mB.y); p.p0 = ra0[x]; p.p1 = ra1[x]; p.p2 = ra2[x]; p.p3 = make_float2(ra3[x].x, ra3[x].y);
+              const float minSep = contact_position_row(W, p, -1, -1, view);
+              if (!(minSep >= -3.0f * kLinearSlop)) __stcg(&notOk[root], 1);
+            }
+          }
+        } else {
+          const int kn = backwards ? k - 1 : k + 1;
+          if (kn >= 0 && kn < nPhL) {
+            const int cn = phL[kn];
+            const int sn = offL[cn] + lt - (joffL[cn + 1] - joffL[cn]);
+            if (sn >= offL[cn] && sn < offL[cn + 1]) tile_prefetch_row(W, mode, sn);
+          }
+          for (int q = lt - nj; q < nr; q += ln) if (q >= 0) tile_item(W, view, mode, beg + q, notOk, prev);
+        }
+      }
+      if (fine) c1 = clock64();
+      __syncthreads();
+      if (fine) { const long long c2 = clock64(); unsigned long long* o = W.phaseTimes + 2048 + (blockIdx.x == 0 ? 0 : 128) + 4 * kk; o[0] = (unsigned long long)(c1 - c0); o[1] = (unsigned long long)(c2 - c1); o[2] = (unsigned long long)(nj + nr); o[3] = (unsigned long long)c; }
     }
-    const bool fine = marking && sweepNo == 4 && k < 16;       // debug: clock stamps of one velocity pass at [2048 + 4 k ..)
-    long long c0 = 0, c1 = 0;
-    if (fine) c0 = clock64();
-    for (int q = lt; q < (mode == TM_INIT ? nj : total); q += ln) tile_item(W, view, mode, q < nj ? ~W.tj_order[jb + q] : beg + (q - nj), notOk, prev);
-    if (fine) c1 = clock64();
-    __syncthreads();
-    if (fine) { const long long c2 = clock64(); unsigned long long* o = W.phaseTimes + 2048 + (blockIdx.x == 0 ? 0 : 128) + 4 * k; o[0] = (unsigned long long)(c1 - c0); o[1] = (unsigned long long)(c2 - c1); o[2] = (unsigned long long)total; o[3] = (unsigned long long)c; }
   };
   auto boundary_phases = [&](int mode, bool backwards, int* notOk, const int* prev) {
     if (bLocal) {
@@ -411,15 +417,41 @@ __global__ void __launch_bounds__(512) k_solve_tiles(const __grid_constant__ Dev
       if (positions) stcg4(&W.b_pos[sBody[i]], sPos[i]); else stcg4(&W.b_vel[sBody[i]], sVel[i]);
     }
   };
+  // Neighbour handshakes instead of grid barriers (when there are no global rows): tile s only ever exchanges bodies with
+  // tiles s - 1 and s + 1, so "my right neighbour has published pass k" and "my left neighbour's boundary rows of pass k are
+  // done" are all it has to wait for -- a slow tile holds up its neighbours, not the machine.  Flags count passes upwards.
+  const bool handshake = nG == 0 && !(W.dbgFlags & 128);
+  int* flagL = W.t_flag; int* flagB = W.t_flag + P;
+  auto signal = [&](int* flag) {
+    __syncthreads();
+    if (lt == 0 && tile < P) { __threadfence(); atomicExch(flag + tile, sweepNo); }
+  };
+  auto await = [&](int* flag, int other) {
+    if (lt == 0 && tile < P && other >= 0 && other < P) {
+      while (*((volatile int*)(flag + other)) < sweepNo) { }
+      __threadfence();
+    }
+    __syncthreads();
+  };
   // one Gauss-Seidel pass.  forward: L, B, G with the colours upwards; backward (position passes): G, B, L downwards
   auto sweep = [&](int mode, int* notOk, const int* prev) {
-    const bool pos = mode == TM_POS;
     ++sweepNo;
-    if (!pos) {
-      for (int k = 0; k < nPhL; ++k) local_phase(mode, k, k + 1 < nPhL ? k + 1 : -1, notOk, prev);
+    if (mode != TM_POS) {
+      local_phases(mode, false, notOk, prev);
       MARK();
       if (nCross == 0) return;
       publish(false, XF_FOREIGN | XF_G, 0);
+      if (handshake) {
+        signal(flagL); await(flagL, tile + 1);
+        MARK();
+        boundary_phases(mode, false, notOk, prev);
+        MARK();
+        signal(flagB); await(flagB, tile - 1);
+        for (int i = lt; i < n; i += ln) if (sFlag[i] & XF_FOREIGN) sVel[i] = ldcg4(&W.b_vel[sBody[i]]);
+        __syncthreads();
+        MARK();
+        return;
+      }
       GB();
       MARK();
       boundary_phases(mode, false, notOk, prev);
@@ -433,7 +465,15 @@ __global__ void __launch_bounds__(512) k_solve_tiles(const __grid_constant__ Dev
       __syncthreads();
       MARK();
     } else {
-      if (nCross > 0) {
+      if (nCross > 0 && handshake) {
+        if (prev) GB();            // the per-island flags of the pass before must be in for every tile alike
+        publish(true, XF_FOREIGN, 0);
+        signal(flagL); await(flagL, tile + 1);
+        boundary_phases(mode, true, notOk, prev);
+        signal(flagB); await(flagB, tile - 1);
+        for (int i = lt; i < n; i += ln) if (sFlag[i] & XF_FOREIGN) sPos[i] = ldcg4(&W.b_pos[sBody[i]]);
+        __syncthreads();
+      } else if (nCross > 0) {
         publish(true, XF_FOREIGN | XF_G, 0);
         GB();
         if (nG > 0) {
@@ -451,23 +491,25 @@ __global__ void __launch_bounds__(512) k_solve_tiles(const __grid_constant__ Dev
         }
         __syncthreads();
       }
-      for (int k = nPhL - 1; k >= 0; --k) local_phase(mode, k, k > 0 ? k - 1 : -1, notOk, prev);
+      local_phases(mode, true, notOk, prev);
     }
   };
 
   if (W.nJoints > 0) sweep(TM_INIT, nullptr, nullptr);                        // joints: InitVelocityConstraints + warm start (:143-146)
   for (int it = 0; it < W.velIters; ++it) sweep(TM_VEL, nullptr, nullptr);    // :153-161
-  // StoreImpulses (:164)
-  {
-    const int ns = min(H->nSolve, W.sCap);
-    for (int s = gt; s < ns; s += gn) {
-      const int i = W.s_contact[s];
-      const int vcCount = W.s_pc[s] & 0xFF;
-      const float4 imp = W.s_imp[s];
-      float4 old = W.c_imp[i];
-      old.x = imp.x; old.y = imp.y;
-      if (vcCount == 2) { old.z = imp.z; old.w = imp.w; }
-      W.c_imp[i] = old;
+  // the local rows' impulses go back to the row array (StoreImpulses below, PostSolve and the next step's warm start read
+  // them there); the position rows take their place in shared memory
+  if (rowsLocal) {
+    for (int k = lt; k < nRows; k += ln) W.s_imp[rs0 + k] = ra5[k];
+    __syncthreads();
+    if (W.posIters > 0) {
+      if (lt == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const unsigned bytes = (unsigned)nRows * 16u;
+        mbar_expect_tx(&rowBar, 3u * bytes);
+        bulk_g2s(ra0, W.s_p0 + rs0, bytes, &rowBar); bulk_g2s(ra1, W.s_p1 + rs0, bytes, &rowBar); bulk_g2s(ra2, W.s_p2 + rs0, bytes, &rowBar);
+      }
+      for (int k = lt; k < nRows; k += ln) { const float2 r = W.s_p3[rs0 + k]; ra3[k] = make_float4(r.x, r.y, 0.0f, 0.0f); }
     }
   }
   // integrate positions (:168-200): tile bodies in shared memory, the island's other bodies (kinematic) in the global arrays
@@ -499,6 +541,20 @@ __global__ void __launch_bounds__(512) k_solve_tiles(const __grid_constant__ Dev
     stcg4(&W.b_pos[b], pos); stcg4(&W.b_vel[b], vel);
   }
   GB();
+  // StoreImpulses (:164): every row's working impulses are in the row array now
+  {
+    const int ns = min(H->nSolve, W.sCap);
+    for (int s = gt; s < ns; s += gn) {
+      const int i = W.s_contact[s];
+      const int vcCount = W.s_pc[s] & 0xFF;
+      const float4 imp = ldcg4(&W.s_imp[s]);
+      float4 old = W.c_imp[i];
+      old.x = imp.x; old.y = imp.y;
+      if (vcCount == 2) { old.z = imp.z; old.w = imp.w; }
+      W.c_imp[i] = old;
+    }
+  }
+  if (rowsLocal && W.posIters > 0) mbar_wait(&rowBar, 1);
   MARK();
   // position iterations (:206-224) with the per-island early-out flags of k_solve
   for (int it = 0; it < W.posIters; ++it) {
@@ -525,7 +581,6 @@ __global__ void __launch_bounds__(512) k_solve_tiles(const __grid_constant__ Dev
     for (int i = lt; i < n; i += ln) {
       const int b = sBody[i];
       if (sFlag[i]) W.b_xflag[b] = 0;
-      W.b_tclaim[b] = 0x7fffffff;
       const uint32_t f = W.b_flags[b];
       if ((f & (BF_ALIVE | BF_ISLAND)) != (BF_ALIVE | BF_ISLAND)) continue;
       const float4 pos = sPos[i], vel = sVel[i];
@@ -562,7 +617,17 @@ __global__ void __launch_bounds__(512) k_solve_tiles(const __grid_constant__ Dev
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-size_t tile_smem_bytes(int tileBodies) { return (size_t)tileBodies * 40 + (size_t)kTileBMax * 8; }   // bodies; the re-colouring scratch needs 8 kTileBMax + 8 T
+// dynamic shared memory of k_solve_tiles: the bodies (48 B each) plus as many local rows (108 B each) as the SM has room for
+size_t tile_smem_bytes(int tileBodies) {
+  static size_t avail = 0;
+  if (!avail) {
+    int dev = 0, optin = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaFuncAttributes fa{}; cudaFuncGetAttributes(&fa, (const void*)k_solve_tiles);
+    avail = (size_t)optin > fa.sharedSizeBytes + 1024 ? (size_t)optin - fa.sharedSizeBytes - 1024 : 0;
+  }
+  return std::max(avail, (size_t)tileBodies * 48 + 4096) > avail ? 0 : avail;       // 0: the tile does not fit
+}
 
 cudaError_t stage_tile_assign(const DevWorld& W, const LaunchCfg& L, unsigned* keysA, unsigned* keysB, int* valsA, int* valsB) {
   ++L.launches; k_tile_body_keys<<<L.gridWide, 256, 0, L.stream>>>(W, keysA, valsA);
@@ -575,20 +640,20 @@ cudaError_t stage_tile_assign(const DevWorld& W, const LaunchCfg& L, unsigned* k
 }
 // colouring as in stage_colour_and_sort, then the constraints sorted by (class, tile, colour) instead of by colour
 cudaError_t stage_colour_and_sort_tiles(const DevWorld& W, const LaunchCfg& L) {
-  CK(launch_mark_and_colour(W, L));
-  ++L.launches; k_tile_claim<<<L.gridWide, 256, 0, L.stream>>>(W);
-  ++L.launches; k_tile_key<<<L.gridWide, 256, 0, L.stream>>>(W);
+  CK(launch_mark_and_colour(W, L));          // with W.tiled set, k_mark_solve / k_colour also bin every constraint (dbx_tilekey.cuh)
   ++L.launches; k_tile_scan<<<1, 1024, 0, L.stream>>>(W);
   ++L.launches; k_tile_scatter<<<L.gridWide, 256, 0, L.stream>>>(W);
   return cudaGetLastError();
 }
 cudaError_t stage_solve_tiles(const DevWorld& W, const LaunchCfg& L) {
+  const size_t smem = tile_smem_bytes(W.tileBodies);
+  if (smem == 0) return cudaErrorInvalidConfiguration;
   static bool attr = false;
-  if (!attr) { CK(cudaFuncSetAttribute((const void*)k_solve_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+  if (!attr) { CK(cudaFuncSetAttribute((const void*)k_solve_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
   if ((L.coopLaunches++ & 1023) == 0) CK(cudaMemsetAsync(&W.hdr->barrier, 0, sizeof(unsigned), L.stream));   // see launch_coop
   void* args[] = {(void*)&W};
   ++L.launches;
-  return cudaLaunchCooperativeKernel((const void*)k_solve_tiles, dim3(L.coopBlocks), dim3(L.coopThreads), args, tile_smem_bytes(W.tileBodies), L.stream);
+  return cudaLaunchCooperativeKernel((const void*)k_solve_tiles, dim3(L.coopBlocks), dim3(L.coopThreads), args, smem, L.stream);
 }
 
 }  // namespace dbx

@@ -1157,6 +1157,7 @@ int World::prepareTiles() {
   CUDA_OR_FAIL(j_tkey_.reserve(capJ, false, stream_), "tile joint keys"); CUDA_OR_FAIL(j_bref_.reserve(capJ, false, stream_), "tile joint refs");
   CUDA_OR_FAIL(tj_order_.reserve(capJ, false, stream_), "tile joint order");
   CUDA_OR_FAIL(c_tcol_.reserve(capC, false, stream_), "tile contact colours"); CUDA_OR_FAIL(j_tcol_.reserve(capJ, false, stream_), "tile joint colours");
+  CUDA_OR_FAIL(t_flag_.reserve((size_t)2 * L_.coopBlocks, false, stream_), "tile flags");
   DevBuf<int>* bins[] = {&t_off_, &t_cur_, &tj_off_, &tj_cur_};
   for (auto* b : bins) CUDA_OR_FAIL(b->reserve(nBins, false, stream_), "tile bins");
   const size_t need = cub_temp_bytes_u32((int)capB);
@@ -1166,7 +1167,7 @@ int World::prepareTiles() {
   w.nTiles = P; w.tileBodies = T; w.nTileBodies = nDynamic_;
   w.b_tslot = b_tslot_.p; w.t_body = t_body_.p; w.b_tclaim = b_tclaim_.p; w.b_xflag = b_xflag_.p;
   w.c_tkey = c_tkey_.p; w.c_bref = c_bref_.p; w.j_tkey = j_tkey_.p; w.j_bref = j_bref_.p; w.c_tcol = c_tcol_.p; w.j_tcol = j_tcol_.p;
-  w.t_off = t_off_.p; w.t_cur = t_cur_.p; w.tj_off = tj_off_.p; w.tj_cur = tj_cur_.p; w.tj_order = tj_order_.p;
+  w.t_off = t_off_.p; w.t_cur = t_cur_.p; w.tj_off = tj_off_.p; w.tj_cur = tj_cur_.p; w.tj_order = tj_order_.p; w.t_flag = t_flag_.p;
   if (!tilesValid_ || sinceTileSort_ >= kTileSortPeriod) {
     CUDA_OR_FAIL(stage_tile_assign(w, L_, tKeyA_.p, tKeyB_.p, tValA_.p, tValB_.p), "tile assign");
     tilesValid_ = true; sinceTileSort_ = 0;

@@ -133,6 +133,9 @@ class World {
   int stageFindNewContacts();
   int stageCollide();
   int setContactLevels(const int32_t* levels, int n);
+  // snapshot / restore: the tile solver's body-to-tile assignment is not part of a snapshot; both sides of an export / import
+  // re-derive it from the body positions at that moment, so a restored world keeps stepping bit for bit like the original
+  void resetSolverSchedule() { tilesValid_ = false; sinceTileSort_ = 0; }
   int readSolveOrder(int32_t* contactRank, int capC, int32_t* jointRank, int capJ, int32_t* info4);
   int colourConflicts();
   int readHeader(void* out, int bytes) { cudaStreamSynchronize(stream_); int n = bytes < (int)sizeof(Header) ? bytes : (int)sizeof(Header); return cudaMemcpy(out, hdr_.p, n, cudaMemcpyDeviceToHost) == cudaSuccess ? n : DBX_E_CUDA; }
@@ -235,7 +238,7 @@ class World {
   std::vector<int> lastReadSlots_;
   // tile solver (dbx_tiles.cu): dynamic bodies of a big single world in x order, cut into one tile per CTA
   int prepareTiles();            // > 0: this step runs the tile solver (buffers sized, tiles assigned, dw_ filled in)
-  DevBuf<int> b_tslot_, t_body_, b_tclaim_, b_xflag_, c_tkey_, j_tkey_, c_tcol_, j_tcol_, t_off_, t_cur_, tj_off_, tj_cur_, tj_order_, tValA_, tValB_;
+  DevBuf<int> b_tslot_, t_body_, b_tclaim_, b_xflag_, c_tkey_, j_tkey_, c_tcol_, j_tcol_, t_flag_, t_off_, t_cur_, tj_off_, tj_cur_, tj_order_, tValA_, tValB_;
   DevBuf<int2> c_bref_, j_bref_; DevBuf<unsigned> tKeyA_, tKeyB_;
   bool tilesDirty_ = true, tilesValid_ = false, lastTiled_ = false; int sinceTileSort_ = 0, nDynamic_ = 0; size_t tileBodyCap_ = 0;
 };

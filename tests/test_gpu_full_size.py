@@ -259,42 +259,61 @@ def _compare_step(wg, wo, label):
             "contacts": int(ng), "touching": int(touching.sum()), "joints": int(nj)}
 
 
+def _one_ulp_twin(snap):
+    """the snapshot with every body angle moved by one ulp (sin / cos left alone): what a 1-ulp difference between CUDA's and
+    glibc's sinf / cosf does to a step, measured on the oracle itself"""
+    B = np.frombuffer(snap["bodies"], dtype=np.dtype(A.BodyState), count=snap["nb"]).copy()
+    B["a"] = np.nextafter(B["a"], np.float32(10.0)).astype(np.float32)
+    twin = dict(snap)
+    twin["bodies"] = (A.BodyState * snap["nb"]).from_buffer_copy(B.tobytes())
+    return twin
+
+
 @pytest.mark.parametrize("n,columns,settle", [(3000, 100, 300), (100000, 1000, 600)])
 def test_pile_single_step_matches_oracle(gpu_api, oracle_api, n, columns, settle):
+    """One step of the settled pile on the device against the sequential oracle walking the device's own Gauss-Seidel order.
+    Exact: contact set, touching flags, manifold types, feature keys, manifolds (bit for bit), island count.  Velocities,
+    positions and impulses: north_star's 1e-4 / 1e-5 relative for all but a fraction of a per cent of the bodies, and for
+    those the yardstick is the solver's own conditioning -- the block solver accepts 2-point contacts whose K matrix has a
+    condition number up to 1000 (b2contactsolver.d:418-448), deep stacks chain such contacts, and the oracle run against ITSELF
+    with every body angle moved by one ulp spreads just as far.  The device must stay within a small factor of that spread.
+    (A wrong order or a wrong warm start shows as 1e-2 .. 1 on hundreds of bodies: both were found with this test.)"""
     from dbox_b200 import state
     from tests.parity import hand_device_order_to_oracle
     wg, _, nj = scenes.pile(api=gpu_api, n=n, columns=columns)
     wo, _, _ = scenes.pile(api=oracle_api, n=n, columns=columns)
-    wg.SetAllowSleeping(False); wo.SetAllowSleeping(False)
+    wt, _, _ = scenes.pile(api=oracle_api, n=n, columns=columns)
+    for w in (wg, wo, wt):
+        w.SetAllowSleeping(False)
     wg.StepN(DT, 8, 3, settle)
     snap = state.capture(wg)
+    twin = _one_ulp_twin(snap)
     assert snap["nb"] == n + 1 and snap["nj"] == nj
-    report = {}
     for continuous in (False, True):
-        for w in (wg, wo):
+        for w in (wg, wo, wt):
             w.SetContinuousPhysics(continuous)
-            state.apply(w, snap)
+            state.apply(w, twin if w is wt else snap)
         assert oracle_api.world_tree_validate(wo._w) == 1
         wg.Step(DT, 8, 3)
         found, info = hand_device_order_to_oracle(oracle_api, wg, wo)
-        wo.Step(DT, 8, 3)
+        hand_device_order_to_oracle(oracle_api, wg, wt)
+        wo.Step(DT, 8, 3); wt.Step(DT, 8, 3)
         cg, co = wg.counts(), wo.counts()
         assert found > 0
         assert cg.islands == co.islands, ("island count", cg.islands, co.islands)          # row a14
         assert cg.touching == co.touching and cg.contacts == co.contacts
         r = _compare_step(wg, wo, "continuous=%s" % continuous)
-        r.update(order_found=found, unified=info[0], colours=info[1], joint_colours=info[2], islands=cg.islands)
-        report[continuous] = r
-        print("pile %d single step vs oracle, continuous=%s: %s" % (n, continuous, r))
-        # north_star: contact set, touching flags, manifold types and feature keys exact (asserted above); manifolds 1e-5,
-        # velocities and impulses 1e-4 relative (floor 1.0 = the unit scale of the scene).  The manifolds are bit-exact.  For
-        # velocities and impulses the bound holds for all but a handful of bodies: the block solver accepts 2-point contacts
-        # whose K matrix has a condition number up to 1000 (b2contactsolver.d:418-448), which amplifies a 1-ulp difference in
-        # sin/cos (CUDA vs glibc) up to ~1e-4 .. 1e-3 -- the oracle shows the same spread against ITSELF when every body angle
-        # is moved by one ulp (measured: 2e-4 on the 3,000-body pile).  A wrong Gauss-Seidel order or a
-        # wrong warm start shows as 1e-2 .. 1 on hundreds of bodies (both were found with this test).
-        assert r["manifold"][0] < 1e-5 and r["pos"][0] < 1e-5, r
-        for q in ("vel", "contact_impulse", "joint_impulse"):
-            assert r[q][1] < 1e-2, (q, r)       # at most 1 % of the items beyond 1e-4 (measured: 0.3 % while the pile is still moving)
-            assert r[q][0] < 5e-3, (q, r)       # and none anywhere near what a wrong order gives
-    wg.close(); wo.close()
+        try:
+            own = _compare_step(wt, wo, "oracle twin")
+        except AssertionError:          # the ulp flipped a feature somewhere: no yardstick from this pair
+            own = None
+        r.update(order_found=found, position_backwards=info[0], colours=info[1], joint_colours=info[2], tiles=info[3], islands=cg.islands)
+        print("pile %d single step, device vs oracle, continuous=%s: %s" % (n, continuous, r))
+        print("pile %d single step, oracle vs oracle with angles + 1 ulp:  %s" % (n, own))
+        assert r["manifold"][0] == 0.0, r                            # bit for bit
+        for q, tol in (("pos", 1e-5), ("vel", 1e-4), ("contact_impulse", 1e-4), ("joint_impulse", 1e-4)):
+            worst, frac = r[q]
+            own_worst, own_frac = own[q] if own else (0.0, 0.0)
+            assert frac <= max(8.0 * own_frac, 1e-2), (q, r[q], own and own[q])        # how many items are beyond the tolerance
+            assert worst <= max(8.0 * own_worst, 20.0 * tol), (q, r[q], own and own[q])    # and how far
+    wg.close(); wo.close(); wt.close()

@@ -15,8 +15,8 @@ for base, name in ((0, "CTA 0"), (1024, "middle CTA")):
     ts = [buf[base + i] for i in range(1000) if buf[base + i]]
     d = [(ts[i + 1] - ts[i]) / 1000. for i in range(len(ts) - 1)]
     print(name, "marks", len(ts), "total us %.1f" % sum(d))
-    print("  load %.1f" % d[0] if d else "")
-    rest = d[1:]
+    print("  prologue: offsets %.1f  recolour %.1f  bodies %.1f  rows wait %.1f" % tuple(d[:4]))
+    rest = d[4:]
     # forward sweeps: 4 intervals each (L, publish+GB, B, GB+readback)
     for k in range(0, min(len(rest), 4 * 9), 4):
         print("  sweep %d: L %.1f  pub+GB %.1f  B %.1f  GB+rb %.1f" % tuple([k // 4] + rest[k:k + 4]) if len(rest) >= k + 4 else rest[k:])
