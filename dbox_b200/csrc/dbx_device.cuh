@@ -245,6 +245,7 @@ struct DevWorld {
   // ---- tile solver (dbx_tiles.cu): dynamic bodies in x order cut into nTiles tiles of tileBodies; constraints by (class, tile, colour)
   int tiled;            // this step's rows / joints carry body references (dbx_solver.cuh, BodyView) and k_solve_tiles runs them
   int nTiles, tileBodies, nTileBodies;
+  int tileKinematic;    // the world holds kinematic bodies (they are integrated outside the tiles)
   int* b_tslot;         // body -> position in tile order (-1: not a dynamic body)
   int* t_body;          // position in tile order -> body
   int* b_tclaim;        // per body: lowest boundary straddled by one of its constraints (0x7fffffff at rest)

@@ -228,6 +228,14 @@ __global__ void __launch_bounds__(512) k_solve_tiles(const __grid_constant__ Dev
   const int rs0 = offL[0], nRows = offL[kTileColours] - rs0;        // the tile's local rows: one contiguous piece of the row arrays
   const bool rowsLocal = nRows > 0 && nRows <= R;                   // they fit: they live in shared memory for the whole solve
   if (lt == 0) {
+    // the tile's local rows into shared memory: the six float4 arrays as TMA bulk copies, under way while the boundary rows
+    // are re-coloured and the bodies come in (the two narrow arrays follow by hand)
+    if (rowsLocal) {
+      const unsigned bytes = (unsigned)nRows * 16u;
+      mbar_expect_tx(&rowBar, 6u * bytes);
+      bulk_g2s(ra0, W.s_v0 + rs0, bytes, &rowBar); bulk_g2s(ra1, W.s_r0 + rs0, bytes, &rowBar); bulk_g2s(ra2, W.s_r1 + rs0, bytes, &rowBar);
+      bulk_g2s(ra3, W.s_q0 + rs0, bytes, &rowBar); bulk_g2s(ra4, W.s_q1 + rs0, bytes, &rowBar); bulk_g2s(ra5, W.s_imp + rs0, bytes, &rowBar);
+    }
     int k = 0;
     for (int c = 0; c < nLoc; ++c) if (offL[c] != offL[c + 1] || joffL[c] != joffL[c + 1]) phL[k++] = c;
     nPhL = k;
@@ -238,7 +246,7 @@ __global__ void __launch_bounds__(512) k_solve_tiles(const __grid_constant__ Dev
   // contacts, then a hash of the item -- so a body still meets its joints first and the outcome does not depend on scheduling).
   {
     const int nBJ = joffB[kTileColours] - joffB[0], nBC = offB[kTileColours] - offB[0], nB = nBJ + nBC;
-    unsigned* sMask = (unsigned*)sm4;                 // scratch in the body / row area (both are filled afterwards)
+    unsigned* sMask = (unsigned*)sMass;               // scratch in the tail of the dynamic area (masses, references, ids: filled afterwards)
     unsigned* sClaim = sMask + 2 * T;                 // [2T] each: own tile's bodies [0, T), the right-hand neighbour's [T, 2T)
     const bool fits = nB <= kTileBMax && (size_t)16 * T <= (size_t)dynBytes;
     if (lt == 0) { bDirect = fits ? 0 : 1; nPhB = 0; }
@@ -301,17 +309,7 @@ __global__ void __launch_bounds__(512) k_solve_tiles(const __grid_constant__ Dev
   const bool bLocal = bDirect == 0;
   MARK();
 
-  // the tile's local rows into shared memory: the six float4 arrays as TMA bulk copies, the two narrow ones by hand
-  if (rowsLocal) {
-    if (lt == 0) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the scratch above was written through the generic proxy
-      const unsigned bytes = (unsigned)nRows * 16u;
-      mbar_expect_tx(&rowBar, 6u * bytes);
-      bulk_g2s(ra0, W.s_v0 + rs0, bytes, &rowBar); bulk_g2s(ra1, W.s_r0 + rs0, bytes, &rowBar); bulk_g2s(ra2, W.s_r1 + rs0, bytes, &rowBar);
-      bulk_g2s(ra3, W.s_q0 + rs0, bytes, &rowBar); bulk_g2s(ra4, W.s_q1 + rs0, bytes, &rowBar); bulk_g2s(ra5, W.s_imp + rs0, bytes, &rowBar);
-    }
-    for (int k = lt; k < nRows; k += ln) { rbd[k] = W.s_body[rs0 + k]; rpc[k] = W.s_pc[rs0 + k]; }
-  }
+  if (rowsLocal) for (int k = lt; k < nRows; k += ln) { rbd[k] = W.s_body[rs0 + k]; rpc[k] = W.s_pc[rs0 + k]; }
   // bodies in: velocities with the contacts' warm start folded in (see k_solve), positions, inverse masses, ids, exchange flags
   {
     const float k = 1.0f / 4294967296.0f;
@@ -497,10 +495,17 @@ __global__ void __launch_bounds__(512) k_solve_tiles(const __grid_constant__ Dev
 
   if (W.nJoints > 0) sweep(TM_INIT, nullptr, nullptr);                        // joints: InitVelocityConstraints + warm start (:143-146)
   for (int it = 0; it < W.velIters; ++it) sweep(TM_VEL, nullptr, nullptr);    // :153-161
-  // the local rows' impulses go back to the row array (StoreImpulses below, PostSolve and the next step's warm start read
-  // them there); the position rows take their place in shared memory
+  // StoreImpulses (:164).  A tile's local rows hold their working impulses in shared memory: they go back to the row array
+  // (PostSolve records read them there) and into the persistent manifolds from here; the position rows take their place.
+  auto store_impulse = [&](int s, float4 imp, int pc) {
+    const int i = W.s_contact[s];
+    float4 old = W.c_imp[i];
+    old.x = imp.x; old.y = imp.y;
+    if ((pc & 0xFF) == 2) { old.z = imp.z; old.w = imp.w; }
+    W.c_imp[i] = old;
+  };
   if (rowsLocal) {
-    for (int k = lt; k < nRows; k += ln) W.s_imp[rs0 + k] = ra5[k];
+    for (int k = lt; k < nRows; k += ln) { const float4 imp = ra5[k]; W.s_imp[rs0 + k] = imp; store_impulse(rs0 + k, imp, rpc[k]); }
     __syncthreads();
     if (W.posIters > 0) {
       if (lt == 0) {
@@ -511,7 +516,11 @@ __global__ void __launch_bounds__(512) k_solve_tiles(const __grid_constant__ Dev
       }
       for (int k = lt; k < nRows; k += ln) { const float2 r = W.s_p3[rs0 + k]; ra3[k] = make_float4(r.x, r.y, 0.0f, 0.0f); }
     }
+  } else if (tile < P) {
+    for (int s = offL[0] + lt; s < offL[kTileColours]; s += ln) store_impulse(s, W.s_imp[s], W.s_pc[s]);
   }
+  if (tile < P) for (int s = offB[0] + lt; s < offB[kTileColours]; s += ln) store_impulse(s, ldcg4(&W.s_imp[s]), W.s_pc[s]);    // this CTA solved them
+  if (nG > 0) for (int s = offG[0] + gt; s < offG[kMaxColours]; s += gn) store_impulse(s, ldcg4(&W.s_imp[s]), W.s_pc[s]);       // (grid barrier after the last global phase)
   // integrate positions (:168-200): tile bodies in shared memory, the island's other bodies (kinematic) in the global arrays
   const float h = W.dt;
   auto integrate = [&](float4& pos, float4& vel) {
@@ -540,20 +549,7 @@ __global__ void __launch_bounds__(512) k_solve_tiles(const __grid_constant__ Dev
     integrate(pos, vel);
     stcg4(&W.b_pos[b], pos); stcg4(&W.b_vel[b], vel);
   }
-  GB();
-  // StoreImpulses (:164): every row's working impulses are in the row array now
-  {
-    const int ns = min(H->nSolve, W.sCap);
-    for (int s = gt; s < ns; s += gn) {
-      const int i = W.s_contact[s];
-      const int vcCount = W.s_pc[s] & 0xFF;
-      const float4 imp = ldcg4(&W.s_imp[s]);
-      float4 old = W.c_imp[i];
-      old.x = imp.x; old.y = imp.y;
-      if (vcCount == 2) { old.z = imp.z; old.w = imp.w; }
-      W.c_imp[i] = old;
-    }
-  }
+  if (W.tileKinematic || nG > 0) GB();      // (kinematic bodies were integrated in the global arrays: the position rows of every tile read them)
   if (rowsLocal && W.posIters > 0) mbar_wait(&rowBar, 1);
   MARK();
   // position iterations (:206-224) with the per-island early-out flags of k_solve

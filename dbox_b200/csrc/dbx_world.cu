@@ -1135,9 +1135,9 @@ int World::prepareTiles() {
   constexpr int kTileMinBodies = 2048, kTileMinPerTile = 256, kTileMaxPerTile = 4800, kTileSortPeriod = 16;
   if (replicated_ || overrideLevels_ || (dw_.dbgFlags & 64)) return 0;
   if (tilesDirty_) {
-    int n = 0;
-    for (const HBody& hb : bodies_) if (hb.alive && hb.st.type == DBX_DYNAMIC_BODY) ++n;
-    nDynamic_ = n; tilesDirty_ = false; tilesValid_ = false;
+    int n = 0, nk = 0;
+    for (const HBody& hb : bodies_) if (hb.alive) { if (hb.st.type == DBX_DYNAMIC_BODY) ++n; else if (hb.st.type == DBX_KINEMATIC_BODY) ++nk; }
+    nDynamic_ = n; dw_.tileKinematic = nk > 0 ? 1 : 0; tilesDirty_ = false; tilesValid_ = false;
   }
   if (nDynamic_ < kTileMinBodies) return 0;
   const int P = std::max(1, std::min(L_.coopBlocks, nDynamic_ / kTileMinPerTile));

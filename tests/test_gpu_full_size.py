@@ -310,7 +310,8 @@ def test_pile_single_step_matches_oracle(gpu_api, oracle_api, n, columns, settle
         r.update(order_found=found, position_backwards=info[0], colours=info[1], joint_colours=info[2], tiles=info[3], islands=cg.islands)
         print("pile %d single step, device vs oracle, continuous=%s: %s" % (n, continuous, r))
         print("pile %d single step, oracle vs oracle with angles + 1 ulp:  %s" % (n, own))
-        assert r["manifold"][0] == 0.0, r                            # bit for bit
+        # bit for bit after Solve; with the TOI sub-steps in, contacts are re-evaluated at positions that carry the deviation below
+        assert r["manifold"][0] == 0.0 if not continuous else r["manifold"][0] < 1e-5, r
         for q, tol in (("pos", 1e-5), ("vel", 1e-4), ("contact_impulse", 1e-4), ("joint_impulse", 1e-4)):
             worst, frac = r[q]
             own_worst, own_frac = own[q] if own else (0.0, 0.0)

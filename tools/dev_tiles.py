@@ -20,6 +20,7 @@ for base, name in ((0, "CTA 0"), (1024, "middle CTA")):
     # forward sweeps: 4 intervals each (L, publish+GB, B, GB+readback)
     for k in range(0, min(len(rest), 4 * 9), 4):
         print("  sweep %d: L %.1f  pub+GB %.1f  B %.1f  GB+rb %.1f" % tuple([k // 4] + rest[k:k + 4]) if len(rest) >= k + 4 else rest[k:])
+    print("  after the velocity passes (store impulses + integrate + GB | position passes ... | write-back + sleep):", " ".join("%.1f" % x for x in rest[36:]))
 for base, name in ((2048, "CTA 0"), (2048 + 128, "middle CTA")):
     print(name, "velocity pass 4, per local colour: (colour, items, cycles own item, cycles waiting at the barrier)")
     print("  ", [(int(buf[base + 4 * k + 3]), int(buf[base + 4 * k + 2]), int(buf[base + 4 * k]), int(buf[base + 4 * k + 1])) for k in range(12)])

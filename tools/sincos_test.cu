@@ -1,0 +1,22 @@
+#include <cstdio>
+#include <cstdint>
+#include <cstring>
+__global__ void k(unsigned long long* bad, unsigned start, unsigned count) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i < count; i += gridDim.x * blockDim.x) {
+    float x = __uint_as_float(start + i);
+    float s1 = sinf(x), c1 = cosf(x), s2, c2;
+    sincosf(x, &s2, &c2);
+    if (__float_as_uint(s1) != __float_as_uint(s2) || __float_as_uint(c1) != __float_as_uint(c2)) atomicAdd(bad, 1ull);
+  }
+}
+int main() {
+  unsigned long long* bad; cudaMallocManaged(&bad, 8); *bad = 0;
+  // every float in [2^-20, 2^20), both signs
+  unsigned lo = 0x35800000u, hi = 0x49800000u;
+  k<<<1184, 256>>>(bad, lo, hi - lo);
+  k<<<1184, 256>>>(bad, lo | 0x80000000u, hi - lo);
+  cudaDeviceSynchronize();
+  printf("sincosf vs sinf+cosf: %llu mismatches over %u values x 2 signs (%s)\n", *bad, hi - lo, cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
