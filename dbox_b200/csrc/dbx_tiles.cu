@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(256) k_tile_scatter(const __grid_constant__ De
 
 // ------------------------------------------------------------------------------------------------ the solver
 enum { TM_INIT = 0, TM_VEL = 1, TM_POS = 2 };
-constexpr int kTileBMax = 1024;      // boundary constraints one CTA re-colours locally (more: it walks them by global colour)
+constexpr int kTileThreads = 384;    // k_solve_tiles: a colour of a tile holds ~300 rows at most; fewer threads leave each more registers (measured: -7 us)
+constexpr int kTileBMax = 2 * kTileThreads;      // boundary constraints one CTA re-colours locally (more: it walks them by global colour)
 constexpr int kTileBColours = 32;
 
 // A constraint that works on rows in the GLOBAL arrays: item >= 0 is a contact row (solver slot), item < 0 a joint
@@ -175,7 +176,7 @@ DBX_D void bulk_g2s(void* dstSmem, const void* srcGlobal, unsigned bytes, unsign
                ::"r"(smem_u32(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(512) k_solve_tiles(const __grid_constant__ DevWorld W) {
+__global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_constant__ DevWorld W) {
   // dynamic shared memory: the tile's bodies [T] and as many of its local rows as fit [R]
   //   float4 vel[T] pos[T] | a0..a5[R] (velocity: v0 r0 r1 q0 q1 imp; position: p0 p1 p2 p3) | float2 mass[T] | int2 bd[R] | int body[T] flag[T] | int pc[R]
   extern __shared__ float4 sm4[];
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(512) k_solve_tiles(const __grid_constant__ Dev
     if (lt < kTileBColours) sBCnt[lt] = 0;
     if (fits && nB > 0) {
       for (int k = lt; k < 2 * T; k += ln) { sMask[k] = 0u; sClaim[k] = 0xFFFFFFFFu; }
-      // every thread keeps at most two items in registers (nB <= 1024 = 2 x 512)
+      // every thread keeps at most two items in registers (nB <= kTileBMax = 2 x kTileThreads)
       int item[2], ia[2], ib[2], lc[2]; unsigned pr[2];
       for (int u = 0; u < 2; ++u) {
         const int k = lt + u * ln;
@@ -649,7 +650,7 @@ cudaError_t stage_solve_tiles(const DevWorld& W, const LaunchCfg& L) {
   if ((L.coopLaunches++ & 1023) == 0) CK(cudaMemsetAsync(&W.hdr->barrier, 0, sizeof(unsigned), L.stream));   // see launch_coop
   void* args[] = {(void*)&W};
   ++L.launches;
-  return cudaLaunchCooperativeKernel((const void*)k_solve_tiles, dim3(L.coopBlocks), dim3(L.coopThreads), args, smem, L.stream);
+  return cudaLaunchCooperativeKernel((const void*)k_solve_tiles, dim3(L.coopBlocks), dim3(kTileThreads), args, smem, L.stream);
 }
 
 }  // namespace dbx
