@@ -83,6 +83,7 @@ struct Header {
   int toiSolved;      // TOI mini-islands solved by the current k_toi launch (sub-stepping stops at the first)
   unsigned long long toiGlobalMin;   // sub-stepping: smallest event priority of the current pass (the ONE event to handle)
   int nTileB, nTileG; // tile solver: boundary / global constraints (contacts + joints) of this step
+  unsigned long long solveStamp[4];   // %globaltimer of CTA 0 in the island solver: start, velocity passes begin, position passes begin, end (b2Profile split)
 };
 
 struct DevWorld {

@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld 
     if (dbgWin && threadIdx.x == 0 && barIdx >= dbgP0 && barIdx < dbgP0 + 8) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); W.phaseTimes[512 + ((barIdx - dbgP0) * nb + blockIdx.x) * 2 + 1] = t_; } \
     ++barIdx; PHASE_MARK(); } while (0)
   const bool haveTail = T < nColours && coff[T] < coff[nColours];
+  solve_stamp(W, 0);
 
   // contacts warm start (b2island.d:138-141): fold the per-body accumulators k_prepare filled into the velocities
   if (W.warmStarting) {
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld 
   const bool unified = W.unifiedColours != 0;
   const int nPhases = unified ? max(T, nJointColours) : nJointColours + T;
   VC pre; int preS = -1;
+  solve_stamp(W, 1);
   for (int it = 0; it < W.velIters; ++it) {
     for (int p = 0; p < nPhases; ++p) {
       const int jc = unified ? (p < nJointColours ? p : -1) : (p < nJointColours ? p : -1);
@@ -152,6 +154,7 @@ __global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld 
     }
   }
   GB();
+  solve_stamp(W, 2);
   // position iterations: contacts then joints, each island stops once all of its constraints are within tolerance
   // (:206-224).  Unified colours run from the highest colour down, so that every body again sees its contacts (higher
   // colours) before its joints; slot q of the pass is the tail colours, a contact colour, a joint colour or both.
@@ -200,6 +203,7 @@ __global__ void __launch_bounds__(512) k_solve(const __grid_constant__ DevWorld 
       if (any) GB();
     }
   }
+  solve_stamp(W, 3);
   // write back + SynchronizeTransform (:227-235), sleep bookkeeping (:241-269), ClearForces (b2world.d:443-450)
   {
     const float h = W.dt;

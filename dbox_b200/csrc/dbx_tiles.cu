@@ -224,6 +224,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   const int markBase = blockIdx.x == 0 ? 0 : 1024;
 #define MARK() do { if (marking && markIdx < 1000) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); W.phaseTimes[markBase + markIdx++] = t_; } } while (0)
   MARK();
+  if (W.phaseTimes != nullptr && lt == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); W.phaseTimes[3300 + blockIdx.x] = t_; }   // debug: start skew of the CTAs
   __syncthreads();
   MARK();
   const int rs0 = offL[0], nRows = offL[kTileColours] - rs0;        // the tile's local rows: one contiguous piece of the row arrays
@@ -494,7 +495,9 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
     }
   };
 
+  solve_stamp(W, 0);
   if (W.nJoints > 0) sweep(TM_INIT, nullptr, nullptr);                        // joints: InitVelocityConstraints + warm start (:143-146)
+  solve_stamp(W, 1);
   for (int it = 0; it < W.velIters; ++it) sweep(TM_VEL, nullptr, nullptr);    // :153-161
   // StoreImpulses (:164).  A tile's local rows hold their working impulses in shared memory: they go back to the row array
   // (PostSolve records read them there) and into the persistent manifolds from here; the position rows take their place.
@@ -552,6 +555,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   }
   if (W.tileKinematic || nG > 0) GB();      // (kinematic bodies were integrated in the global arrays: the position rows of every tile read them)
   if (rowsLocal && W.posIters > 0) mbar_wait(&rowBar, 1);
+  solve_stamp(W, 2);
   MARK();
   // position iterations (:206-224) with the per-island early-out flags of k_solve
   for (int it = 0; it < W.posIters; ++it) {
@@ -560,7 +564,8 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
     sweep(TM_POS, notOk, prev);     // (a pass starts with publish + grid barrier when islands can span tiles: the flags of the pass before are in)
     MARK();
   }
-  // write back + SynchronizeTransform (:227-235), sleep bookkeeping (:241-269); the claim / exchange scratch goes back to rest
+  solve_stamp(W, 3);
+  // write back + SynchronizeTransform (:227-235), sleep bookkeeping (:241-269); the exchange flags go back to rest
   {
     const float linTolSqr = kLinearSleepTolerance * kLinearSleepTolerance;
     const float angTolSqr = kAngularSleepTolerance * kAngularSleepTolerance;

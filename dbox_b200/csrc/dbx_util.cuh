@@ -94,6 +94,10 @@ DBX_D void uf_unite(int* parent, int a, int b, bool hashed) {
   if (b0 != a && parent[b0] != b0) parent[b0] = a;
 }
 
+// b2Profile's solveInit / solveVelocity / solvePosition split (b2timestep.d:37-47): the island solvers stamp their phases
+DBX_D void solve_stamp(const DevWorld& W, int k) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); W.hdr->solveStamp[k] = t; }
+}
 // global barrier for the persistent kernels: all CTAs are co-resident (cooperative launch, one per SM)
 DBX_D void grid_barrier(unsigned* counter, unsigned nblocks) {
   __syncthreads();

@@ -1247,7 +1247,7 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents, int halves) {
       if (tilesPath) CUDA_OR_FAIL(stage_colour_and_sort_tiles(dw_, L_), "colour (tiles)");
       else CUDA_OR_FAIL(stage_colour_and_sort(dw_, L_), "colour");
     }
-    lastTiled_ = tilesPath;
+    lastTiled_ = tilesPath; lastWorldsPath_ = worldsPath;
     mark(3);
     CUDA_OR_FAIL(stage_prepare(dw_, L_), "prepare");
     mark(4);
@@ -1966,6 +1966,16 @@ int World::profile(dbx_profile* out) {
   cudaEventElapsedTime(&total, ev_[0], ev_[9]);
   out->step = total; out->collide = collide; out->solve = pre + solve + bp; out->solveInit = pre; out->solveVelocity = solve;
   out->solvePosition = 0.0f; out->broadphase = bp; out->solveTOI = toi;
+  // the island solver is one kernel; it stamps %globaltimer where the reference's three timers sit (b2island.d:147, 166, 237) and
+  // its event time is split in those proportions (k_solve and k_solve_tiles; the world-local solver of batched replicas has no
+  // single timeline and reports everything as solveVelocity)
+  unsigned long long st[4] = {0, 0, 0, 0};
+  CUDA_OR_FAIL(cudaMemcpy(st, (char*)hdr_.p + offsetof(Header, solveStamp), sizeof(st), cudaMemcpyDeviceToHost), "read stamps");
+  if (!lastWorldsPath_ && st[3] > st[0] && st[1] >= st[0] && st[2] >= st[1] && st[3] >= st[2]) {
+    const double span = (double)(st[3] - st[0]);
+    const float init = (float)(solve * (double)(st[1] - st[0]) / span), pos = (float)(solve * (double)(st[3] - st[2]) / span);
+    out->solveInit = pre + init; out->solvePosition = pos; out->solveVelocity = solve - init - pos;
+  }
   return 0;
 }
 

@@ -110,11 +110,16 @@ class Tumbler:
         """tumbler.d:78-97: one new body per step at the container's centre; spawn_per_step > 1 (grow a big scene in fewer
         steps) lays the extra bodies out side by side, half a unit apart, instead of on top of each other"""
         self.world.Step(dt, vi, pi)
-        for k in range(spawn_per_step):
+        self.spawn(spawn_per_step)
+
+    def spawn(self, n=1):
+        """the body creation half of tumbler.d:84-96, `n` bodies side by side (also used to build a twin of a grown scene
+        without stepping it: same bodies in the same order, state transplanted afterwards)"""
+        for k in range(n):
             if self.m_count < self.count:
                 bd = b2BodyDef()
                 bd.type = b2_dynamicBody
-                bd.position.Set(f32(0.5 * (k - 0.5 * (spawn_per_step - 1))), 10.0 * self.scale)
+                bd.position.Set(f32(0.5 * (k - 0.5 * (n - 1))), 10.0 * self.scale)
                 body = self.world.CreateBody(bd)
                 if self.mixed and (self.m_count & 1):
                     shape = b2CircleShape(self.world._api)

@@ -24,6 +24,8 @@ for base, name in ((0, "CTA 0"), (1024, "middle CTA")):
 for base, name in ((2048, "CTA 0"), (2048 + 128, "middle CTA")):
     print(name, "velocity pass 4, per local colour: (colour, items, cycles own item, cycles waiting at the barrier)")
     print("  ", [(int(buf[base + 4 * k + 3]), int(buf[base + 4 * k + 2]), int(buf[base + 4 * k]), int(buf[base + 4 * k + 1])) for k in range(12)])
+st = [buf[3300 + i] for i in range(148) if buf[3300 + i]]
+print('CTA start skew: %d CTAs, last - first = %.1f us; sorted offsets (us):' % (len(st), (max(st) - min(st)) / 1000.), ' '.join('%.0f' % ((x - min(st)) / 1000.) for x in sorted(st)[::12]))
 hb = (C.c_int32 * 2400)()
 ga.world_debug_header(w._w, hb, 9600)
 c = w.counts()
