@@ -98,6 +98,72 @@ def algorithmic_bytes_solve(ct, nb, n_rev, n_dist, iv, ip):
     return contact + body + joints
 
 
+def algorithmic_bytes_step(c, n_rev, n_dist, iv, ip, proxies, pairs, rebuild_period=8):
+    """SURVEY.md 8(d), the whole step with the run's own counts: bytes_step = 232 Nb + (88 | 192 with LBVH rebuild) Np + 16 pairs
+    + 232 Cc + (568 + 212 Iv + 136 Ip) Ct + joints (prep + Iv vel + Ip pos)."""
+    joints = n_rev * (200 + 164 * iv + 120 * ip) + n_dist * (150 + 116 * iv + 112 * ip)
+    return (232 * c.awakeBodies + (88 + 104.0 / rebuild_period) * proxies + 16 * pairs + 232 * c.contacts
+            + (568 + 212 * iv + 136 * ip) * c.touching + joints)
+
+
+def time_gpu_steps(world, steps, vi, pi, flush=0):
+    tot = C.c_float()
+    rc = world._api.world_time_steps(world._w, DT, vi, pi, steps, flush, C.byref(tot), None)
+    assert rc >= 0, world._api.last_error()
+    return tot.value / steps
+
+
+def bench_small_configs(api, oracle_api, budget_s=90.0):
+    """BASELINE.md section 3's other rows, bounded in time: C1 hello_world and C2 Pyramid (latency-bound on a GPU: microseconds
+    per step, informational), C3 Tumbler at growing populations -- each with the CPU port beside it on the same state
+    (transplanted from the device world, so the CPU times the same scene without simulating its way there)."""
+    from dbox_b200 import scenes, state
+    out = {}
+    t_start = time.time()
+
+    def cpu_ms(world, steps, vi, pi):
+        arr = (C.c_void_p * 1)(world._w)
+        return 1e3 * oracle_api.batch_step(arr, 1, DT, vi, pi, steps, 1) / steps
+    # C1
+    wg, _ = scenes.hello_world(api=api); wo, _ = scenes.hello_world(api=oracle_api)
+    wg.StepN(DT, 6, 2, 3)
+    out["C1_hello_world"] = {"gpu_us_per_step": 1e3 * time_gpu_steps(wg, 60, 6, 2), "cpu_us_per_step": 1e3 * cpu_ms(wo, 60, 6, 2), "iters": "6v/2p", "steps": 60}
+    wg.close(); wo.close()
+    # C2: awake (first 150 steps) and after the pyramid has gone to sleep
+    wg, _ = scenes.pyramid(api=api); wo, _ = scenes.pyramid(api=oracle_api)
+    wg.StepN(DT, 8, 3, 20); wo.StepN(DT, 8, 3, 20)
+    g_awake, c_awake = time_gpu_steps(wg, 130, 8, 3), cpu_ms(wo, 130, 8, 3)
+    wg.StepN(DT, 8, 3, 250); wo.StepN(DT, 8, 3, 250)
+    out["C2_pyramid"] = {"gpu_us_per_step_awake": 1e3 * g_awake, "cpu_us_per_step_awake": 1e3 * c_awake,
+                         "gpu_us_per_step_asleep": 1e3 * time_gpu_steps(wg, 100, 8, 3), "cpu_us_per_step_asleep": 1e3 * cpu_ms(wo, 100, 8, 3),
+                         "awake_bodies_at_end": [wg.counts().awakeBodies, wo.counts().awakeBodies], "iters": "8v/3p"}
+    wg.close(); wo.close()
+    # C3: Tumbler (container x5, mixed boxes / circles), populations reached by spawning 8 bodies per step
+    rows = []
+    tg = scenes.Tumbler(api=api, count=20000, scale=5.0)
+    for target in (1000, 5000, 10000, 20000):
+        if time.time() - t_start > budget_s:
+            break
+        while tg.m_count < target:
+            tg.Step(DT, 8, 3, spawn_per_step=8)
+        for _ in range(60):
+            tg.world.Step(DT, 8, 3)
+        ms = time_gpu_steps(tg.world, 40, 8, 3)
+        row = {"bodies": tg.m_count, "gpu_steps_per_s": 1e3 / ms, "contacts": tg.world.counts().contacts}
+        cpu_steps = 6 if target <= 5000 else 3
+        to = scenes.Tumbler(api=oracle_api, count=20000, scale=5.0)
+        to.spawn(tg.m_count)
+        state.transplant(tg.world, to.world)
+        row["cpu_steps_per_s"] = 1e3 / cpu_ms(to.world, cpu_steps, 8, 3)
+        row["cpu_sample_steps"] = cpu_steps
+        to.world.close()
+        rows.append(row)
+    tg.world.close()
+    out["C3_tumbler"] = rows
+    out["seconds"] = time.time() - t_start
+    return out
+
+
 def run_cpu_port(n_bodies, columns, settle, steps, warmup, threads=1, replicas=1):
     """the reference algorithm's CPU path (oracle/liborc.so, a C++ restatement of dbox): one world per thread"""
     from oracle import orc
@@ -227,8 +293,17 @@ def bench_batched(api, args, rank, world_size, local_rank, barrier, torch):
     t0 = time.time()
     batch.run_pipelined(DT, VEL_ITERS, POS_ITERS, Ke, fp, op)
     barrier()
+    e2e_seconds = time.time() - t0
     local = batch.stats()
-    local.update(ms=ms, seconds=time.time() - t0, launches=launches, sync_seconds=sync_seconds)
+    sleeping_on = None
+    if not args.skip_extras:
+        # second figure: the same batch with sleeping on -- the work collapses once the pyramids rest
+        batch.world.SetAllowSleeping(True)
+        batch.step(DT, VEL_ITERS, POS_ITERS, 300)
+        ms_on, _ = batch.time_steps(DT, VEL_ITERS, POS_ITERS, 20, flush)
+        sleeping_on = {"ms_per_step_rank0": ms_on / 20, "value_rank0_share": batch.count * 20 / (ms_on / 1e3), "unit": "world-steps/s",
+                       "awake_bodies_rank0": int(batch.stats()["awake_bodies"]), "steps_after_enabling": 300}
+    local.update(ms=ms, seconds=e2e_seconds, launches=launches, sync_seconds=sync_seconds)
     tot = reduce_stats(local, maxima=("ms", "seconds", "sync_seconds"))          # the only collective of the batched path: final statistics (NCCL)
     out = {"workload": "C5: %d independent Pyramid worlds (20-row, %d bodies each, per-world random initial velocities), 60 Hz, %dv/%dp, "
                        "sleeping off, partitioned over %d GPU(s)" % (args.worlds, batch.bodies_per_world, VEL_ITERS, POS_ITERS, world_size),
@@ -242,6 +317,8 @@ def bench_batched(api, args, rank, world_size, local_rank, barrier, torch):
                    "mode": "pipelined act/step/observe (dbx_world_apply_forces_async / step_async / read_transforms_async): every step's H2D and D2H are inside the timed region, on copy streams beside the steps",
                    "synchronous_value": args.worlds * Ke / tot["sync_seconds"]},
            "gpu_launches": int(tot["launches"])}
+    if sleeping_on is not None:
+        out["sleeping_on"] = sleeping_on
     # k_solve_worlds (one CTA per replica, rows and bodies stay on chip between passes): compulsory HBM traffic is the rows
     # once (216 B), the impulses (16 + 32 B) and the sort entries (8 B) per solver contact, and 156 B per awake body
     # (velocity, position, transform, flags, sleep time in and out); DESIGN.md 7.2
@@ -276,6 +353,7 @@ def main():
     ap.add_argument("--cpu-warmup", type=int, default=1)
     ap.add_argument("--cpu-settle", type=int, default=240)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true", help="skip the sleeping-on second figures and the C1 / C2 / C3 rows")
     ap.add_argument("--worlds", type=int, default=65536, help="C5: independent Pyramid worlds in the batched leg (0 = skip the leg)")
     ap.add_argument("--batch-steps", type=int, default=100)
     ap.add_argument("--batch-settle", type=int, default=60)
@@ -434,6 +512,20 @@ def main():
     e2e_value = n_gpus * args.bodies * Ke / float(e2e_s.item())
     e2e_sync_value = n_gpus * args.bodies * Ke / float(e2e_sync_s.item())
 
+    # which island solver ran (tile solver: info[3] = tiles), and the second figure of BASELINE.md section 3: the same pile with sleeping ON
+    info = (C.c_int32 * 4)()
+    api.world_debug_read_solve_order(world._w, None, 0, None, 0, info)
+    tiles = int(info[3])
+    proxies, pairs = counts.proxies, counts.pairs
+    sleeping_on = None
+    if not args.skip_extras and rank == 0:
+        world.SetAllowSleeping(True)
+        world.StepN(DT, VEL_ITERS, POS_ITERS, 120)
+        ms_on = time_gpu_steps(world, 50, VEL_ITERS, POS_ITERS, flush)
+        c_on = world.counts()
+        sleeping_on = {"ms_per_step": ms_on, "value": args.bodies / (ms_on / 1e3), "unit": UNIT, "awake_bodies": c_on.awakeBodies,
+                       "note": "sleeping enabled 170 steps before the end of this window; a pile this deep keeps creeping, so only part of it rests"}
+        world.SetAllowSleeping(False)
     js, nj = world.read_joints()
     n_rev = sum(1 for i in range(nj) if js[i].type == A.JOINT_REVOLUTE)
     n_dist = sum(1 for i in range(nj) if js[i].type == A.JOINT_DISTANCE)
@@ -448,26 +540,39 @@ def main():
         solve_ms = stage_ms[4]
         alg = algorithmic_bytes_solve(counts.touching, counts.awakeBodies, n_rev, n_dist, VEL_ITERS, POS_ITERS)
         achieved = alg / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
-        traffic = None
+        traffic, traffic_src = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_solve_traffic.json"))).get("dram_bytes_per_launch")
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_solve_traffic.json" if tiles else "r01_solve_traffic.json")))
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_src = tj.get("source", "profiles/r01d_ncu_pile100k_summary.txt (k_solve, round 1 build)")
         except Exception:
             pass
+        alg_step = algorithmic_bytes_step(counts, n_rev, n_dist, VEL_ITERS, POS_ITERS, proxies, pairs)
+        kernel = ("k_solve_tiles (tile solver, %d tiles: bodies + local rows of a tile in shared memory via TMA bulk copies; " % tiles if tiles else "k_solve (persistent coloured Gauss-Seidel: ") + \
+                 "warm start + %d velocity + %d position iterations + write-back)" % (VEL_ITERS, POS_ITERS)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
                 "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": config, "steps_per_s_per_world": K / (total_ms / 1e3),
                 "counts": {"contacts": counts.contacts, "touching": counts.touching, "awake_bodies": counts.awakeBodies, "joints": counts.joints,
                            "colours": counts.colours, "islands": counts.islands},
                 "stage_ms": dict(zip(["collide", "islands", "colour_sort", "prepare", "solve", "sync_fixtures", "find_new_contacts", "toi", "clear_forces"], stage_ms)),
-                "roofline": {"bound": "hbm", "kernel": "k_solve (persistent coloured Gauss-Seidel: warm start + %d velocity + %d position iterations + write-back)" % (VEL_ITERS, POS_ITERS),
+                "roofline": {"bound": "hbm", "kernel": kernel,
                              "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                             "algorithmic_bytes_per_launch": alg, "kernel_ms": solve_ms, "traffic": traffic},
+                             "algorithmic_bytes_per_launch": alg, "kernel_ms": solve_ms, "traffic": traffic, "traffic_source": traffic_src},
+                "roofline_step": {"bound": "hbm", "what": "the whole step: SURVEY.md 8(d) bytes_step with this run's counts over ms_per_step",
+                                  "algorithmic_bytes_per_step": alg_step, "achieved": alg_step / (total_ms / K * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                  "frac": alg_step / (total_ms / K * 1e-3) / 1e9 / peak},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n, "steps": Ke,
                         "mode": "pipelined act/step/observe (dbx_world_apply_forces_async / step_async / read_transforms_async): every step's H2D and D2H are inside the timed region, on copy streams beside the steps",
                         "synchronous_value": e2e_sync_value},
                 "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall}
         if batched is not None:
             line["batched"] = batched
+        if sleeping_on is not None:
+            line["sleeping_on"] = sleeping_on
+        if n_gpus == 1 and not args.skip_extras:
+            from oracle import orc
+            line["other_configs"] = bench_small_configs(api, orc.api())
         if n_gpus == 1 and not args.skip_cpu_baseline:
             if batched is not None:
                 nw = cores * args.cpu_worlds_per_thread
