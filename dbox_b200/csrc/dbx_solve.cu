@@ -279,7 +279,7 @@ template <bool kLocal> __global__ void __launch_bounds__(128) k_solve_worlds(con
     const int beg = W.w_start[w], end = W.w_end[w];
     // (a replica with no solver contact -- asleep, or in free fall -- has beg == end: only the body loops do anything)
     const int b0 = w * bodiesPerWorld, b1 = b0 + bodiesPerWorld;
-    BodyView bvw; bvw.vel = sBodies; bvw.pos = sBodies + bodiesPerWorld; bvw.off = b0;
+    BodyView bvw; bvw.vel = sBodies; bvw.pos = sBodies + bodiesPerWorld; bvw.off = b0; bvw.mode = 1;
     const BodyView view = kLocal ? bvw : BodyView();
     // colour boundaries of this replica's slot range (sorted by colour): the slots where the colour changes, in order
     if (t == 0) ncol = 0;

@@ -152,21 +152,23 @@ struct BodyVel { v2 vA, vB; float wA, wB; };
 //   * with the tile view of k_solve_tiles: ref >= 0 is the body's position in tile order, owned by THIS CTA (shared memory at
 //     ref - off); ref < 0 carries a body id in its low 31 bits and means "not mine": a static / kinematic body, or a body of
 //     another tile that is currently published in the global arrays.
-struct BodyView { float4* vel = nullptr; float4* pos = nullptr; int off = 0; };   // passed by value; vel == nullptr: no view
+// passed by value.  mode (a literal at every construction site, so the branches below fold away after inlining):
+//   0 no view   1 every reference is a plain body id inside [off, off + n) (k_solve_worlds)   2 tile references (k_solve_tiles)
+struct BodyView { float4* vel = nullptr; float4* pos = nullptr; int off = 0; int mode = 0; };
 constexpr int kRefGlobal = (int)0x80000000;
 DBX_D float4 ld_vel(const DevWorld& W, BodyView view, int ref) {
-  if (view.vel && ref >= 0) return view.vel[ref - view.off];
+  if (view.mode == 1 || (view.mode == 2 && ref >= 0)) return view.vel[ref - view.off];
   return ldcg4(&W.b_vel[ref & 0x7fffffff]);
 }
 DBX_D void st_vel(const DevWorld& W, BodyView view, int ref, float4 v) {
-  if (view.vel && ref >= 0) view.vel[ref - view.off] = v; else stcg4(&W.b_vel[ref & 0x7fffffff], v);
+  if (view.mode == 1 || (view.mode == 2 && ref >= 0)) view.vel[ref - view.off] = v; else stcg4(&W.b_vel[ref & 0x7fffffff], v);
 }
 DBX_D float4 ld_pos(const DevWorld& W, BodyView view, int ref) {
-  if (view.vel && ref >= 0) return view.pos[ref - view.off];
+  if (view.mode == 1 || (view.mode == 2 && ref >= 0)) return view.pos[ref - view.off];
   return ldcg4(&W.b_pos[ref & 0x7fffffff]);
 }
 DBX_D void st_pos(const DevWorld& W, BodyView view, int ref, float4 v) {
-  if (view.vel && ref >= 0) view.pos[ref - view.off] = v; else stcg4(&W.b_pos[ref & 0x7fffffff], v);
+  if (view.mode == 1 || (view.mode == 2 && ref >= 0)) view.pos[ref - view.off] = v; else stcg4(&W.b_pos[ref & 0x7fffffff], v);
 }
 DBX_D BodyVel load_vel(const DevWorld& W, int2 bd, BodyView view = BodyView()) {
   const float4 a = ld_vel(W, view, bd.x), b = ld_vel(W, view, bd.y);
@@ -356,7 +358,7 @@ DBX_D void joint_init(const DevWorld& W, int j, BodyView view = BodyView()) {
   if (!joint_active(W, j)) { W.j_root[j] = -1; return; }   // later phases only look at j_root
   const int4 ids = W.j_ids[j];
   const int bA = ids.y, bB = ids.z;
-  const int2 jb = view.vel ? W.j_bref[j] : make_int2(bA, bB);   // how this joint's two bodies are reached (see BodyView)
+  const int2 jb = view.mode == 2 ? W.j_bref[j] : make_int2(bA, bB);   // how this joint's two bodies are reached (see BodyView)
   const float4 msA = W.b_mass[bA], msB = W.b_mass[bB];
   const float4 lcA4 = W.b_lc[bA], lcB4 = W.b_lc[bB];
   const float4 anc = W.j_anchor[j];
@@ -463,7 +465,7 @@ DBX_D void joint_init(const DevWorld& W, int j, BodyView view = BodyView()) {
 DBX_D void joint_solve_velocity(const DevWorld& W, int j, BodyView view = BodyView()) {
   const int4 ids = W.j_ids[j];
   const int bA = ids.y, bB = ids.z;
-  const int2 jb = view.vel ? W.j_bref[j] : make_int2(bA, bB);   // how this joint's two bodies are reached (see BodyView)
+  const int2 jb = view.mode == 2 ? W.j_bref[j] : make_int2(bA, bB);   // how this joint's two bodies are reached (see BodyView)
   const float4 m = W.j_m[j], r = W.j_r[j];
   const float mA = m.x, iA = m.y, mB = m.z, iB = m.w;
   const v2 rA = V(r.x, r.y), rB = V(r.z, r.w);
@@ -547,7 +549,7 @@ DBX_D void joint_solve_velocity(const DevWorld& W, int j, BodyView view = BodyVi
 DBX_D bool joint_solve_position(const DevWorld& W, int j, BodyView view = BodyView()) {
   const int4 ids = W.j_ids[j];
   const int bA = ids.y, bB = ids.z;
-  const int2 jb = view.vel ? W.j_bref[j] : make_int2(bA, bB);   // how this joint's two bodies are reached (see BodyView)
+  const int2 jb = view.mode == 2 ? W.j_bref[j] : make_int2(bA, bB);   // how this joint's two bodies are reached (see BodyView)
   const float4 m = W.j_m[j], lc = W.j_lc[j], anc = W.j_anchor[j];
   const float mA = m.x, iA = m.y, mB = m.z, iB = m.w;
   float4 pa = ld_pos(W, view, jb.x), pb = ld_pos(W, view, jb.y);

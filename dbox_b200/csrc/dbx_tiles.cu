@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   float2* sMass = (float2*)(ra5 + R);
   int2* rbd = (int2*)(sMass + T);
   int* sBody = (int*)(rbd + R); int* sFlag = sBody + T; int* rpc = sFlag + T;
-  BodyView view; view.vel = sVel; view.pos = sPos; view.off = s0;
+  BodyView view; view.vel = sVel; view.pos = sPos; view.off = s0; view.mode = 2;
   const BodyView noView;
   {
     const int baseG = 2 * P * kTileColours;

@@ -1115,6 +1115,7 @@ int World::findNewContacts(bool deferClear) {
 int World::growContactsIfNeeded() {
   if (!wmPending_ || cudaEventQuery(wmEv_) != cudaSuccess) return 0;
   wmPending_ = false;
+  seenMaxColour_ = std::max(seenMaxColour_, wm_[(int)(offsetof(Header, maxColour) / 4)]);   // (monotonic on the device; the tile solver looks at it)
   const size_t high = (size_t)std::max(wm_[0], 0);          // Header::cHigh
   // a small pool is watched more closely and grown by more: a scene that is just being filled (bodies born on top of each
   // other, tumbler.d:78-97) can double its contacts within a few steps, and the memory at stake is nothing
@@ -1134,6 +1135,10 @@ int World::growContactsIfNeeded() {
 int World::prepareTiles() {
   constexpr int kTileMinBodies = 2048, kTileMinPerTile = 256, kTileMaxPerTile = 4800, kTileSortPeriod = 16;
   if (replicated_ || overrideLevels_ || (dw_.dbgFlags & 64)) return 0;
+  // A body with more than 64 touching contacts (the Tumbler's container) serialises its surplus on overflow colours: hundreds of
+  // one-row phases.  k_solve runs those inside one CTA (its tail); the tile solver would make each a grid-wide phase.  The
+  // watermark copy of the device header (every 8th step, never waited for) tells when a world has such a hub.
+  if (seenMaxColour_ >= kTileColours) return 0;
   if (tilesDirty_) {
     int n = 0, nk = 0;
     for (const HBody& hb : bodies_) if (hb.alive) { if (hb.st.type == DBX_DYNAMIC_BODY) ++n; else if (hb.st.type == DBX_KINEMATIC_BODY) ++nk; }
@@ -1305,7 +1310,7 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents, int halves) {
   if ((stepCount_ & 63) == 0) { int rc2 = compactContacts(); if (rc2 < 0) return rc2; }
   if ((stepCount_ & (c_key.cap <= 65536 ? 1 : 7)) == 0 && !wmPending_) {
     if (!wm_) { CUDA_OR_FAIL(cudaMallocHost((void**)&wm_, 256), "watermark"); CUDA_OR_FAIL(cudaEventCreateWithFlags(&wmEv_, cudaEventDisableTiming), "watermark"); }
-    CUDA_OR_FAIL(cudaMemcpyAsync(wm_, hdr_.p, 64, cudaMemcpyDeviceToHost, stream_), "watermark");
+    CUDA_OR_FAIL(cudaMemcpyAsync(wm_, hdr_.p, 96, cudaMemcpyDeviceToHost, stream_), "watermark");      // cHigh ... maxColour
     CUDA_OR_FAIL(cudaEventRecord(wmEv_, stream_), "watermark");
     wmPending_ = true;
   }

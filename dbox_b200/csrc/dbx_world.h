@@ -233,6 +233,7 @@ class World {
   // the copy that has landed and doubles the pool before it can overflow
   int* wm_ = nullptr; cudaEvent_t wmEv_ = nullptr; bool wmPending_ = false; size_t contactFloor_ = 0;
   int growContactsIfNeeded();
+  int seenMaxColour_ = 0;
   // second stream for the overlapped TOI pre-evaluation (fork after the solver, join before k_toi)
   cudaStream_t aux_ = nullptr; cudaEvent_t evFork_ = nullptr, evJoin_ = nullptr; bool toiClean_ = false; size_t toiBodies_ = 0;
   std::vector<int> lastReadSlots_;
