@@ -1,0 +1,40 @@
+// dbox_b200 D shim -- replaces the module of the same name in d-gamedev-team/dbox (src/dbox/dynamics/...): same public names and
+// signatures, bodies forwarding to the extern(C) ABI of libdbox_b200.so (bindings/d/dbox_b200_c.d, generated from
+// include/dbox_b200.h).  Build recipe: INTEGRATION.md section 3.  No D compiler exists in the image this repository is built
+// in, so this file has not been compiled here; it is written against the reference's own declarations (cited per member).
+module dbox.dynamics.joints.b2motorjoint;
+
+import dbox.common;
+import dbox.dynamics.b2body;
+import dbox.dynamics.joints.b2joint;
+import dbox_b200_c;
+
+/// reference: dynamics/joints/b2motorjoint.d:36-87 (same fields and defaults; the joint itself is solved on the device: dbx_solver.cuh, dbx_joints2.cuh)
+class b2MotorJointDef : b2JointDef
+{
+    this() { type = b2JointType.e_motorJoint; }
+
+    void Initialize(b2Body* bA, b2Body* bB)
+    {
+        bodyA = bA; bodyB = bB;
+        b2Vec2 xB = bodyB.GetPosition();
+        linearOffset = bodyA.GetLocalPoint(xB);
+        angularOffset = bodyB.GetAngle() - bodyA.GetAngle();
+    }
+    b2Vec2 linearOffset = b2Vec2(0, 0);
+    float32 angularOffset = 0;
+    float32 maxForce = 1.0f;
+    float32 maxTorque = 1.0f;
+    float32 correctionFactor = 0.3f;
+
+    override dbx_joint_def toDevice() const
+    {
+        dbx_joint_def d = super.toDevice();
+        d.linearOffset = dbx_vec2(linearOffset.x, linearOffset.y);
+        d.angularOffset = angularOffset;
+        d.maxForce = maxForce;
+        d.maxTorque = maxTorque;
+        d.correctionFactor = correctionFactor;
+        return d;
+    }
+}

@@ -1,0 +1,49 @@
+// dbox_b200 D shim -- replaces the module of the same name in d-gamedev-team/dbox (src/dbox/dynamics/...): same public names and
+// signatures, bodies forwarding to the extern(C) ABI of libdbox_b200.so (bindings/d/dbox_b200_c.d, generated from
+// include/dbox_b200.h).  Build recipe: INTEGRATION.md section 3.  No D compiler exists in the image this repository is built
+// in, so this file has not been compiled here; it is written against the reference's own declarations (cited per member).
+module dbox.dynamics.joints.b2revolutejoint;
+
+import dbox.common;
+import dbox.dynamics.b2body;
+import dbox.dynamics.joints.b2joint;
+import dbox_b200_c;
+
+/// reference: dynamics/joints/b2revolutejoint.d:39-115 (same fields and defaults; the joint itself is solved on the device: dbx_solver.cuh, dbx_joints2.cuh)
+class b2RevoluteJointDef : b2JointDef
+{
+    this() { type = b2JointType.e_revoluteJoint; }
+
+    /// reference: :71-78
+    void Initialize(b2Body* bA, b2Body* bB, b2Vec2 anchor)
+    {
+        bodyA = bA; bodyB = bB;
+        localAnchorA = bodyA.GetLocalPoint(anchor);
+        localAnchorB = bodyB.GetLocalPoint(anchor);
+        referenceAngle = bodyB.GetAngle() - bodyA.GetAngle();
+    }
+    b2Vec2 localAnchorA = b2Vec2(0, 0);
+    b2Vec2 localAnchorB = b2Vec2(0, 0);
+    float32 referenceAngle = 0;
+    bool enableLimit = false;
+    float32 lowerAngle = 0;
+    float32 upperAngle = 0;
+    bool enableMotor = false;
+    float32 motorSpeed = 0;
+    float32 maxMotorTorque = 0;
+
+    override dbx_joint_def toDevice() const
+    {
+        dbx_joint_def d = super.toDevice();
+        d.localAnchorA = dbx_vec2(localAnchorA.x, localAnchorA.y);
+        d.localAnchorB = dbx_vec2(localAnchorB.x, localAnchorB.y);
+        d.referenceAngle = referenceAngle;
+        d.enableLimit = enableLimit ? 1 : 0;
+        d.lowerAngle = lowerAngle;
+        d.upperAngle = upperAngle;
+        d.enableMotor = enableMotor ? 1 : 0;
+        d.motorSpeed = motorSpeed;
+        d.maxMotorTorque = maxMotorTorque;
+        return d;
+    }
+}

@@ -236,6 +236,7 @@ PROTOTYPES = {
     "world_debug_phase_times": (c_i32, [W, P(C.c_uint64), c_i32]),
     "world_debug_header": (c_i32, [W, C.c_void_p, c_i32]),
     "debug_barrier_us": (c_f32, [c_i32, c_i32, c_i32, c_i32]),
+    "stats_allreduce": (c_i32, [C.c_void_p, C.c_void_p, P(C.c_double), c_i32, P(C.c_double), c_i32]),
     "world_replicate": (c_i32, [W, c_i32]),
     "world_replica_count": (c_i32, [W]),
     "world_export_state": (C.c_int64, [W, C.c_void_p, C.c_int64]),

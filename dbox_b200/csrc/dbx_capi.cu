@@ -1,4 +1,5 @@
 // dbx_capi.cu — the extern "C" boundary declared in include/dbox_b200.h.  Plain pointers and sizes only.
+#include <dlfcn.h>
 #include <cstring>
 #include <new>
 #include "dbx_world.h"
@@ -269,6 +270,36 @@ int32_t dbx_world_debug_phase_times(dbx_world* w, uint64_t* out, int32_t cap) { 
 int32_t dbx_world_debug_header(dbx_world* w, void* out, int32_t bytes) { W_OR_INVALID(w); return w->w.readHeader(out, bytes); }
 
 // ---- batched independent worlds
+// final statistics over the ranks: NCCL resolved at run time (no link dependency; the host program owns the communicator)
+int32_t dbx_stats_allreduce(void* comm, void* stream, double* sums, int32_t nSums, double* maxima, int32_t nMax) {
+  typedef int (*AllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  static AllReduceFn allReduce = nullptr;
+  if (!comm || nSums < 0 || nMax < 0 || (nSums > 0 && !sums) || (nMax > 0 && !maxima)) { set_last_error("stats_allreduce: bad arguments"); return DBX_E_INVALID; }
+  if (!allReduce) {
+    void* sym = dlsym(RTLD_DEFAULT, "ncclAllReduce");
+    if (!sym) { void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL); if (lib) sym = dlsym(lib, "ncclAllReduce"); }
+    if (!sym) { set_last_error("stats_allreduce: no NCCL in this process (ncclAllReduce not found, libnccl.so.2 not loadable)"); return DBX_E_UNSUPPORTED; }
+    allReduce = (AllReduceFn)sym;
+  }
+  const int kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;      // ncclDataType_t / ncclRedOp_t (nccl.h)
+  cudaStream_t st = (cudaStream_t)stream;
+  double* d = nullptr;
+  const size_t n = (size_t)nSums + (size_t)nMax;
+  if (n == 0) return 0;
+  if (cudaMalloc((void**)&d, n * sizeof(double)) != cudaSuccess) { set_last_error("stats_allreduce: cudaMalloc"); return DBX_E_CUDA; }
+  int rc = 0;
+  if (nSums) cudaMemcpyAsync(d, sums, (size_t)nSums * 8, cudaMemcpyHostToDevice, st);
+  if (nMax) cudaMemcpyAsync(d + nSums, maxima, (size_t)nMax * 8, cudaMemcpyHostToDevice, st);
+  if (nSums && allReduce(d, d, (size_t)nSums, kNcclFloat64, kNcclSum, comm, st) != 0) rc = DBX_E_CUDA;
+  if (!rc && nMax && allReduce(d + nSums, d + nSums, (size_t)nMax, kNcclFloat64, kNcclMax, comm, st) != 0) rc = DBX_E_CUDA;
+  if (!rc) {
+    if (nSums) cudaMemcpyAsync(sums, d, (size_t)nSums * 8, cudaMemcpyDeviceToHost, st);
+    if (nMax) cudaMemcpyAsync(maxima, d + nSums, (size_t)nMax * 8, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) rc = DBX_E_CUDA;
+  } else set_last_error("stats_allreduce: ncclAllReduce failed");
+  cudaFree(d);
+  return rc;
+}
 int32_t dbx_world_replicate(dbx_world* w, int32_t copies) { W_OR_INVALID(w); return w->w.replicate(copies); }
 int32_t dbx_world_replica_count(dbx_world* w) { W_OR_INVALID(w); return w->w.replicaCount(); }
 // ---- snapshot / restore (SURVEY.md 5 "checkpoint / resume"; the reference only has b2World.Dump, dynamics/b2world.d:796-855)

@@ -345,6 +345,13 @@ int32_t dbx_world_debug_header(dbx_world* w, void* out, int32_t bytes); /* raw c
 float dbx_debug_barrier_us(int32_t device, int32_t blocks, int32_t threads, int32_t iters); /* grid-barrier latency microbenchmark */
 
 /* ---- batched independent worlds (config 5): replicas of a template share one device world ---- */
+/* The one collective of the batched path: the end-of-run statistics of the ranks of a batch, reduced in
+ * place through the caller's NCCL communicator -- sums[0 .. nSums) summed, maxima[0 .. nMax) max-reduced (counts and times:
+ * world-steps, contacts, awake bodies; the slowest rank's seconds).  `ncclComm` is an ncclComm_t, `cudaStream` a cudaStream_t
+ * (NULL: the default stream).  The library does not link NCCL: it resolves ncclAllReduce from the NCCL the host program has
+ * already loaded (or libnccl.so.2).  Nothing in the stepping path communicates; the reference has no counterpart (a dbox user
+ * with many worlds steps many b2World objects, dynamics/b2world.d:34-40). */
+int32_t dbx_stats_allreduce(void* ncclComm, void* cudaStream, double* sums, int32_t nSums, double* maxima, int32_t nMax);
 int32_t dbx_world_replicate(dbx_world* w, int32_t copies);  /* world becomes `copies` disjoint replicas of its current content */
 int32_t dbx_world_replica_count(dbx_world* w);
 

@@ -641,3 +641,32 @@ def test_body_and_fixture_mutators(gpu_api, oracle_api):
             assert abs(pa.x - pb.x) < tol and abs(pa.y - pb.y) < tol and abs(a.GetAngle() - b.GetAngle()) < 5e-3, (k, i, (pa.x, pa.y), (pb.x, pb.y))
     assert 1.4 < bg[5].GetPosition().y < 1.7 and bg[1].GetPosition().y < 0.0 and bg[7].GetPosition().y > 2.0
     assert abs(bg[8].GetMass() - 3.0) < 1e-6 and abs(bg[3].GetMass() - 4.0) < 1e-5
+
+
+def test_stats_allreduce_through_nccl(gpu_api):
+    """dbx_stats_allreduce (the batched path's only collective): sums and maxima through a real NCCL
+    communicator created by the host program -- here a one-rank communicator from ncclCommInitAll, so the reduction must
+    hand back what went in; bad arguments are refused."""
+    import glob
+    import os
+    import sys
+    cands = [f for d in sys.path for f in sorted(glob.glob(os.path.join(d, "nvidia", "nccl", "lib", "libnccl.so*")))] + ["libnccl.so.2"]
+    nccl = None
+    for c in cands:
+        try:
+            nccl = C.CDLL(c, mode=C.RTLD_GLOBAL)
+            break
+        except OSError:
+            continue
+    if nccl is None:
+        pytest.skip("no NCCL library on this box")
+    comm = C.c_void_p()
+    devs = (C.c_int * 1)(0)
+    assert nccl.ncclCommInitAll(C.byref(comm), 1, devs) == 0
+    sums = (C.c_double * 3)(65536.0, 38.7e6, 13.9e6)
+    maxs = (C.c_double * 2)(19.5, 0.25)
+    assert gpu_api.stats_allreduce(comm, None, sums, 3, maxs, 2) == 0, gpu_api.last_error()
+    assert list(sums) == [65536.0, 38.7e6, 13.9e6] and list(maxs) == [19.5, 0.25]
+    assert gpu_api.stats_allreduce(None, None, sums, 3, maxs, 2) == A.DBX_E_INVALID
+    assert gpu_api.stats_allreduce(comm, None, None, 3, maxs, 2) == A.DBX_E_INVALID
+    nccl.ncclCommDestroy(comm)
