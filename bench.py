@@ -251,6 +251,7 @@ def bench_batched(api, args, rank, world_size, local_rank, barrier, torch):
     collective; only the final statistics are reduced), each rank's share as replicas inside one device world.  Every
     world gets its own random initial velocities (the RL reset), so the worlds do not evolve in lockstep."""
     import numpy as np
+    from dbox_b200 import _abi as A
     from dbox_b200 import scenes
     from dbox_b200.batch import WorldBatch, reduce_stats
     batch = WorldBatch(scenes.pyramid, args.worlds, rank, world_size, device=local_rank, api=api, contacts_per_world=700)
@@ -271,8 +272,10 @@ def bench_batched(api, args, rank, world_size, local_rank, barrier, torch):
     barrier()
     launches = api.world_launch_count(batch.world._w) - l0
     # e2e: RL-style loop, per step H2D of one force/torque record per body and D2H of every body transform
-    forces = torch.zeros((nb, 4), dtype=torch.float32).pin_memory()
-    xf_out = torch.empty((nb, 4), dtype=torch.float32).pin_memory()
+    # (12-byte records, DBX_IO_COMPACT: forces (fx, fy, torque) in, poses (x, y, angle) out)
+    assert api.world_set_io_format(batch.world._w, A.IO_COMPACT) == 0
+    forces = torch.zeros((nb, 3), dtype=torch.float32).pin_memory()
+    xf_out = torch.empty((nb, 3), dtype=torch.float32).pin_memory()
     Ke = min(K, 30)
     for _ in range(2):
         batch.apply_forces(forces.data_ptr()); batch.step(DT, VEL_ITERS, POS_ITERS); batch.read_transforms(xf_out.data_ptr())
@@ -285,8 +288,8 @@ def bench_batched(api, args, rank, world_size, local_rank, barrier, torch):
     barrier()
     sync_seconds = time.time() - t0
     # the same loop on the pipelined calls: the copies of step k ride on the copy streams beside steps k and k + 1
-    forces2 = torch.zeros((nb, 4), dtype=torch.float32).pin_memory()
-    xf_out2 = torch.empty((nb, 4), dtype=torch.float32).pin_memory()
+    forces2 = torch.zeros((nb, 3), dtype=torch.float32).pin_memory()
+    xf_out2 = torch.empty((nb, 3), dtype=torch.float32).pin_memory()
     fp, op = (forces.data_ptr(), forces2.data_ptr()), (xf_out.data_ptr(), xf_out2.data_ptr())
     batch.run_pipelined(DT, VEL_ITERS, POS_ITERS, 2, fp, op)
     barrier()
@@ -312,8 +315,8 @@ def bench_batched(api, args, rank, world_size, local_rank, barrier, torch):
            "body_steps_per_s": tot["bodies"] * K / (tot["ms"] / 1e3),
            "counts": {"bodies": int(tot["bodies"]), "contacts": int(tot["contacts"]), "touching": int(tot["touching"])},
            "stage_ms_rank0": dict(zip(["collide", "islands", "colour_sort", "prepare", "solve", "sync_fixtures", "find_new_contacts", "toi", "clear_forces"], stage_ms)),
-           "e2e": {"value": args.worlds * Ke / tot["seconds"], "unit": "world-steps/s", "h2d_bytes_per_step": 16 * int(tot["bodies"]),
-                   "d2h_bytes_per_step": 16 * int(tot["bodies"]), "steps": Ke,
+           "e2e": {"value": args.worlds * Ke / tot["seconds"], "unit": "world-steps/s", "h2d_bytes_per_step": 12 * int(tot["bodies"]),
+                   "d2h_bytes_per_step": 12 * int(tot["bodies"]), "steps": Ke, "record": "12 B per body each way (DBX_IO_COMPACT: forces fx fy torque in, poses x y angle out)",
                    "mode": "pipelined act/step/observe (dbx_world_apply_forces_async / step_async / read_transforms_async): every step's H2D and D2H are inside the timed region, on copy streams beside the steps",
                    "synchronous_value": args.worlds * Ke / tot["sync_seconds"]},
            "gpu_launches": int(tot["launches"])}
@@ -482,8 +485,9 @@ def main():
 
     # ---- e2e: same steps through the public API with host buffers (pinned), H2D + D2H inside the timed region
     n = args.bodies + 1
-    forces = torch.zeros((n, 4), dtype=torch.float32).pin_memory()
-    xf_out = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+    assert api.world_set_io_format(world._w, A.IO_COMPACT) == 0      # 12-byte records: forces (fx, fy, torque) in, poses (x, y, angle) out
+    forces = torch.zeros((n, 3), dtype=torch.float32).pin_memory()
+    xf_out = torch.empty((n, 3), dtype=torch.float32).pin_memory()
     Ke = min(K, 100)
     for _ in range(3):
         api.world_apply_forces(world._w, forces.data_ptr(), n); world.Step(DT, VEL_ITERS, POS_ITERS); api.world_read_transforms(world._w, xf_out.data_ptr(), n)
@@ -497,8 +501,8 @@ def main():
     e2e_sync_s = torch.tensor([time.time() - t0], dtype=torch.float64, device="cuda")
     # the same loop on the pipelined calls (copies on the copy streams beside the steps); this is the e2e headline
     from dbox_b200.batch import run_pipelined
-    forces2 = torch.zeros((n, 4), dtype=torch.float32).pin_memory()
-    xf_out2 = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+    forces2 = torch.zeros((n, 3), dtype=torch.float32).pin_memory()
+    xf_out2 = torch.empty((n, 3), dtype=torch.float32).pin_memory()
     fp, op = (forces.data_ptr(), forces2.data_ptr()), (xf_out.data_ptr(), xf_out2.data_ptr())
     run_pipelined(api, world._w, n, DT, VEL_ITERS, POS_ITERS, 3, fp, op)
     barrier()
@@ -562,7 +566,8 @@ def main():
                 "roofline_step": {"bound": "hbm", "what": "the whole step: SURVEY.md 8(d) bytes_step with this run's counts over ms_per_step",
                                   "algorithmic_bytes_per_step": alg_step, "achieved": alg_step / (total_ms / K * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                   "frac": alg_step / (total_ms / K * 1e-3) / 1e9 / peak},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n, "steps": Ke,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 12 * n, "d2h_bytes_per_step": 12 * n, "steps": Ke,
+                        "record": "12 B per body each way (DBX_IO_COMPACT: forces fx fy torque in, poses x y angle out)",
                         "mode": "pipelined act/step/observe (dbx_world_apply_forces_async / step_async / read_transforms_async): every step's H2D and D2H are inside the timed region, on copy streams beside the steps",
                         "synchronous_value": e2e_sync_value},
                 "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall}

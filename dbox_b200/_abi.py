@@ -18,6 +18,7 @@ MANIFOLD_CIRCLES, MANIFOLD_FACE_A, MANIFOLD_FACE_B = 0, 1, 2
 JOINT_REVOLUTE, JOINT_PRISMATIC, JOINT_DISTANCE, JOINT_PULLEY, JOINT_MOUSE, JOINT_GEAR = 1, 2, 3, 4, 5, 6
 JOINT_WHEEL, JOINT_WELD, JOINT_FRICTION, JOINT_ROPE, JOINT_MOTOR = 7, 8, 9, 10, 11
 WORLD_ALLOW_SLEEP, WORLD_WARM_STARTING, WORLD_CONTINUOUS, WORLD_SUB_STEPPING, WORLD_AUTO_CLEAR_FORCES = 1, 2, 4, 8, 0x10
+IO_FULL, IO_COMPACT = 0, 1      # dbx_world_set_io_format: 16-byte or 12-byte bulk I/O records
 WORLD_DEFAULT_FLAGS = 0x17
 
 
@@ -262,6 +263,7 @@ PROTOTYPES = {
     "world_apply_forces_async": (c_i32, [W, C.c_void_p, c_i32]),
     "world_read_transforms_async": (c_i32, [W, C.c_void_p, c_i32]),
     "world_io_wait": (c_i32, [W, c_i32]),
+    "world_set_io_format": (c_i32, [W, c_i32]),
     "world_sync": (c_i32, [W]),
     "world_poll_new_contacts": (c_i32, [W, P(c_i32), c_i32]),
 }

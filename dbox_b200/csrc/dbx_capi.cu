@@ -369,6 +369,7 @@ int32_t dbx_world_poll_new_contacts(dbx_world* w, int32_t* out, int32_t cap) { W
 int32_t dbx_world_step_async(dbx_world* w, float dt, int32_t vi, int32_t pi) { W_OR_INVALID(w); return w->w.stepAsync(dt, vi, pi); }
 int32_t dbx_world_apply_forces_async(dbx_world* w, const float* f, int32_t n) { W_OR_INVALID(w); return w->w.applyForcesAsync(f, n); }
 int32_t dbx_world_read_transforms_async(dbx_world* w, float* out, int32_t n) { W_OR_INVALID(w); return w->w.readTransformsAsync(out, n); }
+int32_t dbx_world_set_io_format(dbx_world* w, int32_t format) { W_OR_INVALID(w); return w->w.setIoFormat(format); }
 int32_t dbx_world_io_wait(dbx_world* w, int32_t ticket) { W_OR_INVALID(w); return w->w.ioWait(ticket); }
 int32_t dbx_world_sync(dbx_world* w) { W_OR_INVALID(w); return w->w.sync(); }
 int32_t dbx_joint_set_params(dbx_world* w, int32_t joint, const dbx_joint_def* def, uint32_t mask) { W_OR_INVALID(w); if (!def) return DBX_E_INVALID; return w->w.setJointParams(joint, *def, mask); }

@@ -326,6 +326,22 @@ __global__ void __launch_bounds__(256) k_apply_forces(const __grid_constant__ De
     W.b_force[b] = cur;
   }
 }
+// DBX_IO_COMPACT: 12-byte records (fx, fy, torque) in, (p.x, p.y, angle) out
+__global__ void __launch_bounds__(256) k_apply_forces3(const __grid_constant__ DevWorld W, const float* forces, int n) {
+  GRID_STRIDE(b, n) {
+    const uint32_t f = W.b_flags[b];
+    if (!(f & BF_ALIVE) || body_type(f) != BODY_DYNAMIC || !(f & BF_AWAKE)) continue;
+    float4 cur = W.b_force[b];
+    cur.x += forces[3 * b]; cur.y += forces[3 * b + 1]; cur.z += forces[3 * b + 2];
+    W.b_force[b] = cur;
+  }
+}
+__global__ void __launch_bounds__(256) k_pack_poses(const __grid_constant__ DevWorld W, float* out, int n) {
+  GRID_STRIDE(b, n) {
+    const float4 xf = W.b_xf[b];
+    out[3 * b] = xf.x; out[3 * b + 1] = xf.y; out[3 * b + 2] = W.b_pos[b].z;
+  }
+}
 __global__ void __launch_bounds__(256) k_clear_forces(const __grid_constant__ DevWorld W) {
   GRID_STRIDE(b, W.nBodies) W.b_force[b] = make_float4(0, 0, 0, 0);
 }
@@ -1820,6 +1836,14 @@ cudaError_t launch_set_states(const DevWorld& W, const LaunchCfg& L, const int* 
     ++L.launches; k_api_sync_tagged<<<L.gridWide, 256, 0, L.stream>>>(W);
     ++L.launches; k_api_untag<<<L.gridWide, 256, 0, L.stream>>>(W, ids, n);
   }
+  return cudaGetLastError();
+}
+cudaError_t launch_apply_forces3(const DevWorld& W, const LaunchCfg& L, const float* forces, int n) {
+  ++L.launches; k_apply_forces3<<<L.gridWide, 256, 0, L.stream>>>(W, forces, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_poses(const DevWorld& W, const LaunchCfg& L, float* out, int n) {
+  ++L.launches; k_pack_poses<<<L.gridWide, 256, 0, L.stream>>>(W, out, n);
   return cudaGetLastError();
 }
 cudaError_t launch_apply_forces(const DevWorld& W, const LaunchCfg& L, const float4* forces, int n) {

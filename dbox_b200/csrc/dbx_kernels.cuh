@@ -57,6 +57,8 @@ cudaError_t launch_api_wake(const DevWorld& W, const LaunchCfg& L, int a, int b)
 cudaError_t launch_set_motor_speeds(const DevWorld& W, const LaunchCfg& L, const int* slots, const float* speeds, int n);
 cudaError_t launch_set_states(const DevWorld& W, const LaunchCfg& L, const int* ids, const float4* pose, const float4* vel, int n);
 cudaError_t launch_apply_forces(const DevWorld& W, const LaunchCfg& L, const float4* forces, int n);
+cudaError_t launch_apply_forces3(const DevWorld& W, const LaunchCfg& L, const float* forces, int n);   // DBX_IO_COMPACT
+cudaError_t launch_pack_poses(const DevWorld& W, const LaunchCfg& L, float* out, int n);
 cudaError_t launch_clear_forces(const DevWorld& W, const LaunchCfg& L);
 cudaError_t launch_replicate(const DevWorld& W, const LaunchCfg& L, int nB, int nF, int nP, int nMoved, int keyStride, int copies);
 cudaError_t launch_set_levels(const DevWorld& W, const LaunchCfg& L, const int* d_levels, int n);

@@ -1406,8 +1406,9 @@ int World::applyForces(const float* f4, int n) {
   int rc = push(); if (rc < 0) return rc;
   if (n > (int)bodies_.size() * nWorlds_) return DBX_E_INVALID;
   CUDA_OR_FAIL(ioBuf_.reserve(std::max<size_t>(bodies_.size() * (size_t)nWorlds_, 1), false, stream_), "io buffer");
-  CUDA_OR_FAIL(cudaMemcpyAsync(ioBuf_.p, f4, (size_t)n * 16, cudaMemcpyHostToDevice, stream_), "forces h2d");
-  CUDA_OR_FAIL(launch_apply_forces(dw_, L_, ioBuf_.p, n), "apply_forces");
+  CUDA_OR_FAIL(cudaMemcpyAsync(ioBuf_.p, f4, (size_t)n * ioRecordBytes(), cudaMemcpyHostToDevice, stream_), "forces h2d");
+  if (ioCompact_) CUDA_OR_FAIL(launch_apply_forces3(dw_, L_, (const float*)ioBuf_.p, n), "apply_forces");
+  else CUDA_OR_FAIL(launch_apply_forces(dw_, L_, ioBuf_.p, n), "apply_forces");
   hostBodiesValid_ = false;
   return n;
 }
@@ -1754,7 +1755,11 @@ int World::pollContactEvents(dbx_contact_event* out, int cap) {
 int World::readTransforms(float* out, int n) {
   int rc = push(); if (rc < 0) return rc;
   if (n > (int)bodies_.size() * nWorlds_) return DBX_E_INVALID;
-  CUDA_OR_FAIL(cudaMemcpyAsync(out, b_xf.p, (size_t)n * 16, cudaMemcpyDeviceToHost, stream_), "xf d2h");
+  if (ioCompact_) {
+    CUDA_OR_FAIL(ioBuf2_.reserve(std::max<size_t>(bodies_.size() * (size_t)nWorlds_, 1), false, stream_), "io buffer");
+    CUDA_OR_FAIL(launch_pack_poses(dw_, L_, (float*)ioBuf2_.p, n), "pack poses");
+    CUDA_OR_FAIL(cudaMemcpyAsync(out, ioBuf2_.p, (size_t)n * 12, cudaMemcpyDeviceToHost, stream_), "poses d2h");
+  } else CUDA_OR_FAIL(cudaMemcpyAsync(out, b_xf.p, (size_t)n * 16, cudaMemcpyDeviceToHost, stream_), "xf d2h");
   CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
   return n;
 }
@@ -1791,10 +1796,11 @@ int World::applyForcesAsync(const float* f4, int n) {
     inReadValid_[k] = false;
   }
   if (inReadValid_[k]) CUDA_OR_FAIL(cudaStreamWaitEvent(h2d_, inRead_[k], 0), "staging reuse");   // its previous consumer has run
-  CUDA_OR_FAIL(cudaMemcpyAsync(inStage_[k].p, f4, (size_t)n * 16, cudaMemcpyHostToDevice, h2d_), "forces h2d");
+  CUDA_OR_FAIL(cudaMemcpyAsync(inStage_[k].p, f4, (size_t)n * ioRecordBytes(), cudaMemcpyHostToDevice, h2d_), "forces h2d");
   CUDA_OR_FAIL(cudaEventRecord(inCopied_[k], h2d_), "io event");
   CUDA_OR_FAIL(cudaStreamWaitEvent(stream_, inCopied_[k], 0), "forces ready");
-  CUDA_OR_FAIL(launch_apply_forces(dw_, L_, inStage_[k].p, n), "apply_forces");
+  if (ioCompact_) CUDA_OR_FAIL(launch_apply_forces3(dw_, L_, (const float*)inStage_[k].p, n), "apply_forces");
+  else CUDA_OR_FAIL(launch_apply_forces(dw_, L_, inStage_[k].p, n), "apply_forces");
   CUDA_OR_FAIL(cudaEventRecord(inRead_[k], stream_), "io event");
   inReadValid_[k] = true;
   hostBodiesValid_ = false;
@@ -1814,10 +1820,11 @@ int World::readTransformsAsync(float* out, int n) {
     outDoneValid_[k] = false;
   }
   if (outDoneValid_[k]) CUDA_OR_FAIL(cudaStreamWaitEvent(stream_, outDone_[k], 0), "snapshot reuse");   // the read two tickets ago has left
-  CUDA_OR_FAIL(cudaMemcpyAsync(outSnap_[k].p, b_xf.p, (size_t)n * 16, cudaMemcpyDeviceToDevice, stream_), "xf snapshot");
+  if (ioCompact_) CUDA_OR_FAIL(launch_pack_poses(dw_, L_, (float*)outSnap_[k].p, n), "pose snapshot");
+  else CUDA_OR_FAIL(cudaMemcpyAsync(outSnap_[k].p, b_xf.p, (size_t)n * 16, cudaMemcpyDeviceToDevice, stream_), "xf snapshot");
   CUDA_OR_FAIL(cudaEventRecord(snapReady_[k], stream_), "io event");
   CUDA_OR_FAIL(cudaStreamWaitEvent(d2h_, snapReady_[k], 0), "snapshot ready");
-  CUDA_OR_FAIL(cudaMemcpyAsync(out, outSnap_[k].p, (size_t)n * 16, cudaMemcpyDeviceToHost, d2h_), "xf d2h");
+  CUDA_OR_FAIL(cudaMemcpyAsync(out, outSnap_[k].p, (size_t)n * ioRecordBytes(), cudaMemcpyDeviceToHost, d2h_), "xf d2h");
   CUDA_OR_FAIL(cudaEventRecord(outDone_[k], d2h_), "io event");
   outDoneValid_[k] = true;
   return ticket;

@@ -132,6 +132,7 @@ class World {
   int readPairs(int32_t* out, int cap);
   int stageFindNewContacts();
   int stageCollide();
+  int setIoFormat(int format) { if (format != 0 && format != 1) return DBX_E_INVALID; ioCompact_ = format == 1; return 0; }
   int setContactLevels(const int32_t* levels, int n);
   // snapshot / restore: the tile solver's body-to-tile assignment is not part of a snapshot; both sides of an export / import
   // re-derive it from the body positions at that moment, so a restored world keeps stepping bit for bit like the original
@@ -233,6 +234,7 @@ class World {
   // the copy that has landed and doubles the pool before it can overflow
   int* wm_ = nullptr; cudaEvent_t wmEv_ = nullptr; bool wmPending_ = false; size_t contactFloor_ = 0;
   int growContactsIfNeeded();
+  bool ioCompact_ = false; size_t ioRecordBytes() const { return ioCompact_ ? 12 : 16; }
   int seenMaxColour_ = 0;
   // second stream for the overlapped TOI pre-evaluation (fork after the solver, join before k_toi)
   cudaStream_t aux_ = nullptr; cudaEvent_t evFork_ = nullptr, evJoin_ = nullptr; bool toiClean_ = false; size_t toiBodies_ = 0;

@@ -670,3 +670,34 @@ def test_stats_allreduce_through_nccl(gpu_api):
     assert gpu_api.stats_allreduce(None, None, sums, 3, maxs, 2) == A.DBX_E_INVALID
     assert gpu_api.stats_allreduce(comm, None, None, 3, maxs, 2) == A.DBX_E_INVALID
     nccl.ncclCommDestroy(comm)
+
+
+def test_compact_io_records_equal_the_full_ones(gpu_api):
+    """dbx_world_set_io_format(DBX_IO_COMPACT): 12-byte force / pose records move the same numbers as the 16-byte ones --
+    a pyramid pushed by the same per-body forces through both formats evolves bit for bit alike, and the poses read back are
+    (p.x, p.y, angle) of the transforms; the pipelined calls follow the format too."""
+    import numpy as np
+    wa, _ = scenes.pyramid(api=gpu_api); wb, _ = scenes.pyramid(api=gpu_api)
+    n = wa.counts().bodies
+    rng = np.random.RandomState(5)
+    f4 = np.zeros((n, 4), np.float32); f4[:, :3] = rng.uniform(-30, 30, (n, 3))
+    f3 = np.ascontiguousarray(f4[:, :3])
+    assert gpu_api.world_set_io_format(wb._w, A.IO_COMPACT) == 0
+    assert gpu_api.world_set_io_format(wb._w, 7) == A.DBX_E_INVALID
+    xf = np.zeros((n, 4), np.float32); pose = np.zeros((n, 3), np.float32)
+    for k in range(40):
+        assert gpu_api.world_apply_forces(wa._w, f4.ctypes.data, n) == n
+        assert gpu_api.world_apply_forces(wb._w, f3.ctypes.data, n) == n
+        wa.Step(DT, 8, 3); wb.Step(DT, 8, 3)
+    assert gpu_api.world_read_transforms(wa._w, xf.ctypes.data, n) == n
+    assert gpu_api.world_read_transforms(wb._w, pose.ctypes.data, n) == n
+    sa, _ = wa.read_bodies(); sb, _ = wb.read_bodies()
+    for i in range(n):
+        assert (sa[i].c.x, sa[i].c.y, sa[i].a, sa[i].v.x, sa[i].w) == (sb[i].c.x, sb[i].c.y, sb[i].a, sb[i].v.x, sb[i].w), i
+        assert (pose[i, 0], pose[i, 1]) == (xf[i, 0], xf[i, 1]) and pose[i, 2] == np.float32(sb[i].a)
+    # pipelined calls, compact: the same numbers arrive
+    pose2 = np.zeros((n, 3), np.float32)
+    t = gpu_api.world_read_transforms_async(wb._w, pose2.ctypes.data, n)
+    assert t > 0 and gpu_api.world_io_wait(wb._w, t) == 0 and gpu_api.world_sync(wb._w) == 0
+    assert np.array_equal(pose, pose2)
+    wa.close(); wb.close()
