@@ -1,6 +1,7 @@
 """Feature-by-feature parity of the CUDA path (through the C ABI) against the oracle: each scene exercises one part of the
 step pipeline in a configuration where the Gauss-Seidel order cannot matter (one constraint per body, or islands of one
 body), so the two sides must agree to float rounding, not just statistically."""
+import ctypes as C
 import math
 
 import pytest
