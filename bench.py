@@ -433,6 +433,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world_size > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version / debug lines must not share stdout with the JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world_size, device_id=torch.device("cuda", local_rank))
     from dbox_b200 import _abi as A
     from dbox_b200 import lib, scenes
