@@ -122,6 +122,7 @@ enum { TM_INIT = 0, TM_VEL = 1, TM_POS = 2 };
 constexpr int kTileThreads = 384;    // k_solve_tiles: a colour of a tile holds ~300 rows at most; fewer threads leave each more registers (measured: -7 us)
 constexpr int kTileBMax = 2 * kTileThreads;      // boundary constraints one CTA re-colours locally (more: it walks them by global colour)
 constexpr int kTileBColours = 32;
+constexpr int kTileJointsMax = 512;  // local joints of a tile that may live in shared memory
 
 // A constraint that works on rows in the GLOBAL arrays: item >= 0 is a contact row (solver slot), item < 0 a joint
 // (~joint slot).  Boundary and global phases, all joints, and the local rows of a tile too big for shared memory come here;
@@ -185,6 +186,8 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   __shared__ int phL[kTileColours], nPhL;          // the local colours that hold anything, in order
   __shared__ int sBItem[kTileBMax], sBOff[kTileBColours + 1], sBCnt[kTileBColours], nPhB, bDirect;
   __shared__ unsigned long long rowBar;             // mbarrier of the row staging copies
+  __shared__ DevWorld sW;                           // W with the joint arrays pointing at the tile's shared-memory copies (local joints)
+  __shared__ int jointsBad;
   Header* H = W.hdr;
   const unsigned nb = gridDim.x;
   const int lt = threadIdx.x, ln = blockDim.x;
@@ -193,12 +196,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   const int tile = blockIdx.x;
   const int s0 = tile * T, n = tile < P ? max(0, min(T, W.nTileBodies - s0)) : 0;
   unsigned dynBytes; asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dynBytes));
-  const int R = (int)(((long long)dynBytes - 48ll * T) / 108) & ~1;
   float4* sVel = sm4; float4* sPos = sm4 + T;
-  float4* ra0 = sm4 + 2 * T; float4* ra1 = ra0 + R; float4* ra2 = ra1 + R; float4* ra3 = ra2 + R; float4* ra4 = ra3 + R; float4* ra5 = ra4 + R;
-  float2* sMass = (float2*)(ra5 + R);
-  int2* rbd = (int2*)(sMass + T);
-  int* sBody = (int*)(rbd + R); int* sFlag = sBody + T; int* rpc = sFlag + T;
   BodyView view; view.vel = sVel; view.pos = sPos; view.off = s0; view.mode = 2;
   const BodyView noView;
   {
@@ -228,6 +226,17 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   __syncthreads();
   MARK();
   const int rs0 = offL[0], nRows = offL[kTileColours] - rs0;        // the tile's local rows: one contiguous piece of the row arrays
+  // the tile's local joints (revolute / distance) move into shared memory too when they fit beside the rows: 192 B each
+  const int jl0 = joffL[0], nJL = tile < P ? joffL[kTileColours] - jl0 : 0;
+  const int R0 = (int)(((long long)dynBytes - 48ll * T) / 108) & ~1;
+  const int Rj = (int)(((long long)dynBytes - 48ll * T - 192ll * nJL - 32) / 108) & ~1;
+  const bool jointRoom = nJL > 0 && nJL <= kTileJointsMax && Rj > 0 && nRows <= Rj && !(W.dbgFlags & 2048);
+  const int R = jointRoom ? Rj : R0;
+  float4* ra0 = sm4 + 2 * T; float4* ra1 = ra0 + R; float4* ra2 = ra1 + R; float4* ra3 = ra2 + R; float4* ra4 = ra3 + R; float4* ra5 = ra4 + R;
+  float2* sMass = (float2*)(ra5 + R);
+  int2* rbd = (int2*)(sMass + T);
+  int* sBody = (int*)(rbd + R); int* sFlag = sBody + T; int* rpc = sFlag + T;
+  float4* sj = (float4*)(((size_t)(rpc + R) + 15) & ~(size_t)15);  // joints: 11 float4 arrays [nJL], then bref int2, limit, root
   const bool rowsLocal = nRows > 0 && nRows <= R;                   // they fit: they live in shared memory for the whole solve
   if (lt == 0) {
     // the tile's local rows into shared memory: the six float4 arrays as TMA bulk copies, under way while the boundary rows
@@ -312,6 +321,31 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   MARK();
 
   if (rowsLocal) for (int k = lt; k < nRows; k += ln) { rbd[k] = W.s_body[rs0 + k]; rpc[k] = W.s_pc[rs0 + k]; }
+  // local joints in: definition, accumulated impulses, limit state, body references; the per-step temporaries are written by
+  // their own joint_init.  sW is W with the joint arrays redirected, indexed by the joint's position in the tile's list.
+  float4* sjIds = sj; float4* sjAnchor = sj + nJL; float4* sjP0 = sj + 2 * nJL; float4* sjP1 = sj + 3 * nJL; float4* sjImp = sj + 4 * nJL;
+  int2* sjBref = (int2*)(sj + 11 * nJL); int* sjLimit = (int*)(sjBref + nJL); int* sjRoot = sjLimit + nJL;
+  if (lt == 0) jointsBad = 0;
+  __syncthreads();
+  if (jointRoom) {
+    static_assert(sizeof(DevWorld) % 4 == 0, "DevWorld is copied word by word");
+    for (int k = lt; k < (int)(sizeof(DevWorld) / 4); k += ln) ((int*)&sW)[k] = ((const int*)&W)[k];
+    for (int x = lt; x < nJL; x += ln) {
+      const int j = W.tj_order[jl0 + x];
+      const int4 ids = W.j_ids[j];
+      if (ids.x != JT_REVOLUTE && ids.x != JT_DISTANCE) jointsBad = 1;        // (other joint types read more arrays: they stay in L2)
+      ((int4*)sjIds)[x] = ids; sjAnchor[x] = W.j_anchor[j]; sjP0[x] = W.j_p0[j]; sjP1[x] = W.j_p1[j]; sjImp[x] = W.j_imp[j];
+      sjBref[x] = W.j_bref[j]; sjLimit[x] = W.j_limit[j]; sjRoot[x] = -1;
+    }
+  }
+  __syncthreads();
+  const bool jointsLocal = jointRoom && jointsBad == 0;
+  if (jointsLocal && lt == 0) {
+    sW.j_ids = (int4*)sjIds; sW.j_anchor = sjAnchor; sW.j_p0 = sjP0; sW.j_p1 = sjP1; sW.j_imp = sjImp;
+    sW.j_r = sj + 5 * nJL; sW.j_lc = sj + 6 * nJL; sW.j_m = sj + 7 * nJL; sW.j_k0 = sj + 8 * nJL; sW.j_k1 = sj + 9 * nJL; sW.j_k2 = sj + 10 * nJL;
+    sW.j_bref = sjBref; sW.j_limit = sjLimit; sW.j_root = sjRoot;
+  }
+  __syncthreads();
   // bodies in: velocities with the contacts' warm start folded in (see k_solve), positions, inverse masses, ids, exchange flags
   {
     const float k = 1.0f / 4294967296.0f;
@@ -347,7 +381,8 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
       const bool fine = marking && sweepNo == 4 && kk < 16;       // debug: clock stamps of one velocity pass at [2048 + 4 kk ..)
       long long c0 = 0, c1 = 0;
       if (fine) c0 = clock64();
-      for (int q = lt; q < nj; q += ln) tile_item(W, view, mode, ~W.tj_order[jb + q], notOk, prev);
+      if (jointsLocal) { for (int q = lt; q < nj; q += ln) tile_item(sW, view, mode, ~(jb - jl0 + q), notOk, prev); }
+      else for (int q = lt; q < nj; q += ln) tile_item(W, view, mode, ~W.tj_order[jb + q], notOk, prev);
       if (mode != TM_INIT) {
         if (rowsLocal) {
           // (row q of the colour belongs to thread q - nj, as in the global layout, so a jointed colour spreads over all warps)
@@ -564,6 +599,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
     sweep(TM_POS, notOk, prev);     // (a pass starts with publish + grid barrier when islands can span tiles: the flags of the pass before are in)
     MARK();
   }
+  if (jointsLocal) for (int x = lt; x < nJL; x += ln) { const int j = W.tj_order[jl0 + x]; W.j_imp[j] = sjImp[x]; W.j_limit[j] = sjLimit[x]; W.j_root[j] = sjRoot[x]; }
   solve_stamp(W, 3);
   // write back + SynchronizeTransform (:227-235), sleep bookkeeping (:241-269); the exchange flags go back to rest
   {
