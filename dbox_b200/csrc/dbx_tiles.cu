@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(256) k_tile_scatter(const __grid_constant__ De
 // ------------------------------------------------------------------------------------------------ the solver
 enum { TM_INIT = 0, TM_VEL = 1, TM_POS = 2 };
 constexpr int kTileThreads = 384;    // k_solve_tiles: a colour of a tile holds ~300 rows at most; fewer threads leave each more registers (measured: -7 us)
+constexpr int kTileNbrMax = 192;                 // bodies of the right-hand neighbour a CTA's boundary constraints may stage in shared memory
 constexpr int kTileBMax = 2 * kTileThreads;      // boundary constraints one CTA re-colours locally (more: it walks them by global colour)
 constexpr int kTileBColours = 32;
 constexpr int kTileJointsMax = 512;  // local joints of a tile that may live in shared memory
@@ -182,7 +183,8 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   //   float4 vel[T] pos[T] | a0..a5[R] (velocity: v0 r0 r1 q0 q1 imp; position: p0 p1 p2 p3) | float2 mass[T] | int2 bd[R] | int body[T] flag[T] | int pc[R]
   extern __shared__ float4 sm4[];
   __shared__ int offL[kTileColours + 1], joffL[kTileColours + 1], offB[kTileColours + 1], joffB[kTileColours + 1];
-  __shared__ int offG[kMaxColours + 1], joffG[kTileColours + 1];
+  __shared__ int joffG[kTileColours + 1];
+  __shared__ int sNbrBody[kTileNbrMax], nNbr;       // the neighbour's bodies the boundary constraints reach: ids, count
   __shared__ int phL[kTileColours], nPhL;          // the local colours that hold anything, in order
   __shared__ int sBItem[kTileBMax], sBOff[kTileBColours + 1], sBCnt[kTileBColours], nPhB, bDirect;
   __shared__ unsigned long long rowBar;             // mbarrier of the row staging copies
@@ -196,7 +198,9 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   const int tile = blockIdx.x;
   const int s0 = tile * T, n = tile < P ? max(0, min(T, W.nTileBodies - s0)) : 0;
   unsigned dynBytes; asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dynBytes));
-  float4* sVel = sm4; float4* sPos = sm4 + T;
+  const int TX = T + kTileNbrMax;                   // body slots: the tile's own [0, T), staged neighbour bodies [T, T + nNbr)
+  float4* sVel = sm4; float4* sPos = sm4 + TX;
+  const int* offG = W.t_off + 2 * P * kTileColours; // (global rows are the rare case: their offsets stay in L2)
   BodyView view; view.vel = sVel; view.pos = sPos; view.off = s0; view.mode = 2;
   const BodyView noView;
   {
@@ -208,8 +212,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
       } else { offL[c] = offB[c] = joffL[c] = joffB[c] = 0; }
       joffG[c] = W.tj_off[baseG + c];
     }
-    for (int c = lt; c <= kMaxColours; c += ln) offG[c] = W.t_off[baseG + c];
-    if (lt == 0) mbar_init(&rowBar, 1);
+    if (lt == 0) { mbar_init(&rowBar, 1); nNbr = 0; }
   }
   const int nColours = H->nColours;
   const int nG = H->nTileG, nCross = H->nTileB + nG;      // uniform over the grid
@@ -228,11 +231,12 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   const int rs0 = offL[0], nRows = offL[kTileColours] - rs0;        // the tile's local rows: one contiguous piece of the row arrays
   // the tile's local joints (revolute / distance) move into shared memory too when they fit beside the rows: 192 B each
   const int jl0 = joffL[0], nJL = tile < P ? joffL[kTileColours] - jl0 : 0;
-  const int R0 = (int)(((long long)dynBytes - 48ll * T) / 108) & ~1;
-  const int Rj = (int)(((long long)dynBytes - 48ll * T - 192ll * nJL - 32) / 108) & ~1;
+  const long long bodyBytes = 48ll * T + 32ll * kTileNbrMax;
+  const int R0 = (int)(((long long)dynBytes - bodyBytes) / 108) & ~1;
+  const int Rj = (int)(((long long)dynBytes - bodyBytes - 192ll * nJL - 32) / 108) & ~1;
   const bool jointRoom = nJL > 0 && nJL <= kTileJointsMax && Rj > 0 && nRows <= Rj && !(W.dbgFlags & 2048);
   const int R = jointRoom ? Rj : R0;
-  float4* ra0 = sm4 + 2 * T; float4* ra1 = ra0 + R; float4* ra2 = ra1 + R; float4* ra3 = ra2 + R; float4* ra4 = ra3 + R; float4* ra5 = ra4 + R;
+  float4* ra0 = sm4 + 2 * TX; float4* ra1 = ra0 + R; float4* ra2 = ra1 + R; float4* ra3 = ra2 + R; float4* ra4 = ra3 + R; float4* ra5 = ra4 + R;
   float2* sMass = (float2*)(ra5 + R);
   int2* rbd = (int2*)(sMass + T);
   int* sBody = (int*)(rbd + R); int* sFlag = sBody + T; int* rpc = sFlag + T;
@@ -259,16 +263,16 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
     const int nBJ = joffB[kTileColours] - joffB[0], nBC = offB[kTileColours] - offB[0], nB = nBJ + nBC;
     unsigned* sMask = (unsigned*)sMass;               // scratch in the tail of the dynamic area (masses, references, ids: filled afterwards)
     unsigned* sClaim = sMask + 2 * T;                 // [2T] each: own tile's bodies [0, T), the right-hand neighbour's [T, 2T)
-    const bool fits = nB <= kTileBMax && (size_t)16 * T <= (size_t)dynBytes;
+    const bool fits = nB <= kTileBMax && R0 > 0 && (size_t)16 * T <= (size_t)dynBytes - (size_t)(32 * TX + 96 * R);
     if (lt == 0) { bDirect = fits ? 0 : 1; nPhB = 0; }
     if (lt < kTileBColours) sBCnt[lt] = 0;
     if (fits && nB > 0) {
       for (int k = lt; k < 2 * T; k += ln) { sMask[k] = 0u; sClaim[k] = 0xFFFFFFFFu; }
       // every thread keeps at most two items in registers (nB <= kTileBMax = 2 x kTileThreads)
-      int item[2], ia[2], ib[2], lc[2]; unsigned pr[2];
+      int item[2], ia[2], ib[2], lc[2]; unsigned pr[2]; int2 brs[2];
       for (int u = 0; u < 2; ++u) {
         const int k = lt + u * ln;
-        item[u] = 0; ia[u] = ib[u] = -1; lc[u] = k < nB ? -1 : 0; pr[u] = 0xFFFFFFFFu;
+        item[u] = 0; ia[u] = ib[u] = -1; lc[u] = k < nB ? -1 : 0; pr[u] = 0xFFFFFFFFu; brs[u] = make_int2(-1, -1);
         if (k >= nB) continue;
         int2 br;
         if (k < nBJ) { const int j = W.tj_order[joffB[0] + k]; item[u] = ~j; br = W.j_bref[j]; pr[u] = ((unsigned)(mix64((unsigned long long)j + 1ull) >> 33)) & 0x7FFFFC00u; }
@@ -281,6 +285,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
         // index of each body in the scratch: own tile [0, T), the neighbour's [T, 2T), -1 for a body nobody moves
         if (br.x >= 0) ia[u] = br.x - s0; else { const int sl = W.b_tslot[br.x & 0x7fffffff]; if (sl >= 0) ia[u] = sl - s0; }
         if (br.y >= 0) ib[u] = br.y - s0; else { const int sl = W.b_tslot[br.y & 0x7fffffff]; if (sl >= 0) ib[u] = sl - s0; }
+        brs[u] = br;
       }
       __syncthreads();
       for (int round = 0; round < 4096; ++round) {
@@ -314,10 +319,34 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
         sBItem[atomicAdd(&sBCnt[lc[u]], 1)] = item[u];
         if (item[u] >= 0) W.c_tcol[W.s_contact[item[u]]] = lc[u]; else W.j_tcol[~item[u]] = lc[u];    // for dbx_world_debug_read_solve_order
       }
+      // The neighbour's bodies these constraints reach (a hundred or so) get slots of their own behind the tile's bodies: a
+      // boundary pass loads them once, works in shared memory, and writes them back once -- instead of a trip to L2 and back
+      // inside every row.  sClaim is all-ones again by now; its neighbour half serves as the map body -> slot.
+      if (!bDirect && !(W.dbgFlags & 4096)) {
+        for (int u = 0; u < 2; ++u) {
+          const int x[2] = {ia[u], ib[u]}, id[2] = {brs[u].x, brs[u].y};
+          for (int e = 0; e < 2; ++e) if (x[e] >= T && atomicCAS(&sClaim[x[e]], 0xFFFFFFFFu, 0xFFFFFFFEu) == 0xFFFFFFFFu) {
+            const int k = atomicAdd(&nNbr, 1);
+            if (k < kTileNbrMax) { sNbrBody[k] = id[e] & 0x7fffffff; sClaim[x[e]] = (unsigned)k; }
+          }
+        }
+        __syncthreads();
+        if (nNbr <= kTileNbrMax) {
+          for (int u = 0; u < 2; ++u) if (lt + u * ln < nB) {
+            int2 br = brs[u];
+            if (ia[u] >= T) br.x = s0 + T + (int)sClaim[ia[u]];
+            if (ib[u] >= T) br.y = s0 + T + (int)sClaim[ib[u]];
+            if (item[u] >= 0) W.s_body[item[u]] = br; else W.j_bref[~item[u]] = br;      // (both rewritten from scratch every step)
+          }
+        }
+        __syncthreads();
+        if (lt == 0 && nNbr > kTileNbrMax) nNbr = 0;
+      }
     }
     __syncthreads();
   }
   const bool bLocal = bDirect == 0;
+  const int nNb = nNbr;
   MARK();
 
   if (rowsLocal) for (int k = lt; k < nRows; k += ln) { rbd[k] = W.s_body[rs0 + k]; rpc[k] = W.s_pc[rs0 + k]; }
@@ -363,6 +392,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
       sVel[i] = vel; sPos[i] = ldcg4(&W.b_pos[b]); sMass[i] = make_float2(ms.x, ms.y);
       sBody[i] = b; sFlag[i] = W.b_xflag[b];
     }
+    for (int k = lt; k < nNb; k += ln) sPos[T + k] = ldcg4(&W.b_pos[sNbrBody[k]]);      // (boundary joints read positions when they initialise)
     __syncthreads();
   }
   MARK();
@@ -420,11 +450,16 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   };
   auto boundary_phases = [&](int mode, bool backwards, int* notOk, const int* prev) {
     if (bLocal) {
+      if (nNb > 0) {
+        for (int k = lt; k < nNb; k += ln) { if (mode == TM_POS) sPos[T + k] = ldcg4(&W.b_pos[sNbrBody[k]]); else sVel[T + k] = ldcg4(&W.b_vel[sNbrBody[k]]); }
+        __syncthreads();
+      }
       for (int k = 0; k < nPhB; ++k) {
         const int c = backwards ? nPhB - 1 - k : k;
         for (int q = sBOff[c] + lt; q < sBOff[c + 1]; q += ln) { const int item = sBItem[q]; if (mode != TM_INIT || item < 0) tile_item(W, view, mode, item, notOk, prev); }
         __syncthreads();
       }
+      for (int k = lt; k < nNb; k += ln) { if (mode == TM_POS) stcg4(&W.b_pos[sNbrBody[k]], sPos[T + k]); else stcg4(&W.b_vel[sNbrBody[k]], sVel[T + k]); }
     } else {
       for (int k = 0; k < nLoc; ++k) {
         const int c = backwards ? nLoc - 1 - k : k;
@@ -664,7 +699,7 @@ size_t tile_smem_bytes(int tileBodies) {
     cudaFuncAttributes fa{}; cudaFuncGetAttributes(&fa, (const void*)k_solve_tiles);
     avail = (size_t)optin > fa.sharedSizeBytes + 1024 ? (size_t)optin - fa.sharedSizeBytes - 1024 : 0;
   }
-  return std::max(avail, (size_t)tileBodies * 48 + 4096) > avail ? 0 : avail;       // 0: the tile does not fit
+  return std::max(avail, (size_t)tileBodies * 48 + 32 * kTileNbrMax + 4096) > avail ? 0 : avail;       // 0: the tile does not fit
 }
 
 cudaError_t stage_tile_assign(const DevWorld& W, const LaunchCfg& L, unsigned* keysA, unsigned* keysB, int* valsA, int* valsB) {
