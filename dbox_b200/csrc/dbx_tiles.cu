@@ -231,14 +231,18 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   const int rs0 = offL[0], nRows = offL[kTileColours] - rs0;        // the tile's local rows: one contiguous piece of the row arrays
   // the tile's local joints (revolute / distance) move into shared memory too when they fit beside the rows: 192 B each
   const int jl0 = joffL[0], nJL = tile < P ? joffL[kTileColours] - jl0 : 0;
-  const long long bodyBytes = 48ll * T + 32ll * kTileNbrMax;
+  const int jb0 = joffB[0], nBJ = tile < P ? joffB[kTileColours] - jb0 : 0, nBC = tile < P ? offB[kTileColours] - offB[0] : 0, nB = nBJ + nBC;
+  const long long bodyBytes = 48ll * T + 40ll * kTileNbrMax;
+  auto rows_beside = [&](int joints) { return (int)(((long long)dynBytes - bodyBytes - 192ll * joints - 32) / 108) & ~1; };
   const int R0 = (int)(((long long)dynBytes - bodyBytes) / 108) & ~1;
-  const int Rj = (int)(((long long)dynBytes - bodyBytes - 192ll * nJL - 32) / 108) & ~1;
-  const bool jointRoom = nJL > 0 && nJL <= kTileJointsMax && Rj > 0 && nRows <= Rj && !(W.dbgFlags & 2048);
+  // (the boundary's joints join the local ones in shared memory when there is room for them too)
+  const int nJS = (nJL + nBJ <= kTileJointsMax && nRows <= rows_beside(nJL + nBJ)) ? nJL + nBJ : nJL;
+  const int Rj = rows_beside(nJS);
+  const bool jointRoom = nJS > 0 && nJS <= kTileJointsMax && Rj > 0 && nRows <= Rj && !(W.dbgFlags & 2048);
   const int R = jointRoom ? Rj : R0;
   float4* ra0 = sm4 + 2 * TX; float4* ra1 = ra0 + R; float4* ra2 = ra1 + R; float4* ra3 = ra2 + R; float4* ra4 = ra3 + R; float4* ra5 = ra4 + R;
   float2* sMass = (float2*)(ra5 + R);
-  int2* rbd = (int2*)(sMass + T);
+  int2* rbd = (int2*)(sMass + TX);
   int* sBody = (int*)(rbd + R); int* sFlag = sBody + T; int* rpc = sFlag + T;
   float4* sj = (float4*)(((size_t)(rpc + R) + 15) & ~(size_t)15);  // joints: 11 float4 arrays [nJL], then bref int2, limit, root
   const bool rowsLocal = nRows > 0 && nRows <= R;                   // they fit: they live in shared memory for the whole solve
@@ -260,7 +264,6 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   // item takes the lowest colour free on both bodies once it holds the smallest priority on both (priority = joints before
   // contacts, then a hash of the item -- so a body still meets its joints first and the outcome does not depend on scheduling).
   {
-    const int nBJ = joffB[kTileColours] - joffB[0], nBC = offB[kTileColours] - offB[0], nB = nBJ + nBC;
     unsigned* sMask = (unsigned*)sMass;               // scratch in the tail of the dynamic area (masses, references, ids: filled afterwards)
     unsigned* sClaim = sMask + 2 * T;                 // [2T] each: own tile's bodies [0, T), the right-hand neighbour's [T, 2T)
     const bool fits = nB <= kTileBMax && R0 > 0 && (size_t)16 * T <= (size_t)dynBytes - (size_t)(32 * TX + 96 * R);
@@ -269,13 +272,14 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
     if (fits && nB > 0) {
       for (int k = lt; k < 2 * T; k += ln) { sMask[k] = 0u; sClaim[k] = 0xFFFFFFFFu; }
       // every thread keeps at most two items in registers (nB <= kTileBMax = 2 x kTileThreads)
-      int item[2], ia[2], ib[2], lc[2]; unsigned pr[2]; int2 brs[2];
+      int item[2], ia[2], ib[2], lc[2], jg[2]; unsigned pr[2]; int2 brs[2];
       for (int u = 0; u < 2; ++u) {
         const int k = lt + u * ln;
         item[u] = 0; ia[u] = ib[u] = -1; lc[u] = k < nB ? -1 : 0; pr[u] = 0xFFFFFFFFu; brs[u] = make_int2(-1, -1);
         if (k >= nB) continue;
         int2 br;
-        if (k < nBJ) { const int j = W.tj_order[joffB[0] + k]; item[u] = ~j; br = W.j_bref[j]; pr[u] = ((unsigned)(mix64((unsigned long long)j + 1ull) >> 33)) & 0x7FFFFC00u; }
+        jg[u] = -1;
+        if (k < nBJ) { const int j = W.tj_order[joffB[0] + k]; item[u] = ~k; jg[u] = j; br = W.j_bref[j];     /* a joint item: ~index in the boundary's joint list */ pr[u] = ((unsigned)(mix64((unsigned long long)j + 1ull) >> 33)) & 0x7FFFFC00u; }
         else {
           // (the hash is of the pair key, not of the slot: slots inside a bin come out of an atomic scatter in any order)
           const int s = offB[0] + (k - nBJ), i = W.s_contact[s]; item[u] = s; br = W.c_bref[i];
@@ -317,7 +321,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
       __syncthreads();
       if (!bDirect) for (int u = 0; u < 2; ++u) if (lt + u * ln < nB) {
         sBItem[atomicAdd(&sBCnt[lc[u]], 1)] = item[u];
-        if (item[u] >= 0) W.c_tcol[W.s_contact[item[u]]] = lc[u]; else W.j_tcol[~item[u]] = lc[u];    // for dbx_world_debug_read_solve_order
+        if (item[u] >= 0) W.c_tcol[W.s_contact[item[u]]] = lc[u]; else W.j_tcol[jg[u]] = lc[u];    // for dbx_world_debug_read_solve_order
       }
       // The neighbour's bodies these constraints reach (a hundred or so) get slots of their own behind the tile's bodies: a
       // boundary pass loads them once, works in shared memory, and writes them back once -- instead of a trip to L2 and back
@@ -336,7 +340,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
             int2 br = brs[u];
             if (ia[u] >= T) br.x = s0 + T + (int)sClaim[ia[u]];
             if (ib[u] >= T) br.y = s0 + T + (int)sClaim[ib[u]];
-            if (item[u] >= 0) W.s_body[item[u]] = br; else W.j_bref[~item[u]] = br;      // (both rewritten from scratch every step)
+            if (item[u] >= 0) W.s_body[item[u]] = br; else W.j_bref[jg[u]] = br;      // (both rewritten from scratch every step)
           }
         }
         __syncthreads();
@@ -348,19 +352,34 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   const bool bLocal = bDirect == 0;
   const int nNb = nNbr;
   MARK();
+  long long pc0 = 0; if (marking) pc0 = clock64();
+#define PSTAMP(i) do { if (marking) { W.phaseTimes[3900 + (blockIdx.x == 0 ? 0 : 8) + (i)] = (unsigned long long)(clock64() - pc0); } } while (0)
 
   if (rowsLocal) for (int k = lt; k < nRows; k += ln) { rbd[k] = W.s_body[rs0 + k]; rpc[k] = W.s_pc[rs0 + k]; }
+  // Boundary rows too, as many as the spare row slots take, from the END of the boundary's phase order (its later colours are
+  // the small ones: a colour that sits in shared memory whole runs at the local rows' pace).  Position q of the order gets
+  // slot nRows + q - qS0; a joint's position stays empty.
+  const int nBS = (bLocal && rowsLocal && nNb > 0 && !(W.dbgFlags & 8192)) ? min(nB, R - nRows) : 0, qS0 = nB - nBS;
+  for (int q = qS0 + lt; q < nB; q += ln) {
+    const int s = sBItem[q], x = nRows + q - qS0;
+    if (s < 0) continue;
+    ra0[x] = W.s_v0[s]; ra1[x] = W.s_r0[s]; ra2[x] = W.s_r1[s]; ra3[x] = W.s_q0[s]; ra4[x] = W.s_q1[s]; ra5[x] = W.s_imp[s];
+    rbd[x] = W.s_body[s]; rpc[x] = W.s_pc[s];
+  }
+  PSTAMP(0);
   // local joints in: definition, accumulated impulses, limit state, body references; the per-step temporaries are written by
   // their own joint_init.  sW is W with the joint arrays redirected, indexed by the joint's position in the tile's list.
-  float4* sjIds = sj; float4* sjAnchor = sj + nJL; float4* sjP0 = sj + 2 * nJL; float4* sjP1 = sj + 3 * nJL; float4* sjImp = sj + 4 * nJL;
-  int2* sjBref = (int2*)(sj + 11 * nJL); int* sjLimit = (int*)(sjBref + nJL); int* sjRoot = sjLimit + nJL;
+  float4* sjIds = sj; float4* sjAnchor = sj + nJS; float4* sjP0 = sj + 2 * nJS; float4* sjP1 = sj + 3 * nJS; float4* sjImp = sj + 4 * nJS;
+  int2* sjBref = (int2*)(sj + 11 * nJS); int* sjLimit = (int*)(sjBref + nJS); int* sjRoot = sjLimit + nJS;
+  const int nJSe = bLocal ? nJS : nJL;              // (boundary constraints walked by global colour stay in the global arrays)
+  auto staged_joint = [&](int x) { return x < nJL ? W.tj_order[jl0 + x] : W.tj_order[jb0 + (x - nJL)]; };
   if (lt == 0) jointsBad = 0;
   __syncthreads();
   if (jointRoom) {
     static_assert(sizeof(DevWorld) % 4 == 0, "DevWorld is copied word by word");
     for (int k = lt; k < (int)(sizeof(DevWorld) / 4); k += ln) ((int*)&sW)[k] = ((const int*)&W)[k];
-    for (int x = lt; x < nJL; x += ln) {
-      const int j = W.tj_order[jl0 + x];
+    for (int x = lt; x < nJSe; x += ln) {
+      const int j = staged_joint(x);
       const int4 ids = W.j_ids[j];
       if (ids.x != JT_REVOLUTE && ids.x != JT_DISTANCE) jointsBad = 1;        // (other joint types read more arrays: they stay in L2)
       ((int4*)sjIds)[x] = ids; sjAnchor[x] = W.j_anchor[j]; sjP0[x] = W.j_p0[j]; sjP1[x] = W.j_p1[j]; sjImp[x] = W.j_imp[j];
@@ -368,32 +387,50 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
     }
   }
   __syncthreads();
+  PSTAMP(1);
   const bool jointsLocal = jointRoom && jointsBad == 0;
   if (jointsLocal && lt == 0) {
     sW.j_ids = (int4*)sjIds; sW.j_anchor = sjAnchor; sW.j_p0 = sjP0; sW.j_p1 = sjP1; sW.j_imp = sjImp;
-    sW.j_r = sj + 5 * nJL; sW.j_lc = sj + 6 * nJL; sW.j_m = sj + 7 * nJL; sW.j_k0 = sj + 8 * nJL; sW.j_k1 = sj + 9 * nJL; sW.j_k2 = sj + 10 * nJL;
+    sW.j_r = sj + 5 * nJS; sW.j_lc = sj + 6 * nJS; sW.j_m = sj + 7 * nJS; sW.j_k0 = sj + 8 * nJS; sW.j_k1 = sj + 9 * nJS; sW.j_k2 = sj + 10 * nJS;
     sW.j_bref = sjBref; sW.j_limit = sjLimit; sW.j_root = sjRoot;
   }
   __syncthreads();
   // bodies in: velocities with the contacts' warm start folded in (see k_solve), positions, inverse masses, ids, exchange flags
+  PSTAMP(2);
   {
     const float k = 1.0f / 4294967296.0f;
-    for (int i = lt; i < n; i += ln) {
-      const int b = W.t_body[s0 + i];
-      float4 vel = ldcg4(&W.b_vel[b]);
+    // (two bodies per trip, every load of both under way before the first is used)
+    for (int i = lt; i < n; i += 2 * ln) {
+      const int i1 = i + ln;
+      const bool two = i1 < n;
+      const int b0 = W.t_body[s0 + i], b1 = two ? W.t_body[s0 + i1] : b0;
+      float4 vel[2] = {ldcg4(&W.b_vel[b0]), ldcg4(&W.b_vel[b1])};
+      long long acc[2][3] = {{0, 0, 0}, {0, 0, 0}};
       if (W.warmStarting) {
-        const long long ax = (long long)__ldcg(&W.b_acc[3 * b]), ay = (long long)__ldcg(&W.b_acc[3 * b + 1]), aw = (long long)__ldcg(&W.b_acc[3 * b + 2]);
-        if ((ax | ay | aw) != 0) {
-          vel.x += (float)ax * k; vel.y += (float)ay * k; vel.z += (float)aw * k;
+        for (int c = 0; c < 3; ++c) { acc[0][c] = (long long)__ldcg(&W.b_acc[3 * b0 + c]); acc[1][c] = (long long)__ldcg(&W.b_acc[3 * b1 + c]); }
+      }
+      const float4 pos[2] = {ldcg4(&W.b_pos[b0]), ldcg4(&W.b_pos[b1])};
+      const float4 ms[2] = {W.b_mass[b0], W.b_mass[b1]};
+      const int fl[2] = {W.b_xflag[b0], W.b_xflag[b1]};
+      for (int u = 0; u < (two ? 2 : 1); ++u) {
+        const int b = u ? b1 : b0, iu = u ? i1 : i;
+        if ((acc[u][0] | acc[u][1] | acc[u][2]) != 0) {
+          vel[u].x += (float)acc[u][0] * k; vel[u].y += (float)acc[u][1] * k; vel[u].z += (float)acc[u][2] * k;
           __stcg(&W.b_acc[3 * b], 0ull); __stcg(&W.b_acc[3 * b + 1], 0ull); __stcg(&W.b_acc[3 * b + 2], 0ull);
         }
+        sVel[iu] = vel[u]; sPos[iu] = pos[u]; sMass[iu] = make_float2(ms[u].x, ms[u].y);
+        sBody[iu] = b; sFlag[iu] = fl[u];
       }
-      const float4 ms = W.b_mass[b];
-      sVel[i] = vel; sPos[i] = ldcg4(&W.b_pos[b]); sMass[i] = make_float2(ms.x, ms.y);
-      sBody[i] = b; sFlag[i] = W.b_xflag[b];
     }
-    for (int k = lt; k < nNb; k += ln) sPos[T + k] = ldcg4(&W.b_pos[sNbrBody[k]]);      // (boundary joints read positions when they initialise)
+    PSTAMP(3);
+    for (int k = lt; k < nNb; k += ln) {
+      const int b = sNbrBody[k];
+      const float4 ms = W.b_mass[b];
+      sPos[T + k] = ldcg4(&W.b_pos[b]);              // (boundary joints read positions when they initialise)
+      sMass[T + k] = make_float2(ms.x, ms.y);
+    }
     __syncthreads();
+    PSTAMP(4);
   }
   MARK();
   if (rowsLocal) mbar_wait(&rowBar, 0);
@@ -401,6 +438,30 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
 
   // ---- the phases of one class
   int sweepNo = 0;
+  // one row that lives in shared memory (slot x; sg: its slot in the global row arrays)
+  auto smem_row = [&](int mode, int x, int sg, int* notOk, const int* prev) {
+    const int2 bd = rbd[x];
+    const float2 mA = bd.x >= 0 ? sMass[bd.x - s0] : make_float2(0.0f, 0.0f), mB = bd.y >= 0 ? sMass[bd.y - s0] : make_float2(0.0f, 0.0f);
+    if (mode == TM_VEL) {
+      VC v; v.bd = bd; v.pc = rpc[x]; v.v0 = ra0[x]; v.v1 = make_float4(mA.x, mA.y, mB.x, mB.y); v.r0 = ra1[x]; v.r1 = ra2[x]; v.q0 = ra3[x]; v.q1 = ra4[x]; v.imp = ra5[x];
+      if ((v.pc & 0xFF) == 2) { v.nm = W.s_nm[sg]; v.K = W.s_k[sg]; }      // (the block solver's matrices stay in L2: no room; fetching them a phase ahead into registers was measured slower)
+      ra5[x] = contact_velocity_row(W, v, view);
+    } else {
+      const float4 p3 = ra3[x];
+      const int root = __float_as_int(p3.z);                // (staged with the position rows)
+      if (prev && __float_as_int(p3.w) == 0) return;
+      PCn p; p.bd = bd; p.pc = rpc[x]; p.v1 = make_float4(mA.x, mA.y, mB.x, mB.y); p.p0 = ra0[x]; p.p1 = ra1[x]; p.p2 = ra2[x]; p.p3 = make_float2(p3.x, p3.y);
+      const float minSep = contact_position_row(W, p, -1, -1, view);
+      if (!(minSep >= -3.0f * kLinearSlop)) __stcg(&notOk[root], 1);
+    }
+  };
+  // "did my island still move in the pass before", for every row in shared memory: one round of loads at the start of a position
+  // pass (after the barrier that completes the flags) instead of a trip to L2 inside every row
+  auto fetch_prev_flags = [&](const int* prev) {
+    if (!rowsLocal || !prev) return;
+    for (int k = lt; k < nRows + nBS; k += ln) ra3[k].w = __int_as_float(__ldcg(&prev[__float_as_int(ra3[k].z)]));
+    __syncthreads();
+  };
   // local colours of this tile, upwards or downwards: joints first, then rows -- from shared memory when they fit
   auto local_phases = [&](int mode, bool backwards, int* notOk, const int* prev) {
     for (int kk = 0; kk < nPhL; ++kk) {
@@ -408,7 +469,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
       const int c = phL[k];
       const int jb = joffL[c], nj = joffL[c + 1] - jb, beg = offL[c], nr = offL[c + 1] - beg;
       if (mode == TM_INIT && nj == 0) continue;
-      const bool fine = marking && sweepNo == 4 && kk < 16;       // debug: clock stamps of one velocity pass at [2048 + 4 kk ..)
+      const bool fine = marking && (sweepNo == 4 || sweepNo == 11) && kk < 16;       // debug: clock stamps of one velocity pass at [2048 + 4 kk ..), of one position pass at [2304 + 4 kk ..)
       long long c0 = 0, c1 = 0;
       if (fine) c0 = clock64();
       if (jointsLocal) { for (int q = lt; q < nj; q += ln) tile_item(sW, view, mode, ~(jb - jl0 + q), notOk, prev); }
@@ -416,23 +477,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
       if (mode != TM_INIT) {
         if (rowsLocal) {
           // (row q of the colour belongs to thread q - nj, as in the global layout, so a jointed colour spreads over all warps)
-          for (int q = lt - nj; q < nr; q += ln) {
-            if (q < 0) continue;
-            const int x = beg - rs0 + q;
-            const int2 bd = rbd[x];
-            const float2 mA = bd.x >= 0 ? sMass[bd.x - s0] : make_float2(0.0f, 0.0f), mB = bd.y >= 0 ? sMass[bd.y - s0] : make_float2(0.0f, 0.0f);
-            if (mode == TM_VEL) {
-              VC v; v.bd = bd; v.pc = rpc[x]; v.v0 = ra0[x]; v.v1 = make_float4(mA.x, mA.y, mB.x, mB.y); v.r0 = ra1[x]; v.r1 = ra2[x]; v.q0 = ra3[x]; v.q1 = ra4[x]; v.imp = ra5[x];
-              if ((v.pc & 0xFF) == 2) { v.nm = W.s_nm[beg + q]; v.K = W.s_k[beg + q]; }      // (the block solver's matrices stay in L2: no room; fetching them a phase ahead into registers was measured slower)
-              ra5[x] = contact_velocity_row(W, v, view);
-            } else {
-              const int root = W.s_root[beg + q];
-              if (prev && __ldcg(&prev[root]) == 0) continue;
-              PCn p; p.bd = bd; p.pc = rpc[x]; p.v1 = make_float4(mA.x, mA.y, mB.x, mB.y); p.p0 = ra0[x]; p.p1 = ra1[x]; p.p2 = ra2[x]; p.p3 = make_float2(ra3[x].x, ra3[x].y);
-              const float minSep = contact_position_row(W, p, -1, -1, view);
-              if (!(minSep >= -3.0f * kLinearSlop)) __stcg(&notOk[root], 1);
-            }
-          }
+          for (int q = lt - nj; q < nr; q += ln) if (q >= 0) smem_row(mode, beg - rs0 + q, beg + q, notOk, prev);
         } else {
           const int kn = backwards ? k - 1 : k + 1;
           if (kn >= 0 && kn < nPhL) {
@@ -445,9 +490,10 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
       }
       if (fine) c1 = clock64();
       __syncthreads();
-      if (fine) { const long long c2 = clock64(); unsigned long long* o = W.phaseTimes + 2048 + (blockIdx.x == 0 ? 0 : 128) + 4 * kk; o[0] = (unsigned long long)(c1 - c0); o[1] = (unsigned long long)(c2 - c1); o[2] = (unsigned long long)(nj + nr); o[3] = (unsigned long long)c; }
+      if (fine) { const long long c2 = clock64(); unsigned long long* o = W.phaseTimes + 2048 + (sweepNo == 11 ? 256 : 0) + (blockIdx.x == 0 ? 0 : 128) + 4 * kk; o[0] = (unsigned long long)(c1 - c0); o[1] = (unsigned long long)(c2 - c1); o[2] = (unsigned long long)(nj + nr); o[3] = (unsigned long long)c; }
     }
   };
+  const bool bJointsLocal = jointsLocal && nJSe > nJL;
   auto boundary_phases = [&](int mode, bool backwards, int* notOk, const int* prev) {
     if (bLocal) {
       if (nNb > 0) {
@@ -456,8 +502,21 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
       }
       for (int k = 0; k < nPhB; ++k) {
         const int c = backwards ? nPhB - 1 - k : k;
-        for (int q = sBOff[c] + lt; q < sBOff[c + 1]; q += ln) { const int item = sBItem[q]; if (mode != TM_INIT || item < 0) tile_item(W, view, mode, item, notOk, prev); }
+        const bool fine = marking && (sweepNo == 4 || sweepNo == 11) && k < 8;        // debug: [3700 ..)
+        long long c0 = 0, c1 = 0; int nj = 0;
+        if (fine) { c0 = clock64(); for (int q = sBOff[c]; q < sBOff[c + 1]; ++q) nj += sBItem[q] < 0; }
+        for (int q = sBOff[c] + lt; q < sBOff[c + 1]; q += ln) {
+          const int item = sBItem[q];
+          if (item < 0) {                                     // a joint: ~index in the boundary's joint list
+            if (bJointsLocal) tile_item(sW, view, mode, ~(nJL + ~item), notOk, prev);
+            else tile_item(W, view, mode, ~W.tj_order[jb0 + ~item], notOk, prev);
+          } else if (mode != TM_INIT) {
+            if (q >= qS0) smem_row(mode, nRows + q - qS0, item, notOk, prev); else tile_item(W, view, mode, item, notOk, prev);
+          }
+        }
+        if (fine) c1 = clock64();
         __syncthreads();
+        if (fine) { const long long c2 = clock64(); unsigned long long* o = W.phaseTimes + 3700 + (sweepNo == 11 ? 64 : 0) + (blockIdx.x == 0 ? 0 : 32) + 4 * k; o[0] = (unsigned long long)(c1 - c0); o[1] = (unsigned long long)(c2 - c1); o[2] = (unsigned long long)(sBOff[c + 1] - sBOff[c]); o[3] = (unsigned long long)nj; }
       }
       for (int k = lt; k < nNb; k += ln) { if (mode == TM_POS) stcg4(&W.b_pos[sNbrBody[k]], sPos[T + k]); else stcg4(&W.b_vel[sNbrBody[k]], sVel[T + k]); }
     } else {
@@ -537,6 +596,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
     } else {
       if (nCross > 0 && handshake) {
         if (prev) GB();            // the per-island flags of the pass before must be in for every tile alike
+        fetch_prev_flags(prev);
         publish(true, XF_FOREIGN, 0);
         signal(flagL); await(flagL, tile + 1);
         boundary_phases(mode, true, notOk, prev);
@@ -546,6 +606,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
       } else if (nCross > 0) {
         publish(true, XF_FOREIGN | XF_G, 0);
         GB();
+        fetch_prev_flags(prev);
         if (nG > 0) {
           global_phases(mode, true, notOk, prev);
           for (int i = lt; i < n; i += ln) { const int f = sFlag[i]; if ((f & (XF_OWNB | XF_G)) == (XF_OWNB | XF_G)) sPos[i] = ldcg4(&W.b_pos[sBody[i]]); }
@@ -560,7 +621,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
           if ((f & XF_FOREIGN) || ((f & XF_G) && !(f & XF_OWNB))) sPos[i] = ldcg4(&W.b_pos[sBody[i]]);
         }
         __syncthreads();
-      }
+      } else fetch_prev_flags(prev);
       local_phases(mode, true, notOk, prev);
     }
   };
@@ -580,6 +641,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   };
   if (rowsLocal) {
     for (int k = lt; k < nRows; k += ln) { const float4 imp = ra5[k]; W.s_imp[rs0 + k] = imp; store_impulse(rs0 + k, imp, rpc[k]); }
+    for (int q = qS0 + lt; q < nB; q += ln) { const int s = sBItem[q]; if (s >= 0) stcg4(&W.s_imp[s], ra5[nRows + q - qS0]); }     // (into the manifolds with the other boundary rows below)
     __syncthreads();
     if (W.posIters > 0) {
       if (lt == 0) {
@@ -588,7 +650,13 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
         mbar_expect_tx(&rowBar, 3u * bytes);
         bulk_g2s(ra0, W.s_p0 + rs0, bytes, &rowBar); bulk_g2s(ra1, W.s_p1 + rs0, bytes, &rowBar); bulk_g2s(ra2, W.s_p2 + rs0, bytes, &rowBar);
       }
-      for (int k = lt; k < nRows; k += ln) { const float2 r = W.s_p3[rs0 + k]; ra3[k] = make_float4(r.x, r.y, 0.0f, 0.0f); }
+      for (int k = lt; k < nRows; k += ln) { const float2 r = W.s_p3[rs0 + k]; ra3[k] = make_float4(r.x, r.y, __int_as_float(W.s_root[rs0 + k]), 0.0f); }   // .z: the row's island, .w: its flag of the pass before
+      for (int q = qS0 + lt; q < nB; q += ln) {
+        const int s = sBItem[q], x = nRows + q - qS0;
+        if (s < 0) { ra3[x] = make_float4(0.0f, 0.0f, __int_as_float(0), 0.0f); continue; }
+        const float2 r = W.s_p3[s];
+        ra0[x] = W.s_p0[s]; ra1[x] = W.s_p1[s]; ra2[x] = W.s_p2[s]; ra3[x] = make_float4(r.x, r.y, __int_as_float(W.s_root[s]), 0.0f);
+      }
     }
   } else if (tile < P) {
     for (int s = offL[0] + lt; s < offL[kTileColours]; s += ln) store_impulse(s, W.s_imp[s], W.s_pc[s]);
@@ -634,7 +702,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
     sweep(TM_POS, notOk, prev);     // (a pass starts with publish + grid barrier when islands can span tiles: the flags of the pass before are in)
     MARK();
   }
-  if (jointsLocal) for (int x = lt; x < nJL; x += ln) { const int j = W.tj_order[jl0 + x]; W.j_imp[j] = sjImp[x]; W.j_limit[j] = sjLimit[x]; W.j_root[j] = sjRoot[x]; }
+  if (jointsLocal) for (int x = lt; x < nJSe; x += ln) { const int j = staged_joint(x); W.j_imp[j] = sjImp[x]; W.j_limit[j] = sjLimit[x]; W.j_root[j] = sjRoot[x]; }
   solve_stamp(W, 3);
   // write back + SynchronizeTransform (:227-235), sleep bookkeeping (:241-269); the exchange flags go back to rest
   {

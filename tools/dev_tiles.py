@@ -33,3 +33,11 @@ print("colours", c.colours, "touching", c.touching, "tail ints of header (.., nT
 tot = C.c_float(); st = (C.c_float * 9)()
 ga.world_time_steps(w._w, 1 / 60., 8, 3, 50, 1, C.byref(tot), st)
 print("ms/step %.4f" % (tot.value / 50), "stages", ["%.3f" % x for x in st])
+tt = [buf[3000 + i] for i in range(64) if buf[3000 + i]]
+print("k_toi marks of thread 0 (us between):", " ".join("%.1f" % ((tt[i + 1] - tt[i]) / 1000.) for i in range(len(tt) - 1)))
+for base, name in ((3700, "CTA 0 vel"), (3732, "middle vel"), (3764, "CTA 0 pos"), (3796, "middle pos")):
+    print(name, "boundary colours (items, joints, cycles own, cycles wait):", [(int(buf[base + 4 * k + 2]), int(buf[base + 4 * k + 3]), int(buf[base + 4 * k]), int(buf[base + 4 * k + 1])) for k in range(6)])
+for base, name in ((2304, "CTA 0"), (2304 + 128, "middle CTA")):
+    print(name, "position pass 2, per local colour: (colour, items, cycles own item, cycles waiting at the barrier)")
+    print("  ", [(int(buf[base + 4 * k + 3]), int(buf[base + 4 * k + 2]), int(buf[base + 4 * k]), int(buf[base + 4 * k + 1])) for k in range(12)])
+print("prologue cycles (thread 0) after: rbd/rpc, joints staged, sW patched, bodies loaded, bodies synced:", [int(buf[3900 + i]) for i in range(5)], [int(buf[3908 + i]) for i in range(5)])
