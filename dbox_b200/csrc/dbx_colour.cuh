@@ -13,6 +13,14 @@ DBX_D void mark_solve_body(const DevWorld& W) {
     for (int c = threadIdx.x; c <= kMaxJointColours; c += blockDim.x) sjoff[c] = W.hdr->jointColourOff[c];
     __syncthreads();
     tile_key_joints(W, sjoff);
+    // the masses in tile order, for the solver's prologue (a body's mass may change between any two steps)
+    // and "takes part in this step", so that the solver need not gather the body flags
+    GRID_STRIDE(p, W.nTileBodies) {
+      const int b = W.t_body[p];
+      const float4 ms = W.b_mass[b];
+      W.t_mass[p] = make_float2(ms.x, ms.y);
+      if ((W.b_flags[b] & (BF_ALIVE | BF_ISLAND)) == (BF_ALIVE | BF_ISLAND)) atomicOr(&W.b_xflag[p], XF_ISLAND);
+    }
   }
   const int n = W.hdr->cHigh;
   GRID_STRIDE(i, n) {

@@ -43,7 +43,8 @@ constexpr int kSortBlocks = 296;         // 2 CTAs per SM for the colour countin
 constexpr int kMaxPosIters = 8;
 constexpr int kTailContacts = 1024;       // tail colours holding at most this many constraints share one CTA-local phase
 constexpr int kTileColours = 64;         // tile solver: colours a tile walks locally (higher ones, the overflow lanes, run as global phases)
-enum { XF_FOREIGN = 1 /* moved by the left neighbour's boundary rows */, XF_OWNB = 2 /* by this tile's own boundary rows */, XF_G = 4 /* by global rows */ };
+enum { XF_FOREIGN = 1 /* moved by the left neighbour's boundary rows */, XF_OWNB = 2 /* by this tile's own boundary rows */, XF_G = 4 /* by global rows */,
+       XF_ISLAND = 8 /* alive and in an island this step (BF_ALIVE | BF_ISLAND, copied here by k_mark_solve) */ };
 constexpr int kToiCand = 64;             // candidate contacts per event side (mini-island holds at most 32)
 enum { TF_INVAL = 1, TF_SYNC = 2 };
 constexpr unsigned long long kHashEmpty = ~0ull;
@@ -250,7 +251,8 @@ struct DevWorld {
   int* b_tslot;         // body -> position in tile order (-1: not a dynamic body)
   int* t_body;          // position in tile order -> body
   int* b_tclaim;        // per body: lowest boundary straddled by one of its constraints (0x7fffffff at rest)
-  int* b_xflag;         // per body: XF_* (0 at rest)
+  int* b_xflag;         // per TILE SLOT: XF_* (0 at rest)
+  float2* t_mass;       // per tile slot: inverse mass, inverse inertia (refreshed by k_mark_solve every step)
   int* c_tkey; int2* c_bref;     // per contact slot: bin and body references of this step
   int* c_tcol; int* j_tcol;      // boundary constraints: the local colour their tile gave them (k_solve_tiles), -1 otherwise
   int* j_tkey; int2* j_bref;     // per joint slot likewise

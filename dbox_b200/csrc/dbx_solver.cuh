@@ -9,11 +9,14 @@ namespace dbx {
 // ------------------------------------------------------------------------------------------------ contact constraints
 // b2ContactSolver ctor + InitializeVelocityConstraints (contacts/b2contactsolver.d:244-450): one thread per solver contact.
 // `s` = solver slot to fill, `i` = contact slot; warmScale < 0 means "no warm starting" (TOI sub-steps, b2world.d:1419)
+// (tile solver: the accumulators are indexed by tile slot, so that a tile reads and clears its own as one contiguous piece;
+// every body with mass has a slot.  Either way they are all zero again once the solver has started.)
 DBX_D void acc_add(const DevWorld& W, int b, float x, float y, float w) {
   const float k = 4294967296.0f;   // 2^32: scaling a float by a power of two is exact
-  atomicAdd(&W.b_acc[3 * b + 0], (unsigned long long)__float2ll_rn(x * k));
-  atomicAdd(&W.b_acc[3 * b + 1], (unsigned long long)__float2ll_rn(y * k));
-  atomicAdd(&W.b_acc[3 * b + 2], (unsigned long long)__float2ll_rn(w * k));
+  const int e = W.tiled ? W.b_tslot[b] : b;
+  atomicAdd(&W.b_acc[3 * e + 0], (unsigned long long)__float2ll_rn(x * k));
+  atomicAdd(&W.b_acc[3 * e + 1], (unsigned long long)__float2ll_rn(y * k));
+  atomicAdd(&W.b_acc[3 * e + 2], (unsigned long long)__float2ll_rn(w * k));
 }
 DBX_D void prepare_contact(const DevWorld& W, int s, int i, float warmScale) {
   {
@@ -160,15 +163,21 @@ DBX_D float4 ld_vel(const DevWorld& W, BodyView view, int ref) {
   if (view.mode == 1 || (view.mode == 2 && ref >= 0)) return view.vel[ref - view.off];
   return ldcg4(&W.b_vel[ref & 0x7fffffff]);
 }
+// (tile solver: the fourth component of a body's slot holds its inverse mass (velocity) / inverse inertia (position); a store
+// leaves it alone)
 DBX_D void st_vel(const DevWorld& W, BodyView view, int ref, float4 v) {
-  if (view.mode == 1 || (view.mode == 2 && ref >= 0)) view.vel[ref - view.off] = v; else stcg4(&W.b_vel[ref & 0x7fffffff], v);
+  if (view.mode == 1) view.vel[ref - view.off] = v;
+  else if (view.mode == 2 && ref >= 0) { float4* p = &view.vel[ref - view.off]; p->x = v.x; p->y = v.y; p->z = v.z; }
+  else stcg4(&W.b_vel[ref & 0x7fffffff], v);
 }
 DBX_D float4 ld_pos(const DevWorld& W, BodyView view, int ref) {
   if (view.mode == 1 || (view.mode == 2 && ref >= 0)) return view.pos[ref - view.off];
   return ldcg4(&W.b_pos[ref & 0x7fffffff]);
 }
 DBX_D void st_pos(const DevWorld& W, BodyView view, int ref, float4 v) {
-  if (view.mode == 1 || (view.mode == 2 && ref >= 0)) view.pos[ref - view.off] = v; else stcg4(&W.b_pos[ref & 0x7fffffff], v);
+  if (view.mode == 1) view.pos[ref - view.off] = v;
+  else if (view.mode == 2 && ref >= 0) { float4* p = &view.pos[ref - view.off]; p->x = v.x; p->y = v.y; p->z = v.z; }
+  else stcg4(&W.b_pos[ref & 0x7fffffff], v);
 }
 DBX_D BodyVel load_vel(const DevWorld& W, int2 bd, BodyView view = BodyView()) {
   const float4 a = ld_vel(W, view, bd.x), b = ld_vel(W, view, bd.y);

@@ -27,14 +27,14 @@ DBX_D int tile_classify(const DevWorld& W, int bA, int bB, int col, bool forceGl
     if (near) { cls = 1; owner = lo; } else cls = 2;
   }
   if (cls == 2) {
-    if (sA >= 0) atomicOr(&W.b_xflag[bA], XF_G);
-    if (sB >= 0) atomicOr(&W.b_xflag[bB], XF_G);
+    if (sA >= 0) atomicOr(&W.b_xflag[sA], XF_G);
+    if (sB >= 0) atomicOr(&W.b_xflag[sB], XF_G);
     *bref = make_int2(bA | kRefGlobalBit, bB | kRefGlobalBit);
     return 2 * P * kTileColours + min(col, kMaxColours - 1);
   }
   if (cls == 1) {
-    atomicOr(&W.b_xflag[bA], tA == owner ? XF_OWNB : XF_FOREIGN);
-    atomicOr(&W.b_xflag[bB], tB == owner ? XF_OWNB : XF_FOREIGN);
+    atomicOr(&W.b_xflag[sA], tA == owner ? XF_OWNB : XF_FOREIGN);
+    atomicOr(&W.b_xflag[sB], tB == owner ? XF_OWNB : XF_FOREIGN);
   }
   *bref = make_int2(tA == owner ? sA : (bA | kRefGlobalBit), tB == owner ? sB : (bB | kRefGlobalBit));
   return (cls * P + owner) * kTileColours + col;
@@ -60,8 +60,8 @@ DBX_D void tile_key_joints(const DevWorld& W, const int* sjoff) {
     const int bin = tile_classify(W, ids.y, ids.z, lo, gear, &br);
     if (gear) {
       const int4 id2 = W.j_ids2[j];
-      if (W.b_tslot[id2.x] >= 0) atomicOr(&W.b_xflag[id2.x], XF_G);
-      if (W.b_tslot[id2.y] >= 0) atomicOr(&W.b_xflag[id2.y], XF_G);
+      { const int sl = W.b_tslot[id2.x]; if (sl >= 0) atomicOr(&W.b_xflag[sl], XF_G); }
+      { const int sl = W.b_tslot[id2.y]; if (sl >= 0) atomicOr(&W.b_xflag[sl], XF_G); }
     }
     W.j_tkey[j] = bin; W.j_bref[j] = br; W.j_tcol[j] = -1;
     atomicAdd(&W.tj_cur[bin], 1);

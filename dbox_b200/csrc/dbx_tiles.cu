@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) k_tile_scatter(const __grid_constant__ De
 // ------------------------------------------------------------------------------------------------ the solver
 enum { TM_INIT = 0, TM_VEL = 1, TM_POS = 2 };
 constexpr int kTileThreads = 384;    // k_solve_tiles: a colour of a tile holds ~300 rows at most; fewer threads leave each more registers (measured: -7 us)
-constexpr int kTileNbrMax = 192;                 // bodies of the right-hand neighbour a CTA's boundary constraints may stage in shared memory
+constexpr int kTileNbrMax = 128;                 // bodies of the right-hand neighbour a CTA's boundary constraints may stage in shared memory
 constexpr int kTileBMax = 2 * kTileThreads;      // boundary constraints one CTA re-colours locally (more: it walks them by global colour)
 constexpr int kTileBColours = 32;
 constexpr int kTileJointsMax = 512;  // local joints of a tile that may live in shared memory
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   // the tile's local joints (revolute / distance) move into shared memory too when they fit beside the rows: 192 B each
   const int jl0 = joffL[0], nJL = tile < P ? joffL[kTileColours] - jl0 : 0;
   const int jb0 = joffB[0], nBJ = tile < P ? joffB[kTileColours] - jb0 : 0, nBC = tile < P ? offB[kTileColours] - offB[0] : 0, nB = nBJ + nBC;
-  const long long bodyBytes = 48ll * T + 40ll * kTileNbrMax;
+  const long long bodyBytes = 36ll * T + 32ll * kTileNbrMax;
   auto rows_beside = [&](int joints) { return (int)(((long long)dynBytes - bodyBytes - 192ll * joints - 32) / 108) & ~1; };
   const int R0 = (int)(((long long)dynBytes - bodyBytes) / 108) & ~1;
   // (the boundary's joints join the local ones in shared memory when there is room for them too)
@@ -241,9 +241,13 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   const bool jointRoom = nJS > 0 && nJS <= kTileJointsMax && Rj > 0 && nRows <= Rj && !(W.dbgFlags & 2048);
   const int R = jointRoom ? Rj : R0;
   float4* ra0 = sm4 + 2 * TX; float4* ra1 = ra0 + R; float4* ra2 = ra1 + R; float4* ra3 = ra2 + R; float4* ra4 = ra3 + R; float4* ra5 = ra4 + R;
-  float2* sMass = (float2*)(ra5 + R);
-  int2* rbd = (int2*)(sMass + TX);
-  int* sBody = (int*)(rbd + R); int* sFlag = sBody + T; int* rpc = sFlag + T;
+  int2* rbd = (int2*)(ra5 + R);
+  int* sBody = (int*)(rbd + R); int* rpc = sBody + T;      // sBody: body id | exchange flags << 27
+  // (a body's inverse mass rides in the fourth component of its velocity slot, its inverse inertia in that of its position)
+  auto body_id = [&](int i) { return sBody[i] & 0x07FFFFFF; };
+  auto body_xf = [&](int i) { return (int)((unsigned)sBody[i] >> 27); };
+  auto set3 = [](float4* p, float4 v) { p->x = v.x; p->y = v.y; p->z = v.z; };
+  auto xyz0 = [](float4 v) { return make_float4(v.x, v.y, v.z, 0.0f); };
   float4* sj = (float4*)(((size_t)(rpc + R) + 15) & ~(size_t)15);  // joints: 11 float4 arrays [nJL], then bref int2, limit, root
   const bool rowsLocal = nRows > 0 && nRows <= R;                   // they fit: they live in shared memory for the whole solve
   if (lt == 0) {
@@ -264,7 +268,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   // item takes the lowest colour free on both bodies once it holds the smallest priority on both (priority = joints before
   // contacts, then a hash of the item -- so a body still meets its joints first and the outcome does not depend on scheduling).
   {
-    unsigned* sMask = (unsigned*)sMass;               // scratch in the tail of the dynamic area (masses, references, ids: filled afterwards)
+    unsigned* sMask = (unsigned*)rbd;                 // scratch in the tail of the dynamic area (references, ids: filled afterwards)
     unsigned* sClaim = sMask + 2 * T;                 // [2T] each: own tile's bodies [0, T), the right-hand neighbour's [T, 2T)
     const bool fits = nB <= kTileBMax && R0 > 0 && (size_t)16 * T <= (size_t)dynBytes - (size_t)(32 * TX + 96 * R);
     if (lt == 0) { bDirect = fits ? 0 : 1; nPhB = 0; }
@@ -353,7 +357,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   const int nNb = nNbr;
   MARK();
   long long pc0 = 0; if (marking) pc0 = clock64();
-#define PSTAMP(i) do { if (marking) { W.phaseTimes[3900 + (blockIdx.x == 0 ? 0 : 8) + (i)] = (unsigned long long)(clock64() - pc0); } } while (0)
+#define PSTAMP(i) do { if (marking) { W.phaseTimes[3900 + (blockIdx.x == 0 ? 0 : 16) + (i)] = (unsigned long long)(clock64() - pc0); } } while (0)
 
   if (rowsLocal) for (int k = lt; k < nRows; k += ln) { rbd[k] = W.s_body[rs0 + k]; rpc[k] = W.s_pc[rs0 + k]; }
   // Boundary rows too, as many as the spare row slots take, from the END of the boundary's phase order (its later colours are
@@ -399,35 +403,39 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   PSTAMP(2);
   {
     const float k = 1.0f / 4294967296.0f;
-    // (two bodies per trip, every load of both under way before the first is used)
+    // (two bodies per trip, every load of both under way before the first is used; what is kept in tile order -- ids, masses,
+    // exchange flags, warm-start accumulators -- comes in coalesced, only velocity and position are gathered by body id: the
+    // L1 works through a gathered load one 128-byte line at a time, and that queue is what this block waits for)
     for (int i = lt; i < n; i += 2 * ln) {
       const int i1 = i + ln;
       const bool two = i1 < n;
-      const int b0 = W.t_body[s0 + i], b1 = two ? W.t_body[s0 + i1] : b0;
+      const int e0 = s0 + i, e1 = two ? s0 + i1 : e0;
+      const int b0 = W.t_body[e0], b1 = W.t_body[e1];
       float4 vel[2] = {ldcg4(&W.b_vel[b0]), ldcg4(&W.b_vel[b1])};
+      const float4 pos[2] = {ldcg4(&W.b_pos[b0]), ldcg4(&W.b_pos[b1])};
       long long acc[2][3] = {{0, 0, 0}, {0, 0, 0}};
       if (W.warmStarting) {
-        for (int c = 0; c < 3; ++c) { acc[0][c] = (long long)__ldcg(&W.b_acc[3 * b0 + c]); acc[1][c] = (long long)__ldcg(&W.b_acc[3 * b1 + c]); }
+        for (int c = 0; c < 3; ++c) { acc[0][c] = (long long)__ldcg(&W.b_acc[3 * e0 + c]); acc[1][c] = (long long)__ldcg(&W.b_acc[3 * e1 + c]); }
       }
-      const float4 pos[2] = {ldcg4(&W.b_pos[b0]), ldcg4(&W.b_pos[b1])};
-      const float4 ms[2] = {W.b_mass[b0], W.b_mass[b1]};
-      const int fl[2] = {W.b_xflag[b0], W.b_xflag[b1]};
+      const float2 ms[2] = {W.t_mass[e0], W.t_mass[e1]};
+      const int fl[2] = {W.b_xflag[e0], W.b_xflag[e1]};
       for (int u = 0; u < (two ? 2 : 1); ++u) {
-        const int b = u ? b1 : b0, iu = u ? i1 : i;
+        const int e = u ? e1 : e0, iu = u ? i1 : i;
         if ((acc[u][0] | acc[u][1] | acc[u][2]) != 0) {
           vel[u].x += (float)acc[u][0] * k; vel[u].y += (float)acc[u][1] * k; vel[u].z += (float)acc[u][2] * k;
-          __stcg(&W.b_acc[3 * b], 0ull); __stcg(&W.b_acc[3 * b + 1], 0ull); __stcg(&W.b_acc[3 * b + 2], 0ull);
+          __stcg(&W.b_acc[3 * e], 0ull); __stcg(&W.b_acc[3 * e + 1], 0ull); __stcg(&W.b_acc[3 * e + 2], 0ull);
         }
-        sVel[iu] = vel[u]; sPos[iu] = pos[u]; sMass[iu] = make_float2(ms[u].x, ms[u].y);
-        sBody[iu] = b; sFlag[iu] = fl[u];
+        sVel[iu] = make_float4(vel[u].x, vel[u].y, vel[u].z, ms[u].x); sPos[iu] = make_float4(pos[u].x, pos[u].y, pos[u].z, ms[u].y);
+        sBody[iu] = (u ? b1 : b0) | (fl[u] << 27);
       }
     }
     PSTAMP(3);
     for (int k = lt; k < nNb; k += ln) {
       const int b = sNbrBody[k];
       const float4 ms = W.b_mass[b];
-      sPos[T + k] = ldcg4(&W.b_pos[b]);              // (boundary joints read positions when they initialise)
-      sMass[T + k] = make_float2(ms.x, ms.y);
+      const float4 pos = ldcg4(&W.b_pos[b]);          // (boundary joints read positions when they initialise)
+      sPos[T + k] = make_float4(pos.x, pos.y, pos.z, ms.y);
+      sVel[T + k] = make_float4(0.0f, 0.0f, 0.0f, ms.x);
     }
     __syncthreads();
     PSTAMP(4);
@@ -441,7 +449,8 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   // one row that lives in shared memory (slot x; sg: its slot in the global row arrays)
   auto smem_row = [&](int mode, int x, int sg, int* notOk, const int* prev) {
     const int2 bd = rbd[x];
-    const float2 mA = bd.x >= 0 ? sMass[bd.x - s0] : make_float2(0.0f, 0.0f), mB = bd.y >= 0 ? sMass[bd.y - s0] : make_float2(0.0f, 0.0f);
+    const float2 mA = bd.x >= 0 ? make_float2(sVel[bd.x - s0].w, sPos[bd.x - s0].w) : make_float2(0.0f, 0.0f);
+    const float2 mB = bd.y >= 0 ? make_float2(sVel[bd.y - s0].w, sPos[bd.y - s0].w) : make_float2(0.0f, 0.0f);
     if (mode == TM_VEL) {
       VC v; v.bd = bd; v.pc = rpc[x]; v.v0 = ra0[x]; v.v1 = make_float4(mA.x, mA.y, mB.x, mB.y); v.r0 = ra1[x]; v.r1 = ra2[x]; v.q0 = ra3[x]; v.q1 = ra4[x]; v.imp = ra5[x];
       if ((v.pc & 0xFF) == 2) { v.nm = W.s_nm[sg]; v.K = W.s_k[sg]; }      // (the block solver's matrices stay in L2: no room; fetching them a phase ahead into registers was measured slower)
@@ -497,7 +506,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   auto boundary_phases = [&](int mode, bool backwards, int* notOk, const int* prev) {
     if (bLocal) {
       if (nNb > 0) {
-        for (int k = lt; k < nNb; k += ln) { if (mode == TM_POS) sPos[T + k] = ldcg4(&W.b_pos[sNbrBody[k]]); else sVel[T + k] = ldcg4(&W.b_vel[sNbrBody[k]]); }
+        for (int k = lt; k < nNb; k += ln) { if (mode == TM_POS) set3(&sPos[T + k], ldcg4(&W.b_pos[sNbrBody[k]])); else set3(&sVel[T + k], ldcg4(&W.b_vel[sNbrBody[k]])); }
         __syncthreads();
       }
       for (int k = 0; k < nPhB; ++k) {
@@ -518,7 +527,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
         __syncthreads();
         if (fine) { const long long c2 = clock64(); unsigned long long* o = W.phaseTimes + 3700 + (sweepNo == 11 ? 64 : 0) + (blockIdx.x == 0 ? 0 : 32) + 4 * k; o[0] = (unsigned long long)(c1 - c0); o[1] = (unsigned long long)(c2 - c1); o[2] = (unsigned long long)(sBOff[c + 1] - sBOff[c]); o[3] = (unsigned long long)nj; }
       }
-      for (int k = lt; k < nNb; k += ln) { if (mode == TM_POS) stcg4(&W.b_pos[sNbrBody[k]], sPos[T + k]); else stcg4(&W.b_vel[sNbrBody[k]], sVel[T + k]); }
+      for (int k = lt; k < nNb; k += ln) { if (mode == TM_POS) stcg4(&W.b_pos[sNbrBody[k]], xyz0(sPos[T + k])); else stcg4(&W.b_vel[sNbrBody[k]], xyz0(sVel[T + k])); }
     } else {
       for (int k = 0; k < nLoc; ++k) {
         const int c = backwards ? nLoc - 1 - k : k;
@@ -541,9 +550,9 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   // exchange bodies between shared memory and the global arrays, selected by exchange flags
   auto publish = [&](bool positions, int need, int both) {
     for (int i = lt; i < n; i += ln) {
-      const int f = sFlag[i];
+      const int f = body_xf(i);
       if (!(f & need) || (f & both) != both) continue;
-      if (positions) stcg4(&W.b_pos[sBody[i]], sPos[i]); else stcg4(&W.b_vel[sBody[i]], sVel[i]);
+      if (positions) stcg4(&W.b_pos[body_id(i)], xyz0(sPos[i])); else stcg4(&W.b_vel[body_id(i)], xyz0(sVel[i]));
     }
   };
   // Neighbour handshakes instead of grid barriers (when there are no global rows): tile s only ever exchanges bodies with
@@ -576,7 +585,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
         boundary_phases(mode, false, notOk, prev);
         MARK();
         signal(flagB); await(flagB, tile - 1);
-        for (int i = lt; i < n; i += ln) if (sFlag[i] & XF_FOREIGN) sVel[i] = ldcg4(&W.b_vel[sBody[i]]);
+        for (int i = lt; i < n; i += ln) if (body_xf(i) & XF_FOREIGN) set3(&sVel[i], ldcg4(&W.b_vel[body_id(i)]));
         __syncthreads();
         MARK();
         return;
@@ -590,18 +599,25 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
         GB();
         global_phases(mode, false, notOk, prev);
       } else GB();
-      for (int i = lt; i < n; i += ln) if (sFlag[i] & (XF_FOREIGN | XF_G)) sVel[i] = ldcg4(&W.b_vel[sBody[i]]);
+      for (int i = lt; i < n; i += ln) if (body_xf(i) & (XF_FOREIGN | XF_G)) set3(&sVel[i], ldcg4(&W.b_vel[body_id(i)]));
       __syncthreads();
       MARK();
     } else {
       if (nCross > 0 && handshake) {
+        if (prev && W.phaseTimes != nullptr && lt == 0 && sweepNo == W.velIters + (W.nJoints > 0 ? 1 : 0) + 2) {   // debug: arrival at the first grid barrier since the start
+          unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+          W.phaseTimes[3500 + blockIdx.x] = t_;
+          { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); W.phaseTimes[3650 + blockIdx.x] = sm_ + 1; }
+          W.phaseTimes[3940 + blockIdx.x] = (unsigned long long)nPhL * 100000000ull + (unsigned long long)nRows * 10000ull + (unsigned long long)(nPhB * 1000 + nB)
+                                        + ((unsigned long long)nNb << 32) + ((unsigned long long)nJS << 42) + ((unsigned long long)(jointsLocal ? 1 : 0) << 52) + ((unsigned long long)nBS << 53);
+        }
         if (prev) GB();            // the per-island flags of the pass before must be in for every tile alike
         fetch_prev_flags(prev);
         publish(true, XF_FOREIGN, 0);
         signal(flagL); await(flagL, tile + 1);
         boundary_phases(mode, true, notOk, prev);
         signal(flagB); await(flagB, tile - 1);
-        for (int i = lt; i < n; i += ln) if (sFlag[i] & XF_FOREIGN) sPos[i] = ldcg4(&W.b_pos[sBody[i]]);
+        for (int i = lt; i < n; i += ln) if (body_xf(i) & XF_FOREIGN) set3(&sPos[i], ldcg4(&W.b_pos[body_id(i)]));
         __syncthreads();
       } else if (nCross > 0) {
         publish(true, XF_FOREIGN | XF_G, 0);
@@ -609,7 +625,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
         fetch_prev_flags(prev);
         if (nG > 0) {
           global_phases(mode, true, notOk, prev);
-          for (int i = lt; i < n; i += ln) { const int f = sFlag[i]; if ((f & (XF_OWNB | XF_G)) == (XF_OWNB | XF_G)) sPos[i] = ldcg4(&W.b_pos[sBody[i]]); }
+          for (int i = lt; i < n; i += ln) { const int f = body_xf(i); if ((f & (XF_OWNB | XF_G)) == (XF_OWNB | XF_G)) set3(&sPos[i], ldcg4(&W.b_pos[body_id(i)])); }
           __syncthreads();
         }
         boundary_phases(mode, true, notOk, prev);
@@ -617,8 +633,8 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
         // the neighbour's boundary pass and the global phases wrote the global copy; a body this tile's own boundary rows
         // moved after the global phases is newest in shared memory
         for (int i = lt; i < n; i += ln) {
-          const int f = sFlag[i];
-          if ((f & XF_FOREIGN) || ((f & XF_G) && !(f & XF_OWNB))) sPos[i] = ldcg4(&W.b_pos[sBody[i]]);
+          const int f = body_xf(i);
+          if ((f & XF_FOREIGN) || ((f & XF_G) && !(f & XF_OWNB))) set3(&sPos[i], ldcg4(&W.b_pos[body_id(i)]));
         }
         __syncthreads();
       } else fetch_prev_flags(prev);
@@ -677,11 +693,10 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
     pos = make_float4(c.x, c.y, a, 0.0f); vel = make_float4(v.x, v.y, w, 0.0f);
   };
   for (int i = lt; i < n; i += ln) {
-    const uint32_t f = W.b_flags[sBody[i]];
-    if ((f & (BF_ALIVE | BF_ISLAND)) != (BF_ALIVE | BF_ISLAND)) continue;
+    if (!(body_xf(i) & XF_ISLAND)) continue;
     float4 pos = sPos[i], vel = sVel[i];
     integrate(pos, vel);
-    sPos[i] = pos; sVel[i] = vel;
+    set3(&sPos[i], pos); set3(&sVel[i], vel);
   }
   for (int b = gt; b < W.nBodies; b += gn) {
     if (W.b_tslot[b] >= 0) continue;
@@ -720,13 +735,13 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
       }
     };
     for (int i = lt; i < n; i += ln) {
-      const int b = sBody[i];
-      if (sFlag[i]) W.b_xflag[b] = 0;
-      const uint32_t f = W.b_flags[b];
-      if ((f & (BF_ALIVE | BF_ISLAND)) != (BF_ALIVE | BF_ISLAND)) continue;
-      const float4 pos = sPos[i], vel = sVel[i];
+      const int b = body_id(i);
+      const int xf = body_xf(i);
+      if (xf) W.b_xflag[s0 + i] = 0;
+      if (!(xf & XF_ISLAND)) continue;
+      const float4 pos = xyz0(sPos[i]), vel = xyz0(sVel[i]);
       stcg4(&W.b_pos[b], pos); stcg4(&W.b_vel[b], vel);
-      finish(b, f, pos, vel);
+      finish(b, W.allowSleep ? W.b_flags[b] : 0u, pos, vel);
     }
     for (int b = gt; b < W.nBodies; b += gn) {
       if (W.b_tslot[b] >= 0) continue;
@@ -765,9 +780,9 @@ size_t tile_smem_bytes(int tileBodies) {
     int dev = 0, optin = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaFuncAttributes fa{}; cudaFuncGetAttributes(&fa, (const void*)k_solve_tiles);
-    avail = (size_t)optin > fa.sharedSizeBytes + 1024 ? (size_t)optin - fa.sharedSizeBytes - 1024 : 0;
+    avail = (size_t)optin > fa.sharedSizeBytes ? (size_t)optin - fa.sharedSizeBytes : 0;
   }
-  return std::max(avail, (size_t)tileBodies * 48 + 32 * kTileNbrMax + 4096) > avail ? 0 : avail;       // 0: the tile does not fit
+  return std::max(avail, (size_t)tileBodies * 36 + 32 * kTileNbrMax + 4096) > avail ? 0 : avail;       // 0: the tile does not fit
 }
 
 cudaError_t stage_tile_assign(const DevWorld& W, const LaunchCfg& L, unsigned* keysA, unsigned* keysB, int* valsA, int* valsB) {

@@ -1135,6 +1135,7 @@ int World::growContactsIfNeeded() {
 int World::prepareTiles() {
   constexpr int kTileMinBodies = 2048, kTileMinPerTile = 256, kTileMaxPerTile = 4800, kTileSortPeriod = 16;
   if (replicated_ || overrideLevels_ || (dw_.dbgFlags & 64)) return 0;
+  if (bodies_.size() >= ((size_t)1 << 27)) return 0;       // (k_solve_tiles keeps a body's exchange flags above its 27-bit id)
   // A body with more than 64 touching contacts (the Tumbler's container) serialises its surplus on overflow colours: hundreds of
   // one-row phases.  k_solve runs those inside one CTA (its tail); the tile solver would make each a grid-wide phase.  The
   // watermark copy of the device header (every 8th step, never waited for) tells when a world has such a hub.
@@ -1152,6 +1153,7 @@ int World::prepareTiles() {
   const size_t nBins = (size_t)2 * P * kTileColours + kMaxColours + 1;
   DevBuf<int>* perBody[] = {&b_tslot_, &t_body_, &b_tclaim_, &b_xflag_, &tValA_, &tValB_};
   for (auto* b : perBody) CUDA_OR_FAIL(b->reserve(capB, false, stream_), "tile bodies");
+  CUDA_OR_FAIL(t_mass_.reserve(capB, false, stream_), "tile masses");
   CUDA_OR_FAIL(tKeyA_.reserve(capB, false, stream_), "tile keys"); CUDA_OR_FAIL(tKeyB_.reserve(capB, false, stream_), "tile keys");
   if (tileBodyCap_ != b_tclaim_.cap) {       // fresh buffers: claims at rest, no exchange flags, tiles to be assigned
     CUDA_OR_FAIL(cudaMemsetAsync(b_tclaim_.p, 0x7F, b_tclaim_.cap * 4, stream_), "claims");
@@ -1170,7 +1172,7 @@ int World::prepareTiles() {
   DevWorld& w = dw_;
   if (w.nTiles != P || w.tileBodies != T || w.nTileBodies != nDynamic_) tilesValid_ = false;
   w.nTiles = P; w.tileBodies = T; w.nTileBodies = nDynamic_;
-  w.b_tslot = b_tslot_.p; w.t_body = t_body_.p; w.b_tclaim = b_tclaim_.p; w.b_xflag = b_xflag_.p;
+  w.b_tslot = b_tslot_.p; w.t_body = t_body_.p; w.b_tclaim = b_tclaim_.p; w.b_xflag = b_xflag_.p; w.t_mass = t_mass_.p;
   w.c_tkey = c_tkey_.p; w.c_bref = c_bref_.p; w.j_tkey = j_tkey_.p; w.j_bref = j_bref_.p; w.c_tcol = c_tcol_.p; w.j_tcol = j_tcol_.p;
   w.t_off = t_off_.p; w.t_cur = t_cur_.p; w.tj_off = tj_off_.p; w.tj_cur = tj_cur_.p; w.tj_order = tj_order_.p; w.t_flag = t_flag_.p;
   if (!tilesValid_ || sinceTileSort_ >= kTileSortPeriod) {

@@ -241,6 +241,7 @@ class World {
   std::vector<int> lastReadSlots_;
   // tile solver (dbx_tiles.cu): dynamic bodies of a big single world in x order, cut into one tile per CTA
   int prepareTiles();            // > 0: this step runs the tile solver (buffers sized, tiles assigned, dw_ filled in)
+  DevBuf<float2> t_mass_;
   DevBuf<int> b_tslot_, t_body_, b_tclaim_, b_xflag_, c_tkey_, j_tkey_, c_tcol_, j_tcol_, t_flag_, t_off_, t_cur_, tj_off_, tj_cur_, tj_order_, tValA_, tValB_;
   DevBuf<int2> c_bref_, j_bref_; DevBuf<unsigned> tKeyA_, tKeyB_;
   bool tilesDirty_ = true, tilesValid_ = false, lastTiled_ = false, lastWorldsPath_ = false; int sinceTileSort_ = 0, nDynamic_ = 0; size_t tileBodyCap_ = 0;

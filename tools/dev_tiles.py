@@ -40,4 +40,19 @@ for base, name in ((3700, "CTA 0 vel"), (3732, "middle vel"), (3764, "CTA 0 pos"
 for base, name in ((2304, "CTA 0"), (2304 + 128, "middle CTA")):
     print(name, "position pass 2, per local colour: (colour, items, cycles own item, cycles waiting at the barrier)")
     print("  ", [(int(buf[base + 4 * k + 3]), int(buf[base + 4 * k + 2]), int(buf[base + 4 * k]), int(buf[base + 4 * k + 1])) for k in range(12)])
-print("prologue cycles (thread 0) after: rbd/rpc, joints staged, sW patched, bodies loaded, bodies synced:", [int(buf[3900 + i]) for i in range(5)], [int(buf[3908 + i]) for i in range(5)])
+print("prologue cycles (thread 0) after: rbd/rpc, joints staged, sW patched, bodies loaded, bodies synced:", [int(buf[3900 + i]) for i in range(12)], [int(buf[3916 + i]) for i in range(12)])
+arr = [(buf[3500 + i], i) for i in range(148) if buf[3500 + i]]
+if arr:
+    t0 = min(a for a, _ in arr)
+    print("arrival at the first grid barrier (position pass 2), us after the first CTA; (tile: local colours, local rows, boundary colours x1000 + items):")
+    for a, i in sorted(arr)[::-1][:12] + sorted(arr)[:4]:
+        v = int(buf[3940 + i]); hi = v >> 32; v &= 0xFFFFFFFF
+        print("   nbr bodies %d joints staged %d (local: %d) boundary rows staged %d" % (hi & 1023, (hi >> 10) & 1023, (hi >> 20) & 1, hi >> 21), end="")
+        print("   tile %3d  +%.1f us  colours %d rows %d boundary %d" % (i, (a - t0) / 1000., v // 100000000, (v // 10000) % 10000, v % 10000))
+if arr:
+    his = [int(buf[3940 + i]) >> 32 for _, i in arr]
+    print("max neighbour bodies", max(h & 1023 for h in his), "tiles without joints in shared memory", sum(1 for h in his if not (h >> 20) & 1), "min/max boundary rows staged", min(h >> 21 for h in his), max(h >> 21 for h in his))
+if arr:
+    t0 = min(a for a, _ in arr)
+    print("tile: smid, arrival us")
+    print(" ".join("%d:%d:%.0f" % (i, int(buf[3650 + i]) - 1, (a - t0) / 1000.) for a, i in sorted(arr, key=lambda x: x[1])))
