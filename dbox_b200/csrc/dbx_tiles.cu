@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(256) k_tile_scatter(const __grid_constant__ De
 enum { TM_INIT = 0, TM_VEL = 1, TM_POS = 2 };
 constexpr int kTileThreads = 384;    // k_solve_tiles: a colour of a tile holds ~300 rows at most; fewer threads leave each more registers (measured: -7 us)
 constexpr int kTileNbrMax = 128;                 // bodies of the right-hand neighbour a CTA's boundary constraints may stage in shared memory
+constexpr int kTileNoItem = (int)0x80000000;     // an empty position of a tile's boundary order (padding between a colour's joints and rows)
 constexpr int kTileBMax = 2 * kTileThreads;      // boundary constraints one CTA re-colours locally (more: it walks them by global colour)
 constexpr int kTileBColours = 32;
 constexpr int kTileJointsMax = 512;  // local joints of a tile that may live in shared memory
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   __shared__ int joffG[kTileColours + 1];
   __shared__ int sNbrBody[kTileNbrMax], nNbr;       // the neighbour's bodies the boundary constraints reach: ids, count
   __shared__ int phL[kTileColours], nPhL;          // the local colours that hold anything, in order
-  __shared__ int sBItem[kTileBMax], sBOff[kTileBColours + 1], sBCnt[kTileBColours], nPhB, bDirect;
+  __shared__ int sBItem[kTileBMax], sBOff[kTileBColours + 1], sBCnt[kTileBColours], sBCntJ[kTileBColours], nPhB, bDirect, nBLen;
   __shared__ unsigned long long rowBar;             // mbarrier of the row staging copies
   __shared__ DevWorld sW;                           // W with the joint arrays pointing at the tile's shared-memory copies (local joints)
   __shared__ int jointsBad;
@@ -271,8 +272,8 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
     unsigned* sMask = (unsigned*)rbd;                 // scratch in the tail of the dynamic area (references, ids: filled afterwards)
     unsigned* sClaim = sMask + 2 * T;                 // [2T] each: own tile's bodies [0, T), the right-hand neighbour's [T, 2T)
     const bool fits = nB <= kTileBMax && R0 > 0 && (size_t)16 * T <= (size_t)dynBytes - (size_t)(32 * TX + 96 * R);
-    if (lt == 0) { bDirect = fits ? 0 : 1; nPhB = 0; }
-    if (lt < kTileBColours) sBCnt[lt] = 0;
+    if (lt == 0) { bDirect = fits ? 0 : 1; nPhB = 0; nBLen = 0; }
+    if (lt < kTileBColours) { sBCnt[lt] = 0; sBCntJ[lt] = 0; }
     if (fits && nB > 0) {
       for (int k = lt; k < 2 * T; k += ln) { sMask[k] = 0u; sClaim[k] = 0xFFFFFFFFu; }
       // every thread keeps at most two items in registers (nB <= kTileBMax = 2 x kTileThreads)
@@ -313,18 +314,28 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
         for (int u = 0; u < 2; ++u) if (won[u]) { if (ia[u] >= 0) sClaim[ia[u]] = 0xFFFFFFFFu; if (ib[u] >= 0) sClaim[ib[u]] = 0xFFFFFFFFu; }
         __syncthreads();
       }
-      // counting sort of the items by local colour (the order inside a colour is free)
-      for (int u = 0; u < 2; ++u) if (lt + u * ln < nB) atomicAdd(&sBCnt[lc[u]], 1);
+      // counting sort of the items by local colour (the order inside a colour is free).  Inside a colour the joints come first
+      // and the rows start on a warp of their own: a warp that held both would run the two code paths one after the other.
+      for (int u = 0; u < 2; ++u) if (lt + u * ln < nB) atomicAdd(item[u] < 0 ? &sBCntJ[lc[u]] : &sBCnt[lc[u]], 1);
       __syncthreads();
       if (lt == 0) {
+        int padded = 0;
+        for (int c = 0; c < kTileBColours; ++c) padded += ((sBCntJ[c] + 31) & ~31) + sBCnt[c];
+        const bool pad = padded <= kTileBMax;
         int acc = 0, np = 0;
-        for (int c = 0; c < kTileBColours; ++c) { const int v = sBCnt[c]; sBOff[c] = acc; sBCnt[c] = acc; acc += v; if (v) np = c + 1; }
+        for (int c = 0; c < kTileBColours; ++c) {
+          const int nj = sBCntJ[c], nc = sBCnt[c], rowsAt = acc + (pad ? (nj + 31) & ~31 : nj);
+          sBOff[c] = acc; sBCntJ[c] = acc; sBCnt[c] = rowsAt;
+          for (int q = acc + nj; q < rowsAt; ++q) sBItem[q] = kTileNoItem;
+          acc = rowsAt + nc;
+          if (nj + nc) np = c + 1;
+        }
         sBOff[kTileBColours] = acc;
-        nPhB = np;
+        nPhB = np; nBLen = acc;
       }
       __syncthreads();
       if (!bDirect) for (int u = 0; u < 2; ++u) if (lt + u * ln < nB) {
-        sBItem[atomicAdd(&sBCnt[lc[u]], 1)] = item[u];
+        sBItem[atomicAdd(item[u] < 0 ? &sBCntJ[lc[u]] : &sBCnt[lc[u]], 1)] = item[u];
         if (item[u] >= 0) W.c_tcol[W.s_contact[item[u]]] = lc[u]; else W.j_tcol[jg[u]] = lc[u];    // for dbx_world_debug_read_solve_order
       }
       // The neighbour's bodies these constraints reach (a hundred or so) get slots of their own behind the tile's bodies: a
@@ -354,7 +365,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
     __syncthreads();
   }
   const bool bLocal = bDirect == 0;
-  const int nNb = nNbr;
+  const int nNb = nNbr, nBL = nBLen;                // nBL: length of the boundary's phase order (items + padding)
   MARK();
   long long pc0 = 0; if (marking) pc0 = clock64();
 #define PSTAMP(i) do { if (marking) { W.phaseTimes[3900 + (blockIdx.x == 0 ? 0 : 16) + (i)] = (unsigned long long)(clock64() - pc0); } } while (0)
@@ -363,8 +374,8 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   // Boundary rows too, as many as the spare row slots take, from the END of the boundary's phase order (its later colours are
   // the small ones: a colour that sits in shared memory whole runs at the local rows' pace).  Position q of the order gets
   // slot nRows + q - qS0; a joint's position stays empty.
-  const int nBS = (bLocal && rowsLocal && nNb > 0 && !(W.dbgFlags & 8192)) ? min(nB, R - nRows) : 0, qS0 = nB - nBS;
-  for (int q = qS0 + lt; q < nB; q += ln) {
+  const int nBS = (bLocal && rowsLocal && nNb > 0 && !(W.dbgFlags & 8192)) ? min(nBL, R - nRows) : 0, qS0 = nBL - nBS;
+  for (int q = qS0 + lt; q < nBL; q += ln) {
     const int s = sBItem[q], x = nRows + q - qS0;
     if (s < 0) continue;
     ra0[x] = W.s_v0[s]; ra1[x] = W.s_r0[s]; ra2[x] = W.s_r1[s]; ra3[x] = W.s_q0[s]; ra4[x] = W.s_q1[s]; ra5[x] = W.s_imp[s];
@@ -478,6 +489,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
       const int c = phL[k];
       const int jb = joffL[c], nj = joffL[c + 1] - jb, beg = offL[c], nr = offL[c + 1] - beg;
       if (mode == TM_INIT && nj == 0) continue;
+      const int njPad = (nj + 31) & ~31;
       const bool fine = marking && (sweepNo == 4 || sweepNo == 11) && kk < 16;       // debug: clock stamps of one velocity pass at [2048 + 4 kk ..), of one position pass at [2304 + 4 kk ..)
       long long c0 = 0, c1 = 0;
       if (fine) c0 = clock64();
@@ -485,8 +497,8 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
       else for (int q = lt; q < nj; q += ln) tile_item(W, view, mode, ~W.tj_order[jb + q], notOk, prev);
       if (mode != TM_INIT) {
         if (rowsLocal) {
-          // (row q of the colour belongs to thread q - nj, as in the global layout, so a jointed colour spreads over all warps)
-          for (int q = lt - nj; q < nr; q += ln) if (q >= 0) smem_row(mode, beg - rs0 + q, beg + q, notOk, prev);
+          // (the rows start on the first warp after the joints': a warp holding both would run the two code paths in turn)
+          for (int q = lt - njPad; q < nr; q += ln) if (q >= 0) smem_row(mode, beg - rs0 + q, beg + q, notOk, prev);
         } else {
           const int kn = backwards ? k - 1 : k + 1;
           if (kn >= 0 && kn < nPhL) {
@@ -516,6 +528,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
         if (fine) { c0 = clock64(); for (int q = sBOff[c]; q < sBOff[c + 1]; ++q) nj += sBItem[q] < 0; }
         for (int q = sBOff[c] + lt; q < sBOff[c + 1]; q += ln) {
           const int item = sBItem[q];
+          if (item == kTileNoItem) continue;
           if (item < 0) {                                     // a joint: ~index in the boundary's joint list
             if (bJointsLocal) tile_item(sW, view, mode, ~(nJL + ~item), notOk, prev);
             else tile_item(W, view, mode, ~W.tj_order[jb0 + ~item], notOk, prev);
@@ -657,7 +670,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   };
   if (rowsLocal) {
     for (int k = lt; k < nRows; k += ln) { const float4 imp = ra5[k]; W.s_imp[rs0 + k] = imp; store_impulse(rs0 + k, imp, rpc[k]); }
-    for (int q = qS0 + lt; q < nB; q += ln) { const int s = sBItem[q]; if (s >= 0) stcg4(&W.s_imp[s], ra5[nRows + q - qS0]); }     // (into the manifolds with the other boundary rows below)
+    for (int q = qS0 + lt; q < nBL; q += ln) { const int s = sBItem[q]; if (s >= 0) stcg4(&W.s_imp[s], ra5[nRows + q - qS0]); }     // (into the manifolds with the other boundary rows below)
     __syncthreads();
     if (W.posIters > 0) {
       if (lt == 0) {
@@ -667,7 +680,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
         bulk_g2s(ra0, W.s_p0 + rs0, bytes, &rowBar); bulk_g2s(ra1, W.s_p1 + rs0, bytes, &rowBar); bulk_g2s(ra2, W.s_p2 + rs0, bytes, &rowBar);
       }
       for (int k = lt; k < nRows; k += ln) { const float2 r = W.s_p3[rs0 + k]; ra3[k] = make_float4(r.x, r.y, __int_as_float(W.s_root[rs0 + k]), 0.0f); }   // .z: the row's island, .w: its flag of the pass before
-      for (int q = qS0 + lt; q < nB; q += ln) {
+      for (int q = qS0 + lt; q < nBL; q += ln) {
         const int s = sBItem[q], x = nRows + q - qS0;
         if (s < 0) { ra3[x] = make_float4(0.0f, 0.0f, __int_as_float(0), 0.0f); continue; }
         const float2 r = W.s_p3[s];
