@@ -63,6 +63,7 @@ DBX_D void mark_solve_body(const DevWorld& W) {
 // same round are arbitrated Jones-Plassmann style: per body the contact with the highest (key-derived) priority wins,
 // so the outcome is independent of thread scheduling.  Static/kinematic bodies are never written by the solver and do
 // not constrain colours.  Runs as one persistent cooperative kernel; rounds loop on the device.
+constexpr int kColourSoloMax = 8192;
 // pair key with the replica offset removed, so that every replica of a batched world arbitrates (and hence colours) alike
 DBX_D unsigned long long local_key(const DevWorld& W, unsigned long long key, int body) {
   if (W.keyStride == 0) return key;
@@ -70,13 +71,19 @@ DBX_D unsigned long long local_key(const DevWorld& W, unsigned long long key, in
   return key - (o << 32) - o;
 }
 // (every CTA of a cooperative launch calls this; it synchronises the grid through Header::barrier)
+// A short worklist (the few hundred contacts a settled scene gains per step) is coloured by CTA 0 alone: its rounds then meet at
+// block barriers instead of grid barriers (three per round, ~3 us each).  Every CTA takes the same decision: the two header words
+// it depends on are not written while the kernel runs (k_island_init resets / advances them at the start of the next step).
 DBX_D void colour_body(const DevWorld& W) {
   Header* H = W.hdr;
   const unsigned nb = gridDim.x;
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   int* cur = W.c_work; int* nxt = W.c_work2;
   int n = H->nUncoloured;
   unsigned epoch = H->epoch;
+  const bool solo = n <= kColourSoloMax && epoch <= 0xF0000u;
+  if (solo && blockIdx.x != 0) return;
+  const int tid = solo ? (int)threadIdx.x : (int)(blockIdx.x * blockDim.x + threadIdx.x), nth = solo ? (int)blockDim.x : (int)(gridDim.x * blockDim.x);
+#define COLOUR_SYNC() do { if (solo) __syncthreads(); else grid_barrier(&H->barrier, nb); } while (0)
   if (epoch > 0xF0000u) {   // the round stamp is 20 bits wide: recycle it long before it wraps
     for (int b = tid; b < W.nBodies; b += nth) W.b_claim[b] = 0ull;
     epoch = 0;
@@ -94,7 +101,7 @@ DBX_D void colour_body(const DevWorld& W) {
       if (body_type(W.b_flags[ids.w]) == BODY_DYNAMIC) atomicMax(&W.b_claim[ids.w], pr);
     }
     if (tid == 0) H->nUncoloured2 = 0;
-    grid_barrier(&H->barrier, nb);
+    COLOUR_SYNC();
     // phase 2: winners take a colour
     for (int k = tid; k < n; k += nth) {
       int i = cur[k];
@@ -126,12 +133,13 @@ DBX_D void colour_body(const DevWorld& W) {
         nxt[slot] = i;
       }
     }
-    grid_barrier(&H->barrier, nb);
+    COLOUR_SYNC();
     n = *((volatile int*)&H->nUncoloured2);
     int* t = cur; cur = nxt; nxt = t;
-    grid_barrier(&H->barrier, nb);
+    COLOUR_SYNC();
   }
-  if (tid == 0) { H->epoch = epoch; H->nUncoloured = 0; }
+  if (tid == 0) H->epochNext = epoch;
+#undef COLOUR_SYNC
 }
 
 }  // namespace dbx

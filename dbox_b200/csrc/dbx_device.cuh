@@ -71,7 +71,8 @@ struct Header {
   int tailStart;      // first colour of the tail that k_solve runs inside one CTA
   int nCtEvents;      // contact begin/end events recorded since the last poll (may exceed evCap: the surplus is lost and reported)
   unsigned barrier;   // grid barrier ticket counter for the persistent kernels
-  unsigned epoch;     // colouring round stamp
+  unsigned epoch;     // colouring round stamp (k_colour leaves the next one in epochNext; k_island_init moves it here, so that the
+                      // word every CTA of k_colour reads when it starts is not written while that kernel runs)
   int nFresh;         // contacts created by the current FindNewContacts, listed in c_work for k_toi's first pass
   int maxColour;      // largest colour ever handed out (monotonic): bounds the key width of the world-major sort
   float bounds[4];    // world bounds of fat AABB centres (Morton normalisation), as ordered ints
@@ -85,6 +86,7 @@ struct Header {
   unsigned long long toiGlobalMin;   // sub-stepping: smallest event priority of the current pass (the ONE event to handle)
   int nTileB, nTileG; // tile solver: boundary / global constraints (contacts + joints) of this step
   unsigned long long solveStamp[4];   // %globaltimer of CTA 0 in the island solver: start, velocity passes begin, position passes begin, end (b2Profile split)
+  unsigned epochNext; // see epoch
 };
 
 struct DevWorld {

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256, 4) k_collide(const __grid_constant__ DevW
 // ------------------------------------------------------------------------------------------------ islands
 // Replaces the DFS of b2World.Solve (dynamics/b2world.d:943-1095) with a union-find over constraint edges.
 __global__ void __launch_bounds__(256) k_island_init(const __grid_constant__ DevWorld W) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) { W.hdr->nSolve = 0; W.hdr->nColours = 0; W.hdr->nIslands = 0; W.hdr->nUncoloured = 0; W.hdr->nUncoloured2 = 0; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { W.hdr->nSolve = 0; W.hdr->nColours = 0; W.hdr->nIslands = 0; W.hdr->nUncoloured = 0; W.hdr->nUncoloured2 = 0; W.hdr->epoch = W.hdr->epochNext; }
   GRID_STRIDE(b, W.nBodies) {
     W.b_root[b] = b;
     W.b_islAwake[b] = 0;

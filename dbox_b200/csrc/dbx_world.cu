@@ -1146,7 +1146,7 @@ int World::prepareTiles() {
     nDynamic_ = n; dw_.tileKinematic = nk > 0 ? 1 : 0; tilesDirty_ = false; tilesValid_ = false;
   }
   if (nDynamic_ < kTileMinBodies) return 0;
-  const int P = std::max(1, std::min(L_.coopBlocks, nDynamic_ / kTileMinPerTile));
+  const int P = std::max(1, std::min(std::min(L_.coopBlocks, 176), nDynamic_ / kTileMinPerTile));    // (176: what k_tile_scan's histograms in shared memory allow)
   const int T = (nDynamic_ + P - 1) / P;
   if (T > kTileMaxPerTile) return 0;
   const size_t capB = b_root.cap, capC = c_key.cap, capJ = std::max<size_t>(j_ids.cap, 1);
