@@ -1536,10 +1536,12 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
     }
     if (tid == 0) H->nPairs = 0;
     grid_barrier(&H->barrier, nb); TMARK();
+    // (a TOI sub-step rarely carries a proxy out of its fat box: without moved proxies FindNewContacts has nothing to do, and
+    // its two grid barriers are skipped.  The count is final here and every CTA reads the same value.)
+    const int nMovedNow = min(*((volatile int*)&H->nMoved), W.moveCap);
     {
       // the step's LBVH is still valid for every proxy that did not move; widen it for the ones that did
-      const int nMoved = min(*((volatile int*)&H->nMoved), W.moveCap);
-      for (int k = tid; k < nMoved; k += nth) lbvh_enlarge(W, W.moveList[k]);
+      for (int k = tid; k < nMovedNow; k += nth) lbvh_enlarge(W, W.moveList[k]);
       for (int b = tid; b < W.nBodies; b += nth) {
         W.b_toiMin[b] = ~0ull; W.b_toiOther[b] = ~0ull; W.b_toiEvt[b] = -1;
         if (W.b_toiFlags[b] & TF_SYNC) W.b_toiFlags[b] &= ~TF_SYNC;
@@ -1547,21 +1549,17 @@ __global__ void __launch_bounds__(512) k_toi(const __grid_constant__ DevWorld W)
       if (tid == 0) { H->nEvents = 0; H->toiGlobalMin = ~0ull; }
     }
     grid_barrier(&H->barrier, nb); TMARK();
-    {
-      const int nMoved = min(*((volatile int*)&H->nMoved), W.moveCap);
-      for (int k = warp; k < nMoved; k += nwarps) query_proxy(W, W.bv_sorted, stacks[wib], kQueryStackToi, lane, W.moveList[k]);
-    }
-    grid_barrier(&H->barrier, nb); TMARK();
-    {
+    if (nMovedNow > 0) {
+      for (int k = warp; k < nMovedNow; k += nwarps) query_proxy(W, W.bv_sorted, stacks[wib], kQueryStackToi, lane, W.moveList[k]);
+      grid_barrier(&H->barrier, nb); TMARK();
       const int nPairs = min(*((volatile int*)&H->nPairs), W.pairCap);
       for (int k = tid; k < nPairs; k += nth) add_pair(W, W.pairs[k]);
-      const int nMoved = min(*((volatile int*)&H->nMoved), W.moveCap);
-      for (int k = tid; k < nMoved; k += nth) { const int p = W.moveList[k]; W.p_flags[p] &= ~PF_MOVED; }
+      for (int k = tid; k < nMovedNow; k += nth) { const int p = W.moveList[k]; W.p_flags[p] &= ~PF_MOVED; }
+      grid_barrier(&H->barrier, nb); TMARK();
+      if (tid == 0) H->nMoved = 0;      // (next touched by the SynchronizeFixtures of the next pass, four barriers on)
     }
-    grid_barrier(&H->barrier, nb); TMARK();
-    if (tid == 0) H->nMoved = 0;
     const bool stopHere = W.subStep && *((volatile int*)&H->toiSolved) > 0;   // b2world.d:1441-1446: m_stepComplete = false; break
-    grid_barrier(&H->barrier, nb); TMARK();
+    if (W.subStep) { grid_barrier(&H->barrier, nb); TMARK(); }
     if (stopHere) { incomplete = true; break; }
   }
   // leave the per-body scratch clean for the next step (every CTA is past the last arbitration phase here); a sub-stepped
