@@ -1371,8 +1371,32 @@ DBX_D void toi_process_event(const DevWorld& W, int e, float dtStep) {
   }
   // ---- b2Island.SolveTOI with subStep {dt = (1 - alpha) dt, 20 position iterations, no warm starting}
   const int sBase = e * kMaxTOIContacts;
+  // A small mini-island (nearly all are: a body and what it rests on) keeps its bodies in thread-local arrays while the two
+  // solver loops run, the rows referring to them by index (BodyView mode 1): the loops are one thread's chain of dependent
+  // steps, and a trip to L2 and back for the bodies inside every row was a third of it.
+  constexpr int kToiLocalBodies = 8;
+  float4 lpos[kToiLocalBodies], lvel[kToiLocalBodies];
+  const bool local = nb <= kToiLocalBodies;
+  BodyView view; view.vel = lvel; view.pos = lpos; view.off = 0; view.mode = 1;
+  auto rows_to_local = [&]() {
+    for (int k = 0; k < nc; ++k) {
+      int2 bd = W.s_body[sBase + k];
+      int x = 0, y = 0;
+      for (int t = 0; t < nb; ++t) { if (bodies[t] == bd.x) x = t; if (bodies[t] == bd.y) y = t; }
+      W.s_body[sBase + k] = make_int2(x, y);
+    }
+  };
   for (int k = 0; k < nc; ++k) prepare_contact(W, sBase + k, contacts[k], -1.0f);
-  for (int it = 0; it < 20; ++it) {
+  if (local) {
+    for (int t = 0; t < nb; ++t) lpos[t] = ldcg4(&W.b_pos[bodies[t]]);
+    rows_to_local();
+    for (int it = 0; it < 20; ++it) {
+      float minSeparation = 0.0f;
+      for (int k = 0; k < nc; ++k) minSeparation = fminr(minSeparation, contact_solve_position(W, sBase + k, 0, 1, view));   // (bodies[0] = bA, bodies[1] = bB)
+      if (minSeparation >= -1.5f * kLinearSlop) break;
+    }
+    for (int t = 0; t < nb; ++t) if (body_type(W.b_flags[bodies[t]]) == BODY_DYNAMIC) stcg4(&W.b_pos[bodies[t]], lpos[t]);
+  } else for (int it = 0; it < 20; ++it) {
     float minSeparation = 0.0f;
     for (int k = 0; k < nc; ++k) minSeparation = fminr(minSeparation, contact_solve_position(W, sBase + k, bA, bB));
     if (minSeparation >= -1.5f * kLinearSlop) break;
@@ -1391,7 +1415,12 @@ DBX_D void toi_process_event(const DevWorld& W, int e, float dtStep) {
     }
   }
   for (int k = 0; k < nc; ++k) prepare_contact(W, sBase + k, contacts[k], -1.0f);
-  for (int it = 0; it < W.velIters; ++it) for (int k = 0; k < nc; ++k) contact_solve_velocity(W, sBase + k);
+  if (local) {
+    for (int t = 0; t < nb; ++t) lvel[t] = ldcg4(&W.b_vel[bodies[t]]);
+    rows_to_local();
+    for (int it = 0; it < W.velIters; ++it) for (int k = 0; k < nc; ++k) contact_solve_velocity(W, sBase + k, view);
+    for (int t = 0; t < nb; ++t) if (body_type(W.b_flags[bodies[t]]) == BODY_DYNAMIC) stcg4(&W.b_vel[bodies[t]], lvel[t]);
+  } else for (int it = 0; it < W.velIters; ++it) for (int k = 0; k < nc; ++k) contact_solve_velocity(W, sBase + k);
   if (W.psCap > 0) for (int k = 0; k < nc; ++k) emit_post_solve(W, 2, sBase + k, contacts[k]);   // island.Report (b2island.d:414)
   const float h = (1.0f - minAlpha) * dtStep;
   for (int t = 0; t < nb; ++t) {
