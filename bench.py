@@ -553,7 +553,7 @@ def main():
         except Exception:
             pass
         alg_step = algorithmic_bytes_step(counts, n_rev, n_dist, VEL_ITERS, POS_ITERS, proxies, pairs)
-        kernel = ("k_solve_tiles (tile solver, %d tiles: bodies + local rows of a tile in shared memory via TMA bulk copies; " % tiles if tiles else "k_solve (persistent coloured Gauss-Seidel: ") + \
+        kernel = ("k_solve_tiles (tile solver, %d tiles: a tile's bodies, local rows (TMA bulk copies), boundary rows and joints in shared memory; " % tiles if tiles else "k_solve (persistent coloured Gauss-Seidel: ") + \
                  "warm start + %d velocity + %d position iterations + write-back)" % (VEL_ITERS, POS_ITERS)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
                 "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
