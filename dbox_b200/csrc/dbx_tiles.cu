@@ -64,14 +64,22 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const __grid_constant__ DevW
   if (t < 4) stats[t] = 0;
   __syncthreads();
   int nb = 0, ng = 0, maxc = 0;
-  for (int k = t; k < nBins; k += 1024) {
-    const int c = W.t_cur[k], j = W.tj_cur[k];
-    const int ch = k / per, idx = ch * stride + (k - ch * per);
-    A[idx] = c; B[idx] = j;
-    if (c + j > 0) {
-      const int col = k < 2 * P * kTileColours ? k % kTileColours : k - 2 * P * kTileColours;
-      maxc = max(maxc, col + 1);
-      if (k >= 2 * P * kTileColours) ng += c + j; else if (k >= P * kTileColours) nb += c + j;
+  for (int base = t; base < nBins; base += 8 * 1024) {
+    int cs[8], js[8];                                  // eight rounds of loads under way before the first is used
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int k = base + u * 1024; cs[u] = k < nBins ? W.t_cur[k] : 0; js[u] = k < nBins ? W.tj_cur[k] : 0; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = base + u * 1024;
+      if (k >= nBins) break;
+      const int c = cs[u], j = js[u];
+      const int ch = k / per, idx = ch * stride + (k - ch * per);
+      A[idx] = c; B[idx] = j;
+      if (c + j > 0) {
+        const int col = k < 2 * P * kTileColours ? k % kTileColours : k - 2 * P * kTileColours;
+        maxc = max(maxc, col + 1);
+        if (k >= 2 * P * kTileColours) ng += c + j; else if (k >= P * kTileColours) nb += c + j;
+      }
     }
   }
   __syncthreads();

@@ -271,6 +271,31 @@ def _one_ulp_twin(snap):
 
 @pytest.mark.parametrize("n,columns,settle", [(3000, 100, 300), (100000, 1000, 600)])
 def test_pile_single_step_matches_oracle(gpu_api, oracle_api, n, columns, settle):
+    _pile_single_step_vs_oracle(gpu_api, oracle_api, n, columns, settle)
+
+
+@pytest.mark.parametrize("flags,what", [(128, "grid barriers instead of neighbour handshakes"),
+                                        (2048, "joints stay in the global arrays"),
+                                        (4096, "the neighbour's bodies are reached through L2 (no staging, no staged boundary rows)"),
+                                        (8192, "boundary rows stay in the global arrays"),
+                                        (64, "tile solver off: k_solve")])
+def test_pile_single_step_matches_oracle_on_the_fallback_paths(gpu_api, oracle_api, flags, what):
+    """k_solve_tiles takes these branches when something does not fit in a tile's shared memory (a tile richer in joints or
+    boundary rows than the pile's); the DBX_DEBUG bits force them so that they are held to the same oracle as the fast paths.
+    The library reads the variable whenever it rebuilds its device view (world creation included)."""
+    import os
+    old = os.environ.get("DBX_DEBUG")
+    os.environ["DBX_DEBUG"] = str(flags)
+    try:
+        _pile_single_step_vs_oracle(gpu_api, oracle_api, 3000, 100, 300)
+    finally:
+        if old is None:
+            del os.environ["DBX_DEBUG"]
+        else:
+            os.environ["DBX_DEBUG"] = old
+
+
+def _pile_single_step_vs_oracle(gpu_api, oracle_api, n, columns, settle):
     """One step of the settled pile on the device against the sequential oracle walking the device's own Gauss-Seidel order.
     Exact: contact set, touching flags, manifold types, feature keys, manifolds (bit for bit), island count.  Velocities,
     positions and impulses: north_star's 1e-4 / 1e-5 relative for all but a fraction of a per cent of the bodies, and for
