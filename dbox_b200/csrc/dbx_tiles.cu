@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
   const int tile = blockIdx.x;
   const int s0 = tile * T, n = tile < P ? max(0, min(T, W.nTileBodies - s0)) : 0;
   unsigned dynBytes; asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dynBytes));
+  const int nbrMax = (W.dbgFlags & 32768) ? 8 : kTileNbrMax;       // (debug: a tiny limit, so that tests see the overflow branch)
   const int TX = T + kTileNbrMax;                   // body slots: the tile's own [0, T), staged neighbour bodies [T, T + nNbr)
   float4* sVel = sm4; float4* sPos = sm4 + TX;
   const int* offG = W.t_off + 2 * P * kTileColours; // (global rows are the rare case: their offsets stay in L2)
@@ -370,11 +371,11 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
           const int x[2] = {ia[u], ib[u]}, id[2] = {brs[u].x, brs[u].y};
           for (int e = 0; e < 2; ++e) if (x[e] >= T && atomicCAS(&sClaim[x[e]], 0xFFFFFFFFu, 0xFFFFFFFEu) == 0xFFFFFFFFu) {
             const int k = atomicAdd(&nNbr, 1);
-            if (k < kTileNbrMax) { sNbrBody[k] = id[e] & 0x7fffffff; sClaim[x[e]] = (unsigned)k; }
+            if (k < nbrMax) { sNbrBody[k] = id[e] & 0x7fffffff; sClaim[x[e]] = (unsigned)k; }
           }
         }
         __syncthreads();
-        if (nNbr <= kTileNbrMax) {
+        if (nNbr <= nbrMax) {
           for (int u = 0; u < 2; ++u) if (lt + u * ln < nB) {
             int2 br = brs[u];
             if (ia[u] >= T) br.x = s0 + T + (int)sClaim[ia[u]];
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
           }
         }
         __syncthreads();
-        if (lt == 0 && nNbr > kTileNbrMax) nNbr = 0;
+        if (lt == 0 && nNbr > nbrMax) nNbr = 0;
       }
     }
     __syncthreads();

@@ -132,7 +132,7 @@ class Tumbler:
                 self.m_count += 1
 
 
-def pile(api=None, n=100000, columns=1000, joints=True, circles=True, seed=12345, world=None, **kw):
+def pile(api=None, n=100000, columns=1000, joints=True, circles=True, seed=12345, world=None, long_links=0, **kw):
     """Config 4: `n` dynamic bodies in a jittered grid `columns` wide above a static chain floor with
     two edge walls; 70 % boxes (half-extent 0.5, density 1, friction 0.3), 30 % circles r=0.5; every 10th column is
     linked upward into 25-body revolute chains and every 10th row sideways into 25-body rigid distance chains."""
@@ -199,4 +199,17 @@ def pile(api=None, n=100000, columns=1000, joints=True, circles=True, seed=12345
                 jd.collideConnected = True
                 world.CreateJoint(jd)
                 njoints += 1
+    # `long_links` rigid distance joints between bodies half the pile apart (top rows, at their current distance): constraints
+    # that no spatial partition of the bodies can keep local (the tile solver's "global" class)
+    for t in range(long_links):
+        row, col = rows - 1 - (t % 3), (7 * t) % max(1, columns // 2)
+        i, j = row * columns + col, row * columns + col + columns // 2
+        if i < 0 or j >= n:
+            continue
+        jd = b2DistanceJointDef()
+        pa, pb = bodies[i].GetPosition(), bodies[j].GetPosition()
+        jd.Initialize(bodies[i], bodies[j], (pa.x, pa.y), (pb.x, pb.y))
+        jd.collideConnected = True
+        world.CreateJoint(jd)
+        njoints += 1
     return world, bodies, njoints

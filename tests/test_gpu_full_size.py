@@ -278,6 +278,7 @@ def test_pile_single_step_matches_oracle(gpu_api, oracle_api, n, columns, settle
                                         (2048, "joints stay in the global arrays"),
                                         (4096, "the neighbour's bodies are reached through L2 (no staging, no staged boundary rows)"),
                                         (8192, "boundary rows stay in the global arrays"),
+                                        (32768, "more neighbour bodies than slots for them: the whole tile falls back to L2"),
                                         (64, "tile solver off: k_solve")])
 def test_pile_single_step_matches_oracle_on_the_fallback_paths(gpu_api, oracle_api, flags, what):
     """k_solve_tiles takes these branches when something does not fit in a tile's shared memory (a tile richer in joints or
@@ -295,7 +296,14 @@ def test_pile_single_step_matches_oracle_on_the_fallback_paths(gpu_api, oracle_a
             os.environ["DBX_DEBUG"] = old
 
 
-def _pile_single_step_vs_oracle(gpu_api, oracle_api, n, columns, settle):
+def test_pile_with_global_constraints_matches_oracle(gpu_api, oracle_api):
+    """Distance joints across half the pile: constraints of the tile solver's global class (grid-wide phases after the local and
+    boundary ones, grid barriers instead of neighbour handshakes), held to the same oracle."""
+    r = _pile_single_step_vs_oracle(gpu_api, oracle_api, 3000, 100, 300, long_links=12)
+    assert r[False]["tiles"] > 0 and r[False]["global_rows"] > 0, r
+
+
+def _pile_single_step_vs_oracle(gpu_api, oracle_api, n, columns, settle, **scene):
     """One step of the settled pile on the device against the sequential oracle walking the device's own Gauss-Seidel order.
     Exact: contact set, touching flags, manifold types, feature keys, manifolds (bit for bit), island count.  Velocities,
     positions and impulses: north_star's 1e-4 / 1e-5 relative for all but a fraction of a per cent of the bodies, and for
@@ -305,12 +313,13 @@ def _pile_single_step_vs_oracle(gpu_api, oracle_api, n, columns, settle):
     (A wrong order or a wrong warm start shows as 1e-2 .. 1 on hundreds of bodies: both were found with this test.)"""
     from dbox_b200 import state
     from tests.parity import hand_device_order_to_oracle
-    wg, _, nj = scenes.pile(api=gpu_api, n=n, columns=columns)
-    wo, _, _ = scenes.pile(api=oracle_api, n=n, columns=columns)
-    wt, _, _ = scenes.pile(api=oracle_api, n=n, columns=columns)
+    wg, _, nj = scenes.pile(api=gpu_api, n=n, columns=columns, **scene)
+    wo, _, _ = scenes.pile(api=oracle_api, n=n, columns=columns, **scene)
+    wt, _, _ = scenes.pile(api=oracle_api, n=n, columns=columns, **scene)
     for w in (wg, wo, wt):
         w.SetAllowSleeping(False)
     wg.StepN(DT, 8, 3, settle)
+    report = {}
     snap = state.capture(wg)
     twin = _one_ulp_twin(snap)
     assert snap["nb"] == n + 1 and snap["nj"] == nj
@@ -332,7 +341,11 @@ def _pile_single_step_vs_oracle(gpu_api, oracle_api, n, columns, settle):
             own = _compare_step(wt, wo, "oracle twin")
         except AssertionError:          # the ulp flipped a feature somewhere: no yardstick from this pair
             own = None
-        r.update(order_found=found, position_backwards=info[0], colours=info[1], joint_colours=info[2], tiles=info[3], islands=cg.islands)
+        hb = (C.c_int32 * 2400)()
+        gpu_api.world_debug_header(wg._w, hb, 9600)        # Header::nTileB, nTileG (dbx_device.cuh) sit at ints 1124, 1125
+        r.update(order_found=found, position_backwards=info[0], colours=info[1], joint_colours=info[2], tiles=info[3], islands=cg.islands,
+                 boundary_rows=hb[1124], global_rows=hb[1125])
+        report[continuous] = r
         print("pile %d single step, device vs oracle, continuous=%s: %s" % (n, continuous, r))
         print("pile %d single step, oracle vs oracle with angles + 1 ulp:  %s" % (n, own))
         # bit for bit after Solve; with the TOI sub-steps in, contacts are re-evaluated at positions that carry the deviation below
@@ -343,3 +356,4 @@ def _pile_single_step_vs_oracle(gpu_api, oracle_api, n, columns, settle):
             assert frac <= max(8.0 * own_frac, 1e-2), (q, r[q], own and own[q])        # how many items are beyond the tolerance
             assert worst <= max(8.0 * own_worst, 20.0 * tol), (q, r[q], own and own[q])    # and how far
     wg.close(); wo.close(); wt.close()
+    return report
