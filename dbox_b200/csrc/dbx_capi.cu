@@ -168,19 +168,19 @@ int32_t dbx_world_clear_forces(dbx_world* w) { W_OR_INVALID(w); return w->w.clea
 int32_t dbx_body_get_state(dbx_world* w, int32_t body, dbx_body_state* out) { W_OR_INVALID(w); if (!out) return DBX_E_INVALID; return w->w.getBody(body, out); }
 int32_t dbx_body_set_transform(dbx_world* w, int32_t body, float x, float y, float angle) { W_OR_INVALID(w); return w->w.setTransform(body, x, y, angle); }
 int32_t dbx_body_set_linear_velocity(dbx_world* w, int32_t body, float vx, float vy) {
-  W_OR_INVALID(w); HBody* b = w->w.mutBody(body); if (!b) return DBX_E_INVALID;
+  W_OR_INVALID(w); HBody* b = w->w.mutBodyRow(body); if (!b) return DBX_E_INVALID;
   if (b->st.type == DBX_STATIC_BODY) return 0;
   if (vx * vx + vy * vy > 0.0f) w->w.wake(*b, true);
   b->st.v = dbx_vec2{vx, vy}; return 0;
 }
 int32_t dbx_body_set_angular_velocity(dbx_world* w, int32_t body, float omega) {
-  W_OR_INVALID(w); HBody* b = w->w.mutBody(body); if (!b) return DBX_E_INVALID;
+  W_OR_INVALID(w); HBody* b = w->w.mutBodyRow(body); if (!b) return DBX_E_INVALID;
   if (b->st.type == DBX_STATIC_BODY) return 0;
   if (omega * omega > 0.0f) w->w.wake(*b, true);
   b->st.w = omega; return 0;
 }
 int32_t dbx_body_apply_force(dbx_world* w, int32_t body, float fx, float fy, float px, float py, int32_t wake) {
-  W_OR_INVALID(w); HBody* b = w->w.mutBody(body); if (!b) return DBX_E_INVALID;
+  W_OR_INVALID(w); HBody* b = w->w.mutBodyRow(body); if (!b) return DBX_E_INVALID;
   if (b->st.type != DBX_DYNAMIC_BODY) return 0;
   if (wake && (b->st.flags & DBX_BODY_AWAKE) == 0) w->w.wake(*b, true);
   if (b->st.flags & DBX_BODY_AWAKE) {
@@ -190,14 +190,14 @@ int32_t dbx_body_apply_force(dbx_world* w, int32_t body, float fx, float fy, flo
   return 0;
 }
 int32_t dbx_body_apply_torque(dbx_world* w, int32_t body, float torque, int32_t wake) {
-  W_OR_INVALID(w); HBody* b = w->w.mutBody(body); if (!b) return DBX_E_INVALID;
+  W_OR_INVALID(w); HBody* b = w->w.mutBodyRow(body); if (!b) return DBX_E_INVALID;
   if (b->st.type != DBX_DYNAMIC_BODY) return 0;
   if (wake && (b->st.flags & DBX_BODY_AWAKE) == 0) w->w.wake(*b, true);
   if (b->st.flags & DBX_BODY_AWAKE) b->st.torque += torque;
   return 0;
 }
 int32_t dbx_body_apply_linear_impulse(dbx_world* w, int32_t body, float ix, float iy, float px, float py, int32_t wake) {
-  W_OR_INVALID(w); HBody* b = w->w.mutBody(body); if (!b) return DBX_E_INVALID;
+  W_OR_INVALID(w); HBody* b = w->w.mutBodyRow(body); if (!b) return DBX_E_INVALID;
   if (b->st.type != DBX_DYNAMIC_BODY) return 0;
   if (wake && (b->st.flags & DBX_BODY_AWAKE) == 0) w->w.wake(*b, true);
   if (b->st.flags & DBX_BODY_AWAKE) {
@@ -208,17 +208,17 @@ int32_t dbx_body_apply_linear_impulse(dbx_world* w, int32_t body, float ix, floa
   return 0;
 }
 int32_t dbx_body_apply_angular_impulse(dbx_world* w, int32_t body, float impulse, int32_t wake) {
-  W_OR_INVALID(w); HBody* b = w->w.mutBody(body); if (!b) return DBX_E_INVALID;
+  W_OR_INVALID(w); HBody* b = w->w.mutBodyRow(body); if (!b) return DBX_E_INVALID;
   if (b->st.type != DBX_DYNAMIC_BODY) return 0;
   if (wake && (b->st.flags & DBX_BODY_AWAKE) == 0) w->w.wake(*b, true);
   if (b->st.flags & DBX_BODY_AWAKE) b->st.w += b->st.invI * impulse;
   return 0;
 }
 int32_t dbx_body_set_awake(dbx_world* w, int32_t body, int32_t flag) {
-  W_OR_INVALID(w); HBody* b = w->w.mutBody(body); if (!b) return DBX_E_INVALID; w->w.wake(*b, flag != 0); return 0;
+  W_OR_INVALID(w); HBody* b = w->w.mutBodyRow(body); if (!b) return DBX_E_INVALID; w->w.wake(*b, flag != 0); return 0;
 }
 int32_t dbx_body_set_bullet(dbx_world* w, int32_t body, int32_t flag) {
-  W_OR_INVALID(w); HBody* b = w->w.mutBody(body); if (!b) return DBX_E_INVALID;
+  W_OR_INVALID(w); HBody* b = w->w.mutBodyRow(body); if (!b) return DBX_E_INVALID;
   if (flag) b->st.flags |= DBX_BODY_BULLET; else b->st.flags &= ~DBX_BODY_BULLET; return 0;
 }
 int32_t dbx_body_set_type(dbx_world* w, int32_t body, int32_t type) { W_OR_INVALID(w); return w->w.setBodyType(body, type); }
@@ -235,7 +235,7 @@ int32_t dbx_fixture_set_friction(dbx_world* w, int32_t fixture, float v) { W_OR_
 int32_t dbx_fixture_set_restitution(dbx_world* w, int32_t fixture, float v) { W_OR_INVALID(w); return w->w.setFixtureMaterial(fixture, nullptr, &v, nullptr); }
 int32_t dbx_fixture_set_density(dbx_world* w, int32_t fixture, float v) { W_OR_INVALID(w); return w->w.setFixtureMaterial(fixture, nullptr, nullptr, &v); }
 int32_t dbx_body_set_sleeping_allowed(dbx_world* w, int32_t body, int32_t flag) {
-  W_OR_INVALID(w); HBody* b = w->w.mutBody(body); if (!b) return DBX_E_INVALID;
+  W_OR_INVALID(w); HBody* b = w->w.mutBodyRow(body); if (!b) return DBX_E_INVALID;
   if (flag) b->st.flags |= DBX_BODY_AUTOSLEEP; else { b->st.flags &= ~DBX_BODY_AUTOSLEEP; w->w.wake(*b, true); }
   return 0;
 }

@@ -1853,6 +1853,32 @@ cudaError_t launch_set_motor_speeds(const DevWorld& W, const LaunchCfg& L, const
   ++L.launches; k_api_motor_speeds<<<(n + 255) / 256, 256, 0, L.stream>>>(W, slots, speeds, n);
   return cudaGetLastError();
 }
+// Row-granular body sync (World::pullBodyRow / push of edited rows): n bodies' rows as nine float4 each -- xf, xf0, pos, pos0, vel,
+// force, mass, lc, (gravityScale, sleepTime, flags bits, -) -- so that a per-body edit costs one small copy each way, not ten
+constexpr int kBodyRowQuads = 9;
+__global__ void __launch_bounds__(64) k_body_rows_get(const __grid_constant__ DevWorld W, const int* ids, float4* rows, int n) {
+  GRID_STRIDE(k, n) {
+    const int b = ids[k];
+    float4* r = rows + (size_t)k * kBodyRowQuads;
+    const float2 gs = W.b_gs[b];
+    r[0] = W.b_xf[b]; r[1] = W.b_xf0[b]; r[2] = W.b_pos[b]; r[3] = W.b_pos0[b]; r[4] = W.b_vel[b]; r[5] = W.b_force[b]; r[6] = W.b_mass[b]; r[7] = W.b_lc[b];
+    r[8] = make_float4(gs.x, gs.y, __uint_as_float(W.b_flags[b]), 0.0f);
+  }
+}
+__global__ void __launch_bounds__(64) k_body_rows_set(const __grid_constant__ DevWorld W, const int* ids, const float4* rows, int n) {
+  GRID_STRIDE(k, n) {
+    const int b = ids[k];
+    const float4* r = rows + (size_t)k * kBodyRowQuads;
+    W.b_xf[b] = r[0]; W.b_xf0[b] = r[1]; W.b_pos[b] = r[2]; W.b_pos0[b] = r[3]; W.b_vel[b] = r[4]; W.b_force[b] = r[5]; W.b_mass[b] = r[6]; W.b_lc[b] = r[7];
+    W.b_gs[b] = make_float2(r[8].x, r[8].y); W.b_flags[b] = __float_as_uint(r[8].z);
+  }
+}
+cudaError_t launch_body_rows(const DevWorld& W, const LaunchCfg& L, const int* ids, float4* rows, int n, bool set) {
+  ++L.launches;
+  if (set) k_body_rows_set<<<(n + 63) / 64, 64, 0, L.stream>>>(W, ids, rows, n);
+  else k_body_rows_get<<<(n + 63) / 64, 64, 0, L.stream>>>(W, ids, rows, n);
+  return cudaGetLastError();
+}
 cudaError_t launch_api_wake(const DevWorld& W, const LaunchCfg& L, int a, int b) {
   ++L.launches; k_api_wake<<<1, 1, 0, L.stream>>>(W, a, b);
   return cudaGetLastError();

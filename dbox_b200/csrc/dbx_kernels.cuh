@@ -54,6 +54,7 @@ size_t cub_temp_bytes(int maxProxies);
 cudaError_t launch_insert_contacts(const DevWorld& W, const LaunchCfg& L, int n);  // (re)build hash + free list for slots [0,n)
 cudaError_t launch_api_contacts(const DevWorld& W, const LaunchCfg& L, int body, int fixture, int otherBody, int flagOnly);
 cudaError_t launch_api_wake(const DevWorld& W, const LaunchCfg& L, int a, int b);
+cudaError_t launch_body_rows(const DevWorld& W, const LaunchCfg& L, const int* ids, float4* rows, int n, bool set);   // nine float4 per row
 cudaError_t launch_set_motor_speeds(const DevWorld& W, const LaunchCfg& L, const int* slots, const float* speeds, int n);
 cudaError_t launch_set_states(const DevWorld& W, const LaunchCfg& L, const int* ids, const float4* pose, const float4* vel, int n);
 cudaError_t launch_apply_forces(const DevWorld& W, const LaunchCfg& L, const float4* forces, int n);

@@ -54,6 +54,7 @@ World::~World() {
   for (auto* b : f4) b->release();
   j_ids2.release();
   b_toiMin.release(); b_toiOther.release(); b_acc.release(); jp_bits.release(); b_jmask.release();
+  rowStage_.release(); rowIds_.release(); t_mass_.release();
   DevBuf<int>* i1[] = {&b_toiEvt, &b_toiFlags, &e_contact, &e_ncand, &e_cand, &bv_pos, &b_wake, &b_root, &b_islAwake, &b_islMinSleep, &b_posNotOk, &b_ovf, &b_world, &f_body, &f_group, &p_key, &moveList, &bv_leaf, &bv_leafAlt,
                        &bv_parent, &bv_visit, &c_toiList, &c_toiCount, &c_colour, &c_free, &c_work, &c_work2, &h_val, &s_contact, &s_hist, &s_pc, &s_root, &j_limit, &j_colour, &j_order, &j_root, &d_levels};
   for (auto* b : i1) b->release();
@@ -425,7 +426,7 @@ int World::setBodyActive(int b, bool flag) {
 int World::destroyContactsWhere(int body, int fixture, int otherBody, bool flagOnly) {
   int rc = push(); if (rc < 0) return rc;
   CUDA_OR_FAIL(launch_api_contacts(dw_, L_, body, fixture, otherBody, flagOnly ? 1 : 0), "api_contacts");
-  hostBodiesValid_ = false;
+  hostBodiesValid_ = false, ++bodyEpoch_;
   return 0;
 }
 
@@ -559,7 +560,7 @@ int World::destroyJoint(int jid) {
   jointsChanged_ = true; fullPushJoints_ = true;
   rc = push(); if (rc < 0) return rc;
   CUDA_OR_FAIL(launch_api_wake(dw_, L_, a, b), "api_wake");          // b2world.d:297-298
-  hostBodiesValid_ = false;
+  hostBodiesValid_ = false, ++bodyEpoch_;
   if (!j.def.collideConnected) { rc = destroyContactsWhere(a, -1, b, true); if (rc < 0) return rc; }
   return 0;
 }
@@ -586,18 +587,19 @@ int World::pullBodies() {
   std::vector<float2> gs(n); std::vector<uint32_t> fl(n);
   CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
   CUDA_OR_FAIL(cudaMemcpy(xf.data(), b_xf.p, n * 16, cudaMemcpyDeviceToHost), "pull xf");
-  cudaMemcpy(xf0.data(), b_xf0.p, n * 16, cudaMemcpyDeviceToHost);
-  cudaMemcpy(pos.data(), b_pos.p, n * 16, cudaMemcpyDeviceToHost);
-  cudaMemcpy(pos0.data(), b_pos0.p, n * 16, cudaMemcpyDeviceToHost);
-  cudaMemcpy(vel.data(), b_vel.p, n * 16, cudaMemcpyDeviceToHost);
-  cudaMemcpy(frc.data(), b_force.p, n * 16, cudaMemcpyDeviceToHost);
-  cudaMemcpy(ms.data(), b_mass.p, n * 16, cudaMemcpyDeviceToHost);
-  cudaMemcpy(lc.data(), b_lc.p, n * 16, cudaMemcpyDeviceToHost);
-  cudaMemcpy(gs.data(), b_gs.p, n * 8, cudaMemcpyDeviceToHost);
+  CUDA_OR_FAIL(cudaMemcpy(xf0.data(), b_xf0.p, n * 16, cudaMemcpyDeviceToHost), "pull xf0");
+  CUDA_OR_FAIL(cudaMemcpy(pos.data(), b_pos.p, n * 16, cudaMemcpyDeviceToHost), "pull pos");
+  CUDA_OR_FAIL(cudaMemcpy(pos0.data(), b_pos0.p, n * 16, cudaMemcpyDeviceToHost), "pull pos0");
+  CUDA_OR_FAIL(cudaMemcpy(vel.data(), b_vel.p, n * 16, cudaMemcpyDeviceToHost), "pull vel");
+  CUDA_OR_FAIL(cudaMemcpy(frc.data(), b_force.p, n * 16, cudaMemcpyDeviceToHost), "pull force");
+  CUDA_OR_FAIL(cudaMemcpy(ms.data(), b_mass.p, n * 16, cudaMemcpyDeviceToHost), "pull mass");
+  CUDA_OR_FAIL(cudaMemcpy(lc.data(), b_lc.p, n * 16, cudaMemcpyDeviceToHost), "pull lc");
+  CUDA_OR_FAIL(cudaMemcpy(gs.data(), b_gs.p, n * 8, cudaMemcpyDeviceToHost), "pull gs");
   CUDA_OR_FAIL(cudaMemcpy(fl.data(), b_flags.p, n * 4, cudaMemcpyDeviceToHost), "pull flags");
   for (size_t i = 0; i < n; ++i) {
     HBody& hb = bodies_[i];
     if (!hb.alive) continue;
+    if (hb.dirty) continue;             // edited on the host since (mutBodyRow): the host row is the newer one
     dbx_body_state& st = hb.st;
     st.p = dbx_vec2{xf[i].x, xf[i].y}; st.qs = xf[i].z; st.qc = xf[i].w;
     hb.xf0 = xf0[i];
@@ -611,6 +613,55 @@ int World::pullBodies() {
     st.flags = fl[i] & 0xFFFF; st.type = body_type(fl[i]);
   }
   hostBodiesValid_ = true;
+  return 0;
+}
+
+// one body's row (see bodyEpoch_ in dbx_world.h)
+int World::pullBodyRow(int b) {
+  HBody& hb = bodies_[b];
+  if (hostBodiesValid_ || (size_t)b >= bodiesSynced_ || hb.dirty || hb.validEpoch == bodyEpoch_) return 0;
+  CUDA_OR_FAIL(rowStage_.reserve(64 * 9, false, stream_), "row stage"); CUDA_OR_FAIL(rowIds_.reserve(64, false, stream_), "row ids");
+  float4 r[9];
+  CUDA_OR_FAIL(cudaMemcpyAsync(rowIds_.p, &b, 4, cudaMemcpyHostToDevice, stream_), "row id");
+  CUDA_OR_FAIL(launch_body_rows(dw_, L_, rowIds_.p, rowStage_.p, 1, false), "row get");
+  CUDA_OR_FAIL(cudaMemcpyAsync(r, rowStage_.p, sizeof(r), cudaMemcpyDeviceToHost, stream_), "row d2h");
+  CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
+  const float4 xf = r[0], xf0 = r[1], pos = r[2], pos0 = r[3], vel = r[4], frc = r[5], ms = r[6], lc = r[7];
+  const float2 gs = make_float2(r[8].x, r[8].y);
+  uint32_t fl; std::memcpy(&fl, &r[8].z, 4);
+  dbx_body_state& st = hb.st;
+  st.p = dbx_vec2{xf.x, xf.y}; st.qs = xf.z; st.qc = xf.w;
+  hb.xf0 = xf0;
+  st.c = dbx_vec2{pos.x, pos.y}; st.a = pos.z;
+  st.c0 = dbx_vec2{pos0.x, pos0.y}; st.a0 = pos0.z; st.alpha0 = pos0.w;
+  st.v = dbx_vec2{vel.x, vel.y}; st.w = vel.z;
+  st.force = dbx_vec2{frc.x, frc.y}; st.torque = frc.z;
+  st.invMass = ms.x; st.invI = ms.y; st.mass = ms.z; st.I = ms.w;
+  st.localCenter = dbx_vec2{lc.x, lc.y}; st.linearDamping = lc.z; st.angularDamping = lc.w;
+  st.gravityScale = gs.x; st.sleepTime = gs.y;
+  st.flags = fl & 0xFFFF; st.type = body_type(fl);
+  hb.validEpoch = bodyEpoch_;
+  return 0;
+}
+int World::pushBodyRows() {
+  const int n = (int)dirtyBodies_.size();
+  if (n == 0) return 0;
+  CUDA_OR_FAIL(rowStage_.reserve(64 * 9, false, stream_), "row stage"); CUDA_OR_FAIL(rowIds_.reserve(64, false, stream_), "row ids");
+  std::vector<float4> rows((size_t)n * 9);
+  for (int k = 0; k < n; ++k) {
+    const HBody& hb = bodies_[dirtyBodies_[k]];
+    const dbx_body_state& st = hb.st;
+    float4* r = rows.data() + (size_t)k * 9;
+    const uint32_t fl = hb.alive ? (uint32_t)((st.flags & 0xFFFF) | ((uint32_t)st.type << BF_TYPE_SHIFT) | BF_ALIVE) : (uint32_t)0;
+    r[0] = f4(st.p.x, st.p.y, st.qs, st.qc); r[1] = hb.xf0; r[2] = f4(st.c.x, st.c.y, st.a, 0.0f); r[3] = f4(st.c0.x, st.c0.y, st.a0, st.alpha0);
+    r[4] = f4(st.v.x, st.v.y, st.w, 0.0f); r[5] = f4(st.force.x, st.force.y, st.torque, 0.0f); r[6] = f4(st.invMass, st.invI, st.mass, st.I);
+    r[7] = f4(st.localCenter.x, st.localCenter.y, st.linearDamping, st.angularDamping);
+    r[8] = f4(st.gravityScale, st.sleepTime, 0.0f, 0.0f); std::memcpy(&r[8].z, &fl, 4);
+  }
+  // (pageable sources: both copies are complete on return, the vectors may go)
+  CUDA_OR_FAIL(cudaMemcpy(rowIds_.p, dirtyBodies_.data(), (size_t)n * 4, cudaMemcpyHostToDevice), "row ids");
+  CUDA_OR_FAIL(cudaMemcpy(rowStage_.p, rows.data(), rows.size() * 16, cudaMemcpyHostToDevice), "rows h2d");
+  CUDA_OR_FAIL(launch_body_rows(dw_, L_, rowIds_.p, rowStage_.p, n, true), "rows set");
   return 0;
 }
 
@@ -671,7 +722,7 @@ int World::setJointTarget(int jid, float x, float y) {
   fullPushJoints_ = true;
   rc = push(); if (rc < 0) return rc;
   CUDA_OR_FAIL(launch_api_wake(dw_, L_, joints_[jid].def.bodyB, -1), "api_wake");
-  hostBodiesValid_ = false;
+  hostBodiesValid_ = false, ++bodyEpoch_;
   return 0;
 }
 
@@ -717,7 +768,7 @@ int World::setJointParams(int jid, const dbx_joint_def& d, uint32_t mask) {
   CUDA_OR_FAIL(cudaMemcpyAsync(j_p0.p + slot, &p0, 16, cudaMemcpyHostToDevice, stream_), "joint patch");
   CUDA_OR_FAIL(cudaMemcpyAsync(j_p1.p + slot, &p1, 16, cudaMemcpyHostToDevice, stream_), "joint patch");
   if (zeroLimitImpulse) CUDA_OR_FAIL(cudaMemcpyAsync(j_imp.p + slot, &imp, 16, cudaMemcpyHostToDevice, stream_), "joint patch");
-  if (wakeBoth) { CUDA_OR_FAIL(launch_api_wake(dw_, L_, o.bodyA, o.bodyB), "api_wake"); hostBodiesValid_ = false; }
+  if (wakeBoth) { CUDA_OR_FAIL(launch_api_wake(dw_, L_, o.bodyA, o.bodyB), "api_wake"); hostBodiesValid_ = false, ++bodyEpoch_; }
   CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");      // the host temporaries go away
   return 0;
 }
@@ -747,7 +798,7 @@ int World::setMotorSpeeds(const int32_t* joints, const float* speeds, int n) {
   CUDA_OR_FAIL(cudaMemcpyAsync(qIn_.p, speeds, (size_t)n * 4, cudaMemcpyHostToDevice, stream_), "speeds h2d");
   CUDA_OR_FAIL(launch_set_motor_speeds(dw_, L_, ioIds_.p, (const float*)qIn_.p, n), "motor_speeds");
   CUDA_OR_FAIL(cudaStreamSynchronize(stream_), "sync");
-  hostBodiesValid_ = false;
+  hostBodiesValid_ = false, ++bodyEpoch_;
   return n;
 }
 
@@ -933,12 +984,13 @@ int World::push() {
   if (replicated_) return 0;   // nothing on the host can be newer than the device any more
   const size_t nB = bodies_.size(), nF = fixtures_.size(), nP = proxies_.size(), nS = shapes_.size(), nJ = joints_.size();
   const bool anyBody = fullPushBodies_ || nB > bodiesSynced_;
+  const bool anyRow = !dirtyBodies_.empty();
   const bool anyFix = fullPushFixtures_ || nF > fixturesSynced_;
   const bool anyProxy = fullPushProxies_ || nP > proxiesSynced_ || !pendingMoves_.empty();
   const size_t proxiesKnown = proxiesSynced_;      // proxies the device had before this push
   const bool anyShape = nS > shapesSynced_;
   const bool anyJoint = fullPushJoints_ || nJ > jointsSynced_ || jointsChanged_;
-  if (!anyBody && !anyFix && !anyProxy && !anyShape && !anyJoint && dw_.hdr) return 0;
+  if (!anyBody && !anyRow && !anyFix && !anyProxy && !anyShape && !anyJoint && dw_.hdr) return 0;
   if (anyBody) tilesDirty_ = true;       // body set or body types may have changed: the tile solver re-counts and re-sorts
   if (fullPushBodies_ && !hostBodiesValid_) { int rc = pullBodies(); if (rc < 0) return rc; }
   if (fullPushProxies_ && !hostProxiesValid_) { int rc = pullProxies(); if (rc < 0) return rc; }
@@ -965,6 +1017,9 @@ int World::push() {
       if (!bodies_[i].alive) return (uint32_t)0;
       return (uint32_t)((S(i).flags & 0xFFFF) | ((uint32_t)S(i).type << BF_TYPE_SHIFT) | BF_ALIVE); }), "up flags");
     CUDA_OR_FAIL(upload_range(b_world, from, nB, [&](size_t i) { return bodies_[i].world; }), "up world");
+    if (!fullPushBodies_ && !dirtyBodies_.empty()) { refreshView(); int rcr = pushBodyRows(); if (rcr < 0) return rcr; }    // (the pools may just have moved)
+    for (int b : dirtyBodies_) bodies_[b].dirty = false;
+    dirtyBodies_.clear();
     bodiesSynced_ = nB; fullPushBodies_ = false;
   }
   // ---- fixtures, shapes
@@ -1211,7 +1266,7 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents, int halves) {
     CUDA_OR_FAIL(stage_collide(dw_, L_), "collide");
     mark(1);
   }
-  if (!(halves & 2)) { hostBodiesValid_ = false; return 0; }
+  if (!(halves & 2)) { hostBodiesValid_ = false, ++bodyEpoch_; return 0; }
   if (dw_.psCap > 0) CUDA_OR_FAIL(cudaMemsetAsync((char*)hdr_.p + offsetof(Header, nPostSolve), 0, 4, stream_), "post-solve reset");
   if (stepComplete_ && dt > 0.0f) {
     CUDA_OR_FAIL(stage_islands_and_integrate(dw_, L_), "islands");
@@ -1316,7 +1371,7 @@ int World::enqueueStep(float dt, int vi, int pi, bool fineEvents, int halves) {
     CUDA_OR_FAIL(cudaEventRecord(wmEv_, stream_), "watermark");
     wmPending_ = true;
   }
-  hostBodiesValid_ = false; hostProxiesValid_ = false; hostJointsValid_ = false;
+  hostBodiesValid_ = false, ++bodyEpoch_; hostProxiesValid_ = false; hostJointsValid_ = false;
   return 0;
 }
 
@@ -1411,7 +1466,7 @@ int World::applyForces(const float* f4, int n) {
   CUDA_OR_FAIL(cudaMemcpyAsync(ioBuf_.p, f4, (size_t)n * ioRecordBytes(), cudaMemcpyHostToDevice, stream_), "forces h2d");
   if (ioCompact_) CUDA_OR_FAIL(launch_apply_forces3(dw_, L_, (const float*)ioBuf_.p, n), "apply_forces");
   else CUDA_OR_FAIL(launch_apply_forces(dw_, L_, ioBuf_.p, n), "apply_forces");
-  hostBodiesValid_ = false;
+  hostBodiesValid_ = false, ++bodyEpoch_;
   return n;
 }
 // bulk SetTransform / SetLinearVelocity / SetAngularVelocity from host arrays (either may be null); ids null = bodies 0..n-1
@@ -1427,7 +1482,7 @@ int World::setBodyStates(const int* ids, const float* pose4, const float* vel4, 
   if (pose4) CUDA_OR_FAIL(cudaMemcpyAsync(ioBuf_.p, pose4, (size_t)n * 16, cudaMemcpyHostToDevice, stream_), "pose h2d");
   if (vel4) CUDA_OR_FAIL(cudaMemcpyAsync(ioBuf2_.p, vel4, (size_t)n * 16, cudaMemcpyHostToDevice, stream_), "vel h2d");
   CUDA_OR_FAIL(launch_set_states(dw_, L_, ids ? ioIds_.p : nullptr, pose4 ? ioBuf_.p : nullptr, vel4 ? ioBuf2_.p : nullptr, n), "set_states");
-  hostBodiesValid_ = false; hostProxiesValid_ = false;
+  hostBodiesValid_ = false, ++bodyEpoch_; hostProxiesValid_ = false;
   return n;
 }
 // world queries (b2world.d:563-587) see the world as it is now: pending host edits are pushed, and the LBVH is rebuilt if
@@ -1595,7 +1650,7 @@ int World::shiftOrigin(float x, float y) {
   }
   CUDA_OR_FAIL(launch_shift_origin(dw_, L_, x, y), "shift_origin");
   treeValid_ = false;                       // the LBVH boxes are stale: rebuilt before the next pair query / world query
-  hostBodiesValid_ = false; hostProxiesValid_ = false;
+  hostBodiesValid_ = false, ++bodyEpoch_; hostProxiesValid_ = false;
   if (anyJoint) { rc = push(); if (rc < 0) return rc; }
   return 0;
 }
@@ -1805,7 +1860,7 @@ int World::applyForcesAsync(const float* f4, int n) {
   else CUDA_OR_FAIL(launch_apply_forces(dw_, L_, inStage_[k].p, n), "apply_forces");
   CUDA_OR_FAIL(cudaEventRecord(inRead_[k], stream_), "io event");
   inReadValid_[k] = true;
-  hostBodiesValid_ = false;
+  hostBodiesValid_ = false, ++bodyEpoch_;
   return n;
 }
 int World::readTransformsAsync(float* out, int n) {
@@ -1850,7 +1905,7 @@ int World::clearForces() {
   int rc = push(); if (rc < 0) return rc;
   if (bodies_.empty()) return 0;
   CUDA_OR_FAIL(launch_clear_forces(dw_, L_), "clear_forces");
-  hostBodiesValid_ = false;
+  hostBodiesValid_ = false, ++bodyEpoch_;
   return 0;
 }
 
@@ -1859,7 +1914,7 @@ int World::stageFindNewContacts() {
   if (bodies_.empty()) return 0;
   { int rf = findNewContacts(); if (rf < 0) return rf; }
   newFixture_ = false;
-  hostBodiesValid_ = false; hostProxiesValid_ = false;
+  hostBodiesValid_ = false, ++bodyEpoch_; hostProxiesValid_ = false;
   return checkDeviceError(true);
 }
 
@@ -1868,7 +1923,7 @@ int World::stageCollide() {
   if (bodies_.empty()) return 0;
   setStepParams(0.0f, 0, 0);
   CUDA_OR_FAIL(stage_collide(dw_, L_), "collide");
-  hostBodiesValid_ = false;
+  hostBodiesValid_ = false, ++bodyEpoch_;
   return checkDeviceError(true);
 }
 
@@ -1904,7 +1959,7 @@ int World::getBody(int b, dbx_body_state* out) {
     int rc = readBodiesDevice(b, 1, out); return rc < 0 ? rc : 0;
   }
   if (b < 0 || b >= (int)bodies_.size() || !bodies_[b].alive) return DBX_E_INVALID;
-  int rc = pullBodies(); if (rc < 0) return rc;
+  int rc = pullBodyRow(b); if (rc < 0) return rc;         // (one row, not the world: b2Body.GetPosition in a game loop)
   *out = bodies_[b].st;
   return 0;
 }
@@ -1915,6 +1970,19 @@ HBody* World::mutBody(int b) {
   if (pullBodies() < 0) return nullptr;
   if ((size_t)b < bodiesSynced_) fullPushBodies_ = true;
   return &bodies_[b];
+}
+// An edit of this body's own row (velocity, force, awake / bullet / autosleep flags): one row comes back from the device and one
+// row goes out with the next push -- not every body array of the world both ways (b2Body.ApplyForce once per frame on the 100,000
+// body pile used to cost 12 MB each way and a host loop over all bodies per step).  Past 64 edited bodies between two pushes the
+// whole-array path is the cheaper one.
+HBody* World::mutBodyRow(int b) {
+  if (replicated_) return nullptr;
+  if (b < 0 || b >= (int)bodies_.size() || !bodies_[b].alive) return nullptr;
+  HBody& hb = bodies_[b];
+  if ((size_t)b >= bodiesSynced_ || fullPushBodies_ || dirtyBodies_.size() >= 64) return mutBody(b);
+  if (pullBodyRow(b) < 0) return nullptr;
+  if (!hb.dirty) { hb.dirty = true; dirtyBodies_.push_back(b); }
+  return &hb;
 }
 
 // b2Body.SetTransform (dynamics/b2body.d:261-285) incl. b2Fixture.Synchronize with xf1 == xf2

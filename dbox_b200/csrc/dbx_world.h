@@ -13,6 +13,10 @@ namespace dbx {
 
 template <class T> struct DevBuf {
   T* p = nullptr; size_t cap = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }           // (World::~World releases most pools by name; whatever it does not list goes here)
   cudaError_t reserve(size_t n, bool keep, cudaStream_t st) {
     if (n <= cap) return cudaSuccess;
     size_t ncap = cap ? cap : 64;
@@ -43,6 +47,8 @@ struct HProxy {
 };
 struct HBody {
   bool alive = false; dbx_body_state st{}; float4 xf0{}; std::vector<int> fixtures, joints; int world = 0;
+  unsigned long long validEpoch = 0;   // host row read back at this World::bodyEpoch_ (row-granular sync: World::mutBodyRow)
+  bool dirty = false;                  // host row newer than the device's (listed in World::dirtyBodies_)
 };
 struct HJoint {
   bool alive = false; dbx_joint_def def{}; float imp[4] = {0, 0, 0, 0}; int limit = 0; int colour = -1;
@@ -101,7 +107,9 @@ class World {
 
   int getBody(int b, dbx_body_state* out);
   int readBodiesDevice(int from, int count, dbx_body_state* out);
-  HBody* mutBody(int b);   // pulls, marks dirty; nullptr if invalid
+  HBody* mutBody(int b);
+  // pulls, marks dirty; nullptr if invalid
+  HBody* mutBodyRow(int b);            // as mutBody, for edits that touch this body's row only
   int setTransform(int b, float x, float y, float angle);
   int setBodyType(int b, int type);
   int setBodyActive(int b, bool flag);
@@ -188,6 +196,14 @@ class World {
   // mirror state
   size_t bodiesSynced_ = 0, fixturesSynced_ = 0, proxiesSynced_ = 0, shapesSynced_ = 0, jointsSynced_ = 0;
   bool hostBodiesValid_ = true, hostProxiesValid_ = true, hostJointsValid_ = true;
+  // Row-granular body sync for the per-body calls a game makes every frame (b2Body.ApplyForce, SetLinearVelocity, SetAwake ...):
+  // one body's row is read back and written instead of every array of the world.  bodyEpoch_ counts the device-side changes;
+  // a host row is current when the whole mirror is (hostBodiesValid_) or when it was read at this epoch or edited since.
+  unsigned long long bodyEpoch_ = 1;
+  std::vector<int> dirtyBodies_;
+  int pullBodyRow(int b);
+  int pushBodyRows();
+  DevBuf<float4> rowStage_; DevBuf<int> rowIds_;
   bool fullPushBodies_ = false, fullPushProxies_ = false, fullPushJoints_ = false, fullPushFixtures_ = false;
   bool jointsChanged_ = false;
   std::vector<int> movesOnDevice_; std::unordered_set<int> movesUploaded_;   // host moves already in the device move list since the last FindNewContacts

@@ -644,6 +644,89 @@ def test_body_and_fixture_mutators(gpu_api, oracle_api):
     assert abs(bg[8].GetMass() - 3.0) < 1e-6 and abs(bg[3].GetMass() - 4.0) < 1e-5
 
 
+def test_per_frame_body_calls_touch_one_row(gpu_api, oracle_api):
+    """b2Body.ApplyForce / ApplyTorque / ApplyLinearImpulse / SetLinearVelocity / SetAngularVelocity / SetAwake / SetBullet /
+    SetSleepingAllowed (b2body.d:287-500, 827-922) between steps, the way a game drives a few bodies every frame: the same
+    trajectory as the reference, and each call moves ONE body's row between host and device -- on a 20,000-body pile a frame
+    with such calls must cost about what a frame without them does (it used to copy every body array both ways)."""
+    import time
+
+    def build(api):
+        w = b2World((0.0, -10.0), api=api)
+        _ground(w, api)
+        bs = [_box_body(w, api, -8.0 + 4.0 * k, 0.52) for k in range(5)] + [_box_body(w, api, -8.0 + 4.0 * k, 1.55) for k in range(5)]
+        return w, bs
+
+    def drive(k, bs):
+        # (gentle pushes: with 8 iterations a violent shove leaves the device's coloured order and the reference's list order
+        # several per cent apart, which is the solver's convergence and not what this test is about)
+        bs[0].ApplyForce((2.0, 0.0), (bs[0].GetPosition().x, bs[0].GetPosition().y + 0.05))
+        bs[6].ApplyTorque(0.2)
+        if k % 20 == 5:
+            bs[7].ApplyLinearImpulse((0.0, 1.5), (bs[7].GetPosition().x + 0.05, bs[7].GetPosition().y))
+            bs[8].ApplyAngularImpulse(0.05)
+        if k == 30:
+            bs[2].SetLinearVelocity((1.5, 0.0)); bs[2].SetAngularVelocity(0.5)
+            bs[3].SetBullet(True); bs[4].SetSleepingAllowed(False)
+        if k == 90:
+            bs[9].SetAwake(False)
+        if k == 100:
+            bs[9].SetAwake(True); bs[9].SetLinearVelocity((0.0, 2.0))
+    wg, bg = build(gpu_api); wo, bo = build(oracle_api)
+    for k in range(140):
+        drive(k, bg); drive(k, bo)
+        wg.Step(DT, 8, 3); wo.Step(DT, 8, 3)
+        for i, (a, b) in enumerate(zip(bg, bo)):
+            pa, pb = a.GetPosition(), b.GetPosition()
+            tol = 2e-3 * max(1.0, abs(pb.x), abs(pb.y))
+            assert abs(pa.x - pb.x) < tol and abs(pa.y - pb.y) < tol and abs(a.GetAngle() - b.GetAngle()) < 5e-3, (k, i, (pa.x, pa.y), (pb.x, pb.y))
+            assert a.IsAwake() == b.IsAwake(), (k, i)
+    wg.close(); wo.close()
+    # cost: frames with per-body calls against frames without, same world
+    w, bodies, _ = scenes.pile(api=gpu_api, n=20000, columns=400)
+    w.SetAllowSleeping(False)
+    w.StepN(DT, 8, 3, 60)
+
+    def frames(n, calls):
+        w.Step(DT, 8, 3); bodies[0].GetPosition()
+        t0 = time.perf_counter()
+        for k in range(n):
+            if calls:
+                bodies[17].ApplyForce((5.0, 0.0), (bodies[17].GetPosition().x, bodies[17].GetPosition().y))
+                bodies[4011].ApplyTorque(0.5)
+                bodies[9000 + k].SetLinearVelocity((0.0, 0.1))
+            w.Step(DT, 8, 3)
+        bodies[0].GetPosition()
+        return (time.perf_counter() - t0) / n
+    plain = min(frames(30, False) for _ in range(2))
+    driven = min(frames(30, True) for _ in range(2))
+    print("20,000-body pile: %.3f ms per frame, %.3f ms with three per-body calls and two reads per frame" % (plain * 1e3, driven * 1e3))
+    assert driven < plain + 0.6e-3, (plain, driven)      # three rows out, two back: ~0.1 ms (measured); the whole-array path took ~5 ms here
+    w.close()
+
+
+def test_world_close_returns_device_memory(gpu_api):
+    """dbx_world_destroy frees every device pool of the world, the tile solver's and the I/O staging included (a jointed pile
+    large enough for k_solve_tiles, stepped, read in bulk, closed -- ten times over)"""
+    import torch
+
+    def cycle():
+        w, bodies, _ = scenes.pile(api=gpu_api, n=6000, columns=120)
+        w.StepN(DT, 8, 3, 20)
+        bodies[5].ApplyTorque(0.1); bodies[5].GetPosition()
+        w.Step(DT, 8, 3)
+        w.read_contacts(); w.counts()
+        w.close()
+    cycle()
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(10):
+        cycle()
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < (8 << 20), (free0, free1)          # ten leaked worlds of this size would be ~300 MB
+
+
 def test_stats_allreduce_through_nccl(gpu_api):
     """dbx_stats_allreduce (the batched path's only collective): sums and maxima through a real NCCL
     communicator created by the host program -- here a one-rank communicator from ncclCommInitAll, so the reduction must
