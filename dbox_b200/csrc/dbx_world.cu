@@ -620,6 +620,10 @@ int World::pullBodies() {
 int World::pullBodyRow(int b) {
   HBody& hb = bodies_[b];
   if (hostBodiesValid_ || (size_t)b >= bodiesSynced_ || hb.dirty || hb.validEpoch == bodyEpoch_) return 0;
+  // a program that reads many bodies after a step (drawing all of them) is better served by the bulk copy: past 16 single rows
+  // since the device last changed, fetch everything once
+  if (rowPullEpoch_ != bodyEpoch_) { rowPullEpoch_ = bodyEpoch_; rowPulls_ = 0; }
+  if (++rowPulls_ > 16) return pullBodies();
   CUDA_OR_FAIL(rowStage_.reserve(64 * 9, false, stream_), "row stage"); CUDA_OR_FAIL(rowIds_.reserve(64, false, stream_), "row ids");
   float4 r[9];
   CUDA_OR_FAIL(cudaMemcpyAsync(rowIds_.p, &b, 4, cudaMemcpyHostToDevice, stream_), "row id");

@@ -199,7 +199,7 @@ class World {
   // Row-granular body sync for the per-body calls a game makes every frame (b2Body.ApplyForce, SetLinearVelocity, SetAwake ...):
   // one body's row is read back and written instead of every array of the world.  bodyEpoch_ counts the device-side changes;
   // a host row is current when the whole mirror is (hostBodiesValid_) or when it was read at this epoch or edited since.
-  unsigned long long bodyEpoch_ = 1;
+  unsigned long long bodyEpoch_ = 1, rowPullEpoch_ = 0; int rowPulls_ = 0;
   std::vector<int> dirtyBodies_;
   int pullBodyRow(int b);
   int pushBodyRows();

@@ -702,6 +702,13 @@ def test_per_frame_body_calls_touch_one_row(gpu_api, oracle_api):
     driven = min(frames(30, True) for _ in range(2))
     print("20,000-body pile: %.3f ms per frame, %.3f ms with three per-body calls and two reads per frame" % (plain * 1e3, driven * 1e3))
     assert driven < plain + 0.6e-3, (plain, driven)      # three rows out, two back: ~0.1 ms (measured); the whole-array path took ~5 ms here
+    # a program that reads MANY bodies after a step (drawing them) gets the bulk copy after a few single rows, not 20,000 row trips
+    w.Step(DT, 8, 3)
+    t0 = time.perf_counter()
+    ys = [b.GetPosition().y for b in bodies]
+    read_all = time.perf_counter() - t0
+    print("reading all 20,000 positions after a step: %.1f ms" % (read_all * 1e3))
+    assert read_all < 1.0 and min(ys) > 0.0, read_all       # (row by row: 20,000 x ~25 us of device round trips + the Python calls)
     w.close()
 
 
