@@ -4,18 +4,28 @@
 // k_solve (dbx_solve.cu) runs every colour of every Gauss-Seidel pass as a grid-wide phase: ~104 dependent phases of ~4 us on
 // the 100,000-body pile, each a grid barrier plus an L2 round trip for two bodies.  Here the dynamic bodies are sorted along x
 // and cut into P tiles of T bodies (P <= one CTA per SM).  A constraint whose dynamic bodies sit in one tile is LOCAL (class L):
-// its CTA walks the local colours with __syncthreads() between them, velocities and positions in shared memory.  A constraint
-// between tiles s and s + 1 whose two bodies are both claimed by boundary s is a BOUNDARY constraint (class B), solved by CTA s
-// with its own body in shared memory and the neighbour's body in the global arrays; everything else (a body reaching over two
-// tiles, a gear joint, an overflow colour of a hub body) is GLOBAL (class G) and runs as grid-wide colour phases like k_solve's.
-// One pass = L colours (block barriers) -> publish the exchange bodies -> grid barrier -> B colours (block barriers)
-// [-> publish -> grid barrier -> G colours, a grid barrier each] -> grid barrier -> read the exchange bodies back:
-// two grid barriers per pass instead of one per colour.  Position passes run the same schedule backwards, so that a body
+// its CTA walks the local colours with __syncthreads() between them, bodies and rows in shared memory.  A constraint between
+// tiles s and s + 1 whose bodies sit in the right half of s and the left half of s + 1 is a BOUNDARY constraint (class B),
+// solved by CTA s after its local ones; the halves make that claim exclusive without arbitration.  Everything else (a reach
+// over more than one boundary or from the wrong half, a gear joint, an overflow colour of a hub body) is GLOBAL (class G) and
+// runs as grid-wide colour phases like k_solve's.
+//
+// What lives in a tile's shared memory for the whole solve: its bodies (velocity and position slots whose fourth components
+// carry the inverse mass and inertia; id + exchange flags), its local rows (six float4 arrays, staged with TMA bulk copies),
+// its local and boundary joints (revolute / distance), its boundary rows, and slots for the bodies of the right-hand neighbour
+// those boundary constraints touch (loaded at the start of a boundary pass, written back at its end).  Whatever does not fit
+// stays in the global arrays and is reached through L2 (every such branch is forced by a DBX_DEBUG bit in the tests).
+//
+// One pass without global constraints = L colours (block barriers) -> publish the exchange bodies -> wait for the right-hand
+// neighbour's publication (a flag per tile) -> B colours, re-coloured per tile (block barriers) -> signal -> wait for the left-hand
+// neighbour's boundary pass -> read the exchange bodies back: no grid barrier.  With global constraints the two waits become grid
+// barriers and the G colours follow, a grid barrier each.  Position passes run the same schedule backwards, so that a body
 // still meets its contacts before its joints (b2island.d:206-216), as in k_solve's unified phases.
 //
 // The order is a Gauss-Seidel sweep like any other: within a phase no two constraints share a dynamic body (the global
-// colouring is proper, and L / B / G phases never overlap in time on a body: boundary claims are exclusive).  The schedule
-// is reported by dbx_world_debug_read_solve_order, and tests hand it to the sequential oracle.
+// colouring is proper, the boundary re-colouring is proper among a tile's boundary constraints, and L / B / G phases never
+// overlap in time on a body).  The schedule is reported by dbx_world_debug_read_solve_order, and tests hand it to the
+// sequential oracle.  Measurements and what bounds the kernel: DESIGN.md section 7.0.
 #include <cub/cub.cuh>
 #include "dbx_solver.cuh"
 #include "dbx_kernels.cuh"
@@ -204,8 +214,9 @@ DBX_D void bulk_g2s(void* dstSmem, const void* srcGlobal, unsigned bytes, unsign
 }
 
 __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_constant__ DevWorld W) {
-  // dynamic shared memory: the tile's bodies [T] and as many of its local rows as fit [R]
-  //   float4 vel[T] pos[T] | a0..a5[R] (velocity: v0 r0 r1 q0 q1 imp; position: p0 p1 p2 p3) | float2 mass[T] | int2 bd[R] | int body[T] flag[T] | int pc[R]
+  // dynamic shared memory: body slots [TX = T + kTileNbrMax] (own bodies, then staged neighbour bodies), row slots [R] (local rows,
+  // then staged boundary rows), joints [nJS]
+  //   float4 vel[TX] pos[TX] | a0..a5[R] (velocity: v0 r0 r1 q0 q1 imp; position: p0 p1 p2, p3 + island + flag) | int2 bd[R] | int body[T] | int pc[R] | joints 192 B each
   extern __shared__ float4 sm4[];
   __shared__ int offL[kTileColours + 1], joffL[kTileColours + 1], offB[kTileColours + 1], joffB[kTileColours + 1];
   __shared__ int joffG[kTileColours + 1];
