@@ -822,7 +822,7 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-// dynamic shared memory of k_solve_tiles: the bodies (48 B each) plus as many local rows (108 B each) as the SM has room for
+// dynamic shared memory of k_solve_tiles: everything the SM offers (bodies 36 B each + neighbour slots, then rows of 108 B, joints of 192 B)
 size_t tile_smem_bytes(int tileBodies) {
   static size_t avail = 0;
   if (!avail) {
