@@ -7,7 +7,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     ga = lib.api()
     w, b, nj = scenes.pile(api=ga, n=100000, columns=1000)
     w.SetAllowSleeping(False)
-    p = "gpurun_out/pile100k_settled.pkl"
+    p = "/tmp/pile100k_settled.pkl"      # (scratch on the GPU box: gpurun_out/ is copied back and capped at 64 MiB)
     if os.path.exists(p):
         state.load(w, p); w.StepN(1 / 60., 8, 3, 30)
     else:
