@@ -17,7 +17,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     out = []
     for rep in range(3):
         ga.world_time_steps(w._w, 1 / 60., 8, 3, 200, 1, C.byref(tot), st)
-        out.append((tot.value / 200, st[2], st[4]))
+        out.append((round(tot.value / 200, 4), round(st[1], 4), round(st[2], 4), round(st[4], 4)))
     print(json.dumps(out))
 else:
     variants = [int(x) for x in sys.argv[1:]] or [0, 2048]
@@ -26,4 +26,4 @@ else:
             env = dict(os.environ, DBX_DEBUG=str(v))
             r = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
             line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:]
-            print("DBX_DEBUG=%d" % v, "(ms/step, colour+sort, solve) x3:", line, flush=True)
+            print("DBX_DEBUG=%d" % v, "(ms/step, islands, colour+sort, solve) x3:", line, flush=True)
