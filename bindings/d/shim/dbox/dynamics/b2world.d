@@ -313,14 +313,19 @@ private:
         }
     }
     /// PreSolve for every touching, enabled, non-sensor contact after Collide (b2contact.d:348-355); what the callback changed on
-    /// the contact goes back to the device as patches before Solve runs
+    /// the contact goes back to the device as patches before Solve runs.  SetEnabled(false) then holds for the whole step, the
+    /// TOI loop's re-evaluations included (where the reference would call PreSolve again, b2world.d:1295,1379).
+    /// preSolveLookahead (off by default: the reference never does this): with continuous physics on, also ask about contacts that
+    /// are not touching yet -- their manifold is empty -- because a fast body can first touch INSIDE the TOI loop, where the
+    /// listener cannot be reached; the answer given here is the one that loop applies (include/dbox_b200.h, "PreSolve").
+    bool preSolveLookahead = false;
     void preSolve()
     {
         dbx_contact_patch[] patches;
         b2Manifold oldManifold;          // (the manifold before this step's Update is not kept on the device)
         foreach (ref r; readContacts())
         {
-            if ((r.flags & 0x0002) == 0) continue;
+            if ((r.flags & 0x0002) == 0 && !(preSolveLookahead && GetContinuousPhysics())) continue;
             auto c = contactFor(r.fixtureA, r.childA, r.fixtureB, r.childB);
             if (c.m_fixtureA is null || c.m_fixtureB is null || c.m_fixtureA.IsSensor() || c.m_fixtureB.IsSensor()) continue;
             fill(c, r);

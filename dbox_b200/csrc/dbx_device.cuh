@@ -26,7 +26,8 @@ enum : uint32_t {
   CF_ISLAND = 0x0001, CF_TOUCHING = 0x0002, CF_ENABLED = 0x0004, CF_FILTER = 0x0008, CF_BULLET_HIT = 0x0010, CF_TOI = 0x0020,
   CF_ALIVE = 0x0100, CF_SENSOR = 0x0200, CF_SOLVE = 0x0400 /* in an awake island this step */,
   CF_FRESH = 0x0800 /* created by this step's FindNewContacts: the overlapped TOI pre-evaluation must not look at it */,
-  CF_NEW = 0x1000 /* created since the host last polled the new-contact list (user contact filter, deferred) */
+  CF_NEW = 0x1000 /* created since the host last polled the new-contact list (user contact filter, deferred) */,
+  CF_PRESOLVE_OFF = 0x2000 /* this step's PreSolve patch said SetEnabled(false): the Update calls of the TOI loop re-apply it */
 };
 // what a kernel stores in Header::error: DBX_E_CAPACITY (-5) in the low bits, the pool that overflowed above (host: checkDeviceError)
 enum { E_CONTACTS = -5 - 16 * 1, E_PAIRS = -5 - 16 * 2, E_MOVES = -5 - 16 * 3, E_COLOURS = -5 - 16 * 4, E_SOLVER_ROWS = -5 - 16 * 5,

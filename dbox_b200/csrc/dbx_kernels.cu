@@ -60,6 +60,7 @@ DBX_D void destroy_contact(const DevWorld& W, int i, uint32_t flags, int bodyA, 
 DBX_D uint32_t update_contact(const DevWorld& W, int i, uint32_t flags, const int4 ids, const int4 fx, bool immediateWake) {
   uint4 mk = W.c_mk[i];
   flags |= CF_ENABLED;
+  if (!immediateWake) flags &= ~CF_PRESOLVE_OFF;      // (Collide: the decision of a step's PreSolve ends with that step)
   const bool wasTouching = (flags & CF_TOUCHING) != 0;
   const Xf xfA = XF(ldcg4(&W.b_xf[ids.z])), xfB = XF(ldcg4(&W.b_xf[ids.w]));
   const DShape* sA = W.shapes + fx.z;
@@ -102,6 +103,9 @@ DBX_D uint32_t update_contact(const DevWorld& W, int i, uint32_t flags, const in
   }
   if (touching != wasTouching) emit_contact_event(W, touching ? EV_BEGIN : EV_END, immediateWake ? 2 : 1, i, ids, fx);
   flags = touching ? (flags | CF_TOUCHING) : (flags & ~CF_TOUCHING);
+  // b2ContactListener.PreSolve inside the TOI loop (b2contact.d:348-355 reached from b2world.d:1295,1379): no call-back from the
+  // device, so the answer the listener gave after this step's Collide (dbx_world_patch_contacts) is taken to stand
+  if (immediateWake && touching && !(flags & CF_SENSOR) && (flags & CF_PRESOLVE_OFF)) flags &= ~CF_ENABLED;
   W.c_flags[i] = flags;
   return flags;
 }
@@ -1057,7 +1061,7 @@ __global__ void __launch_bounds__(256) k_patch_contacts(const __grid_constant__ 
       W.c_free[slot] = i;
       continue;
     }
-    if (m & 1) { uint32_t f = W.c_flags[i]; W.c_flags[i] = (m & 0x100) ? (f | CF_ENABLED) : (f & ~CF_ENABLED); }
+    if (m & 1) { uint32_t f = W.c_flags[i]; W.c_flags[i] = (m & 0x100) ? ((f | CF_ENABLED) & ~CF_PRESOLVE_OFF) : ((f & ~CF_ENABLED) | CF_PRESOLVE_OFF); }
     if (m & 14) {
       float4 mat = W.c_mat[i];
       const float4 v = vals[k];

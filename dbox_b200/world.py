@@ -459,6 +459,10 @@ class b2Fixture:
     def SetSensor(self, flag):
         w = self.body.world
         w._ck(w._api.fixture_set_sensor(w._w, self.id, int(flag)))
+        self.sensor = bool(flag)
+
+    def IsSensor(self):
+        return getattr(self, "sensor", False)
 
     def SetFriction(self, v):
         w = self.body.world
@@ -583,6 +587,7 @@ class b2Body:
         fid = self.world._ck(self.world._api.fixture_create(self.world._w, self.id, C.byref(pod), C.byref(shape._pod)))
         f = b2Fixture(self, fid)
         f.filter = (fd.filter.categoryBits, fd.filter.maskBits, fd.filter.groupIndex)
+        f.sensor = bool(fd.isSensor)
         self.fixtures.append(f)
         self.world._fixtures[fid] = f
         return f
@@ -892,16 +897,23 @@ class b2World:
             self._deliver_contact_events()
 
     # PreSolve: the step cut after Collide (include/dbox_b200.h "PreSolve") ---------------------------------
-    def StepWithPreSolve(self, dt, velocityIterations, positionIterations, pre_solve):
+    def StepWithPreSolve(self, dt, velocityIterations, positionIterations, pre_solve, toi_lookahead=False):
         """pre_solve(contact_rec) is called for every touching non-sensor contact after Collide and may return a dict with any
-        of enabled / friction / restitution / tangentSpeed (what a b2ContactListener.PreSolve would set on the contact)"""
+        of enabled / friction / restitution / tangentSpeed (what a b2ContactListener.PreSolve would set on the contact).
+        SetEnabled(false) holds for the rest of the step, the TOI loop's re-evaluations of the contact included (where the
+        reference would call PreSolve again).  toi_lookahead=True also asks about contacts that are not touching yet (empty
+        manifold): a fast body can first touch INSIDE the TOI loop (b2world.d:1295), where nobody can be asked any more, and the
+        answer given here is the one that loop applies."""
         self._ck(self._api.world_step_begin(self._w, dt, velocityIterations, positionIterations))
         recs, n = self.read_contacts()
         patches = []
         for i in range(n):
             r = recs[i]
-            if not (r.flags & A.CONTACT_TOUCHING) or r.manifold.pointCount == 0:      # PreSolve skips sensors (b2contact.d:352)
-                continue
+            touching = bool(r.flags & A.CONTACT_TOUCHING) and r.manifold.pointCount > 0      # PreSolve skips sensors (b2contact.d:352)
+            if not touching:
+                fa, fb = self._fixtures.get(r.fixtureA), self._fixtures.get(r.fixtureB)
+                if not toi_lookahead or (fa is not None and fa.IsSensor()) or (fb is not None and fb.IsSensor()):
+                    continue
             ch = pre_solve(r)
             if not ch:
                 continue

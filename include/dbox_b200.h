@@ -411,8 +411,16 @@ int32_t dbx_world_poll_contact_events(dbx_world* w, dbx_contact_event* out, int3
  *     dbx_world_read_contacts(...)                  // touching, non-sensor contacts -> listener.PreSolve(contact, oldManifold = none)
  *     dbx_world_patch_contacts(w, patches, n);      // what the listener changed
  *     dbx_world_step_end(w);                        // Solve, SolveTOI, ClearForces (b2world.d:401-431)
- * and is bit-identical to dbx_world_step when nothing is patched.  Not covered: the Update calls inside the TOI loop
- * (b2world.d:1295,1379) and the old manifold argument. */
+ * and is bit-identical to dbx_world_step when nothing is patched.
+ * The TOI loop calls b2Contact.Update -- and with it PreSolve -- again for the contacts of a TOI event (b2world.d:1295,1379), in
+ * the middle of step_end where no listener can be reached.  There the answer already given stands: a contact patched with
+ * enabled = 0 stays disabled through every re-evaluation of this step (the listener, asked again about the same contact in the
+ * same step, is taken to answer the same) and is enabled again by the next step's Collide, as in the reference (b2contact.d:272).
+ * A fast body may TOUCH for the first time inside the TOI loop; patches are accepted for contacts that are not touching yet
+ * (they exist as soon as the fat AABBs overlap), so a shim can ask its listener ahead of time ("if this pair touches during
+ * this step ...") -- dbox_b200.world.b2World.StepWithPreSolve(..., toi_lookahead=True) does.  Not covered: contacts that are
+ * CREATED inside the TOI loop (its own FindNewContacts, b2world.d:1444) and used by a later TOI event of the same step, and the
+ * old-manifold argument. */
 typedef struct dbx_contact_patch {
   int32_t fixtureA, childA, fixtureB, childB;   /* either order */
   int32_t mask;                                 /* DBX_PATCH_* of the fields to apply */

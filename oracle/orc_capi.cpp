@@ -435,7 +435,9 @@ int32_t orc_world_patch_contacts(orc_world* w, const dbx_contact_patch* p, int32
       const bool same = c->fixtureA->id == p[k].fixtureA && c->indexA == p[k].childA && c->fixtureB->id == p[k].fixtureB && c->indexB == p[k].childB;
       const bool swapped = c->fixtureA->id == p[k].fixtureB && c->indexA == p[k].childB && c->fixtureB->id == p[k].fixtureA && c->indexB == p[k].childA;
       if (!same && !swapped) continue;
-      if (p[k].mask & DBX_PATCH_ENABLED) { if (p[k].enabled) c->flags |= cEnabled; else c->flags &= ~cEnabled; }   // b2contact.d:137-147
+      if (p[k].mask & DBX_PATCH_ENABLED) {                                                                          // b2contact.d:137-147
+        if (p[k].enabled) { c->flags |= cEnabled; c->flags &= ~cPreSolveOff; } else { c->flags &= ~cEnabled; c->flags |= cPreSolveOff; }
+      }
       if (p[k].mask & DBX_PATCH_FRICTION) c->friction = p[k].friction;
       if (p[k].mask & DBX_PATCH_RESTITUTION) c->restitution = p[k].restitution;
       if (p[k].mask & DBX_PATCH_TANGENT_SPEED) c->tangentSpeed = p[k].tangentSpeed;

@@ -109,6 +109,7 @@ void Contact::evaluate(Manifold* m, const Xf& xfA, const Xf& xfB) const {
 void Contact::update(World* w) {
   Manifold oldManifold = manifold;
   flags |= cEnabled;
+  if (!w || w->evPhase != 2) flags &= ~cPreSolveOff;       // the decision of a step's PreSolve ends with that step
   bool touching = false;
   bool wasTouching = (flags & cTouching) == cTouching;
   bool sensor = fixtureA->isSensor || fixtureB->isSensor;
@@ -138,6 +139,7 @@ void Contact::update(World* w) {
     if (touching != wasTouching) { bodyA->setAwake(true); bodyB->setAwake(true); }
   }
   if (touching) flags |= cTouching; else flags &= ~cTouching;
+  if (!sensor && touching && (flags & cPreSolveOff)) flags &= ~cEnabled;       // PreSolve (b2contact.d:348-355), see cPreSolveOff
   // listener callbacks (b2contact.d:338-355): BeginContact / EndContact are logged, PreSolve is the default no-op
   if (w && wasTouching == false && touching == true) w->logContactEvent(1, this);
   if (w && wasTouching == true && touching == false) w->logContactEvent(2, this);

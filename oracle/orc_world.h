@@ -19,7 +19,10 @@ struct Body; struct Fixture; struct Contact; struct Joint; struct World;
 
 enum BodyType { kStatic = 0, kKinematic = 1, kDynamic = 2 };
 enum BodyFlags { bIsland = 1, bAwake = 2, bAutoSleep = 4, bBullet = 8, bFixedRotation = 0x10, bActive = 0x20, bToi = 0x40 };
-enum ContactFlags { cIsland = 1, cTouching = 2, cEnabled = 4, cFilter = 8, cBulletHit = 0x10, cToi = 0x20 };
+enum ContactFlags { cIsland = 1, cTouching = 2, cEnabled = 4, cFilter = 8, cBulletHit = 0x10, cToi = 0x20,
+                    cPreSolveOff = 0x40 /* not in the reference: this step's PreSolve said SetEnabled(false) (orc_world_patch_contacts);
+                                           the Update calls of the TOI loop (b2world.d:1295,1379) re-apply it, standing in for a
+                                           listener that answers the same when asked again */ };
 enum JointType { jUnknown, jRevolute, jPrismatic, jDistance, jPulley, jMouse, jGear, jWheel, jWeld, jFriction, jRope, jMotor };
 enum LimitState { kInactiveLimit, kAtLowerLimit, kAtUpperLimit, kEqualLimits };
 
