@@ -8,7 +8,6 @@ as the reference programs are written against dbox, so one function builds the s
  config 4  pile          SURVEY.md 8(d): jittered box/circle grid on a chain floor with revolute + distance chains
 """
 import ctypes as C
-import random
 
 from .world import (b2BodyDef, b2ChainShape, b2CircleShape, b2DistanceJointDef, b2EdgeShape, b2FixtureDef,
                     b2PolygonShape, b2RevoluteJointDef, b2Vec2, b2World, b2_dynamicBody, b2_pi)
@@ -16,6 +15,44 @@ from .world import (b2BodyDef, b2ChainShape, b2CircleShape, b2DistanceJointDef, 
 
 def f32(x):
     return C.c_float(x).value
+
+
+class Mt19937:
+    """std::mt19937 (SURVEY.md 8(d) names `std::mt19937(12345)` for the pile's jitter): MT19937 seeded with init_genrand(seed),
+    one 32-bit draw per call, and uniform(a, b) the way libstdc++'s uniform_real_distribution<float> maps a draw
+    (generate_canonical<float, 24>: float(draw) / 2^32, below 1; then r * (b - a) + a in float arithmetic)."""
+
+    def __init__(self, seed):
+        mt = [0] * 624
+        mt[0] = seed & 0xFFFFFFFF
+        for i in range(1, 624):
+            mt[i] = (1812433253 * (mt[i - 1] ^ (mt[i - 1] >> 30)) + i) & 0xFFFFFFFF
+        self.mt, self.idx = mt, 624
+
+    def _twist(self):
+        mt = self.mt
+        for k in range(624):
+            y = (mt[k] & 0x80000000) | (mt[(k + 1) % 624] & 0x7FFFFFFF)
+            mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ (0x9908B0DF if y & 1 else 0)
+        self.idx = 0
+
+    def draw(self):
+        if self.idx >= 624:
+            self._twist()
+        y = self.mt[self.idx]
+        self.idx += 1
+        y ^= y >> 11
+        y ^= (y << 7) & 0x9D2C5680
+        y ^= (y << 15) & 0xEFC60000
+        y ^= y >> 18
+        return y & 0xFFFFFFFF
+
+    def canonical(self):
+        r = f32(f32(self.draw()) / 4294967296.0)
+        return r if r < 1.0 else f32(1.0 - 2.0 ** -24)
+
+    def uniform(self, a, b):
+        return f32(f32(self.canonical() * f32(b - a)) + f32(a))
 
 
 def hello_world(api=None, **kw):
@@ -134,11 +171,12 @@ class Tumbler:
 
 def pile(api=None, n=100000, columns=1000, joints=True, circles=True, seed=12345, world=None, long_links=0, **kw):
     """Config 4: `n` dynamic bodies in a jittered grid `columns` wide above a static chain floor with
-    two edge walls; 70 % boxes (half-extent 0.5, density 1, friction 0.3), 30 % circles r=0.5; every 10th column is
+    two edge walls, the jitter U(-0.01, 0.01) and the shape choice drawn from std::mt19937(seed) (x, y, shape per body, in body
+    order); 70 % boxes (half-extent 0.5, density 1, friction 0.3), 30 % circles r=0.5; every 10th column is
     linked upward into 25-body revolute chains and every 10th row sideways into 25-body rigid distance chains."""
     if world is None:
         world = b2World((0.0, -10.0), api=api, **kw)
-    rng = random.Random(seed)
+    rng = Mt19937(seed)
     half_w = f32(1.05 * columns * 0.5 + 5.0)
     rows = (n + columns - 1) // columns
     ground = world.CreateBody(b2BodyDef())
@@ -167,7 +205,7 @@ def pile(api=None, n=100000, columns=1000, joints=True, circles=True, seed=12345
         bd.type = b2_dynamicBody
         bd.position.Set(f32(x0 + 1.05 * col + rng.uniform(-0.01, 0.01)), f32(0.55 + 1.05 * row + rng.uniform(-0.01, 0.01)))
         body = world.CreateBody(bd)
-        fd.shape = circle if (circles and rng.random() < 0.3) else box
+        fd.shape = circle if (circles and rng.canonical() < 0.3) else box
         body.CreateFixture(fd)
         bodies.append(body)
     njoints = 0
