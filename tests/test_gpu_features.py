@@ -568,6 +568,47 @@ def test_everything_asleep_costs_nothing_wrong(gpu_api, oracle_api):
     assert woke
 
 
+def test_islands_sleep_and_wake_one_by_one_like_the_reference(gpu_api, oracle_api):
+    """islands are found per step and each keeps its own sleep clock (b2island.d:241-279: the
+    minimum sleep time over ITS bodies, asleep together when it passes b2_timeToSleep and the position solver has converged).
+    Five separate stacks, nudged at different times: the island count and the awake flag of every body must follow the oracle
+    step by step (two steps of slack where a sleep clock crosses the threshold), a stack sleeps and wakes as one, and some stacks
+    are asleep while others are awake."""
+    def build(api):
+        w = b2World((0.0, -10.0), api=api)
+        _ground(w, api)
+        return w, [[_box_body(w, api, -16.0 + 8.0 * k, 0.51 + 1.01 * r) for r in range(3)] for k in range(5)]
+    wg, sg = build(gpu_api); wo, so = build(oracle_api)
+    nudges = {60: (2, 2, (0.3, 0.0)), 150: (4, 1, (0.0, 0.6)), 260: (0, 0, (0.2, 0.0)), 262: (1, 2, (-0.2, 0.0))}
+    mismatch, partial, prev_awake = {}, 0, None
+    for k in range(420):
+        if k in nudges:
+            st, r, imp = nudges[k]
+            for stacks in (sg, so):
+                p = stacks[st][r].GetPosition()
+                stacks[st][r].ApplyLinearImpulse(imp, (p.x, p.y + 0.2))
+        wg.Step(DT, 8, 3); wo.Step(DT, 8, 3)
+        cg, co = wg.counts(), wo.counts()
+        ag = [[b.IsAwake() for b in st] for st in sg]
+        ao = [[b.IsAwake() for b in st] for st in so]
+        for st in ag:
+            assert len(set(st)) == 1, (k, ag)                # the three boxes of a stack are one island
+        if ag == ao:
+            assert cg.islands == co.islands, (k, cg.islands, co.islands, ao)        # (islands SOLVED in the step: a stack that just fell asleep counts)
+            assert prev_awake is None or cg.islands >= sum(1 for st in ao if st[0])
+            assert cg.awakeBodies == co.awakeBodies
+        else:
+            for i, (x, y) in enumerate(zip(ag, ao)):
+                if x != y:
+                    mismatch[i] = mismatch.get(i, 0) + 1
+        partial += 0 < sum(1 for st in ao if st[0]) < 5
+        prev_awake = ao
+    assert partial > 100                                      # the clocks are per island: long stretches with some asleep, some awake
+    assert all(v <= 2 for v in mismatch.values()), mismatch  # a sleep clock crossing 0.5 s a step or two apart, nothing more
+    assert not any(x for st in ag for x in st)
+    wg.close(); wo.close()
+
+
 def test_set_type_and_set_active(gpu_api, oracle_api):
     """b2Body.SetType (b2body.d:867-914: mass reset, contacts destroyed, proxies touched) and SetActive (:718-775: proxies
     destroyed / re-created in fixture-list order, contacts destroyed) between steps, against the oracle: same contact and
