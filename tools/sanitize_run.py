@@ -10,6 +10,9 @@ DT = 1 / 60.
 n = int(os.environ.get("STEPS", "6"))
 w, b, nj = scenes.pile(api=ga, n=3000, columns=100)
 w.StepN(DT, 8, 3, n)
+for k in range(3):                      # row-granular body sync (k_body_rows_get / _set) between steps
+    b[7 + k].ApplyTorque(0.1); b[40].SetLinearVelocity((0.0, 0.1)); b[7 + k].GetPosition()
+    w.Step(DT, 8, 3)
 print("pile 3000 (tile solver):", w.counts().touching, "touching")
 w.close()
 w, b = scenes.pyramid(api=ga)
