@@ -756,6 +756,8 @@ __global__ void __launch_bounds__(kTileThreads) k_solve_tiles(const __grid_const
     stcg4(&W.b_pos[b], pos); stcg4(&W.b_vel[b], vel);
   }
   if (W.tileKinematic || nG > 0) GB();      // (kinematic bodies were integrated in the global arrays: the position rows of every tile read them)
+  __syncthreads();                          // integrated bodies and hand-staged position rows: written by one thread, read by any (a tile
+                                            // without boundary or global constraints reaches its first position colour with no other barrier)
   if (rowsLocal && W.posIters > 0) mbar_wait(&rowBar, 1);
   solve_stamp(W, 2);
   MARK();

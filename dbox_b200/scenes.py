@@ -169,6 +169,34 @@ class Tumbler:
                 self.m_count += 1
 
 
+def islands_of_boxes(api=None, clusters=12, side=16, gap=40.0, seed=7, **kw):
+    """`clusters` separate side x side grids of boxes on one long floor, `gap` metres apart: enough dynamic bodies for the tile
+    solver, cut so that every tile is one cluster -- no boundary and no global constraint anywhere"""
+    world = b2World((0.0, -10.0), api=api, **kw)
+    rng = Mt19937(seed)
+    ground = world.CreateBody(b2BodyDef())
+    floor = b2EdgeShape(world._api)
+    half = f32(0.5 * clusters * gap + 20.0)
+    floor.Set((-half, 0.0), (half, 0.0))
+    ground.CreateFixture(floor, 0.0)
+    box = b2PolygonShape(world._api)
+    box.SetAsBox(0.5, 0.5)
+    fd = b2FixtureDef()
+    fd.shape, fd.density, fd.friction = box, 1.0, 0.3
+    bodies = []
+    for c in range(clusters):
+        cx = f32(-0.5 * (clusters - 1) * gap + c * gap)
+        for i in range(side * side):
+            col, row = i % side, i // side
+            bd = b2BodyDef()
+            bd.type = b2_dynamicBody
+            bd.position.Set(f32(cx + 1.05 * (col - 0.5 * (side - 1)) + rng.uniform(-0.01, 0.01)), f32(0.55 + 1.05 * row + rng.uniform(-0.01, 0.01)))
+            b = world.CreateBody(bd)
+            b.CreateFixture(fd)
+            bodies.append(b)
+    return world, bodies
+
+
 def pile(api=None, n=100000, columns=1000, joints=True, circles=True, seed=12345, world=None, long_links=0, **kw):
     """Config 4: `n` dynamic bodies in a jittered grid `columns` wide above a static chain floor with
     two edge walls, the jitter U(-0.01, 0.01) and the shape choice drawn from std::mt19937(seed) (x, y, shape per body, in body

@@ -303,6 +303,34 @@ def test_pile_with_global_constraints_matches_oracle(gpu_api, oracle_api):
     assert r[False]["tiles"] > 0 and r[False]["global_rows"] > 0, r
 
 
+def test_tiles_without_any_boundary_constraint_match_oracle(gpu_api, oracle_api):
+    """Twelve separate clusters of 256 boxes: twelve tiles, not one boundary or global constraint -- the tile solver's passes then
+    run with no exchange and no barrier between tiles at all (the path a world of scattered piles takes)."""
+    from dbox_b200 import state
+    from tests.parity import hand_device_order_to_oracle
+    wg, _ = scenes.islands_of_boxes(api=gpu_api)
+    wo, _ = scenes.islands_of_boxes(api=oracle_api)
+    for w in (wg, wo):
+        w.SetAllowSleeping(False)
+    wg.StepN(DT, 8, 3, 150)
+    snap = state.capture(wg)
+    for continuous in (False, True):
+        for w in (wg, wo):
+            w.SetContinuousPhysics(continuous)
+            state.apply(w, snap)
+        wg.Step(DT, 8, 3)
+        found, info = hand_device_order_to_oracle(oracle_api, wg, wo)
+        wo.Step(DT, 8, 3)
+        hb = (C.c_int32 * 2400)()
+        gpu_api.world_debug_header(wg._w, hb, 9600)
+        assert info[3] == 12 and hb[1124] == 0 and hb[1125] == 0, (info, hb[1124], hb[1125])      # tiles, boundary rows, global rows
+        cg, co = wg.counts(), wo.counts()
+        assert cg.touching == co.touching and cg.contacts == co.contacts and cg.islands == co.islands >= 12, (cg.touching, co.touching, cg.contacts, co.contacts, cg.islands, co.islands)
+        r = _compare_step(wg, wo, "continuous=%s" % continuous)
+        assert r["manifold"][0] < 1e-5 and r["pos"][0] < 2e-5 and r["vel"][0] < 2e-3, r
+    wg.close(); wo.close()
+
+
 def _pile_single_step_vs_oracle(gpu_api, oracle_api, n, columns, settle, **scene):
     """One step of the settled pile on the device against the sequential oracle walking the device's own Gauss-Seidel order.
     Exact: contact set, touching flags, manifold types, feature keys, manifolds (bit for bit), island count.  Velocities,

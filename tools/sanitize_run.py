@@ -15,6 +15,10 @@ for k in range(3):                      # row-granular body sync (k_body_rows_ge
     w.Step(DT, 8, 3)
 print("pile 3000 (tile solver):", w.counts().touching, "touching")
 w.close()
+w, b = scenes.islands_of_boxes(api=ga)          # twelve tiles without a boundary constraint between them
+w.StepN(DT, 8, 3, n)
+print("12 separate clusters (tile solver, no exchange):", w.counts().touching, "touching")
+w.close()
 w, b = scenes.pyramid(api=ga)
 bd = b2BodyDef(); bd.type = b2_dynamicBody; bd.bullet = True; bd.position.Set(-30.0, 5.0); bd.linearVelocity.Set(200.0, 0.0)
 bullet = w.CreateBody(bd); s = b2CircleShape(ga); s.m_radius = 0.25; bullet.CreateFixture(s, 20.0)
