@@ -851,8 +851,10 @@ cudaError_t stage_colour_and_sort_tiles(const DevWorld& W, const LaunchCfg& L) {
   {
     const int nBins = 2 * W.nTiles * kTileColours + kMaxColours;
     const size_t smem = (size_t)2 * 1024 * ((((size_t)nBins + 1023) >> 10) | 1) * sizeof(int);
-    static size_t allowed = 0;
-    if (smem > allowed) { CK(cudaFuncSetAttribute((const void*)k_tile_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); allowed = smem; }
+    // (function attributes are per device: a process may hold worlds on several)
+    static size_t allowed[64] = {};
+    int dev = 0; CK(cudaGetDevice(&dev)); dev &= 63;
+    if (smem > allowed[dev]) { CK(cudaFuncSetAttribute((const void*)k_tile_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); allowed[dev] = smem; }
     ++L.launches; k_tile_scan<<<1, 1024, smem, L.stream>>>(W);
   }
   ++L.launches; k_tile_scatter<<<L.gridWide, 256, 0, L.stream>>>(W);
@@ -861,8 +863,9 @@ cudaError_t stage_colour_and_sort_tiles(const DevWorld& W, const LaunchCfg& L) {
 cudaError_t stage_solve_tiles(const DevWorld& W, const LaunchCfg& L) {
   const size_t smem = tile_smem_bytes(W.tileBodies);
   if (smem == 0) return cudaErrorInvalidConfiguration;
-  static bool attr = false;
-  if (!attr) { CK(cudaFuncSetAttribute((const void*)k_solve_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  static bool attr[64] = {};
+  int dev = 0; CK(cudaGetDevice(&dev)); dev &= 63;
+  if (!attr[dev]) { CK(cudaFuncSetAttribute((const void*)k_solve_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr[dev] = true; }
   if ((L.coopLaunches++ & 1023) == 0) CK(cudaMemsetAsync(&W.hdr->barrier, 0, sizeof(unsigned), L.stream));   // see launch_coop
   void* args[] = {(void*)&W};
   ++L.launches;
