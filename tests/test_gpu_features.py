@@ -778,6 +778,22 @@ def test_world_close_returns_device_memory(gpu_api):
     assert free0 - free1 < (8 << 20), (free0, free1)          # ten leaked worlds of this size would be ~300 MB
 
 
+def test_worlds_on_two_devices_in_one_process(gpu_api):
+    """A process may hold worlds on several GPUs (one host thread driving two agents' worlds): the tile solver's launch attributes
+    are per device, and the same scene steps to the same bits on either."""
+    if gpu_api.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    states = []
+    for dev in (0, 1):
+        w, _, _ = scenes.pile(api=gpu_api, n=3000, columns=100, device=dev)
+        w.SetAllowSleeping(False)
+        w.StepN(DT, 8, 3, 40)
+        sb, n = w.read_bodies()
+        states.append([(sb[i].c.x, sb[i].c.y, sb[i].a, sb[i].v.x, sb[i].v.y, sb[i].w) for i in range(n)])
+        w.close()
+    assert states[0] == states[1]
+
+
 def test_stats_allreduce_through_nccl(gpu_api):
     """dbx_stats_allreduce (the batched path's only collective): sums and maxima through a real NCCL
     communicator created by the host program -- here a one-rank communicator from ncclCommInitAll, so the reduction must
