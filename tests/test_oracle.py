@@ -258,6 +258,61 @@ def test_state_import_round_trip_and_ordered_step(oracle_api):
     assert bytes(a)[:na * C.sizeof(A.BodyState)] != bytes(b)[:nb * C.sizeof(A.BodyState)]
 
 
+def test_pile_generator_draws_from_std_mt19937():
+    """SURVEY.md 8(d) names std::mt19937(12345) for the pile's jitter.  scenes.Mt19937 against the generator's known answers (the
+    C++ standard's check value: the 10,000th output of a default-constructed mt19937 is 4123659995) and numpy's legacy stream
+    (init_genrand seeding, the same as std::mt19937(seed)); the pile built from it is the same scene every time."""
+    import numpy as np
+    r = scenes.Mt19937(5489)
+    first = r.draw()
+    for _ in range(9998):
+        r.draw()
+    assert first == 3499211612 and r.draw() == 4123659995
+    r = scenes.Mt19937(12345)
+    ref = np.random.RandomState(12345).randint(0, 2 ** 32, size=2000, dtype=np.uint64)
+    assert [r.draw() for _ in range(2000)] == [int(x) for x in ref]
+    r = scenes.Mt19937(12345)
+    us = [r.uniform(-0.01, 0.01) for _ in range(5000)]
+    assert min(us) >= -0.01 and max(us) < 0.01 and abs(sum(us) / len(us)) < 5e-4
+    # (x, y, shape) per body, in body order: body 0 of the pile sits at the first two draws
+    r = scenes.Mt19937(12345)
+    jx, jy = r.uniform(-0.01, 0.01), r.uniform(-0.01, 0.01)
+    from oracle import orc
+    w, bodies, _ = scenes.pile(api=orc.api(), n=40, columns=10, joints=False)
+    p = bodies[0].GetPosition()
+    assert p.x == scenes.f32(scenes.f32(-1.05 * 10 * 0.5 + 0.525) + jx) and p.y == scenes.f32(0.55 + jy)
+    w.close()
+
+
+def test_one_way_platform_with_continuous_physics_on_the_oracle(oracle_api):
+    """The PreSolve decision of a step stands through the TOI loop's re-evaluations, and the listener can be asked ahead of a first
+    touch that happens there (include/dbox_b200.h, "PreSolve"): the oracle's side of tests/test_gpu_features.py::
+    test_pre_solve_split_step[True] -- a box shot upwards passes a one-way platform with continuous physics on, and is stopped
+    by it when nobody is asked ahead."""
+    from dbox_b200.world import b2BodyDef, b2EdgeShape, b2PolygonShape, b2World, b2_dynamicBody
+
+    def run(lookahead):
+        w = b2World((0.0, -10.0), api=oracle_api)
+        g = w.CreateBody(b2BodyDef()); e = b2EdgeShape(oracle_api); e.Set((-40.0, 0.0), (40.0, 0.0)); g.CreateFixture(e, 0.0)
+        plat = w.CreateBody(b2BodyDef()); ps = b2PolygonShape(oracle_api); ps.SetAsBox(3.0, 0.25, (0.0, 6.0), 0.0)
+        pf = plat.CreateFixture(ps, 0.0).id
+        bd = b2BodyDef(); bd.type = b2_dynamicBody; bd.position.Set(0.0, 3.0)
+        up = w.CreateBody(bd); s = b2PolygonShape(oracle_api); s.SetAsBox(0.5, 0.5); up.CreateFixture(s, 1.0)
+        up.SetLinearVelocity((0.0, 14.0))
+
+        def pre_solve(c):
+            if pf in (c.fixtureA, c.fixtureB):
+                return {"enabled": up.GetLinearVelocity().y <= 0.0}
+            return None
+        for _ in range(150):
+            w.StepWithPreSolve(DT, 8, 3, pre_solve, toi_lookahead=lookahead)
+        y = up.GetPosition().y
+        w.close()
+        return y
+    assert 6.7 < run(True) < 6.85          # through the platform on the way up, resting on it afterwards
+    assert run(False) < 1.0                 # first touch inside the TOI loop, nobody asked: the platform is solid from below
+
+
 def test_oracle_matches_reference_golden():
     """tests/golden/reference_golden.json = output of oracle/dref/harness.d linked against the UNMODIFIED dbox (oracle/dref/build.sh,
     needs a D compiler).  When the file is there, the oracle's own goldens must equal it bit for bit; while it is not, the oracle is
